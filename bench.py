@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""Benchmark of the OCR4All pixel-classifier inference hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (our arm)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+One "step" = one pass of the hot path (prepare_images -> fcn_skip forward ->
+softmax/argmax -> colour masks) over one batch of 64 synthetic A4-300dpi pages per
+GPU (BASELINE.json configs[1]).  Pages are sharded page-wise over ranks with no
+collective on the data path ("weak" scaling: the per-GPU batch is fixed).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from page_segmentation_b200 import synth  # noqa: E402
+
+ARCH = "fcn_skip"
+N_CLASSES = 3
+LINE_HEIGHT = 18
+TARGET_LH = 6
+SCALE = TARGET_LH / LINE_HEIGHT
+LUT = np.array([[255, 255, 255], [255, 0, 0], [0, 255, 0]], dtype=np.uint8)
+GFLOP_PER_PAGE = {"fcn_skip": 111.999, "fcn": 101.97, "unet": 1639.684}
+# algorithmic GFLOP of the single layers at the 1184x832 grid (2 * GMAC of appendix E)
+LAYER_GFLOP = {"conv1": 0.985, "conv2": 29.553, "conv3": 14.776, "conv4": 19.702, "conv5": 7.388, "conv6": 11.082,
+               "conv7": 3.694, "deconv1": 4.925, "deconv2": 0.591, "deconv3": 14.776, "deconv4": 1.478, "head": 3.048}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_pages_per_s(n_pages, warm=1):
+    """The reference's CPU path restated (oracle port): dataset.py prepare_images ->
+    model_fcn_skip (torch-CPU fp32, oneDNN, all host threads) -> softmax/argmax ->
+    generate_output_masks, batch 1 like predictor.py:27-30."""
+    import torch
+    from oracle import network as onet
+    from oracle import pipeline as opipe
+    weights = synth.make_weights(ARCH, N_CLASSES, seed=0)
+    fwd = onet.Forward(ARCH, weights, N_CLASSES)
+    lut = {i: tuple(int(v) for v in LUT[i]) for i in range(N_CLASSES)}
+    pages = [synth.make_page(s) for s in range(max(1, min(2, n_pages + warm)))]
+
+    def one(page):
+        img, b = opipe.prepare_images(page, page, TARGET_LH, LINE_HEIGHT)
+        logit, prob, pred = fwd.predict(img)
+        return opipe.generate_output_masks(b, pred, lut)
+
+    for i in range(warm):
+        one(pages[i % len(pages)])
+    t0 = time.perf_counter()
+    for i in range(n_pages):
+        one(pages[i % len(pages)])
+    dt = time.perf_counter() - t0
+    return n_pages / dt, torch.get_num_threads()
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    per_step = 2
+    for _ in range(args.warmup):
+        cpu_reference_pages_per_s(1, warm=0)
+    t0 = time.perf_counter()
+    pps = []
+    cores = 1
+    for _ in range(args.steps):
+        v, cores = cpu_reference_pages_per_s(per_step, warm=0)
+        pps.append(v)
+    dt = time.perf_counter() - t0
+    value = per_step * args.steps / sum(per_step / v for v in pps)
+    line = {
+        "impl": "reference", "metric": "pages_per_sec", "value": value, "unit": "pages/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "mpixel_per_sec": value * synth.A4_MPX,
+        "config": {"workload": f"{ARCH} predict, synthetic 2480x3508 binarised pages, line_height_px=18, "
+                               f"random-init weights; {per_step} pages per step (bounded sample), batch 1",
+                   "arch": ARCH, "n_classes": N_CLASSES},
+        "cpu_baseline": {"value": value, "unit": "pages/s", "cores": cores, "kind": "port",
+                         "sample": f"{per_step} pages per step x {args.steps} steps; oracle port of the reference's "
+                                   "TF/skimage CPU path (torch-CPU fp32 convs + numpy), TF itself is not installable here"},
+        "e2e": {"value": value, "unit": "pages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pages", type=int, default=64, help="pages per GPU per step")
+    ap.add_argument("--precision", default=os.environ.get("PCSEG_PRECISION", "bf16"), choices=["bf16", "fp16"])
+    ap.add_argument("--engine", default=os.environ.get("PCSEG_ENGINE", "umma"), choices=["umma", "direct"])
+    ap.add_argument("--arch", default=ARCH, choices=["fcn_skip", "fcn", "unet"])
+    ap.add_argument("--cpu-pages", type=int, default=3, help="pages of the CPU-baseline sample (rank 0, N=1)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from page_segmentation_b200.runtime import PageBatchEngine
+    assert torch.cuda.is_available(), "bench.py needs a B200; there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    arch = args.arch
+    weights = synth.make_weights(arch, N_CLASSES, seed=0)
+    eng = PageBatchEngine(arch, weights, N_CLASSES, precision=args.precision, device=local_rank, lut=LUT,
+                          engine=args.engine)
+    n = args.pages
+    distinct = min(n, 8)
+    base = np.stack([synth.make_page(rank * 1000 + s) for s in range(distinct)])
+    h_pages = torch.empty((n, synth.A4_H, synth.A4_W), dtype=torch.uint8).pin_memory()
+    for i in range(n):
+        h_pages[i] = torch.from_numpy(base[i % distinct])
+    d_pages = h_pages.to(dev)
+    Hs, Ws = synth.scaled_shape(synth.A4_H, synth.A4_W, SCALE)
+    h_out = {k: torch.empty((n, Hs, Ws) + ((3,) if k != "labels" else ()), dtype=torch.uint8).pin_memory()
+             for k in ("labels", "color", "overlay", "inverted")}
+    h_out_np = {k: v.numpy() for k, v in h_out.items()}
+    h_pages_np = h_pages.numpy()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput ----------------
+    for _ in range(args.warmup):
+        eng.run_device(d_pages, SCALE)
+    eng.ctx.set_timing(True)
+    stage_ms = {}
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        eng.run_device(d_pages, SCALE)
+        if rank == 0:
+            for k, v in eng.ctx.timings():      # syncs; outside the event bracket it would hide launch gaps
+                stage_ms[k] = stage_ms.get(k, 0.0) + v
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    launches = eng.ctx.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    eng.ctx.set_timing(False)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * n * args.steps / (ms_max / 1e3)
+
+    # ---------------- end to end through the host-buffer C ABI ----------------
+    for _ in range(max(1, args.warmup // 2)):
+        eng.run_host(h_pages_np, SCALE, h_out_np)
+    sync_all()
+    e0.record()
+    for _ in range(args.steps):
+        eng.run_host(h_pages_np, SCALE, h_out_np)
+    e1.record()
+    sync_all()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * args.steps / (float(t.item()) / 1e3)
+    h2d = int(h_pages_np.nbytes)
+    d2h = int(sum(v.nbytes for v in h_out_np.values()))
+
+    if rank == 0:
+        hbm_peak, tf_peak, which = peaks()
+        # dominant kernel = the slowest stage of the step
+        per_step = {k: v / args.steps for k, v in stage_ms.items()}
+        dom = max((k for k in per_step if k in LAYER_GFLOP), key=lambda k: per_step[k], default=None)
+        roofline = None
+        if dom is not None and arch == "fcn_skip":
+            tflops = LAYER_GFLOP[dom] * n / per_step[dom]          # GFLOP / ms == TFLOP/s
+            roofline = {"bound": "tensor", "kernel": dom, "achieved": tflops, "peak": tf_peak, "unit": "TFLOP/s",
+                        "frac": tflops / tf_peak, "traffic": None, "peak_source": f"{which} (sustained bf16)",
+                        "whole_body_tflops": GFLOP_PER_PAGE[arch] * n / sum(
+                            v for k, v in per_step.items() if k not in ("preprocess",)),
+                        "stage_ms_per_step": {k: round(v, 4) for k, v in per_step.items()}}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            v, cores = cpu_reference_pages_per_s(args.cpu_pages)
+            cpu = {"value": v, "unit": "pages/s", "cores": cores, "kind": "port",
+                   "sample": f"{args.cpu_pages} synthetic A4 pages after 1 warm-up, batch 1: oracle port of the "
+                             "reference CPU path (numpy/skimage-restated preprocess, torch-CPU fp32 fcn_skip, "
+                             "scipy softmax, numpy masks)"}
+        line = {
+            "metric": "pages_per_sec", "value": value, "unit": "pages/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "mpixel_per_sec": value * synth.A4_MPX,
+            "config": {"workload": f"{arch} predict, {n} synthetic 2480x3508 binarised pages per GPU per step "
+                                   f"(BASELINE configs[1]), line_height_px=18 -> 1169x827, random-init weights, "
+                                   f"preprocess + network + argmax + colour masks",
+                       "arch": arch, "n_classes": N_CLASSES, "pages_per_gpu": n, "engine": args.engine,
+                       "l2": "inputs larger than L2 (557 MB of pages per step)", "distinct_pages": distinct},
+            "e2e": {"value": e2e_value, "unit": "pages/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,178 @@
+/*
+ * pcseg_b200 - C ABI of the B200-native (sm_100a) OCR4All pixel-classifier
+ * inference hot path.
+ *
+ * The reference (ocr4all_pixel_classifier 0.6.5) is pure Python and has no FFI;
+ * its hot path is the Python API of lib/predictor.py, lib/network.py,
+ * lib/dataset.py, lib/output.py and lib/postprocess.py.  Every entry point
+ * below names the reference function (file:line under
+ * ocr4all_pixel_classifier/) whose arithmetic it replaces.  The Python shim in
+ * page_segmentation_b200/lib/ binds these symbols with ctypes and re-exposes
+ * the reference's class / function names on top of them.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative pcs_status;
+ *     pcs_last_error(ctx) returns a message for the last failure on that ctx;
+ *   - no exceptions and no ownership cross the ABI: all in/out buffers are
+ *     caller-allocated; activations/workspace are owned by the ctx;
+ *   - pointers named d_* are DEVICE pointers on the ctx's device, pointers
+ *     named h_* are HOST pointers (pinned memory makes the copies async);
+ *   - all work is enqueued on the ctx's stream (pcs_set_stream); functions are
+ *     asynchronous with respect to that stream unless stated otherwise;
+ *   - one ctx per GPU per host thread (thread-compatible, not thread-safe);
+ *   - images are row-major, pages of a batch are contiguous ([n][H][W]...).
+ */
+#ifndef PCSEG_B200_H
+#define PCSEG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCS_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define PCS_API __attribute__((visibility("default")))
+#else
+#define PCS_API
+#endif
+
+typedef struct pcs_ctx pcs_ctx;
+
+typedef enum {
+    PCS_OK = 0,
+    PCS_ERR_ARG = -1,       /* bad argument / unsupported configuration */
+    PCS_ERR_CUDA = -2,      /* CUDA runtime or driver error (see pcs_last_error) */
+    PCS_ERR_STATE = -3,     /* call order: e.g. forward before model load */
+    PCS_ERR_NOMEM = -4,     /* device allocation failed */
+    PCS_ERR_DEVICE = -5     /* not an sm_100 device */
+} pcs_status;
+
+/* Architecture.value strings of lib/architecture.py:6-11 that are in scope. */
+typedef enum { PCS_ARCH_FCN_SKIP = 0, PCS_ARCH_FCN = 1, PCS_ARCH_UNET = 2 } pcs_arch;
+
+/* Operand type of the tensor-core convolutions (accumulation is always fp32). */
+typedef enum { PCS_PREC_BF16 = 0, PCS_PREC_FP16 = 1 } pcs_precision;
+
+/* Which convolution engine runs the body: hand-written tcgen05/TMEM/TMA
+ * implicit GEMM (default) or the CUDA-core direct kernels (numerics twin). */
+typedef enum { PCS_ENGINE_UMMA = 0, PCS_ENGINE_DIRECT = 1 } pcs_engine;
+
+/* One layer's weights exactly as Keras stores them (lib/model.py:45-92,
+ * :151-203, :206-234): Conv2D kernel (kh,kw,C_in,C_out), Conv2DTranspose
+ * kernel (kh,kw,C_out,C_in), both float32 row-major; bias (C_out). */
+typedef struct {
+    const float* kernel;
+    const float* bias;
+    int32_t shape[4];
+} pcs_layer_weights;
+
+/* ---- context -------------------------------------------------------- */
+PCS_API int pcs_abi_version(void);
+PCS_API int pcs_ctx_create(int device, pcs_ctx** out);
+PCS_API void pcs_ctx_destroy(pcs_ctx* ctx);
+PCS_API const char* pcs_last_error(const pcs_ctx* ctx);
+PCS_API int pcs_set_stream(pcs_ctx* ctx, void* cuda_stream);
+PCS_API int pcs_synchronize(pcs_ctx* ctx);
+/* number of kernels this library launched on ctx since creation */
+PCS_API int64_t pcs_launch_count(const pcs_ctx* ctx);
+
+/* ---- model: replaces Network.__init__ weight loading, lib/network.py:75-107
+ * (the .h5 container is parsed on the host side; this uploads the tensors in
+ * Keras layer order, pre-transformed for the kernels).  Synchronous. */
+PCS_API int pcs_model_load(pcs_ctx* ctx, int arch, int n_classes, int precision,
+                   const pcs_layer_weights* layers, int n_layers);
+PCS_API int pcs_set_engine(pcs_ctx* ctx, int engine);
+
+/* ---- preprocess: replaces prepare_images, lib/dataset.py:131-150 (with
+ * scale_binary :114-119 and scale_image :122-128, i.e. skimage rescale order 0
+ * / resize order 3, mode='reflect', clip, preserve_range).
+ *   d_grey, d_bin : [n][H][W] uint8 source pages (may alias, dataset.py:169-172)
+ *   Hs, Ws        : np.round(scale * (H, W)) computed by the caller
+ *   d_image       : [n][Hs][Ws] uint8  `data.image`  (inverted, truncated)
+ *   d_binary      : [n][Hs][Ws] uint8  `data.binary` in {0,1}, 1 = ink
+ *   d_orig_binary : [n][H][W] uint8 `data.orig_binary` or NULL
+ * The anti-aliasing Gaussian of resize() is applied per page when the page has
+ * more than two grey levels, as dataset.py:127 decides. */
+PCS_API int pcs_preprocess(pcs_ctx* ctx, const uint8_t* d_grey, const uint8_t* d_bin,
+                   int n, int H, int W, int Hs, int Ws,
+                   uint8_t* d_image, uint8_t* d_binary, uint8_t* d_orig_binary);
+
+/* ---- network body + head: replaces Network.predict_single_data,
+ * lib/network.py:248-260 = default_preprocess x/255 (architecture.py:67-68),
+ * the Keras graph (model.py:45-92 / :206-234 / :151-203 incl. pad :20-26 and
+ * crop :29-42), scipy softmax and np.argmax; optionally fused with the colour
+ * epilogue generate_output_masks, lib/output.py:44-60.
+ *   d_image  : [n][Hs][Ws] uint8 network input (`data.image`)
+ *   d_binary : [n][Hs][Ws] uint8 {0,1} (only read when masks are requested)
+ *   d_labels : [n][Hs][Ws] uint8 argmax class (ties -> lowest index)
+ *   d_logits, d_prob : [n][Hs][Ws][n_classes] float32 or NULL
+ *   lut      : n_classes x 3 uint8 HOST array (ColorMap label -> rgb) or NULL
+ *   d_color, d_overlay, d_inverted : [n][Hs][Ws][3] uint8 or NULL */
+PCS_API int pcs_forward(pcs_ctx* ctx, const uint8_t* d_image, const uint8_t* d_binary,
+                int n, int Hs, int Ws,
+                uint8_t* d_labels, float* d_logits, float* d_prob,
+                const uint8_t* lut, uint8_t* d_color, uint8_t* d_overlay, uint8_t* d_inverted);
+
+/* ---- colour epilogue on an existing class map: replaces
+ * generate_output_masks, lib/output.py:44-60 (fg_color_mask == inverted). */
+PCS_API int pcs_masks(pcs_ctx* ctx, const uint8_t* d_labels, const uint8_t* d_binary,
+              int n, int H, int W, const uint8_t* lut, int n_lut,
+              uint8_t* d_color, uint8_t* d_overlay, uint8_t* d_inverted);
+
+/* ---- nearest-neighbour resize: replaces preserving_resize, lib/util.py:21-29
+ * as used by scale_to_original_shape, lib/output.py:63-79 (uint8 planes). */
+PCS_API int pcs_resize_nearest(pcs_ctx* ctx, const uint8_t* d_src, int n, int H, int W,
+                       uint8_t* d_dst, int Ho, int Wo);
+
+/* ---- connected components, 4-connectivity: replaces
+ * cv2.connectedComponentsWithStats(img, connectivity=4) as called at
+ * lib/postprocess.py:10,33 and lib/image_ops.py:68.  Labels are numbered in
+ * raster order of each component's first pixel (label 0 = background).
+ *   d_img     : [n][H][W] uint8, nonzero = foreground
+ *   d_labels  : [n][H][W] int32
+ *   d_stats   : [n][max_components][5] int32 (left, top, width, height, area),
+ *               row 0 = background, or NULL
+ *   d_ncomp   : [n] int32 number of labels incl. background */
+PCS_API int pcs_ccl(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W,
+            int32_t* d_labels, int32_t* d_stats, int max_components, int32_t* d_ncomp);
+
+/* ---- replaces vote_connected_component_class, lib/postprocess.py:9-26:
+ * every 4-connected component of d_binary gets the most frequent class of
+ * d_pred inside it (ties -> lowest class); in place on d_pred. */
+PCS_API int pcs_cc_majority(pcs_ctx* ctx, uint8_t* d_pred, const uint8_t* d_binary,
+                    int n, int H, int W, int n_classes);
+
+/* ---- replaces add_bounding_boxes, lib/postprocess.py:29-42 (evident intent:
+ * per class c ascending, every component of pred==c paints its bbox with c). */
+PCS_API int pcs_bounding_boxes(pcs_ctx* ctx, const uint8_t* d_pred, int n, int H, int W,
+                       int n_classes, uint8_t* d_out);
+
+/* ---- whole page batch through the pipeline with HOST buffers (the copies are
+ * part of the call): prepare_images -> predict_single_data -> optional
+ * cc_majority -> generate_output_masks.  Synchronous.  Any output may be NULL.
+ *   h_grey/h_bin  : [n][H][W] uint8;  h_labels : [n][Hs][Ws] uint8;
+ *   h_color/h_overlay/h_inverted : [n][Hs][Ws][3] uint8 */
+PCS_API int pcs_predict_pages_host(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h_bin,
+                           int n, int H, int W, int Hs, int Ws, int cc_majority,
+                           const uint8_t* lut,
+                           uint8_t* h_image, uint8_t* h_binary, uint8_t* h_labels,
+                           uint8_t* h_color, uint8_t* h_overlay, uint8_t* h_inverted);
+
+/* ---- diagnostics ------------------------------------------------------ */
+/* copies one named internal activation of the last pcs_forward to a float32
+ * NHWC host buffer (real channels only); returns the channel count or <0. */
+PCS_API int pcs_debug_activation(pcs_ctx* ctx, const char* name, float* h_out, size_t capacity_floats,
+                         int32_t* shape4);
+/* enable (1) / disable (0) CUDA-event timing of every stage of the next calls */
+PCS_API int pcs_set_timing(pcs_ctx* ctx, int enabled);
+/* device time in ms of the stages since the last pcs_forward began ("name:ms;"...) */
+PCS_API const char* pcs_last_timings(pcs_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCSEG_B200_H */

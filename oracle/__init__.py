@@ -1,0 +1,16 @@
+"""CPU oracle for the OCR4All pixel-classifier inference hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in `page_segmentation_b200/` may import this
+package; only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s CPU-baseline
+/ `--impl reference` legs use it, and there only as the checker or as the timed
+CPU arm - never as the product path.
+
+PARITY UNPINNED: the reference (`ocr4all_pixel_classifier` 0.6.5) ships no
+tests, golden vectors or fixtures, and its arithmetic lives in third-party
+packages that are not installed here and cannot be (tensorflow==2.5.0,
+scikit-image==0.17.2, ocr4all-pylib==0.2.6, h5py==3.1.0; SURVEY.md section
+8(c)).  This oracle therefore restates those packages' published algorithms at
+the reference's own call sites (each function cites the reference file:line it
+follows) and is pinned by hand-computed known-answer tests plus cv2 4.13
+(installed) as a live oracle for connected components.
+"""

@@ -1,0 +1,241 @@
+"""ctypes binding of libpcseg_b200.so (the C ABI in include/pcseg_b200.h).
+
+There is deliberately no CPU or PyTorch fallback: if the shared library is
+missing or the device is not an sm_100 GPU every compute entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpcseg_b200.so")
+
+ARCH_IDS = {"fcn_skip": 0, "fcn": 1, "unet": 2}
+PRECISIONS = {"bf16": 0, "fp16": 1}
+ENGINES = {"umma": 0, "direct": 1}
+
+EXPORTS = [
+    "pcs_abi_version", "pcs_ctx_create", "pcs_ctx_destroy", "pcs_last_error", "pcs_set_stream",
+    "pcs_synchronize", "pcs_launch_count", "pcs_model_load", "pcs_set_engine", "pcs_preprocess",
+    "pcs_forward", "pcs_masks", "pcs_resize_nearest", "pcs_ccl", "pcs_cc_majority",
+    "pcs_bounding_boxes", "pcs_predict_pages_host", "pcs_debug_activation", "pcs_set_timing",
+    "pcs_last_timings",
+]
+
+
+class PcsError(RuntimeError):
+    pass
+
+
+class LayerWeights(C.Structure):
+    _fields_ = [("kernel", C.c_void_p), ("bias", C.c_void_p), ("shape", C.c_int32 * 4)]
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the in-tree shared library (built by page_segmentation_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PcsError(
+            f"{LIB_PATH} is missing: run `python -m page_segmentation_b200.build` "
+            "(there is no CPU fallback for the hot path)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, u8p = C.c_void_p, C.c_int, C.c_void_p
+    lib.pcs_abi_version.restype = C.c_int
+    lib.pcs_ctx_create.argtypes = [i32, C.POINTER(vp)]
+    lib.pcs_ctx_destroy.argtypes = [vp]
+    lib.pcs_ctx_destroy.restype = None
+    lib.pcs_last_error.argtypes = [vp]
+    lib.pcs_last_error.restype = C.c_char_p
+    lib.pcs_set_stream.argtypes = [vp, vp]
+    lib.pcs_synchronize.argtypes = [vp]
+    lib.pcs_launch_count.argtypes = [vp]
+    lib.pcs_launch_count.restype = C.c_int64
+    lib.pcs_model_load.argtypes = [vp, i32, i32, i32, C.POINTER(LayerWeights), i32]
+    lib.pcs_set_engine.argtypes = [vp, i32]
+    lib.pcs_preprocess.argtypes = [vp, u8p, u8p, i32, i32, i32, i32, i32, u8p, u8p, u8p]
+    lib.pcs_forward.argtypes = [vp, u8p, u8p, i32, i32, i32, u8p, vp, vp, vp, u8p, u8p, u8p]
+    lib.pcs_masks.argtypes = [vp, u8p, u8p, i32, i32, i32, vp, i32, u8p, u8p, u8p]
+    lib.pcs_resize_nearest.argtypes = [vp, u8p, i32, i32, i32, u8p, i32, i32]
+    lib.pcs_ccl.argtypes = [vp, u8p, i32, i32, i32, vp, vp, i32, vp]
+    lib.pcs_cc_majority.argtypes = [vp, u8p, u8p, i32, i32, i32, i32]
+    lib.pcs_bounding_boxes.argtypes = [vp, u8p, i32, i32, i32, i32, u8p]
+    lib.pcs_predict_pages_host.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
+    lib.pcs_debug_activation.argtypes = [vp, C.c_char_p, vp, C.c_size_t, C.POINTER(C.c_int32)]
+    lib.pcs_set_timing.argtypes = [vp, i32]
+    lib.pcs_last_timings.argtypes = [vp]
+    lib.pcs_last_timings.restype = C.c_char_p
+    if lib.pcs_abi_version() != 1:
+        raise PcsError("libpcseg_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def _ptr(t) -> Optional[int]:
+    """Device/host pointer of a torch tensor / numpy array / None."""
+    if t is None:
+        return None
+    if isinstance(t, np.ndarray):
+        if not t.flags["C_CONTIGUOUS"]:
+            raise PcsError("numpy buffer must be C-contiguous")
+        return t.ctypes.data
+    if not t.is_contiguous():
+        raise PcsError("tensor must be contiguous")
+    return t.data_ptr()
+
+
+class Context:
+    """One pcs_ctx: one GPU, one stream, one loaded model."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load()
+        self.device = int(device)
+        h = C.c_void_p()
+        rc = self.lib.pcs_ctx_create(self.device, C.byref(h))
+        if rc != 0:
+            raise PcsError(f"pcs_ctx_create(device={device}) failed with status {rc} "
+                           "(needs a CUDA sm_100 / B200 device; no fallback exists)")
+        self.h = h
+        self.model: Optional[Tuple[str, int, str]] = None
+        self._keepalive = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pcs_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            msg = self.lib.pcs_last_error(self.h)
+            raise PcsError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    # -- plumbing ----------------------------------------------------------
+    def set_stream(self, cuda_stream: int):
+        self._check(self.lib.pcs_set_stream(self.h, C.c_void_p(cuda_stream)), "pcs_set_stream")
+
+    def use_torch_stream(self):
+        import torch
+        self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def synchronize(self):
+        self._check(self.lib.pcs_synchronize(self.h), "pcs_synchronize")
+
+    def launch_count(self) -> int:
+        return int(self.lib.pcs_launch_count(self.h))
+
+    def set_engine(self, engine: str):
+        self._check(self.lib.pcs_set_engine(self.h, ENGINES[engine]), "pcs_set_engine")
+
+    def set_timing(self, enabled: bool):
+        self._check(self.lib.pcs_set_timing(self.h, 1 if enabled else 0), "pcs_set_timing")
+
+    def timings(self):
+        s = self.lib.pcs_last_timings(self.h).decode()
+        out = []
+        for item in s.split(";"):
+            if item:
+                k, v = item.rsplit(":", 1)
+                out.append((k, float(v)))
+        return out
+
+    # -- model ---------------------------------------------------------------
+    def load_model(self, arch: str, n_classes: int, weights: Sequence[Tuple[np.ndarray, np.ndarray]],
+                   precision: str = "bf16"):
+        arr = (LayerWeights * len(weights))()
+        keep = []
+        for i, (k, b) in enumerate(weights):
+            k = np.ascontiguousarray(k, dtype=np.float32)
+            b = np.ascontiguousarray(b, dtype=np.float32)
+            if k.ndim != 4:
+                raise PcsError(f"layer {i}: kernel must be 4-D, got shape {k.shape}")
+            keep.append((k, b))
+            arr[i].kernel = k.ctypes.data
+            arr[i].bias = b.ctypes.data
+            for d in range(4):
+                arr[i].shape[d] = k.shape[d]
+            if b.ndim != 1:
+                raise PcsError(f"layer {i}: bias must be 1-D")
+        self._check(self.lib.pcs_model_load(self.h, ARCH_IDS[arch], int(n_classes), PRECISIONS[precision],
+                                            arr, len(weights)), "pcs_model_load")
+        self.model = (arch, int(n_classes), precision)
+
+    # -- stages (device pointers) ----------------------------------------------
+    def preprocess(self, d_grey, d_bin, n, H, W, Hs, Ws, d_image, d_binary, d_orig_binary=None):
+        self._check(self.lib.pcs_preprocess(self.h, _ptr(d_grey), _ptr(d_bin), n, H, W, Hs, Ws, _ptr(d_image),
+                                            _ptr(d_binary), _ptr(d_orig_binary)), "pcs_preprocess")
+
+    def forward(self, d_image, d_binary, n, Hs, Ws, d_labels, d_logits=None, d_prob=None, lut=None,
+                d_color=None, d_overlay=None, d_inverted=None):
+        lut_arr = None if lut is None else np.ascontiguousarray(lut, dtype=np.uint8)
+        self._check(self.lib.pcs_forward(self.h, _ptr(d_image), _ptr(d_binary), n, Hs, Ws, _ptr(d_labels),
+                                         _ptr(d_logits), _ptr(d_prob), _ptr(lut_arr), _ptr(d_color),
+                                         _ptr(d_overlay), _ptr(d_inverted)), "pcs_forward")
+
+    def masks(self, d_labels, d_binary, n, H, W, lut, d_color, d_overlay, d_inverted):
+        lut_arr = np.ascontiguousarray(lut, dtype=np.uint8)
+        self._check(self.lib.pcs_masks(self.h, _ptr(d_labels), _ptr(d_binary), n, H, W, _ptr(lut_arr),
+                                       lut_arr.shape[0], _ptr(d_color), _ptr(d_overlay), _ptr(d_inverted)),
+                    "pcs_masks")
+
+    def resize_nearest(self, d_src, n, H, W, d_dst, Ho, Wo):
+        self._check(self.lib.pcs_resize_nearest(self.h, _ptr(d_src), n, H, W, _ptr(d_dst), Ho, Wo),
+                    "pcs_resize_nearest")
+
+    def ccl(self, d_img, n, H, W, d_labels, d_stats=None, max_components=0, d_ncomp=None):
+        self._check(self.lib.pcs_ccl(self.h, _ptr(d_img), n, H, W, _ptr(d_labels), _ptr(d_stats),
+                                     int(max_components), _ptr(d_ncomp)), "pcs_ccl")
+
+    def cc_majority(self, d_pred, d_binary, n, H, W, n_classes):
+        self._check(self.lib.pcs_cc_majority(self.h, _ptr(d_pred), _ptr(d_binary), n, H, W, n_classes),
+                    "pcs_cc_majority")
+
+    def bounding_boxes(self, d_pred, n, H, W, n_classes, d_out):
+        self._check(self.lib.pcs_bounding_boxes(self.h, _ptr(d_pred), n, H, W, n_classes, _ptr(d_out)),
+                    "pcs_bounding_boxes")
+
+    # -- whole pipeline, host buffers ----------------------------------------
+    def predict_pages_host(self, h_grey, h_bin, n, H, W, Hs, Ws, cc_majority=False, lut=None, h_image=None,
+                           h_binary=None, h_labels=None, h_color=None, h_overlay=None, h_inverted=None):
+        lut_arr = None if lut is None else np.ascontiguousarray(lut, dtype=np.uint8)
+        self._check(self.lib.pcs_predict_pages_host(
+            self.h, _ptr(h_grey), _ptr(h_bin), n, H, W, Hs, Ws, 1 if cc_majority else 0, _ptr(lut_arr),
+            _ptr(h_image), _ptr(h_binary), _ptr(h_labels), _ptr(h_color), _ptr(h_overlay), _ptr(h_inverted)),
+            "pcs_predict_pages_host")
+
+    # -- diagnostics -----------------------------------------------------------
+    def debug_activation(self, name: str) -> np.ndarray:
+        shape = (C.c_int32 * 4)()
+        c = self.lib.pcs_debug_activation(self.h, name.encode(), None, 0, shape)
+        if c < 0:
+            self._check(c, "pcs_debug_activation")
+        out = np.empty(tuple(shape), dtype=np.float32)
+        c = self.lib.pcs_debug_activation(self.h, name.encode(), out.ctypes.data, out.size, shape)
+        if c < 0:
+            self._check(c, "pcs_debug_activation")
+        return out
+
+
+_contexts = {}
+
+
+def context(device: int = 0) -> Context:
+    """Process-wide Context per device (created on first use)."""
+    ctx = _contexts.get(device)
+    if ctx is None:
+        ctx = Context(device)
+        _contexts[device] = ctx
+    return ctx

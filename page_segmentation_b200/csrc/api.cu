@@ -1,0 +1,657 @@
+// C ABI of pcseg_b200 (see include/pcseg_b200.h): context, model upload, the
+// per-architecture forward schedules and the page-batch pipeline.
+#include "common.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+
+namespace pcs {
+
+int set_err(pcs_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+int arena_reserve(pcs_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->arena_bytes) return PCS_OK;
+    if (ctx->arena_used != 0 && ctx->arena) {
+        // growing while allocations are live would invalidate them
+        return set_err(ctx, PCS_ERR_STATE, "arena grow requested with live allocations (%zu > %zu)", bytes, ctx->arena_bytes);
+    }
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->arena) cudaFree(ctx->arena);
+    ctx->arena = nullptr;
+    ctx->arena_bytes = 0;
+    const size_t want = bytes + bytes / 16 + (1u << 20);
+    if (cudaMalloc(&ctx->arena, want) != cudaSuccess) {
+        cudaGetLastError();
+        return set_err(ctx, PCS_ERR_NOMEM, "cudaMalloc of %zu bytes for the activation arena failed", want);
+    }
+    ctx->arena_bytes = want;
+    return PCS_OK;
+}
+
+void* arena_alloc(pcs_ctx* ctx, size_t bytes) {
+    const size_t off = (ctx->arena_used + 255) / 256 * 256;
+    if (off + bytes > ctx->arena_bytes) return nullptr;
+    ctx->arena_used = off + bytes;
+    return ctx->arena + off;
+}
+
+int scratch_reserve(pcs_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->scratch_bytes) return PCS_OK;
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    ctx->scratch = nullptr;
+    ctx->scratch_bytes = 0;
+    const size_t want = bytes + bytes / 8 + 4096;
+    if (cudaMalloc(&ctx->scratch, want) != cudaSuccess) {
+        cudaGetLastError();
+        return set_err(ctx, PCS_ERR_NOMEM, "cudaMalloc of %zu bytes of scratch failed", want);
+    }
+    ctx->scratch_bytes = want;
+    return PCS_OK;
+}
+
+// ---------------------------------------------------------------------------
+// layer tables (Keras creation order; ocr4all_pixel_classifier/lib/model.py)
+// ---------------------------------------------------------------------------
+struct LayerSpec { const char* name; int kind; int k; int cin; int cout; int relu; };
+enum { K_CONV = 0, K_DECONV = 1, K_DECONV_S2 = 2, K_LOGITS = 3 };
+
+static const LayerSpec kFcnSkip[] = {   // model.py:45-92
+    {"conv1", K_CONV, 5, 1, 20, 1},      {"conv2", K_CONV, 5, 20, 30, 0},    {"conv3", K_CONV, 5, 30, 40, 1},
+    {"conv4", K_CONV, 5, 40, 40, 0},     {"conv5", K_CONV, 5, 40, 60, 1},    {"conv6", K_CONV, 5, 60, 60, 0},
+    {"conv7", K_CONV, 5, 60, 80, 1},     {"deconv1", K_DECONV, 5, 80, 80, 1}, {"deconv2", K_DECONV_S2, 2, 80, 60, 1},
+    {"deconv3", K_DECONV, 5, 120, 40, 1}, {"deconv4", K_DECONV_S2, 2, 100, 30, 1},
+    {"deconv5", K_DECONV_S2, 2, 70, 20, 0}, {"logits", K_LOGITS, 1, 50, -1, 0}};
+static const LayerSpec kFcn[] = {       // model.py:206-234
+    {"conv1", K_CONV, 5, 1, 20, 1},      {"conv2", K_CONV, 5, 20, 30, 0},    {"conv3", K_CONV, 5, 30, 40, 1},
+    {"conv4", K_CONV, 5, 40, 40, 0},     {"conv5", K_CONV, 5, 40, 60, 1},    {"conv6", K_CONV, 5, 60, 60, 0},
+    {"conv7", K_CONV, 5, 60, 80, 1},     {"deconv1", K_DECONV, 5, 80, 80, 1}, {"deconv2", K_DECONV_S2, 2, 80, 60, 1},
+    {"deconv3", K_DECONV, 5, 60, 40, 1}, {"deconv4", K_DECONV_S2, 2, 40, 30, 1},
+    {"deconv5", K_DECONV_S2, 2, 30, 20, 0}, {"logits", K_LOGITS, 1, 20, -1, 0}};
+static const LayerSpec kUnet[] = {      // model.py:151-203
+    {"conv1a", K_CONV, 3, 1, 64, 1},     {"conv1b", K_CONV, 3, 64, 64, 1},   {"conv2a", K_CONV, 3, 64, 128, 1},
+    {"conv2b", K_CONV, 3, 128, 128, 1},  {"conv3a", K_CONV, 3, 128, 256, 1}, {"conv3b", K_CONV, 3, 256, 256, 1},
+    {"conv4a", K_CONV, 3, 256, 512, 1},  {"conv4b", K_CONV, 3, 512, 512, 1}, {"conv5a", K_CONV, 3, 512, 1024, 1},
+    {"conv5b", K_CONV, 3, 1024, 1024, 1}, {"up6", K_CONV, 2, 1024, 512, 1},  {"conv6a", K_CONV, 3, 1024, 512, 1},
+    {"conv6b", K_CONV, 3, 512, 512, 1},  {"up7", K_CONV, 2, 512, 256, 1},    {"conv7a", K_CONV, 3, 512, 256, 1},
+    {"conv7b", K_CONV, 3, 256, 256, 1},  {"up8", K_CONV, 2, 256, 128, 1},    {"conv8a", K_CONV, 3, 256, 128, 1},
+    {"conv8b", K_CONV, 3, 128, 128, 1},  {"up9", K_CONV, 2, 128, 64, 1},     {"conv9a", K_CONV, 3, 128, 64, 1},
+    {"conv9b", K_CONV, 3, 64, 64, 1},    {"logits", K_LOGITS, 1, 64, -1, 0}};
+
+static void arch_table(int arch, const LayerSpec** t, int* n) {
+    switch (arch) {
+        case PCS_ARCH_FCN_SKIP: *t = kFcnSkip; *n = (int)(sizeof(kFcnSkip) / sizeof(LayerSpec)); break;
+        case PCS_ARCH_FCN: *t = kFcn; *n = (int)(sizeof(kFcn) / sizeof(LayerSpec)); break;
+        case PCS_ARCH_UNET: *t = kUnet; *n = (int)(sizeof(kUnet) / sizeof(LayerSpec)); break;
+        default: *t = nullptr; *n = 0;
+    }
+}
+
+static void free_layers(pcs_ctx* ctx) {
+    for (auto& l : ctx->layers) {
+        if (l.d_w32) cudaFree(l.d_w32);
+        if (l.d_b32) cudaFree(l.d_b32);
+        if (l.d_wmma) cudaFree(l.d_wmma);
+    }
+    ctx->layers.clear();
+    ctx->model_ready = false;
+}
+
+static Layer* find_layer(pcs_ctx* ctx, const char* name) {
+    for (auto& l : ctx->layers)
+        if (l.name == name) return &l;
+    return nullptr;
+}
+
+// ---------------------------------------------------------------------------
+// stage timing
+// ---------------------------------------------------------------------------
+struct StageScope {
+    pcs_ctx* ctx; size_t idx; bool on;
+    StageScope(pcs_ctx* c, const char* name) : ctx(c), idx(0), on(c->timing_enabled) {
+        if (!on) return;
+        StageTime st; st.name = name;
+        cudaEventCreate(&st.e0); cudaEventCreate(&st.e1);
+        cudaEventRecord(st.e0, ctx->stream);
+        ctx->stage_times.push_back(st);
+        idx = ctx->stage_times.size() - 1;
+    }
+    ~StageScope() { if (on) cudaEventRecord(ctx->stage_times[idx].e1, ctx->stream); }
+};
+
+static void clear_stage_times(pcs_ctx* ctx) {
+    for (auto& s : ctx->stage_times) { cudaEventDestroy(s.e0); cudaEventDestroy(s.e1); }
+    ctx->stage_times.clear();
+}
+
+// ---------------------------------------------------------------------------
+// forward schedules
+// ---------------------------------------------------------------------------
+static int new_act(pcs_ctx* ctx, const char* name, int n, int h, int w, int c, Act* out) {
+    Act a; a.n = n; a.h = h; a.w = w; a.c = c; a.cp = pad16(c);
+    a.p = arena_alloc(ctx, a.bytes());
+    if (!a.p) return set_err(ctx, PCS_ERR_NOMEM, "activation arena exhausted at %s", name);
+    ctx->acts[name] = a;
+    *out = a;
+    return PCS_OK;
+}
+
+static ConvSrc src_of(const Act& a) { ConvSrc s; s.p = a.p; s.c = a.c; s.cp = a.cp; return s; }
+
+// conv / deconv-s1 layer ('same', stride 1) on 1 or 2 concatenated sources
+static int run_conv(pcs_ctx* ctx, const char* lname, const Act* s0, const Act* s1, Act* out, Act* pool_out,
+                    bool upsample = false) {
+    Layer* L = find_layer(ctx, lname);
+    if (!L) return set_err(ctx, PCS_ERR_STATE, "layer %s missing", lname);
+    StageScope ts(ctx, lname);
+    const Act& any = out ? *out : *pool_out;
+    const int n = any.n;
+    const int h = out ? out->h : pool_out->h * 2, w = out ? out->w : pool_out->w * 2;
+    if (ctx->engine == PCS_ENGINE_UMMA && !upsample && L->d_wmma && umma_supported(L->k, L->npad)) {
+        UmmaConvArgs a;
+        a.src[0] = src_of(*s0); a.nsrc = 1;
+        if (s1) { a.src[1] = src_of(*s1); a.nsrc = 2; }
+        a.n = n; a.h = h; a.w = w; a.k = L->k; a.pad = (L->k % 2) ? L->k / 2 : 0;
+        a.wmma = L->d_wmma; a.b32 = L->d_b32; a.cout = L->cout; a.npad = L->npad; a.nchunks = L->nchunks; a.relu = L->relu;
+        a.out = out ? out->p : nullptr; a.out_cp = out ? out->cp : 0;
+        a.pool_out = pool_out ? pool_out->p : nullptr; a.pool_cp = pool_out ? pool_out->cp : 0;
+        return launch_conv_umma(ctx, a);
+    }
+    DirectConvArgs a;
+    a.src[0] = src_of(*s0); a.nsrc = 1;
+    if (s1) { a.src[1] = src_of(*s1); a.nsrc = 2; }
+    a.upsample = upsample ? 1 : 0;
+    a.n = n; a.h = h; a.w = w; a.k = L->k; a.pad = (L->k % 2) ? L->k / 2 : 0;
+    a.w32 = L->d_w32; a.b32 = L->d_b32; a.cin = L->cin; a.cout = L->cout; a.relu = L->relu;
+    a.out = out ? out->p : nullptr; a.out_cp = out ? out->cp : 0;
+    a.pool_out = pool_out ? pool_out->p : nullptr; a.pool_cp = pool_out ? pool_out->cp : 0;
+    return launch_conv_direct(ctx, a);
+}
+
+static int run_conv1_u8(pcs_ctx* ctx, const char* lname, const uint8_t* d_image, int n, int hs, int ws, Act* out) {
+    Layer* L = find_layer(ctx, lname);
+    if (!L) return set_err(ctx, PCS_ERR_STATE, "layer %s missing", lname);
+    StageScope ts(ctx, lname);
+    DirectConvArgs a;
+    a.src[0].p = d_image; a.src[0].c = 1; a.src[0].cp = 1; a.nsrc = 1;
+    a.src_u8 = 1; a.img_h = hs; a.img_w = ws;
+    a.n = n; a.h = out->h; a.w = out->w; a.k = L->k; a.pad = L->k / 2;
+    a.w32 = L->d_w32; a.b32 = L->d_b32; a.cin = 1; a.cout = L->cout; a.relu = L->relu;
+    a.out = out->p; a.out_cp = out->cp;
+    return launch_conv_direct(ctx, a);
+}
+
+static int run_deconv_s2(pcs_ctx* ctx, const char* lname, const Act* s0, const Act* s1, Act* out) {
+    Layer* L = find_layer(ctx, lname);
+    if (!L) return set_err(ctx, PCS_ERR_STATE, "layer %s missing", lname);
+    StageScope ts(ctx, lname);
+    DeconvS2Args a;
+    a.src[0] = src_of(*s0); a.nsrc = 1;
+    if (s1) { a.src[1] = src_of(*s1); a.nsrc = 2; }
+    a.n = s0->n; a.h = s0->h; a.w = s0->w;
+    a.w32 = L->d_w32; a.b32 = L->d_b32; a.cin = L->cin; a.cout = L->cout; a.relu = L->relu;
+    a.out = out->p; a.out_cp = out->cp;
+    return launch_deconv_s2_direct(ctx, a);
+}
+
+struct HeadIO {
+    const uint8_t* binary; uint8_t* labels; float* logits; float* prob;
+    const uint8_t* d_lut; uint8_t* color; uint8_t* overlay; uint8_t* inverted;
+};
+
+static int forward_fcn(pcs_ctx* ctx, bool skip, const uint8_t* d_image, int n, int hs, int ws, const HeadIO& io) {
+    const int hp = hs + (32 - hs % 32) % 32, wp = ws + (32 - ws % 32) % 32;    // model.py:10-26
+    Act conv1, conv2, pool2, conv3, pool4, conv5, conv6, pool6, conv7, d1, d2, d3, d4;
+    PCS_TRY(new_act(ctx, "conv1", n, hp, wp, 20, &conv1));
+    PCS_TRY(run_conv1_u8(ctx, "conv1", d_image, n, hs, ws, &conv1));
+    PCS_TRY(new_act(ctx, "conv2", n, hp, wp, 30, &conv2));
+    PCS_TRY(new_act(ctx, "pool2", n, hp / 2, wp / 2, 30, &pool2));
+    PCS_TRY(run_conv(ctx, "conv2", &conv1, nullptr, &conv2, &pool2));
+    PCS_TRY(new_act(ctx, "conv3", n, hp / 2, wp / 2, 40, &conv3));
+    PCS_TRY(run_conv(ctx, "conv3", &pool2, nullptr, &conv3, nullptr));
+    PCS_TRY(new_act(ctx, "pool4", n, hp / 4, wp / 4, 40, &pool4));
+    PCS_TRY(run_conv(ctx, "conv4", &conv3, nullptr, nullptr, &pool4));      // conv4 itself is never re-read
+    PCS_TRY(new_act(ctx, "conv5", n, hp / 4, wp / 4, 60, &conv5));
+    PCS_TRY(run_conv(ctx, "conv5", &pool4, nullptr, &conv5, nullptr));
+    PCS_TRY(new_act(ctx, "pool6", n, hp / 8, wp / 8, 60, &pool6));
+    if (skip) {
+        PCS_TRY(new_act(ctx, "conv6", n, hp / 4, wp / 4, 60, &conv6));
+        PCS_TRY(run_conv(ctx, "conv6", &conv5, nullptr, &conv6, &pool6));
+    } else {
+        PCS_TRY(run_conv(ctx, "conv6", &conv5, nullptr, nullptr, &pool6));
+    }
+    PCS_TRY(new_act(ctx, "conv7", n, hp / 8, wp / 8, 80, &conv7));
+    PCS_TRY(run_conv(ctx, "conv7", &pool6, nullptr, &conv7, nullptr));
+    PCS_TRY(new_act(ctx, "deconv1", n, hp / 8, wp / 8, 80, &d1));
+    PCS_TRY(run_conv(ctx, "deconv1", &conv7, nullptr, &d1, nullptr));
+    PCS_TRY(new_act(ctx, "deconv2", n, hp / 4, wp / 4, 60, &d2));
+    PCS_TRY(run_deconv_s2(ctx, "deconv2", &d1, nullptr, &d2));
+    PCS_TRY(new_act(ctx, "deconv3", n, hp / 4, wp / 4, 40, &d3));
+    PCS_TRY(run_conv(ctx, "deconv3", &d2, skip ? &conv6 : nullptr, &d3, nullptr));     // concat [deconv2, conv6]
+    PCS_TRY(new_act(ctx, "deconv4", n, hp / 2, wp / 2, 30, &d4));
+    PCS_TRY(run_deconv_s2(ctx, "deconv4", &d3, skip ? &conv5 : nullptr, &d4));         // concat [deconv3, conv5]
+
+    Layer* L5 = find_layer(ctx, "deconv5");
+    Layer* LL = find_layer(ctx, "logits");
+    StageScope ts(ctx, "head");
+    HeadArgs a;
+    a.has_deconv = 1;
+    a.dsrc[0] = src_of(d4); a.dnsrc = 1;
+    if (skip) { a.dsrc[1] = src_of(conv3); a.dnsrc = 2; }                              // concat [deconv4, conv3]
+    a.dw32 = L5->d_w32; a.db32 = L5->d_b32; a.dcin = L5->cin; a.dcout = L5->cout;
+    if (skip) { a.skip = src_of(conv2); a.has_skip = 1; }                              // concat [deconv5, conv2]
+    a.lw32 = LL->d_w32; a.lb32 = LL->d_b32; a.n_classes = ctx->n_classes;
+    a.n = n; a.hp = hp; a.wp = wp; a.h = hs; a.w = ws;
+    a.binary = io.binary; a.labels = io.labels; a.logits = io.logits; a.prob = io.prob;
+    a.lut = io.d_lut; a.color = io.color; a.overlay = io.overlay; a.inverted = io.inverted;
+    return launch_head(ctx, a);
+}
+
+static int forward_unet(pcs_ctx* ctx, const uint8_t* d_image, int n, int hs, int ws, const HeadIO& io) {
+    const int hp = hs + (32 - hs % 32) % 32, wp = ws + (32 - ws % 32) % 32;
+    Act c1a, c1, p1, c2a, c2, p2, c3a, c3, p3, c4a, c4, p4, c5a, c5, u6, c6a, c6, u7, c7a, c7, u8, c8a, c8, u9, c9a, c9;
+    PCS_TRY(new_act(ctx, "conv1a", n, hp, wp, 64, &c1a));
+    PCS_TRY(run_conv1_u8(ctx, "conv1a", d_image, n, hs, ws, &c1a));
+    PCS_TRY(new_act(ctx, "conv1b", n, hp, wp, 64, &c1));
+    PCS_TRY(new_act(ctx, "pool1", n, hp / 2, wp / 2, 64, &p1));
+    PCS_TRY(run_conv(ctx, "conv1b", &c1a, nullptr, &c1, &p1));
+    PCS_TRY(new_act(ctx, "conv2a", n, hp / 2, wp / 2, 128, &c2a));
+    PCS_TRY(run_conv(ctx, "conv2a", &p1, nullptr, &c2a, nullptr));
+    PCS_TRY(new_act(ctx, "conv2b", n, hp / 2, wp / 2, 128, &c2));
+    PCS_TRY(new_act(ctx, "pool2", n, hp / 4, wp / 4, 128, &p2));
+    PCS_TRY(run_conv(ctx, "conv2b", &c2a, nullptr, &c2, &p2));
+    PCS_TRY(new_act(ctx, "conv3a", n, hp / 4, wp / 4, 256, &c3a));
+    PCS_TRY(run_conv(ctx, "conv3a", &p2, nullptr, &c3a, nullptr));
+    PCS_TRY(new_act(ctx, "conv3b", n, hp / 4, wp / 4, 256, &c3));
+    PCS_TRY(new_act(ctx, "pool3", n, hp / 8, wp / 8, 256, &p3));
+    PCS_TRY(run_conv(ctx, "conv3b", &c3a, nullptr, &c3, &p3));
+    PCS_TRY(new_act(ctx, "conv4a", n, hp / 8, wp / 8, 512, &c4a));
+    PCS_TRY(run_conv(ctx, "conv4a", &p3, nullptr, &c4a, nullptr));
+    PCS_TRY(new_act(ctx, "conv4b", n, hp / 8, wp / 8, 512, &c4));                     // drop4 = identity at inference
+    PCS_TRY(new_act(ctx, "pool4", n, hp / 16, wp / 16, 512, &p4));
+    PCS_TRY(run_conv(ctx, "conv4b", &c4a, nullptr, &c4, &p4));
+    PCS_TRY(new_act(ctx, "conv5a", n, hp / 16, wp / 16, 1024, &c5a));
+    PCS_TRY(run_conv(ctx, "conv5a", &p4, nullptr, &c5a, nullptr));
+    PCS_TRY(new_act(ctx, "conv5b", n, hp / 16, wp / 16, 1024, &c5));
+    PCS_TRY(run_conv(ctx, "conv5b", &c5a, nullptr, &c5, nullptr));
+    PCS_TRY(new_act(ctx, "up6", n, hp / 8, wp / 8, 512, &u6));
+    PCS_TRY(run_conv(ctx, "up6", &c5, nullptr, &u6, nullptr, true));                 // UpSampling2D fused
+    PCS_TRY(new_act(ctx, "conv6a", n, hp / 8, wp / 8, 512, &c6a));
+    PCS_TRY(run_conv(ctx, "conv6a", &c4, &u6, &c6a, nullptr));                       // concat [drop4, up6]
+    PCS_TRY(new_act(ctx, "conv6b", n, hp / 8, wp / 8, 512, &c6));
+    PCS_TRY(run_conv(ctx, "conv6b", &c6a, nullptr, &c6, nullptr));
+    PCS_TRY(new_act(ctx, "up7", n, hp / 4, wp / 4, 256, &u7));
+    PCS_TRY(run_conv(ctx, "up7", &c6, nullptr, &u7, nullptr, true));
+    PCS_TRY(new_act(ctx, "conv7a", n, hp / 4, wp / 4, 256, &c7a));
+    PCS_TRY(run_conv(ctx, "conv7a", &c3, &u7, &c7a, nullptr));
+    PCS_TRY(new_act(ctx, "conv7b", n, hp / 4, wp / 4, 256, &c7));
+    PCS_TRY(run_conv(ctx, "conv7b", &c7a, nullptr, &c7, nullptr));
+    PCS_TRY(new_act(ctx, "up8", n, hp / 2, wp / 2, 128, &u8));
+    PCS_TRY(run_conv(ctx, "up8", &c7, nullptr, &u8, nullptr, true));
+    PCS_TRY(new_act(ctx, "conv8a", n, hp / 2, wp / 2, 128, &c8a));
+    PCS_TRY(run_conv(ctx, "conv8a", &c2, &u8, &c8a, nullptr));
+    PCS_TRY(new_act(ctx, "conv8b", n, hp / 2, wp / 2, 128, &c8));
+    PCS_TRY(run_conv(ctx, "conv8b", &c8a, nullptr, &c8, nullptr));
+    PCS_TRY(new_act(ctx, "up9", n, hp, wp, 64, &u9));
+    PCS_TRY(run_conv(ctx, "up9", &c8, nullptr, &u9, nullptr, true));
+    PCS_TRY(new_act(ctx, "conv9a", n, hp, wp, 64, &c9a));
+    PCS_TRY(run_conv(ctx, "conv9a", &c1, &u9, &c9a, nullptr));
+    PCS_TRY(new_act(ctx, "conv9b", n, hp, wp, 64, &c9));
+    PCS_TRY(run_conv(ctx, "conv9b", &c9a, nullptr, &c9, nullptr));
+
+    Layer* LL = find_layer(ctx, "logits");
+    StageScope ts(ctx, "head");
+    HeadArgs a;
+    a.has_deconv = 0;
+    a.skip = src_of(c9); a.has_skip = 1;
+    a.lw32 = LL->d_w32; a.lb32 = LL->d_b32; a.n_classes = ctx->n_classes;
+    a.n = n; a.hp = hp; a.wp = wp; a.h = hs; a.w = ws;
+    a.binary = io.binary; a.labels = io.labels; a.logits = io.logits; a.prob = io.prob;
+    a.lut = io.d_lut; a.color = io.color; a.overlay = io.overlay; a.inverted = io.inverted;
+    return launch_head(ctx, a);
+}
+
+static size_t arena_need(int arch, int n, int hs, int ws) {
+    const size_t hp = hs + (32 - hs % 32) % 32, wp = ws + (32 - ws % 32) % 32;
+    const size_t px = (size_t)n * hp * wp;
+    // sum over activations of (pixels at level) * padded channels * 2 bytes (+ slack)
+    double ch;   // channel-pixels in units of full-resolution pixels
+    if (arch == PCS_ARCH_UNET)
+        ch = 64 * 5 + (64 + 128 * 5) / 4.0 + (128 + 256 * 5) / 16.0 + (256 + 512 * 5) / 64.0 + (512 + 1024 * 2) / 256.0;
+    else
+        ch = 32 + 32 + (32 + 48 + 32) / 4.0 + (48 + 64 + 64 + 64 + 48) / 16.0 + (64 + 80 + 80) / 64.0;
+    return (size_t)(px * ch * 2.0) + (size_t)64 * 4096 + (1u << 20);
+}
+
+}  // namespace pcs
+
+using namespace pcs;
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+int pcs_abi_version(void) { return PCS_ABI_VERSION; }
+
+int pcs_ctx_create(int device, pcs_ctx** out) {
+    if (!out) return PCS_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+        cudaGetLastError();
+        return PCS_ERR_CUDA;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return PCS_ERR_CUDA;
+    if (prop.major != 10) return PCS_ERR_DEVICE;      // sm_100a code only; no fallback by design
+    if (cudaSetDevice(device) != cudaSuccess) return PCS_ERR_CUDA;
+    pcs_ctx* ctx = new pcs_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    const char* t = getenv("PCSEG_TIMING");
+    ctx->timing_enabled = t && t[0] == '1';
+    const char* e = getenv("PCSEG_ENGINE");
+    if (e && !strcmp(e, "direct")) ctx->engine = PCS_ENGINE_DIRECT;
+    *out = ctx;
+    return PCS_OK;
+}
+
+void pcs_ctx_destroy(pcs_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_layers(ctx);
+    clear_stage_times(ctx);
+    if (ctx->arena) cudaFree(ctx->arena);
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->stage) cudaFree(ctx->stage);
+    delete ctx;
+}
+
+const char* pcs_last_error(const pcs_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+
+int pcs_set_stream(pcs_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return PCS_ERR_ARG;
+    ctx->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    return PCS_OK;
+}
+
+int pcs_synchronize(pcs_ctx* ctx) {
+    if (!ctx) return PCS_ERR_ARG;
+    PCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PCS_OK;
+}
+
+int64_t pcs_launch_count(const pcs_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+int pcs_set_engine(pcs_ctx* ctx, int engine) {
+    if (!ctx || (engine != PCS_ENGINE_UMMA && engine != PCS_ENGINE_DIRECT)) return PCS_ERR_ARG;
+    ctx->engine = engine;
+    return PCS_OK;
+}
+
+int pcs_model_load(pcs_ctx* ctx, int arch, int n_classes, int precision, const pcs_layer_weights* layers, int n_layers) {
+    if (!ctx) return PCS_ERR_ARG;
+    PCS_CUDA(ctx, cudaSetDevice(ctx->device));
+    const LayerSpec* table; int nt;
+    arch_table(arch, &table, &nt);
+    if (!table) return set_err(ctx, PCS_ERR_ARG, "unknown architecture id %d", arch);
+    if (n_layers != nt) return set_err(ctx, PCS_ERR_ARG, "architecture %d expects %d weighted layers, got %d", arch, nt, n_layers);
+    if (n_classes < 1 || n_classes > kMaxClasses) return set_err(ctx, PCS_ERR_ARG, "n_classes %d out of range 1..%d", n_classes, kMaxClasses);
+    if (precision != PCS_PREC_BF16 && precision != PCS_PREC_FP16) return set_err(ctx, PCS_ERR_ARG, "unknown precision %d", precision);
+    PCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    free_layers(ctx);
+    ctx->arch = arch; ctx->n_classes = n_classes; ctx->precision = precision;
+    for (int li = 0; li < nt; ++li) {
+        const LayerSpec& s = table[li];
+        const pcs_layer_weights& w = layers[li];
+        const int cout = s.cout < 0 ? n_classes : s.cout;
+        const bool transposed = s.kind == K_DECONV || s.kind == K_DECONV_S2;
+        const int e2 = transposed ? cout : s.cin, e3 = transposed ? s.cin : cout;
+        if (!w.kernel || !w.bias || w.shape[0] != s.k || w.shape[1] != s.k || w.shape[2] != e2 || w.shape[3] != e3) {
+            free_layers(ctx);
+            return set_err(ctx, PCS_ERR_ARG, "layer %d (%s): kernel shape (%d,%d,%d,%d) != expected (%d,%d,%d,%d)", li, s.name,
+                           w.shape[0], w.shape[1], w.shape[2], w.shape[3], s.k, s.k, e2, e3);
+        }
+        Layer L;
+        L.name = s.name; L.kind = s.kind; L.k = s.k; L.cin = s.cin; L.cout = cout; L.relu = s.relu;
+        const int taps = s.k * s.k;
+        L.h_w32.assign((size_t)taps * s.cin * cout, 0.f);
+        for (int i = 0; i < s.k; ++i)
+            for (int j = 0; j < s.k; ++j)
+                for (int c = 0; c < s.cin; ++c)
+                    for (int o = 0; o < cout; ++o) {
+                        float v;
+                        if (s.kind == K_DECONV) {
+                            // gradient-of-conv form -> correlation: K'[i,j,c,o] = K[k-1-i, k-1-j, o, c]
+                            v = w.kernel[(((size_t)(s.k - 1 - i) * s.k + (s.k - 1 - j)) * cout + o) * s.cin + c];
+                        } else if (s.kind == K_DECONV_S2) {
+                            v = w.kernel[(((size_t)i * s.k + j) * cout + o) * s.cin + c];
+                        } else {
+                            v = w.kernel[(((size_t)i * s.k + j) * s.cin + c) * cout + o];
+                        }
+                        L.h_w32[(((size_t)i * s.k + j) * s.cin + c) * cout + o] = v;
+                    }
+        L.h_b32.assign(w.bias, w.bias + cout);
+        // every layer except the first and the logits consumes operands rounded to the model precision
+        const bool rounded = li != 0 && s.kind != K_LOGITS;
+        if (rounded) {
+            for (float& v : L.h_w32)
+                v = precision == PCS_PREC_BF16 ? __bfloat162float(__float2bfloat16_rn(v)) : __half2float(__float2half_rn(v));
+        }
+        PCS_CUDA(ctx, cudaMalloc(&L.d_w32, L.h_w32.size() * 4));
+        PCS_CUDA(ctx, cudaMalloc(&L.d_b32, L.h_b32.size() * 4));
+        PCS_CUDA(ctx, cudaMemcpy(L.d_w32, L.h_w32.data(), L.h_w32.size() * 4, cudaMemcpyHostToDevice));
+        PCS_CUDA(ctx, cudaMemcpy(L.d_b32, L.h_b32.data(), L.h_b32.size() * 4, cudaMemcpyHostToDevice));
+        ctx->layers.push_back(std::move(L));
+    }
+    // tensor-core operand images for the stride-1 convolutions with C_in > 1
+    for (size_t li = 1; li < ctx->layers.size(); ++li) {
+        Layer& L = ctx->layers[li];
+        if (L.kind != K_CONV && L.kind != K_DECONV) continue;
+        int src_c[2] = {L.cin, 0}, nsrc = 1;
+        if (arch == PCS_ARCH_FCN_SKIP && L.name == "deconv3") { src_c[0] = 60; src_c[1] = 60; nsrc = 2; }
+        if (arch == PCS_ARCH_UNET && (L.name == "conv6a" || L.name == "conv7a" || L.name == "conv8a" || L.name == "conv9a")) {
+            src_c[0] = L.cin / 2; src_c[1] = L.cin / 2; nsrc = 2;
+        }
+        L.npad = pad16(L.cout);
+        if (!umma_supported(L.k, L.npad)) continue;
+        std::vector<uint16_t> img;
+        L.wmma_bytes = umma_weight_image(L.h_w32.data(), L.k * L.k, src_c, nsrc, L.cout, L.npad, precision, img);
+        L.nchunks = 0;
+        for (int s = 0; s < nsrc; ++s) L.nchunks += pad16(src_c[s]) / 16;
+        PCS_CUDA(ctx, cudaMalloc(&L.d_wmma, L.wmma_bytes));
+        PCS_CUDA(ctx, cudaMemcpy(L.d_wmma, img.data(), L.wmma_bytes, cudaMemcpyHostToDevice));
+    }
+    ctx->model_ready = true;
+    return PCS_OK;
+}
+
+int pcs_preprocess(pcs_ctx* ctx, const uint8_t* d_grey, const uint8_t* d_bin, int n, int H, int W, int Hs, int Ws,
+                   uint8_t* d_image, uint8_t* d_binary, uint8_t* d_orig_binary) {
+    if (!ctx || !d_bin || (!d_grey && d_image)) return ctx ? set_err(ctx, PCS_ERR_ARG, "preprocess: null input") : PCS_ERR_ARG;
+    PCS_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->timing_enabled) clear_stage_times(ctx);
+    StageScope ts(ctx, "preprocess");
+    return launch_preprocess(ctx, d_grey, d_bin, n, H, W, Hs, Ws, d_image, d_binary, d_orig_binary);
+}
+
+int pcs_forward(pcs_ctx* ctx, const uint8_t* d_image, const uint8_t* d_binary, int n, int Hs, int Ws, uint8_t* d_labels,
+                float* d_logits, float* d_prob, const uint8_t* lut, uint8_t* d_color, uint8_t* d_overlay,
+                uint8_t* d_inverted) {
+    if (!ctx) return PCS_ERR_ARG;
+    if (!ctx->model_ready) return set_err(ctx, PCS_ERR_STATE, "pcs_forward before pcs_model_load");
+    if (!d_image || n <= 0 || Hs <= 0 || Ws <= 0) return set_err(ctx, PCS_ERR_ARG, "forward: bad argument");
+    const bool want_masks = d_color || d_overlay || d_inverted;
+    if (want_masks && !lut) return set_err(ctx, PCS_ERR_ARG, "forward: colour outputs need a LUT");
+    if ((d_overlay || d_inverted) && !d_binary) return set_err(ctx, PCS_ERR_ARG, "forward: overlay outputs need the binary page");
+    PCS_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->timing_enabled && (ctx->stage_times.empty() || ctx->stage_times.back().name != "preprocess"))
+        clear_stage_times(ctx);
+    ctx->arena_used = 0;
+    ctx->acts.clear();
+    PCS_TRY(arena_reserve(ctx, arena_need(ctx->arch, n, Hs, Ws)));
+    HeadIO io{d_binary, d_labels, d_logits, d_prob, nullptr, d_color, d_overlay, d_inverted};
+    if (want_masks) {
+        uint8_t* d_lut = reinterpret_cast<uint8_t*>(arena_alloc(ctx, 256 * 3));
+        if (!d_lut) return set_err(ctx, PCS_ERR_NOMEM, "arena exhausted (lut)");
+        PCS_CUDA(ctx, cudaMemcpyAsync(d_lut, lut, (size_t)ctx->n_classes * 3, cudaMemcpyHostToDevice, ctx->stream));
+        io.d_lut = d_lut;
+    }
+    if (ctx->arch == PCS_ARCH_UNET) return forward_unet(ctx, d_image, n, Hs, Ws, io);
+    return forward_fcn(ctx, ctx->arch == PCS_ARCH_FCN_SKIP, d_image, n, Hs, Ws, io);
+}
+
+int pcs_masks(pcs_ctx* ctx, const uint8_t* d_labels, const uint8_t* d_binary, int n, int H, int W, const uint8_t* lut,
+              int n_lut, uint8_t* d_color, uint8_t* d_overlay, uint8_t* d_inverted) {
+    if (!ctx || !d_labels || !d_binary || !lut) return ctx ? set_err(ctx, PCS_ERR_ARG, "masks: null argument") : PCS_ERR_ARG;
+    if (n_lut < 0 || n_lut > 256) return set_err(ctx, PCS_ERR_ARG, "masks: LUT size %d", n_lut);
+    PCS_CUDA(ctx, cudaSetDevice(ctx->device));
+    PCS_TRY(scratch_reserve(ctx, 1024));
+    uint8_t* d_lut = reinterpret_cast<uint8_t*>(ctx->scratch);
+    PCS_CUDA(ctx, cudaMemcpyAsync(d_lut, lut, (size_t)n_lut * 3, cudaMemcpyHostToDevice, ctx->stream));
+    StageScope ts(ctx, "masks");
+    return launch_masks(ctx, d_labels, d_binary, n, H, W, d_lut, n_lut, d_color, d_overlay, d_inverted);
+}
+
+int pcs_resize_nearest(pcs_ctx* ctx, const uint8_t* d_src, int n, int H, int W, uint8_t* d_dst, int Ho, int Wo) {
+    if (!ctx || !d_src || !d_dst) return ctx ? set_err(ctx, PCS_ERR_ARG, "resize_nearest: null argument") : PCS_ERR_ARG;
+    PCS_CUDA(ctx, cudaSetDevice(ctx->device));
+    return launch_resize_nearest(ctx, d_src, n, H, W, d_dst, Ho, Wo);
+}
+
+int pcs_ccl(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, int32_t* d_labels, int32_t* d_stats,
+            int max_components, int32_t* d_ncomp) {
+    if (!ctx || !d_img || !d_labels) return ctx ? set_err(ctx, PCS_ERR_ARG, "ccl: null argument") : PCS_ERR_ARG;
+    PCS_CUDA(ctx, cudaSetDevice(ctx->device));
+    StageScope ts(ctx, "ccl");
+    return launch_ccl(ctx, d_img, n, H, W, d_labels, d_stats, max_components, d_ncomp);
+}
+
+int pcs_cc_majority(pcs_ctx* ctx, uint8_t* d_pred, const uint8_t* d_binary, int n, int H, int W, int n_classes) {
+    if (!ctx || !d_pred || !d_binary) return ctx ? set_err(ctx, PCS_ERR_ARG, "cc_majority: null argument") : PCS_ERR_ARG;
+    PCS_CUDA(ctx, cudaSetDevice(ctx->device));
+    StageScope ts(ctx, "cc_majority");
+    return launch_cc_majority(ctx, d_pred, d_binary, n, H, W, n_classes);
+}
+
+int pcs_bounding_boxes(pcs_ctx* ctx, const uint8_t* d_pred, int n, int H, int W, int n_classes, uint8_t* d_out) {
+    if (!ctx || !d_pred || !d_out) return ctx ? set_err(ctx, PCS_ERR_ARG, "bounding_boxes: null argument") : PCS_ERR_ARG;
+    PCS_CUDA(ctx, cudaSetDevice(ctx->device));
+    StageScope ts(ctx, "bounding_boxes");
+    return launch_bounding_boxes(ctx, d_pred, n, H, W, n_classes, d_out);
+}
+
+int pcs_predict_pages_host(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h_bin, int n, int H, int W, int Hs, int Ws,
+                           int cc_majority, const uint8_t* lut, uint8_t* h_image, uint8_t* h_binary, uint8_t* h_labels,
+                           uint8_t* h_color, uint8_t* h_overlay, uint8_t* h_inverted) {
+    if (!ctx || !h_grey || !h_bin) return ctx ? set_err(ctx, PCS_ERR_ARG, "predict_pages_host: null input") : PCS_ERR_ARG;
+    if (!ctx->model_ready) return set_err(ctx, PCS_ERR_STATE, "pcs_predict_pages_host before pcs_model_load");
+    if (n <= 0 || H <= 0 || W <= 0 || Hs <= 0 || Ws <= 0) return set_err(ctx, PCS_ERR_ARG, "predict_pages_host: bad shape");
+    const bool want_masks = h_color || h_overlay || h_inverted;
+    if (want_masks && !lut) return set_err(ctx, PCS_ERR_ARG, "predict_pages_host: colour outputs need a LUT");
+    PCS_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t src = (size_t)n * H * W, dst = (size_t)n * Hs * Ws;
+    const bool same = h_grey == h_bin;
+    const size_t need = (same ? src : 2 * src) + dst * (3 + 9) + 4096;
+    if (need > ctx->stage_bytes) {
+        PCS_CUDA(ctx, cudaStreamSynchronize(st));
+        if (ctx->stage) cudaFree(ctx->stage);
+        ctx->stage = nullptr; ctx->stage_bytes = 0;
+        if (cudaMalloc(&ctx->stage, need) != cudaSuccess) {
+            cudaGetLastError();
+            return set_err(ctx, PCS_ERR_NOMEM, "cudaMalloc of %zu staging bytes failed", need);
+        }
+        ctx->stage_bytes = need;
+    }
+    uint8_t* p = reinterpret_cast<uint8_t*>(ctx->stage);
+    auto take = [&](size_t b) { uint8_t* r = p; p += (b + 255) / 256 * 256; return r; };
+    uint8_t* d_grey = take(src);
+    uint8_t* d_bin = same ? d_grey : take(src);
+    uint8_t* d_image = take(dst);
+    uint8_t* d_binary = take(dst);
+    uint8_t* d_labels = take(dst);
+    uint8_t* d_color = h_color ? take(dst * 3) : nullptr;
+    uint8_t* d_overlay = h_overlay ? take(dst * 3) : nullptr;
+    uint8_t* d_inverted = h_inverted ? take(dst * 3) : nullptr;
+    PCS_CUDA(ctx, cudaMemcpyAsync(d_grey, h_grey, src, cudaMemcpyHostToDevice, st));
+    if (!same) PCS_CUDA(ctx, cudaMemcpyAsync(d_bin, h_bin, src, cudaMemcpyHostToDevice, st));
+    PCS_TRY(pcs_preprocess(ctx, d_grey, d_bin, n, H, W, Hs, Ws, d_image, d_binary, nullptr));
+    if (cc_majority) {
+        PCS_TRY(pcs_forward(ctx, d_image, d_binary, n, Hs, Ws, d_labels, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
+        PCS_TRY(pcs_cc_majority(ctx, d_labels, d_binary, n, Hs, Ws, ctx->n_classes));
+        if (want_masks) PCS_TRY(pcs_masks(ctx, d_labels, d_binary, n, Hs, Ws, lut, ctx->n_classes, d_color, d_overlay, d_inverted));
+    } else {
+        PCS_TRY(pcs_forward(ctx, d_image, d_binary, n, Hs, Ws, d_labels, nullptr, nullptr, lut, d_color, d_overlay, d_inverted));
+    }
+    if (h_image) PCS_CUDA(ctx, cudaMemcpyAsync(h_image, d_image, dst, cudaMemcpyDeviceToHost, st));
+    if (h_binary) PCS_CUDA(ctx, cudaMemcpyAsync(h_binary, d_binary, dst, cudaMemcpyDeviceToHost, st));
+    if (h_labels) PCS_CUDA(ctx, cudaMemcpyAsync(h_labels, d_labels, dst, cudaMemcpyDeviceToHost, st));
+    if (h_color) PCS_CUDA(ctx, cudaMemcpyAsync(h_color, d_color, dst * 3, cudaMemcpyDeviceToHost, st));
+    if (h_overlay) PCS_CUDA(ctx, cudaMemcpyAsync(h_overlay, d_overlay, dst * 3, cudaMemcpyDeviceToHost, st));
+    if (h_inverted) PCS_CUDA(ctx, cudaMemcpyAsync(h_inverted, d_inverted, dst * 3, cudaMemcpyDeviceToHost, st));
+    PCS_CUDA(ctx, cudaStreamSynchronize(st));
+    return PCS_OK;
+}
+
+int pcs_debug_activation(pcs_ctx* ctx, const char* name, float* h_out, size_t capacity_floats, int32_t* shape4) {
+    if (!ctx || !name) return PCS_ERR_ARG;
+    auto it = ctx->acts.find(name);
+    if (it == ctx->acts.end()) return set_err(ctx, PCS_ERR_ARG, "no activation named %s in the last forward", name);
+    const Act& a = it->second;
+    if (shape4) { shape4[0] = a.n; shape4[1] = a.h; shape4[2] = a.w; shape4[3] = a.c; }
+    if (!h_out) return a.c;
+    const size_t px = (size_t)a.n * a.h * a.w;
+    if (px * a.c > capacity_floats) return set_err(ctx, PCS_ERR_ARG, "debug_activation: buffer too small");
+    PCS_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<uint16_t> raw(px * a.cp);
+    PCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    PCS_CUDA(ctx, cudaMemcpy(raw.data(), a.p, raw.size() * 2, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < px; ++i)
+        for (int c = 0; c < a.c; ++c) {
+            const uint16_t v = raw[i * a.cp + c];
+            float f;
+            if (ctx->precision == PCS_PREC_BF16) {
+                uint32_t u = (uint32_t)v << 16;
+                memcpy(&f, &u, 4);
+            } else {
+                __half_raw hr; hr.x = v;
+                f = __half2float(__half(hr));
+            }
+            h_out[i * a.c + c] = f;
+        }
+    return a.c;
+}
+
+int pcs_set_timing(pcs_ctx* ctx, int enabled) {
+    if (!ctx) return PCS_ERR_ARG;
+    ctx->timing_enabled = enabled != 0;
+    if (!enabled) clear_stage_times(ctx);
+    return PCS_OK;
+}
+
+const char* pcs_last_timings(pcs_ctx* ctx) {
+    if (!ctx) return "";
+    ctx->timings.clear();
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& s : ctx->stage_times) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, s.e0, s.e1) != cudaSuccess) { cudaGetLastError(); continue; }
+        char buf[128];
+        snprintf(buf, sizeof(buf), "%s:%.4f;", s.name.c_str(), ms);
+        ctx->timings += buf;
+    }
+    return ctx->timings.c_str();
+}
+
+}  // extern "C"

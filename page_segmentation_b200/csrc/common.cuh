@@ -1,0 +1,224 @@
+// Shared declarations for the pcseg_b200 CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/pcseg_b200.h"
+
+namespace pcs {
+
+constexpr int kMaxClasses = 16;
+
+// ---------------------------------------------------------------------------
+// Activation tensors: NHWC, channel count padded to a multiple of 16 with zeros.
+// ---------------------------------------------------------------------------
+struct Act {
+    void* p = nullptr;      // device pointer, element type = model precision (bf16 / fp16)
+    int n = 0, h = 0, w = 0;
+    int c = 0;              // real channels
+    int cp = 0;             // padded channels (stride between pixels, elements)
+    size_t bytes() const { return (size_t)n * h * w * cp * 2; }
+};
+
+inline int pad16(int c) { return (c + 15) / 16 * 16; }
+
+// One network layer after host-side weight transformation.
+struct Layer {
+    std::string name;
+    int kind = 0;           // 0 conv (same, s1), 1 deconv s1 (stored flipped as conv), 2 deconv 2x2 s2, 3 logits 1x1
+    int k = 0;              // kernel size
+    int cin = 0, cout = 0;  // real channel counts (cin over all concatenated sources)
+    int relu = 0;
+    // fp32 weights in "correlation" form [tap][cin][cout] (deconv s1 flipped + transposed;
+    // deconv s2: tap = i*2+j) and bias [cout]; device copies.
+    float* d_w32 = nullptr;
+    float* d_b32 = nullptr;
+    std::vector<float> h_w32, h_b32;
+    // tensor-core operand image (precision type): see conv_umma.cu for the layout
+    void* d_wmma = nullptr;
+    size_t wmma_bytes = 0;
+    int npad = 0;           // padded C_out of the UMMA tile
+    int nchunks = 0;        // number of 16-channel K chunks over all sources
+};
+
+struct StageTime { std::string name; cudaEvent_t e0, e1; };
+
+}  // namespace pcs
+
+struct pcs_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+
+    // model
+    int arch = -1, n_classes = 0, precision = PCS_PREC_BF16, engine = PCS_ENGINE_UMMA;
+    std::vector<pcs::Layer> layers;
+    bool model_ready = false;
+
+    // workspace arena (activations), grown on demand
+    char* arena = nullptr;
+    size_t arena_bytes = 0;
+    size_t arena_used = 0;
+    std::map<std::string, pcs::Act> acts;   // activations of the last forward (debug / reuse)
+
+    // small scratch
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+
+    // staging buffers of pcs_predict_pages_host
+    char* stage = nullptr;
+    size_t stage_bytes = 0;
+
+    std::string timings;
+    std::vector<pcs::StageTime> stage_times;
+    bool timing_enabled = false;
+};
+
+namespace pcs {
+
+int set_err(pcs_ctx* ctx, int code, const char* fmt, ...);
+
+#define PCS_CUDA(ctx, call)                                                                  \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess)                                                              \
+            return pcs::set_err((ctx), PCS_ERR_CUDA, "%s failed: %s (%s:%d)", #call,         \
+                                cudaGetErrorString(e__), __FILE__, __LINE__);                \
+    } while (0)
+
+#define PCS_LAUNCH_CHECK(ctx, what)                                                          \
+    do {                                                                                     \
+        (ctx)->launches++;                                                                   \
+        cudaError_t e__ = cudaGetLastError();                                                \
+        if (e__ != cudaSuccess)                                                              \
+            return pcs::set_err((ctx), PCS_ERR_CUDA, "launch of %s failed: %s (%s:%d)", what, \
+                                cudaGetErrorString(e__), __FILE__, __LINE__);                \
+    } while (0)
+
+#define PCS_TRY(expr)                 \
+    do {                              \
+        int rc__ = (expr);            \
+        if (rc__ != PCS_OK) return rc__; \
+    } while (0)
+
+// arena
+int arena_reserve(pcs_ctx* ctx, size_t bytes);
+void* arena_alloc(pcs_ctx* ctx, size_t bytes);      // 256-B aligned bump allocation; nullptr if full
+int scratch_reserve(pcs_ctx* ctx, size_t bytes);
+
+// ---- kernels implemented in the other translation units --------------------
+// preprocess.cu
+int launch_preprocess(pcs_ctx* ctx, const uint8_t* d_grey, const uint8_t* d_bin, int n, int H, int W,
+                      int Hs, int Ws, uint8_t* d_image, uint8_t* d_binary, uint8_t* d_orig_binary);
+int launch_resize_nearest(pcs_ctx* ctx, const uint8_t* d_src, int n, int H, int W, uint8_t* d_dst,
+                          int Ho, int Wo);
+
+// conv_direct.cu  (CUDA-core fp32-accumulate kernels)
+struct ConvSrc {
+    const void* p = nullptr;   // activation (precision type) or uint8 image for the first layer
+    int c = 0;                 // real channels taken from this source
+    int cp = 0;                // pixel stride in elements
+};
+struct DirectConvArgs {
+    ConvSrc src[2];
+    int nsrc = 1;
+    int src_u8 = 0;            // src[0] is the uint8 network input (value/255), H,W below are the padded grid
+    int img_h = 0, img_w = 0;  // real (unpadded) size of the uint8 input
+    int upsample = 0;          // read input at (y/2, x/2): UpSampling2D fused (U-Net up*)
+    int n = 0, h = 0, w = 0;   // output grid (== input grid unless upsample)
+    int k = 0, pad = 0;        // kernel size, pad-before
+    const float* w32 = nullptr;   // [k*k][cin][cout]
+    const float* b32 = nullptr;
+    int cin = 0, cout = 0, relu = 0;
+    void* out = nullptr;       // full-resolution output (may be null if only pooled output is needed)
+    int out_cp = 0;
+    void* pool_out = nullptr;  // optional fused 2x2 max-pool output
+    int pool_cp = 0;
+};
+int launch_conv_direct(pcs_ctx* ctx, const DirectConvArgs& a);
+
+struct DeconvS2Args {
+    ConvSrc src[2];
+    int nsrc = 1;
+    int n = 0, h = 0, w = 0;   // INPUT grid; output is 2h x 2w
+    const float* w32 = nullptr;   // [4][cin][cout], tap = i*2+j
+    const float* b32 = nullptr;
+    int cin = 0, cout = 0, relu = 0;
+    void* out = nullptr;
+    int out_cp = 0;
+};
+int launch_deconv_s2_direct(pcs_ctx* ctx, const DeconvS2Args& a);
+
+// epilogue.cu
+struct HeadArgs {
+    // optional fused stride-2 deconv feeding the logits (FCN deconv5): inputs at half resolution
+    int has_deconv = 0;
+    ConvSrc dsrc[2];
+    int dnsrc = 0;
+    const float* dw32 = nullptr;   // [4][dcin][dcout]
+    const float* db32 = nullptr;
+    int dcin = 0, dcout = 0;
+    // optional direct (full-resolution) source concatenated after the deconv output
+    ConvSrc skip;
+    int has_skip = 0;
+    // logits 1x1: [cin_total][n_classes], bias
+    const float* lw32 = nullptr;
+    const float* lb32 = nullptr;
+    int n_classes = 0;
+    int n = 0, hp = 0, wp = 0;     // padded full-resolution grid of the sources
+    int h = 0, w = 0;              // cropped output size
+    const uint8_t* binary = nullptr;
+    uint8_t* labels = nullptr;
+    float* logits = nullptr;
+    float* prob = nullptr;
+    const uint8_t* lut = nullptr;  // device copy, n_classes*3
+    uint8_t* color = nullptr;
+    uint8_t* overlay = nullptr;
+    uint8_t* inverted = nullptr;
+};
+int launch_head(pcs_ctx* ctx, const HeadArgs& a);
+int launch_masks(pcs_ctx* ctx, const uint8_t* d_labels, const uint8_t* d_binary, int n, int H, int W,
+                 const uint8_t* d_lut, int n_lut, uint8_t* d_color, uint8_t* d_overlay, uint8_t* d_inverted);
+
+// ccl.cu
+int launch_ccl(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, int32_t* d_labels,
+               int32_t* d_stats, int max_components, int32_t* d_ncomp);
+int launch_cc_majority(pcs_ctx* ctx, uint8_t* d_pred, const uint8_t* d_binary, int n, int H, int W,
+                       int n_classes);
+int launch_bounding_boxes(pcs_ctx* ctx, const uint8_t* d_pred, int n, int H, int W, int n_classes,
+                          uint8_t* d_out);
+
+// conv_umma.cu  (tcgen05 / TMEM / TMA implicit GEMM)
+struct UmmaConvArgs {
+    ConvSrc src[2];
+    int nsrc = 1;
+    int n = 0, h = 0, w = 0;
+    int k = 0, pad = 0;
+    const void* wmma = nullptr;    // pre-arranged operand image, see conv_umma.cu
+    const float* b32 = nullptr;
+    int cout = 0, npad = 0, nchunks = 0, relu = 0;
+    void* out = nullptr;
+    int out_cp = 0;
+    void* pool_out = nullptr;
+    int pool_cp = 0;
+};
+int launch_conv_umma(pcs_ctx* ctx, const UmmaConvArgs& a);
+// host-side operand image builder; returns bytes written (precision: PCS_PREC_*)
+size_t umma_weight_image(const float* w32 /*[taps][cin][cout]*/, int taps, const int* src_c, int nsrc,
+                         int cout, int npad, int precision, std::vector<uint16_t>& out);
+bool umma_supported(int k, int npad);
+
+}  // namespace pcs

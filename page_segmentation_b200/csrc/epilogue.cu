@@ -1,0 +1,209 @@
+// Network head + colour epilogue.
+//
+// Fuses, per output pixel of the cropped grid (model.py:29-42 crop):
+//   [FCN] deconv5 = Conv2DTranspose(20, 2x2, s2, linear) over concat[deconv4, conv3]   model.py:83
+//         concat [deconv5, conv2]                                                      model.py:85
+//   logits = Conv2D(n_classes, 1x1) + bias                                            model.py:88 / :199 / :231
+//   prob = softmax(logit), pred = argmax(logit) (first max wins)                       network.py:258-259
+//   color = LUT[pred]; overlay[(1-binary)==0] = 0; inverted[binary==0] = 0             output.py:44-60
+// The deconv5 result stays in fp32 registers; logits weights are fp32.
+#include "common.cuh"
+
+namespace pcs {
+
+template <typename T> __device__ __forceinline__ float hf(T v);
+template <> __device__ __forceinline__ float hf<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float hf<__half>(__half v) { return __half2float(v); }
+
+constexpr int DCO = 20;      // deconv5 output channels of both FCN variants
+
+struct HeadParams {
+    int has_deconv;
+    const void* d0; const void* d1; int dc0, dcp0, dc1, dcp1;
+    const float* dw32; const float* db32; int dcin;
+    const void* skip; int skip_c, skip_cp; int has_skip;
+    const float* lw32; const float* lb32; int n_classes;
+    int hp, wp, h, w;
+    const uint8_t* binary; uint8_t* labels; float* logits; float* prob;
+    const uint8_t* lut; uint8_t* color; uint8_t* overlay; uint8_t* inverted;
+};
+
+template <typename T, int NC>
+__global__ void __launch_bounds__(256) head_kernel(HeadParams p) {
+    extern __shared__ __align__(16) float s_head[];
+    // layout: dw [4][dcin][DCO] | db [DCO] | lw [cin_total][NC] | lb [NC]
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const int dcin = p.has_deconv ? p.dcin : 0;
+    float* s_dw = s_head;
+    float* s_db = s_dw + 4 * dcin * DCO;
+    float* s_lw = s_db + DCO;
+    const int cin_total = (p.has_deconv ? DCO : 0) + (p.has_skip ? p.skip_c : 0);
+    float* s_lb = s_lw + cin_total * NC;
+    for (int i = tid; i < 4 * dcin * DCO; i += 256) s_dw[i] = __ldg(p.dw32 + i);
+    if (p.has_deconv && tid < DCO) s_db[tid] = __ldg(p.db32 + tid);
+    for (int i = tid; i < cin_total * NC; i += 256) {
+        const int k = i % NC, c = i / NC;
+        s_lw[i] = k < p.n_classes ? __ldg(p.lw32 + (size_t)c * p.n_classes + k) : 0.f;
+    }
+    if (tid < NC) s_lb[tid] = tid < p.n_classes ? __ldg(p.lb32 + tid) : 0.f;
+    __syncthreads();
+
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, page = blockIdx.z;
+    if (x >= p.w || y >= p.h) return;
+
+    float lg[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) lg[k] = s_lb[k];
+    int row = 0;
+    if (p.has_deconv) {
+        float d5[DCO];
+#pragma unroll
+        for (int o = 0; o < DCO; ++o) d5[o] = s_db[o];
+        const int t = (y & 1) * 2 + (x & 1);
+        const int hh = p.hp / 2, wh = p.wp / 2;
+        const size_t ipix = ((size_t)page * hh + (y >> 1)) * wh + (x >> 1);
+        const T* a0 = reinterpret_cast<const T*>(p.d0) + ipix * p.dcp0;
+        const T* a1 = p.d1 ? reinterpret_cast<const T*>(p.d1) + ipix * p.dcp1 : nullptr;
+        for (int c = 0; c < dcin; ++c) {
+            const float a = hf(c < p.dc0 ? a0[c] : a1[c - p.dc0]);
+            const float4* wv = reinterpret_cast<const float4*>(s_dw + ((size_t)t * dcin + c) * DCO);
+#pragma unroll
+            for (int q = 0; q < DCO / 4; ++q) {
+                const float4 w4 = wv[q];
+                d5[4 * q + 0] = fmaf(a, w4.x, d5[4 * q + 0]);
+                d5[4 * q + 1] = fmaf(a, w4.y, d5[4 * q + 1]);
+                d5[4 * q + 2] = fmaf(a, w4.z, d5[4 * q + 2]);
+                d5[4 * q + 3] = fmaf(a, w4.w, d5[4 * q + 3]);
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < DCO; ++o)
+#pragma unroll
+            for (int k = 0; k < NC; ++k) lg[k] = fmaf(d5[o], s_lw[o * NC + k], lg[k]);
+        row = DCO;
+    }
+    if (p.has_skip) {
+        const T* s = reinterpret_cast<const T*>(p.skip) + (((size_t)page * p.hp + y) * p.wp + x) * p.skip_cp;
+        for (int c = 0; c < p.skip_c; ++c) {
+            const float a = hf(s[c]);
+#pragma unroll
+            for (int k = 0; k < NC; ++k) lg[k] = fmaf(a, s_lw[(row + c) * NC + k], lg[k]);
+        }
+    }
+
+    // argmax, first maximum wins (np.argmax)
+    int best = 0;
+    float bv = lg[0];
+#pragma unroll
+    for (int k = 1; k < NC; ++k)
+        if (k < p.n_classes && lg[k] > bv) { bv = lg[k]; best = k; }
+    const size_t opix = ((size_t)page * p.h + y) * p.w + x;
+    if (p.labels) p.labels[opix] = (uint8_t)best;
+    if (p.logits)
+        for (int k = 0; k < p.n_classes; ++k) p.logits[opix * p.n_classes + k] = lg[k];
+    if (p.prob) {
+        float e[NC], sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            e[k] = k < p.n_classes ? expf(lg[k] - bv) : 0.f;
+            sum += e[k];
+        }
+        for (int k = 0; k < p.n_classes; ++k) p.prob[opix * p.n_classes + k] = e[k] / sum;
+    }
+    if (p.color || p.overlay || p.inverted) {
+        const uint8_t r = p.lut[best * 3 + 0], g = p.lut[best * 3 + 1], b = p.lut[best * 3 + 2];
+        const uint8_t bin = p.binary ? p.binary[opix] : 1;
+        if (p.color) { p.color[opix * 3 + 0] = r; p.color[opix * 3 + 1] = g; p.color[opix * 3 + 2] = b; }
+        if (p.overlay) {
+            // overlay[(1 - binary) == 0] = 0  -> kept where binary != 1
+            const bool keep = (uint8_t)(1 - bin) != 0;
+            p.overlay[opix * 3 + 0] = keep ? r : 0; p.overlay[opix * 3 + 1] = keep ? g : 0; p.overlay[opix * 3 + 2] = keep ? b : 0;
+        }
+        if (p.inverted) {
+            const bool keep = bin != 0;                     // inverted[binary == 0] = 0
+            p.inverted[opix * 3 + 0] = keep ? r : 0; p.inverted[opix * 3 + 1] = keep ? g : 0; p.inverted[opix * 3 + 2] = keep ? b : 0;
+        }
+    }
+}
+
+template <typename T, int NC>
+static int launch_head_nc(pcs_ctx* ctx, const HeadParams& p, int n) {
+    const int dcin = p.has_deconv ? p.dcin : 0;
+    const int cin_total = (p.has_deconv ? DCO : 0) + (p.has_skip ? p.skip_c : 0);
+    const size_t smem = ((size_t)4 * dcin * DCO + DCO + (size_t)cin_total * NC + NC) * sizeof(float);
+    if (smem > 200 * 1024) return set_err(ctx, PCS_ERR_ARG, "head: weights do not fit in shared memory");
+    if (smem > 48 * 1024)
+        PCS_CUDA(ctx, cudaFuncSetAttribute(head_kernel<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((p.w + 31) / 32, (p.h + 7) / 8, n), block(32, 8);
+    head_kernel<T, NC><<<grid, block, smem, ctx->stream>>>(p);
+    PCS_LAUNCH_CHECK(ctx, "head_kernel");
+    return PCS_OK;
+}
+
+template <typename T>
+static int launch_head_t(pcs_ctx* ctx, const HeadParams& p, int n) {
+    const int nc = p.n_classes;
+    if (nc <= 2) return launch_head_nc<T, 2>(ctx, p, n);
+    if (nc <= 3) return launch_head_nc<T, 3>(ctx, p, n);
+    if (nc <= 4) return launch_head_nc<T, 4>(ctx, p, n);
+    if (nc <= 6) return launch_head_nc<T, 6>(ctx, p, n);
+    if (nc <= 8) return launch_head_nc<T, 8>(ctx, p, n);
+    if (nc <= 16) return launch_head_nc<T, 16>(ctx, p, n);
+    return set_err(ctx, PCS_ERR_ARG, "head: n_classes %d > %d", nc, kMaxClasses);
+}
+
+int launch_head(pcs_ctx* ctx, const HeadArgs& a) {
+    if (a.has_deconv && a.dcout != DCO) return set_err(ctx, PCS_ERR_ARG, "head: fused deconv expects %d channels", DCO);
+    if (a.has_deconv && (a.dcin % 1)) return PCS_ERR_ARG;
+    HeadParams p{};
+    p.has_deconv = a.has_deconv;
+    p.d0 = a.dsrc[0].p; p.dc0 = a.dsrc[0].c; p.dcp0 = a.dsrc[0].cp;
+    p.d1 = a.dnsrc > 1 ? a.dsrc[1].p : nullptr; p.dc1 = a.dnsrc > 1 ? a.dsrc[1].c : 0; p.dcp1 = a.dnsrc > 1 ? a.dsrc[1].cp : 0;
+    p.dw32 = a.dw32; p.db32 = a.db32; p.dcin = a.dcin;
+    p.skip = a.skip.p; p.skip_c = a.skip.c; p.skip_cp = a.skip.cp; p.has_skip = a.has_skip;
+    p.lw32 = a.lw32; p.lb32 = a.lb32; p.n_classes = a.n_classes;
+    p.hp = a.hp; p.wp = a.wp; p.h = a.h; p.w = a.w;
+    p.binary = a.binary; p.labels = a.labels; p.logits = a.logits; p.prob = a.prob;
+    p.lut = a.lut; p.color = a.color; p.overlay = a.overlay; p.inverted = a.inverted;
+    if (ctx->precision == PCS_PREC_BF16) return launch_head_t<__nv_bfloat16>(ctx, p, a.n);
+    return launch_head_t<__half>(ctx, p, a.n);
+}
+
+// ---------------------------------------------------------------------------
+// generate_output_masks on an existing class map (output.py:44-60).
+// Labels not present in the LUT map to (0,0,0).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+masks_kernel(const uint8_t* __restrict__ labels, const uint8_t* __restrict__ binary, size_t npix,
+             const uint8_t* __restrict__ lut, int n_lut, uint8_t* __restrict__ color, uint8_t* __restrict__ overlay,
+             uint8_t* __restrict__ inverted) {
+    __shared__ uint8_t s_lut[256 * 3];
+    for (int i = threadIdx.x; i < 256 * 3; i += blockDim.x) s_lut[i] = (i < n_lut * 3) ? lut[i] : 0;
+    __syncthreads();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+        const int l = labels[i];
+        const uint8_t r = s_lut[l * 3], g = s_lut[l * 3 + 1], b = s_lut[l * 3 + 2];
+        const uint8_t bin = binary[i];
+        if (color) { color[i * 3] = r; color[i * 3 + 1] = g; color[i * 3 + 2] = b; }
+        if (overlay) {
+            const bool keep = (uint8_t)(1 - bin) != 0;
+            overlay[i * 3] = keep ? r : 0; overlay[i * 3 + 1] = keep ? g : 0; overlay[i * 3 + 2] = keep ? b : 0;
+        }
+        if (inverted) {
+            const bool keep = bin != 0;
+            inverted[i * 3] = keep ? r : 0; inverted[i * 3 + 1] = keep ? g : 0; inverted[i * 3 + 2] = keep ? b : 0;
+        }
+    }
+}
+
+int launch_masks(pcs_ctx* ctx, const uint8_t* d_labels, const uint8_t* d_binary, int n, int H, int W,
+                 const uint8_t* d_lut, int n_lut, uint8_t* d_color, uint8_t* d_overlay, uint8_t* d_inverted) {
+    if (n <= 0 || H <= 0 || W <= 0 || n_lut < 0 || n_lut > 256) return set_err(ctx, PCS_ERR_ARG, "masks: bad argument");
+    const size_t npix = (size_t)n * H * W;
+    const unsigned blocks = (unsigned)std::min<size_t>((size_t)ctx->sm_count * 8, (npix + 255) / 256);
+    masks_kernel<<<blocks, 256, 0, ctx->stream>>>(d_labels, d_binary, npix, d_lut, n_lut, d_color, d_overlay, d_inverted);
+    PCS_LAUNCH_CHECK(ctx, "masks_kernel");
+    return PCS_OK;
+}
+
+}  // namespace pcs

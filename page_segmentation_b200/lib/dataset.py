@@ -1,0 +1,116 @@
+"""Mirror of ocr4all_pixel_classifier/lib/dataset.py for the prediction path:
+SingleData (:17-29), Dataset (:32-41), prepare_images (:131-150) and
+DatasetLoader (:153-208).  Training-only helpers (list_dataset, splits) are out
+of scope."""
+from __future__ import annotations
+
+import json
+from dataclasses import dataclass
+from typing import Any, Callable, List, Optional, Tuple
+
+import numpy as np
+
+from .colors import ColorMap
+
+
+@dataclass
+class SingleData:
+    image: np.ndarray = None
+    binary: Optional[np.ndarray] = None
+    orig_binary: Optional[np.ndarray] = None
+    mask: np.ndarray = None
+    image_path: Optional[str] = None
+    binary_path: Optional[str] = None
+    mask_path: Optional[str] = None
+    line_height_px: Optional[int] = 1
+    original_shape: Tuple[int, int] = None
+    output_path: Optional[str] = None
+    user_data: Any = None
+
+
+@dataclass
+class Dataset:
+    data: List[SingleData]
+    color_map: ColorMap
+
+    def __len__(self):
+        return len(self.data)
+
+    def __iter__(self):
+        return self.data.__iter__()
+
+
+def imread(path: str, as_gray: bool = True) -> np.ndarray:
+    """Stand-in for ocr4all.files.imread (dataset.py:169): 8-bit grey page."""
+    import cv2
+    img = cv2.imread(path, cv2.IMREAD_GRAYSCALE if as_gray else cv2.IMREAD_COLOR)
+    if img is None:
+        raise FileNotFoundError(path)
+    return img
+
+
+def imread_bin(path: str, white_is_fg: bool = True) -> np.ndarray:
+    """Stand-in for ocr4all.files.imread_bin (dataset.py:172): {0,255} page,
+    paper = 255 (threshold at mid-grey; pylib's exact rule is unpinned)."""
+    img = imread(path, True)
+    return np.where(img > 127, 255, 0).astype(np.uint8)
+
+
+def prepare_images(image: np.ndarray, binary: np.ndarray, target_line_height: int, line_height_px: int,
+                   max_width: Optional[int] = None, keep_orig_bin=False):
+    """dataset.py:131-150 (device kernel behind pcs_preprocess)."""
+    from ..runtime import prepare_images_device
+    return prepare_images_device(image, binary, target_line_height, line_height_px, max_width, keep_orig_bin)
+
+
+class DatasetLoader:
+    def __init__(self, target_line_height, color_map: ColorMap, prediction=False, max_width=None):
+        self.target_line_height = target_line_height
+        self.prediction = prediction
+        self.color_map = color_map
+        self.max_width = max_width
+
+    def load_images(self, dataset_file_entry: SingleData) -> SingleData:
+        """dataset.py:160-191, including its quirk that the binary page is
+        derived from `image` / `image_path` (attribute name 'image', :172)."""
+        def load_cached(data: SingleData, attr: str, loader: Callable[[str], np.ndarray]) -> np.ndarray:
+            file = getattr(data, attr)
+            if file is not None:
+                return file
+            return loader(getattr(data, attr + '_path'))
+
+        img = load_cached(dataset_file_entry, 'image', lambda path: imread(path, as_gray=True))
+        original_shape = img.shape
+        bin = load_cached(dataset_file_entry, 'image', lambda path: imread_bin(path, True))
+        img, bin, orig_bin = prepare_images(img, bin, self.target_line_height, dataset_file_entry.line_height_px,
+                                            self.max_width, keep_orig_bin=True)
+        scaled_shape = img.shape
+        if not self.prediction:
+            from .util import preserving_resize
+            mask = load_cached(dataset_file_entry, 'mask', self.color_map.imread_labels)
+            mask = preserving_resize(mask, scaled_shape)
+            assert (mask.shape == img.shape)
+            dataset_file_entry.mask = mask.astype(np.uint8)
+        dataset_file_entry.binary = bin
+        dataset_file_entry.orig_binary = orig_bin
+        dataset_file_entry.image = img
+        dataset_file_entry.original_shape = original_shape
+        return dataset_file_entry
+
+    def load_data(self, all_dataset_files) -> Dataset:
+        """dataset.py:193-198.  The reference fans pages out to a 12-process pool
+        because its rescale is CPU bound; here the rescale is a GPU kernel, so
+        pages are processed in order on the caller's device."""
+        out = [self.load_images(d) for d in all_dataset_files]
+        return Dataset(out, self.color_map)
+
+    def load_data_from_json(self, files, type) -> Dataset:
+        """dataset.py:200-208."""
+        all_files = []
+        for f in files:
+            if type == "all":
+                all_files += [SingleData(**d) for t in ["train", "test", "eval"] for d in json.load(open(f, 'r'))[t]]
+            else:
+                all_files += [SingleData(**d) for d in json.load(open(f, 'r'))[type]]
+        print(f"Loading {len(all_files)} data of type {type}")
+        return self.load_data(all_files)

@@ -1,0 +1,131 @@
+"""Mirror of ocr4all_pixel_classifier/lib/network.py for prediction:
+`Network.__init__` model loading (:19-107) and `predict_single_data` (:248-260).
+Training (`train_dataset`, :167-242) is out of scope."""
+from __future__ import annotations
+
+import logging
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .architecture import Architecture
+from .dataset import Dataset, SingleData
+from .colors import ColorMap
+
+logger = logging.getLogger(__name__)
+
+DEFAULT_PRECISION = os.environ.get("PCSEG_PRECISION", "bf16")
+
+
+class _ModelHandle:
+    """What `self.model` of the reference exposes to its callers: `.name`."""
+
+    def __init__(self, name: str, weights):
+        self.name = name
+        self.weights = weights
+
+
+class Network:
+    def __init__(self,
+                 type: str,
+                 n_classes: int = -1,
+                 model_constructor: Architecture = Architecture.FCN_SKIP,
+                 l_rate: float = 1e-4,
+                 has_binary: bool = False,
+                 foreground_masks: bool = False,
+                 model: str = None,
+                 continue_training: bool = False,
+                 input_image_dimension: int = 1,
+                 optimizer=None,
+                 optimizer_norm_clipping: bool = True,
+                 optimizer_norm_clip_value: float = 1.0,
+                 optimizer_clipping=False,
+                 optimizer_clip_value=1,
+                 loss_func=None,
+                 weights: Optional[Sequence[Tuple[np.ndarray, np.ndarray]]] = None,
+                 precision: Optional[str] = None,
+                 device: Optional[int] = None,
+                 ):
+        """Same leading parameters as the reference (network.py:19-35).  Extra
+        keyword-only-in-practice parameters: `weights` (Keras-ordered list of
+        (kernel, bias) instead of a file), `precision` ('bf16' | 'fp16' tensor-core
+        operand type) and `device`."""
+        if type.lower() == "train":
+            raise NotImplementedError("training is outside the B200 inference hot path")
+        self.architecture = model_constructor.value
+        self._data: Dataset = Dataset([], ColorMap({}))
+        self.type = type
+        self.has_binary = has_binary
+        self.foreground_masks = foreground_masks
+        self.n_classes = n_classes
+        self.precision = precision or DEFAULT_PRECISION
+        self.device = device
+        Architecture(self.architecture).preprocess()   # raises for out-of-scope architectures
+
+        name = 'model'
+        if weights is None:
+            if not model:
+                raise ValueError("Network needs `model` (a Keras .h5 path) or `weights`")
+            model = model if '.' in model else model + '.h5'                 # network.py:59
+            if not os.path.exists(model):
+                raise FileNotFoundError(f"model file {model} does not exist (TF1 .meta migration, network.py:60-68, "
+                                        "is not available)")
+            from . import h5
+            # network.py:75-84 load_model, falling back to load_weights (:106-107): both layouts are read
+            loaded = h5.load_keras_model(model)
+            weights = loaded.weights
+            if loaded.name:
+                name = loaded.name
+            if loaded.name in ('fcn_skip', 'fcn', 'unet'):
+                self.architecture = loaded.name                               # network.py:251
+        self.model = _ModelHandle(name, list(weights))
+        arch = self.architecture if self.model.name == 'model' else self.model.name
+        n_from_weights = int(self.model.weights[-1][0].shape[-1])
+        if self.n_classes is None or self.n_classes < 0:
+            self.n_classes = n_from_weights
+        elif self.n_classes != n_from_weights:
+            raise ValueError(f"n_classes={self.n_classes} but the logits layer has {n_from_weights} outputs")
+        self._arch = arch
+        self._ctx = None
+
+    # -- device state ----------------------------------------------------------
+    def _context(self):
+        from ..runtime import get_context
+        ctx = get_context(self.device)
+        want = (self._arch, self.n_classes, self.precision, id(self.model))
+        if getattr(ctx, "_loaded_key", None) != want:
+            ctx.load_model(self._arch, self.n_classes, self.model.weights, self.precision)
+            ctx._loaded_key = want
+        return ctx
+
+    def predict_single_data(self, data: SingleData):
+        """network.py:248-260 -> (logit f32 HWC, prob f32 HWC, pred int64 HW)."""
+        import torch
+        ctx = self._context()
+        image = np.ascontiguousarray(data.image)
+        if image.dtype != np.uint8 or image.ndim != 2:
+            raise ValueError("data.image must be a 2-D uint8 array (DatasetLoader output)")
+        h, w = image.shape
+        dev = f"cuda:{ctx.device}"
+        d_image = torch.from_numpy(image).to(dev)
+        d_labels = torch.empty((h, w), dtype=torch.uint8, device=dev)
+        d_logits = torch.empty((h, w, self.n_classes), dtype=torch.float32, device=dev)
+        d_prob = torch.empty((h, w, self.n_classes), dtype=torch.float32, device=dev)
+        ctx.forward(d_image, None, 1, h, w, d_labels, d_logits, d_prob)
+        logit = d_logits.cpu().numpy()
+        prob = d_prob.cpu().numpy()
+        pred = d_labels.cpu().numpy().astype(np.int64)
+        return logit, prob, pred
+
+    def predict_labels_device(self, d_image, d_labels):
+        """Device-resident variant: (n,H,W) uint8 CUDA tensors in/out."""
+        ctx = self._context()
+        n, h, w = d_image.shape
+        ctx.forward(d_image, None, n, h, w, d_labels)
+        return d_labels
+
+
+def tf_backend_allow_growth():
+    """network.py:263-268 configures TensorFlow's allocator; nothing to do here."""
+    return None

@@ -1,0 +1,49 @@
+"""Mirror of ocr4all_pixel_classifier/lib/predictor.py:10-54."""
+import os
+from typing import Generator
+
+from .predictor_data import Prediction, PredictSettings
+from .dataset import Dataset, SingleData
+from .network import Network, tf_backend_allow_growth
+from .output import Masks, scale_to_original_shape, generate_output_masks
+
+
+class Predictor:
+    def __init__(self, settings: PredictSettings, network: Network = None):
+        self.settings = settings
+        self.network = network
+
+        if settings.gpu_allow_growth:
+            tf_backend_allow_growth()
+
+        if not network:
+            self.network = Network("Predict", n_classes=settings.n_classes,
+                                   model=os.path.abspath(self.settings.network))
+        if settings.output:
+            output_dir = settings.output
+            os.makedirs(os.path.join(output_dir, "overlay"), exist_ok=True)
+            os.makedirs(os.path.join(output_dir, "color"), exist_ok=True)
+            os.makedirs(os.path.join(output_dir, "inverted"), exist_ok=True)
+
+    def predict(self, dataset: Dataset) -> Generator[Prediction, None, None]:
+        for data in dataset.data:
+            prediction = self.predict_single(data)
+            yield prediction
+
+    def _post(self, data: SingleData, pred):
+        if self.settings.high_res_output:
+            data, pred = scale_to_original_shape(data, pred)
+        if self.settings.post_process:
+            for processor in self.settings.post_process:
+                pred = processor(pred, data)
+        return data, pred
+
+    def predict_single(self, data: SingleData) -> Prediction:
+        logit, prob, pred = self.network.predict_single_data(data)
+        data, pred = self._post(data, pred)
+        return Prediction(pred, prob, data)
+
+    def predict_masks(self, data: SingleData) -> Masks:
+        logit, prob, pred = self.network.predict_single_data(data)
+        data, pred = self._post(data, pred)
+        return generate_output_masks(data, pred, self.settings.color_map)

@@ -1,0 +1,179 @@
+"""Host-side runtime: one `Context` per GPU, numpy <-> device staging helpers and
+the page-batch engine used by the Predictor mirror, bench.py and the tests.
+
+PyTorch is plumbing only (device tensors, pinned host memory, streams,
+torch.distributed); all arithmetic is in libpcseg_b200.so.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native
+from .synth import scaled_shape
+
+
+def default_device() -> int:
+    return int(os.environ.get("LOCAL_RANK", os.environ.get("PCSEG_DEVICE", "0")))
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise _native.PcsError("no CUDA device visible: the B200 hot path has no CPU fallback")
+    return torch
+
+
+def get_context(device: Optional[int] = None) -> _native.Context:
+    torch = _torch()
+    dev = default_device() if device is None else int(device)
+    torch.cuda.set_device(dev)
+    ctx = _native.context(dev)
+    ctx.use_torch_stream()
+    return ctx
+
+
+def to_device_u8(arr: np.ndarray, device: int):
+    torch = _torch()
+    a = np.ascontiguousarray(arr)
+    if a.dtype == np.bool_:
+        a = a.astype(np.uint8)
+    if a.dtype != np.uint8:
+        if a.size and (a.min() < 0 or a.max() > 255):
+            raise ValueError("values outside 0..255 cannot be staged as uint8")
+        a = a.astype(np.uint8)
+    return torch.from_numpy(a).to(f"cuda:{device}", non_blocking=False)
+
+
+# ---------------------------------------------------------------------------
+# single-page helpers behind the reference-named functions
+# ---------------------------------------------------------------------------
+def prepare_images_device(image: np.ndarray, binary: np.ndarray, target_line_height: int, line_height_px: int,
+                          max_width: Optional[int] = None, keep_orig_bin: bool = False, device: Optional[int] = None):
+    """dataset.py:131-150 on the GPU; returns numpy uint8 arrays like the reference."""
+    torch = _torch()
+    ctx = get_context(device)
+    dev = ctx.device
+    image = np.asarray(image)
+    binary = np.asarray(binary)
+    if image.ndim != 2 or binary.shape != image.shape:
+        raise ValueError("prepare_images expects 2-D image and binary of equal shape")
+    if image.dtype != np.uint8:
+        raise NotImplementedError("the device preprocess takes uint8 grey pages (as imread(as_gray=True) of 8-bit scans yields)")
+    scale = target_line_height / line_height_px
+    H, W = image.shape
+    Hs, Ws = scaled_shape(H, W, scale)
+    if max_width is not None and max_width / Ws < 1.0:
+        raise NotImplementedError("max_width second rescale pass is not implemented on the device path yet")
+    same = binary is image or (binary.dtype == np.uint8 and np.shares_memory(binary, image))
+    d_grey = to_device_u8(image, dev)
+    d_bin = d_grey if same else to_device_u8(binary, dev)
+    d_image = torch.empty((Hs, Ws), dtype=torch.uint8, device=d_grey.device)
+    d_binary = torch.empty((Hs, Ws), dtype=torch.uint8, device=d_grey.device)
+    d_orig = torch.empty((H, W), dtype=torch.uint8, device=d_grey.device) if keep_orig_bin else None
+    ctx.preprocess(d_grey, d_bin, 1, H, W, Hs, Ws, d_image, d_binary, d_orig)
+    img, bin_ = d_image.cpu().numpy(), d_binary.cpu().numpy()
+    if keep_orig_bin:
+        return img, bin_, d_orig.cpu().numpy()
+    return img, bin_
+
+
+def resize_nearest_plane(arr: np.ndarray, target_shape: Tuple[int, int], device: Optional[int] = None) -> np.ndarray:
+    """util.py:21-29 preserving_resize for a uint8-representable plane."""
+    torch = _torch()
+    ctx = get_context(device)
+    if arr.ndim != 2:
+        raise ValueError("preserving_resize expects a 2-D plane")
+    d_src = to_device_u8(arr, ctx.device)
+    Ho, Wo = int(target_shape[0]), int(target_shape[1])
+    d_dst = torch.empty((Ho, Wo), dtype=torch.uint8, device=d_src.device)
+    ctx.resize_nearest(d_src, 1, arr.shape[0], arr.shape[1], d_dst, Ho, Wo)
+    return d_dst.cpu().numpy()
+
+
+def connected_components_with_stats(img: np.ndarray, device: Optional[int] = None):
+    """cv2.connectedComponentsWithStats(img, connectivity=4) -> (n, labels i32, stats i32 (n,5))."""
+    torch = _torch()
+    ctx = get_context(device)
+    H, W = img.shape
+    d_img = to_device_u8((np.asarray(img) != 0), ctx.device)
+    d_labels = torch.empty((H, W), dtype=torch.int32, device=d_img.device)
+    d_ncomp = torch.zeros((1,), dtype=torch.int32, device=d_img.device)
+    ctx.ccl(d_img, 1, H, W, d_labels, None, 0, d_ncomp)
+    n = int(d_ncomp.cpu()[0])
+    d_stats = torch.empty((n, 5), dtype=torch.int32, device=d_img.device)
+    ctx.ccl(d_img, 1, H, W, d_labels, d_stats, n, d_ncomp)
+    return n, d_labels.cpu().numpy(), d_stats.cpu().numpy()
+
+
+# ---------------------------------------------------------------------------
+# page-batch engine (device-resident or host-staged)
+# ---------------------------------------------------------------------------
+class PageBatchEngine:
+    """Runs prepare_images -> network -> [cc_majority] -> masks for batches of
+    equally sized pages on one GPU.  Buffers are allocated once per shape."""
+
+    def __init__(self, arch: str, weights, n_classes: int, precision: str = "bf16", device: Optional[int] = None,
+                 lut: Optional[np.ndarray] = None, engine: str = "umma"):
+        self.torch = _torch()
+        self.ctx = get_context(device)
+        self.ctx.load_model(arch, n_classes, weights, precision)
+        self.ctx.set_engine(engine)
+        self.n_classes = n_classes
+        self.lut = None if lut is None else np.ascontiguousarray(lut, dtype=np.uint8)
+        self._bufs: Dict[tuple, dict] = {}
+
+    def buffers(self, n: int, H: int, W: int, Hs: int, Ws: int) -> dict:
+        key = (n, H, W, Hs, Ws)
+        b = self._bufs.get(key)
+        if b is None:
+            t, dev = self.torch, f"cuda:{self.ctx.device}"
+            b = dict(
+                image=t.empty((n, Hs, Ws), dtype=t.uint8, device=dev),
+                binary=t.empty((n, Hs, Ws), dtype=t.uint8, device=dev),
+                labels=t.empty((n, Hs, Ws), dtype=t.uint8, device=dev),
+                color=t.empty((n, Hs, Ws, 3), dtype=t.uint8, device=dev),
+                overlay=t.empty((n, Hs, Ws, 3), dtype=t.uint8, device=dev),
+                inverted=t.empty((n, Hs, Ws, 3), dtype=t.uint8, device=dev),
+            )
+            self._bufs[key] = b
+        return b
+
+    def run_device(self, d_pages, scale: float, cc_majority: bool = False, masks: bool = True) -> dict:
+        """d_pages: (n, H, W) uint8 CUDA tensor used as grey and binary page."""
+        n, H, W = d_pages.shape
+        Hs, Ws = scaled_shape(H, W, scale)
+        b = self.buffers(n, H, W, Hs, Ws)
+        ctx = self.ctx
+        ctx.use_torch_stream()
+        ctx.preprocess(d_pages, d_pages, n, H, W, Hs, Ws, b["image"], b["binary"], None)
+        want = masks and self.lut is not None
+        if cc_majority:
+            ctx.forward(b["image"], b["binary"], n, Hs, Ws, b["labels"])
+            ctx.cc_majority(b["labels"], b["binary"], n, Hs, Ws, self.n_classes)
+            if want:
+                ctx.masks(b["labels"], b["binary"], n, Hs, Ws, self.lut, b["color"], b["overlay"], b["inverted"])
+        else:
+            ctx.forward(b["image"], b["binary"], n, Hs, Ws, b["labels"], None, None,
+                        self.lut if want else None, b["color"] if want else None,
+                        b["overlay"] if want else None, b["inverted"] if want else None)
+        return b
+
+    def run_host(self, h_pages: np.ndarray, scale: float, out: dict, cc_majority: bool = False):
+        """h_pages: (n, H, W) uint8 host array (ideally pinned); `out` holds host
+        arrays 'labels' and optionally 'color','overlay','inverted' (pinned)."""
+        n, H, W = h_pages.shape
+        Hs, Ws = scaled_shape(H, W, scale)
+        self.ctx.use_torch_stream()
+        self.ctx.predict_pages_host(h_pages, h_pages, n, H, W, Hs, Ws, cc_majority, self.lut,
+                                    None, None, out.get("labels"), out.get("color"), out.get("overlay"),
+                                    out.get("inverted"))
+        return out
+
+
+def shard_pages(n_pages: int, rank: int, world: int) -> List[int]:
+    """Static round-robin page sharding over ranks (pages are independent;
+    predictor.py:27-30 has batch 1 everywhere)."""
+    return list(range(rank, n_pages, world))

@@ -1,0 +1,124 @@
+"""Bit-exact parity of the colour epilogue (output.py:44-60) and of the
+connected-component post-processors (postprocess.py:9-42, cv2 4-connectivity)."""
+import cv2
+import numpy as np
+import pytest
+
+from oracle import pipeline as opipe
+from page_segmentation_b200 import synth
+from page_segmentation_b200.lib.colors import ColorMap, DEFAULT_COLOR_MAP
+from page_segmentation_b200.lib.dataset import SingleData
+
+pytestmark = pytest.mark.gpu
+
+
+def _pred_and_binary(seed, h, w, n_classes=3):
+    rng = np.random.default_rng(seed)
+    page = synth.make_page(seed, h * 3, w * 3, 18)
+    _, b = opipe.prepare_images(page, page, 6, 18)
+    # blocky class map so that components see mixed classes
+    coarse = rng.integers(0, n_classes, size=(h // 7 + 1, w // 9 + 1))
+    pred = np.kron(coarse, np.ones((7, 9), dtype=np.int64))[:b.shape[0], :b.shape[1]]
+    noise = rng.random(b.shape) < 0.15
+    pred = np.where(noise, rng.integers(0, n_classes, size=b.shape), pred).astype(np.int64)
+    return pred, b
+
+
+@pytest.mark.parametrize("hw", [(2, 2), (61, 83), (389, 275), (1169, 827)])
+def test_generate_output_masks_bit_exact(ctx, hw):
+    from page_segmentation_b200.lib.output import generate_output_masks
+    pred, b = _pred_and_binary(1, *hw)
+    m = generate_output_masks(SingleData(binary=b), pred, DEFAULT_COLOR_MAP)
+    lut = {0: (255, 255, 255), 1: (255, 0, 0), 2: (0, 255, 0)}
+    c, o, i, f = opipe.generate_output_masks(b, pred, lut)
+    np.testing.assert_array_equal(m.color, c)
+    np.testing.assert_array_equal(m.overlay, o)
+    np.testing.assert_array_equal(m.inverted_overlay, i)
+    np.testing.assert_array_equal(m.fg_color_mask, f)
+
+
+def test_masks_unknown_label_is_black(ctx):
+    from page_segmentation_b200.lib.output import generate_output_masks
+    pred = np.array([[0, 1], [2, 3]], dtype=np.int64)
+    b = np.array([[1, 0], [1, 1]], dtype=np.uint8)
+    cm = ColorMap({(255, 255, 255): (0, "background"), (255, 0, 0): (1, "text"), (0, 0, 255): (3, "x")})
+    m = generate_output_masks(SingleData(binary=b), pred, cm)
+    assert m.color[1, 0].tolist() == [0, 0, 0]
+    assert m.color[1, 1].tolist() == [0, 0, 255]
+    assert m.overlay[0, 0].tolist() == [0, 0, 0] and m.overlay[0, 1].tolist() == [255, 0, 0]
+    assert m.inverted_overlay[0, 1].tolist() == [0, 0, 0] and m.inverted_overlay[0, 0].tolist() == [255, 255, 255]
+
+
+@pytest.mark.parametrize("hw", [(6, 8), (61, 83), (389, 275), (1169, 827)])
+def test_ccl_matches_cv2(ctx, hw):
+    from page_segmentation_b200.runtime import connected_components_with_stats
+    _, b = _pred_and_binary(2, *hw)
+    n, labels, stats = connected_components_with_stats(b)
+    en, elabels, estats, _ = cv2.connectedComponentsWithStats(b, connectivity=4)
+    assert n == en
+    np.testing.assert_array_equal(labels, elabels)
+    np.testing.assert_array_equal(stats, estats)
+
+
+@pytest.mark.parametrize("pattern", ["empty", "full", "checker", "hstripes", "vstripes", "spiral", "wide"])
+def test_ccl_patterns(ctx, pattern):
+    from page_segmentation_b200.runtime import connected_components_with_stats
+    h, w = 70, 131
+    a = np.zeros((h, w), np.uint8)
+    if pattern == "full":
+        a[:] = 1
+    elif pattern == "checker":
+        a[::2, ::2] = 1
+        a[1::2, 1::2] = 1
+    elif pattern == "hstripes":
+        a[::2, :] = 1
+    elif pattern == "vstripes":
+        a[:, ::2] = 1
+    elif pattern == "spiral":
+        for k in range(0, 30, 2):
+            a[k, k:w - k] = 1
+            a[k:h - k, w - 1 - k] = 1
+            a[h - 1 - k, k:w - k] = 1
+            a[k + 2:h - k, k] = 1
+    elif pattern == "wide":
+        a[10, :] = 1
+        a[5:40, 64] = 1
+        a[30, 3:100] = 1
+    n, labels, stats = connected_components_with_stats(a)
+    en, elabels, estats, _ = cv2.connectedComponentsWithStats(a, connectivity=4)
+    assert n == en
+    np.testing.assert_array_equal(labels, elabels)
+    if pattern not in ("full",):          # cv2's background row is undefined when there is no background
+        np.testing.assert_array_equal(stats, estats)
+    else:
+        np.testing.assert_array_equal(stats[1:], estats[1:])
+
+
+@pytest.mark.parametrize("hw", [(61, 83), (389, 275), (1169, 827)])
+def test_cc_majority_bit_exact(ctx, hw):
+    from page_segmentation_b200.lib.postprocess import vote_connected_component_class
+    pred, b = _pred_and_binary(3, *hw)
+    exp = opipe.vote_connected_component_class(pred.copy(), b)
+    got_in = pred.copy()
+    got = vote_connected_component_class(got_in, SingleData(binary=b))
+    assert got is got_in                        # the reference mutates in place
+    np.testing.assert_array_equal(got, exp)
+
+
+@pytest.mark.parametrize("hw", [(61, 83), (200, 160)])
+def test_bounding_boxes(ctx, hw):
+    from page_segmentation_b200.lib.postprocess import add_bounding_boxes
+    pred, b = _pred_and_binary(4, *hw)
+    pred = np.where(b > 0, pred, 0)
+    exp = opipe.add_bounding_boxes(pred.copy())
+    got = add_bounding_boxes(pred.copy(), SingleData(binary=b))
+    np.testing.assert_array_equal(got, exp)
+
+
+def test_find_postprocessor(ctx):
+    from page_segmentation_b200.lib import postprocess as pp
+    assert pp.find_postprocessor("cc_majority") is pp.vote_connected_component_class
+    assert pp.find_postprocessor("CC-Vote") is pp.vote_connected_component_class
+    assert pp.find_postprocessor("bounding_boxes") is pp.add_bounding_boxes
+    with pytest.raises(KeyError):
+        pp.find_postprocessor("nope")

@@ -1,0 +1,145 @@
+"""Parity of the device network (pcs_forward) with the CPU oracle restating
+model.py / network.py:248-260.
+
+Tolerances (stated, see DESIGN.md "precision"):
+  * device vs numerics twin (same bf16|fp16 rounding points, fp32 accumulate):
+    logits max |d| <= 2e-3 (bf16) / 3e-4 (fp16), mean |d| <= 2e-5 / 4e-6 -- only
+    accumulation order and rare 1-ulp operand flips differ;
+  * device vs fp32 oracle: logits max |d| <= 8e-3 (bf16) / 1e-3 (fp16);
+  * argmax vs the fp64 oracle: agreement >= 99.9 % for fp16 operands, >= 99.7 % for
+    bf16 operands, and every disagreeing pixel is a near-tie: fp64 top-2 margin
+    <= 2 * max logit error.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import network as onet
+from oracle import pipeline as opipe
+from page_segmentation_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"bf16": dict(twin_max=2e-3, twin_mean=2e-5, f32_max=8e-3, agree=0.997),
+       "fp16": dict(twin_max=3e-4, twin_mean=4e-6, f32_max=1e-3, agree=0.999)}
+
+
+def _device_predict(arch, weights, n_classes, image, precision, engine):
+    from page_segmentation_b200.lib.network import Network
+    from page_segmentation_b200.lib.architecture import Architecture
+    from page_segmentation_b200.lib.dataset import SingleData
+    net = Network("Predict", n_classes=n_classes, model_constructor=Architecture(arch), weights=weights,
+                  precision=precision)
+    net._context().set_engine(engine)
+    return net, net.predict_single_data(SingleData(image=image))
+
+
+def _small_input(seed, h, w):
+    page = synth.make_page(seed, h * 3, w * 3, 18)
+    img, b = opipe.prepare_images(page, page, 6, 18)
+    return img, b
+
+
+@pytest.mark.parametrize("engine", ["direct", "umma"])
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+@pytest.mark.parametrize("arch,hw", [("fcn_skip", (150, 203)), ("fcn", (97, 64)), ("fcn_skip", (32, 32))])
+def test_fcn_logits_and_argmax(ctx, arch, hw, precision, engine):
+    img, _ = _small_input(1, *hw)
+    W = synth.make_weights(arch, 3, seed=2)
+    net, (logit, prob, pred) = _device_predict(arch, W, 3, img, precision, engine)
+    assert logit.shape == img.shape + (3,) and logit.dtype == np.float32
+    assert prob.shape == logit.shape and prob.dtype == np.float32
+    assert pred.shape == img.shape and pred.dtype == np.int64
+    tol = TOL[precision]
+
+    twin = onet.Forward(arch, W, 3, bf16=True)
+    if precision == "fp16":
+        onet._bf16, saved = (lambda t: t.to(torch.float16).to(t.dtype)), onet._bf16
+        try:
+            twin = onet.Forward(arch, W, 3, bf16=True)
+            lt, _ = twin.logits(img)
+        finally:
+            onet._bf16 = saved
+    else:
+        lt, _ = twin.logits(img)
+    d = np.abs(logit - lt)
+    assert d.max() <= tol["twin_max"], d.max()
+    assert d.mean() <= tol["twin_mean"], d.mean()
+
+    l32, _ = onet.Forward(arch, W, 3).logits(img)
+    assert np.abs(logit - l32).max() <= tol["f32_max"]
+
+    l64, _ = onet.Forward(arch, W, 3, dtype=torch.float64).logits(img)
+    ref = l64.argmax(-1)
+    agree = (pred == ref).mean()
+    assert agree >= tol["agree"], agree
+    s = np.sort(l64, -1)
+    margin = s[..., -1] - s[..., -2]
+    bad = pred != ref
+    if bad.any():
+        assert margin[bad].max() <= 2 * np.abs(logit - l64).max()
+
+    # softmax / argmax are exact functions of the returned logits
+    np.testing.assert_array_equal(pred, logit.argmax(-1))
+    eprob, _ = opipe.softmax_argmax(logit)
+    np.testing.assert_allclose(prob, eprob, rtol=0, atol=2e-6)
+
+
+@pytest.mark.parametrize("engine", ["direct", "umma"])
+def test_fcn_skip_layerwise_vs_twin(ctx, engine):
+    """Every stored activation against the twin: localises layout / weight-transform errors."""
+    img, _ = _small_input(3, 96, 128)
+    W = synth.make_weights("fcn_skip", 3, seed=5)
+    net, (logit, _, _) = _device_predict("fcn_skip", W, 3, img, "bf16", engine)
+    c = net._context()
+    names = ["conv1", "conv2", "conv3", "conv5", "conv6", "conv7", "deconv1", "deconv2", "deconv3", "deconv4"]
+    twin = onet.Forward("fcn_skip", W, 3, bf16=True)
+    _, kept = twin.logits(img, keep=names)
+    for nme in names:
+        got = c.debug_activation(nme)[0]
+        exp = kept[nme]
+        assert got.shape == exp.shape, (nme, got.shape, exp.shape)
+        d = np.abs(got - exp)
+        scale = max(1e-3, np.abs(exp).max())
+        assert d.max() <= 2 ** -7 * scale + 1e-6, (nme, d.max(), scale)      # <= ~1 bf16 ulp of the range
+        assert d.mean() <= 2e-5 * scale + 1e-7, (nme, d.mean())
+
+
+@pytest.mark.parametrize("n_classes", [2, 5, 8])
+def test_n_classes(ctx, n_classes):
+    img, _ = _small_input(7, 64, 96)
+    W = synth.make_weights("fcn_skip", n_classes, seed=3)
+    _, (logit, prob, pred) = _device_predict("fcn_skip", W, n_classes, img, "fp16", "direct")
+    lt, _ = onet.Forward("fcn_skip", W, n_classes).logits(img)
+    assert np.abs(logit - lt).max() <= 1e-3
+    np.testing.assert_array_equal(pred, logit.argmax(-1))
+    np.testing.assert_allclose(prob.sum(-1), 1.0, atol=1e-5)
+
+
+def test_unet_small(ctx):
+    img, _ = _small_input(2, 32, 64)
+    W = synth.make_weights("unet", 3, seed=1)
+    _, (logit, prob, pred) = _device_predict("unet", W, 3, img, "fp16", "direct")
+    onet._bf16, saved = (lambda t: t.to(torch.float16).to(t.dtype)), onet._bf16
+    try:
+        lt, _ = onet.Forward("unet", W, 3, bf16=True).logits(img)
+    finally:
+        onet._bf16 = saved
+    scale = np.abs(lt).max()
+    assert np.abs(logit - lt).max() <= 2e-3 * max(1.0, scale)
+    l32, _ = onet.Forward("unet", W, 3).logits(img)
+    assert (pred == l32.argmax(-1)).mean() >= 0.995
+
+
+def test_batch_equals_single(ctx):
+    imgs = [_small_input(s, 64, 96)[0] for s in range(3)]
+    W = synth.make_weights("fcn_skip", 3, seed=2)
+    from page_segmentation_b200.lib.network import Network
+    net = Network("Predict", n_classes=3, weights=W, precision="bf16")
+    d = torch.from_numpy(np.stack(imgs)).cuda()
+    out = torch.empty_like(d)
+    net.predict_labels_device(d, out)
+    from page_segmentation_b200.lib.dataset import SingleData
+    for i, im in enumerate(imgs):
+        _, _, pred = net.predict_single_data(SingleData(image=im))
+        np.testing.assert_array_equal(out[i].cpu().numpy(), pred)

@@ -1,0 +1,95 @@
+"""Parity of the device preprocess (pcs_preprocess / pcs_resize_nearest) with the
+CPU oracle restating dataset.py:114-150 and util.py:21-29.  Bit-exact bar."""
+import numpy as np
+import pytest
+
+from oracle import pipeline as opipe
+from oracle import resize as osk
+from page_segmentation_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(page_grey, page_bin, target_lh, lh):
+    from page_segmentation_b200.lib.dataset import prepare_images
+    return prepare_images(page_grey, page_bin, target_lh, lh, keep_orig_bin=True)
+
+
+@pytest.mark.parametrize("shape,lh", [((3508, 2480), 18), ((700, 500), 18), ((333, 517), 11), ((64, 64), 6),
+                                      ((97, 131), 5), ((1200, 900), 24)])
+def test_binarised_page_bit_exact(ctx, shape, lh):
+    page = synth.make_page(3, shape[0], shape[1], lh)
+    img, b, ob = _run(page, page, 6, lh)
+    eimg, eb, eob = opipe.prepare_images(page, page, 6, lh, keep_orig_bin=True)
+    assert img.shape == eimg.shape and img.dtype == np.uint8
+    np.testing.assert_array_equal(b, eb)
+    np.testing.assert_array_equal(ob, eob)
+    np.testing.assert_array_equal(img, eimg)
+
+
+def test_upscale_reflect_borders(ctx):
+    # scale > 1 exercises the reflect border handling of the 4x4 cubic taps
+    page = synth.make_page(5, 120, 90, 4)
+    img, b, ob = _run(page, page, 6, 4)
+    eimg, eb, eob = opipe.prepare_images(page, page, 6, 4, keep_orig_bin=True)
+    np.testing.assert_array_equal(b, eb)
+    np.testing.assert_array_equal(img, eimg)
+
+
+def test_separate_binary_input(ctx):
+    grey = synth.make_page(1, 400, 300, 18)
+    binary = synth.make_page(2, 400, 300, 18)
+    img, b, ob = _run(grey, binary, 6, 18)
+    eimg, eb, eob = opipe.prepare_images(grey, binary, 6, 18, keep_orig_bin=True)
+    np.testing.assert_array_equal(b, eb)
+    np.testing.assert_array_equal(ob, eob)
+    np.testing.assert_array_equal(img, eimg)
+
+
+def test_binary_01_input(ctx):
+    # `binary / 255 if max > 1 else binary` (dataset.py:135): a {0,1} page is used as is
+    grey = synth.make_page(1, 300, 200, 18)
+    b01 = (synth.make_page(2, 300, 200, 18) > 0).astype(np.uint8)
+    img, b, ob = _run(grey, b01, 6, 18)
+    eimg, eb, eob = opipe.prepare_images(grey, b01, 6, 18, keep_orig_bin=True)
+    np.testing.assert_array_equal(b, eb)
+    np.testing.assert_array_equal(ob, eob)
+
+
+@pytest.mark.parametrize("shape,lh", [((600, 420), 18), ((301, 203), 9)])
+def test_grey_page_antialiased(ctx, shape, lh):
+    """>2 grey levels => anti_aliasing=True (dataset.py:127).  The Gaussian
+    weights go through exp(); tolerance: <= 1 grey level on <= 1e-4 of pixels."""
+    grey = synth.make_grey_page(4, shape[0], shape[1], lh)
+    assert len(np.unique(grey)) > 2
+    img, b, ob = _run(grey, grey, 6, lh)
+    eimg, eb, eob = opipe.prepare_images(grey, grey, 6, lh, keep_orig_bin=True)
+    np.testing.assert_array_equal(b, eb)
+    diff = np.abs(img.astype(int) - eimg.astype(int))
+    assert diff.max() <= 1
+    assert (diff > 0).mean() <= 1e-4
+
+
+def test_batched_pages_match_single(ctx):
+    import torch
+    pages = np.stack([synth.make_page(s, 480, 360, 18) for s in range(3)])
+    Hs, Ws = synth.scaled_shape(480, 360, 6 / 18)
+    d = torch.from_numpy(pages).cuda()
+    d_img = torch.empty((3, Hs, Ws), dtype=torch.uint8, device="cuda")
+    d_bin = torch.empty_like(d_img)
+    ctx.preprocess(d, d, 3, 480, 360, Hs, Ws, d_img, d_bin, None)
+    for i in range(3):
+        eimg, eb = opipe.prepare_images(pages[i], pages[i], 6, 18)
+        np.testing.assert_array_equal(d_img[i].cpu().numpy(), eimg)
+        np.testing.assert_array_equal(d_bin[i].cpu().numpy(), eb)
+
+
+@pytest.mark.parametrize("src,dst", [((50, 40), (150, 121)), ((389, 275), (1169, 827)), ((120, 90), (40, 30))])
+def test_preserving_resize(ctx, src, dst):
+    from page_segmentation_b200.lib.util import preserving_resize
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 4, size=src).astype(np.int64)
+    got = preserving_resize(a, dst)
+    exp = osk.resize(a, dst, order=0)
+    assert got.dtype == np.float64
+    np.testing.assert_array_equal(got, exp)
