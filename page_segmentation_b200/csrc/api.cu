@@ -463,8 +463,8 @@ int pcs_model_load(pcs_ctx* ctx, int arch, int n_classes, int precision, const p
         if (arch == PCS_ARCH_UNET && (L.name == "conv6a" || L.name == "conv7a" || L.name == "conv8a" || L.name == "conv9a")) {
             src_c[0] = L.cin / 2; src_c[1] = L.cin / 2; nsrc = 2;
         }
-        L.npad = pad16(L.cout);
-        if (!umma_supported(L.k, L.npad)) continue;
+        L.npad = std::min(pad16(L.cout), 128);
+        if (!umma_supported(L.k, L.npad) || (L.cout > 128 && L.cout % 128)) continue;
         std::vector<uint16_t> img;
         L.wmma_bytes = umma_weight_image(L.h_w32.data(), L.k * L.k, src_c, nsrc, L.cout, L.npad, precision, img);
         L.nchunks = 0;

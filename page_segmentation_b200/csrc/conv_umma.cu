@@ -1,7 +1,455 @@
-// placeholder replaced below in the same round
+// Implicit-GEMM 'same' convolution on the 5th-generation tensor cores:
+// tcgen05.mma (kind::f16, bf16|fp16 operands, fp32 accumulators in TMEM) fed by
+// TMA, warp-specialised, persistent.
+//
+// Reference layers served: Conv2D k5/k3 'same' and Conv2DTranspose k5 s1 (as a
+// pre-flipped correlation) of ocr4all_pixel_classifier/lib/model.py:45-92,
+// :151-203, :206-234, with the channel concatenation of the skip connections
+// read as two K segments (the concat tensor is never materialised) and
+// MaxPooling2D(2,2) fused into the epilogue.
+//
+// GEMM view per CTA tile:  D[128 px, NPAD] += A[128 px, 16 ch] * B[16 ch, NPAD]
+//   M = 128 consecutive pixels of one image row (one TMEM lane per pixel),
+//   N = C_out padded to 16 (tile of <= 128),
+//   K = taps x C_in, walked as (16-channel chunk) x (tap).
+// A CTA owns a strip of 128 px x R rows and keeps R accumulators (R x NPAD TMEM
+// columns).  Per 16-channel chunk the producer brings in, with TMA,
+//   * the input patch  [2 planes][R+k-1 rows][128+k-1 px][8 ch]  (zero filled
+//     outside the image = the 'same' zero border), and
+//   * the weights      [taps][2 planes][NPAD][8 ch]  (host pre-arranged image).
+// Both are K-major, SWIZZLE_NONE canonical layouts: a "plane" holds 8 channels
+// (16 B) per pixel at a 16-byte pixel pitch, so the A operand of tap (dy,dx) for
+// accumulator row r is the SAME shared-memory patch addressed at byte offset
+// ((r+dy)*PXW + dx)*16 -- the im2col expansion never exists anywhere.
 #include "common.cuh"
+
 namespace pcs {
-bool umma_supported(int, int) { return false; }
-size_t umma_weight_image(const float*, int, const int*, int, int, int, int, std::vector<uint16_t>&) { return 0; }
-int launch_conv_umma(pcs_ctx* ctx, const UmmaConvArgs&) { return set_err(ctx, PCS_ERR_STATE, "umma engine not built"); }
+namespace {
+
+constexpr int TILE_M = 128;
+constexpr int kThreads = 192;       // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int kMaxStages = 4;
+
+template <int NPAD> struct Cfg {
+    static constexpr int R = NPAD <= 64 ? 8 : (NPAD <= 80 ? 6 : 4);      // accumulator rows per tile
+    static constexpr int ACC = (2 * R * NPAD <= 512) ? 2 : 1;             // TMEM accumulator stages
+};
+
+struct UmmaParams {
+    int n, h, w;
+    int k, pad;
+    int nch0, nchunks;          // 16-channel chunks of source 0 / of all sources
+    const uint8_t* wimg;        // [ntile][chunk][tap][plane][NPAD][8] operand image
+    const float* bias;
+    int cout, relu;
+    void* out; int out_cp;
+    void* pool; int pool_cp;
+    int strips, rowblocks, ntiles_n, num_tiles;
+    int a_rows, pxw;            // R + k - 1, 128 + k - 1
+    uint32_t a_plane_bytes, a_plane_stride, a_bytes, b_bytes, stage_bytes;   // a_bytes = 2 * a_plane_stride
+    int nstages;
+};
+
+// ---- PTX wrappers -----------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 24)) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+//   [0,14) start>>4 | [16,30) LBO>>4 (stride between the two 8-element K halves)
+//   [32,46) SBO>>4 (stride between 8-row groups) | [46,48) version = 1 | [61,64) layout = 0
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
+}
+
+template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+    __half2 v = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+template <typename T, int NPAD>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1) {
+    constexpr int R = Cfg<NPAD>::R;
+    constexpr int ACC = Cfg<NPAD>::ACC;
+    constexpr uint32_t IDESC = (1u << 4)                                            // D = f32
+                               | ((sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value ? 1u : 0u) << 7)    // A format
+                               | ((std::is_same<T, __nv_bfloat16>::value ? 1u : 0u) << 10)                    // B format
+                               | ((uint32_t)(NPAD >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);            // N, M; K-major A and B
+
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t s_full[kMaxStages], s_empty[kMaxStages], s_tfull[2], s_tempty[2];
+    __shared__ uint32_t s_tmem_base;
+    __shared__ float s_bias[NPAD];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* stages = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < p.nstages; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 1); }
+        for (int a = 0; a < ACC; ++a) { mbar_init(&s_tfull[a], 1); mbar_init(&s_tempty[a], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem_base;
+
+    const int tiles_per_page = p.strips * p.rowblocks * p.ntiles_n;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int page = tile / tiles_per_page;
+                int rem = tile - page * tiles_per_page;
+                const int nt = rem % p.ntiles_n; rem /= p.ntiles_n;
+                const int rb = rem % p.rowblocks;
+                const int strip = rem / p.rowblocks;
+                const int x0 = strip * TILE_M - p.pad, y0 = rb * R - p.pad;
+                const uint8_t* wsrc = p.wimg + (size_t)nt * p.nchunks * p.b_bytes;
+                for (int kc = 0; kc < p.nchunks; ++kc) {
+                    mbar_wait(&s_empty[stage], phase ^ 1u);
+                    uint8_t* a_dst = stages + (size_t)stage * p.stage_bytes;
+                    uint8_t* b_dst = a_dst + p.a_bytes;
+                    mbar_expect_tx(&s_full[stage], 2 * p.a_plane_bytes + p.b_bytes);
+                    const CUtensorMap* tm = kc < p.nch0 ? &tm0 : &tm1;
+                    const int c0 = (kc < p.nch0 ? kc : kc - p.nch0) * 16;
+                    tma_load_4d(a_dst, tm, &s_full[stage], c0, x0, y0, page);
+                    tma_load_4d(a_dst + p.a_plane_stride, tm, &s_full[stage], c0 + 8, x0, y0, page);
+                    bulk_load(b_dst, wsrc + (size_t)kc * p.b_bytes, p.b_bytes, &s_full[stage]);
+                    if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0;
+        const uint32_t a_lbo = p.a_plane_stride, b_lbo = NPAD * 16, b_tap_bytes = 2 * NPAD * 16;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            mbar_wait(&s_tempty[acc], acc_phase ^ 1u);
+            tc_fence_after();
+            for (int kc = 0; kc < p.nchunks; ++kc) {
+                mbar_wait(&s_full[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_base = smem_u32(stages + (size_t)stage * p.stage_bytes);
+                    const uint32_t b_base = a_base + p.a_bytes;
+                    const uint64_t a_desc0 = make_desc(a_base, a_lbo, 128);
+                    const uint64_t b_desc0 = make_desc(b_base, b_lbo, 128);
+#pragma unroll 1
+                    for (int r = 0; r < R; ++r) {
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * R * NPAD + r * NPAD);
+                        int t = 0;
+                        for (int dy = 0; dy < p.k; ++dy) {
+                            for (int dx = 0; dx < p.k; ++dx, ++t) {
+                                const uint32_t a_off = (uint32_t)((r + dy) * p.pxw + dx);     // in 16-byte units
+                                const uint32_t b_off = (uint32_t)t * (b_tap_bytes >> 4);
+                                tc_mma(d_tmem, a_desc0 + a_off, b_desc0 + b_off, IDESC, (kc | t) ? 1u : 0u);
+                            }
+                        }
+                    }
+                    tc_commit(&s_empty[stage]);                    // smem slot free once these MMAs retire
+                    if (kc == p.nchunks - 1) tc_commit(&s_tfull[acc]);
+                }
+                __syncwarp();
+                if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
+            }
+            if (++acc == ACC) { acc = 0; acc_phase ^= 1u; }
+        }
+    } else {
+        // ===================== epilogue warps =====================
+        const int quarter = warp & 3;                              // TMEM lane quarter this warp may touch
+        for (int i = threadIdx.x - 64; i < NPAD; i += 128) s_bias[i] = 0.f;   // filled per N tile below
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const int page = tile / tiles_per_page;
+            int rem = tile - page * tiles_per_page;
+            const int nt = rem % p.ntiles_n; rem /= p.ntiles_n;
+            const int rb = rem % p.rowblocks;
+            const int strip = rem / p.rowblocks;
+            const int x = strip * TILE_M + quarter * 32 + lane;
+            const int y0 = rb * R;
+            const int cbase = nt * NPAD;
+            // bias of this N tile (named barrier 1 over the 4 epilogue warps)
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int i = threadIdx.x - 64; i < NPAD; i += 128) s_bias[i] = (cbase + i < p.cout) ? __ldg(p.bias + cbase + i) : 0.f;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+
+            mbar_wait(&s_tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * R * NPAD);
+            T* out = reinterpret_cast<T*>(p.out);
+            T* pool = reinterpret_cast<T*>(p.pool);
+#pragma unroll 1
+            for (int rp = 0; rp < R / 2; ++rp) {
+                const int ya = y0 + 2 * rp;
+#pragma unroll 1
+                for (int c16 = 0; c16 < NPAD / 16; ++c16) {
+                    uint32_t v0[16], v1[16];
+                    tmem_ld16(t_lane + (uint32_t)((2 * rp) * NPAD + c16 * 16), v0);
+                    tmem_ld16(t_lane + (uint32_t)((2 * rp + 1) * NPAD + c16 * 16), v1);
+                    tmem_ld_wait();
+                    float f0[16], f1[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float b = s_bias[c16 * 16 + i];
+                        f0[i] = __uint_as_float(v0[i]) + b;
+                        f1[i] = __uint_as_float(v1[i]) + b;
+                        if (p.relu) { f0[i] = fmaxf(f0[i], 0.f); f1[i] = fmaxf(f1[i], 0.f); }
+                    }
+                    if (out && x < p.w) {
+                        if (ya < p.h) {
+                            uint4* d = reinterpret_cast<uint4*>(out + (((size_t)page * p.h + ya) * p.w + x) * p.out_cp + cbase + c16 * 16);
+                            d[0] = make_uint4(pack2<T>(f0[0], f0[1]), pack2<T>(f0[2], f0[3]), pack2<T>(f0[4], f0[5]), pack2<T>(f0[6], f0[7]));
+                            d[1] = make_uint4(pack2<T>(f0[8], f0[9]), pack2<T>(f0[10], f0[11]), pack2<T>(f0[12], f0[13]), pack2<T>(f0[14], f0[15]));
+                        }
+                        if (ya + 1 < p.h) {
+                            uint4* d = reinterpret_cast<uint4*>(out + (((size_t)page * p.h + ya + 1) * p.w + x) * p.out_cp + cbase + c16 * 16);
+                            d[0] = make_uint4(pack2<T>(f1[0], f1[1]), pack2<T>(f1[2], f1[3]), pack2<T>(f1[4], f1[5]), pack2<T>(f1[6], f1[7]));
+                            d[1] = make_uint4(pack2<T>(f1[8], f1[9]), pack2<T>(f1[10], f1[11]), pack2<T>(f1[12], f1[13]), pack2<T>(f1[14], f1[15]));
+                        }
+                    }
+                    if (pool) {
+                        float m[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float a = fmaxf(f0[i], f1[i]);
+                            m[i] = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, 1));
+                        }
+                        if (!(lane & 1) && x < p.w && ya < p.h) {
+                            uint4* d = reinterpret_cast<uint4*>(pool + (((size_t)page * (p.h >> 1) + (ya >> 1)) * (p.w >> 1) + (x >> 1)) * p.pool_cp + cbase + c16 * 16);
+                            d[0] = make_uint4(pack2<T>(m[0], m[1]), pack2<T>(m[2], m[3]), pack2<T>(m[4], m[5]), pack2<T>(m[6], m[7]));
+                            d[1] = make_uint4(pack2<T>(m[8], m[9]), pack2<T>(m[10], m[11]), pack2<T>(m[12], m[13]), pack2<T>(m[14], m[15]));
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_tempty[acc]);
+            if (++acc == ACC) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---- host side ----------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// activation [n][h][w][cp] (2-byte elements) seen as (channel, x, y, page); box = 8 ch x PXW x rows x 1
+int make_act_map(pcs_ctx* ctx, CUtensorMap* tm, const ConvSrc& s, int n, int h, int w, int pxw, int rows, bool bf16) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return set_err(ctx, PCS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    const cuuint64_t dims[4] = {(cuuint64_t)s.cp, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+    const cuuint64_t strides[3] = {(cuuint64_t)s.cp * 2, (cuuint64_t)w * s.cp * 2, (cuuint64_t)h * w * s.cp * 2};
+    const cuuint32_t box[4] = {8, (cuuint32_t)pxw, (cuuint32_t)rows, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(s.p), dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_err(ctx, PCS_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d (cp=%d w=%d h=%d n=%d box=%d,%d)", (int)r, s.cp, w, h, n, pxw, rows);
+    return PCS_OK;
+}
+
+template <typename T, int NPAD>
+int launch_t(pcs_ctx* ctx, const UmmaConvArgs& a) {
+    constexpr int R = Cfg<NPAD>::R;
+    UmmaParams p{};
+    p.n = a.n; p.h = a.h; p.w = a.w; p.k = a.k; p.pad = a.pad;
+    p.nch0 = a.src[0].cp / 16;
+    p.nchunks = p.nch0 + (a.nsrc > 1 ? a.src[1].cp / 16 : 0);
+    if (p.nchunks != a.nchunks) return set_err(ctx, PCS_ERR_ARG, "conv_umma: source channel chunks %d != weight image chunks %d", p.nchunks, a.nchunks);
+    p.wimg = reinterpret_cast<const uint8_t*>(a.wmma); p.bias = a.b32; p.cout = a.cout; p.relu = a.relu;
+    p.out = a.out; p.out_cp = a.out_cp; p.pool = a.pool_out; p.pool_cp = a.pool_cp;
+    p.strips = (a.w + TILE_M - 1) / TILE_M;
+    p.rowblocks = (a.h + R - 1) / R;
+    p.ntiles_n = (a.cout + NPAD - 1) / NPAD;
+    p.num_tiles = a.n * p.strips * p.rowblocks * p.ntiles_n;
+    p.a_rows = R + a.k - 1;
+    p.pxw = TILE_M + a.k - 1;
+    p.a_plane_bytes = (uint32_t)p.a_rows * p.pxw * 16;
+    p.a_plane_stride = (p.a_plane_bytes + 127) / 128 * 128;       // TMA destinations are 128-byte aligned
+    p.a_bytes = 2 * p.a_plane_stride;
+    p.b_bytes = (uint32_t)a.k * a.k * 2 * NPAD * 16;
+    p.stage_bytes = (p.a_bytes + p.b_bytes + 1023) / 1024 * 1024;
+    // the B block must start 16-byte aligned inside the stage: a_bytes is a multiple of 32
+    const uint32_t budget = 225 * 1024 - 1024;
+    p.nstages = (int)std::min<uint32_t>(kMaxStages, budget / p.stage_bytes);
+    if (p.nstages < 2) return set_err(ctx, PCS_ERR_ARG, "conv_umma: stage of %u bytes does not fit twice in shared memory", p.stage_bytes);
+    if ((a.h & 1) || (a.w & 1)) return set_err(ctx, PCS_ERR_ARG, "conv_umma: odd grid");
+    const size_t smem = (size_t)p.nstages * p.stage_bytes + 1024;
+    const bool bf = ctx->precision == PCS_PREC_BF16;
+    CUtensorMap tm0, tm1;
+    PCS_TRY(make_act_map(ctx, &tm0, a.src[0], a.n, a.h, a.w, p.pxw, p.a_rows, bf));
+    if (a.nsrc > 1) PCS_TRY(make_act_map(ctx, &tm1, a.src[1], a.n, a.h, a.w, p.pxw, p.a_rows, bf));
+    else tm1 = tm0;
+    static bool attr_set = false;
+    if (!attr_set) {
+        PCS_CUDA(ctx, cudaFuncSetAttribute(conv_umma_kernel<T, NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        attr_set = true;
+    }
+    const int grid = std::min(p.num_tiles, ctx->sm_count);
+    conv_umma_kernel<T, NPAD><<<grid, kThreads, smem, ctx->stream>>>(p, tm0, tm1);
+    PCS_LAUNCH_CHECK(ctx, "conv_umma_kernel");
+    return PCS_OK;
+}
+
+template <typename T>
+int launch_npad(pcs_ctx* ctx, const UmmaConvArgs& a) {
+    switch (a.npad) {
+        case 32: return launch_t<T, 32>(ctx, a);
+        case 48: return launch_t<T, 48>(ctx, a);
+        case 64: return launch_t<T, 64>(ctx, a);
+        case 80: return launch_t<T, 80>(ctx, a);
+        case 128: return launch_t<T, 128>(ctx, a);
+        default: return set_err(ctx, PCS_ERR_ARG, "conv_umma: no instantiation for N tile %d", a.npad);
+    }
+}
+
+}  // namespace
+
+bool umma_supported(int k, int npad) {
+    if (k < 1 || k > 5) return false;
+    return npad == 32 || npad == 48 || npad == 64 || npad == 80 || npad == 128;
+}
+
+// Operand image [ntile][chunk][tap][plane][NPAD][8]; chunk runs over the 16-channel groups of
+// source 0 then source 1 (each padded to a multiple of 16 channels with zeros).
+size_t umma_weight_image(const float* w32, int taps, const int* src_c, int nsrc, int cout, int npad, int precision,
+                         std::vector<uint16_t>& out) {
+    int cin = 0, nchunks = 0;
+    for (int s = 0; s < nsrc; ++s) { cin += src_c[s]; nchunks += pad16(src_c[s]) / 16; }
+    const int ntiles = (cout + npad - 1) / npad;
+    out.assign((size_t)ntiles * nchunks * taps * 2 * npad * 8, 0);
+    auto conv = [&](float v) -> uint16_t {
+        if (precision == PCS_PREC_BF16) {
+            __nv_bfloat16 b = __float2bfloat16_rn(v);
+            return *reinterpret_cast<uint16_t*>(&b);
+        }
+        __half h = __float2half_rn(v);
+        return *reinterpret_cast<uint16_t*>(&h);
+    };
+    for (int nt = 0; nt < ntiles; ++nt) {
+        int chunk = 0, cbase = 0;
+        for (int s = 0; s < nsrc; ++s) {
+            for (int lc = 0; lc < pad16(src_c[s]) / 16; ++lc, ++chunk)
+                for (int t = 0; t < taps; ++t)
+                    for (int pl = 0; pl < 2; ++pl)
+                        for (int nn = 0; nn < npad; ++nn)
+                            for (int e = 0; e < 8; ++e) {
+                                const int c = lc * 16 + pl * 8 + e, o = nt * npad + nn;
+                                if (c >= src_c[s] || o >= cout) continue;
+                                const float v = w32[((size_t)t * cin + cbase + c) * cout + o];
+                                out[(((((size_t)nt * nchunks + chunk) * taps + t) * 2 + pl) * npad + nn) * 8 + e] = conv(v);
+                            }
+            cbase += src_c[s];
+        }
+    }
+    return out.size() * sizeof(uint16_t);
+}
+
+int launch_conv_umma(pcs_ctx* ctx, const UmmaConvArgs& a) {
+    if (!umma_supported(a.k, a.npad)) return set_err(ctx, PCS_ERR_ARG, "conv_umma: unsupported k=%d N=%d", a.k, a.npad);
+    if (a.src[0].cp % 16 || (a.nsrc > 1 && a.src[1].cp % 16)) return set_err(ctx, PCS_ERR_ARG, "conv_umma: channel stride not a multiple of 16");
+    if (a.out && a.out_cp % 16) return set_err(ctx, PCS_ERR_ARG, "conv_umma: output stride");
+    if (ctx->precision == PCS_PREC_BF16) return launch_npad<__nv_bfloat16>(ctx, a);
+    return launch_npad<__half>(ctx, a);
+}
+
+}  // namespace pcs

@@ -3,7 +3,7 @@ model.py / network.py:248-260.
 
 Tolerances (stated, see DESIGN.md "precision"):
   * device vs numerics twin (same bf16|fp16 rounding points, fp32 accumulate):
-    logits max |d| <= 2e-3 (bf16) / 3e-4 (fp16), mean |d| <= 2e-5 / 4e-6 -- only
+    logits max |d| <= 2e-3 (bf16) / 3e-4 (fp16), mean |d| <= 6e-5 / 4e-6 -- only
     accumulation order and rare 1-ulp operand flips differ;
   * device vs fp32 oracle: logits max |d| <= 8e-3 (bf16) / 1e-3 (fp16);
   * argmax vs the fp64 oracle: agreement >= 99.9 % for fp16 operands, >= 99.7 % for
@@ -20,7 +20,7 @@ from page_segmentation_b200 import synth
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"bf16": dict(twin_max=2e-3, twin_mean=2e-5, f32_max=8e-3, agree=0.997),
+TOL = {"bf16": dict(twin_max=2e-3, twin_mean=6e-5, f32_max=8e-3, agree=0.997),
        "fp16": dict(twin_max=3e-4, twin_mean=4e-6, f32_max=1e-3, agree=0.999)}
 
 
@@ -143,3 +143,30 @@ def test_batch_equals_single(ctx):
     for i, im in enumerate(imgs):
         _, _, pred = net.predict_single_data(SingleData(image=im))
         np.testing.assert_array_equal(out[i].cpu().numpy(), pred)
+
+
+@pytest.mark.parametrize("tap", [(2, 2), (0, 0), (4, 4), (1, 3), (3, 0)])
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+def test_umma_one_hot_tap_is_a_shifted_copy(ctx, tap, precision):
+    """Sharp layout check of the tcgen05 path: with one-hot conv2 weights at a single tap,
+    conv2 must be a bit-exact shifted copy of conv1 (1.0 * x accumulates exactly)."""
+    ty, tx = tap
+    img, _ = _small_input(4, 70, 300)
+    W = [(np.zeros_like(k), np.zeros_like(b)) for k, b in synth.make_weights("fcn_skip", 3, seed=0)]
+    for c in range(20):
+        W[0][0][2, 2, 0, c] = (c + 1) / 32.0
+        W[1][0][ty, tx, c, c] = 1.0
+    net, _ = _device_predict("fcn_skip", W, 3, img, precision, "umma")
+    c = net._context()
+    conv1 = c.debug_activation("conv1")[0]
+    conv2 = c.debug_activation("conv2")[0]
+    pool2 = c.debug_activation("pool2")[0]
+    H, Wd, _ = conv1.shape
+    exp = np.zeros((H, Wd, 30), np.float32)
+    ys, xs = np.arange(H)[:, None] + ty - 2, np.arange(Wd)[None, :] + tx - 2
+    ok = (ys >= 0) & (ys < H) & (xs >= 0) & (xs < Wd)
+    src = conv1[np.clip(ys, 0, H - 1), np.clip(xs, 0, Wd - 1), :]
+    exp[..., :20] = np.where(ok[..., None], src, 0.0)
+    assert conv1.max() > 0
+    np.testing.assert_array_equal(conv2, exp)
+    np.testing.assert_array_equal(pool2, exp.reshape(H // 2, 2, Wd // 2, 2, 30).max(axis=(1, 3)))
