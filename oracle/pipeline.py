@@ -34,8 +34,8 @@ def prepare_images(image: np.ndarray, binary: np.ndarray, target_line_height: in
         if n_scale < 1.0:
             bin_ = sk.rescale(bin_, n_scale, order=0, anti_aliasing=False)
             img = sk.resize(img, bin_.shape, order=3, anti_aliasing=len(np.unique(img)) > 2)
-    img = (img * 255).astype(np.uint8)
-    bin_ = bin_.astype(np.uint8)
+    img = np.ascontiguousarray((img * 255).astype(np.uint8))
+    bin_ = np.ascontiguousarray(bin_.astype(np.uint8))
     if keep_orig_bin:
         return img, bin_, (1 - orig_bin).astype(np.uint8)
     return img, bin_

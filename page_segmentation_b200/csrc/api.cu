@@ -193,6 +193,16 @@ static int run_deconv_s2(pcs_ctx* ctx, const char* lname, const Act* s0, const A
     Layer* L = find_layer(ctx, lname);
     if (!L) return set_err(ctx, PCS_ERR_STATE, "layer %s missing", lname);
     StageScope ts(ctx, lname);
+    if (ctx->engine == PCS_ENGINE_UMMA && L->d_wmma) {
+        UmmaConvArgs a;
+        a.src[0] = src_of(*s0); a.nsrc = 1;
+        if (s1) { a.src[1] = src_of(*s1); a.nsrc = 2; }
+        a.n = s0->n; a.h = s0->h; a.w = s0->w; a.k = 1; a.pad = 0;
+        a.wmma = L->d_wmma; a.b32 = L->d_b32; a.cout = L->cout; a.npad = L->npad; a.nchunks = L->nchunks; a.relu = L->relu;
+        a.mode = 1; a.co_t = L->co_t;
+        a.out = out->p; a.out_cp = out->cp;
+        return launch_conv_umma(ctx, a);
+    }
     DeconvS2Args a;
     a.src[0] = src_of(*s0); a.nsrc = 1;
     if (s1) { a.src[1] = src_of(*s1); a.nsrc = 2; }
@@ -454,19 +464,31 @@ int pcs_model_load(pcs_ctx* ctx, int arch, int n_classes, int precision, const p
         PCS_CUDA(ctx, cudaMemcpy(L.d_b32, L.h_b32.data(), L.h_b32.size() * 4, cudaMemcpyHostToDevice));
         ctx->layers.push_back(std::move(L));
     }
-    // tensor-core operand images for the stride-1 convolutions with C_in > 1
+    // tensor-core operand images: stride-1 convolutions with C_in > 1 and the 2x2 stride-2
+    // transposed convolutions that are not fused into the head
     for (size_t li = 1; li < ctx->layers.size(); ++li) {
         Layer& L = ctx->layers[li];
-        if (L.kind != K_CONV && L.kind != K_DECONV) continue;
         int src_c[2] = {L.cin, 0}, nsrc = 1;
-        if (arch == PCS_ARCH_FCN_SKIP && L.name == "deconv3") { src_c[0] = 60; src_c[1] = 60; nsrc = 2; }
+        if (arch == PCS_ARCH_FCN_SKIP) {
+            if (L.name == "deconv3") { src_c[0] = 60; src_c[1] = 60; nsrc = 2; }      // [deconv2, conv6]
+            if (L.name == "deconv4") { src_c[0] = 40; src_c[1] = 60; nsrc = 2; }      // [deconv3, conv5]
+        }
         if (arch == PCS_ARCH_UNET && (L.name == "conv6a" || L.name == "conv7a" || L.name == "conv8a" || L.name == "conv9a")) {
             src_c[0] = L.cin / 2; src_c[1] = L.cin / 2; nsrc = 2;
         }
-        L.npad = std::min(pad16(L.cout), 128);
-        if (!umma_supported(L.k, L.npad) || (L.cout > 128 && L.cout % 128)) continue;
         std::vector<uint16_t> img;
-        L.wmma_bytes = umma_weight_image(L.h_w32.data(), L.k * L.k, src_c, nsrc, L.cout, L.npad, precision, img);
+        if (L.kind == K_CONV || L.kind == K_DECONV) {
+            L.npad = std::min(pad16(L.cout), 128);
+            if (!umma_supported(L.k, L.npad) || (L.cout > 128 && L.cout % 128)) continue;
+            L.wmma_bytes = umma_weight_image(L.h_w32.data(), L.k * L.k, src_c, nsrc, L.cout, L.npad, precision, img);
+        } else if (L.kind == K_DECONV_S2 && L.name != "deconv5") {
+            L.co_t = pad16(L.cout);
+            L.npad = std::min(4 * L.co_t, 128);
+            if (!umma_supported(1, L.npad) || (4 * L.co_t) % L.npad) continue;
+            L.wmma_bytes = umma_weight_image_deconv(L.h_w32.data(), src_c, nsrc, L.cout, L.co_t, L.npad, precision, img);
+        } else {
+            continue;
+        }
         L.nchunks = 0;
         for (int s = 0; s < nsrc; ++s) L.nchunks += pad16(src_c[s]) / 16;
         PCS_CUDA(ctx, cudaMalloc(&L.d_wmma, L.wmma_bytes));
@@ -619,7 +641,8 @@ int pcs_debug_activation(pcs_ctx* ctx, const char* name, float* h_out, size_t ca
     PCS_CUDA(ctx, cudaMemcpy(raw.data(), a.p, raw.size() * 2, cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < px; ++i)
         for (int c = 0; c < a.c; ++c) {
-            const uint16_t v = raw[i * a.cp + c];
+            const int x = (int)(i % a.w), y = (int)((i / a.w) % a.h), pg = (int)(i / ((size_t)a.w * a.h));
+            const uint16_t v = raw[act_idx(pg, a.cp, a.h, a.w, c, y, x)];
             float f;
             if (ctx->precision == PCS_PREC_BF16) {
                 uint32_t u = (uint32_t)v << 16;

@@ -21,7 +21,11 @@ namespace pcs {
 constexpr int kMaxClasses = 16;
 
 // ---------------------------------------------------------------------------
-// Activation tensors: NHWC, channel count padded to a multiple of 16 with zeros.
+// Activation tensors: plane-major "NC/8HW8": [n][cp/8][h][w][8 channels], i.e. one
+// 16-byte unit per (pixel, 8-channel group); channel count padded to a multiple
+// of 16 with zeros.  A plane row is contiguous in memory, which is what makes the
+// TMA boxes of the tensor-core kernel 2 KB wide and every epilogue store a
+// 512-byte coalesced warp store.
 // ---------------------------------------------------------------------------
 struct Act {
     void* p = nullptr;      // device pointer, element type = model precision (bf16 / fp16)
@@ -32,6 +36,11 @@ struct Act {
 };
 
 inline int pad16(int c) { return (c + 15) / 16 * 16; }
+
+// element index of channel c at (page, y, x) of an activation with cp padded channels
+__host__ __device__ __forceinline__ size_t act_idx(int page, int cp, int h, int w, int c, int y, int x) {
+    return ((((size_t)page * (cp >> 3) + (c >> 3)) * h + y) * w + x) * 8 + (c & 7);
+}
 
 // One network layer after host-side weight transformation.
 struct Layer {
@@ -49,6 +58,7 @@ struct Layer {
     void* d_wmma = nullptr;
     size_t wmma_bytes = 0;
     int npad = 0;           // padded C_out of the UMMA tile
+    int co_t = 0;           // deconv s2 on the tensor path: padded channels per tap
     int nchunks = 0;        // number of 16-channel K chunks over all sources
 };
 
@@ -210,6 +220,8 @@ struct UmmaConvArgs {
     const void* wmma = nullptr;    // pre-arranged operand image, see conv_umma.cu
     const float* b32 = nullptr;
     int cout = 0, npad = 0, nchunks = 0, relu = 0;
+    int mode = 0;                  // 0 = 'same' conv store (+pool), 1 = 2x2 stride-2 transposed conv scatter
+    int co_t = 0;                  // mode 1: padded channels per tap
     void* out = nullptr;
     int out_cp = 0;
     void* pool_out = nullptr;
@@ -219,6 +231,8 @@ int launch_conv_umma(pcs_ctx* ctx, const UmmaConvArgs& a);
 // host-side operand image builder; returns bytes written (precision: PCS_PREC_*)
 size_t umma_weight_image(const float* w32 /*[taps][cin][cout]*/, int taps, const int* src_c, int nsrc,
                          int cout, int npad, int precision, std::vector<uint16_t>& out);
+size_t umma_weight_image_deconv(const float* w32 /*[4][cin][cout]*/, const int* src_c, int nsrc, int cout, int co_t,
+                                int npad, int precision, std::vector<uint16_t>& out);
 bool umma_supported(int k, int npad);
 
 }  // namespace pcs

@@ -88,9 +88,9 @@ __global__ void __launch_bounds__(256) conv_direct_kernel(DirectParams p) {
                     if (gy < p.img_h && gx < p.img_w)
                         v = c_u8_lut[reinterpret_cast<const uint8_t*>(p.s0)[((size_t)page * p.img_h + gy) * p.img_w + gx]];
                 } else if (ci < p.c0) {
-                    v = to_f(reinterpret_cast<const T*>(p.s0)[(((size_t)page * in_h + gy) * in_w + gx) * p.cp0 + ci]);
+                    v = to_f(reinterpret_cast<const T*>(p.s0)[act_idx(page, p.cp0, in_h, in_w, ci, gy, gx)]);
                 } else {
-                    v = to_f(reinterpret_cast<const T*>(p.s1)[(((size_t)page * in_h + gy) * in_w + gx) * p.cp1 + (ci - p.c0)]);
+                    v = to_f(reinterpret_cast<const T*>(p.s1)[act_idx(page, p.cp1, in_h, in_w, ci - p.c0, gy, gx)]);
                 }
             }
             s_in[c][py][px] = v;
@@ -148,11 +148,10 @@ __global__ void __launch_bounds__(256) conv_direct_kernel(DirectParams p) {
         for (int r = 0; r < 2; ++r) {
             const int y = yA + r;
             if (y < p.h) {
-                T* dst = reinterpret_cast<T*>(p.out) + (((size_t)page * p.h + y) * p.w + x) * p.out_cp + o0;
-                uint4* d4 = reinterpret_cast<uint4*>(dst);
+                T* base = reinterpret_cast<T*>(p.out);
                 const uint4* s4 = reinterpret_cast<const uint4*>(&vals[r][0]);
-                d4[0] = s4[0];
-                d4[1] = s4[1];
+                *reinterpret_cast<uint4*>(base + act_idx(page, p.out_cp, p.h, p.w, o0, y, x)) = s4[0];
+                *reinterpret_cast<uint4*>(base + act_idx(page, p.out_cp, p.h, p.w, o0 + 8, y, x)) = s4[1];
             }
         }
     }
@@ -166,12 +165,10 @@ __global__ void __launch_bounds__(256) conv_direct_kernel(DirectParams p) {
             pooled[o] = from_f<T>(fmaxf(m, other));
         }
         if ((tx & 1) == 0 && x < p.w && yA < p.h) {
-            T* dst = reinterpret_cast<T*>(p.pool) +
-                     (((size_t)page * (p.h / 2) + yA / 2) * (p.w / 2) + x / 2) * p.pool_cp + o0;
-            uint4* d4 = reinterpret_cast<uint4*>(dst);
+            T* base = reinterpret_cast<T*>(p.pool);
             const uint4* s4 = reinterpret_cast<const uint4*>(&pooled[0]);
-            d4[0] = s4[0];
-            d4[1] = s4[1];
+            *reinterpret_cast<uint4*>(base + act_idx(page, p.pool_cp, p.h / 2, p.w / 2, o0, yA / 2, x / 2)) = s4[0];
+            *reinterpret_cast<uint4*>(base + act_idx(page, p.pool_cp, p.h / 2, p.w / 2, o0 + 8, yA / 2, x / 2)) = s4[1];
         }
     }
 }
@@ -231,14 +228,14 @@ __global__ void __launch_bounds__(256) deconv_s2_direct_kernel(DeconvParams p) {
     const int X = blockIdx.x * 32 + tx, Y = blockIdx.y * 8 + ty;
     if (X >= 2 * p.w || Y >= 2 * p.h) return;
     const int t = (Y & 1) * 2 + (X & 1);
-    const size_t ipix = ((size_t)page * p.h + (Y >> 1)) * p.w + (X >> 1);
     float acc[COT];
 #pragma unroll
     for (int o = 0; o < COT; ++o) acc[o] = 0.f;
-    const T* a0 = reinterpret_cast<const T*>(p.s0) + ipix * p.cp0;
-    const T* a1 = p.s1 ? reinterpret_cast<const T*>(p.s1) + ipix * p.cp1 : nullptr;
+    const T* a0 = reinterpret_cast<const T*>(p.s0);
+    const T* a1 = reinterpret_cast<const T*>(p.s1);
     for (int c = 0; c < p.cin; ++c) {
-        const float a = to_f(c < p.c0 ? a0[c] : a1[c - p.c0]);
+        const float a = to_f(c < p.c0 ? a0[act_idx(page, p.cp0, p.h, p.w, c, Y >> 1, X >> 1)]
+                                      : a1[act_idx(page, p.cp1, p.h, p.w, c - p.c0, Y >> 1, X >> 1)]);
         const float4* wv = reinterpret_cast<const float4*>(s_dw + ((size_t)t * p.cin + c) * COT);
 #pragma unroll
         for (int q = 0; q < COT / 4; ++q) {
@@ -259,11 +256,10 @@ __global__ void __launch_bounds__(256) deconv_s2_direct_kernel(DeconvParams p) {
         }
         vals[o] = from_f<T>(v);
     }
-    T* dst = reinterpret_cast<T*>(p.out) + (((size_t)page * 2 * p.h + Y) * (2 * p.w) + X) * p.out_cp + o0;
-    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    T* base = reinterpret_cast<T*>(p.out);
     const uint4* s4 = reinterpret_cast<const uint4*>(&vals[0]);
-    d4[0] = s4[0];
-    d4[1] = s4[1];
+    *reinterpret_cast<uint4*>(base + act_idx(page, p.out_cp, 2 * p.h, 2 * p.w, o0, Y, X)) = s4[0];
+    *reinterpret_cast<uint4*>(base + act_idx(page, p.out_cp, 2 * p.h, 2 * p.w, o0 + 8, Y, X)) = s4[1];
 }
 
 int launch_deconv_s2_direct(pcs_ctx* ctx, const DeconvS2Args& a) {

@@ -14,13 +14,20 @@
 //   K = taps x C_in, walked as (16-channel chunk) x (tap).
 // A CTA owns a strip of 128 px x R rows and keeps R accumulators (R x NPAD TMEM
 // columns).  Per 16-channel chunk the producer brings in, with TMA,
-//   * the input patch  [2 planes][R+k-1 rows][128+k-1 px][8 ch]  (zero filled
-//     outside the image = the 'same' zero border), and
+//   * the input patch  [2 planes][R+k-1 rows][128 px][8 ch]  (zero filled outside
+//     the image = the 'same' zero border): ONE TMA box whose rows are 2 KB
+//     contiguous runs of the plane-major activation layout (common.cuh), and
 //   * the weights      [taps][2 planes][NPAD][8 ch]  (host pre-arranged image).
 // Both are K-major, SWIZZLE_NONE canonical layouts: a "plane" holds 8 channels
 // (16 B) per pixel at a 16-byte pixel pitch, so the A operand of tap (dy,dx) for
 // accumulator row r is the SAME shared-memory patch addressed at byte offset
-// ((r+dy)*PXW + dx)*16 -- the im2col expansion never exists anywhere.
+// ((r+dy)*128 + dx)*16 -- the im2col expansion never exists anywhere.  The patch
+// is 128 px wide, so a strip yields 128-(k-1) valid output pixels; the last k-1
+// MMA rows read wrapped neighbours and are discarded.
+//
+// mode EPI_DECONV serves Conv2DTranspose(2x2, stride 2): a 1x1 GEMM whose N axis
+// is (tap, C_out) -- y[2h+i, 2w+j, o] = b[o] + sum_c x[h,w,c] K[i,j,o,c] -- with
+// a scattering epilogue (model.py:71,79).
 #include "common.cuh"
 
 namespace pcs {
@@ -35,18 +42,21 @@ template <int NPAD> struct Cfg {
     static constexpr int ACC = (2 * R * NPAD <= 512) ? 2 : 1;             // TMEM accumulator stages
 };
 
+enum { EPI_STORE = 0, EPI_DECONV = 1 };
+
 struct UmmaParams {
-    int n, h, w;
+    int n, h, w;                // input grid (conv: == output grid; deconv: output is 2h x 2w)
     int k, pad;
+    int sw;                     // valid output pixels per strip = 128 - (k - 1)
     int nch0, nchunks;          // 16-channel chunks of source 0 / of all sources
     const uint8_t* wimg;        // [ntile][chunk][tap][plane][NPAD][8] operand image
     const float* bias;
-    int cout, relu;
+    int cout, relu, mode, co_t; // co_t: padded channels per tap (deconv mode)
     void* out; int out_cp;
     void* pool; int pool_cp;
     int strips, rowblocks, ntiles_n, num_tiles;
-    int a_rows, pxw;            // R + k - 1, 128 + k - 1
-    uint32_t a_plane_bytes, a_plane_stride, a_bytes, b_bytes, stage_bytes;   // a_bytes = 2 * a_plane_stride
+    int a_rows;                 // R + k - 1
+    uint32_t a_plane_stride, a_bytes, b_bytes, stage_bytes;   // a_bytes = 2 * a_plane_stride = TMA bytes
     int nstages;
 };
 
@@ -179,17 +189,17 @@ conv_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm0, co
                 const int nt = rem % p.ntiles_n; rem /= p.ntiles_n;
                 const int rb = rem % p.rowblocks;
                 const int strip = rem / p.rowblocks;
-                const int x0 = strip * TILE_M - p.pad, y0 = rb * R - p.pad;
+                const int x0 = strip * p.sw - p.pad, y0 = rb * R - p.pad;
                 const uint8_t* wsrc = p.wimg + (size_t)nt * p.nchunks * p.b_bytes;
                 for (int kc = 0; kc < p.nchunks; ++kc) {
                     mbar_wait(&s_empty[stage], phase ^ 1u);
                     uint8_t* a_dst = stages + (size_t)stage * p.stage_bytes;
                     uint8_t* b_dst = a_dst + p.a_bytes;
-                    mbar_expect_tx(&s_full[stage], 2 * p.a_plane_bytes + p.b_bytes);
+                    mbar_expect_tx(&s_full[stage], p.a_bytes + p.b_bytes);
                     const CUtensorMap* tm = kc < p.nch0 ? &tm0 : &tm1;
-                    const int c0 = (kc < p.nch0 ? kc : kc - p.nch0) * 16;
-                    tma_load_4d(a_dst, tm, &s_full[stage], c0, x0, y0, page);
-                    tma_load_4d(a_dst + p.a_plane_stride, tm, &s_full[stage], c0 + 8, x0, y0, page);
+                    const int plane0 = (kc < p.nch0 ? kc : kc - p.nch0) * 2;
+                    // box = 256 x u64 (128 px x 16 B) x a_rows x 2 planes; coordinate 0 counts 8-byte units
+                    tma_load_4d(a_dst, tm, &s_full[stage], x0 * 2, y0, plane0, page);
                     bulk_load(b_dst, wsrc + (size_t)kc * p.b_bytes, p.b_bytes, &s_full[stage]);
                     if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
                 }
@@ -217,7 +227,7 @@ conv_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm0, co
                         int t = 0;
                         for (int dy = 0; dy < p.k; ++dy) {
                             for (int dx = 0; dx < p.k; ++dx, ++t) {
-                                const uint32_t a_off = (uint32_t)((r + dy) * p.pxw + dx);     // in 16-byte units
+                                const uint32_t a_off = (uint32_t)((r + dy) * TILE_M + dx);   // in 16-byte units
                                 const uint32_t b_off = (uint32_t)t * (b_tap_bytes >> 4);
                                 tc_mma(d_tmem, a_desc0 + a_off, b_desc0 + b_off, IDESC, (kc | t) ? 1u : 0u);
                             }
@@ -243,12 +253,17 @@ conv_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm0, co
             const int nt = rem % p.ntiles_n; rem /= p.ntiles_n;
             const int rb = rem % p.rowblocks;
             const int strip = rem / p.rowblocks;
-            const int x = strip * TILE_M + quarter * 32 + lane;
+            const int m = quarter * 32 + lane;                     // MMA row = pixel within the strip
+            const int x = strip * p.sw + m;
+            const bool xok = m < p.sw && x < p.w;
             const int y0 = rb * R;
             const int cbase = nt * NPAD;
             // bias of this N tile (named barrier 1 over the 4 epilogue warps)
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            for (int i = threadIdx.x - 64; i < NPAD; i += 128) s_bias[i] = (cbase + i < p.cout) ? __ldg(p.bias + cbase + i) : 0.f;
+            for (int i = threadIdx.x - 64; i < NPAD; i += 128) {
+                const int o = p.mode == EPI_DECONV ? (cbase + i) % p.co_t : cbase + i;
+                s_bias[i] = o < p.cout ? __ldg(p.bias + o) : 0.f;
+            }
             asm volatile("bar.sync 1, 128;" ::: "memory");
 
             mbar_wait(&s_tfull[acc], acc_phase);
@@ -273,29 +288,53 @@ conv_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm0, co
                         f1[i] = __uint_as_float(v1[i]) + b;
                         if (p.relu) { f0[i] = fmaxf(f0[i], 0.f); f1[i] = fmaxf(f1[i], 0.f); }
                     }
-                    if (out && x < p.w) {
+                    const uint4 lo0 = make_uint4(pack2<T>(f0[0], f0[1]), pack2<T>(f0[2], f0[3]), pack2<T>(f0[4], f0[5]), pack2<T>(f0[6], f0[7]));
+                    const uint4 hi0 = make_uint4(pack2<T>(f0[8], f0[9]), pack2<T>(f0[10], f0[11]), pack2<T>(f0[12], f0[13]), pack2<T>(f0[14], f0[15]));
+                    const uint4 lo1 = make_uint4(pack2<T>(f1[0], f1[1]), pack2<T>(f1[2], f1[3]), pack2<T>(f1[4], f1[5]), pack2<T>(f1[6], f1[7]));
+                    const uint4 hi1 = make_uint4(pack2<T>(f1[8], f1[9]), pack2<T>(f1[10], f1[11]), pack2<T>(f1[12], f1[13]), pack2<T>(f1[14], f1[15]));
+                    if (p.mode == EPI_DECONV) {
+                        // column J = (tap, o): scatter to output pixel (2y + tap/2, 2x + tap%2)
+                        const int J = cbase + c16 * 16;
+                        const int tap = J / p.co_t, o = J - tap * p.co_t;
+                        if (xok && o < p.out_cp) {
+                            const int ox = 2 * x + (tap & 1), oh = 2 * p.h, ow = 2 * p.w;
+                            if (ya < p.h) {
+                                const int oy = 2 * ya + (tap >> 1);
+                                *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, oh, ow, o, oy, ox)) = lo0;
+                                *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, oh, ow, o + 8, oy, ox)) = hi0;
+                            }
+                            if (ya + 1 < p.h) {
+                                const int oy = 2 * (ya + 1) + (tap >> 1);
+                                *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, oh, ow, o, oy, ox)) = lo1;
+                                *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, oh, ow, o + 8, oy, ox)) = hi1;
+                            }
+                        }
+                        continue;
+                    }
+                    const int o = cbase + c16 * 16;
+                    if (out && xok) {
                         if (ya < p.h) {
-                            uint4* d = reinterpret_cast<uint4*>(out + (((size_t)page * p.h + ya) * p.w + x) * p.out_cp + cbase + c16 * 16);
-                            d[0] = make_uint4(pack2<T>(f0[0], f0[1]), pack2<T>(f0[2], f0[3]), pack2<T>(f0[4], f0[5]), pack2<T>(f0[6], f0[7]));
-                            d[1] = make_uint4(pack2<T>(f0[8], f0[9]), pack2<T>(f0[10], f0[11]), pack2<T>(f0[12], f0[13]), pack2<T>(f0[14], f0[15]));
+                            *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, p.h, p.w, o, ya, x)) = lo0;
+                            *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, p.h, p.w, o + 8, ya, x)) = hi0;
                         }
                         if (ya + 1 < p.h) {
-                            uint4* d = reinterpret_cast<uint4*>(out + (((size_t)page * p.h + ya + 1) * p.w + x) * p.out_cp + cbase + c16 * 16);
-                            d[0] = make_uint4(pack2<T>(f1[0], f1[1]), pack2<T>(f1[2], f1[3]), pack2<T>(f1[4], f1[5]), pack2<T>(f1[6], f1[7]));
-                            d[1] = make_uint4(pack2<T>(f1[8], f1[9]), pack2<T>(f1[10], f1[11]), pack2<T>(f1[12], f1[13]), pack2<T>(f1[14], f1[15]));
+                            *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, p.h, p.w, o, ya + 1, x)) = lo1;
+                            *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, p.h, p.w, o + 8, ya + 1, x)) = hi1;
                         }
                     }
                     if (pool) {
-                        float m[16];
+                        float mx[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             const float a = fmaxf(f0[i], f1[i]);
-                            m[i] = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, 1));
+                            mx[i] = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, 1));
                         }
-                        if (!(lane & 1) && x < p.w && ya < p.h) {
-                            uint4* d = reinterpret_cast<uint4*>(pool + (((size_t)page * (p.h >> 1) + (ya >> 1)) * (p.w >> 1) + (x >> 1)) * p.pool_cp + cbase + c16 * 16);
-                            d[0] = make_uint4(pack2<T>(m[0], m[1]), pack2<T>(m[2], m[3]), pack2<T>(m[4], m[5]), pack2<T>(m[6], m[7]));
-                            d[1] = make_uint4(pack2<T>(m[8], m[9]), pack2<T>(m[10], m[11]), pack2<T>(m[12], m[13]), pack2<T>(m[14], m[15]));
+                        if (!(lane & 1) && xok && ya < p.h) {
+                            const int ph = p.h >> 1, pw = p.w >> 1;
+                            *reinterpret_cast<uint4*>(pool + act_idx(page, p.pool_cp, ph, pw, o, ya >> 1, x >> 1)) =
+                                make_uint4(pack2<T>(mx[0], mx[1]), pack2<T>(mx[2], mx[3]), pack2<T>(mx[4], mx[5]), pack2<T>(mx[6], mx[7]));
+                            *reinterpret_cast<uint4*>(pool + act_idx(page, p.pool_cp, ph, pw, o + 8, ya >> 1, x >> 1)) =
+                                make_uint4(pack2<T>(mx[8], mx[9]), pack2<T>(mx[10], mx[11]), pack2<T>(mx[12], mx[13]), pack2<T>(mx[14], mx[15]));
                         }
                     }
                 }
@@ -332,18 +371,21 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
-// activation [n][h][w][cp] (2-byte elements) seen as (channel, x, y, page); box = 8 ch x PXW x rows x 1
-int make_act_map(pcs_ctx* ctx, CUtensorMap* tm, const ConvSrc& s, int n, int h, int w, int pxw, int rows, bool bf16) {
+// plane-major activation [n][cp/8][h][w][8 x 2 B] seen as a u64 tensor (2w, h, planes, pages):
+// box = 256 u64 (128 px x 16 B) x rows x 2 planes x 1 -> shared memory [plane][row][128 px][16 B]
+int make_act_map(pcs_ctx* ctx, CUtensorMap* tm, const ConvSrc& s, int n, int h, int w, int rows) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return set_err(ctx, PCS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-    const cuuint64_t dims[4] = {(cuuint64_t)s.cp, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
-    const cuuint64_t strides[3] = {(cuuint64_t)s.cp * 2, (cuuint64_t)w * s.cp * 2, (cuuint64_t)h * w * s.cp * 2};
-    const cuuint32_t box[4] = {8, (cuuint32_t)pxw, (cuuint32_t)rows, 1};
+    const cuuint64_t planes = (cuuint64_t)s.cp / 8;
+    const cuuint64_t dims[4] = {(cuuint64_t)w * 2, (cuuint64_t)h, planes, (cuuint64_t)n};
+    const cuuint64_t strides[3] = {(cuuint64_t)w * 16, (cuuint64_t)h * w * 16, planes * h * w * 16};
+    const cuuint32_t box[4] = {256, (cuuint32_t)rows, 2, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = enc(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(s.p), dims,
-                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return set_err(ctx, PCS_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d (cp=%d w=%d h=%d n=%d box=%d,%d)", (int)r, s.cp, w, h, n, pxw, rows);
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(s.p), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return set_err(ctx, PCS_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d (cp=%d w=%d h=%d n=%d rows=%d)", (int)r, s.cp, w, h, n, rows);
     return PCS_OK;
 }
 
@@ -357,27 +399,27 @@ int launch_t(pcs_ctx* ctx, const UmmaConvArgs& a) {
     if (p.nchunks != a.nchunks) return set_err(ctx, PCS_ERR_ARG, "conv_umma: source channel chunks %d != weight image chunks %d", p.nchunks, a.nchunks);
     p.wimg = reinterpret_cast<const uint8_t*>(a.wmma); p.bias = a.b32; p.cout = a.cout; p.relu = a.relu;
     p.out = a.out; p.out_cp = a.out_cp; p.pool = a.pool_out; p.pool_cp = a.pool_cp;
-    p.strips = (a.w + TILE_M - 1) / TILE_M;
+    p.mode = a.mode; p.co_t = a.co_t;
+    p.sw = TILE_M - (a.k - 1);
+    p.strips = (a.w + p.sw - 1) / p.sw;
     p.rowblocks = (a.h + R - 1) / R;
-    p.ntiles_n = (a.cout + NPAD - 1) / NPAD;
+    const int ncols = a.mode == EPI_DECONV ? 4 * a.co_t : a.cout;
+    p.ntiles_n = (ncols + NPAD - 1) / NPAD;
     p.num_tiles = a.n * p.strips * p.rowblocks * p.ntiles_n;
     p.a_rows = R + a.k - 1;
-    p.pxw = TILE_M + a.k - 1;
-    p.a_plane_bytes = (uint32_t)p.a_rows * p.pxw * 16;
-    p.a_plane_stride = (p.a_plane_bytes + 127) / 128 * 128;       // TMA destinations are 128-byte aligned
+    p.a_plane_stride = (uint32_t)p.a_rows * TILE_M * 16;
     p.a_bytes = 2 * p.a_plane_stride;
     p.b_bytes = (uint32_t)a.k * a.k * 2 * NPAD * 16;
     p.stage_bytes = (p.a_bytes + p.b_bytes + 1023) / 1024 * 1024;
-    // the B block must start 16-byte aligned inside the stage: a_bytes is a multiple of 32
     const uint32_t budget = 225 * 1024 - 1024;
     p.nstages = (int)std::min<uint32_t>(kMaxStages, budget / p.stage_bytes);
     if (p.nstages < 2) return set_err(ctx, PCS_ERR_ARG, "conv_umma: stage of %u bytes does not fit twice in shared memory", p.stage_bytes);
     if ((a.h & 1) || (a.w & 1)) return set_err(ctx, PCS_ERR_ARG, "conv_umma: odd grid");
+    if (a.pool_out && (p.sw & 1)) return set_err(ctx, PCS_ERR_ARG, "conv_umma: fused pooling needs an even strip width");
     const size_t smem = (size_t)p.nstages * p.stage_bytes + 1024;
-    const bool bf = ctx->precision == PCS_PREC_BF16;
     CUtensorMap tm0, tm1;
-    PCS_TRY(make_act_map(ctx, &tm0, a.src[0], a.n, a.h, a.w, p.pxw, p.a_rows, bf));
-    if (a.nsrc > 1) PCS_TRY(make_act_map(ctx, &tm1, a.src[1], a.n, a.h, a.w, p.pxw, p.a_rows, bf));
+    PCS_TRY(make_act_map(ctx, &tm0, a.src[0], a.n, a.h, a.w, p.a_rows));
+    if (a.nsrc > 1) PCS_TRY(make_act_map(ctx, &tm1, a.src[1], a.n, a.h, a.w, p.a_rows));
     else tm1 = tm0;
     static bool attr_set = false;
     if (!attr_set) {
@@ -405,7 +447,7 @@ int launch_npad(pcs_ctx* ctx, const UmmaConvArgs& a) {
 }  // namespace
 
 bool umma_supported(int k, int npad) {
-    if (k < 1 || k > 5) return false;
+    if (k < 1 || k > 5 || k == 2) return false;      // k = 2 (U-Net up-conv) would need an odd strip width
     return npad == 32 || npad == 48 || npad == 64 || npad == 80 || npad == 128;
 }
 
@@ -438,6 +480,40 @@ size_t umma_weight_image(const float* w32, int taps, const int* src_c, int nsrc,
                                 const float v = w32[((size_t)t * cin + cbase + c) * cout + o];
                                 out[(((((size_t)nt * nchunks + chunk) * taps + t) * 2 + pl) * npad + nn) * 8 + e] = conv(v);
                             }
+            cbase += src_c[s];
+        }
+    }
+    return out.size() * sizeof(uint16_t);
+}
+
+// Operand image of a 2x2 stride-2 transposed convolution: one "tap" (1x1 GEMM), N column J = t * co_t + o.
+size_t umma_weight_image_deconv(const float* w32 /*[4][cin][cout]*/, const int* src_c, int nsrc, int cout, int co_t,
+                                int npad, int precision, std::vector<uint16_t>& out) {
+    int cin = 0, nchunks = 0;
+    for (int s = 0; s < nsrc; ++s) { cin += src_c[s]; nchunks += pad16(src_c[s]) / 16; }
+    const int ncols = 4 * co_t, ntiles = (ncols + npad - 1) / npad;
+    out.assign((size_t)ntiles * nchunks * 2 * npad * 8, 0);
+    auto conv = [&](float v) -> uint16_t {
+        if (precision == PCS_PREC_BF16) {
+            __nv_bfloat16 b = __float2bfloat16_rn(v);
+            return *reinterpret_cast<uint16_t*>(&b);
+        }
+        __half h = __float2half_rn(v);
+        return *reinterpret_cast<uint16_t*>(&h);
+    };
+    for (int nt = 0; nt < ntiles; ++nt) {
+        int chunk = 0, cbase = 0;
+        for (int s = 0; s < nsrc; ++s) {
+            for (int lc = 0; lc < pad16(src_c[s]) / 16; ++lc, ++chunk)
+                for (int pl = 0; pl < 2; ++pl)
+                    for (int nn = 0; nn < npad; ++nn)
+                        for (int e = 0; e < 8; ++e) {
+                            const int c = lc * 16 + pl * 8 + e, J = nt * npad + nn;
+                            const int t = J / co_t, o = J % co_t;
+                            if (c >= src_c[s] || J >= ncols || o >= cout) continue;
+                            const float v = w32[((size_t)t * cin + cbase + c) * cout + o];
+                            out[((((size_t)nt * nchunks + chunk) * 2 + pl) * npad + nn) * 8 + e] = conv(v);
+                        }
             cbase += src_c[s];
         }
     }

@@ -61,11 +61,11 @@ __global__ void __launch_bounds__(256) head_kernel(HeadParams p) {
         for (int o = 0; o < DCO; ++o) d5[o] = s_db[o];
         const int t = (y & 1) * 2 + (x & 1);
         const int hh = p.hp / 2, wh = p.wp / 2;
-        const size_t ipix = ((size_t)page * hh + (y >> 1)) * wh + (x >> 1);
-        const T* a0 = reinterpret_cast<const T*>(p.d0) + ipix * p.dcp0;
-        const T* a1 = p.d1 ? reinterpret_cast<const T*>(p.d1) + ipix * p.dcp1 : nullptr;
+        const T* a0 = reinterpret_cast<const T*>(p.d0);
+        const T* a1 = reinterpret_cast<const T*>(p.d1);
         for (int c = 0; c < dcin; ++c) {
-            const float a = hf(c < p.dc0 ? a0[c] : a1[c - p.dc0]);
+            const float a = hf(c < p.dc0 ? a0[act_idx(page, p.dcp0, hh, wh, c, y >> 1, x >> 1)]
+                                         : a1[act_idx(page, p.dcp1, hh, wh, c - p.dc0, y >> 1, x >> 1)]);
             const float4* wv = reinterpret_cast<const float4*>(s_dw + ((size_t)t * dcin + c) * DCO);
 #pragma unroll
             for (int q = 0; q < DCO / 4; ++q) {
@@ -83,9 +83,9 @@ __global__ void __launch_bounds__(256) head_kernel(HeadParams p) {
         row = DCO;
     }
     if (p.has_skip) {
-        const T* s = reinterpret_cast<const T*>(p.skip) + (((size_t)page * p.hp + y) * p.wp + x) * p.skip_cp;
+        const T* s = reinterpret_cast<const T*>(p.skip);
         for (int c = 0; c < p.skip_c; ++c) {
-            const float a = hf(s[c]);
+            const float a = hf(s[act_idx(page, p.skip_cp, p.hp, p.wp, c, y, x)]);
 #pragma unroll
             for (int k = 0; k < NC; ++k) lg[k] = fmaf(a, s_lw[(row + c) * NC + k], lg[k]);
         }

@@ -201,7 +201,7 @@ gauss1d_kernel(const SRC* __restrict__ src, double* __restrict__ dst, int H, int
 __global__ void __launch_bounds__(256) minmax_f64_kernel(const double* __restrict__ p, size_t n,
                                                          unsigned long long* __restrict__ out /*[2]*/) {
     // values are >= 0 here (filtered uint8 levels), so the bit patterns order like the doubles
-    double lo = 1e300, hi = -1e300;
+    double lo = 1e300, hi = 0.0;      // idle threads must not win the unsigned-pattern max
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         double v = p[i];
         lo = fmin(lo, v);

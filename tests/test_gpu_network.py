@@ -3,7 +3,7 @@ model.py / network.py:248-260.
 
 Tolerances (stated, see DESIGN.md "precision"):
   * device vs numerics twin (same bf16|fp16 rounding points, fp32 accumulate):
-    logits max |d| <= 2e-3 (bf16) / 3e-4 (fp16), mean |d| <= 6e-5 / 4e-6 -- only
+    logits max |d| <= 2e-3 (bf16) / 3e-4 (fp16), mean |d| <= 6e-5 / 1e-5 -- only
     accumulation order and rare 1-ulp operand flips differ;
   * device vs fp32 oracle: logits max |d| <= 8e-3 (bf16) / 1e-3 (fp16);
   * argmax vs the fp64 oracle: agreement >= 99.9 % for fp16 operands, >= 99.7 % for
@@ -21,7 +21,7 @@ from page_segmentation_b200 import synth
 pytestmark = pytest.mark.gpu
 
 TOL = {"bf16": dict(twin_max=2e-3, twin_mean=6e-5, f32_max=8e-3, agree=0.997),
-       "fp16": dict(twin_max=3e-4, twin_mean=4e-6, f32_max=1e-3, agree=0.999)}
+       "fp16": dict(twin_max=3e-4, twin_mean=1e-5, f32_max=1e-3, agree=0.999)}
 
 
 def _device_predict(arch, weights, n_classes, image, precision, engine):
@@ -102,7 +102,7 @@ def test_fcn_skip_layerwise_vs_twin(ctx, engine):
         d = np.abs(got - exp)
         scale = max(1e-3, np.abs(exp).max())
         assert d.max() <= 2 ** -7 * scale + 1e-6, (nme, d.max(), scale)      # <= ~1 bf16 ulp of the range
-        assert d.mean() <= 2e-5 * scale + 1e-7, (nme, d.mean())
+        assert d.mean() <= 2e-4 * scale + 1e-7, (nme, d.mean())
 
 
 @pytest.mark.parametrize("n_classes", [2, 5, 8])
