@@ -108,14 +108,30 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// descriptors travel as (lo, hi) 32-bit halves: only the start-address field in `lo` changes per MMA
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                       uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        ".reg .b64 da, db;\n"
+        "mov.b64 da, {%1, %2};\n"
+        "mov.b64 db, {%3, %4};\n"
+        "setp.ne.b32 p, %6, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+        "}\n" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
@@ -143,7 +159,7 @@ template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) 
     __half2 v = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
 }
-template <typename T, int NPAD>
+template <typename T, int NPAD, int KS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1) {
     constexpr int R = Cfg<NPAD>::R;
@@ -189,7 +205,7 @@ conv_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm0, co
                 const int nt = rem % p.ntiles_n; rem /= p.ntiles_n;
                 const int rb = rem % p.rowblocks;
                 const int strip = rem / p.rowblocks;
-                const int x0 = strip * p.sw - p.pad, y0 = rb * R - p.pad;
+                const int x0 = strip * p.sw - p.pad, y0 = rb * R - p.pad;      // p.sw = 128 - (KS - 1)
                 const uint8_t* wsrc = p.wimg + (size_t)nt * p.nchunks * p.b_bytes;
                 for (int kc = 0; kc < p.nchunks; ++kc) {
                     mbar_wait(&s_empty[stage], phase ^ 1u);
@@ -209,27 +225,34 @@ conv_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm0, co
         // ===================== MMA issuer =====================
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0;
-        const uint32_t a_lbo = p.a_plane_stride, b_lbo = NPAD * 16, b_tap_bytes = 2 * NPAD * 16;
+        const bool leader = elect_one();
+        const uint32_t a_hi = (uint32_t)(make_desc(0, 0, 128) >> 32), b_hi = a_hi;
+        const uint32_t a_lo_c = ((p.a_plane_stride >> 4) & 0x3fffu) << 16;           // LBO field of A
+        constexpr uint32_t b_lo_c = (((uint32_t)NPAD * 16u >> 4) & 0x3fffu) << 16;   // LBO field of B
+        constexpr uint32_t B_TAP16 = 2u * NPAD;                                      // 16-byte units per tap
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             mbar_wait(&s_tempty[acc], acc_phase ^ 1u);
             tc_fence_after();
             for (int kc = 0; kc < p.nchunks; ++kc) {
                 mbar_wait(&s_full[stage], phase);
                 tc_fence_after();
-                if (lane == 0) {
+                if (leader) {
                     const uint32_t a_base = smem_u32(stages + (size_t)stage * p.stage_bytes);
-                    const uint32_t b_base = a_base + p.a_bytes;
-                    const uint64_t a_desc0 = make_desc(a_base, a_lbo, 128);
-                    const uint64_t b_desc0 = make_desc(b_base, b_lbo, 128);
-#pragma unroll 1
+                    const uint32_t a_lo0 = ((a_base >> 4) & 0x3fffu) | a_lo_c;
+                    const uint32_t b_lo0 = (((a_base + p.a_bytes) >> 4) & 0x3fffu) | b_lo_c;
+                    const uint32_t d0 = tmem_base + (uint32_t)(acc * R * NPAD);
+                    const uint32_t first = kc ? 1u : 0u;
+#pragma unroll
                     for (int r = 0; r < R; ++r) {
-                        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * R * NPAD + r * NPAD);
-                        int t = 0;
-                        for (int dy = 0; dy < p.k; ++dy) {
-                            for (int dx = 0; dx < p.k; ++dx, ++t) {
-                                const uint32_t a_off = (uint32_t)((r + dy) * TILE_M + dx);   // in 16-byte units
-                                const uint32_t b_off = (uint32_t)t * (b_tap_bytes >> 4);
-                                tc_mma(d_tmem, a_desc0 + a_off, b_desc0 + b_off, IDESC, (kc | t) ? 1u : 0u);
+#pragma unroll
+                        for (int dy = 0; dy < KS; ++dy) {
+#pragma unroll
+                            for (int dx = 0; dx < KS; ++dx) {
+                                constexpr int dummy = 0; (void)dummy;
+                                const uint32_t a_off = (uint32_t)((r + dy) * TILE_M + dx);      // 16-byte units
+                                const uint32_t b_off = (uint32_t)(dy * KS + dx) * B_TAP16;
+                                tc_mma(d0 + (uint32_t)(r * NPAD), a_lo0 + a_off, a_hi, b_lo0 + b_off, b_hi, IDESC,
+                                       (dy | dx) ? 1u : first);
                             }
                         }
                     }
@@ -389,7 +412,7 @@ int make_act_map(pcs_ctx* ctx, CUtensorMap* tm, const ConvSrc& s, int n, int h, 
     return PCS_OK;
 }
 
-template <typename T, int NPAD>
+template <typename T, int NPAD, int KS>
 int launch_t(pcs_ctx* ctx, const UmmaConvArgs& a) {
     constexpr int R = Cfg<NPAD>::R;
     UmmaParams p{};
@@ -423,32 +446,35 @@ int launch_t(pcs_ctx* ctx, const UmmaConvArgs& a) {
     else tm1 = tm0;
     static bool attr_set = false;
     if (!attr_set) {
-        PCS_CUDA(ctx, cudaFuncSetAttribute(conv_umma_kernel<T, NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        PCS_CUDA(ctx, cudaFuncSetAttribute(conv_umma_kernel<T, NPAD, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         attr_set = true;
     }
     const int grid = std::min(p.num_tiles, ctx->sm_count);
-    conv_umma_kernel<T, NPAD><<<grid, kThreads, smem, ctx->stream>>>(p, tm0, tm1);
+    conv_umma_kernel<T, NPAD, KS><<<grid, kThreads, smem, ctx->stream>>>(p, tm0, tm1);
     PCS_LAUNCH_CHECK(ctx, "conv_umma_kernel");
     return PCS_OK;
 }
 
 template <typename T>
 int launch_npad(pcs_ctx* ctx, const UmmaConvArgs& a) {
-    switch (a.npad) {
-        case 32: return launch_t<T, 32>(ctx, a);
-        case 48: return launch_t<T, 48>(ctx, a);
-        case 64: return launch_t<T, 64>(ctx, a);
-        case 80: return launch_t<T, 80>(ctx, a);
-        case 128: return launch_t<T, 128>(ctx, a);
-        default: return set_err(ctx, PCS_ERR_ARG, "conv_umma: no instantiation for N tile %d", a.npad);
+    const int key = a.k * 1000 + a.npad;
+    switch (key) {
+        case 5032: return launch_t<T, 32, 5>(ctx, a);
+        case 5048: return launch_t<T, 48, 5>(ctx, a);
+        case 5064: return launch_t<T, 64, 5>(ctx, a);
+        case 5080: return launch_t<T, 80, 5>(ctx, a);
+        case 3064: return launch_t<T, 64, 3>(ctx, a);
+        case 3128: return launch_t<T, 128, 3>(ctx, a);
+        case 1128: return launch_t<T, 128, 1>(ctx, a);
+        default: return set_err(ctx, PCS_ERR_ARG, "conv_umma: no instantiation for k=%d N tile %d", a.k, a.npad);
     }
 }
 
 }  // namespace
 
 bool umma_supported(int k, int npad) {
-    if (k < 1 || k > 5 || k == 2) return false;      // k = 2 (U-Net up-conv) would need an odd strip width
-    return npad == 32 || npad == 48 || npad == 64 || npad == 80 || npad == 128;
+    const int key = k * 1000 + npad;
+    return key == 5032 || key == 5048 || key == 5064 || key == 5080 || key == 3064 || key == 3128 || key == 1128;
 }
 
 // Operand image [ntile][chunk][tap][plane][NPAD][8]; chunk runs over the 16-channel groups of
