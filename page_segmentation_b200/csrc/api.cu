@@ -100,6 +100,8 @@ static void free_layers(pcs_ctx* ctx) {
         if (l.d_w32) cudaFree(l.d_w32);
         if (l.d_b32) cudaFree(l.d_b32);
         if (l.d_wmma) cudaFree(l.d_wmma);
+        if (l.d_head_lw) cudaFree(l.d_head_lw);
+        if (l.d_head_lb) cudaFree(l.d_head_lb);
     }
     ctx->layers.clear();
     ctx->model_ready = false;
@@ -183,6 +185,7 @@ static int run_conv1_u8(pcs_ctx* ctx, const char* lname, const uint8_t* d_image,
     DirectConvArgs a;
     a.src[0].p = d_image; a.src[0].c = 1; a.src[0].cp = 1; a.nsrc = 1;
     a.src_u8 = 1; a.img_h = hs; a.img_w = ws;
+    a.fast_first = ctx->engine == PCS_ENGINE_UMMA;     // the DIRECT engine keeps the generic kernel as reference
     a.n = n; a.h = out->h; a.w = out->w; a.k = L->k; a.pad = L->k / 2;
     a.w32 = L->d_w32; a.b32 = L->d_b32; a.cin = 1; a.cout = L->cout; a.relu = L->relu;
     a.out = out->p; a.out_cp = out->cp;
@@ -252,6 +255,21 @@ static int forward_fcn(pcs_ctx* ctx, bool skip, const uint8_t* d_image, int n, i
     Layer* L5 = find_layer(ctx, "deconv5");
     Layer* LL = find_layer(ctx, "logits");
     StageScope ts(ctx, "head");
+    if (ctx->engine == PCS_ENGINE_UMMA && L5->d_wmma && LL->d_head_lw) {
+        UmmaHeadArgs hd;
+        if (skip) { hd.skip = conv2.p; hd.skip_cp = conv2.cp; }
+        hd.lw_padded = LL->d_head_lw; hd.lb_folded = LL->d_head_lb;
+        hd.n_classes = ctx->n_classes; hd.hs = hs; hd.ws = ws;
+        hd.binary = io.binary; hd.labels = io.labels; hd.logits = io.logits; hd.prob = io.prob;
+        hd.lut = io.d_lut; hd.color = io.color; hd.overlay = io.overlay; hd.inverted = io.inverted;
+        UmmaConvArgs u;
+        u.src[0] = src_of(d4); u.nsrc = 1;
+        if (skip) { u.src[1] = src_of(conv3); u.nsrc = 2; }
+        u.n = n; u.h = hp / 2; u.w = wp / 2; u.k = 1; u.pad = 0;
+        u.wmma = L5->d_wmma; u.b32 = L5->d_b32; u.cout = L5->cout; u.npad = L5->npad; u.nchunks = L5->nchunks; u.relu = 0;
+        u.mode = skip ? 3 : 2; u.co_t = L5->co_t; u.head = &hd;
+        return launch_conv_umma(ctx, u);
+    }
     HeadArgs a;
     a.has_deconv = 1;
     a.dsrc[0] = src_of(d4); a.dnsrc = 1;
@@ -421,6 +439,7 @@ int pcs_model_load(pcs_ctx* ctx, int arch, int n_classes, int precision, const p
     PCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     free_layers(ctx);
     ctx->arch = arch; ctx->n_classes = n_classes; ctx->precision = precision;
+    { static int64_t next_stamp = 0; ctx->model_stamp = ++next_stamp; }
     for (int li = 0; li < nt; ++li) {
         const LayerSpec& s = table[li];
         const pcs_layer_weights& w = layers[li];
@@ -481,7 +500,15 @@ int pcs_model_load(pcs_ctx* ctx, int arch, int n_classes, int precision, const p
             L.npad = std::min(pad16(L.cout), 128);
             if (!umma_supported(L.k, L.npad) || (L.cout > 128 && L.cout % 128)) continue;
             L.wmma_bytes = umma_weight_image(L.h_w32.data(), L.k * L.k, src_c, nsrc, L.cout, L.npad, precision, img);
-        } else if (L.kind == K_DECONV_S2 && L.name != "deconv5") {
+        } else if (L.kind == K_DECONV_S2 && L.name == "deconv5") {
+            // fused head: N column J = tap * 20 + o (see conv_umma.cu EPI_HEAD)
+            if (arch == PCS_ARCH_FCN_SKIP) { src_c[0] = 30; src_c[1] = 40; nsrc = 2; }     // [deconv4, conv3]
+            if (L.cout != 20 || n_classes > 4) continue;
+            L.co_t = L.cout;
+            L.npad = 4 * L.cout;
+            if (!umma_supported(1, L.npad)) continue;
+            L.wmma_bytes = umma_weight_image_deconv(L.h_w32.data(), src_c, nsrc, L.cout, L.co_t, L.npad, precision, img);
+        } else if (L.kind == K_DECONV_S2) {
             L.co_t = pad16(L.cout);
             L.npad = std::min(4 * L.co_t, 128);
             if (!umma_supported(1, L.npad) || (4 * L.co_t) % L.npad) continue;
@@ -494,6 +521,24 @@ int pcs_model_load(pcs_ctx* ctx, int arch, int n_classes, int precision, const p
         PCS_CUDA(ctx, cudaMalloc(&L.d_wmma, L.wmma_bytes));
         PCS_CUDA(ctx, cudaMemcpy(L.d_wmma, img.data(), L.wmma_bytes, cudaMemcpyHostToDevice));
     }
+    if (arch != PCS_ARCH_UNET && n_classes <= 4) {
+        // logits weights padded to 4 classes; deconv5 bias folded through them: lb' = lb + b5 . lw[0:20]
+        Layer* L5 = find_layer(ctx, "deconv5");
+        Layer* LL = find_layer(ctx, "logits");
+        std::vector<float> lw(50 * 4, 0.f), lb(4, 0.f);
+        for (int c = 0; c < LL->cin; ++c)
+            for (int k = 0; k < n_classes; ++k) lw[(size_t)c * 4 + k] = LL->h_w32[(size_t)c * n_classes + k];
+        for (int k = 0; k < n_classes; ++k) {
+            double v = LL->h_b32[k];
+            for (int o = 0; o < L5->cout; ++o) v += (double)L5->h_b32[o] * (double)LL->h_w32[(size_t)o * n_classes + k];
+            lb[k] = (float)v;
+        }
+        PCS_CUDA(ctx, cudaMalloc(&LL->d_head_lw, lw.size() * 4));
+        PCS_CUDA(ctx, cudaMalloc(&LL->d_head_lb, lb.size() * 4));
+        PCS_CUDA(ctx, cudaMemcpy(LL->d_head_lw, lw.data(), lw.size() * 4, cudaMemcpyHostToDevice));
+        PCS_CUDA(ctx, cudaMemcpy(LL->d_head_lb, lb.data(), lb.size() * 4, cudaMemcpyHostToDevice));
+    }
+    if (getenv("PCSEG_DEBUG_SYNC_LOAD")) PCS_CUDA(ctx, cudaDeviceSynchronize());
     ctx->model_ready = true;
     return PCS_OK;
 }

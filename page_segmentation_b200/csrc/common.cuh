@@ -59,6 +59,8 @@ struct Layer {
     size_t wmma_bytes = 0;
     int npad = 0;           // padded C_out of the UMMA tile
     int co_t = 0;           // deconv s2 on the tensor path: padded channels per tap
+    float* d_head_lw = nullptr;   // logits layer: [50][4] padded weights for the fused head
+    float* d_head_lb = nullptr;   // logits layer: [4] bias with the deconv5 bias folded in
     int nchunks = 0;        // number of 16-channel K chunks over all sources
 };
 
@@ -77,6 +79,7 @@ struct pcs_ctx {
     int arch = -1, n_classes = 0, precision = PCS_PREC_BF16, engine = PCS_ENGINE_UMMA;
     std::vector<pcs::Layer> layers;
     bool model_ready = false;
+    int64_t model_stamp = 0;                // process-unique id of the loaded model (never reused)
 
     // workspace arena (activations), grown on demand
     char* arena = nullptr;
@@ -148,6 +151,7 @@ struct DirectConvArgs {
     int src_u8 = 0;            // src[0] is the uint8 network input (value/255), H,W below are the padded grid
     int img_h = 0, img_w = 0;  // real (unpadded) size of the uint8 input
     int upsample = 0;          // read input at (y/2, x/2): UpSampling2D fused (U-Net up*)
+    int fast_first = 0;        // allow the specialised first-layer kernel (constant-bank weights)
     int n = 0, h = 0, w = 0;   // output grid (== input grid unless upsample)
     int k = 0, pad = 0;        // kernel size, pad-before
     const float* w32 = nullptr;   // [k*k][cin][cout]
@@ -212,6 +216,14 @@ int launch_bounding_boxes(pcs_ctx* ctx, const uint8_t* d_pred, int n, int H, int
                           uint8_t* d_out);
 
 // conv_umma.cu  (tcgen05 / TMEM / TMA implicit GEMM)
+struct UmmaHeadArgs {              // fused FCN head epilogue (conv_umma.cu modes 2/3)
+    const void* skip = nullptr; int skip_cp = 0;
+    const float* lw_padded = nullptr;   // device [50][4]: logits weights, classes zero-padded to 4
+    const float* lb_folded = nullptr;   // device [4]: logits bias + deconv5 bias folded through the logits weights
+    int n_classes = 0, hs = 0, ws = 0;
+    const uint8_t* binary = nullptr; uint8_t* labels = nullptr; float* logits = nullptr; float* prob = nullptr;
+    const uint8_t* lut = nullptr; uint8_t* color = nullptr; uint8_t* overlay = nullptr; uint8_t* inverted = nullptr;
+};
 struct UmmaConvArgs {
     ConvSrc src[2];
     int nsrc = 1;
@@ -220,7 +232,9 @@ struct UmmaConvArgs {
     const void* wmma = nullptr;    // pre-arranged operand image, see conv_umma.cu
     const float* b32 = nullptr;
     int cout = 0, npad = 0, nchunks = 0, relu = 0;
-    int mode = 0;                  // 0 = 'same' conv store (+pool), 1 = 2x2 stride-2 transposed conv scatter
+    int mode = 0;                  // 0 = 'same' conv store (+pool), 1 = 2x2 stride-2 transposed conv scatter,
+                                   // 2 / 3 = fused FCN head without / with the conv2 skip
+    const UmmaHeadArgs* head = nullptr;
     int co_t = 0;                  // mode 1: padded channels per tap
     void* out = nullptr;
     int out_cp = 0;

@@ -173,12 +173,98 @@ __global__ void __launch_bounds__(256) conv_direct_kernel(DirectParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------
+// First layer of both FCN variants: Conv2D(20, 5x5, 'same', relu) on the uint8 page
+// (model.py:50 / :211).  C_in = 1, so there is no contraction to hand to the tensor
+// cores; instead every weight is an immediate constant-bank operand of an FFMA
+// (fully unrolled 25 taps x 20 outputs), each thread owns 4 consecutive pixels and
+// the stream is pure FFMA.  fp32 math on the exact (float)(v/255.0) inputs.
+// ---------------------------------------------------------------------------
+constexpr int C1_K = 5, C1_CO = 20, C1_PX = 4;
+__constant__ float c_conv1_w[C1_K * C1_K * C1_CO];
+__constant__ float c_conv1_b[C1_CO];
+static int64_t g_conv1_owner[64] = {0};      // generation stamp of the model whose weights sit in the constant bank
+
+template <typename T>
+__global__ void __launch_bounds__(256) conv1_c20_kernel(const uint8_t* __restrict__ img, int img_h, int img_w, int h, int w,
+                                                       T* __restrict__ out, int out_cp) {
+    constexpr int TWX = 32 * C1_PX, THY = 8;
+    __shared__ float s_in[THY + C1_K - 1][TWX + C1_K - 1 + 1];
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
+    const int x0 = blockIdx.x * TWX, y0 = blockIdx.y * THY, page = blockIdx.z;
+    const uint8_t* src = img + (size_t)page * img_h * img_w;
+    for (int i = tid; i < (THY + 4) * (TWX + 4); i += 256) {
+        const int px = i % (TWX + 4), py = i / (TWX + 4);
+        const int gy = y0 + py - 2, gx = x0 + px - 2;
+        float v = 0.f;
+        if (gy >= 0 && gy < img_h && gx >= 0 && gx < img_w) v = c_u8_lut[src[(size_t)gy * img_w + gx]];
+        s_in[py][px] = v;
+    }
+    __syncthreads();
+    float acc[C1_PX][C1_CO];
+#pragma unroll
+    for (int q = 0; q < C1_PX; ++q)
+#pragma unroll
+        for (int o = 0; o < C1_CO; ++o) acc[q][o] = c_conv1_b[o];
+#pragma unroll
+    for (int dy = 0; dy < C1_K; ++dy) {
+        float row[C1_PX + C1_K - 1];
+#pragma unroll
+        for (int i = 0; i < C1_PX + C1_K - 1; ++i) row[i] = s_in[ty + dy][tx * C1_PX + i];
+#pragma unroll
+        for (int dx = 0; dx < C1_K; ++dx)
+#pragma unroll
+            for (int o = 0; o < C1_CO; ++o) {
+                const float wv = c_conv1_w[(dy * C1_K + dx) * C1_CO + o];
+#pragma unroll
+                for (int q = 0; q < C1_PX; ++q) acc[q][o] = fmaf(row[q + dx], wv, acc[q][o]);
+            }
+    }
+    const int y = y0 + ty;
+    if (y >= h) return;
+#pragma unroll
+    for (int q = 0; q < C1_PX; ++q) {
+        const int x = x0 + tx * C1_PX + q;
+        if (x >= w) continue;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {            // 32 padded channels = 4 planes of 8
+            T v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int o = g * 8 + e;
+                v[e] = from_f<T>(o < C1_CO ? fmaxf(acc[q][o < C1_CO ? o : 0], 0.f) : 0.f);
+            }
+            *reinterpret_cast<uint4*>(out + act_idx(page, out_cp, h, w, g * 8, y, x)) = *reinterpret_cast<const uint4*>(v);
+        }
+    }
+}
+
+static int launch_conv1_c20(pcs_ctx* ctx, const DirectConvArgs& a) {
+    if (ctx->device >= 64 || g_conv1_owner[ctx->device] != ctx->model_stamp) {
+        // w32 is [25][1][20] == the constant-bank layout; device-to-device copy on the stream
+        PCS_CUDA(ctx, cudaMemcpyToSymbolAsync(c_conv1_w, a.w32, sizeof(float) * C1_K * C1_K * C1_CO, 0, cudaMemcpyDeviceToDevice, ctx->stream));
+        PCS_CUDA(ctx, cudaMemcpyToSymbolAsync(c_conv1_b, a.b32, sizeof(float) * C1_CO, 0, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (ctx->device < 64) g_conv1_owner[ctx->device] = ctx->model_stamp;
+    }
+    dim3 grid((a.w + 127) / 128, (a.h + 7) / 8, a.n), block(32, 8);
+    if (ctx->precision == PCS_PREC_BF16)
+        conv1_c20_kernel<__nv_bfloat16><<<grid, block, 0, ctx->stream>>>(reinterpret_cast<const uint8_t*>(a.src[0].p), a.img_h, a.img_w, a.h, a.w,
+                                                                         reinterpret_cast<__nv_bfloat16*>(a.out), a.out_cp);
+    else
+        conv1_c20_kernel<__half><<<grid, block, 0, ctx->stream>>>(reinterpret_cast<const uint8_t*>(a.src[0].p), a.img_h, a.img_w, a.h, a.w,
+                                                                  reinterpret_cast<__half*>(a.out), a.out_cp);
+    PCS_LAUNCH_CHECK(ctx, "conv1_c20_kernel");
+    return PCS_OK;
+}
+
 int launch_conv_direct(pcs_ctx* ctx, const DirectConvArgs& a) {
     if (a.k < 1 || a.k > KMAX) return set_err(ctx, PCS_ERR_ARG, "conv_direct: kernel size %d unsupported", a.k);
     if (a.out_cp % COT || (a.pool_out && a.pool_cp % COT))
         return set_err(ctx, PCS_ERR_ARG, "conv_direct: channel stride must be a multiple of %d", COT);
     if ((a.h & 1) || (a.w & 1)) return set_err(ctx, PCS_ERR_ARG, "conv_direct: odd grid %dx%d", a.h, a.w);
     PCS_TRY(ensure_lut(ctx));
+    if (a.src_u8 && a.k == C1_K && a.cout == C1_CO && a.relu && a.out_cp == 32 && !a.pool_out && !a.upsample && a.fast_first)
+        return launch_conv1_c20(ctx, a);
     DirectParams p{};
     p.s0 = a.src[0].p; p.c0 = a.src[0].c; p.cp0 = a.src[0].cp;
     p.s1 = a.nsrc > 1 ? a.src[1].p : nullptr; p.c1 = a.nsrc > 1 ? a.src[1].c : 0; p.cp1 = a.nsrc > 1 ? a.src[1].cp : 0;

@@ -42,7 +42,23 @@ template <int NPAD> struct Cfg {
     static constexpr int ACC = (2 * R * NPAD <= 512) ? 2 : 1;             // TMEM accumulator stages
 };
 
-enum { EPI_STORE = 0, EPI_DECONV = 1 };
+enum { EPI_STORE = 0, EPI_DECONV = 1, EPI_HEAD = 2, EPI_HEAD_SKIP = 3 };
+
+// Fused FCN head (modes EPI_HEAD*): the GEMM is deconv5 = Conv2DTranspose(20, 2x2, s2, linear)
+// (model.py:83 / :229) with N column J = tap * 20 + o; its epilogue keeps deconv5 in fp32
+// registers and applies concat[deconv5, conv2] -> logits 1x1 -> softmax/argmax (model.py:85-88,
+// network.py:258-259) and the colour masks (output.py:44-60) per cropped output pixel.
+constexpr int HEAD_DCO = 20, HEAD_SKIPC = 30, HEAD_NC = 4;
+__constant__ float c_head_lw[(HEAD_DCO + HEAD_SKIPC) * HEAD_NC];   // logits weights [cin][4 classes], zero padded
+__constant__ float c_head_lb[HEAD_NC];                             // logits bias (+ folded deconv5 bias)
+int64_t g_head_owner[64] = {0};
+
+struct HeadEpi {
+    const void* skip; int skip_cp;         // conv2 activation at full resolution (2h x 2w grid)
+    int n_classes, hs, ws;                 // crop (model.py:29-42)
+    const uint8_t* binary; uint8_t* labels; float* logits; float* prob;
+    const uint8_t* lut; uint8_t* color; uint8_t* overlay; uint8_t* inverted;
+};
 
 struct UmmaParams {
     int n, h, w;                // input grid (conv: == output grid; deconv: output is 2h x 2w)
@@ -58,6 +74,8 @@ struct UmmaParams {
     int a_rows;                 // R + k - 1
     uint32_t a_plane_stride, a_bytes, b_bytes, stage_bytes;   // a_bytes = 2 * a_plane_stride = TMA bytes
     int nstages;
+    int debug_poison;
+    HeadEpi head;
 };
 
 // ---- PTX wrappers -----------------------------------------------------------
@@ -140,6 +158,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
           "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+                 : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
@@ -159,8 +182,16 @@ template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) 
     __half2 v = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
 }
-template <typename T, int NPAD, int KS>
-__global__ void __launch_bounds__(kThreads, 1)
+template <typename T> __device__ __forceinline__ float2 unpack2(uint32_t v);
+template <> __device__ __forceinline__ float2 unpack2<__nv_bfloat16>(uint32_t v) {
+    return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+}
+template <> __device__ __forceinline__ float2 unpack2<__half>(uint32_t v) {
+    return __half22float2(*reinterpret_cast<const __half2*>(&v));
+}
+
+template <typename T, int NPAD, int KS, int MODE>
+__global__ void __launch_bounds__(MODE >= EPI_HEAD ? 320 : kThreads, 1)
 conv_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1) {
     constexpr int R = Cfg<NPAD>::R;
     constexpr int ACC = Cfg<NPAD>::ACC;
@@ -177,9 +208,14 @@ conv_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm0, co
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* stages = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
 
+    if (p.debug_poison) {      // diagnosis: NaN-fill the stage buffers so that an early operand read is visible
+        uint32_t* w = reinterpret_cast<uint32_t*>(stages);
+        for (uint32_t i = threadIdx.x; i < (uint32_t)p.nstages * p.stage_bytes / 4; i += blockDim.x) w[i] = 0x7fc07fc0u;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < p.nstages; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 1); }
-        for (int a = 0; a < ACC; ++a) { mbar_init(&s_tfull[a], 1); mbar_init(&s_tempty[a], 4); }
+        for (int a = 0; a < ACC; ++a) { mbar_init(&s_tfull[a], 1); mbar_init(&s_tempty[a], (blockDim.x >> 5) - 2); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -191,6 +227,18 @@ conv_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm0, co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = s_tmem_base;
+    if (p.debug_poison && warp >= 2) {     // diagnosis: NaN-fill all accumulator columns of this warp's lane quarter
+        const uint32_t nanv = 0x7fc00000u;
+        for (int c = 0; c < 512; c += 16) {
+            const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c;
+            asm volatile(
+                "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+                ::"r"(ta), "r"(nanv) : "memory");
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+    }
+    if (p.debug_poison) { __syncthreads(); tc_fence_after(); }
 
     const int tiles_per_page = p.strips * p.rowblocks * p.ntiles_n;
 
@@ -266,8 +314,11 @@ conv_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm0, co
         }
     } else {
         // ===================== epilogue warps =====================
-        const int quarter = warp & 3;                              // TMEM lane quarter this warp may touch
-        for (int i = threadIdx.x - 64; i < NPAD; i += 128) s_bias[i] = 0.f;   // filled per N tile below
+        // warps 2.. : TMEM lane quarter = warp & 3; with 8 epilogue warps two warps share a quarter
+        // and split the accumulator rows between them (group 0 / 1)
+        const int quarter = warp & 3;
+        const int group = (warp - 2) >> 2, ngroups = ((blockDim.x >> 5) - 2) >> 2;
+        const int epi_threads = blockDim.x - 64;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -281,83 +332,170 @@ conv_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm0, co
             const bool xok = m < p.sw && x < p.w;
             const int y0 = rb * R;
             const int cbase = nt * NPAD;
-            // bias of this N tile (named barrier 1 over the 4 epilogue warps)
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            for (int i = threadIdx.x - 64; i < NPAD; i += 128) {
-                const int o = p.mode == EPI_DECONV ? (cbase + i) % p.co_t : cbase + i;
+            // per-column bias of this N tile (named barrier 1 over the epilogue warps)
+            asm volatile("bar.sync 1, %0;" ::"r"(epi_threads) : "memory");
+            for (int i = threadIdx.x - 64; i < NPAD; i += epi_threads) {
+                int o = cbase + i;
+                if (MODE == EPI_DECONV) o = (cbase + i) % p.co_t;
+                if (MODE >= EPI_HEAD) o = 0x7fffffff;              // deconv5 bias is folded into c_head_lb
                 s_bias[i] = o < p.cout ? __ldg(p.bias + o) : 0.f;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"r"(epi_threads) : "memory");
 
             mbar_wait(&s_tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * R * NPAD);
-            T* out = reinterpret_cast<T*>(p.out);
-            T* pool = reinterpret_cast<T*>(p.pool);
+
+            if constexpr (MODE >= EPI_HEAD) {
+                const HeadEpi& hd = p.head;
+                const int oh = 2 * p.h, ow = 2 * p.w;
 #pragma unroll 1
-            for (int rp = 0; rp < R / 2; ++rp) {
-                const int ya = y0 + 2 * rp;
+                for (int r = group; r < R; r += ngroups) {
+                    const int y = y0 + r;
 #pragma unroll 1
-                for (int c16 = 0; c16 < NPAD / 16; ++c16) {
-                    uint32_t v0[16], v1[16];
-                    tmem_ld16(t_lane + (uint32_t)((2 * rp) * NPAD + c16 * 16), v0);
-                    tmem_ld16(t_lane + (uint32_t)((2 * rp + 1) * NPAD + c16 * 16), v1);
-                    tmem_ld_wait();
-                    float f0[16], f1[16];
+                    for (int t = 0; t < 4; ++t) {
+                        uint32_t va[16], vb[4];
+                        tmem_ld16(t_lane + (uint32_t)(r * NPAD + t * HEAD_DCO), va);
+                        tmem_ld4(t_lane + (uint32_t)(r * NPAD + t * HEAD_DCO + 16), vb);
+                        tmem_ld_wait();
+                        const int oy = 2 * y + (t >> 1), ox = 2 * x + (t & 1);
+                        const bool valid = xok && y < p.h && oy < hd.hs && ox < hd.ws;
+                        float lg[HEAD_NC];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float b = s_bias[c16 * 16 + i];
-                        f0[i] = __uint_as_float(v0[i]) + b;
-                        f1[i] = __uint_as_float(v1[i]) + b;
-                        if (p.relu) { f0[i] = fmaxf(f0[i], 0.f); f1[i] = fmaxf(f1[i], 0.f); }
-                    }
-                    const uint4 lo0 = make_uint4(pack2<T>(f0[0], f0[1]), pack2<T>(f0[2], f0[3]), pack2<T>(f0[4], f0[5]), pack2<T>(f0[6], f0[7]));
-                    const uint4 hi0 = make_uint4(pack2<T>(f0[8], f0[9]), pack2<T>(f0[10], f0[11]), pack2<T>(f0[12], f0[13]), pack2<T>(f0[14], f0[15]));
-                    const uint4 lo1 = make_uint4(pack2<T>(f1[0], f1[1]), pack2<T>(f1[2], f1[3]), pack2<T>(f1[4], f1[5]), pack2<T>(f1[6], f1[7]));
-                    const uint4 hi1 = make_uint4(pack2<T>(f1[8], f1[9]), pack2<T>(f1[10], f1[11]), pack2<T>(f1[12], f1[13]), pack2<T>(f1[14], f1[15]));
-                    if (p.mode == EPI_DECONV) {
-                        // column J = (tap, o): scatter to output pixel (2y + tap/2, 2x + tap%2)
-                        const int J = cbase + c16 * 16;
-                        const int tap = J / p.co_t, o = J - tap * p.co_t;
-                        if (xok && o < p.out_cp) {
-                            const int ox = 2 * x + (tap & 1), oh = 2 * p.h, ow = 2 * p.w;
-                            if (ya < p.h) {
-                                const int oy = 2 * ya + (tap >> 1);
-                                *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, oh, ow, o, oy, ox)) = lo0;
-                                *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, oh, ow, o + 8, oy, ox)) = hi0;
+                        for (int k = 0; k < HEAD_NC; ++k) lg[k] = c_head_lb[k];
+#pragma unroll
+                        for (int o = 0; o < HEAD_DCO; ++o) {
+                            const float d = __uint_as_float(o < 16 ? va[o < 16 ? o : 0] : vb[o >= 16 ? o - 16 : 0]);
+#pragma unroll
+                            for (int k = 0; k < HEAD_NC; ++k) lg[k] = fmaf(d, c_head_lw[o * HEAD_NC + k], lg[k]);
+                        }
+                        if constexpr (MODE == EPI_HEAD_SKIP) {
+                            if (valid) {
+                                const T* sk = reinterpret_cast<const T*>(hd.skip);
+#pragma unroll
+                                for (int g = 0; g < 4; ++g) {          // 30 channels live in 4 planes of 8
+                                    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(sk + act_idx(page, hd.skip_cp, oh, ow, g * 8, oy, ox)));
+                                    const uint32_t wds[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        const float2 f = unpack2<T>(wds[e]);
+                                        const int c0 = g * 8 + 2 * e;
+                                        if (c0 < HEAD_SKIPC) {
+#pragma unroll
+                                            for (int k = 0; k < HEAD_NC; ++k) lg[k] = fmaf(f.x, c_head_lw[(HEAD_DCO + c0) * HEAD_NC + k], lg[k]);
+                                        }
+                                        if (c0 + 1 < HEAD_SKIPC) {
+#pragma unroll
+                                            for (int k = 0; k < HEAD_NC; ++k) lg[k] = fmaf(f.y, c_head_lw[(HEAD_DCO + c0 + 1) * HEAD_NC + k], lg[k]);
+                                        }
+                                    }
+                                }
                             }
-                            if (ya + 1 < p.h) {
-                                const int oy = 2 * (ya + 1) + (tap >> 1);
-                                *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, oh, ow, o, oy, ox)) = lo1;
-                                *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, oh, ow, o + 8, oy, ox)) = hi1;
+                        }
+                        if (!valid) continue;
+                        int best = 0;
+                        float bv = lg[0];
+#pragma unroll
+                        for (int k = 1; k < HEAD_NC; ++k)
+                            if (k < hd.n_classes && lg[k] > bv) { bv = lg[k]; best = k; }      // first maximum wins
+                        const size_t opix = ((size_t)page * hd.hs + oy) * hd.ws + ox;
+                        if (hd.labels) hd.labels[opix] = (uint8_t)best;
+                        if (hd.logits) {
+#pragma unroll
+                            for (int k = 0; k < HEAD_NC; ++k)
+                                if (k < hd.n_classes) hd.logits[opix * hd.n_classes + k] = lg[k];
+                        }
+                        if (hd.prob) {
+                            float e[HEAD_NC], sum = 0.f;
+#pragma unroll
+                            for (int k = 0; k < HEAD_NC; ++k) { e[k] = k < hd.n_classes ? expf(lg[k] - bv) : 0.f; sum += e[k]; }
+#pragma unroll
+                            for (int k = 0; k < HEAD_NC; ++k)
+                                if (k < hd.n_classes) hd.prob[opix * hd.n_classes + k] = e[k] / sum;
+                        }
+                        if (hd.color || hd.overlay || hd.inverted) {
+                            const uint8_t cr = hd.lut[best * 3 + 0], cg = hd.lut[best * 3 + 1], cb = hd.lut[best * 3 + 2];
+                            const uint8_t bin = hd.binary ? hd.binary[opix] : 1;
+                            if (hd.color) { hd.color[opix * 3 + 0] = cr; hd.color[opix * 3 + 1] = cg; hd.color[opix * 3 + 2] = cb; }
+                            if (hd.overlay) {
+                                const bool keep = (uint8_t)(1 - bin) != 0;          // overlay[(1 - binary) == 0] = 0
+                                hd.overlay[opix * 3 + 0] = keep ? cr : 0; hd.overlay[opix * 3 + 1] = keep ? cg : 0; hd.overlay[opix * 3 + 2] = keep ? cb : 0;
+                            }
+                            if (hd.inverted) {
+                                const bool keep = bin != 0;                         // inverted[binary == 0] = 0
+                                hd.inverted[opix * 3 + 0] = keep ? cr : 0; hd.inverted[opix * 3 + 1] = keep ? cg : 0; hd.inverted[opix * 3 + 2] = keep ? cb : 0;
                             }
                         }
-                        continue;
                     }
-                    const int o = cbase + c16 * 16;
-                    if (out && xok) {
-                        if (ya < p.h) {
-                            *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, p.h, p.w, o, ya, x)) = lo0;
-                            *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, p.h, p.w, o + 8, ya, x)) = hi0;
-                        }
-                        if (ya + 1 < p.h) {
-                            *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, p.h, p.w, o, ya + 1, x)) = lo1;
-                            *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, p.h, p.w, o + 8, ya + 1, x)) = hi1;
-                        }
-                    }
-                    if (pool) {
-                        float mx[16];
+                }
+            } else {
+                T* out = reinterpret_cast<T*>(p.out);
+                T* pool = reinterpret_cast<T*>(p.pool);
+#pragma unroll 1
+                for (int rp = group; rp < R / 2; rp += ngroups) {
+                    const int ya = y0 + 2 * rp;
+#pragma unroll 1
+                    for (int c16 = 0; c16 < NPAD / 16; ++c16) {
+                        uint32_t v0[16], v1[16];
+                        tmem_ld16(t_lane + (uint32_t)((2 * rp) * NPAD + c16 * 16), v0);
+                        tmem_ld16(t_lane + (uint32_t)((2 * rp + 1) * NPAD + c16 * 16), v1);
+                        tmem_ld_wait();
+                        float f0[16], f1[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
-                            const float a = fmaxf(f0[i], f1[i]);
-                            mx[i] = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, 1));
+                            const float b = s_bias[c16 * 16 + i];
+                            f0[i] = __uint_as_float(v0[i]) + b;
+                            f1[i] = __uint_as_float(v1[i]) + b;
+                            if (p.relu) { f0[i] = fmaxf(f0[i], 0.f); f1[i] = fmaxf(f1[i], 0.f); }
                         }
-                        if (!(lane & 1) && xok && ya < p.h) {
-                            const int ph = p.h >> 1, pw = p.w >> 1;
-                            *reinterpret_cast<uint4*>(pool + act_idx(page, p.pool_cp, ph, pw, o, ya >> 1, x >> 1)) =
-                                make_uint4(pack2<T>(mx[0], mx[1]), pack2<T>(mx[2], mx[3]), pack2<T>(mx[4], mx[5]), pack2<T>(mx[6], mx[7]));
-                            *reinterpret_cast<uint4*>(pool + act_idx(page, p.pool_cp, ph, pw, o + 8, ya >> 1, x >> 1)) =
-                                make_uint4(pack2<T>(mx[8], mx[9]), pack2<T>(mx[10], mx[11]), pack2<T>(mx[12], mx[13]), pack2<T>(mx[14], mx[15]));
+                        const uint4 lo0 = make_uint4(pack2<T>(f0[0], f0[1]), pack2<T>(f0[2], f0[3]), pack2<T>(f0[4], f0[5]), pack2<T>(f0[6], f0[7]));
+                        const uint4 hi0 = make_uint4(pack2<T>(f0[8], f0[9]), pack2<T>(f0[10], f0[11]), pack2<T>(f0[12], f0[13]), pack2<T>(f0[14], f0[15]));
+                        const uint4 lo1 = make_uint4(pack2<T>(f1[0], f1[1]), pack2<T>(f1[2], f1[3]), pack2<T>(f1[4], f1[5]), pack2<T>(f1[6], f1[7]));
+                        const uint4 hi1 = make_uint4(pack2<T>(f1[8], f1[9]), pack2<T>(f1[10], f1[11]), pack2<T>(f1[12], f1[13]), pack2<T>(f1[14], f1[15]));
+                        if constexpr (MODE == EPI_DECONV) {
+                            // column J = (tap, o): scatter to output pixel (2y + tap/2, 2x + tap%2)
+                            const int J = cbase + c16 * 16;
+                            const int tap = J / p.co_t, o = J - tap * p.co_t;
+                            if (xok && o < p.out_cp) {
+                                const int ox = 2 * x + (tap & 1), oh = 2 * p.h, ow = 2 * p.w;
+                                if (ya < p.h) {
+                                    const int oy = 2 * ya + (tap >> 1);
+                                    *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, oh, ow, o, oy, ox)) = lo0;
+                                    *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, oh, ow, o + 8, oy, ox)) = hi0;
+                                }
+                                if (ya + 1 < p.h) {
+                                    const int oy = 2 * (ya + 1) + (tap >> 1);
+                                    *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, oh, ow, o, oy, ox)) = lo1;
+                                    *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, oh, ow, o + 8, oy, ox)) = hi1;
+                                }
+                            }
+                        } else {
+                            const int o = cbase + c16 * 16;
+                            if (out && xok) {
+                                if (ya < p.h) {
+                                    *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, p.h, p.w, o, ya, x)) = lo0;
+                                    *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, p.h, p.w, o + 8, ya, x)) = hi0;
+                                }
+                                if (ya + 1 < p.h) {
+                                    *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, p.h, p.w, o, ya + 1, x)) = lo1;
+                                    *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, p.h, p.w, o + 8, ya + 1, x)) = hi1;
+                                }
+                            }
+                            if (pool) {
+                                float mx[16];
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) {
+                                    const float a = fmaxf(f0[i], f1[i]);
+                                    mx[i] = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, 1));
+                                }
+                                if (!(lane & 1) && xok && ya < p.h) {
+                                    const int ph = p.h >> 1, pw = p.w >> 1;
+                                    *reinterpret_cast<uint4*>(pool + act_idx(page, p.pool_cp, ph, pw, o, ya >> 1, x >> 1)) =
+                                        make_uint4(pack2<T>(mx[0], mx[1]), pack2<T>(mx[2], mx[3]), pack2<T>(mx[4], mx[5]), pack2<T>(mx[6], mx[7]));
+                                    *reinterpret_cast<uint4*>(pool + act_idx(page, p.pool_cp, ph, pw, o + 8, ya >> 1, x >> 1)) =
+                                        make_uint4(pack2<T>(mx[8], mx[9]), pack2<T>(mx[10], mx[11]), pack2<T>(mx[12], mx[13]), pack2<T>(mx[14], mx[15]));
+                                }
+                            }
                         }
                     }
                 }
@@ -412,7 +550,7 @@ int make_act_map(pcs_ctx* ctx, CUtensorMap* tm, const ConvSrc& s, int n, int h, 
     return PCS_OK;
 }
 
-template <typename T, int NPAD, int KS>
+template <typename T, int NPAD, int KS, int MODE>
 int launch_t(pcs_ctx* ctx, const UmmaConvArgs& a) {
     constexpr int R = Cfg<NPAD>::R;
     UmmaParams p{};
@@ -422,11 +560,13 @@ int launch_t(pcs_ctx* ctx, const UmmaConvArgs& a) {
     if (p.nchunks != a.nchunks) return set_err(ctx, PCS_ERR_ARG, "conv_umma: source channel chunks %d != weight image chunks %d", p.nchunks, a.nchunks);
     p.wimg = reinterpret_cast<const uint8_t*>(a.wmma); p.bias = a.b32; p.cout = a.cout; p.relu = a.relu;
     p.out = a.out; p.out_cp = a.out_cp; p.pool = a.pool_out; p.pool_cp = a.pool_cp;
+    if (a.mode != MODE) return set_err(ctx, PCS_ERR_ARG, "conv_umma: mode dispatch mismatch");
     p.mode = a.mode; p.co_t = a.co_t;
+    { const char* e = getenv("PCSEG_DEBUG_POISON"); p.debug_poison = e && e[0] == '1'; }
     p.sw = TILE_M - (a.k - 1);
     p.strips = (a.w + p.sw - 1) / p.sw;
     p.rowblocks = (a.h + R - 1) / R;
-    const int ncols = a.mode == EPI_DECONV ? 4 * a.co_t : a.cout;
+    const int ncols = a.mode == EPI_STORE ? a.cout : 4 * a.co_t;
     p.ntiles_n = (ncols + NPAD - 1) / NPAD;
     p.num_tiles = a.n * p.strips * p.rowblocks * p.ntiles_n;
     p.a_rows = R + a.k - 1;
@@ -446,27 +586,40 @@ int launch_t(pcs_ctx* ctx, const UmmaConvArgs& a) {
     else tm1 = tm0;
     static bool attr_set = false;
     if (!attr_set) {
-        PCS_CUDA(ctx, cudaFuncSetAttribute(conv_umma_kernel<T, NPAD, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        PCS_CUDA(ctx, cudaFuncSetAttribute(conv_umma_kernel<T, NPAD, KS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         attr_set = true;
     }
     const int grid = std::min(p.num_tiles, ctx->sm_count);
-    conv_umma_kernel<T, NPAD, KS><<<grid, kThreads, smem, ctx->stream>>>(p, tm0, tm1);
+    if constexpr (MODE >= EPI_HEAD) {
+        const UmmaHeadArgs& h = *a.head;
+        p.head.skip = h.skip; p.head.skip_cp = h.skip_cp; p.head.n_classes = h.n_classes; p.head.hs = h.hs; p.head.ws = h.ws;
+        p.head.binary = h.binary; p.head.labels = h.labels; p.head.logits = h.logits; p.head.prob = h.prob;
+        p.head.lut = h.lut; p.head.color = h.color; p.head.overlay = h.overlay; p.head.inverted = h.inverted;
+        if (ctx->device >= 64 || g_head_owner[ctx->device] != ctx->model_stamp) {
+            PCS_CUDA(ctx, cudaMemcpyToSymbolAsync(c_head_lw, h.lw_padded, sizeof(float) * (HEAD_DCO + HEAD_SKIPC) * HEAD_NC, 0, cudaMemcpyDeviceToDevice, ctx->stream));
+            PCS_CUDA(ctx, cudaMemcpyToSymbolAsync(c_head_lb, h.lb_folded, sizeof(float) * HEAD_NC, 0, cudaMemcpyDeviceToDevice, ctx->stream));
+            if (ctx->device < 64) g_head_owner[ctx->device] = ctx->model_stamp;
+        }
+    }
+    conv_umma_kernel<T, NPAD, KS, MODE><<<grid, MODE >= EPI_HEAD ? 320 : kThreads, smem, ctx->stream>>>(p, tm0, tm1);
     PCS_LAUNCH_CHECK(ctx, "conv_umma_kernel");
     return PCS_OK;
 }
 
 template <typename T>
 int launch_npad(pcs_ctx* ctx, const UmmaConvArgs& a) {
-    const int key = a.k * 1000 + a.npad;
+    const int key = a.mode * 100000 + a.k * 1000 + a.npad;
     switch (key) {
-        case 5032: return launch_t<T, 32, 5>(ctx, a);
-        case 5048: return launch_t<T, 48, 5>(ctx, a);
-        case 5064: return launch_t<T, 64, 5>(ctx, a);
-        case 5080: return launch_t<T, 80, 5>(ctx, a);
-        case 3064: return launch_t<T, 64, 3>(ctx, a);
-        case 3128: return launch_t<T, 128, 3>(ctx, a);
-        case 1128: return launch_t<T, 128, 1>(ctx, a);
-        default: return set_err(ctx, PCS_ERR_ARG, "conv_umma: no instantiation for k=%d N tile %d", a.k, a.npad);
+        case 5032: return launch_t<T, 32, 5, EPI_STORE>(ctx, a);
+        case 5048: return launch_t<T, 48, 5, EPI_STORE>(ctx, a);
+        case 5064: return launch_t<T, 64, 5, EPI_STORE>(ctx, a);
+        case 5080: return launch_t<T, 80, 5, EPI_STORE>(ctx, a);
+        case 3064: return launch_t<T, 64, 3, EPI_STORE>(ctx, a);
+        case 3128: return launch_t<T, 128, 3, EPI_STORE>(ctx, a);
+        case 101128: return launch_t<T, 128, 1, EPI_DECONV>(ctx, a);
+        case 201080: return launch_t<T, 80, 1, EPI_HEAD>(ctx, a);
+        case 301080: return launch_t<T, 80, 1, EPI_HEAD_SKIP>(ctx, a);
+        default: return set_err(ctx, PCS_ERR_ARG, "conv_umma: no instantiation for mode=%d k=%d N tile %d", a.mode, a.k, a.npad);
     }
 }
 
@@ -474,7 +627,7 @@ int launch_npad(pcs_ctx* ctx, const UmmaConvArgs& a) {
 
 bool umma_supported(int k, int npad) {
     const int key = k * 1000 + npad;
-    return key == 5032 || key == 5048 || key == 5064 || key == 5080 || key == 3064 || key == 3128 || key == 1128;
+    return key == 5032 || key == 5048 || key == 5064 || key == 5080 || key == 3064 || key == 3128 || key == 1128 || key == 1080;
 }
 
 // Operand image [ntile][chunk][tap][plane][NPAD][8]; chunk runs over the 16-channel groups of
@@ -547,6 +700,8 @@ size_t umma_weight_image_deconv(const float* w32 /*[4][cin][cout]*/, const int* 
 }
 
 int launch_conv_umma(pcs_ctx* ctx, const UmmaConvArgs& a) {
+    if (a.mode >= EPI_HEAD && (!a.head || a.co_t != HEAD_DCO || a.head->n_classes > HEAD_NC))
+        return set_err(ctx, PCS_ERR_ARG, "conv_umma: fused head needs 20 deconv channels and <= %d classes", HEAD_NC);
     if (!umma_supported(a.k, a.npad)) return set_err(ctx, PCS_ERR_ARG, "conv_umma: unsupported k=%d N=%d", a.k, a.npad);
     if (a.src[0].cp % 16 || (a.nsrc > 1 && a.src[1].cp % 16)) return set_err(ctx, PCS_ERR_ARG, "conv_umma: channel stride not a multiple of 16");
     if (a.out && a.out_cp % 16) return set_err(ctx, PCS_ERR_ARG, "conv_umma: output stride");

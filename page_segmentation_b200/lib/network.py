@@ -14,6 +14,7 @@ from .dataset import Dataset, SingleData
 from .colors import ColorMap
 
 logger = logging.getLogger(__name__)
+_model_tokens = __import__("itertools").count(1)     # id() values are recycled by the allocator; tokens are not
 
 DEFAULT_PRECISION = os.environ.get("PCSEG_PRECISION", "bf16")
 
@@ -87,13 +88,13 @@ class Network:
         elif self.n_classes != n_from_weights:
             raise ValueError(f"n_classes={self.n_classes} but the logits layer has {n_from_weights} outputs")
         self._arch = arch
-        self._ctx = None
+        self._token = next(_model_tokens)
 
     # -- device state ----------------------------------------------------------
     def _context(self):
         from ..runtime import get_context
         ctx = get_context(self.device)
-        want = (self._arch, self.n_classes, self.precision, id(self.model))
+        want = (self._arch, self.n_classes, self.precision, self._token)
         if getattr(ctx, "_loaded_key", None) != want:
             ctx.load_model(self._arch, self.n_classes, self.model.weights, self.precision)
             ctx._loaded_key = want

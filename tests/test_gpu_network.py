@@ -105,11 +105,12 @@ def test_fcn_skip_layerwise_vs_twin(ctx, engine):
         assert d.mean() <= 2e-4 * scale + 1e-7, (nme, d.mean())
 
 
-@pytest.mark.parametrize("n_classes", [2, 5, 8])
-def test_n_classes(ctx, n_classes):
+@pytest.mark.parametrize("n_classes,engine", [(2, "umma"), (4, "umma"), (5, "umma"), (2, "direct"), (5, "direct"), (8, "direct")])
+def test_n_classes(ctx, n_classes, engine):
+    """<= 4 classes run the fused tensor-core head, more fall back to the CUDA-core head kernel."""
     img, _ = _small_input(7, 64, 96)
     W = synth.make_weights("fcn_skip", n_classes, seed=3)
-    _, (logit, prob, pred) = _device_predict("fcn_skip", W, n_classes, img, "fp16", "direct")
+    _, (logit, prob, pred) = _device_predict("fcn_skip", W, n_classes, img, "fp16", engine)
     lt, _ = onet.Forward("fcn_skip", W, n_classes).logits(img)
     assert np.abs(logit - lt).max() <= 1e-3
     np.testing.assert_array_equal(pred, logit.argmax(-1))
@@ -168,5 +169,18 @@ def test_umma_one_hot_tap_is_a_shifted_copy(ctx, tap, precision):
     src = conv1[np.clip(ys, 0, H - 1), np.clip(xs, 0, Wd - 1), :]
     exp[..., :20] = np.where(ok[..., None], src, 0.0)
     assert conv1.max() > 0
+    # conv1 itself in closed form (guards against a stale model on the device)
+    x32 = (np.pad(img, ((0, H - img.shape[0]), (0, Wd - img.shape[1]))).astype(np.float64) / 255.0).astype(np.float32)
+    c1 = torch.from_numpy(x32[..., None] * (np.arange(1, 21, dtype=np.float32) / np.float32(32.0)))
+    c1 = c1.to(torch.bfloat16 if precision == "bf16" else torch.float16).to(torch.float32).numpy()
+    np.testing.assert_array_equal(conv1, c1)
+    bad = (conv2 != exp).any(-1)
+    if bad.any():       # tile map of the mismatches (8 rows x 124 px tiles) for diagnosis
+        lines = []
+        for rb in range(H // 8):
+            lines.append(" ".join(f"{int(bad[rb * 8:(rb + 1) * 8, st * 124:(st + 1) * 124].sum()):4d}"
+                                  for st in range((Wd + 123) // 124)))
+        yy, xx = np.nonzero(bad)
+        print("mismatch tile map:\n" + "\n".join(lines))
     np.testing.assert_array_equal(conv2, exp)
     np.testing.assert_array_equal(pool2, exp.reshape(H // 2, 2, Wd // 2, 2, 30).max(axis=(1, 3)))
