@@ -1,0 +1,85 @@
+"""Committed golden vectors (tests/golden/*.npz, written by tests/golden/make_golden.py with
+the CPU oracle - the reference cannot run here).  CPU: the oracle still reproduces them.
+GPU: the device path reproduces them through the drop-in API."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import network as onet
+from oracle import pipeline as opipe
+from page_segmentation_b200 import synth
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CASES = sorted(glob.glob(os.path.join(HERE, "golden", "*.npz")))
+LUT = {0: (255, 255, 255), 1: (255, 0, 0), 2: (0, 255, 0)}
+
+
+def test_golden_files_exist():
+    assert len(CASES) >= 3
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p) for p in CASES])
+def test_oracle_reproduces_golden(path):
+    g = np.load(path)
+    page_seed, weight_seed, lh, grey = (int(v) for v in g["meta"])
+    arch = str(g["arch"])
+    page = g["page"]
+    gen = synth.make_grey_page if grey else synth.make_page
+    np.testing.assert_array_equal(gen(page_seed, *page.shape, lh), page)          # generator is stable
+    img, b, ob = opipe.prepare_images(page, page, 6, lh, keep_orig_bin=True)
+    np.testing.assert_array_equal(img, g["image"])
+    np.testing.assert_array_equal(b, g["binary"])
+    np.testing.assert_array_equal(ob, g["orig_binary"])
+    W = synth.make_weights(arch, 3, seed=weight_seed)
+    l32, _ = onet.Forward(arch, W, 3).logits(img)
+    np.testing.assert_allclose(l32, g["logits32"], rtol=0, atol=2e-6)              # oneDNN thread-count jitter only
+    voted = opipe.vote_connected_component_class(g["pred32"].astype(np.int64), b)
+    np.testing.assert_array_equal(voted, g["voted"])
+    color, overlay, inverted, _ = opipe.generate_output_masks(b, voted, LUT)
+    np.testing.assert_array_equal(color, g["color"])
+    np.testing.assert_array_equal(overlay, g["overlay"])
+    np.testing.assert_array_equal(inverted, g["inverted"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p) for p in CASES])
+def test_device_reproduces_golden(ctx, path, precision):
+    from page_segmentation_b200.lib.architecture import Architecture
+    from page_segmentation_b200.lib.colors import DEFAULT_COLOR_MAP
+    from page_segmentation_b200.lib.dataset import DatasetLoader, SingleData
+    from page_segmentation_b200.lib.network import Network
+    from page_segmentation_b200.lib.output import generate_output_masks
+    from page_segmentation_b200.lib.postprocess import add_bounding_boxes, vote_connected_component_class
+    g = np.load(path)
+    page_seed, weight_seed, lh, grey = (int(v) for v in g["meta"])
+    arch = str(g["arch"])
+    data = DatasetLoader(6, DEFAULT_COLOR_MAP, prediction=True).load_images(SingleData(image=g["page"], line_height_px=lh))
+    np.testing.assert_array_equal(data.binary, g["binary"])
+    np.testing.assert_array_equal(data.orig_binary, g["orig_binary"])
+    if grey:                                                 # Gaussian weights go through exp(): <= 1 level
+        assert np.abs(data.image.astype(int) - g["image"].astype(int)).max() <= 1
+    else:
+        np.testing.assert_array_equal(data.image, g["image"])
+    assert data.original_shape == g["page"].shape
+    data.image = g["image"]                                   # the golden network input
+    net = Network("Predict", n_classes=3, model_constructor=Architecture(arch),
+                  weights=synth.make_weights(arch, 3, seed=weight_seed), precision=precision)
+    logit, prob, pred = net.predict_single_data(data)
+    tol = 8e-3 if precision == "bf16" else 1e-3
+    err = np.abs(logit - g["logits32"]).max()
+    assert err <= tol, err
+    bad = pred != g["pred64"]
+    assert bad.mean() <= (3e-3 if precision == "bf16" else 1e-3)
+    if bad.any():                                             # disagreements only at near-ties of the fp64 oracle
+        assert g["margin64"][bad].max() <= 2 * tol
+    # integer stages are bit-exact given the same class map
+    voted = vote_connected_component_class(g["pred32"].astype(np.int64), data)
+    np.testing.assert_array_equal(voted, g["voted"])
+    np.testing.assert_array_equal(add_bounding_boxes(np.where(g["binary"] > 0, g["pred32"], 0).astype(np.int64), data), g["boxes"])
+    m = generate_output_masks(data, g["voted"].astype(np.int64), DEFAULT_COLOR_MAP)
+    np.testing.assert_array_equal(m.color, g["color"])
+    np.testing.assert_array_equal(m.overlay, g["overlay"])
+    np.testing.assert_array_equal(m.inverted_overlay, g["inverted"])
