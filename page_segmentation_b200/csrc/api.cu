@@ -402,6 +402,10 @@ void pcs_ctx_destroy(pcs_ctx* ctx) {
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->stage) cudaFree(ctx->stage);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->copy_streams[i]) cudaStreamDestroy(ctx->copy_streams[i]);
+        if (ctx->ev_h2d[i]) { cudaEventDestroy(ctx->ev_h2d[i]); cudaEventDestroy(ctx->ev_comp[i]); cudaEventDestroy(ctx->ev_d2h[i]); }
+    }
     delete ctx;
 }
 
@@ -627,12 +631,30 @@ int pcs_predict_pages_host(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h
     const bool want_masks = h_color || h_overlay || h_inverted;
     if (want_masks && !lut) return set_err(ctx, PCS_ERR_ARG, "predict_pages_host: colour outputs need a LUT");
     PCS_CUDA(ctx, cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
-    const size_t src = (size_t)n * H * W, dst = (size_t)n * Hs * Ws;
+    // Three-stage pipeline over sub-batches of pages: H2D copy stream -> compute stream (ctx->stream) ->
+    // D2H copy stream, double-buffered on the device, so that with pinned host memory the PCIe traffic
+    // of neighbouring sub-batches hides behind the kernels.
+    if (!ctx->copy_streams[0]) {
+        PCS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_streams[0], cudaStreamNonBlocking));
+        PCS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_streams[1], cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            PCS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
+            PCS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_comp[i], cudaEventDisableTiming));
+            PCS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming));
+        }
+    }
+    cudaStream_t s_in = ctx->copy_streams[0], s_out = ctx->copy_streams[1], st = ctx->stream;
+    int chunk = 8;
+    if (const char* e = getenv("PCSEG_HOST_CHUNK")) chunk = std::max(1, atoi(e));
+    chunk = std::min(chunk, n);
+    const size_t src1 = (size_t)H * W, dst1 = (size_t)Hs * Ws;
     const bool same = h_grey == h_bin;
-    const size_t need = (same ? src : 2 * src) + dst * (3 + 9) + 4096;
+    auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+    const size_t in_bytes = al(src1 * chunk) * (same ? 1 : 2);
+    const size_t out_bytes = al(dst1 * chunk) * 3 + al(dst1 * chunk * 3) * 3;
+    const size_t need = 2 * (in_bytes + out_bytes) + 4096;
     if (need > ctx->stage_bytes) {
-        PCS_CUDA(ctx, cudaStreamSynchronize(st));
+        PCS_CUDA(ctx, cudaDeviceSynchronize());
         if (ctx->stage) cudaFree(ctx->stage);
         ctx->stage = nullptr; ctx->stage_bytes = 0;
         if (cudaMalloc(&ctx->stage, need) != cudaSuccess) {
@@ -641,32 +663,62 @@ int pcs_predict_pages_host(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h
         }
         ctx->stage_bytes = need;
     }
-    uint8_t* p = reinterpret_cast<uint8_t*>(ctx->stage);
-    auto take = [&](size_t b) { uint8_t* r = p; p += (b + 255) / 256 * 256; return r; };
-    uint8_t* d_grey = take(src);
-    uint8_t* d_bin = same ? d_grey : take(src);
-    uint8_t* d_image = take(dst);
-    uint8_t* d_binary = take(dst);
-    uint8_t* d_labels = take(dst);
-    uint8_t* d_color = h_color ? take(dst * 3) : nullptr;
-    uint8_t* d_overlay = h_overlay ? take(dst * 3) : nullptr;
-    uint8_t* d_inverted = h_inverted ? take(dst * 3) : nullptr;
-    PCS_CUDA(ctx, cudaMemcpyAsync(d_grey, h_grey, src, cudaMemcpyHostToDevice, st));
-    if (!same) PCS_CUDA(ctx, cudaMemcpyAsync(d_bin, h_bin, src, cudaMemcpyHostToDevice, st));
-    PCS_TRY(pcs_preprocess(ctx, d_grey, d_bin, n, H, W, Hs, Ws, d_image, d_binary, nullptr));
-    if (cc_majority) {
-        PCS_TRY(pcs_forward(ctx, d_image, d_binary, n, Hs, Ws, d_labels, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
-        PCS_TRY(pcs_cc_majority(ctx, d_labels, d_binary, n, Hs, Ws, ctx->n_classes));
-        if (want_masks) PCS_TRY(pcs_masks(ctx, d_labels, d_binary, n, Hs, Ws, lut, ctx->n_classes, d_color, d_overlay, d_inverted));
-    } else {
-        PCS_TRY(pcs_forward(ctx, d_image, d_binary, n, Hs, Ws, d_labels, nullptr, nullptr, lut, d_color, d_overlay, d_inverted));
+    struct Buf { uint8_t *grey, *bin, *image, *binary, *labels, *color, *overlay, *inverted; } buf[2];
+    {
+        uint8_t* p = reinterpret_cast<uint8_t*>(ctx->stage);
+        for (int i = 0; i < 2; ++i) {
+            buf[i].grey = p; p += al(src1 * chunk);
+            buf[i].bin = same ? buf[i].grey : p; if (!same) p += al(src1 * chunk);
+            buf[i].image = p; p += al(dst1 * chunk);
+            buf[i].binary = p; p += al(dst1 * chunk);
+            buf[i].labels = p; p += al(dst1 * chunk);
+            buf[i].color = p; p += al(dst1 * chunk * 3);
+            buf[i].overlay = p; p += al(dst1 * chunk * 3);
+            buf[i].inverted = p; p += al(dst1 * chunk * 3);
+        }
     }
-    if (h_image) PCS_CUDA(ctx, cudaMemcpyAsync(h_image, d_image, dst, cudaMemcpyDeviceToHost, st));
-    if (h_binary) PCS_CUDA(ctx, cudaMemcpyAsync(h_binary, d_binary, dst, cudaMemcpyDeviceToHost, st));
-    if (h_labels) PCS_CUDA(ctx, cudaMemcpyAsync(h_labels, d_labels, dst, cudaMemcpyDeviceToHost, st));
-    if (h_color) PCS_CUDA(ctx, cudaMemcpyAsync(h_color, d_color, dst * 3, cudaMemcpyDeviceToHost, st));
-    if (h_overlay) PCS_CUDA(ctx, cudaMemcpyAsync(h_overlay, d_overlay, dst * 3, cudaMemcpyDeviceToHost, st));
-    if (h_inverted) PCS_CUDA(ctx, cudaMemcpyAsync(h_inverted, d_inverted, dst * 3, cudaMemcpyDeviceToHost, st));
+    const int nchunks = (n + chunk - 1) / chunk;
+    auto enqueue_h2d = [&](int c) -> int {
+        const int b = c & 1, p0 = c * chunk, m = std::min(chunk, n - p0);
+        if (c >= 2) PCS_CUDA(ctx, cudaStreamWaitEvent(s_in, ctx->ev_comp[b], 0));      // input buffer consumed by chunk c-2
+        PCS_CUDA(ctx, cudaMemcpyAsync(buf[b].grey, h_grey + (size_t)p0 * src1, src1 * m, cudaMemcpyHostToDevice, s_in));
+        if (!same) PCS_CUDA(ctx, cudaMemcpyAsync(buf[b].bin, h_bin + (size_t)p0 * src1, src1 * m, cudaMemcpyHostToDevice, s_in));
+        PCS_CUDA(ctx, cudaEventRecord(ctx->ev_h2d[b], s_in));
+        return PCS_OK;
+    };
+    // order the pipeline after whatever the caller already queued on the compute stream
+    PCS_CUDA(ctx, cudaEventRecord(ctx->ev_comp[0], st));
+    PCS_CUDA(ctx, cudaStreamWaitEvent(s_in, ctx->ev_comp[0], 0));
+    PCS_CUDA(ctx, cudaStreamWaitEvent(s_out, ctx->ev_comp[0], 0));
+    PCS_TRY(enqueue_h2d(0));
+    for (int c = 0; c < nchunks; ++c) {
+        const int b = c & 1, p0 = c * chunk, m = std::min(chunk, n - p0);
+        if (c + 1 < nchunks) PCS_TRY(enqueue_h2d(c + 1));                                // next copy flies during this compute
+        PCS_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_h2d[b], 0));
+        if (c >= 2) PCS_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_d2h[b], 0));          // output buffer drained by chunk c-2
+        PCS_TRY(pcs_preprocess(ctx, buf[b].grey, buf[b].bin, m, H, W, Hs, Ws, buf[b].image, buf[b].binary, nullptr));
+        if (cc_majority) {
+            PCS_TRY(pcs_forward(ctx, buf[b].image, buf[b].binary, m, Hs, Ws, buf[b].labels, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
+            PCS_TRY(pcs_cc_majority(ctx, buf[b].labels, buf[b].binary, m, Hs, Ws, ctx->n_classes));
+            if (want_masks)
+                PCS_TRY(pcs_masks(ctx, buf[b].labels, buf[b].binary, m, Hs, Ws, lut, ctx->n_classes, h_color ? buf[b].color : nullptr,
+                                  h_overlay ? buf[b].overlay : nullptr, h_inverted ? buf[b].inverted : nullptr));
+        } else {
+            PCS_TRY(pcs_forward(ctx, buf[b].image, buf[b].binary, m, Hs, Ws, buf[b].labels, nullptr, nullptr, want_masks ? lut : nullptr,
+                                h_color ? buf[b].color : nullptr, h_overlay ? buf[b].overlay : nullptr, h_inverted ? buf[b].inverted : nullptr));
+        }
+        PCS_CUDA(ctx, cudaEventRecord(ctx->ev_comp[b], st));
+        PCS_CUDA(ctx, cudaStreamWaitEvent(s_out, ctx->ev_comp[b], 0));
+        const size_t o1 = (size_t)p0 * dst1, o3 = o1 * 3;
+        if (h_image) PCS_CUDA(ctx, cudaMemcpyAsync(h_image + o1, buf[b].image, dst1 * m, cudaMemcpyDeviceToHost, s_out));
+        if (h_binary) PCS_CUDA(ctx, cudaMemcpyAsync(h_binary + o1, buf[b].binary, dst1 * m, cudaMemcpyDeviceToHost, s_out));
+        if (h_labels) PCS_CUDA(ctx, cudaMemcpyAsync(h_labels + o1, buf[b].labels, dst1 * m, cudaMemcpyDeviceToHost, s_out));
+        if (h_color) PCS_CUDA(ctx, cudaMemcpyAsync(h_color + o3, buf[b].color, dst1 * m * 3, cudaMemcpyDeviceToHost, s_out));
+        if (h_overlay) PCS_CUDA(ctx, cudaMemcpyAsync(h_overlay + o3, buf[b].overlay, dst1 * m * 3, cudaMemcpyDeviceToHost, s_out));
+        if (h_inverted) PCS_CUDA(ctx, cudaMemcpyAsync(h_inverted + o3, buf[b].inverted, dst1 * m * 3, cudaMemcpyDeviceToHost, s_out));
+        PCS_CUDA(ctx, cudaEventRecord(ctx->ev_d2h[b], s_out));
+    }
+    PCS_CUDA(ctx, cudaStreamSynchronize(s_out));
     PCS_CUDA(ctx, cudaStreamSynchronize(st));
     return PCS_OK;
 }

@@ -94,6 +94,8 @@ struct pcs_ctx {
     // staging buffers of pcs_predict_pages_host
     char* stage = nullptr;
     size_t stage_bytes = 0;
+    cudaStream_t copy_streams[2] = {nullptr, nullptr};     // H2D / D2H streams of the host pipeline
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
 
     std::string timings;
     std::vector<pcs::StageTime> stage_times;

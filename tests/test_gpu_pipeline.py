@@ -1,0 +1,172 @@
+"""End-to-end drop-in surface on the device: DatasetLoader -> Predictor -> Masks / files, the
+host-buffer batch pipeline (pcs_predict_pages_host) and model loading from a Keras .h5."""
+import os
+
+import cv2
+import numpy as np
+import pytest
+import torch
+
+from oracle import network as onet
+from oracle import pipeline as opipe
+from page_segmentation_b200 import synth
+from page_segmentation_b200.lib.colors import DEFAULT_COLOR_MAP
+
+pytestmark = pytest.mark.gpu
+LUT = {0: (255, 255, 255), 1: (255, 0, 0), 2: (0, 255, 0)}
+
+
+def _loaded(seed, h=450, w=330, lh=18):
+    from page_segmentation_b200.lib.dataset import DatasetLoader, SingleData
+    page = synth.make_page(seed, h, w, lh)
+    data = DatasetLoader(6, DEFAULT_COLOR_MAP, prediction=True).load_images(SingleData(image=page, line_height_px=lh))
+    return page, data
+
+
+def test_dataset_loader_quirks(ctx):
+    from page_segmentation_b200.lib.dataset import DatasetLoader, SingleData
+    page = synth.make_page(1, 300, 240, 18)
+    other = synth.make_page(2, 300, 240, 18)
+    # dataset.py:172: the binary is derived from `image`; a caller-supplied `binary` is ignored and overwritten
+    d = DatasetLoader(6, DEFAULT_COLOR_MAP, prediction=True).load_images(SingleData(image=page, binary=other, line_height_px=18))
+    eimg, eb, eob = opipe.prepare_images(page, page, 6, 18, keep_orig_bin=True)
+    np.testing.assert_array_equal(d.image, eimg)
+    np.testing.assert_array_equal(d.binary, eb)
+    np.testing.assert_array_equal(d.orig_binary, eob)
+    assert d.original_shape == (300, 240) and d.mask is None
+
+
+def test_predictor_predict_and_masks_with_postprocessing(ctx):
+    from page_segmentation_b200.lib.dataset import Dataset
+    from page_segmentation_b200.lib.network import Network
+    from page_segmentation_b200.lib.postprocess import find_postprocessor
+    from page_segmentation_b200.lib.predictor import Predictor
+    from page_segmentation_b200.lib.predictor_data import PredictSettings
+    W = synth.make_weights("fcn_skip", 3, seed=1)
+    net = Network("Predict", n_classes=3, weights=W, precision="fp16")
+    pages = [_loaded(s) for s in (3, 4)]
+    settings = PredictSettings(n_classes=3, color_map=DEFAULT_COLOR_MAP, post_process=[find_postprocessor("cc_majority")])
+    pred = Predictor(settings, network=net)
+    gen = pred.predict(Dataset([d for _, d in pages], DEFAULT_COLOR_MAP))
+    assert hasattr(gen, "__next__")                                # lazy generator like predictor.py:27-30
+    for (page, data), p in zip(pages, gen):
+        logit, prob, raw = net.predict_single_data(data)
+        exp = opipe.vote_connected_component_class(raw.copy(), data.binary)
+        assert p.labels.dtype == np.int64 and p.probabilities.dtype == np.float32 and p.data is data
+        np.testing.assert_array_equal(p.labels, exp)
+        l64 = onet.Forward("fcn_skip", W, 3, dtype=torch.float64).logits(data.image)[0]
+        assert (raw == l64.argmax(-1)).mean() >= 0.999
+        m = pred.predict_masks(data)
+        c, o, i, f = opipe.generate_output_masks(data.binary, exp, LUT)
+        np.testing.assert_array_equal(m.color, c)
+        np.testing.assert_array_equal(m.overlay, o)
+        np.testing.assert_array_equal(m.inverted_overlay, i)
+        np.testing.assert_array_equal(m.fg_color_mask, f)
+
+
+def test_high_res_output(ctx):
+    from page_segmentation_b200.lib.network import Network
+    from page_segmentation_b200.lib.predictor import Predictor
+    from page_segmentation_b200.lib.predictor_data import PredictSettings
+    W = synth.make_weights("fcn_skip", 3, seed=2)
+    net = Network("Predict", n_classes=3, weights=W)
+    page, data = _loaded(5, 333, 241)
+    p = Predictor(PredictSettings(n_classes=3, color_map=DEFAULT_COLOR_MAP, high_res_output=True), network=net).predict_single(data)
+    _, _, raw = net.predict_single_data(data)
+    eimg, ebin, epred = opipe.scale_to_original_shape(data.image, data.binary, data.orig_binary, data.original_shape, raw)
+    assert p.labels.shape == page.shape and p.labels.dtype == np.int64
+    np.testing.assert_array_equal(p.labels, epred)
+    np.testing.assert_array_equal(p.data.image, eimg)
+    np.testing.assert_array_equal(p.data.binary, data.orig_binary)      # output.py:70-71
+    assert data.image.shape != page.shape                                # the input SingleData is not mutated (replace())
+
+
+def test_output_data_writes_three_images(ctx, tmp_path):
+    from page_segmentation_b200.lib.output import output_data
+    from page_segmentation_b200.lib.predictor import Predictor
+    from page_segmentation_b200.lib.predictor_data import PredictSettings
+    from page_segmentation_b200.lib.network import Network
+    net = Network("Predict", n_classes=3, weights=synth.make_weights("fcn_skip", 3, seed=3))
+    _, data = _loaded(6, 240, 200)
+    data.image_path = "/somewhere/page_0001.png"
+    out = str(tmp_path / "out")
+    Predictor(PredictSettings(n_classes=3, color_map=DEFAULT_COLOR_MAP, output=out), network=net)
+    for sub in ("color", "overlay", "inverted"):
+        assert os.path.isdir(os.path.join(out, sub))                     # predictor.py:21-25
+    _, _, pred = net.predict_single_data(data)
+    output_data(out, pred[None], data, DEFAULT_COLOR_MAP)                 # leading batch dim is squeezed (output.py:21-23)
+    c, o, i, _ = opipe.generate_output_masks(data.binary, pred, LUT)
+    for sub, exp in (("color", c), ("overlay", o), ("inverted", i)):
+        img = cv2.imread(os.path.join(out, sub, "page_0001.png"), cv2.IMREAD_COLOR)[..., ::-1]
+        np.testing.assert_array_equal(img, exp)
+
+
+def test_model_from_keras_h5(ctx, tmp_path):
+    from page_segmentation_b200.lib import h5
+    from page_segmentation_b200.lib.network import Network
+    from page_segmentation_b200.lib.predictor import Predictor
+    from page_segmentation_b200.lib.predictor_data import PredictSettings
+    W = synth.make_weights("fcn", 3, seed=7)
+    path = str(tmp_path / "model.h5")
+    h5.write_keras_h5(path, W, "fcn", extra_layers=["lambda", "max_pooling2d"])
+    _, data = _loaded(7, 200, 260)
+    pred = Predictor(PredictSettings(network=path, n_classes=3, color_map=DEFAULT_COLOR_MAP))     # builds its own Network
+    assert pred.network.model.name == "fcn"
+    logit, _, labels = pred.network.predict_single_data(data)
+    l32 = onet.Forward("fcn", W, 3).logits(data.image)[0]
+    assert np.abs(logit - l32).max() <= 8e-3
+    assert (labels == l32.argmax(-1)).mean() >= 0.995
+
+
+@pytest.mark.parametrize("cc", [False, True])
+def test_host_batch_pipeline_matches_stagewise(ctx, cc, monkeypatch):
+    """pcs_predict_pages_host (sub-batched, copy/compute overlapped) == stage-by-stage device calls."""
+    from page_segmentation_b200.runtime import PageBatchEngine
+    monkeypatch.setenv("PCSEG_HOST_CHUNK", "2")
+    n, H, W_ = 5, 360, 300
+    pages = np.stack([synth.make_page(10 + s, H, W_, 18) for s in range(n)])
+    weights = synth.make_weights("fcn_skip", 3, seed=9)
+    lut = np.array([LUT[i] for i in range(3)], dtype=np.uint8)
+    eng = PageBatchEngine("fcn_skip", weights, 3, precision="bf16", lut=lut)
+    Hs, Ws = synth.scaled_shape(H, W_, 6 / 18)
+    h_pages = torch.from_numpy(pages).pin_memory()
+    out = {k: torch.empty((n, Hs, Ws) + ((3,) if k != "labels" else ()), dtype=torch.uint8).pin_memory().numpy()
+           for k in ("labels", "color", "overlay", "inverted")}
+    eng.run_host(h_pages.numpy(), 6 / 18, out, cc_majority=cc)
+    dev = eng.run_device(torch.from_numpy(pages).cuda(), 6 / 18, cc_majority=cc)
+    torch.cuda.synchronize()
+    for k in out:
+        np.testing.assert_array_equal(out[k], dev[k].cpu().numpy())
+    for i in range(n):
+        eimg, eb = opipe.prepare_images(pages[i], pages[i], 6, 18)
+        np.testing.assert_array_equal(dev["image"][i].cpu().numpy(), eimg)
+        c, o, inv, _ = opipe.generate_output_masks(eb, out["labels"][i].astype(np.int64), LUT)
+        np.testing.assert_array_equal(out["color"][i], c)
+        np.testing.assert_array_equal(out["overlay"][i], o)
+        np.testing.assert_array_equal(out["inverted"][i], inv)
+        if cc:      # voting is idempotent: a voted map is its own vote
+            again = opipe.vote_connected_component_class(out["labels"][i].astype(np.int64), eb)
+            np.testing.assert_array_equal(again, out["labels"][i])
+
+
+def test_full_size_a4_page_properties(ctx):
+    """BASELINE config 1 shape (2480x3508 -> 1169x827): size-independent properties at full size."""
+    from page_segmentation_b200.lib.dataset import DatasetLoader, SingleData
+    from page_segmentation_b200.lib.network import Network
+    from page_segmentation_b200.lib.postprocess import vote_connected_component_class
+    page = synth.make_page(0)
+    data = DatasetLoader(6, DEFAULT_COLOR_MAP, prediction=True).load_images(SingleData(image=page, line_height_px=18))
+    assert data.image.shape == (1169, 827)
+    eimg, eb = opipe.prepare_images(page, page, 6, 18)
+    np.testing.assert_array_equal(data.image, eimg)
+    np.testing.assert_array_equal(data.binary, eb)
+    W = synth.make_weights("fcn_skip", 3, seed=0)
+    net = Network("Predict", n_classes=3, weights=W, precision="fp16")
+    logit, prob, pred = net.predict_single_data(data)
+    l32 = onet.Forward("fcn_skip", W, 3).logits(data.image)[0]
+    assert np.abs(logit - l32).max() <= 1e-3
+    assert (pred == l32.argmax(-1)).mean() >= 0.999
+    np.testing.assert_allclose(prob.sum(-1), 1.0, atol=1e-5)
+    voted = vote_connected_component_class(pred.copy(), data)
+    np.testing.assert_array_equal(vote_connected_component_class(voted.copy(), data), voted)      # idempotent
+    assert np.array_equal(voted[data.binary == 0], pred[data.binary == 0])                          # paper untouched
