@@ -226,6 +226,24 @@ def main():
     ms_max = float(t.item())
     value = world * n * args.steps / (ms_max / 1e3)
 
+    # ---------------- PCIe context for the end-to-end number ----------------
+    pcie = None
+    if rank == 0:
+        big = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
+        dbig = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        res = {}
+        for name, (dst, src) in (("h2d_gbs", (dbig, big)), ("d2h_gbs", (big, dbig))):
+            dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(3):
+                dst.copy_(src, non_blocking=True)
+            e1.record()
+            torch.cuda.synchronize()
+            res[name] = 3 * big.numel() / (e0.elapsed_time(e1) * 1e6)
+        pcie = res
+        del big, dbig
+
     # ---------------- end to end through the host-buffer C ABI ----------------
     for _ in range(max(1, args.warmup // 2)):
         eng.run_host(h_pages_np, SCALE, h_out_np)
@@ -274,6 +292,7 @@ def main():
                        "l2": "inputs larger than L2 (557 MB of pages per step)", "distinct_pages": distinct},
             "e2e": {"value": e2e_value, "unit": "pages/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "pcie_pinned_copy": pcie,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -3,6 +3,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 
 namespace pcs {
@@ -678,6 +679,9 @@ int pcs_predict_pages_host(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h
         }
     }
     const int nchunks = (n + chunk - 1) / chunk;
+    const bool trace = getenv("PCSEG_TRACE_HOST") != nullptr;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto now_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
     auto enqueue_h2d = [&](int c) -> int {
         const int b = c & 1, p0 = c * chunk, m = std::min(chunk, n - p0);
         if (c >= 2) PCS_CUDA(ctx, cudaStreamWaitEvent(s_in, ctx->ev_comp[b], 0));      // input buffer consumed by chunk c-2
@@ -707,6 +711,7 @@ int pcs_predict_pages_host(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h
             PCS_TRY(pcs_forward(ctx, buf[b].image, buf[b].binary, m, Hs, Ws, buf[b].labels, nullptr, nullptr, want_masks ? lut : nullptr,
                                 h_color ? buf[b].color : nullptr, h_overlay ? buf[b].overlay : nullptr, h_inverted ? buf[b].inverted : nullptr));
         }
+        const double t_enq = now_ms();
         PCS_CUDA(ctx, cudaEventRecord(ctx->ev_comp[b], st));
         PCS_CUDA(ctx, cudaStreamWaitEvent(s_out, ctx->ev_comp[b], 0));
         const size_t o1 = (size_t)p0 * dst1, o3 = o1 * 3;
@@ -717,6 +722,7 @@ int pcs_predict_pages_host(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h
         if (h_overlay) PCS_CUDA(ctx, cudaMemcpyAsync(h_overlay + o3, buf[b].overlay, dst1 * m * 3, cudaMemcpyDeviceToHost, s_out));
         if (h_inverted) PCS_CUDA(ctx, cudaMemcpyAsync(h_inverted + o3, buf[b].inverted, dst1 * m * 3, cudaMemcpyDeviceToHost, s_out));
         PCS_CUDA(ctx, cudaEventRecord(ctx->ev_d2h[b], s_out));
+        if (trace) fprintf(stderr, "[pcs host] chunk %d: compute enqueued at %.3f ms, d2h enqueued at %.3f ms\n", c, t_enq, now_ms());
     }
     PCS_CUDA(ctx, cudaStreamSynchronize(s_out));
     PCS_CUDA(ctx, cudaStreamSynchronize(st));

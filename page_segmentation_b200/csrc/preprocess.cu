@@ -73,21 +73,27 @@ __device__ __forceinline__ double cubic_rn(double x, double f0, double f1, doubl
     return __dadd_rn(f1, __dmul_rn(__dmul_rn(0.5, x), i1));
 }
 
-template <typename SRC>
-__device__ __forceinline__ double load_px(const SRC* p, size_t i) { return (double)p[i]; }
+__device__ __forceinline__ int level_count(const uint32_t* bits) {
+    int c = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) c += __popc(bits[k]);
+    return c;
+}
 
-// One thread per output pixel.  grid = (ceil(Ws/32), ceil(Hs/8), n).
-// SRC = uint8_t (plain page) or double (anti-aliased page, one page per launch).
-template <typename SRC>
+// One thread per output pixel.  grid = (ceil(Ws/32), ceil(Hs/8), pages of the group).
+// Per page (block-uniform): more than two grey levels => the bicubic source is the Gaussian-
+// filtered fp64 plane of that page (anti_aliasing=True, dataset.py:127) and the clip range its
+// min/max; otherwise the uint8 page itself and the min/max from the level bitmap.  No host
+// decision is involved, so the whole preprocess is asynchronous.
 __global__ void __launch_bounds__(256)
-resample_kernel(const SRC* __restrict__ grey, const uint8_t* __restrict__ bin, int H, int W, int Hs, int Ws,
-                const uint32_t* __restrict__ level_bits, const int* __restrict__ page_list,
-                double fmin_in, double fmax_in, uint8_t* __restrict__ image_out,
+resample_kernel(const uint8_t* __restrict__ grey, const uint8_t* __restrict__ bin, int H, int W, int Hs, int Ws,
+                const uint32_t* __restrict__ level_bits, const double* __restrict__ aa_planes,
+                const unsigned long long* __restrict__ aa_minmax, int page0, uint8_t* __restrict__ image_out,
                 uint8_t* __restrict__ binary_out) {
     const int x = blockIdx.x * 32 + threadIdx.x;
     const int y = blockIdx.y * 8 + threadIdx.y;
     if (x >= Ws || y >= Hs) return;
-    const int page = page_list ? page_list[blockIdx.z] : blockIdx.z;
+    const int page = page0 + blockIdx.z;
     const size_t src_off = (size_t)page * H * W;
     const size_t dst_off = (size_t)page * Hs * Ws + (size_t)y * Ws + x;
 
@@ -105,9 +111,13 @@ resample_kernel(const SRC* __restrict__ grey, const uint8_t* __restrict__ bin, i
         binary_out[dst_off] = (v == 0) ? 1 : 0;
     }
     if (image_out) {
+        const uint32_t* bits = level_bits + (size_t)page * 8;
+        const bool aa = aa_planes != nullptr && level_count(bits) > 2;
         double vmin, vmax;
-        if constexpr (sizeof(SRC) == 1) {
-            const uint32_t* bits = level_bits + page * 8;
+        if (aa) {
+            vmin = __longlong_as_double((long long)aa_minmax[2 * blockIdx.z]);
+            vmax = __longlong_as_double((long long)aa_minmax[2 * blockIdx.z + 1]);
+        } else {
             int lo = 0, hi = 255;
             for (int wv = 0; wv < 8; ++wv)
                 if (bits[wv]) { lo = wv * 32 + __ffs(bits[wv]) - 1; break; }
@@ -115,9 +125,6 @@ resample_kernel(const SRC* __restrict__ grey, const uint8_t* __restrict__ bin, i
                 if (bits[wv]) { hi = wv * 32 + 31 - __clz(bits[wv]); break; }
             vmin = (double)lo;
             vmax = (double)hi;
-        } else {
-            vmin = fmin_in;
-            vmax = fmax_in;
         }
         const double r0f = floor(r), c0f = floor(c);
         const double xr = __dsub_rn(r, r0f), xc = __dsub_rn(c, c0f);
@@ -128,13 +135,22 @@ resample_kernel(const SRC* __restrict__ grey, const uint8_t* __restrict__ bin, i
             cols[k] = reflect_coord(c0 + k, W);
             rows[k] = reflect_coord(r0 + k, H);
         }
-        const SRC* g = grey + (sizeof(SRC) == 1 ? src_off : 0);
         double frow[4];
+        if (aa) {
+            const double* g = aa_planes + (size_t)blockIdx.z * H * W;
 #pragma unroll
-        for (int pr = 0; pr < 4; ++pr) {
-            const size_t ro = (size_t)rows[pr] * W;
-            frow[pr] = cubic_rn(xc, load_px(g, ro + cols[0]), load_px(g, ro + cols[1]), load_px(g, ro + cols[2]),
-                                load_px(g, ro + cols[3]));
+            for (int pr = 0; pr < 4; ++pr) {
+                const size_t ro = (size_t)rows[pr] * W;
+                frow[pr] = cubic_rn(xc, g[ro + cols[0]], g[ro + cols[1]], g[ro + cols[2]], g[ro + cols[3]]);
+            }
+        } else {
+            const uint8_t* g = grey + src_off;
+#pragma unroll
+            for (int pr = 0; pr < 4; ++pr) {
+                const size_t ro = (size_t)rows[pr] * W;
+                frow[pr] = cubic_rn(xc, (double)g[ro + cols[0]], (double)g[ro + cols[1]], (double)g[ro + cols[2]],
+                                    (double)g[ro + cols[3]]);
+            }
         }
         double v = cubic_rn(xr, frow[0], frow[1], frow[2], frow[3]);
         v = fmin(fmax(v, vmin), vmax);                       // clip=True
@@ -182,25 +198,33 @@ __device__ __forceinline__ int mirror_idx(int i, int n) {
 constexpr int kMaxGaussRadius = 63;   // 2R+1 <= 128: numpy pairwise_sum single block
 __constant__ double c_gauss_w[2][kMaxGaussRadius + 1];   // [axis][0..R], w[0] = centre
 
+// grid = (ceil(W/32), ceil(H/8), pages of the group); pages with <= 2 grey levels exit at once.
+// AXIS 0 reads the uint8 page, AXIS 1 the fp64 result of axis 0 (or the page when axis 0 is skipped).
 template <typename SRC, int AXIS>
 __global__ void __launch_bounds__(256)
-gauss1d_kernel(const SRC* __restrict__ src, double* __restrict__ dst, int H, int W, int radius) {
+gauss1d_kernel(const SRC* __restrict__ src, size_t src_page_stride, double* __restrict__ dst, int H, int W, int radius,
+               const uint32_t* __restrict__ level_bits, int page0) {
+    if (level_count(level_bits + (size_t)(page0 + blockIdx.z) * 8) <= 2) return;
     const int x = blockIdx.x * 32 + threadIdx.x;
     const int y = blockIdx.y * 8 + threadIdx.y;
     if (x >= W || y >= H) return;
+    const SRC* sp = src + (size_t)blockIdx.z * src_page_stride;
     const double* wts = c_gauss_w[AXIS];
     auto at = [&](int d) -> double {
-        if (AXIS == 0) return (double)src[(size_t)mirror_idx(y + d, H) * W + x];
-        return (double)src[(size_t)y * W + mirror_idx(x + d, W)];
+        if (AXIS == 0) return (double)sp[(size_t)mirror_idx(y + d, H) * W + x];
+        return (double)sp[(size_t)y * W + mirror_idx(x + d, W)];
     };
     double tmp = __dmul_rn(at(0), wts[0]);
     for (int j = radius; j >= 1; --j) tmp = __dadd_rn(tmp, __dmul_rn(__dadd_rn(at(-j), at(j)), wts[j]));
-    dst[(size_t)y * W + x] = tmp;
+    dst[(size_t)blockIdx.z * H * W + (size_t)y * W + x] = tmp;
 }
 
-__global__ void __launch_bounds__(256) minmax_f64_kernel(const double* __restrict__ p, size_t n,
-                                                         unsigned long long* __restrict__ out /*[2]*/) {
-    // values are >= 0 here (filtered uint8 levels), so the bit patterns order like the doubles
+// per-page min/max of the filtered plane (values >= 0: the bit patterns order like the doubles)
+__global__ void __launch_bounds__(256)
+minmax_f64_kernel(const double* __restrict__ planes, size_t n, unsigned long long* __restrict__ out /*[pages][2]*/,
+                  const uint32_t* __restrict__ level_bits, int page0) {
+    if (level_count(level_bits + (size_t)(page0 + blockIdx.y) * 8) <= 2) return;
+    const double* p = planes + (size_t)blockIdx.y * n;
     double lo = 1e300, hi = 0.0;      // idle threads must not win the unsigned-pattern max
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         double v = p[i];
@@ -212,9 +236,14 @@ __global__ void __launch_bounds__(256) minmax_f64_kernel(const double* __restric
         hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
     }
     if ((threadIdx.x & 31) == 0) {
-        atomicMin(out, (unsigned long long)__double_as_longlong(lo));
-        atomicMax(out + 1, (unsigned long long)__double_as_longlong(hi));
+        atomicMin(out + 2 * blockIdx.y, (unsigned long long)__double_as_longlong(lo));
+        atomicMax(out + 2 * blockIdx.y + 1, (unsigned long long)__double_as_longlong(hi));
     }
+}
+
+__global__ void minmax_init_kernel(unsigned long long* out, int pages) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < pages) { out[2 * i] = 0x7ff0000000000000ull; out[2 * i + 1] = 0ull; }
 }
 
 static int gauss_weights(double sigma, std::vector<double>& w) {
@@ -244,117 +273,76 @@ static int gauss_weights(double sigma, std::vector<double>& w) {
     return radius;
 }
 
+constexpr int kAaGroup = 8;      // pages whose fp64 anti-aliasing planes live in scratch at the same time
+
 int launch_preprocess(pcs_ctx* ctx, const uint8_t* d_grey, const uint8_t* d_bin, int n, int H, int W, int Hs,
                       int Ws, uint8_t* d_image, uint8_t* d_binary, uint8_t* d_orig_binary) {
     if (n <= 0 || H <= 0 || W <= 0 || Hs <= 0 || Ws <= 0) return set_err(ctx, PCS_ERR_ARG, "preprocess: bad shape");
     cudaStream_t st = ctx->stream;
-    const size_t page_bytes = (size_t)H * W;
-    PCS_TRY(scratch_reserve(ctx, (size_t)n * 8 * sizeof(uint32_t) + (size_t)n * sizeof(int) + 128));
-    uint32_t* d_bits = reinterpret_cast<uint32_t*>(ctx->scratch);
-    int* d_list = reinterpret_cast<int*>(d_bits + (size_t)n * 8);
-    unsigned long long* d_mm = reinterpret_cast<unsigned long long*>(
-        reinterpret_cast<char*>(ctx->scratch) + (((size_t)n * 8 * 4 + (size_t)n * 4 + 15) / 16) * 16);
-
-    std::vector<int> plain, aa;
-    std::vector<uint32_t> h_bits((size_t)n * 8);
-    if (d_image) {
-        PCS_CUDA(ctx, cudaMemsetAsync(d_bits, 0, (size_t)n * 8 * sizeof(uint32_t), st));
-        dim3 grid((unsigned)std::min<size_t>(296, (page_bytes / 16 + 255) / 256 + 1), n);
-        level_bits_kernel<<<grid, 256, 0, st>>>(d_grey, page_bytes, d_bits);
-        PCS_LAUNCH_CHECK(ctx, "level_bits_kernel");
-        // the anti-aliasing decision (dataset.py:127) is data dependent: read the 32 B/page back
-        PCS_CUDA(ctx, cudaMemcpyAsync(h_bits.data(), d_bits, h_bits.size() * 4, cudaMemcpyDeviceToHost, st));
-        PCS_CUDA(ctx, cudaStreamSynchronize(st));
-        for (int p = 0; p < n; ++p) {
-            int levels = 0;
-            for (int k = 0; k < 8; ++k) levels += __builtin_popcount(h_bits[(size_t)p * 8 + k]);
-            (levels > 2 ? aa : plain).push_back(p);
-        }
-    } else {
-        for (int p = 0; p < n; ++p) plain.push_back(p);
-    }
-
+    const size_t page_px = (size_t)H * W;
     dim3 block(32, 8);
-    if (!plain.empty()) {
-        const int* list = nullptr;
-        if ((int)plain.size() != n) {
-            PCS_CUDA(ctx, cudaMemcpyAsync(d_list, plain.data(), plain.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-            PCS_CUDA(ctx, cudaStreamSynchronize(st));   // plain is a stack vector
-            list = d_list;
-        }
-        dim3 grid((Ws + 31) / 32, (Hs + 7) / 8, (unsigned)plain.size());
-        resample_kernel<uint8_t><<<grid, block, 0, st>>>(d_grey, d_bin, H, W, Hs, Ws, d_bits, list, 0.0, 0.0, d_image,
-                                                         d_binary);
-        PCS_LAUNCH_CHECK(ctx, "resample_kernel<u8>");
-    }
-    if (!aa.empty()) {
-        // per page: gaussian (axis 0, axis 1) into fp64 scratch, min/max, bicubic from fp64
+    if (d_image || d_binary) {
+        // anti-aliasing parameters depend on the shapes only (skimage: sigma = (in/out - 1) / 2 per axis)
         const double fr = (double)H / (double)Hs, fc = (double)W / (double)Ws;
         const double sig[2] = {std::max(0.0, (fr - 1.0) / 2.0), std::max(0.0, (fc - 1.0) / 2.0)};
+        const bool may_aa = d_image && (sig[0] > 1e-15 || sig[1] > 1e-15);
         std::vector<double> w0, w1;
-        int r0 = sig[0] > 1e-15 ? gauss_weights(sig[0], w0) : -1;
-        int r1 = sig[1] > 1e-15 ? gauss_weights(sig[1], w1) : -1;
+        const int r0 = (d_image && sig[0] > 1e-15) ? gauss_weights(sig[0], w0) : -1;
+        const int r1 = (d_image && sig[1] > 1e-15) ? gauss_weights(sig[1], w1) : -1;
         if (r0 > kMaxGaussRadius || r1 > kMaxGaussRadius)
             return set_err(ctx, PCS_ERR_ARG, "preprocess: anti-aliasing radius %d/%d exceeds %d", r0, r1, kMaxGaussRadius);
-        if (r0 >= 0) PCS_CUDA(ctx, cudaMemcpyToSymbolAsync(c_gauss_w, w0.data(), w0.size() * 8, 0, cudaMemcpyHostToDevice, st));
-        if (r1 >= 0)
-            PCS_CUDA(ctx, cudaMemcpyToSymbolAsync(c_gauss_w, w1.data(), w1.size() * 8, sizeof(double) * (kMaxGaussRadius + 1),
-                                                  cudaMemcpyHostToDevice, st));
-        PCS_CUDA(ctx, cudaStreamSynchronize(st));
-        // two fp64 planes of one page behind the bitmap block; growing the scratch drops its
-        // contents, so the level bitmaps are re-uploaded from the host copy
-        const size_t plane = page_bytes * sizeof(double);
-        const size_t head = (((size_t)n * 8 * 4 + (size_t)n * 4 + 15) / 16) * 16 + 64;
-        const size_t head_al = (head + 255) / 256 * 256;
-        PCS_TRY(scratch_reserve(ctx, head_al + 2 * plane + 256));
-        d_bits = reinterpret_cast<uint32_t*>(ctx->scratch);
-        d_list = reinterpret_cast<int*>(d_bits + (size_t)n * 8);
-        d_mm = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(ctx->scratch) + head - 64);
-        PCS_CUDA(ctx, cudaMemcpyAsync(d_bits, h_bits.data(), h_bits.size() * 4, cudaMemcpyHostToDevice, st));
-        PCS_CUDA(ctx, cudaStreamSynchronize(st));
-        double* t0 = reinterpret_cast<double*>(reinterpret_cast<char*>(ctx->scratch) + head_al);
-        double* t1 = t0 + page_bytes;
-        dim3 gfull((W + 31) / 32, (H + 7) / 8);
-        for (int p : aa) {
-            const uint8_t* src = d_grey + (size_t)p * page_bytes;
-            const double* cur = nullptr;
-            if (r0 >= 0) {
-                gauss1d_kernel<uint8_t, 0><<<gfull, block, 0, st>>>(src, t0, H, W, r0);
-                PCS_LAUNCH_CHECK(ctx, "gauss1d<0>");
-                cur = t0;
+        const int group = std::min(n, kAaGroup);
+        const size_t head = (((size_t)n * 8 * 4 + 255) / 256) * 256;
+        const size_t mm_bytes = (((size_t)group * 16 + 255) / 256) * 256;
+        const size_t plane_bytes = may_aa ? (size_t)group * page_px * sizeof(double) : 0;
+        PCS_TRY(scratch_reserve(ctx, head + mm_bytes + 2 * plane_bytes + 256));
+        uint32_t* d_bits = reinterpret_cast<uint32_t*>(ctx->scratch);
+        unsigned long long* d_mm = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(ctx->scratch) + head);
+        double* t0 = reinterpret_cast<double*>(reinterpret_cast<char*>(ctx->scratch) + head + mm_bytes);
+        double* t1 = t0 + (size_t)group * page_px;
+        if (d_image) {
+            PCS_CUDA(ctx, cudaMemsetAsync(d_bits, 0, (size_t)n * 8 * sizeof(uint32_t), st));
+            dim3 grid((unsigned)std::min<size_t>(296, (page_px / 16 + 255) / 256 + 1), n);
+            level_bits_kernel<<<grid, 256, 0, st>>>(d_grey, page_px, d_bits);
+            PCS_LAUNCH_CHECK(ctx, "level_bits_kernel");
+            if (may_aa) {
+                // pageable host -> constant: staged synchronously, ordered on the stream
+                if (r0 >= 0) PCS_CUDA(ctx, cudaMemcpyToSymbolAsync(c_gauss_w, w0.data(), w0.size() * 8, 0, cudaMemcpyHostToDevice, st));
+                if (r1 >= 0)
+                    PCS_CUDA(ctx, cudaMemcpyToSymbolAsync(c_gauss_w, w1.data(), w1.size() * 8, sizeof(double) * (kMaxGaussRadius + 1),
+                                                          cudaMemcpyHostToDevice, st));
             }
-            if (r1 >= 0) {
-                if (cur) gauss1d_kernel<double, 1><<<gfull, block, 0, st>>>(cur, t1, H, W, r1);
-                else gauss1d_kernel<uint8_t, 1><<<gfull, block, 0, st>>>(src, t1, H, W, r1);
-                PCS_LAUNCH_CHECK(ctx, "gauss1d<1>");
-                cur = t1;
+        }
+        for (int p0 = 0; p0 < n; p0 += group) {
+            const int m = std::min(group, n - p0);
+            const double* planes = nullptr;
+            if (may_aa) {
+                // pages with <= 2 grey levels leave every one of these kernels in their first instruction
+                dim3 gfull((W + 31) / 32, (H + 7) / 8, m);
+                const uint8_t* src = d_grey + (size_t)p0 * page_px;
+                if (r0 >= 0) {
+                    gauss1d_kernel<uint8_t, 0><<<gfull, block, 0, st>>>(src, page_px, t0, H, W, r0, d_bits, p0);
+                    PCS_LAUNCH_CHECK(ctx, "gauss1d<axis 0>");
+                    planes = t0;
+                }
+                if (r1 >= 0) {
+                    if (planes) gauss1d_kernel<double, 1><<<gfull, block, 0, st>>>(t0, page_px, t1, H, W, r1, d_bits, p0);
+                    else gauss1d_kernel<uint8_t, 1><<<gfull, block, 0, st>>>(src, page_px, t1, H, W, r1, d_bits, p0);
+                    PCS_LAUNCH_CHECK(ctx, "gauss1d<axis 1>");
+                    planes = t1;
+                }
+                minmax_init_kernel<<<1, 32, 0, st>>>(d_mm, m);
+                PCS_LAUNCH_CHECK(ctx, "minmax_init_kernel");
+                minmax_f64_kernel<<<dim3(148, m), 256, 0, st>>>(planes, page_px, d_mm, d_bits, p0);
+                PCS_LAUNCH_CHECK(ctx, "minmax_f64_kernel");
             }
-            if (!cur) {   // both sigmas zero: plain conversion path
-                gauss1d_kernel<uint8_t, 0><<<gfull, block, 0, st>>>(src, t0, H, W, 0);
-                PCS_LAUNCH_CHECK(ctx, "gauss1d<copy>");
-                cur = t0;
-            }
-            const unsigned long long init[2] = {0x7ff0000000000000ull, 0ull};
-            PCS_CUDA(ctx, cudaMemcpyAsync(d_mm, init, sizeof(init), cudaMemcpyHostToDevice, st));
-            minmax_f64_kernel<<<296, 256, 0, st>>>(cur, page_bytes, d_mm);
-            PCS_LAUNCH_CHECK(ctx, "minmax_f64");
-            unsigned long long mm[2];
-            PCS_CUDA(ctx, cudaMemcpyAsync(mm, d_mm, sizeof(mm), cudaMemcpyDeviceToHost, st));
-            PCS_CUDA(ctx, cudaStreamSynchronize(st));
-            double vmin, vmax;
-            memcpy(&vmin, &mm[0], 8);
-            memcpy(&vmax, &mm[1], 8);
-            int pidx = p;
-            PCS_CUDA(ctx, cudaMemcpyAsync(d_list, &pidx, sizeof(int), cudaMemcpyHostToDevice, st));
-            PCS_CUDA(ctx, cudaStreamSynchronize(st));
-            dim3 grid((Ws + 31) / 32, (Hs + 7) / 8, 1);
-            resample_kernel<double><<<grid, block, 0, st>>>(cur, d_bin, H, W, Hs, Ws, d_bits, d_list, vmin, vmax, d_image,
-                                                            d_binary);
-            PCS_LAUNCH_CHECK(ctx, "resample_kernel<f64>");
+            dim3 grid((Ws + 31) / 32, (Hs + 7) / 8, m);
+            resample_kernel<<<grid, block, 0, st>>>(d_grey, d_bin, H, W, Hs, Ws, d_bits, planes, d_mm, p0, d_image, d_binary);
+            PCS_LAUNCH_CHECK(ctx, "resample_kernel");
         }
     }
     if (d_orig_binary) {
-        const size_t nbytes = (size_t)n * page_bytes;
+        const size_t nbytes = (size_t)n * page_px;
         orig_binary_kernel<<<(unsigned)std::min<size_t>(148 * 8, (nbytes / 16 + 255) / 256 + 1), 256, 0, st>>>(d_bin, nbytes,
                                                                                                           d_orig_binary);
         PCS_LAUNCH_CHECK(ctx, "orig_binary_kernel");
