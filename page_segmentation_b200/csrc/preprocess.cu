@@ -198,25 +198,32 @@ __device__ __forceinline__ int mirror_idx(int i, int n) {
 constexpr int kMaxGaussRadius = 63;   // 2R+1 <= 128: numpy pairwise_sum single block
 __constant__ double c_gauss_w[2][kMaxGaussRadius + 1];   // [axis][0..R], w[0] = centre
 
-// grid = (ceil(W/32), ceil(H/8), pages of the group); pages with <= 2 grey levels exit at once.
-// AXIS 0 reads the uint8 page, AXIS 1 the fp64 result of axis 0 (or the page when axis 0 is skipped).
+// Persistent grid (a few blocks per SM) looping over (page, 32x8 tile): pages with <= 2 grey levels are
+// skipped, so a batch of binarised pages pays one near-empty launch.  AXIS 0 reads the uint8 page,
+// AXIS 1 the fp64 result of axis 0 (or the page when axis 0 is skipped).
 template <typename SRC, int AXIS>
 __global__ void __launch_bounds__(256)
 gauss1d_kernel(const SRC* __restrict__ src, size_t src_page_stride, double* __restrict__ dst, int H, int W, int radius,
-               const uint32_t* __restrict__ level_bits, int page0) {
-    if (level_count(level_bits + (size_t)(page0 + blockIdx.z) * 8) <= 2) return;
-    const int x = blockIdx.x * 32 + threadIdx.x;
-    const int y = blockIdx.y * 8 + threadIdx.y;
-    if (x >= W || y >= H) return;
-    const SRC* sp = src + (size_t)blockIdx.z * src_page_stride;
+               const uint32_t* __restrict__ level_bits, int page0, int pages) {
     const double* wts = c_gauss_w[AXIS];
-    auto at = [&](int d) -> double {
-        if (AXIS == 0) return (double)sp[(size_t)mirror_idx(y + d, H) * W + x];
-        return (double)sp[(size_t)y * W + mirror_idx(x + d, W)];
-    };
-    double tmp = __dmul_rn(at(0), wts[0]);
-    for (int j = radius; j >= 1; --j) tmp = __dadd_rn(tmp, __dmul_rn(__dadd_rn(at(-j), at(j)), wts[j]));
-    dst[(size_t)blockIdx.z * H * W + (size_t)y * W + x] = tmp;
+    const int tiles_x = (W + 31) / 32, tiles_y = (H + 7) / 8;
+    for (int pg = 0; pg < pages; ++pg) {
+        if (level_count(level_bits + (size_t)(page0 + pg) * 8) <= 2) continue;
+        const SRC* sp = src + (size_t)pg * src_page_stride;
+        double* dp = dst + (size_t)pg * H * W;
+        for (int tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
+            const int x = (tile % tiles_x) * 32 + (threadIdx.x & 31);
+            const int y = (tile / tiles_x) * 8 + (threadIdx.x >> 5);
+            if (x >= W || y >= H) continue;
+            auto at = [&](int d) -> double {
+                if (AXIS == 0) return (double)sp[(size_t)mirror_idx(y + d, H) * W + x];
+                return (double)sp[(size_t)y * W + mirror_idx(x + d, W)];
+            };
+            double tmp = __dmul_rn(at(0), wts[0]);
+            for (int j = radius; j >= 1; --j) tmp = __dadd_rn(tmp, __dmul_rn(__dadd_rn(at(-j), at(j)), wts[j]));
+            dp[(size_t)y * W + x] = tmp;
+        }
+    }
 }
 
 // per-page min/max of the filtered plane (values >= 0: the bit patterns order like the doubles)
@@ -318,16 +325,16 @@ int launch_preprocess(pcs_ctx* ctx, const uint8_t* d_grey, const uint8_t* d_bin,
             const double* planes = nullptr;
             if (may_aa) {
                 // pages with <= 2 grey levels leave every one of these kernels in their first instruction
-                dim3 gfull((W + 31) / 32, (H + 7) / 8, m);
+                const unsigned gfull = (unsigned)ctx->sm_count * 8;
                 const uint8_t* src = d_grey + (size_t)p0 * page_px;
                 if (r0 >= 0) {
-                    gauss1d_kernel<uint8_t, 0><<<gfull, block, 0, st>>>(src, page_px, t0, H, W, r0, d_bits, p0);
+                    gauss1d_kernel<uint8_t, 0><<<gfull, 256, 0, st>>>(src, page_px, t0, H, W, r0, d_bits, p0, m);
                     PCS_LAUNCH_CHECK(ctx, "gauss1d<axis 0>");
                     planes = t0;
                 }
                 if (r1 >= 0) {
-                    if (planes) gauss1d_kernel<double, 1><<<gfull, block, 0, st>>>(t0, page_px, t1, H, W, r1, d_bits, p0);
-                    else gauss1d_kernel<uint8_t, 1><<<gfull, block, 0, st>>>(src, page_px, t1, H, W, r1, d_bits, p0);
+                    if (planes) gauss1d_kernel<double, 1><<<gfull, 256, 0, st>>>(t0, page_px, t1, H, W, r1, d_bits, p0, m);
+                    else gauss1d_kernel<uint8_t, 1><<<gfull, 256, 0, st>>>(src, page_px, t1, H, W, r1, d_bits, p0, m);
                     PCS_LAUNCH_CHECK(ctx, "gauss1d<axis 1>");
                     planes = t1;
                 }
