@@ -183,6 +183,9 @@ static int run_conv1_u8(pcs_ctx* ctx, const char* lname, const uint8_t* d_image,
     Layer* L = find_layer(ctx, lname);
     if (!L) return set_err(ctx, PCS_ERR_STATE, "layer %s missing", lname);
     StageScope ts(ctx, lname);
+    static const bool use_ffma = getenv("PCSEG_CONV1") && !strcmp(getenv("PCSEG_CONV1"), "ffma");
+    if (ctx->engine == PCS_ENGINE_UMMA && L->d_wmma && L->k == 5 && L->cout == 20 && !use_ffma)
+        return launch_conv1_umma(ctx, d_image, n, hs, ws, out->h, out->w, L->d_wmma, L->d_b32, out->p, out->cp);
     DirectConvArgs a;
     a.src[0].p = d_image; a.src[0].c = 1; a.src[0].cp = 1; a.nsrc = 1;
     a.src_u8 = 1; a.img_h = hs; a.img_w = ws;
@@ -487,6 +490,14 @@ int pcs_model_load(pcs_ctx* ctx, int arch, int n_classes, int precision, const p
         PCS_CUDA(ctx, cudaMemcpy(L.d_w32, L.h_w32.data(), L.h_w32.size() * 4, cudaMemcpyHostToDevice));
         PCS_CUDA(ctx, cudaMemcpy(L.d_b32, L.h_b32.data(), L.h_b32.size() * 4, cudaMemcpyHostToDevice));
         ctx->layers.push_back(std::move(L));
+    }
+    // first FCN layer (C_in = 1, 5x5, 20 outputs): tap-contraction operand image, weights split hi + lo
+    if (arch != PCS_ARCH_UNET) {
+        Layer& L = ctx->layers[0];
+        std::vector<uint16_t> img;
+        L.wmma_bytes = conv1_umma_weight_image(L.h_w32.data(), L.cout, precision, img);
+        PCS_CUDA(ctx, cudaMalloc(&L.d_wmma, L.wmma_bytes));
+        PCS_CUDA(ctx, cudaMemcpy(L.d_wmma, img.data(), L.wmma_bytes, cudaMemcpyHostToDevice));
     }
     // tensor-core operand images: stride-1 convolutions with C_in > 1 and the 2x2 stride-2
     // transposed convolutions that are not fused into the head

@@ -251,4 +251,9 @@ size_t umma_weight_image_deconv(const float* w32 /*[4][cin][cout]*/, const int* 
                                 int npad, int precision, std::vector<uint16_t>& out);
 bool umma_supported(int k, int npad);
 
+// conv1_umma.cu  (first FCN layer on the tensor cores)
+size_t conv1_umma_weight_image(const float* w32 /*[25][1][cout]*/, int cout, int precision, std::vector<uint16_t>& out);
+int launch_conv1_umma(pcs_ctx* ctx, const uint8_t* d_image, int n, int img_h, int img_w, int h, int w, const void* wimg,
+                      const float* bias, void* out, int out_cp);
+
 }  // namespace pcs

@@ -1,0 +1,259 @@
+// First layer of the FCN variants on the tensor cores:
+//   Conv2D(20, 5x5, 'same', relu) over the uint8 page  (model.py:50 / :211, x/255 of architecture.py:67-68).
+//
+// C_in = 1, so the contraction runs over the 25 taps.  The builder warps expand every input row rho
+// of the tile once into shared memory as   E_rho[x'] = (in[rho][x0-2+x' + 0..7])  -- one 16-byte unit
+// (8 operand elements) per pixel, i.e. exactly one K-major SWIZZLE_NONE "plane" of the canonical UMMA
+// layout.  Output row r then needs K = (dy, dx-slot): its A operand for the K=16 step ks is the pair of
+// expanded rows (r+2ks, r+2ks+1) -- the same smem rows serve five different output rows -- and the B
+// operand holds W[dy][dx] in slot dx < 5 and zeros elsewhere.  Pixels 0..255 are exact in bf16/fp16; the
+// fp32 weights are split into hi + lo operand halves (two MMAs, ~16 mantissa bits) and 1/255 is applied
+// to the fp32 accumulator, so the result matches the fp32 CUDA-core kernel to fp32 rounding.
+//
+// Warp roles (320 threads): warp 0 loads the weight image; warp 1 = MMA issuer + TMEM owner;
+// warps 2-5 = epilogue (bias, ReLU, pack, plane-major stores); warps 6-9 = builders.
+#include "common.cuh"
+#include "umma_ptx.cuh"
+
+namespace pcs {
+namespace {
+using namespace ptx;
+
+constexpr int C1_R = 8;            // output rows per tile
+constexpr int C1_N = 32;           // padded C_out
+constexpr int C1_ROWS = C1_R + 5;  // expanded rows per stage (r + 2ks + 1 <= R - 1 + 5)
+constexpr int C1_SW = 124;         // valid output pixels per 128-pixel strip
+constexpr int C1_STAGES = 2;
+constexpr int C1_ROW_BYTES = 128 * 16;
+constexpr int C1_STAGE_BYTES = C1_ROWS * C1_ROW_BYTES;
+constexpr int C1_B_BYTES = 2 * 3 * 2 * C1_N * 16;      // [hi|lo][ks][plane][n][8]
+constexpr int C1_THREADS = 320;
+
+struct Conv1Params {
+    const uint8_t* img; int img_h, img_w;   // real page
+    int n, h, w;                            // padded grid
+    const uint8_t* wimg;                    // C1_B_BYTES operand image
+    const float* bias;
+    void* out; int out_cp;
+    int strips, rowblocks, num_tiles;
+};
+
+template <typename T> __device__ __forceinline__ uint32_t pack_u8x2(uint32_t a, uint32_t b);
+template <> __device__ __forceinline__ uint32_t pack_u8x2<__nv_bfloat16>(uint32_t a, uint32_t b) {
+    return pack2<__nv_bfloat16>((float)a, (float)b);
+}
+template <> __device__ __forceinline__ uint32_t pack_u8x2<__half>(uint32_t a, uint32_t b) {
+    return pack2<__half>((float)a, (float)b);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(C1_THREADS, 1) conv1_umma_kernel(const Conv1Params p) {
+    constexpr uint32_t IDESC = (1u << 4) | ((std::is_same<T, __nv_bfloat16>::value ? 1u : 0u) << 7) |
+                               ((std::is_same<T, __nv_bfloat16>::value ? 1u : 0u) << 10) |
+                               ((uint32_t)(C1_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t s_full[C1_STAGES], s_empty[C1_STAGES], s_tfull[2], s_tempty[2];
+    __shared__ uint32_t s_tmem_base;
+    __shared__ float s_bias[C1_N];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* s_b = base;                                   // weight image
+    uint8_t* stages = base + ((C1_B_BYTES + 1023) / 1024) * 1024;
+
+    if (warp == 0) {
+        const uint4* src = reinterpret_cast<const uint4*>(p.wimg);
+        uint4* dst = reinterpret_cast<uint4*>(s_b);
+        for (int i = lane; i < C1_B_BYTES / 16; i += 32) dst[i] = __ldg(src + i);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (lane == 0) {
+            for (int s = 0; s < C1_STAGES; ++s) { mbar_init(&s_full[s], 128); mbar_init(&s_empty[s], 1); }
+            for (int a = 0; a < 2; ++a) { mbar_init(&s_tfull[a], 1); mbar_init(&s_tempty[a], 4); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (threadIdx.x < C1_N) s_bias[threadIdx.x] = threadIdx.x < 20 ? __ldg(p.bias + threadIdx.x) : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem_base;
+    const int tiles_per_page = p.strips * p.rowblocks;
+
+    if (warp == 1) {
+        // ===================== MMA issuer =====================
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0;
+        const bool leader = elect_one();
+        const uint32_t hi = (uint32_t)(make_desc(0, 0, 128) >> 32);
+        constexpr uint32_t a_lbo = ((uint32_t)(C1_ROW_BYTES >> 4) & 0x3fffu) << 16;       // K halves = consecutive rows
+        constexpr uint32_t b_lbo = (((uint32_t)C1_N * 16u >> 4) & 0x3fffu) << 16;
+        const uint32_t b_lo0 = ((smem_u32(s_b) >> 4) & 0x3fffu) | b_lbo;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            mbar_wait(&s_tempty[acc], acc_phase ^ 1u);
+            mbar_wait(&s_full[stage], phase);
+            tc_fence_after();
+            if (leader) {
+                const uint32_t a_lo0 = ((smem_u32(stages + (size_t)stage * C1_STAGE_BYTES) >> 4) & 0x3fffu) | a_lbo;
+                const uint32_t d0 = tmem_base + (uint32_t)(acc * C1_R * C1_N);
+#pragma unroll
+                for (int r = 0; r < C1_R; ++r) {
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {        // weights hi, then lo
+#pragma unroll
+                        for (int ks = 0; ks < 3; ++ks) {
+                            const uint32_t a_off = (uint32_t)((r + 2 * ks) * (C1_ROW_BYTES >> 4));
+                            const uint32_t b_off = (uint32_t)((half * 3 + ks) * (2 * C1_N));    // 16-byte units
+                            tc_mma(d0 + (uint32_t)(r * C1_N), a_lo0 + a_off, hi, b_lo0 + b_off, hi, IDESC, (half | ks) ? 1u : 0u);
+                        }
+                    }
+                }
+                tc_commit(&s_empty[stage]);
+                tc_commit(&s_tfull[acc]);
+            }
+            __syncwarp();
+            if (++stage == C1_STAGES) { stage = 0; phase ^= 1u; }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    } else if (warp >= 2 && warp < 6) {
+        // ===================== epilogue =====================
+        const int quarter = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        T* out = reinterpret_cast<T*>(p.out);
+        const float inv255 = 1.0f / 255.0f;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const int page = tile / tiles_per_page;
+            const int rem = tile - page * tiles_per_page;
+            const int rb = rem % p.rowblocks, strip = rem / p.rowblocks;
+            const int m = quarter * 32 + lane;
+            const int x = strip * C1_SW + m;
+            const bool xok = m < C1_SW && x < p.w;
+            const int y0 = rb * C1_R;
+            mbar_wait(&s_tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * C1_R * C1_N);
+#pragma unroll 1
+            for (int r = 0; r < C1_R; ++r) {
+                uint32_t v0[16], v1[16];
+                tmem_ld16(t_lane + (uint32_t)(r * C1_N), v0);
+                tmem_ld16(t_lane + (uint32_t)(r * C1_N + 16), v1);
+                tmem_ld_wait();
+                const int y = y0 + r;
+                if (xok && y < p.h) {
+                    float f[32];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        f[i] = fmaxf(fmaf(__uint_as_float(v0[i]), inv255, s_bias[i]), 0.f);
+                        f[16 + i] = fmaxf(fmaf(__uint_as_float(v1[i]), inv255, s_bias[16 + i]), 0.f);
+                    }
+#pragma unroll
+                    for (int g = 0; g < 4; ++g)
+                        *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, p.h, p.w, g * 8, y, x)) =
+                            make_uint4(pack2<T>(f[g * 8 + 0], f[g * 8 + 1]), pack2<T>(f[g * 8 + 2], f[g * 8 + 3]),
+                                       pack2<T>(f[g * 8 + 4], f[g * 8 + 5]), pack2<T>(f[g * 8 + 6], f[g * 8 + 7]));
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_tempty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    } else if (warp >= 6) {
+        // ===================== builders: expand input rows into K-major planes =====================
+        const int xq = threadIdx.x - 192;                 // 0..127 = pixel slot of the strip patch
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const int page = tile / tiles_per_page;
+            const int rem = tile - page * tiles_per_page;
+            const int rb = rem % p.rowblocks, strip = rem / p.rowblocks;
+            const int gx0 = strip * C1_SW - 2 + xq, gy0 = rb * C1_R - 2;
+            const uint8_t* src = p.img + (size_t)page * p.img_h * p.img_w;
+            mbar_wait(&s_empty[stage], phase ^ 1u);
+            uint8_t* dst = stages + (size_t)stage * C1_STAGE_BYTES + (size_t)xq * 16;
+#pragma unroll 1
+            for (int row = 0; row < C1_ROWS; ++row) {
+                const int gy = gy0 + row;
+                uint32_t px[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int gx = gx0 + e;
+                    px[e] = (gy >= 0 && gy < p.img_h && gx >= 0 && gx < p.img_w) ? (uint32_t)__ldg(src + (size_t)gy * p.img_w + gx) : 0u;
+                }
+                *reinterpret_cast<uint4*>(dst + (size_t)row * C1_ROW_BYTES) =
+                    make_uint4(pack_u8x2<T>(px[0], px[1]), pack_u8x2<T>(px[2], px[3]), pack_u8x2<T>(px[4], px[5]),
+                               pack_u8x2<T>(px[6], px[7]));
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the MMA
+            mbar_arrive(&s_full[stage]);
+            if (++stage == C1_STAGES) { stage = 0; phase ^= 1u; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+}  // namespace
+
+// Operand image [hi|lo][ks 0..2][plane 0..1][n 0..31][e 0..7]: value W[dy = 2ks+plane][dx = e][n] for dy, e < 5.
+size_t conv1_umma_weight_image(const float* w32 /*[25][1][cout]*/, int cout, int precision, std::vector<uint16_t>& out) {
+    out.assign(C1_B_BYTES / 2, 0);
+    auto to16 = [&](float v) -> uint16_t {
+        if (precision == PCS_PREC_BF16) { __nv_bfloat16 b = __float2bfloat16_rn(v); return *reinterpret_cast<uint16_t*>(&b); }
+        __half h = __float2half_rn(v); return *reinterpret_cast<uint16_t*>(&h);
+    };
+    auto from16 = [&](uint16_t u) -> float {
+        if (precision == PCS_PREC_BF16) { uint32_t x = (uint32_t)u << 16; float f; memcpy(&f, &x, 4); return f; }
+        __half_raw hr; hr.x = u; return __half2float(__half(hr));
+    };
+    for (int ks = 0; ks < 3; ++ks)
+        for (int pl = 0; pl < 2; ++pl)
+            for (int n = 0; n < C1_N; ++n)
+                for (int e = 0; e < 8; ++e) {
+                    const int dy = 2 * ks + pl;
+                    if (dy >= 5 || e >= 5 || n >= cout) continue;
+                    const float w = w32[(size_t)(dy * 5 + e) * cout + n];
+                    const uint16_t hi = to16(w);
+                    const uint16_t lo = to16(w - from16(hi));
+                    const size_t idx = (((size_t)ks * 2 + pl) * C1_N + n) * 8 + e;
+                    out[idx] = hi;
+                    out[(size_t)3 * 2 * C1_N * 8 + idx] = lo;
+                }
+    return out.size() * sizeof(uint16_t);
+}
+
+int launch_conv1_umma(pcs_ctx* ctx, const uint8_t* d_image, int n, int img_h, int img_w, int h, int w, const void* wimg,
+                      const float* bias, void* out, int out_cp) {
+    if (out_cp != C1_N) return set_err(ctx, PCS_ERR_ARG, "conv1_umma: output stride must be %d channels", C1_N);
+    Conv1Params p{};
+    p.img = d_image; p.img_h = img_h; p.img_w = img_w; p.n = n; p.h = h; p.w = w;
+    p.wimg = reinterpret_cast<const uint8_t*>(wimg); p.bias = bias; p.out = out; p.out_cp = out_cp;
+    p.strips = (w + C1_SW - 1) / C1_SW;
+    p.rowblocks = (h + C1_R - 1) / C1_R;
+    p.num_tiles = n * p.strips * p.rowblocks;
+    const size_t smem = ((C1_B_BYTES + 1023) / 1024) * 1024 + (size_t)C1_STAGES * C1_STAGE_BYTES + 1024;
+    const int grid = std::min(p.num_tiles, ctx->sm_count);
+    if (ctx->precision == PCS_PREC_BF16) {
+        static bool set = false;
+        if (!set) { PCS_CUDA(ctx, cudaFuncSetAttribute(conv1_umma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = true; }
+        conv1_umma_kernel<__nv_bfloat16><<<grid, C1_THREADS, smem, ctx->stream>>>(p);
+    } else {
+        static bool set = false;
+        if (!set) { PCS_CUDA(ctx, cudaFuncSetAttribute(conv1_umma_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = true; }
+        conv1_umma_kernel<__half><<<grid, C1_THREADS, smem, ctx->stream>>>(p);
+    }
+    PCS_LAUNCH_CHECK(ctx, "conv1_umma_kernel");
+    return PCS_OK;
+}
+
+}  // namespace pcs

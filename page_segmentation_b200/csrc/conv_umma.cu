@@ -29,6 +29,7 @@
 // is (tap, C_out) -- y[2h+i, 2w+j, o] = b[o] + sum_c x[h,w,c] K[i,j,o,c] -- with
 // a scattering epilogue (model.py:71,79).
 #include "common.cuh"
+#include "umma_ptx.cuh"
 
 namespace pcs {
 namespace {
@@ -36,6 +37,7 @@ namespace {
 constexpr int TILE_M = 128;
 constexpr int kThreads = 192;       // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 constexpr int kMaxStages = 4;
+constexpr int kHeadThreads = 64 + 12 * 32;   // fused head: 12 epilogue warps (3 per TMEM lane quarter)
 
 template <int NPAD> struct Cfg {
     static constexpr int R = NPAD <= 64 ? 8 : (NPAD <= 80 ? 6 : 4);      // accumulator rows per tile
@@ -78,110 +80,8 @@ struct UmmaParams {
     HeadEpi head;
 };
 
-// ---- PTX wrappers -----------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+using namespace ptx;
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 24)) __trap();
-    }
-}
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// descriptors travel as (lo, hi) 32-bit halves: only the start-address field in `lo` changes per MMA
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                       uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        ".reg .b64 da, db;\n"
-        "mov.b64 da, {%1, %2};\n"
-        "mov.b64 db, {%3, %4};\n"
-        "setp.ne.b32 p, %6, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
-        "}\n" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "elect.sync _|p, 0xffffffff;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
-                 : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
-//   [0,14) start>>4 | [16,30) LBO>>4 (stride between the two 8-element K halves)
-//   [32,46) SBO>>4 (stride between 8-row groups) | [46,48) version = 1 | [61,64) layout = 0
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
-}
-
-template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
-template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&v);
-}
-template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
-    __half2 v = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&v);
-}
 template <typename T> __device__ __forceinline__ float2 unpack2(uint32_t v);
 template <> __device__ __forceinline__ float2 unpack2<__nv_bfloat16>(uint32_t v) {
     return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
@@ -191,7 +91,7 @@ template <> __device__ __forceinline__ float2 unpack2<__half>(uint32_t v) {
 }
 
 template <typename T, int NPAD, int KS, int MODE>
-__global__ void __launch_bounds__(MODE >= EPI_HEAD ? 320 : kThreads, 1)
+__global__ void __launch_bounds__(MODE >= EPI_HEAD ? kHeadThreads : kThreads, 1)
 conv_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1) {
     constexpr int R = Cfg<NPAD>::R;
     constexpr int ACC = Cfg<NPAD>::ACC;
@@ -601,7 +501,7 @@ int launch_t(pcs_ctx* ctx, const UmmaConvArgs& a) {
             if (ctx->device < 64) g_head_owner[ctx->device] = ctx->model_stamp;
         }
     }
-    conv_umma_kernel<T, NPAD, KS, MODE><<<grid, MODE >= EPI_HEAD ? 320 : kThreads, smem, ctx->stream>>>(p, tm0, tm1);
+    conv_umma_kernel<T, NPAD, KS, MODE><<<grid, MODE >= EPI_HEAD ? kHeadThreads : kThreads, smem, ctx->stream>>>(p, tm0, tm1);
     PCS_LAUNCH_CHECK(ctx, "conv_umma_kernel");
     return PCS_OK;
 }

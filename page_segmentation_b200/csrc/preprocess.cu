@@ -90,6 +90,30 @@ resample_kernel(const uint8_t* __restrict__ grey, const uint8_t* __restrict__ bi
                 const uint32_t* __restrict__ level_bits, const double* __restrict__ aa_planes,
                 const unsigned long long* __restrict__ aa_minmax, int page0, uint8_t* __restrict__ image_out,
                 uint8_t* __restrict__ binary_out) {
+    // per-block coordinate tables: the sampling positions depend on the column (row) only
+    __shared__ int s_cols[32][4], s_rows[8][4], s_ci[32], s_ri[8];
+    __shared__ double s_xc[32], s_xr[8];
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    if (tid < 40) {
+        const bool is_col = tid < 32;
+        const int i = is_col ? tid : tid - 32;
+        const int o = is_col ? blockIdx.x * 32 + i : blockIdx.y * 8 + i;
+        const int n_in = is_col ? W : H, n_out = is_col ? Ws : Hs;
+        const double f = __ddiv_rn((double)n_in, (double)n_out);
+        const double p = __dadd_rn(__dmul_rn(f, (double)o), __dsub_rn(__dmul_rn(0.5, f), 0.5));
+        const int nn = reflect_coord((long long)round(p), n_in);        // order 0: C round(), then reflect
+        const double pf = floor(p);
+        const double frac = __dsub_rn(p, pf);
+        const long long p0 = (long long)pf - 1;
+        if (is_col) {
+            s_ci[i] = nn; s_xc[i] = frac;
+            for (int k = 0; k < 4; ++k) s_cols[i][k] = reflect_coord(p0 + k, n_in);
+        } else {
+            s_ri[i] = nn; s_xr[i] = frac;
+            for (int k = 0; k < 4; ++k) s_rows[i][k] = reflect_coord(p0 + k, n_in);
+        }
+    }
+    __syncthreads();
     const int x = blockIdx.x * 32 + threadIdx.x;
     const int y = blockIdx.y * 8 + threadIdx.y;
     if (x >= Ws || y >= Hs) return;
@@ -97,16 +121,8 @@ resample_kernel(const uint8_t* __restrict__ grey, const uint8_t* __restrict__ bi
     const size_t src_off = (size_t)page * H * W;
     const size_t dst_off = (size_t)page * Hs * Ws + (size_t)y * Ws + x;
 
-    const double fr = __ddiv_rn((double)H, (double)Hs);
-    const double fc = __ddiv_rn((double)W, (double)Ws);
-    const double r = __dadd_rn(__dmul_rn(fr, (double)y), __dsub_rn(__dmul_rn(0.5, fr), 0.5));
-    const double c = __dadd_rn(__dmul_rn(fc, (double)x), __dsub_rn(__dmul_rn(0.5, fc), 0.5));
-
     if (binary_out) {
-        // order 0: C round() (half away from zero), then reflect
-        const int ri = reflect_coord((long long)round(r), H);
-        const int ci = reflect_coord((long long)round(c), W);
-        const uint8_t v = bin[src_off + (size_t)ri * W + ci];
+        const uint8_t v = bin[src_off + (size_t)s_ri[threadIdx.y] * W + s_ci[threadIdx.x]];
         // bin = (1.0 - NN(binary/255 or binary)).astype(uint8): 1 iff v == 0
         binary_out[dst_off] = (v == 0) ? 1 : 0;
     }
@@ -126,30 +142,22 @@ resample_kernel(const uint8_t* __restrict__ grey, const uint8_t* __restrict__ bi
             vmin = (double)lo;
             vmax = (double)hi;
         }
-        const double r0f = floor(r), c0f = floor(c);
-        const double xr = __dsub_rn(r, r0f), xc = __dsub_rn(c, c0f);
-        const long long r0 = (long long)r0f - 1, c0 = (long long)c0f - 1;
-        int cols[4], rows[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            cols[k] = reflect_coord(c0 + k, W);
-            rows[k] = reflect_coord(r0 + k, H);
-        }
+        const double xr = s_xr[threadIdx.y], xc = s_xc[threadIdx.x];
+        const int c0 = s_cols[threadIdx.x][0], c1 = s_cols[threadIdx.x][1], c2 = s_cols[threadIdx.x][2], c3 = s_cols[threadIdx.x][3];
         double frow[4];
         if (aa) {
             const double* g = aa_planes + (size_t)blockIdx.z * H * W;
 #pragma unroll
             for (int pr = 0; pr < 4; ++pr) {
-                const size_t ro = (size_t)rows[pr] * W;
-                frow[pr] = cubic_rn(xc, g[ro + cols[0]], g[ro + cols[1]], g[ro + cols[2]], g[ro + cols[3]]);
+                const size_t ro = (size_t)s_rows[threadIdx.y][pr] * W;
+                frow[pr] = cubic_rn(xc, g[ro + c0], g[ro + c1], g[ro + c2], g[ro + c3]);
             }
         } else {
             const uint8_t* g = grey + src_off;
 #pragma unroll
             for (int pr = 0; pr < 4; ++pr) {
-                const size_t ro = (size_t)rows[pr] * W;
-                frow[pr] = cubic_rn(xc, (double)g[ro + cols[0]], (double)g[ro + cols[1]], (double)g[ro + cols[2]],
-                                    (double)g[ro + cols[3]]);
+                const size_t ro = (size_t)s_rows[threadIdx.y][pr] * W;
+                frow[pr] = cubic_rn(xc, (double)g[ro + c0], (double)g[ro + c1], (double)g[ro + c2], (double)g[ro + c3]);
             }
         }
         double v = cubic_rn(xr, frow[0], frow[1], frow[2], frow[3]);
