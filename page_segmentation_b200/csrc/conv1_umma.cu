@@ -28,6 +28,7 @@ constexpr int C1_ROW_BYTES = 128 * 16;
 constexpr int C1_STAGE_BYTES = C1_ROWS * C1_ROW_BYTES;
 constexpr int C1_B_BYTES = 2 * 3 * 2 * C1_N * 16;      // [hi|lo][ks][plane][n][8]
 constexpr int C1_THREADS = 320;
+constexpr int C1_RAW_W = 136;      // bytes per raw patch row: 128 pixel slots + 7 look-ahead (+1 pad)
 
 struct Conv1Params {
     const uint8_t* img; int img_h, img_w;   // real page
@@ -55,6 +56,7 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv1_umma_kernel(const Conv1Pa
     __shared__ __align__(8) uint64_t s_full[C1_STAGES], s_empty[C1_STAGES], s_tfull[2], s_tempty[2];
     __shared__ uint32_t s_tmem_base;
     __shared__ float s_bias[C1_N];
+    __shared__ uint8_t s_raw[C1_STAGES][C1_ROWS * C1_RAW_W];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -165,6 +167,8 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv1_umma_kernel(const Conv1Pa
         }
     } else if (warp >= 6) {
         // ===================== builders: expand input rows into K-major planes =====================
+        // phase 1: the 13 x 135-byte uint8 patch is fetched with independent, coalesced byte loads (one
+        // latency round); phase 2: every thread assembles the 16-byte unit of "its" pixel for all rows.
         const int xq = threadIdx.x - 192;                 // 0..127 = pixel slot of the strip patch
         int stage = 0;
         uint32_t phase = 0;
@@ -172,22 +176,32 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv1_umma_kernel(const Conv1Pa
             const int page = tile / tiles_per_page;
             const int rem = tile - page * tiles_per_page;
             const int rb = rem % p.rowblocks, strip = rem / p.rowblocks;
-            const int gx0 = strip * C1_SW - 2 + xq, gy0 = rb * C1_R - 2;
+            const int gxb = strip * C1_SW - 2, gy0 = rb * C1_R - 2;
             const uint8_t* src = p.img + (size_t)page * p.img_h * p.img_w;
-            mbar_wait(&s_empty[stage], phase ^ 1u);
-            uint8_t* dst = stages + (size_t)stage * C1_STAGE_BYTES + (size_t)xq * 16;
-#pragma unroll 1
-            for (int row = 0; row < C1_ROWS; ++row) {
-                const int gy = gy0 + row;
-                uint32_t px[8];
+            uint8_t vals[(C1_ROWS * C1_RAW_W + 127) / 128];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const int gx = gx0 + e;
-                    px[e] = (gy >= 0 && gy < p.img_h && gx >= 0 && gx < p.img_w) ? (uint32_t)__ldg(src + (size_t)gy * p.img_w + gx) : 0u;
-                }
+            for (int j = 0; j < (C1_ROWS * C1_RAW_W + 127) / 128; ++j) {
+                const int i = xq + 128 * j;
+                const int row = i / C1_RAW_W, col = i - row * C1_RAW_W;
+                const int gy = gy0 + row, gx = gxb + col;
+                vals[j] = (i < C1_ROWS * C1_RAW_W && gy >= 0 && gy < p.img_h && gx >= 0 && gx < p.img_w)
+                              ? __ldg(src + (size_t)gy * p.img_w + gx) : (uint8_t)0;
+            }
+            mbar_wait(&s_empty[stage], phase ^ 1u);           // stage (incl. its raw buffer) is free
+            uint8_t* raw = s_raw[stage];
+#pragma unroll
+            for (int j = 0; j < (C1_ROWS * C1_RAW_W + 127) / 128; ++j) {
+                const int i = xq + 128 * j;
+                if (i < C1_ROWS * C1_RAW_W) raw[i] = vals[j];
+            }
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            uint8_t* dst = stages + (size_t)stage * C1_STAGE_BYTES + (size_t)xq * 16;
+#pragma unroll
+            for (int row = 0; row < C1_ROWS; ++row) {
+                const uint8_t* r8 = raw + row * C1_RAW_W + xq;
                 *reinterpret_cast<uint4*>(dst + (size_t)row * C1_ROW_BYTES) =
-                    make_uint4(pack_u8x2<T>(px[0], px[1]), pack_u8x2<T>(px[2], px[3]), pack_u8x2<T>(px[4], px[5]),
-                               pack_u8x2<T>(px[6], px[7]));
+                    make_uint4(pack_u8x2<T>(r8[0], r8[1]), pack_u8x2<T>(r8[2], r8[3]), pack_u8x2<T>(r8[4], r8[5]),
+                               pack_u8x2<T>(r8[6], r8[7]));
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the MMA
             mbar_arrive(&s_full[stage]);

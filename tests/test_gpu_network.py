@@ -102,7 +102,7 @@ def test_fcn_skip_layerwise_vs_twin(ctx, engine):
         d = np.abs(got - exp)
         scale = max(1e-3, np.abs(exp).max())
         assert d.max() <= 2 ** -7 * scale + 1e-6, (nme, d.max(), scale)      # <= ~1 bf16 ulp of the range
-        assert d.mean() <= 2e-4 * scale + 1e-7, (nme, d.mean())
+        assert d.mean() <= 4e-4 * scale + 1e-7, (nme, d.mean())
 
 
 @pytest.mark.parametrize("n_classes,engine", [(2, "umma"), (4, "umma"), (5, "umma"), (2, "direct"), (5, "direct"), (8, "direct")])
