@@ -101,6 +101,7 @@ static void free_layers(pcs_ctx* ctx) {
         if (l.d_w32) cudaFree(l.d_w32);
         if (l.d_b32) cudaFree(l.d_b32);
         if (l.d_wmma) cudaFree(l.d_wmma);
+        if (l.d_wfold) cudaFree(l.d_wfold);
         if (l.d_head_lw) cudaFree(l.d_head_lw);
         if (l.d_head_lb) cudaFree(l.d_head_lb);
     }
@@ -158,6 +159,16 @@ static int run_conv(pcs_ctx* ctx, const char* lname, const Act* s0, const Act* s
     const Act& any = out ? *out : *pool_out;
     const int n = any.n;
     const int h = out ? out->h : pool_out->h * 2, w = out ? out->w : pool_out->w * 2;
+    static const bool no_fold = getenv("PCSEG_FOLD") && !strcmp(getenv("PCSEG_FOLD"), "0");
+    if (ctx->engine == PCS_ENGINE_UMMA && !upsample && !s1 && L->d_wfold && !no_fold && (h % 4) == 0) {
+        FoldConvArgs f;
+        f.src = src_of(*s0);
+        f.n = n; f.h = h; f.w = w; f.k = L->k;
+        f.wimg = L->d_wfold; f.b32 = L->d_b32; f.cout = L->cout; f.npad = L->npad; f.nchunks = s0->cp / 16; f.relu = L->relu;
+        f.out = out ? out->p : nullptr; f.out_cp = out ? out->cp : 0;
+        f.pool_out = pool_out ? pool_out->p : nullptr; f.pool_cp = pool_out ? pool_out->cp : 0;
+        return launch_conv_fold(ctx, f);
+    }
     if (ctx->engine == PCS_ENGINE_UMMA && !upsample && L->d_wmma && umma_supported(L->k, L->npad)) {
         UmmaConvArgs a;
         a.src[0] = src_of(*s0); a.nsrc = 1;
@@ -516,6 +527,12 @@ int pcs_model_load(pcs_ctx* ctx, int arch, int n_classes, int precision, const p
             L.npad = std::min(pad16(L.cout), 128);
             if (!umma_supported(L.k, L.npad) || (L.cout > 128 && L.cout % 128)) continue;
             L.wmma_bytes = umma_weight_image(L.h_w32.data(), L.k * L.k, src_c, nsrc, L.cout, L.npad, precision, img);
+            if (fold_supported(L.k, L.npad, pad16(L.cin) / 16, nsrc)) {
+                std::vector<uint16_t> fimg;
+                const size_t fb = fold_weight_image(L.h_w32.data(), L.cin, L.cout, L.npad, precision, fimg);
+                PCS_CUDA(ctx, cudaMalloc(&L.d_wfold, fb));
+                PCS_CUDA(ctx, cudaMemcpy(L.d_wfold, fimg.data(), fb, cudaMemcpyHostToDevice));
+            }
         } else if (L.kind == K_DECONV_S2 && L.name == "deconv5") {
             // fused head: N column J = tap * 20 + o (see conv_umma.cu EPI_HEAD)
             if (arch == PCS_ARCH_FCN_SKIP) { src_c[0] = 30; src_c[1] = 40; nsrc = 2; }     // [deconv4, conv3]

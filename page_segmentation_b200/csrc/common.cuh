@@ -59,6 +59,7 @@ struct Layer {
     size_t wmma_bytes = 0;
     int npad = 0;           // padded C_out of the UMMA tile
     int co_t = 0;           // deconv s2 on the tensor path: padded channels per tap
+    void* d_wfold = nullptr;      // resident operand image of the dx-folded kernel (conv_fold.cu)
     float* d_head_lw = nullptr;   // logits layer: [50][4] padded weights for the fused head
     float* d_head_lb = nullptr;   // logits layer: [4] bias with the deconv5 bias folded in
     int nchunks = 0;        // number of 16-channel K chunks over all sources
@@ -250,6 +251,20 @@ size_t umma_weight_image(const float* w32 /*[taps][cin][cout]*/, int taps, const
 size_t umma_weight_image_deconv(const float* w32 /*[4][cin][cout]*/, const int* src_c, int nsrc, int cout, int co_t,
                                 int npad, int precision, std::vector<uint16_t>& out);
 bool umma_supported(int k, int npad);
+
+// conv_fold.cu  (marching, dx-folded 5x5 convolution for the small-channel layers)
+struct FoldConvArgs {
+    ConvSrc src;
+    int n = 0, h = 0, w = 0, k = 5;
+    const void* wimg = nullptr;
+    const float* b32 = nullptr;
+    int cout = 0, npad = 0, nchunks = 0, relu = 0;
+    void* out = nullptr; int out_cp = 0;
+    void* pool_out = nullptr; int pool_cp = 0;
+};
+bool fold_supported(int k, int npad, int nchunks, int nsrc);
+size_t fold_weight_image(const float* w32 /*[25][cin][cout]*/, int cin, int cout, int npad, int precision, std::vector<uint16_t>& out);
+int launch_conv_fold(pcs_ctx* ctx, const FoldConvArgs& a);
 
 // conv1_umma.cu  (first FCN layer on the tensor cores)
 size_t conv1_umma_weight_image(const float* w32 /*[25][1][cout]*/, int cout, int precision, std::vector<uint16_t>& out);
