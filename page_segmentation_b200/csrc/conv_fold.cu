@@ -324,11 +324,11 @@ int launch_fold_t(pcs_ctx* ctx, const FoldConvArgs& a) {
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_err(ctx, PCS_ERR_CUDA, "conv_fold: cuTensorMapEncodeTiled failed with %d", (int)r);
     const size_t smem = ((p.w_bytes + 1023) / 1024) * 1024 + (size_t)F_RING * NCH * 4096 + 1024;
-    if (smem > 226 * 1024) return set_err(ctx, PCS_ERR_ARG, "conv_fold: %zu bytes of shared memory needed", smem);
-    static bool attr_set = false;
-    if (!attr_set) {
-        PCS_CUDA(ctx, cudaFuncSetAttribute(conv_fold_kernel<T, NPAD, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-        attr_set = true;
+    if (smem + 11 * 1024 > 227 * 1024) return set_err(ctx, PCS_ERR_ARG, "conv_fold: %zu bytes of shared memory needed", smem);
+    static size_t attr_set = 0;                    // static shared memory (exchange buffers) counts against the 227 KB too
+    if (attr_set < smem) {
+        PCS_CUDA(ctx, cudaFuncSetAttribute(conv_fold_kernel<T, NPAD, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = smem;
     }
     const int grid = std::min(p.num_items, ctx->sm_count);
     conv_fold_kernel<T, NPAD, NCH><<<grid, F_THREADS, smem, ctx->stream>>>(p, tm);
