@@ -1,18 +1,22 @@
-// "Marching, dx-folded" implicit-GEMM 5x5 'same' convolution for the small-channel encoder layers
-// (conv2, conv3, conv4 of ocr4all_pixel_classifier/lib/model.py:52-57 / :212-215).
+// "Marching, dy-folded" implicit-GEMM 5x5 'same' convolution for the small-channel encoder layers
+// (conv2 ... conv5 of ocr4all_pixel_classifier/lib/model.py:52-60 / :212-217).
 //
-// With C_out of 30-40 the plain kernel (conv_umma.cu) issues one N=32..48 MMA per tap and re-reads the
+// With C_out of 30-60 the plain kernel (conv_umma.cu) issues one N=32..64 MMA per tap and re-reads the
 // 4 KB A operand from shared memory for each of them: it is shared-memory-read bound at ~40 % tensor
-// activity.  Here the five horizontal taps are folded into the N dimension:
-//     D_y[j][dx*NPAD + o] = sum_{dy, c} in[y+dy-2][x0-2+j][c] * W[dy][dx][c][o]        (one N' = 5*NPAD MMA per (chunk, dy))
-//     out[y][x0+t][o]     = b[o] + sum_dx D_y[t+dx][dx*NPAD + o]                       (shifted sum in the epilogue)
-// so A is read once per 5 taps and the MMA (N' = 160 / 240) is tensor-bound.  Further:
-//   * all weights of the layer stay resident in shared memory (51-115 KB), loaded once per CTA;
-//   * a CTA marches down a 124-pixel strip: input rows stream through a ring (one TMA box per row holding
-//     all channel chunks), every output row needs ONE new input row (halo re-read 132/128 instead of 12/8);
-//   * two TMEM accumulator stages (2 x N' columns) let the epilogue of row y overlap the MMAs of row y+1;
-//   * 8 epilogue warps in two groups; a group owns a row pair (keeps the even row for the fused 2x2
-//     max-pool); the dx shift is a warp shuffle plus a 10-value-per-warp exchange through shared memory.
+// activity.  Here the five VERTICAL taps are folded into the N dimension.  An input row rho contributes
+// to the five output rows y = rho+2-dy, so TMEM holds a ring of 8 output-row accumulators (NPAD columns
+// each) and ONE MMA of N' = 5*NPAD adds
+//     D[slot(y)][j][o] += sum_c in[rho][x0-2+j+dx][c] * W[dy = rho+2-y][dx][c][o]      for the 5 rows y at once
+// (A = the input row shifted by dx, B = [W[4] | W[3] | W[2] | W[1] | W[0]] stacked along N; when the
+// 5-slot window wraps around the ring the MMA is split in two).  A is read once per 5 taps, the MMA is
+// tensor-bound, the epilogue stays as cheap as in the plain kernel (it drains ONE NPAD-column slot per
+// output row, same TMEM lane, no cross-lane traffic) and re-zeroes the slot for its next use.  Further:
+//   * all weights of the layer stay resident in shared memory (51-154 KB), loaded once per CTA;
+//   * a CTA marches down a 124-pixel strip: every output row needs ONE new input row (one TMA box holding
+//     all channel chunks), halo re-read 132/128 instead of 12/8;
+//   * the accumulator ring decouples the epilogue from the MMAs by up to three rows;
+//   * segments start with four "virtual" output rows (their slots collect the partial sums left over by
+//     the previous segment); they are drained and re-zeroed like real rows but never stored.
 #include "common.cuh"
 #include "umma_ptx.cuh"
 
@@ -26,14 +30,23 @@ template <> __device__ __forceinline__ float2 unpack2f<__nv_bfloat16>(uint32_t v
 }
 template <> __device__ __forceinline__ float2 unpack2f<__half>(uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
 
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
+    const uint32_t z = 0u;
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+        ::"r"(taddr), "r"(z) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 constexpr int F_THREADS = 64 + 8 * 32;      // warp 0 producer, warp 1 MMA, warps 2-9 epilogue (2 groups x 4 quarters)
-constexpr int F_RING = 8;                   // input-row ring entries
+constexpr int F_RING = 4;                   // input-row ring entries (one row is consumed per step)
+constexpr int F_SLOTS = 8;                  // output-row accumulator slots in TMEM
 constexpr int F_SW = 124;                   // valid output pixels per strip
 
 struct FoldParams {
     int n, h, w;
     int seg_rows, segs, strips, num_items;  // work item = (page, strip, segment of seg_rows output rows)
-    const uint8_t* wimg;                    // [chunk][dy][plane][N' rows][8]: resident operand image
+    const uint8_t* wimg;                    // [chunk][dx][plane][row = (4-dy)*NPAD + o][8]: resident operand image
     const float* bias;
     int cout, relu;
     void* out; int out_cp;
@@ -46,18 +59,16 @@ __global__ void __launch_bounds__(F_THREADS, 1)
 conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
     constexpr int NF = 5 * NPAD;                                     // folded N
     constexpr uint32_t ROW_BYTES = NCH * 2 * 2048;                   // one ring entry: all chunks of one input row
-    constexpr uint32_t WDY_BYTES = 2 * NF * 16;                      // weights of one (chunk, dy)
-    constexpr uint32_t IDESC = (1u << 4) | ((std::is_same<T, __nv_bfloat16>::value ? 1u : 0u) << 7) |
-                               ((std::is_same<T, __nv_bfloat16>::value ? 1u : 0u) << 10) |
-                               ((uint32_t)(NF >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr uint32_t WDX_BYTES = 2 * NF * 16;                      // weights of one (chunk, dx)
+    constexpr uint32_t IDESC0 = (1u << 4) | ((std::is_same<T, __nv_bfloat16>::value ? 1u : 0u) << 7) |
+                                ((std::is_same<T, __nv_bfloat16>::value ? 1u : 0u) << 10) | ((uint32_t)(128 >> 4) << 24);
     static_assert(NF <= 256 && NF % 16 == 0, "folded N must be a legal UMMA N");
-    static_assert(2 * NF <= 512, "two accumulator stages must fit TMEM");
+    static_assert(F_SLOTS * NPAD <= 512, "accumulator ring must fit TMEM");
 
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t s_full[F_RING], s_empty[F_RING], s_wfull, s_tfull[2][2], s_tempty[2];
+    __shared__ __align__(8) uint64_t s_full[F_RING], s_empty[F_RING], s_wfull, s_tfull[F_SLOTS], s_tempty[F_SLOTS];
     __shared__ uint32_t s_tmem_base;
     __shared__ float s_bias[NPAD];
-    __shared__ __align__(16) float s_xchg[2][2][4][10][16];          // [group][parity][quarter][(lane,dx) slot][16 ch]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -67,9 +78,7 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < F_RING; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 1); }
         mbar_init(&s_wfull, 1);
-        for (int g = 0; g < 2; ++g)
-            for (int a = 0; a < 2; ++a) mbar_init(&s_tfull[g][a], 1);
-        for (int a = 0; a < 2; ++a) mbar_init(&s_tempty[a], 4);       // TMEM stage drained (whichever group read it)
+        for (int s = 0; s < F_SLOTS; ++s) { mbar_init(&s_tfull[s], 1); mbar_init(&s_tempty[s], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -88,8 +97,8 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
         // ===================== producer: resident weights, then the input-row stream =====================
         if (lane == 0) {
             mbar_expect_tx(&s_wfull, p.w_bytes);
-            for (uint32_t off = 0; off < p.w_bytes; off += WDY_BYTES) bulk_load(s_w + off, p.wimg + off, WDY_BYTES, &s_wfull);
-            uint32_t k = 0;                                           // running ring position
+            for (uint32_t off = 0; off < p.w_bytes; off += WDX_BYTES) bulk_load(s_w + off, p.wimg + off, WDX_BYTES, &s_wfull);
+            uint32_t k = 0;                                           // running input-row counter
             for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
                 const int page = item / items_per_page;
                 const int rem = item - page * items_per_page;
@@ -108,6 +117,7 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
+        // step k (one input row) accumulates into the output slots k .. k+4 (mod 8) and completes slot k
         const bool leader = elect_one();
         const uint32_t hi = (uint32_t)(make_desc(0, 0, 128) >> 32);
         constexpr uint32_t a_lbo = ((2048u >> 4) & 0x3fffu) << 16;                    // the two K planes of a chunk
@@ -115,58 +125,62 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
         mbar_wait(&s_wfull, 0);
         const uint32_t ring_lo = (smem_u32(ring) >> 4) & 0x3fffu;
         const uint32_t b_lo0 = ((smem_u32(s_w) >> 4) & 0x3fffu) | b_lbo;
-        uint32_t k = 0;                                                               // ring position of input row 0 of the item
-        uint32_t use[2] = {0, 0};                                                     // uses of TMEM stage 0 / 1
+        for (int s = 0; s < F_SLOTS; ++s) mbar_wait(&s_tempty[s], 0);                  // every slot zeroed once
+        uint32_t k = 0;
         for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-            const int page = item / items_per_page;
-            const int rem = item - page * items_per_page;
+            const int rem = item % items_per_page;
             const int seg = rem % p.segs;
             const int ys = seg * p.seg_rows;
             const int rows = min(p.seg_rows, p.h - ys);
-            (void)page;
-            for (int i = 0; i < 4; ++i) {                                            // halo rows of the segment
-                const uint32_t kk = k + i;
-                mbar_wait(&s_full[kk % F_RING], (kk / F_RING) & 1u);
-            }
-            for (int r = 0; r < rows; ++r) {
-                const int g = (r >> 1) & 1, st = r & 1;
-                const uint32_t kn = k + r + 4;                                       // newest input row needed
-                mbar_wait(&s_full[kn % F_RING], (kn / F_RING) & 1u);
-                mbar_wait(&s_tempty[st], (use[st] & 1u) ^ 1u);
+            for (int i = 0; i < rows + 4; ++i, ++k) {
+                const uint32_t in_slot = k % F_RING;
+                mbar_wait(&s_full[in_slot], (k / F_RING) & 1u);
+                // the newest output slot of the window must have been drained and re-zeroed by the epilogue
+                const uint32_t g_new = k + 4;
+                // tempty phase 0 = initial zeroing, phase n = drain of use n-1: use n waits for phase n
+                mbar_wait(&s_tempty[g_new % F_SLOTS], (g_new / F_SLOTS) & 1u);
                 tc_fence_after();
                 if (leader) {
-                    const uint32_t d = tmem_base + (uint32_t)(st * NF);
+                    const uint32_t s0 = k % F_SLOTS;
+                    const uint32_t n1 = min(5u, (uint32_t)F_SLOTS - s0);              // blocks before the ring wraps
+                    const uint32_t a_row = ring_lo + in_slot * (ROW_BYTES >> 4);
+                    const uint32_t d1 = tmem_base + s0 * NPAD;
+                    const uint32_t idesc1 = IDESC0 | (((n1 * NPAD) >> 3) << 17);
+                    const uint32_t idesc2 = IDESC0 | ((((5u - n1) * NPAD) >> 3) << 17);
 #pragma unroll
-                    for (int dy = 0; dy < 5; ++dy) {
-                        const uint32_t slot = (k + r + dy) % F_RING;
-                        const uint32_t a_row = ring_lo + slot * (ROW_BYTES >> 4);
+                    for (int c = 0; c < NCH; ++c) {
 #pragma unroll
-                        for (int c = 0; c < NCH; ++c) {
-                            const uint32_t a_lo = (a_row + (uint32_t)c * (4096u >> 4)) | a_lbo;
-                            const uint32_t b_lo = b_lo0 + (uint32_t)((c * 5 + dy) * (WDY_BYTES >> 4));
-                            tc_mma(d, a_lo, hi, b_lo, hi, IDESC, (dy | c) ? 1u : 0u);
+                        for (int dx = 0; dx < 5; ++dx) {
+                            const uint32_t a_lo = (a_row + (uint32_t)c * (4096u >> 4) + (uint32_t)dx) | a_lbo;
+                            const uint32_t b_lo = b_lo0 + (uint32_t)((c * 5 + dx) * (WDX_BYTES >> 4));
+                            tc_mma(d1, a_lo, hi, b_lo, hi, idesc1, 1u);               // slots are pre-zeroed: always accumulate
+                            if (n1 < 5u) tc_mma(tmem_base, a_lo, hi, b_lo + n1 * NPAD, hi, idesc2, 1u);
                         }
                     }
-                    tc_commit(&s_empty[(k + r) % F_RING]);                            // input row r of the segment is dead
-                    tc_commit(&s_tfull[g][st]);
-                    if (r == rows - 1)
-                        for (int i = 1; i <= 4; ++i) tc_commit(&s_empty[(k + r + i) % F_RING]);
+                    tc_commit(&s_empty[in_slot]);                                     // input row consumed
+                    tc_commit(&s_tfull[k % F_SLOTS]);                                 // output slot k is complete
                 }
                 __syncwarp();
-                ++use[st];
             }
-            k += rows + 4;
         }
     } else {
-        // ===================== epilogue: shifted sum over dx, bias, activation, store, pool =====================
+        // ===================== epilogue: drain one slot per output row =====================
         const int quarter = warp & 3, group = (warp - 2) >> 2;
-        const int j = quarter * 32 + lane;                           // patch column; output pixel t = j
+        const int j = quarter * 32 + lane;                           // patch column = output pixel of the strip
         const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        const uint32_t bar_id = 2 + group;
         T* out = reinterpret_cast<T*>(p.out);
         T* pool = reinterpret_cast<T*>(p.pool);
-        uint32_t cnt[2] = {0, 0};                                     // uses of my group's accumulator stages
-        uint32_t xpar = 0;                                            // exchange-buffer parity
+        // zero the whole accumulator ring once (both groups: each its own slots {0,1,4,5} / {2,3,6,7})
+        for (int s = 0; s < F_SLOTS; ++s) {
+            if (((s >> 1) & 1) != group) continue;
+            for (int c = 0; c < NPAD; c += 16) tmem_st16_zero(t_lane + (uint32_t)(s * NPAD + c));
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        for (int s = 0; s < F_SLOTS; ++s)
+            if (((s >> 1) & 1) == group && lane == 0) mbar_arrive(&s_tempty[s]);     // completes phase 0 of every slot
+        uint32_t g = 0;                                               // running output counter (incl. virtual rows)
         for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
             const int page = item / items_per_page;
             const int rem = item - page * items_per_page;
@@ -175,64 +189,35 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
             const int rows = min(p.seg_rows, p.h - ys);
             const int x = strip * F_SW + j;
             const bool xok = j < F_SW && x < p.w;
-            for (int r0 = 2 * group; r0 < rows; r0 += 4) {           // my group's row pairs
-                uint32_t kept[NPAD / 2];                               // even row, packed, for the 2x2 max-pool
+            for (int o2 = 2 * group; o2 < rows + 4; o2 += 4) {        // my group's row pairs (o = o2 - 4 + st)
+                uint32_t kept[NPAD / 2];
 #pragma unroll
                 for (int st = 0; st < 2; ++st) {
-                    const int y = ys + r0 + st;
-                    mbar_wait(&s_tfull[group][st], cnt[st] & 1u);
+                    const uint32_t gg = g + (uint32_t)(o2 + st);
+                    const uint32_t slot = gg % F_SLOTS;
+                    const int y = ys + o2 + st - 4;                   // < ys: virtual row
+                    const bool real = o2 >= 4;
+                    mbar_wait(&s_tfull[slot], (gg / F_SLOTS) & 1u);
                     tc_fence_after();
-                    const uint32_t tacc = t_lane + (uint32_t)(st * NF);
+                    const uint32_t tacc = t_lane + slot * NPAD;
+                    uint32_t v[NPAD];
+#pragma unroll
+                    for (int c = 0; c < NPAD; c += 16) tmem_ld16(tacc + (uint32_t)c, *reinterpret_cast<uint32_t(*)[16]>(&v[c]));
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < NPAD; c += 16) tmem_st16_zero(tacc + (uint32_t)c);
+                    tmem_st_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&s_tempty[slot]);      // slot free for the window of input row gg+4
+                    if (!real) continue;
 #pragma unroll
                     for (int hb = 0; hb < NPAD / 16; ++hb) {
-                        float accv[16];
-                        uint32_t v[16];
-                        tmem_ld16(tacc + (uint32_t)(hb * 16), v);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) accv[i] = __uint_as_float(v[i]);
-                        uint32_t vd[4][16];
-#pragma unroll
-                        for (int dx = 1; dx <= 4; ++dx) tmem_ld16(tacc + (uint32_t)(dx * NPAD + hb * 16), vd[dx - 1]);
-                        tmem_ld_wait();
-                        // publish what the previous quarter's top lanes need: lane l < dx publishes (l, dx)
-#pragma unroll
-                        for (int dx = 1; dx <= 4; ++dx) {
-                            if (lane < dx) {
-                                const int slot = (dx * (dx - 1)) / 2 + lane;          // 0 | 1,2 | 3,4,5 | 6,7,8,9
-                                float4* dst = reinterpret_cast<float4*>(&s_xchg[group][xpar][quarter][slot][0]);
-                                dst[0] = make_float4(__uint_as_float(vd[dx - 1][0]), __uint_as_float(vd[dx - 1][1]), __uint_as_float(vd[dx - 1][2]), __uint_as_float(vd[dx - 1][3]));
-                                dst[1] = make_float4(__uint_as_float(vd[dx - 1][4]), __uint_as_float(vd[dx - 1][5]), __uint_as_float(vd[dx - 1][6]), __uint_as_float(vd[dx - 1][7]));
-                                dst[2] = make_float4(__uint_as_float(vd[dx - 1][8]), __uint_as_float(vd[dx - 1][9]), __uint_as_float(vd[dx - 1][10]), __uint_as_float(vd[dx - 1][11]));
-                                dst[3] = make_float4(__uint_as_float(vd[dx - 1][12]), __uint_as_float(vd[dx - 1][13]), __uint_as_float(vd[dx - 1][14]), __uint_as_float(vd[dx - 1][15]));
-                            }
-                        }
-                        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-#pragma unroll
-                        for (int dx = 1; dx <= 4; ++dx) {
-                            const int src_lane = lane + dx;
-                            float wv[16];
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) wv[i] = __uint_as_float(__shfl_down_sync(0xffffffffu, vd[dx - 1][i], dx));   // all lanes
-                            if (src_lane >= 32) {
-                                // pixels t+dx of the next TMEM lane quarter: published through shared memory
-                                const int l2 = src_lane - 32;
-                                const float4* srcp = reinterpret_cast<const float4*>(&s_xchg[group][xpar][(quarter + 1) & 3][(dx * (dx - 1)) / 2 + l2][0]);
-#pragma unroll
-                                for (int q4 = 0; q4 < 4; ++q4) {
-                                    const float4 f = srcp[q4];
-                                    wv[4 * q4 + 0] = f.x; wv[4 * q4 + 1] = f.y; wv[4 * q4 + 2] = f.z; wv[4 * q4 + 3] = f.w;
-                                }
-                            }
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) accv[i] += wv[i];      // quarter 3, lanes >= 28: garbage, never stored (j >= 124)
-                        }
-                        xpar ^= 1u;
-                        // bias, activation, rounding
                         uint32_t pk[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            float a = accv[2 * i] + s_bias[hb * 16 + 2 * i], b = accv[2 * i + 1] + s_bias[hb * 16 + 2 * i + 1];
+                            float a = __uint_as_float(v[hb * 16 + 2 * i]) + s_bias[hb * 16 + 2 * i];
+                            float b = __uint_as_float(v[hb * 16 + 2 * i + 1]) + s_bias[hb * 16 + 2 * i + 1];
                             if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
                             pk[i] = pack2<T>(a, b);
                         }
@@ -262,12 +247,9 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
                             }
                         }
                     }
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&s_tempty[st]);
-                    ++cnt[st];
                 }
             }
+            g += (uint32_t)(rows + 4);
         }
     }
 
@@ -301,7 +283,7 @@ int launch_fold_t(pcs_ctx* ctx, const FoldConvArgs& a) {
     p.n = a.n; p.h = a.h; p.w = a.w;
     p.wimg = reinterpret_cast<const uint8_t*>(a.wimg); p.bias = a.b32; p.cout = a.cout; p.relu = a.relu;
     p.out = a.out; p.out_cp = a.out_cp; p.pool = a.pool_out; p.pool_cp = a.pool_cp;
-    p.w_bytes = (uint32_t)NCH * 5 * 2 * NF * 16;
+    p.w_bytes = (uint32_t)NCH * 5 * 2 * NF * 16;          // [chunk][dx][plane][N' rows][16 B]
     p.strips = (a.w + F_SW - 1) / F_SW;
     // segments: multiples of 4 rows (row pairs x 2 groups); aim at >= 4 items per CTA
     int segs = 1;
@@ -324,8 +306,8 @@ int launch_fold_t(pcs_ctx* ctx, const FoldConvArgs& a) {
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_err(ctx, PCS_ERR_CUDA, "conv_fold: cuTensorMapEncodeTiled failed with %d", (int)r);
     const size_t smem = ((p.w_bytes + 1023) / 1024) * 1024 + (size_t)F_RING * NCH * 4096 + 1024;
-    if (smem + 11 * 1024 > 227 * 1024) return set_err(ctx, PCS_ERR_ARG, "conv_fold: %zu bytes of shared memory needed", smem);
-    static size_t attr_set = 0;                    // static shared memory (exchange buffers) counts against the 227 KB too
+    if (smem + 2 * 1024 > 227 * 1024) return set_err(ctx, PCS_ERR_ARG, "conv_fold: %zu bytes of shared memory needed", smem);
+    static size_t attr_set = 0;
     if (attr_set < smem) {
         PCS_CUDA(ctx, cudaFuncSetAttribute(conv_fold_kernel<T, NPAD, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = smem;
@@ -352,10 +334,11 @@ int launch_fold_dispatch(pcs_ctx* ctx, const FoldConvArgs& a) {
 bool fold_supported(int k, int npad, int nchunks, int nsrc) {
     if (k != 5 || nsrc != 1) return false;
     const int key = npad * 10 + nchunks;
-    return key == 322 || key == 482 || key == 483;
+    return key == 322 || key == 482 || key == 483;          // conv5+ (N' = 5*64 = 320) exceeds the UMMA N limit of 256
 }
 
-// Resident operand image [chunk][dy][plane][row = dx*NPAD + o][8]
+// Resident operand image [chunk][dx][plane][row = (4-dy)*NPAD + o][8]: the N blocks run from the oldest
+// output row of the window (dy = 4) to the newest (dy = 0).
 size_t fold_weight_image(const float* w32 /*[25][cin][cout]*/, int cin, int cout, int npad, int precision, std::vector<uint16_t>& out) {
     const int nch = pad16(cin) / 16, nf = 5 * npad;
     out.assign((size_t)nch * 5 * 2 * nf * 8, 0);
@@ -364,15 +347,15 @@ size_t fold_weight_image(const float* w32 /*[25][cin][cout]*/, int cin, int cout
         __half h = __float2half_rn(v); return *reinterpret_cast<uint16_t*>(&h);
     };
     for (int c = 0; c < nch; ++c)
-        for (int dy = 0; dy < 5; ++dy)
+        for (int dx = 0; dx < 5; ++dx)
             for (int pl = 0; pl < 2; ++pl)
-                for (int dx = 0; dx < 5; ++dx)
+                for (int dy = 0; dy < 5; ++dy)
                     for (int o = 0; o < npad; ++o)
                         for (int e = 0; e < 8; ++e) {
                             const int ci = c * 16 + pl * 8 + e;
                             if (ci >= cin || o >= cout) continue;
                             const float v = w32[((size_t)(dy * 5 + dx) * cin + ci) * cout + o];
-                            out[((((size_t)c * 5 + dy) * 2 + pl) * nf + dx * npad + o) * 8 + e] = conv(v);
+                            out[((((size_t)c * 5 + dx) * 2 + pl) * nf + (4 - dy) * npad + o) * 8 + e] = conv(v);
                         }
     return out.size() * sizeof(uint16_t);
 }
