@@ -39,7 +39,7 @@ __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 constexpr int F_THREADS = 64 + 8 * 32;      // warp 0 producer, warp 1 MMA, warps 2-9 epilogue (2 groups x 4 quarters)
-constexpr int F_RING = 4;                   // input-row ring entries (one row is consumed per step)
+constexpr int F_RING_MAX = 16;              // input-row ring entries (one row is consumed per step); actual depth fits smem
 constexpr int F_SLOTS = 8;                  // output-row accumulator slots in TMEM
 constexpr int F_SW = 124;                   // valid output pixels per strip
 
@@ -52,6 +52,7 @@ struct FoldParams {
     void* out; int out_cp;
     void* pool; int pool_cp;
     uint32_t w_bytes;
+    int ring;                               // input-row ring depth
 };
 
 template <typename T, int NPAD, int NCH>
@@ -66,7 +67,7 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
     static_assert(F_SLOTS * NPAD <= 512, "accumulator ring must fit TMEM");
 
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t s_full[F_RING], s_empty[F_RING], s_wfull, s_tfull[F_SLOTS], s_tempty[F_SLOTS];
+    __shared__ __align__(8) uint64_t s_full[F_RING_MAX], s_empty[F_RING_MAX], s_wfull, s_tfull[F_SLOTS], s_tempty[F_SLOTS];
     __shared__ uint32_t s_tmem_base;
     __shared__ float s_bias[NPAD];
 
@@ -76,7 +77,7 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
     uint8_t* ring = base + ((p.w_bytes + 1023) / 1024) * 1024;
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < F_RING; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 1); }
+        for (int s = 0; s < p.ring; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 1); }
         mbar_init(&s_wfull, 1);
         for (int s = 0; s < F_SLOTS; ++s) { mbar_init(&s_tfull[s], 1); mbar_init(&s_tempty[s], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -107,7 +108,7 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
                 const int rows = min(p.seg_rows, p.h - ys);
                 const int x0 = strip * F_SW - 2;
                 for (int i = 0; i < rows + 4; ++i, ++k) {
-                    const uint32_t slot = k % F_RING, pass = k / F_RING;
+                    const uint32_t slot = k % (uint32_t)p.ring, pass = k / (uint32_t)p.ring;
                     mbar_wait(&s_empty[slot], (pass & 1u) ^ 1u);
                     mbar_expect_tx(&s_full[slot], ROW_BYTES);
                     // box = 256 u64 (128 px x 16 B) x 1 row x (2 * NCH) planes
@@ -133,8 +134,8 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
             const int ys = seg * p.seg_rows;
             const int rows = min(p.seg_rows, p.h - ys);
             for (int i = 0; i < rows + 4; ++i, ++k) {
-                const uint32_t in_slot = k % F_RING;
-                mbar_wait(&s_full[in_slot], (k / F_RING) & 1u);
+                const uint32_t in_slot = k % (uint32_t)p.ring;
+                mbar_wait(&s_full[in_slot], (k / (uint32_t)p.ring) & 1u);
                 // the newest output slot of the window must have been drained and re-zeroed by the epilogue
                 const uint32_t g_new = k + 4;
                 // tempty phase 0 = initial zeroing, phase n = drain of use n-1: use n waits for phase n
@@ -287,7 +288,7 @@ int launch_fold_t(pcs_ctx* ctx, const FoldConvArgs& a) {
     p.strips = (a.w + F_SW - 1) / F_SW;
     // segments: multiples of 4 rows (row pairs x 2 groups); aim at >= 4 items per CTA
     int segs = 1;
-    while (segs < 64 && (size_t)a.n * p.strips * segs < (size_t)4 * ctx->sm_count && a.h / (segs * 2) >= 16) segs *= 2;
+    while (segs < 64 && (size_t)a.n * p.strips * segs < (size_t)24 * ctx->sm_count && a.h / (segs * 2) >= 32) segs *= 2;
     p.seg_rows = ((a.h + segs - 1) / segs + 3) / 4 * 4;
     p.segs = (a.h + p.seg_rows - 1) / p.seg_rows;
     p.num_items = a.n * p.strips * p.segs;
@@ -305,7 +306,10 @@ int launch_fold_t(pcs_ctx* ctx, const FoldConvArgs& a) {
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_err(ctx, PCS_ERR_CUDA, "conv_fold: cuTensorMapEncodeTiled failed with %d", (int)r);
-    const size_t smem = ((p.w_bytes + 1023) / 1024) * 1024 + (size_t)F_RING * NCH * 4096 + 1024;
+    const size_t w_al = ((p.w_bytes + 1023) / 1024) * 1024;
+    p.ring = (int)std::min<size_t>(F_RING_MAX, (224 * 1024 - w_al) / ((size_t)NCH * 4096));
+    if (p.ring < 3) return set_err(ctx, PCS_ERR_ARG, "conv_fold: weights leave no room for the input ring");
+    const size_t smem = w_al + (size_t)p.ring * NCH * 4096 + 1024;
     if (smem + 2 * 1024 > 227 * 1024) return set_err(ctx, PCS_ERR_ARG, "conv_fold: %zu bytes of shared memory needed", smem);
     static size_t attr_set = 0;
     if (attr_set < smem) {
