@@ -288,7 +288,7 @@ int launch_fold_t(pcs_ctx* ctx, const FoldConvArgs& a) {
     p.strips = (a.w + F_SW - 1) / F_SW;
     // segments: multiples of 4 rows (row pairs x 2 groups); aim at >= 4 items per CTA
     int segs = 1;
-    while (segs < 64 && (size_t)a.n * p.strips * segs < (size_t)24 * ctx->sm_count && a.h / (segs * 2) >= 32) segs *= 2;
+    while (segs < 64 && (size_t)a.n * p.strips * segs < (size_t)6 * ctx->sm_count && a.h / (segs * 2) >= 32) segs *= 2;
     p.seg_rows = ((a.h + segs - 1) / segs + 3) / 4 * 4;
     p.segs = (a.h + p.seg_rows - 1) / p.seg_rows;
     p.num_items = a.n * p.strips * p.segs;
