@@ -275,15 +275,24 @@ static int forward_fcn(pcs_ctx* ctx, bool skip, const uint8_t* d_image, int n, i
         if (skip) { hd.skip = conv2.p; hd.skip_cp = conv2.cp; }
         hd.lw_padded = LL->d_head_lw; hd.lb_folded = LL->d_head_lb;
         hd.n_classes = ctx->n_classes; hd.hs = hs; hd.ws = ws;
-        hd.binary = io.binary; hd.labels = io.labels; hd.logits = io.logits; hd.prob = io.prob;
-        hd.lut = io.d_lut; hd.color = io.color; hd.overlay = io.overlay; hd.inverted = io.inverted;
+        // the class map is always produced (the colour pass reads it); colour masks follow as one vectorised kernel
+        uint8_t* labels = io.labels;
+        const bool want_masks = io.color || io.overlay || io.inverted;
+        if (!labels && want_masks) {
+            labels = reinterpret_cast<uint8_t*>(arena_alloc(ctx, (size_t)n * hs * ws));
+            if (!labels) return set_err(ctx, PCS_ERR_NOMEM, "activation arena exhausted at labels");
+        }
+        hd.labels = labels; hd.logits = io.logits; hd.prob = io.prob;
         UmmaConvArgs u;
         u.src[0] = src_of(d4); u.nsrc = 1;
         if (skip) { u.src[1] = src_of(conv3); u.nsrc = 2; }
         u.n = n; u.h = hp / 2; u.w = wp / 2; u.k = 1; u.pad = 0;
         u.wmma = L5->d_wmma; u.b32 = L5->d_b32; u.cout = L5->cout; u.npad = L5->npad; u.nchunks = L5->nchunks; u.relu = 0;
         u.mode = skip ? 3 : 2; u.co_t = L5->co_t; u.head = &hd;
-        return launch_conv_umma(ctx, u);
+        PCS_TRY(launch_conv_umma(ctx, u));
+        if (want_masks)
+            return launch_masks(ctx, labels, io.binary, n, hs, ws, io.d_lut, ctx->n_classes, io.color, io.overlay, io.inverted);
+        return PCS_OK;
     }
     HeadArgs a;
     a.has_deconv = 1;

@@ -224,8 +224,7 @@ struct UmmaHeadArgs {              // fused FCN head epilogue (conv_umma.cu mode
     const float* lw_padded = nullptr;   // device [50][4]: logits weights, classes zero-padded to 4
     const float* lb_folded = nullptr;   // device [4]: logits bias + deconv5 bias folded through the logits weights
     int n_classes = 0, hs = 0, ws = 0;
-    const uint8_t* binary = nullptr; uint8_t* labels = nullptr; float* logits = nullptr; float* prob = nullptr;
-    const uint8_t* lut = nullptr; uint8_t* color = nullptr; uint8_t* overlay = nullptr; uint8_t* inverted = nullptr;
+    uint8_t* labels = nullptr; float* logits = nullptr; float* prob = nullptr;
 };
 struct UmmaConvArgs {
     ConvSrc src[2];

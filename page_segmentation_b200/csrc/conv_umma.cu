@@ -58,8 +58,7 @@ int64_t g_head_owner[64] = {0};
 struct HeadEpi {
     const void* skip; int skip_cp;         // conv2 activation at full resolution (2h x 2w grid)
     int n_classes, hs, ws;                 // crop (model.py:29-42)
-    const uint8_t* binary; uint8_t* labels; float* logits; float* prob;
-    const uint8_t* lut; uint8_t* color; uint8_t* overlay; uint8_t* inverted;
+    uint8_t* labels; float* logits; float* prob;       // the colour masks are a separate, fully vectorised pass
 };
 
 struct UmmaParams {
@@ -247,35 +246,51 @@ conv_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm0, co
             const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * R * NPAD);
 
             if constexpr (MODE >= EPI_HEAD) {
+                // one thread = one deconv5 input pixel = a 2x2 block of output pixels; the two pixels of an
+                // output row are handled together: their conv2 skip units are 32 contiguous bytes per plane
+                // (fully coalesced across the warp) and all loads are issued before the first use.
                 const HeadEpi& hd = p.head;
                 const int oh = 2 * p.h, ow = 2 * p.w;
+                const T* sk = reinterpret_cast<const T*>(hd.skip);
 #pragma unroll 1
                 for (int r = group; r < R; r += ngroups) {
                     const int y = y0 + r;
 #pragma unroll 1
-                    for (int t = 0; t < 4; ++t) {
-                        uint32_t va[16], vb[4];
-                        tmem_ld16(t_lane + (uint32_t)(r * NPAD + t * HEAD_DCO), va);
-                        tmem_ld4(t_lane + (uint32_t)(r * NPAD + t * HEAD_DCO + 16), vb);
-                        tmem_ld_wait();
-                        const int oy = 2 * y + (t >> 1), ox = 2 * x + (t & 1);
-                        const bool valid = xok && y < p.h && oy < hd.hs && ox < hd.ws;
-                        float lg[HEAD_NC];
+                    for (int i2 = 0; i2 < 2; ++i2) {                  // output row 2y + i2, taps t = 2*i2 + {0,1}
+                        const int oy = 2 * y + i2, ox = 2 * x;
+                        const bool rowok = xok && y < p.h && oy < hd.hs;
+                        const bool v0ok = rowok && ox < hd.ws, v1ok = rowok && ox + 1 < hd.ws;
+                        uint32_t va[2][16], vb[2][4];
 #pragma unroll
-                        for (int k = 0; k < HEAD_NC; ++k) lg[k] = c_head_lb[k];
-#pragma unroll
-                        for (int o = 0; o < HEAD_DCO; ++o) {
-                            const float d = __uint_as_float(o < 16 ? va[o < 16 ? o : 0] : vb[o >= 16 ? o - 16 : 0]);
-#pragma unroll
-                            for (int k = 0; k < HEAD_NC; ++k) lg[k] = fmaf(d, c_head_lw[o * HEAD_NC + k], lg[k]);
+                        for (int j = 0; j < 2; ++j) {
+                            tmem_ld16(t_lane + (uint32_t)(r * NPAD + (2 * i2 + j) * HEAD_DCO), va[j]);
+                            tmem_ld4(t_lane + (uint32_t)(r * NPAD + (2 * i2 + j) * HEAD_DCO + 16), vb[j]);
                         }
+                        uint4 raw[2][4];
                         if constexpr (MODE == EPI_HEAD_SKIP) {
-                            if (valid) {
-                                const T* sk = reinterpret_cast<const T*>(hd.skip);
 #pragma unroll
-                                for (int g = 0; g < 4; ++g) {          // 30 channels live in 4 planes of 8
-                                    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(sk + act_idx(page, hd.skip_cp, oh, ow, g * 8, oy, ox)));
-                                    const uint32_t wds[4] = {raw.x, raw.y, raw.z, raw.w};
+                            for (int g = 0; g < 4; ++g) {              // 30 channels live in 4 planes of 8
+                                const uint4* src = reinterpret_cast<const uint4*>(sk + act_idx(page, hd.skip_cp, oh, ow, g * 8, rowok ? oy : 0, rowok ? ox : 0));
+                                raw[0][g] = rowok ? __ldg(src) : make_uint4(0, 0, 0, 0);
+                                raw[1][g] = rowok ? __ldg(src + 1) : make_uint4(0, 0, 0, 0);   // ox + 1 < ow always (ow even)
+                            }
+                        }
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            float lg[HEAD_NC];
+#pragma unroll
+                            for (int k = 0; k < HEAD_NC; ++k) lg[k] = c_head_lb[k];
+#pragma unroll
+                            for (int o = 0; o < HEAD_DCO; ++o) {
+                                const float d = __uint_as_float(o < 16 ? va[j][o < 16 ? o : 0] : vb[j][o >= 16 ? o - 16 : 0]);
+#pragma unroll
+                                for (int k = 0; k < HEAD_NC; ++k) lg[k] = fmaf(d, c_head_lw[o * HEAD_NC + k], lg[k]);
+                            }
+                            if constexpr (MODE == EPI_HEAD_SKIP) {
+#pragma unroll
+                                for (int g = 0; g < 4; ++g) {
+                                    const uint32_t wds[4] = {raw[j][g].x, raw[j][g].y, raw[j][g].z, raw[j][g].w};
 #pragma unroll
                                     for (int e = 0; e < 4; ++e) {
                                         const float2 f = unpack2<T>(wds[e]);
@@ -291,39 +306,26 @@ conv_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm0, co
                                     }
                                 }
                             }
-                        }
-                        if (!valid) continue;
-                        int best = 0;
-                        float bv = lg[0];
+                            if (!(j ? v1ok : v0ok)) continue;
+                            int best = 0;
+                            float bv = lg[0];
 #pragma unroll
-                        for (int k = 1; k < HEAD_NC; ++k)
-                            if (k < hd.n_classes && lg[k] > bv) { bv = lg[k]; best = k; }      // first maximum wins
-                        const size_t opix = ((size_t)page * hd.hs + oy) * hd.ws + ox;
-                        if (hd.labels) hd.labels[opix] = (uint8_t)best;
-                        if (hd.logits) {
+                            for (int k = 1; k < HEAD_NC; ++k)
+                                if (k < hd.n_classes && lg[k] > bv) { bv = lg[k]; best = k; }      // first maximum wins
+                            const size_t opix = ((size_t)page * hd.hs + oy) * hd.ws + ox + j;
+                            if (hd.labels) hd.labels[opix] = (uint8_t)best;
+                            if (hd.logits) {
 #pragma unroll
-                            for (int k = 0; k < HEAD_NC; ++k)
-                                if (k < hd.n_classes) hd.logits[opix * hd.n_classes + k] = lg[k];
-                        }
-                        if (hd.prob) {
-                            float e[HEAD_NC], sum = 0.f;
-#pragma unroll
-                            for (int k = 0; k < HEAD_NC; ++k) { e[k] = k < hd.n_classes ? expf(lg[k] - bv) : 0.f; sum += e[k]; }
-#pragma unroll
-                            for (int k = 0; k < HEAD_NC; ++k)
-                                if (k < hd.n_classes) hd.prob[opix * hd.n_classes + k] = e[k] / sum;
-                        }
-                        if (hd.color || hd.overlay || hd.inverted) {
-                            const uint8_t cr = hd.lut[best * 3 + 0], cg = hd.lut[best * 3 + 1], cb = hd.lut[best * 3 + 2];
-                            const uint8_t bin = hd.binary ? hd.binary[opix] : 1;
-                            if (hd.color) { hd.color[opix * 3 + 0] = cr; hd.color[opix * 3 + 1] = cg; hd.color[opix * 3 + 2] = cb; }
-                            if (hd.overlay) {
-                                const bool keep = (uint8_t)(1 - bin) != 0;          // overlay[(1 - binary) == 0] = 0
-                                hd.overlay[opix * 3 + 0] = keep ? cr : 0; hd.overlay[opix * 3 + 1] = keep ? cg : 0; hd.overlay[opix * 3 + 2] = keep ? cb : 0;
+                                for (int k = 0; k < HEAD_NC; ++k)
+                                    if (k < hd.n_classes) hd.logits[opix * hd.n_classes + k] = lg[k];
                             }
-                            if (hd.inverted) {
-                                const bool keep = bin != 0;                         // inverted[binary == 0] = 0
-                                hd.inverted[opix * 3 + 0] = keep ? cr : 0; hd.inverted[opix * 3 + 1] = keep ? cg : 0; hd.inverted[opix * 3 + 2] = keep ? cb : 0;
+                            if (hd.prob) {
+                                float e[HEAD_NC], sum = 0.f;
+#pragma unroll
+                                for (int k = 0; k < HEAD_NC; ++k) { e[k] = k < hd.n_classes ? expf(lg[k] - bv) : 0.f; sum += e[k]; }
+#pragma unroll
+                                for (int k = 0; k < HEAD_NC; ++k)
+                                    if (k < hd.n_classes) hd.prob[opix * hd.n_classes + k] = e[k] / sum;
                             }
                         }
                     }
@@ -493,8 +495,7 @@ int launch_t(pcs_ctx* ctx, const UmmaConvArgs& a) {
     if constexpr (MODE >= EPI_HEAD) {
         const UmmaHeadArgs& h = *a.head;
         p.head.skip = h.skip; p.head.skip_cp = h.skip_cp; p.head.n_classes = h.n_classes; p.head.hs = h.hs; p.head.ws = h.ws;
-        p.head.binary = h.binary; p.head.labels = h.labels; p.head.logits = h.logits; p.head.prob = h.prob;
-        p.head.lut = h.lut; p.head.color = h.color; p.head.overlay = h.overlay; p.head.inverted = h.inverted;
+        p.head.labels = h.labels; p.head.logits = h.logits; p.head.prob = h.prob;
         if (ctx->device >= 64 || g_head_owner[ctx->device] != ctx->model_stamp) {
             PCS_CUDA(ctx, cudaMemcpyToSymbolAsync(c_head_lw, h.lw_padded, sizeof(float) * (HEAD_DCO + HEAD_SKIPC) * HEAD_NC, 0, cudaMemcpyDeviceToDevice, ctx->stream));
             PCS_CUDA(ctx, cudaMemcpyToSymbolAsync(c_head_lb, h.lb_folded, sizeof(float) * HEAD_NC, 0, cudaMemcpyDeviceToDevice, ctx->stream));

@@ -173,25 +173,50 @@ int launch_head(pcs_ctx* ctx, const HeadArgs& a) {
 // generate_output_masks on an existing class map (output.py:44-60).
 // Labels not present in the LUT map to (0,0,0).
 // ---------------------------------------------------------------------------
+// One thread = 16 consecutive output BYTES of the flat [npix][3] images (one aligned 128-bit store per
+// image); they cover at most 6 pixels, whose class / binary bytes are read once.
 __global__ void __launch_bounds__(256)
 masks_kernel(const uint8_t* __restrict__ labels, const uint8_t* __restrict__ binary, size_t npix,
              const uint8_t* __restrict__ lut, int n_lut, uint8_t* __restrict__ color, uint8_t* __restrict__ overlay,
-             uint8_t* __restrict__ inverted) {
+             uint8_t* __restrict__ inverted, int vec_ok) {
     __shared__ uint8_t s_lut[256 * 3];
     for (int i = threadIdx.x; i < 256 * 3; i += blockDim.x) s_lut[i] = (i < n_lut * 3) ? lut[i] : 0;
     __syncthreads();
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
-        const int l = labels[i];
-        const uint8_t r = s_lut[l * 3], g = s_lut[l * 3 + 1], b = s_lut[l * 3 + 2];
-        const uint8_t bin = binary[i];
-        if (color) { color[i * 3] = r; color[i * 3 + 1] = g; color[i * 3 + 2] = b; }
-        if (overlay) {
-            const bool keep = (uint8_t)(1 - bin) != 0;
-            overlay[i * 3] = keep ? r : 0; overlay[i * 3 + 1] = keep ? g : 0; overlay[i * 3 + 2] = keep ? b : 0;
+    const size_t nbytes = npix * 3;
+    const size_t nchunks = (nbytes + 15) / 16;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < nchunks; k += (size_t)gridDim.x * blockDim.x) {
+        const size_t b0 = k * 16;
+        const size_t p0 = b0 / 3;
+        const int phase = (int)(b0 - p0 * 3);
+        uint8_t lab[6], bin[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            const size_t pi = p0 + q;
+            lab[q] = pi < npix ? labels[pi] : 0;
+            bin[q] = (pi < npix && binary) ? binary[pi] : 1;
         }
-        if (inverted) {
-            const bool keep = bin != 0;
-            inverted[i * 3] = keep ? r : 0; inverted[i * 3 + 1] = keep ? g : 0; inverted[i * 3 + 2] = keep ? b : 0;
+        uint32_t wc[4] = {0, 0, 0, 0}, wo[4] = {0, 0, 0, 0}, wi[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int b = 0; b < 16; ++b) {
+            const int q = phase + b;
+            const int pi = q / 3, ch = q - 3 * pi;
+            const uint32_t v = s_lut[lab[pi] * 3 + ch];
+            const bool keep_o = (uint8_t)(1 - bin[pi]) != 0;        // overlay[(1 - binary) == 0] = 0
+            const bool keep_i = bin[pi] != 0;                        // inverted[binary == 0] = 0
+            wc[b >> 2] |= v << (8 * (b & 3));
+            wo[b >> 2] |= (keep_o ? v : 0u) << (8 * (b & 3));
+            wi[b >> 2] |= (keep_i ? v : 0u) << (8 * (b & 3));
+        }
+        if (vec_ok && b0 + 16 <= nbytes) {
+            if (color) *reinterpret_cast<uint4*>(color + b0) = make_uint4(wc[0], wc[1], wc[2], wc[3]);
+            if (overlay) *reinterpret_cast<uint4*>(overlay + b0) = make_uint4(wo[0], wo[1], wo[2], wo[3]);
+            if (inverted) *reinterpret_cast<uint4*>(inverted + b0) = make_uint4(wi[0], wi[1], wi[2], wi[3]);
+        } else {
+            for (int b = 0; b < 16 && b0 + b < nbytes; ++b) {
+                if (color) color[b0 + b] = (uint8_t)(wc[b >> 2] >> (8 * (b & 3)));
+                if (overlay) overlay[b0 + b] = (uint8_t)(wo[b >> 2] >> (8 * (b & 3)));
+                if (inverted) inverted[b0 + b] = (uint8_t)(wi[b >> 2] >> (8 * (b & 3)));
+            }
         }
     }
 }
@@ -200,8 +225,10 @@ int launch_masks(pcs_ctx* ctx, const uint8_t* d_labels, const uint8_t* d_binary,
                  const uint8_t* d_lut, int n_lut, uint8_t* d_color, uint8_t* d_overlay, uint8_t* d_inverted) {
     if (n <= 0 || H <= 0 || W <= 0 || n_lut < 0 || n_lut > 256) return set_err(ctx, PCS_ERR_ARG, "masks: bad argument");
     const size_t npix = (size_t)n * H * W;
-    const unsigned blocks = (unsigned)std::min<size_t>((size_t)ctx->sm_count * 8, (npix + 255) / 256);
-    masks_kernel<<<blocks, 256, 0, ctx->stream>>>(d_labels, d_binary, npix, d_lut, n_lut, d_color, d_overlay, d_inverted);
+    const size_t nchunks = (npix * 3 + 15) / 16;
+    const unsigned blocks = (unsigned)std::min<size_t>((size_t)ctx->sm_count * 16, (nchunks + 255) / 256);
+    const int vec_ok = (((uintptr_t)d_color | (uintptr_t)d_overlay | (uintptr_t)d_inverted) & 15) == 0;
+    masks_kernel<<<blocks, 256, 0, ctx->stream>>>(d_labels, d_binary, npix, d_lut, n_lut, d_color, d_overlay, d_inverted, vec_ok);
     PCS_LAUNCH_CHECK(ctx, "masks_kernel");
     return PCS_OK;
 }
