@@ -167,6 +167,10 @@ PCS_API int pcs_predict_pages_host(pcs_ctx* ctx, const uint8_t* h_grey, const ui
  * NHWC host buffer (real channels only); returns the channel count or <0. */
 PCS_API int pcs_debug_activation(pcs_ctx* ctx, const char* name, float* h_out, size_t capacity_floats,
                          int32_t* shape4);
+/* 1: the next pcs_forward calls also store the activations that the fused kernels
+ * normally never write (fcn_skip conv2 at full resolution), so that
+ * pcs_debug_activation can return them; 0 (default): production schedule */
+PCS_API int pcs_set_keep_activations(pcs_ctx* ctx, int enabled);
 /* enable (1) / disable (0) CUDA-event timing of every stage of the next calls */
 PCS_API int pcs_set_timing(pcs_ctx* ctx, int enabled);
 /* device time in ms of the stages since the last pcs_forward began ("name:ms;"...) */

@@ -17,7 +17,10 @@ TF semantics restated:
 
 `bf16=True` gives the numerics twin of the device path: weights of every layer
 but conv1 and logits are rounded to bf16, every stored activation is rounded to
-bf16, accumulation stays fp32 (see DESIGN.md "precision").
+bf16, accumulation stays fp32 (see DESIGN.md "precision").  `fused_head=True`
+additionally mirrors the tensor-engine head: deconv5 keeps its fp32 weights (it is
+composed with the logits layer on the host and split into two bf16 operand halves)
+and the conv2 skip enters the logits unrounded (taken from conv2's fp32 accumulators).
 """
 from __future__ import annotations
 
@@ -64,18 +67,19 @@ class Forward:
     """Runs one of the three reference graphs on a single page."""
 
     def __init__(self, arch: str, weights: Sequence[Tuple[np.ndarray, np.ndarray]], n_classes: int,
-                 dtype=torch.float32, bf16: bool = False):
+                 dtype=torch.float32, bf16: bool = False, fused_head: bool = False):
         from page_segmentation_b200.synth import layer_table
         self.arch = arch
         self.table = layer_table(arch, n_classes)
         assert len(weights) == len(self.table)
         self.dtype = dtype
         self.bf16 = bf16
+        self.fused_head = fused_head and bf16
         self.params: Dict[str, Tuple[torch.Tensor, torch.Tensor, tuple]] = {}
         for (name, kind, k, ci, co, act), (w, b) in zip(self.table, weights):
             wt = torch.from_numpy(np.ascontiguousarray(w)).to(dtype)
             bt = torch.from_numpy(np.ascontiguousarray(b)).to(dtype)
-            if bf16 and name not in ("conv1", "conv1a", "logits"):
+            if bf16 and name not in ("conv1", "conv1a", "logits") and not (self.fused_head and name == "deconv5"):
                 wt = _bf16(wt)
             self.params[name] = (wt, bt, (kind, k, ci, co, act))
 
@@ -113,7 +117,8 @@ class Forward:
         if self.arch in ("fcn_skip", "fcn"):
             skip = self.arch == "fcn_skip"
             conv1 = K("conv1", L("conv1", x))
-            conv2 = K("conv2", L("conv2", conv1))
+            conv2_f32 = L("conv2", conv1, store=False)
+            conv2 = K("conv2", _bf16(conv2_f32) if self.bf16 else conv2_f32)
             pool2 = F.max_pool2d(conv2, 2, 2)
             conv3 = K("conv3", L("conv3", pool2))
             conv4 = K("conv4", L("conv4", conv3))
@@ -135,7 +140,7 @@ class Forward:
             # device path keeps deconv5 in fp32 registers and feeds the logits directly
             d5 = K("deconv5", L("deconv5", d4, store=False))
             if skip:
-                d5 = torch.cat([d5, conv2], 1)
+                d5 = torch.cat([d5, conv2_f32 if self.fused_head else conv2], 1)
             last = d5
         elif self.arch == "unet":
             def up(name, t):

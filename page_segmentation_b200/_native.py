@@ -22,7 +22,7 @@ EXPORTS = [
     "pcs_abi_version", "pcs_ctx_create", "pcs_ctx_destroy", "pcs_last_error", "pcs_set_stream",
     "pcs_synchronize", "pcs_launch_count", "pcs_model_load", "pcs_set_engine", "pcs_preprocess",
     "pcs_forward", "pcs_masks", "pcs_resize_nearest", "pcs_ccl", "pcs_cc_majority",
-    "pcs_bounding_boxes", "pcs_predict_pages_host", "pcs_debug_activation", "pcs_set_timing",
+    "pcs_bounding_boxes", "pcs_predict_pages_host", "pcs_debug_activation", "pcs_set_keep_activations", "pcs_set_timing",
     "pcs_last_timings",
 ]
 
@@ -70,6 +70,7 @@ def load() -> C.CDLL:
     lib.pcs_bounding_boxes.argtypes = [vp, u8p, i32, i32, i32, i32, u8p]
     lib.pcs_predict_pages_host.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
     lib.pcs_debug_activation.argtypes = [vp, C.c_char_p, vp, C.c_size_t, C.POINTER(C.c_int32)]
+    lib.pcs_set_keep_activations.argtypes = [vp, i32]
     lib.pcs_set_timing.argtypes = [vp, i32]
     lib.pcs_last_timings.argtypes = [vp]
     lib.pcs_last_timings.restype = C.c_char_p
@@ -139,6 +140,10 @@ class Context:
 
     def set_engine(self, engine: str):
         self._check(self.lib.pcs_set_engine(self.h, ENGINES[engine]), "pcs_set_engine")
+
+    def set_keep_activations(self, enabled: bool):
+        """Diagnostics: also store the activations the fused kernels never write (fcn_skip conv2)."""
+        self._check(self.lib.pcs_set_keep_activations(self.h, 1 if enabled else 0), "pcs_set_keep_activations")
 
     def set_timing(self, enabled: bool):
         self._check(self.lib.pcs_set_timing(self.h, 1 if enabled else 0), "pcs_set_timing")

@@ -151,24 +151,30 @@ static int new_act(pcs_ctx* ctx, const char* name, int n, int h, int w, int c, A
 static ConvSrc src_of(const Act& a) { ConvSrc s; s.p = a.p; s.c = a.c; s.cp = a.cp; return s; }
 
 // conv / deconv-s1 layer ('same', stride 1) on 1 or 2 concatenated sources
+static bool fold_disabled() {
+    static const bool no_fold = getenv("PCSEG_FOLD") && !strcmp(getenv("PCSEG_FOLD"), "0");
+    return no_fold;
+}
+
 static int run_conv(pcs_ctx* ctx, const char* lname, const Act* s0, const Act* s1, Act* out, Act* pool_out,
-                    bool upsample = false) {
+                    bool upsample = false, void* plog = nullptr, const float* skip_lw = nullptr) {
     Layer* L = find_layer(ctx, lname);
     if (!L) return set_err(ctx, PCS_ERR_STATE, "layer %s missing", lname);
     StageScope ts(ctx, lname);
     const Act& any = out ? *out : *pool_out;
     const int n = any.n;
     const int h = out ? out->h : pool_out->h * 2, w = out ? out->w : pool_out->w * 2;
-    static const bool no_fold = getenv("PCSEG_FOLD") && !strcmp(getenv("PCSEG_FOLD"), "0");
-    if (ctx->engine == PCS_ENGINE_UMMA && !upsample && !s1 && L->d_wfold && !no_fold && (h % 4) == 0) {
+    if (ctx->engine == PCS_ENGINE_UMMA && !upsample && !s1 && L->d_wfold && !fold_disabled() && (h % 4) == 0) {
         FoldConvArgs f;
         f.src = src_of(*s0);
         f.n = n; f.h = h; f.w = w; f.k = L->k;
         f.wimg = L->d_wfold; f.b32 = L->d_b32; f.cout = L->cout; f.npad = L->npad; f.nchunks = s0->cp / 16; f.relu = L->relu;
         f.out = out ? out->p : nullptr; f.out_cp = out ? out->cp : 0;
         f.pool_out = pool_out ? pool_out->p : nullptr; f.pool_cp = pool_out ? pool_out->cp : 0;
+        f.plog = plog; f.skip_lw = skip_lw;
         return launch_conv_fold(ctx, f);
     }
+    if (plog) return set_err(ctx, PCS_ERR_STATE, "layer %s: partial logits requested off the folded kernel", lname);
     if (ctx->engine == PCS_ENGINE_UMMA && !upsample && L->d_wmma && umma_supported(L->k, L->npad)) {
         UmmaConvArgs a;
         a.src[0] = src_of(*s0); a.nsrc = 1;
@@ -240,9 +246,22 @@ static int forward_fcn(pcs_ctx* ctx, bool skip, const uint8_t* d_image, int n, i
     Act conv1, conv2, pool2, conv3, pool4, conv5, conv6, pool6, conv7, d1, d2, d3, d4;
     PCS_TRY(new_act(ctx, "conv1", n, hp, wp, 20, &conv1));
     PCS_TRY(run_conv1_u8(ctx, "conv1", d_image, n, hs, ws, &conv1));
-    PCS_TRY(new_act(ctx, "conv2", n, hp, wp, 30, &conv2));
+    // fused head (<= 4 classes, tensor engine): conv2 hands its share of the logits to the head as fp32
+    // partial sums and its full-resolution tensor is not stored at all
+    Layer* L2 = find_layer(ctx, "conv2");
+    Layer* L5 = find_layer(ctx, "deconv5");
+    Layer* LL = find_layer(ctx, "logits");
+    const bool conv2_folds = L2 && L2->d_wfold && !fold_disabled();
+    const bool fused_head = ctx->engine == PCS_ENGINE_UMMA && L5->d_wmma && LL->d_head_lb && (!skip || (conv2_folds && LL->d_head_lw));
+    void* plog = nullptr;
+    if (fused_head && skip) {
+        plog = arena_alloc(ctx, (size_t)n * hp * wp * sizeof(float4));
+        if (!plog) return set_err(ctx, PCS_ERR_NOMEM, "activation arena exhausted at the partial logits");
+    }
+    const bool store_conv2 = (skip && !fused_head) || ctx->keep_acts;
+    if (store_conv2) PCS_TRY(new_act(ctx, "conv2", n, hp, wp, 30, &conv2));
     PCS_TRY(new_act(ctx, "pool2", n, hp / 2, wp / 2, 30, &pool2));
-    PCS_TRY(run_conv(ctx, "conv2", &conv1, nullptr, &conv2, &pool2));
+    PCS_TRY(run_conv(ctx, "conv2", &conv1, nullptr, store_conv2 ? &conv2 : nullptr, &pool2, false, plog, plog ? LL->d_head_lw : nullptr));
     PCS_TRY(new_act(ctx, "conv3", n, hp / 2, wp / 2, 40, &conv3));
     PCS_TRY(run_conv(ctx, "conv3", &pool2, nullptr, &conv3, nullptr));
     PCS_TRY(new_act(ctx, "pool4", n, hp / 4, wp / 4, 40, &pool4));
@@ -267,13 +286,10 @@ static int forward_fcn(pcs_ctx* ctx, bool skip, const uint8_t* d_image, int n, i
     PCS_TRY(new_act(ctx, "deconv4", n, hp / 2, wp / 2, 30, &d4));
     PCS_TRY(run_deconv_s2(ctx, "deconv4", &d3, skip ? &conv5 : nullptr, &d4));         // concat [deconv3, conv5]
 
-    Layer* L5 = find_layer(ctx, "deconv5");
-    Layer* LL = find_layer(ctx, "logits");
     StageScope ts(ctx, "head");
-    if (ctx->engine == PCS_ENGINE_UMMA && L5->d_wmma && LL->d_head_lw) {
+    if (fused_head) {
         UmmaHeadArgs hd;
-        if (skip) { hd.skip = conv2.p; hd.skip_cp = conv2.cp; }
-        hd.lw_padded = LL->d_head_lw; hd.lb_folded = LL->d_head_lb;
+        hd.plog = plog; hd.lb_folded = LL->d_head_lb;
         hd.n_classes = ctx->n_classes; hd.hs = hs; hd.ws = ws;
         // the class map is always produced (the colour pass reads it); colour masks follow as one vectorised kernel
         uint8_t* labels = io.labels;
@@ -288,7 +304,7 @@ static int forward_fcn(pcs_ctx* ctx, bool skip, const uint8_t* d_image, int n, i
         if (skip) { u.src[1] = src_of(conv3); u.nsrc = 2; }
         u.n = n; u.h = hp / 2; u.w = wp / 2; u.k = 1; u.pad = 0;
         u.wmma = L5->d_wmma; u.b32 = L5->d_b32; u.cout = L5->cout; u.npad = L5->npad; u.nchunks = L5->nchunks; u.relu = 0;
-        u.mode = skip ? 3 : 2; u.co_t = L5->co_t; u.head = &hd;
+        u.mode = 2; u.co_t = 0; u.head = &hd;
         PCS_TRY(launch_conv_umma(ctx, u));
         if (want_masks)
             return launch_masks(ctx, labels, io.binary, n, hs, ws, io.d_lut, ctx->n_classes, io.color, io.overlay, io.inverted);
@@ -379,7 +395,7 @@ static size_t arena_need(int arch, int n, int hs, int ws) {
     if (arch == PCS_ARCH_UNET)
         ch = 64 * 5 + (64 + 128 * 5) / 4.0 + (128 + 256 * 5) / 16.0 + (256 + 512 * 5) / 64.0 + (512 + 1024 * 2) / 256.0;
     else
-        ch = 32 + 32 + (32 + 48 + 32) / 4.0 + (48 + 64 + 64 + 64 + 48) / 16.0 + (64 + 80 + 80) / 64.0;
+        ch = 32 + 32 + 8 + (32 + 48 + 32) / 4.0 + (48 + 64 + 64 + 64 + 48) / 16.0 + (64 + 80 + 80) / 64.0;
     return (size_t)(px * ch * 2.0) + (size_t)64 * 4096 + (1u << 20);
 }
 
@@ -501,6 +517,7 @@ int pcs_model_load(pcs_ctx* ctx, int arch, int n_classes, int precision, const p
         L.h_b32.assign(w.bias, w.bias + cout);
         // every layer except the first and the logits consumes operands rounded to the model precision
         const bool rounded = li != 0 && s.kind != K_LOGITS;
+        if (L.name == "deconv5") L.h_w32_raw = L.h_w32;
         if (rounded) {
             for (float& v : L.h_w32)
                 v = precision == PCS_PREC_BF16 ? __bfloat162float(__float2bfloat16_rn(v)) : __half2float(__float2half_rn(v));
@@ -543,13 +560,21 @@ int pcs_model_load(pcs_ctx* ctx, int arch, int n_classes, int precision, const p
                 PCS_CUDA(ctx, cudaMemcpy(L.d_wfold, fimg.data(), fb, cudaMemcpyHostToDevice));
             }
         } else if (L.kind == K_DECONV_S2 && L.name == "deconv5") {
-            // fused head: N column J = tap * 20 + o (see conv_umma.cu EPI_HEAD)
+            // fused head: deconv5 composed with the logits layer on the host (conv_umma.cu EPI_HEAD)
             if (arch == PCS_ARCH_FCN_SKIP) { src_c[0] = 30; src_c[1] = 40; nsrc = 2; }     // [deconv4, conv3]
-            if (L.cout != 20 || n_classes > 4) continue;
-            L.co_t = L.cout;
-            L.npad = 4 * L.cout;
-            if (!umma_supported(1, L.npad)) continue;
-            L.wmma_bytes = umma_weight_image_deconv(L.h_w32.data(), src_c, nsrc, L.cout, L.co_t, L.npad, precision, img);
+            if (n_classes > 4) continue;
+            const Layer& LG = ctx->layers.back();                                           // logits: [cin][n_classes]
+            std::vector<double> m((size_t)4 * L.cin * 4, 0.0);
+            for (int t = 0; t < 4; ++t)
+                for (int c = 0; c < L.cin; ++c)
+                    for (int k = 0; k < n_classes; ++k) {
+                        double v = 0.0;
+                        for (int o = 0; o < L.cout; ++o)
+                            v += (double)L.h_w32_raw[((size_t)t * L.cin + c) * L.cout + o] * (double)LG.h_w32[(size_t)o * n_classes + k];
+                        m[((size_t)t * L.cin + c) * 4 + k] = v;
+                    }
+            L.npad = 32;
+            L.wmma_bytes = umma_weight_image_head(m.data(), src_c, nsrc, precision, img);
         } else if (L.kind == K_DECONV_S2) {
             L.co_t = pad16(L.cout);
             L.npad = std::min(4 * L.co_t, 128);
@@ -564,20 +589,29 @@ int pcs_model_load(pcs_ctx* ctx, int arch, int n_classes, int precision, const p
         PCS_CUDA(ctx, cudaMemcpy(L.d_wmma, img.data(), L.wmma_bytes, cudaMemcpyHostToDevice));
     }
     if (arch != PCS_ARCH_UNET && n_classes <= 4) {
-        // logits weights padded to 4 classes; deconv5 bias folded through them: lb' = lb + b5 . lw[0:20]
+        // fused head constants: bias lb' = lb + b5 . lw[0:20] (+ b2 . lw[20:50]) and, for fcn_skip, the
+        // logits rows of the conv2 skip channels [32][4] that conv2's epilogue applies (conv_fold.cu)
+        Layer* L2 = find_layer(ctx, "conv2");
         Layer* L5 = find_layer(ctx, "deconv5");
         Layer* LL = find_layer(ctx, "logits");
-        std::vector<float> lw(50 * 4, 0.f), lb(4, 0.f);
-        for (int c = 0; c < LL->cin; ++c)
-            for (int k = 0; k < n_classes; ++k) lw[(size_t)c * 4 + k] = LL->h_w32[(size_t)c * n_classes + k];
+        std::vector<float> lw(32 * 4, 0.f), lb(4, 0.f);
+        const bool skip = arch == PCS_ARCH_FCN_SKIP;
         for (int k = 0; k < n_classes; ++k) {
             double v = LL->h_b32[k];
             for (int o = 0; o < L5->cout; ++o) v += (double)L5->h_b32[o] * (double)LL->h_w32[(size_t)o * n_classes + k];
+            if (skip)
+                for (int c = 0; c < L2->cout; ++c) {
+                    const float w = LL->h_w32[(size_t)(L5->cout + c) * n_classes + k];
+                    lw[(size_t)c * 4 + k] = w;
+                    v += (double)L2->h_b32[c] * (double)w;
+                }
             lb[k] = (float)v;
         }
-        PCS_CUDA(ctx, cudaMalloc(&LL->d_head_lw, lw.size() * 4));
+        if (skip) {
+            PCS_CUDA(ctx, cudaMalloc(&LL->d_head_lw, lw.size() * 4));
+            PCS_CUDA(ctx, cudaMemcpy(LL->d_head_lw, lw.data(), lw.size() * 4, cudaMemcpyHostToDevice));
+        }
         PCS_CUDA(ctx, cudaMalloc(&LL->d_head_lb, lb.size() * 4));
-        PCS_CUDA(ctx, cudaMemcpy(LL->d_head_lw, lw.data(), lw.size() * 4, cudaMemcpyHostToDevice));
         PCS_CUDA(ctx, cudaMemcpy(LL->d_head_lb, lb.data(), lb.size() * 4, cudaMemcpyHostToDevice));
     }
     if (getenv("PCSEG_DEBUG_SYNC_LOAD")) PCS_CUDA(ctx, cudaDeviceSynchronize());
@@ -794,6 +828,12 @@ int pcs_debug_activation(pcs_ctx* ctx, const char* name, float* h_out, size_t ca
             h_out[i * a.c + c] = f;
         }
     return a.c;
+}
+
+int pcs_set_keep_activations(pcs_ctx* ctx, int enabled) {
+    if (!ctx) return PCS_ERR_ARG;
+    ctx->keep_acts = enabled != 0;
+    return PCS_OK;
 }
 
 int pcs_set_timing(pcs_ctx* ctx, int enabled) {

@@ -60,8 +60,9 @@ struct Layer {
     int npad = 0;           // padded C_out of the UMMA tile
     int co_t = 0;           // deconv s2 on the tensor path: padded channels per tap
     void* d_wfold = nullptr;      // resident operand image of the dx-folded kernel (conv_fold.cu)
-    float* d_head_lw = nullptr;   // logits layer: [50][4] padded weights for the fused head
-    float* d_head_lb = nullptr;   // logits layer: [4] bias with the deconv5 bias folded in
+    std::vector<float> h_w32_raw; // deconv5 only: weights before rounding (composed with the logits on the host)
+    float* d_head_lw = nullptr;   // logits layer: [32][4] rows of the conv2 skip channels, zero padded (fcn_skip)
+    float* d_head_lb = nullptr;   // logits layer: [4] bias with the deconv5 / conv2 biases folded in
     int nchunks = 0;        // number of 16-channel K chunks over all sources
 };
 
@@ -101,6 +102,7 @@ struct pcs_ctx {
     std::string timings;
     std::vector<pcs::StageTime> stage_times;
     bool timing_enabled = false;
+    bool keep_acts = false;                 // diagnostics: also store activations the fused kernels normally skip
 };
 
 namespace pcs {
@@ -219,10 +221,9 @@ int launch_bounding_boxes(pcs_ctx* ctx, const uint8_t* d_pred, int n, int H, int
                           uint8_t* d_out);
 
 // conv_umma.cu  (tcgen05 / TMEM / TMA implicit GEMM)
-struct UmmaHeadArgs {              // fused FCN head epilogue (conv_umma.cu modes 2/3)
-    const void* skip = nullptr; int skip_cp = 0;
-    const float* lw_padded = nullptr;   // device [50][4]: logits weights, classes zero-padded to 4
-    const float* lb_folded = nullptr;   // device [4]: logits bias + deconv5 bias folded through the logits weights
+struct UmmaHeadArgs {              // fused FCN head epilogue (conv_umma.cu mode 2)
+    const void* plog = nullptr;         // device float4 [n][2h][2w]: conv2 share of the logits (fcn_skip) or null
+    const float* lb_folded = nullptr;   // device [4]: logits bias with the deconv5 (and conv2) bias folded through
     int n_classes = 0, hs = 0, ws = 0;
     uint8_t* labels = nullptr; float* logits = nullptr; float* prob = nullptr;
 };
@@ -235,7 +236,7 @@ struct UmmaConvArgs {
     const float* b32 = nullptr;
     int cout = 0, npad = 0, nchunks = 0, relu = 0;
     int mode = 0;                  // 0 = 'same' conv store (+pool), 1 = 2x2 stride-2 transposed conv scatter,
-                                   // 2 / 3 = fused FCN head without / with the conv2 skip
+                                   // 2 = fused FCN head (composed deconv5 x logits GEMM)
     const UmmaHeadArgs* head = nullptr;
     int co_t = 0;                  // mode 1: padded channels per tap
     void* out = nullptr;
@@ -249,6 +250,8 @@ size_t umma_weight_image(const float* w32 /*[taps][cin][cout]*/, int taps, const
                          int cout, int npad, int precision, std::vector<uint16_t>& out);
 size_t umma_weight_image_deconv(const float* w32 /*[4][cin][cout]*/, const int* src_c, int nsrc, int cout, int co_t,
                                 int npad, int precision, std::vector<uint16_t>& out);
+size_t umma_weight_image_head(const double* m /*[4][cin][4]*/, const int* src_c, int nsrc, int precision,
+                              std::vector<uint16_t>& out);
 bool umma_supported(int k, int npad);
 
 // conv_fold.cu  (marching, dx-folded 5x5 convolution for the small-channel layers)
@@ -260,6 +263,8 @@ struct FoldConvArgs {
     int cout = 0, npad = 0, nchunks = 0, relu = 0;
     void* out = nullptr; int out_cp = 0;
     void* pool_out = nullptr; int pool_cp = 0;
+    void* plog = nullptr;              // optional float4 [n][h][w]: this layer's share of the logits (fcn_skip conv2)
+    const float* skip_lw = nullptr;    // device [32][4]: logits rows of this layer's channels, zero padded
 };
 bool fold_supported(int k, int npad, int nchunks, int nsrc);
 size_t fold_weight_image(const float* w32 /*[25][cin][cout]*/, int cin, int cout, int npad, int precision, std::vector<uint16_t>& out);

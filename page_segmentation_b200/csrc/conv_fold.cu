@@ -43,6 +43,13 @@ constexpr int F_RING_MAX = 16;              // input-row ring entries (one row i
 constexpr int F_SLOTS = 8;                  // output-row accumulator slots in TMEM
 constexpr int F_SW = 124;                   // valid output pixels per strip
 
+// conv2 -> logits partial sums (fcn_skip): concat[deconv5, conv2] -> logits 1x1 (model.py:85-88) is linear
+// in conv2, so its share  P[y,x,k] = sum_o conv2[y,x,o] * lw[20+o][k]  is taken here from the fp32
+// accumulators (before the bf16 rounding) and the full-resolution conv2 tensor is never written.
+constexpr int F_LOGC = 32, F_NC = 4;
+__constant__ float c_skip_lw[F_LOGC * F_NC];
+int64_t g_skip_owner[64] = {0};
+
 struct FoldParams {
     int n, h, w;
     int seg_rows, segs, strips, num_items;  // work item = (page, strip, segment of seg_rows output rows)
@@ -51,6 +58,7 @@ struct FoldParams {
     int cout, relu;
     void* out; int out_cp;
     void* pool; int pool_cp;
+    float4* plog;                           // [n][h][w] partial logits (4 classes, zero padded) or null
     uint32_t w_bytes;
     int ring;                               // input-row ring depth
 };
@@ -212,6 +220,20 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&s_tempty[slot]);      // slot free for the window of input row gg+4
                     if (!real) continue;
+                    if constexpr (NPAD == F_LOGC) {
+                        if (p.plog) {
+                            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                            for (int o = 0; o < NPAD; ++o) {
+                                const float a = __uint_as_float(v[o]);
+                                acc.x = fmaf(a, c_skip_lw[o * F_NC + 0], acc.x);
+                                acc.y = fmaf(a, c_skip_lw[o * F_NC + 1], acc.y);
+                                acc.z = fmaf(a, c_skip_lw[o * F_NC + 2], acc.z);
+                                acc.w = fmaf(a, c_skip_lw[o * F_NC + 3], acc.w);
+                            }
+                            if (xok && y < p.h) p.plog[((size_t)page * p.h + y) * p.w + x] = acc;
+                        }
+                    }
 #pragma unroll
                     for (int hb = 0; hb < NPAD / 16; ++hb) {
                         uint32_t pk[8];
@@ -284,6 +306,15 @@ int launch_fold_t(pcs_ctx* ctx, const FoldConvArgs& a) {
     p.n = a.n; p.h = a.h; p.w = a.w;
     p.wimg = reinterpret_cast<const uint8_t*>(a.wimg); p.bias = a.b32; p.cout = a.cout; p.relu = a.relu;
     p.out = a.out; p.out_cp = a.out_cp; p.pool = a.pool_out; p.pool_cp = a.pool_cp;
+    p.plog = nullptr;
+    if (a.plog) {
+        if (NPAD != F_LOGC || !a.skip_lw) return set_err(ctx, PCS_ERR_ARG, "conv_fold: partial logits need the N=32 kernel and weights");
+        p.plog = reinterpret_cast<float4*>(a.plog);
+        if (ctx->device >= 64 || g_skip_owner[ctx->device] != ctx->model_stamp) {
+            PCS_CUDA(ctx, cudaMemcpyToSymbolAsync(c_skip_lw, a.skip_lw, sizeof(float) * F_LOGC * F_NC, 0, cudaMemcpyDeviceToDevice, ctx->stream));
+            if (ctx->device < 64) g_skip_owner[ctx->device] = ctx->model_stamp;
+        }
+    }
     p.w_bytes = (uint32_t)NCH * 5 * 2 * NF * 16;          // [chunk][dx][plane][N' rows][16 B]
     p.strips = (a.w + F_SW - 1) / F_SW;
     // segments: multiples of 4 rows (row pairs x 2 groups); aim at >= 4 items per CTA

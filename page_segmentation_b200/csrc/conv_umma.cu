@@ -37,26 +37,29 @@ namespace {
 constexpr int TILE_M = 128;
 constexpr int kThreads = 192;       // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 constexpr int kMaxStages = 4;
-constexpr int kHeadThreads = 64 + 12 * 32;   // fused head: 12 epilogue warps (3 per TMEM lane quarter)
+constexpr int kHeadThreads = 64 + 8 * 32;    // fused head: 8 epilogue warps (2 per TMEM lane quarter)
 
 template <int NPAD> struct Cfg {
     static constexpr int R = NPAD <= 64 ? 8 : (NPAD <= 80 ? 6 : 4);      // accumulator rows per tile
     static constexpr int ACC = (2 * R * NPAD <= 512) ? 2 : 1;             // TMEM accumulator stages
 };
 
-enum { EPI_STORE = 0, EPI_DECONV = 1, EPI_HEAD = 2, EPI_HEAD_SKIP = 3 };
+enum { EPI_STORE = 0, EPI_DECONV = 1, EPI_HEAD = 2 };
 
-// Fused FCN head (modes EPI_HEAD*): the GEMM is deconv5 = Conv2DTranspose(20, 2x2, s2, linear)
-// (model.py:83 / :229) with N column J = tap * 20 + o; its epilogue keeps deconv5 in fp32
-// registers and applies concat[deconv5, conv2] -> logits 1x1 -> softmax/argmax (model.py:85-88,
-// network.py:258-259) and the colour masks (output.py:44-60) per cropped output pixel.
-constexpr int HEAD_DCO = 20, HEAD_SKIPC = 30, HEAD_NC = 4;
-__constant__ float c_head_lw[(HEAD_DCO + HEAD_SKIPC) * HEAD_NC];   // logits weights [cin][4 classes], zero padded
-__constant__ float c_head_lb[HEAD_NC];                             // logits bias (+ folded deconv5 bias)
+// Fused FCN head (mode EPI_HEAD).  deconv5 = Conv2DTranspose(20, 2x2, s2, linear) (model.py:83 / :229)
+// feeds the 1x1 logits layer (model.py:88 / :232) with no activation in between, so the two compose into
+// ONE linear map per 2x2 tap:  M[tap][c][k] = sum_o K5[tap][c][o] * lw[o][k]  (host, double precision).
+// The GEMM has N = 32 columns: J = tap*4 + k holds the high operand half of M, J = 16 + tap*4 + k the low
+// half (M = hi + lo, both in the model precision: the composed weights keep ~16 mantissa bits).  The
+// epilogue adds the conv2 share of the logits (written by conv2's own epilogue from its fp32
+// accumulators, conv_fold.cu) and the folded bias, then takes softmax/argmax (network.py:258-259) per
+// cropped output pixel (model.py:29-42).  deconv5, the concat and the logits tensor never exist in HBM.
+constexpr int HEAD_NC = 4;
+__constant__ float c_head_lb[HEAD_NC];     // logits bias + deconv5 bias + conv2 bias folded through the logits weights
 int64_t g_head_owner[64] = {0};
 
 struct HeadEpi {
-    const void* skip; int skip_cp;         // conv2 activation at full resolution (2h x 2w grid)
+    const float4* plog;                    // [n][2h][2w] conv2 share of the logits or null (model_fcn)
     int n_classes, hs, ws;                 // crop (model.py:29-42)
     uint8_t* labels; float* logits; float* prob;       // the colour masks are a separate, fully vectorised pass
 };
@@ -236,7 +239,7 @@ conv_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm0, co
             for (int i = threadIdx.x - 64; i < NPAD; i += epi_threads) {
                 int o = cbase + i;
                 if (MODE == EPI_DECONV) o = (cbase + i) % p.co_t;
-                if (MODE >= EPI_HEAD) o = 0x7fffffff;              // deconv5 bias is folded into c_head_lb
+                if (MODE >= EPI_HEAD) o = 0x7fffffff;              // all biases are folded into c_head_lb
                 s_bias[i] = o < p.cout ? __ldg(p.bias + o) : 0.f;
             }
             asm volatile("bar.sync 1, %0;" ::"r"(epi_threads) : "memory");
@@ -246,87 +249,59 @@ conv_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm0, co
             const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * R * NPAD);
 
             if constexpr (MODE >= EPI_HEAD) {
-                // one thread = one deconv5 input pixel = a 2x2 block of output pixels; the two pixels of an
-                // output row are handled together: their conv2 skip units are 32 contiguous bytes per plane
-                // (fully coalesced across the warp) and all loads are issued before the first use.
+                // one thread = one input pixel of deconv5 = a 2x2 block of output pixels x 4 classes
                 const HeadEpi& hd = p.head;
                 const int oh = 2 * p.h, ow = 2 * p.w;
-                const T* sk = reinterpret_cast<const T*>(hd.skip);
 #pragma unroll 1
                 for (int r = group; r < R; r += ngroups) {
                     const int y = y0 + r;
-#pragma unroll 1
-                    for (int i2 = 0; i2 < 2; ++i2) {                  // output row 2y + i2, taps t = 2*i2 + {0,1}
-                        const int oy = 2 * y + i2, ox = 2 * x;
-                        const bool rowok = xok && y < p.h && oy < hd.hs;
-                        const bool v0ok = rowok && ox < hd.ws, v1ok = rowok && ox + 1 < hd.ws;
-                        uint32_t va[2][16], vb[2][4];
+                    uint32_t vh[16], vl[16];
+                    tmem_ld16(t_lane + (uint32_t)(r * NPAD), vh);
+                    tmem_ld16(t_lane + (uint32_t)(r * NPAD + 16), vl);
+                    const bool rok = xok && y < p.h;
+                    float4 pl[2][2];
 #pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            tmem_ld16(t_lane + (uint32_t)(r * NPAD + (2 * i2 + j) * HEAD_DCO), va[j]);
-                            tmem_ld4(t_lane + (uint32_t)(r * NPAD + (2 * i2 + j) * HEAD_DCO + 16), vb[j]);
+                    for (int i2 = 0; i2 < 2; ++i2) {
+                        const int oy = 2 * y + i2;
+                        if (hd.plog && rok && oy < hd.hs) {
+                            // the two pixels of an output row: 32 contiguous bytes per thread, 1 KB per warp
+                            const float4* src = hd.plog + ((size_t)page * oh + oy) * ow + 2 * x;
+                            pl[i2][0] = __ldg(src);
+                            pl[i2][1] = __ldg(src + 1);
+                        } else {
+                            pl[i2][0] = pl[i2][1] = make_float4(0.f, 0.f, 0.f, 0.f);
                         }
-                        uint4 raw[2][4];
-                        if constexpr (MODE == EPI_HEAD_SKIP) {
+                    }
+                    tmem_ld_wait();
 #pragma unroll
-                            for (int g = 0; g < 4; ++g) {              // 30 channels live in 4 planes of 8
-                                const uint4* src = reinterpret_cast<const uint4*>(sk + act_idx(page, hd.skip_cp, oh, ow, g * 8, rowok ? oy : 0, rowok ? ox : 0));
-                                raw[0][g] = rowok ? __ldg(src) : make_uint4(0, 0, 0, 0);
-                                raw[1][g] = rowok ? __ldg(src + 1) : make_uint4(0, 0, 0, 0);   // ox + 1 < ow always (ow even)
-                            }
+                    for (int t = 0; t < 4; ++t) {                      // tap = 2*i2 + j -> output pixel (2y+i2, 2x+j)
+                        const int oy = 2 * y + (t >> 1), ox = 2 * x + (t & 1);
+                        if (!(rok && oy < hd.hs && ox < hd.ws)) continue;
+                        const float4 pp = pl[t >> 1][t & 1];
+                        float lg[HEAD_NC];
+                        lg[0] = (__uint_as_float(vh[t * 4 + 0]) + __uint_as_float(vl[t * 4 + 0])) + pp.x + c_head_lb[0];
+                        lg[1] = (__uint_as_float(vh[t * 4 + 1]) + __uint_as_float(vl[t * 4 + 1])) + pp.y + c_head_lb[1];
+                        lg[2] = (__uint_as_float(vh[t * 4 + 2]) + __uint_as_float(vl[t * 4 + 2])) + pp.z + c_head_lb[2];
+                        lg[3] = (__uint_as_float(vh[t * 4 + 3]) + __uint_as_float(vl[t * 4 + 3])) + pp.w + c_head_lb[3];
+                        int best = 0;
+                        float bv = lg[0];
+#pragma unroll
+                        for (int k = 1; k < HEAD_NC; ++k)
+                            if (k < hd.n_classes && lg[k] > bv) { bv = lg[k]; best = k; }      // first maximum wins
+                        const size_t opix = ((size_t)page * hd.hs + oy) * hd.ws + ox;
+                        if (hd.labels) hd.labels[opix] = (uint8_t)best;
+                        if (hd.logits) {
+#pragma unroll
+                            for (int k = 0; k < HEAD_NC; ++k)
+                                if (k < hd.n_classes) hd.logits[opix * hd.n_classes + k] = lg[k];
                         }
-                        tmem_ld_wait();
+                        if (hd.prob) {
+                            float e[HEAD_NC], sum = 0.f;
 #pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            float lg[HEAD_NC];
+                            for (int k = 0; k < HEAD_NC; ++k) { e[k] = k < hd.n_classes ? expf(lg[k] - bv) : 0.f; sum += e[k]; }
 #pragma unroll
-                            for (int k = 0; k < HEAD_NC; ++k) lg[k] = c_head_lb[k];
-#pragma unroll
-                            for (int o = 0; o < HEAD_DCO; ++o) {
-                                const float d = __uint_as_float(o < 16 ? va[j][o < 16 ? o : 0] : vb[j][o >= 16 ? o - 16 : 0]);
-#pragma unroll
-                                for (int k = 0; k < HEAD_NC; ++k) lg[k] = fmaf(d, c_head_lw[o * HEAD_NC + k], lg[k]);
-                            }
-                            if constexpr (MODE == EPI_HEAD_SKIP) {
-#pragma unroll
-                                for (int g = 0; g < 4; ++g) {
-                                    const uint32_t wds[4] = {raw[j][g].x, raw[j][g].y, raw[j][g].z, raw[j][g].w};
-#pragma unroll
-                                    for (int e = 0; e < 4; ++e) {
-                                        const float2 f = unpack2<T>(wds[e]);
-                                        const int c0 = g * 8 + 2 * e;
-                                        if (c0 < HEAD_SKIPC) {
-#pragma unroll
-                                            for (int k = 0; k < HEAD_NC; ++k) lg[k] = fmaf(f.x, c_head_lw[(HEAD_DCO + c0) * HEAD_NC + k], lg[k]);
-                                        }
-                                        if (c0 + 1 < HEAD_SKIPC) {
-#pragma unroll
-                                            for (int k = 0; k < HEAD_NC; ++k) lg[k] = fmaf(f.y, c_head_lw[(HEAD_DCO + c0 + 1) * HEAD_NC + k], lg[k]);
-                                        }
-                                    }
-                                }
-                            }
-                            if (!(j ? v1ok : v0ok)) continue;
-                            int best = 0;
-                            float bv = lg[0];
-#pragma unroll
-                            for (int k = 1; k < HEAD_NC; ++k)
-                                if (k < hd.n_classes && lg[k] > bv) { bv = lg[k]; best = k; }      // first maximum wins
-                            const size_t opix = ((size_t)page * hd.hs + oy) * hd.ws + ox + j;
-                            if (hd.labels) hd.labels[opix] = (uint8_t)best;
-                            if (hd.logits) {
-#pragma unroll
-                                for (int k = 0; k < HEAD_NC; ++k)
-                                    if (k < hd.n_classes) hd.logits[opix * hd.n_classes + k] = lg[k];
-                            }
-                            if (hd.prob) {
-                                float e[HEAD_NC], sum = 0.f;
-#pragma unroll
-                                for (int k = 0; k < HEAD_NC; ++k) { e[k] = k < hd.n_classes ? expf(lg[k] - bv) : 0.f; sum += e[k]; }
-#pragma unroll
-                                for (int k = 0; k < HEAD_NC; ++k)
-                                    if (k < hd.n_classes) hd.prob[opix * hd.n_classes + k] = e[k] / sum;
-                            }
+                            for (int k = 0; k < HEAD_NC; ++k)
+                                if (k < hd.n_classes) hd.prob[opix * hd.n_classes + k] = e[k] / sum;
                         }
                     }
                 }
@@ -468,7 +443,7 @@ int launch_t(pcs_ctx* ctx, const UmmaConvArgs& a) {
     p.sw = TILE_M - (a.k - 1);
     p.strips = (a.w + p.sw - 1) / p.sw;
     p.rowblocks = (a.h + R - 1) / R;
-    const int ncols = a.mode == EPI_STORE ? a.cout : 4 * a.co_t;
+    const int ncols = a.mode == EPI_STORE ? a.cout : (a.mode == EPI_DECONV ? 4 * a.co_t : NPAD);
     p.ntiles_n = (ncols + NPAD - 1) / NPAD;
     p.num_tiles = a.n * p.strips * p.rowblocks * p.ntiles_n;
     p.a_rows = R + a.k - 1;
@@ -494,10 +469,9 @@ int launch_t(pcs_ctx* ctx, const UmmaConvArgs& a) {
     const int grid = std::min(p.num_tiles, ctx->sm_count);
     if constexpr (MODE >= EPI_HEAD) {
         const UmmaHeadArgs& h = *a.head;
-        p.head.skip = h.skip; p.head.skip_cp = h.skip_cp; p.head.n_classes = h.n_classes; p.head.hs = h.hs; p.head.ws = h.ws;
+        p.head.plog = reinterpret_cast<const float4*>(h.plog); p.head.n_classes = h.n_classes; p.head.hs = h.hs; p.head.ws = h.ws;
         p.head.labels = h.labels; p.head.logits = h.logits; p.head.prob = h.prob;
         if (ctx->device >= 64 || g_head_owner[ctx->device] != ctx->model_stamp) {
-            PCS_CUDA(ctx, cudaMemcpyToSymbolAsync(c_head_lw, h.lw_padded, sizeof(float) * (HEAD_DCO + HEAD_SKIPC) * HEAD_NC, 0, cudaMemcpyDeviceToDevice, ctx->stream));
             PCS_CUDA(ctx, cudaMemcpyToSymbolAsync(c_head_lb, h.lb_folded, sizeof(float) * HEAD_NC, 0, cudaMemcpyDeviceToDevice, ctx->stream));
             if (ctx->device < 64) g_head_owner[ctx->device] = ctx->model_stamp;
         }
@@ -518,8 +492,7 @@ int launch_npad(pcs_ctx* ctx, const UmmaConvArgs& a) {
         case 3064: return launch_t<T, 64, 3, EPI_STORE>(ctx, a);
         case 3128: return launch_t<T, 128, 3, EPI_STORE>(ctx, a);
         case 101128: return launch_t<T, 128, 1, EPI_DECONV>(ctx, a);
-        case 201080: return launch_t<T, 80, 1, EPI_HEAD>(ctx, a);
-        case 301080: return launch_t<T, 80, 1, EPI_HEAD_SKIP>(ctx, a);
+        case 201032: return launch_t<T, 32, 1, EPI_HEAD>(ctx, a);
         default: return set_err(ctx, PCS_ERR_ARG, "conv_umma: no instantiation for mode=%d k=%d N tile %d", a.mode, a.k, a.npad);
     }
 }
@@ -528,7 +501,7 @@ int launch_npad(pcs_ctx* ctx, const UmmaConvArgs& a) {
 
 bool umma_supported(int k, int npad) {
     const int key = k * 1000 + npad;
-    return key == 5032 || key == 5048 || key == 5064 || key == 5080 || key == 3064 || key == 3128 || key == 1128 || key == 1080;
+    return key == 5032 || key == 5048 || key == 5064 || key == 5080 || key == 3064 || key == 3128 || key == 1128 || key == 1032;
 }
 
 // Operand image [ntile][chunk][tap][plane][NPAD][8]; chunk runs over the 16-channel groups of
@@ -600,9 +573,48 @@ size_t umma_weight_image_deconv(const float* w32 /*[4][cin][cout]*/, const int* 
     return out.size() * sizeof(uint16_t);
 }
 
+// Operand image of the fused head: composed deconv5 x logits map m[tap][cin][4] split into two operand
+// halves; N column J = tap*4 + k (high half), 16 + tap*4 + k (low half); layout [chunk][plane][32][8].
+size_t umma_weight_image_head(const double* m /*[4][cin][4]*/, const int* src_c, int nsrc, int precision,
+                              std::vector<uint16_t>& out) {
+    int cin = 0, nchunks = 0;
+    for (int s = 0; s < nsrc; ++s) { cin += src_c[s]; nchunks += pad16(src_c[s]) / 16; }
+    constexpr int npad = 32;
+    out.assign((size_t)nchunks * 2 * npad * 8, 0);
+    auto split = [&](double v, uint16_t& hi, uint16_t& lo) {
+        if (precision == PCS_PREC_BF16) {
+            __nv_bfloat16 h = __float2bfloat16_rn((float)v);
+            __nv_bfloat16 l = __float2bfloat16_rn((float)(v - (double)__bfloat162float(h)));
+            hi = *reinterpret_cast<uint16_t*>(&h); lo = *reinterpret_cast<uint16_t*>(&l);
+        } else {
+            __half h = __float2half_rn((float)v);
+            __half l = __float2half_rn((float)(v - (double)__half2float(h)));
+            hi = *reinterpret_cast<uint16_t*>(&h); lo = *reinterpret_cast<uint16_t*>(&l);
+        }
+    };
+    int chunk = 0, cbase = 0;
+    for (int s = 0; s < nsrc; ++s) {
+        for (int lc = 0; lc < pad16(src_c[s]) / 16; ++lc, ++chunk)
+            for (int pl = 0; pl < 2; ++pl)
+                for (int e = 0; e < 8; ++e) {
+                    const int c = lc * 16 + pl * 8 + e;
+                    if (c >= src_c[s]) continue;
+                    for (int t = 0; t < 4; ++t)
+                        for (int k = 0; k < 4; ++k) {
+                            uint16_t hi, lo;
+                            split(m[((size_t)t * cin + cbase + c) * 4 + k], hi, lo);
+                            out[(((size_t)chunk * 2 + pl) * npad + t * 4 + k) * 8 + e] = hi;
+                            out[(((size_t)chunk * 2 + pl) * npad + 16 + t * 4 + k) * 8 + e] = lo;
+                        }
+                }
+        cbase += src_c[s];
+    }
+    return out.size() * sizeof(uint16_t);
+}
+
 int launch_conv_umma(pcs_ctx* ctx, const UmmaConvArgs& a) {
-    if (a.mode >= EPI_HEAD && (!a.head || a.co_t != HEAD_DCO || a.head->n_classes > HEAD_NC))
-        return set_err(ctx, PCS_ERR_ARG, "conv_umma: fused head needs 20 deconv channels and <= %d classes", HEAD_NC);
+    if (a.mode >= EPI_HEAD && (!a.head || a.npad != 32 || a.head->n_classes > HEAD_NC))
+        return set_err(ctx, PCS_ERR_ARG, "conv_umma: fused head needs the N=32 operand image and <= %d classes", HEAD_NC);
     if (!umma_supported(a.k, a.npad)) return set_err(ctx, PCS_ERR_ARG, "conv_umma: unsupported k=%d N=%d", a.k, a.npad);
     if (a.src[0].cp % 16 || (a.nsrc > 1 && a.src[1].cp % 16)) return set_err(ctx, PCS_ERR_ARG, "conv_umma: channel stride not a multiple of 16");
     if (a.out && a.out_cp % 16) return set_err(ctx, PCS_ERR_ARG, "conv_umma: output stride");

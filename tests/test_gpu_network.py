@@ -24,14 +24,19 @@ TOL = {"bf16": dict(twin_max=2e-3, twin_mean=6e-5, f32_max=8e-3, agree=0.997),
        "fp16": dict(twin_max=3e-4, twin_mean=1e-5, f32_max=1e-3, agree=0.999)}
 
 
-def _device_predict(arch, weights, n_classes, image, precision, engine):
+def _device_predict(arch, weights, n_classes, image, precision, engine, keep=False):
     from page_segmentation_b200.lib.network import Network
     from page_segmentation_b200.lib.architecture import Architecture
     from page_segmentation_b200.lib.dataset import SingleData
     net = Network("Predict", n_classes=n_classes, model_constructor=Architecture(arch), weights=weights,
                   precision=precision)
     net._context().set_engine(engine)
-    return net, net.predict_single_data(SingleData(image=image))
+    # keep=True: also store the activations the fused kernels never write (conv2 of fcn_skip)
+    net._context().set_keep_activations(keep)
+    try:
+        return net, net.predict_single_data(SingleData(image=image))
+    finally:
+        net._context().set_keep_activations(False)
 
 
 def _small_input(seed, h, w):
@@ -52,11 +57,12 @@ def test_fcn_logits_and_argmax(ctx, arch, hw, precision, engine):
     assert pred.shape == img.shape and pred.dtype == np.int64
     tol = TOL[precision]
 
-    twin = onet.Forward(arch, W, 3, bf16=True)
+    fused = engine == "umma"          # the tensor engine composes deconv5 with the logits (fp32-grade weights)
+    twin = onet.Forward(arch, W, 3, bf16=True, fused_head=fused)
     if precision == "fp16":
         onet._bf16, saved = (lambda t: t.to(torch.float16).to(t.dtype)), onet._bf16
         try:
-            twin = onet.Forward(arch, W, 3, bf16=True)
+            twin = onet.Forward(arch, W, 3, bf16=True, fused_head=fused)
             lt, _ = twin.logits(img)
         finally:
             onet._bf16 = saved
@@ -90,7 +96,7 @@ def test_fcn_skip_layerwise_vs_twin(ctx, engine):
     """Every stored activation against the twin: localises layout / weight-transform errors."""
     img, _ = _small_input(3, 96, 128)
     W = synth.make_weights("fcn_skip", 3, seed=5)
-    net, (logit, _, _) = _device_predict("fcn_skip", W, 3, img, "bf16", engine)
+    net, (logit, _, _) = _device_predict("fcn_skip", W, 3, img, "bf16", engine, keep=True)
     c = net._context()
     names = ["conv1", "conv2", "conv3", "conv5", "conv6", "conv7", "deconv1", "deconv2", "deconv3", "deconv4"]
     twin = onet.Forward("fcn_skip", W, 3, bf16=True)
@@ -157,7 +163,7 @@ def test_umma_one_hot_tap_is_a_shifted_copy(ctx, tap, precision):
     for c in range(20):
         W[0][0][2, 2, 0, c] = (c + 1) / 32.0
         W[1][0][ty, tx, c, c] = 1.0
-    net, _ = _device_predict("fcn_skip", W, 3, img, precision, "umma")
+    net, _ = _device_predict("fcn_skip", W, 3, img, precision, "umma", keep=True)
     c = net._context()
     conv1 = c.debug_activation("conv1")[0]
     conv2 = c.debug_activation("conv2")[0]
