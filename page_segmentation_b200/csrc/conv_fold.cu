@@ -63,7 +63,7 @@ struct FoldParams {
     int ring;                               // input-row ring depth
 };
 
-template <typename T, int NPAD, int NCH>
+template <typename T, int NPAD, int NCH, int RING>
 __global__ void __launch_bounds__(F_THREADS, 1)
 conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
     constexpr int NF = 5 * NPAD;                                     // folded N
@@ -73,6 +73,7 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
                                 ((std::is_same<T, __nv_bfloat16>::value ? 1u : 0u) << 10) | ((uint32_t)(128 >> 4) << 24);
     static_assert(NF <= 256 && NF % 16 == 0, "folded N must be a legal UMMA N");
     static_assert(F_SLOTS * NPAD <= 512, "accumulator ring must fit TMEM");
+    static_assert(RING % F_SLOTS == 0 && RING <= F_RING_MAX, "the issue loop is unrolled over one ring period");
 
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_full[F_RING_MAX], s_empty[F_RING_MAX], s_wfull, s_tfull[F_SLOTS], s_tempty[F_SLOTS];
@@ -85,7 +86,7 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
     uint8_t* ring = base + ((p.w_bytes + 1023) / 1024) * 1024;
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < p.ring; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 1); }
+        for (int s = 0; s < RING; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 1); }
         mbar_init(&s_wfull, 1);
         for (int s = 0; s < F_SLOTS; ++s) { mbar_init(&s_tfull[s], 1); mbar_init(&s_tempty[s], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -116,7 +117,7 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
                 const int rows = min(p.seg_rows, p.h - ys);
                 const int x0 = strip * F_SW - 2;
                 for (int i = 0; i < rows + 4; ++i, ++k) {
-                    const uint32_t slot = k % (uint32_t)p.ring, pass = k / (uint32_t)p.ring;
+                    const uint32_t slot = k % (uint32_t)RING, pass = k / (uint32_t)RING;
                     mbar_wait(&s_empty[slot], (pass & 1u) ^ 1u);
                     mbar_expect_tx(&s_full[slot], ROW_BYTES);
                     // box = 256 u64 (128 px x 16 B) x 1 row x (2 * NCH) planes
@@ -126,52 +127,60 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        // step k (one input row) accumulates into the output slots k .. k+4 (mod 8) and completes slot k
-        const bool leader = elect_one();
-        const uint32_t hi = (uint32_t)(make_desc(0, 0, 128) >> 32);
-        constexpr uint32_t a_lbo = ((2048u >> 4) & 0x3fffu) << 16;                    // the two K planes of a chunk
-        constexpr uint32_t b_lbo = (((uint32_t)NF * 16u >> 4) & 0x3fffu) << 16;
-        mbar_wait(&s_wfull, 0);
-        const uint32_t ring_lo = (smem_u32(ring) >> 4) & 0x3fffu;
-        const uint32_t b_lo0 = ((smem_u32(s_w) >> 4) & 0x3fffu) | b_lbo;
-        for (int s = 0; s < F_SLOTS; ++s) mbar_wait(&s_tempty[s], 0);                  // every slot zeroed once
-        uint32_t k = 0;
-        for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-            const int rem = item % items_per_page;
-            const int seg = rem % p.segs;
-            const int ys = seg * p.seg_rows;
-            const int rows = min(p.seg_rows, p.h - ys);
-            for (int i = 0; i < rows + 4; ++i, ++k) {
-                const uint32_t in_slot = k % (uint32_t)p.ring;
-                mbar_wait(&s_full[in_slot], (k / (uint32_t)p.ring) & 1u);
-                // the newest output slot of the window must have been drained and re-zeroed by the epilogue
-                const uint32_t g_new = k + 4;
-                // tempty phase 0 = initial zeroing, phase n = drain of use n-1: use n waits for phase n
-                mbar_wait(&s_tempty[g_new % F_SLOTS], (g_new / F_SLOTS) & 1u);
-                tc_fence_after();
-                if (leader) {
-                    const uint32_t s0 = k % F_SLOTS;
-                    const uint32_t n1 = min(5u, (uint32_t)F_SLOTS - s0);              // blocks before the ring wraps
-                    const uint32_t a_row = ring_lo + in_slot * (ROW_BYTES >> 4);
-                    const uint32_t d1 = tmem_base + s0 * NPAD;
-                    const uint32_t idesc1 = IDESC0 | (((n1 * NPAD) >> 3) << 17);
-                    const uint32_t idesc2 = IDESC0 | ((((5u - n1) * NPAD) >> 3) << 17);
+        // step k (one input row) accumulates into the output slots k .. k+4 (mod 8) and completes slot k.
+        // The issuer does not care about work items, only about the number of input rows of this CTA, and
+        // the loop is unrolled over one ring period so that every shared-memory / TMEM address and the
+        // split of the window at the ring wrap are compile-time immediates: one thread must keep the
+        // tensor pipe fed, ~200 uniform-datapath instructions per row (the first version) did not.
+        if (elect_one()) {
+            uint32_t total = 0;
+            for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+                const int seg = (item % items_per_page) % p.segs;
+                total += (uint32_t)(min(p.seg_rows, p.h - seg * p.seg_rows) + 4);
+            }
+            const uint32_t hi = (uint32_t)(make_desc(0, 0, 128) >> 32);
+            constexpr uint32_t a_lbo = ((2048u >> 4) & 0x3fffu) << 16;                    // the two K planes of a chunk
+            constexpr uint32_t b_lbo = (((uint32_t)NF * 16u >> 4) & 0x3fffu) << 16;
+            mbar_wait(&s_wfull, 0);
+            const uint32_t a_lo0 = ((smem_u32(ring) >> 4) & 0x3fffu) | a_lbo;
+            const uint32_t b_lo0 = ((smem_u32(s_w) >> 4) & 0x3fffu) | b_lbo;
+            for (int s = 0; s < F_SLOTS; ++s) mbar_wait(&s_tempty[s], 0);                  // every slot zeroed once
+            tc_fence_after();
+            for (uint32_t kk = 0; kk < total; kk += RING) {
+                const uint32_t ring_phase = (kk / RING) & 1u;
+#pragma unroll
+                for (int u = 0; u < RING; ++u) {
+                    if (kk + u >= total) break;
+                    mbar_wait(&s_full[u], ring_phase);
+                    // the newest output slot of the window must have been drained and re-zeroed by the epilogue:
+                    // tempty phase 0 = initial zeroing, phase n = drain of use n-1: use n waits for phase n
+                    mbar_wait(&s_tempty[(u + 4) % F_SLOTS], ((kk + u + 4) / F_SLOTS) & 1u);
+                    tc_fence_after();
+                    // opaque copies: keeps the descriptor arithmetic (base + immediate) next to its MMA instead of
+                    // having every one of the RING x NCH x 5 sums hoisted out of the loop into spilled registers
+                    uint32_t a_step, b_step, d_step;
+                    asm volatile("mov.u32 %0, %3;\n\tmov.u32 %1, %4;\n\tmov.u32 %2, %5;"
+                                 : "=r"(a_step), "=r"(b_step), "=r"(d_step) : "r"(a_lo0), "r"(b_lo0), "r"(tmem_base));
+                    const int s0 = u % F_SLOTS;
+                    const int n1 = (F_SLOTS - s0) < 5 ? (F_SLOTS - s0) : 5;           // blocks before the ring wraps
+                    const uint32_t idesc1 = IDESC0 | ((uint32_t)((n1 * NPAD) >> 3) << 17);
+                    const uint32_t idesc2 = IDESC0 | ((uint32_t)(((5 - n1) * NPAD) >> 3) << 17);
 #pragma unroll
                     for (int c = 0; c < NCH; ++c) {
 #pragma unroll
                         for (int dx = 0; dx < 5; ++dx) {
-                            const uint32_t a_lo = (a_row + (uint32_t)c * (4096u >> 4) + (uint32_t)dx) | a_lbo;
-                            const uint32_t b_lo = b_lo0 + (uint32_t)((c * 5 + dx) * (WDX_BYTES >> 4));
-                            tc_mma(d1, a_lo, hi, b_lo, hi, idesc1, 1u);               // slots are pre-zeroed: always accumulate
-                            if (n1 < 5u) tc_mma(tmem_base, a_lo, hi, b_lo + n1 * NPAD, hi, idesc2, 1u);
+                            const uint32_t a_lo = a_step + (uint32_t)(u * (ROW_BYTES >> 4) + c * (4096 >> 4) + dx);
+                            const uint32_t b_lo = b_step + (uint32_t)((c * 5 + dx) * (WDX_BYTES >> 4));
+                            tc_mma(d_step + (uint32_t)(s0 * NPAD), a_lo, hi, b_lo, hi, idesc1, 1u);   // slots are pre-zeroed
+                            if (n1 < 5) tc_mma(d_step, a_lo, hi, b_lo + (uint32_t)(n1 * NPAD), hi, idesc2, 1u);
                         }
                     }
-                    tc_commit(&s_empty[in_slot]);                                     // input row consumed
-                    tc_commit(&s_tfull[k % F_SLOTS]);                                 // output slot k is complete
+                    tc_commit(&s_empty[u]);                                               // input row consumed
+                    tc_commit(&s_tfull[s0]);                                              // output slot k is complete
                 }
-                __syncwarp();
             }
         }
+        __syncwarp();
     } else {
         // ===================== epilogue: drain one slot per output row =====================
         const int quarter = warp & 3, group = (warp - 2) >> 2;
@@ -299,7 +308,7 @@ EncodeTiledFn fold_get_encode() {
     return fn;
 }
 
-template <typename T, int NPAD, int NCH>
+template <typename T, int NPAD, int NCH, int RING>
 int launch_fold_t(pcs_ctx* ctx, const FoldConvArgs& a) {
     constexpr int NF = 5 * NPAD;
     FoldParams p{};
@@ -338,17 +347,16 @@ int launch_fold_t(pcs_ctx* ctx, const FoldConvArgs& a) {
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_err(ctx, PCS_ERR_CUDA, "conv_fold: cuTensorMapEncodeTiled failed with %d", (int)r);
     const size_t w_al = ((p.w_bytes + 1023) / 1024) * 1024;
-    p.ring = (int)std::min<size_t>(F_RING_MAX, (224 * 1024 - w_al) / ((size_t)NCH * 4096));
-    if (p.ring < 3) return set_err(ctx, PCS_ERR_ARG, "conv_fold: weights leave no room for the input ring");
-    const size_t smem = w_al + (size_t)p.ring * NCH * 4096 + 1024;
+    p.ring = RING;
+    const size_t smem = w_al + (size_t)RING * NCH * 4096 + 1024;
     if (smem + 2 * 1024 > 227 * 1024) return set_err(ctx, PCS_ERR_ARG, "conv_fold: %zu bytes of shared memory needed", smem);
     static size_t attr_set = 0;
     if (attr_set < smem) {
-        PCS_CUDA(ctx, cudaFuncSetAttribute(conv_fold_kernel<T, NPAD, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PCS_CUDA(ctx, cudaFuncSetAttribute(conv_fold_kernel<T, NPAD, NCH, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = smem;
     }
     const int grid = std::min(p.num_items, ctx->sm_count);
-    conv_fold_kernel<T, NPAD, NCH><<<grid, F_THREADS, smem, ctx->stream>>>(p, tm);
+    conv_fold_kernel<T, NPAD, NCH, RING><<<grid, F_THREADS, smem, ctx->stream>>>(p, tm);
     PCS_LAUNCH_CHECK(ctx, "conv_fold_kernel");
     return PCS_OK;
 }
@@ -357,9 +365,9 @@ template <typename T>
 int launch_fold_dispatch(pcs_ctx* ctx, const FoldConvArgs& a) {
     const int key = a.npad * 10 + a.nchunks;
     switch (key) {
-        case 322: return launch_fold_t<T, 32, 2>(ctx, a);     // conv2: 20(32) -> 30(32)
-        case 482: return launch_fold_t<T, 48, 2>(ctx, a);     // conv3: 30(32) -> 40(48)
-        case 483: return launch_fold_t<T, 48, 3>(ctx, a);     // conv4: 40(48) -> 40(48)
+        case 322: return launch_fold_t<T, 32, 2, 16>(ctx, a);     // conv2: 20(32) -> 30(32)
+        case 482: return launch_fold_t<T, 48, 2, 16>(ctx, a);     // conv3: 30(32) -> 40(48)
+        case 483: return launch_fold_t<T, 48, 3, 8>(ctx, a);     // conv4: 40(48) -> 40(48)
         default: return set_err(ctx, PCS_ERR_ARG, "conv_fold: no instantiation for N=%d chunks=%d", a.npad, a.nchunks);
     }
 }
