@@ -139,8 +139,10 @@ static void clear_stage_times(pcs_ctx* ctx) {
 // ---------------------------------------------------------------------------
 // forward schedules
 // ---------------------------------------------------------------------------
+// channel padding: whole 8-channel planes for the tensor engine (its kernels read planes through TMA and
+// take an odd plane count in their stride), pairs of planes for the CUDA-core kernels (16-channel tiles)
 static int new_act(pcs_ctx* ctx, const char* name, int n, int h, int w, int c, Act* out) {
-    Act a; a.n = n; a.h = h; a.w = w; a.c = c; a.cp = pad16(c);
+    Act a; a.n = n; a.h = h; a.w = w; a.c = c; a.cp = ctx->engine == PCS_ENGINE_UMMA ? pad8(c) : pad16(c);
     a.p = arena_alloc(ctx, a.bytes());
     if (!a.p) return set_err(ctx, PCS_ERR_NOMEM, "activation arena exhausted at %s", name);
     ctx->acts[name] = a;
@@ -168,7 +170,7 @@ static int run_conv(pcs_ctx* ctx, const char* lname, const Act* s0, const Act* s
         FoldConvArgs f;
         f.src = src_of(*s0);
         f.n = n; f.h = h; f.w = w; f.k = L->k;
-        f.wimg = L->d_wfold; f.b32 = L->d_b32; f.cout = L->cout; f.npad = L->npad; f.nchunks = s0->cp / 16; f.relu = L->relu;
+        f.wimg = L->d_wfold; f.b32 = L->d_b32; f.cout = L->cout; f.npad = L->npad; f.nplanes = s0->cp / 8; f.relu = L->relu;
         f.out = out ? out->p : nullptr; f.out_cp = out ? out->cp : 0;
         f.pool_out = pool_out ? pool_out->p : nullptr; f.pool_cp = pool_out ? pool_out->cp : 0;
         f.plog = plog; f.skip_lw = skip_lw;
@@ -200,13 +202,11 @@ static int run_conv1_u8(pcs_ctx* ctx, const char* lname, const uint8_t* d_image,
     Layer* L = find_layer(ctx, lname);
     if (!L) return set_err(ctx, PCS_ERR_STATE, "layer %s missing", lname);
     StageScope ts(ctx, lname);
-    static const bool use_ffma = getenv("PCSEG_CONV1") && !strcmp(getenv("PCSEG_CONV1"), "ffma");
-    if (ctx->engine == PCS_ENGINE_UMMA && L->d_wmma && L->k == 5 && L->cout == 20 && !use_ffma)
+    if (ctx->engine == PCS_ENGINE_UMMA && L->d_wmma && L->k == 5 && L->cout == 20)
         return launch_conv1_umma(ctx, d_image, n, hs, ws, out->h, out->w, L->d_wmma, L->d_b32, out->p, out->cp);
     DirectConvArgs a;
     a.src[0].p = d_image; a.src[0].c = 1; a.src[0].cp = 1; a.nsrc = 1;
     a.src_u8 = 1; a.img_h = hs; a.img_w = ws;
-    a.fast_first = ctx->engine == PCS_ENGINE_UMMA;     // the DIRECT engine keeps the generic kernel as reference
     a.n = n; a.h = out->h; a.w = out->w; a.k = L->k; a.pad = L->k / 2;
     a.w32 = L->d_w32; a.b32 = L->d_b32; a.cin = 1; a.cout = L->cout; a.relu = L->relu;
     a.out = out->p; a.out_cp = out->cp;
@@ -553,7 +553,7 @@ int pcs_model_load(pcs_ctx* ctx, int arch, int n_classes, int precision, const p
             L.npad = std::min(pad16(L.cout), 128);
             if (!umma_supported(L.k, L.npad) || (L.cout > 128 && L.cout % 128)) continue;
             L.wmma_bytes = umma_weight_image(L.h_w32.data(), L.k * L.k, src_c, nsrc, L.cout, L.npad, precision, img);
-            if (fold_supported(L.k, L.npad, pad16(L.cin) / 16, nsrc)) {
+            if (fold_supported(L.k, L.npad, pad8(L.cin) / 8, nsrc)) {
                 std::vector<uint16_t> fimg;
                 const size_t fb = fold_weight_image(L.h_w32.data(), L.cin, L.cout, L.npad, precision, fimg);
                 PCS_CUDA(ctx, cudaMalloc(&L.d_wfold, fb));

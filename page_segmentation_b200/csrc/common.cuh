@@ -23,7 +23,7 @@ constexpr int kMaxClasses = 16;
 // ---------------------------------------------------------------------------
 // Activation tensors: plane-major "NC/8HW8": [n][cp/8][h][w][8 channels], i.e. one
 // 16-byte unit per (pixel, 8-channel group); channel count padded to a multiple
-// of 16 with zeros.  A plane row is contiguous in memory, which is what makes the
+// of 8 (tensor engine) or 16 (CUDA-core engine) with zeros.  A plane row is contiguous in memory, which is what makes the
 // TMA boxes of the tensor-core kernel 2 KB wide and every epilogue store a
 // 512-byte coalesced warp store.
 // ---------------------------------------------------------------------------
@@ -36,6 +36,7 @@ struct Act {
 };
 
 inline int pad16(int c) { return (c + 15) / 16 * 16; }
+inline int pad8(int c) { return (c + 7) / 8 * 8; }
 
 // element index of channel c at (page, y, x) of an activation with cp padded channels
 __host__ __device__ __forceinline__ size_t act_idx(int page, int cp, int h, int w, int c, int y, int x) {
@@ -260,13 +261,13 @@ struct FoldConvArgs {
     int n = 0, h = 0, w = 0, k = 5;
     const void* wimg = nullptr;
     const float* b32 = nullptr;
-    int cout = 0, npad = 0, nchunks = 0, relu = 0;
+    int cout = 0, npad = 0, nplanes = 0, relu = 0;      // nplanes: 8-channel planes of the source
     void* out = nullptr; int out_cp = 0;
     void* pool_out = nullptr; int pool_cp = 0;
     void* plog = nullptr;              // optional float4 [n][h][w]: this layer's share of the logits (fcn_skip conv2)
     const float* skip_lw = nullptr;    // device [32][4]: logits rows of this layer's channels, zero padded
 };
-bool fold_supported(int k, int npad, int nchunks, int nsrc);
+bool fold_supported(int k, int npad, int nplanes, int nsrc);
 size_t fold_weight_image(const float* w32 /*[25][cin][cout]*/, int cin, int cout, int npad, int precision, std::vector<uint16_t>& out);
 int launch_conv_fold(pcs_ctx* ctx, const FoldConvArgs& a);
 

@@ -11,7 +11,8 @@
 // to the fp32 accumulator, so the result matches the fp32 CUDA-core kernel to fp32 rounding.
 //
 // Warp roles (320 threads): warp 0 loads the weight image; warp 1 = MMA issuer + TMEM owner;
-// warps 2-5 = epilogue (bias, ReLU, pack, plane-major stores); warps 6-9 = builders.
+// warps 2-5 and 10-13 = epilogue (bias, ReLU, pack, plane-major stores; two warps per TMEM lane quarter
+// splitting the rows); warps 6-9 = builders.
 #include "common.cuh"
 #include "umma_ptx.cuh"
 
@@ -27,7 +28,7 @@ constexpr int C1_STAGES = 2;
 constexpr int C1_ROW_BYTES = 128 * 16;
 constexpr int C1_STAGE_BYTES = C1_ROWS * C1_ROW_BYTES;
 constexpr int C1_B_BYTES = 2 * 3 * 2 * C1_N * 16;      // [hi|lo][ks][plane][n][8]
-constexpr int C1_THREADS = 320;
+constexpr int C1_THREADS = 448;     // warp 0 weights, warp 1 MMA, warps 2-5 + 10-13 epilogue (2 per lane quarter), warps 6-9 builders
 constexpr int C1_RAW_W = 136;      // bytes per raw patch row: 128 pixel slots + 7 look-ahead (+1 pad)
 
 struct Conv1Params {
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv1_umma_kernel(const Conv1Pa
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         if (lane == 0) {
             for (int s = 0; s < C1_STAGES; ++s) { mbar_init(&s_full[s], 128); mbar_init(&s_empty[s], 1); }
-            for (int a = 0; a < 2; ++a) { mbar_init(&s_tfull[a], 1); mbar_init(&s_tempty[a], 4); }
+            for (int a = 0; a < 2; ++a) { mbar_init(&s_tfull[a], 1); mbar_init(&s_tempty[a], 8); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         }
@@ -121,9 +122,10 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv1_umma_kernel(const Conv1Pa
             if (++stage == C1_STAGES) { stage = 0; phase ^= 1u; }
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
-    } else if (warp >= 2 && warp < 6) {
+    } else if ((warp >= 2 && warp < 6) || warp >= 10) {
         // ===================== epilogue =====================
-        const int quarter = warp & 3;
+        const int quarter = warp & 3, rgroup = warp >= 10 ? 1 : 0;
+        const int nplanes = p.out_cp >> 3;                 // 3 (tensor engine: 20 -> 24 channels) or 4
         int acc = 0;
         uint32_t acc_phase = 0;
         T* out = reinterpret_cast<T*>(p.out);
@@ -140,7 +142,7 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv1_umma_kernel(const Conv1Pa
             tc_fence_after();
             const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * C1_R * C1_N);
 #pragma unroll 1
-            for (int r = 0; r < C1_R; ++r) {
+            for (int r = rgroup; r < C1_R; r += 2) {
                 uint32_t v0[16], v1[16];
                 tmem_ld16(t_lane + (uint32_t)(r * C1_N), v0);
                 tmem_ld16(t_lane + (uint32_t)(r * C1_N + 16), v1);
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv1_umma_kernel(const Conv1Pa
                     }
 #pragma unroll
                     for (int g = 0; g < 4; ++g)
-                        *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, p.h, p.w, g * 8, y, x)) =
+                        if (g < nplanes) *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, p.h, p.w, g * 8, y, x)) =
                             make_uint4(pack2<T>(f[g * 8 + 0], f[g * 8 + 1]), pack2<T>(f[g * 8 + 2], f[g * 8 + 3]),
                                        pack2<T>(f[g * 8 + 4], f[g * 8 + 5]), pack2<T>(f[g * 8 + 6], f[g * 8 + 7]));
                 }
@@ -165,7 +167,7 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv1_umma_kernel(const Conv1Pa
             if (lane == 0) mbar_arrive(&s_tempty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
-    } else if (warp >= 6) {
+    } else if (warp >= 6 && warp < 10) {
         // ===================== builders: expand input rows into K-major planes =====================
         // phase 1: the 13 x 135-byte uint8 patch is fetched with independent, coalesced byte loads (one
         // latency round); phase 2: every thread assembles the 16-byte unit of "its" pixel for all rows.
@@ -248,7 +250,7 @@ size_t conv1_umma_weight_image(const float* w32 /*[25][1][cout]*/, int cout, int
 
 int launch_conv1_umma(pcs_ctx* ctx, const uint8_t* d_image, int n, int img_h, int img_w, int h, int w, const void* wimg,
                       const float* bias, void* out, int out_cp) {
-    if (out_cp != C1_N) return set_err(ctx, PCS_ERR_ARG, "conv1_umma: output stride must be %d channels", C1_N);
+    if (out_cp != C1_N && out_cp != 24) return set_err(ctx, PCS_ERR_ARG, "conv1_umma: output stride must be 24 or %d channels", C1_N);
     Conv1Params p{};
     p.img = d_image; p.img_h = img_h; p.img_w = img_w; p.n = n; p.h = h; p.w = w;
     p.wimg = reinterpret_cast<const uint8_t*>(wimg); p.bias = bias; p.out = out; p.out_cp = out_cp;

@@ -24,11 +24,16 @@ namespace pcs {
 namespace {
 using namespace ptx;
 
-template <typename T> __device__ __forceinline__ float2 unpack2f(uint32_t v);
-template <> __device__ __forceinline__ float2 unpack2f<__nv_bfloat16>(uint32_t v) {
-    return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+// element-wise maximum of two packed operand pairs (max of rounded values == rounded max: rounding is monotonic)
+template <typename T> __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b);
+template <> __device__ __forceinline__ uint32_t max2<__nv_bfloat16>(uint32_t a, uint32_t b) {
+    const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
 }
-template <> __device__ __forceinline__ float2 unpack2f<__half>(uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
+template <> __device__ __forceinline__ uint32_t max2<__half>(uint32_t a, uint32_t b) {
+    const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+}
 
 __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
     const uint32_t z = 0u;
@@ -38,9 +43,10 @@ __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-constexpr int F_THREADS = 64 + 8 * 32;      // warp 0 producer, warp 1 MMA, warps 2-9 epilogue (2 groups x 4 quarters)
-constexpr int F_RING_MAX = 16;              // input-row ring entries (one row is consumed per step); actual depth fits smem
-constexpr int F_SLOTS = 8;                  // output-row accumulator slots in TMEM
+constexpr int F_EG = 3;                     // epilogue warp groups (4 warps = 4 TMEM lane quarters each)
+constexpr int F_THREADS = 64 + F_EG * 128;  // warp 0 producer, warp 1 MMA issuer, then the epilogue groups
+constexpr int F_RING_MAX = 20;              // input-row ring entries (one row is consumed per step)
+constexpr int F_SLOTS_MAX = 16;             // output-row accumulator slots in TMEM (512 columns / NPAD)
 constexpr int F_SW = 124;                   // valid output pixels per strip
 
 // conv2 -> logits partial sums (fcn_skip): concat[deconv5, conv2] -> logits 1x1 (model.py:85-88) is linear
@@ -63,20 +69,31 @@ struct FoldParams {
     int ring;                               // input-row ring depth
 };
 
-template <typename T, int NPAD, int NCH, int RING>
+// K steps of one input row (NPL = 8-channel planes of the source).  Plane pairs (2q, 2q+1) give one
+// K=16 MMA per dx (the two K halves are the two planes, LBO = plane pitch).  An odd last plane is paired
+// with ITSELF one pixel further: the K halves of one MMA are the taps (dx, dx+1) of that plane, LBO = 16 B
+// (one pixel), so 5 taps x 8 channels cost 3 MMAs -- (0,1), (2,3), (3,4) with zero weights for the
+// repeated tap 3 -- instead of the 5 that padding the plane count to even would cost.
+template <int NPL> struct FoldK {
+    static constexpr int PAIRS = NPL / 2, ODD = NPL & 1;
+    static constexpr int NMMA = PAIRS * 5 + ODD * 3;
+};
+
+template <typename T, int NPAD, int NPL, int RING, int SLOTS>
 __global__ void __launch_bounds__(F_THREADS, 1)
 conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
     constexpr int NF = 5 * NPAD;                                     // folded N
-    constexpr uint32_t ROW_BYTES = NCH * 2 * 2048;                   // one ring entry: all chunks of one input row
-    constexpr uint32_t WDX_BYTES = 2 * NF * 16;                      // weights of one (chunk, dx)
+    constexpr uint32_t ROW_BYTES = NPL * 2048;                       // one ring entry: all planes of one input row
+    constexpr uint32_t WDX_BYTES = 2 * NF * 16;                      // weights of one K step
+    constexpr int NMMA = FoldK<NPL>::NMMA;
     constexpr uint32_t IDESC0 = (1u << 4) | ((std::is_same<T, __nv_bfloat16>::value ? 1u : 0u) << 7) |
                                 ((std::is_same<T, __nv_bfloat16>::value ? 1u : 0u) << 10) | ((uint32_t)(128 >> 4) << 24);
     static_assert(NF <= 256 && NF % 16 == 0, "folded N must be a legal UMMA N");
-    static_assert(F_SLOTS * NPAD <= 512, "accumulator ring must fit TMEM");
-    static_assert(RING % F_SLOTS == 0 && RING <= F_RING_MAX, "the issue loop is unrolled over one ring period");
+    static_assert(SLOTS * NPAD <= 512 && SLOTS <= F_SLOTS_MAX && SLOTS >= 8, "accumulator ring must fit TMEM");
+    static_assert(RING % SLOTS == 0 && RING <= F_RING_MAX, "the issue loop is unrolled over one ring period");
 
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t s_full[F_RING_MAX], s_empty[F_RING_MAX], s_wfull, s_tfull[F_SLOTS], s_tempty[F_SLOTS];
+    __shared__ __align__(8) uint64_t s_full[F_RING_MAX], s_empty[F_RING_MAX], s_wfull, s_tfull[F_SLOTS_MAX], s_tempty[F_SLOTS_MAX];
     __shared__ uint32_t s_tmem_base;
     __shared__ float s_bias[NPAD];
 
@@ -88,7 +105,7 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < RING; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 1); }
         mbar_init(&s_wfull, 1);
-        for (int s = 0; s < F_SLOTS; ++s) { mbar_init(&s_tfull[s], 1); mbar_init(&s_tempty[s], 4); }
+        for (int s = 0; s < SLOTS; ++s) { mbar_init(&s_tfull[s], 1); mbar_init(&s_tempty[s], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -120,7 +137,7 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
                     const uint32_t slot = k % (uint32_t)RING, pass = k / (uint32_t)RING;
                     mbar_wait(&s_empty[slot], (pass & 1u) ^ 1u);
                     mbar_expect_tx(&s_full[slot], ROW_BYTES);
-                    // box = 256 u64 (128 px x 16 B) x 1 row x (2 * NCH) planes
+                    // box = 256 u64 (128 px x 16 B) x 1 row x NPL planes
                     tma_load_4d(ring + (size_t)slot * ROW_BYTES, &tm, &s_full[slot], x0 * 2, ys - 2 + i, 0, page);
                 }
             }
@@ -139,12 +156,13 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
                 total += (uint32_t)(min(p.seg_rows, p.h - seg * p.seg_rows) + 4);
             }
             const uint32_t hi = (uint32_t)(make_desc(0, 0, 128) >> 32);
-            constexpr uint32_t a_lbo = ((2048u >> 4) & 0x3fffu) << 16;                    // the two K planes of a chunk
+            constexpr uint32_t a_lbo_pair = ((2048u >> 4) & 0x3fffu) << 16;               // K halves = two planes
+            constexpr uint32_t a_lbo_self = ((16u >> 4) & 0x3fffu) << 16;                 // K halves = two taps of one plane
             constexpr uint32_t b_lbo = (((uint32_t)NF * 16u >> 4) & 0x3fffu) << 16;
             mbar_wait(&s_wfull, 0);
-            const uint32_t a_lo0 = ((smem_u32(ring) >> 4) & 0x3fffu) | a_lbo;
+            const uint32_t a_lo0 = (smem_u32(ring) >> 4) & 0x3fffu;
             const uint32_t b_lo0 = ((smem_u32(s_w) >> 4) & 0x3fffu) | b_lbo;
-            for (int s = 0; s < F_SLOTS; ++s) mbar_wait(&s_tempty[s], 0);                  // every slot zeroed once
+            for (int s = 0; s < SLOTS; ++s) mbar_wait(&s_tempty[s], 0);                    // every slot zeroed once
             tc_fence_after();
             for (uint32_t kk = 0; kk < total; kk += RING) {
                 const uint32_t ring_phase = (kk / RING) & 1u;
@@ -154,26 +172,29 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
                     mbar_wait(&s_full[u], ring_phase);
                     // the newest output slot of the window must have been drained and re-zeroed by the epilogue:
                     // tempty phase 0 = initial zeroing, phase n = drain of use n-1: use n waits for phase n
-                    mbar_wait(&s_tempty[(u + 4) % F_SLOTS], ((kk + u + 4) / F_SLOTS) & 1u);
+                    mbar_wait(&s_tempty[(u + 4) % SLOTS], ((kk + u + 4) / SLOTS) & 1u);
                     tc_fence_after();
                     // opaque copies: keeps the descriptor arithmetic (base + immediate) next to its MMA instead of
                     // having every one of the RING x NCH x 5 sums hoisted out of the loop into spilled registers
                     uint32_t a_step, b_step, d_step;
                     asm volatile("mov.u32 %0, %3;\n\tmov.u32 %1, %4;\n\tmov.u32 %2, %5;"
                                  : "=r"(a_step), "=r"(b_step), "=r"(d_step) : "r"(a_lo0), "r"(b_lo0), "r"(tmem_base));
-                    const int s0 = u % F_SLOTS;
-                    const int n1 = (F_SLOTS - s0) < 5 ? (F_SLOTS - s0) : 5;           // blocks before the ring wraps
+                    const int s0 = u % SLOTS;
+                    const int n1 = (SLOTS - s0) < 5 ? (SLOTS - s0) : 5;           // blocks before the ring wraps
                     const uint32_t idesc1 = IDESC0 | ((uint32_t)((n1 * NPAD) >> 3) << 17);
                     const uint32_t idesc2 = IDESC0 | ((uint32_t)(((5 - n1) * NPAD) >> 3) << 17);
 #pragma unroll
-                    for (int c = 0; c < NCH; ++c) {
-#pragma unroll
-                        for (int dx = 0; dx < 5; ++dx) {
-                            const uint32_t a_lo = a_step + (uint32_t)(u * (ROW_BYTES >> 4) + c * (4096 >> 4) + dx);
-                            const uint32_t b_lo = b_step + (uint32_t)((c * 5 + dx) * (WDX_BYTES >> 4));
-                            tc_mma(d_step + (uint32_t)(s0 * NPAD), a_lo, hi, b_lo, hi, idesc1, 1u);   // slots are pre-zeroed
-                            if (n1 < 5) tc_mma(d_step, a_lo, hi, b_lo + (uint32_t)(n1 * NPAD), hi, idesc2, 1u);
-                        }
+                    for (int q = 0; q < NMMA; ++q) {
+                        // K step q: plane pair (q / 5) at tap q % 5, or the odd last plane at taps {0, 2, 3} (+1)
+                        const bool pair = q < FoldK<NPL>::PAIRS * 5;
+                        const int t = q - FoldK<NPL>::PAIRS * 5;
+                        const int plane = pair ? 2 * (q / 5) : NPL - 1;
+                        const int dx = pair ? q % 5 : (t == 0 ? 0 : t + 1);
+                        const uint32_t a_lo = (a_step + (uint32_t)(u * (ROW_BYTES >> 4) + plane * (2048 >> 4) + dx)) |
+                                              (pair ? a_lbo_pair : a_lbo_self);
+                        const uint32_t b_lo = b_step + (uint32_t)(q * (WDX_BYTES >> 4));
+                        tc_mma(d_step + (uint32_t)(s0 * NPAD), a_lo, hi, b_lo, hi, idesc1, 1u);   // slots are pre-zeroed
+                        if (n1 < 5) tc_mma(d_step, a_lo, hi, b_lo + (uint32_t)(n1 * NPAD), hi, idesc2, 1u);
                     }
                     tc_commit(&s_empty[u]);                                               // input row consumed
                     tc_commit(&s_tfull[s0]);                                              // output slot k is complete
@@ -188,17 +209,17 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
         const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
         T* out = reinterpret_cast<T*>(p.out);
         T* pool = reinterpret_cast<T*>(p.pool);
-        // zero the whole accumulator ring once (both groups: each its own slots {0,1,4,5} / {2,3,6,7})
-        for (int s = 0; s < F_SLOTS; ++s) {
-            if (((s >> 1) & 1) != group) continue;
-            for (int c = 0; c < NPAD; c += 16) tmem_st16_zero(t_lane + (uint32_t)(s * NPAD + c));
+        // group 0 zeroes the whole accumulator ring once
+        if (group == 0) {
+            for (int s = 0; s < SLOTS; ++s)
+                for (int c = 0; c < NPAD; c += 16) tmem_st16_zero(t_lane + (uint32_t)(s * NPAD + c));
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0)
+                for (int s = 0; s < SLOTS; ++s) mbar_arrive(&s_tempty[s]);            // completes phase 0 of every slot
         }
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        for (int s = 0; s < F_SLOTS; ++s)
-            if (((s >> 1) & 1) == group && lane == 0) mbar_arrive(&s_tempty[s]);     // completes phase 0 of every slot
-        uint32_t g = 0;                                               // running output counter (incl. virtual rows)
+        uint32_t g = 0;                                               // running output counter (incl. virtual rows), even
         for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
             const int page = item / items_per_page;
             const int rem = item - page * items_per_page;
@@ -207,15 +228,16 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
             const int rows = min(p.seg_rows, p.h - ys);
             const int x = strip * F_SW + j;
             const bool xok = j < F_SW && x < p.w;
-            for (int o2 = 2 * group; o2 < rows + 4; o2 += 4) {        // my group's row pairs (o = o2 - 4 + st)
+            // row pairs (o = o2 - 4 + st) go round-robin over the epilogue groups, across work items
+            for (int o2 = 2 * (int)((F_EG + group - (g >> 1) % F_EG) % F_EG); o2 < rows + 4; o2 += 2 * F_EG) {
                 uint32_t kept[NPAD / 2];
 #pragma unroll
                 for (int st = 0; st < 2; ++st) {
                     const uint32_t gg = g + (uint32_t)(o2 + st);
-                    const uint32_t slot = gg % F_SLOTS;
+                    const uint32_t slot = gg % SLOTS;
                     const int y = ys + o2 + st - 4;                   // < ys: virtual row
                     const bool real = o2 >= 4;
-                    mbar_wait(&s_tfull[slot], (gg / F_SLOTS) & 1u);
+                    mbar_wait(&s_tfull[slot], (gg / SLOTS) & 1u);
                     tc_fence_after();
                     const uint32_t tacc = t_lane + slot * NPAD;
                     uint32_t v[NPAD];
@@ -253,9 +275,10 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
                             if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
                             pk[i] = pack2<T>(a, b);
                         }
-                        if (out && xok && y < p.h) {
+                        if (out && xok && y < p.h && hb * 16 < p.out_cp) {
                             *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, p.h, p.w, hb * 16, y, x)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                            *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, p.h, p.w, hb * 16 + 8, y, x)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                            if (hb * 16 + 8 < p.out_cp)
+                                *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, p.h, p.w, hb * 16 + 8, y, x)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                         }
                         if (pool) {
                             if (st == 0) {
@@ -265,16 +288,14 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
                                 uint32_t pm[8];
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) {
-                                    const float2 a = unpack2f<T>(pk[i]), b = unpack2f<T>(kept[hb * 8 + i]);
-                                    float mx = fmaxf(a.x, b.x), my = fmaxf(a.y, b.y);
-                                    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-                                    my = fmaxf(my, __shfl_xor_sync(0xffffffffu, my, 1));
-                                    pm[i] = pack2<T>(mx, my);
+                                    const uint32_t m = max2<T>(pk[i], kept[hb * 8 + i]);
+                                    pm[i] = max2<T>(m, __shfl_xor_sync(0xffffffffu, m, 1));
                                 }
-                                if (!(lane & 1) && xok && y < p.h) {
+                                if (!(lane & 1) && xok && y < p.h && hb * 16 < p.pool_cp) {
                                     const int ph = p.h >> 1, pw = p.w >> 1;
                                     *reinterpret_cast<uint4*>(pool + act_idx(page, p.pool_cp, ph, pw, hb * 16, y >> 1, x >> 1)) = make_uint4(pm[0], pm[1], pm[2], pm[3]);
-                                    *reinterpret_cast<uint4*>(pool + act_idx(page, p.pool_cp, ph, pw, hb * 16 + 8, y >> 1, x >> 1)) = make_uint4(pm[4], pm[5], pm[6], pm[7]);
+                                    if (hb * 16 + 8 < p.pool_cp)
+                                        *reinterpret_cast<uint4*>(pool + act_idx(page, p.pool_cp, ph, pw, hb * 16 + 8, y >> 1, x >> 1)) = make_uint4(pm[4], pm[5], pm[6], pm[7]);
                                 }
                             }
                         }
@@ -308,7 +329,7 @@ EncodeTiledFn fold_get_encode() {
     return fn;
 }
 
-template <typename T, int NPAD, int NCH, int RING>
+template <typename T, int NPAD, int NPL, int RING, int SLOTS>
 int launch_fold_t(pcs_ctx* ctx, const FoldConvArgs& a) {
     constexpr int NF = 5 * NPAD;
     FoldParams p{};
@@ -324,7 +345,7 @@ int launch_fold_t(pcs_ctx* ctx, const FoldConvArgs& a) {
             if (ctx->device < 64) g_skip_owner[ctx->device] = ctx->model_stamp;
         }
     }
-    p.w_bytes = (uint32_t)NCH * 5 * 2 * NF * 16;          // [chunk][dx][plane][N' rows][16 B]
+    p.w_bytes = (uint32_t)FoldK<NPL>::NMMA * 2 * NF * 16;  // [K step][K half][N' rows][16 B]
     p.strips = (a.w + F_SW - 1) / F_SW;
     // segments: multiples of 4 rows (row pairs x 2 groups); aim at >= 4 items per CTA
     int segs = 1;
@@ -336,10 +357,10 @@ int launch_fold_t(pcs_ctx* ctx, const FoldConvArgs& a) {
     EncodeTiledFn enc = fold_get_encode();
     if (!enc) return set_err(ctx, PCS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     const cuuint64_t planes = (cuuint64_t)a.src.cp / 8;
-    if ((int)planes != 2 * NCH) return set_err(ctx, PCS_ERR_ARG, "conv_fold: source has %d planes, kernel expects %d", (int)planes, 2 * NCH);
+    if ((int)planes != NPL) return set_err(ctx, PCS_ERR_ARG, "conv_fold: source has %d planes, kernel expects %d", (int)planes, NPL);
     const cuuint64_t dims[4] = {(cuuint64_t)a.w * 2, (cuuint64_t)a.h, planes, (cuuint64_t)a.n};
     const cuuint64_t strides[3] = {(cuuint64_t)a.w * 16, (cuuint64_t)a.h * a.w * 16, planes * a.h * a.w * 16};
-    const cuuint32_t box[4] = {256, 1, (cuuint32_t)(2 * NCH), 1};
+    const cuuint32_t box[4] = {256, 1, (cuuint32_t)NPL, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     CUtensorMap tm;
     CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(a.src.p), dims, strides, box, estr,
@@ -348,63 +369,71 @@ int launch_fold_t(pcs_ctx* ctx, const FoldConvArgs& a) {
     if (r != CUDA_SUCCESS) return set_err(ctx, PCS_ERR_CUDA, "conv_fold: cuTensorMapEncodeTiled failed with %d", (int)r);
     const size_t w_al = ((p.w_bytes + 1023) / 1024) * 1024;
     p.ring = RING;
-    const size_t smem = w_al + (size_t)RING * NCH * 4096 + 1024;
+    const size_t smem = w_al + (size_t)RING * NPL * 2048 + 1024;
     if (smem + 2 * 1024 > 227 * 1024) return set_err(ctx, PCS_ERR_ARG, "conv_fold: %zu bytes of shared memory needed", smem);
     static size_t attr_set = 0;
     if (attr_set < smem) {
-        PCS_CUDA(ctx, cudaFuncSetAttribute(conv_fold_kernel<T, NPAD, NCH, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PCS_CUDA(ctx, cudaFuncSetAttribute(conv_fold_kernel<T, NPAD, NPL, RING, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = smem;
     }
     const int grid = std::min(p.num_items, ctx->sm_count);
-    conv_fold_kernel<T, NPAD, NCH, RING><<<grid, F_THREADS, smem, ctx->stream>>>(p, tm);
+    conv_fold_kernel<T, NPAD, NPL, RING, SLOTS><<<grid, F_THREADS, smem, ctx->stream>>>(p, tm);
     PCS_LAUNCH_CHECK(ctx, "conv_fold_kernel");
     return PCS_OK;
 }
 
 template <typename T>
 int launch_fold_dispatch(pcs_ctx* ctx, const FoldConvArgs& a) {
-    const int key = a.npad * 10 + a.nchunks;
+    const int key = a.npad * 10 + a.nplanes;
     switch (key) {
-        case 322: return launch_fold_t<T, 32, 2, 16>(ctx, a);     // conv2: 20(32) -> 30(32)
-        case 482: return launch_fold_t<T, 48, 2, 16>(ctx, a);     // conv3: 30(32) -> 40(48)
-        case 483: return launch_fold_t<T, 48, 3, 8>(ctx, a);     // conv4: 40(48) -> 40(48)
-        default: return set_err(ctx, PCS_ERR_ARG, "conv_fold: no instantiation for N=%d chunks=%d", a.npad, a.nchunks);
+        case 323: return launch_fold_t<T, 32, 3, 16, 16>(ctx, a);     // conv2: 20(24) -> 30(32)
+        case 484: return launch_fold_t<T, 48, 4, 10, 10>(ctx, a);     // conv3: 30(32) -> 40(48)
+        case 485: return launch_fold_t<T, 48, 5, 10, 10>(ctx, a);      // conv4: 40(40) -> 40(48)
+        default: return set_err(ctx, PCS_ERR_ARG, "conv_fold: no instantiation for N=%d planes=%d", a.npad, a.nplanes);
     }
 }
 
 }  // namespace
 
-bool fold_supported(int k, int npad, int nchunks, int nsrc) {
+bool fold_supported(int k, int npad, int nplanes, int nsrc) {
     if (k != 5 || nsrc != 1) return false;
-    const int key = npad * 10 + nchunks;
-    return key == 322 || key == 482 || key == 483;          // conv5+ (N' = 5*64 = 320) exceeds the UMMA N limit of 256
+    const int key = npad * 10 + nplanes;
+    return key == 323 || key == 484 || key == 485;          // conv5+ (N' = 5*64 = 320) exceeds the UMMA N limit of 256
 }
 
-// Resident operand image [chunk][dx][plane][row = (4-dy)*NPAD + o][8]: the N blocks run from the oldest
-// output row of the window (dy = 4) to the newest (dy = 0).
+// Resident operand image [K step][K half][row = (4-dy)*NPAD + o][8] (K steps as in FoldK): the N blocks run
+// from the oldest output row of the window (dy = 4) to the newest (dy = 0).
 size_t fold_weight_image(const float* w32 /*[25][cin][cout]*/, int cin, int cout, int npad, int precision, std::vector<uint16_t>& out) {
-    const int nch = pad16(cin) / 16, nf = 5 * npad;
-    out.assign((size_t)nch * 5 * 2 * nf * 8, 0);
+    const int npl = pad8(cin) / 8, pairs = npl / 2, odd = npl & 1, nmma = pairs * 5 + odd * 3, nf = 5 * npad;
+    out.assign((size_t)nmma * 2 * nf * 8, 0);
     auto conv = [&](float v) -> uint16_t {
         if (precision == PCS_PREC_BF16) { __nv_bfloat16 b = __float2bfloat16_rn(v); return *reinterpret_cast<uint16_t*>(&b); }
         __half h = __float2half_rn(v); return *reinterpret_cast<uint16_t*>(&h);
     };
-    for (int c = 0; c < nch; ++c)
-        for (int dx = 0; dx < 5; ++dx)
-            for (int pl = 0; pl < 2; ++pl)
-                for (int dy = 0; dy < 5; ++dy)
-                    for (int o = 0; o < npad; ++o)
-                        for (int e = 0; e < 8; ++e) {
-                            const int ci = c * 16 + pl * 8 + e;
-                            if (ci >= cin || o >= cout) continue;
-                            const float v = w32[((size_t)(dy * 5 + dx) * cin + ci) * cout + o];
-                            out[((((size_t)c * 5 + dx) * 2 + pl) * nf + (4 - dy) * npad + o) * 8 + e] = conv(v);
-                        }
+    for (int q = 0; q < nmma; ++q)
+        for (int half = 0; half < 2; ++half) {
+            int plane, dx;
+            if (q < pairs * 5) { plane = 2 * (q / 5) + half; dx = q % 5; }
+            else {
+                const int t = q - pairs * 5;                  // taps (0,1), (2,3), (3,4); the repeated tap 3 gets zeros
+                plane = npl - 1;
+                dx = (t == 0 ? 0 : t + 1) + half;
+                if (t == 2 && half == 0) continue;
+            }
+            for (int dy = 0; dy < 5; ++dy)
+                for (int o = 0; o < cout; ++o)
+                    for (int e = 0; e < 8; ++e) {
+                        const int ci = plane * 8 + e;
+                        if (ci >= cin) continue;
+                        const float v = w32[((size_t)(dy * 5 + dx) * cin + ci) * cout + o];
+                        out[(((size_t)q * 2 + half) * nf + (4 - dy) * npad + o) * 8 + e] = conv(v);
+                    }
+        }
     return out.size() * sizeof(uint16_t);
 }
 
 int launch_conv_fold(pcs_ctx* ctx, const FoldConvArgs& a) {
-    if (!fold_supported(a.k, a.npad, a.nchunks, 1)) return set_err(ctx, PCS_ERR_ARG, "conv_fold: unsupported layer");
+    if (!fold_supported(a.k, a.npad, a.nplanes, 1)) return set_err(ctx, PCS_ERR_ARG, "conv_fold: unsupported layer");
     if (ctx->precision == PCS_PREC_BF16) return launch_fold_dispatch<__nv_bfloat16>(ctx, a);
     return launch_fold_dispatch<__half>(ctx, a);
 }

@@ -335,27 +335,29 @@ conv_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm0, co
                             const int tap = J / p.co_t, o = J - tap * p.co_t;
                             if (xok && o < p.out_cp) {
                                 const int ox = 2 * x + (tap & 1), oh = 2 * p.h, ow = 2 * p.w;
+                                const bool two = o + 8 < p.out_cp;
                                 if (ya < p.h) {
                                     const int oy = 2 * ya + (tap >> 1);
                                     *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, oh, ow, o, oy, ox)) = lo0;
-                                    *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, oh, ow, o + 8, oy, ox)) = hi0;
+                                    if (two) *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, oh, ow, o + 8, oy, ox)) = hi0;
                                 }
                                 if (ya + 1 < p.h) {
                                     const int oy = 2 * (ya + 1) + (tap >> 1);
                                     *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, oh, ow, o, oy, ox)) = lo1;
-                                    *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, oh, ow, o + 8, oy, ox)) = hi1;
+                                    if (two) *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, oh, ow, o + 8, oy, ox)) = hi1;
                                 }
                             }
                         } else {
                             const int o = cbase + c16 * 16;
-                            if (out && xok) {
+                            if (out && xok && o < p.out_cp) {
+                                const bool two = o + 8 < p.out_cp;
                                 if (ya < p.h) {
                                     *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, p.h, p.w, o, ya, x)) = lo0;
-                                    *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, p.h, p.w, o + 8, ya, x)) = hi0;
+                                    if (two) *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, p.h, p.w, o + 8, ya, x)) = hi0;
                                 }
                                 if (ya + 1 < p.h) {
                                     *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, p.h, p.w, o, ya + 1, x)) = lo1;
-                                    *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, p.h, p.w, o + 8, ya + 1, x)) = hi1;
+                                    if (two) *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, p.h, p.w, o + 8, ya + 1, x)) = hi1;
                                 }
                             }
                             if (pool) {
@@ -365,11 +367,12 @@ conv_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm0, co
                                     const float a = fmaxf(f0[i], f1[i]);
                                     mx[i] = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, 1));
                                 }
-                                if (!(lane & 1) && xok && ya < p.h) {
+                                if (!(lane & 1) && xok && ya < p.h && o < p.pool_cp) {
                                     const int ph = p.h >> 1, pw = p.w >> 1;
                                     *reinterpret_cast<uint4*>(pool + act_idx(page, p.pool_cp, ph, pw, o, ya >> 1, x >> 1)) =
                                         make_uint4(pack2<T>(mx[0], mx[1]), pack2<T>(mx[2], mx[3]), pack2<T>(mx[4], mx[5]), pack2<T>(mx[6], mx[7]));
-                                    *reinterpret_cast<uint4*>(pool + act_idx(page, p.pool_cp, ph, pw, o + 8, ya >> 1, x >> 1)) =
+                                    if (o + 8 < p.pool_cp)
+                                        *reinterpret_cast<uint4*>(pool + act_idx(page, p.pool_cp, ph, pw, o + 8, ya >> 1, x >> 1)) =
                                         make_uint4(pack2<T>(mx[8], mx[9]), pack2<T>(mx[10], mx[11]), pack2<T>(mx[12], mx[13]), pack2<T>(mx[14], mx[15]));
                                 }
                             }
@@ -432,8 +435,10 @@ int launch_t(pcs_ctx* ctx, const UmmaConvArgs& a) {
     constexpr int R = Cfg<NPAD>::R;
     UmmaParams p{};
     p.n = a.n; p.h = a.h; p.w = a.w; p.k = a.k; p.pad = a.pad;
-    p.nch0 = a.src[0].cp / 16;
-    p.nchunks = p.nch0 + (a.nsrc > 1 ? a.src[1].cp / 16 : 0);
+    // 16-channel K chunks; a source with an odd number of 8-channel planes ends in a half-empty chunk whose
+    // second plane is out of bounds for the tensor map (TMA zero fill) and has zero weights
+    p.nch0 = (a.src[0].cp + 15) / 16;
+    p.nchunks = p.nch0 + (a.nsrc > 1 ? (a.src[1].cp + 15) / 16 : 0);
     if (p.nchunks != a.nchunks) return set_err(ctx, PCS_ERR_ARG, "conv_umma: source channel chunks %d != weight image chunks %d", p.nchunks, a.nchunks);
     p.wimg = reinterpret_cast<const uint8_t*>(a.wmma); p.bias = a.b32; p.cout = a.cout; p.relu = a.relu;
     p.out = a.out; p.out_cp = a.out_cp; p.pool = a.pool_out; p.pool_cp = a.pool_cp;
@@ -616,8 +621,8 @@ int launch_conv_umma(pcs_ctx* ctx, const UmmaConvArgs& a) {
     if (a.mode >= EPI_HEAD && (!a.head || a.npad != 32 || a.head->n_classes > HEAD_NC))
         return set_err(ctx, PCS_ERR_ARG, "conv_umma: fused head needs the N=32 operand image and <= %d classes", HEAD_NC);
     if (!umma_supported(a.k, a.npad)) return set_err(ctx, PCS_ERR_ARG, "conv_umma: unsupported k=%d N=%d", a.k, a.npad);
-    if (a.src[0].cp % 16 || (a.nsrc > 1 && a.src[1].cp % 16)) return set_err(ctx, PCS_ERR_ARG, "conv_umma: channel stride not a multiple of 16");
-    if (a.out && a.out_cp % 16) return set_err(ctx, PCS_ERR_ARG, "conv_umma: output stride");
+    if (a.src[0].cp % 8 || (a.nsrc > 1 && a.src[1].cp % 8)) return set_err(ctx, PCS_ERR_ARG, "conv_umma: channel stride not a multiple of 8");
+    if ((a.out && a.out_cp % 8) || (a.pool_out && a.pool_cp % 8)) return set_err(ctx, PCS_ERR_ARG, "conv_umma: output stride");
     if (ctx->precision == PCS_PREC_BF16) return launch_npad<__nv_bfloat16>(ctx, a);
     return launch_npad<__half>(ctx, a);
 }
