@@ -43,8 +43,7 @@ __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-constexpr int F_EG = 3;                     // epilogue warp groups (4 warps = 4 TMEM lane quarters each)
-constexpr int F_THREADS = 64 + F_EG * 128;  // warp 0 producer, warp 1 MMA issuer, then the epilogue groups
+// threads = warp 0 producer, warp 1 MMA issuer, then EG epilogue groups of 4 warps (4 TMEM lane quarters)
 constexpr int F_RING_MAX = 20;              // input-row ring entries (one row is consumed per step)
 constexpr int F_SLOTS_MAX = 16;             // output-row accumulator slots in TMEM (512 columns / NPAD)
 constexpr int F_SW = 124;                   // valid output pixels per strip
@@ -65,6 +64,7 @@ struct FoldParams {
     void* out; int out_cp;
     void* pool; int pool_cp;
     float4* plog;                           // [n][h][w] partial logits (4 classes, zero padded) or null
+    int plog_nc;                            // classes actually present (the 4th FMA chain is skipped for <= 3)
     uint32_t w_bytes;
     int ring;                               // input-row ring depth
 };
@@ -79,8 +79,8 @@ template <int NPL> struct FoldK {
     static constexpr int NMMA = PAIRS * 5 + ODD * 3;
 };
 
-template <typename T, int NPAD, int NPL, int RING, int SLOTS>
-__global__ void __launch_bounds__(F_THREADS, 1)
+template <typename T, int NPAD, int NPL, int RING, int SLOTS, int EG>
+__global__ void __launch_bounds__(64 + EG * 128, 1)
 conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
     constexpr int NF = 5 * NPAD;                                     // folded N
     constexpr uint32_t ROW_BYTES = NPL * 2048;                       // one ring entry: all planes of one input row
@@ -229,7 +229,7 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
             const int x = strip * F_SW + j;
             const bool xok = j < F_SW && x < p.w;
             // row pairs (o = o2 - 4 + st) go round-robin over the epilogue groups, across work items
-            for (int o2 = 2 * (int)((F_EG + group - (g >> 1) % F_EG) % F_EG); o2 < rows + 4; o2 += 2 * F_EG) {
+            for (int o2 = 2 * (int)((EG + group - (g >> 1) % EG) % EG); o2 < rows + 4; o2 += 2 * EG) {
                 uint32_t kept[NPAD / 2];
 #pragma unroll
                 for (int st = 0; st < 2; ++st) {
@@ -260,7 +260,10 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
                                 acc.x = fmaf(a, c_skip_lw[o * F_NC + 0], acc.x);
                                 acc.y = fmaf(a, c_skip_lw[o * F_NC + 1], acc.y);
                                 acc.z = fmaf(a, c_skip_lw[o * F_NC + 2], acc.z);
-                                acc.w = fmaf(a, c_skip_lw[o * F_NC + 3], acc.w);
+                            }
+                            if (p.plog_nc > 3) {
+#pragma unroll
+                                for (int o = 0; o < NPAD; ++o) acc.w = fmaf(__uint_as_float(v[o]), c_skip_lw[o * F_NC + 3], acc.w);
                             }
                             if (xok && y < p.h) p.plog[((size_t)page * p.h + y) * p.w + x] = acc;
                         }
@@ -329,7 +332,7 @@ EncodeTiledFn fold_get_encode() {
     return fn;
 }
 
-template <typename T, int NPAD, int NPL, int RING, int SLOTS>
+template <typename T, int NPAD, int NPL, int RING, int SLOTS, int EG>
 int launch_fold_t(pcs_ctx* ctx, const FoldConvArgs& a) {
     constexpr int NF = 5 * NPAD;
     FoldParams p{};
@@ -340,6 +343,7 @@ int launch_fold_t(pcs_ctx* ctx, const FoldConvArgs& a) {
     if (a.plog) {
         if (NPAD != F_LOGC || !a.skip_lw) return set_err(ctx, PCS_ERR_ARG, "conv_fold: partial logits need the N=32 kernel and weights");
         p.plog = reinterpret_cast<float4*>(a.plog);
+        p.plog_nc = ctx->n_classes;
         if (ctx->device >= 64 || g_skip_owner[ctx->device] != ctx->model_stamp) {
             PCS_CUDA(ctx, cudaMemcpyToSymbolAsync(c_skip_lw, a.skip_lw, sizeof(float) * F_LOGC * F_NC, 0, cudaMemcpyDeviceToDevice, ctx->stream));
             if (ctx->device < 64) g_skip_owner[ctx->device] = ctx->model_stamp;
@@ -373,11 +377,11 @@ int launch_fold_t(pcs_ctx* ctx, const FoldConvArgs& a) {
     if (smem + 2 * 1024 > 227 * 1024) return set_err(ctx, PCS_ERR_ARG, "conv_fold: %zu bytes of shared memory needed", smem);
     static size_t attr_set = 0;
     if (attr_set < smem) {
-        PCS_CUDA(ctx, cudaFuncSetAttribute(conv_fold_kernel<T, NPAD, NPL, RING, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PCS_CUDA(ctx, cudaFuncSetAttribute(conv_fold_kernel<T, NPAD, NPL, RING, SLOTS, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = smem;
     }
     const int grid = std::min(p.num_items, ctx->sm_count);
-    conv_fold_kernel<T, NPAD, NPL, RING, SLOTS><<<grid, F_THREADS, smem, ctx->stream>>>(p, tm);
+    conv_fold_kernel<T, NPAD, NPL, RING, SLOTS, EG><<<grid, 64 + EG * 128, smem, ctx->stream>>>(p, tm);
     PCS_LAUNCH_CHECK(ctx, "conv_fold_kernel");
     return PCS_OK;
 }
@@ -386,9 +390,9 @@ template <typename T>
 int launch_fold_dispatch(pcs_ctx* ctx, const FoldConvArgs& a) {
     const int key = a.npad * 10 + a.nplanes;
     switch (key) {
-        case 323: return launch_fold_t<T, 32, 3, 16, 16>(ctx, a);     // conv2: 20(24) -> 30(32)
-        case 484: return launch_fold_t<T, 48, 4, 10, 10>(ctx, a);     // conv3: 30(32) -> 40(48)
-        case 485: return launch_fold_t<T, 48, 5, 10, 10>(ctx, a);      // conv4: 40(40) -> 40(48)
+        case 323: return launch_fold_t<T, 32, 3, 16, 16, 4>(ctx, a);     // conv2: 20(24) -> 30(32)
+        case 484: return launch_fold_t<T, 48, 4, 10, 10, 3>(ctx, a);     // conv3: 30(32) -> 40(48)
+        case 485: return launch_fold_t<T, 48, 5, 10, 10, 3>(ctx, a);      // conv4: 40(40) -> 40(48)
         default: return set_err(ctx, PCS_ERR_ARG, "conv_fold: no instantiation for N=%d planes=%d", a.npad, a.nplanes);
     }
 }
