@@ -84,14 +84,6 @@ struct UmmaParams {
 
 using namespace ptx;
 
-template <typename T> __device__ __forceinline__ float2 unpack2(uint32_t v);
-template <> __device__ __forceinline__ float2 unpack2<__nv_bfloat16>(uint32_t v) {
-    return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
-}
-template <> __device__ __forceinline__ float2 unpack2<__half>(uint32_t v) {
-    return __half22float2(*reinterpret_cast<const __half2*>(&v));
-}
-
 template <typename T, int NPAD, int KS, int MODE>
 __global__ void __launch_bounds__(MODE >= EPI_HEAD ? kHeadThreads : kThreads, 1)
 conv_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1) {

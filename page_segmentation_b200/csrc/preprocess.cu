@@ -80,7 +80,199 @@ __device__ __forceinline__ int level_count(const uint32_t* bits) {
     return c;
 }
 
-// One thread per output pixel.  grid = (ceil(Ws/32), ceil(Hs/8), pages of the group).
+// ---------------------------------------------------------------------------
+// Fast path for pages with at most two grey levels (binarised scans: the case dataset.py:169-172 makes
+// the normal one).  One streaming pass over the page produces the level bitmap AND a 1-bit-per-pixel
+// plane  bit(i) = (page[i] != page[0]);  the resampler then never touches the 8.7 MB page again: a
+// source value is  bit ? other level : page[0].
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ne_bits4(uint32_t w, uint32_t ref4) {
+    const uint32_t x = w ^ ref4;
+    const uint32_t t = (x | ((x | 0x80808080u) - 0x01010101u)) & 0x80808080u;      // high bit set iff byte != 0
+    return (((t >> 7) * 0x01020408u) >> 24) & 0xfu;                                 // byte k -> bit k
+}
+__device__ __forceinline__ uint32_t ne_bits16(const uint4 v, uint32_t ref4) {
+    return ne_bits4(v.x, ref4) | (ne_bits4(v.y, ref4) << 4) | (ne_bits4(v.z, ref4) << 8) | (ne_bits4(v.w, ref4) << 12);
+}
+
+// grid = (blocks, pages); every thread turns 32 page bytes into one bitmap word.  Requires 16-byte aligned
+// pages whose size is a multiple of 32 bytes (checked by the host; other shapes take the general kernels).
+__global__ void __launch_bounds__(256) scan_pack_kernel(const uint8_t* __restrict__ src, size_t page_bytes,
+                                                        uint32_t* __restrict__ bits /*[n][8]*/,
+                                                        uint32_t* __restrict__ bitmap, size_t bitmap_words /*per page, padded*/) {
+    __shared__ uint32_t s_bits[8];
+    if (threadIdx.x < 8) s_bits[threadIdx.x] = 0;
+    __syncthreads();
+    const int page = blockIdx.y;
+    const uint8_t* p = src + (size_t)page * page_bytes;
+    const uint4* pv = reinterpret_cast<const uint4*>(p);
+    uint32_t* bm = bitmap + (size_t)page * bitmap_words;
+    const uint32_t ref4 = (uint32_t)__ldg(p) * 0x01010101u;
+    const size_t nwords = page_bytes / 32;
+    auto mark = [&](uint32_t val) {
+        if (!((s_bits[val >> 5] >> (val & 31)) & 1u)) atomicOr(&s_bits[val >> 5], 1u << (val & 31));
+    };
+    // high bit of every byte of w that is NOT zero
+    auto nz = [](uint32_t w) -> uint32_t { return (w | ((w | 0x80808080u) - 0x01010101u)) & 0x80808080u; };
+    // per-thread cache of the second value: words made of {page[0], oth} bytes only need no set update
+    uint32_t oth4 = ref4;
+    bool have_oth = false;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 a = __ldg(pv + 2 * i), b = __ldg(pv + 2 * i + 1);
+        const uint32_t words[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint32_t out = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t wv = words[k];
+            const uint32_t dif = nz(wv ^ ref4);                         // bytes that differ from page[0]
+            out |= ((((dif >> 7) * 0x01020408u) >> 24) & 0xfu) << (4 * k);
+            if (dif & nz(wv ^ oth4)) {                                  // some byte is neither page[0] nor oth
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t v = (wv >> (8 * q)) & 0xff;
+                    if (v != (ref4 & 0xff)) { mark(v); if (!have_oth) { oth4 = v * 0x01010101u; have_oth = true; } }
+                }
+            }
+        }
+        bm[i] = out;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { mark(ref4 & 0xff); bm[nwords] = 0; }       // pad word read by the funnel shift
+    __syncthreads();
+    if (threadIdx.x < 8 && s_bits[threadIdx.x]) atomicOr(&bits[page * 8 + threadIdx.x], s_bits[threadIdx.x]);
+}
+
+constexpr int RB_T = 32, RB_TY = 64;             // output tile of the fast resampler: 32 x 64 (256 threads, 8 rows each)
+constexpr int RB_MAX_SPAN = 4 * RB_TY + 8;       // staged source rows for scale factors up to 4
+constexpr int RB_ROW_WORDS = 8;                  // staged words per source row: (4*32 + 8 + 31 + 31) / 32
+
+// grid = (ceil(Ws/32), ceil(Hs/64), pages).  Pages with more than two grey levels return at once (the
+// general kernel below handles them).  Bit-identical to the general kernel:
+//   * the horizontal cubic of a two-level row has only 16 possible operand patterns per output column;
+//     they are evaluated once per block with the same fp64 operation order (cubic_rn) and looked up;
+//   * a pixel whose 4x4 neighbourhood is all one level v gets cubic(v,v,v,v) = v exactly (every
+//     intermediate of cubic_rn is an exact small integer or zero), so warps over blank paper or solid ink
+//     store the precomputed constant and skip the fp64 arithmetic;
+//   * the vertical cubic, clip and the (1 - v/255) * 255 truncation are otherwise unchanged.
+__global__ void __launch_bounds__(256)
+resample_bits_kernel(const uint8_t* __restrict__ grey, const uint8_t* __restrict__ bin, int bin_is_grey, int H, int W,
+                     int Hs, int Ws, const uint32_t* __restrict__ level_bits, const uint32_t* __restrict__ bitmap,
+                     size_t bitmap_words, uint8_t* __restrict__ image_out, uint8_t* __restrict__ binary_out) {
+    __shared__ double s_lut[16][RB_T];            // [pattern][column]: a warp reads 32 consecutive doubles (no bank conflicts)
+    __shared__ double s_cfrac[RB_T], s_rfrac[RB_TY];                  // fractional sampling offsets of columns / rows
+    __shared__ uint32_t s_bm[RB_MAX_SPAN][RB_ROW_WORDS];
+    __shared__ __align__(16) int s_ctap[RB_T][4], s_rtap[RB_TY][4];   // the four (reflected) source columns / rows
+    __shared__ int s_cnn[RB_T], s_rnn[RB_TY], s_off[RB_MAX_SPAN], s_rng[6];
+    const int page = blockIdx.z;
+    const uint32_t* bits = level_bits + (size_t)page * 8;
+    if (level_count(bits) > 2) return;
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    if (wrp < 3) {                                // warp 0: the 32 columns, warps 1-2: the 64 rows of the tile
+        const int n_in = wrp == 0 ? W : H, n_out = wrp == 0 ? Ws : Hs;
+        const int o = min(wrp == 0 ? blockIdx.x * RB_T + lane : blockIdx.y * RB_TY + (wrp - 1) * 32 + lane, n_out - 1);   // replicate past the edge
+        const double f = __ddiv_rn((double)n_in, (double)n_out);
+        const double pc = __dadd_rn(__dmul_rn(f, (double)o), __dsub_rn(__dmul_rn(0.5, f), 0.5));
+        const int nn = reflect_coord((long long)round(pc), n_in);        // order 0: C round(), then reflect
+        const double pf = floor(pc);
+        const int ti = wrp == 0 ? lane : (wrp - 1) * 32 + lane;
+        (wrp == 0 ? s_cfrac : s_rfrac)[ti] = __dsub_rn(pc, pf);
+        (wrp == 0 ? s_cnn : s_rnn)[ti] = nn;
+        int lo = nn, hi = nn;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = reflect_coord((long long)pf - 1 + k, n_in);
+            (wrp == 0 ? s_ctap : s_rtap)[ti][k] = c;
+            lo = min(lo, c); hi = max(hi, c);
+        }
+        lo = __reduce_min_sync(0xffffffffu, lo);
+        hi = __reduce_max_sync(0xffffffffu, hi);
+        if (lane == 0) { s_rng[2 * wrp] = lo; s_rng[2 * wrp + 1] = hi; }
+    }
+    __syncthreads();
+    const int cmin = s_rng[0], cmax = s_rng[1], rmin = min(s_rng[2], s_rng[4]), rmax = max(s_rng[3], s_rng[5]);
+    const int nrows = rmax - rmin + 1;
+    if (nrows > RB_MAX_SPAN || cmax - cmin + 1 + 62 > RB_ROW_WORDS * 32) { __trap(); }      // host guarantees scale <= 4
+    const uint32_t* bm = bitmap + (size_t)page * bitmap_words;
+    const size_t last_word = (size_t)H * W / 32;
+    for (int i = tid; i < nrows * RB_ROW_WORDS; i += 256) {
+        const int r = i / RB_ROW_WORDS, wq = i - r * RB_ROW_WORDS;
+        const size_t b0 = (size_t)(rmin + r) * W + cmin;
+        const size_t w0 = (b0 >> 5) + wq;
+        s_bm[r][wq] = w0 <= last_word ? __ldg(bm + w0) : 0u;
+        if (wq == 0) s_off[r] = (int)(b0 & 31) - cmin;        // bit (r, c) sits at bit s_off[r] + c of the staged row
+    }
+    // the two levels: a = page[0] (bit 0), b = the other one (bit 1)
+    int l0 = -1, l1 = -1;
+#pragma unroll
+    for (int wv = 7; wv >= 0; --wv) {
+        const uint32_t m = bits[wv];
+        if (m) {
+            const int hi = wv * 32 + 31 - __clz(m), lo = wv * 32 + __ffs(m) - 1;
+            if (l1 < 0) l1 = hi;
+            l0 = lo;
+        }
+    }
+    const int va = (int)__ldg(grey + (size_t)page * H * W);
+    const int vb = va == l0 ? l1 : l0;
+    const double vmin = (double)l0, vmax = (double)l1;
+    if (image_out) {
+        const double fa = (double)va, fb = (double)vb;
+        for (int i = tid; i < RB_T * 16; i += 256) {
+            const int c = i & 31, pat = i >> 5;
+            s_lut[pat][c] = cubic_rn(s_cfrac[c], (pat & 1) ? fb : fa, (pat & 2) ? fb : fa, (pat & 4) ? fb : fa, (pat & 8) ? fb : fa);
+        }
+    }
+    __syncthreads();
+    const int x = blockIdx.x * RB_T + lane;
+    auto bit_at = [&](int rl, int c) -> uint32_t {
+        const int b = s_off[rl] + c;
+        return (s_bm[rl][b >> 5] >> (b & 31)) & 1u;
+    };
+    auto finish = [&](double v) -> uint8_t {          // clip=True, then img = 1.0 - v/255 ; (img*255).astype(uint8)
+        v = fmin(fmax(v, vmin), vmax);
+        return (uint8_t)(int)__dmul_rn(__dsub_rn(1.0, __ddiv_rn(v, 255.0)), 255.0);
+    };
+    const uint8_t out_a = finish((double)va), out_b = finish((double)vb);
+    const int c0 = s_ctap[lane][0], c1 = s_ctap[lane][1], c2 = s_ctap[lane][2], c3 = s_ctap[lane][3];
+    const bool consec = c1 == c0 + 1 && c2 == c0 + 2 && c3 == c0 + 3;
+    const int nnc = s_cnn[lane];
+    const bool xok = x < Ws;
+#pragma unroll 1
+    for (int q = 0; q < RB_TY / 8; ++q) {
+        const int ty = wrp + 8 * q, y = blockIdx.y * RB_TY + ty;
+        if (y >= Hs) break;                                            // warp-uniform
+        const size_t dst = (size_t)page * Hs * Ws + (size_t)y * Ws + x;
+        if (binary_out && xok) {
+            int v;
+            if (bin_is_grey) v = bit_at(s_rnn[ty] - rmin, nnc) ? vb : va;
+            else v = bin[(size_t)page * H * W + (size_t)s_rnn[ty] * W + nnc];
+            binary_out[dst] = v == 0 ? 1 : 0;      // bin = (1.0 - NN(binary/255 or binary)).astype(uint8)
+        }
+        if (image_out) {
+            const int4 rr = *reinterpret_cast<const int4*>(s_rtap[ty]);
+            const int rl[4] = {rr.x - rmin, rr.y - rmin, rr.z - rmin, rr.w - rmin};
+            uint32_t pat[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (consec) {
+                    const int b = s_off[rl[k]] + c0;
+                    pat[k] = __funnelshift_r(s_bm[rl[k]][b >> 5], s_bm[rl[k]][(b >> 5) + 1], b & 31) & 15u;
+                } else {
+                    pat[k] = bit_at(rl[k], c0) | (bit_at(rl[k], c1) << 1) | (bit_at(rl[k], c2) << 2) | (bit_at(rl[k], c3) << 3);
+                }
+            }
+            const bool all_a = (pat[0] | pat[1] | pat[2] | pat[3]) == 0u;
+            const bool all_b = (pat[0] & pat[1] & pat[2] & pat[3]) == 15u;
+            uint8_t o = all_a ? out_a : out_b;
+            if (!__all_sync(0xffffffffu, all_a || all_b)) {
+                const double v = cubic_rn(s_rfrac[ty], s_lut[pat[0]][lane], s_lut[pat[1]][lane], s_lut[pat[2]][lane], s_lut[pat[3]][lane]);
+                o = finish(v);
+            }
+            if (xok) image_out[dst] = o;
+        }
+    }
+}
+
+// General resampler: one thread per output pixel, persistent grid over 32x8 tiles of the pages of a group.
 // Per page (block-uniform): more than two grey levels => the bicubic source is the Gaussian-
 // filtered fp64 plane of that page (anti_aliasing=True, dataset.py:127) and the clip range its
 // min/max; otherwise the uint8 page itself and the min/max from the level bitmap.  No host
@@ -89,82 +281,92 @@ __global__ void __launch_bounds__(256)
 resample_kernel(const uint8_t* __restrict__ grey, const uint8_t* __restrict__ bin, int H, int W, int Hs, int Ws,
                 const uint32_t* __restrict__ level_bits, const double* __restrict__ aa_planes,
                 const unsigned long long* __restrict__ aa_minmax, int page0, uint8_t* __restrict__ image_out,
-                uint8_t* __restrict__ binary_out) {
-    // per-block coordinate tables: the sampling positions depend on the column (row) only
+                uint8_t* __restrict__ binary_out, int skip_two_level, const int* __restrict__ group_flag, int pages) {
+    // skip_two_level: pages with at most two grey levels were already done by resample_bits_kernel; when
+    // no page of the group has more (group_flag == 0) the whole persistent grid leaves at once
+    if (skip_two_level && group_flag && !*group_flag) return;
+    // per-tile coordinate tables: the sampling positions depend on the column (row) only
     __shared__ int s_cols[32][4], s_rows[8][4], s_ci[32], s_ri[8];
     __shared__ double s_xc[32], s_xr[8];
-    const int tid = threadIdx.y * 32 + threadIdx.x;
-    if (tid < 40) {
-        const bool is_col = tid < 32;
-        const int i = is_col ? tid : tid - 32;
-        const int o = is_col ? blockIdx.x * 32 + i : blockIdx.y * 8 + i;
-        const int n_in = is_col ? W : H, n_out = is_col ? Ws : Hs;
-        const double f = __ddiv_rn((double)n_in, (double)n_out);
-        const double p = __dadd_rn(__dmul_rn(f, (double)o), __dsub_rn(__dmul_rn(0.5, f), 0.5));
-        const int nn = reflect_coord((long long)round(p), n_in);        // order 0: C round(), then reflect
-        const double pf = floor(p);
-        const double frac = __dsub_rn(p, pf);
-        const long long p0 = (long long)pf - 1;
-        if (is_col) {
-            s_ci[i] = nn; s_xc[i] = frac;
-            for (int k = 0; k < 4; ++k) s_cols[i][k] = reflect_coord(p0 + k, n_in);
-        } else {
-            s_ri[i] = nn; s_xr[i] = frac;
-            for (int k = 0; k < 4; ++k) s_rows[i][k] = reflect_coord(p0 + k, n_in);
+    const int tiles_x = (Ws + 31) / 32, tiles_y = (Hs + 7) / 8;
+    for (int tile = blockIdx.x; tile < tiles_x * tiles_y * pages; tile += gridDim.x) {
+        const int bz = tile / (tiles_x * tiles_y), bxy = tile - bz * (tiles_x * tiles_y);
+        const int by = bxy / tiles_x, bx = bxy - by * tiles_x;
+        __syncthreads();                               // the coordinate tables of the previous tile are no longer read
+        if (skip_two_level && level_count(level_bits + (size_t)(page0 + bz) * 8) <= 2) continue;
+        const int tid = threadIdx.y * 32 + threadIdx.x;
+        if (tid < 40) {
+            const bool is_col = tid < 32;
+            const int i = is_col ? tid : tid - 32;
+            const int o = is_col ? bx * 32 + i : by * 8 + i;
+            const int n_in = is_col ? W : H, n_out = is_col ? Ws : Hs;
+            const double f = __ddiv_rn((double)n_in, (double)n_out);
+            const double p = __dadd_rn(__dmul_rn(f, (double)o), __dsub_rn(__dmul_rn(0.5, f), 0.5));
+            const int nn = reflect_coord((long long)round(p), n_in);        // order 0: C round(), then reflect
+            const double pf = floor(p);
+            const double frac = __dsub_rn(p, pf);
+            const long long p0 = (long long)pf - 1;
+            if (is_col) {
+                s_ci[i] = nn; s_xc[i] = frac;
+                for (int k = 0; k < 4; ++k) s_cols[i][k] = reflect_coord(p0 + k, n_in);
+            } else {
+                s_ri[i] = nn; s_xr[i] = frac;
+                for (int k = 0; k < 4; ++k) s_rows[i][k] = reflect_coord(p0 + k, n_in);
+            }
         }
-    }
-    __syncthreads();
-    const int x = blockIdx.x * 32 + threadIdx.x;
-    const int y = blockIdx.y * 8 + threadIdx.y;
-    if (x >= Ws || y >= Hs) return;
-    const int page = page0 + blockIdx.z;
-    const size_t src_off = (size_t)page * H * W;
-    const size_t dst_off = (size_t)page * Hs * Ws + (size_t)y * Ws + x;
+        __syncthreads();
+        const int x = bx * 32 + threadIdx.x;
+        const int y = by * 8 + threadIdx.y;
+        if (x >= Ws || y >= Hs) continue;
+        const int page = page0 + bz;
+        const size_t src_off = (size_t)page * H * W;
+        const size_t dst_off = (size_t)page * Hs * Ws + (size_t)y * Ws + x;
 
-    if (binary_out) {
-        const uint8_t v = bin[src_off + (size_t)s_ri[threadIdx.y] * W + s_ci[threadIdx.x]];
-        // bin = (1.0 - NN(binary/255 or binary)).astype(uint8): 1 iff v == 0
-        binary_out[dst_off] = (v == 0) ? 1 : 0;
-    }
-    if (image_out) {
-        const uint32_t* bits = level_bits + (size_t)page * 8;
-        const bool aa = aa_planes != nullptr && level_count(bits) > 2;
-        double vmin, vmax;
-        if (aa) {
-            vmin = __longlong_as_double((long long)aa_minmax[2 * blockIdx.z]);
-            vmax = __longlong_as_double((long long)aa_minmax[2 * blockIdx.z + 1]);
-        } else {
-            int lo = 0, hi = 255;
-            for (int wv = 0; wv < 8; ++wv)
-                if (bits[wv]) { lo = wv * 32 + __ffs(bits[wv]) - 1; break; }
-            for (int wv = 7; wv >= 0; --wv)
-                if (bits[wv]) { hi = wv * 32 + 31 - __clz(bits[wv]); break; }
-            vmin = (double)lo;
-            vmax = (double)hi;
+        if (binary_out) {
+            const uint8_t v = bin[src_off + (size_t)s_ri[threadIdx.y] * W + s_ci[threadIdx.x]];
+            // bin = (1.0 - NN(binary/255 or binary)).astype(uint8): 1 iff v == 0
+            binary_out[dst_off] = (v == 0) ? 1 : 0;
         }
-        const double xr = s_xr[threadIdx.y], xc = s_xc[threadIdx.x];
-        const int c0 = s_cols[threadIdx.x][0], c1 = s_cols[threadIdx.x][1], c2 = s_cols[threadIdx.x][2], c3 = s_cols[threadIdx.x][3];
-        double frow[4];
-        if (aa) {
-            const double* g = aa_planes + (size_t)blockIdx.z * H * W;
-#pragma unroll
-            for (int pr = 0; pr < 4; ++pr) {
-                const size_t ro = (size_t)s_rows[threadIdx.y][pr] * W;
-                frow[pr] = cubic_rn(xc, g[ro + c0], g[ro + c1], g[ro + c2], g[ro + c3]);
+        if (image_out) {
+            const uint32_t* bits = level_bits + (size_t)page * 8;
+            const bool aa = aa_planes != nullptr && level_count(bits) > 2;
+            double vmin, vmax;
+            if (aa) {
+                vmin = __longlong_as_double((long long)aa_minmax[2 * bz]);
+                vmax = __longlong_as_double((long long)aa_minmax[2 * bz + 1]);
+            } else {
+                int lo = 0, hi = 255;
+                for (int wv = 0; wv < 8; ++wv)
+                    if (bits[wv]) { lo = wv * 32 + __ffs(bits[wv]) - 1; break; }
+                for (int wv = 7; wv >= 0; --wv)
+                    if (bits[wv]) { hi = wv * 32 + 31 - __clz(bits[wv]); break; }
+                vmin = (double)lo;
+                vmax = (double)hi;
             }
-        } else {
-            const uint8_t* g = grey + src_off;
-#pragma unroll
-            for (int pr = 0; pr < 4; ++pr) {
-                const size_t ro = (size_t)s_rows[threadIdx.y][pr] * W;
-                frow[pr] = cubic_rn(xc, (double)g[ro + c0], (double)g[ro + c1], (double)g[ro + c2], (double)g[ro + c3]);
+            const double xr = s_xr[threadIdx.y], xc = s_xc[threadIdx.x];
+            const int c0 = s_cols[threadIdx.x][0], c1 = s_cols[threadIdx.x][1], c2 = s_cols[threadIdx.x][2], c3 = s_cols[threadIdx.x][3];
+            double frow[4];
+            if (aa) {
+                const double* g = aa_planes + (size_t)bz * H * W;
+    #pragma unroll
+                for (int pr = 0; pr < 4; ++pr) {
+                    const size_t ro = (size_t)s_rows[threadIdx.y][pr] * W;
+                    frow[pr] = cubic_rn(xc, g[ro + c0], g[ro + c1], g[ro + c2], g[ro + c3]);
+                }
+            } else {
+                const uint8_t* g = grey + src_off;
+    #pragma unroll
+                for (int pr = 0; pr < 4; ++pr) {
+                    const size_t ro = (size_t)s_rows[threadIdx.y][pr] * W;
+                    frow[pr] = cubic_rn(xc, (double)g[ro + c0], (double)g[ro + c1], (double)g[ro + c2], (double)g[ro + c3]);
+                }
             }
+            double v = cubic_rn(xr, frow[0], frow[1], frow[2], frow[3]);
+            v = fmin(fmax(v, vmin), vmax);                       // clip=True
+            // img = 1.0 - v/255 ; (img*255).astype(uint8)
+            const double t = __dmul_rn(__dsub_rn(1.0, __ddiv_rn(v, 255.0)), 255.0);
+            image_out[dst_off] = (uint8_t)(int)t;                // C truncation
         }
-        double v = cubic_rn(xr, frow[0], frow[1], frow[2], frow[3]);
-        v = fmin(fmax(v, vmin), vmax);                       // clip=True
-        // img = 1.0 - v/255 ; (img*255).astype(uint8)
-        const double t = __dmul_rn(__dsub_rn(1.0, __ddiv_rn(v, 255.0)), 255.0);
-        image_out[dst_off] = (uint8_t)(int)t;                // C truncation
     }
 }
 
@@ -209,10 +411,21 @@ __constant__ double c_gauss_w[2][kMaxGaussRadius + 1];   // [axis][0..R], w[0] =
 // Persistent grid (a few blocks per SM) looping over (page, 32x8 tile): pages with <= 2 grey levels are
 // skipped, so a batch of binarised pages pays one near-empty launch.  AXIS 0 reads the uint8 page,
 // AXIS 1 the fp64 result of axis 0 (or the page when axis 0 is skipped).
+// group_flag[g] = 1 iff some page of group g has more than two grey levels: the general-path kernels of a
+// group of binarised pages leave on one load instead of scanning the level bitmaps of all its pages
+__global__ void group_flags_kernel(const uint32_t* __restrict__ level_bits, int n, int group, int* __restrict__ flags) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g * group >= n) return;
+    int f = 0;
+    for (int pg = g * group; pg < min(n, (g + 1) * group); ++pg) f |= level_count(level_bits + (size_t)pg * 8) > 2;
+    flags[g] = f;
+}
+
 template <typename SRC, int AXIS>
 __global__ void __launch_bounds__(256)
 gauss1d_kernel(const SRC* __restrict__ src, size_t src_page_stride, double* __restrict__ dst, int H, int W, int radius,
-               const uint32_t* __restrict__ level_bits, int page0, int pages) {
+               const uint32_t* __restrict__ level_bits, int page0, int pages, const int* __restrict__ group_flag) {
+    if (!*group_flag) return;
     const double* wts = c_gauss_w[AXIS];
     const int tiles_x = (W + 31) / 32, tiles_y = (H + 7) / 8;
     for (int pg = 0; pg < pages; ++pg) {
@@ -237,8 +450,8 @@ gauss1d_kernel(const SRC* __restrict__ src, size_t src_page_stride, double* __re
 // per-page min/max of the filtered plane (values >= 0: the bit patterns order like the doubles)
 __global__ void __launch_bounds__(256)
 minmax_f64_kernel(const double* __restrict__ planes, size_t n, unsigned long long* __restrict__ out /*[pages][2]*/,
-                  const uint32_t* __restrict__ level_bits, int page0) {
-    if (level_count(level_bits + (size_t)(page0 + blockIdx.y) * 8) <= 2) return;
+                  const uint32_t* __restrict__ level_bits, int page0, const int* __restrict__ group_flag) {
+    if (!*group_flag || level_count(level_bits + (size_t)(page0 + blockIdx.y) * 8) <= 2) return;
     const double* p = planes + (size_t)blockIdx.y * n;
     double lo = 1e300, hi = 0.0;      // idle threads must not win the unsigned-pattern max
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -288,7 +501,7 @@ static int gauss_weights(double sigma, std::vector<double>& w) {
     return radius;
 }
 
-constexpr int kAaGroup = 8;      // pages whose fp64 anti-aliasing planes live in scratch at the same time
+constexpr int kAaGroup = 16;     // pages whose fp64 anti-aliasing planes live in scratch at the same time
 
 int launch_preprocess(pcs_ctx* ctx, const uint8_t* d_grey, const uint8_t* d_bin, int n, int H, int W, int Hs,
                       int Ws, uint8_t* d_image, uint8_t* d_binary, uint8_t* d_orig_binary) {
@@ -307,19 +520,38 @@ int launch_preprocess(pcs_ctx* ctx, const uint8_t* d_grey, const uint8_t* d_bin,
         if (r0 > kMaxGaussRadius || r1 > kMaxGaussRadius)
             return set_err(ctx, PCS_ERR_ARG, "preprocess: anti-aliasing radius %d/%d exceeds %d", r0, r1, kMaxGaussRadius);
         const int group = std::min(n, kAaGroup);
-        const size_t head = (((size_t)n * 8 * 4 + 255) / 256) * 256;
+        // two-level fast path: 16-byte aligned pages of a multiple of 32 bytes, scale factors up to 4
+        const bool fast = d_image && (reinterpret_cast<uintptr_t>(d_grey) & 15) == 0 && page_px % 32 == 0 && fr <= 4.0 && fc <= 4.0;
+        const size_t bitmap_words = fast ? (page_px / 32 + 1 + 3) / 4 * 4 : 0;
+        const int ngroups = (n + group - 1) / group;
+        const size_t head = (((size_t)n * 8 * 4 + (size_t)ngroups * 4 + 255) / 256) * 256;     // level bitmaps, then group flags
         const size_t mm_bytes = (((size_t)group * 16 + 255) / 256) * 256;
+        const size_t bm_bytes = (((size_t)n * bitmap_words * 4 + 255) / 256) * 256;
         const size_t plane_bytes = may_aa ? (size_t)group * page_px * sizeof(double) : 0;
-        PCS_TRY(scratch_reserve(ctx, head + mm_bytes + 2 * plane_bytes + 256));
+        PCS_TRY(scratch_reserve(ctx, head + mm_bytes + bm_bytes + 2 * plane_bytes + 256));
         uint32_t* d_bits = reinterpret_cast<uint32_t*>(ctx->scratch);
+        int* d_gflags = reinterpret_cast<int*>(d_bits + (size_t)n * 8);
         unsigned long long* d_mm = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(ctx->scratch) + head);
-        double* t0 = reinterpret_cast<double*>(reinterpret_cast<char*>(ctx->scratch) + head + mm_bytes);
+        uint32_t* d_bitmap = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ctx->scratch) + head + mm_bytes);
+        double* t0 = reinterpret_cast<double*>(reinterpret_cast<char*>(ctx->scratch) + head + mm_bytes + bm_bytes);
         double* t1 = t0 + (size_t)group * page_px;
         if (d_image) {
             PCS_CUDA(ctx, cudaMemsetAsync(d_bits, 0, (size_t)n * 8 * sizeof(uint32_t), st));
-            dim3 grid((unsigned)std::min<size_t>(296, (page_px / 16 + 255) / 256 + 1), n);
-            level_bits_kernel<<<grid, 256, 0, st>>>(d_grey, page_px, d_bits);
-            PCS_LAUNCH_CHECK(ctx, "level_bits_kernel");
+            if (fast) {
+                dim3 grid((unsigned)std::min<size_t>((size_t)ctx->sm_count * 4, (page_px / 32 + 255) / 256), n);
+                scan_pack_kernel<<<grid, 256, 0, st>>>(d_grey, page_px, d_bits, d_bitmap, bitmap_words);
+                PCS_LAUNCH_CHECK(ctx, "scan_pack_kernel");
+                dim3 rgrid((Ws + RB_T - 1) / RB_T, (Hs + RB_TY - 1) / RB_TY, n);
+                resample_bits_kernel<<<rgrid, 256, 0, st>>>(d_grey, d_bin, d_bin == d_grey ? 1 : 0, H, W, Hs, Ws, d_bits, d_bitmap,
+                                                            bitmap_words, d_image, d_binary);
+                PCS_LAUNCH_CHECK(ctx, "resample_bits_kernel");
+            } else {
+                dim3 grid((unsigned)std::min<size_t>(296, (page_px / 16 + 255) / 256 + 1), n);
+                level_bits_kernel<<<grid, 256, 0, st>>>(d_grey, page_px, d_bits);
+                PCS_LAUNCH_CHECK(ctx, "level_bits_kernel");
+            }
+            group_flags_kernel<<<(ngroups + 63) / 64, 64, 0, st>>>(d_bits, n, group, d_gflags);
+            PCS_LAUNCH_CHECK(ctx, "group_flags_kernel");
             if (may_aa) {
                 // pageable host -> constant: staged synchronously, ordered on the stream
                 if (r0 >= 0) PCS_CUDA(ctx, cudaMemcpyToSymbolAsync(c_gauss_w, w0.data(), w0.size() * 8, 0, cudaMemcpyHostToDevice, st));
@@ -336,23 +568,25 @@ int launch_preprocess(pcs_ctx* ctx, const uint8_t* d_grey, const uint8_t* d_bin,
                 const unsigned gfull = (unsigned)ctx->sm_count * 8;
                 const uint8_t* src = d_grey + (size_t)p0 * page_px;
                 if (r0 >= 0) {
-                    gauss1d_kernel<uint8_t, 0><<<gfull, 256, 0, st>>>(src, page_px, t0, H, W, r0, d_bits, p0, m);
+                    gauss1d_kernel<uint8_t, 0><<<gfull, 256, 0, st>>>(src, page_px, t0, H, W, r0, d_bits, p0, m, d_gflags + p0 / group);
                     PCS_LAUNCH_CHECK(ctx, "gauss1d<axis 0>");
                     planes = t0;
                 }
                 if (r1 >= 0) {
-                    if (planes) gauss1d_kernel<double, 1><<<gfull, 256, 0, st>>>(t0, page_px, t1, H, W, r1, d_bits, p0, m);
-                    else gauss1d_kernel<uint8_t, 1><<<gfull, 256, 0, st>>>(src, page_px, t1, H, W, r1, d_bits, p0, m);
+                    if (planes) gauss1d_kernel<double, 1><<<gfull, 256, 0, st>>>(t0, page_px, t1, H, W, r1, d_bits, p0, m, d_gflags + p0 / group);
+                    else gauss1d_kernel<uint8_t, 1><<<gfull, 256, 0, st>>>(src, page_px, t1, H, W, r1, d_bits, p0, m, d_gflags + p0 / group);
                     PCS_LAUNCH_CHECK(ctx, "gauss1d<axis 1>");
                     planes = t1;
                 }
                 minmax_init_kernel<<<1, 32, 0, st>>>(d_mm, m);
                 PCS_LAUNCH_CHECK(ctx, "minmax_init_kernel");
-                minmax_f64_kernel<<<dim3(148, m), 256, 0, st>>>(planes, page_px, d_mm, d_bits, p0);
+                minmax_f64_kernel<<<dim3(148, m), 256, 0, st>>>(planes, page_px, d_mm, d_bits, p0, d_gflags + p0 / group);
                 PCS_LAUNCH_CHECK(ctx, "minmax_f64_kernel");
             }
-            dim3 grid((Ws + 31) / 32, (Hs + 7) / 8, m);
-            resample_kernel<<<grid, block, 0, st>>>(d_grey, d_bin, H, W, Hs, Ws, d_bits, planes, d_mm, p0, d_image, d_binary);
+            const long long tiles = (long long)((Ws + 31) / 32) * ((Hs + 7) / 8) * m;
+            const unsigned rgrid = (unsigned)std::min<long long>(tiles, (long long)ctx->sm_count * 8);
+            resample_kernel<<<rgrid, block, 0, st>>>(d_grey, d_bin, H, W, Hs, Ws, d_bits, planes, d_mm, p0, d_image, d_binary, fast ? 1 : 0,
+                                                     d_image ? d_gflags + p0 / group : nullptr, m);
             PCS_LAUNCH_CHECK(ctx, "resample_kernel");
         }
     }

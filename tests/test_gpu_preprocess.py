@@ -84,6 +84,70 @@ def test_batched_pages_match_single(ctx):
         np.testing.assert_array_equal(d_bin[i].cpu().numpy(), eb)
 
 
+# ---- two-level fast path (bitmap + 16-pattern LUT): pages of a multiple of 32 bytes, scale factor <= 4 ----
+@pytest.mark.parametrize("shape,lh,target", [((128, 96), 4, 6), ((256, 160), 6, 6), ((640, 480), 20, 6), ((352, 512), 23, 6),
+                                             ((640, 480), 30, 6)])
+def test_fast_path_shapes_and_scales(ctx, shape, lh, target):
+    """up-scale (reflect borders inside the tile), scale 1, ~1/3.3, ~1/3.8 and 1/5 (beyond the fast path's
+    span limit -> general kernel) on shapes that are eligible for the fast path"""
+    page = synth.make_page(11, shape[0], shape[1], max(lh, 6))
+    img, b, ob = _run(page, page, target, lh)
+    eimg, eb, eob = opipe.prepare_images(page, page, target, lh, keep_orig_bin=True)
+    np.testing.assert_array_equal(b, eb)
+    np.testing.assert_array_equal(ob, eob)
+    np.testing.assert_array_equal(img, eimg)
+
+
+@pytest.mark.parametrize("levels,first_is_ink", [((0, 255), False), ((0, 255), True), ((10, 200), True), ((1, 2), False)])
+def test_fast_path_levels(ctx, levels, first_is_ink):
+    """the bitmap is relative to page[0]: either level may come first; levels need not be 0/255"""
+    rng = np.random.default_rng(5)
+    mask = rng.random((320, 256)) < 0.3
+    mask[0, 0] = first_is_ink
+    page = np.where(mask, levels[0], levels[1]).astype(np.uint8)
+    img, b, ob = _run(page, page, 6, 15)
+    eimg, eb, eob = opipe.prepare_images(page, page, 6, 15, keep_orig_bin=True)
+    np.testing.assert_array_equal(b, eb)
+    np.testing.assert_array_equal(ob, eob)
+    np.testing.assert_array_equal(img, eimg)
+
+
+def test_fast_path_mixed_batch(ctx):
+    """one call, pages of different kinds: binarised, blank (one level), three levels (anti-aliased general
+    path), grey; each page must match its own single-page oracle result"""
+    import torch
+    H, W, lh = 480, 352, 18
+    two = synth.make_page(2, H, W, lh)
+    blank = np.full((H, W), 255, np.uint8)
+    three = two.copy(); three[100:140, 50:90] = 128
+    grey = synth.make_grey_page(4, H, W, lh)
+    pages = np.stack([two, blank, three, grey, two[::-1].copy()])
+    n = len(pages)
+    Hs, Ws = synth.scaled_shape(H, W, 6 / lh)
+    d = torch.from_numpy(pages).cuda()
+    d_img = torch.empty((n, Hs, Ws), dtype=torch.uint8, device="cuda")
+    d_bin = torch.empty_like(d_img)
+    ctx.preprocess(d, d, n, H, W, Hs, Ws, d_img, d_bin, None)
+    for i in range(n):
+        eimg, eb = opipe.prepare_images(pages[i], pages[i], 6, lh)
+        np.testing.assert_array_equal(d_bin[i].cpu().numpy(), eb)
+        diff = np.abs(d_img[i].cpu().numpy().astype(int) - eimg.astype(int))
+        if len(np.unique(pages[i])) <= 2:
+            assert diff.max() == 0, i
+        else:
+            assert diff.max() <= 1 and (diff > 0).mean() <= 1e-4, i
+
+
+def test_fast_path_separate_binary(ctx):
+    grey = synth.make_page(1, 384, 320, 18)
+    binary = synth.make_page(2, 384, 320, 18)
+    img, b, ob = _run(grey, binary, 6, 18)
+    eimg, eb, eob = opipe.prepare_images(grey, binary, 6, 18, keep_orig_bin=True)
+    np.testing.assert_array_equal(b, eb)
+    np.testing.assert_array_equal(ob, eob)
+    np.testing.assert_array_equal(img, eimg)
+
+
 @pytest.mark.parametrize("src,dst", [((50, 40), (150, 121)), ((389, 275), (1169, 827)), ((120, 90), (40, 30))])
 def test_preserving_resize(ctx, src, dst):
     from page_segmentation_b200.lib.util import preserving_resize
