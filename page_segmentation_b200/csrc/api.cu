@@ -170,7 +170,7 @@ static int run_conv(pcs_ctx* ctx, const char* lname, const Act* s0, const Act* s
         FoldConvArgs f;
         f.src = src_of(*s0);
         f.n = n; f.h = h; f.w = w; f.k = L->k;
-        f.wimg = L->d_wfold; f.b32 = L->d_b32; f.cout = L->cout; f.npad = L->npad; f.nplanes = s0->cp / 8; f.relu = L->relu;
+        f.wimg = L->d_wfold; f.h_bias = L->h_b32.data(); f.cout = L->cout; f.npad = L->npad; f.nplanes = s0->cp / 8; f.relu = L->relu;
         f.out = out ? out->p : nullptr; f.out_cp = out ? out->cp : 0;
         f.pool_out = pool_out ? pool_out->p : nullptr; f.pool_cp = pool_out ? pool_out->cp : 0;
         f.plog = plog; f.skip_lw = skip_lw;
@@ -203,7 +203,7 @@ static int run_conv1_u8(pcs_ctx* ctx, const char* lname, const uint8_t* d_image,
     if (!L) return set_err(ctx, PCS_ERR_STATE, "layer %s missing", lname);
     StageScope ts(ctx, lname);
     if (ctx->engine == PCS_ENGINE_UMMA && L->d_wmma && L->k == 5 && L->cout == 20)
-        return launch_conv1_umma(ctx, d_image, n, hs, ws, out->h, out->w, L->d_wmma, L->d_b32, out->p, out->cp);
+        return launch_conv1_umma(ctx, d_image, n, hs, ws, out->h, out->w, L->d_wmma, L->h_b32.data(), out->p, out->cp);
     DirectConvArgs a;
     a.src[0].p = d_image; a.src[0].c = 1; a.src[0].cp = 1; a.nsrc = 1;
     a.src_u8 = 1; a.img_h = hs; a.img_w = ws;

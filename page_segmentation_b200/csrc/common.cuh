@@ -260,7 +260,7 @@ struct FoldConvArgs {
     ConvSrc src;
     int n = 0, h = 0, w = 0, k = 5;
     const void* wimg = nullptr;
-    const float* b32 = nullptr;
+    const float* h_bias = nullptr;     // HOST pointer: the bias travels in the kernel parameter block
     int cout = 0, npad = 0, nplanes = 0, relu = 0;      // nplanes: 8-channel planes of the source
     void* out = nullptr; int out_cp = 0;
     void* pool_out = nullptr; int pool_cp = 0;
@@ -274,6 +274,6 @@ int launch_conv_fold(pcs_ctx* ctx, const FoldConvArgs& a);
 // conv1_umma.cu  (first FCN layer on the tensor cores)
 size_t conv1_umma_weight_image(const float* w32 /*[25][1][cout]*/, int cout, int precision, std::vector<uint16_t>& out);
 int launch_conv1_umma(pcs_ctx* ctx, const uint8_t* d_image, int n, int img_h, int img_w, int h, int w, const void* wimg,
-                      const float* bias, void* out, int out_cp);
+                      const float* h_bias, void* out, int out_cp);
 
 }  // namespace pcs

@@ -24,29 +24,25 @@ constexpr int C1_R = 8;            // output rows per tile
 constexpr int C1_N = 32;           // padded C_out
 constexpr int C1_ROWS = C1_R + 5;  // expanded rows per stage (r + 2ks + 1 <= R - 1 + 5)
 constexpr int C1_SW = 124;         // valid output pixels per 128-pixel strip
-constexpr int C1_STAGES = 2;
+constexpr int C1_STAGES = 3;
 constexpr int C1_ROW_BYTES = 128 * 16;
 constexpr int C1_STAGE_BYTES = C1_ROWS * C1_ROW_BYTES;
 constexpr int C1_B_BYTES = 2 * 3 * 2 * C1_N * 16;      // [hi|lo][ks][plane][n][8]
 constexpr int C1_THREADS = 448;     // warp 0 weights, warp 1 MMA, warps 2-5 + 10-13 epilogue (2 per lane quarter), warps 6-9 builders
 constexpr int C1_RAW_W = 136;      // bytes per raw patch row: 128 pixel slots + 7 look-ahead (+1 pad)
+constexpr int C1_CVT_W = 144;      // operand elements per converted patch row (4-byte aligned rows)
+constexpr int C1_CVT_COPY = C1_ROWS * C1_CVT_W + 14;   // elements per converted copy: 943 words = 15 mod 32, so the windows of odd
+                                                       // pixel slots (copy 1, word m+1) use the 16 banks the even ones (word m) do not
 
 struct Conv1Params {
     const uint8_t* img; int img_h, img_w;   // real page
     int n, h, w;                            // padded grid
     const uint8_t* wimg;                    // C1_B_BYTES operand image
-    const float* bias;
+    float bias[C1_N];                       // by value: read as constant-bank FFMA operands, no shared-memory traffic
     void* out; int out_cp;
     int strips, rowblocks, num_tiles;
+    int dbg;                                // diagnosis only (PCSEG_C1_DEBUG): 1 = no output stores, 2 = hi MMAs only, 4 = no expansion
 };
-
-template <typename T> __device__ __forceinline__ uint32_t pack_u8x2(uint32_t a, uint32_t b);
-template <> __device__ __forceinline__ uint32_t pack_u8x2<__nv_bfloat16>(uint32_t a, uint32_t b) {
-    return pack2<__nv_bfloat16>((float)a, (float)b);
-}
-template <> __device__ __forceinline__ uint32_t pack_u8x2<__half>(uint32_t a, uint32_t b) {
-    return pack2<__half>((float)a, (float)b);
-}
 
 template <typename T>
 __global__ void __launch_bounds__(C1_THREADS, 1) conv1_umma_kernel(const Conv1Params p) {
@@ -56,8 +52,9 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv1_umma_kernel(const Conv1Pa
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_full[C1_STAGES], s_empty[C1_STAGES], s_tfull[2], s_tempty[2];
     __shared__ uint32_t s_tmem_base;
-    __shared__ float s_bias[C1_N];
-    __shared__ uint8_t s_raw[C1_STAGES][C1_ROWS * C1_RAW_W];
+    // every patch pixel converted ONCE to the operand type, stored twice: copy c holds element e at index e + c, so
+    // that the 8-element window of an odd pixel slot is 4-byte aligned in copy 1 (and of an even slot in copy 0)
+    __shared__ __align__(16) T s_cvt[C1_STAGES][2 * C1_CVT_COPY];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -70,7 +67,7 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv1_umma_kernel(const Conv1Pa
         for (int i = lane; i < C1_B_BYTES / 16; i += 32) dst[i] = __ldg(src + i);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         if (lane == 0) {
-            for (int s = 0; s < C1_STAGES; ++s) { mbar_init(&s_full[s], 128); mbar_init(&s_empty[s], 1); }
+            for (int s = 0; s < C1_STAGES; ++s) { mbar_init(&s_full[s], 4); mbar_init(&s_empty[s], 1); }
             for (int a = 0; a < 2; ++a) { mbar_init(&s_tfull[a], 1); mbar_init(&s_tempty[a], 8); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -80,7 +77,6 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv1_umma_kernel(const Conv1Pa
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (threadIdx.x < C1_N) s_bias[threadIdx.x] = threadIdx.x < 20 ? __ldg(p.bias + threadIdx.x) : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -106,7 +102,7 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv1_umma_kernel(const Conv1Pa
 #pragma unroll
                 for (int r = 0; r < C1_R; ++r) {
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {        // weights hi, then lo
+                    for (int half = 0; half < ((p.dbg & 2) ? 1 : 2); ++half) {        // weights hi, then lo
 #pragma unroll
                         for (int ks = 0; ks < 3; ++ks) {
                             const uint32_t a_off = (uint32_t)((r + 2 * ks) * (C1_ROW_BYTES >> 4));
@@ -148,12 +144,12 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv1_umma_kernel(const Conv1Pa
                 tmem_ld16(t_lane + (uint32_t)(r * C1_N + 16), v1);
                 tmem_ld_wait();
                 const int y = y0 + r;
-                if (xok && y < p.h) {
+                if (xok && y < p.h && !(p.dbg & 1)) {
                     float f[32];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        f[i] = fmaxf(fmaf(__uint_as_float(v0[i]), inv255, s_bias[i]), 0.f);
-                        f[16 + i] = fmaxf(fmaf(__uint_as_float(v1[i]), inv255, s_bias[16 + i]), 0.f);
+                        f[i] = fmaxf(fmaf(__uint_as_float(v0[i]), inv255, p.bias[i]), 0.f);
+                        f[16 + i] = fmaxf(fmaf(__uint_as_float(v1[i]), inv255, p.bias[16 + i]), 0.f);
                     }
 #pragma unroll
                     for (int g = 0; g < 4; ++g)
@@ -169,44 +165,65 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv1_umma_kernel(const Conv1Pa
         }
     } else if (warp >= 6 && warp < 10) {
         // ===================== builders: expand input rows into K-major planes =====================
-        // phase 1: the 13 x 135-byte uint8 patch is fetched with independent, coalesced byte loads (one
-        // latency round); phase 2: every thread assembles the 16-byte unit of "its" pixel for all rows.
+        // phase 1: the 13 x 135-byte uint8 patch is fetched with independent, coalesced byte loads -- for the
+        // NEXT tile, so that the global-load latency hides behind the current tile's work; phase 2: each byte is
+        // converted once (pixels 0..255 are exact in bf16/fp16) into the two shifted copies; phase 3: every
+        // thread assembles the 16-byte unit (8 consecutive pixels) of "its" pixel slot for all 13 rows with four
+        // aligned 32-bit loads and one 128-bit store per row.
         const int xq = threadIdx.x - 192;                 // 0..127 = pixel slot of the strip patch
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        // byte (row j, column xq) for the 13 rows, plus one of the 13 x 8 look-ahead bytes (columns 128..135)
+        constexpr int NV = C1_ROWS + 1;
+        uint8_t next[NV];
+        const int xrow = xq >> 3, xcol = 128 + (xq & 7);  // the look-ahead byte of this thread (xq < 104)
+        auto fetch = [&](int tile, uint8_t (&dst)[NV]) {
             const int page = tile / tiles_per_page;
             const int rem = tile - page * tiles_per_page;
             const int rb = rem % p.rowblocks, strip = rem / p.rowblocks;
             const int gxb = strip * C1_SW - 2, gy0 = rb * C1_R - 2;
             const uint8_t* src = p.img + (size_t)page * p.img_h * p.img_w;
-            uint8_t vals[(C1_ROWS * C1_RAW_W + 127) / 128];
+            const int gx = gxb + xq;
+            const bool xin = gx >= 0 && gx < p.img_w;
+            const uint8_t* col = src + (ptrdiff_t)gy0 * p.img_w + gx;
 #pragma unroll
-            for (int j = 0; j < (C1_ROWS * C1_RAW_W + 127) / 128; ++j) {
-                const int i = xq + 128 * j;
-                const int row = i / C1_RAW_W, col = i - row * C1_RAW_W;
-                const int gy = gy0 + row, gx = gxb + col;
-                vals[j] = (i < C1_ROWS * C1_RAW_W && gy >= 0 && gy < p.img_h && gx >= 0 && gx < p.img_w)
-                              ? __ldg(src + (size_t)gy * p.img_w + gx) : (uint8_t)0;
+            for (int j = 0; j < C1_ROWS; ++j) {
+                const int gy = gy0 + j;
+                dst[j] = (xin && gy >= 0 && gy < p.img_h) ? __ldg(col + (ptrdiff_t)j * p.img_w) : (uint8_t)0;
             }
-            mbar_wait(&s_empty[stage], phase ^ 1u);           // stage (incl. its raw buffer) is free
-            uint8_t* raw = s_raw[stage];
+            const int gy = gy0 + xrow, gx2 = gxb + xcol;
+            dst[C1_ROWS] = (xrow < C1_ROWS && gy >= 0 && gy < p.img_h && gx2 < p.img_w)
+                               ? __ldg(src + (size_t)gy * p.img_w + gx2) : (uint8_t)0;
+        };
+        if ((int)blockIdx.x < p.num_tiles) fetch(blockIdx.x, next);
+        const int par = xq & 1;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            mbar_wait(&s_empty[stage], phase ^ 1u);           // stage (incl. its conversion buffer) is free
+            T* cvt = s_cvt[stage];
 #pragma unroll
-            for (int j = 0; j < (C1_ROWS * C1_RAW_W + 127) / 128; ++j) {
-                const int i = xq + 128 * j;
-                if (i < C1_ROWS * C1_RAW_W) raw[i] = vals[j];
+            for (int j = 0; j < C1_ROWS; ++j) {
+                const T v = T((float)next[j]);
+                cvt[j * C1_CVT_W + xq] = v;
+                cvt[C1_CVT_COPY + j * C1_CVT_W + xq + 1] = v;
+            }
+            if (xrow < C1_ROWS) {
+                const T v = T((float)next[C1_ROWS]);
+                cvt[xrow * C1_CVT_W + xcol] = v;
+                cvt[C1_CVT_COPY + xrow * C1_CVT_W + xcol + 1] = v;
             }
             asm volatile("bar.sync 2, 128;" ::: "memory");
+            if (tile + (int)gridDim.x < p.num_tiles) fetch(tile + gridDim.x, next);
             uint8_t* dst = stages + (size_t)stage * C1_STAGE_BYTES + (size_t)xq * 16;
+            const uint32_t* win = reinterpret_cast<const uint32_t*>(cvt + par * C1_CVT_COPY) + ((xq + par) >> 1);
 #pragma unroll
-            for (int row = 0; row < C1_ROWS; ++row) {
-                const uint8_t* r8 = raw + row * C1_RAW_W + xq;
-                *reinterpret_cast<uint4*>(dst + (size_t)row * C1_ROW_BYTES) =
-                    make_uint4(pack_u8x2<T>(r8[0], r8[1]), pack_u8x2<T>(r8[2], r8[3]), pack_u8x2<T>(r8[4], r8[5]),
-                               pack_u8x2<T>(r8[6], r8[7]));
+            for (int row = 0; row < ((p.dbg & 4) ? 1 : C1_ROWS); ++row) {
+                const uint32_t* w4 = win + row * (C1_CVT_W / 2);
+                *reinterpret_cast<uint4*>(dst + (size_t)row * C1_ROW_BYTES) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the MMA
-            mbar_arrive(&s_full[stage]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_full[stage]);                      // one arrival per builder warp
+            // (the conversion buffer is reused three tiles later, after s_empty: every builder has arrived, hence read it)
             if (++stage == C1_STAGES) { stage = 0; phase ^= 1u; }
         }
     }
@@ -249,14 +266,16 @@ size_t conv1_umma_weight_image(const float* w32 /*[25][1][cout]*/, int cout, int
 }
 
 int launch_conv1_umma(pcs_ctx* ctx, const uint8_t* d_image, int n, int img_h, int img_w, int h, int w, const void* wimg,
-                      const float* bias, void* out, int out_cp) {
+                      const float* h_bias /*host, 20 values*/, void* out, int out_cp) {
     if (out_cp != C1_N && out_cp != 24) return set_err(ctx, PCS_ERR_ARG, "conv1_umma: output stride must be 24 or %d channels", C1_N);
     Conv1Params p{};
     p.img = d_image; p.img_h = img_h; p.img_w = img_w; p.n = n; p.h = h; p.w = w;
-    p.wimg = reinterpret_cast<const uint8_t*>(wimg); p.bias = bias; p.out = out; p.out_cp = out_cp;
+    p.wimg = reinterpret_cast<const uint8_t*>(wimg); p.out = out; p.out_cp = out_cp;
+    for (int i = 0; i < C1_N; ++i) p.bias[i] = i < 20 ? h_bias[i] : 0.f;
     p.strips = (w + C1_SW - 1) / C1_SW;
     p.rowblocks = (h + C1_R - 1) / C1_R;
     p.num_tiles = n * p.strips * p.rowblocks;
+    { const char* e = getenv("PCSEG_C1_DEBUG"); p.dbg = e ? atoi(e) : 0; }
     const size_t smem = ((C1_B_BYTES + 1023) / 1024) * 1024 + (size_t)C1_STAGES * C1_STAGE_BYTES + 1024;
     const int grid = std::min(p.num_tiles, ctx->sm_count);
     if (ctx->precision == PCS_PREC_BF16) {

@@ -59,7 +59,7 @@ struct FoldParams {
     int n, h, w;
     int seg_rows, segs, strips, num_items;  // work item = (page, strip, segment of seg_rows output rows)
     const uint8_t* wimg;                    // [chunk][dx][plane][row = (4-dy)*NPAD + o][8]: resident operand image
-    const float* bias;
+    float bias[48];                         // by value (zero padded): constant-bank operands of the epilogue's adds
     int cout, relu;
     void* out; int out_cp;
     void* pool; int pool_cp;
@@ -95,7 +95,6 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_full[F_RING_MAX], s_empty[F_RING_MAX], s_wfull, s_tfull[F_SLOTS_MAX], s_tempty[F_SLOTS_MAX];
     __shared__ uint32_t s_tmem_base;
-    __shared__ float s_bias[NPAD];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -113,7 +112,6 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < NPAD; i += blockDim.x) s_bias[i] = i < p.cout ? __ldg(p.bias + i) : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -273,8 +271,8 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
                         uint32_t pk[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            float a = __uint_as_float(v[hb * 16 + 2 * i]) + s_bias[hb * 16 + 2 * i];
-                            float b = __uint_as_float(v[hb * 16 + 2 * i + 1]) + s_bias[hb * 16 + 2 * i + 1];
+                            float a = __uint_as_float(v[hb * 16 + 2 * i]) + p.bias[hb * 16 + 2 * i];
+                            float b = __uint_as_float(v[hb * 16 + 2 * i + 1]) + p.bias[hb * 16 + 2 * i + 1];
                             if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
                             pk[i] = pack2<T>(a, b);
                         }
@@ -337,7 +335,9 @@ int launch_fold_t(pcs_ctx* ctx, const FoldConvArgs& a) {
     constexpr int NF = 5 * NPAD;
     FoldParams p{};
     p.n = a.n; p.h = a.h; p.w = a.w;
-    p.wimg = reinterpret_cast<const uint8_t*>(a.wimg); p.bias = a.b32; p.cout = a.cout; p.relu = a.relu;
+    p.wimg = reinterpret_cast<const uint8_t*>(a.wimg); p.cout = a.cout; p.relu = a.relu;
+    static_assert(NPAD <= 48, "bias travels in the parameter block");
+    for (int i = 0; i < 48; ++i) p.bias[i] = i < a.cout ? a.h_bias[i] : 0.f;
     p.out = a.out; p.out_cp = a.out_cp; p.pool = a.pool_out; p.pool_cp = a.pool_cp;
     p.plog = nullptr;
     if (a.plog) {
