@@ -101,7 +101,7 @@ static void free_layers(pcs_ctx* ctx) {
         if (l.d_w32) cudaFree(l.d_w32);
         if (l.d_b32) cudaFree(l.d_b32);
         if (l.d_wmma) cudaFree(l.d_wmma);
-        if (l.d_wfold) cudaFree(l.d_wfold);
+        for (auto& f : l.fold) if (f.d_w) cudaFree(f.d_w);
         if (l.d_head_lw) cudaFree(l.d_head_lw);
         if (l.d_head_lb) cudaFree(l.d_head_lb);
     }
@@ -166,15 +166,28 @@ static int run_conv(pcs_ctx* ctx, const char* lname, const Act* s0, const Act* s
     const Act& any = out ? *out : *pool_out;
     const int n = any.n;
     const int h = out ? out->h : pool_out->h * 2, w = out ? out->w : pool_out->w * 2;
-    if (ctx->engine == PCS_ENGINE_UMMA && !upsample && !s1 && L->d_wfold && !fold_disabled() && (h % 4) == 0) {
-        FoldConvArgs f;
-        f.src = src_of(*s0);
-        f.n = n; f.h = h; f.w = w; f.k = L->k;
-        f.wimg = L->d_wfold; f.h_bias = L->h_b32.data(); f.cout = L->cout; f.npad = L->npad; f.nplanes = s0->cp / 8; f.relu = L->relu;
-        f.out = out ? out->p : nullptr; f.out_cp = out ? out->cp : 0;
-        f.pool_out = pool_out ? pool_out->p : nullptr; f.pool_cp = pool_out ? pool_out->cp : 0;
-        f.plog = plog; f.skip_lw = skip_lw;
-        return launch_conv_fold(ctx, f);
+    if (ctx->engine == PCS_ENGINE_UMMA && !upsample && !L->fold.empty() && !fold_disabled() && (h % 4) == 0) {
+        void* psum = nullptr;
+        for (const Layer::FoldPart& part : L->fold) {
+            const Act* src = part.src == 0 ? s0 : s1;
+            if (!src) return set_err(ctx, PCS_ERR_STATE, "layer %s: folded part reads a missing source", lname);
+            if (part.psum && !psum) {
+                psum = arena_alloc(ctx, (size_t)n * h * w * part.npad * sizeof(float));
+                if (!psum) return set_err(ctx, PCS_ERR_NOMEM, "activation arena exhausted at the partial sums of %s", lname);
+            }
+            FoldConvArgs f;
+            f.src = src_of(*src);
+            f.n = n; f.h = h; f.w = w; f.k = L->k;
+            f.wimg = part.d_w; f.h_bias = L->h_b32.data() + part.o0; f.cout = part.ncols; f.npad = part.npad;
+            f.nplanes = src->cp / 8; f.relu = L->relu; f.o0 = part.o0;
+            f.out = out ? out->p : nullptr; f.out_cp = out ? out->cp : 0;
+            f.pool_out = pool_out ? pool_out->p : nullptr; f.pool_cp = pool_out ? pool_out->cp : 0;
+            f.psum_out = part.psum == 1 ? psum : nullptr;
+            f.psum_in = part.psum == 2 ? psum : nullptr;
+            f.plog = plog; f.skip_lw = skip_lw;
+            PCS_TRY(launch_conv_fold(ctx, f));
+        }
+        return PCS_OK;
     }
     if (plog) return set_err(ctx, PCS_ERR_STATE, "layer %s: partial logits requested off the folded kernel", lname);
     if (ctx->engine == PCS_ENGINE_UMMA && !upsample && L->d_wmma && umma_supported(L->k, L->npad)) {
@@ -251,7 +264,7 @@ static int forward_fcn(pcs_ctx* ctx, bool skip, const uint8_t* d_image, int n, i
     Layer* L2 = find_layer(ctx, "conv2");
     Layer* L5 = find_layer(ctx, "deconv5");
     Layer* LL = find_layer(ctx, "logits");
-    const bool conv2_folds = L2 && L2->d_wfold && !fold_disabled();
+    const bool conv2_folds = L2 && L2->fold.size() == 1 && !fold_disabled();
     const bool fused_head = ctx->engine == PCS_ENGINE_UMMA && L5->d_wmma && LL->d_head_lb && (!skip || (conv2_folds && LL->d_head_lw));
     void* plog = nullptr;
     if (fused_head && skip) {
@@ -395,7 +408,7 @@ static size_t arena_need(int arch, int n, int hs, int ws) {
     if (arch == PCS_ARCH_UNET)
         ch = 64 * 5 + (64 + 128 * 5) / 4.0 + (128 + 256 * 5) / 16.0 + (256 + 512 * 5) / 64.0 + (512 + 1024 * 2) / 256.0;
     else
-        ch = 32 + 32 + 8 + (32 + 48 + 32) / 4.0 + (48 + 64 + 64 + 64 + 48) / 16.0 + (64 + 80 + 80) / 64.0;
+        ch = 32 + 32 + 8 + (32 + 48 + 32) / 4.0 + (48 + 64 + 64 + 64 + 48 + 96) / 16.0 + (64 + 80 + 80) / 64.0;
     return (size_t)(px * ch * 2.0) + (size_t)64 * 4096 + (1u << 20);
 }
 
@@ -553,11 +566,27 @@ int pcs_model_load(pcs_ctx* ctx, int arch, int n_classes, int precision, const p
             L.npad = std::min(pad16(L.cout), 128);
             if (!umma_supported(L.k, L.npad) || (L.cout > 128 && L.cout % 128)) continue;
             L.wmma_bytes = umma_weight_image(L.h_w32.data(), L.k * L.k, src_c, nsrc, L.cout, L.npad, precision, img);
-            if (fold_supported(L.k, L.npad, pad8(L.cin) / 8, nsrc)) {
+            // dy-folded marching kernel: whole layer if its resident weights fit, else split along N (output
+            // channels, two launches) or along K (one launch per concatenated source)
+            auto add_part = [&](int src, int ci0, int cin, int o0, int ncols, int npad, int psum) -> int {
                 std::vector<uint16_t> fimg;
-                const size_t fb = fold_weight_image(L.h_w32.data(), L.cin, L.cout, L.npad, precision, fimg);
-                PCS_CUDA(ctx, cudaMalloc(&L.d_wfold, fb));
-                PCS_CUDA(ctx, cudaMemcpy(L.d_wfold, fimg.data(), fb, cudaMemcpyHostToDevice));
+                const size_t fb = fold_weight_image(L.h_w32.data(), L.cin, L.cout, ci0, cin, o0, ncols, npad, precision, fimg);
+                Layer::FoldPart part;
+                part.src = src; part.o0 = o0; part.ncols = ncols; part.npad = npad; part.nplanes = pad8(cin) / 8; part.psum = psum;
+                PCS_CUDA(ctx, cudaMalloc(&part.d_w, fb));
+                PCS_CUDA(ctx, cudaMemcpy(part.d_w, fimg.data(), fb, cudaMemcpyHostToDevice));
+                L.fold.push_back(part);
+                return PCS_OK;
+            };
+            if (L.k == 5 && nsrc == 1 && fold_supported(5, L.npad, pad8(L.cin) / 8)) {
+                PCS_TRY(add_part(0, 0, L.cin, 0, L.cout, L.npad, 0));
+            } else if (L.k == 5 && nsrc == 1 && L.cout > 32 && L.cout <= 64 && fold_supported(5, 32, pad8(L.cin) / 8)) {
+                PCS_TRY(add_part(0, 0, L.cin, 0, 32, 32, 0));
+                PCS_TRY(add_part(0, 0, L.cin, 32, L.cout - 32, 32, 0));
+            } else if (L.k == 5 && nsrc == 2 && fold_supported(5, L.npad, pad8(src_c[0]) / 8) &&
+                       fold_supported(5, L.npad, pad8(src_c[1]) / 8)) {
+                PCS_TRY(add_part(0, 0, src_c[0], 0, L.cout, L.npad, 1));
+                PCS_TRY(add_part(1, src_c[0], src_c[1], 0, L.cout, L.npad, 2));
             }
         } else if (L.kind == K_DECONV_S2 && L.name == "deconv5") {
             // fused head: deconv5 composed with the logits layer on the host (conv_umma.cu EPI_HEAD)

@@ -60,7 +60,17 @@ struct Layer {
     size_t wmma_bytes = 0;
     int npad = 0;           // padded C_out of the UMMA tile
     int co_t = 0;           // deconv s2 on the tensor path: padded channels per tap
-    void* d_wfold = nullptr;      // resident operand image of the dx-folded kernel (conv_fold.cu)
+    // launches of the dy-folded marching kernel (conv_fold.cu) that together compute this layer: a layer whose
+    // resident weights do not fit shared memory is split along N (output channels) or along K (one part per
+    // concatenated source, fp32 partial sums handed from the first part to the last)
+    struct FoldPart {
+        void* d_w = nullptr;      // resident operand image
+        int src = 0;              // concatenated source read by this part
+        int o0 = 0, ncols = 0;    // output channels [o0, o0 + ncols)
+        int npad = 0, nplanes = 0;
+        int psum = 0;             // 0 complete, 1 writes partial sums, 2 adds them
+    };
+    std::vector<FoldPart> fold;
     std::vector<float> h_w32_raw; // deconv5 only: weights before rounding (composed with the logits on the host)
     float* d_head_lw = nullptr;   // logits layer: [32][4] rows of the conv2 skip channels, zero padded (fcn_skip)
     float* d_head_lb = nullptr;   // logits layer: [4] bias with the deconv5 / conv2 biases folded in
@@ -264,11 +274,15 @@ struct FoldConvArgs {
     int cout = 0, npad = 0, nplanes = 0, relu = 0;      // nplanes: 8-channel planes of the source
     void* out = nullptr; int out_cp = 0;
     void* pool_out = nullptr; int pool_cp = 0;
+    int o0 = 0;                        // first output channel written by this launch (N split; whole planes)
+    void* psum_out = nullptr;          // K split: fp32 partial sums [n][npad/4][h][w][4] written instead of the output ...
+    const void* psum_in = nullptr;     // ... and added by the last part before bias / activation
     void* plog = nullptr;              // optional float4 [n][h][w]: this layer's share of the logits (fcn_skip conv2)
     const float* skip_lw = nullptr;    // device [32][4]: logits rows of this layer's channels, zero padded
 };
-bool fold_supported(int k, int npad, int nplanes, int nsrc);
-size_t fold_weight_image(const float* w32 /*[25][cin][cout]*/, int cin, int cout, int npad, int precision, std::vector<uint16_t>& out);
+bool fold_supported(int k, int npad, int nplanes);
+size_t fold_weight_image(const float* w32 /*[25][cin_total][cout_total]*/, int cin_total, int cout_total, int ci0, int cin,
+                         int o0, int ncols, int npad, int precision, std::vector<uint16_t>& out);
 int launch_conv_fold(pcs_ctx* ctx, const FoldConvArgs& a);
 
 // conv1_umma.cu  (first FCN layer on the tensor cores)

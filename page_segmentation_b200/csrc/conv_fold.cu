@@ -63,6 +63,9 @@ struct FoldParams {
     int cout, relu;
     void* out; int out_cp;
     void* pool; int pool_cp;
+    int out_c0;                             // first output channel of this launch (a multiple of 8): layers split along N
+    float4* psum_out;                       // [n][NPAD/4][h][w] fp32 partial sums written INSTEAD of the output (K split, first part)
+    const float4* psum_in;                  // ... added before bias / activation (K split, last part)
     float4* plog;                           // [n][h][w] partial logits (4 classes, zero padded) or null
     int plog_nc;                            // classes actually present (the 4th FMA chain is skipped for <= 3)
     uint32_t w_bytes;
@@ -90,7 +93,9 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
                                 ((std::is_same<T, __nv_bfloat16>::value ? 1u : 0u) << 10) | ((uint32_t)(128 >> 4) << 24);
     static_assert(NF <= 256 && NF % 16 == 0, "folded N must be a legal UMMA N");
     static_assert(SLOTS * NPAD <= 512 && SLOTS <= F_SLOTS_MAX && SLOTS >= 8, "accumulator ring must fit TMEM");
-    static_assert(RING % SLOTS == 0 && RING <= F_RING_MAX, "the issue loop is unrolled over one ring period");
+    constexpr int PERIOD = (RING % SLOTS == 0) ? RING : ((SLOTS % RING == 0) ? SLOTS : RING * SLOTS);   // lcm for the shapes used
+    static_assert(PERIOD % RING == 0 && PERIOD % SLOTS == 0 && PERIOD <= 20 && RING <= F_RING_MAX,
+                  "the issue loop is unrolled over one common period of the input ring and the accumulator ring");
 
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_full[F_RING_MAX], s_empty[F_RING_MAX], s_wfull, s_tfull[F_SLOTS_MAX], s_tempty[F_SLOTS_MAX];
@@ -162,12 +167,11 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
             const uint32_t b_lo0 = ((smem_u32(s_w) >> 4) & 0x3fffu) | b_lbo;
             for (int s = 0; s < SLOTS; ++s) mbar_wait(&s_tempty[s], 0);                    // every slot zeroed once
             tc_fence_after();
-            for (uint32_t kk = 0; kk < total; kk += RING) {
-                const uint32_t ring_phase = (kk / RING) & 1u;
+            for (uint32_t kk = 0; kk < total; kk += PERIOD) {
 #pragma unroll
-                for (int u = 0; u < RING; ++u) {
+                for (int u = 0; u < PERIOD; ++u) {
                     if (kk + u >= total) break;
-                    mbar_wait(&s_full[u], ring_phase);
+                    mbar_wait(&s_full[u % RING], ((kk + u) / RING) & 1u);
                     // the newest output slot of the window must have been drained and re-zeroed by the epilogue:
                     // tempty phase 0 = initial zeroing, phase n = drain of use n-1: use n waits for phase n
                     mbar_wait(&s_tempty[(u + 4) % SLOTS], ((kk + u + 4) / SLOTS) & 1u);
@@ -188,13 +192,13 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
                         const int t = q - FoldK<NPL>::PAIRS * 5;
                         const int plane = pair ? 2 * (q / 5) : NPL - 1;
                         const int dx = pair ? q % 5 : (t == 0 ? 0 : t + 1);
-                        const uint32_t a_lo = (a_step + (uint32_t)(u * (ROW_BYTES >> 4) + plane * (2048 >> 4) + dx)) |
+                        const uint32_t a_lo = (a_step + (uint32_t)((u % RING) * (ROW_BYTES >> 4) + plane * (2048 >> 4) + dx)) |
                                               (pair ? a_lbo_pair : a_lbo_self);
                         const uint32_t b_lo = b_step + (uint32_t)(q * (WDX_BYTES >> 4));
                         tc_mma(d_step + (uint32_t)(s0 * NPAD), a_lo, hi, b_lo, hi, idesc1, 1u);   // slots are pre-zeroed
                         if (n1 < 5) tc_mma(d_step, a_lo, hi, b_lo + (uint32_t)(n1 * NPAD), hi, idesc2, 1u);
                     }
-                    tc_commit(&s_empty[u]);                                               // input row consumed
+                    tc_commit(&s_empty[u % RING]);                                        // input row consumed
                     tc_commit(&s_tfull[s0]);                                              // output slot k is complete
                 }
             }
@@ -249,6 +253,28 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&s_tempty[slot]);      // slot free for the window of input row gg+4
                     if (!real) continue;
+                    if (p.psum_out) {                                   // K split, first part: raw fp32 sums, nothing else
+                        if (xok && y < p.h) {
+#pragma unroll
+                            for (int c4 = 0; c4 < NPAD / 4; ++c4)
+                                p.psum_out[(((size_t)page * (NPAD / 4) + c4) * p.h + y) * p.w + x] =
+                                    make_float4(__uint_as_float(v[4 * c4]), __uint_as_float(v[4 * c4 + 1]),
+                                                __uint_as_float(v[4 * c4 + 2]), __uint_as_float(v[4 * c4 + 3]));
+                        }
+                        continue;
+                    }
+                    if (p.psum_in) {                                    // K split, last part: add what the first part left
+                        const bool ok = xok && y < p.h;
+#pragma unroll
+                        for (int c4 = 0; c4 < NPAD / 4; ++c4) {
+                            const float4 q = ok ? __ldg(p.psum_in + (((size_t)page * (NPAD / 4) + c4) * p.h + y) * p.w + x)
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+                            v[4 * c4] = __float_as_uint(__uint_as_float(v[4 * c4]) + q.x);
+                            v[4 * c4 + 1] = __float_as_uint(__uint_as_float(v[4 * c4 + 1]) + q.y);
+                            v[4 * c4 + 2] = __float_as_uint(__uint_as_float(v[4 * c4 + 2]) + q.z);
+                            v[4 * c4 + 3] = __float_as_uint(__uint_as_float(v[4 * c4 + 3]) + q.w);
+                        }
+                    }
                     if constexpr (NPAD == F_LOGC) {
                         if (p.plog) {
                             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -276,10 +302,11 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
                             if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
                             pk[i] = pack2<T>(a, b);
                         }
-                        if (out && xok && y < p.h && hb * 16 < p.out_cp) {
-                            *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, p.h, p.w, hb * 16, y, x)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                            if (hb * 16 + 8 < p.out_cp)
-                                *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, p.h, p.w, hb * 16 + 8, y, x)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                        const int oc = p.out_c0 + hb * 16;            // first of the 16 output channels of this block
+                        if (out && xok && y < p.h && oc < p.out_cp) {
+                            *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, p.h, p.w, oc, y, x)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            if (oc + 8 < p.out_cp)
+                                *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, p.h, p.w, oc + 8, y, x)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                         }
                         if (pool) {
                             if (st == 0) {
@@ -292,11 +319,11 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
                                     const uint32_t m = max2<T>(pk[i], kept[hb * 8 + i]);
                                     pm[i] = max2<T>(m, __shfl_xor_sync(0xffffffffu, m, 1));
                                 }
-                                if (!(lane & 1) && xok && y < p.h && hb * 16 < p.pool_cp) {
+                                if (!(lane & 1) && xok && y < p.h && oc < p.pool_cp) {
                                     const int ph = p.h >> 1, pw = p.w >> 1;
-                                    *reinterpret_cast<uint4*>(pool + act_idx(page, p.pool_cp, ph, pw, hb * 16, y >> 1, x >> 1)) = make_uint4(pm[0], pm[1], pm[2], pm[3]);
-                                    if (hb * 16 + 8 < p.pool_cp)
-                                        *reinterpret_cast<uint4*>(pool + act_idx(page, p.pool_cp, ph, pw, hb * 16 + 8, y >> 1, x >> 1)) = make_uint4(pm[4], pm[5], pm[6], pm[7]);
+                                    *reinterpret_cast<uint4*>(pool + act_idx(page, p.pool_cp, ph, pw, oc, y >> 1, x >> 1)) = make_uint4(pm[0], pm[1], pm[2], pm[3]);
+                                    if (oc + 8 < p.pool_cp)
+                                        *reinterpret_cast<uint4*>(pool + act_idx(page, p.pool_cp, ph, pw, oc + 8, y >> 1, x >> 1)) = make_uint4(pm[4], pm[5], pm[6], pm[7]);
                                 }
                             }
                         }
@@ -339,6 +366,10 @@ int launch_fold_t(pcs_ctx* ctx, const FoldConvArgs& a) {
     static_assert(NPAD <= 48, "bias travels in the parameter block");
     for (int i = 0; i < 48; ++i) p.bias[i] = i < a.cout ? a.h_bias[i] : 0.f;
     p.out = a.out; p.out_cp = a.out_cp; p.pool = a.pool_out; p.pool_cp = a.pool_cp;
+    p.out_c0 = a.o0;
+    p.psum_out = reinterpret_cast<float4*>(a.psum_out);
+    p.psum_in = reinterpret_cast<const float4*>(a.psum_in);
+    if (a.o0 & 7) return set_err(ctx, PCS_ERR_ARG, "conv_fold: output channel offset %d is not a whole plane", a.o0);
     p.plog = nullptr;
     if (a.plog) {
         if (NPAD != F_LOGC || !a.skip_lw) return set_err(ctx, PCS_ERR_ARG, "conv_fold: partial logits need the N=32 kernel and weights");
@@ -389,25 +420,31 @@ int launch_fold_t(pcs_ctx* ctx, const FoldConvArgs& a) {
 template <typename T>
 int launch_fold_dispatch(pcs_ctx* ctx, const FoldConvArgs& a) {
     const int key = a.npad * 10 + a.nplanes;
-    switch (key) {
+    switch (key) {          //               NPAD planes RING SLOTS epilogue groups
         case 323: return launch_fold_t<T, 32, 3, 16, 16, 4>(ctx, a);     // conv2: 20(24) -> 30(32)
         case 484: return launch_fold_t<T, 48, 4, 10, 10, 3>(ctx, a);     // conv3: 30(32) -> 40(48)
-        case 485: return launch_fold_t<T, 48, 5, 10, 10, 3>(ctx, a);      // conv4: 40(40) -> 40(48)
+        case 485: return launch_fold_t<T, 48, 5, 10, 10, 3>(ctx, a);     // conv4: 40(40) -> 40(48)
+        case 325: return launch_fold_t<T, 32, 5, 8, 16, 4>(ctx, a);      // conv5: 40(40) -> 60 as 32 + 28 output channels
+        case 328: return launch_fold_t<T, 32, 8, 4, 8, 4>(ctx, a);       // conv6: 60(64) -> 60 as 32 + 28 output channels
+        case 488: return launch_fold_t<T, 48, 8, 4, 8, 3>(ctx, a);       // deconv3: 60(64) [+ 60(64)] -> 40(48), one launch per source
         default: return set_err(ctx, PCS_ERR_ARG, "conv_fold: no instantiation for N=%d planes=%d", a.npad, a.nplanes);
     }
 }
 
 }  // namespace
 
-bool fold_supported(int k, int npad, int nplanes, int nsrc) {
-    if (k != 5 || nsrc != 1) return false;
+// (N tile, source planes) pairs with an instantiation; the resident weights + input ring must fit shared memory
+bool fold_supported(int k, int npad, int nplanes) {
+    if (k != 5) return false;
     const int key = npad * 10 + nplanes;
-    return key == 323 || key == 484 || key == 485;          // conv5+ (N' = 5*64 = 320) exceeds the UMMA N limit of 256
+    return key == 323 || key == 484 || key == 485 || key == 325 || key == 328 || key == 488;
 }
 
-// Resident operand image [K step][K half][row = (4-dy)*NPAD + o][8] (K steps as in FoldK): the N blocks run
-// from the oldest output row of the window (dy = 4) to the newest (dy = 0).
-size_t fold_weight_image(const float* w32 /*[25][cin][cout]*/, int cin, int cout, int npad, int precision, std::vector<uint16_t>& out) {
+// Resident operand image [K step][K half][row = (4-dy)*NPAD + o][8] (K steps as in FoldK) for the input channels
+// [ci0, ci0 + cin) and the output channels [o0, o0 + ncols) of a layer with weights w32[25][cin_total][cout_total]:
+// the N blocks run from the oldest output row of the window (dy = 4) to the newest (dy = 0).
+size_t fold_weight_image(const float* w32, int cin_total, int cout_total, int ci0, int cin, int o0, int ncols, int npad,
+                         int precision, std::vector<uint16_t>& out) {
     const int npl = pad8(cin) / 8, pairs = npl / 2, odd = npl & 1, nmma = pairs * 5 + odd * 3, nf = 5 * npad;
     out.assign((size_t)nmma * 2 * nf * 8, 0);
     auto conv = [&](float v) -> uint16_t {
@@ -425,11 +462,11 @@ size_t fold_weight_image(const float* w32 /*[25][cin][cout]*/, int cin, int cout
                 if (t == 2 && half == 0) continue;
             }
             for (int dy = 0; dy < 5; ++dy)
-                for (int o = 0; o < cout; ++o)
+                for (int o = 0; o < ncols; ++o)
                     for (int e = 0; e < 8; ++e) {
                         const int ci = plane * 8 + e;
                         if (ci >= cin) continue;
-                        const float v = w32[((size_t)(dy * 5 + dx) * cin + ci) * cout + o];
+                        const float v = w32[((size_t)(dy * 5 + dx) * cin_total + ci0 + ci) * cout_total + o0 + o];
                         out[(((size_t)q * 2 + half) * nf + (4 - dy) * npad + o) * 8 + e] = conv(v);
                     }
         }
@@ -437,7 +474,7 @@ size_t fold_weight_image(const float* w32 /*[25][cin][cout]*/, int cin, int cout
 }
 
 int launch_conv_fold(pcs_ctx* ctx, const FoldConvArgs& a) {
-    if (!fold_supported(a.k, a.npad, a.nplanes, 1)) return set_err(ctx, PCS_ERR_ARG, "conv_fold: unsupported layer");
+    if (!fold_supported(a.k, a.npad, a.nplanes)) return set_err(ctx, PCS_ERR_ARG, "conv_fold: unsupported layer");
     if (ctx->precision == PCS_PREC_BF16) return launch_fold_dispatch<__nv_bfloat16>(ctx, a);
     return launch_fold_dispatch<__half>(ctx, a);
 }
