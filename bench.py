@@ -36,6 +36,18 @@ LAYER_GFLOP = {"conv1": 0.985, "conv2": 29.553, "conv3": 14.776, "conv4": 19.702
                "conv7": 3.694, "deconv1": 4.925, "deconv2": 0.591, "deconv3": 14.776, "deconv4": 1.478, "head": 3.048}
 
 
+def measured_traffic(kernel, pages):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed
+    `ncu --set full` capture (profiles/ncu_traffic.json); only valid for the launch size it was taken at."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p)).get(kernel)
+    if not d or d.get("pages_per_launch") != pages:
+        return None
+    return d["dram_bytes_read"] + d["dram_bytes_write"]
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -269,7 +281,9 @@ def main():
         if dom is not None and arch == "fcn_skip":
             tflops = LAYER_GFLOP[dom] * n / per_step[dom]          # GFLOP / ms == TFLOP/s
             roofline = {"bound": "tensor", "kernel": dom, "achieved": tflops, "peak": tf_peak, "unit": "TFLOP/s",
-                        "frac": tflops / tf_peak, "traffic": None, "peak_source": f"{which} (sustained bf16)",
+                        "frac": tflops / tf_peak, "traffic": measured_traffic(dom, n),
+                        "traffic_unit": "bytes per launch (ncu dram read + write)",
+                        "peak_source": f"{which} (sustained bf16: the kernel is timed inside a long step)",
                         "whole_body_tflops": GFLOP_PER_PAGE[arch] * n / sum(
                             v for k, v in per_step.items() if k not in ("preprocess",)),
                         "stage_ms_per_step": {k: round(v, 4) for k, v in per_step.items()}}

@@ -77,6 +77,8 @@ struct FoldParams {
 // with ITSELF one pixel further: the K halves of one MMA are the taps (dx, dx+1) of that plane, LBO = 16 B
 // (one pixel), so 5 taps x 8 channels cost 3 MMAs -- (0,1), (2,3), (3,4) with zero weights for the
 // repeated tap 3 -- instead of the 5 that padding the plane count to even would cost.
+constexpr int fold_gcd(int a, int b) { return b == 0 ? a : fold_gcd(b, a % b); }
+
 template <int NPL> struct FoldK {
     static constexpr int PAIRS = NPL / 2, ODD = NPL & 1;
     static constexpr int NMMA = PAIRS * 5 + ODD * 3;
@@ -93,7 +95,7 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
                                 ((std::is_same<T, __nv_bfloat16>::value ? 1u : 0u) << 10) | ((uint32_t)(128 >> 4) << 24);
     static_assert(NF <= 256 && NF % 16 == 0, "folded N must be a legal UMMA N");
     static_assert(SLOTS * NPAD <= 512 && SLOTS <= F_SLOTS_MAX && SLOTS >= 8, "accumulator ring must fit TMEM");
-    constexpr int PERIOD = (RING % SLOTS == 0) ? RING : ((SLOTS % RING == 0) ? SLOTS : RING * SLOTS);   // lcm for the shapes used
+    constexpr int PERIOD = RING / fold_gcd(RING, SLOTS) * SLOTS;     // least common multiple
     static_assert(PERIOD % RING == 0 && PERIOD % SLOTS == 0 && PERIOD <= 20 && RING <= F_RING_MAX,
                   "the issue loop is unrolled over one common period of the input ring and the accumulator ring");
 
@@ -425,7 +427,7 @@ int launch_fold_dispatch(pcs_ctx* ctx, const FoldConvArgs& a) {
         case 484: return launch_fold_t<T, 48, 4, 10, 10, 3>(ctx, a);     // conv3: 30(32) -> 40(48)
         case 485: return launch_fold_t<T, 48, 5, 10, 10, 3>(ctx, a);     // conv4: 40(40) -> 40(48)
         case 325: return launch_fold_t<T, 32, 5, 8, 16, 4>(ctx, a);      // conv5: 40(40) -> 60 as 32 + 28 output channels
-        case 328: return launch_fold_t<T, 32, 8, 4, 8, 4>(ctx, a);       // conv6: 60(64) -> 60 as 32 + 28 output channels
+        case 328: return launch_fold_t<T, 32, 8, 4, 16, 4>(ctx, a);       // conv6: 60(64) -> 60 as 32 + 28 output channels
         case 488: return launch_fold_t<T, 48, 8, 4, 8, 3>(ctx, a);       // deconv3: 60(64) [+ 60(64)] -> 40(48), one launch per source
         default: return set_err(ctx, PCS_ERR_ARG, "conv_fold: no instantiation for N=%d planes=%d", a.npad, a.nplanes);
     }
