@@ -101,6 +101,16 @@ PCS_API int pcs_preprocess(pcs_ctx* ctx, const uint8_t* d_grey, const uint8_t* d
                    int n, int H, int W, int Hs, int Ws,
                    uint8_t* d_image, uint8_t* d_binary, uint8_t* d_orig_binary);
 
+/* ---- prepare_images with max_width (lib/dataset.py:139-143): after the first
+ * rescale to (H1, W1) = np.round(scale * (H, W)), `n_scale = max_width / W1 < 1`
+ * triggers a second one to (H2, W2) = np.round(n_scale * (H1, W1)): order 0 for
+ * the binary, order 3 for the fp64 image (anti-aliased when it holds more than
+ * two distinct values), then (img * 255).astype(uint8).  The caller computes the
+ * two shapes.  d_image, d_binary: [n][H2][W2]; d_orig_binary: [n][H][W] or NULL. */
+PCS_API int pcs_preprocess_max_width(pcs_ctx* ctx, const uint8_t* d_grey, const uint8_t* d_bin,
+                             int n, int H, int W, int H1, int W1, int H2, int W2,
+                             uint8_t* d_image, uint8_t* d_binary, uint8_t* d_orig_binary);
+
 /* ---- network body + head: replaces Network.predict_single_data,
  * lib/network.py:248-260 = default_preprocess x/255 (architecture.py:67-68),
  * the Keras graph (model.py:45-92 / :206-234 / :151-203 incl. pad :20-26 and

@@ -21,6 +21,7 @@ ENGINES = {"umma": 0, "direct": 1}
 EXPORTS = [
     "pcs_abi_version", "pcs_ctx_create", "pcs_ctx_destroy", "pcs_last_error", "pcs_set_stream",
     "pcs_synchronize", "pcs_launch_count", "pcs_model_load", "pcs_set_engine", "pcs_preprocess",
+    "pcs_preprocess_max_width",
     "pcs_forward", "pcs_masks", "pcs_resize_nearest", "pcs_ccl", "pcs_cc_majority",
     "pcs_bounding_boxes", "pcs_predict_pages_host", "pcs_debug_activation", "pcs_set_keep_activations", "pcs_set_timing",
     "pcs_last_timings",
@@ -62,6 +63,7 @@ def load() -> C.CDLL:
     lib.pcs_model_load.argtypes = [vp, i32, i32, i32, C.POINTER(LayerWeights), i32]
     lib.pcs_set_engine.argtypes = [vp, i32]
     lib.pcs_preprocess.argtypes = [vp, u8p, u8p, i32, i32, i32, i32, i32, u8p, u8p, u8p]
+    lib.pcs_preprocess_max_width.argtypes = [vp, u8p, u8p, i32, i32, i32, i32, i32, i32, i32, u8p, u8p, u8p]
     lib.pcs_forward.argtypes = [vp, u8p, u8p, i32, i32, i32, u8p, vp, vp, vp, u8p, u8p, u8p]
     lib.pcs_masks.argtypes = [vp, u8p, u8p, i32, i32, i32, vp, i32, u8p, u8p, u8p]
     lib.pcs_resize_nearest.argtypes = [vp, u8p, i32, i32, i32, u8p, i32, i32]
@@ -182,6 +184,11 @@ class Context:
     def preprocess(self, d_grey, d_bin, n, H, W, Hs, Ws, d_image, d_binary, d_orig_binary=None):
         self._check(self.lib.pcs_preprocess(self.h, _ptr(d_grey), _ptr(d_bin), n, H, W, Hs, Ws, _ptr(d_image),
                                             _ptr(d_binary), _ptr(d_orig_binary)), "pcs_preprocess")
+
+    def preprocess_max_width(self, d_grey, d_bin, n, H, W, H1, W1, H2, W2, d_image, d_binary, d_orig_binary=None):
+        self._check(self.lib.pcs_preprocess_max_width(self.h, _ptr(d_grey), _ptr(d_bin), n, H, W, H1, W1, H2, W2,
+                                                      _ptr(d_image), _ptr(d_binary), _ptr(d_orig_binary)),
+                    "pcs_preprocess_max_width")
 
     def forward(self, d_image, d_binary, n, Hs, Ws, d_labels, d_logits=None, d_prob=None, lut=None,
                 d_color=None, d_overlay=None, d_inverted=None):

@@ -48,6 +48,7 @@ int scratch_reserve(pcs_ctx* ctx, size_t bytes) {
     if (bytes <= ctx->scratch_bytes) return PCS_OK;
     cudaStreamSynchronize(ctx->stream);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->scratch2) cudaFree(ctx->scratch2);
     ctx->scratch = nullptr;
     ctx->scratch_bytes = 0;
     const size_t want = bytes + bytes / 8 + 4096;
@@ -454,6 +455,7 @@ void pcs_ctx_destroy(pcs_ctx* ctx) {
     clear_stage_times(ctx);
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->scratch2) cudaFree(ctx->scratch2);
     if (ctx->stage) cudaFree(ctx->stage);
     for (int i = 0; i < 2; ++i) {
         if (ctx->copy_streams[i]) cudaStreamDestroy(ctx->copy_streams[i]);
@@ -655,6 +657,15 @@ int pcs_preprocess(pcs_ctx* ctx, const uint8_t* d_grey, const uint8_t* d_bin, in
     if (ctx->timing_enabled) clear_stage_times(ctx);
     StageScope ts(ctx, "preprocess");
     return launch_preprocess(ctx, d_grey, d_bin, n, H, W, Hs, Ws, d_image, d_binary, d_orig_binary);
+}
+
+int pcs_preprocess_max_width(pcs_ctx* ctx, const uint8_t* d_grey, const uint8_t* d_bin, int n, int H, int W, int H1, int W1,
+                             int H2, int W2, uint8_t* d_image, uint8_t* d_binary, uint8_t* d_orig_binary) {
+    if (!ctx || !d_bin || !d_grey) return ctx ? set_err(ctx, PCS_ERR_ARG, "preprocess: null input") : PCS_ERR_ARG;
+    PCS_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->timing_enabled) clear_stage_times(ctx);
+    StageScope ts(ctx, "preprocess");
+    return launch_preprocess_max_width(ctx, d_grey, d_bin, n, H, W, H1, W1, H2, W2, d_image, d_binary, d_orig_binary);
 }
 
 int pcs_forward(pcs_ctx* ctx, const uint8_t* d_image, const uint8_t* d_binary, int n, int Hs, int Ws, uint8_t* d_labels,

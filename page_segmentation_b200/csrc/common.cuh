@@ -100,9 +100,11 @@ struct pcs_ctx {
     size_t arena_used = 0;
     std::map<std::string, pcs::Act> acts;   // activations of the last forward (debug / reuse)
 
-    // small scratch
+    // small scratch (+ a second one for the max_width pass, which runs the first pass inside)
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
+    void* scratch2 = nullptr;
+    size_t scratch2_bytes = 0;
 
     // staging buffers of pcs_predict_pages_host
     char* stage = nullptr;
@@ -152,6 +154,8 @@ int scratch_reserve(pcs_ctx* ctx, size_t bytes);
 // preprocess.cu
 int launch_preprocess(pcs_ctx* ctx, const uint8_t* d_grey, const uint8_t* d_bin, int n, int H, int W,
                       int Hs, int Ws, uint8_t* d_image, uint8_t* d_binary, uint8_t* d_orig_binary);
+int launch_preprocess_max_width(pcs_ctx* ctx, const uint8_t* d_grey, const uint8_t* d_bin, int n, int H, int W, int H1, int W1,
+                                int H2, int W2, uint8_t* d_image, uint8_t* d_binary, uint8_t* d_orig_binary);
 int launch_resize_nearest(pcs_ctx* ctx, const uint8_t* d_src, int n, int H, int W, uint8_t* d_dst,
                           int Ho, int Wo);
 

@@ -281,7 +281,8 @@ __global__ void __launch_bounds__(256)
 resample_kernel(const uint8_t* __restrict__ grey, const uint8_t* __restrict__ bin, int H, int W, int Hs, int Ws,
                 const uint32_t* __restrict__ level_bits, const double* __restrict__ aa_planes,
                 const unsigned long long* __restrict__ aa_minmax, int page0, uint8_t* __restrict__ image_out,
-                uint8_t* __restrict__ binary_out, int skip_two_level, const int* __restrict__ group_flag, int pages) {
+                uint8_t* __restrict__ binary_out, int skip_two_level, const int* __restrict__ group_flag, int pages,
+                double* __restrict__ image_f64 /* [pages][Hs][Ws]: img = 1 - v/255 kept in fp64 (max_width pass) or null */) {
     // skip_two_level: pages with at most two grey levels were already done by resample_bits_kernel; when
     // no page of the group has more (group_flag == 0) the whole persistent grid leaves at once
     if (skip_two_level && group_flag && !*group_flag) return;
@@ -327,7 +328,7 @@ resample_kernel(const uint8_t* __restrict__ grey, const uint8_t* __restrict__ bi
             // bin = (1.0 - NN(binary/255 or binary)).astype(uint8): 1 iff v == 0
             binary_out[dst_off] = (v == 0) ? 1 : 0;
         }
-        if (image_out) {
+        if (image_out || image_f64) {
             const uint32_t* bits = level_bits + (size_t)page * 8;
             const bool aa = aa_planes != nullptr && level_count(bits) > 2;
             double vmin, vmax;
@@ -364,8 +365,9 @@ resample_kernel(const uint8_t* __restrict__ grey, const uint8_t* __restrict__ bi
             double v = cubic_rn(xr, frow[0], frow[1], frow[2], frow[3]);
             v = fmin(fmax(v, vmin), vmax);                       // clip=True
             // img = 1.0 - v/255 ; (img*255).astype(uint8)
-            const double t = __dmul_rn(__dsub_rn(1.0, __ddiv_rn(v, 255.0)), 255.0);
-            image_out[dst_off] = (uint8_t)(int)t;                // C truncation
+            const double img = __dsub_rn(1.0, __ddiv_rn(v, 255.0));
+            if (image_f64) image_f64[(size_t)bz * Hs * Ws + (size_t)y * Ws + x] = img;
+            else image_out[dst_off] = (uint8_t)(int)__dmul_rn(img, 255.0);      // C truncation
         }
     }
 }
@@ -503,20 +505,24 @@ static int gauss_weights(double sigma, std::vector<double>& w) {
 
 constexpr int kAaGroup = 16;     // pages whose fp64 anti-aliasing planes live in scratch at the same time
 
-int launch_preprocess(pcs_ctx* ctx, const uint8_t* d_grey, const uint8_t* d_bin, int n, int H, int W, int Hs,
-                      int Ws, uint8_t* d_image, uint8_t* d_binary, uint8_t* d_orig_binary) {
+// d_image_f64 (internal, max_width pass): the image of the first rescale kept as fp64 `1 - v/255` planes
+// [n][Hs][Ws] instead of the truncated uint8 image; n must not exceed kAaGroup then.
+static int preprocess_impl(pcs_ctx* ctx, const uint8_t* d_grey, const uint8_t* d_bin, int n, int H, int W, int Hs,
+                           int Ws, uint8_t* d_image, uint8_t* d_binary, uint8_t* d_orig_binary, double* d_image_f64) {
     if (n <= 0 || H <= 0 || W <= 0 || Hs <= 0 || Ws <= 0) return set_err(ctx, PCS_ERR_ARG, "preprocess: bad shape");
+    if (d_image_f64 && (d_image || n > kAaGroup)) return set_err(ctx, PCS_ERR_ARG, "preprocess: fp64 image output is per group");
+    const bool want_image = d_image || d_image_f64;
     cudaStream_t st = ctx->stream;
     const size_t page_px = (size_t)H * W;
     dim3 block(32, 8);
-    if (d_image || d_binary) {
+    if (want_image || d_binary) {
         // anti-aliasing parameters depend on the shapes only (skimage: sigma = (in/out - 1) / 2 per axis)
         const double fr = (double)H / (double)Hs, fc = (double)W / (double)Ws;
         const double sig[2] = {std::max(0.0, (fr - 1.0) / 2.0), std::max(0.0, (fc - 1.0) / 2.0)};
-        const bool may_aa = d_image && (sig[0] > 1e-15 || sig[1] > 1e-15);
+        const bool may_aa = want_image && (sig[0] > 1e-15 || sig[1] > 1e-15);
         std::vector<double> w0, w1;
-        const int r0 = (d_image && sig[0] > 1e-15) ? gauss_weights(sig[0], w0) : -1;
-        const int r1 = (d_image && sig[1] > 1e-15) ? gauss_weights(sig[1], w1) : -1;
+        const int r0 = (want_image && sig[0] > 1e-15) ? gauss_weights(sig[0], w0) : -1;
+        const int r1 = (want_image && sig[1] > 1e-15) ? gauss_weights(sig[1], w1) : -1;
         if (r0 > kMaxGaussRadius || r1 > kMaxGaussRadius)
             return set_err(ctx, PCS_ERR_ARG, "preprocess: anti-aliasing radius %d/%d exceeds %d", r0, r1, kMaxGaussRadius);
         const int group = std::min(n, kAaGroup);
@@ -535,7 +541,7 @@ int launch_preprocess(pcs_ctx* ctx, const uint8_t* d_grey, const uint8_t* d_bin,
         uint32_t* d_bitmap = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ctx->scratch) + head + mm_bytes);
         double* t0 = reinterpret_cast<double*>(reinterpret_cast<char*>(ctx->scratch) + head + mm_bytes + bm_bytes);
         double* t1 = t0 + (size_t)group * page_px;
-        if (d_image) {
+        if (want_image) {
             PCS_CUDA(ctx, cudaMemsetAsync(d_bits, 0, (size_t)n * 8 * sizeof(uint32_t), st));
             if (fast) {
                 dim3 grid((unsigned)std::min<size_t>((size_t)ctx->sm_count * 4, (page_px / 32 + 255) / 256), n);
@@ -586,7 +592,7 @@ int launch_preprocess(pcs_ctx* ctx, const uint8_t* d_grey, const uint8_t* d_bin,
             const long long tiles = (long long)((Ws + 31) / 32) * ((Hs + 7) / 8) * m;
             const unsigned rgrid = (unsigned)std::min<long long>(tiles, (long long)ctx->sm_count * 8);
             resample_kernel<<<rgrid, block, 0, st>>>(d_grey, d_bin, H, W, Hs, Ws, d_bits, planes, d_mm, p0, d_image, d_binary, fast ? 1 : 0,
-                                                     d_image ? d_gflags + p0 / group : nullptr, m);
+                                                     want_image ? d_gflags + p0 / group : nullptr, m, d_image_f64);
             PCS_LAUNCH_CHECK(ctx, "resample_kernel");
         }
     }
@@ -594,6 +600,170 @@ int launch_preprocess(pcs_ctx* ctx, const uint8_t* d_grey, const uint8_t* d_bin,
         const size_t nbytes = (size_t)n * page_px;
         orig_binary_kernel<<<(unsigned)std::min<size_t>(148 * 8, (nbytes / 16 + 255) / 256 + 1), 256, 0, st>>>(d_bin, nbytes,
                                                                                                           d_orig_binary);
+        PCS_LAUNCH_CHECK(ctx, "orig_binary_kernel");
+    }
+    return PCS_OK;
+}
+
+int launch_preprocess(pcs_ctx* ctx, const uint8_t* d_grey, const uint8_t* d_bin, int n, int H, int W, int Hs,
+                      int Ws, uint8_t* d_image, uint8_t* d_binary, uint8_t* d_orig_binary) {
+    return preprocess_impl(ctx, d_grey, d_bin, n, H, W, Hs, Ws, d_image, d_binary, d_orig_binary, nullptr);
+}
+
+// ---------------------------------------------------------------------------
+// max_width second pass (dataset.py:139-143):  bin = scale_binary(bin, n_scale);  img = scale_image(img, bin.shape)
+// on the fp64 image `1 - v/255` of the first pass; anti-aliased when that image has more than two distinct
+// values (`len(np.unique(img)) > 2`), clipped to the min/max of the image that is warped, then
+// (img * 255).astype(uint8).  A rarely used option: plain per-pixel kernels.
+// ---------------------------------------------------------------------------
+constexpr unsigned long long kNoValue = 0xffffffffffffffffull;     // a NaN pattern: never a pixel value
+
+__global__ void distinct_init_kernel(unsigned long long* slots, int* flags, int pages) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < pages) { slots[i] = kNoValue; flags[i] = 0; }
+}
+
+// flags[page] = 1 iff the plane holds more than two distinct values
+__global__ void __launch_bounds__(256)
+distinct_kernel(const double* __restrict__ planes, size_t npx, unsigned long long* __restrict__ slots, int* __restrict__ flags) {
+    const int page = blockIdx.y;
+    const double* p = planes + (size_t)page * npx;
+    const unsigned long long v0 = (unsigned long long)__double_as_longlong(p[0]);
+    unsigned long long seen = v0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += (size_t)gridDim.x * blockDim.x) {
+        const unsigned long long v = (unsigned long long)__double_as_longlong(p[i]);
+        if (v == v0 || v == seen) continue;
+        seen = v;
+        const unsigned long long old = atomicCAS(slots + page, kNoValue, v);
+        if (old != kNoValue && old != v) flags[page] = 1;
+    }
+}
+
+template <int AXIS>
+__global__ void __launch_bounds__(256)
+gauss_plane_kernel(const double* __restrict__ src, double* __restrict__ dst, int H, int W, int radius,
+                   const double* __restrict__ wts, const int* __restrict__ flags) {
+    const int page = blockIdx.y;
+    if (!flags[page]) return;
+    const double* sp = src + (size_t)page * H * W;
+    double* dp = dst + (size_t)page * H * W;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)H * W; i += (size_t)gridDim.x * blockDim.x) {
+        const int y = (int)(i / W), x = (int)(i - (size_t)y * W);
+        auto at = [&](int d) -> double {
+            if (AXIS == 0) return sp[(size_t)mirror_idx(y + d, H) * W + x];
+            return sp[(size_t)y * W + mirror_idx(x + d, W)];
+        };
+        double tmp = __dmul_rn(at(0), wts[0]);
+        for (int j = radius; j >= 1; --j) tmp = __dadd_rn(tmp, __dmul_rn(__dadd_rn(at(-j), at(j)), wts[j]));
+        dp[i] = tmp;
+    }
+}
+
+// min / max of the plane that is warped (the filtered one when flags[page], else the raw one); values >= 0
+__global__ void __launch_bounds__(256)
+minmax_plane_kernel(const double* __restrict__ raw, const double* __restrict__ filt, size_t npx, const int* __restrict__ flags,
+                    unsigned long long* __restrict__ out /*[pages][2], initialised*/) {
+    const int page = blockIdx.y;
+    const double* p = (flags[page] ? filt : raw) + (size_t)page * npx;
+    double lo = 1e300, hi = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += (size_t)gridDim.x * blockDim.x) {
+        const double v = p[i];
+        lo = fmin(lo, v);
+        hi = fmax(hi, v);
+    }
+    for (int o = 16; o; o >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(out + 2 * page, (unsigned long long)__double_as_longlong(lo));
+        atomicMax(out + 2 * page + 1, (unsigned long long)__double_as_longlong(hi));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+resample_plane_kernel(const double* __restrict__ raw, const double* __restrict__ filt, const int* __restrict__ flags,
+                      const unsigned long long* __restrict__ mm, int H, int W, int Ho, int Wo, uint8_t* __restrict__ out) {
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, page = blockIdx.z;
+    if (x >= Wo || y >= Ho) return;
+    const double* g = (flags[page] ? filt : raw) + (size_t)page * H * W;
+    const double fr = __ddiv_rn((double)H, (double)Ho), fc = __ddiv_rn((double)W, (double)Wo);
+    const double pr = __dadd_rn(__dmul_rn(fr, (double)y), __dsub_rn(__dmul_rn(0.5, fr), 0.5));
+    const double pc = __dadd_rn(__dmul_rn(fc, (double)x), __dsub_rn(__dmul_rn(0.5, fc), 0.5));
+    const double rf = floor(pr), cf = floor(pc);
+    const double xr = __dsub_rn(pr, rf), xc = __dsub_rn(pc, cf);
+    int cols[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cols[k] = reflect_coord((long long)cf - 1 + k, W);
+    double frow[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const size_t ro = (size_t)reflect_coord((long long)rf - 1 + k, H) * W;
+        frow[k] = cubic_rn(xc, g[ro + cols[0]], g[ro + cols[1]], g[ro + cols[2]], g[ro + cols[3]]);
+    }
+    double v = cubic_rn(xr, frow[0], frow[1], frow[2], frow[3]);
+    v = fmin(fmax(v, __longlong_as_double((long long)mm[2 * page])), __longlong_as_double((long long)mm[2 * page + 1]));
+    out[(size_t)page * Ho * Wo + (size_t)y * Wo + x] = (uint8_t)(int)__dmul_rn(v, 255.0);      // (img * 255).astype(uint8)
+}
+
+int launch_preprocess_max_width(pcs_ctx* ctx, const uint8_t* d_grey, const uint8_t* d_bin, int n, int H, int W, int H1, int W1,
+                                int H2, int W2, uint8_t* d_image, uint8_t* d_binary, uint8_t* d_orig_binary) {
+    if (n <= 0 || H2 <= 0 || W2 <= 0 || H1 <= 0 || W1 <= 0) return set_err(ctx, PCS_ERR_ARG, "preprocess(max_width): bad shape");
+    if (!d_image || !d_binary) return set_err(ctx, PCS_ERR_ARG, "preprocess(max_width): image and binary outputs are required");
+    cudaStream_t st = ctx->stream;
+    const size_t px1 = (size_t)H1 * W1;
+    const int group = std::min(n, kAaGroup);
+    const double f2[2] = {(double)H1 / (double)H2, (double)W1 / (double)W2};
+    std::vector<double> w[2];
+    int rad[2];
+    for (int a = 0; a < 2; ++a) {
+        const double sg = std::max(0.0, (f2[a] - 1.0) / 2.0);
+        rad[a] = sg > 1e-15 ? gauss_weights(sg, w[a]) : -1;
+        if (rad[a] > kMaxGaussRadius) return set_err(ctx, PCS_ERR_ARG, "preprocess(max_width): anti-aliasing radius %d", rad[a]);
+    }
+    // second scratch (the first pass uses ctx->scratch): fp64 planes img1, t0, t1; bin1; small control words
+    auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+    const size_t need = 3 * al((size_t)group * px1 * 8) + al((size_t)group * px1) + al((size_t)group * 32) + al(2 * 64 * 8) + 256;
+    if (need > ctx->scratch2_bytes) {
+        PCS_CUDA(ctx, cudaStreamSynchronize(st));
+        if (ctx->scratch2) cudaFree(ctx->scratch2);
+        ctx->scratch2 = nullptr; ctx->scratch2_bytes = 0;
+        if (cudaMalloc(&ctx->scratch2, need) != cudaSuccess) { cudaGetLastError(); return set_err(ctx, PCS_ERR_NOMEM, "cudaMalloc of %zu bytes failed", need); }
+        ctx->scratch2_bytes = need;
+    }
+    char* q = reinterpret_cast<char*>(ctx->scratch2);
+    double* img1 = reinterpret_cast<double*>(q); q += al((size_t)group * px1 * 8);
+    double* t0 = reinterpret_cast<double*>(q); q += al((size_t)group * px1 * 8);
+    double* t1 = reinterpret_cast<double*>(q); q += al((size_t)group * px1 * 8);
+    uint8_t* bin1 = reinterpret_cast<uint8_t*>(q); q += al((size_t)group * px1);
+    unsigned long long* slots = reinterpret_cast<unsigned long long*>(q);           // [group] second value, then [group][2] min/max
+    unsigned long long* mm = slots + group;
+    int* flags = reinterpret_cast<int*>(mm + 2 * group); q += al((size_t)group * 32);
+    double* d_w = reinterpret_cast<double*>(q);
+    for (int a = 0; a < 2; ++a)
+        if (rad[a] >= 0) PCS_CUDA(ctx, cudaMemcpyAsync(d_w + 64 * a, w[a].data(), w[a].size() * 8, cudaMemcpyHostToDevice, st));
+    for (int p0 = 0; p0 < n; p0 += group) {
+        const int m = std::min(group, n - p0);
+        const size_t so = (size_t)p0 * H * W;
+        PCS_TRY(preprocess_impl(ctx, d_grey + so, d_bin + so, m, H, W, H1, W1, nullptr, bin1, nullptr, img1));
+        PCS_TRY(launch_resize_nearest(ctx, bin1, m, H1, W1, d_binary + (size_t)p0 * H2 * W2, H2, W2));
+        distinct_init_kernel<<<1, 64, 0, st>>>(slots, flags, m);
+        minmax_init_kernel<<<1, 32, 0, st>>>(mm, m);
+        distinct_kernel<<<dim3(64, m), 256, 0, st>>>(img1, px1, slots, flags);
+        PCS_LAUNCH_CHECK(ctx, "distinct_kernel");
+        const double* filt = img1;
+        if (rad[0] >= 0) { gauss_plane_kernel<0><<<dim3(296, m), 256, 0, st>>>(img1, t0, H1, W1, rad[0], d_w, flags); filt = t0; }
+        if (rad[1] >= 0) { gauss_plane_kernel<1><<<dim3(296, m), 256, 0, st>>>(filt, t1, H1, W1, rad[1], d_w + 64, flags); filt = t1; }
+        PCS_LAUNCH_CHECK(ctx, "gauss_plane_kernel");
+        minmax_plane_kernel<<<dim3(148, m), 256, 0, st>>>(img1, filt, px1, flags, mm);
+        PCS_LAUNCH_CHECK(ctx, "minmax_plane_kernel");
+        resample_plane_kernel<<<dim3((W2 + 31) / 32, (H2 + 7) / 8, m), dim3(32, 8), 0, st>>>(img1, filt, flags, mm, H1, W1, H2, W2,
+                                                                                             d_image + (size_t)p0 * H2 * W2);
+        PCS_LAUNCH_CHECK(ctx, "resample_plane_kernel");
+    }
+    if (d_orig_binary) {
+        const size_t nbytes = (size_t)n * H * W;
+        orig_binary_kernel<<<(unsigned)std::min<size_t>(148 * 8, (nbytes / 16 + 255) / 256 + 1), 256, 0, st>>>(d_bin, nbytes, d_orig_binary);
         PCS_LAUNCH_CHECK(ctx, "orig_binary_kernel");
     }
     return PCS_OK;

@@ -65,15 +65,20 @@ def prepare_images_device(image: np.ndarray, binary: np.ndarray, target_line_hei
     scale = target_line_height / line_height_px
     H, W = image.shape
     Hs, Ws = scaled_shape(H, W, scale)
-    if max_width is not None and max_width / Ws < 1.0:
-        raise NotImplementedError("max_width second rescale pass is not implemented on the device path yet")
+    second = max_width is not None and max_width / Ws < 1.0            # dataset.py:139-141
+    H1, W1 = Hs, Ws
+    if second:
+        Hs, Ws = scaled_shape(H1, W1, max_width / W1)
     same = binary is image or (binary.dtype == np.uint8 and np.shares_memory(binary, image))
     d_grey = to_device_u8(image, dev)
     d_bin = d_grey if same else to_device_u8(binary, dev)
     d_image = torch.empty((Hs, Ws), dtype=torch.uint8, device=d_grey.device)
     d_binary = torch.empty((Hs, Ws), dtype=torch.uint8, device=d_grey.device)
     d_orig = torch.empty((H, W), dtype=torch.uint8, device=d_grey.device) if keep_orig_bin else None
-    ctx.preprocess(d_grey, d_bin, 1, H, W, Hs, Ws, d_image, d_binary, d_orig)
+    if second:
+        ctx.preprocess_max_width(d_grey, d_bin, 1, H, W, H1, W1, Hs, Ws, d_image, d_binary, d_orig)
+    else:
+        ctx.preprocess(d_grey, d_bin, 1, H, W, Hs, Ws, d_image, d_binary, d_orig)
     img, bin_ = d_image.cpu().numpy(), d_binary.cpu().numpy()
     if keep_orig_bin:
         return img, bin_, d_orig.cpu().numpy()

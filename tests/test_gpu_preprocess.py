@@ -148,6 +148,25 @@ def test_fast_path_separate_binary(ctx):
     np.testing.assert_array_equal(img, eimg)
 
 
+@pytest.mark.parametrize("kind,shape,lh,max_width", [("bin", (600, 480), 18, 100), ("bin", (333, 517), 11, 200),
+                                                     ("grey", (480, 360), 12, 90), ("bin", (640, 480), 18, 1000)])
+def test_max_width_second_pass(ctx, kind, shape, lh, max_width):
+    """dataset.py:139-143: a second rescale when the first result is wider than max_width (the last case is
+    not: no second pass).  The second pass anti-aliases the fp64 image with Gaussian weights that go through
+    exp(): tolerance <= 1 grey level on <= 1e-3 of the pixels; the binary is exact."""
+    from page_segmentation_b200.lib.dataset import prepare_images
+    page = synth.make_page(7, *shape, lh) if kind == "bin" else synth.make_grey_page(7, *shape, lh)
+    img, b, ob = prepare_images(page, page, 6, lh, max_width=max_width, keep_orig_bin=True)
+    eimg, eb, eob = opipe.prepare_images(page, page, 6, lh, max_width=max_width, keep_orig_bin=True)
+    assert img.shape == eimg.shape and b.shape == eb.shape
+    assert img.shape[1] <= max(max_width, 1) or max_width >= round(shape[1] * 6 / lh)
+    np.testing.assert_array_equal(b, eb)
+    np.testing.assert_array_equal(ob, eob)
+    diff = np.abs(img.astype(int) - eimg.astype(int))
+    assert diff.max() <= 1, diff.max()
+    assert (diff > 0).mean() <= 1e-3, (diff > 0).mean()
+
+
 @pytest.mark.parametrize("src,dst", [((50, 40), (150, 121)), ((389, 275), (1169, 827)), ((120, 90), (40, 30))])
 def test_preserving_resize(ctx, src, dst):
     from page_segmentation_b200.lib.util import preserving_resize
