@@ -191,6 +191,16 @@ static int run_conv(pcs_ctx* ctx, const char* lname, const Act* s0, const Act* s
         return PCS_OK;
     }
     if (plog) return set_err(ctx, PCS_ERR_STATE, "layer %s: partial logits requested off the folded kernel", lname);
+    if (ctx->engine == PCS_ENGINE_UMMA && upsample && L->d_wmma && L->k == 2 && !s1 && out) {
+        // UpSampling2D(2) + Conv2D(2x2) as a 2x2 convolution on the low-resolution grid, N = (parity, C_out)
+        UmmaConvArgs a;
+        a.src[0] = src_of(*s0); a.nsrc = 1;
+        a.n = n; a.h = s0->h; a.w = s0->w; a.k = 2; a.pad = 0;
+        a.wmma = L->d_wmma; a.b32 = L->d_b32; a.cout = L->cout; a.npad = L->npad; a.nchunks = L->nchunks; a.relu = L->relu;
+        a.mode = 1; a.co_t = L->co_t;
+        a.out = out->p; a.out_cp = out->cp;
+        return launch_conv_umma(ctx, a);
+    }
     if (ctx->engine == PCS_ENGINE_UMMA && !upsample && L->d_wmma && umma_supported(L->k, L->npad)) {
         UmmaConvArgs a;
         a.src[0] = src_of(*s0); a.nsrc = 1;
@@ -532,7 +542,7 @@ int pcs_model_load(pcs_ctx* ctx, int arch, int n_classes, int precision, const p
         L.h_b32.assign(w.bias, w.bias + cout);
         // every layer except the first and the logits consumes operands rounded to the model precision
         const bool rounded = li != 0 && s.kind != K_LOGITS;
-        if (L.name == "deconv5") L.h_w32_raw = L.h_w32;
+        if (L.name == "deconv5" || (arch == PCS_ARCH_UNET && s.kind == K_CONV && s.k == 2)) L.h_w32_raw = L.h_w32;
         if (rounded) {
             for (float& v : L.h_w32)
                 v = precision == PCS_PREC_BF16 ? __bfloat162float(__float2bfloat16_rn(v)) : __half2float(__float2half_rn(v));
@@ -564,7 +574,13 @@ int pcs_model_load(pcs_ctx* ctx, int arch, int n_classes, int precision, const p
             src_c[0] = L.cin / 2; src_c[1] = L.cin / 2; nsrc = 2;
         }
         std::vector<uint16_t> img;
-        if (L.kind == K_CONV || L.kind == K_DECONV) {
+        if (arch == PCS_ARCH_UNET && L.kind == K_CONV && L.k == 2) {
+            // up6..up9: UpSampling2D + 2x2 convolution folded onto the low-resolution grid
+            L.co_t = pad16(L.cout);
+            L.npad = 128;
+            if ((4 * L.co_t) % L.npad) continue;
+            L.wmma_bytes = umma_weight_image_up2(L.h_w32_raw.data(), L.cin, L.cout, L.co_t, L.npad, precision, img);
+        } else if (L.kind == K_CONV || L.kind == K_DECONV) {
             L.npad = std::min(pad16(L.cout), 128);
             if (!umma_supported(L.k, L.npad) || (L.cout > 128 && L.cout % 128)) continue;
             L.wmma_bytes = umma_weight_image(L.h_w32.data(), L.k * L.k, src_c, nsrc, L.cout, L.npad, precision, img);

@@ -71,7 +71,7 @@ struct Layer {
         int psum = 0;             // 0 complete, 1 writes partial sums, 2 adds them
     };
     std::vector<FoldPart> fold;
-    std::vector<float> h_w32_raw; // deconv5 only: weights before rounding (composed with the logits on the host)
+    std::vector<float> h_w32_raw; // deconv5, U-Net up*: weights before rounding (composed / summed on the host, rounded once)
     float* d_head_lw = nullptr;   // logits layer: [32][4] rows of the conv2 skip channels, zero padded (fcn_skip)
     float* d_head_lb = nullptr;   // logits layer: [4] bias with the deconv5 / conv2 biases folded in
     int nchunks = 0;        // number of 16-channel K chunks over all sources
@@ -265,6 +265,8 @@ size_t umma_weight_image(const float* w32 /*[taps][cin][cout]*/, int taps, const
                          int cout, int npad, int precision, std::vector<uint16_t>& out);
 size_t umma_weight_image_deconv(const float* w32 /*[4][cin][cout]*/, const int* src_c, int nsrc, int cout, int co_t,
                                 int npad, int precision, std::vector<uint16_t>& out);
+size_t umma_weight_image_up2(const float* w32 /*[4][cin][cout]*/, int cin, int cout, int co_t, int npad, int precision,
+                             std::vector<uint16_t>& out);
 size_t umma_weight_image_head(const double* m /*[4][cin][4]*/, const int* src_c, int nsrc, int precision,
                               std::vector<uint16_t>& out);
 bool umma_supported(int k, int npad);

@@ -489,6 +489,7 @@ int launch_npad(pcs_ctx* ctx, const UmmaConvArgs& a) {
         case 3064: return launch_t<T, 64, 3, EPI_STORE>(ctx, a);
         case 3128: return launch_t<T, 128, 3, EPI_STORE>(ctx, a);
         case 101128: return launch_t<T, 128, 1, EPI_DECONV>(ctx, a);
+        case 102128: return launch_t<T, 128, 2, EPI_DECONV>(ctx, a);      // UpSampling2D(2) + Conv2D(2x2) of the U-Net
         case 201032: return launch_t<T, 32, 1, EPI_HEAD>(ctx, a);
         default: return set_err(ctx, PCS_ERR_ARG, "conv_umma: no instantiation for mode=%d k=%d N tile %d", a.mode, a.k, a.npad);
     }
@@ -498,7 +499,7 @@ int launch_npad(pcs_ctx* ctx, const UmmaConvArgs& a) {
 
 bool umma_supported(int k, int npad) {
     const int key = k * 1000 + npad;
-    return key == 5032 || key == 5048 || key == 5064 || key == 5080 || key == 3064 || key == 3128 || key == 1128 || key == 1032;
+    return key == 5032 || key == 5048 || key == 5064 || key == 5080 || key == 3064 || key == 3128 || key == 1128 || key == 1032 || key == 2128;
 }
 
 // Operand image [ntile][chunk][tap][plane][NPAD][8]; chunk runs over the 16-channel groups of
@@ -567,6 +568,42 @@ size_t umma_weight_image_deconv(const float* w32 /*[4][cin][cout]*/, const int* 
             cbase += src_c[s];
         }
     }
+    return out.size() * sizeof(uint16_t);
+}
+
+// Operand image of UpSampling2D(2, nearest) -> Conv2D(2x2, 'same') (model.py:176-196) as ONE 2x2 convolution on
+// the low-resolution grid with N column J = parity * co_t + o, parity = (i, j) of the output pixel (2y+i, 2x+j):
+//   out[2y+i][2x+j] = sum_{u,v} W[u][v] . in[(2y+i+u) >> 1][(2x+j+v) >> 1]
+// so the low-resolution tap (dy, dx) of parity (i, j) carries  sum of W[u][v] over (i+u)>>1 == dy, (j+v)>>1 == dx
+// (9 of the 16 (parity, tap) blocks are non-zero).  Layout [ntile][chunk][tap = dy*2+dx][plane][npad][8].
+size_t umma_weight_image_up2(const float* w32 /*[4][cin][cout], tap = u*2+v*/, int cin, int cout, int co_t, int npad,
+                             int precision, std::vector<uint16_t>& out) {
+    const int nchunks = pad16(cin) / 16, ncols = 4 * co_t, ntiles = (ncols + npad - 1) / npad;
+    out.assign((size_t)ntiles * nchunks * 4 * 2 * npad * 8, 0);
+    auto conv = [&](float v) -> uint16_t {
+        if (precision == PCS_PREC_BF16) { __nv_bfloat16 b = __float2bfloat16_rn(v); return *reinterpret_cast<uint16_t*>(&b); }
+        __half h = __float2half_rn(v); return *reinterpret_cast<uint16_t*>(&h);
+    };
+    for (int nt = 0; nt < ntiles; ++nt)
+        for (int ch = 0; ch < nchunks; ++ch)
+            for (int t = 0; t < 4; ++t)
+                for (int pl = 0; pl < 2; ++pl)
+                    for (int nn = 0; nn < npad; ++nn)
+                        for (int e = 0; e < 8; ++e) {
+                            const int c = ch * 16 + pl * 8 + e, J = nt * npad + nn;
+                            const int par = J / co_t, o = J % co_t;
+                            if (c >= cin || J >= ncols || o >= cout) continue;
+                            const int i = par >> 1, j = par & 1, dy = t >> 1, dx = t & 1;
+                            float sum = 0.f;
+                            bool any = false;
+                            for (int u = 0; u < 2; ++u)
+                                for (int v = 0; v < 2; ++v)
+                                    if (((i + u) >> 1) == dy && ((j + v) >> 1) == dx) {
+                                        sum += w32[((size_t)(u * 2 + v) * cin + c) * cout + o];
+                                        any = true;
+                                    }
+                            if (any) out[(((((size_t)nt * nchunks + ch) * 4 + t) * 2 + pl) * npad + nn) * 8 + e] = conv(sum);
+                        }
     return out.size() * sizeof(uint16_t);
 }
 

@@ -123,10 +123,14 @@ def test_n_classes(ctx, n_classes, engine):
     np.testing.assert_allclose(prob.sum(-1), 1.0, atol=1e-5)
 
 
-def test_unet_small(ctx):
-    img, _ = _small_input(2, 32, 64)
+@pytest.mark.parametrize("engine,hw", [("direct", (32, 64)), ("umma", (32, 64)), ("umma", (70, 150))])
+def test_unet_small(ctx, engine, hw):
+    """U-Net (model.py:151-203); on the tensor engine the four UpSampling2D + Conv2D(2x2) blocks run as 2x2
+    convolutions on the low-resolution grid with pre-summed weights (rounded once, so a little closer to the
+    fp32 graph than the twin, which rounds every tap)"""
+    img, _ = _small_input(2, *hw)
     W = synth.make_weights("unet", 3, seed=1)
-    _, (logit, prob, pred) = _device_predict("unet", W, 3, img, "fp16", "direct")
+    _, (logit, prob, pred) = _device_predict("unet", W, 3, img, "fp16", engine)
     onet._bf16, saved = (lambda t: t.to(torch.float16).to(t.dtype)), onet._bf16
     try:
         lt, _ = onet.Forward("unet", W, 3, bf16=True).logits(img)
