@@ -167,6 +167,8 @@ def main():
     ap.add_argument("--arch", default=ARCH, choices=["fcn_skip", "fcn", "unet"])
     ap.add_argument("--cpu-pages", type=int, default=3, help="pages of the CPU-baseline sample (rank 0, N=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cc-majority", action="store_true",
+                    help="also run the cc_majority post-processor (BASELINE configs[3] pipeline); not the default workload")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -211,7 +213,7 @@ def main():
 
     # ---------------- device-resident throughput ----------------
     for _ in range(args.warmup):
-        eng.run_device(d_pages, SCALE)
+        eng.run_device(d_pages, SCALE, cc_majority=args.cc_majority)
     eng.ctx.set_timing(True)
     stage_ms = {}
     sync_all()
@@ -222,7 +224,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        eng.run_device(d_pages, SCALE)
+        eng.run_device(d_pages, SCALE, cc_majority=args.cc_majority)
         if rank == 0:
             for k, v in eng.ctx.timings():      # syncs; outside the event bracket it would hide launch gaps
                 stage_ms[k] = stage_ms.get(k, 0.0) + v
@@ -258,11 +260,11 @@ def main():
 
     # ---------------- end to end through the host-buffer C ABI ----------------
     for _ in range(max(1, args.warmup // 2)):
-        eng.run_host(h_pages_np, SCALE, h_out_np)
+        eng.run_host(h_pages_np, SCALE, h_out_np, cc_majority=args.cc_majority)
     sync_all()
     e0.record()
     for _ in range(args.steps):
-        eng.run_host(h_pages_np, SCALE, h_out_np)
+        eng.run_host(h_pages_np, SCALE, h_out_np, cc_majority=args.cc_majority)
     e1.record()
     sync_all()
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -301,7 +303,7 @@ def main():
             "mpixel_per_sec": value * synth.A4_MPX,
             "config": {"workload": f"{arch} predict, {n} synthetic 2480x3508 binarised pages per GPU per step "
                                    f"(BASELINE configs[1]), line_height_px=18 -> 1169x827, random-init weights, "
-                                   f"preprocess + network + argmax + colour masks",
+                                   f"preprocess + network + argmax{' + cc_majority' if args.cc_majority else ''} + colour masks",
                        "arch": arch, "n_classes": N_CLASSES, "pages_per_gpu": n, "engine": args.engine,
                        "l2": "inputs larger than L2 (557 MB of pages per step)", "distinct_pages": distinct},
             "e2e": {"value": e2e_value, "unit": "pages/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -57,7 +57,10 @@ int64_t g_skip_owner[64] = {0};
 
 struct FoldParams {
     int n, h, w;
-    int seg_rows, segs, strips, num_items;  // work item = (page, strip, segment of seg_rows output rows)
+    int strips;                             // 124-pixel strips per page
+    long long total_rows, rows_per_cta;     // the (page, strip, row) space is cut into equal contiguous ranges, one per CTA:
+                                            // perfect balance, and a strip restart (4 virtual rows) only where a range or a
+                                            // strip begins
     const uint8_t* wimg;                    // [chunk][dx][plane][row = (4-dy)*NPAD + o][8]: resident operand image
     float bias[48];                         // by value (zero padded): constant-bank operands of the epilogue's adds
     int cout, relu;
@@ -123,7 +126,9 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = s_tmem_base;
-    const int items_per_page = p.strips * p.segs;
+    // this CTA's range of the concatenated (page * strips + strip) * h + y space; segments = its pieces inside one strip
+    const long long pos0 = (long long)blockIdx.x * p.rows_per_cta;
+    const long long pos1 = pos0 + p.rows_per_cta < p.total_rows ? pos0 + p.rows_per_cta : p.total_rows;
 
     if (warp == 0) {
         // ===================== producer: resident weights, then the input-row stream =====================
@@ -131,12 +136,11 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
             mbar_expect_tx(&s_wfull, p.w_bytes);
             for (uint32_t off = 0; off < p.w_bytes; off += WDX_BYTES) bulk_load(s_w + off, p.wimg + off, WDX_BYTES, &s_wfull);
             uint32_t k = 0;                                           // running input-row counter
-            for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-                const int page = item / items_per_page;
-                const int rem = item - page * items_per_page;
-                const int seg = rem % p.segs, strip = rem / p.segs;
-                const int ys = seg * p.seg_rows;
-                const int rows = min(p.seg_rows, p.h - ys);
+            for (long long pos = pos0; pos < pos1;) {
+                const int sg = (int)(pos / p.h), ys = (int)(pos - (long long)sg * p.h);
+                const int rows = (int)((long long)(p.h - ys) < pos1 - pos ? (long long)(p.h - ys) : pos1 - pos);
+                const int page = sg / p.strips, strip = sg - page * p.strips;
+                pos += rows;
                 const int x0 = strip * F_SW - 2;
                 for (int i = 0; i < rows + 4; ++i, ++k) {
                     const uint32_t slot = k % (uint32_t)RING, pass = k / (uint32_t)RING;
@@ -156,9 +160,11 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
         // tensor pipe fed, ~200 uniform-datapath instructions per row (the first version) did not.
         if (elect_one()) {
             uint32_t total = 0;
-            for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-                const int seg = (item % items_per_page) % p.segs;
-                total += (uint32_t)(min(p.seg_rows, p.h - seg * p.seg_rows) + 4);
+            for (long long pos = pos0; pos < pos1;) {
+                const int ys = (int)(pos % p.h);
+                const int rows = (int)((long long)(p.h - ys) < pos1 - pos ? (long long)(p.h - ys) : pos1 - pos);
+                pos += rows;
+                total += (uint32_t)(rows + 4);
             }
             const uint32_t hi = (uint32_t)(make_desc(0, 0, 128) >> 32);
             constexpr uint32_t a_lbo_pair = ((2048u >> 4) & 0x3fffu) << 16;               // K halves = two planes
@@ -224,12 +230,11 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
                 for (int s = 0; s < SLOTS; ++s) mbar_arrive(&s_tempty[s]);            // completes phase 0 of every slot
         }
         uint32_t g = 0;                                               // running output counter (incl. virtual rows), even
-        for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-            const int page = item / items_per_page;
-            const int rem = item - page * items_per_page;
-            const int seg = rem % p.segs, strip = rem / p.segs;
-            const int ys = seg * p.seg_rows;
-            const int rows = min(p.seg_rows, p.h - ys);
+        for (long long pos = pos0; pos < pos1;) {
+            const int sg = (int)(pos / p.h), ys = (int)(pos - (long long)sg * p.h);
+            const int rows = (int)((long long)(p.h - ys) < pos1 - pos ? (long long)(p.h - ys) : pos1 - pos);
+            const int page = sg / p.strips, strip = sg - page * p.strips;
+            pos += rows;
             const int x = strip * F_SW + j;
             const bool xok = j < F_SW && x < p.w;
             // row pairs (o = o2 - 4 + st) go round-robin over the epilogue groups, across work items
@@ -384,12 +389,10 @@ int launch_fold_t(pcs_ctx* ctx, const FoldConvArgs& a) {
     }
     p.w_bytes = (uint32_t)FoldK<NPL>::NMMA * 2 * NF * 16;  // [K step][K half][N' rows][16 B]
     p.strips = (a.w + F_SW - 1) / F_SW;
-    // segments: multiples of 4 rows (row pairs x 2 groups); aim at >= 4 items per CTA
-    int segs = 1;
-    while (segs < 64 && (size_t)a.n * p.strips * segs < (size_t)6 * ctx->sm_count && a.h / (segs * 2) >= 32) segs *= 2;
-    p.seg_rows = ((a.h + segs - 1) / segs + 3) / 4 * 4;
-    p.segs = (a.h + p.seg_rows - 1) / p.seg_rows;
-    p.num_items = a.n * p.strips * p.segs;
+    // equal ranges of whole row quads (row pairs for the pooling, pair rotation over the epilogue groups)
+    p.total_rows = (long long)a.n * p.strips * a.h;
+    p.rows_per_cta = ((p.total_rows + ctx->sm_count - 1) / ctx->sm_count + 3) / 4 * 4;
+    if (p.rows_per_cta < 16) p.rows_per_cta = 16;
     if ((a.h & 3) || (a.w & 1)) return set_err(ctx, PCS_ERR_ARG, "conv_fold: grid %dx%d must be a multiple of 4 x 2", a.h, a.w);
     EncodeTiledFn enc = fold_get_encode();
     if (!enc) return set_err(ctx, PCS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
@@ -413,7 +416,7 @@ int launch_fold_t(pcs_ctx* ctx, const FoldConvArgs& a) {
         PCS_CUDA(ctx, cudaFuncSetAttribute(conv_fold_kernel<T, NPAD, NPL, RING, SLOTS, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = smem;
     }
-    const int grid = std::min(p.num_items, ctx->sm_count);
+    const int grid = (int)((p.total_rows + p.rows_per_cta - 1) / p.rows_per_cta);
     conv_fold_kernel<T, NPAD, NPL, RING, SLOTS, EG><<<grid, 64 + EG * 128, smem, ctx->stream>>>(p, tm);
     PCS_LAUNCH_CHECK(ctx, "conv_fold_kernel");
     return PCS_OK;
