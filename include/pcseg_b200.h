@@ -161,6 +161,17 @@ PCS_API int pcs_cc_majority(pcs_ctx* ctx, uint8_t* d_pred, const uint8_t* d_bina
 PCS_API int pcs_bounding_boxes(pcs_ctx* ctx, const uint8_t* d_pred, int n, int H, int W,
                        int n_classes, uint8_t* d_out);
 
+/* ---- replaces compute_char_height, lib/image_ops.py:58-82 (the producer of
+ * `line_height_px`): cv2 Otsu threshold of the grey page, inversion unless
+ * `inverse`, connected components (8-connected: the reference's positional `4`
+ * lands in cv2's `labels` slot, so cv2's default connectivity applies), boxes
+ * with 0.5 < w/h < 2, 10 < h < 60, 5 < w < 50, and the height at index len/2 of
+ * the sorted valid heights.
+ *   d_img    : [n][H][W] uint8 grey pages
+ *   d_height : [n] int32, -1 where the reference returns None (no valid box) */
+PCS_API int pcs_char_height(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W,
+                    int inverse, int32_t* d_height);
+
 /* ---- whole page batch through the pipeline with HOST buffers (the copies are
  * part of the call): prepare_images -> predict_single_data -> optional
  * cc_majority -> generate_output_masks.  Synchronous.  Any output may be NULL.

@@ -23,7 +23,7 @@ EXPORTS = [
     "pcs_synchronize", "pcs_launch_count", "pcs_model_load", "pcs_set_engine", "pcs_preprocess",
     "pcs_preprocess_max_width",
     "pcs_forward", "pcs_masks", "pcs_resize_nearest", "pcs_ccl", "pcs_cc_majority",
-    "pcs_bounding_boxes", "pcs_predict_pages_host", "pcs_debug_activation", "pcs_set_keep_activations", "pcs_set_timing",
+    "pcs_bounding_boxes", "pcs_char_height", "pcs_predict_pages_host", "pcs_debug_activation", "pcs_set_keep_activations", "pcs_set_timing",
     "pcs_last_timings",
 ]
 
@@ -70,6 +70,7 @@ def load() -> C.CDLL:
     lib.pcs_ccl.argtypes = [vp, u8p, i32, i32, i32, vp, vp, i32, vp]
     lib.pcs_cc_majority.argtypes = [vp, u8p, u8p, i32, i32, i32, i32]
     lib.pcs_bounding_boxes.argtypes = [vp, u8p, i32, i32, i32, i32, u8p]
+    lib.pcs_char_height.argtypes = [vp, u8p, i32, i32, i32, i32, vp]
     lib.pcs_predict_pages_host.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
     lib.pcs_debug_activation.argtypes = [vp, C.c_char_p, vp, C.c_size_t, C.POINTER(C.c_int32)]
     lib.pcs_set_keep_activations.argtypes = [vp, i32]
@@ -218,6 +219,10 @@ class Context:
     def bounding_boxes(self, d_pred, n, H, W, n_classes, d_out):
         self._check(self.lib.pcs_bounding_boxes(self.h, _ptr(d_pred), n, H, W, n_classes, _ptr(d_out)),
                     "pcs_bounding_boxes")
+
+    def char_height(self, d_img, n, H, W, inverse, d_height):
+        self._check(self.lib.pcs_char_height(self.h, _ptr(d_img), n, H, W, 1 if inverse else 0, _ptr(d_height)),
+                    "pcs_char_height")
 
     # -- whole pipeline, host buffers ----------------------------------------
     def predict_pages_host(self, h_grey, h_bin, n, H, W, Hs, Ws, cc_majority=False, lut=None, h_image=None,

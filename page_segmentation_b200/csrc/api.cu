@@ -750,6 +750,13 @@ int pcs_bounding_boxes(pcs_ctx* ctx, const uint8_t* d_pred, int n, int H, int W,
     return launch_bounding_boxes(ctx, d_pred, n, H, W, n_classes, d_out);
 }
 
+int pcs_char_height(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, int inverse, int32_t* d_height) {
+    if (!ctx || !d_img || !d_height) return ctx ? set_err(ctx, PCS_ERR_ARG, "char_height: null argument") : PCS_ERR_ARG;
+    PCS_CUDA(ctx, cudaSetDevice(ctx->device));
+    StageScope ts(ctx, "char_height");
+    return launch_char_height(ctx, d_img, n, H, W, inverse, d_height);
+}
+
 int pcs_predict_pages_host(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h_bin, int n, int H, int W, int Hs, int Ws,
                            int cc_majority, const uint8_t* lut, uint8_t* h_image, uint8_t* h_binary, uint8_t* h_labels,
                            uint8_t* h_color, uint8_t* h_overlay, uint8_t* h_inverted) {

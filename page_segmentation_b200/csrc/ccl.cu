@@ -76,7 +76,7 @@ ccl_init_kernel(const uint8_t* __restrict__ img, int H, int W, int cls, int* __r
     }
 }
 
-template <bool MATCH_CLASS>
+template <bool MATCH_CLASS, bool CONN8>
 __global__ void __launch_bounds__(256)
 ccl_merge_kernel(const uint8_t* __restrict__ img, int H, int W, int cls, int* __restrict__ parent) {
     const int x = blockIdx.x * 256 + threadIdx.x;
@@ -96,6 +96,11 @@ ccl_merge_kernel(const uint8_t* __restrict__ img, int H, int W, int cls, int* __
     if (y > 0 && isfg(y - 1, x)) {
         const bool upleft = x > 0 && isfg(y - 1, x - 1);
         if (!left || !upleft) uf_union(par, idx, idx - W);
+    } else if (CONN8 && y > 0) {
+        // 8-connectivity: the diagonal neighbours matter only when the pixel above is background (otherwise they
+        // are in its run); a diagonal that the horizontal neighbour reaches through ITS upper pixel is skipped
+        if (!left && x > 0 && isfg(y - 1, x - 1)) uf_union(par, idx, idx - W - 1);
+        if (x + 1 < W && isfg(y - 1, x + 1) && !isfg(y, x + 1)) uf_union(par, idx, idx - W + 1);
     }
 }
 
@@ -256,15 +261,16 @@ ccl_stats_finish_kernel(int32_t* __restrict__ stats, const int32_t* __restrict__
 }
 
 static int ccl_roots(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, int cls, bool match, int* parent,
-                     int* zero_aux, int aux_stride) {
+                     int* zero_aux, int aux_stride, bool conn8 = false) {
     cudaStream_t st = ctx->stream;
     dim3 ginit(((W + 31) / 32 + 7) / 8, H, n);
     if (match) ccl_init_kernel<true><<<ginit, 256, 0, st>>>(d_img, H, W, cls, parent, zero_aux, aux_stride);
     else ccl_init_kernel<false><<<ginit, 256, 0, st>>>(d_img, H, W, cls, parent, zero_aux, aux_stride);
     PCS_LAUNCH_CHECK(ctx, "ccl_init_kernel");
     dim3 gmerge((W + 255) / 256, H, n);
-    if (match) ccl_merge_kernel<true><<<gmerge, 256, 0, st>>>(d_img, H, W, cls, parent);
-    else ccl_merge_kernel<false><<<gmerge, 256, 0, st>>>(d_img, H, W, cls, parent);
+    if (match) ccl_merge_kernel<true, false><<<gmerge, 256, 0, st>>>(d_img, H, W, cls, parent);
+    else if (conn8) ccl_merge_kernel<false, true><<<gmerge, 256, 0, st>>>(d_img, H, W, cls, parent);
+    else ccl_merge_kernel<false, false><<<gmerge, 256, 0, st>>>(d_img, H, W, cls, parent);
     PCS_LAUNCH_CHECK(ctx, "ccl_merge_kernel");
     const size_t page_px = (size_t)H * W;
     dim3 gflat((unsigned)std::min<size_t>(2048, (page_px + 255) / 256), n);
@@ -446,6 +452,123 @@ int launch_bounding_boxes(pcs_ctx* ctx, const uint8_t* d_pred, int n, int H, int
         diff_colscan_paint_kernel<<<dim3((W + 255) / 256, n), 256, 0, st>>>(diff, H, W, c, d_out);
         PCS_LAUNCH_CHECK(ctx, "diff_colscan_paint_kernel");
     }
+    return PCS_OK;
+}
+
+// ---------------------------------------------------------------------------
+// compute_char_height (lib/image_ops.py:58-82): Otsu threshold, connected components, letter-like boxes
+// (0.5 < w/h < 2, 10 < h < 60, 5 < w < 50), the height at index len/2 of the sorted valid heights.
+// The reference calls cv2.connectedComponentsWithStats(img, 4): the positional 4 lands in the `labels`
+// output slot and is ignored, so the components are 8-CONNECTED (cv2 default); restated as such.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) hist256_kernel(const uint8_t* __restrict__ img, size_t page_px, unsigned* __restrict__ hist) {
+    __shared__ unsigned s_h[256];
+    s_h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint8_t* p = img + (size_t)blockIdx.y * page_px;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < page_px; i += (size_t)gridDim.x * blockDim.x)
+        atomicAdd(&s_h[p[i]], 1u);
+    __syncthreads();
+    if (s_h[threadIdx.x]) atomicAdd(&hist[(size_t)blockIdx.y * 256 + threadIdx.x], s_h[threadIdx.x]);
+}
+
+// cv2 getThreshVal_Otsu_8u in its operation order (double precision, no contraction); one thread per page
+__global__ void otsu_kernel(const unsigned* __restrict__ hist, size_t page_px, int n, int* __restrict__ thresh) {
+    const int page = blockIdx.x * blockDim.x + threadIdx.x;
+    if (page >= n) return;
+    const unsigned* h = hist + (size_t)page * 256;
+    const double scale = __ddiv_rn(1.0, (double)page_px);
+    double mu = 0.0;
+    for (int i = 0; i < 256; ++i) mu = __dadd_rn(mu, __dmul_rn((double)i, (double)h[i]));
+    mu = __dmul_rn(mu, scale);
+    double mu1 = 0.0, q1 = 0.0, max_sigma = 0.0;
+    int max_val = 0;
+    for (int i = 0; i < 256; ++i) {
+        const double p_i = __dmul_rn((double)h[i], scale);
+        mu1 = __dmul_rn(mu1, q1);
+        q1 = __dadd_rn(q1, p_i);
+        const double q2 = __dsub_rn(1.0, q1);
+        if (fmin(q1, q2) < 1.1920928955078125e-07 || fmax(q1, q2) > 1.0 - 1.1920928955078125e-07) continue;
+        mu1 = __ddiv_rn(__dadd_rn(mu1, __dmul_rn((double)i, p_i)), q1);
+        const double mu2 = __ddiv_rn(__dsub_rn(mu, __dmul_rn(q1, mu1)), q2);
+        const double d = __dsub_rn(mu1, mu2);
+        const double sigma = __dmul_rn(__dmul_rn(__dmul_rn(q1, q2), d), d);
+        if (sigma > max_sigma) { max_sigma = sigma; max_val = i; }
+    }
+    thresh[page] = max_val;
+}
+
+// foreground of the component analysis: THRESH_BINARY (v > t -> 255), inverted unless `inverse`
+__global__ void __launch_bounds__(256)
+otsu_fg_kernel(const uint8_t* __restrict__ img, size_t page_px, const int* __restrict__ thresh, int inverse, uint8_t* __restrict__ fg) {
+    const int t = thresh[blockIdx.y];
+    const size_t off = (size_t)blockIdx.y * page_px;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < page_px; i += (size_t)gridDim.x * blockDim.x) {
+        const bool above = img[off + i] > t;
+        fg[off + i] = (above == (inverse != 0)) ? 1 : 0;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+letter_heights_kernel(const int* __restrict__ parent, int H, int W, const int* __restrict__ box, unsigned* __restrict__ hh /*[n][64]*/) {
+    const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    const size_t page_off = (size_t)blockIdx.z * H * W;
+    const int idx = y * W + x;
+    if (parent[page_off + idx] != idx) return;            // roots only
+    const int* b = box + (page_off + idx) * 4;
+    const int w = b[2] - (W - b[0]) + 1, h = b[3] - (H - b[1]) + 1;
+    // 0.5 < w/h < 2  <=>  h < 2w and w < 2h (exact for these small integers)
+    if (h < 2 * w && w < 2 * h && h > 10 && h < 60 && w > 5 && w < 50) atomicAdd(&hh[(size_t)blockIdx.z * 64 + h], 1u);
+}
+
+// sorted(valid heights)[len / 2], or -1 when there is no valid letter (the reference returns None)
+__global__ void median_height_kernel(const unsigned* __restrict__ hh, int n, int32_t* __restrict__ out) {
+    const int page = blockIdx.x * blockDim.x + threadIdx.x;
+    if (page >= n) return;
+    const unsigned* h = hh + (size_t)page * 64;
+    unsigned total = 0;
+    for (int i = 0; i < 64; ++i) total += h[i];
+    int res = -1;
+    if (total) {
+        const unsigned k = total / 2;
+        unsigned cum = 0;
+        for (int i = 0; i < 64; ++i) { cum += h[i]; if (cum > k) { res = i; break; } }
+    }
+    out[page] = res;
+}
+
+int launch_char_height(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, int inverse, int32_t* d_out) {
+    if (n <= 0 || H <= 0 || W <= 0 || (size_t)H * W >= (size_t)INT_MAX) return set_err(ctx, PCS_ERR_ARG, "char_height: bad shape");
+    const size_t page_px = (size_t)H * W, total = page_px * n;
+    auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+    const size_t need = al(total * 4) + al(total * 16) + al(total) + al((size_t)n * 256 * 4) + al((size_t)n * 64 * 4) + al((size_t)n * 4) + 256;
+    PCS_TRY(scratch_reserve(ctx, need));
+    char* q = reinterpret_cast<char*>(ctx->scratch);
+    int* parent = reinterpret_cast<int*>(q); q += al(total * 4);
+    int* box = reinterpret_cast<int*>(q); q += al(total * 16);
+    uint8_t* fg = reinterpret_cast<uint8_t*>(q); q += al(total);
+    unsigned* hist = reinterpret_cast<unsigned*>(q); q += al((size_t)n * 256 * 4);
+    unsigned* hh = reinterpret_cast<unsigned*>(q); q += al((size_t)n * 64 * 4);
+    int* thresh = reinterpret_cast<int*>(q);
+    cudaStream_t st = ctx->stream;
+    PCS_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)n * 256 * 4, st));
+    PCS_CUDA(ctx, cudaMemsetAsync(hh, 0, (size_t)n * 64 * 4, st));
+    const dim3 gflat((unsigned)std::min<size_t>(1184, (page_px + 255) / 256), n);
+    hist256_kernel<<<gflat, 256, 0, st>>>(d_img, page_px, hist);
+    PCS_LAUNCH_CHECK(ctx, "hist256_kernel");
+    otsu_kernel<<<(n + 63) / 64, 64, 0, st>>>(hist, page_px, n, thresh);
+    PCS_LAUNCH_CHECK(ctx, "otsu_kernel");
+    otsu_fg_kernel<<<gflat, 256, 0, st>>>(d_img, page_px, thresh, inverse, fg);
+    PCS_LAUNCH_CHECK(ctx, "otsu_fg_kernel");
+    PCS_TRY(ccl_roots(ctx, fg, n, H, W, 0, false, parent, box, 4, /*conn8=*/true));
+    const dim3 g((W + 255) / 256, H, n);
+    bbox_accum_kernel<<<g, 256, 0, st>>>(parent, H, W, box);
+    PCS_LAUNCH_CHECK(ctx, "bbox_accum_kernel");
+    letter_heights_kernel<<<g, 256, 0, st>>>(parent, H, W, box, hh);
+    PCS_LAUNCH_CHECK(ctx, "letter_heights_kernel");
+    median_height_kernel<<<(n + 63) / 64, 64, 0, st>>>(hh, n, d_out);
+    PCS_LAUNCH_CHECK(ctx, "median_height_kernel");
     return PCS_OK;
 }
 

@@ -232,6 +232,7 @@ int launch_ccl(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, int32_t*
                int32_t* d_stats, int max_components, int32_t* d_ncomp);
 int launch_cc_majority(pcs_ctx* ctx, uint8_t* d_pred, const uint8_t* d_binary, int n, int H, int W,
                        int n_classes);
+int launch_char_height(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, int inverse, int32_t* d_out);
 int launch_bounding_boxes(pcs_ctx* ctx, const uint8_t* d_pred, int n, int H, int W, int n_classes,
                           uint8_t* d_out);
 

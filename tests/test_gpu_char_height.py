@@ -1,0 +1,74 @@
+"""Parity of pcs_char_height with the CPU oracle restating compute_char_height (image_ops.py:58-82).
+Integer result: bit-exact bar."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import image_ops as oio
+from page_segmentation_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _text_page(seed, h, w, glyph_h):
+    """grey page with glyph-like boxes of about glyph_h pixels plus noise, so that Otsu has work to do"""
+    rng = np.random.default_rng(seed)
+    page = rng.normal(215, 8, (h, w))
+    y = 20
+    while y + glyph_h + 10 < h:
+        x = 15
+        while x + 40 < w:
+            gh = int(glyph_h + rng.integers(-3, 4))
+            gw = int(max(6, gh * rng.uniform(0.45, 1.4)))
+            page[y:y + gh, x:x + gw] = rng.normal(40, 10, (gh, gw))
+            if rng.random() < 0.2:                     # a dot touching the glyph only through a corner
+                page[y + gh:y + gh + 3, x + gw:x + gw + 3] = 35
+            x += gw + int(rng.integers(4, 14))
+        y += glyph_h + int(rng.integers(8, 20))
+    return np.clip(page, 0, 255).astype(np.uint8)
+
+
+@pytest.mark.parametrize("inverse", [False, True])
+@pytest.mark.parametrize("seed,shape,gh", [(0, (400, 600), 18), (1, (700, 500), 30), (2, (333, 517), 12), (3, (256, 256), 45)])
+def test_char_height_matches_oracle(ctx, seed, shape, gh, inverse):
+    from page_segmentation_b200.lib.image_ops import compute_char_height_array
+    page = _text_page(seed, *shape, gh)
+    if inverse:
+        page = 255 - page
+    got = compute_char_height_array(page, inverse)
+    exp = oio.compute_char_height_array(page, inverse)
+    assert (got is None) == (exp is None)
+    if exp is not None:
+        assert int(got) == int(exp)
+        assert abs(int(got) - gh) <= 4
+
+
+def test_char_height_binarised_page_and_none(ctx):
+    from page_segmentation_b200.lib.image_ops import compute_char_height_array
+    page = synth.make_page(3, 900, 700, 18)
+    assert compute_char_height_array(page, False) == oio.compute_char_height_array(page, False)
+    blank = np.full((200, 300), 255, np.uint8)
+    blank[0, 0] = 0                                      # Otsu needs two levels; a single dot is no letter
+    assert compute_char_height_array(blank, False) is None and oio.compute_char_height_array(blank, False) is None
+
+
+def test_char_height_file_api(ctx, tmp_path):
+    import cv2
+    from page_segmentation_b200.lib.image_ops import compute_char_height
+    page = _text_page(5, 300, 420, 20)
+    f = os.path.join(tmp_path, "page.png")
+    cv2.imwrite(f, page)
+    assert int(compute_char_height(f, False)) == int(oio.compute_char_height_array(page, False))
+    with pytest.raises(Exception, match="File does not exist"):
+        compute_char_height(os.path.join(tmp_path, "missing.png"), False)
+
+
+def test_char_height_batch(ctx):
+    import torch
+    pages = np.stack([_text_page(s, 320, 480, 14 + 6 * s) for s in range(3)])
+    d = torch.from_numpy(pages).cuda()
+    out = torch.empty((3,), dtype=torch.int32, device="cuda")
+    ctx.char_height(d, 3, 320, 480, False, out)
+    for i in range(3):
+        assert int(out[i].cpu()) == int(oio.compute_char_height_array(pages[i], False))

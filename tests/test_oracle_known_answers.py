@@ -245,3 +245,45 @@ def test_bf16_twin_rounding_points():
     lt, _ = twin.logits(img)
     l32, _ = onet.Forward("fcn_skip", W, 3).logits(img)
     assert 0 < np.abs(lt - l32).max() < 8e-3
+
+
+# ---------------------------------------------------------------------------
+# compute_char_height (image_ops.py:58-82)
+# ---------------------------------------------------------------------------
+def _glyph_page(h=300, w=400, sizes=((20, 12), (22, 14), (30, 20), (8, 8), (70, 30), (16, 40)), paper=230, ink=30):
+    page = np.full((h, w), paper, np.uint8)
+    x = 10
+    for gh, gw in sizes:
+        page[50:50 + gh, x:x + gw] = ink
+        x += gw + 15
+    return page
+
+
+def test_char_height_positional_4_means_8_connectivity():
+    """the reference's `cv2.connectedComponentsWithStats(img, 4)` ignores the 4 (it fills the `labels` slot):
+    cv2's default 8-connectivity applies -- two diagonal squares are ONE component"""
+    import cv2
+    img = np.zeros((40, 40), np.uint8)
+    img[5:10, 5:10] = 255
+    img[10:15, 10:15] = 255           # touches the first square only through a corner
+    n_ref = cv2.connectedComponentsWithStats(img, 4)[0]
+    assert n_ref == cv2.connectedComponentsWithStats(img, connectivity=8)[0] == 2
+    assert cv2.connectedComponentsWithStats(img, connectivity=4)[0] == 3
+
+
+def test_char_height_known_answer():
+    from oracle import image_ops as oio
+    page = _glyph_page()
+    # letter-like boxes: (20x12), (22x14), (30x20); (8x8) too small, (70x30) too tall, (16x40): w/h = 2.5
+    assert oio.compute_char_height_array(page, inverse=False) == 22       # sorted [20, 22, 30][3 // 2]
+    # inverse=True analyses the paper instead: one huge component, no letters
+    assert oio.compute_char_height_array(page, inverse=True) is None
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_otsu_restatement_matches_cv2(seed):
+    import cv2
+    from oracle import image_ops as oio
+    rng = np.random.default_rng(seed)
+    img = np.clip(rng.normal(90, 30, (120, 160)) + (rng.random((120, 160)) < 0.3) * 110, 0, 255).astype(np.uint8)
+    assert oio.otsu_threshold(img) == int(cv2.threshold(img, 0, 255, cv2.THRESH_BINARY + cv2.THRESH_OTSU)[0])
