@@ -162,7 +162,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pages", type=int, default=64, help="pages per GPU per step")
-    ap.add_argument("--precision", default=os.environ.get("PCSEG_PRECISION", "bf16"), choices=["bf16", "fp16"])
+    ap.add_argument("--precision", default=os.environ.get("PCSEG_PRECISION", "fp16"), choices=["bf16", "fp16"])
     ap.add_argument("--engine", default=os.environ.get("PCSEG_ENGINE", "umma"), choices=["umma", "direct"])
     ap.add_argument("--arch", default=ARCH, choices=["fcn_skip", "fcn", "unet"])
     ap.add_argument("--cpu-pages", type=int, default=3, help="pages of the CPU-baseline sample (rank 0, N=1)")

@@ -162,7 +162,7 @@ class Context:
 
     # -- model ---------------------------------------------------------------
     def load_model(self, arch: str, n_classes: int, weights: Sequence[Tuple[np.ndarray, np.ndarray]],
-                   precision: str = "bf16"):
+                   precision: str = "fp16"):
         arr = (LayerWeights * len(weights))()
         keep = []
         for i, (k, b) in enumerate(weights):

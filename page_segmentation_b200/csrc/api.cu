@@ -467,10 +467,11 @@ void pcs_ctx_destroy(pcs_ctx* ctx) {
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->scratch2) cudaFree(ctx->scratch2);
     if (ctx->stage) cudaFree(ctx->stage);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 2; ++i)
         if (ctx->copy_streams[i]) cudaStreamDestroy(ctx->copy_streams[i]);
+    for (int i = 0; i < pcs_ctx::kHostBufs; ++i)
         if (ctx->ev_h2d[i]) { cudaEventDestroy(ctx->ev_h2d[i]); cudaEventDestroy(ctx->ev_comp[i]); cudaEventDestroy(ctx->ev_d2h[i]); }
-    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     delete ctx;
 }
 
@@ -766,28 +767,58 @@ int pcs_predict_pages_host(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h
     const bool want_masks = h_color || h_overlay || h_inverted;
     if (want_masks && !lut) return set_err(ctx, PCS_ERR_ARG, "predict_pages_host: colour outputs need a LUT");
     PCS_CUDA(ctx, cudaSetDevice(ctx->device));
-    // Three-stage pipeline over sub-batches of pages: H2D copy stream -> compute stream (ctx->stream) ->
-    // D2H copy stream, double-buffered on the device, so that with pinned host memory the PCIe traffic
-    // of neighbouring sub-batches hides behind the kernels.
+    // Three-stage pipeline over sub-batches ("chunks") of pages: H2D copy stream -> compute stream
+    // (ctx->stream) -> D2H copy stream, rotating over `nbuf` device staging buffers, so that with pinned
+    // host memory the PCIe traffic of neighbouring chunks hides behind the kernels.  Per page the three
+    // stages cost about the same on a B200 behind PCIe 5 x16 (8.7 MB in, 9.7 MB out, ~0.16 ms of
+    // kernels), so what is left outside the overlap is the fill (first H2D) and the drain (last D2H):
+    // the schedule therefore starts and ends with small chunks and runs large ones in between.
     if (!ctx->copy_streams[0]) {
         PCS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_streams[0], cudaStreamNonBlocking));
         PCS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_streams[1], cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < pcs_ctx::kHostBufs; ++i) {
             PCS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
             PCS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_comp[i], cudaEventDisableTiming));
             PCS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming));
         }
+        PCS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     }
     cudaStream_t s_in = ctx->copy_streams[0], s_out = ctx->copy_streams[1], st = ctx->stream;
-    int chunk = 8;
-    if (const char* e = getenv("PCSEG_HOST_CHUNK")) chunk = std::max(1, atoi(e));
-    chunk = std::min(chunk, n);
+    // schedule "head,chunk,tail[,nbuf]": pages of the first chunk, of the steady chunks, of the last chunk
+    int head = 2, chunk = 8, tail = 2, nbuf = 3;
+    if (const char* e = getenv("PCSEG_HOST_SCHED")) sscanf(e, "%d,%d,%d,%d", &head, &chunk, &tail, &nbuf);
+    if (const char* e = getenv("PCSEG_HOST_CHUNK")) head = chunk = tail = std::max(1, atoi(e));
+    chunk = std::max(1, std::min(chunk, n));
+    head = std::max(1, std::min(head, chunk));
+    tail = std::max(1, std::min(tail, chunk));
+    nbuf = std::max(2, std::min(nbuf, (int)pcs_ctx::kHostBufs));
+    std::vector<int> first, count;             // first page and page count of every chunk
+    {
+        int p = 0;
+        auto push = [&](int m) { first.push_back(p); count.push_back(m); p += m; };
+        if (n <= chunk) push(n);
+        else {
+            push(head);
+            // grow geometrically to the steady size, keep `tail` pages (and a shrinking ramp) for the end
+            int m = head;
+            std::vector<int> ramp_down;
+            for (int t = tail, left = n - head; t < chunk && left - t > 0; t *= 2) { ramp_down.push_back(t); left -= t; }
+            int reserve = 0;
+            for (int t : ramp_down) reserve += t;
+            while (n - p - reserve > 0) {
+                m = std::min(chunk, m * 2);
+                push(std::min(m, n - p - reserve));
+            }
+            for (auto it = ramp_down.rbegin(); it != ramp_down.rend(); ++it) push(*it);
+        }
+    }
+    const int nchunks = (int)first.size();
     const size_t src1 = (size_t)H * W, dst1 = (size_t)Hs * Ws;
     const bool same = h_grey == h_bin;
     auto al = [](size_t b) { return (b + 255) / 256 * 256; };
     const size_t in_bytes = al(src1 * chunk) * (same ? 1 : 2);
     const size_t out_bytes = al(dst1 * chunk) * 3 + al(dst1 * chunk * 3) * 3;
-    const size_t need = 2 * (in_bytes + out_bytes) + 4096;
+    const size_t need = (size_t)nbuf * (in_bytes + out_bytes) + 4096;
     if (need > ctx->stage_bytes) {
         PCS_CUDA(ctx, cudaDeviceSynchronize());
         if (ctx->stage) cudaFree(ctx->stage);
@@ -798,10 +829,10 @@ int pcs_predict_pages_host(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h
         }
         ctx->stage_bytes = need;
     }
-    struct Buf { uint8_t *grey, *bin, *image, *binary, *labels, *color, *overlay, *inverted; } buf[2];
+    struct Buf { uint8_t *grey, *bin, *image, *binary, *labels, *color, *overlay, *inverted; } buf[pcs_ctx::kHostBufs];
     {
         uint8_t* p = reinterpret_cast<uint8_t*>(ctx->stage);
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < nbuf; ++i) {
             buf[i].grey = p; p += al(src1 * chunk);
             buf[i].bin = same ? buf[i].grey : p; if (!same) p += al(src1 * chunk);
             buf[i].image = p; p += al(dst1 * chunk);
@@ -812,28 +843,37 @@ int pcs_predict_pages_host(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h
             buf[i].inverted = p; p += al(dst1 * chunk * 3);
         }
     }
-    const int nchunks = (n + chunk - 1) / chunk;
+    // PCSEG_TRACE_HOST: per-chunk device timeline (timing events on the three streams), printed at the end
     const bool trace = getenv("PCSEG_TRACE_HOST") != nullptr;
-    const auto t_start = std::chrono::steady_clock::now();
-    auto now_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
+    std::vector<cudaEvent_t> tev;
+    cudaEvent_t t0 = nullptr;
+    auto mark = [&](cudaStream_t s) {
+        if (!trace) return;
+        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); tev.push_back(e);
+    };
     auto enqueue_h2d = [&](int c) -> int {
-        const int b = c & 1, p0 = c * chunk, m = std::min(chunk, n - p0);
-        if (c >= 2) PCS_CUDA(ctx, cudaStreamWaitEvent(s_in, ctx->ev_comp[b], 0));      // input buffer consumed by chunk c-2
+        const int b = c % nbuf, p0 = first[c], m = count[c];
+        if (c >= nbuf) PCS_CUDA(ctx, cudaStreamWaitEvent(s_in, ctx->ev_comp[b], 0));   // input buffer consumed by chunk c-nbuf
+        mark(s_in);
         PCS_CUDA(ctx, cudaMemcpyAsync(buf[b].grey, h_grey + (size_t)p0 * src1, src1 * m, cudaMemcpyHostToDevice, s_in));
         if (!same) PCS_CUDA(ctx, cudaMemcpyAsync(buf[b].bin, h_bin + (size_t)p0 * src1, src1 * m, cudaMemcpyHostToDevice, s_in));
+        mark(s_in);
         PCS_CUDA(ctx, cudaEventRecord(ctx->ev_h2d[b], s_in));
         return PCS_OK;
     };
     // order the pipeline after whatever the caller already queued on the compute stream
-    PCS_CUDA(ctx, cudaEventRecord(ctx->ev_comp[0], st));
-    PCS_CUDA(ctx, cudaStreamWaitEvent(s_in, ctx->ev_comp[0], 0));
-    PCS_CUDA(ctx, cudaStreamWaitEvent(s_out, ctx->ev_comp[0], 0));
-    PCS_TRY(enqueue_h2d(0));
+    if (trace) { cudaEventCreate(&t0); cudaEventRecord(t0, st); }
+    PCS_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+    PCS_CUDA(ctx, cudaStreamWaitEvent(s_in, ctx->ev_fork, 0));
+    PCS_CUDA(ctx, cudaStreamWaitEvent(s_out, ctx->ev_fork, 0));
+    const int ahead = nbuf - 1;                                                        // copies in flight ahead of the compute
+    for (int c = 0; c < std::min(ahead, nchunks); ++c) PCS_TRY(enqueue_h2d(c));
     for (int c = 0; c < nchunks; ++c) {
-        const int b = c & 1, p0 = c * chunk, m = std::min(chunk, n - p0);
-        if (c + 1 < nchunks) PCS_TRY(enqueue_h2d(c + 1));                                // next copy flies during this compute
+        const int b = c % nbuf, p0 = first[c], m = count[c];
+        if (c + ahead < nchunks) PCS_TRY(enqueue_h2d(c + ahead));
         PCS_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_h2d[b], 0));
-        if (c >= 2) PCS_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_d2h[b], 0));          // output buffer drained by chunk c-2
+        if (c >= nbuf) PCS_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_d2h[b], 0));       // output buffer drained by chunk c-nbuf
+        mark(st);
         PCS_TRY(pcs_preprocess(ctx, buf[b].grey, buf[b].bin, m, H, W, Hs, Ws, buf[b].image, buf[b].binary, nullptr));
         if (cc_majority) {
             PCS_TRY(pcs_forward(ctx, buf[b].image, buf[b].binary, m, Hs, Ws, buf[b].labels, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
@@ -845,9 +885,10 @@ int pcs_predict_pages_host(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h
             PCS_TRY(pcs_forward(ctx, buf[b].image, buf[b].binary, m, Hs, Ws, buf[b].labels, nullptr, nullptr, want_masks ? lut : nullptr,
                                 h_color ? buf[b].color : nullptr, h_overlay ? buf[b].overlay : nullptr, h_inverted ? buf[b].inverted : nullptr));
         }
-        const double t_enq = now_ms();
+        mark(st);
         PCS_CUDA(ctx, cudaEventRecord(ctx->ev_comp[b], st));
         PCS_CUDA(ctx, cudaStreamWaitEvent(s_out, ctx->ev_comp[b], 0));
+        mark(s_out);
         const size_t o1 = (size_t)p0 * dst1, o3 = o1 * 3;
         if (h_image) PCS_CUDA(ctx, cudaMemcpyAsync(h_image + o1, buf[b].image, dst1 * m, cudaMemcpyDeviceToHost, s_out));
         if (h_binary) PCS_CUDA(ctx, cudaMemcpyAsync(h_binary + o1, buf[b].binary, dst1 * m, cudaMemcpyDeviceToHost, s_out));
@@ -855,11 +896,34 @@ int pcs_predict_pages_host(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h
         if (h_color) PCS_CUDA(ctx, cudaMemcpyAsync(h_color + o3, buf[b].color, dst1 * m * 3, cudaMemcpyDeviceToHost, s_out));
         if (h_overlay) PCS_CUDA(ctx, cudaMemcpyAsync(h_overlay + o3, buf[b].overlay, dst1 * m * 3, cudaMemcpyDeviceToHost, s_out));
         if (h_inverted) PCS_CUDA(ctx, cudaMemcpyAsync(h_inverted + o3, buf[b].inverted, dst1 * m * 3, cudaMemcpyDeviceToHost, s_out));
+        mark(s_out);
         PCS_CUDA(ctx, cudaEventRecord(ctx->ev_d2h[b], s_out));
-        if (trace) fprintf(stderr, "[pcs host] chunk %d: compute enqueued at %.3f ms, d2h enqueued at %.3f ms\n", c, t_enq, now_ms());
     }
+    // the compute stream joins the output stream, so the caller's stream order covers the whole call
+    PCS_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_d2h[(nchunks - 1) % nbuf], 0));
     PCS_CUDA(ctx, cudaStreamSynchronize(s_out));
     PCS_CUDA(ctx, cudaStreamSynchronize(st));
+    if (trace) {
+        // events were pushed in enqueue order: reconstruct (kind, chunk) by replaying that order
+        std::vector<std::pair<char, int>> tag;
+        for (int c = 0; c < std::min(ahead, nchunks); ++c) tag.push_back({'i', c});
+        for (int c = 0; c < nchunks; ++c) {
+            if (c + ahead < nchunks) tag.push_back({'i', c + ahead});
+            tag.push_back({'k', c});
+            tag.push_back({'o', c});
+        }
+        fprintf(stderr, "[pcs host] n=%d chunks=%d nbuf=%d  (ms since call start: begin-end)\n", n, nchunks, nbuf);
+        for (size_t i = 0; i < tag.size(); ++i) {
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, t0, tev[2 * i]);
+            cudaEventElapsedTime(&b, t0, tev[2 * i + 1]);
+            fprintf(stderr, "[pcs host]   %s chunk %2d (%2d pages): %7.3f - %7.3f  (%.3f ms)\n",
+                    tag[i].first == 'i' ? "h2d    " : tag[i].first == 'k' ? "kernels" : "d2h    ", tag[i].second,
+                    count[tag[i].second], a, b, b - a);
+        }
+        for (cudaEvent_t e : tev) cudaEventDestroy(e);
+        cudaEventDestroy(t0);
+    }
     return PCS_OK;
 }
 

@@ -110,7 +110,8 @@ struct pcs_ctx {
     char* stage = nullptr;
     size_t stage_bytes = 0;
     cudaStream_t copy_streams[2] = {nullptr, nullptr};     // H2D / D2H streams of the host pipeline
-    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+    static constexpr int kHostBufs = 4;                    // staging buffers the host pipeline may rotate over
+    cudaEvent_t ev_h2d[kHostBufs] = {}, ev_comp[kHostBufs] = {}, ev_d2h[kHostBufs] = {}, ev_fork = nullptr;
 
     std::string timings;
     std::vector<pcs::StageTime> stage_times;

@@ -131,8 +131,10 @@ template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, fl
     return *reinterpret_cast<uint32_t*>(&v);
 }
 template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
-    __half2 v = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&v);
+    // saturating: an activation beyond the fp16 range is stored as +-65504 instead of inf (one F2FP either way)
+    uint32_t v;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(v) : "f"(b), "f"(a));
+    return v;
 }
 
 }  // namespace ptx

@@ -120,7 +120,7 @@ class PageBatchEngine:
     """Runs prepare_images -> network -> [cc_majority] -> masks for batches of
     equally sized pages on one GPU.  Buffers are allocated once per shape."""
 
-    def __init__(self, arch: str, weights, n_classes: int, precision: str = "bf16", device: Optional[int] = None,
+    def __init__(self, arch: str, weights, n_classes: int, precision: str = "fp16", device: Optional[int] = None,
                  lut: Optional[np.ndarray] = None, engine: str = "umma"):
         self.torch = _torch()
         self.ctx = get_context(device)
