@@ -183,6 +183,38 @@ PCS_API int pcs_predict_pages_host(pcs_ctx* ctx, const uint8_t* h_grey, const ui
                            uint8_t* h_image, uint8_t* h_binary, uint8_t* h_labels,
                            uint8_t* h_color, uint8_t* h_overlay, uint8_t* h_inverted);
 
+/* ---- region extraction (downstream consumer of the `inverted` colour image):
+ * the pixel work of lib/pc_segmentation.py and lib/xycut.py; the data-dependent
+ * parts (XY-cut recursion, contour tracing) stay on the host. -------------- */
+
+/* find_segments, lib/pc_segmentation.py:28-33 + :48/:56: cv2.resize(image,
+ * (Wo, Ho), INTER_NEAREST) -> dilate with a 3x3 rectangle (:63-67) ->
+ * color_map.filter_label for each of the m <= 8 colours.
+ *   d_rgb    : [H][W][3] uint8 colour image
+ *   colours  : HOST [m][3] uint8
+ *   d_masks  : [m][Ho][Wo] uint8 in {0,1} */
+PCS_API int pcs_segment_masks(pcs_ctx* ctx, const uint8_t* d_rgb, int H, int W, int Ho, int Wo,
+                      const uint8_t* colours, int m, uint8_t* d_masks);
+
+/* dilate, lib/pc_segmentation.py:63-67: cv2.dilate with a 3x3 rectangle of an
+ * interleaved uint8 image [H][W][C]; d_dst must not alias d_src. */
+PCS_API int pcs_dilate3x3(pcs_ctx* ctx, const uint8_t* d_src, int H, int W, int C, uint8_t* d_dst);
+
+/* projection profiles of do_xy_cut / recursive_cut, lib/xycut.py:95-161: the
+ * recursion evaluates np.count_nonzero(sub_image, axis) on nested sub-rectangles
+ * (:135); all of them are differences of rows / columns of the summed-area table
+ *   d_sat : [n][H+1][W+1] int32, sat[y][x] = #{mask[y'<y][x'<x] != 0}. */
+PCS_API int pcs_integral_image(pcs_ctx* ctx, const uint8_t* d_mask, int n, int H, int W, int32_t* d_sat);
+
+/* get_text_contours, lib/pc_segmentation.py:70-96: cv2.inRange(image, colour,
+ * colour) -> MORPH_CLOSE with a k_close x k_close rectangle -> MORPH_OPEN with
+ * k_open -> dilate with k_region -> MORPH_CLOSE with k_region (OpenCV anchors,
+ * borders and even-sized elements).  Outputs, both [H][W] uint8 or NULL:
+ *   d_text_inv : 255 - image after the opening (:96, the canvas the contours are drawn on)
+ *   d_region   : region_text (:93, the input of the first cv2.findContours) */
+PCS_API int pcs_text_regions(pcs_ctx* ctx, const uint8_t* d_rgb, int H, int W, const uint8_t* colour,
+                     int k_close, int k_open, int k_region, uint8_t* d_text_inv, uint8_t* d_region);
+
 /* ---- diagnostics ------------------------------------------------------ */
 /* copies one named internal activation of the last pcs_forward to a float32
  * NHWC host buffer (real channels only); returns the channel count or <0. */

@@ -23,7 +23,7 @@ EXPORTS = [
     "pcs_synchronize", "pcs_launch_count", "pcs_model_load", "pcs_set_engine", "pcs_preprocess",
     "pcs_preprocess_max_width",
     "pcs_forward", "pcs_masks", "pcs_resize_nearest", "pcs_ccl", "pcs_cc_majority",
-    "pcs_bounding_boxes", "pcs_char_height", "pcs_predict_pages_host", "pcs_debug_activation", "pcs_set_keep_activations", "pcs_set_timing",
+    "pcs_bounding_boxes", "pcs_char_height", "pcs_segment_masks", "pcs_dilate3x3", "pcs_integral_image", "pcs_text_regions", "pcs_predict_pages_host", "pcs_debug_activation", "pcs_set_keep_activations", "pcs_set_timing",
     "pcs_last_timings",
 ]
 
@@ -71,6 +71,10 @@ def load() -> C.CDLL:
     lib.pcs_cc_majority.argtypes = [vp, u8p, u8p, i32, i32, i32, i32]
     lib.pcs_bounding_boxes.argtypes = [vp, u8p, i32, i32, i32, i32, u8p]
     lib.pcs_char_height.argtypes = [vp, u8p, i32, i32, i32, i32, vp]
+    lib.pcs_segment_masks.argtypes = [vp, u8p, i32, i32, i32, i32, vp, i32, u8p]
+    lib.pcs_dilate3x3.argtypes = [vp, u8p, i32, i32, i32, u8p]
+    lib.pcs_integral_image.argtypes = [vp, u8p, i32, i32, i32, vp]
+    lib.pcs_text_regions.argtypes = [vp, u8p, i32, i32, vp, i32, i32, i32, u8p, u8p]
     lib.pcs_predict_pages_host.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
     lib.pcs_debug_activation.argtypes = [vp, C.c_char_p, vp, C.c_size_t, C.POINTER(C.c_int32)]
     lib.pcs_set_keep_activations.argtypes = [vp, i32]
@@ -223,6 +227,23 @@ class Context:
     def char_height(self, d_img, n, H, W, inverse, d_height):
         self._check(self.lib.pcs_char_height(self.h, _ptr(d_img), n, H, W, 1 if inverse else 0, _ptr(d_height)),
                     "pcs_char_height")
+
+    # -- region extraction ---------------------------------------------------
+    def segment_masks(self, d_rgb, H, W, Ho, Wo, colours, d_masks):
+        cols = np.ascontiguousarray(colours, dtype=np.uint8).reshape(-1, 3)
+        self._check(self.lib.pcs_segment_masks(self.h, _ptr(d_rgb), H, W, Ho, Wo, _ptr(cols), cols.shape[0], _ptr(d_masks)),
+                    "pcs_segment_masks")
+
+    def dilate3x3(self, d_src, H, W, C, d_dst):
+        self._check(self.lib.pcs_dilate3x3(self.h, _ptr(d_src), H, W, C, _ptr(d_dst)), "pcs_dilate3x3")
+
+    def integral_image(self, d_mask, n, H, W, d_sat):
+        self._check(self.lib.pcs_integral_image(self.h, _ptr(d_mask), n, H, W, _ptr(d_sat)), "pcs_integral_image")
+
+    def text_regions(self, d_rgb, H, W, colour, k_close, k_open, k_region, d_text_inv, d_region):
+        col = np.ascontiguousarray(colour, dtype=np.uint8).reshape(3)
+        self._check(self.lib.pcs_text_regions(self.h, _ptr(d_rgb), H, W, _ptr(col), int(k_close), int(k_open), int(k_region),
+                                              _ptr(d_text_inv), _ptr(d_region)), "pcs_text_regions")
 
     # -- whole pipeline, host buffers ----------------------------------------
     def predict_pages_host(self, h_grey, h_bin, n, H, W, Hs, Ws, cc_majority=False, lut=None, h_image=None,

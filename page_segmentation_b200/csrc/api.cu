@@ -758,6 +758,42 @@ int pcs_char_height(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, int
     return launch_char_height(ctx, d_img, n, H, W, inverse, d_height);
 }
 
+int pcs_segment_masks(pcs_ctx* ctx, const uint8_t* d_rgb, int H, int W, int Ho, int Wo, const uint8_t* colours, int m,
+                      uint8_t* d_masks) {
+    if (!ctx || !d_rgb || !colours || !d_masks) return ctx ? set_err(ctx, PCS_ERR_ARG, "segment_masks: null argument") : PCS_ERR_ARG;
+    if (H <= 0 || W <= 0 || Ho <= 0 || Wo <= 0) return set_err(ctx, PCS_ERR_ARG, "segment_masks: bad shape");
+    PCS_CUDA(ctx, cudaSetDevice(ctx->device));
+    StageScope ts(ctx, "segment_masks");
+    return launch_segment_masks(ctx, d_rgb, H, W, Ho, Wo, colours, m, d_masks);
+}
+
+int pcs_dilate3x3(pcs_ctx* ctx, const uint8_t* d_src, int H, int W, int C, uint8_t* d_dst) {
+    if (!ctx || !d_src || !d_dst) return ctx ? set_err(ctx, PCS_ERR_ARG, "dilate3x3: null argument") : PCS_ERR_ARG;
+    if (H <= 0 || W <= 0 || C <= 0 || d_src == d_dst) return set_err(ctx, PCS_ERR_ARG, "dilate3x3: bad shape or in-place call");
+    PCS_CUDA(ctx, cudaSetDevice(ctx->device));
+    return launch_dilate3x3(ctx, d_src, H, W, C, d_dst);
+}
+
+int pcs_integral_image(pcs_ctx* ctx, const uint8_t* d_mask, int n, int H, int W, int32_t* d_sat) {
+    if (!ctx || !d_mask || !d_sat) return ctx ? set_err(ctx, PCS_ERR_ARG, "integral_image: null argument") : PCS_ERR_ARG;
+    if (n <= 0 || H <= 0 || W <= 0 || (long long)H * W >= (1ll << 31)) return set_err(ctx, PCS_ERR_ARG, "integral_image: bad shape");
+    PCS_CUDA(ctx, cudaSetDevice(ctx->device));
+    StageScope ts(ctx, "integral_image");
+    return launch_integral_image(ctx, d_mask, n, H, W, d_sat);
+}
+
+int pcs_text_regions(pcs_ctx* ctx, const uint8_t* d_rgb, int H, int W, const uint8_t* colour, int k_close, int k_open,
+                     int k_region, uint8_t* d_text_inv, uint8_t* d_region) {
+    if (!ctx || !d_rgb || !colour) return ctx ? set_err(ctx, PCS_ERR_ARG, "text_regions: null argument") : PCS_ERR_ARG;
+    if (H <= 0 || W <= 0 || H > 65535) return set_err(ctx, PCS_ERR_ARG, "text_regions: bad shape");
+    // cv2.getStructuringElement rejects empty elements (char_height < 3 makes int(char_height / 3) zero)
+    if (k_close < 1 || k_open < 1 || k_region < 1)
+        return set_err(ctx, PCS_ERR_ARG, "text_regions: structuring elements must be at least 1x1 (got %d, %d, %d)", k_close, k_open, k_region);
+    PCS_CUDA(ctx, cudaSetDevice(ctx->device));
+    StageScope ts(ctx, "text_regions");
+    return launch_text_regions(ctx, d_rgb, H, W, colour, k_close, k_open, k_region, d_text_inv, d_region);
+}
+
 int pcs_predict_pages_host(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h_bin, int n, int H, int W, int Hs, int Ws,
                            int cc_majority, const uint8_t* lut, uint8_t* h_image, uint8_t* h_binary, uint8_t* h_labels,
                            uint8_t* h_color, uint8_t* h_overlay, uint8_t* h_inverted) {

@@ -237,6 +237,14 @@ int launch_char_height(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, 
 int launch_bounding_boxes(pcs_ctx* ctx, const uint8_t* d_pred, int n, int H, int W, int n_classes,
                           uint8_t* d_out);
 
+// regions.cu
+int launch_segment_masks(pcs_ctx* ctx, const uint8_t* d_rgb, int H, int W, int Ho, int Wo, const uint8_t* colours, int m,
+                         uint8_t* d_masks);
+int launch_dilate3x3(pcs_ctx* ctx, const uint8_t* d_src, int H, int W, int C, uint8_t* d_dst);
+int launch_integral_image(pcs_ctx* ctx, const uint8_t* d_mask, int n, int H, int W, int32_t* d_sat);
+int launch_text_regions(pcs_ctx* ctx, const uint8_t* d_rgb, int H, int W, const uint8_t* colour, int k_close, int k_open,
+                        int k_region, uint8_t* d_text_inv, uint8_t* d_region);
+
 // conv_umma.cu  (tcgen05 / TMEM / TMA implicit GEMM)
 struct UmmaHeadArgs {              // fused FCN head epilogue (conv_umma.cu mode 2)
     const void* plog = nullptr;         // device float4 [n][2h][2w]: conv2 share of the logits (fcn_skip) or null

@@ -196,3 +196,52 @@ def scaled_shape(h: int, w: int, scale: float) -> Tuple[int, int]:
 def padded_shape(h: int, w: int, f: int = 32) -> Tuple[int, int]:
     """model.py:10-17 calculate_padding applied to (H, W)."""
     return h + (f - h % f) % f, w + (f - w % f) % f
+
+
+def make_inverted_image(seed: int = 0, height: int = 700, width: int = 500, char_height: int = 18,
+                        text_colour=(255, 0, 0), image_colour=(0, 255, 0)) -> np.ndarray:
+    """A synthetic `inverted` output image (output.py:50-51: class colour where ink, black elsewhere) as the
+    region-extraction stage reads it: text lines of glyph blobs in `text_colour` arranged in one or two columns,
+    one or two noisy picture blocks in `image_colour`, and a sprinkle of misclassified specks of either colour."""
+    rng = np.random.default_rng(seed + 104729)
+    img = np.zeros((height, width, 3), dtype=np.uint8)
+    ch = max(3, int(char_height))
+    margin = max(4, min(height, width) // 12)
+    two_cols = bool(rng.integers(0, 2)) and width > 20 * ch
+    gutter = 4 * ch
+    cols = [(margin, width - margin)] if not two_cols else [(margin, width // 2 - gutter // 2), (width // 2 + gutter // 2, width - margin)]
+    # picture blocks at the bottom of a column
+    pic_top = {}
+    for ci, (x0, x1) in enumerate(cols):
+        if rng.random() < 0.7:
+            bh = int(rng.integers(height // 6, height // 3))
+            top = height - margin - bh
+            block = rng.random((bh, x1 - x0)) < 0.5
+            img[top:top + bh, x0:x1][block] = image_colour
+            pic_top[ci] = top
+    for ci, (x0, x1) in enumerate(cols):
+        y = margin
+        bottom = pic_top.get(ci, height - margin) - 2 * ch
+        para_left = int(rng.integers(4, 9))
+        while y + ch < bottom:
+            x = x0 + int(rng.integers(0, ch))
+            while x + ch < x1:
+                gw = int(rng.integers(max(2, ch // 3), max(3, ch * 9 // 10)))
+                gh = int(rng.integers(max(2, ch * 2 // 3), ch + 1))
+                glyph = rng.random((gh, gw)) < 0.7
+                glyph[:, :max(1, gw // 4)] = True
+                img[y + ch - gh:y + ch, x:x + gw][glyph[:, :max(0, min(gw, x1 - x))]] = text_colour
+                x += gw + int(rng.integers(1, max(2, ch // 4)))
+                if rng.random() < 0.15:
+                    x += ch
+            y += int(ch * rng.uniform(1.5, 1.9))
+            para_left -= 1
+            if para_left == 0:
+                y += int(ch * rng.uniform(2.5, 4.0))
+                para_left = int(rng.integers(4, 9))
+    n = int(0.001 * height * width)
+    ys, xs = rng.integers(0, height, n), rng.integers(0, width, n)
+    pick = rng.random(n) < 0.5
+    img[ys[pick], xs[pick]] = text_colour
+    img[ys[~pick], xs[~pick]] = image_colour
+    return img
