@@ -374,8 +374,21 @@ bbox_accum_kernel(const int* __restrict__ parent, int H, int W, int* __restrict_
     const int p = parent[page_off + (size_t)y * W + x];
     if (p == kBG) return;
     int* b = box + (page_off + p) * 4;
-    // accumulators are zero-initialised at run starts: keep (W - min x, H - min y, max x, max y) as maxima
-    atomicMax(&b[0], W - x); atomicMax(&b[1], H - y); atomicMax(&b[2], x); atomicMax(&b[3], y);
+    // accumulators are zero-initialised at run starts: keep (W - min x, H - min y, max x, max y) as maxima.
+    // A large component (a picture block, the page background of add_bounding_boxes) would send every one of
+    // its pixels to the same four words: lanes of a warp that share a root first reduce among themselves, and
+    // the leader only issues the atomics that can still grow the box (a stale read merely costs an atomic).
+    const unsigned act = __activemask();
+    const unsigned peers = __match_any_sync(act, p);
+    const int v0 = __reduce_max_sync(peers, W - x), v1 = __reduce_max_sync(peers, H - y);
+    const int v2 = __reduce_max_sync(peers, x), v3 = __reduce_max_sync(peers, y);
+    if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) {
+        const int4 cur = __ldcg(reinterpret_cast<const int4*>(b));
+        if (v0 > cur.x) atomicMax(&b[0], v0);
+        if (v1 > cur.y) atomicMax(&b[1], v1);
+        if (v2 > cur.z) atomicMax(&b[2], v2);
+        if (v3 > cur.w) atomicMax(&b[3], v3);
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -432,10 +445,11 @@ int launch_bounding_boxes(pcs_ctx* ctx, const uint8_t* d_pred, int n, int H, int
         return set_err(ctx, PCS_ERR_ARG, "bounding_boxes: bad argument");
     const size_t page_px = (size_t)H * W, total = page_px * n;
     const size_t diff_elems = (size_t)n * (H + 1) * (W + 1);
-    PCS_TRY(scratch_reserve(ctx, total * 4 * 5 + diff_elems * 4 + 512));
+    const size_t total4 = (total + 3) / 4 * 4;                           // keeps the int4 box records 16-byte aligned
+    PCS_TRY(scratch_reserve(ctx, total4 * 4 * 5 + diff_elems * 4 + 512));
     int* parent = reinterpret_cast<int*>(ctx->scratch);
-    int* box = parent + total;
-    int* diff = box + total * 4;
+    int* box = parent + total4;
+    int* diff = box + total4 * 4;
     cudaStream_t st = ctx->stream;
     PCS_CUDA(ctx, cudaMemsetAsync(d_out, 0, total, st));                 // newpred = zeros_like(pred)
     // classes = np.unique(pred) per page in the reference; painting an absent class is a no-op
@@ -466,7 +480,26 @@ __global__ void __launch_bounds__(256) hist256_kernel(const uint8_t* __restrict_
     s_h[threadIdx.x] = 0;
     __syncthreads();
     const uint8_t* p = img + (size_t)blockIdx.y * page_px;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < page_px; i += (size_t)gridDim.x * blockDim.x)
+    // 16 consecutive pixels per thread, equal neighbours counted as one run: scans are mostly paper, so a thread
+    // usually issues one shared-memory atomic per 16 pixels instead of 16 to the same bin
+    const size_t chunks = page_px / 16;
+    const bool aligned = (reinterpret_cast<uintptr_t>(p) & 15) == 0;
+    if (aligned) {
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < chunks; i += (size_t)gridDim.x * blockDim.x) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(p) + i);
+            const unsigned w[4] = {q.x, q.y, q.z, q.w};
+            unsigned cur = w[0] & 0xffu, run = 0;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const unsigned v = (w[k >> 2] >> ((k & 3) * 8)) & 0xffu;
+                if (v != cur) { atomicAdd(&s_h[cur], run); cur = v; run = 0; }
+                ++run;
+            }
+            atomicAdd(&s_h[cur], run);
+        }
+    }
+    for (size_t i = (aligned ? chunks * 16 : 0) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < page_px;
+         i += (size_t)gridDim.x * blockDim.x)
         atomicAdd(&s_h[p[i]], 1u);
     __syncthreads();
     if (s_h[threadIdx.x]) atomicAdd(&hist[(size_t)blockIdx.y * 256 + threadIdx.x], s_h[threadIdx.x]);

@@ -771,24 +771,42 @@ int launch_preprocess_max_width(pcs_ctx* ctx, const uint8_t* d_grey, const uint8
 
 // preserving_resize (util.py:21-29): order-0 resize of uint8 planes
 __global__ void __launch_bounds__(256)
-resize_nearest_kernel(const uint8_t* __restrict__ src, int H, int W, uint8_t* __restrict__ dst, int Ho, int Wo) {
-    const int x = blockIdx.x * 32 + threadIdx.x;
+resize_nearest_kernel(const uint8_t* __restrict__ src, int H, int W, uint8_t* __restrict__ dst, int Ho, int Wo, double fr,
+                      double fc, int vec) {
+    // 16 output pixels per thread (one 16-byte store when the row is aligned); fr = H / Ho, fc = W / Wo
+    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 16;
     const int y = blockIdx.y * 8 + threadIdx.y;
-    if (x >= Wo || y >= Ho) return;
+    if (x0 >= Wo || y >= Ho) return;
     const int page = blockIdx.z;
-    const double fr = __ddiv_rn((double)H, (double)Ho);
-    const double fc = __ddiv_rn((double)W, (double)Wo);
     const double r = __dadd_rn(__dmul_rn(fr, (double)y), __dsub_rn(__dmul_rn(0.5, fr), 0.5));
-    const double c = __dadd_rn(__dmul_rn(fc, (double)x), __dsub_rn(__dmul_rn(0.5, fc), 0.5));
     const int ri = reflect_coord((long long)round(r), H);
-    const int ci = reflect_coord((long long)round(c), W);
-    dst[(size_t)page * Ho * Wo + (size_t)y * Wo + x] = src[(size_t)page * H * W + (size_t)ri * W + ci];
+    const uint8_t* srow = src + (size_t)page * H * W + (size_t)ri * W;
+    uint8_t* drow = dst + (size_t)page * Ho * Wo + (size_t)y * Wo;
+    const double c_off = __dsub_rn(__dmul_rn(0.5, fc), 0.5);
+    unsigned w[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int x = x0 + k;
+        if (x < Wo) {
+            const double c = __dadd_rn(__dmul_rn(fc, (double)x), c_off);
+            const unsigned v = __ldg(srow + reflect_coord((long long)round(c), W));
+            if (vec) w[k >> 2] |= v << ((k & 3) * 8);
+            else drow[x] = (uint8_t)v;
+        }
+    }
+    if (vec) {
+        if (x0 + 16 <= Wo) *reinterpret_cast<uint4*>(drow + x0) = make_uint4(w[0], w[1], w[2], w[3]);
+        else
+            for (int k = 0; x0 + k < Wo; ++k) drow[x0 + k] = (uint8_t)((w[k >> 2] >> ((k & 3) * 8)) & 0xffu);
+    }
 }
 
 int launch_resize_nearest(pcs_ctx* ctx, const uint8_t* d_src, int n, int H, int W, uint8_t* d_dst, int Ho, int Wo) {
     if (n <= 0 || H <= 0 || W <= 0 || Ho <= 0 || Wo <= 0) return set_err(ctx, PCS_ERR_ARG, "resize_nearest: bad shape");
-    dim3 grid((Wo + 31) / 32, (Ho + 7) / 8, n), block(32, 8);
-    resize_nearest_kernel<<<grid, block, 0, ctx->stream>>>(d_src, H, W, d_dst, Ho, Wo);
+    dim3 grid((Wo + 511) / 512, (Ho + 7) / 8, n), block(32, 8);
+    const int vec = (Wo % 16 == 0) && (reinterpret_cast<uintptr_t>(d_dst) % 16 == 0);
+    resize_nearest_kernel<<<grid, block, 0, ctx->stream>>>(d_src, H, W, d_dst, Ho, Wo, (double)H / (double)Ho,
+                                                           (double)W / (double)Wo, vec);
     PCS_LAUNCH_CHECK(ctx, "resize_nearest_kernel");
     return PCS_OK;
 }

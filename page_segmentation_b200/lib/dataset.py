@@ -1,7 +1,8 @@
 """Mirror of ocr4all_pixel_classifier/lib/dataset.py for the prediction path:
 SingleData (:17-29), Dataset (:32-41), prepare_images (:131-150) and
-DatasetLoader (:153-208).  Training-only helpers (list_dataset, splits) are out
-of scope."""
+DatasetLoader (:153-208) and the directory listing `list_dataset` (:44-111) that
+feeds it (dataset layout + per-page normalisation JSON).  The train/test split
+helpers (:247-289) belong to training and are out of scope."""
 from __future__ import annotations
 
 import json
@@ -9,6 +10,8 @@ from dataclasses import dataclass
 from typing import Any, Callable, List, Optional, Tuple
 
 import numpy as np
+
+import os
 
 from .colors import ColorMap
 
@@ -38,6 +41,57 @@ class Dataset:
 
     def __iter__(self):
         return self.data.__iter__()
+
+
+def list_dataset(root_dir, line_height_px=None, binary_dir_="binary_images", images_dir_="images", masks_dir_="masks",
+                 masks_postfix="", normalizations_dir="normalizations", verify_filenames=False):
+    """dataset.py:44-111: one {binary_path, image_path, mask_path, line_height_px} record per page of a dataset
+    directory; without a fixed `line_height_px` every page takes "char_height" from its normalisation JSON
+    (<root>/<normalizations_dir>/*, what `compute-image-normalizations` / compute_char_height writes)."""
+    def files_in(folder, keep):
+        return [os.path.join(folder, name) for name in sorted(os.listdir(folder)) if keep(name)]
+
+    dirs = {k: os.path.join(root_dir, v) for k, v in (("bin", binary_dir_), ("img", images_dir_), ("mask", masks_dir_))}
+    for d in (root_dir, dirs["bin"], dirs["img"], dirs["mask"]):
+        if not os.path.exists(d):
+            raise Exception("Dataset dir does not exist at '%s'" % d)
+
+    bins = files_in(dirs["bin"], lambda n: True)
+    # images may live next to the masks: with a postfix, everything NOT carrying it is an image (:73)
+    imgs = files_in(dirs["img"], (lambda n: not n.endswith(masks_postfix)) if masks_postfix else (lambda n: True))
+    masks = files_in(dirs["mask"], lambda n: n.endswith(masks_postfix))
+
+    base_names = None
+    if verify_filenames:
+        def by_stem(paths, postfix=None):
+            if postfix:
+                stripped = [p[:-len(postfix)] if p.endswith(postfix) else p for p in paths]
+                return {os.path.basename(p).split('.')[0]: p + postfix for p in stripped}
+            return {os.path.basename(p).split('.')[0]: p for p in paths}
+
+        b, i, m = by_stem(bins), by_stem(imgs), by_stem(masks, masks_postfix)
+        base_names = set(b.keys()).intersection(set(i.keys())).intersection(set(m.keys()))
+        bins, imgs, masks = ([table.get(name) for name in base_names] for table in (b, i, m))
+
+    if not line_height_px:
+        norm_dir = os.path.join(root_dir, normalizations_dir)
+        if not os.path.exists(norm_dir):
+            raise Exception(f"Norm dir does not exist at '{norm_dir}'")
+        norm_files = files_in(norm_dir, lambda n: True)
+        if verify_filenames:
+            norm_files = [f for f in norm_files if any(os.path.basename(f).startswith(s) for s in base_names)]
+        heights = []
+        for f in norm_files:
+            with open(f, 'r') as fh:
+                heights.append(json.load(fh)["char_height"])
+        assert (len(heights) == len(masks))
+    else:
+        heights = [line_height_px] * len(masks)
+
+    if not (len(bins) == len(imgs) == len(masks)):
+        raise Exception("Mismatch in dataset files length: %d, %d, %d!" % (len(bins), len(imgs), len(masks)))
+    return [{"binary_path": bp, "image_path": ip, "mask_path": mp, "line_height_px": lh}
+            for bp, ip, mp, lh in zip(bins, imgs, masks, heights)]
 
 
 def imread(path: str, as_gray: bool = True) -> np.ndarray:

@@ -173,3 +173,70 @@ def test_live_reference_region_extraction_and_vote():
     pred = rng.integers(0, 4, binary.shape).astype(np.int64)
     exp = pp.vote_connected_component_class(pred.copy(), ds.SingleData(binary=binary))
     assert np.array_equal(opipe.vote_connected_component_class(pred.copy(), binary), exp)
+
+
+@live
+def test_live_reference_api_surface():
+    """Field names / order / defaults of the value types, the Architecture enum and the two pure helpers."""
+    import dataclasses
+    import importlib
+
+    def fields(c):
+        if dataclasses.is_dataclass(c):
+            return [(f.name, None if f.default is dataclasses.MISSING else f.default) for f in dataclasses.fields(c)]
+        return [(f, c._field_defaults.get(f)) for f in c._fields]
+
+    for mod, names in [("dataset", ["SingleData", "Dataset"]), ("predictor_data", ["PredictSettings", "Prediction"]),
+                       ("output", ["Masks"]), ("xycut", ["RectSegment", "CVContour", "Segment1D", "Gap"])]:
+        theirs, ours = ref.load(mod), importlib.import_module("page_segmentation_b200.lib." + mod)
+        for n in names:
+            assert fields(getattr(theirs, n)) == fields(getattr(ours, n)), n
+    ra = ref.load("architecture")
+    from page_segmentation_b200.lib import architecture as ma
+    assert [(a.name, a.value) for a in ra.Architecture] == [(a.name, a.value) for a in ma.Architecture]
+    x = np.arange(12, dtype=np.uint8).reshape(3, 4)
+    assert np.array_equal(ra.default_preprocess(x), ma.default_preprocess(x))
+    ru = ref.load("util")
+    from page_segmentation_b200.lib import util as mu
+    assert np.array_equal(ru.gray_to_rgb(x), mu.gray_to_rgb(x))
+    assert np.array_equal(ru.image_to_batch(x), mu.image_to_batch(x))
+    rp = ref.load("postprocess")
+    from page_segmentation_b200.lib import postprocess as mp
+    assert sorted(rp.POSTPROCESSORS) == sorted(mp.POSTPROCESSORS) and rp.postprocess_help() == mp.postprocess_help()
+
+
+@live
+def test_live_reference_list_dataset(tmp_path):
+    import json
+    from page_segmentation_b200.lib import dataset as md
+    rd = ref.load("dataset")
+    root = tmp_path / "ds"
+    for sub in ("binary_images", "images", "masks", "normalizations", "together"):
+        (root / sub).mkdir(parents=True)
+    names = ["p003", "p001", "p010", "p002"]
+    for i, n in enumerate(names):
+        (root / "binary_images" / f"{n}.bin.png").write_bytes(b"x")
+        (root / "images" / f"{n}.png").write_bytes(b"x")
+        (root / "masks" / f"{n}.mask.png").write_bytes(b"x")
+        (root / "normalizations" / f"{n}.norm").write_text(json.dumps({"char_height": 17 + i}))
+        (root / "together" / f"{n}.png").write_bytes(b"x")
+        (root / "together" / f"{n}_GT.png").write_bytes(b"x")
+    (root / "images" / "extra.png").write_bytes(b"x")                       # page without mask / binary
+    key = lambda rec: rec["image_path"]                                      # noqa: E731
+    assert md.list_dataset(str(root), line_height_px=9, images_dir_="together", masks_dir_="together",
+                           masks_postfix="_GT.png") == \
+        rd.list_dataset(str(root), line_height_px=9, images_dir_="together", masks_dir_="together", masks_postfix="_GT.png")
+    for kw in (dict(verify_filenames=True), dict(verify_filenames=True, line_height_px=12)):
+        assert sorted(md.list_dataset(str(root), **kw), key=key) == sorted(rd.list_dataset(str(root), **kw), key=key)
+    for kw in (dict(), dict(line_height_px=5)):                             # 5 images vs 4 masks
+        with pytest.raises(Exception) as e1:
+            md.list_dataset(str(root), **kw)
+        with pytest.raises(Exception) as e2:
+            rd.list_dataset(str(root), **kw)
+        assert type(e1.value) is type(e2.value) and str(e1.value) == str(e2.value)
+    (root / "images" / "extra.png").unlink()
+    assert md.list_dataset(str(root)) == rd.list_dataset(str(root))
+    with pytest.raises(Exception, match="Dataset dir does not exist"):
+        md.list_dataset(str(root / "nope"))
+    with pytest.raises(Exception, match="Norm dir does not exist"):
+        md.list_dataset(str(root), normalizations_dir="absent")
