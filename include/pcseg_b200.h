@@ -224,6 +224,10 @@ PCS_API int pcs_debug_activation(pcs_ctx* ctx, const char* name, float* h_out, s
  * normally never write (fcn_skip conv2 at full resolution), so that
  * pcs_debug_activation can return them; 0 (default): production schedule */
 PCS_API int pcs_set_keep_activations(pcs_ctx* ctx, int enabled);
+/* 1 (or PCSEG_PDL=1 at context creation; default 0, measured neutral on B200): launch the tensor-core kernels with programmatic dependent
+ * launch, so that a layer's prologue (barrier init, TMEM allocation, resident weights) overlaps the tail of
+ * the previous layer; 0: plain stream-ordered launches */
+PCS_API int pcs_set_pdl(pcs_ctx* ctx, int enabled);
 /* enable (1) / disable (0) CUDA-event timing of every stage of the next calls */
 PCS_API int pcs_set_timing(pcs_ctx* ctx, int enabled);
 /* device time in ms of the stages since the last pcs_forward began ("name:ms;"...) */

@@ -23,7 +23,7 @@ EXPORTS = [
     "pcs_synchronize", "pcs_launch_count", "pcs_model_load", "pcs_set_engine", "pcs_preprocess",
     "pcs_preprocess_max_width",
     "pcs_forward", "pcs_masks", "pcs_resize_nearest", "pcs_ccl", "pcs_cc_majority",
-    "pcs_bounding_boxes", "pcs_char_height", "pcs_segment_masks", "pcs_dilate3x3", "pcs_integral_image", "pcs_text_regions", "pcs_predict_pages_host", "pcs_debug_activation", "pcs_set_keep_activations", "pcs_set_timing",
+    "pcs_bounding_boxes", "pcs_char_height", "pcs_segment_masks", "pcs_dilate3x3", "pcs_integral_image", "pcs_text_regions", "pcs_predict_pages_host", "pcs_debug_activation", "pcs_set_keep_activations", "pcs_set_timing", "pcs_set_pdl",
     "pcs_last_timings",
 ]
 
@@ -79,6 +79,7 @@ def load() -> C.CDLL:
     lib.pcs_debug_activation.argtypes = [vp, C.c_char_p, vp, C.c_size_t, C.POINTER(C.c_int32)]
     lib.pcs_set_keep_activations.argtypes = [vp, i32]
     lib.pcs_set_timing.argtypes = [vp, i32]
+    lib.pcs_set_pdl.argtypes = [vp, i32]
     lib.pcs_last_timings.argtypes = [vp]
     lib.pcs_last_timings.restype = C.c_char_p
     if lib.pcs_abi_version() != 1:
@@ -151,6 +152,9 @@ class Context:
     def set_keep_activations(self, enabled: bool):
         """Diagnostics: also store the activations the fused kernels never write (fcn_skip conv2)."""
         self._check(self.lib.pcs_set_keep_activations(self.h, 1 if enabled else 0), "pcs_set_keep_activations")
+
+    def set_pdl(self, enabled: bool):
+        self._check(self.lib.pcs_set_pdl(self.h, 1 if enabled else 0), "pcs_set_pdl")
 
     def set_timing(self, enabled: bool):
         self._check(self.lib.pcs_set_timing(self.h, 1 if enabled else 0), "pcs_set_timing")

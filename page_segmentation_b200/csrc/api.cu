@@ -449,6 +449,7 @@ int pcs_ctx_create(int device, pcs_ctx** out) {
     pcs_ctx* ctx = new pcs_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    if (const char* e = getenv("PCSEG_PDL")) ctx->pdl = atoi(e) != 0;
     const char* t = getenv("PCSEG_TIMING");
     ctx->timing_enabled = t && t[0] == '1';
     const char* e = getenv("PCSEG_ENGINE");
@@ -996,6 +997,12 @@ int pcs_debug_activation(pcs_ctx* ctx, const char* name, float* h_out, size_t ca
 int pcs_set_keep_activations(pcs_ctx* ctx, int enabled) {
     if (!ctx) return PCS_ERR_ARG;
     ctx->keep_acts = enabled != 0;
+    return PCS_OK;
+}
+
+int pcs_set_pdl(pcs_ctx* ctx, int enabled) {
+    if (!ctx) return PCS_ERR_ARG;
+    ctx->pdl = enabled != 0;
     return PCS_OK;
 }
 

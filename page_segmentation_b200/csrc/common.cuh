@@ -116,6 +116,8 @@ struct pcs_ctx {
     std::string timings;
     std::vector<pcs::StageTime> stage_times;
     bool timing_enabled = false;
+    bool pdl = false;                       // launch the tensor-core kernels with programmatic dependent launch (PCSEG_PDL=1 / pcs_set_pdl);
+                                            // measured neutral on B200 (interleaved A/B), so off by default
     bool keep_acts = false;                 // diagnostics: also store activations the fused kernels normally skip
 };
 
@@ -145,6 +147,25 @@ int set_err(pcs_ctx* ctx, int code, const char* fmt, ...);
         int rc__ = (expr);            \
         if (rc__ != PCS_OK) return rc__; \
     } while (0)
+
+// Dynamic shared memory every tensor-core kernel asks for at least: more than half an SM, so that two of their CTAs
+// never share an SM (each allocates all 512 TMEM columns: a second CTA would sit in tcgen05.alloc while other SMs
+// idle - which is what the block scheduler does when CTAs trickle in under programmatic dependent launch).
+constexpr size_t kSoloSmem = 116 * 1024;
+
+// kernel launch with the programmatic-dependent-launch attribute (see ptx::griddep_wait); `pdl` false = plain launch
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
+                                     Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // arena
 int arena_reserve(pcs_ctx* ctx, size_t bytes);

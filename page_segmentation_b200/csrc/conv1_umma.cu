@@ -80,6 +80,8 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv1_umma_kernel(const Conv1Pa
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    griddep_launch();
+    griddep_wait();
     const uint32_t tmem_base = s_tmem_base;
     const int tiles_per_page = p.strips * p.rowblocks;
 
@@ -276,16 +278,16 @@ int launch_conv1_umma(pcs_ctx* ctx, const uint8_t* d_image, int n, int img_h, in
     p.rowblocks = (h + C1_R - 1) / C1_R;
     p.num_tiles = n * p.strips * p.rowblocks;
     { const char* e = getenv("PCSEG_C1_DEBUG"); p.dbg = e ? atoi(e) : 0; }
-    const size_t smem = ((C1_B_BYTES + 1023) / 1024) * 1024 + (size_t)C1_STAGES * C1_STAGE_BYTES + 1024;
+    const size_t smem = std::max<size_t>(((C1_B_BYTES + 1023) / 1024) * 1024 + (size_t)C1_STAGES * C1_STAGE_BYTES + 1024, kSoloSmem);
     const int grid = std::min(p.num_tiles, ctx->sm_count);
     if (ctx->precision == PCS_PREC_BF16) {
         static bool set = false;
         if (!set) { PCS_CUDA(ctx, cudaFuncSetAttribute(conv1_umma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = true; }
-        conv1_umma_kernel<__nv_bfloat16><<<grid, C1_THREADS, smem, ctx->stream>>>(p);
+        PCS_CUDA(ctx, launch_kernel_pdl(conv1_umma_kernel<__nv_bfloat16>, dim3(grid), dim3(C1_THREADS), smem, ctx->stream, ctx->pdl, p));
     } else {
         static bool set = false;
         if (!set) { PCS_CUDA(ctx, cudaFuncSetAttribute(conv1_umma_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = true; }
-        conv1_umma_kernel<__half><<<grid, C1_THREADS, smem, ctx->stream>>>(p);
+        PCS_CUDA(ctx, launch_kernel_pdl(conv1_umma_kernel<__half>, dim3(grid), dim3(C1_THREADS), smem, ctx->stream, ctx->pdl, p));
     }
     PCS_LAUNCH_CHECK(ctx, "conv1_umma_kernel");
     return PCS_OK;

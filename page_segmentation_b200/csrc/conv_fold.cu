@@ -125,6 +125,8 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    griddep_launch();
+    if (threadIdx.x != 0) griddep_wait();          // thread 0 (the producer) first queues the weight loads, see below
     const uint32_t tmem_base = s_tmem_base;
     // this CTA's range of the concatenated (page * strips + strip) * h + y space; segments = its pieces inside one strip
     const long long pos0 = (long long)blockIdx.x * p.rows_per_cta;
@@ -135,6 +137,7 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
         if (lane == 0) {
             mbar_expect_tx(&s_wfull, p.w_bytes);
             for (uint32_t off = 0; off < p.w_bytes; off += WDX_BYTES) bulk_load(s_w + off, p.wimg + off, WDX_BYTES, &s_wfull);
+            griddep_wait();                         // weights are constants; the input rows are the previous layer's output
             uint32_t k = 0;                                           // running input-row counter
             for (long long pos = pos0; pos < pos1;) {
                 const int sg = (int)(pos / p.h), ys = (int)(pos - (long long)sg * p.h);
@@ -409,7 +412,7 @@ int launch_fold_t(pcs_ctx* ctx, const FoldConvArgs& a) {
     if (r != CUDA_SUCCESS) return set_err(ctx, PCS_ERR_CUDA, "conv_fold: cuTensorMapEncodeTiled failed with %d", (int)r);
     const size_t w_al = ((p.w_bytes + 1023) / 1024) * 1024;
     p.ring = RING;
-    const size_t smem = w_al + (size_t)RING * NPL * 2048 + 1024;
+    const size_t smem = std::max<size_t>(w_al + (size_t)RING * NPL * 2048 + 1024, kSoloSmem);
     if (smem + 2 * 1024 > 227 * 1024) return set_err(ctx, PCS_ERR_ARG, "conv_fold: %zu bytes of shared memory needed", smem);
     static size_t attr_set = 0;
     if (attr_set < smem) {
@@ -417,7 +420,8 @@ int launch_fold_t(pcs_ctx* ctx, const FoldConvArgs& a) {
         attr_set = smem;
     }
     const int grid = (int)((p.total_rows + p.rows_per_cta - 1) / p.rows_per_cta);
-    conv_fold_kernel<T, NPAD, NPL, RING, SLOTS, EG><<<grid, 64 + EG * 128, smem, ctx->stream>>>(p, tm);
+    PCS_CUDA(ctx, launch_kernel_pdl(conv_fold_kernel<T, NPAD, NPL, RING, SLOTS, EG>, dim3(grid), dim3(64 + EG * 128), smem, ctx->stream,
+                                    ctx->pdl, p, tm));
     PCS_LAUNCH_CHECK(ctx, "conv_fold_kernel");
     return PCS_OK;
 }

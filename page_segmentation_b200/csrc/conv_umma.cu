@@ -35,14 +35,25 @@ namespace pcs {
 namespace {
 
 constexpr int TILE_M = 128;
-constexpr int kThreads = 192;       // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
-constexpr int kMaxStages = 4;
+constexpr int kMaxStages = 8;       // barrier arrays; the stage count in use is capped per mode (Cfg::STAGE_CAP)
 constexpr int kHeadThreads = 64 + 8 * 32;    // fused head: 8 epilogue warps (2 per TMEM lane quarter)
 
-template <int NPAD> struct Cfg {
-    static constexpr int R = NPAD <= 64 ? 8 : (NPAD <= 80 ? 6 : 4);      // accumulator rows per tile
+template <int NPAD, int KS = 5, int MODE = 0> struct Cfg {
+    // The stride-2 transposed conv (1x1 GEMM, N = 128) is bound by its output stream, not by the tensor pipe: two
+    // rows per tile so that TWO accumulator stages fit TMEM (the MMAs of the next tile run under this tile's
+    // stores), eight epilogue warps, a deeper ring of small stages.
+    static constexpr bool STREAMING_DECONV = (MODE == 1 && KS == 1 && NPAD == 128);
+    static constexpr int R = STREAMING_DECONV ? 2 : (NPAD <= 64 ? 8 : (NPAD <= 80 ? 6 : 4));      // accumulator rows per tile
     static constexpr int ACC = (2 * R * NPAD <= 512) ? 2 : 1;             // TMEM accumulator stages
+    static constexpr int THREADS = (MODE >= 2 || STREAMING_DECONV) ? kHeadThreads : 192;
+    static constexpr int STAGE_CAP = STREAMING_DECONV ? 8 : 4;
 };
+
+// one 32-byte store (STG.256): two neighbouring pixels of one channel plane
+__device__ __forceinline__ void st_global_v8(void* ptr, const uint4& a, const uint4& b) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x),
+                 "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
 
 enum { EPI_STORE = 0, EPI_DECONV = 1, EPI_HEAD = 2 };
 
@@ -85,10 +96,10 @@ struct UmmaParams {
 using namespace ptx;
 
 template <typename T, int NPAD, int KS, int MODE>
-__global__ void __launch_bounds__(MODE >= EPI_HEAD ? kHeadThreads : kThreads, 1)
+__global__ void __launch_bounds__(Cfg<NPAD, KS, MODE>::THREADS, 1)
 conv_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1) {
-    constexpr int R = Cfg<NPAD>::R;
-    constexpr int ACC = Cfg<NPAD>::ACC;
+    constexpr int R = Cfg<NPAD, KS, MODE>::R;
+    constexpr int ACC = Cfg<NPAD, KS, MODE>::ACC;
     constexpr uint32_t IDESC = (1u << 4)                                            // D = f32
                                | ((sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value ? 1u : 0u) << 7)    // A format
                                | ((std::is_same<T, __nv_bfloat16>::value ? 1u : 0u) << 10)                    // B format
@@ -120,6 +131,8 @@ conv_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm0, co
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    griddep_launch();
+    griddep_wait();
     const uint32_t tmem_base = s_tmem_base;
     if (p.debug_poison && warp >= 2) {     // diagnosis: NaN-fill all accumulator columns of this warp's lane quarter
         const uint32_t nanv = 0x7fc00000u;
@@ -297,6 +310,44 @@ conv_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm0, co
                         }
                     }
                 }
+            } else if (MODE == EPI_DECONV && 2 * p.co_t <= NPAD && (p.co_t & 15) == 0) {
+                // both horizontal taps (2i, 2i+1) of an output row lie in this N tile: one thread owns the output pixel
+                // pair (2y+i, 2x), (2y+i, 2x+1) of a plane = 32 contiguous bytes = one STG.256; a warp writes 1 KB runs
+                T* out = reinterpret_cast<T*>(p.out);
+                const int oh = 2 * p.h, ow = 2 * p.w;
+                const int tap_base = cbase / p.co_t;                       // first tap of this N tile (even)
+#pragma unroll 1
+                for (int r = group; r < R; r += ngroups) {
+                    const int y = y0 + r;
+                    const bool ok = xok && y < p.h;
+#pragma unroll 1
+                    for (int c = 0; c < NPAD / 2; c += 16) {               // 16 channels of the even tap of a pair
+                        const int tp = c / p.co_t, o = c - tp * p.co_t;    // tap pair within the tile, first channel
+                        const int c0 = 2 * tp * p.co_t + o, c1 = c0 + p.co_t;
+                        uint32_t v0[16], v1[16];
+                        tmem_ld16(t_lane + (uint32_t)(r * NPAD + c0), v0);
+                        tmem_ld16(t_lane + (uint32_t)(r * NPAD + c1), v1);
+                        tmem_ld_wait();
+                        float f0[16], f1[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float b = s_bias[c0 + i];                // same channel, same bias for both taps
+                            f0[i] = __uint_as_float(v0[i]) + b;
+                            f1[i] = __uint_as_float(v1[i]) + b;
+                            if (p.relu) { f0[i] = fmaxf(f0[i], 0.f); f1[i] = fmaxf(f1[i], 0.f); }
+                        }
+                        if (ok && o < p.out_cp) {
+                            const int oy = 2 * y + ((tap_base + 2 * tp) >> 1);
+                            st_global_v8(out + act_idx(page, p.out_cp, oh, ow, o, oy, 2 * x),
+                                         make_uint4(pack2<T>(f0[0], f0[1]), pack2<T>(f0[2], f0[3]), pack2<T>(f0[4], f0[5]), pack2<T>(f0[6], f0[7])),
+                                         make_uint4(pack2<T>(f1[0], f1[1]), pack2<T>(f1[2], f1[3]), pack2<T>(f1[4], f1[5]), pack2<T>(f1[6], f1[7])));
+                            if (o + 8 < p.out_cp)
+                                st_global_v8(out + act_idx(page, p.out_cp, oh, ow, o + 8, oy, 2 * x),
+                                             make_uint4(pack2<T>(f0[8], f0[9]), pack2<T>(f0[10], f0[11]), pack2<T>(f0[12], f0[13]), pack2<T>(f0[14], f0[15])),
+                                             make_uint4(pack2<T>(f1[8], f1[9]), pack2<T>(f1[10], f1[11]), pack2<T>(f1[12], f1[13]), pack2<T>(f1[14], f1[15])));
+                        }
+                    }
+                }
             } else {
                 T* out = reinterpret_cast<T*>(p.out);
                 T* pool = reinterpret_cast<T*>(p.pool);
@@ -424,7 +475,7 @@ int make_act_map(pcs_ctx* ctx, CUtensorMap* tm, const ConvSrc& s, int n, int h, 
 
 template <typename T, int NPAD, int KS, int MODE>
 int launch_t(pcs_ctx* ctx, const UmmaConvArgs& a) {
-    constexpr int R = Cfg<NPAD>::R;
+    constexpr int R = Cfg<NPAD, KS, MODE>::R;
     UmmaParams p{};
     p.n = a.n; p.h = a.h; p.w = a.w; p.k = a.k; p.pad = a.pad;
     // 16-channel K chunks; a source with an odd number of 8-channel planes ends in a half-empty chunk whose
@@ -449,11 +500,11 @@ int launch_t(pcs_ctx* ctx, const UmmaConvArgs& a) {
     p.b_bytes = (uint32_t)a.k * a.k * 2 * NPAD * 16;
     p.stage_bytes = (p.a_bytes + p.b_bytes + 1023) / 1024 * 1024;
     const uint32_t budget = 225 * 1024 - 1024;
-    p.nstages = (int)std::min<uint32_t>(kMaxStages, budget / p.stage_bytes);
+    p.nstages = (int)std::min<uint32_t>(Cfg<NPAD, KS, MODE>::STAGE_CAP, budget / p.stage_bytes);
     if (p.nstages < 2) return set_err(ctx, PCS_ERR_ARG, "conv_umma: stage of %u bytes does not fit twice in shared memory", p.stage_bytes);
     if ((a.h & 1) || (a.w & 1)) return set_err(ctx, PCS_ERR_ARG, "conv_umma: odd grid");
     if (a.pool_out && (p.sw & 1)) return set_err(ctx, PCS_ERR_ARG, "conv_umma: fused pooling needs an even strip width");
-    const size_t smem = (size_t)p.nstages * p.stage_bytes + 1024;
+    const size_t smem = std::max<size_t>((size_t)p.nstages * p.stage_bytes + 1024, kSoloSmem);
     CUtensorMap tm0, tm1;
     PCS_TRY(make_act_map(ctx, &tm0, a.src[0], a.n, a.h, a.w, p.a_rows));
     if (a.nsrc > 1) PCS_TRY(make_act_map(ctx, &tm1, a.src[1], a.n, a.h, a.w, p.a_rows));
@@ -473,7 +524,8 @@ int launch_t(pcs_ctx* ctx, const UmmaConvArgs& a) {
             if (ctx->device < 64) g_head_owner[ctx->device] = ctx->model_stamp;
         }
     }
-    conv_umma_kernel<T, NPAD, KS, MODE><<<grid, MODE >= EPI_HEAD ? kHeadThreads : kThreads, smem, ctx->stream>>>(p, tm0, tm1);
+    PCS_CUDA(ctx, launch_kernel_pdl(conv_umma_kernel<T, NPAD, KS, MODE>, dim3(grid), dim3(Cfg<NPAD, KS, MODE>::THREADS), smem,
+                                    ctx->stream, ctx->pdl, p, tm0, tm1));
     PCS_LAUNCH_CHECK(ctx, "conv_umma_kernel");
     return PCS_OK;
 }

@@ -173,49 +173,75 @@ int launch_head(pcs_ctx* ctx, const HeadArgs& a) {
 // generate_output_masks on an existing class map (output.py:44-60).
 // Labels not present in the LUT map to (0,0,0).
 // ---------------------------------------------------------------------------
-// One thread = 16 consecutive output BYTES of the flat [npix][3] images (one aligned 128-bit store per
-// image); they cover at most 6 pixels, whose class / binary bytes are read once.
+// One thread = 16 consecutive pixels: one aligned 128-bit load of the class bytes and one of the binary bytes,
+// three aligned 128-bit stores (48 bytes) per image; every register index is a compile-time constant.
 __global__ void __launch_bounds__(256)
 masks_kernel(const uint8_t* __restrict__ labels, const uint8_t* __restrict__ binary, size_t npix,
              const uint8_t* __restrict__ lut, int n_lut, uint8_t* __restrict__ color, uint8_t* __restrict__ overlay,
              uint8_t* __restrict__ inverted, int vec_ok) {
-    __shared__ uint8_t s_lut[256 * 3];
-    for (int i = threadIdx.x; i < 256 * 3; i += blockDim.x) s_lut[i] = (i < n_lut * 3) ? lut[i] : 0;
+    __shared__ uint32_t s_lut[256];                               // r | g << 8 | b << 16
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        s_lut[i] = i < n_lut ? ((uint32_t)lut[i * 3] | ((uint32_t)lut[i * 3 + 1] << 8) | ((uint32_t)lut[i * 3 + 2] << 16)) : 0u;
     __syncthreads();
-    const size_t nbytes = npix * 3;
-    const size_t nchunks = (nbytes + 15) / 16;
+    const size_t nchunks = (npix + 15) / 16;
     for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < nchunks; k += (size_t)gridDim.x * blockDim.x) {
-        const size_t b0 = k * 16;
-        const size_t p0 = b0 / 3;
-        const int phase = (int)(b0 - p0 * 3);
-        uint8_t lab[6], bin[6];
-#pragma unroll
-        for (int q = 0; q < 6; ++q) {
-            const size_t pi = p0 + q;
-            lab[q] = pi < npix ? labels[pi] : 0;
-            bin[q] = (pi < npix && binary) ? binary[pi] : 1;
-        }
-        uint32_t wc[4] = {0, 0, 0, 0}, wo[4] = {0, 0, 0, 0}, wi[4] = {0, 0, 0, 0};
-#pragma unroll
-        for (int b = 0; b < 16; ++b) {
-            const int q = phase + b;
-            const int pi = q / 3, ch = q - 3 * pi;
-            const uint32_t v = s_lut[lab[pi] * 3 + ch];
-            const bool keep_o = (uint8_t)(1 - bin[pi]) != 0;        // overlay[(1 - binary) == 0] = 0
-            const bool keep_i = bin[pi] != 0;                        // inverted[binary == 0] = 0
-            wc[b >> 2] |= v << (8 * (b & 3));
-            wo[b >> 2] |= (keep_o ? v : 0u) << (8 * (b & 3));
-            wi[b >> 2] |= (keep_i ? v : 0u) << (8 * (b & 3));
-        }
-        if (vec_ok && b0 + 16 <= nbytes) {
-            if (color) *reinterpret_cast<uint4*>(color + b0) = make_uint4(wc[0], wc[1], wc[2], wc[3]);
-            if (overlay) *reinterpret_cast<uint4*>(overlay + b0) = make_uint4(wo[0], wo[1], wo[2], wo[3]);
-            if (inverted) *reinterpret_cast<uint4*>(inverted + b0) = make_uint4(wi[0], wi[1], wi[2], wi[3]);
+        const size_t p0 = k * 16;
+        const bool full = vec_ok && p0 + 16 <= npix;
+        uint32_t lw[4], bw[4];
+        if (full) {
+            const uint4 l4 = __ldg(reinterpret_cast<const uint4*>(labels + p0));
+            lw[0] = l4.x; lw[1] = l4.y; lw[2] = l4.z; lw[3] = l4.w;
+            if (binary) {
+                const uint4 b4 = __ldg(reinterpret_cast<const uint4*>(binary + p0));
+                bw[0] = b4.x; bw[1] = b4.y; bw[2] = b4.z; bw[3] = b4.w;
+            } else {
+                bw[0] = bw[1] = bw[2] = bw[3] = 0x01010101u;
+            }
         } else {
-            for (int b = 0; b < 16 && b0 + b < nbytes; ++b) {
-                if (color) color[b0 + b] = (uint8_t)(wc[b >> 2] >> (8 * (b & 3)));
-                if (overlay) overlay[b0 + b] = (uint8_t)(wo[b >> 2] >> (8 * (b & 3)));
-                if (inverted) inverted[b0 + b] = (uint8_t)(wi[b >> 2] >> (8 * (b & 3)));
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                lw[w] = 0; bw[w] = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const size_t pi = p0 + w * 4 + q;
+                    const uint32_t l = pi < npix ? labels[pi] : 0, b = (pi < npix && binary) ? binary[pi] : 1;
+                    lw[w] |= l << (8 * q); bw[w] |= b << (8 * q);
+                }
+            }
+        }
+        // 16 pixels x 3 bytes = 12 words per image; pixel q contributes bytes 3q .. 3q+2
+        uint32_t wc[12], wo[12], wi[12];
+#pragma unroll
+        for (int w = 0; w < 12; ++w) { wc[w] = 0; wo[w] = 0; wi[w] = 0; }
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const uint32_t lab = (lw[q >> 2] >> (8 * (q & 3))) & 0xffu, bin = (bw[q >> 2] >> (8 * (q & 3))) & 0xffu;
+            const uint32_t v = s_lut[lab];
+            const uint32_t vo = ((uint8_t)(1u - bin) != 0) ? v : 0u;       // overlay[(1 - binary) == 0] = 0
+            const uint32_t vi = bin != 0 ? v : 0u;                          // inverted[binary == 0] = 0
+            const int byte0 = 3 * q, w0 = byte0 >> 2, sh = 8 * (byte0 & 3);
+            wc[w0] |= v << sh; wo[w0] |= vo << sh; wi[w0] |= vi << sh;
+            if (sh > 8) {                                                    // the 3 bytes straddle a word boundary
+                wc[w0 + 1] |= v >> (32 - sh); wo[w0 + 1] |= vo >> (32 - sh); wi[w0 + 1] |= vi >> (32 - sh);
+            }
+        }
+        const size_t b0 = p0 * 3;
+        if (full) {
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                if (color) *reinterpret_cast<uint4*>(color + b0 + 16 * t) = make_uint4(wc[4 * t], wc[4 * t + 1], wc[4 * t + 2], wc[4 * t + 3]);
+                if (overlay) *reinterpret_cast<uint4*>(overlay + b0 + 16 * t) = make_uint4(wo[4 * t], wo[4 * t + 1], wo[4 * t + 2], wo[4 * t + 3]);
+                if (inverted) *reinterpret_cast<uint4*>(inverted + b0 + 16 * t) = make_uint4(wi[4 * t], wi[4 * t + 1], wi[4 * t + 2], wi[4 * t + 3]);
+            }
+        } else {
+            const size_t nbytes = npix * 3;
+#pragma unroll
+            for (int b = 0; b < 48; ++b) {
+                if (b0 + b < nbytes) {
+                    if (color) color[b0 + b] = (uint8_t)(wc[b >> 2] >> (8 * (b & 3)));
+                    if (overlay) overlay[b0 + b] = (uint8_t)(wo[b >> 2] >> (8 * (b & 3)));
+                    if (inverted) inverted[b0 + b] = (uint8_t)(wi[b >> 2] >> (8 * (b & 3)));
+                }
             }
         }
     }
@@ -225,9 +251,9 @@ int launch_masks(pcs_ctx* ctx, const uint8_t* d_labels, const uint8_t* d_binary,
                  const uint8_t* d_lut, int n_lut, uint8_t* d_color, uint8_t* d_overlay, uint8_t* d_inverted) {
     if (n <= 0 || H <= 0 || W <= 0 || n_lut < 0 || n_lut > 256) return set_err(ctx, PCS_ERR_ARG, "masks: bad argument");
     const size_t npix = (size_t)n * H * W;
-    const size_t nchunks = (npix * 3 + 15) / 16;
+    const size_t nchunks = (npix + 15) / 16;
     const unsigned blocks = (unsigned)std::min<size_t>((size_t)ctx->sm_count * 16, (nchunks + 255) / 256);
-    const int vec_ok = (((uintptr_t)d_color | (uintptr_t)d_overlay | (uintptr_t)d_inverted) & 15) == 0;
+    const int vec_ok = (((uintptr_t)d_color | (uintptr_t)d_overlay | (uintptr_t)d_inverted | (uintptr_t)d_labels | (uintptr_t)d_binary) & 15) == 0;
     masks_kernel<<<blocks, 256, 0, ctx->stream>>>(d_labels, d_binary, npix, d_lut, n_lut, d_color, d_overlay, d_inverted, vec_ok);
     PCS_LAUNCH_CHECK(ctx, "masks_kernel");
     return PCS_OK;

@@ -125,6 +125,14 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
            ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
 }
 
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may be
+// scheduled while its predecessor in the stream drains.  griddep_launch() lets the NEXT kernel's CTAs take SMs as
+// this kernel's CTAs leave them (its barrier init, TMEM allocation and resident-weight loads then overlap our
+// tail); griddep_wait() blocks until every earlier kernel has completed and its writes are visible, and must
+// precede the first access to activations.  Both are no-ops for a plain launch.
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
 template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
