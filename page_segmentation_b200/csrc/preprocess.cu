@@ -141,7 +141,9 @@ __global__ void __launch_bounds__(256) scan_pack_kernel(const uint8_t* __restric
     if (threadIdx.x < 8 && s_bits[threadIdx.x]) atomicOr(&bits[page * 8 + threadIdx.x], s_bits[threadIdx.x]);
 }
 
-constexpr int RB_T = 32, RB_TY = 64;             // output tile of the fast resampler: 32 x 64 (256 threads, 8 rows each)
+constexpr int RB_T = 32, RB_TY = 128;            // output tile of the fast resampler: 32 x 128 (256 threads, 16 rows each): the
+                                                 // per-block setup (coordinates, 16-pattern table) is a quarter of the work at 64 rows
+constexpr int RB_RW = RB_TY / 32;                // warps that set up the rows
 constexpr int RB_MAX_SPAN = 4 * RB_TY + 8;       // staged source rows for scale factors up to 4
 constexpr int RB_ROW_WORDS = 8;                  // staged words per source row: (4*32 + 8 + 31 + 31) / 32
 
@@ -161,12 +163,16 @@ resample_bits_kernel(const uint8_t* __restrict__ grey, const uint8_t* __restrict
     __shared__ double s_cfrac[RB_T], s_rfrac[RB_TY];                  // fractional sampling offsets of columns / rows
     __shared__ uint32_t s_bm[RB_MAX_SPAN][RB_ROW_WORDS];
     __shared__ __align__(16) int s_ctap[RB_T][4], s_rtap[RB_TY][4];   // the four (reflected) source columns / rows
-    __shared__ int s_cnn[RB_T], s_rnn[RB_TY], s_off[RB_MAX_SPAN], s_rng[6];
+    __shared__ int s_cnn[RB_T], s_rnn[RB_TY], s_off[RB_MAX_SPAN], s_rng[2 + 2 * RB_RW];
+    // bit address (within the flat staged bitmap) of column 0 of the four tap rows / the nearest row of every output
+    // row: the per-pixel work is then one add, one shift and a funnel shift per tap row
+    __shared__ __align__(16) int s_tapbit[RB_TY][4];
+    __shared__ int s_nnbit[RB_TY];
     const int page = blockIdx.z;
     const uint32_t* bits = level_bits + (size_t)page * 8;
     if (level_count(bits) > 2) return;
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
-    if (wrp < 3) {                                // warp 0: the 32 columns, warps 1-2: the 64 rows of the tile
+    if (wrp < 1 + RB_RW) {                        // warp 0: the 32 columns, warps 1..: the rows of the tile
         const int n_in = wrp == 0 ? W : H, n_out = wrp == 0 ? Ws : Hs;
         const int o = min(wrp == 0 ? blockIdx.x * RB_T + lane : blockIdx.y * RB_TY + (wrp - 1) * 32 + lane, n_out - 1);   // replicate past the edge
         const double f = __ddiv_rn((double)n_in, (double)n_out);
@@ -188,7 +194,10 @@ resample_bits_kernel(const uint8_t* __restrict__ grey, const uint8_t* __restrict
         if (lane == 0) { s_rng[2 * wrp] = lo; s_rng[2 * wrp + 1] = hi; }
     }
     __syncthreads();
-    const int cmin = s_rng[0], cmax = s_rng[1], rmin = min(s_rng[2], s_rng[4]), rmax = max(s_rng[3], s_rng[5]);
+    const int cmin = s_rng[0], cmax = s_rng[1];
+    int rmin = s_rng[2], rmax = s_rng[3];
+#pragma unroll
+    for (int k = 1; k < RB_RW; ++k) { rmin = min(rmin, s_rng[2 + 2 * k]); rmax = max(rmax, s_rng[3 + 2 * k]); }
     const int nrows = rmax - rmin + 1;
     if (nrows > RB_MAX_SPAN || cmax - cmin + 1 + 62 > RB_ROW_WORDS * 32) { __trap(); }      // host guarantees scale <= 4
     const uint32_t* bm = bitmap + (size_t)page * bitmap_words;
@@ -199,6 +208,16 @@ resample_bits_kernel(const uint8_t* __restrict__ grey, const uint8_t* __restrict
         const size_t w0 = (b0 >> 5) + wq;
         s_bm[r][wq] = w0 <= last_word ? __ldg(bm + w0) : 0u;
         if (wq == 0) s_off[r] = (int)(b0 & 31) - cmin;        // bit (r, c) sits at bit s_off[r] + c of the staged row
+    }
+    __syncthreads();
+    if (tid < RB_TY) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int rl = s_rtap[tid][k] - rmin;
+            s_tapbit[tid][k] = rl * (RB_ROW_WORDS * 32) + s_off[rl];
+        }
+        const int rl = s_rnn[tid] - rmin;
+        s_nnbit[tid] = rl * (RB_ROW_WORDS * 32) + s_off[rl];
     }
     // the two levels: a = page[0] (bit 0), b = the other one (bit 1)
     int l0 = -1, l1 = -1;
@@ -223,9 +242,10 @@ resample_bits_kernel(const uint8_t* __restrict__ grey, const uint8_t* __restrict
     }
     __syncthreads();
     const int x = blockIdx.x * RB_T + lane;
-    auto bit_at = [&](int rl, int c) -> uint32_t {
-        const int b = s_off[rl] + c;
-        return (s_bm[rl][b >> 5] >> (b & 31)) & 1u;
+    const uint32_t* bmflat = &s_bm[0][0];
+    auto bit_at = [&](int rowbit, int c) -> uint32_t {          // rowbit: flat bit address of column 0 of a staged row
+        const int b = rowbit + c;
+        return (bmflat[b >> 5] >> (b & 31)) & 1u;
     };
     auto finish = [&](double v) -> uint8_t {          // clip=True, then img = 1.0 - v/255 ; (img*255).astype(uint8)
         v = fmin(fmax(v, vmin), vmax);
@@ -236,28 +256,29 @@ resample_bits_kernel(const uint8_t* __restrict__ grey, const uint8_t* __restrict
     const bool consec = c1 == c0 + 1 && c2 == c0 + 2 && c3 == c0 + 3;
     const int nnc = s_cnn[lane];
     const bool xok = x < Ws;
+    const uint8_t bin_a = va == 0 ? 1 : 0, bin_b = vb == 0 ? 1 : 0;   // bin = (1.0 - NN(binary/255 or binary)).astype(uint8)
+    const int y_first = blockIdx.y * RB_TY + wrp;
+    size_t dst = (size_t)page * Hs * Ws + (size_t)y_first * Ws + x;
+    const size_t dst_step = (size_t)8 * Ws;
 #pragma unroll 1
-    for (int q = 0; q < RB_TY / 8; ++q) {
-        const int ty = wrp + 8 * q, y = blockIdx.y * RB_TY + ty;
-        if (y >= Hs) break;                                            // warp-uniform
-        const size_t dst = (size_t)page * Hs * Ws + (size_t)y * Ws + x;
+    for (int ty = wrp; ty < RB_TY && blockIdx.y * RB_TY + ty < Hs; ty += 8, dst += dst_step) {     // warp-uniform bounds
         if (binary_out && xok) {
-            int v;
-            if (bin_is_grey) v = bit_at(s_rnn[ty] - rmin, nnc) ? vb : va;
-            else v = bin[(size_t)page * H * W + (size_t)s_rnn[ty] * W + nnc];
-            binary_out[dst] = v == 0 ? 1 : 0;      // bin = (1.0 - NN(binary/255 or binary)).astype(uint8)
+            uint8_t v;
+            if (bin_is_grey) v = bit_at(s_nnbit[ty], nnc) ? bin_b : bin_a;
+            else v = bin[(size_t)page * H * W + (size_t)s_rnn[ty] * W + nnc] == 0 ? 1 : 0;
+            binary_out[dst] = v;
         }
         if (image_out) {
-            const int4 rr = *reinterpret_cast<const int4*>(s_rtap[ty]);
-            const int rl[4] = {rr.x - rmin, rr.y - rmin, rr.z - rmin, rr.w - rmin};
+            const int4 rr = *reinterpret_cast<const int4*>(s_tapbit[ty]);
+            const int rb[4] = {rr.x, rr.y, rr.z, rr.w};
             uint32_t pat[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 if (consec) {
-                    const int b = s_off[rl[k]] + c0;
-                    pat[k] = __funnelshift_r(s_bm[rl[k]][b >> 5], s_bm[rl[k]][(b >> 5) + 1], b & 31) & 15u;
+                    const int b = rb[k] + c0;
+                    pat[k] = __funnelshift_r(bmflat[b >> 5], bmflat[(b >> 5) + 1], b & 31) & 15u;
                 } else {
-                    pat[k] = bit_at(rl[k], c0) | (bit_at(rl[k], c1) << 1) | (bit_at(rl[k], c2) << 2) | (bit_at(rl[k], c3) << 3);
+                    pat[k] = bit_at(rb[k], c0) | (bit_at(rb[k], c1) << 1) | (bit_at(rb[k], c2) << 2) | (bit_at(rb[k], c3) << 3);
                 }
             }
             const bool all_a = (pat[0] | pat[1] | pat[2] | pat[3]) == 0u;
