@@ -183,6 +183,15 @@ PCS_API int pcs_predict_pages_host(pcs_ctx* ctx, const uint8_t* h_grey, const ui
                            uint8_t* h_image, uint8_t* h_binary, uint8_t* h_labels,
                            uint8_t* h_color, uint8_t* h_overlay, uint8_t* h_inverted);
 
+/* ---- image files: the encoder of output_data, lib/output.py:38-41 (skimage.io.imsave of the three masks).
+ * Builds n complete PNG files on the device from [n][H][W][channels] uint8 images (channels 1 = grey, 3 = RGB,
+ * 4 = RGBA): signature, IHDR, one IDAT whose zlib stream uses stored deflate blocks, Adler-32, CRC-32, IEND.
+ * File i starts at d_out + i * stride and is pcs_png_bytes(H, W, channels) bytes long (also written to
+ * d_sizes[i] when d_sizes is not NULL); any PNG reader decodes it to exactly the input bytes. */
+PCS_API size_t pcs_png_bytes(int H, int W, int channels);          /* 0 if the shape is unsupported */
+PCS_API int pcs_png_encode(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, int channels,
+                   uint8_t* d_out, size_t stride, uint64_t* d_sizes);
+
 /* ---- region extraction (downstream consumer of the `inverted` colour image):
  * the pixel work of lib/pc_segmentation.py and lib/xycut.py; the data-dependent
  * parts (XY-cut recursion, contour tracing) stay on the host. -------------- */

@@ -23,7 +23,7 @@ EXPORTS = [
     "pcs_synchronize", "pcs_launch_count", "pcs_model_load", "pcs_set_engine", "pcs_preprocess",
     "pcs_preprocess_max_width",
     "pcs_forward", "pcs_masks", "pcs_resize_nearest", "pcs_ccl", "pcs_cc_majority",
-    "pcs_bounding_boxes", "pcs_char_height", "pcs_segment_masks", "pcs_dilate3x3", "pcs_integral_image", "pcs_text_regions", "pcs_predict_pages_host", "pcs_debug_activation", "pcs_set_keep_activations", "pcs_set_timing", "pcs_set_pdl",
+    "pcs_bounding_boxes", "pcs_char_height", "pcs_png_bytes", "pcs_png_encode", "pcs_segment_masks", "pcs_dilate3x3", "pcs_integral_image", "pcs_text_regions", "pcs_predict_pages_host", "pcs_debug_activation", "pcs_set_keep_activations", "pcs_set_timing", "pcs_set_pdl",
     "pcs_last_timings",
 ]
 
@@ -71,6 +71,9 @@ def load() -> C.CDLL:
     lib.pcs_cc_majority.argtypes = [vp, u8p, u8p, i32, i32, i32, i32]
     lib.pcs_bounding_boxes.argtypes = [vp, u8p, i32, i32, i32, i32, u8p]
     lib.pcs_char_height.argtypes = [vp, u8p, i32, i32, i32, i32, vp]
+    lib.pcs_png_bytes.argtypes = [i32, i32, i32]
+    lib.pcs_png_bytes.restype = C.c_size_t
+    lib.pcs_png_encode.argtypes = [vp, u8p, i32, i32, i32, i32, u8p, C.c_size_t, vp]
     lib.pcs_segment_masks.argtypes = [vp, u8p, i32, i32, i32, i32, vp, i32, u8p]
     lib.pcs_dilate3x3.argtypes = [vp, u8p, i32, i32, i32, u8p]
     lib.pcs_integral_image.argtypes = [vp, u8p, i32, i32, i32, vp]
@@ -231,6 +234,14 @@ class Context:
     def char_height(self, d_img, n, H, W, inverse, d_height):
         self._check(self.lib.pcs_char_height(self.h, _ptr(d_img), n, H, W, 1 if inverse else 0, _ptr(d_height)),
                     "pcs_char_height")
+
+    # -- image files ------------------------------------------------------------
+    def png_bytes(self, H, W, channels) -> int:
+        return int(self.lib.pcs_png_bytes(H, W, channels))
+
+    def png_encode(self, d_img, n, H, W, channels, d_out, stride, d_sizes=None):
+        self._check(self.lib.pcs_png_encode(self.h, _ptr(d_img), n, H, W, channels, _ptr(d_out), stride, _ptr(d_sizes)),
+                    "pcs_png_encode")
 
     # -- region extraction ---------------------------------------------------
     def segment_masks(self, d_rgb, H, W, Ho, Wo, colours, d_masks):

@@ -266,6 +266,11 @@ int launch_integral_image(pcs_ctx* ctx, const uint8_t* d_mask, int n, int H, int
 int launch_text_regions(pcs_ctx* ctx, const uint8_t* d_rgb, int H, int W, const uint8_t* colour, int k_close, int k_open,
                         int k_region, uint8_t* d_text_inv, uint8_t* d_region);
 
+// png.cu
+size_t png_file_bytes(int H, int W, int C);
+int launch_png_encode(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, int C, uint8_t* d_out, size_t stride,
+                      unsigned long long* d_sizes);
+
 // conv_umma.cu  (tcgen05 / TMEM / TMA implicit GEMM)
 struct UmmaHeadArgs {              // fused FCN head epilogue (conv_umma.cu mode 2)
     const void* plog = nullptr;         // device float4 [n][2h][2w]: conv2 share of the logits (fcn_skip) or null

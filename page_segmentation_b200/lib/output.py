@@ -21,8 +21,8 @@ class Masks:
     fg_color_mask: Optional[np.ndarray] = None
 
 
-def generate_output_masks(data: SingleData, pred: np.ndarray, color_map: ColorMap) -> Masks:
-    """output.py:44-60 through the device epilogue (pcs_masks)."""
+def _masks_on_device(data: SingleData, pred: np.ndarray, color_map: ColorMap):
+    """The three masks as one (3, H, W, 3) uint8 device tensor: color, overlay, inverted."""
     import torch
     from ..runtime import get_context, to_device_u8
     ctx = get_context()
@@ -34,16 +34,44 @@ def generate_output_masks(data: SingleData, pred: np.ndarray, color_map: ColorMa
     binary = np.asarray(data.binary)
     d_pred = to_device_u8(pred, ctx.device)
     d_bin = to_device_u8(binary, ctx.device)
-    outs = [torch.empty((h, w, 3), dtype=torch.uint8, device=d_pred.device) for _ in range(3)]
+    outs = torch.empty((3, h, w, 3), dtype=torch.uint8, device=d_pred.device)
     ctx.masks(d_pred, d_bin, 1, h, w, lut, outs[0], outs[1], outs[2])
-    color, overlay, inverted = (o.cpu().numpy() for o in outs)
+    return ctx, outs
+
+
+def encode_png(images) -> list:
+    """PNG files (bytes) of a stack of equally sized uint8 images (n, H, W) or (n, H, W, 3|4), built on the device
+    (pcs_png_encode: stored deflate blocks, so a file is the raw image plus 0.2 %; lossless like any PNG).
+    `images` may be a numpy array or a CUDA tensor."""
+    import torch
+    from ..runtime import get_context
+    ctx = get_context()
+    d_img = images if isinstance(images, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(images)).to(f"cuda:{ctx.device}")
+    if d_img.dtype != torch.uint8 or d_img.dim() not in (3, 4):
+        raise ValueError("encode_png expects uint8 images (n, H, W) or (n, H, W, C)")
+    n, h, w = d_img.shape[:3]
+    c = 1 if d_img.dim() == 3 else d_img.shape[3]
+    size = ctx.png_bytes(h, w, c)
+    if size == 0:
+        raise ValueError(f"images of shape {h} x {w} x {c} cannot be written as PNG by the device encoder")
+    stride = (size + 255) // 256 * 256
+    d_out = torch.empty((n, stride), dtype=torch.uint8, device=d_img.device)
+    ctx.png_encode(d_img.contiguous(), n, h, w, c, d_out, stride)
+    files = d_out.cpu().numpy()
+    return [files[i, :size].tobytes() for i in range(n)]
+
+
+def generate_output_masks(data: SingleData, pred: np.ndarray, color_map: ColorMap) -> Masks:
+    """output.py:44-60 through the device epilogue (pcs_masks)."""
+    _, outs = _masks_on_device(data, pred, color_map)
+    color, overlay, inverted = outs.cpu().numpy()
     # fg_color_mask[foreground != 0] = 0 is arithmetically the inverted overlay (output.py:50-53)
     return Masks(color=color, overlay=overlay, inverted_overlay=inverted, fg_color_mask=inverted.copy())
 
 
 def output_data(output_dir, pred, data: SingleData, color_map):
-    """output.py:20-41 (cv2.imwrite in place of skimage.io.imsave)."""
-    import cv2
+    """output.py:20-41.  `.png` targets (the frontend's default) are encoded on the device (encode_png) and written
+    with one file write each; other extensions go through cv2.imwrite in place of skimage.io.imsave."""
     if len(pred.shape) == 3:
         assert (pred.shape[0] == 1)
         pred = pred[0]
@@ -57,8 +85,15 @@ def output_data(output_dir, pred, data: SingleData, color_map):
                 os.makedirs(os.path.join(output_dir, category, dir), exist_ok=True)
     else:
         filename = os.path.basename(data.image_path)
-    masks = generate_output_masks(data, pred, color_map)
-    for category, img in (("color", masks.color), ("overlay", masks.overlay), ("inverted", masks.inverted_overlay)):
+    categories = ("color", "overlay", "inverted")
+    _, d_masks = _masks_on_device(data, pred, color_map)
+    if filename.lower().endswith(".png"):
+        for category, blob in zip(categories, encode_png(d_masks)):
+            with open(os.path.join(output_dir, category, filename), "wb") as f:
+                f.write(blob)
+        return
+    import cv2
+    for category, img in zip(categories, d_masks.cpu().numpy()):
         path = os.path.join(output_dir, category, filename)
         if not cv2.imwrite(path, np.ascontiguousarray(img[..., ::-1])):
             raise IOError(f"could not write {path}")

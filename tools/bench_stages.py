@@ -82,6 +82,13 @@ def main():
     timed("generate_output_masks", lambda: ctx.masks(d_pred0, d_binary, n, Hs, Ws, lut, *d_c), n, 2 * px + 9 * px,
           "labels + binary in, three colour images out")
 
+    size = ctx.png_bytes(Hs, Ws, 3)
+    stride = (size + 255) // 256 * 256
+    d_png = torch.empty((3 * n, stride), dtype=torch.uint8, device="cuda")
+    d_all = torch.cat(d_c)                                    # (3n, Hs, Ws, 3): the three masks of every page
+    timed("png_encode (three masks per page)", lambda: ctx.png_encode(d_all, 3 * n, Hs, Ws, 3, d_png, stride), n, 2 * 9 * px,
+          "three colour masks in, three complete PNG files out (stored deflate blocks, Adler-32, CRC-32)")
+
     # region extraction works page by page on the full-resolution `inverted` image (26 MB each)
     inv = [torch.from_numpy(synth.make_inverted_image(s, H, W, 40)).cuda() for s in range(4)]
     d_text = torch.empty((H, W), dtype=torch.uint8, device="cuda")
