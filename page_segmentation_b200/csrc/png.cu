@@ -4,11 +4,11 @@
 //
 // A PNG is  signature | IHDR | IDAT(zlib(filtered scanlines)) | IEND.  Everything is data parallel except the entropy
 // coder, so the device writes a valid file with the deflate stream in STORED blocks (RFC 1951 section 3.2.4):
-//   scanline r      = filter byte 0 + W*C pixel bytes                       (png_rows_kernel, one pass over the image)
+//   scanline r      = filter byte 0 + W*C pixel bytes                       (png_body_kernel, one pass over the image)
 //   stored block b  = 5-byte header + as many whole scanlines as fit 65535 bytes
 //   Adler-32        = per-scanline partial sums, combined in closed form     (png_adler_rows_kernel / png_adler_kernel)
-//   CRC-32 of IDAT  = per-2-KB-chunk CRCs, each shifted by x^(8 * bytes after it) mod P and XOR-ed (crc32_combine is
-//                     linear, so the shifts run in parallel)                  (png_crc_kernel)
+//   CRC-32 of IDAT  = 256-byte CRCs combined by a tree per 32-KB tile, every tile shifted by x^(8 * bytes after it)
+//                     mod P and XOR-ed (crc32_combine is linear, so all of it runs in parallel)   (png_crc_kernel)
 // The file is 1.002x the raw image (no compression): the masks are then written with one memcpy per file instead of
 // ~10 ms of zlib each.  Any PNG reader decodes them to exactly the mask bytes (tests decode with OpenCV and zlib).
 #include "common.cuh"
@@ -20,7 +20,6 @@ namespace pcs {
 namespace {
 
 constexpr uint32_t kCrcPoly = 0xedb88320u;
-constexpr int kCrcChunk = 2048;                 // bytes per thread of the CRC pass
 constexpr size_t kHead = 8 + 25 + 8;            // signature, IHDR chunk, IDAT length + type
 
 struct PngPlan {
@@ -60,32 +59,44 @@ __device__ uint32_t x8n_modp(uint64_t n, const uint32_t* x2n /*[32]: x^(2^k)*/) 
     return p;
 }
 
-__device__ __forceinline__ uint64_t row_offset(const PngPlan& pl, int row) {             // file offset of a scanline
-    const uint32_t blk = (uint32_t)row / pl.lines_per_block;
-    return kHead + 2 + (uint64_t)blk * ((uint64_t)pl.lines_per_block * pl.line + 5) + 5 +
-           (uint64_t)((uint32_t)row - blk * pl.lines_per_block) * pl.line;
-}
-
-// grid = (ceil(line / 256), H, n): scanlines, stored-block headers, file head, zlib header
-__global__ void __launch_bounds__(256) png_rows_kernel(const uint8_t* __restrict__ img, uint8_t* __restrict__ out, const PngPlan pl) {
-    const uint32_t x = blockIdx.x * 256 + threadIdx.x;
-    const int row = blockIdx.y;
-    uint8_t* f = out + (uint64_t)blockIdx.z * pl.stride;
-    const uint8_t* src = img + (uint64_t)blockIdx.z * pl.H * (pl.line - 1) + (uint64_t)row * (pl.line - 1);
-    const uint64_t off = row_offset(pl, row);
-    if (x < pl.line) f[off + x] = x == 0 ? 0 : __ldg(src + x - 1);
-    if (x < 5 && (uint32_t)row % pl.lines_per_block == 0) {       // this scanline opens a stored block
-        const uint32_t blk = (uint32_t)row / pl.lines_per_block;
-        const uint32_t rows = min(pl.lines_per_block, (uint32_t)pl.H - blk * pl.lines_per_block);
-        const uint32_t len = rows * pl.line;
-        const uint8_t hdr[5] = {(uint8_t)(blk + 1 == pl.nblocks ? 1 : 0), (uint8_t)(len & 0xff), (uint8_t)(len >> 8),
-                                (uint8_t)(~len & 0xff), (uint8_t)((~len >> 8) & 0xff)};
-        f[off - 5 + x] = hdr[x];
+// Everything in front of the Adler-32: file head, zlib header, stored-block headers and the scanlines.  One thread
+// assembles one aligned 32-bit word of the file (four consecutive bytes, decoded once and then advanced byte by byte)
+// and stores it whole: the scanlines sit at arbitrary byte offsets, so byte stores would quarter the store throughput.
+// grid = (ceil(words / 256), n).  The word that straddles the Adler-32 is completed by png_adler_kernel afterwards.
+__global__ void __launch_bounds__(256) png_body_kernel(const uint8_t* __restrict__ img, uint8_t* __restrict__ out, const PngPlan pl) {
+    const uint32_t limit = (uint32_t)(kHead + pl.zlib_bytes - 4);                       // first byte of the Adler-32
+    const uint32_t o0 = (blockIdx.x * 256u + threadIdx.x) * 4u;
+    if (o0 >= limit) return;
+    const uint32_t npx = pl.line - 1, pitch = pl.lines_per_block * pl.line + 5;         // bytes from one block header to the next
+    const uint8_t* src = img + (uint64_t)blockIdx.y * pl.H * npx;
+    // position of byte o0 inside the block structure (only meaningful from the first block header on)
+    uint32_t blk = 0, t = 0, row_in = 0, col = 0;
+    if (o0 >= kHead + 2) {
+        const uint32_t z = o0 - (uint32_t)(kHead + 2);
+        blk = z / pitch; t = z - blk * pitch;
+        if (t >= 5) { row_in = (t - 5) / pl.line; col = (t - 5) - row_in * pl.line; }
     }
-    if (row == 0 && blockIdx.x == 0) {
-        if (threadIdx.x < kHead) f[threadIdx.x] = pl.head[threadIdx.x];
-        if (threadIdx.x == 64) { f[kHead] = 0x78; f[kHead + 1] = 0x01; }               // zlib: deflate, 32K window, no dictionary
+    uint32_t word = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t o = o0 + k;
+        uint32_t b = 0;
+        if (o < kHead) b = pl.head[o];
+        else if (o < kHead + 2) b = o == kHead ? 0x78u : 0x01u;                          // zlib: deflate, 32K window, no dictionary
+        else if (o < limit) {
+            if (t < 5) {                                                                 // stored-block header: final flag, LEN, ~LEN
+                const uint32_t rows = min(pl.lines_per_block, (uint32_t)pl.H - blk * pl.lines_per_block), len = rows * pl.line;
+                b = t == 0 ? (blk + 1 == pl.nblocks ? 1u : 0u) : (t == 1 ? (len & 0xffu) : (t == 2 ? (len >> 8) : (t == 3 ? (~len & 0xffu) : ((~len >> 8) & 0xffu))));
+            } else if (col != 0) {
+                b = __ldg(src + (uint64_t)(blk * pl.lines_per_block + row_in) * npx + (col - 1));
+            }                                                                            // col == 0: filter type 0
+            if (++t > 5) { if (++col == pl.line) { col = 0; ++row_in; } }
+            if (t == 5) { row_in = 0; col = 0; }
+            if (t == pitch) { ++blk; t = 0; }
+        }
+        word |= b << (8 * k);
     }
+    *reinterpret_cast<uint32_t*>(out + (uint64_t)blockIdx.y * pl.stride + o0) = word;
 }
 
 // per scanline: A = sum of bytes, B = sum of (line - j) * byte_j  (the filter byte is zero and contributes nothing)
@@ -135,25 +146,47 @@ __global__ void __launch_bounds__(256) png_adler_kernel(const unsigned long long
     }
 }
 
-// CRC-32 of the IDAT chunk (type + data): thread t takes bytes [t*2048, ...) of it; grid = (blocks, n)
-__global__ void __launch_bounds__(128) png_crc_kernel(const uint8_t* __restrict__ out, const PngPlan pl, uint32_t* __restrict__ crc /*[n], zeroed*/) {
-    __shared__ uint32_t tab[256], x2n[32];
-    for (int i = threadIdx.x; i < 256; i += 128) tab[i] = crc_step((uint32_t)i);
-    if (threadIdx.x == 0) {
+// CRC-32 of the IDAT chunk (type + data).  A block takes 32 KB of it: coalesced copy into shared memory (chunk rows
+// padded by one word against bank conflicts), one 256-byte CRC per thread, a 7-level combine tree inside the block
+// with the precomputed shifts x^(8 * 256 * 2^j), and one general shift by the bytes that follow the tile.
+constexpr int kCrcThreads = 128, kCrcBytes = 256, kCrcTile = kCrcThreads * kCrcBytes, kCrcPitch = kCrcBytes + 4;
+
+__global__ void __launch_bounds__(kCrcThreads) png_crc_kernel(const uint8_t* __restrict__ out, const PngPlan pl,
+                                                              uint32_t* __restrict__ crc /*[n], zeroed*/) {
+    __shared__ uint32_t tab[256], x2n[32], lvl[7], part[kCrcThreads];
+    __shared__ __align__(4) uint8_t tile[kCrcThreads * kCrcPitch];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 256; i += kCrcThreads) tab[i] = crc_step((uint32_t)i);
+    if (tid == 0) {
         uint32_t p = 1u << 30;                                                           // x^1
         x2n[0] = p;
         for (int k = 1; k < 32; ++k) x2n[k] = p = multmodp(p, p);
     }
-    __syncthreads();
     const uint64_t total = 4 + pl.zlib_bytes;                                            // "IDAT" + data
-    const uint64_t begin = ((uint64_t)blockIdx.x * 128 + threadIdx.x) * kCrcChunk;
-    if (begin >= total) return;
-    const uint64_t end = min(begin + (uint64_t)kCrcChunk, total);
-    const uint8_t* p = out + (uint64_t)blockIdx.y * pl.stride + (kHead - 4) + begin;
+    const uint64_t tile_begin = (uint64_t)blockIdx.x * kCrcTile;
+    const int nbytes = (int)min((uint64_t)kCrcTile, total - tile_begin);
+    const uint8_t* src = out + (uint64_t)blockIdx.y * pl.stride + (kHead - 4) + tile_begin;
+    for (int i = tid; i < nbytes; i += kCrcThreads) tile[(i >> 8) * kCrcPitch + (i & 255)] = src[i];
+    __syncthreads();
+    if (tid < 7) lvl[tid] = x8n_modp((uint64_t)kCrcBytes << tid, x2n);
+    const int len = max(0, min(kCrcBytes, nbytes - tid * kCrcBytes));
     uint32_t c = 0xffffffffu;
-    for (uint64_t i = 0; i < end - begin; ++i) c = tab[(c ^ p[i]) & 0xffu] ^ (c >> 8);
-    c ^= 0xffffffffu;
-    atomicXor(&crc[blockIdx.y], multmodp(x8n_modp(total - end, x2n), c));
+    const uint8_t* mine = tile + tid * kCrcPitch;
+    for (int i = 0; i < len; ++i) c = tab[(c ^ mine[i]) & 0xffu] ^ (c >> 8);
+    part[tid] = c ^ 0xffffffffu;                                                         // the CRC of an empty chunk is 0
+    __syncthreads();
+#pragma unroll 1
+    for (int j = 0; j < 7; ++j) {
+        const int stride = 1 << j;
+        if ((tid & (2 * stride - 1)) == 0) {
+            const int right = tid + stride;
+            const int len_r = max(0, min(stride * kCrcBytes, nbytes - right * kCrcBytes));        // bytes under the right subtree
+            const uint32_t shift = len_r == stride * kCrcBytes ? lvl[j] : x8n_modp((uint64_t)len_r, x2n);
+            part[tid] = multmodp(shift, part[tid]) ^ part[right];
+        }
+        __syncthreads();
+    }
+    if (tid == 0) atomicXor(&crc[blockIdx.y], multmodp(x8n_modp(total - (tile_begin + (uint64_t)nbytes), x2n), part[0]));
 }
 
 __global__ void png_finish_kernel(uint8_t* __restrict__ out, const PngPlan pl, const uint32_t* __restrict__ crc, int n,
@@ -208,6 +241,7 @@ int launch_png_encode(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, i
                       unsigned long long* d_sizes) {
     PngPlan pl{};
     if (n <= 0 || !make_plan(H, W, C, pl)) return set_err(ctx, PCS_ERR_ARG, "png_encode: unsupported shape %d x %d x %d", H, W, C);
+    if ((stride & 3) || (reinterpret_cast<uintptr_t>(d_out) & 3)) return set_err(ctx, PCS_ERR_ARG, "png_encode: output and stride must be 4-byte aligned");
     if (stride < pl.file_bytes) return set_err(ctx, PCS_ERR_ARG, "png_encode: %zu bytes per file needed, stride is %zu", (size_t)pl.file_bytes, stride);
     if (H > 65535) return set_err(ctx, PCS_ERR_ARG, "png_encode: more than 65535 rows");
     pl.stride = stride;
@@ -217,14 +251,15 @@ int launch_png_encode(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, i
     uint32_t* crc = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ctx->scratch) + ((size_t)n * H * 2 * 8 + 255) / 256 * 256);
     cudaStream_t st = ctx->stream;
     PCS_CUDA(ctx, cudaMemsetAsync(crc, 0, (size_t)n * 4, st));
-    png_rows_kernel<<<dim3((pl.line + 255) / 256, H, n), 256, 0, st>>>(d_img, d_out, pl);
-    PCS_LAUNCH_CHECK(ctx, "png_rows_kernel");
+    const uint64_t words = (kHead + pl.zlib_bytes - 4 + 3) / 4;
+    png_body_kernel<<<dim3((unsigned)((words + 255) / 256), n), 256, 0, st>>>(d_img, d_out, pl);
+    PCS_LAUNCH_CHECK(ctx, "png_body_kernel");
     png_adler_rows_kernel<<<dim3(H, n), 256, 0, st>>>(d_img, pl, ab);
     PCS_LAUNCH_CHECK(ctx, "png_adler_rows_kernel");
     png_adler_kernel<<<n, 256, 0, st>>>(ab, d_out, pl);
     PCS_LAUNCH_CHECK(ctx, "png_adler_kernel");
-    const uint64_t chunks = (4 + pl.zlib_bytes + kCrcChunk - 1) / kCrcChunk;
-    png_crc_kernel<<<dim3((unsigned)((chunks + 127) / 128), n), 128, 0, st>>>(d_out, pl, crc);
+    const uint64_t tiles = (4 + pl.zlib_bytes + kCrcTile - 1) / kCrcTile;
+    png_crc_kernel<<<dim3((unsigned)tiles, n), kCrcThreads, 0, st>>>(d_out, pl, crc);
     PCS_LAUNCH_CHECK(ctx, "png_crc_kernel");
     png_finish_kernel<<<(n + 63) / 64, 64, 0, st>>>(d_out, pl, crc, n, d_sizes);
     PCS_LAUNCH_CHECK(ctx, "png_finish_kernel");
