@@ -105,7 +105,13 @@ class Network:
 
     def predict_single_data(self, data: SingleData):
         """network.py:248-260 -> (logit f32 HWC, prob f32 HWC, pred int64 HW)."""
+        return self._predict(data, want_logits=True)
+
+    def _predict(self, data: SingleData, want_logits: bool):
+        """`want_logits=False` (Predictor: predictor.py:33 drops the logits at once) skips their 12 bytes per pixel of
+        device-to-host traffic and returns None in their place."""
         import torch
+        from ..runtime import to_host
         ctx = self._context()
         image = np.ascontiguousarray(data.image)
         if image.dtype != np.uint8 or image.ndim != 2:
@@ -114,12 +120,12 @@ class Network:
         dev = f"cuda:{ctx.device}"
         d_image = torch.from_numpy(image).to(dev)
         d_labels = torch.empty((h, w), dtype=torch.uint8, device=dev)
-        d_logits = torch.empty((h, w, self.n_classes), dtype=torch.float32, device=dev)
+        d_logits = torch.empty((h, w, self.n_classes), dtype=torch.float32, device=dev) if want_logits else None
         d_prob = torch.empty((h, w, self.n_classes), dtype=torch.float32, device=dev)
         ctx.forward(d_image, None, 1, h, w, d_labels, d_logits, d_prob)
-        logit = d_logits.cpu().numpy()
-        prob = d_prob.cpu().numpy()
-        pred = d_labels.cpu().numpy().astype(np.int64)
+        logit = to_host(d_logits) if want_logits else None
+        prob = to_host(d_prob)
+        pred = to_host(d_labels.to(torch.int64))          # np.argmax yields int64; widened on the device, not by a host pass
         return logit, prob, pred
 
     def predict_labels_device(self, d_image, d_labels):

@@ -57,14 +57,16 @@ def encode_png(images) -> list:
     stride = (size + 255) // 256 * 256
     d_out = torch.empty((n, stride), dtype=torch.uint8, device=d_img.device)
     ctx.png_encode(d_img.contiguous(), n, h, w, c, d_out, stride)
-    files = d_out.cpu().numpy()
+    from ..runtime import to_host
+    files = to_host(d_out)
     return [files[i, :size].tobytes() for i in range(n)]
 
 
 def generate_output_masks(data: SingleData, pred: np.ndarray, color_map: ColorMap) -> Masks:
     """output.py:44-60 through the device epilogue (pcs_masks)."""
     _, outs = _masks_on_device(data, pred, color_map)
-    color, overlay, inverted = outs.cpu().numpy()
+    from ..runtime import to_host
+    color, overlay, inverted = to_host(outs)
     # fg_color_mask[foreground != 0] = 0 is arithmetically the inverted overlay (output.py:50-53)
     return Masks(color=color, overlay=overlay, inverted_overlay=inverted, fg_color_mask=inverted.copy())
 

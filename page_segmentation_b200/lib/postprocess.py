@@ -20,7 +20,8 @@ def vote_connected_component_class(pred: np.ndarray, data: SingleData) -> np.nda
     d_pred = to_device_u8(pred, ctx.device)
     d_bin = to_device_u8(np.asarray(data.binary) != 0, ctx.device)
     ctx.cc_majority(d_pred, d_bin, 1, h, w, _n_classes(pred))
-    pred[...] = d_pred.cpu().numpy().astype(pred.dtype)
+    from ..runtime import to_host
+    pred[...] = to_host(d_pred.to(torch.int64)) if pred.dtype == np.int64 else to_host(d_pred).astype(pred.dtype)
     return pred
 
 

@@ -38,12 +38,18 @@ class Predictor:
                 pred = processor(pred, data)
         return data, pred
 
+    def _forward(self, data: SingleData):
+        # the logits are dropped right away (predictor.py:33), so the device path does not copy them back; a
+        # caller-supplied network object without that shortcut is used through the reference's method
+        fast = getattr(self.network, "_predict", None)
+        return fast(data, want_logits=False) if fast else self.network.predict_single_data(data)
+
     def predict_single(self, data: SingleData) -> Prediction:
-        logit, prob, pred = self.network.predict_single_data(data)
+        logit, prob, pred = self._forward(data)
         data, pred = self._post(data, pred)
         return Prediction(pred, prob, data)
 
     def predict_masks(self, data: SingleData) -> Masks:
-        logit, prob, pred = self.network.predict_single_data(data)
+        logit, prob, pred = self._forward(data)
         data, pred = self._post(data, pred)
         return generate_output_masks(data, pred, self.settings.color_map)
