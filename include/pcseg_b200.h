@@ -185,11 +185,14 @@ PCS_API int pcs_predict_pages_host(pcs_ctx* ctx, const uint8_t* h_grey, const ui
 
 /* ---- image files: the encoder of output_data, lib/output.py:38-41 (skimage.io.imsave of the three masks).
  * Builds n complete PNG files on the device from [n][H][W][channels] uint8 images (channels 1 = grey, 3 = RGB,
- * 4 = RGBA): signature, IHDR, one IDAT whose zlib stream uses stored deflate blocks, Adler-32, CRC-32, IEND.
- * File i starts at d_out + i * stride and is pcs_png_bytes(H, W, channels) bytes long (also written to
- * d_sizes[i] when d_sizes is not NULL); any PNG reader decodes it to exactly the input bytes. */
-PCS_API size_t pcs_png_bytes(int H, int W, int channels);          /* 0 if the shape is unsupported */
-PCS_API int pcs_png_encode(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, int channels,
+ * 4 = RGBA): signature, IHDR, one IDAT, Adler-32, CRC-32, IEND.  level 0: stored deflate blocks, the file is the
+ * raw image + 0.2 %; level 1: Sub-filtered scanlines, fixed-Huffman deflate with run-length matches (class-colour
+ * masks shrink 30-100x, scanlines up to 16384 bytes).  File i starts at d_out + i * stride (stride a multiple of 4
+ * and >= pcs_png_bytes rounded up to 4; at level 1 the buffer is zero-filled first); its length is written to
+ * d_sizes[i] (device, may be NULL at level 0 where it equals pcs_png_bytes).  Any PNG reader decodes the files to
+ * exactly the input bytes. */
+PCS_API size_t pcs_png_bytes(int H, int W, int channels, int level);   /* exact (level 0) / upper bound (level 1); 0 = unsupported */
+PCS_API int pcs_png_encode(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, int channels, int level,
                    uint8_t* d_out, size_t stride, uint64_t* d_sizes);
 
 /* ---- region extraction (downstream consumer of the `inverted` colour image):

@@ -71,9 +71,9 @@ def load() -> C.CDLL:
     lib.pcs_cc_majority.argtypes = [vp, u8p, u8p, i32, i32, i32, i32]
     lib.pcs_bounding_boxes.argtypes = [vp, u8p, i32, i32, i32, i32, u8p]
     lib.pcs_char_height.argtypes = [vp, u8p, i32, i32, i32, i32, vp]
-    lib.pcs_png_bytes.argtypes = [i32, i32, i32]
+    lib.pcs_png_bytes.argtypes = [i32, i32, i32, i32]
     lib.pcs_png_bytes.restype = C.c_size_t
-    lib.pcs_png_encode.argtypes = [vp, u8p, i32, i32, i32, i32, u8p, C.c_size_t, vp]
+    lib.pcs_png_encode.argtypes = [vp, u8p, i32, i32, i32, i32, i32, u8p, C.c_size_t, vp]
     lib.pcs_segment_masks.argtypes = [vp, u8p, i32, i32, i32, i32, vp, i32, u8p]
     lib.pcs_dilate3x3.argtypes = [vp, u8p, i32, i32, i32, u8p]
     lib.pcs_integral_image.argtypes = [vp, u8p, i32, i32, i32, vp]
@@ -236,11 +236,11 @@ class Context:
                     "pcs_char_height")
 
     # -- image files ------------------------------------------------------------
-    def png_bytes(self, H, W, channels) -> int:
-        return int(self.lib.pcs_png_bytes(H, W, channels))
+    def png_bytes(self, H, W, channels, level=1) -> int:
+        return int(self.lib.pcs_png_bytes(H, W, channels, level))
 
-    def png_encode(self, d_img, n, H, W, channels, d_out, stride, d_sizes=None):
-        self._check(self.lib.pcs_png_encode(self.h, _ptr(d_img), n, H, W, channels, _ptr(d_out), stride, _ptr(d_sizes)),
+    def png_encode(self, d_img, n, H, W, channels, d_out, stride, d_sizes=None, level=1):
+        self._check(self.lib.pcs_png_encode(self.h, _ptr(d_img), n, H, W, channels, level, _ptr(d_out), stride, _ptr(d_sizes)),
                     "pcs_png_encode")
 
     # -- region extraction ---------------------------------------------------

@@ -795,14 +795,14 @@ int pcs_text_regions(pcs_ctx* ctx, const uint8_t* d_rgb, int H, int W, const uin
     return launch_text_regions(ctx, d_rgb, H, W, colour, k_close, k_open, k_region, d_text_inv, d_region);
 }
 
-size_t pcs_png_bytes(int H, int W, int channels) { return png_file_bytes(H, W, channels); }
+size_t pcs_png_bytes(int H, int W, int channels, int level) { return png_file_bytes(H, W, channels, level); }
 
-int pcs_png_encode(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, int channels, uint8_t* d_out, size_t stride,
+int pcs_png_encode(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, int channels, int level, uint8_t* d_out, size_t stride,
                    uint64_t* d_sizes) {
     if (!ctx || !d_img || !d_out) return ctx ? set_err(ctx, PCS_ERR_ARG, "png_encode: null argument") : PCS_ERR_ARG;
     PCS_CUDA(ctx, cudaSetDevice(ctx->device));
     StageScope ts(ctx, "png_encode");
-    return launch_png_encode(ctx, d_img, n, H, W, channels, d_out, stride, reinterpret_cast<unsigned long long*>(d_sizes));
+    return launch_png_encode(ctx, d_img, n, H, W, channels, level, d_out, stride, reinterpret_cast<unsigned long long*>(d_sizes));
 }
 
 int pcs_predict_pages_host(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h_bin, int n, int H, int W, int Hs, int Ws,

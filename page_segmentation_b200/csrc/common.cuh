@@ -267,8 +267,8 @@ int launch_text_regions(pcs_ctx* ctx, const uint8_t* d_rgb, int H, int W, const 
                         int k_region, uint8_t* d_text_inv, uint8_t* d_region);
 
 // png.cu
-size_t png_file_bytes(int H, int W, int C);
-int launch_png_encode(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, int C, uint8_t* d_out, size_t stride,
+size_t png_file_bytes(int H, int W, int C, int level);
+int launch_png_encode(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, int C, int level, uint8_t* d_out, size_t stride,
                       unsigned long long* d_sizes);
 
 // conv_umma.cu  (tcgen05 / TMEM / TMA implicit GEMM)

@@ -39,9 +39,10 @@ def _masks_on_device(data: SingleData, pred: np.ndarray, color_map: ColorMap):
     return ctx, outs
 
 
-def encode_png(images) -> list:
+def encode_png(images, level: int = 1) -> list:
     """PNG files (bytes) of a stack of equally sized uint8 images (n, H, W) or (n, H, W, 3|4), built on the device
-    (pcs_png_encode: stored deflate blocks, so a file is the raw image plus 0.2 %; lossless like any PNG).
+    (pcs_png_encode).  level 1 (default): Sub filter + fixed-Huffman deflate with run-length matches - class-colour
+    masks come out 30-100x smaller than raw; level 0: stored blocks, raw size + 0.2 %.  Lossless like any PNG.
     `images` may be a numpy array or a CUDA tensor."""
     import torch
     from ..runtime import get_context
@@ -51,15 +52,21 @@ def encode_png(images) -> list:
         raise ValueError("encode_png expects uint8 images (n, H, W) or (n, H, W, C)")
     n, h, w = d_img.shape[:3]
     c = 1 if d_img.dim() == 3 else d_img.shape[3]
-    size = ctx.png_bytes(h, w, c)
+    if level and ctx.png_bytes(h, w, c, level) == 0:
+        level = 0                                        # scanlines too long for the run tables: stored blocks
+    size = ctx.png_bytes(h, w, c, level)
     if size == 0:
         raise ValueError(f"images of shape {h} x {w} x {c} cannot be written as PNG by the device encoder")
     stride = (size + 255) // 256 * 256
     d_out = torch.empty((n, stride), dtype=torch.uint8, device=d_img.device)
-    ctx.png_encode(d_img.contiguous(), n, h, w, c, d_out, stride)
+    d_sizes = torch.empty((n,), dtype=torch.int64, device=d_img.device)
+    ctx.png_encode(d_img.contiguous(), n, h, w, c, d_out, stride, d_sizes, level)
+    sizes = d_sizes.cpu().tolist()
+    if level:                                            # only the bytes of the files travel, not the worst-case buffers
+        return [d_out[i, :sizes[i]].cpu().numpy().tobytes() for i in range(n)]
     from ..runtime import to_host
     files = to_host(d_out)
-    return [files[i, :size].tobytes() for i in range(n)]
+    return [files[i, :sizes[i]].tobytes() for i in range(n)]
 
 
 def generate_output_masks(data: SingleData, pred: np.ndarray, color_map: ColorMap) -> Masks:

@@ -32,13 +32,84 @@ def host_png(img: np.ndarray) -> bytes:
     return b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", ihdr) + chunk(b"IDAT", z) + chunk(b"IEND", b"")
 
 
+def check_container(blob: bytes, img: np.ndarray, sub_filter: bool):
+    """Chunk structure, both checksums, the zlib stream and the decoded pixels of one PNG file."""
+    assert blob[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, kinds, idat = 8, [], b""
+    while pos < len(blob):
+        (length,), kind = struct.unpack(">I", blob[pos:pos + 4]), blob[pos + 4:pos + 8]
+        data = blob[pos + 8:pos + 8 + length]
+        assert struct.unpack(">I", blob[pos + 8 + length:pos + 12 + length])[0] == zlib.crc32(kind + data), kind
+        kinds.append(kind)
+        if kind == b"IDAT":
+            idat += data
+        pos += 12 + length
+    assert kinds == [b"IHDR", b"IDAT", b"IEND"] and pos == len(blob)
+    h = img.shape[0]
+    c = 1 if img.ndim == 2 else img.shape[2]
+    stream = zlib.decompress(idat)                                  # inflate also verifies the Adler-32
+    line = 1 + img.shape[1] * c
+    assert len(stream) == h * line
+    lines = np.frombuffer(stream, np.uint8).reshape(h, line)
+    if sub_filter:                                                  # level 1: Sub or Up per scanline, undone here by hand
+        assert set(np.unique(lines[:, 0])) <= {1, 2}
+        prev = np.zeros(line - 1, np.uint8)
+        for r in range(h):
+            f = lines[r, 1:]
+            if lines[r, 0] == 1:
+                cur = np.cumsum(f.reshape(-1, c).astype(np.uint64), axis=0).astype(np.uint8).reshape(-1)
+            else:
+                cur = (f.astype(np.uint16) + prev).astype(np.uint8)
+            assert np.array_equal(cur, img[r].reshape(-1)), r
+            prev = cur
+    else:
+        assert stream == b"".join(b"\x00" + img[r].tobytes() for r in range(h))
+    dec = cv2.imdecode(np.frombuffer(blob, np.uint8), cv2.IMREAD_UNCHANGED)
+    assert dec is not None
+    np.testing.assert_array_equal(dec if img.ndim == 2 else (dec[..., ::-1] if c == 3 else dec[..., [2, 1, 0, 3]]), img)
+
+
+def mask_like(rng, shape):
+    """Blocky class-colour image with some speckle: what the encoder is for."""
+    h, w = shape[:2]
+    lut = np.array([[255, 255, 255], [255, 0, 0], [0, 255, 0], [0, 0, 0]], np.uint8)
+    coarse = rng.integers(0, 4, (h // 24 + 1, w // 24 + 1))
+    lab = np.kron(coarse, np.ones((24, 24), np.int64))[:h, :w]
+    flip = rng.random((h, w)) < 0.01
+    lab[flip] = rng.integers(0, 4, int(flip.sum()))
+    img = lut[lab]
+    return img if len(shape) == 3 else img[..., 0]
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 3), (7, 5, 3), (61, 83, 3), (389, 275, 3), (1169, 827, 3), (5, 5461, 3), (33, 65), (300, 260, 4)])
+def test_png_level1_is_valid_lossless_and_small(ctx, shape):
+    from page_segmentation_b200.lib.output import encode_png
+    rng = np.random.default_rng(shape[0] + 1)
+    noise = rng.integers(0, 256, shape, dtype=np.uint8)             # worst case: no runs at all, 9-bit literals
+    runs = np.zeros(shape, np.uint8)
+    runs[shape[0] // 3:] = 200                                       # runs far longer than 258 bytes, literals >= 144
+    if len(shape) == 3 and shape[2] == 3:
+        masks = mask_like(rng, shape)
+    else:
+        masks = (rng.random(shape) < 0.5).astype(np.uint8) * 255
+    imgs = np.stack([noise, runs, masks])
+    files = encode_png(imgs, level=1)
+    for img, blob in zip(imgs, files):
+        check_container(blob, img, sub_filter=True)
+    assert len(files[0]) <= imgs[0].size * 9 // 8 + shape[0] * 2 + 80
+    if shape[0] * shape[1] > 10000:
+        assert len(files[1]) < imgs[1].size // 50
+        if len(shape) == 3 and shape[2] == 3:
+            assert len(files[2]) < imgs[2].size // 15, (len(files[2]), imgs[2].size)
+
+
 @pytest.mark.parametrize("shape", [(1, 1, 3), (7, 5, 3), (61, 83, 3), (389, 275, 3), (1169, 827, 3), (40, 21844, 3), (33, 65)])
 def test_png_files_are_valid_and_lossless(ctx, shape):
     from page_segmentation_b200.lib.output import encode_png
     rng = np.random.default_rng(shape[0])
     imgs = rng.integers(0, 256, (2,) + shape, dtype=np.uint8)
     imgs[1][: shape[0] // 2] = 255                                   # long runs of 0xff stress the Adler sums
-    files = encode_png(imgs)
+    files = encode_png(imgs, level=0)
     assert len(files) == 2
     for img, blob in zip(imgs, files):
         assert blob == host_png(img)                                 # every byte: headers, block framing, Adler-32, CRC-32
@@ -53,14 +124,19 @@ def test_png_full_a4_masks(ctx):
     from page_segmentation_b200.lib.output import encode_png
     inv = synth.make_inverted_image(5, synth.A4_H, synth.A4_W, 40)
     imgs = np.stack([inv, 255 - inv, inv[::-1].copy()])
-    for img, blob in zip(imgs, encode_png(imgs)):
+    for img, blob in zip(imgs, encode_png(imgs, level=0)):
         assert len(blob) == len(host_png(img)) and blob == host_png(img)
+    for img, blob in zip(imgs, encode_png(imgs, level=1)):
+        check_container(blob, img, sub_filter=True)
+        assert len(blob) < img.size // 4
 
 
 def test_png_rejects_unsupported_shapes(ctx):
     from page_segmentation_b200.lib.output import encode_png
     with pytest.raises(ValueError):
         encode_png(np.zeros((1, 4, 30000, 3), np.uint8))             # a scanline longer than one stored block
+    long_lines = np.zeros((1, 3, 6000, 3), np.uint8)                 # too long for the run tables: falls back to stored blocks
+    assert encode_png(long_lines, level=1) == encode_png(long_lines, level=0)
     with pytest.raises(ValueError):
         encode_png(np.zeros((1, 4, 4, 2), np.uint8))                 # grey + alpha is not offered
 
