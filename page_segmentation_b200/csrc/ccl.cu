@@ -47,7 +47,7 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
 
 // grid: (ceil(W/32) * rows_per_block..., H, n) -- one warp per 32-pixel row segment.
 // block = 256 threads = 8 segments of one row.
-template <bool MATCH_CLASS>
+template <bool MATCH_CLASS, bool WRITE_BG = true>
 __global__ void __launch_bounds__(256)
 ccl_init_kernel(const uint8_t* __restrict__ img, int H, int W, int cls, int* __restrict__ parent,
                 int* __restrict__ zero_aux, int aux_stride) {
@@ -65,7 +65,7 @@ ccl_init_kernel(const uint8_t* __restrict__ img, int H, int W, int cls, int* __r
     }
     const unsigned mask = __ballot_sync(0xffffffffu, fg);
     if (!inb) return;
-    if (!fg) { parent[page_off + idx] = kBG; return; }
+    if (!fg) { if (WRITE_BG) parent[page_off + idx] = kBG; return; }      // !WRITE_BG: every later pass tests the image first
     const unsigned below = ~mask & ((1u << lane) - 1u);     // background lanes left of me
     const int start = below ? 32 - __clz(below) : 0;
     parent[page_off + idx] = y * W + seg * 32 + start;
@@ -104,11 +104,14 @@ ccl_merge_kernel(const uint8_t* __restrict__ img, int H, int W, int cls, int* __
     }
 }
 
-__global__ void __launch_bounds__(256) ccl_flatten_kernel(int* __restrict__ parent, size_t page_px) {
+// `fg` (optional): the image whose non-zero pixels are the foreground.  Nine tenths of a page are background, and
+// testing the 1-byte pixel first spares the 4-byte parent read of those pixels (and lets cc_majority leave the
+// parents of background pixels unwritten).
+__global__ void __launch_bounds__(256) ccl_flatten_kernel(int* __restrict__ parent, size_t page_px, const uint8_t* __restrict__ fg) {
     const size_t page_off = (size_t)blockIdx.y * page_px;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < page_px; i += (size_t)gridDim.x * blockDim.x) {
-        const int p = parent[page_off + i];
-        if (p == kBG) continue;
+        if (fg) { if (!fg[page_off + i]) continue; }
+        else if (parent[page_off + i] == kBG) continue;
         parent[page_off + i] = uf_find(parent + page_off, (int)i);
     }
 }
@@ -261,10 +264,12 @@ ccl_stats_finish_kernel(int32_t* __restrict__ stats, const int32_t* __restrict__
 }
 
 static int ccl_roots(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, int cls, bool match, int* parent,
-                     int* zero_aux, int aux_stride, bool conn8 = false) {
+                     int* zero_aux, int aux_stride, bool conn8 = false, bool fg_only = false) {
+    // fg_only: the caller's later passes test the image before they touch a parent, so background parents are not written
     cudaStream_t st = ctx->stream;
     dim3 ginit(((W + 31) / 32 + 7) / 8, H, n);
     if (match) ccl_init_kernel<true><<<ginit, 256, 0, st>>>(d_img, H, W, cls, parent, zero_aux, aux_stride);
+    else if (fg_only) ccl_init_kernel<false, false><<<ginit, 256, 0, st>>>(d_img, H, W, cls, parent, zero_aux, aux_stride);
     else ccl_init_kernel<false><<<ginit, 256, 0, st>>>(d_img, H, W, cls, parent, zero_aux, aux_stride);
     PCS_LAUNCH_CHECK(ctx, "ccl_init_kernel");
     dim3 gmerge((W + 255) / 256, H, n);
@@ -274,7 +279,7 @@ static int ccl_roots(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, in
     PCS_LAUNCH_CHECK(ctx, "ccl_merge_kernel");
     const size_t page_px = (size_t)H * W;
     dim3 gflat((unsigned)std::min<size_t>(2048, (page_px + 255) / 256), n);
-    ccl_flatten_kernel<<<gflat, 256, 0, st>>>(parent, page_px);
+    ccl_flatten_kernel<<<gflat, 256, 0, st>>>(parent, page_px, match ? nullptr : d_img);
     PCS_LAUNCH_CHECK(ctx, "ccl_flatten_kernel");
     return PCS_OK;
 }
@@ -319,24 +324,24 @@ int launch_ccl(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, int32_t*
 // vote_connected_component_class (postprocess.py:9-26)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-cc_vote_kernel(const uint8_t* __restrict__ pred, const int* __restrict__ parent, size_t page_px, int n_classes,
-               int* __restrict__ hist) {
+cc_vote_kernel(const uint8_t* __restrict__ pred, const uint8_t* __restrict__ fg, const int* __restrict__ parent, size_t page_px,
+               int n_classes, int* __restrict__ hist) {
     const size_t page_off = (size_t)blockIdx.y * page_px;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < page_px; i += (size_t)gridDim.x * blockDim.x) {
+        if (!fg[page_off + i]) continue;
         const int p = parent[page_off + i];
-        if (p == kBG) continue;
         const int c = pred[page_off + i];
         if (c < n_classes) atomicAdd(&hist[(page_off + p) * n_classes + c], 1);
     }
 }
 
 __global__ void __launch_bounds__(256)
-cc_apply_kernel(uint8_t* __restrict__ pred, const int* __restrict__ parent, size_t page_px, int n_classes,
-                const int* __restrict__ hist) {
+cc_apply_kernel(uint8_t* __restrict__ pred, const uint8_t* __restrict__ fg, const int* __restrict__ parent, size_t page_px,
+                int n_classes, const int* __restrict__ hist) {
     const size_t page_off = (size_t)blockIdx.y * page_px;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < page_px; i += (size_t)gridDim.x * blockDim.x) {
+        if (!fg[page_off + i]) continue;
         const int p = parent[page_off + i];
-        if (p == kBG) continue;
         const int* h = hist + (page_off + p) * n_classes;
         int best = 0, bv = h[0];
         for (int c = 1; c < n_classes; ++c)
@@ -352,11 +357,11 @@ int launch_cc_majority(pcs_ctx* ctx, uint8_t* d_pred, const uint8_t* d_binary, i
     PCS_TRY(scratch_reserve(ctx, total * 4 * (1 + (size_t)n_classes) + 256));
     int* parent = reinterpret_cast<int*>(ctx->scratch);
     int* hist = parent + total;
-    PCS_TRY(ccl_roots(ctx, d_binary, n, H, W, 0, false, parent, hist, n_classes));
+    PCS_TRY(ccl_roots(ctx, d_binary, n, H, W, 0, false, parent, hist, n_classes, false, /*fg_only=*/true));
     dim3 grid((unsigned)std::min<size_t>(2048, (page_px + 255) / 256), n);
-    cc_vote_kernel<<<grid, 256, 0, ctx->stream>>>(d_pred, parent, page_px, n_classes, hist);
+    cc_vote_kernel<<<grid, 256, 0, ctx->stream>>>(d_pred, d_binary, parent, page_px, n_classes, hist);
     PCS_LAUNCH_CHECK(ctx, "cc_vote_kernel");
-    cc_apply_kernel<<<grid, 256, 0, ctx->stream>>>(d_pred, parent, page_px, n_classes, hist);
+    cc_apply_kernel<<<grid, 256, 0, ctx->stream>>>(d_pred, d_binary, parent, page_px, n_classes, hist);
     PCS_LAUNCH_CHECK(ctx, "cc_apply_kernel");
     return PCS_OK;
 }
