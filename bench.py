@@ -127,6 +127,13 @@ def cpu_reference_pages_per_s(n_pages, warm=1):
 def run_reference(args, rank, world):
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 for its workers; the CPU arm is meant to use every host core of the box
+    import torch
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    torch.set_num_threads(max(1, cores))
     per_step = 2
     for _ in range(args.warmup):
         cpu_reference_pages_per_s(1, warm=0)
