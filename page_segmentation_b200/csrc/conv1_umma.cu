@@ -281,12 +281,18 @@ int launch_conv1_umma(pcs_ctx* ctx, const uint8_t* d_image, int n, int img_h, in
     const size_t smem = std::max<size_t>(((C1_B_BYTES + 1023) / 1024) * 1024 + (size_t)C1_STAGES * C1_STAGE_BYTES + 1024, kSoloSmem);
     const int grid = std::min(p.num_tiles, ctx->sm_count);
     if (ctx->precision == PCS_PREC_BF16) {
-        static bool set = false;
-        if (!set) { PCS_CUDA(ctx, cudaFuncSetAttribute(conv1_umma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = true; }
+        static bool set[64] = {};                // the attribute is per device
+        if (ctx->device >= 64 || !set[ctx->device]) {
+            PCS_CUDA(ctx, cudaFuncSetAttribute(conv1_umma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (ctx->device < 64) set[ctx->device] = true;
+        }
         PCS_CUDA(ctx, launch_kernel_pdl(conv1_umma_kernel<__nv_bfloat16>, dim3(grid), dim3(C1_THREADS), smem, ctx->stream, ctx->pdl, p));
     } else {
-        static bool set = false;
-        if (!set) { PCS_CUDA(ctx, cudaFuncSetAttribute(conv1_umma_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = true; }
+        static bool set[64] = {};
+        if (ctx->device >= 64 || !set[ctx->device]) {
+            PCS_CUDA(ctx, cudaFuncSetAttribute(conv1_umma_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (ctx->device < 64) set[ctx->device] = true;
+        }
         PCS_CUDA(ctx, launch_kernel_pdl(conv1_umma_kernel<__half>, dim3(grid), dim3(C1_THREADS), smem, ctx->stream, ctx->pdl, p));
     }
     PCS_LAUNCH_CHECK(ctx, "conv1_umma_kernel");

@@ -414,10 +414,10 @@ int launch_fold_t(pcs_ctx* ctx, const FoldConvArgs& a) {
     p.ring = RING;
     const size_t smem = std::max<size_t>(w_al + (size_t)RING * NPL * 2048 + 1024, kSoloSmem);
     if (smem + 2 * 1024 > 227 * 1024) return set_err(ctx, PCS_ERR_ARG, "conv_fold: %zu bytes of shared memory needed", smem);
-    static size_t attr_set = 0;
-    if (attr_set < smem) {
+    static size_t attr_set[64] = {};             // the attribute is per device
+    if (ctx->device >= 64 || attr_set[ctx->device] < smem) {
         PCS_CUDA(ctx, cudaFuncSetAttribute(conv_fold_kernel<T, NPAD, NPL, RING, SLOTS, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = smem;
+        if (ctx->device < 64) attr_set[ctx->device] = smem;
     }
     const int grid = (int)((p.total_rows + p.rows_per_cta - 1) / p.rows_per_cta);
     PCS_CUDA(ctx, launch_kernel_pdl(conv_fold_kernel<T, NPAD, NPL, RING, SLOTS, EG>, dim3(grid), dim3(64 + EG * 128), smem, ctx->stream,

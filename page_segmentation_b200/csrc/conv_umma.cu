@@ -509,10 +509,10 @@ int launch_t(pcs_ctx* ctx, const UmmaConvArgs& a) {
     PCS_TRY(make_act_map(ctx, &tm0, a.src[0], a.n, a.h, a.w, p.a_rows));
     if (a.nsrc > 1) PCS_TRY(make_act_map(ctx, &tm1, a.src[1], a.n, a.h, a.w, p.a_rows));
     else tm1 = tm0;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};               // the attribute is per device
+    if (ctx->device >= 64 || !attr_set[ctx->device]) {
         PCS_CUDA(ctx, cudaFuncSetAttribute(conv_umma_kernel<T, NPAD, KS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-        attr_set = true;
+        if (ctx->device < 64) attr_set[ctx->device] = true;
     }
     const int grid = std::min(p.num_tiles, ctx->sm_count);
     if constexpr (MODE >= EPI_HEAD) {
