@@ -183,6 +183,17 @@ PCS_API int pcs_predict_pages_host(pcs_ctx* ctx, const uint8_t* h_grey, const ui
                            uint8_t* h_image, uint8_t* h_binary, uint8_t* h_labels,
                            uint8_t* h_color, uint8_t* h_overlay, uint8_t* h_inverted);
 
+/* The same pipeline with the three masks leaving the device as PNG files (pcs_png_encode, level 1) instead of raw
+ * arrays - Predictor.predict + output_data (lib/predictor.py:27-42, lib/output.py:20-41) for a batch, minus the
+ * file write.  The device-to-host traffic drops from 9.7 MB to about 1.3 MB per A4 page.
+ *   h_labels    : [n][Hs][Ws] uint8 or NULL
+ *   h_png       : file (page p, kind k) starts at h_png + (3 p + k) * png_stride; kind 0 = color, 1 = overlay,
+ *                 2 = inverted; png_stride >= pcs_png_bytes(Hs, Ws, 3, 1)
+ *   h_png_sizes : [n][3] uint64 file lengths */
+PCS_API int pcs_predict_pages_files(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h_bin,
+                            int n, int H, int W, int Hs, int Ws, int cc_majority, const uint8_t* lut,
+                            uint8_t* h_labels, uint8_t* h_png, size_t png_stride, uint64_t* h_png_sizes);
+
 /* ---- image files: the encoder of output_data, lib/output.py:38-41 (skimage.io.imsave of the three masks).
  * Builds n complete PNG files on the device from [n][H][W][channels] uint8 images (channels 1 = grey, 3 = RGB,
  * 4 = RGBA): signature, IHDR, one IDAT, Adler-32, CRC-32, IEND.  level 0: stored deflate blocks, the file is the

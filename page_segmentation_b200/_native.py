@@ -23,7 +23,7 @@ EXPORTS = [
     "pcs_synchronize", "pcs_launch_count", "pcs_model_load", "pcs_set_engine", "pcs_preprocess",
     "pcs_preprocess_max_width",
     "pcs_forward", "pcs_masks", "pcs_resize_nearest", "pcs_ccl", "pcs_cc_majority",
-    "pcs_bounding_boxes", "pcs_char_height", "pcs_png_bytes", "pcs_png_encode", "pcs_segment_masks", "pcs_dilate3x3", "pcs_integral_image", "pcs_text_regions", "pcs_predict_pages_host", "pcs_debug_activation", "pcs_set_keep_activations", "pcs_set_timing", "pcs_set_pdl",
+    "pcs_bounding_boxes", "pcs_char_height", "pcs_png_bytes", "pcs_png_encode", "pcs_segment_masks", "pcs_dilate3x3", "pcs_integral_image", "pcs_text_regions", "pcs_predict_pages_host", "pcs_predict_pages_files", "pcs_debug_activation", "pcs_set_keep_activations", "pcs_set_timing", "pcs_set_pdl",
     "pcs_last_timings",
 ]
 
@@ -79,6 +79,7 @@ def load() -> C.CDLL:
     lib.pcs_integral_image.argtypes = [vp, u8p, i32, i32, i32, vp]
     lib.pcs_text_regions.argtypes = [vp, u8p, i32, i32, vp, i32, i32, i32, u8p, u8p]
     lib.pcs_predict_pages_host.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
+    lib.pcs_predict_pages_files.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, C.c_size_t, vp]
     lib.pcs_debug_activation.argtypes = [vp, C.c_char_p, vp, C.c_size_t, C.POINTER(C.c_int32)]
     lib.pcs_set_keep_activations.argtypes = [vp, i32]
     lib.pcs_set_timing.argtypes = [vp, i32]
@@ -268,6 +269,12 @@ class Context:
             self.h, _ptr(h_grey), _ptr(h_bin), n, H, W, Hs, Ws, 1 if cc_majority else 0, _ptr(lut_arr),
             _ptr(h_image), _ptr(h_binary), _ptr(h_labels), _ptr(h_color), _ptr(h_overlay), _ptr(h_inverted)),
             "pcs_predict_pages_host")
+
+    def predict_pages_files(self, h_grey, h_bin, n, H, W, Hs, Ws, cc_majority, lut, h_labels, h_png, png_stride, h_png_sizes):
+        lut_arr = np.ascontiguousarray(lut, dtype=np.uint8)
+        self._check(self.lib.pcs_predict_pages_files(
+            self.h, _ptr(h_grey), _ptr(h_bin), n, H, W, Hs, Ws, 1 if cc_majority else 0, _ptr(lut_arr),
+            _ptr(h_labels), _ptr(h_png), png_stride, _ptr(h_png_sizes)), "pcs_predict_pages_files")
 
     # -- diagnostics -----------------------------------------------------------
     def debug_activation(self, name: str) -> np.ndarray:

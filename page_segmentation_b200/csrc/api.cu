@@ -468,10 +468,11 @@ void pcs_ctx_destroy(pcs_ctx* ctx) {
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->scratch2) cudaFree(ctx->scratch2);
     if (ctx->stage) cudaFree(ctx->stage);
+    if (ctx->h_png_sizes) cudaFreeHost(ctx->h_png_sizes);
     for (int i = 0; i < 2; ++i)
         if (ctx->copy_streams[i]) cudaStreamDestroy(ctx->copy_streams[i]);
     for (int i = 0; i < pcs_ctx::kHostBufs; ++i)
-        if (ctx->ev_h2d[i]) { cudaEventDestroy(ctx->ev_h2d[i]); cudaEventDestroy(ctx->ev_comp[i]); cudaEventDestroy(ctx->ev_d2h[i]); }
+        if (ctx->ev_h2d[i]) { cudaEventDestroy(ctx->ev_h2d[i]); cudaEventDestroy(ctx->ev_comp[i]); cudaEventDestroy(ctx->ev_d2h[i]); cudaEventDestroy(ctx->ev_sizes[i]); }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     delete ctx;
 }
@@ -805,14 +806,22 @@ int pcs_png_encode(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, int 
     return launch_png_encode(ctx, d_img, n, H, W, channels, level, d_out, stride, reinterpret_cast<unsigned long long*>(d_sizes));
 }
 
-int pcs_predict_pages_host(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h_bin, int n, int H, int W, int Hs, int Ws,
-                           int cc_majority, const uint8_t* lut, uint8_t* h_image, uint8_t* h_binary, uint8_t* h_labels,
-                           uint8_t* h_color, uint8_t* h_overlay, uint8_t* h_inverted) {
+// h_png != nullptr: the three masks leave the device as PNG files (level 1) instead of raw arrays: file (page p, kind k)
+// at h_png + (3 p + k) * png_stride, its length in h_png_sizes[3 p + k]; kind 0 = color, 1 = overlay, 2 = inverted.
+static int predict_pages_host_impl(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h_bin, int n, int H, int W, int Hs, int Ws,
+                                   int cc_majority, const uint8_t* lut, uint8_t* h_image, uint8_t* h_binary, uint8_t* h_labels,
+                                   uint8_t* h_color, uint8_t* h_overlay, uint8_t* h_inverted, uint8_t* h_png, size_t png_stride,
+                                   uint64_t* h_png_sizes) {
     if (!ctx || !h_grey || !h_bin) return ctx ? set_err(ctx, PCS_ERR_ARG, "predict_pages_host: null input") : PCS_ERR_ARG;
     if (!ctx->model_ready) return set_err(ctx, PCS_ERR_STATE, "pcs_predict_pages_host before pcs_model_load");
     if (n <= 0 || H <= 0 || W <= 0 || Hs <= 0 || Ws <= 0) return set_err(ctx, PCS_ERR_ARG, "predict_pages_host: bad shape");
-    const bool want_masks = h_color || h_overlay || h_inverted;
+    const bool want_png = h_png != nullptr;
+    const bool want_masks = h_color || h_overlay || h_inverted || want_png;
     if (want_masks && !lut) return set_err(ctx, PCS_ERR_ARG, "predict_pages_host: colour outputs need a LUT");
+    const size_t png_bound = want_png ? png_file_bytes(Hs, Ws, 3, 1) : 0;
+    if (want_png && (!h_png_sizes || !png_bound || png_stride < png_bound))
+        return set_err(ctx, PCS_ERR_ARG, "predict_pages_files: %zu bytes per file needed (stride %zu), sizes array required", png_bound, png_stride);
+    const size_t dpng_stride = (png_bound + 255) / 256 * 256;
     PCS_CUDA(ctx, cudaSetDevice(ctx->device));
     // Three-stage pipeline over sub-batches ("chunks") of pages: H2D copy stream -> compute stream
     // (ctx->stream) -> D2H copy stream, rotating over `nbuf` device staging buffers, so that with pinned
@@ -827,6 +836,7 @@ int pcs_predict_pages_host(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h
             PCS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
             PCS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_comp[i], cudaEventDisableTiming));
             PCS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming));
+            PCS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_sizes[i], cudaEventDisableTiming));
         }
         PCS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     }
@@ -864,8 +874,11 @@ int pcs_predict_pages_host(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h
     const bool same = h_grey == h_bin;
     auto al = [](size_t b) { return (b + 255) / 256 * 256; };
     const size_t in_bytes = al(src1 * chunk) * (same ? 1 : 2);
-    const size_t out_bytes = al(dst1 * chunk) * 3 + al(dst1 * chunk * 3) * 3;
+    const size_t png_bytes = want_png ? 3 * (size_t)chunk * dpng_stride + al(3 * (size_t)chunk * 8) : 0;
+    const size_t out_bytes = al(dst1 * chunk) * 3 + al(dst1 * chunk * 3) * 3 + png_bytes;
     const size_t need = (size_t)nbuf * (in_bytes + out_bytes) + 4096;
+    if (want_png && !ctx->h_png_sizes) PCS_CUDA(ctx, cudaHostAlloc(&ctx->h_png_sizes, pcs_ctx::kHostBufs * 3 * 64 * sizeof(uint64_t), cudaHostAllocDefault));
+    if (want_png && chunk > 64) return set_err(ctx, PCS_ERR_ARG, "predict_pages_files: chunks of more than 64 pages");
     if (need > ctx->stage_bytes) {
         PCS_CUDA(ctx, cudaDeviceSynchronize());
         if (ctx->stage) cudaFree(ctx->stage);
@@ -876,7 +889,7 @@ int pcs_predict_pages_host(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h
         }
         ctx->stage_bytes = need;
     }
-    struct Buf { uint8_t *grey, *bin, *image, *binary, *labels, *color, *overlay, *inverted; } buf[pcs_ctx::kHostBufs];
+    struct Buf { uint8_t *grey, *bin, *image, *binary, *labels, *color, *overlay, *inverted, *png; uint64_t* png_sizes; } buf[pcs_ctx::kHostBufs];
     {
         uint8_t* p = reinterpret_cast<uint8_t*>(ctx->stage);
         for (int i = 0; i < nbuf; ++i) {
@@ -888,6 +901,7 @@ int pcs_predict_pages_host(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h
             buf[i].color = p; p += al(dst1 * chunk * 3);
             buf[i].overlay = p; p += al(dst1 * chunk * 3);
             buf[i].inverted = p; p += al(dst1 * chunk * 3);
+            buf[i].png = p; buf[i].png_sizes = reinterpret_cast<uint64_t*>(p + 3 * (size_t)chunk * dpng_stride); p += png_bytes;
         }
     }
     // PCSEG_TRACE_HOST: per-chunk device timeline (timing events on the three streams), printed at the end
@@ -914,6 +928,23 @@ int pcs_predict_pages_host(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h
     PCS_CUDA(ctx, cudaStreamWaitEvent(s_in, ctx->ev_fork, 0));
     PCS_CUDA(ctx, cudaStreamWaitEvent(s_out, ctx->ev_fork, 0));
     const int ahead = nbuf - 1;                                                        // copies in flight ahead of the compute
+    // PNG mode: the file lengths of a chunk reach the host first; once they are there the files themselves are copied
+    // (only their bytes, not the worst-case buffers).  The host waits for chunk c-1 after it has queued chunk c.
+    auto finish_files = [&](int c) -> int {
+        const int b = c % nbuf, p0 = first[c], m = count[c];
+        PCS_CUDA(ctx, cudaEventSynchronize(ctx->ev_sizes[b]));
+        const uint64_t* sz = ctx->h_png_sizes + (size_t)b * 3 * 64;
+        for (int k = 0; k < 3; ++k)
+            for (int j = 0; j < m; ++j) {
+                const uint64_t bytes = sz[k * 64 + j];
+                if (bytes > png_bound) return set_err(ctx, PCS_ERR_CUDA, "predict_pages_files: encoder reported %llu bytes", (unsigned long long)bytes);
+                h_png_sizes[(size_t)(p0 + j) * 3 + k] = bytes;
+                PCS_CUDA(ctx, cudaMemcpyAsync(h_png + ((size_t)(p0 + j) * 3 + k) * png_stride, buf[b].png + ((size_t)k * chunk + j) * dpng_stride,
+                                              bytes, cudaMemcpyDeviceToHost, s_out));
+            }
+        PCS_CUDA(ctx, cudaEventRecord(ctx->ev_d2h[b], s_out));
+        return PCS_OK;
+    };
     for (int c = 0; c < std::min(ahead, nchunks); ++c) PCS_TRY(enqueue_h2d(c));
     for (int c = 0; c < nchunks; ++c) {
         const int b = c % nbuf, p0 = first[c], m = count[c];
@@ -926,11 +957,18 @@ int pcs_predict_pages_host(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h
             PCS_TRY(pcs_forward(ctx, buf[b].image, buf[b].binary, m, Hs, Ws, buf[b].labels, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
             PCS_TRY(pcs_cc_majority(ctx, buf[b].labels, buf[b].binary, m, Hs, Ws, ctx->n_classes));
             if (want_masks)
-                PCS_TRY(pcs_masks(ctx, buf[b].labels, buf[b].binary, m, Hs, Ws, lut, ctx->n_classes, h_color ? buf[b].color : nullptr,
-                                  h_overlay ? buf[b].overlay : nullptr, h_inverted ? buf[b].inverted : nullptr));
+                PCS_TRY(pcs_masks(ctx, buf[b].labels, buf[b].binary, m, Hs, Ws, lut, ctx->n_classes, (h_color || want_png) ? buf[b].color : nullptr,
+                                  (h_overlay || want_png) ? buf[b].overlay : nullptr, (h_inverted || want_png) ? buf[b].inverted : nullptr));
         } else {
             PCS_TRY(pcs_forward(ctx, buf[b].image, buf[b].binary, m, Hs, Ws, buf[b].labels, nullptr, nullptr, want_masks ? lut : nullptr,
-                                h_color ? buf[b].color : nullptr, h_overlay ? buf[b].overlay : nullptr, h_inverted ? buf[b].inverted : nullptr));
+                                (h_color || want_png) ? buf[b].color : nullptr, (h_overlay || want_png) ? buf[b].overlay : nullptr,
+                                (h_inverted || want_png) ? buf[b].inverted : nullptr));
+        }
+        if (want_png) {
+            uint8_t* const kinds[3] = {buf[b].color, buf[b].overlay, buf[b].inverted};
+            for (int k = 0; k < 3; ++k)
+                PCS_TRY(pcs_png_encode(ctx, kinds[k], m, Hs, Ws, 3, 1, buf[b].png + (size_t)k * chunk * dpng_stride, dpng_stride,
+                                       buf[b].png_sizes + (size_t)k * chunk));
         }
         mark(st);
         PCS_CUDA(ctx, cudaEventRecord(ctx->ev_comp[b], st));
@@ -944,8 +982,17 @@ int pcs_predict_pages_host(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h
         if (h_overlay) PCS_CUDA(ctx, cudaMemcpyAsync(h_overlay + o3, buf[b].overlay, dst1 * m * 3, cudaMemcpyDeviceToHost, s_out));
         if (h_inverted) PCS_CUDA(ctx, cudaMemcpyAsync(h_inverted + o3, buf[b].inverted, dst1 * m * 3, cudaMemcpyDeviceToHost, s_out));
         mark(s_out);
-        PCS_CUDA(ctx, cudaEventRecord(ctx->ev_d2h[b], s_out));
+        if (want_png) {
+            for (int k = 0; k < 3; ++k)
+                PCS_CUDA(ctx, cudaMemcpyAsync(ctx->h_png_sizes + (size_t)b * 3 * 64 + k * 64, buf[b].png_sizes + (size_t)k * chunk, (size_t)m * 8,
+                                              cudaMemcpyDeviceToHost, s_out));
+            PCS_CUDA(ctx, cudaEventRecord(ctx->ev_sizes[b], s_out));
+            if (c >= 1) PCS_TRY(finish_files(c - 1));
+        } else {
+            PCS_CUDA(ctx, cudaEventRecord(ctx->ev_d2h[b], s_out));
+        }
     }
+    if (want_png) PCS_TRY(finish_files(nchunks - 1));
     // the compute stream joins the output stream, so the caller's stream order covers the whole call
     PCS_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_d2h[(nchunks - 1) % nbuf], 0));
     PCS_CUDA(ctx, cudaStreamSynchronize(s_out));
@@ -972,6 +1019,21 @@ int pcs_predict_pages_host(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h
         cudaEventDestroy(t0);
     }
     return PCS_OK;
+}
+
+int pcs_predict_pages_host(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h_bin, int n, int H, int W, int Hs, int Ws,
+                           int cc_majority, const uint8_t* lut, uint8_t* h_image, uint8_t* h_binary, uint8_t* h_labels,
+                           uint8_t* h_color, uint8_t* h_overlay, uint8_t* h_inverted) {
+    return predict_pages_host_impl(ctx, h_grey, h_bin, n, H, W, Hs, Ws, cc_majority, lut, h_image, h_binary, h_labels, h_color, h_overlay,
+                                   h_inverted, nullptr, 0, nullptr);
+}
+
+int pcs_predict_pages_files(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h_bin, int n, int H, int W, int Hs, int Ws,
+                            int cc_majority, const uint8_t* lut, uint8_t* h_labels, uint8_t* h_png, size_t png_stride,
+                            uint64_t* h_png_sizes) {
+    if (ctx && !h_png) return set_err(ctx, PCS_ERR_ARG, "predict_pages_files: null output");
+    return predict_pages_host_impl(ctx, h_grey, h_bin, n, H, W, Hs, Ws, cc_majority, lut, nullptr, nullptr, h_labels, nullptr, nullptr, nullptr,
+                                   h_png, png_stride, h_png_sizes);
 }
 
 int pcs_debug_activation(pcs_ctx* ctx, const char* name, float* h_out, size_t capacity_floats, int32_t* shape4) {

@@ -111,7 +111,8 @@ struct pcs_ctx {
     size_t stage_bytes = 0;
     cudaStream_t copy_streams[2] = {nullptr, nullptr};     // H2D / D2H streams of the host pipeline
     static constexpr int kHostBufs = 4;                    // staging buffers the host pipeline may rotate over
-    cudaEvent_t ev_h2d[kHostBufs] = {}, ev_comp[kHostBufs] = {}, ev_d2h[kHostBufs] = {}, ev_fork = nullptr;
+    cudaEvent_t ev_h2d[kHostBufs] = {}, ev_comp[kHostBufs] = {}, ev_d2h[kHostBufs] = {}, ev_sizes[kHostBufs] = {}, ev_fork = nullptr;
+    uint64_t* h_png_sizes = nullptr;                       // pinned [kHostBufs][3][64]: file lengths of the chunk in flight (PNG mode)
 
     std::string timings;
     std::vector<pcs::StageTime> stage_times;

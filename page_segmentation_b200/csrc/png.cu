@@ -214,18 +214,18 @@ __device__ __forceinline__ uint32_t run_bits(uint32_t v, uint32_t n) {
     const uint32_t m = n - 1, k = m / 258u, rem = m - 258u * k;
     return lit_bits(v) + 13u * k + (rem >= 3u ? match_bits(rem) : rem * lit_bits(v));
 }
-__device__ __forceinline__ void put_bits(uint32_t* __restrict__ w, unsigned long long& pos, uint32_t val, uint32_t nbits) {
-    const unsigned long long word = pos >> 5;
-    const uint32_t sh = (uint32_t)pos & 31u;
+// `w` is the scanline's bit buffer in SHARED memory (zeroed, OR-ed by the lanes of the warp), `pos` a bit offset in it
+__device__ __forceinline__ void put_bits(uint32_t* w, uint32_t& pos, uint32_t val, uint32_t nbits) {
+    const uint32_t word = pos >> 5, sh = pos & 31u;
     atomicOr(&w[word], val << sh);
     if (sh + nbits > 32u) atomicOr(&w[word + 1], val >> (32u - sh));
     pos += nbits;
 }
-__device__ __forceinline__ void put_literal(uint32_t* w, unsigned long long& pos, uint32_t v) {
+__device__ __forceinline__ void put_literal(uint32_t* w, uint32_t& pos, uint32_t v) {
     const uint32_t nb = lit_bits(v), code = v < 144u ? 0x30u + v : 0x190u + (v - 144u);
     put_bits(w, pos, __brev(code) >> (32u - nb), nb);                         // Huffman codes go in most significant bit first
 }
-__device__ __forceinline__ void put_match(uint32_t* w, unsigned long long& pos, uint32_t len) {
+__device__ __forceinline__ void put_match(uint32_t* w, uint32_t& pos, uint32_t len) {
     const uint32_t l = len - 3;
     uint32_t sym, e = 0;
     if (len == 258u) sym = 285u;
@@ -344,7 +344,10 @@ __global__ void __launch_bounds__(1024) png_rle_scan_kernel(const uint32_t* __re
     }
 }
 
-// one warp per scanline: the codes of its runs, OR-ed into the zero-filled file at their final bit positions
+// one warp per scanline: the codes of its runs are assembled in a shared-memory bit buffer (the lanes own consecutive
+// runs, i.e. adjacent bit ranges: shared-memory atomics) that starts at the scanline's bit offset inside its first file
+// word; whole words are then stored, and only the first and the last word - shared with the neighbouring scanlines -
+// are OR-ed into the zero-filled file
 __global__ void __launch_bounds__(32) png_rle_emit_kernel(const uint8_t* __restrict__ img, const PngPlan pl,
                                                           const unsigned long long* __restrict__ bitbase,
                                                           const uint8_t* __restrict__ ftypes, uint8_t* __restrict__ out) {
@@ -354,8 +357,13 @@ __global__ void __launch_bounds__(32) png_rle_emit_kernel(const uint8_t* __restr
     const uint32_t row = blockIdx.x, page = blockIdx.y, lane = threadIdx.x, npx = pl.line - 1;
     const uint8_t* raw = img + ((uint64_t)page * pl.H + row) * npx;
     const uint32_t R = rle_prepare(raw, row ? raw - npx : nullptr, ftypes[(uint64_t)page * pl.H + row], pl.line, (uint32_t)pl.C, fb, starts);
-    uint32_t* w = reinterpret_cast<uint32_t*>(out + (uint64_t)page * pl.stride);
-    unsigned long long carry = bitbase[(uint64_t)page * pl.H + row];
+    uint32_t* bitbuf = reinterpret_cast<uint32_t*>(sm + ((pl.line + 15u) & ~15u) + ((2u * pl.line + 15u) & ~15u));
+    const uint32_t buf_words = (9u * pl.line + 31u + 31u) / 32u + 1u;                      // worst case 9 bits per byte + the offset
+    for (uint32_t i = lane; i < buf_words; i += 32) bitbuf[i] = 0;
+    __syncwarp();
+    const unsigned long long base = bitbase[(uint64_t)page * pl.H + row];
+    uint32_t carry = (uint32_t)(base & 31ull);                                               // bit offset inside the first file word
+    uint32_t* const w = bitbuf;
     for (uint32_t r0 = 0; r0 < R; r0 += 32) {
         const uint32_t r = r0 + lane;
         uint32_t v = 0, n = 0, cost = 0;
@@ -369,7 +377,7 @@ __global__ void __launch_bounds__(32) png_rle_emit_kernel(const uint8_t* __restr
             if (lane >= (uint32_t)o) incl += t;
         }
         if (r < R) {
-            unsigned long long pos = carry + incl - cost;
+            uint32_t pos = carry + incl - cost;
             put_literal(w, pos, v);
             uint32_t m = n - 1;
             for (; m >= 258u; m -= 258u) put_match(w, pos, 258u);
@@ -377,6 +385,15 @@ __global__ void __launch_bounds__(32) png_rle_emit_kernel(const uint8_t* __restr
             else for (; m; --m) put_literal(w, pos, v);
         }
         carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    __syncwarp();
+    // carry = offset + bits of the scanline: words [0, nwords) of the buffer go to file words first_word + ...
+    uint32_t* fw = reinterpret_cast<uint32_t*>(out + (uint64_t)page * pl.stride) + (base >> 5);
+    const uint32_t nwords = (carry + 31u) >> 5;
+    for (uint32_t i = lane; i < nwords; i += 32) {
+        const uint32_t v = bitbuf[i];
+        if (i == 0 || i + 1 == nwords) { if (v) atomicOr(&fw[i], v); }
+        else fw[i] = v;
     }
 }
 
@@ -466,13 +483,21 @@ int launch_png_encode(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, i
         zbytes = nullptr;
     } else {
         zlib_max = bound - kHead - 16;
-        const size_t smem = ((pl.line + 15u) & ~15u) + 2 * (size_t)pl.line;
+        const size_t smem_count = ((pl.line + 15u) & ~15u) + 2 * (size_t)pl.line;
+        const size_t smem_emit = ((pl.line + 15u) & ~15u) + ((2 * (size_t)pl.line + 15u) & ~(size_t)15u) + ((9 * (size_t)pl.line + 62) / 32 + 2) * 4;
+        if (smem_emit > 48 * 1024) {
+            static bool set[64] = {};
+            if (ctx->device >= 64 || !set[ctx->device]) {
+                PCS_CUDA(ctx, cudaFuncSetAttribute(png_rle_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+                if (ctx->device < 64) set[ctx->device] = true;
+            }
+        }
         PCS_CUDA(ctx, cudaMemsetAsync(d_out, 0, (size_t)n * stride, st));               // the codes are OR-ed into place
-        png_rle_count_kernel<<<dim3(H, n), 32, smem, st>>>(d_img, pl, ab, bits, ftypes);
+        png_rle_count_kernel<<<dim3(H, n), 32, smem_count, st>>>(d_img, pl, ab, bits, ftypes);
         PCS_LAUNCH_CHECK(ctx, "png_rle_count_kernel");
         png_rle_scan_kernel<<<n, 1024, 0, st>>>(bits, pl, d_out, bitbase, zbytes);
         PCS_LAUNCH_CHECK(ctx, "png_rle_scan_kernel");
-        png_rle_emit_kernel<<<dim3(H, n), 32, smem, st>>>(d_img, pl, bitbase, ftypes, d_out);
+        png_rle_emit_kernel<<<dim3(H, n), 32, smem_emit, st>>>(d_img, pl, bitbase, ftypes, d_out);
         PCS_LAUNCH_CHECK(ctx, "png_rle_emit_kernel");
     }
     png_adler_kernel<<<n, 256, 0, st>>>(ab, d_out, pl, zbytes);

@@ -185,6 +185,17 @@ class PageBatchEngine:
                                     out.get("inverted"))
         return out
 
+    def run_host_files(self, h_pages: np.ndarray, scale: float, out: dict, cc_majority: bool = False):
+        """Like run_host, but the three masks of every page come back as PNG files (pcs_predict_pages_files): `out` holds
+        host arrays 'png' (n, 3, stride) uint8, 'png_sizes' (n, 3) uint64 and optionally 'labels' (ideally pinned).
+        Returns `out`; file (p, k) is out['png'][p, k, :out['png_sizes'][p, k]], k = 0 color, 1 overlay, 2 inverted."""
+        n, H, W = h_pages.shape
+        Hs, Ws = scaled_shape(H, W, scale)
+        self.ctx.use_torch_stream()
+        self.ctx.predict_pages_files(h_pages, h_pages, n, H, W, Hs, Ws, cc_majority, self.lut, out.get("labels"), out["png"],
+                                     out["png"].shape[2], out["png_sizes"])
+        return out
+
 
 def shard_pages(n_pages: int, rank: int, world: int) -> List[int]:
     """Static round-robin page sharding over ranks (pages are independent;

@@ -158,3 +158,27 @@ def test_output_data_writes_device_encoded_pngs(ctx, tmp_path):
     for sub, e in zip(("color", "overlay", "inverted"), exp[:3]):
         got = cv2.imread(str(tmp_path / sub / "page_0001.png"), cv2.IMREAD_COLOR)[..., ::-1]
         np.testing.assert_array_equal(got, e)
+
+
+@pytest.mark.parametrize("cc", [False, True])
+def test_batch_pipeline_with_png_output_matches_raw_masks(ctx, cc):
+    """pcs_predict_pages_files: the PNG files of a page batch decode to exactly the raw masks of pcs_predict_pages_host."""
+    import torch
+    from page_segmentation_b200.runtime import PageBatchEngine
+    lut = np.array([[255, 255, 255], [255, 0, 0], [0, 255, 0]], dtype=np.uint8)
+    eng = PageBatchEngine("fcn_skip", synth.make_weights("fcn_skip", 3, seed=4), 3, lut=lut)
+    n, H, W = 11, 420, 333                                          # 11 pages: ragged chunk schedule 2, 4, 1, 2, 2
+    pages = np.stack([synth.make_page(s, H, W, 18) for s in range(n)])
+    Hs, Ws = synth.scaled_shape(H, W, 1 / 3)
+    raw = {k: np.zeros((n, Hs, Ws) + ((3,) if k != "labels" else ()), np.uint8) for k in ("labels", "color", "overlay", "inverted")}
+    eng.run_host(pages, 1 / 3, raw, cc_majority=cc)
+    stride = (eng.ctx.png_bytes(Hs, Ws, 3, 1) + 255) // 256 * 256
+    out = {"labels": np.zeros((n, Hs, Ws), np.uint8), "png": torch.zeros((n, 3, stride), dtype=torch.uint8).pin_memory().numpy(),
+           "png_sizes": np.zeros((n, 3), np.uint64)}
+    eng.run_host_files(pages, 1 / 3, out, cc_majority=cc)
+    np.testing.assert_array_equal(out["labels"], raw["labels"])
+    for p in range(n):
+        for k, kind in enumerate(("color", "overlay", "inverted")):
+            blob = out["png"][p, k, :int(out["png_sizes"][p, k])].tobytes()
+            check_container(blob, raw[kind][p], sub_filter=True)
+    assert int(out["png_sizes"].max()) < raw["color"][0].size // 2
