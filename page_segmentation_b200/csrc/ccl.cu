@@ -372,10 +372,13 @@ int launch_cc_majority(pcs_ctx* ctx, uint8_t* d_pred, const uint8_t* d_binary, i
 // Boxes are rasterised through a 2-D difference array + prefix sums.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-bbox_accum_kernel(const int* __restrict__ parent, int H, int W, int* __restrict__ box /*[px][4]*/) {
+bbox_accum_kernel(const int* __restrict__ parent, int H, int W, int* __restrict__ box /*[px][4]*/, const uint8_t* __restrict__ fg) {
+    // fg (optional): the labelled image; when given, background pixels are recognised by their byte and their
+    // (then unwritten) parents are never read
     const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
     if (x >= W) return;
     const size_t page_off = (size_t)blockIdx.z * H * W;
+    if (fg && !fg[page_off + (size_t)y * W + x]) return;
     const int p = parent[page_off + (size_t)y * W + x];
     if (p == kBG) return;
     int* b = box + (page_off + p) * 4;
@@ -461,7 +464,7 @@ int launch_bounding_boxes(pcs_ctx* ctx, const uint8_t* d_pred, int n, int H, int
     for (int c = 0; c < n_classes; ++c) {
         PCS_TRY(ccl_roots(ctx, d_pred, n, H, W, c, true, parent, box, 4));
         dim3 g((W + 255) / 256, H, n);
-        bbox_accum_kernel<<<g, 256, 0, st>>>(parent, H, W, box);
+        bbox_accum_kernel<<<g, 256, 0, st>>>(parent, H, W, box, nullptr);
         PCS_LAUNCH_CHECK(ctx, "bbox_accum_kernel");
         PCS_CUDA(ctx, cudaMemsetAsync(diff, 0, diff_elems * 4, st));
         bbox_diff_kernel<<<g, 256, 0, st>>>(parent, H, W, box, diff);
@@ -548,12 +551,13 @@ otsu_fg_kernel(const uint8_t* __restrict__ img, size_t page_px, const int* __res
 }
 
 __global__ void __launch_bounds__(256)
-letter_heights_kernel(const int* __restrict__ parent, int H, int W, const int* __restrict__ box, unsigned* __restrict__ hh /*[n][64]*/) {
+letter_heights_kernel(const int* __restrict__ parent, const uint8_t* __restrict__ fg, int H, int W, const int* __restrict__ box,
+                      unsigned* __restrict__ hh /*[n][64]*/) {
     const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
     if (x >= W) return;
     const size_t page_off = (size_t)blockIdx.z * H * W;
     const int idx = y * W + x;
-    if (parent[page_off + idx] != idx) return;            // roots only
+    if (!fg[page_off + idx] || parent[page_off + idx] != idx) return;            // roots only (background parents are unwritten)
     const int* b = box + (page_off + idx) * 4;
     const int w = b[2] - (W - b[0]) + 1, h = b[3] - (H - b[1]) + 1;
     // 0.5 < w/h < 2  <=>  h < 2w and w < 2h (exact for these small integers)
@@ -599,11 +603,11 @@ int launch_char_height(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, 
     PCS_LAUNCH_CHECK(ctx, "otsu_kernel");
     otsu_fg_kernel<<<gflat, 256, 0, st>>>(d_img, page_px, thresh, inverse, fg);
     PCS_LAUNCH_CHECK(ctx, "otsu_fg_kernel");
-    PCS_TRY(ccl_roots(ctx, fg, n, H, W, 0, false, parent, box, 4, /*conn8=*/true));
+    PCS_TRY(ccl_roots(ctx, fg, n, H, W, 0, false, parent, box, 4, /*conn8=*/true, /*fg_only=*/true));
     const dim3 g((W + 255) / 256, H, n);
-    bbox_accum_kernel<<<g, 256, 0, st>>>(parent, H, W, box);
+    bbox_accum_kernel<<<g, 256, 0, st>>>(parent, H, W, box, fg);
     PCS_LAUNCH_CHECK(ctx, "bbox_accum_kernel");
-    letter_heights_kernel<<<g, 256, 0, st>>>(parent, H, W, box, hh);
+    letter_heights_kernel<<<g, 256, 0, st>>>(parent, fg, H, W, box, hh);
     PCS_LAUNCH_CHECK(ctx, "letter_heights_kernel");
     median_height_kernel<<<(n + 63) / 64, 64, 0, st>>>(hh, n, d_out);
     PCS_LAUNCH_CHECK(ctx, "median_height_kernel");
