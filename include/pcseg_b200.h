@@ -238,6 +238,35 @@ PCS_API int pcs_integral_image(pcs_ctx* ctx, const uint8_t* d_mask, int n, int H
 PCS_API int pcs_text_regions(pcs_ctx* ctx, const uint8_t* d_rgb, int H, int W, const uint8_t* colour,
                      int k_close, int k_open, int k_region, uint8_t* d_text_inv, uint8_t* d_region);
 
+/* ---- training step primitives (first version: fp32 on the CUDA cores): Network.train_dataset with batch 1,
+ * lib/network.py:151-161,167-242; metrics.loss, lib/metrics.py:8-9; Keras Adam with per-variable clipnorm as compiled
+ * at lib/network.py:91-103.  Tensors are planar float32 [C][H][W] on the device; the host side (lib/trainer.py)
+ * walks the graph of lib/model.py:45-92 / :206-234.
+ *   corr2d      : 'same' correlation, k in {1, 5}: y = act(b + x (*) w), w[c_out][c_in][k][k].  Serves Conv2D, the
+ *                 stride-1 Conv2DTranspose (flipped kernel), both input gradients (transposed / flipped kernel) and
+ *                 the logits; accumulate = 1 adds to y (gradients meeting at a skip connection).
+ *   wgrad       : dw[c_out][c_in][k][k] = sum over pixels of dy * shifted x
+ *   deconv2_*   : Conv2DTranspose(2x2, stride 2), k2[tap = 2i + j][c_out][c_in]
+ *   softmax_ce  : mean sparse cross entropy from logits over the Hc x Wc crop; d_loss_sum receives the SUM over pixels
+ *   adam        : one variable per offsets[i] .. offsets[i+1]: g *= grad_scale, clip_by_norm(g, clipnorm) when
+ *                 clipnorm > 0, m / v update, p -= lr_t * m / (sqrt(v) + eps) with lr_t computed by the caller */
+PCS_API int pcs_train_input(pcs_ctx* ctx, const uint8_t* d_image, int h, int w, float* d_plane, int H, int W);
+PCS_API int pcs_train_corr2d(pcs_ctx* ctx, const float* d_x, const float* d_w, const float* d_b, float* d_y,
+                     int c_in, int c_out, int H, int W, int k, int relu, int accumulate);
+PCS_API int pcs_train_wgrad(pcs_ctx* ctx, const float* d_x, const float* d_dy, float* d_dw, int c_in, int c_out, int H, int W, int k);
+PCS_API int pcs_train_bias_grad(pcs_ctx* ctx, const float* d_dy, float* d_db, int channels, size_t plane);
+PCS_API int pcs_train_relu_bwd(pcs_ctx* ctx, float* d_dy, const float* d_y, size_t n);
+PCS_API int pcs_train_maxpool_fwd(pcs_ctx* ctx, const float* d_x, float* d_y, int channels, int H, int W);
+PCS_API int pcs_train_maxpool_bwd(pcs_ctx* ctx, const float* d_x, const float* d_dy, float* d_dx, int channels, int H, int W, int accumulate);
+PCS_API int pcs_train_deconv2_fwd(pcs_ctx* ctx, const float* d_x, const float* d_k2, const float* d_b, float* d_y,
+                          int c_in, int c_out, int h, int w, int relu);
+PCS_API int pcs_train_deconv2_bwd_data(pcs_ctx* ctx, const float* d_dy, const float* d_k2, float* d_dx, int c_in, int c_out, int h, int w);
+PCS_API int pcs_train_deconv2_wgrad(pcs_ctx* ctx, const float* d_x, const float* d_dy, float* d_dk2, int c_in, int c_out, int h, int w);
+PCS_API int pcs_train_softmax_ce(pcs_ctx* ctx, const float* d_logits, const uint8_t* d_labels, int n_classes, int H, int W,
+                         int Hc, int Wc, float* d_dlogits, double* d_loss_sum);
+PCS_API int pcs_train_adam(pcs_ctx* ctx, float* d_params, const float* d_grads, float* d_m, float* d_v, const int64_t* d_offsets,
+                   int n_vars, float lr_t, float beta1, float beta2, float eps, float clipnorm, float grad_scale);
+
 /* ---- diagnostics ------------------------------------------------------ */
 /* copies one named internal activation of the last pcs_forward to a float32
  * NHWC host buffer (real channels only); returns the channel count or <0. */

@@ -796,6 +796,64 @@ int pcs_text_regions(pcs_ctx* ctx, const uint8_t* d_rgb, int H, int W, const uin
     return launch_text_regions(ctx, d_rgb, H, W, colour, k_close, k_open, k_region, d_text_inv, d_region);
 }
 
+// ---- training primitives (train.cu): thin argument checks, everything on the ctx stream
+#define PCS_TRAIN_ENTER(ctx, cond, what)                                                        \
+    if (!(ctx)) return PCS_ERR_ARG;                                                             \
+    if (!(cond)) return set_err((ctx), PCS_ERR_ARG, what ": null or bad argument");             \
+    PCS_CUDA((ctx), cudaSetDevice((ctx)->device));
+
+int pcs_train_corr2d(pcs_ctx* ctx, const float* d_x, const float* d_w, const float* d_b, float* d_y, int c_in, int c_out, int H, int W, int k,
+                     int relu, int accumulate) {
+    PCS_TRAIN_ENTER(ctx, d_x && d_w && d_y, "train_corr2d");
+    return train_corr2d(ctx, d_x, d_w, d_b, d_y, c_in, c_out, H, W, k, relu, accumulate);
+}
+int pcs_train_wgrad(pcs_ctx* ctx, const float* d_x, const float* d_dy, float* d_dw, int c_in, int c_out, int H, int W, int k) {
+    PCS_TRAIN_ENTER(ctx, d_x && d_dy && d_dw, "train_wgrad");
+    return train_wgrad(ctx, d_x, d_dy, d_dw, c_in, c_out, H, W, k);
+}
+int pcs_train_bias_grad(pcs_ctx* ctx, const float* d_dy, float* d_db, int channels, size_t plane) {
+    PCS_TRAIN_ENTER(ctx, d_dy && d_db && channels > 0 && plane > 0, "train_bias_grad");
+    return train_plane_sum(ctx, d_dy, d_db, channels, plane);
+}
+int pcs_train_relu_bwd(pcs_ctx* ctx, float* d_dy, const float* d_y, size_t n) {
+    PCS_TRAIN_ENTER(ctx, d_dy && d_y && n > 0, "train_relu_bwd");
+    return train_relu_bwd(ctx, d_dy, d_y, n);
+}
+int pcs_train_maxpool_fwd(pcs_ctx* ctx, const float* d_x, float* d_y, int channels, int H, int W) {
+    PCS_TRAIN_ENTER(ctx, d_x && d_y && channels > 0 && H > 0 && W > 0, "train_maxpool_fwd");
+    return train_maxpool(ctx, d_x, d_y, nullptr, nullptr, channels, H, W, 0);
+}
+int pcs_train_maxpool_bwd(pcs_ctx* ctx, const float* d_x, const float* d_dy, float* d_dx, int channels, int H, int W, int accumulate) {
+    PCS_TRAIN_ENTER(ctx, d_x && d_dy && d_dx && channels > 0 && H > 0 && W > 0, "train_maxpool_bwd");
+    return train_maxpool(ctx, d_x, nullptr, d_dy, d_dx, channels, H, W, accumulate);
+}
+int pcs_train_deconv2_fwd(pcs_ctx* ctx, const float* d_x, const float* d_k2, const float* d_b, float* d_y, int c_in, int c_out, int h, int w, int relu) {
+    PCS_TRAIN_ENTER(ctx, d_x && d_k2 && d_b && d_y && c_in > 0 && c_out > 0 && h > 0 && w > 0, "train_deconv2_fwd");
+    return train_deconv2(ctx, 0, d_x, d_k2, d_b, d_y, nullptr, nullptr, nullptr, c_in, c_out, h, w, relu);
+}
+int pcs_train_deconv2_bwd_data(pcs_ctx* ctx, const float* d_dy, const float* d_k2, float* d_dx, int c_in, int c_out, int h, int w) {
+    PCS_TRAIN_ENTER(ctx, d_dy && d_k2 && d_dx && c_in > 0 && c_out > 0 && h > 0 && w > 0, "train_deconv2_bwd_data");
+    return train_deconv2(ctx, 1, nullptr, d_k2, nullptr, nullptr, d_dy, d_dx, nullptr, c_in, c_out, h, w, 0);
+}
+int pcs_train_deconv2_wgrad(pcs_ctx* ctx, const float* d_x, const float* d_dy, float* d_dk2, int c_in, int c_out, int h, int w) {
+    PCS_TRAIN_ENTER(ctx, d_x && d_dy && d_dk2 && c_in > 0 && c_in < 65536 && c_out > 0 && h > 0 && w > 0, "train_deconv2_wgrad");
+    return train_deconv2(ctx, 2, d_x, nullptr, nullptr, nullptr, d_dy, nullptr, d_dk2, c_in, c_out, h, w, 0);
+}
+int pcs_train_softmax_ce(pcs_ctx* ctx, const float* d_logits, const uint8_t* d_labels, int n_classes, int H, int W, int Hc, int Wc,
+                         float* d_dlogits, double* d_loss_sum) {
+    PCS_TRAIN_ENTER(ctx, d_logits && d_labels && d_dlogits && d_loss_sum && n_classes > 0 && Hc > 0 && Wc > 0 && Hc <= H && Wc <= W, "train_softmax_ce");
+    return train_softmax_ce(ctx, d_logits, d_labels, n_classes, H, W, Hc, Wc, d_dlogits, d_loss_sum);
+}
+int pcs_train_input(pcs_ctx* ctx, const uint8_t* d_image, int h, int w, float* d_plane, int H, int W) {
+    PCS_TRAIN_ENTER(ctx, d_image && d_plane && h > 0 && w > 0 && H >= h && W >= w, "train_input");
+    return train_input_plane(ctx, d_image, h, w, d_plane, H, W);
+}
+int pcs_train_adam(pcs_ctx* ctx, float* d_params, const float* d_grads, float* d_m, float* d_v, const int64_t* d_offsets, int n_vars, float lr_t,
+                   float beta1, float beta2, float eps, float clipnorm, float grad_scale) {
+    PCS_TRAIN_ENTER(ctx, d_params && d_grads && d_m && d_v && d_offsets && n_vars > 0, "train_adam");
+    return train_adam(ctx, d_params, d_grads, d_m, d_v, reinterpret_cast<const long long*>(d_offsets), n_vars, lr_t, beta1, beta2, eps, clipnorm, grad_scale);
+}
+
 size_t pcs_png_bytes(int H, int W, int channels, int level) { return png_file_bytes(H, W, channels, level); }
 
 int pcs_png_encode(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, int channels, int level, uint8_t* d_out, size_t stride,

@@ -272,6 +272,19 @@ size_t png_file_bytes(int H, int W, int C, int level);
 int launch_png_encode(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, int C, int level, uint8_t* d_out, size_t stride,
                       unsigned long long* d_sizes);
 
+// train.cu  (fp32 CUDA-core training primitives, planar [C][H][W])
+int train_corr2d(pcs_ctx* ctx, const float* x, const float* w, const float* b, float* y, int Ci, int Co, int H, int W, int k, int relu, int acc);
+int train_wgrad(pcs_ctx* ctx, const float* x, const float* dy, float* dw, int Ci, int Co, int H, int W, int k);
+int train_plane_sum(pcs_ctx* ctx, const float* dy, float* db, int C, size_t plane);
+int train_relu_bwd(pcs_ctx* ctx, float* dy, const float* y, size_t n);
+int train_maxpool(pcs_ctx* ctx, const float* x, float* y, const float* dy, float* dx, int C, int H, int W, int acc);
+int train_deconv2(pcs_ctx* ctx, int mode, const float* x, const float* k2, const float* b, float* y, const float* dy, float* dx, float* dk2,
+                  int Ci, int Co, int h, int w, int relu);
+int train_softmax_ce(pcs_ctx* ctx, const float* logits, const uint8_t* labels, int C, int H, int W, int Hc, int Wc, float* dlogits, double* loss_sum);
+int train_input_plane(pcs_ctx* ctx, const uint8_t* img, int h, int w, float* out, int H, int W);
+int train_adam(pcs_ctx* ctx, float* p, const float* g, float* m, float* v, const long long* d_offsets, int nvars, float lr_t, float b1,
+               float b2, float eps, float clipnorm, float gscale);
+
 // conv_umma.cu  (tcgen05 / TMEM / TMA implicit GEMM)
 struct UmmaHeadArgs {              // fused FCN head epilogue (conv_umma.cu mode 2)
     const void* plog = nullptr;         // device float4 [n][2h][2w]: conv2 share of the logits (fcn_skip) or null

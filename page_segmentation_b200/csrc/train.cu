@@ -1,0 +1,335 @@
+// Training step primitives (BASELINE configs[4]; ocr4all_pixel_classifier/lib/network.py:167-242 `train_dataset`,
+// lib/metrics.py:8-9 `loss`, Keras Adam with clipnorm as compiled at network.py:91-103): forward with kept
+// activations, backward, loss and the optimizer for the FCN graphs of lib/model.py:45-92 / :206-234.
+//
+// First version: fp32 on the CUDA cores, one page per step per GPU (the reference trains with batch 1,
+// network.py:151-161), planar [C][H][W] tensors.  Every convolution of the graph - Conv2D, Conv2DTranspose with
+// stride 1 (a correlation with the flipped kernel), their input gradients (correlations with the transposed /
+// flipped kernel) and the 1x1 logits - is ONE 'same' correlation kernel over host-arranged weights
+// w[C_out][C_in][k][k]; weight gradients are pixel reductions per (C_out, C_in) pair.  The tensor-core forward of the
+// inference path is not used here: training needs the fp32 activations the reference keeps.
+#include "common.cuh"
+
+#include <cstdint>
+
+namespace pcs {
+namespace {
+
+constexpr int TX = 32, TY = 8, CO_T = 8;
+
+// y[co][r][c] = act(b[co] + sum_ci sum_t x[ci][r + ky - P][c + kx - P] * w[co][ci][t]), zero padding, P = (K - 1) / 2.
+// ACC: add to y instead of overwriting (second source of a concatenation, gradient accumulation).
+template <int K>
+__global__ void __launch_bounds__(TX * TY)
+corr2d_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ y, int Ci,
+              int Co, int H, int W, int relu, int acc_out) {
+    constexpr int P = (K - 1) / 2, IW = TX + K - 1, IH = TY + K - 1, KK = K * K;
+    __shared__ float s_in[IH][IW + 1];
+    __shared__ __align__(16) float s_w[KK][CO_T];
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY, co0 = blockIdx.z * CO_T;
+    float acc[CO_T];
+#pragma unroll
+    for (int o = 0; o < CO_T; ++o) acc[o] = 0.f;
+    for (int ci = 0; ci < Ci; ++ci) {
+        __syncthreads();
+        const float* xp = x + (size_t)ci * H * W;
+        for (int i = tid; i < IH * IW; i += TX * TY) {
+            const int r = i / IW, c = i - r * IW, gy = y0 + r - P, gx = x0 + c - P;
+            s_in[r][c] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(xp + (size_t)gy * W + gx) : 0.f;
+        }
+        for (int i = tid; i < KK * CO_T; i += TX * TY) {
+            const int t = i / CO_T, o = i - t * CO_T;
+            s_w[t][o] = (co0 + o < Co) ? __ldg(w + ((size_t)(co0 + o) * Ci + ci) * KK + t) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx) {
+                const float v = s_in[ty + ky][tx + kx];
+                const float4 w0 = *reinterpret_cast<const float4*>(&s_w[ky * K + kx][0]);
+                const float4 w1 = *reinterpret_cast<const float4*>(&s_w[ky * K + kx][4]);
+                acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]); acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
+                acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]); acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
+            }
+    }
+    const int gx = x0 + tx, gy = y0 + ty;
+    if (gx >= W || gy >= H) return;
+#pragma unroll
+    for (int o = 0; o < CO_T; ++o) {
+        if (co0 + o >= Co) break;
+        float* dst = y + ((size_t)(co0 + o) * H + gy) * W + gx;
+        float v = acc[o] + (b ? __ldg(b + co0 + o) : 0.f);
+        if (acc_out) v += *dst;
+        if (relu) v = fmaxf(v, 0.f);
+        *dst = v;
+    }
+}
+
+// dw[co][ci][t] = sum_{r,c} dy[co][r][c] * x[ci][r + ky - P][c + kx - P]; one block per (co, ci)
+template <int K>
+__global__ void __launch_bounds__(256)
+wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw, int Ci, int Co, int H, int W) {
+    constexpr int P = (K - 1) / 2, KK = K * K;
+    const int co = blockIdx.x, ci = blockIdx.y;
+    const float* xp = x + (size_t)ci * H * W;
+    const float* gp = dy + (size_t)co * H * W;
+    float acc[KK];
+#pragma unroll
+    for (int t = 0; t < KK; ++t) acc[t] = 0.f;
+    const int lane_x = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    for (int r = wrp; r < H; r += 8) {
+        for (int c = lane_x; c < W; c += 32) {
+            const float g = __ldg(gp + (size_t)r * W + c);
+            if (g == 0.f) continue;
+#pragma unroll
+            for (int ky = 0; ky < K; ++ky) {
+                const int yy = r + ky - P;
+                if (yy < 0 || yy >= H) continue;
+#pragma unroll
+                for (int kx = 0; kx < K; ++kx) {
+                    const int xx = c + kx - P;
+                    if (xx >= 0 && xx < W) acc[ky * K + kx] = fmaf(g, __ldg(xp + (size_t)yy * W + xx), acc[ky * K + kx]);
+                }
+            }
+        }
+    }
+    __shared__ float s_red[8][KK];
+#pragma unroll
+    for (int t = 0; t < KK; ++t) {
+        float v = acc[t];
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane_x == 0) s_red[wrp][t] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < KK) {
+        float v = 0.f;
+        for (int k = 0; k < 8; ++k) v += s_red[k][threadIdx.x];
+        dw[((size_t)co * Ci + ci) * KK + threadIdx.x] = v;
+    }
+}
+
+// db[c] = sum over the plane; one block per channel
+__global__ void __launch_bounds__(256) plane_sum_kernel(const float* __restrict__ dy, float* __restrict__ db, size_t plane) {
+    const float* p = dy + (size_t)blockIdx.x * plane;
+    float v = 0.f;
+    for (size_t i = threadIdx.x; i < plane; i += 256) v += p[i];
+    __shared__ float s[8];
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) { for (int k = 1; k < 8; ++k) v += s[k]; db[blockIdx.x] = v; }
+}
+
+__global__ void __launch_bounds__(256) relu_bwd_kernel(float* __restrict__ dy, const float* __restrict__ y, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256)
+        if (!(y[i] > 0.f)) dy[i] = 0.f;
+}
+
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int H, int W) {
+    const int ho = H / 2, wo = W / 2;
+    const size_t n = (size_t)C * ho * wo;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        const int c = (int)(i / ((size_t)ho * wo)), r = (int)((i / wo) % ho), q = (int)(i % wo);
+        const float* p = x + ((size_t)c * H + 2 * r) * W + 2 * q;
+        y[i] = fmaxf(fmaxf(p[0], p[1]), fmaxf(p[W], p[W + 1]));
+    }
+}
+// the gradient goes to the first maximum of the window in row-major order (TensorFlow / torch argmax convention)
+__global__ void __launch_bounds__(256)
+maxpool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, int C, int H, int W, int acc_out) {
+    const int ho = H / 2, wo = W / 2;
+    const size_t n = (size_t)C * ho * wo;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        const int c = (int)(i / ((size_t)ho * wo)), r = (int)((i / wo) % ho), q = (int)(i % wo);
+        const size_t o = ((size_t)c * H + 2 * r) * W + 2 * q;
+        const float v[4] = {x[o], x[o + 1], x[o + W], x[o + W + 1]};
+        int best = 0;
+        for (int k = 1; k < 4; ++k) if (v[k] > v[best]) best = k;
+        const float g = dy[i];
+        const size_t off[4] = {o, o + 1, o + W, o + W + 1};
+        for (int k = 0; k < 4; ++k) {
+            const float d = k == best ? g : 0.f;
+            dx[off[k]] = acc_out ? dx[off[k]] + d : d;
+        }
+    }
+}
+
+// Conv2DTranspose(2x2, stride 2): y[o][2r+i][2c+j] = act(b[o] + sum_ci x[ci][r][c] * k2[i*2+j][o][ci])
+__global__ void __launch_bounds__(256)
+deconv2_fwd_kernel(const float* __restrict__ x, const float* __restrict__ k2, const float* __restrict__ b, float* __restrict__ y, int Ci,
+                   int Co, int h, int w, int relu) {
+    const size_t n = (size_t)Co * 4 * h * w;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        const int W2 = 2 * w, H2 = 2 * h;
+        const int o = (int)(i / ((size_t)H2 * W2)), R = (int)((i / W2) % H2), Cc = (int)(i % W2);
+        const int r = R >> 1, c = Cc >> 1, tap = (R & 1) * 2 + (Cc & 1);
+        const float* kp = k2 + ((size_t)tap * Co + o) * Ci;
+        float v = b[o];
+        for (int ci = 0; ci < Ci; ++ci) v = fmaf(__ldg(x + ((size_t)ci * h + r) * w + c), __ldg(kp + ci), v);
+        y[i] = relu ? fmaxf(v, 0.f) : v;
+    }
+}
+// dx[ci][r][c] = sum_{tap,o} dy[o][2r+i][2c+j] * k2[tap][o][ci]
+__global__ void __launch_bounds__(256)
+deconv2_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ k2, float* __restrict__ dx, int Ci, int Co, int h, int w) {
+    const size_t n = (size_t)Ci * h * w;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        const int ci = (int)(i / ((size_t)h * w)), r = (int)((i / w) % h), c = (int)(i % w);
+        float v = 0.f;
+        for (int tap = 0; tap < 4; ++tap)
+            for (int o = 0; o < Co; ++o)
+                v = fmaf(__ldg(dy + ((size_t)o * 2 * h + 2 * r + (tap >> 1)) * 2 * w + 2 * c + (tap & 1)), __ldg(k2 + ((size_t)tap * Co + o) * Ci + ci), v);
+        dx[i] = v;
+    }
+}
+// dk2[tap][o][ci] = sum_{r,c} dy[o][2r+i][2c+j] * x[ci][r][c]; one block per (tap * Co + o, ci)
+__global__ void __launch_bounds__(256)
+deconv2_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dk2, int Ci, int Co, int h, int w) {
+    const int to = blockIdx.x, ci = blockIdx.y, tap = to / Co, o = to - tap * Co;
+    float v = 0.f;
+    for (int p = threadIdx.x; p < h * w; p += 256) {
+        const int r = p / w, c = p - r * w;
+        v = fmaf(__ldg(dy + ((size_t)o * 2 * h + 2 * r + (tap >> 1)) * 2 * w + 2 * c + (tap & 1)), __ldg(x + ((size_t)ci * h + r) * w + c), v);
+    }
+    __shared__ float s[8];
+    for (int k = 16; k; k >>= 1) v += __shfl_xor_sync(0xffffffffu, v, k);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) { for (int k = 1; k < 8; ++k) v += s[k]; dk2[((size_t)tap * Co + o) * Ci + ci] = v; }
+}
+
+// metrics.loss: mean over the Hc x Wc crop of the sparse softmax cross entropy from logits [C][H][W];
+// dlogits = (softmax - onehot) / (Hc * Wc) inside the crop, 0 outside; loss_sum accumulates the un-normalised sum
+__global__ void __launch_bounds__(256)
+softmax_ce_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ labels, int C, int H, int W, int Hc, int Wc,
+                  float* __restrict__ dlogits, double* __restrict__ loss_sum) {
+    const size_t plane = (size_t)H * W;
+    double local = 0.0;
+    const float inv = 1.f / ((float)Hc * (float)Wc);
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < plane; i += (size_t)gridDim.x * 256) {
+        const int r = (int)(i / W), c = (int)(i % W);
+        if (r >= Hc || c >= Wc) { for (int k = 0; k < C; ++k) dlogits[k * plane + i] = 0.f; continue; }
+        float mx = logits[i];
+        for (int k = 1; k < C; ++k) mx = fmaxf(mx, logits[k * plane + i]);
+        float sum = 0.f;
+        for (int k = 0; k < C; ++k) sum += expf(logits[k * plane + i] - mx);
+        const int lab = labels[(size_t)r * Wc + c];
+        const float lse = mx + logf(sum);
+        local += (double)(lse - logits[(size_t)lab * plane + i]);
+        for (int k = 0; k < C; ++k) dlogits[k * plane + i] = (expf(logits[k * plane + i] - lse) - (k == lab ? 1.f : 0.f)) * inv;
+    }
+    for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(loss_sum, local);
+}
+
+// x/255 of the uint8 page into the zero-padded fp32 plane (architecture.py:67-68, model.py:20-26)
+__global__ void __launch_bounds__(256) input_plane_kernel(const uint8_t* __restrict__ img, int h, int w, float* __restrict__ out, int H, int W) {
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < (size_t)H * W; i += (size_t)gridDim.x * 256) {
+        const int r = (int)(i / W), c = (int)(i % W);
+        out[i] = (r < h && c < w) ? (float)img[(size_t)r * w + c] / 255.0f : 0.f;
+    }
+}
+
+// Keras Adam with clipnorm (TF <= 2.5 clips every variable separately): one block per variable computes the norm,
+// then updates  m, v, p  with lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t),  p -= lr_t * m / (sqrt(v) + eps)
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, const long long* __restrict__ offs,
+            float lr_t, float b1, float b2, float eps, float clipnorm, float gscale) {
+    const long long a = offs[blockIdx.x], b = offs[blockIdx.x + 1];
+    float ss = 0.f;
+    for (long long i = a + threadIdx.x; i < b; i += 256) { const float gi = g[i] * gscale; ss = fmaf(gi, gi, ss); }
+    __shared__ float s[8];
+    __shared__ float s_scale;
+    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; ++k) ss += s[k];
+        const float norm = sqrtf(ss);
+        s_scale = (clipnorm > 0.f && norm > clipnorm) ? clipnorm / norm : 1.f;       // tf.clip_by_norm
+    }
+    __syncthreads();
+    const float sc = s_scale * gscale;
+    for (long long i = a + threadIdx.x; i < b; i += 256) {
+        const float gi = g[i] * sc;
+        const float mi = b1 * m[i] + (1.f - b1) * gi, vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+    }
+}
+
+inline unsigned blocks_for(size_t n) { return (unsigned)std::min<size_t>((n + 255) / 256, 148 * 16); }
+
+}  // namespace
+
+int train_corr2d(pcs_ctx* ctx, const float* x, const float* w, const float* b, float* y, int Ci, int Co, int H, int W, int k, int relu, int acc) {
+    if (Ci <= 0 || Co <= 0 || H <= 0 || W <= 0 || (k != 1 && k != 5)) return set_err(ctx, PCS_ERR_ARG, "train_corr2d: bad shape or kernel size %d", k);
+    dim3 grid((W + TX - 1) / TX, (H + TY - 1) / TY, (Co + CO_T - 1) / CO_T), block(TX, TY);
+    if (grid.y > 65535 || grid.z > 65535) return set_err(ctx, PCS_ERR_ARG, "train_corr2d: grid too large");
+    if (k == 5) corr2d_kernel<5><<<grid, block, 0, ctx->stream>>>(x, w, b, y, Ci, Co, H, W, relu, acc);
+    else corr2d_kernel<1><<<grid, block, 0, ctx->stream>>>(x, w, b, y, Ci, Co, H, W, relu, acc);
+    PCS_LAUNCH_CHECK(ctx, "corr2d_kernel");
+    return PCS_OK;
+}
+
+int train_wgrad(pcs_ctx* ctx, const float* x, const float* dy, float* dw, int Ci, int Co, int H, int W, int k) {
+    if (Ci <= 0 || Co <= 0 || H <= 0 || W <= 0 || (k != 1 && k != 5) || Ci > 65535) return set_err(ctx, PCS_ERR_ARG, "train_wgrad: bad shape");
+    if (k == 5) wgrad_kernel<5><<<dim3(Co, Ci), 256, 0, ctx->stream>>>(x, dy, dw, Ci, Co, H, W);
+    else wgrad_kernel<1><<<dim3(Co, Ci), 256, 0, ctx->stream>>>(x, dy, dw, Ci, Co, H, W);
+    PCS_LAUNCH_CHECK(ctx, "wgrad_kernel");
+    return PCS_OK;
+}
+
+int train_plane_sum(pcs_ctx* ctx, const float* dy, float* db, int C, size_t plane) {
+    plane_sum_kernel<<<C, 256, 0, ctx->stream>>>(dy, db, plane);
+    PCS_LAUNCH_CHECK(ctx, "plane_sum_kernel");
+    return PCS_OK;
+}
+
+int train_relu_bwd(pcs_ctx* ctx, float* dy, const float* y, size_t n) {
+    relu_bwd_kernel<<<blocks_for(n), 256, 0, ctx->stream>>>(dy, y, n);
+    PCS_LAUNCH_CHECK(ctx, "relu_bwd_kernel");
+    return PCS_OK;
+}
+
+int train_maxpool(pcs_ctx* ctx, const float* x, float* y, const float* dy, float* dx, int C, int H, int W, int acc) {
+    if ((H | W) & 1) return set_err(ctx, PCS_ERR_ARG, "train_maxpool: odd plane");
+    const size_t n = (size_t)C * (H / 2) * (W / 2);
+    if (dx) maxpool_bwd_kernel<<<blocks_for(n), 256, 0, ctx->stream>>>(x, dy, dx, C, H, W, acc);
+    else maxpool_fwd_kernel<<<blocks_for(n), 256, 0, ctx->stream>>>(x, y, C, H, W);
+    PCS_LAUNCH_CHECK(ctx, "maxpool kernel");
+    return PCS_OK;
+}
+
+int train_deconv2(pcs_ctx* ctx, int mode, const float* x, const float* k2, const float* b, float* y, const float* dy, float* dx, float* dk2,
+                  int Ci, int Co, int h, int w, int relu) {
+    if (mode == 0) deconv2_fwd_kernel<<<blocks_for((size_t)Co * 4 * h * w), 256, 0, ctx->stream>>>(x, k2, b, y, Ci, Co, h, w, relu);
+    else if (mode == 1) deconv2_bwd_data_kernel<<<blocks_for((size_t)Ci * h * w), 256, 0, ctx->stream>>>(dy, k2, dx, Ci, Co, h, w);
+    else deconv2_wgrad_kernel<<<dim3(4 * Co, Ci), 256, 0, ctx->stream>>>(x, dy, dk2, Ci, Co, h, w);
+    PCS_LAUNCH_CHECK(ctx, "deconv2 kernel");
+    return PCS_OK;
+}
+
+int train_softmax_ce(pcs_ctx* ctx, const float* logits, const uint8_t* labels, int C, int H, int W, int Hc, int Wc, float* dlogits, double* loss_sum) {
+    PCS_CUDA(ctx, cudaMemsetAsync(loss_sum, 0, sizeof(double), ctx->stream));
+    softmax_ce_kernel<<<blocks_for((size_t)H * W), 256, 0, ctx->stream>>>(logits, labels, C, H, W, Hc, Wc, dlogits, loss_sum);
+    PCS_LAUNCH_CHECK(ctx, "softmax_ce_kernel");
+    return PCS_OK;
+}
+
+int train_input_plane(pcs_ctx* ctx, const uint8_t* img, int h, int w, float* out, int H, int W) {
+    input_plane_kernel<<<blocks_for((size_t)H * W), 256, 0, ctx->stream>>>(img, h, w, out, H, W);
+    PCS_LAUNCH_CHECK(ctx, "input_plane_kernel");
+    return PCS_OK;
+}
+
+int train_adam(pcs_ctx* ctx, float* p, const float* g, float* m, float* v, const long long* d_offsets, int nvars, float lr_t, float b1,
+               float b2, float eps, float clipnorm, float gscale) {
+    adam_kernel<<<nvars, 256, 0, ctx->stream>>>(p, g, m, v, d_offsets, lr_t, b1, b2, eps, clipnorm, gscale);
+    PCS_LAUNCH_CHECK(ctx, "adam_kernel");
+    return PCS_OK;
+}
+
+}  // namespace pcs
