@@ -67,22 +67,36 @@ corr2d_kernel(const float* __restrict__ x, const float* __restrict__ w, const fl
     }
 }
 
-// dw[co][ci][t] = sum_{r,c} dy[co][r][c] * x[ci][r + ky - P][c + kx - P]; one block per (co, ci)
+// dw[co][ci][t] = sum_{r,c} dy[co][r][c] * x[ci][r + ky - P][c + kx - P].  A block owns WG_CO output channels of one input
+// channel over a band of rows: the K*K shifted x values of a pixel are loaded once and used for all WG_CO gradients
+// (one block per (co, ci) pair re-read them per output channel, and conv1's 20 pairs left 128 SMs idle); bands are
+// combined with atomicAdd into the zero-filled dw.
+constexpr int WG_CO = 4;
+
 template <int K>
 __global__ void __launch_bounds__(256)
-wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw, int Ci, int Co, int H, int W) {
+wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw, int Ci, int Co, int H, int W, int band) {
     constexpr int P = (K - 1) / 2, KK = K * K;
-    const int co = blockIdx.x, ci = blockIdx.y;
+    const int co0 = blockIdx.x * WG_CO, ci = blockIdx.y;
+    const int r0 = blockIdx.z * band, r1 = min(H, r0 + band);
     const float* xp = x + (size_t)ci * H * W;
-    const float* gp = dy + (size_t)co * H * W;
-    float acc[KK];
+    const size_t plane = (size_t)H * W;
+    float acc[WG_CO][KK];
 #pragma unroll
-    for (int t = 0; t < KK; ++t) acc[t] = 0.f;
+    for (int o = 0; o < WG_CO; ++o)
+#pragma unroll
+        for (int t = 0; t < KK; ++t) acc[o][t] = 0.f;
     const int lane_x = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-    for (int r = wrp; r < H; r += 8) {
+    for (int r = r0 + wrp; r < r1; r += 8) {
         for (int c = lane_x; c < W; c += 32) {
-            const float g = __ldg(gp + (size_t)r * W + c);
-            if (g == 0.f) continue;
+            float g[WG_CO];
+            bool any = false;
+#pragma unroll
+            for (int o = 0; o < WG_CO; ++o) {
+                g[o] = (co0 + o < Co) ? __ldg(dy + (size_t)(co0 + o) * plane + (size_t)r * W + c) : 0.f;
+                any |= g[o] != 0.f;
+            }
+            if (!any) continue;
 #pragma unroll
             for (int ky = 0; ky < K; ++ky) {
                 const int yy = r + ky - P;
@@ -90,23 +104,31 @@ wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* _
 #pragma unroll
                 for (int kx = 0; kx < K; ++kx) {
                     const int xx = c + kx - P;
-                    if (xx >= 0 && xx < W) acc[ky * K + kx] = fmaf(g, __ldg(xp + (size_t)yy * W + xx), acc[ky * K + kx]);
+                    if (xx < 0 || xx >= W) continue;
+                    const float xv = __ldg(xp + (size_t)yy * W + xx);
+#pragma unroll
+                    for (int o = 0; o < WG_CO; ++o) acc[o][ky * K + kx] = fmaf(g[o], xv, acc[o][ky * K + kx]);
                 }
             }
         }
     }
-    __shared__ float s_red[8][KK];
+    __shared__ float s_red[8][WG_CO * KK];
 #pragma unroll
-    for (int t = 0; t < KK; ++t) {
-        float v = acc[t];
-        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane_x == 0) s_red[wrp][t] = v;
-    }
+    for (int o = 0; o < WG_CO; ++o)
+#pragma unroll
+        for (int t = 0; t < KK; ++t) {
+            float v = acc[o][t];
+            for (int k = 16; k; k >>= 1) v += __shfl_xor_sync(0xffffffffu, v, k);
+            if (lane_x == 0) s_red[wrp][o * KK + t] = v;
+        }
     __syncthreads();
-    if (threadIdx.x < KK) {
-        float v = 0.f;
-        for (int k = 0; k < 8; ++k) v += s_red[k][threadIdx.x];
-        dw[((size_t)co * Ci + ci) * KK + threadIdx.x] = v;
+    if (threadIdx.x < WG_CO * KK) {
+        const int o = threadIdx.x / KK, t = threadIdx.x - o * KK;
+        if (co0 + o < Co) {
+            float v = 0.f;
+            for (int k = 0; k < 8; ++k) v += s_red[k][threadIdx.x];
+            atomicAdd(dw + ((size_t)(co0 + o) * Ci + ci) * KK + t, v);
+        }
     }
 }
 
@@ -276,8 +298,14 @@ int train_corr2d(pcs_ctx* ctx, const float* x, const float* w, const float* b, f
 
 int train_wgrad(pcs_ctx* ctx, const float* x, const float* dy, float* dw, int Ci, int Co, int H, int W, int k) {
     if (Ci <= 0 || Co <= 0 || H <= 0 || W <= 0 || (k != 1 && k != 5) || Ci > 65535) return set_err(ctx, PCS_ERR_ARG, "train_wgrad: bad shape");
-    if (k == 5) wgrad_kernel<5><<<dim3(Co, Ci), 256, 0, ctx->stream>>>(x, dy, dw, Ci, Co, H, W);
-    else wgrad_kernel<1><<<dim3(Co, Ci), 256, 0, ctx->stream>>>(x, dy, dw, Ci, Co, H, W);
+    PCS_CUDA(ctx, cudaMemsetAsync(dw, 0, (size_t)Co * Ci * k * k * sizeof(float), ctx->stream));
+    const int pairs = ((Co + WG_CO - 1) / WG_CO) * Ci;
+    int bands = std::max(1, std::min((H + 7) / 8, (148 * 6 + pairs - 1) / pairs));       // enough blocks to fill the GPU a few times
+    const int band = ((H + bands - 1) / bands + 7) / 8 * 8;
+    bands = (H + band - 1) / band;
+    const dim3 grid((Co + WG_CO - 1) / WG_CO, Ci, bands);
+    if (k == 5) wgrad_kernel<5><<<grid, 256, 0, ctx->stream>>>(x, dy, dw, Ci, Co, H, W, band);
+    else wgrad_kernel<1><<<grid, 256, 0, ctx->stream>>>(x, dy, dw, Ci, Co, H, W, band);
     PCS_LAUNCH_CHECK(ctx, "wgrad_kernel");
     return PCS_OK;
 }
