@@ -74,59 +74,65 @@ corr2d_kernel(const float* __restrict__ x, const float* __restrict__ w, const fl
 constexpr int WG_CO = 4;
 
 template <int K>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(TX * TY)
 wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw, int Ci, int Co, int H, int W, int band) {
-    constexpr int P = (K - 1) / 2, KK = K * K;
+    // the band is walked in 32 x 8 pixel tiles staged in shared memory (x with its halo, dy of the WG_CO channels):
+    // no bounds tests and no repeated global loads in the 25 x WG_CO inner products
+    constexpr int P = (K - 1) / 2, KK = K * K, IW = TX + K - 1, IH = TY + K - 1;
+    __shared__ float s_in[IH][IW + 1];
+    __shared__ float s_red[TY][WG_CO * KK];
     const int co0 = blockIdx.x * WG_CO, ci = blockIdx.y;
     const int r0 = blockIdx.z * band, r1 = min(H, r0 + band);
     const float* xp = x + (size_t)ci * H * W;
     const size_t plane = (size_t)H * W;
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
     float acc[WG_CO][KK];
 #pragma unroll
     for (int o = 0; o < WG_CO; ++o)
 #pragma unroll
         for (int t = 0; t < KK; ++t) acc[o][t] = 0.f;
-    const int lane_x = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-    for (int r = r0 + wrp; r < r1; r += 8) {
-        for (int c = lane_x; c < W; c += 32) {
+    for (int y0 = r0; y0 < r1; y0 += TY)
+        for (int x0 = 0; x0 < W; x0 += TX) {
+            __syncthreads();
+            for (int i = tid; i < IH * IW; i += TX * TY) {
+                const int r = i / IW, c = i - r * IW, gy = y0 + r - P, gx = x0 + c - P;
+                s_in[r][c] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(xp + (size_t)gy * W + gx) : 0.f;
+            }
+            __syncthreads();
+            const int gy = y0 + ty, gx = x0 + tx;
+            if (gy >= r1 || gx >= W) continue;
             float g[WG_CO];
             bool any = false;
 #pragma unroll
             for (int o = 0; o < WG_CO; ++o) {
-                g[o] = (co0 + o < Co) ? __ldg(dy + (size_t)(co0 + o) * plane + (size_t)r * W + c) : 0.f;
+                g[o] = (co0 + o < Co) ? __ldg(dy + (size_t)(co0 + o) * plane + (size_t)gy * W + gx) : 0.f;
                 any |= g[o] != 0.f;
             }
             if (!any) continue;
 #pragma unroll
-            for (int ky = 0; ky < K; ++ky) {
-                const int yy = r + ky - P;
-                if (yy < 0 || yy >= H) continue;
+            for (int ky = 0; ky < K; ++ky)
 #pragma unroll
                 for (int kx = 0; kx < K; ++kx) {
-                    const int xx = c + kx - P;
-                    if (xx < 0 || xx >= W) continue;
-                    const float xv = __ldg(xp + (size_t)yy * W + xx);
+                    const float xv = s_in[ty + ky][tx + kx];
 #pragma unroll
                     for (int o = 0; o < WG_CO; ++o) acc[o][ky * K + kx] = fmaf(g[o], xv, acc[o][ky * K + kx]);
                 }
-            }
         }
-    }
-    __shared__ float s_red[8][WG_CO * KK];
+    __syncthreads();
 #pragma unroll
     for (int o = 0; o < WG_CO; ++o)
 #pragma unroll
         for (int t = 0; t < KK; ++t) {
             float v = acc[o][t];
             for (int k = 16; k; k >>= 1) v += __shfl_xor_sync(0xffffffffu, v, k);
-            if (lane_x == 0) s_red[wrp][o * KK + t] = v;
+            if (tx == 0) s_red[ty][o * KK + t] = v;
         }
     __syncthreads();
-    if (threadIdx.x < WG_CO * KK) {
-        const int o = threadIdx.x / KK, t = threadIdx.x - o * KK;
+    if (tid < WG_CO * KK) {
+        const int o = tid / KK, t = tid - o * KK;
         if (co0 + o < Co) {
             float v = 0.f;
-            for (int k = 0; k < 8; ++k) v += s_red[k][threadIdx.x];
+            for (int k = 0; k < TY; ++k) v += s_red[k][tid];
             atomicAdd(dw + ((size_t)(co0 + o) * Ci + ci) * KK + t, v);
         }
     }
@@ -254,27 +260,33 @@ __global__ void __launch_bounds__(256) input_plane_kernel(const uint8_t* __restr
     }
 }
 
-// Keras Adam with clipnorm (TF <= 2.5 clips every variable separately): one block per variable computes the norm,
-// then updates  m, v, p  with lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t),  p -= lr_t * m / (sqrt(v) + eps)
+// Keras Adam with clipnorm (TF <= 2.5 clips every variable separately).  grid = (variables, kAdamBlocks): first the
+// squared norms (atomicAdd per block into sumsq[var]), then  m, v, p  with lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t),
+// p -= lr_t * m / (sqrt(v) + eps)
+constexpr int kAdamBlocks = 16;
+
 __global__ void __launch_bounds__(256)
-adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, const long long* __restrict__ offs,
-            float lr_t, float b1, float b2, float eps, float clipnorm, float gscale) {
+grad_sumsq_kernel(const float* __restrict__ g, const long long* __restrict__ offs, float gscale, float* __restrict__ sumsq) {
     const long long a = offs[blockIdx.x], b = offs[blockIdx.x + 1];
     float ss = 0.f;
-    for (long long i = a + threadIdx.x; i < b; i += 256) { const float gi = g[i] * gscale; ss = fmaf(gi, gi, ss); }
+    for (long long i = a + (long long)blockIdx.y * 256 + threadIdx.x; i < b; i += 256LL * gridDim.y) { const float gi = g[i] * gscale; ss = fmaf(gi, gi, ss); }
     __shared__ float s[8];
-    __shared__ float s_scale;
     for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = ss;
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int k = 1; k < 8; ++k) ss += s[k];
-        const float norm = sqrtf(ss);
-        s_scale = (clipnorm > 0.f && norm > clipnorm) ? clipnorm / norm : 1.f;       // tf.clip_by_norm
+        if (ss != 0.f) atomicAdd(&sumsq[blockIdx.x], ss);
     }
-    __syncthreads();
-    const float sc = s_scale * gscale;
-    for (long long i = a + threadIdx.x; i < b; i += 256) {
+}
+
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, const long long* __restrict__ offs,
+            const float* __restrict__ sumsq, float lr_t, float b1, float b2, float eps, float clipnorm, float gscale) {
+    const long long a = offs[blockIdx.x], b = offs[blockIdx.x + 1];
+    const float norm = sqrtf(sumsq[blockIdx.x]);
+    const float sc = ((clipnorm > 0.f && norm > clipnorm) ? clipnorm / norm : 1.f) * gscale;       // tf.clip_by_norm
+    for (long long i = a + (long long)blockIdx.y * 256 + threadIdx.x; i < b; i += 256LL * gridDim.y) {
         const float gi = g[i] * sc;
         const float mi = b1 * m[i] + (1.f - b1) * gi, vi = b2 * v[i] + (1.f - b2) * gi * gi;
         m[i] = mi; v[i] = vi;
@@ -304,8 +316,8 @@ int train_wgrad(pcs_ctx* ctx, const float* x, const float* dy, float* dw, int Ci
     const int band = ((H + bands - 1) / bands + 7) / 8 * 8;
     bands = (H + band - 1) / band;
     const dim3 grid((Co + WG_CO - 1) / WG_CO, Ci, bands);
-    if (k == 5) wgrad_kernel<5><<<grid, 256, 0, ctx->stream>>>(x, dy, dw, Ci, Co, H, W, band);
-    else wgrad_kernel<1><<<grid, 256, 0, ctx->stream>>>(x, dy, dw, Ci, Co, H, W, band);
+    if (k == 5) wgrad_kernel<5><<<grid, dim3(TX, TY), 0, ctx->stream>>>(x, dy, dw, Ci, Co, H, W, band);
+    else wgrad_kernel<1><<<grid, dim3(TX, TY), 0, ctx->stream>>>(x, dy, dw, Ci, Co, H, W, band);
     PCS_LAUNCH_CHECK(ctx, "wgrad_kernel");
     return PCS_OK;
 }
@@ -355,7 +367,12 @@ int train_input_plane(pcs_ctx* ctx, const uint8_t* img, int h, int w, float* out
 
 int train_adam(pcs_ctx* ctx, float* p, const float* g, float* m, float* v, const long long* d_offsets, int nvars, float lr_t, float b1,
                float b2, float eps, float clipnorm, float gscale) {
-    adam_kernel<<<nvars, 256, 0, ctx->stream>>>(p, g, m, v, d_offsets, lr_t, b1, b2, eps, clipnorm, gscale);
+    PCS_TRY(scratch_reserve(ctx, (size_t)nvars * sizeof(float) + 256));
+    float* sumsq = reinterpret_cast<float*>(ctx->scratch);
+    PCS_CUDA(ctx, cudaMemsetAsync(sumsq, 0, (size_t)nvars * sizeof(float), ctx->stream));
+    grad_sumsq_kernel<<<dim3(nvars, kAdamBlocks), 256, 0, ctx->stream>>>(g, d_offsets, gscale, sumsq);
+    PCS_LAUNCH_CHECK(ctx, "grad_sumsq_kernel");
+    adam_kernel<<<dim3(nvars, kAdamBlocks), 256, 0, ctx->stream>>>(p, g, m, v, d_offsets, sumsq, lr_t, b1, b2, eps, clipnorm, gscale);
     PCS_LAUNCH_CHECK(ctx, "adam_kernel");
     return PCS_OK;
 }
