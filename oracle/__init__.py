@@ -15,6 +15,9 @@ PARITY, per stage:
   * UNPINNED: prepare_images (scikit-image 0.17.2 resize / rescale), the network graphs (tensorflow 2.5), the
     Keras HDF5 container (h5py) and ColorMap (ocr4all-pylib) - see below.
 
+The training step (oracle/train.py: torch autograd on the restated graph + a numpy restatement of Keras' Adam with
+clipnorm) inherits the network's status: unpinned, checked against finite differences and a hand-computed Adam step.
+
 For the unpinned stages: the reference (`ocr4all_pixel_classifier` 0.6.5) ships no
 tests, golden vectors or fixtures, and its arithmetic lives in third-party
 packages that are not installed here and cannot be (tensorflow==2.5.0,
