@@ -184,48 +184,122 @@ maxpool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, fl
     }
 }
 
-// Conv2DTranspose(2x2, stride 2): y[o][2r+i][2c+j] = act(b[o] + sum_ci x[ci][r][c] * k2[i*2+j][o][ci])
+// Conv2DTranspose(2x2, stride 2): y[o][2r+i][2c+j] = act(b[o] + sum_ci x[ci][r][c] * k2[i*2+j][o][ci]).
+// The three kernels tile one channel axis by D2_T in registers, so that a value loaded from the big tensor feeds D2_T
+// multiply-adds, with the matching weight slice in shared memory (the first versions did one load per multiply-add).
+constexpr int D2_T = 8;
+
+// grid = (pixel blocks of the INPUT grid, ceil(Co / D2_T)); a thread owns one input pixel and D2_T output channels (x 4 taps)
 __global__ void __launch_bounds__(256)
 deconv2_fwd_kernel(const float* __restrict__ x, const float* __restrict__ k2, const float* __restrict__ b, float* __restrict__ y, int Ci,
                    int Co, int h, int w, int relu) {
-    const size_t n = (size_t)Co * 4 * h * w;
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
-        const int W2 = 2 * w, H2 = 2 * h;
-        const int o = (int)(i / ((size_t)H2 * W2)), R = (int)((i / W2) % H2), Cc = (int)(i % W2);
-        const int r = R >> 1, c = Cc >> 1, tap = (R & 1) * 2 + (Cc & 1);
-        const float* kp = k2 + ((size_t)tap * Co + o) * Ci;
-        float v = b[o];
-        for (int ci = 0; ci < Ci; ++ci) v = fmaf(__ldg(x + ((size_t)ci * h + r) * w + c), __ldg(kp + ci), v);
-        y[i] = relu ? fmaxf(v, 0.f) : v;
+    extern __shared__ float s_k[];                                  // [4][D2_T][Ci]
+    const int o0 = blockIdx.y * D2_T;
+    for (int i = threadIdx.x; i < 4 * D2_T * Ci; i += 256) {
+        const int tap = i / (D2_T * Ci), rem = i - tap * D2_T * Ci, o = rem / Ci, ci = rem - o * Ci;
+        s_k[i] = (o0 + o < Co) ? __ldg(k2 + ((size_t)tap * Co + o0 + o) * Ci + ci) : 0.f;
+    }
+    __syncthreads();
+    const size_t p = (size_t)blockIdx.x * 256 + threadIdx.x, plane = (size_t)h * w;
+    if (p >= plane) return;
+    const int r = (int)(p / w), c = (int)(p % w);
+    float acc[4][D2_T];
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int o = 0; o < D2_T; ++o) acc[t][o] = 0.f;
+    for (int ci = 0; ci < Ci; ++ci) {
+        const float xv = __ldg(x + (size_t)ci * plane + p);
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+            for (int o = 0; o < D2_T; ++o) acc[t][o] = fmaf(xv, s_k[(t * D2_T + o) * Ci + ci], acc[t][o]);
+    }
+#pragma unroll
+    for (int o = 0; o < D2_T; ++o) {
+        if (o0 + o >= Co) break;
+        const float bias = __ldg(b + o0 + o);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            float v = acc[t][o] + bias;
+            if (relu) v = fmaxf(v, 0.f);
+            y[((size_t)(o0 + o) * 2 * h + 2 * r + (t >> 1)) * 2 * w + 2 * c + (t & 1)] = v;
+        }
     }
 }
-// dx[ci][r][c] = sum_{tap,o} dy[o][2r+i][2c+j] * k2[tap][o][ci]
+
+// dx[ci][r][c] = sum_{tap,o} dy[o][2r+i][2c+j] * k2[tap][o][ci]; grid = (pixel blocks, ceil(Ci / D2_T))
 __global__ void __launch_bounds__(256)
 deconv2_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ k2, float* __restrict__ dx, int Ci, int Co, int h, int w) {
-    const size_t n = (size_t)Ci * h * w;
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
-        const int ci = (int)(i / ((size_t)h * w)), r = (int)((i / w) % h), c = (int)(i % w);
-        float v = 0.f;
-        for (int tap = 0; tap < 4; ++tap)
-            for (int o = 0; o < Co; ++o)
-                v = fmaf(__ldg(dy + ((size_t)o * 2 * h + 2 * r + (tap >> 1)) * 2 * w + 2 * c + (tap & 1)), __ldg(k2 + ((size_t)tap * Co + o) * Ci + ci), v);
-        dx[i] = v;
+    extern __shared__ float s_k[];                                  // [4][Co][D2_T]
+    const int c0 = blockIdx.y * D2_T;
+    for (int i = threadIdx.x; i < 4 * Co * D2_T; i += 256) {
+        const int to = i / D2_T, q = i - to * D2_T;
+        s_k[i] = (c0 + q < Ci) ? __ldg(k2 + (size_t)to * Ci + c0 + q) : 0.f;
     }
+    __syncthreads();
+    const size_t p = (size_t)blockIdx.x * 256 + threadIdx.x, plane = (size_t)h * w;
+    if (p >= plane) return;
+    const int r = (int)(p / w), c = (int)(p % w);
+    float acc[D2_T];
+#pragma unroll
+    for (int q = 0; q < D2_T; ++q) acc[q] = 0.f;
+    for (int o = 0; o < Co; ++o) {
+        const float* g = dy + ((size_t)o * 2 * h + 2 * r) * 2 * w + 2 * c;
+        const float2 top = *reinterpret_cast<const float2*>(g), bot = *reinterpret_cast<const float2*>(g + 2 * w);
+        const float gv[4] = {top.x, top.y, bot.x, bot.y};
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+            for (int q = 0; q < D2_T; ++q) acc[q] = fmaf(gv[t], s_k[(t * Co + o) * D2_T + q], acc[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < D2_T; ++q)
+        if (c0 + q < Ci) dx[(size_t)(c0 + q) * plane + p] = acc[q];
 }
-// dk2[tap][o][ci] = sum_{r,c} dy[o][2r+i][2c+j] * x[ci][r][c]; one block per (tap * Co + o, ci)
+
+// dk2[tap][o][ci] = sum_{r,c} dy[o][2r+i][2c+j] * x[ci][r][c]; grid = (Co, ceil(Ci / D2_T)): a block owns one output channel,
+// D2_T input channels and all four taps
 __global__ void __launch_bounds__(256)
 deconv2_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dk2, int Ci, int Co, int h, int w) {
-    const int to = blockIdx.x, ci = blockIdx.y, tap = to / Co, o = to - tap * Co;
-    float v = 0.f;
-    for (int p = threadIdx.x; p < h * w; p += 256) {
-        const int r = p / w, c = p - r * w;
-        v = fmaf(__ldg(dy + ((size_t)o * 2 * h + 2 * r + (tap >> 1)) * 2 * w + 2 * c + (tap & 1)), __ldg(x + ((size_t)ci * h + r) * w + c), v);
+    const int o = blockIdx.x, c0 = blockIdx.y * D2_T;
+    const size_t plane = (size_t)h * w;
+    float acc[4][D2_T];
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int q = 0; q < D2_T; ++q) acc[t][q] = 0.f;
+    for (size_t p = threadIdx.x; p < plane; p += 256) {
+        const int r = (int)(p / w), c = (int)(p % w);
+        const float* g = dy + ((size_t)o * 2 * h + 2 * r) * 2 * w + 2 * c;
+        const float2 top = *reinterpret_cast<const float2*>(g), bot = *reinterpret_cast<const float2*>(g + 2 * w);
+        const float gv[4] = {top.x, top.y, bot.x, bot.y};
+        if (gv[0] == 0.f && gv[1] == 0.f && gv[2] == 0.f && gv[3] == 0.f) continue;
+#pragma unroll
+        for (int q = 0; q < D2_T; ++q) {
+            const float xv = (c0 + q < Ci) ? __ldg(x + (size_t)(c0 + q) * plane + p) : 0.f;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) acc[t][q] = fmaf(gv[t], xv, acc[t][q]);
+        }
     }
-    __shared__ float s[8];
-    for (int k = 16; k; k >>= 1) v += __shfl_xor_sync(0xffffffffu, v, k);
-    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+    __shared__ float s_red[8][4 * D2_T];
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int q = 0; q < D2_T; ++q) {
+            float v = acc[t][q];
+            for (int k = 16; k; k >>= 1) v += __shfl_xor_sync(0xffffffffu, v, k);
+            if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5][t * D2_T + q] = v;
+        }
     __syncthreads();
-    if (threadIdx.x == 0) { for (int k = 1; k < 8; ++k) v += s[k]; dk2[((size_t)tap * Co + o) * Ci + ci] = v; }
+    if (threadIdx.x < 4 * D2_T) {
+        const int t = threadIdx.x / D2_T, q = threadIdx.x - t * D2_T;
+        if (c0 + q < Ci) {
+            float v = 0.f;
+            for (int k = 0; k < 8; ++k) v += s_red[k][threadIdx.x];
+            dk2[((size_t)t * Co + o) * Ci + c0 + q] = v;
+        }
+    }
 }
 
 // metrics.loss: mean over the Hc x Wc crop of the sparse softmax cross entropy from logits [C][H][W];
@@ -345,9 +419,13 @@ int train_maxpool(pcs_ctx* ctx, const float* x, float* y, const float* dy, float
 
 int train_deconv2(pcs_ctx* ctx, int mode, const float* x, const float* k2, const float* b, float* y, const float* dy, float* dx, float* dk2,
                   int Ci, int Co, int h, int w, int relu) {
-    if (mode == 0) deconv2_fwd_kernel<<<blocks_for((size_t)Co * 4 * h * w), 256, 0, ctx->stream>>>(x, k2, b, y, Ci, Co, h, w, relu);
-    else if (mode == 1) deconv2_bwd_data_kernel<<<blocks_for((size_t)Ci * h * w), 256, 0, ctx->stream>>>(dy, k2, dx, Ci, Co, h, w);
-    else deconv2_wgrad_kernel<<<dim3(4 * Co, Ci), 256, 0, ctx->stream>>>(x, dy, dk2, Ci, Co, h, w);
+    const unsigned pblocks = (unsigned)(((size_t)h * w + 255) / 256);
+    const size_t smem = (size_t)4 * D2_T * (mode == 0 ? Ci : Co) * sizeof(float);
+    if (smem > 48 * 1024) return set_err(ctx, PCS_ERR_ARG, "train_deconv2: %d channels exceed the shared-memory weight slice", mode == 0 ? Ci : Co);
+    if (mode != 0 && (reinterpret_cast<uintptr_t>(dy) & 7)) return set_err(ctx, PCS_ERR_ARG, "train_deconv2: dy must be 8-byte aligned");
+    if (mode == 0) deconv2_fwd_kernel<<<dim3(pblocks, (Co + D2_T - 1) / D2_T), 256, smem, ctx->stream>>>(x, k2, b, y, Ci, Co, h, w, relu);
+    else if (mode == 1) deconv2_bwd_data_kernel<<<dim3(pblocks, (Ci + D2_T - 1) / D2_T), 256, smem, ctx->stream>>>(dy, k2, dx, Ci, Co, h, w);
+    else deconv2_wgrad_kernel<<<dim3(Co, (Ci + D2_T - 1) / D2_T), 256, 0, ctx->stream>>>(x, dy, dk2, Ci, Co, h, w);
     PCS_LAUNCH_CHECK(ctx, "deconv2 kernel");
     return PCS_OK;
 }
