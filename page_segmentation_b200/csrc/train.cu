@@ -19,18 +19,24 @@ constexpr int TX = 32, TY = 8, CO_T = 8;
 
 // y[co][r][c] = act(b[co] + sum_ci sum_t x[ci][r + ky - P][c + kx - P] * w[co][ci][t]), zero padding, P = (K - 1) / 2.
 // ACC: add to y instead of overwriting (second source of a concatenation, gradient accumulation).
+// A block computes a 32 x (TY * RPT) pixel tile for CO_T output channels; a thread owns RPT pixels of one column
+// (rows ty, ty + TY, ...), so that the two float4 weight loads of a tap feed RPT * CO_T multiply-adds.
+constexpr int RPT = 2;
+
 template <int K>
 __global__ void __launch_bounds__(TX * TY)
 corr2d_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ y, int Ci,
               int Co, int H, int W, int relu, int acc_out) {
-    constexpr int P = (K - 1) / 2, IW = TX + K - 1, IH = TY + K - 1, KK = K * K;
+    constexpr int P = (K - 1) / 2, IW = TX + K - 1, IH = TY * RPT + K - 1, KK = K * K;
     __shared__ float s_in[IH][IW + 1];
     __shared__ __align__(16) float s_w[KK][CO_T];
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
-    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY, co0 = blockIdx.z * CO_T;
-    float acc[CO_T];
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY * RPT, co0 = blockIdx.z * CO_T;
+    float acc[RPT][CO_T];
 #pragma unroll
-    for (int o = 0; o < CO_T; ++o) acc[o] = 0.f;
+    for (int p = 0; p < RPT; ++p)
+#pragma unroll
+        for (int o = 0; o < CO_T; ++o) acc[p][o] = 0.f;
     for (int ci = 0; ci < Ci; ++ci) {
         __syncthreads();
         const float* xp = x + (size_t)ci * H * W;
@@ -47,23 +53,33 @@ corr2d_kernel(const float* __restrict__ x, const float* __restrict__ w, const fl
         for (int ky = 0; ky < K; ++ky)
 #pragma unroll
             for (int kx = 0; kx < K; ++kx) {
-                const float v = s_in[ty + ky][tx + kx];
                 const float4 w0 = *reinterpret_cast<const float4*>(&s_w[ky * K + kx][0]);
                 const float4 w1 = *reinterpret_cast<const float4*>(&s_w[ky * K + kx][4]);
-                acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]); acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
-                acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]); acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
+#pragma unroll
+                for (int p = 0; p < RPT; ++p) {
+                    const float v = s_in[ty + p * TY + ky][tx + kx];
+                    acc[p][0] = fmaf(v, w0.x, acc[p][0]); acc[p][1] = fmaf(v, w0.y, acc[p][1]);
+                    acc[p][2] = fmaf(v, w0.z, acc[p][2]); acc[p][3] = fmaf(v, w0.w, acc[p][3]);
+                    acc[p][4] = fmaf(v, w1.x, acc[p][4]); acc[p][5] = fmaf(v, w1.y, acc[p][5]);
+                    acc[p][6] = fmaf(v, w1.z, acc[p][6]); acc[p][7] = fmaf(v, w1.w, acc[p][7]);
+                }
             }
     }
-    const int gx = x0 + tx, gy = y0 + ty;
-    if (gx >= W || gy >= H) return;
+    const int gx = x0 + tx;
+    if (gx >= W) return;
 #pragma unroll
-    for (int o = 0; o < CO_T; ++o) {
-        if (co0 + o >= Co) break;
-        float* dst = y + ((size_t)(co0 + o) * H + gy) * W + gx;
-        float v = acc[o] + (b ? __ldg(b + co0 + o) : 0.f);
-        if (acc_out) v += *dst;
-        if (relu) v = fmaxf(v, 0.f);
-        *dst = v;
+    for (int p = 0; p < RPT; ++p) {
+        const int gy = y0 + ty + p * TY;
+        if (gy >= H) continue;
+#pragma unroll
+        for (int o = 0; o < CO_T; ++o) {
+            if (co0 + o >= Co) break;
+            float* dst = y + ((size_t)(co0 + o) * H + gy) * W + gx;
+            float v = acc[p][o] + (b ? __ldg(b + co0 + o) : 0.f);
+            if (acc_out) v += *dst;
+            if (relu) v = fmaxf(v, 0.f);
+            *dst = v;
+        }
     }
 }
 
@@ -374,7 +390,7 @@ inline unsigned blocks_for(size_t n) { return (unsigned)std::min<size_t>((n + 25
 
 int train_corr2d(pcs_ctx* ctx, const float* x, const float* w, const float* b, float* y, int Ci, int Co, int H, int W, int k, int relu, int acc) {
     if (Ci <= 0 || Co <= 0 || H <= 0 || W <= 0 || (k != 1 && k != 5)) return set_err(ctx, PCS_ERR_ARG, "train_corr2d: bad shape or kernel size %d", k);
-    dim3 grid((W + TX - 1) / TX, (H + TY - 1) / TY, (Co + CO_T - 1) / CO_T), block(TX, TY);
+    dim3 grid((W + TX - 1) / TX, (H + TY * RPT - 1) / (TY * RPT), (Co + CO_T - 1) / CO_T), block(TX, TY);
     if (grid.y > 65535 || grid.z > 65535) return set_err(ctx, PCS_ERR_ARG, "train_corr2d: grid too large");
     if (k == 5) corr2d_kernel<5><<<grid, block, 0, ctx->stream>>>(x, w, b, y, Ci, Co, H, W, relu, acc);
     else corr2d_kernel<1><<<grid, block, 0, ctx->stream>>>(x, w, b, y, Ci, Co, H, W, relu, acc);
