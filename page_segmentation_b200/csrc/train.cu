@@ -94,7 +94,8 @@ __global__ void __launch_bounds__(TX * TY)
 wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw, int Ci, int Co, int H, int W, int band) {
     // the band is walked in 32 x 8 pixel tiles staged in shared memory (x with its halo, dy of the WG_CO channels):
     // no bounds tests and no repeated global loads in the 25 x WG_CO inner products
-    constexpr int P = (K - 1) / 2, KK = K * K, IW = TX + K - 1, IH = TY + K - 1;
+    constexpr int WG_R = 4;                                          // tile rows per thread: 32 x 32 pixel tiles, a quarter of the barriers
+    constexpr int P = (K - 1) / 2, KK = K * K, IW = TX + K - 1, IH = TY * WG_R + K - 1;
     __shared__ float s_in[IH][IW + 1];
     __shared__ float s_red[TY][WG_CO * KK];
     const int co0 = blockIdx.x * WG_CO, ci = blockIdx.y;
@@ -107,7 +108,7 @@ wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* _
     for (int o = 0; o < WG_CO; ++o)
 #pragma unroll
         for (int t = 0; t < KK; ++t) acc[o][t] = 0.f;
-    for (int y0 = r0; y0 < r1; y0 += TY)
+    for (int y0 = r0; y0 < r1; y0 += TY * WG_R)
         for (int x0 = 0; x0 < W; x0 += TX) {
             __syncthreads();
             for (int i = tid; i < IH * IW; i += TX * TY) {
@@ -115,24 +116,29 @@ wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* _
                 s_in[r][c] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(xp + (size_t)gy * W + gx) : 0.f;
             }
             __syncthreads();
-            const int gy = y0 + ty, gx = x0 + tx;
-            if (gy >= r1 || gx >= W) continue;
-            float g[WG_CO];
-            bool any = false;
+            const int gx = x0 + tx;
+            if (gx >= W) continue;
+#pragma unroll 1
+            for (int q = 0; q < WG_R; ++q) {
+                const int ly = ty + q * TY, gy = y0 + ly;
+                if (gy >= r1) break;
+                float g[WG_CO];
+                bool any = false;
 #pragma unroll
-            for (int o = 0; o < WG_CO; ++o) {
-                g[o] = (co0 + o < Co) ? __ldg(dy + (size_t)(co0 + o) * plane + (size_t)gy * W + gx) : 0.f;
-                any |= g[o] != 0.f;
-            }
-            if (!any) continue;
-#pragma unroll
-            for (int ky = 0; ky < K; ++ky)
-#pragma unroll
-                for (int kx = 0; kx < K; ++kx) {
-                    const float xv = s_in[ty + ky][tx + kx];
-#pragma unroll
-                    for (int o = 0; o < WG_CO; ++o) acc[o][ky * K + kx] = fmaf(g[o], xv, acc[o][ky * K + kx]);
+                for (int o = 0; o < WG_CO; ++o) {
+                    g[o] = (co0 + o < Co) ? __ldg(dy + (size_t)(co0 + o) * plane + (size_t)gy * W + gx) : 0.f;
+                    any |= g[o] != 0.f;
                 }
+                if (!any) continue;
+#pragma unroll
+                for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < K; ++kx) {
+                        const float xv = s_in[ly + ky][tx + kx];
+#pragma unroll
+                        for (int o = 0; o < WG_CO; ++o) acc[o][ky * K + kx] = fmaf(g[o], xv, acc[o][ky * K + kx]);
+                    }
+            }
         }
     __syncthreads();
 #pragma unroll
@@ -403,7 +409,7 @@ int train_wgrad(pcs_ctx* ctx, const float* x, const float* dy, float* dw, int Ci
     PCS_CUDA(ctx, cudaMemsetAsync(dw, 0, (size_t)Co * Ci * k * k * sizeof(float), ctx->stream));
     const int pairs = ((Co + WG_CO - 1) / WG_CO) * Ci;
     int bands = std::max(1, std::min((H + 7) / 8, (148 * 6 + pairs - 1) / pairs));       // enough blocks to fill the GPU a few times
-    const int band = ((H + bands - 1) / bands + 7) / 8 * 8;
+    const int band = ((H + bands - 1) / bands + 31) / 32 * 32;
     bands = (H + band - 1) / band;
     const dim3 grid((Co + WG_CO - 1) / WG_CO, Ci, bands);
     if (k == 5) wgrad_kernel<5><<<grid, dim3(TX, TY), 0, ctx->stream>>>(x, dy, dw, Ci, Co, H, W, band);
