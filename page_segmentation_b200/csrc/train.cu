@@ -28,8 +28,9 @@ __global__ void __launch_bounds__(TX * TY)
 corr2d_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ y, int Ci,
               int Co, int H, int W, int relu, int acc_out) {
     constexpr int P = (K - 1) / 2, IW = TX + K - 1, IH = TY * RPT + K - 1, KK = K * K;
-    __shared__ float s_in[IH][IW + 1];
-    __shared__ __align__(16) float s_w[KK][CO_T];
+    constexpr int CI_T = K == 1 ? 8 : 4;                             // input channels staged per barrier pair
+    __shared__ float s_in[CI_T][IH][IW + 1];
+    __shared__ __align__(16) float s_w[CI_T][KK][CO_T];
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
     const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY * RPT, co0 = blockIdx.z * CO_T;
     float acc[RPT][CO_T];
@@ -37,33 +38,35 @@ corr2d_kernel(const float* __restrict__ x, const float* __restrict__ w, const fl
     for (int p = 0; p < RPT; ++p)
 #pragma unroll
         for (int o = 0; o < CO_T; ++o) acc[p][o] = 0.f;
-    for (int ci = 0; ci < Ci; ++ci) {
+    for (int ci0 = 0; ci0 < Ci; ci0 += CI_T) {
+        const int nci = min(CI_T, Ci - ci0);
         __syncthreads();
-        const float* xp = x + (size_t)ci * H * W;
-        for (int i = tid; i < IH * IW; i += TX * TY) {
-            const int r = i / IW, c = i - r * IW, gy = y0 + r - P, gx = x0 + c - P;
-            s_in[r][c] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(xp + (size_t)gy * W + gx) : 0.f;
+        for (int i = tid; i < nci * IH * IW; i += TX * TY) {
+            const int q = i / (IH * IW), rem = i - q * IH * IW, r = rem / IW, c = rem - r * IW, gy = y0 + r - P, gx = x0 + c - P;
+            s_in[q][r][c] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(x + (size_t)(ci0 + q) * H * W + (size_t)gy * W + gx) : 0.f;
         }
-        for (int i = tid; i < KK * CO_T; i += TX * TY) {
-            const int t = i / CO_T, o = i - t * CO_T;
-            s_w[t][o] = (co0 + o < Co) ? __ldg(w + ((size_t)(co0 + o) * Ci + ci) * KK + t) : 0.f;
+        for (int i = tid; i < nci * KK * CO_T; i += TX * TY) {
+            const int q = i / (KK * CO_T), rem = i - q * KK * CO_T, t = rem / CO_T, o = rem - t * CO_T;
+            s_w[q][t][o] = (co0 + o < Co) ? __ldg(w + ((size_t)(co0 + o) * Ci + ci0 + q) * KK + t) : 0.f;
         }
         __syncthreads();
+        for (int q = 0; q < nci; ++q) {
 #pragma unroll
-        for (int ky = 0; ky < K; ++ky)
+            for (int ky = 0; ky < K; ++ky)
 #pragma unroll
-            for (int kx = 0; kx < K; ++kx) {
-                const float4 w0 = *reinterpret_cast<const float4*>(&s_w[ky * K + kx][0]);
-                const float4 w1 = *reinterpret_cast<const float4*>(&s_w[ky * K + kx][4]);
+                for (int kx = 0; kx < K; ++kx) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(&s_w[q][ky * K + kx][0]);
+                    const float4 w1 = *reinterpret_cast<const float4*>(&s_w[q][ky * K + kx][4]);
 #pragma unroll
-                for (int p = 0; p < RPT; ++p) {
-                    const float v = s_in[ty + p * TY + ky][tx + kx];
-                    acc[p][0] = fmaf(v, w0.x, acc[p][0]); acc[p][1] = fmaf(v, w0.y, acc[p][1]);
-                    acc[p][2] = fmaf(v, w0.z, acc[p][2]); acc[p][3] = fmaf(v, w0.w, acc[p][3]);
-                    acc[p][4] = fmaf(v, w1.x, acc[p][4]); acc[p][5] = fmaf(v, w1.y, acc[p][5]);
-                    acc[p][6] = fmaf(v, w1.z, acc[p][6]); acc[p][7] = fmaf(v, w1.w, acc[p][7]);
+                    for (int p = 0; p < RPT; ++p) {
+                        const float v = s_in[q][ty + p * TY + ky][tx + kx];
+                        acc[p][0] = fmaf(v, w0.x, acc[p][0]); acc[p][1] = fmaf(v, w0.y, acc[p][1]);
+                        acc[p][2] = fmaf(v, w0.z, acc[p][2]); acc[p][3] = fmaf(v, w0.w, acc[p][3]);
+                        acc[p][4] = fmaf(v, w1.x, acc[p][4]); acc[p][5] = fmaf(v, w1.y, acc[p][5]);
+                        acc[p][6] = fmaf(v, w1.z, acc[p][6]); acc[p][7] = fmaf(v, w1.w, acc[p][7]);
+                    }
                 }
-            }
+        }
     }
     const int gx = x0 + tx;
     if (gx >= W) return;
