@@ -216,6 +216,9 @@ def main():
     ap.add_argument("--arch", default=ARCH, choices=["fcn_skip", "fcn", "unet"])
     ap.add_argument("--cpu-pages", type=int, default=3, help="pages of the CPU-baseline sample (rank 0, N=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="predict", choices=["predict", "train"],
+                    help="predict = BASELINE configs[1] (default, the contract line); train = configs[4]: one training step per page per "
+                         "rank with the NCCL gradient all-reduce (tools/bench_train.py)")
     ap.add_argument("--cc-majority", action="store_true",
                     help="also run the cc_majority post-processor (BASELINE configs[3] pipeline); not the default workload")
     args = ap.parse_args()
@@ -226,6 +229,13 @@ def main():
 
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.workload == "train":
+        sys.argv = [os.path.join(ROOT, "tools", "bench_train.py"), "--steps", str(args.steps), "--warmup", str(args.warmup),
+                    "--arch", args.arch if args.arch != "unet" else "fcn_skip"]
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_train
+        bench_train.main()
         return
 
     import torch
