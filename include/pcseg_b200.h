@@ -238,6 +238,12 @@ PCS_API int pcs_integral_image(pcs_ctx* ctx, const uint8_t* d_mask, int n, int H
 PCS_API int pcs_text_regions(pcs_ctx* ctx, const uint8_t* d_rgb, int H, int W, const uint8_t* colour,
                      int k_close, int k_open, int k_region, uint8_t* d_text_inv, uint8_t* d_region);
 
+/* ---- evaluation counts: the reductions of fgpa and fgoverlap_per_class, lib/image_ops.py:8-55.  Over the pixels with
+ * bin != 0: d_out[0] = their number, d_out[1] = those with pred != mask, d_out[2 + p * (n_classes + 2) + m] = the
+ * confusion matrix of (pred, mask), class values above n_classes folded into the last bucket.  uint8 class maps. */
+PCS_API int pcs_eval_counts(pcs_ctx* ctx, const uint8_t* d_pred, const uint8_t* d_mask, const uint8_t* d_bin,
+                    size_t n_pixels, int n_classes, uint64_t* d_out);
+
 /* ---- training step primitives (first version: fp32 on the CUDA cores): Network.train_dataset with batch 1,
  * lib/network.py:151-161,167-242; metrics.loss, lib/metrics.py:8-9; Keras Adam with per-variable clipnorm as compiled
  * at lib/network.py:91-103.  Tensors are planar float32 [C][H][W] on the device; the host side (lib/trainer.py)

@@ -50,3 +50,23 @@ def compute_char_height_array(img: np.ndarray, inverse: bool):
     if len(heights) == 0:
         return None
     return heights[int(len(heights) / 2)]
+
+
+def fgpa(pred: np.ndarray, mask: np.ndarray, bin: np.ndarray) -> float:
+    """image_ops.py:8-19."""
+    fg = np.count_nonzero(bin)
+    with np.errstate(invalid="ignore"):
+        return np.float64(fg - np.count_nonzero((pred * bin) != (mask * bin))) / np.float64(fg)      # nan without foreground
+
+
+def fgoverlap_per_class(pred: np.ndarray, mask: np.ndarray, bin: np.ndarray, n_classes: int):
+    """image_ops.py:22-55 -> (overlaps, tps, fps, fns), n_classes + 1 entries each."""
+    pfg, mfg = (pred.astype(np.int64) + 1) * bin - 1, (mask.astype(np.int64) + 1) * bin - 1
+    out = ([], [], [], [])
+    for i in range(n_classes + 1):
+        a, e = pfg == i, mfg == i
+        tp, fp, fn = int((a & e).sum()), int((a & ~e).sum()), int((e & ~a).sum())
+        vals = (np.nan, 0, 0, 0) if tp + fp + fn == 0 else (tp / (tp + fp + fn), tp, fp, fn)
+        for lst, v in zip(out, vals):
+            lst.append(v)
+    return out

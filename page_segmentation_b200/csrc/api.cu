@@ -854,6 +854,13 @@ int pcs_train_adam(pcs_ctx* ctx, float* d_params, const float* d_grads, float* d
     return train_adam(ctx, d_params, d_grads, d_m, d_v, reinterpret_cast<const long long*>(d_offsets), n_vars, lr_t, beta1, beta2, eps, clipnorm, grad_scale);
 }
 
+int pcs_eval_counts(pcs_ctx* ctx, const uint8_t* d_pred, const uint8_t* d_mask, const uint8_t* d_bin, size_t n_pixels, int n_classes,
+                    uint64_t* d_out) {
+    if (!ctx || !d_pred || !d_mask || !d_bin || !d_out || !n_pixels) return ctx ? set_err(ctx, PCS_ERR_ARG, "eval_counts: null or empty argument") : PCS_ERR_ARG;
+    PCS_CUDA(ctx, cudaSetDevice(ctx->device));
+    return launch_eval_counts(ctx, d_pred, d_mask, d_bin, n_pixels, n_classes, reinterpret_cast<unsigned long long*>(d_out));
+}
+
 size_t pcs_png_bytes(int H, int W, int channels, int level) { return png_file_bytes(H, W, channels, level); }
 
 int pcs_png_encode(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, int channels, int level, uint8_t* d_out, size_t stride,

@@ -250,6 +250,9 @@ int launch_head(pcs_ctx* ctx, const HeadArgs& a);
 int launch_masks(pcs_ctx* ctx, const uint8_t* d_labels, const uint8_t* d_binary, int n, int H, int W,
                  const uint8_t* d_lut, int n_lut, uint8_t* d_color, uint8_t* d_overlay, uint8_t* d_inverted);
 
+int launch_eval_counts(pcs_ctx* ctx, const uint8_t* d_pred, const uint8_t* d_mask, const uint8_t* d_bin, size_t n, int n_classes,
+                       unsigned long long* d_out);
+
 // ccl.cu
 int launch_ccl(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, int32_t* d_labels,
                int32_t* d_stats, int max_components, int32_t* d_ncomp);

@@ -259,4 +259,41 @@ int launch_masks(pcs_ctx* ctx, const uint8_t* d_labels, const uint8_t* d_binary,
     return PCS_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Evaluation counts behind fgpa / fgoverlap_per_class (lib/image_ops.py:8-55): over the foreground pixels (bin != 0)
+// out[0] = their number, out[1] = those with pred != mask, out[2 + p * (n + 2) + m] = the confusion matrix of
+// (pred, mask) with every class value above n_classes folded into the last bucket.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+eval_counts_kernel(const uint8_t* __restrict__ pred, const uint8_t* __restrict__ mask, const uint8_t* __restrict__ bin, size_t n,
+                   int n_classes, unsigned long long* __restrict__ out) {
+    extern __shared__ unsigned int s_cnt[];                       // [2 + (n_classes + 2)^2]
+    const int nb = n_classes + 2, total = 2 + nb * nb;
+    for (int i = threadIdx.x; i < total; i += 256) s_cnt[i] = 0;
+    __syncthreads();
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        if (!bin[i]) continue;
+        const int p = pred[i], m = mask[i];
+        atomicAdd(&s_cnt[0], 1u);
+        if (p != m) atomicAdd(&s_cnt[1], 1u);
+        atomicAdd(&s_cnt[2 + min(p, nb - 1) * nb + min(m, nb - 1)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < total; i += 256)
+        if (s_cnt[i]) atomicAdd(&out[i], (unsigned long long)s_cnt[i]);
+}
+
+int launch_eval_counts(pcs_ctx* ctx, const uint8_t* d_pred, const uint8_t* d_mask, const uint8_t* d_bin, size_t n, int n_classes,
+                       unsigned long long* d_out) {
+    if (n_classes < 1 || n_classes > 62) return set_err(ctx, PCS_ERR_ARG, "eval_counts: 1..62 classes");
+    const int nb = n_classes + 2;
+    const size_t words = 2 + (size_t)nb * nb;
+    PCS_CUDA(ctx, cudaMemsetAsync(d_out, 0, words * sizeof(unsigned long long), ctx->stream));
+    // a block's shared counters are 32 bit: keep a block's share of the pixels below 2^32
+    const unsigned blocks = (unsigned)std::max<size_t>(std::min<size_t>((size_t)ctx->sm_count * 8, (n + 255) / 256), (n >> 31) + 1);
+    eval_counts_kernel<<<blocks, 256, words * sizeof(unsigned int), ctx->stream>>>(d_pred, d_mask, d_bin, n, n_classes, d_out);
+    PCS_LAUNCH_CHECK(ctx, "eval_counts_kernel");
+    return PCS_OK;
+}
+
 }  // namespace pcs

@@ -1,11 +1,14 @@
-"""Mirror of ocr4all_pixel_classifier/lib/image_ops.py:58-82 (`compute_char_height`), the producer of the
-`line_height_px` normalisation input, on the B200 path (pcs_char_height)."""
+"""Mirror of ocr4all_pixel_classifier/lib/image_ops.py on the B200 path: `compute_char_height` (:58-82, the producer of
+the `line_height_px` normalisation input; pcs_char_height) and the evaluation metrics `fgpa` (:8-19) and
+`fgoverlap_per_class` (:22-55) as one masked counting pass (pcs_eval_counts)."""
 from __future__ import annotations
 
 import os
 from typing import Optional
 
 import numpy as np
+
+from typing import List, Tuple
 
 from .. import runtime
 
@@ -32,3 +35,43 @@ def compute_char_height(file_name: str, inverse: bool):
     import cv2                      # file decoding stays on the host, as in the reference (cv2.imread)
     img = cv2.imread(file_name, cv2.IMREAD_GRAYSCALE)
     return compute_char_height_array(img, inverse)
+
+
+def _eval_counts(pred: np.ndarray, mask: np.ndarray, bin: np.ndarray, n_classes: int, device: Optional[int] = None):
+    torch = runtime._torch()
+    ctx = runtime.get_context(device)
+    pred, mask, bin = np.asarray(pred), np.asarray(mask), np.asarray(bin)
+    if pred.shape != mask.shape or pred.shape != bin.shape:
+        raise ValueError("pred, mask and bin must have one shape")
+    if bin.size and (bin.min() < 0 or bin.max() > 1):
+        raise ValueError("bin must be a {0, 1} foreground map (1 is foreground), as dataset.py:146 leaves it")
+    d = [runtime.to_device_u8(a, ctx.device) for a in (pred, mask, bin)]
+    nb = n_classes + 2
+    d_out = torch.zeros((2 + nb * nb,), dtype=torch.int64, device=d[0].device)
+    ctx.eval_counts(d[0], d[1], d[2], pred.size, n_classes, d_out)
+    out = d_out.cpu().numpy()
+    return int(out[0]), int(out[1]), out[2:].reshape(nb, nb)
+
+
+def fgpa(pred: np.ndarray, mask: np.ndarray, bin: np.ndarray):
+    """image_ops.py:8-19: foreground pixel accuracy.  A page without foreground gives nan, as the reference does with the
+    numpy scalars np.count_nonzero returns today (with numpy 1.x ints it raised ZeroDivisionError)."""
+    fg_count, neq, _ = _eval_counts(pred, mask, bin, 1)
+    return np.float64(fg_count - neq) / np.float64(fg_count) if fg_count else np.float64("nan")
+
+
+def fgoverlap_per_class(pred: np.ndarray, mask: np.ndarray, bin: np.ndarray, n_classes: int) \
+        -> Tuple[List[float], List[int], List[int], List[int]]:
+    """image_ops.py:22-55: per class 0..n_classes (n_classes + 1 entries) the foreground overlap tp / (tp + fp + fn) and
+    tp, fp, fn; nan and zeros for a class that occurs in neither map."""
+    _, _, conf = _eval_counts(pred, mask, bin, n_classes)
+    overlaps, tps, fps, fns = [], [], [], []
+    for i in range(n_classes + 1):
+        tp = int(conf[i, i])
+        fp = int(conf[i, :].sum()) - tp          # predicted i, expected something else
+        fn = int(conf[:, i].sum()) - tp          # expected i, predicted something else
+        if tp + fp + fn == 0:
+            overlaps.append(np.nan); tps.append(0); fps.append(0); fns.append(0)
+        else:
+            overlaps.append(tp / (tp + fp + fn)); tps.append(tp); fps.append(fp); fns.append(fn)
+    return overlaps, tps, fps, fns

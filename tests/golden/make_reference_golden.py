@@ -89,6 +89,13 @@ def main():
             got = iops.compute_char_height(path, inverse)
             store[f"char{i}_page"], store[f"char{i}_inverse"] = page, np.array(inverse)
             store[f"char{i}_height"] = np.array(-1 if got is None else int(got))
+    # evaluation metrics (image_ops.fgpa / fgoverlap_per_class) on the vote cases: the voted map against the raw one
+    for i, (seed, h, w, lh, ncls) in enumerate(cases):
+        pred, voted, binary = store[f"vote{i}_pred"].astype(np.int64), store[f"vote{i}_voted"].astype(np.int64), store[f"vote{i}_binary"].astype(np.int64)
+        store[f"eval{i}_fgpa"] = np.array(iops.fgpa(voted, pred, binary))
+        ov, tp, fp, fn = iops.fgoverlap_per_class(voted, pred, binary, ncls)
+        store[f"eval{i}_overlap"], store[f"eval{i}_tp"], store[f"eval{i}_fp"], store[f"eval{i}_fn"] = np.array(ov), np.array(tp), np.array(fp), np.array(fn)
+        store[f"eval{i}_ncls"] = np.array(ncls)
     np.savez_compressed(os.path.join(HERE, "ref_postprocess.npz"), **store)
 
     # ---------------- region extraction ----------------

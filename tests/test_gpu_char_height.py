@@ -72,3 +72,22 @@ def test_char_height_batch(ctx):
     ctx.char_height(d, 3, 320, 480, False, out)
     for i in range(3):
         assert int(out[i].cpu()) == int(oio.compute_char_height_array(pages[i], False))
+
+
+def test_eval_metrics_reproduce_reference(ctx):
+    """fgpa / fgoverlap_per_class (image_ops.py:8-55) against vectors produced by the reference's own functions."""
+    from page_segmentation_b200.lib.image_ops import fgoverlap_per_class, fgpa
+    post = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_postprocess.npz"))
+    for i in range(int(post["n_vote"])):
+        pred, voted, binary = (post[f"vote{i}_{k}"] for k in ("pred", "voted", "binary"))
+        assert fgpa(voted, pred, binary) == float(post[f"eval{i}_fgpa"])
+        ov, tp, fp, fn = fgoverlap_per_class(voted, pred, binary, int(post[f"eval{i}_ncls"]))
+        assert np.array_equal(np.array(ov), post[f"eval{i}_overlap"], equal_nan=True)
+        assert tp == post[f"eval{i}_tp"].tolist() and fp == post[f"eval{i}_fp"].tolist() and fn == post[f"eval{i}_fn"].tolist()
+    rng = np.random.default_rng(4)
+    pred, mask = rng.integers(0, 6, (1169, 827)), rng.integers(0, 4, (1169, 827))        # classes above n_classes in pred
+    binary = (rng.random(pred.shape) < 0.3).astype(np.uint8)
+    assert fgpa(pred, mask, binary) == oio.fgpa(pred, mask, binary)
+    got, exp = fgoverlap_per_class(pred, mask, binary, 4), oio.fgoverlap_per_class(pred, mask, binary, 4)
+    assert np.array_equal(np.array(got[0]), np.array(exp[0]), equal_nan=True) and list(got[1:]) == list(exp[1:])
+    assert np.isnan(fgpa(pred, mask, np.zeros_like(binary)))

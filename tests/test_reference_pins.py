@@ -240,3 +240,26 @@ def test_live_reference_list_dataset(tmp_path):
         md.list_dataset(str(root / "nope"))
     with pytest.raises(Exception, match="Norm dir does not exist"):
         md.list_dataset(str(root), normalizations_dir="absent")
+
+
+@pytest.mark.parametrize("i", range(int(POST["n_vote"])))
+def test_oracle_eval_metrics_match_reference_vectors(i):
+    pred, voted, binary = (POST[f"vote{i}_{k}"].astype(np.int64) for k in ("pred", "voted", "binary"))
+    assert oio.fgpa(voted, pred, binary) == float(POST[f"eval{i}_fgpa"])
+    ov, tp, fp, fn = oio.fgoverlap_per_class(voted, pred, binary, int(POST[f"eval{i}_ncls"]))
+    assert np.array_equal(np.array(ov), POST[f"eval{i}_overlap"], equal_nan=True)
+    assert tp == POST[f"eval{i}_tp"].tolist() and fp == POST[f"eval{i}_fp"].tolist() and fn == POST[f"eval{i}_fn"].tolist()
+
+
+@live
+def test_live_reference_eval_metrics():
+    iops = ref.load("image_ops")
+    rng = np.random.default_rng(9)
+    for n_classes, shape in ((3, (50, 70)), (5, (33, 20)), (2, (8, 8))):
+        pred, mask = rng.integers(0, n_classes + 2, shape), rng.integers(0, n_classes, shape)       # pred also holds out-of-range classes
+        binary = (rng.random(shape) < 0.4).astype(np.int64)
+        assert oio.fgpa(pred, mask, binary) == iops.fgpa(pred, mask, binary)
+        exp, got = iops.fgoverlap_per_class(pred, mask, binary, n_classes), oio.fgoverlap_per_class(pred, mask, binary, n_classes)
+        assert np.array_equal(np.array(exp[0]), np.array(got[0]), equal_nan=True) and list(exp[1:]) == list(got[1:])
+    with np.errstate(invalid="ignore"):
+        assert np.isnan(iops.fgpa(pred, mask, np.zeros(shape, np.int64))) and np.isnan(oio.fgpa(pred, mask, np.zeros(shape, np.int64)))
