@@ -244,6 +244,8 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a B200; there is no CPU fallback"
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
+    from page_segmentation_b200.runtime import bind_to_gpu_numa_node
+    numa = bind_to_gpu_numa_node(local_rank)            # before any pinned allocation: host buffers local to the GPU's PCIe root
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -367,7 +369,7 @@ def main():
                        "l2": "inputs larger than L2 (557 MB of pages per step)", "distinct_pages": distinct},
             "e2e": {"value": e2e_value, "unit": "pages/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "pcie_pinned_copy": pcie,
+            "pcie_pinned_copy": pcie, "numa_binding": numa,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

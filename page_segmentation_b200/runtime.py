@@ -35,6 +35,34 @@ def get_context(device: Optional[int] = None) -> _native.Context:
     return ctx
 
 
+def bind_to_gpu_numa_node(device: int) -> Optional[dict]:
+    """Pins the calling process to the CPUs of the NUMA node its GPU hangs off (sysfs: the PCI device's `numa_node` and
+    that node's `cpulist`), so that host buffers allocated afterwards - first touch - and the copy threads are local to
+    the GPU's PCIe root.  With one process per GPU on a two-socket box this is what keeps eight host<->device streams
+    from crossing the socket interconnect.  Returns what it did, or None when the topology is not exposed."""
+    torch = _torch()
+    try:
+        p = torch.cuda.get_device_properties(device)
+        addr = f"{getattr(p, 'pci_domain_id', 0):04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{addr}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return {"pci": addr, "numa_node": node, "cpus": len(allowed)}
+    except (OSError, ValueError, AttributeError):
+        return None
+
+
 def to_device_u8(arr: np.ndarray, device: int):
     torch = _torch()
     a = np.ascontiguousarray(arr)
