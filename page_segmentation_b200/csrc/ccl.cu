@@ -20,6 +20,8 @@
 #include "common.cuh"
 
 #include <climits>
+#include <cstdlib>
+#include <cstring>
 
 namespace pcs {
 
@@ -33,7 +35,17 @@ __device__ __forceinline__ int uf_find(const int* parent, int x) {
     return x;
 }
 
+// COMPRESS: the two starting nodes are re-linked to the roots found on the first walk (atomicMin towards an ancestor
+// of the same tree: pointers only ever decrease, so no cycle can form and no link between two sets is lost)
+template <bool COMPRESS>
 __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
+    if (COMPRESS) {
+        const int ra = uf_find(parent, a), rb = uf_find(parent, b);
+        if (ra < a) atomicMin(&parent[a], ra);
+        if (rb < b) atomicMin(&parent[b], rb);
+        if (ra == rb) return;
+        a = ra; b = rb;
+    }
     while (true) {
         a = uf_find(parent, a);
         b = uf_find(parent, b);
@@ -45,74 +57,174 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
     }
 }
 
-// grid: (ceil(W/32) * rows_per_block..., H, n) -- one warp per 32-pixel row segment.
-// block = 256 threads = 8 segments of one row.
-template <bool MATCH_CLASS, bool WRITE_BG = true>
+// ---------------------------------------------------------------------------------------------------
+// Segment-wise passes.  A page is nine tenths background, so the passes over the image do not spend a thread per
+// pixel: a thread owns one 32-pixel segment of a row, reads it with two 128-bit loads (32-bit words and a funnel
+// shift when the row is not 16-byte aligned), turns it into a bit mask and is done when the mask is empty;
+// neighbour relations (left / upper / diagonal) are bit operations between the masks of two rows.
+// ---------------------------------------------------------------------------------------------------
+// MODE 0: foreground = non-zero byte; MODE 1: foreground = byte equal to `cls`
+template <int MODE>
+__device__ __forceinline__ unsigned bytes4_to_bits(unsigned w, unsigned cls4) {
+    unsigned c = MODE == 1 ? __vcmpeq4(w, cls4) : __vcmpne4(w, 0u);     // 0xff per matching byte
+    c &= 0x08040201u;                                                   // byte k keeps bit k of itself
+    c |= c >> 8;
+    c |= c >> 16;
+    return c & 0xfu;
+}
+
+// bit k = pixel x0 + k of this row is foreground; pixels at or beyond W read as background.
+// `last_row`: the row is the last one of the whole buffer (the word path may read 3 bytes past pixel x0 + 31).
+template <int MODE>
+__device__ __forceinline__ unsigned fg_bits(const uint8_t* __restrict__ row, int x0, int W, int cls, bool last_row) {
+    const uint8_t* p = row + x0;
+    const unsigned cls4 = (unsigned)cls * 0x01010101u;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    unsigned m = 0;
+    if (x0 + 32 <= W && (a & 15) == 0) {
+        const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(p));
+        const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+        m = bytes4_to_bits<MODE>(q0.x, cls4) | bytes4_to_bits<MODE>(q0.y, cls4) << 4 | bytes4_to_bits<MODE>(q0.z, cls4) << 8 |
+            bytes4_to_bits<MODE>(q0.w, cls4) << 12 | bytes4_to_bits<MODE>(q1.x, cls4) << 16 | bytes4_to_bits<MODE>(q1.y, cls4) << 20 |
+            bytes4_to_bits<MODE>(q1.z, cls4) << 24 | bytes4_to_bits<MODE>(q1.w, cls4) << 28;
+    } else if (x0 + 32 <= W && (!last_row || x0 + 36 <= W)) {
+        const unsigned* pa = reinterpret_cast<const unsigned*>(a & ~(uintptr_t)3);
+        const unsigned sh = (unsigned)(a & 3) * 8;
+        unsigned lo = __ldg(pa);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const unsigned hi = (k < 7 || sh) ? __ldg(pa + k + 1) : 0u;
+            m |= bytes4_to_bits<MODE>(__funnelshift_r(lo, hi, sh), cls4) << (4 * k);
+            lo = hi;
+        }
+    } else {
+        const int nx = min(32, W - x0);
+        for (int k = 0; k < nx; ++k) {
+            const uint8_t v = __ldg(p + k);
+            m |= (unsigned)(MODE == 1 ? (v == cls) : (v != 0)) << k;
+        }
+    }
+    return m;
+}
+
+// pops the lowest run of set bits of mm: pixels s .. s + len - 1
+__device__ __forceinline__ bool next_run(unsigned& mm, int& s, int& len) {
+    if (!mm) return false;
+    s = __ffs(mm) - 1;
+    len = __ffs(~(mm >> s)) - 1;
+    if (len < 0) len = 32;                                              // s == 0 and all 32 pixels set
+    mm &= ~((len >= 32 ? 0xffffffffu : ((1u << len) - 1u)) << s);
+    return true;
+}
+
+// thread -> (row y, first pixel x0 of its segment); grid = (ceil(segs * H / 256), n pages)
+#define PCS_SEG_THREAD()                                                     \
+    const int segs = (W + 31) >> 5;                                          \
+    const int t = blockIdx.x * 256 + threadIdx.x;                            \
+    const bool valid = t < segs * H;                                         \
+    const int y = valid ? t / segs : 0;                                      \
+    const int x0 = valid ? (t - y * segs) * 32 : 0;                          \
+    const size_t page_off = (size_t)blockIdx.y * H * W;                      \
+    const bool last_row = y == H - 1 && blockIdx.y == gridDim.y - 1
+
+static inline dim3 seg_grid(int H, int W, int n) { return dim3((unsigned)((((size_t)(W + 31) / 32) * H + 255) / 256), n); }
+
+// A  init: parent = first pixel of the pixel's run inside its 32-pixel segment.  The 32 masks of a warp are handed
+// round so that every store instruction writes 32 consecutive parents.
+template <int MODE, bool WRITE_BG>
 __global__ void __launch_bounds__(256)
 ccl_init_kernel(const uint8_t* __restrict__ img, int H, int W, int cls, int* __restrict__ parent,
                 int* __restrict__ zero_aux, int aux_stride) {
+    PCS_SEG_THREAD();
     const int lane = threadIdx.x & 31;
-    const int seg = blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int x = seg * 32 + lane;
-    const int y = blockIdx.y;
-    const size_t page_off = (size_t)blockIdx.z * H * W;
-    const bool inb = x < W;
-    const int idx = y * W + x;
-    bool fg = false;
-    if (inb) {
-        const uint8_t v = img[page_off + idx];
-        fg = MATCH_CLASS ? (v == cls) : (v != 0);
-    }
-    const unsigned mask = __ballot_sync(0xffffffffu, fg);
-    if (!inb) return;
-    if (!fg) { if (WRITE_BG) parent[page_off + idx] = kBG; return; }      // !WRITE_BG: every later pass tests the image first
-    const unsigned below = ~mask & ((1u << lane) - 1u);     // background lanes left of me
-    const int start = below ? 32 - __clz(below) : 0;
-    parent[page_off + idx] = y * W + seg * 32 + start;
-    if (zero_aux && start == lane) {
-        // run starts are the only root candidates: clear their accumulators
-        int* a = zero_aux + (page_off + idx) * aux_stride;
-        for (int k = 0; k < aux_stride; ++k) a[k] = 0;
+    const unsigned m = valid ? fg_bits<MODE>(img + page_off + (size_t)y * W, x0, W, cls, last_row) : 0u;
+    const int base = y * W + x0;
+    const int nx = valid ? min(32, W - x0) : 0;
+    int* par = parent + page_off;
+    if (!WRITE_BG && !__any_sync(0xffffffffu, m != 0)) return;          // !WRITE_BG: every later pass tests the image first
+    for (int j = 0; j < 32; ++j) {
+        const unsigned mj = __shfl_sync(0xffffffffu, m, j);
+        const int bj = __shfl_sync(0xffffffffu, base, j), nj = __shfl_sync(0xffffffffu, nx, j);
+        if (!WRITE_BG && mj == 0) continue;                             // warp-uniform
+        if (lane < nj) {
+            if ((mj >> lane) & 1u) {
+                const unsigned below = ~mj & ((1u << lane) - 1u);       // background lanes left of me
+                const int start = below ? 32 - __clz(below) : 0;
+                par[bj + lane] = bj + start;
+                if (zero_aux && start == lane) {
+                    // run starts are the only root candidates: clear their accumulators
+                    int* z = zero_aux + (page_off + bj + lane) * aux_stride;
+                    for (int k = 0; k < aux_stride; ++k) z[k] = 0;
+                }
+            } else if (WRITE_BG) {
+                par[bj + lane] = kBG;
+            }
+        }
     }
 }
 
-template <bool MATCH_CLASS, bool CONN8>
+// B  merge: one union per touching run pair (vertical unions only where a run starts or the upper-left neighbour
+// is background), plus one union per run crossing a segment border.
+template <int MODE, bool CONN8, bool COMPRESS>
 __global__ void __launch_bounds__(256)
 ccl_merge_kernel(const uint8_t* __restrict__ img, int H, int W, int cls, int* __restrict__ parent) {
-    const int x = blockIdx.x * 256 + threadIdx.x;
-    const int y = blockIdx.y;
-    if (x >= W) return;
-    const size_t page_off = (size_t)blockIdx.z * H * W;
+    PCS_SEG_THREAD();
+    if (!valid) return;
     const uint8_t* im = img + page_off;
-    int* par = parent + page_off;
-    auto isfg = [&](int yy, int xx) -> bool {
-        const uint8_t v = im[yy * W + xx];
-        return MATCH_CLASS ? (v == cls) : (v != 0);
+    const uint8_t* row = im + (size_t)y * W;
+    const unsigned m = fg_bits<MODE>(row, x0, W, cls, last_row);
+    if (!m) return;
+    auto isfg = [&](const uint8_t* r, int xx) -> unsigned {
+        const uint8_t v = __ldg(r + xx);
+        return MODE == 1 ? (v == cls) : (v != 0);
     };
-    if (!isfg(y, x)) return;
-    const int idx = y * W + x;
-    const bool left = x > 0 && isfg(y, x - 1);
-    if (left && (x & 31) == 0) uf_union(par, idx, idx - 1);          // run crosses a segment border
-    if (y > 0 && isfg(y - 1, x)) {
-        const bool upleft = x > 0 && isfg(y - 1, x - 1);
-        if (!left || !upleft) uf_union(par, idx, idx - W);
-    } else if (CONN8 && y > 0) {
+    int* par = parent + page_off;
+    const int idx0 = y * W + x0;
+    const unsigned lb = ((m & 1u) && x0 > 0) ? isfg(row, x0 - 1) : 0u;
+    if (lb) uf_union<COMPRESS>(par, idx0, idx0 - 1);                    // run crosses a segment border
+    if (y == 0) return;
+    const uint8_t* rup = row - W;
+    const unsigned up = fg_bits<MODE>(rup, x0, W, cls, false);
+    const unsigned ulb = ((m & 1u) && x0 > 0) ? isfg(rup, x0 - 1) : 0u;
+    const unsigned leftm = (m << 1) | lb;                               // bit k: pixel left of k
+    const unsigned upleftm = (up << 1) | ulb;                           // bit k: pixel above-left of k
+    unsigned v = m & up & ~(leftm & upleftm);
+    while (v) {
+        const int k = __ffs(v) - 1;
+        v &= v - 1;
+        uf_union<COMPRESS>(par, idx0 + k, idx0 + k - W);
+    }
+    if (CONN8) {
         // 8-connectivity: the diagonal neighbours matter only when the pixel above is background (otherwise they
         // are in its run); a diagonal that the horizontal neighbour reaches through ITS upper pixel is skipped
-        if (!left && x > 0 && isfg(y - 1, x - 1)) uf_union(par, idx, idx - W - 1);
-        if (x + 1 < W && isfg(y - 1, x + 1) && !isfg(y, x + 1)) uf_union(par, idx, idx - W + 1);
+        unsigned d1 = m & ~up & ~leftm & upleftm;
+        while (d1) {
+            const int k = __ffs(d1) - 1;
+            d1 &= d1 - 1;
+            uf_union<COMPRESS>(par, idx0 + k, idx0 + k - W - 1);
+        }
+        const bool edge = (m >> 31) && x0 + 32 < W;
+        const unsigned rb = edge ? isfg(row, x0 + 32) : 0u, urb = edge ? isfg(rup, x0 + 32) : 0u;
+        unsigned d2 = m & ~up & ((up >> 1) | (urb << 31)) & ~((m >> 1) | (rb << 31));
+        while (d2) {
+            const int k = __ffs(d2) - 1;
+            d2 &= d2 - 1;
+            uf_union<COMPRESS>(par, idx0 + k, idx0 + k - W + 1);
+        }
     }
 }
 
-// `fg` (optional): the image whose non-zero pixels are the foreground.  Nine tenths of a page are background, and
-// testing the 1-byte pixel first spares the 4-byte parent read of those pixels (and lets cc_majority leave the
-// parents of background pixels unwritten).
-__global__ void __launch_bounds__(256) ccl_flatten_kernel(int* __restrict__ parent, size_t page_px, const uint8_t* __restrict__ fg) {
-    const size_t page_off = (size_t)blockIdx.y * page_px;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < page_px; i += (size_t)gridDim.x * blockDim.x) {
-        if (fg) { if (!fg[page_off + i]) continue; }
-        else if (parent[page_off + i] == kBG) continue;
-        parent[page_off + i] = uf_find(parent + page_off, (int)i);
+// C  flatten: one find per run (all pixels of a run still point at its first pixel), written to every pixel of it
+__global__ void __launch_bounds__(256) ccl_flatten_kernel(const uint8_t* __restrict__ img, int H, int W, int* __restrict__ parent) {
+    PCS_SEG_THREAD();
+    if (!valid) return;
+    unsigned mm = fg_bits<0>(img + page_off + (size_t)y * W, x0, W, 0, last_row);
+    int* par = parent + page_off;
+    const int base = y * W + x0;
+    int s, len;
+    while (next_run(mm, s, len)) {
+        const int root = uf_find(par, base + s);
+        for (int k = 0; k < len; ++k) par[base + s + k] = root;
     }
 }
 // NOTE: flatten races are benign: a concurrent writer only replaces a parent by
@@ -263,24 +375,43 @@ ccl_stats_finish_kernel(int32_t* __restrict__ stats, const int32_t* __restrict__
     }
 }
 
+// Re-linking of union operands: measured on 32 A4 pages it pays where components are huge (the page background of
+// add_bounding_boxes: 1.91 -> 1.80 ms) and costs where they are letters (compute_char_height 2.62 -> 2.84 ms,
+// cc_majority 0.44 -> 0.46 ms), so it is on for class-match labelling only.  PCSEG_CCL_COMPRESS=0/1 forces it.
+static bool ccl_compress(bool match) {
+    static const char* e = getenv("PCSEG_CCL_COMPRESS");
+    return e ? atoi(e) != 0 : match;
+}
+
+// init + merge (+ flatten).  After the merge every tree's root is the component's first pixel in raster order;
+// `flatten` additionally makes every foreground pixel point at it (callers that only walk runs find the root
+// themselves and skip that pass).
 static int ccl_roots(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, int cls, bool match, int* parent,
-                     int* zero_aux, int aux_stride, bool conn8 = false, bool fg_only = false) {
+                     int* zero_aux, int aux_stride, bool conn8 = false, bool fg_only = false, bool flatten = true) {
     // fg_only: the caller's later passes test the image before they touch a parent, so background parents are not written
     cudaStream_t st = ctx->stream;
-    dim3 ginit(((W + 31) / 32 + 7) / 8, H, n);
-    if (match) ccl_init_kernel<true><<<ginit, 256, 0, st>>>(d_img, H, W, cls, parent, zero_aux, aux_stride);
-    else if (fg_only) ccl_init_kernel<false, false><<<ginit, 256, 0, st>>>(d_img, H, W, cls, parent, zero_aux, aux_stride);
-    else ccl_init_kernel<false><<<ginit, 256, 0, st>>>(d_img, H, W, cls, parent, zero_aux, aux_stride);
+    const dim3 g = seg_grid(H, W, n);
+    if (match) ccl_init_kernel<1, true><<<g, 256, 0, st>>>(d_img, H, W, cls, parent, zero_aux, aux_stride);
+    else if (fg_only) ccl_init_kernel<0, false><<<g, 256, 0, st>>>(d_img, H, W, cls, parent, zero_aux, aux_stride);
+    else ccl_init_kernel<0, true><<<g, 256, 0, st>>>(d_img, H, W, cls, parent, zero_aux, aux_stride);
     PCS_LAUNCH_CHECK(ctx, "ccl_init_kernel");
-    dim3 gmerge((W + 255) / 256, H, n);
-    if (match) ccl_merge_kernel<true, false><<<gmerge, 256, 0, st>>>(d_img, H, W, cls, parent);
-    else if (conn8) ccl_merge_kernel<false, true><<<gmerge, 256, 0, st>>>(d_img, H, W, cls, parent);
-    else ccl_merge_kernel<false, false><<<gmerge, 256, 0, st>>>(d_img, H, W, cls, parent);
+    const bool cz = ccl_compress(match);
+    if (match) {
+        if (cz) ccl_merge_kernel<1, false, true><<<g, 256, 0, st>>>(d_img, H, W, cls, parent);
+        else ccl_merge_kernel<1, false, false><<<g, 256, 0, st>>>(d_img, H, W, cls, parent);
+    } else if (conn8) {
+        if (cz) ccl_merge_kernel<0, true, true><<<g, 256, 0, st>>>(d_img, H, W, cls, parent);
+        else ccl_merge_kernel<0, true, false><<<g, 256, 0, st>>>(d_img, H, W, cls, parent);
+    } else {
+        if (cz) ccl_merge_kernel<0, false, true><<<g, 256, 0, st>>>(d_img, H, W, cls, parent);
+        else ccl_merge_kernel<0, false, false><<<g, 256, 0, st>>>(d_img, H, W, cls, parent);
+    }
     PCS_LAUNCH_CHECK(ctx, "ccl_merge_kernel");
-    const size_t page_px = (size_t)H * W;
-    dim3 gflat((unsigned)std::min<size_t>(2048, (page_px + 255) / 256), n);
-    ccl_flatten_kernel<<<gflat, 256, 0, st>>>(parent, page_px, match ? nullptr : d_img);
-    PCS_LAUNCH_CHECK(ctx, "ccl_flatten_kernel");
+    if (flatten) {
+        if (match) return set_err(ctx, PCS_ERR_ARG, "ccl_roots: flatten needs a non-zero-foreground image");
+        ccl_flatten_kernel<<<g, 256, 0, st>>>(d_img, H, W, parent);
+        PCS_LAUNCH_CHECK(ctx, "ccl_flatten_kernel");
+    }
     return PCS_OK;
 }
 
@@ -371,26 +502,23 @@ int launch_cc_majority(pcs_ctx* ctx, uint8_t* d_pred, const uint8_t* d_binary, i
 // every 4-connected component of (pred == c) paints its bounding box with c.
 // Boxes are rasterised through a 2-D difference array + prefix sums.
 // ---------------------------------------------------------------------------
+template <int MODE>
 __global__ void __launch_bounds__(256)
-bbox_accum_kernel(const int* __restrict__ parent, int H, int W, int* __restrict__ box /*[px][4]*/, const uint8_t* __restrict__ fg) {
-    // fg (optional): the labelled image; when given, background pixels are recognised by their byte and their
-    // (then unwritten) parents are never read
-    const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
-    if (x >= W) return;
-    const size_t page_off = (size_t)blockIdx.z * H * W;
-    if (fg && !fg[page_off + (size_t)y * W + x]) return;
-    const int p = parent[page_off + (size_t)y * W + x];
-    if (p == kBG) return;
-    int* b = box + (page_off + p) * 4;
-    // accumulators are zero-initialised at run starts: keep (W - min x, H - min y, max x, max y) as maxima.
-    // A large component (a picture block, the page background of add_bounding_boxes) would send every one of
-    // its pixels to the same four words: lanes of a warp that share a root first reduce among themselves, and
-    // the leader only issues the atomics that can still grow the box (a stale read merely costs an atomic).
-    const unsigned act = __activemask();
-    const unsigned peers = __match_any_sync(act, p);
-    const int v0 = __reduce_max_sync(peers, W - x), v1 = __reduce_max_sync(peers, H - y);
-    const int v2 = __reduce_max_sync(peers, x), v3 = __reduce_max_sync(peers, y);
-    if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) {
+bbox_accum_kernel(const uint8_t* __restrict__ img, int H, int W, int cls, const int* __restrict__ parent, int* __restrict__ box /*[px][4]*/) {
+    // one update per RUN: the root is found from the run's first pixel (no flatten pass needed), the run
+    // contributes (first x, y, last x, y).  Accumulators are zero-initialised at run starts: keep
+    // (W - min x, H - min y, max x, max y) as maxima.  A large component (a picture block, the page background of
+    // add_bounding_boxes) would send every run to the same four words: the box is read first and only the atomics
+    // that can still grow it are issued (a stale read merely costs an atomic).
+    PCS_SEG_THREAD();
+    if (!valid) return;
+    unsigned mm = fg_bits<MODE>(img + page_off + (size_t)y * W, x0, W, cls, last_row);
+    const int base = y * W + x0;
+    int s, len;
+    while (next_run(mm, s, len)) {
+        const int p = uf_find(parent + page_off, base + s);
+        int* b = box + (page_off + p) * 4;
+        const int v0 = W - (x0 + s), v1 = H - y, v2 = x0 + s + len - 1, v3 = y;
         const int4 cur = __ldcg(reinterpret_cast<const int4*>(b));
         if (v0 > cur.x) atomicMax(&b[0], v0);
         if (v1 > cur.y) atomicMax(&b[1], v1);
@@ -399,20 +527,26 @@ bbox_accum_kernel(const int* __restrict__ parent, int H, int W, int* __restrict_
     }
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(256)
-bbox_diff_kernel(const int* __restrict__ parent, int H, int W, const int* __restrict__ box, int* __restrict__ diff) {
-    const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
-    if (x >= W) return;
-    const size_t page_off = (size_t)blockIdx.z * H * W;
-    const int idx = y * W + x;
-    if (parent[page_off + idx] != idx) return;            // roots only
-    const int* b = box + (page_off + idx) * 4;
-    const int x0 = W - b[0], y0 = H - b[1], x1 = b[2], y1 = b[3];
-    int* d = diff + (size_t)blockIdx.z * (H + 1) * (W + 1);
-    atomicAdd(&d[(size_t)y0 * (W + 1) + x0], 1);
-    atomicAdd(&d[(size_t)y0 * (W + 1) + x1 + 1], -1);
-    atomicAdd(&d[(size_t)(y1 + 1) * (W + 1) + x0], -1);
-    atomicAdd(&d[(size_t)(y1 + 1) * (W + 1) + x1 + 1], 1);
+bbox_diff_kernel(const uint8_t* __restrict__ img, int H, int W, int cls, const int* __restrict__ parent, const int* __restrict__ box,
+                 int* __restrict__ diff) {
+    PCS_SEG_THREAD();
+    if (!valid) return;
+    unsigned mm = fg_bits<MODE>(img + page_off + (size_t)y * W, x0, W, cls, last_row);
+    const int base = y * W + x0;
+    int* d = diff + (size_t)blockIdx.y * (H + 1) * (W + 1);
+    int s, len;
+    while (next_run(mm, s, len)) {
+        const int idx = base + s;
+        if (parent[page_off + idx] != idx) continue;        // roots only (a root is the first pixel of its run)
+        const int* b = box + (page_off + idx) * 4;
+        const int bx0 = W - b[0], by0 = H - b[1], bx1 = b[2], by1 = b[3];
+        atomicAdd(&d[(size_t)by0 * (W + 1) + bx0], 1);
+        atomicAdd(&d[(size_t)by0 * (W + 1) + bx1 + 1], -1);
+        atomicAdd(&d[(size_t)(by1 + 1) * (W + 1) + bx0], -1);
+        atomicAdd(&d[(size_t)(by1 + 1) * (W + 1) + bx1 + 1], 1);
+    }
 }
 
 // in-place inclusive scan along rows: one warp per row
@@ -434,15 +568,34 @@ __global__ void __launch_bounds__(256) diff_rowscan_kernel(int* __restrict__ dif
     }
 }
 
-// column scan fused with the paint: coverage > 0 -> out = cls
+// column scan in kColBands row bands (a thread walking all H rows of its column leaves the device idle):
+// per-band column sums first, then every band scans its rows from the sum of the bands above it.
+constexpr int kColBands = 16;
+
 __global__ void __launch_bounds__(256)
-diff_colscan_paint_kernel(const int* __restrict__ diff, int H, int W, int cls, uint8_t* __restrict__ out) {
+diff_colband_sum_kernel(const int* __restrict__ diff, int H, int W, int* __restrict__ bandsum) {
     const int x = blockIdx.x * 256 + threadIdx.x;
     if (x >= W) return;
-    const int* d = diff + (size_t)blockIdx.y * (H + 1) * (W + 1);
-    uint8_t* o = out + (size_t)blockIdx.y * H * W;
+    const int rows = (H + kColBands - 1) / kColBands;
+    const int y0 = blockIdx.y * rows, y1 = min(H, y0 + rows);
+    const int* d = diff + (size_t)blockIdx.z * (H + 1) * (W + 1);
     int acc = 0;
-    for (int y = 0; y < H; ++y) {
+    for (int y = y0; y < y1; ++y) acc += d[(size_t)y * (W + 1) + x];
+    bandsum[((size_t)blockIdx.z * kColBands + blockIdx.y) * W + x] = acc;
+}
+
+// column scan fused with the paint: coverage > 0 -> out = cls
+__global__ void __launch_bounds__(256)
+diff_colscan_paint_kernel(const int* __restrict__ diff, int H, int W, int cls, const int* __restrict__ bandsum, uint8_t* __restrict__ out) {
+    const int x = blockIdx.x * 256 + threadIdx.x;
+    if (x >= W) return;
+    const int rows = (H + kColBands - 1) / kColBands;
+    const int y0 = blockIdx.y * rows, y1 = min(H, y0 + rows);
+    const int* d = diff + (size_t)blockIdx.z * (H + 1) * (W + 1);
+    uint8_t* o = out + (size_t)blockIdx.z * H * W;
+    int acc = 0;
+    for (int b = 0; b < (int)blockIdx.y; ++b) acc += bandsum[((size_t)blockIdx.z * kColBands + b) * W + x];
+    for (int y = y0; y < y1; ++y) {
         acc += d[(size_t)y * (W + 1) + x];
         if (acc > 0) o[(size_t)y * W + x] = (uint8_t)cls;
     }
@@ -454,24 +607,29 @@ int launch_bounding_boxes(pcs_ctx* ctx, const uint8_t* d_pred, int n, int H, int
     const size_t page_px = (size_t)H * W, total = page_px * n;
     const size_t diff_elems = (size_t)n * (H + 1) * (W + 1);
     const size_t total4 = (total + 3) / 4 * 4;                           // keeps the int4 box records 16-byte aligned
-    PCS_TRY(scratch_reserve(ctx, total4 * 4 * 5 + diff_elems * 4 + 512));
+    const size_t band_elems = (size_t)n * kColBands * W;
+    PCS_TRY(scratch_reserve(ctx, total4 * 4 * 5 + (diff_elems + band_elems) * 4 + 512));
     int* parent = reinterpret_cast<int*>(ctx->scratch);
     int* box = parent + total4;
     int* diff = box + total4 * 4;
+    int* bandsum = diff + diff_elems;
     cudaStream_t st = ctx->stream;
     PCS_CUDA(ctx, cudaMemsetAsync(d_out, 0, total, st));                 // newpred = zeros_like(pred)
     // classes = np.unique(pred) per page in the reference; painting an absent class is a no-op
     for (int c = 0; c < n_classes; ++c) {
-        PCS_TRY(ccl_roots(ctx, d_pred, n, H, W, c, true, parent, box, 4));
-        dim3 g((W + 255) / 256, H, n);
-        bbox_accum_kernel<<<g, 256, 0, st>>>(parent, H, W, box, nullptr);
+        PCS_TRY(ccl_roots(ctx, d_pred, n, H, W, c, true, parent, box, 4, false, false, /*flatten=*/false));
+        const dim3 g = seg_grid(H, W, n);
+        bbox_accum_kernel<1><<<g, 256, 0, st>>>(d_pred, H, W, c, parent, box);
         PCS_LAUNCH_CHECK(ctx, "bbox_accum_kernel");
         PCS_CUDA(ctx, cudaMemsetAsync(diff, 0, diff_elems * 4, st));
-        bbox_diff_kernel<<<g, 256, 0, st>>>(parent, H, W, box, diff);
+        bbox_diff_kernel<1><<<g, 256, 0, st>>>(d_pred, H, W, c, parent, box, diff);
         PCS_LAUNCH_CHECK(ctx, "bbox_diff_kernel");
         diff_rowscan_kernel<<<dim3((H + 1 + 7) / 8, n), 256, 0, st>>>(diff, H + 1, W + 1);
         PCS_LAUNCH_CHECK(ctx, "diff_rowscan_kernel");
-        diff_colscan_paint_kernel<<<dim3((W + 255) / 256, n), 256, 0, st>>>(diff, H, W, c, d_out);
+        const dim3 gc((W + 255) / 256, kColBands, n);
+        diff_colband_sum_kernel<<<gc, 256, 0, st>>>(diff, H, W, bandsum);
+        PCS_LAUNCH_CHECK(ctx, "diff_colband_sum_kernel");
+        diff_colscan_paint_kernel<<<gc, 256, 0, st>>>(diff, H, W, c, bandsum, d_out);
         PCS_LAUNCH_CHECK(ctx, "diff_colscan_paint_kernel");
     }
     return PCS_OK;
@@ -544,24 +702,40 @@ __global__ void __launch_bounds__(256)
 otsu_fg_kernel(const uint8_t* __restrict__ img, size_t page_px, const int* __restrict__ thresh, int inverse, uint8_t* __restrict__ fg) {
     const int t = thresh[blockIdx.y];
     const size_t off = (size_t)blockIdx.y * page_px;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < page_px; i += (size_t)gridDim.x * blockDim.x) {
+    const bool aligned = ((reinterpret_cast<uintptr_t>(img + off) | reinterpret_cast<uintptr_t>(fg + off)) & 15) == 0;
+    const size_t chunks = aligned ? page_px / 16 : 0;
+    const unsigned t4 = (unsigned)t * 0x01010101u, flip = inverse ? 0u : 0xffffffffu;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < chunks; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(img + off) + i);
+        uint4 r;
+        r.x = (__vcmpgtu4(q.x, t4) ^ flip) & 0x01010101u;
+        r.y = (__vcmpgtu4(q.y, t4) ^ flip) & 0x01010101u;
+        r.z = (__vcmpgtu4(q.z, t4) ^ flip) & 0x01010101u;
+        r.w = (__vcmpgtu4(q.w, t4) ^ flip) & 0x01010101u;
+        reinterpret_cast<uint4*>(fg + off)[i] = r;
+    }
+    for (size_t i = chunks * 16 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < page_px; i += (size_t)gridDim.x * blockDim.x) {
         const bool above = img[off + i] > t;
         fg[off + i] = (above == (inverse != 0)) ? 1 : 0;
     }
 }
 
 __global__ void __launch_bounds__(256)
-letter_heights_kernel(const int* __restrict__ parent, const uint8_t* __restrict__ fg, int H, int W, const int* __restrict__ box,
+letter_heights_kernel(const uint8_t* __restrict__ fg, int H, int W, const int* __restrict__ parent, const int* __restrict__ box,
                       unsigned* __restrict__ hh /*[n][64]*/) {
-    const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
-    if (x >= W) return;
-    const size_t page_off = (size_t)blockIdx.z * H * W;
-    const int idx = y * W + x;
-    if (!fg[page_off + idx] || parent[page_off + idx] != idx) return;            // roots only (background parents are unwritten)
-    const int* b = box + (page_off + idx) * 4;
-    const int w = b[2] - (W - b[0]) + 1, h = b[3] - (H - b[1]) + 1;
-    // 0.5 < w/h < 2  <=>  h < 2w and w < 2h (exact for these small integers)
-    if (h < 2 * w && w < 2 * h && h > 10 && h < 60 && w > 5 && w < 50) atomicAdd(&hh[(size_t)blockIdx.z * 64 + h], 1u);
+    PCS_SEG_THREAD();
+    if (!valid) return;
+    unsigned mm = fg_bits<0>(fg + page_off + (size_t)y * W, x0, W, 0, last_row);
+    const int base = y * W + x0;
+    int s, len;
+    while (next_run(mm, s, len)) {
+        const int idx = base + s;
+        if (parent[page_off + idx] != idx) continue;            // roots only (a root is the first pixel of its run)
+        const int* b = box + (page_off + idx) * 4;
+        const int w = b[2] - (W - b[0]) + 1, h = b[3] - (H - b[1]) + 1;
+        // 0.5 < w/h < 2  <=>  h < 2w and w < 2h (exact for these small integers)
+        if (h < 2 * w && w < 2 * h && h > 10 && h < 60 && w > 5 && w < 50) atomicAdd(&hh[(size_t)blockIdx.y * 64 + h], 1u);
+    }
 }
 
 // sorted(valid heights)[len / 2], or -1 when there is no valid letter (the reference returns None)
@@ -603,11 +777,11 @@ int launch_char_height(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, 
     PCS_LAUNCH_CHECK(ctx, "otsu_kernel");
     otsu_fg_kernel<<<gflat, 256, 0, st>>>(d_img, page_px, thresh, inverse, fg);
     PCS_LAUNCH_CHECK(ctx, "otsu_fg_kernel");
-    PCS_TRY(ccl_roots(ctx, fg, n, H, W, 0, false, parent, box, 4, /*conn8=*/true, /*fg_only=*/true));
-    const dim3 g((W + 255) / 256, H, n);
-    bbox_accum_kernel<<<g, 256, 0, st>>>(parent, H, W, box, fg);
+    PCS_TRY(ccl_roots(ctx, fg, n, H, W, 0, false, parent, box, 4, /*conn8=*/true, /*fg_only=*/true, /*flatten=*/false));
+    const dim3 g = seg_grid(H, W, n);
+    bbox_accum_kernel<0><<<g, 256, 0, st>>>(fg, H, W, 0, parent, box);
     PCS_LAUNCH_CHECK(ctx, "bbox_accum_kernel");
-    letter_heights_kernel<<<g, 256, 0, st>>>(parent, fg, H, W, box, hh);
+    letter_heights_kernel<<<g, 256, 0, st>>>(fg, H, W, parent, box, hh);
     PCS_LAUNCH_CHECK(ctx, "letter_heights_kernel");
     median_height_kernel<<<(n + 63) / 64, 64, 0, st>>>(hh, n, d_out);
     PCS_LAUNCH_CHECK(ctx, "median_height_kernel");
