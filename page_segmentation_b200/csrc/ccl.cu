@@ -5,16 +5,18 @@
 // ocr4all_pixel_classifier/lib/postprocess.py:10 (vote_connected_component_class),
 // :33 (add_bounding_boxes) and lib/image_ops.py:68 (compute_char_height).
 //
-// Algorithm: union-find over pixels with warp-ballot run detection.
-//   A  init     : every warp owns 32 consecutive pixels of a row; the ballot of
-//                 the foreground bits gives each pixel its run start, so all
-//                 horizontal merges inside a segment cost no atomics;
-//   B  merge    : vertical unions only where a run starts or the upper-left
-//                 neighbour is background (one union per touching run pair),
-//                 plus one union per run crossing a 32-pixel segment border;
-//                 union = atomicMin on the larger root (roots only decrease);
+// Algorithm: union-find over pixels; a thread owns a 32-pixel row segment as a bit mask.
+//   A  tile     : every 256 x 32 tile is labelled on its own in shared memory: parent =
+//                 first pixel of the pixel's run inside its segment (horizontal merges
+//                 inside a segment cost nothing), vertical unions only where a run
+//                 starts or the upper-left neighbour is background (one union per
+//                 touching run pair), plus one union per run crossing a segment border;
+//                 the global parent of a pixel is its tile-local root;
+//   B  borders  : the same unions for pixel pairs in different tiles, on the global
+//                 parents; union = atomicMin on the larger root (roots only decrease);
 //   C  flatten  : label = root = smallest linear index of the component = its
-//                 first pixel in raster order;
+//                 first pixel in raster order (one find per run; consumers that walk
+//                 runs themselves -- bounding boxes -- skip this pass);
 //   D  rank     : exclusive scan of the root flags -> OpenCV numbering
 //                 (components numbered by raster order of their first pixel).
 #include "common.cuh"
@@ -129,28 +131,116 @@ __device__ __forceinline__ bool next_run(unsigned& mm, int& s, int& len) {
 
 static inline dim3 seg_grid(int H, int W, int n) { return dim3((unsigned)((((size_t)(W + 31) / 32) * H + 255) / 256), n); }
 
-// A  init: parent = first pixel of the pixel's run inside its 32-pixel segment.  The 32 masks of a warp are handed
-// round so that every store instruction writes 32 consecutive parents.
-template <int MODE, bool WRITE_BG>
+// union-find inside one tile, in shared memory (local pixel index = thread * 32 + bit)
+__device__ __forceinline__ int suf_find(const volatile int* lp, int x) {
+    int p = lp[x];
+    while (p != x) { x = p; p = lp[x]; }
+    return x;
+}
+
+__device__ __forceinline__ void suf_union(int* lp, int a, int b) {
+    while (true) {
+        a = suf_find(lp, a);
+        b = suf_find(lp, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }
+        const int old = atomicMin(&lp[a], b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
+constexpr int kTileSegs = 8, kTileRows = 32;        // a block labels a tile of 256 x 32 pixels
+
+// A  tile: every 256 x 32 tile is labelled on its own in shared memory (pixels outside the tile count as
+// background): parent = first pixel of the run inside the 32-pixel segment, one union per touching run pair
+// (vertical unions only where a run starts or the upper-left neighbour is background) with shared-memory atomics,
+// one find per run; then every pixel's parent is written as the GLOBAL index of its tile-local root.  The local
+// order (row, then x) is the global raster order, so the local root is the tile's first pixel of the component.
+// The 32 masks of a warp are handed round so that every store instruction writes 32 consecutive parents.
+template <int MODE, bool CONN8, bool WRITE_BG>
 __global__ void __launch_bounds__(256)
-ccl_init_kernel(const uint8_t* __restrict__ img, int H, int W, int cls, int* __restrict__ parent,
+ccl_tile_kernel(const uint8_t* __restrict__ img, int H, int W, int cls, int* __restrict__ parent,
                 int* __restrict__ zero_aux, int aux_stride) {
-    PCS_SEG_THREAD();
-    const int lane = threadIdx.x & 31;
+    __shared__ int lpar[kTileRows * kTileSegs * 32];
+    __shared__ unsigned smask[kTileRows][kTileSegs];
+    const int tid = threadIdx.x, lane = tid & 31, sx = tid & (kTileSegs - 1), ry = tid / kTileSegs;
+    const int ty0 = blockIdx.y * kTileRows, tx0 = blockIdx.x * kTileSegs * 32;
+    const int y = ty0 + ry, x0 = tx0 + sx * 32;
+    const size_t page_off = (size_t)blockIdx.z * H * W;
+    const bool valid = y < H && x0 < W;
+    const bool last_row = y == H - 1 && blockIdx.z == gridDim.z - 1;
     const unsigned m = valid ? fg_bits<MODE>(img + page_off + (size_t)y * W, x0, W, cls, last_row) : 0u;
-    const int base = y * W + x0;
-    const int nx = valid ? min(32, W - x0) : 0;
-    int* par = parent + page_off;
-    if (!WRITE_BG && !__any_sync(0xffffffffu, m != 0)) return;          // !WRITE_BG: every later pass tests the image first
-    for (int j = 0; j < 32; ++j) {
+    smask[ry][sx] = m;
+    const int l0 = tid * 32;                                            // = ry * 256 + sx * 32
+    const unsigned nz = __ballot_sync(0xffffffffu, m != 0);            // segments of this warp that hold foreground
+    for (unsigned todo = nz; todo; todo &= todo - 1) {                  // warp-uniform loop
+        const int j = __ffs(todo) - 1;
         const unsigned mj = __shfl_sync(0xffffffffu, m, j);
-        const int bj = __shfl_sync(0xffffffffu, base, j), nj = __shfl_sync(0xffffffffu, nx, j);
-        if (!WRITE_BG && mj == 0) continue;                             // warp-uniform
+        if ((mj >> lane) & 1u) {
+            const unsigned below = ~mj & ((1u << lane) - 1u);           // background lanes left of me
+            const int lb = (tid - lane + j) * 32;
+            lpar[lb + lane] = lb + (below ? 32 - __clz(below) : 0);
+        }
+    }
+    __syncthreads();
+    if (m) {
+        const unsigned lb = sx > 0 ? smask[ry][sx - 1] >> 31 : 0u;
+        if ((m & 1u) && lb) suf_union(lpar, l0, l0 - 1);                // run crosses a segment border
+        if (ry > 0) {
+            const unsigned up = smask[ry - 1][sx];
+            const unsigned ulb = sx > 0 ? smask[ry - 1][sx - 1] >> 31 : 0u;
+            const unsigned leftm = (m << 1) | lb, upleftm = (up << 1) | ulb;
+            unsigned v = m & up & ~(leftm & upleftm);
+            while (v) {
+                const int k = __ffs(v) - 1;
+                v &= v - 1;
+                suf_union(lpar, l0 + k, l0 + k - 256);
+            }
+            if (CONN8) {
+                // 8-connectivity: the diagonal neighbours matter only when the pixel above is background (otherwise
+                // they are in its run); a diagonal that the horizontal neighbour reaches through ITS upper pixel is skipped
+                unsigned d1 = m & ~up & ~leftm & upleftm;
+                while (d1) {
+                    const int k = __ffs(d1) - 1;
+                    d1 &= d1 - 1;
+                    suf_union(lpar, l0 + k, l0 + k - 256 - 1);
+                }
+                const unsigned rb = sx + 1 < kTileSegs ? smask[ry][sx + 1] & 1u : 0u;
+                const unsigned urb = sx + 1 < kTileSegs ? smask[ry - 1][sx + 1] & 1u : 0u;
+                unsigned d2 = m & ~up & ((up >> 1) | (urb << 31)) & ~((m >> 1) | (rb << 31));
+                while (d2) {
+                    const int k = __ffs(d2) - 1;
+                    d2 &= d2 - 1;
+                    suf_union(lpar, l0 + k, l0 + k - 256 + 1);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    {   // one find per run, kept at the run's first pixel (a concurrent walker reads the old or the new ancestor)
+        unsigned mm = m;
+        int s, len;
+        while (next_run(mm, s, len)) {
+            const int r = suf_find(lpar, l0 + s);
+            lpar[l0 + s] = r;
+        }
+    }
+    __syncthreads();
+    int* par = parent + page_off;
+    // segments to write: the ones with foreground, or (WRITE_BG) every segment inside the page
+    for (unsigned todo = WRITE_BG ? __ballot_sync(0xffffffffu, valid) : nz; todo; todo &= todo - 1) {
+        const int j = __ffs(todo) - 1;
+        const unsigned mj = __shfl_sync(0xffffffffu, m, j);
+        const int tj = tid - lane + j;                                  // the thread that owns segment j: warp-uniform
+        const int xj = tx0 + (tj & (kTileSegs - 1)) * 32;
+        const int bj = (ty0 + tj / kTileSegs) * W + xj, nj = min(32, W - xj);
         if (lane < nj) {
             if ((mj >> lane) & 1u) {
-                const unsigned below = ~mj & ((1u << lane) - 1u);       // background lanes left of me
+                const unsigned below = ~mj & ((1u << lane) - 1u);
                 const int start = below ? 32 - __clz(below) : 0;
-                par[bj + lane] = bj + start;
+                const int r = lpar[(tid - lane + j) * 32 + start];
+                par[bj + lane] = (ty0 + (r >> 8)) * W + tx0 + (r & 255);
                 if (zero_aux && start == lane) {
                     // run starts are the only root candidates: clear their accumulators
                     int* z = zero_aux + (page_off + bj + lane) * aux_stride;
@@ -163,13 +253,18 @@ ccl_init_kernel(const uint8_t* __restrict__ img, int H, int W, int cls, int* __r
     }
 }
 
-// B  merge: one union per touching run pair (vertical unions only where a run starts or the upper-left neighbour
-// is background), plus one union per run crossing a segment border.
+// B  borders: the unions between pixels of different tiles, on the global parents.  Rows that start a tile run the
+// complete rule set against the row above; elsewhere only the first segment of a tile has a neighbour outside it
+// (to the left; with 8-connectivity also the upper-left diagonal of its first pixel, and the upper-right diagonal
+// of the last pixel of the tile's last segment).
 template <int MODE, bool CONN8, bool COMPRESS>
 __global__ void __launch_bounds__(256)
-ccl_merge_kernel(const uint8_t* __restrict__ img, int H, int W, int cls, int* __restrict__ parent) {
+ccl_border_kernel(const uint8_t* __restrict__ img, int H, int W, int cls, int* __restrict__ parent) {
     PCS_SEG_THREAD();
     if (!valid) return;
+    const int sx = (x0 >> 5) & (kTileSegs - 1);
+    const bool hrow = (y & (kTileRows - 1)) == 0;
+    if (!hrow && sx != 0 && !(CONN8 && sx == kTileSegs - 1)) return;
     const uint8_t* im = img + page_off;
     const uint8_t* row = im + (size_t)y * W;
     const unsigned m = fg_bits<MODE>(row, x0, W, cls, last_row);
@@ -181,23 +276,22 @@ ccl_merge_kernel(const uint8_t* __restrict__ img, int H, int W, int cls, int* __
     int* par = parent + page_off;
     const int idx0 = y * W + x0;
     const unsigned lb = ((m & 1u) && x0 > 0) ? isfg(row, x0 - 1) : 0u;
-    if (lb) uf_union<COMPRESS>(par, idx0, idx0 - 1);                    // run crosses a segment border
-    if (y == 0) return;
+    if (lb && sx == 0) uf_union<COMPRESS>(par, idx0, idx0 - 1);         // run crosses a tile border
+    if (y == 0 || (!hrow && !CONN8)) return;
     const uint8_t* rup = row - W;
     const unsigned up = fg_bits<MODE>(rup, x0, W, cls, false);
     const unsigned ulb = ((m & 1u) && x0 > 0) ? isfg(rup, x0 - 1) : 0u;
     const unsigned leftm = (m << 1) | lb;                               // bit k: pixel left of k
     const unsigned upleftm = (up << 1) | ulb;                           // bit k: pixel above-left of k
-    unsigned v = m & up & ~(leftm & upleftm);
+    unsigned v = hrow ? m & up & ~(leftm & upleftm) : 0u;
     while (v) {
         const int k = __ffs(v) - 1;
         v &= v - 1;
         uf_union<COMPRESS>(par, idx0 + k, idx0 + k - W);
     }
     if (CONN8) {
-        // 8-connectivity: the diagonal neighbours matter only when the pixel above is background (otherwise they
-        // are in its run); a diagonal that the horizontal neighbour reaches through ITS upper pixel is skipped
         unsigned d1 = m & ~up & ~leftm & upleftm;
+        if (!hrow) d1 &= sx == 0 ? 1u : 0u;
         while (d1) {
             const int k = __ffs(d1) - 1;
             d1 &= d1 - 1;
@@ -206,6 +300,7 @@ ccl_merge_kernel(const uint8_t* __restrict__ img, int H, int W, int cls, int* __
         const bool edge = (m >> 31) && x0 + 32 < W;
         const unsigned rb = edge ? isfg(row, x0 + 32) : 0u, urb = edge ? isfg(rup, x0 + 32) : 0u;
         unsigned d2 = m & ~up & ((up >> 1) | (urb << 31)) & ~((m >> 1) | (rb << 31));
+        if (!hrow) d2 &= sx == kTileSegs - 1 ? 0x80000000u : 0u;
         while (d2) {
             const int k = __ffs(d2) - 1;
             d2 &= d2 - 1;
@@ -391,22 +486,25 @@ static int ccl_roots(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, in
     // fg_only: the caller's later passes test the image before they touch a parent, so background parents are not written
     cudaStream_t st = ctx->stream;
     const dim3 g = seg_grid(H, W, n);
-    if (match) ccl_init_kernel<1, true><<<g, 256, 0, st>>>(d_img, H, W, cls, parent, zero_aux, aux_stride);
-    else if (fg_only) ccl_init_kernel<0, false><<<g, 256, 0, st>>>(d_img, H, W, cls, parent, zero_aux, aux_stride);
-    else ccl_init_kernel<0, true><<<g, 256, 0, st>>>(d_img, H, W, cls, parent, zero_aux, aux_stride);
-    PCS_LAUNCH_CHECK(ctx, "ccl_init_kernel");
+    const dim3 gt((W + kTileSegs * 32 - 1) / (kTileSegs * 32), (H + kTileRows - 1) / kTileRows, n);
+    if (match) ccl_tile_kernel<1, false, true><<<gt, 256, 0, st>>>(d_img, H, W, cls, parent, zero_aux, aux_stride);
+    else if (conn8 && fg_only) ccl_tile_kernel<0, true, false><<<gt, 256, 0, st>>>(d_img, H, W, cls, parent, zero_aux, aux_stride);
+    else if (conn8) ccl_tile_kernel<0, true, true><<<gt, 256, 0, st>>>(d_img, H, W, cls, parent, zero_aux, aux_stride);
+    else if (fg_only) ccl_tile_kernel<0, false, false><<<gt, 256, 0, st>>>(d_img, H, W, cls, parent, zero_aux, aux_stride);
+    else ccl_tile_kernel<0, false, true><<<gt, 256, 0, st>>>(d_img, H, W, cls, parent, zero_aux, aux_stride);
+    PCS_LAUNCH_CHECK(ctx, "ccl_tile_kernel");
     const bool cz = ccl_compress(match);
     if (match) {
-        if (cz) ccl_merge_kernel<1, false, true><<<g, 256, 0, st>>>(d_img, H, W, cls, parent);
-        else ccl_merge_kernel<1, false, false><<<g, 256, 0, st>>>(d_img, H, W, cls, parent);
+        if (cz) ccl_border_kernel<1, false, true><<<g, 256, 0, st>>>(d_img, H, W, cls, parent);
+        else ccl_border_kernel<1, false, false><<<g, 256, 0, st>>>(d_img, H, W, cls, parent);
     } else if (conn8) {
-        if (cz) ccl_merge_kernel<0, true, true><<<g, 256, 0, st>>>(d_img, H, W, cls, parent);
-        else ccl_merge_kernel<0, true, false><<<g, 256, 0, st>>>(d_img, H, W, cls, parent);
+        if (cz) ccl_border_kernel<0, true, true><<<g, 256, 0, st>>>(d_img, H, W, cls, parent);
+        else ccl_border_kernel<0, true, false><<<g, 256, 0, st>>>(d_img, H, W, cls, parent);
     } else {
-        if (cz) ccl_merge_kernel<0, false, true><<<g, 256, 0, st>>>(d_img, H, W, cls, parent);
-        else ccl_merge_kernel<0, false, false><<<g, 256, 0, st>>>(d_img, H, W, cls, parent);
+        if (cz) ccl_border_kernel<0, false, true><<<g, 256, 0, st>>>(d_img, H, W, cls, parent);
+        else ccl_border_kernel<0, false, false><<<g, 256, 0, st>>>(d_img, H, W, cls, parent);
     }
-    PCS_LAUNCH_CHECK(ctx, "ccl_merge_kernel");
+    PCS_LAUNCH_CHECK(ctx, "ccl_border_kernel");
     if (flatten) {
         if (match) return set_err(ctx, PCS_ERR_ARG, "ccl_roots: flatten needs a non-zero-foreground image");
         ccl_flatten_kernel<<<g, 256, 0, st>>>(d_img, H, W, parent);
