@@ -75,20 +75,15 @@ __device__ __forceinline__ unsigned bytes4_to_bits(unsigned w, unsigned cls4) {
     return c & 0xfu;
 }
 
-// bit k = pixel x0 + k of this row is foreground; pixels at or beyond W read as background.
+// the 32 bytes of a segment as eight words; bytes at or beyond W read as `fill`.
 // `last_row`: the row is the last one of the whole buffer (the word path may read 3 bytes past pixel x0 + 31).
-template <int MODE>
-__device__ __forceinline__ unsigned fg_bits(const uint8_t* __restrict__ row, int x0, int W, int cls, bool last_row) {
+__device__ __forceinline__ void load_seg32(const uint8_t* __restrict__ row, int x0, int W, bool last_row, unsigned fill, unsigned (&w)[8]) {
     const uint8_t* p = row + x0;
-    const unsigned cls4 = (unsigned)cls * 0x01010101u;
     const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-    unsigned m = 0;
     if (x0 + 32 <= W && (a & 15) == 0) {
         const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(p));
         const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(p) + 1);
-        m = bytes4_to_bits<MODE>(q0.x, cls4) | bytes4_to_bits<MODE>(q0.y, cls4) << 4 | bytes4_to_bits<MODE>(q0.z, cls4) << 8 |
-            bytes4_to_bits<MODE>(q0.w, cls4) << 12 | bytes4_to_bits<MODE>(q1.x, cls4) << 16 | bytes4_to_bits<MODE>(q1.y, cls4) << 20 |
-            bytes4_to_bits<MODE>(q1.z, cls4) << 24 | bytes4_to_bits<MODE>(q1.w, cls4) << 28;
+        w[0] = q0.x; w[1] = q0.y; w[2] = q0.z; w[3] = q0.w; w[4] = q1.x; w[5] = q1.y; w[6] = q1.z; w[7] = q1.w;
     } else if (x0 + 32 <= W && (!last_row || x0 + 36 <= W)) {
         const unsigned* pa = reinterpret_cast<const unsigned*>(a & ~(uintptr_t)3);
         const unsigned sh = (unsigned)(a & 3) * 8;
@@ -96,17 +91,33 @@ __device__ __forceinline__ unsigned fg_bits(const uint8_t* __restrict__ row, int
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const unsigned hi = (k < 7 || sh) ? __ldg(pa + k + 1) : 0u;
-            m |= bytes4_to_bits<MODE>(__funnelshift_r(lo, hi, sh), cls4) << (4 * k);
+            w[k] = __funnelshift_r(lo, hi, sh);
             lo = hi;
         }
     } else {
         const int nx = min(32, W - x0);
-        for (int k = 0; k < nx; ++k) {
-            const uint8_t v = __ldg(p + k);
-            m |= (unsigned)(MODE == 1 ? (v == cls) : (v != 0)) << k;
-        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) w[k] = 0u;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) w[k >> 2] |= (unsigned)(k < nx ? __ldg(p + k) : (uint8_t)fill) << ((k & 3) * 8);
     }
+}
+
+template <int MODE>
+__device__ __forceinline__ unsigned seg_bits(const unsigned (&w)[8], int cls) {
+    const unsigned cls4 = (unsigned)cls * 0x01010101u;
+    unsigned m = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m |= bytes4_to_bits<MODE>(w[k], cls4) << (4 * k);
     return m;
+}
+
+// bit k = pixel x0 + k of this row is foreground; pixels at or beyond W read as background.
+template <int MODE>
+__device__ __forceinline__ unsigned fg_bits(const uint8_t* __restrict__ row, int x0, int W, int cls, bool last_row) {
+    unsigned w[8];
+    load_seg32(row, x0, W, last_row, MODE == 1 ? ~(unsigned)cls : 0u, w);
+    return seg_bits<MODE>(w, cls);
 }
 
 // pops the lowest run of set bits of mm: pixels s .. s + len - 1
@@ -552,30 +563,52 @@ int launch_ccl(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, int32_t*
 // ---------------------------------------------------------------------------
 // vote_connected_component_class (postprocess.py:9-26)
 // ---------------------------------------------------------------------------
+// one histogram update per RUN and class: the root is found from the run's first pixel and kept there for the
+// apply pass (no flatten pass), the classes of the run's pixels are counted on bit masks
 __global__ void __launch_bounds__(256)
-cc_vote_kernel(const uint8_t* __restrict__ pred, const uint8_t* __restrict__ fg, const int* __restrict__ parent, size_t page_px,
+cc_vote_kernel(const uint8_t* __restrict__ pred, const uint8_t* __restrict__ fg, int H, int W, int* __restrict__ parent,
                int n_classes, int* __restrict__ hist) {
-    const size_t page_off = (size_t)blockIdx.y * page_px;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < page_px; i += (size_t)gridDim.x * blockDim.x) {
-        if (!fg[page_off + i]) continue;
-        const int p = parent[page_off + i];
-        const int c = pred[page_off + i];
-        if (c < n_classes) atomicAdd(&hist[(page_off + p) * n_classes + c], 1);
+    PCS_SEG_THREAD();
+    if (!valid) return;
+    const unsigned m = fg_bits<0>(fg + page_off + (size_t)y * W, x0, W, 0, last_row);
+    if (!m) return;
+    unsigned w[8];
+    load_seg32(pred + page_off + (size_t)y * W, x0, W, last_row, 0xffu, w);
+    int* par = parent + page_off;
+    const int base = y * W + x0;
+    unsigned mm = m;
+    int s, len;
+    while (next_run(mm, s, len)) {                                      // roots first: the class loop re-reads them
+        const int root = uf_find(par, base + s);
+        par[base + s] = root;
+    }
+    for (int c = 0; c < n_classes; ++c) {
+        const unsigned bc = seg_bits<1>(w, c) & m;
+        if (!bc) continue;
+        mm = m;
+        while (next_run(mm, s, len)) {
+            const unsigned run = (len >= 32 ? 0xffffffffu : ((1u << len) - 1u)) << s;
+            const int cnt = __popc(bc & run);
+            if (cnt) atomicAdd(&hist[(page_off + par[base + s]) * n_classes + c], cnt);
+        }
     }
 }
 
 __global__ void __launch_bounds__(256)
-cc_apply_kernel(uint8_t* __restrict__ pred, const uint8_t* __restrict__ fg, const int* __restrict__ parent, size_t page_px,
+cc_apply_kernel(uint8_t* __restrict__ pred, const uint8_t* __restrict__ fg, int H, int W, const int* __restrict__ parent,
                 int n_classes, const int* __restrict__ hist) {
-    const size_t page_off = (size_t)blockIdx.y * page_px;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < page_px; i += (size_t)gridDim.x * blockDim.x) {
-        if (!fg[page_off + i]) continue;
-        const int p = parent[page_off + i];
-        const int* h = hist + (page_off + p) * n_classes;
+    PCS_SEG_THREAD();
+    if (!valid) return;
+    unsigned mm = fg_bits<0>(fg + page_off + (size_t)y * W, x0, W, 0, last_row);
+    const int base = y * W + x0;
+    int s, len;
+    while (next_run(mm, s, len)) {
+        const int* h = hist + (page_off + parent[page_off + base + s]) * n_classes;
         int best = 0, bv = h[0];
         for (int c = 1; c < n_classes; ++c)
             if (h[c] > bv) { bv = h[c]; best = c; }          // ties -> lowest class (np.argmax)
-        pred[page_off + i] = (uint8_t)best;
+        uint8_t* o = pred + page_off + base + s;
+        for (int k = 0; k < len; ++k) o[k] = (uint8_t)best;
     }
 }
 
@@ -586,11 +619,11 @@ int launch_cc_majority(pcs_ctx* ctx, uint8_t* d_pred, const uint8_t* d_binary, i
     PCS_TRY(scratch_reserve(ctx, total * 4 * (1 + (size_t)n_classes) + 256));
     int* parent = reinterpret_cast<int*>(ctx->scratch);
     int* hist = parent + total;
-    PCS_TRY(ccl_roots(ctx, d_binary, n, H, W, 0, false, parent, hist, n_classes, false, /*fg_only=*/true));
-    dim3 grid((unsigned)std::min<size_t>(2048, (page_px + 255) / 256), n);
-    cc_vote_kernel<<<grid, 256, 0, ctx->stream>>>(d_pred, d_binary, parent, page_px, n_classes, hist);
+    PCS_TRY(ccl_roots(ctx, d_binary, n, H, W, 0, false, parent, hist, n_classes, false, /*fg_only=*/true, /*flatten=*/false));
+    const dim3 grid = seg_grid(H, W, n);
+    cc_vote_kernel<<<grid, 256, 0, ctx->stream>>>(d_pred, d_binary, H, W, parent, n_classes, hist);
     PCS_LAUNCH_CHECK(ctx, "cc_vote_kernel");
-    cc_apply_kernel<<<grid, 256, 0, ctx->stream>>>(d_pred, d_binary, parent, page_px, n_classes, hist);
+    cc_apply_kernel<<<grid, 256, 0, ctx->stream>>>(d_pred, d_binary, H, W, parent, n_classes, hist);
     PCS_LAUNCH_CHECK(ctx, "cc_apply_kernel");
     return PCS_OK;
 }
