@@ -111,7 +111,7 @@ class Network:
         """`want_logits=False` (Predictor: predictor.py:33 drops the logits at once) skips their 12 bytes per pixel of
         device-to-host traffic and returns None in their place."""
         import torch
-        from ..runtime import to_host
+        from ..runtime import results_to_host
         ctx = self._context()
         image = np.ascontiguousarray(data.image)
         if image.dtype != np.uint8 or image.ndim != 2:
@@ -123,9 +123,8 @@ class Network:
         d_logits = torch.empty((h, w, self.n_classes), dtype=torch.float32, device=dev) if want_logits else None
         d_prob = torch.empty((h, w, self.n_classes), dtype=torch.float32, device=dev)
         ctx.forward(d_image, None, 1, h, w, d_labels, d_logits, d_prob)
-        logit = to_host(d_logits) if want_logits else None
-        prob = to_host(d_prob)
-        pred = to_host(d_labels.to(torch.int64))          # np.argmax yields int64; widened on the device, not by a host pass
+        # np.argmax yields int64; widened on the device, not by a host pass
+        logit, prob, pred = results_to_host(d_logits, d_prob, d_labels.to(torch.int64))
         return logit, prob, pred
 
     def predict_labels_device(self, d_image, d_labels):

@@ -11,31 +11,59 @@ def _n_classes(pred: np.ndarray) -> int:
     return int(pred.max()) + 1 if pred.size else 1
 
 
+def _pred_to_device(pred: np.ndarray, device: int):
+    """Class map of any integer dtype -> (uint8 device tensor, n_classes).  The array goes up as it is (from
+    Predictor.predict it is page-locked int64) and is range-checked and narrowed on the device, not by host passes."""
+    import torch
+    from ..runtime import to_device_u8
+    if pred.size == 0 or pred.dtype not in (np.int64, np.int32, np.int16, np.uint8, np.int8):
+        return to_device_u8(pred, device), _n_classes(pred)
+    t = torch.from_numpy(np.ascontiguousarray(pred)).to(f"cuda:{device}")
+    lo, hi = (int(v) for v in torch.aminmax(t))
+    if lo < 0 or hi > 255:
+        raise ValueError("values outside 0..255 cannot be staged as uint8")
+    return t.to(torch.uint8), hi + 1
+
+
+def _store(pred: np.ndarray, d_pred) -> np.ndarray:
+    """Device class map -> the caller's array, widened on the device and copied straight into its memory."""
+    import torch
+    if pred.size and pred.flags.c_contiguous and pred.flags.writeable and pred.dtype in (np.int64, np.int32, np.int16, np.uint8):
+        torch.from_numpy(pred).copy_(d_pred.to(getattr(torch, pred.dtype.name)))
+    else:
+        pred[...] = d_pred.cpu().numpy().astype(pred.dtype)
+    return pred
+
+
 def vote_connected_component_class(pred: np.ndarray, data: SingleData) -> np.ndarray:
     """postprocess.py:9-26; like the reference, writes into `pred` and returns it."""
     import torch
-    from ..runtime import get_context, to_device_u8
+    from ..runtime import get_context
     ctx = get_context()
     h, w = pred.shape
-    d_pred = to_device_u8(pred, ctx.device)
-    d_bin = to_device_u8(np.asarray(data.binary) != 0, ctx.device)
-    ctx.cc_majority(d_pred, d_bin, 1, h, w, _n_classes(pred))
-    from ..runtime import to_host
-    pred[...] = to_host(d_pred.to(torch.int64)) if pred.dtype == np.int64 else to_host(d_pred).astype(pred.dtype)
-    return pred
+    d_pred, n_classes = _pred_to_device(pred, ctx.device)
+    binary = np.ascontiguousarray(data.binary)
+    if binary.dtype == np.bool_:
+        binary = binary.view(np.uint8)
+    if binary.dtype == np.uint8:
+        d_bin = torch.from_numpy(binary).to(d_pred.device)            # the kernels take non-zero as foreground
+    else:
+        d_bin = torch.from_numpy(np.ascontiguousarray(binary != 0).view(np.uint8)).to(d_pred.device)
+    ctx.cc_majority(d_pred, d_bin, 1, h, w, n_classes)
+    return _store(pred, d_pred)
 
 
 def add_bounding_boxes(pred: np.ndarray, data: SingleData) -> np.ndarray:
     """postprocess.py:29-42.  The reference hands cv2 a bool array, which cv2
     rejects; this implements the evident intent (components of pred == c)."""
     import torch
-    from ..runtime import get_context, to_device_u8
+    from ..runtime import get_context
     ctx = get_context()
     h, w = pred.shape
-    d_pred = to_device_u8(pred, ctx.device)
+    d_pred, n_classes = _pred_to_device(pred, ctx.device)
     d_out = torch.empty((h, w), dtype=torch.uint8, device=d_pred.device)
-    ctx.bounding_boxes(d_pred, 1, h, w, _n_classes(pred), d_out)
-    return d_out.cpu().numpy().astype(pred.dtype)
+    ctx.bounding_boxes(d_pred, 1, h, w, n_classes, d_out)
+    return _store(np.empty_like(pred), d_out)
 
 
 def find_postprocessor(key: str) -> Callable[[np.ndarray, SingleData], np.ndarray]:
