@@ -29,10 +29,9 @@ def _masks_on_device(data: SingleData, pred: np.ndarray, color_map: ColorMap):
     pred = np.asarray(pred)
     h, w = pred.shape
     lut = color_map.lut()
-    if pred.size and (pred.min() < 0 or pred.max() > 255):
-        raise ValueError("labels outside 0..255")
+    from .postprocess import _pred_to_device
     binary = np.asarray(data.binary)
-    d_pred = to_device_u8(pred, ctx.device)
+    d_pred, _ = _pred_to_device(pred, ctx.device)        # int64 from Predictor.predict: checked and narrowed on the device
     d_bin = to_device_u8(binary, ctx.device)
     outs = torch.empty((3, h, w, 3), dtype=torch.uint8, device=d_pred.device)
     ctx.masks(d_pred, d_bin, 1, h, w, lut, outs[0], outs[1], outs[2])
@@ -72,10 +71,10 @@ def encode_png(images, level: int = 1) -> list:
 def generate_output_masks(data: SingleData, pred: np.ndarray, color_map: ColorMap) -> Masks:
     """output.py:44-60 through the device epilogue (pcs_masks)."""
     _, outs = _masks_on_device(data, pred, color_map)
-    from ..runtime import to_host
-    color, overlay, inverted = to_host(outs)
+    from ..runtime import results_to_host
     # fg_color_mask[foreground != 0] = 0 is arithmetically the inverted overlay (output.py:50-53)
-    return Masks(color=color, overlay=overlay, inverted_overlay=inverted, fg_color_mask=inverted.copy())
+    (color, overlay, inverted), fg_color = results_to_host(outs, outs[2])
+    return Masks(color=color, overlay=overlay, inverted_overlay=inverted, fg_color_mask=fg_color)
 
 
 def output_data(output_dir, pred, data: SingleData, color_map):

@@ -83,38 +83,51 @@ def to_host(t) -> np.ndarray:
     return t.cpu().numpy()
 
 
-# Page-sized results (probabilities, class map) of the per-page API.  A pageable copy of a page's 19 MB costs ~9 ms
-# (first-touch faults of a fresh block plus the driver's bounce buffers); page-locking a NEW block per result costs
-# more still.  torch's caching host allocator keeps freed page-locked blocks, so a caller that consumes a Prediction
-# and drops it (the reference's front ends: predict -> write masks -> next page) gets the same few blocks back and the
-# copy runs at PCIe speed (measured: 1 070 instead of 105 pages/s through Predictor.predict).  A caller that keeps every
-# result would make each one a cudaHostAlloc: past `PCSEG_PINNED_RESULTS` live page-locked arrays (the current and the
-# next Prediction, plus slack) the pageable copy is used, so at most that many blocks are ever page-locked.  The arrays are ordinary numpy arrays the
-# caller owns either way (the counter is only a heuristic; lifetime is by reference count).
-_PINNED_RESULT_LIMIT = int(os.environ.get("PCSEG_PINNED_RESULTS", "6"))
-_pinned_live = [0]
+# Page-sized results (probabilities, class map, masks) of the per-page API.  A pageable copy of a page's 19 MB costs
+# ~9 ms (first-touch faults of a fresh block plus the driver's bounce buffers); page-locking a NEW block per result
+# costs more still.  torch's caching host allocator keeps freed page-locked blocks, so a caller that consumes a
+# Prediction and drops it (the reference's front ends: predict -> write masks -> next page) gets the same few blocks
+# back and the copy runs at PCIe speed (measured: 1 070 instead of 105 pages/s through Predictor.predict).  A caller
+# that keeps every result makes each allocation a cudaHostAlloc; that shows as a slow allocation, and after
+# `_PIN_MISSES` slow ones in a row the pageable copy is used for a while (doubling each time it happens again, back to
+# page-locked at the first fast allocation).  The arrays are ordinary numpy arrays the caller owns either way.
+_PIN_MISSES = 10
+_PIN_SLOW_S = 3e-4          # a cache hit takes ~10 us, a cudaHostAlloc of a page-sized block milliseconds
+_pin = {"misses": 0, "skip": 0, "pause": 32, "enabled": os.environ.get("PCSEG_PINNED_RESULTS", "1") != "0"}
 
 
-def _pinned_released():
-    _pinned_live[0] -= 1
+def _pinned_empty(torch, shape, dtype):
+    import time
+    st = _pin
+    if not st["enabled"]:
+        return None
+    if st["skip"] > 0:
+        st["skip"] -= 1
+        return None
+    t0 = time.perf_counter()
+    h = torch.empty(shape, dtype=dtype, pin_memory=True)
+    if time.perf_counter() - t0 > _PIN_SLOW_S:
+        st["misses"] += 1
+        if st["misses"] >= _PIN_MISSES:
+            st["pause"] = min(st["pause"] * 2, 8192)
+            st["skip"], st["misses"] = st["pause"], _PIN_MISSES // 2
+    else:
+        st["misses"], st["pause"] = 0, 32
+    return h
 
 
 def results_to_host(*tensors):
     """Device tensors (None allowed) -> fresh numpy arrays, all copies issued before one synchronisation."""
-    import weakref
     torch = _torch()
     outs, stream = [], None
     for t in tensors:
+        h = None if t is None or t.numel() < (1 << 16) else _pinned_empty(torch, t.shape, t.dtype)
         if t is None:
             outs.append(None)
-        elif _pinned_live[0] < _PINNED_RESULT_LIMIT:
-            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        elif h is not None:
             h.copy_(t, non_blocking=True)
             stream = torch.cuda.current_stream(t.device)
-            arr = h.numpy()
-            _pinned_live[0] += 1
-            weakref.finalize(arr, _pinned_released)
-            outs.append(arr)
+            outs.append(h.numpy())
         else:
             outs.append(t.cpu().numpy())
     if stream is not None:

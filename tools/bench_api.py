@@ -47,6 +47,7 @@ def main():
             for p in pred.predict(ds):
                 k += int(p.labels[0, 0]) + 1
             return k
+        preds = None                                    # kept results of the previous round would hold page-locked blocks
         consume()
         _, t = clock(consume)
         print(json.dumps({"stage": f"Predictor.{label}, each result consumed and dropped", "pages": n, "s": round(t, 4),
