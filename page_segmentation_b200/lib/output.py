@@ -73,7 +73,7 @@ def generate_output_masks(data: SingleData, pred: np.ndarray, color_map: ColorMa
     _, outs = _masks_on_device(data, pred, color_map)
     from ..runtime import results_to_host
     # fg_color_mask[foreground != 0] = 0 is arithmetically the inverted overlay (output.py:50-53)
-    (color, overlay, inverted), fg_color = results_to_host(outs, outs[2])
+    (color, overlay, inverted), fg_color = results_to_host(outs, outs[2], site="masks")
     return Masks(color=color, overlay=overlay, inverted_overlay=inverted, fg_color_mask=fg_color)
 
 

@@ -93,14 +93,16 @@ def to_host(t) -> np.ndarray:
 # page-locked at the first fast allocation).  The arrays are ordinary numpy arrays the caller owns either way.
 _PIN_MISSES = 10
 _PIN_SLOW_S = 3e-4          # a cache hit takes ~10 us, a cudaHostAlloc of a page-sized block milliseconds
-_pin = {"misses": 0, "skip": 0, "pause": 32, "enabled": os.environ.get("PCSEG_PINNED_RESULTS", "1") != "0"}
+_PIN_ENABLED = os.environ.get("PCSEG_PINNED_RESULTS", "1") != "0"
+_PIN_LOAD = os.environ.get("PCSEG_PINNED_LOAD", "0") == "1"      # page-by-page loaders that drop each page may opt in
+_pin_sites: Dict[str, dict] = {}        # one state per call site: a dataset that is kept must not slow the predictions down
 
 
-def _pinned_empty(torch, shape, dtype):
+def _pinned_empty(torch, shape, dtype, site):
     import time
-    st = _pin
-    if not st["enabled"]:
+    if not _PIN_ENABLED or site is None:
         return None
+    st = _pin_sites.setdefault(site, {"misses": 0, "skip": 0, "pause": 32})
     if st["skip"] > 0:
         st["skip"] -= 1
         return None
@@ -116,12 +118,12 @@ def _pinned_empty(torch, shape, dtype):
     return h
 
 
-def results_to_host(*tensors):
+def results_to_host(*tensors, site: str = "predict"):
     """Device tensors (None allowed) -> fresh numpy arrays, all copies issued before one synchronisation."""
     torch = _torch()
     outs, stream = [], None
     for t in tensors:
-        h = None if t is None or t.numel() < (1 << 16) else _pinned_empty(torch, t.shape, t.dtype)
+        h = None if t is None or t.numel() < (1 << 16) else _pinned_empty(torch, t.shape, t.dtype, site)
         if t is None:
             outs.append(None)
         elif h is not None:
@@ -167,9 +169,11 @@ def prepare_images_device(image: np.ndarray, binary: np.ndarray, target_line_hei
         ctx.preprocess_max_width(d_grey, d_bin, 1, H, W, H1, W1, Hs, Ws, d_image, d_binary, d_orig)
     else:
         ctx.preprocess(d_grey, d_bin, 1, H, W, Hs, Ws, d_image, d_binary, d_orig)
-    img, bin_ = to_host(d_image), to_host(d_binary)
+    # datasets are kept (DatasetLoader.load_data returns all pages), and page-locking a fresh 8.7 MB block per page
+    # costs ~60 ms (measured: 38 instead of 170 pages/s), so these results are pageable unless the caller opts in
+    img, bin_, orig = results_to_host(d_image, d_binary, d_orig, site="load" if _PIN_LOAD else None)
     if keep_orig_bin:
-        return img, bin_, to_host(d_orig)
+        return img, bin_, orig
     return img, bin_
 
 

@@ -64,6 +64,18 @@ def main():
         _, t = clock(lambda: [output_data(out, p.labels, p.data, DEFAULT_COLOR_MAP) for p in preds])
         print(json.dumps({"stage": "output_data (three PNG files per page, device encoder)", "pages": n, "s": round(t, 4),
                           "pages_per_s": round(n / t, 1)}), flush=True)
+        del preds, ds
+
+        def flow():
+            # one page at a time through the whole per-page API, nothing kept
+            for i in range(n):
+                e = SingleData(image=pages[i % 8], line_height_px=18, image_path=f"/in/page_{i:04d}.png")
+                p = pred.predict_single(loader.load_images(e))
+                output_data(out, p.labels, p.data, DEFAULT_COLOR_MAP)
+        flow()
+        _, t = clock(flow)
+        print(json.dumps({"stage": "load_images -> predict_single (+ cc_majority) -> output_data, page by page, nothing kept",
+                          "pages": n, "s": round(t, 4), "pages_per_s": round(n / t, 1)}), flush=True)
 
 
 if __name__ == "__main__":
