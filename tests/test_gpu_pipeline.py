@@ -64,6 +64,45 @@ def test_predictor_predict_and_masks_with_postprocessing(ctx):
         np.testing.assert_array_equal(m.fg_color_mask, f)
 
 
+def test_results_are_owned_by_the_caller(ctx):
+    """Results travel through recycled page-locked blocks (runtime.results_to_host): an array a caller keeps must
+    never be rewritten by a later call, arrays that are dropped may be recycled, and the pageable path (forced, or
+    chosen after a run of slow allocations) gives the same values."""
+    import gc
+    from page_segmentation_b200 import runtime
+    from page_segmentation_b200.lib.network import Network
+    from page_segmentation_b200.lib.predictor import Predictor
+    from page_segmentation_b200.lib.predictor_data import PredictSettings
+    W = synth.make_weights("fcn_skip", 3, seed=2)
+    net = Network("Predict", n_classes=3, weights=W, precision="fp16")
+    pred = Predictor(PredictSettings(n_classes=3, color_map=DEFAULT_COLOR_MAP), network=net)
+    datas = [_loaded(s, h=1350, w=990)[1] for s in (5, 6, 7)]        # large enough for the page-locked path
+    kept = [pred.predict_single(d) for d in datas]
+    snap = [(p.labels.copy(), p.probabilities.copy()) for p in kept]
+    assert len({p.labels.ctypes.data for p in kept}) == 3 and len({p.probabilities.ctypes.data for p in kept}) == 3
+    for _ in range(3):                                         # dropped results: their blocks go round
+        for d in datas:
+            p = pred.predict_single(d)
+            m = pred.predict_masks(d)
+            del p, m
+        gc.collect()
+    for p, (l, q), d in zip(kept, snap, datas):
+        np.testing.assert_array_equal(p.labels, l)
+        np.testing.assert_array_equal(p.probabilities, q)
+        assert p.labels.flags.writeable and p.labels.flags.c_contiguous
+        again = pred.predict_single(d)
+        np.testing.assert_array_equal(again.labels, l)
+        np.testing.assert_array_equal(again.probabilities, q)
+    saved = runtime._PIN_ENABLED
+    try:
+        runtime._PIN_ENABLED = False                           # the pageable copy
+        p = pred.predict_single(datas[0])
+        np.testing.assert_array_equal(p.labels, snap[0][0])
+        np.testing.assert_array_equal(p.probabilities, snap[0][1])
+    finally:
+        runtime._PIN_ENABLED = saved
+
+
 def test_high_res_output(ctx):
     from page_segmentation_b200.lib.network import Network
     from page_segmentation_b200.lib.predictor import Predictor
