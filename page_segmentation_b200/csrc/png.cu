@@ -236,9 +236,29 @@ __device__ __forceinline__ void put_match(uint32_t* w, uint32_t& pos, uint32_t l
     put_bits(w, pos, (__brev(code) >> (32u - nb)) | ((l & ((1u << e) - 1u)) << nb), nb + e + 5u);
 }
 
-// Filtered scanline and its run starts in shared memory; returns the number of runs (warp-uniform).
+// A scanline staged in shared memory with aligned 32-bit loads (a warp reading it byte by byte issues one 32-byte
+// request per instruction); byte j of the row is s[mis + j], `mis` (returned) = the row's misalignment.  The first / last
+// word of the whole image buffer is assembled from byte loads instead of reaching across the buffer's ends.
+__device__ __forceinline__ uint32_t stage_row(const uint8_t* __restrict__ src, uint32_t nbytes, bool guard_head, bool guard_tail,
+                                              uint8_t* s) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(src);
+    const uint32_t mis = (uint32_t)(a & 3);
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(a - mis);
+    const uint32_t words = (mis + nbytes + 3) >> 2;
+    const uint32_t w0 = (guard_head && mis) ? 1u : 0u, w1 = (guard_tail && ((mis + nbytes) & 3u)) ? words - 1 : words;
+    uint32_t* sw = reinterpret_cast<uint32_t*>(s);
+    for (uint32_t w = w0 + threadIdx.x; w < w1; w += 32) sw[w] = __ldg(p + w);
+    if (threadIdx.x == 0) {
+        if (w0) for (uint32_t b = mis; b < min(4u, mis + nbytes); ++b) s[b] = __ldg(src + (b - mis));
+        if (w1 < words) for (uint32_t b = max(w1 * 4u, mis); b < mis + nbytes; ++b) s[b] = __ldg(src + (b - mis));
+    }
+    return mis;
+}
+
+// Filtered scanline and its run starts in shared memory; returns the number of runs (warp-uniform).  `raw` / `above`
+// are the staged rows (shared memory; `above` null on the first row).
 // fb[0] is the filter type: 1 (Sub) fb[i] = raw[i-1] - raw[i-1-C];  2 (Up) fb[i] = raw[i-1] - above[i-1]  (zeros above row 0).
-__device__ uint32_t rle_prepare(const uint8_t* __restrict__ raw, const uint8_t* __restrict__ above, uint32_t ftype, uint32_t line,
+__device__ uint32_t rle_prepare(const uint8_t* raw, const uint8_t* above, uint32_t ftype, uint32_t line,
                                 uint32_t C, uint8_t* fb, uint16_t* starts) {
     const uint32_t lane = threadIdx.x;
     __syncwarp();
@@ -246,8 +266,8 @@ __device__ uint32_t rle_prepare(const uint8_t* __restrict__ raw, const uint8_t* 
         uint32_t v = ftype;
         if (i) {
             const uint32_t j = i - 1;
-            const uint32_t pred = ftype == 1u ? (j >= C ? (uint32_t)__ldg(raw + j - C) : 0u) : (above ? (uint32_t)__ldg(above + j) : 0u);
-            v = (uint32_t)__ldg(raw + j) - pred;
+            const uint32_t pred = ftype == 1u ? (j >= C ? (uint32_t)raw[j - C] : 0u) : (above ? (uint32_t)above[j] : 0u);
+            v = (uint32_t)raw[j] - pred;
         }
         fb[i] = (uint8_t)v;
     }
@@ -274,8 +294,12 @@ __global__ void __launch_bounds__(32) png_rle_count_kernel(const uint8_t* __rest
     uint8_t* fb = sm;
     uint16_t* starts = reinterpret_cast<uint16_t*>(sm + ((pl.line + 15u) & ~15u));
     const uint32_t row = blockIdx.x, page = blockIdx.y, lane = threadIdx.x, npx = pl.line - 1;
-    const uint8_t* raw = img + ((uint64_t)page * pl.H + row) * npx;
-    const uint8_t* above = row ? raw - npx : nullptr;
+    const uint8_t* graw = img + ((uint64_t)page * pl.H + row) * npx;
+    uint8_t* sraw = sm + ((pl.line + 15u) & ~15u) + ((2u * pl.line + 15u) & ~15u);
+    uint8_t* sabove = sraw + ((pl.line + 8u + 15u) & ~15u);
+    const bool first = page == 0 && row == 0, last = page + 1 == gridDim.y && row + 1 == (uint32_t)pl.H;
+    const uint8_t* raw = sraw + stage_row(graw, npx, first, last, sraw);
+    const uint8_t* above = row ? sabove + stage_row(graw - npx, npx, page == 0 && row == 1, false, sabove) : nullptr;
     unsigned long long best_a = 0, best_b = 0;
     uint32_t best_t = 0xffffffffu, best_f = 1;
     for (uint32_t ftype = 1; ftype <= 2; ++ftype) {
@@ -355,10 +379,16 @@ __global__ void __launch_bounds__(32) png_rle_emit_kernel(const uint8_t* __restr
     uint8_t* fb = sm;
     uint16_t* starts = reinterpret_cast<uint16_t*>(sm + ((pl.line + 15u) & ~15u));
     const uint32_t row = blockIdx.x, page = blockIdx.y, lane = threadIdx.x, npx = pl.line - 1;
-    const uint8_t* raw = img + ((uint64_t)page * pl.H + row) * npx;
-    const uint32_t R = rle_prepare(raw, row ? raw - npx : nullptr, ftypes[(uint64_t)page * pl.H + row], pl.line, (uint32_t)pl.C, fb, starts);
+    const uint8_t* graw = img + ((uint64_t)page * pl.H + row) * npx;
     uint32_t* bitbuf = reinterpret_cast<uint32_t*>(sm + ((pl.line + 15u) & ~15u) + ((2u * pl.line + 15u) & ~15u));
     const uint32_t buf_words = (9u * pl.line + 31u + 31u) / 32u + 1u;                      // worst case 9 bits per byte + the offset
+    uint8_t* sraw = reinterpret_cast<uint8_t*>(bitbuf) + ((buf_words * 4u + 15u) & ~15u);
+    uint8_t* sabove = sraw + ((pl.line + 8u + 15u) & ~15u);
+    const uint32_t ftype = ftypes[(uint64_t)page * pl.H + row];
+    const bool first = page == 0 && row == 0, last = page + 1 == gridDim.y && row + 1 == (uint32_t)pl.H;
+    const uint8_t* raw = sraw + stage_row(graw, npx, first, last, sraw);
+    const uint8_t* above = (row && ftype == 2u) ? sabove + stage_row(graw - npx, npx, page == 0 && row == 1, false, sabove) : nullptr;
+    const uint32_t R = rle_prepare(raw, above, ftype, pl.line, (uint32_t)pl.C, fb, starts);
     for (uint32_t i = lane; i < buf_words; i += 32) bitbuf[i] = 0;
     __syncwarp();
     const unsigned long long base = bitbase[(uint64_t)page * pl.H + row];
@@ -483,12 +513,15 @@ int launch_png_encode(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, i
         zbytes = nullptr;
     } else {
         zlib_max = bound - kHead - 16;
-        const size_t smem_count = ((pl.line + 15u) & ~15u) + 2 * (size_t)pl.line;
-        const size_t smem_emit = ((pl.line + 15u) & ~15u) + ((2 * (size_t)pl.line + 15u) & ~(size_t)15u) + ((9 * (size_t)pl.line + 62) / 32 + 2) * 4;
+        const size_t staged = 2 * (((size_t)pl.line + 8 + 15) & ~(size_t)15);                // the scanline and the one above it
+        const size_t smem_count = ((pl.line + 15u) & ~15u) + ((2 * (size_t)pl.line + 15u) & ~(size_t)15u) + staged;
+        const size_t smem_emit = ((pl.line + 15u) & ~15u) + ((2 * (size_t)pl.line + 15u) & ~(size_t)15u) +
+                                 ((((9 * (size_t)pl.line + 62) / 32 + 1) * 4 + 15) & ~(size_t)15) + staged;
         if (smem_emit > 48 * 1024) {
             static bool set[64] = {};
             if (ctx->device >= 64 || !set[ctx->device]) {
-                PCS_CUDA(ctx, cudaFuncSetAttribute(png_rle_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+                PCS_CUDA(ctx, cudaFuncSetAttribute(png_rle_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+                PCS_CUDA(ctx, cudaFuncSetAttribute(png_rle_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
                 if (ctx->device < 64) set[ctx->device] = true;
             }
         }
