@@ -258,27 +258,33 @@ __device__ __forceinline__ uint32_t stage_row(const uint8_t* __restrict__ src, u
 // Filtered scanline and its run starts in shared memory; returns the number of runs (warp-uniform).  `raw` / `above`
 // are the staged rows (shared memory; `above` null on the first row).
 // fb[0] is the filter type: 1 (Sub) fb[i] = raw[i-1] - raw[i-1-C];  2 (Up) fb[i] = raw[i-1] - above[i-1]  (zeros above row 0).
+// One pass: filter, Adler partial sums (ADLER: lane-local, of the FILTERED bytes incl. the filter byte) and run starts;
+// the previous byte comes from the neighbouring lane, not from shared memory.
+template <bool ADLER>
 __device__ uint32_t rle_prepare(const uint8_t* raw, const uint8_t* above, uint32_t ftype, uint32_t line,
-                                uint32_t C, uint8_t* fb, uint16_t* starts) {
+                                uint32_t C, uint8_t* fb, uint16_t* starts, unsigned long long& a, unsigned long long& b) {
     const uint32_t lane = threadIdx.x;
     __syncwarp();
-    for (uint32_t i = lane; i < line; i += 32) {
-        uint32_t v = ftype;
-        if (i) {
-            const uint32_t j = i - 1;
-            const uint32_t pred = ftype == 1u ? (j >= C ? (uint32_t)raw[j - C] : 0u) : (above ? (uint32_t)above[j] : 0u);
-            v = (uint32_t)raw[j] - pred;
-        }
-        fb[i] = (uint8_t)v;
-    }
-    __syncwarp();
-    uint32_t count = 0;
+    uint32_t count = 0, carry = 0;
     for (uint32_t base = 0; base < line; base += 32) {
         const uint32_t i = base + lane;
-        const bool st = i < line && (i == 0 || fb[i] != fb[i - 1]);
+        uint32_t v = ftype;
+        if (i && i < line) {
+            const uint32_t j = i - 1;
+            const uint32_t pred = ftype == 1u ? (j >= C ? (uint32_t)raw[j - C] : 0u) : (above ? (uint32_t)above[j] : 0u);
+            v = ((uint32_t)raw[j] - pred) & 0xffu;
+        }
+        if (i < line) {
+            fb[i] = (uint8_t)v;
+            if (ADLER) { a += v; b += (unsigned long long)(line - i) * v; }
+        }
+        uint32_t prev = __shfl_up_sync(0xffffffffu, v, 1);
+        if (lane == 0) prev = carry;
+        const bool st = i < line && (i == 0 || v != prev);
         const uint32_t m = __ballot_sync(0xffffffffu, st);
         if (st) starts[count + __popc(m & ((1u << lane) - 1u))] = (uint16_t)i;
         count += __popc(m);
+        carry = __shfl_sync(0xffffffffu, v, 31);
     }
     __syncwarp();
     return count;
@@ -303,9 +309,8 @@ __global__ void __launch_bounds__(32) png_rle_count_kernel(const uint8_t* __rest
     unsigned long long best_a = 0, best_b = 0;
     uint32_t best_t = 0xffffffffu, best_f = 1;
     for (uint32_t ftype = 1; ftype <= 2; ++ftype) {
-        const uint32_t R = rle_prepare(raw, above, ftype, pl.line, (uint32_t)pl.C, fb, starts);
         unsigned long long a = 0, b = 0;
-        for (uint32_t i = lane; i < pl.line; i += 32) { a += fb[i]; b += (unsigned long long)(pl.line - i) * fb[i]; }
+        const uint32_t R = rle_prepare<true>(raw, above, ftype, pl.line, (uint32_t)pl.C, fb, starts, a, b);
         uint32_t t = 0;
         for (uint32_t r = lane; r < R; r += 32) {
             const uint32_t s0 = starts[r], s1 = r + 1 < R ? starts[r + 1] : pl.line;
@@ -388,7 +393,8 @@ __global__ void __launch_bounds__(32) png_rle_emit_kernel(const uint8_t* __restr
     const bool first = page == 0 && row == 0, last = page + 1 == gridDim.y && row + 1 == (uint32_t)pl.H;
     const uint8_t* raw = sraw + stage_row(graw, npx, first, last, sraw);
     const uint8_t* above = (row && ftype == 2u) ? sabove + stage_row(graw - npx, npx, page == 0 && row == 1, false, sabove) : nullptr;
-    const uint32_t R = rle_prepare(raw, above, ftype, pl.line, (uint32_t)pl.C, fb, starts);
+    unsigned long long unused_a = 0, unused_b = 0;
+    const uint32_t R = rle_prepare<false>(raw, above, ftype, pl.line, (uint32_t)pl.C, fb, starts, unused_a, unused_b);
     for (uint32_t i = lane; i < buf_words; i += 32) bitbuf[i] = 0;
     __syncwarp();
     const unsigned long long base = bitbase[(uint64_t)page * pl.H + row];
