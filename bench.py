@@ -219,6 +219,8 @@ def main():
     ap.add_argument("--workload", default="predict", choices=["predict", "train"],
                     help="predict = BASELINE configs[1] (default, the contract line); train = configs[4]: one training step per page per "
                          "rank with the NCCL gradient all-reduce (tools/bench_train.py)")
+    ap.add_argument("--png-files", action="store_true",
+                    help="adds e2e_png_files: the host-buffer call with the masks returned as PNG files (pcs_predict_pages_files)")
     ap.add_argument("--cc-majority", action="store_true",
                     help="also run the cc_majority post-processor (BASELINE configs[3] pipeline); not the default workload")
     args = ap.parse_args()
@@ -335,6 +337,27 @@ def main():
     h2d = int(h_pages_np.nbytes)
     d2h = int(sum(v.nbytes for v in h_out_np.values()))
 
+    # ---------------- optional: the same call with the masks leaving the device as PNG files ----------------
+    png_files = None
+    if args.png_files:
+        stride = (eng.ctx.png_bytes(Hs, Ws, 3, 1) + 255) // 256 * 256
+        f_out = {"labels": h_out["labels"].numpy(),
+                 "png": torch.empty((n, 3, stride), dtype=torch.uint8).pin_memory().numpy(),
+                 "png_sizes": torch.zeros((n, 3), dtype=torch.int64).pin_memory().numpy().view(np.uint64)}
+        eng.run_host_files(h_pages_np, SCALE, f_out, cc_majority=args.cc_majority)
+        sync_all()
+        e0.record()
+        for _ in range(args.steps):
+            eng.run_host_files(h_pages_np, SCALE, f_out, cc_majority=args.cc_majority)
+        e1.record()
+        sync_all()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        png_files = {"value": world * n * args.steps / (float(t.item()) / 1e3), "unit": "pages/s", "h2d_bytes_per_step": h2d,
+                     "d2h_bytes_per_step": int(f_out["labels"].nbytes + int(f_out["png_sizes"].sum()) + f_out["png_sizes"].nbytes),
+                     "what": "pcs_predict_pages_files: class map + the three masks as PNG files (device encoder, level 1) per page"}
+
     if rank == 0:
         hbm_peak, tf_peak, which = peaks()
         # dominant kernel = the slowest stage of the step
@@ -369,7 +392,7 @@ def main():
                        "l2": "inputs larger than L2 (557 MB of pages per step)", "distinct_pages": distinct},
             "e2e": {"value": e2e_value, "unit": "pages/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "pcie_pinned_copy": pcie, "numa_binding": numa,
+            "pcie_pinned_copy": pcie, "numa_binding": numa, **({"e2e_png_files": png_files} if png_files else {}),
         }
         print(json.dumps(line), flush=True)
     if world > 1:
