@@ -44,6 +44,36 @@ def test_char_height_matches_oracle(ctx, seed, shape, gh, inverse):
         assert abs(int(got) - gh) <= 4
 
 
+# Two half glyphs that touch only through one corner, placed so that the corner sits on a border of the 256 x 32
+# labelling tiles (csrc/ccl.cu): merged (8-connectivity) the glyph is 24 rows high, unmerged there are two of 12.
+_CORNERS = {
+    "tile corner, down-right": ((20, 249), (32, 256)),          # (31,255) - (32,256): row 32 starts a tile row
+    "tile corner, down-left": ((20, 256), (32, 249)),           # (31,256) - (32,255)
+    "vertical tile border, down-right": ((40, 249), (52, 256)),  # (51,255) - (52,256): inside a tile row
+    "vertical tile border, down-left": ((40, 256), (52, 249)),   # (51,256) - (52,255): last pixel of a tile's last segment
+    "horizontal tile border, down-right": ((52, 100), (64, 107)),  # (63,106) - (64,107): inside a tile column
+    "horizontal tile border, down-left": ((52, 107), (64, 100)),
+    "segment border inside a tile, down-right": ((70, 57), (82, 64)),  # (81,63) - (82,64)
+    "segment border inside a tile, down-left": ((70, 64), (82, 57)),
+}
+
+
+@pytest.mark.parametrize("case", sorted(_CORNERS))
+def test_char_height_diagonal_contacts_on_tile_borders(ctx, case):
+    from page_segmentation_b200.lib.image_ops import compute_char_height_array
+    (ya, xa), (yb, xb) = _CORNERS[case]
+    page = np.full((128, 600), 255, np.uint8)
+    page[ya:ya + 12, xa:xa + 7] = 0
+    page[yb:yb + 12, xb:xb + 7] = 0
+    got, exp = compute_char_height_array(page, False), oio.compute_char_height_array(page, False)
+    assert exp == 24 and got == exp
+    page[yb:yb + 12, xb:xb + 7] = 255                       # the same halves one column apart: two letters of 12 rows
+    xb += 1 if xb > xa else -1
+    page[yb:yb + 12, xb:xb + 7] = 0
+    got, exp = compute_char_height_array(page, False), oio.compute_char_height_array(page, False)
+    assert exp == 12 and got == exp
+
+
 def test_char_height_binarised_page_and_none(ctx):
     from page_segmentation_b200.lib.image_ops import compute_char_height_array
     page = synth.make_page(3, 900, 700, 18)

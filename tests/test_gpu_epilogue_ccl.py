@@ -105,7 +105,7 @@ def test_cc_majority_bit_exact(ctx, hw):
     np.testing.assert_array_equal(got, exp)
 
 
-@pytest.mark.parametrize("hw", [(61, 83), (200, 160)])
+@pytest.mark.parametrize("hw", [(61, 83), (200, 160), (97, 530)])         # the last one spans three labelling tiles across
 def test_bounding_boxes(ctx, hw):
     from page_segmentation_b200.lib.postprocess import add_bounding_boxes
     pred, b = _pred_and_binary(4, *hw)
