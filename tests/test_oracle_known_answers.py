@@ -280,6 +280,22 @@ def test_char_height_known_answer():
     assert oio.compute_char_height_array(page, inverse=True) is None
 
 
+@pytest.mark.parametrize("down_right", [True, False])
+def test_char_height_half_glyphs_touching_through_a_corner(down_right):
+    """known answer behind tests/test_gpu_char_height.py::test_char_height_diagonal_contacts_on_tile_borders: two 12 x 7
+    halves touching through one corner are ONE letter of 24 rows (8-connectivity); one column apart they are two of 12"""
+    from oracle import image_ops as oio
+    page = np.full((128, 600), 255, np.uint8)
+    xa, xb = (249, 256) if down_right else (256, 249)
+    page[20:32, xa:xa + 7] = 0
+    page[32:44, xb:xb + 7] = 0
+    assert oio.compute_char_height_array(page, inverse=False) == 24
+    page[32:44, xb:xb + 7] = 255
+    xb += 1 if down_right else -1
+    page[32:44, xb:xb + 7] = 0
+    assert oio.compute_char_height_array(page, inverse=False) == 12
+
+
 @pytest.mark.parametrize("seed", [0, 1, 2])
 def test_otsu_restatement_matches_cv2(seed):
     import cv2
