@@ -87,7 +87,7 @@ def main():
     d_png = torch.empty((3 * n, stride), dtype=torch.uint8, device="cuda")
     d_all = torch.cat(d_c)                                    # (3n, Hs, Ws, 3): the three masks of every page
     timed("png_encode (three masks per page)", lambda: ctx.png_encode(d_all, 3 * n, Hs, Ws, 3, d_png, stride), n, 2 * 9 * px,
-          "three colour masks in, three complete PNG files out (stored deflate blocks, Adler-32, CRC-32)")
+          "three colour masks in, three complete PNG files out (level 1: Sub/Up filter choice, fixed-Huffman run-length deflate, Adler-32, CRC-32)")
 
     # region extraction works page by page on the full-resolution `inverted` image (26 MB each)
     inv = [torch.from_numpy(synth.make_inverted_image(s, H, W, 40)).cuda() for s in range(4)]
