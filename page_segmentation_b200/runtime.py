@@ -7,6 +7,7 @@ torch.distributed); all arithmetic is in libpcseg_b200.so.
 from __future__ import annotations
 
 import os
+import time
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -92,21 +93,21 @@ def to_host(t) -> np.ndarray:
 _PIN_MISSES = 10
 _PIN_SLOW_S = 3e-4          # a cache hit takes ~10 us, a cudaHostAlloc of a page-sized block milliseconds
 _PIN_ENABLED = os.environ.get("PCSEG_PINNED_RESULTS", "1") != "0"
+_clock = time.perf_counter
 _PIN_LOAD = os.environ.get("PCSEG_PINNED_LOAD", "0") == "1"      # page-by-page loaders that drop each page may opt in
 _pin_sites: Dict[str, dict] = {}        # one state per call site: a dataset that is kept must not slow the predictions down
 
 
 def _pinned_empty(torch, shape, dtype, site):
-    import time
     if not _PIN_ENABLED or site is None:
         return None
     st = _pin_sites.setdefault(site, {"misses": 0, "skip": 0, "pause": 32})
     if st["skip"] > 0:
         st["skip"] -= 1
         return None
-    t0 = time.perf_counter()
+    t0 = _clock()
     h = torch.empty(shape, dtype=dtype, pin_memory=True)
-    if time.perf_counter() - t0 > _PIN_SLOW_S:
+    if _clock() - t0 > _PIN_SLOW_S:
         st["misses"] += 1
         if st["misses"] >= _PIN_MISSES:
             st["pause"] = min(st["pause"] * 2, 8192)

@@ -185,3 +185,39 @@ def test_synthetic_page_is_deterministic_and_binarised():
     np.testing.assert_array_equal(a, b)
     assert set(np.unique(a)) <= {0, 255} and 0.02 < (a == 0).mean() < 0.5
     assert len(np.unique(synth.make_grey_page(3, 200, 150))) > 2
+
+
+def test_page_locked_result_policy(monkeypatch):
+    """runtime._pinned_empty: fast allocations (blocks recycled by the caching host allocator) stay page-locked; a run of
+    slow ones (a caller that keeps every result: each block is a fresh cudaHostAlloc) switches to the pageable copy for a
+    doubling number of results and comes back at the first fast one; one state per call site."""
+    from page_segmentation_b200 import runtime
+    now = [0.0]
+
+    class FakeTorch:
+        slow = False
+
+        def empty(self, shape, dtype=None, pin_memory=False):
+            assert pin_memory
+            now[0] += runtime._PIN_SLOW_S * (4 if self.slow else 0.01)
+            return ("block", shape)
+
+    t = FakeTorch()
+    monkeypatch.setattr(runtime, "_clock", lambda: now[0])
+    monkeypatch.setattr(runtime, "_pin_sites", {})
+    monkeypatch.setattr(runtime, "_PIN_ENABLED", True)
+    assert runtime._pinned_empty(t, (4,), None, None) is None                     # site None: always pageable
+    for _ in range(3 * runtime._PIN_MISSES):
+        assert runtime._pinned_empty(t, (4,), None, "a") is not None              # streaming caller: hits
+    t.slow = True
+    got = [runtime._pinned_empty(t, (4,), None, "a") is not None for _ in range(runtime._PIN_MISSES + 64)]
+    assert all(got[:runtime._PIN_MISSES]) and not any(got[runtime._PIN_MISSES:])  # then 64 pageable results
+    t.slow = False
+    assert runtime._pinned_empty(t, (4,), None, "b") is not None                  # another site is unaffected
+    probes = [runtime._pinned_empty(t, (4,), None, "a") is not None for _ in range(4)]
+    assert all(probes) and runtime._pin_sites["a"]["misses"] == 0 and runtime._pin_sites["a"]["pause"] == 32
+    t.slow = True                                                                 # keep-all again: the pause doubles
+    n_pinned = sum(runtime._pinned_empty(t, (4,), None, "a") is not None for _ in range(400))
+    assert n_pinned <= runtime._PIN_MISSES + 3 * (runtime._PIN_MISSES - runtime._PIN_MISSES // 2)
+    monkeypatch.setattr(runtime, "_PIN_ENABLED", False)
+    assert runtime._pinned_empty(t, (4,), None, "b") is None
