@@ -109,6 +109,21 @@ def load() -> C.CDLL:
     return lib
 
 
+def _lut256(lut, n_classes: Optional[int] = None):
+    """Colour LUT as a (256, 3) uint8 array (zero rows past the caller's table): the library reads n_classes rows of
+    it (pcs_forward, pcs_predict_pages_*), so a table shorter than the model's class count must not reach it."""
+    if lut is None:
+        return None
+    a = np.ascontiguousarray(lut, dtype=np.uint8).reshape(-1, 3)
+    if a.shape[0] > 256:
+        raise PcsError(f"colour LUT has {a.shape[0]} rows (at most 256)")
+    if n_classes is not None and a.shape[0] < n_classes:
+        raise PcsError(f"colour LUT has {a.shape[0]} rows but the model predicts {n_classes} classes")
+    out = np.zeros((256, 3), dtype=np.uint8)
+    out[:a.shape[0]] = a
+    return out
+
+
 def _ptr(t) -> Optional[int]:
     """Device/host pointer of a torch tensor / numpy array / None."""
     if t is None:
@@ -135,6 +150,7 @@ class Context:
                            "(needs a CUDA sm_100 / B200 device; no fallback exists)")
         self.h = h
         self.model: Optional[Tuple[str, int, str]] = None
+        self.loaded_key = None
         self._keepalive = None
 
     def close(self):
@@ -191,7 +207,11 @@ class Context:
 
     # -- model ---------------------------------------------------------------
     def load_model(self, arch: str, n_classes: int, weights: Sequence[Tuple[np.ndarray, np.ndarray]],
-                   precision: str = "fp16"):
+                   precision: str = "fp16", key=None):
+        """Uploads a model.  The context holds ONE model; `key` names its owner (a Network / PageBatchEngine token) and
+        is what `loaded_key` answers afterwards, so that every owner can tell whether the context still holds its
+        weights.  A load without a key invalidates every owner's cache."""
+        self.loaded_key = None
         arr = (LayerWeights * len(weights))()
         keep = []
         for i, (k, b) in enumerate(weights):
@@ -209,6 +229,7 @@ class Context:
         self._check(self.lib.pcs_model_load(self.h, ARCH_IDS[arch], int(n_classes), PRECISIONS[precision],
                                             arr, len(weights)), "pcs_model_load")
         self.model = (arch, int(n_classes), precision)
+        self.loaded_key = key
 
     # -- stages (device pointers) ----------------------------------------------
     def preprocess(self, d_grey, d_bin, n, H, W, Hs, Ws, d_image, d_binary, d_orig_binary=None):
@@ -222,7 +243,7 @@ class Context:
 
     def forward(self, d_image, d_binary, n, Hs, Ws, d_labels, d_logits=None, d_prob=None, lut=None,
                 d_color=None, d_overlay=None, d_inverted=None):
-        lut_arr = None if lut is None else np.ascontiguousarray(lut, dtype=np.uint8)
+        lut_arr = _lut256(lut, self.model[1] if self.model else None)
         self._check(self.lib.pcs_forward(self.h, _ptr(d_image), _ptr(d_binary), n, Hs, Ws, _ptr(d_labels),
                                          _ptr(d_logits), _ptr(d_prob), _ptr(lut_arr), _ptr(d_color),
                                          _ptr(d_overlay), _ptr(d_inverted)), "pcs_forward")
@@ -281,14 +302,14 @@ class Context:
     # -- whole pipeline, host buffers ----------------------------------------
     def predict_pages_host(self, h_grey, h_bin, n, H, W, Hs, Ws, cc_majority=False, lut=None, h_image=None,
                            h_binary=None, h_labels=None, h_color=None, h_overlay=None, h_inverted=None):
-        lut_arr = None if lut is None else np.ascontiguousarray(lut, dtype=np.uint8)
+        lut_arr = _lut256(lut, self.model[1] if self.model else None)
         self._check(self.lib.pcs_predict_pages_host(
             self.h, _ptr(h_grey), _ptr(h_bin), n, H, W, Hs, Ws, 1 if cc_majority else 0, _ptr(lut_arr),
             _ptr(h_image), _ptr(h_binary), _ptr(h_labels), _ptr(h_color), _ptr(h_overlay), _ptr(h_inverted)),
             "pcs_predict_pages_host")
 
     def predict_pages_files(self, h_grey, h_bin, n, H, W, Hs, Ws, cc_majority, lut, h_labels, h_png, png_stride, h_png_sizes):
-        lut_arr = np.ascontiguousarray(lut, dtype=np.uint8)
+        lut_arr = _lut256(lut, self.model[1] if self.model else None)
         self._check(self.lib.pcs_predict_pages_files(
             self.h, _ptr(h_grey), _ptr(h_bin), n, H, W, Hs, Ws, 1 if cc_majority else 0, _ptr(lut_arr),
             _ptr(h_labels), _ptr(h_png), png_stride, _ptr(h_png_sizes)), "pcs_predict_pages_files")

@@ -47,8 +47,9 @@ void* arena_alloc(pcs_ctx* ctx, size_t bytes) {
 int scratch_reserve(pcs_ctx* ctx, size_t bytes) {
     if (bytes <= ctx->scratch_bytes) return PCS_OK;
     cudaStreamSynchronize(ctx->stream);
+    // only ctx->scratch: scratch2 (the max_width pass, which runs a whole first pass - and therefore this function -
+    // while it holds pointers into scratch2) has its own grow path in launch_preprocess_max_width
     if (ctx->scratch) cudaFree(ctx->scratch);
-    if (ctx->scratch2) cudaFree(ctx->scratch2);
     ctx->scratch = nullptr;
     ctx->scratch_bytes = 0;
     const size_t want = bytes + bytes / 8 + 4096;
@@ -873,7 +874,7 @@ int pcs_png_encode(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, int 
 
 // h_png != nullptr: the three masks leave the device as PNG files (level 1) instead of raw arrays: file (page p, kind k)
 // at h_png + (3 p + k) * png_stride, its length in h_png_sizes[3 p + k]; kind 0 = color, 1 = overlay, 2 = inverted.
-static int predict_pages_host_impl(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h_bin, int n, int H, int W, int Hs, int Ws,
+static int predict_pages_host_body(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h_bin, int n, int H, int W, int Hs, int Ws,
                                    int cc_majority, const uint8_t* lut, uint8_t* h_image, uint8_t* h_binary, uint8_t* h_labels,
                                    uint8_t* h_color, uint8_t* h_overlay, uint8_t* h_inverted, uint8_t* h_png, size_t png_stride,
                                    uint64_t* h_png_sizes) {
@@ -1084,6 +1085,24 @@ static int predict_pages_host_impl(pcs_ctx* ctx, const uint8_t* h_grey, const ui
         cudaEventDestroy(t0);
     }
     return PCS_OK;
+}
+
+// A failure in the middle of the pipeline (arena exhaustion on a later chunk, an encoder size check) must not return
+// while copies into the caller's host buffers or the rotating staging buffers are still in flight: drain the three
+// streams first, so that the caller may free its buffers and the next call starts from idle events.
+static int predict_pages_host_impl(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h_bin, int n, int H, int W, int Hs, int Ws,
+                                   int cc_majority, const uint8_t* lut, uint8_t* h_image, uint8_t* h_binary, uint8_t* h_labels,
+                                   uint8_t* h_color, uint8_t* h_overlay, uint8_t* h_inverted, uint8_t* h_png, size_t png_stride,
+                                   uint64_t* h_png_sizes) {
+    const int rc = predict_pages_host_body(ctx, h_grey, h_bin, n, H, W, Hs, Ws, cc_majority, lut, h_image, h_binary, h_labels, h_color,
+                                           h_overlay, h_inverted, h_png, png_stride, h_png_sizes);
+    if (rc != PCS_OK && ctx) {
+        for (cudaStream_t s : {ctx->copy_streams[0], ctx->copy_streams[1]})
+            if (s) cudaStreamSynchronize(s);
+        cudaStreamSynchronize(ctx->stream);
+        cudaGetLastError();
+    }
+    return rc;
 }
 
 int pcs_predict_pages_host(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h_bin, int n, int H, int W, int Hs, int Ws,

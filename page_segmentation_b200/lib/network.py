@@ -92,15 +92,16 @@ class Network:
             raise ValueError(f"n_classes={self.n_classes} but the logits layer has {n_from_weights} outputs")
         self._arch = arch
         self._token = next(_model_tokens)
+        self.engine = os.environ.get("PCSEG_ENGINE", "umma")      # 'direct' = the CUDA-core numerics twin
 
     # -- device state ----------------------------------------------------------
     def _context(self):
         from ..runtime import get_context
         ctx = get_context(self.device)
         want = (self._arch, self.n_classes, self.precision, self._token)
-        if getattr(ctx, "_loaded_key", None) != want:
-            ctx.load_model(self._arch, self.n_classes, self.model.weights, self.precision)
-            ctx._loaded_key = want
+        if ctx.loaded_key != want:                  # the context holds one model; whoever loaded last owns it
+            ctx.load_model(self._arch, self.n_classes, self.model.weights, self.precision, key=want)
+        ctx.set_engine(self.engine)
         return ctx
 
     def predict_single_data(self, data: SingleData):

@@ -16,6 +16,9 @@ from . import _native
 from .synth import scaled_shape
 
 
+_engine_tokens = __import__("itertools").count(1)
+
+
 def default_device() -> int:
     return int(os.environ.get("LOCAL_RANK", os.environ.get("PCSEG_DEVICE", "0")))
 
@@ -251,11 +254,21 @@ class PageBatchEngine:
                  lut: Optional[np.ndarray] = None, engine: str = "umma"):
         self.torch = _torch()
         self.ctx = get_context(device)
-        self.ctx.load_model(arch, n_classes, weights, precision)
-        self.ctx.set_engine(engine)
+        self._model = (arch, n_classes, list(weights), precision)
+        self._engine = engine
+        self._key = ("engine", next(_engine_tokens))
         self.n_classes = n_classes
+        self._ensure_model()
         self.lut = None if lut is None else np.ascontiguousarray(lut, dtype=np.uint8)
         self._bufs: Dict[tuple, dict] = {}
+
+    def _ensure_model(self):
+        """The per-device context is shared and holds one model: reload ours if a Network or another engine has used
+        the context since, and select our convolution engine (both are no-ops in the steady state)."""
+        if self.ctx.loaded_key != self._key:
+            arch, n_classes, weights, precision = self._model
+            self.ctx.load_model(arch, n_classes, weights, precision, key=self._key)
+        self.ctx.set_engine(self._engine)
 
     def buffers(self, n: int, H: int, W: int, Hs: int, Ws: int) -> dict:
         key = (n, H, W, Hs, Ws)
@@ -279,6 +292,7 @@ class PageBatchEngine:
         Hs, Ws = scaled_shape(H, W, scale)
         b = self.buffers(n, H, W, Hs, Ws)
         ctx = self.ctx
+        self._ensure_model()
         ctx.use_torch_stream()
         ctx.preprocess(d_pages, d_pages, n, H, W, Hs, Ws, b["image"], b["binary"], None)
         want = masks and self.lut is not None
@@ -298,6 +312,7 @@ class PageBatchEngine:
         arrays 'labels' and optionally 'color','overlay','inverted' (pinned)."""
         n, H, W = h_pages.shape
         Hs, Ws = scaled_shape(H, W, scale)
+        self._ensure_model()
         self.ctx.use_torch_stream()
         self.ctx.predict_pages_host(h_pages, h_pages, n, H, W, Hs, Ws, cc_majority, self.lut,
                                     None, None, out.get("labels"), out.get("color"), out.get("overlay"),
@@ -310,6 +325,7 @@ class PageBatchEngine:
         Returns `out`; file (p, k) is out['png'][p, k, :out['png_sizes'][p, k]], k = 0 color, 1 overlay, 2 inverted."""
         n, H, W = h_pages.shape
         Hs, Ws = scaled_shape(H, W, scale)
+        self._ensure_model()
         self.ctx.use_torch_stream()
         self.ctx.predict_pages_files(h_pages, h_pages, n, H, W, Hs, Ws, cc_majority, self.lut, out.get("labels"), out["png"],
                                      out["png"].shape[2], out["png_sizes"])

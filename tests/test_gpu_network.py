@@ -30,7 +30,7 @@ def _device_predict(arch, weights, n_classes, image, precision, engine, keep=Fal
     from page_segmentation_b200.lib.dataset import SingleData
     net = Network("Predict", n_classes=n_classes, model_constructor=Architecture(arch), weights=weights,
                   precision=precision)
-    net._context().set_engine(engine)
+    net.engine = engine
     # keep=True: also store the activations the fused kernels never write (conv2 of fcn_skip)
     net._context().set_keep_activations(keep)
     try:

@@ -176,3 +176,63 @@ def test_preserving_resize(ctx, src, dst):
     exp = osk.resize(a, dst, order=0)
     assert got.dtype == np.float64
     np.testing.assert_array_equal(got, exp)
+
+
+def _max_width_on(c, page, lh, max_width):
+    """pcs_preprocess_max_width on context `c` -> (image, binary) numpy."""
+    import torch
+    H, W = page.shape
+    H1, W1 = synth.scaled_shape(H, W, 6 / lh)
+    H2, W2 = synth.scaled_shape(H1, W1, max_width / W1)
+    d = torch.from_numpy(page).cuda()
+    d_img = torch.empty((H2, W2), dtype=torch.uint8, device="cuda")
+    d_bin = torch.empty((H2, W2), dtype=torch.uint8, device="cuda")
+    c.preprocess_max_width(d, d, 1, H, W, H1, W1, H2, W2, d_img, d_bin, None)
+    c.synchronize()
+    return d_img.cpu().numpy(), d_bin.cpu().numpy()
+
+
+def _assert_max_width(got, page, lh, max_width):
+    eimg, eb = opipe.prepare_images(page, page, 6, lh, max_width=max_width)
+    np.testing.assert_array_equal(got[1], eb)
+    diff = np.abs(got[0].astype(int) - eimg.astype(int))
+    assert diff.max() <= 1 and (diff > 0).mean() <= 1e-3, (diff.max(), (diff > 0).mean())
+
+
+def test_max_width_is_the_first_call_on_a_fresh_context():
+    """the max_width pass carves its fp64 planes out of a second scratch buffer and then runs a whole
+    first pass, which grows the first scratch buffer; growing it must not free the second one under its feet.  A fresh
+    pcs_ctx (not the session's, whose scratch has long been grown) makes the first pass grow scratch inside the call."""
+    import torch
+    from page_segmentation_b200 import _native
+    assert torch.cuda.is_available()
+    c = _native.Context(0)
+    try:
+        c.use_torch_stream()
+        page = synth.make_page(7, 600, 480, 18)
+        _assert_max_width(_max_width_on(c, page, 18, 100), page, 18, 100)
+    finally:
+        c.close()
+
+
+def test_scratch_growth_between_two_max_width_calls():
+    """... and a scratch-growing call (connected components of a much larger page) between two max_width calls must
+    leave the second scratch buffer alive: the second call re-uses it."""
+    import torch
+    from page_segmentation_b200 import _native
+    c = _native.Context(0)
+    try:
+        c.use_torch_stream()
+        page = synth.make_page(8, 333, 517, 11)
+        first = _max_width_on(c, page, 11, 200)
+        _assert_max_width(first, page, 11, 200)
+        big = torch.from_numpy((synth.make_page(9, 2000, 1500, 18) < 128).astype(np.uint8)).cuda()
+        labels = torch.empty(big.shape, dtype=torch.int32, device="cuda")
+        ncomp = torch.zeros((1,), dtype=torch.int32, device="cuda")
+        c.ccl(big, 1, big.shape[0], big.shape[1], labels, None, 0, ncomp)          # grows ctx->scratch
+        c.synchronize()
+        second = _max_width_on(c, page, 11, 200)
+        np.testing.assert_array_equal(first[0], second[0])
+        np.testing.assert_array_equal(first[1], second[1])
+    finally:
+        c.close()

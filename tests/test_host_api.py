@@ -221,3 +221,17 @@ def test_page_locked_result_policy(monkeypatch):
     assert n_pinned <= runtime._PIN_MISSES + 3 * (runtime._PIN_MISSES - runtime._PIN_MISSES // 2)
     monkeypatch.setattr(runtime, "_PIN_ENABLED", False)
     assert runtime._pinned_empty(t, (4,), None, "b") is None
+
+
+def test_colour_lut_is_padded_and_checked_before_it_reaches_the_library():
+    """pcs_forward / pcs_predict_pages_* read n_classes rows of the caller's LUT; the binding pads the table
+    to 256 rows and refuses one that is shorter than the model's class count."""
+    from page_segmentation_b200 import _native
+    lut = _native._lut256([[255, 255, 255], [255, 0, 0]])
+    assert lut.shape == (256, 3) and lut.dtype == np.uint8 and lut.flags["C_CONTIGUOUS"]
+    assert lut[1].tolist() == [255, 0, 0] and not lut[2:].any()
+    assert _native._lut256(None) is None
+    with pytest.raises(_native.PcsError):
+        _native._lut256([[0, 0, 0], [1, 1, 1]], n_classes=3)
+    with pytest.raises(_native.PcsError):
+        _native._lut256(np.zeros((257, 3), np.uint8))

@@ -16,7 +16,7 @@ for rep in range(int(sys.argv[1]) if len(sys.argv) > 1 else 6):
             W[0][0][2, 2, 0, c] = (c + 1) / 32.0
             W[1][0][ty, tx, c, c] = 1.0
         net = Network("Predict", n_classes=3, weights=W, precision="bf16")
-        ctx = net._context(); ctx.set_engine("umma")
+        net.engine = "umma"; ctx = net._context()
         net.predict_single_data(SingleData(image=img))
         conv1 = ctx.debug_activation("conv1")[0]; conv2 = ctx.debug_activation("conv2")[0]
         H, Wd, _ = conv1.shape
