@@ -161,6 +161,18 @@ PCS_API int pcs_cc_majority(pcs_ctx* ctx, uint8_t* d_pred, const uint8_t* d_bina
 PCS_API int pcs_bounding_boxes(pcs_ctx* ctx, const uint8_t* d_pred, int n, int H, int W,
                        int n_classes, uint8_t* d_out);
 
+/* ---- segment extraction: the per-class labelling of add_bounding_boxes, lib/postprocess.py:31-33
+ * (cv2.connectedComponentsWithStats(pred == c, connectivity=4) for every class c), returning the stats table that
+ * lib/cc.py:4-18 (cc_bbox / cc_bbox_func) indexes instead of a painted map: BASELINE configs[3]'s "connected-component
+ * segment extraction".
+ *   d_pred  : [n][H][W] uint8 class map
+ *   d_stats : [n][n_classes][max_components][5] int32 (left, top, width, height, area); row 0 = the labelling's
+ *             background (every pixel != c), rows 1.. = the components of class c in raster order of their first
+ *             pixel, rows at or beyond the label count are zero; components beyond max_components are dropped
+ *   d_ncomp : [n][n_classes] int32 number of labels incl. background (may exceed max_components), or NULL */
+PCS_API int pcs_class_components(pcs_ctx* ctx, const uint8_t* d_pred, int n, int H, int W, int n_classes,
+                         int32_t* d_stats, int max_components, int32_t* d_ncomp);
+
 /* ---- replaces compute_char_height, lib/image_ops.py:58-82 (the producer of
  * `line_height_px`): cv2 Otsu threshold of the grey page, inversion unless
  * `inverse`, connected components (8-connected: the reference's positional `4`
@@ -193,6 +205,14 @@ PCS_API int pcs_predict_pages_host(pcs_ctx* ctx, const uint8_t* h_grey, const ui
 PCS_API int pcs_predict_pages_files(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h_bin,
                             int n, int H, int W, int Hs, int Ws, int cc_majority, const uint8_t* lut,
                             uint8_t* h_labels, uint8_t* h_png, size_t png_stride, uint64_t* h_png_sizes);
+
+/* The same pipeline followed by segment extraction (pcs_class_components on the final class map): BASELINE configs[3],
+ * "normalization rescale + FCN + connected-component segment extraction".  The masks are optional.
+ *   h_stats : [n][n_classes][max_components][5] int32;  h_ncomp : [n][n_classes] int32 or NULL */
+PCS_API int pcs_predict_pages_segments(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h_bin,
+                               int n, int H, int W, int Hs, int Ws, int cc_majority, const uint8_t* lut,
+                               uint8_t* h_labels, uint8_t* h_color, uint8_t* h_overlay, uint8_t* h_inverted,
+                               int32_t* h_stats, int max_components, int32_t* h_ncomp);
 
 /* ---- image files: the encoder of output_data, lib/output.py:38-41 (skimage.io.imsave of the three masks).
  * Builds n complete PNG files on the device from [n][H][W][channels] uint8 images (channels 1 = grey, 3 = RGB,

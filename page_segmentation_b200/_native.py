@@ -23,7 +23,7 @@ EXPORTS = [
     "pcs_synchronize", "pcs_launch_count", "pcs_model_load", "pcs_set_engine", "pcs_preprocess",
     "pcs_preprocess_max_width",
     "pcs_forward", "pcs_masks", "pcs_resize_nearest", "pcs_ccl", "pcs_cc_majority",
-    "pcs_bounding_boxes", "pcs_char_height", "pcs_png_bytes", "pcs_png_encode", "pcs_segment_masks", "pcs_dilate3x3", "pcs_integral_image", "pcs_text_regions", "pcs_predict_pages_host", "pcs_predict_pages_files", "pcs_eval_counts",
+    "pcs_bounding_boxes", "pcs_class_components", "pcs_char_height", "pcs_png_bytes", "pcs_png_encode", "pcs_segment_masks", "pcs_dilate3x3", "pcs_integral_image", "pcs_text_regions", "pcs_predict_pages_host", "pcs_predict_pages_files", "pcs_predict_pages_segments", "pcs_eval_counts",
     "pcs_train_input", "pcs_train_corr2d", "pcs_train_wgrad", "pcs_train_bias_grad", "pcs_train_relu_bwd", "pcs_train_maxpool_fwd",
     "pcs_train_maxpool_bwd", "pcs_train_deconv2_fwd", "pcs_train_deconv2_bwd_data", "pcs_train_deconv2_wgrad", "pcs_train_softmax_ce",
     "pcs_train_adam", "pcs_debug_activation", "pcs_set_keep_activations", "pcs_set_timing", "pcs_set_pdl",
@@ -74,6 +74,7 @@ def load() -> C.CDLL:
     lib.pcs_cc_majority.argtypes = [vp, u8p, u8p, i32, i32, i32, i32]
     lib.pcs_bounding_boxes.argtypes = [vp, u8p, i32, i32, i32, i32, u8p]
     lib.pcs_char_height.argtypes = [vp, u8p, i32, i32, i32, i32, vp]
+    lib.pcs_class_components.argtypes = [vp, u8p, i32, i32, i32, i32, vp, i32, vp]
     lib.pcs_png_bytes.argtypes = [i32, i32, i32, i32]
     lib.pcs_png_bytes.restype = C.c_size_t
     lib.pcs_png_encode.argtypes = [vp, u8p, i32, i32, i32, i32, i32, u8p, C.c_size_t, vp]
@@ -83,6 +84,7 @@ def load() -> C.CDLL:
     lib.pcs_text_regions.argtypes = [vp, u8p, i32, i32, vp, i32, i32, i32, u8p, u8p]
     lib.pcs_predict_pages_host.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
     lib.pcs_predict_pages_files.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, C.c_size_t, vp]
+    lib.pcs_predict_pages_segments.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp]
     lib.pcs_eval_counts.argtypes = [vp, vp, vp, vp, C.c_size_t, i32, vp]
     f32 = C.c_float
     lib.pcs_train_input.argtypes = [vp, vp, i32, i32, vp, i32, i32]
@@ -270,6 +272,10 @@ class Context:
         self._check(self.lib.pcs_bounding_boxes(self.h, _ptr(d_pred), n, H, W, n_classes, _ptr(d_out)),
                     "pcs_bounding_boxes")
 
+    def class_components(self, d_pred, n, H, W, n_classes, d_stats, max_components, d_ncomp=None):
+        self._check(self.lib.pcs_class_components(self.h, _ptr(d_pred), n, H, W, n_classes, _ptr(d_stats), int(max_components),
+                                                  _ptr(d_ncomp)), "pcs_class_components")
+
     def char_height(self, d_img, n, H, W, inverse, d_height):
         self._check(self.lib.pcs_char_height(self.h, _ptr(d_img), n, H, W, 1 if inverse else 0, _ptr(d_height)),
                     "pcs_char_height")
@@ -313,6 +319,14 @@ class Context:
         self._check(self.lib.pcs_predict_pages_files(
             self.h, _ptr(h_grey), _ptr(h_bin), n, H, W, Hs, Ws, 1 if cc_majority else 0, _ptr(lut_arr),
             _ptr(h_labels), _ptr(h_png), png_stride, _ptr(h_png_sizes)), "pcs_predict_pages_files")
+
+    def predict_pages_segments(self, h_grey, h_bin, n, H, W, Hs, Ws, cc_majority, lut, h_labels, h_stats, max_components,
+                               h_ncomp=None, h_color=None, h_overlay=None, h_inverted=None):
+        lut_arr = _lut256(lut, self.model[1] if self.model else None)
+        self._check(self.lib.pcs_predict_pages_segments(
+            self.h, _ptr(h_grey), _ptr(h_bin), n, H, W, Hs, Ws, 1 if cc_majority else 0, _ptr(lut_arr), _ptr(h_labels),
+            _ptr(h_color), _ptr(h_overlay), _ptr(h_inverted), _ptr(h_stats), int(max_components), _ptr(h_ncomp)),
+            "pcs_predict_pages_segments")
 
     def eval_counts(self, d_pred, d_mask, d_bin, n_pixels, n_classes, d_out):
         self._check(self.lib.pcs_eval_counts(self.h, _ptr(d_pred), _ptr(d_mask), _ptr(d_bin), n_pixels, n_classes, _ptr(d_out)), "pcs_eval_counts")

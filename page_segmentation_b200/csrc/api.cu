@@ -754,6 +754,14 @@ int pcs_bounding_boxes(pcs_ctx* ctx, const uint8_t* d_pred, int n, int H, int W,
     return launch_bounding_boxes(ctx, d_pred, n, H, W, n_classes, d_out);
 }
 
+int pcs_class_components(pcs_ctx* ctx, const uint8_t* d_pred, int n, int H, int W, int n_classes, int32_t* d_stats, int max_components,
+                         int32_t* d_ncomp) {
+    if (!ctx || !d_pred || !d_stats) return ctx ? set_err(ctx, PCS_ERR_ARG, "class_components: null argument") : PCS_ERR_ARG;
+    PCS_CUDA(ctx, cudaSetDevice(ctx->device));
+    StageScope ts(ctx, "class_components");
+    return launch_class_components(ctx, d_pred, n, H, W, n_classes, d_stats, max_components, d_ncomp);
+}
+
 int pcs_char_height(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, int inverse, int32_t* d_height) {
     if (!ctx || !d_img || !d_height) return ctx ? set_err(ctx, PCS_ERR_ARG, "char_height: null argument") : PCS_ERR_ARG;
     PCS_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -877,8 +885,9 @@ int pcs_png_encode(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, int 
 static int predict_pages_host_body(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h_bin, int n, int H, int W, int Hs, int Ws,
                                    int cc_majority, const uint8_t* lut, uint8_t* h_image, uint8_t* h_binary, uint8_t* h_labels,
                                    uint8_t* h_color, uint8_t* h_overlay, uint8_t* h_inverted, uint8_t* h_png, size_t png_stride,
-                                   uint64_t* h_png_sizes) {
+                                   uint64_t* h_png_sizes, int32_t* h_stats = nullptr, int max_components = 0, int32_t* h_ncomp = nullptr) {
     if (!ctx || !h_grey || !h_bin) return ctx ? set_err(ctx, PCS_ERR_ARG, "predict_pages_host: null input") : PCS_ERR_ARG;
+    if (h_stats && (max_components <= 0 || !h_labels)) return set_err(ctx, PCS_ERR_ARG, "predict_pages_segments: max_components and the class map are required");
     if (!ctx->model_ready) return set_err(ctx, PCS_ERR_STATE, "pcs_predict_pages_host before pcs_model_load");
     if (n <= 0 || H <= 0 || W <= 0 || Hs <= 0 || Ws <= 0) return set_err(ctx, PCS_ERR_ARG, "predict_pages_host: bad shape");
     const bool want_png = h_png != nullptr;
@@ -941,7 +950,9 @@ static int predict_pages_host_body(pcs_ctx* ctx, const uint8_t* h_grey, const ui
     auto al = [](size_t b) { return (b + 255) / 256 * 256; };
     const size_t in_bytes = al(src1 * chunk) * (same ? 1 : 2);
     const size_t png_bytes = want_png ? 3 * (size_t)chunk * dpng_stride + al(3 * (size_t)chunk * 8) : 0;
-    const size_t out_bytes = al(dst1 * chunk) * 3 + al(dst1 * chunk * 3) * 3 + png_bytes;
+    const size_t stats1 = h_stats ? (size_t)ctx->n_classes * max_components * 5 * sizeof(int32_t) : 0;      // per page
+    const size_t seg_bytes = h_stats ? al(stats1 * chunk) + al((size_t)chunk * ctx->n_classes * sizeof(int32_t)) : 0;
+    const size_t out_bytes = al(dst1 * chunk) * 3 + al(dst1 * chunk * 3) * 3 + png_bytes + seg_bytes;
     const size_t need = (size_t)nbuf * (in_bytes + out_bytes) + 4096;
     if (want_png && !ctx->h_png_sizes) PCS_CUDA(ctx, cudaHostAlloc(&ctx->h_png_sizes, pcs_ctx::kHostBufs * 3 * 64 * sizeof(uint64_t), cudaHostAllocDefault));
     if (want_png && chunk > 64) return set_err(ctx, PCS_ERR_ARG, "predict_pages_files: chunks of more than 64 pages");
@@ -955,7 +966,7 @@ static int predict_pages_host_body(pcs_ctx* ctx, const uint8_t* h_grey, const ui
         }
         ctx->stage_bytes = need;
     }
-    struct Buf { uint8_t *grey, *bin, *image, *binary, *labels, *color, *overlay, *inverted, *png; uint64_t* png_sizes; } buf[pcs_ctx::kHostBufs];
+    struct Buf { uint8_t *grey, *bin, *image, *binary, *labels, *color, *overlay, *inverted, *png; uint64_t* png_sizes; int32_t *stats, *ncomp; } buf[pcs_ctx::kHostBufs];
     {
         uint8_t* p = reinterpret_cast<uint8_t*>(ctx->stage);
         for (int i = 0; i < nbuf; ++i) {
@@ -968,6 +979,7 @@ static int predict_pages_host_body(pcs_ctx* ctx, const uint8_t* h_grey, const ui
             buf[i].overlay = p; p += al(dst1 * chunk * 3);
             buf[i].inverted = p; p += al(dst1 * chunk * 3);
             buf[i].png = p; buf[i].png_sizes = reinterpret_cast<uint64_t*>(p + 3 * (size_t)chunk * dpng_stride); p += png_bytes;
+            buf[i].stats = reinterpret_cast<int32_t*>(p); buf[i].ncomp = reinterpret_cast<int32_t*>(p + al(stats1 * chunk)); p += seg_bytes;
         }
     }
     // PCSEG_TRACE_HOST: per-chunk device timeline (timing events on the three streams), printed at the end
@@ -1030,6 +1042,8 @@ static int predict_pages_host_body(pcs_ctx* ctx, const uint8_t* h_grey, const ui
                                 (h_color || want_png) ? buf[b].color : nullptr, (h_overlay || want_png) ? buf[b].overlay : nullptr,
                                 (h_inverted || want_png) ? buf[b].inverted : nullptr));
         }
+        if (h_stats)        // segment extraction on the final class map (after the vote, when one runs)
+            PCS_TRY(pcs_class_components(ctx, buf[b].labels, m, Hs, Ws, ctx->n_classes, buf[b].stats, max_components, buf[b].ncomp));
         if (want_png) {
             uint8_t* const kinds[3] = {buf[b].color, buf[b].overlay, buf[b].inverted};
             for (int k = 0; k < 3; ++k)
@@ -1047,6 +1061,11 @@ static int predict_pages_host_body(pcs_ctx* ctx, const uint8_t* h_grey, const ui
         if (h_color) PCS_CUDA(ctx, cudaMemcpyAsync(h_color + o3, buf[b].color, dst1 * m * 3, cudaMemcpyDeviceToHost, s_out));
         if (h_overlay) PCS_CUDA(ctx, cudaMemcpyAsync(h_overlay + o3, buf[b].overlay, dst1 * m * 3, cudaMemcpyDeviceToHost, s_out));
         if (h_inverted) PCS_CUDA(ctx, cudaMemcpyAsync(h_inverted + o3, buf[b].inverted, dst1 * m * 3, cudaMemcpyDeviceToHost, s_out));
+        if (h_stats) {
+            PCS_CUDA(ctx, cudaMemcpyAsync(reinterpret_cast<char*>(h_stats) + (size_t)p0 * stats1, buf[b].stats, stats1 * m, cudaMemcpyDeviceToHost, s_out));
+            if (h_ncomp) PCS_CUDA(ctx, cudaMemcpyAsync(h_ncomp + (size_t)p0 * ctx->n_classes, buf[b].ncomp, (size_t)m * ctx->n_classes * sizeof(int32_t),
+                                                       cudaMemcpyDeviceToHost, s_out));
+        }
         mark(s_out);
         if (want_png) {
             for (int k = 0; k < 3; ++k)
@@ -1093,9 +1112,9 @@ static int predict_pages_host_body(pcs_ctx* ctx, const uint8_t* h_grey, const ui
 static int predict_pages_host_impl(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h_bin, int n, int H, int W, int Hs, int Ws,
                                    int cc_majority, const uint8_t* lut, uint8_t* h_image, uint8_t* h_binary, uint8_t* h_labels,
                                    uint8_t* h_color, uint8_t* h_overlay, uint8_t* h_inverted, uint8_t* h_png, size_t png_stride,
-                                   uint64_t* h_png_sizes) {
+                                   uint64_t* h_png_sizes, int32_t* h_stats = nullptr, int max_components = 0, int32_t* h_ncomp = nullptr) {
     const int rc = predict_pages_host_body(ctx, h_grey, h_bin, n, H, W, Hs, Ws, cc_majority, lut, h_image, h_binary, h_labels, h_color,
-                                           h_overlay, h_inverted, h_png, png_stride, h_png_sizes);
+                                           h_overlay, h_inverted, h_png, png_stride, h_png_sizes, h_stats, max_components, h_ncomp);
     if (rc != PCS_OK && ctx) {
         for (cudaStream_t s : {ctx->copy_streams[0], ctx->copy_streams[1]})
             if (s) cudaStreamSynchronize(s);
@@ -1118,6 +1137,14 @@ int pcs_predict_pages_files(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* 
     if (ctx && !h_png) return set_err(ctx, PCS_ERR_ARG, "predict_pages_files: null output");
     return predict_pages_host_impl(ctx, h_grey, h_bin, n, H, W, Hs, Ws, cc_majority, lut, nullptr, nullptr, h_labels, nullptr, nullptr, nullptr,
                                    h_png, png_stride, h_png_sizes);
+}
+
+int pcs_predict_pages_segments(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h_bin, int n, int H, int W, int Hs, int Ws,
+                               int cc_majority, const uint8_t* lut, uint8_t* h_labels, uint8_t* h_color, uint8_t* h_overlay,
+                               uint8_t* h_inverted, int32_t* h_stats, int max_components, int32_t* h_ncomp) {
+    if (ctx && (!h_stats || !h_labels)) return set_err(ctx, PCS_ERR_ARG, "predict_pages_segments: null output");
+    return predict_pages_host_impl(ctx, h_grey, h_bin, n, H, W, Hs, Ws, cc_majority, lut, nullptr, nullptr, h_labels, h_color, h_overlay,
+                                   h_inverted, nullptr, 0, nullptr, h_stats, max_components, h_ncomp);
 }
 
 int pcs_debug_activation(pcs_ctx* ctx, const char* name, float* h_out, size_t capacity_floats, int32_t* shape4) {

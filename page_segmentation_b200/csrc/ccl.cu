@@ -767,6 +767,117 @@ int launch_bounding_boxes(pcs_ctx* ctx, const uint8_t* d_pred, int n, int H, int
 }
 
 // ---------------------------------------------------------------------------
+// Segment extraction: the labelling add_bounding_boxes runs per class (postprocess.py:31-33,
+// cv2.connectedComponentsWithStats(pred == c, connectivity=4)) with its stats table (what cc.py:4-18 indexes) as the
+// result instead of a painted map: per page and class the number of labels (background included, like cv2) and the
+// rows [left, top, width, height, area], row 0 = the "background" of that labelling (every pixel != c), rows
+// 1.. = the components of class c numbered in raster order of their first pixel.
+// One accumulator record per root (W - min x, H - min y, max x, max y, area), one update per RUN.
+// ---------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256)
+cstats_accum_kernel(const uint8_t* __restrict__ img, int H, int W, int cls, const int* __restrict__ parent, int* __restrict__ acc /*[px][5]*/,
+                    int* __restrict__ bg /*[n][5]: W - min x, H - min y, max x, max y, count of the pixels != cls*/) {
+    PCS_SEG_THREAD();
+    const unsigned m = valid ? fg_bits<MODE>(img + page_off + (size_t)y * W, x0, W, cls, last_row) : 0u;
+    {   // pixels outside the class: one warp-aggregated update per warp (a warp never straddles two pages)
+        const int nx = valid ? min(32, W - x0) : 0;
+        const unsigned b = ~m & (nx >= 32 ? 0xffffffffu : ((1u << nx) - 1u));
+        const int v0 = b ? W - (x0 + __ffs(b) - 1) : 0, v1 = b ? H - y : 0, v2 = b ? x0 + 31 - __clz(b) : -1, v3 = b ? y : -1;
+        const int r0 = __reduce_max_sync(0xffffffffu, v0), r1 = __reduce_max_sync(0xffffffffu, v1);
+        const int r2 = __reduce_max_sync(0xffffffffu, v2), r3 = __reduce_max_sync(0xffffffffu, v3);
+        const int cnt = __reduce_add_sync(0xffffffffu, __popc(b));
+        if ((threadIdx.x & 31) == 0 && cnt) {
+            int* g = bg + (size_t)blockIdx.y * 5;
+            if (r0 > g[0]) atomicMax(&g[0], r0);
+            if (r1 > g[1]) atomicMax(&g[1], r1);
+            if (r2 > g[2]) atomicMax(&g[2], r2);
+            if (r3 > g[3]) atomicMax(&g[3], r3);
+            atomicAdd(&g[4], cnt);
+        }
+    }
+    if (!m) return;
+    const int base = y * W + x0;
+    unsigned mm = m;
+    int s, len;
+    while (next_run(mm, s, len)) {
+        const int p = uf_find(parent + page_off, base + s);
+        int* a = acc + (page_off + p) * 5;
+        const int v0 = W - (x0 + s), v1 = H - y, v2 = x0 + s + len - 1, v3 = y;
+        if (v0 > __ldcg(a + 0)) atomicMax(&a[0], v0);
+        if (v1 > __ldcg(a + 1)) atomicMax(&a[1], v1);
+        if (v2 > __ldcg(a + 2)) atomicMax(&a[2], v2);
+        if (v3 > __ldcg(a + 3)) atomicMax(&a[3], v3);
+        atomicAdd(&a[4], len);
+    }
+}
+
+// stats row of every root (label = rank of the root) and row 0; rows at or beyond the label count stay zero
+__global__ void __launch_bounds__(256)
+cstats_write_kernel(const int* __restrict__ parent, const int* __restrict__ rank, const int* __restrict__ acc, const int* __restrict__ bg,
+                    int H, int W, int32_t* __restrict__ stats, size_t page_stride /*ints between pages*/, int max_components) {
+    const size_t page_px = (size_t)H * W, page_off = (size_t)blockIdx.y * page_px;
+    int32_t* st = stats + (size_t)blockIdx.y * page_stride;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const int* g = bg + (size_t)blockIdx.y * 5;
+        if (g[4] > 0) { st[0] = W - g[0]; st[1] = H - g[1]; st[2] = g[2] - (W - g[0]) + 1; st[3] = g[3] - (H - g[1]) + 1; st[4] = g[4]; }
+        else { st[0] = 0; st[1] = 0; st[2] = 0; st[3] = 0; st[4] = 0; }     // cv2 leaves an empty label's box at zero extent
+    }
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < page_px; i += (size_t)gridDim.x * blockDim.x) {
+        if (parent[page_off + i] != (int)i) continue;
+        const int l = rank[page_off + i];
+        if (l >= max_components) continue;
+        const int* a = acc + (page_off + i) * 5;
+        int32_t* o = st + (size_t)l * 5;
+        const int left = W - a[0], top = H - a[1];
+        o[0] = left; o[1] = top; o[2] = a[2] - left + 1; o[3] = a[3] - top + 1; o[4] = a[4];
+    }
+}
+
+__global__ void cstats_ncomp_kernel(const int* __restrict__ ncomp_tmp, int n, int n_classes, int cls, int32_t* __restrict__ d_ncomp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) d_ncomp[(size_t)i * n_classes + cls] = ncomp_tmp[i];
+}
+
+int launch_class_components(pcs_ctx* ctx, const uint8_t* d_pred, int n, int H, int W, int n_classes, int32_t* d_stats, int max_components,
+                            int32_t* d_ncomp) {
+    if (n <= 0 || H <= 0 || W <= 0 || n_classes <= 0 || n_classes > 255 || (size_t)H * W >= (size_t)INT_MAX || max_components <= 0)
+        return set_err(ctx, PCS_ERR_ARG, "class_components: bad argument");
+    const size_t page_px = (size_t)H * W, total = page_px * n;
+    const int nblocks = (int)((page_px + kScanBlock - 1) / kScanBlock);
+    PCS_TRY(scratch_reserve(ctx, total * 4 * 7 + ((size_t)n * nblocks + n + (size_t)n * 5) * 4 + 512));
+    int* parent = reinterpret_cast<int*>(ctx->scratch);
+    int* rank = parent + total;
+    int* acc = rank + total;
+    int* blocksum = acc + total * 5;
+    int* ncomp_tmp = blocksum + (size_t)n * nblocks;
+    int* bg = ncomp_tmp + n;
+    cudaStream_t st = ctx->stream;
+    PCS_CUDA(ctx, cudaMemsetAsync(d_stats, 0, (size_t)n * n_classes * max_components * 5 * sizeof(int32_t), st));
+    const dim3 g = seg_grid(H, W, n);
+    for (int c = 0; c < n_classes; ++c) {
+        PCS_TRY(ccl_roots(ctx, d_pred, n, H, W, c, true, parent, acc, 5, false, false, /*flatten=*/false));
+        PCS_CUDA(ctx, cudaMemsetAsync(bg, 0, (size_t)n * 5 * sizeof(int), st));
+        cstats_accum_kernel<1><<<g, 256, 0, st>>>(d_pred, H, W, c, parent, acc, bg);
+        PCS_LAUNCH_CHECK(ctx, "cstats_accum_kernel");
+        ccl_count_roots_kernel<<<dim3(nblocks, n), 256, 0, st>>>(parent, page_px, nblocks, blocksum);
+        PCS_LAUNCH_CHECK(ctx, "ccl_count_roots_kernel");
+        ccl_scan_blocks_kernel<<<n, 1024, 0, st>>>(blocksum, nblocks, ncomp_tmp);
+        PCS_LAUNCH_CHECK(ctx, "ccl_scan_blocks_kernel");
+        ccl_rank_kernel<<<dim3(nblocks, n), 256, 0, st>>>(parent, page_px, nblocks, blocksum, rank);
+        PCS_LAUNCH_CHECK(ctx, "ccl_rank_kernel");
+        cstats_write_kernel<<<dim3((unsigned)std::min<size_t>(512, (page_px + 255) / 256), n), 256, 0, st>>>(
+            parent, rank, acc, bg, H, W, d_stats + (size_t)c * max_components * 5, (size_t)n_classes * max_components * 5, max_components);
+        PCS_LAUNCH_CHECK(ctx, "cstats_write_kernel");
+        if (d_ncomp) {
+            cstats_ncomp_kernel<<<(n + 255) / 256, 256, 0, st>>>(ncomp_tmp, n, n_classes, c, d_ncomp);
+            PCS_LAUNCH_CHECK(ctx, "cstats_ncomp_kernel");
+        }
+    }
+    return PCS_OK;
+}
+
+// ---------------------------------------------------------------------------
 // compute_char_height (lib/image_ops.py:58-82): Otsu threshold, connected components, letter-like boxes
 // (0.5 < w/h < 2, 10 < h < 60, 5 < w < 50), the height at index len/2 of the sorted valid heights.
 // The reference calls cv2.connectedComponentsWithStats(img, 4): the positional 4 lands in the `labels`

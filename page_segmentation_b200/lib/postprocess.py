@@ -66,6 +66,26 @@ def add_bounding_boxes(pred: np.ndarray, data: SingleData) -> np.ndarray:
     return _store(np.empty_like(pred), d_out)
 
 
+def class_components(pred: np.ndarray, n_classes: int = None, max_components: int = 65536):
+    """Segment extraction (BASELINE configs[3]): what add_bounding_boxes computes per class before it paints
+    (postprocess.py:31-33) -- `cv2.connectedComponentsWithStats(pred == c, connectivity=4)` for every class c -- as a
+    list of `(num_labels, stats)` pairs, `stats` int32 (num_labels, 5) in cv2's column order (cc.py:4-18).  Not part
+    of the reference's API: the reference throws these tables away after painting."""
+    import torch
+    from ..runtime import get_context
+    ctx = get_context()
+    h, w = pred.shape
+    d_pred, seen = _pred_to_device(pred, ctx.device)
+    n_classes = seen if n_classes is None else int(n_classes)
+    d_stats = torch.empty((1, n_classes, max_components, 5), dtype=torch.int32, device=d_pred.device)
+    d_ncomp = torch.empty((1, n_classes), dtype=torch.int32, device=d_pred.device)
+    ctx.class_components(d_pred, 1, h, w, n_classes, d_stats, max_components, d_ncomp)
+    ncomp = d_ncomp.cpu().numpy()[0]
+    if int(ncomp.max()) > max_components:
+        return class_components(pred, n_classes, int(ncomp.max()))
+    return [(int(ncomp[c]), d_stats[0, c, :int(ncomp[c])].cpu().numpy()) for c in range(n_classes)]
+
+
 def find_postprocessor(key: str) -> Callable[[np.ndarray, SingleData], np.ndarray]:
     return POSTPROCESSORS[key.lower().replace('_', '').replace('-', '')]
 

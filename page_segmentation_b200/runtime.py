@@ -319,6 +319,18 @@ class PageBatchEngine:
                                     out.get("inverted"))
         return out
 
+    def run_host_segments(self, h_pages: np.ndarray, scale: float, out: dict, max_components: int, cc_majority: bool = True):
+        """run_host followed by segment extraction (pcs_predict_pages_segments, BASELINE configs[3]): `out` holds host
+        arrays 'labels' (n, Hs, Ws) uint8, 'stats' (n, n_classes, max_components, 5) int32, optionally 'ncomp'
+        (n, n_classes) int32 and the masks 'color' / 'overlay' / 'inverted'."""
+        n, H, W = h_pages.shape
+        Hs, Ws = scaled_shape(H, W, scale)
+        self._ensure_model()
+        self.ctx.use_torch_stream()
+        self.ctx.predict_pages_segments(h_pages, h_pages, n, H, W, Hs, Ws, cc_majority, self.lut, out["labels"], out["stats"],
+                                        max_components, out.get("ncomp"), out.get("color"), out.get("overlay"), out.get("inverted"))
+        return out
+
     def run_host_files(self, h_pages: np.ndarray, scale: float, out: dict, cc_majority: bool = False):
         """Like run_host, but the three masks of every page come back as PNG files (pcs_predict_pages_files): `out` holds
         host arrays 'png' (n, 3, stride) uint8, 'png_sizes' (n, 3) uint64 and optionally 'labels' (ideally pinned).

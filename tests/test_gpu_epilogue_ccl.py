@@ -122,3 +122,39 @@ def test_find_postprocessor(ctx):
     assert pp.find_postprocessor("bounding_boxes") is pp.add_bounding_boxes
     with pytest.raises(KeyError):
         pp.find_postprocessor("nope")
+
+
+@pytest.mark.parametrize("hw", [(61, 83), (200, 160), (97, 530), (389, 275), (1169, 827)])
+def test_class_components_match_cv2_stats(ctx, hw):
+    """pcs_class_components: per class c the label count and stats table of
+    cv2.connectedComponentsWithStats(pred == c, connectivity=4) (postprocess.py:31-33), bit-exact incl. row 0."""
+    from page_segmentation_b200.lib.postprocess import class_components
+    pred, b = _pred_and_binary(6, *hw)
+    pred = np.where(b > 0, pred, 0)
+    got = class_components(pred, 3, max_components=64)          # small table first: exercises the regrow path
+    for c in range(3):
+        n, _, stats, _ = cv2.connectedComponentsWithStats((pred == c).astype(np.uint8), connectivity=4)
+        assert got[c][0] == n, (c, got[c][0], n)
+        np.testing.assert_array_equal(got[c][1], stats)
+
+
+def test_class_components_batched_and_truncated(ctx):
+    """n pages in one call; a class that is absent yields one label (the background) covering the page; components beyond
+    max_components are dropped while the count still reports them."""
+    import torch
+    preds = [np.where(_pred_and_binary(20 + s, 150, 203)[1] > 0, _pred_and_binary(20 + s, 150, 203)[0], 0) for s in range(3)]
+    preds[1][preds[1] == 2] = 1                                    # page 1 has no class 2
+    d = torch.from_numpy(np.stack(preds).astype(np.uint8)).cuda()
+    maxc = 16
+    d_stats = torch.full((3, 3, maxc, 5), -7, dtype=torch.int32, device="cuda")
+    d_ncomp = torch.zeros((3, 3), dtype=torch.int32, device="cuda")
+    ctx.class_components(d, 3, 150, 203, 3, d_stats, maxc, d_ncomp)
+    stats, ncomp = d_stats.cpu().numpy(), d_ncomp.cpu().numpy()
+    for p in range(3):
+        for c in range(3):
+            n, _, exp, _ = cv2.connectedComponentsWithStats((preds[p] == c).astype(np.uint8), connectivity=4)
+            assert ncomp[p, c] == n
+            k = min(n, maxc)
+            np.testing.assert_array_equal(stats[p, c, :k], exp[:k])
+            assert not stats[p, c, k:].any()
+    assert ncomp[1, 2] == 1 and stats[1, 2, 0].tolist() == [0, 0, 203, 150, 150 * 203]

@@ -209,3 +209,34 @@ def test_full_size_a4_page_properties(ctx):
     voted = vote_connected_component_class(pred.copy(), data)
     np.testing.assert_array_equal(vote_connected_component_class(voted.copy(), data), voted)      # idempotent
     assert np.array_equal(voted[data.binary == 0], pred[data.binary == 0])                          # paper untouched
+
+
+@pytest.mark.parametrize("cc", [False, True])
+def test_host_batch_pipeline_with_segment_extraction(ctx, cc, monkeypatch):
+    """pcs_predict_pages_segments (BASELINE configs[3]): the stats tables that come back with the class maps are cv2's
+    for exactly those class maps (postprocess.py:31-33), page by page, over a chunked call."""
+    from page_segmentation_b200.runtime import PageBatchEngine
+    monkeypatch.setenv("PCSEG_HOST_CHUNK", "2")
+    n, H, W_ = 5, 360, 300
+    pages = np.stack([synth.make_page(30 + s, H, W_, 18) for s in range(n)])
+    weights = synth.make_weights("fcn_skip", 3, seed=9)
+    lut = np.array([LUT[i] for i in range(3)], dtype=np.uint8)
+    eng = PageBatchEngine("fcn_skip", weights, 3, precision="fp16", lut=lut)
+    Hs, Ws = synth.scaled_shape(H, W_, 6 / 18)
+    maxc = 2048
+    out = {"labels": np.zeros((n, Hs, Ws), np.uint8), "color": np.zeros((n, Hs, Ws, 3), np.uint8),
+           "stats": np.full((n, 3, maxc, 5), -1, np.int32), "ncomp": np.zeros((n, 3), np.int32)}
+    eng.run_host_segments(pages, 6 / 18, out, max_components=maxc, cc_majority=cc)
+    ref = {"labels": np.zeros((n, Hs, Ws), np.uint8)}
+    eng.run_host(pages, 6 / 18, ref, cc_majority=cc)
+    np.testing.assert_array_equal(out["labels"], ref["labels"])
+    for i in range(n):
+        _, eb = opipe.prepare_images(pages[i], pages[i], 6, 18)
+        c, _, _, _ = opipe.generate_output_masks(eb, out["labels"][i].astype(np.int64), LUT)
+        np.testing.assert_array_equal(out["color"][i], c)
+        for k in range(3):
+            m, _, stats, _ = cv2.connectedComponentsWithStats((out["labels"][i] == k).astype(np.uint8), connectivity=4)
+            assert out["ncomp"][i, k] == m
+            kk = min(m, maxc)
+            np.testing.assert_array_equal(out["stats"][i, k, :kk], stats[:kk])
+            assert not out["stats"][i, k, kk:].any()
