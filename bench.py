@@ -49,11 +49,38 @@ def measured_traffic(kernel, pages):
 
 
 def peaks():
+    """(HBM GB/s, bf16 TFLOP/s burst, bf16 TFLOP/s sustained, source).  The timed region of this bench is K steps of
+    ~10 ms at ~1.9 GHz SM clock -- far shorter than the 4 s back-to-back run behind the sustained figure (1.25 GHz median)
+    -- so the roofline fraction is quoted against the BURST peak; the sustained one is printed beside it."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
-    return 6650.0, 1590.0, "fallback"
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1650.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+def tensor_roofline(kernel, gflop_per_launch, ms, traffic=None, extra=None):
+    hbm, burst, sustained, which = peaks()
+    tflops = gflop_per_launch / ms
+    r = {"bound": "tensor", "kernel": kernel, "achieved": tflops, "peak": burst, "unit": "TFLOP/s", "frac": tflops / burst,
+         "frac_burst": tflops / burst, "frac_sustained": tflops / sustained, "peak_sustained": sustained,
+         "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read + write)",
+         "peak_source": f"{which}: burst cuBLAS bf16 (the kernel is timed inside a short region at boost clocks)"}
+    if extra:
+        r.update(extra)
+    return r
+
+
+def unet_layer_gflop(hp, wp):
+    """Algorithmic GFLOP per page of every U-Net layer (model.py:151-203) on the padded hp x wp grid: 2 * H_l * W_l * k^2 *
+    C_in * C_out, true channel counts (SURVEY.md appendix E sums these to 1 639.684 at 1184 x 832)."""
+    t = [("conv1a", 3, 1, 64, 1), ("conv1b", 3, 64, 64, 1), ("conv2a", 3, 64, 128, 2), ("conv2b", 3, 128, 128, 2),
+         ("conv3a", 3, 128, 256, 4), ("conv3b", 3, 256, 256, 4), ("conv4a", 3, 256, 512, 8), ("conv4b", 3, 512, 512, 8),
+         ("conv5a", 3, 512, 1024, 16), ("conv5b", 3, 1024, 1024, 16), ("up6", 2, 1024, 512, 8), ("conv6a", 3, 1024, 512, 8),
+         ("conv6b", 3, 512, 512, 8), ("up7", 2, 512, 256, 4), ("conv7a", 3, 512, 256, 4), ("conv7b", 3, 256, 256, 4),
+         ("up8", 2, 256, 128, 2), ("conv8a", 3, 256, 128, 2), ("conv8b", 3, 128, 128, 2), ("up9", 2, 128, 64, 1),
+         ("conv9a", 3, 128, 64, 1), ("conv9b", 3, 64, 64, 1), ("head", 1, 64, N_CLASSES, 1)]
+    return {name: 2.0 * (hp // lv) * (wp // lv) * k * k * ci * co / 1e9 for name, k, ci, co, lv in t}
 
 
 class ClockSampler:
@@ -204,6 +231,217 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------
+# Sub-benchmarks carried as extra objects of the default line (the headline stays BASELINE configs[1]).  Each runs a
+# bounded number of its own steps (stated in the object), is timed with CUDA events on the launch stream between
+# barriers, max over ranks, and reports whole-job pages/s.
+# ---------------------------------------------------------------------------
+def _timed(env, fn, steps):
+    torch, dist = env["torch"], env["dist"]
+    env["sync_all"]()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    env["sync_all"]()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=env["dev"])
+    if env["world"] > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()) / steps
+
+
+def _stage_times(ctx, fn):
+    """per-stage device ms of one call of fn (CUDA events recorded by the library on the launch stream)"""
+    ctx.set_timing(True)
+    fn()
+    out = {}
+    for k, v in ctx.timings():
+        out[k] = out.get(k, 0.0) + v
+    ctx.set_timing(False)
+    return out
+
+
+def bench_pipeline_cc(eng, env):
+    """BASELINE configs[3]: normalisation rescale + fcn_skip + cc_majority + connected-component segment extraction
+    (per-class CC stats tables) + colour masks; 1024 pages on 8 GPUs = 128 pages per GPU per step (weak scaling)."""
+    torch, world = env["torch"], env["world"]
+    per_gpu, sub, maxc, steps = 128, 64, 4096, 3
+    d_pages, h_pages = env["d_pages"][:sub], env["h_pages_np"][:sub]
+    Hs, Ws = synth.scaled_shape(synth.A4_H, synth.A4_W, SCALE)
+    d_stats = torch.empty((sub, N_CLASSES, maxc, 5), dtype=torch.int32, device=env["dev"])
+    d_ncomp = torch.empty((sub, N_CLASSES), dtype=torch.int32, device=env["dev"])
+
+    def device_step():
+        for _ in range(per_gpu // sub):
+            b = eng.run_device(d_pages, SCALE, cc_majority=True)
+            eng.ctx.class_components(b["labels"], sub, Hs, Ws, N_CLASSES, d_stats, maxc, d_ncomp)
+
+    def one_sub_batch():
+        b = eng.run_device(d_pages, SCALE, cc_majority=True)
+        eng.ctx.class_components(b["labels"], sub, Hs, Ws, N_CLASSES, d_stats, maxc, d_ncomp)
+
+    device_step()
+    st = _stage_times(eng.ctx, one_sub_batch)
+    ms = _timed(env, device_step, steps)
+    out = {k: v[:sub] for k, v in env["h_out_np"].items()}
+    out["stats"] = torch.empty((sub, N_CLASSES, maxc, 5), dtype=torch.int32).pin_memory().numpy()
+    out["ncomp"] = torch.empty((sub, N_CLASSES), dtype=torch.int32).pin_memory().numpy()
+
+    def host_step():
+        for _ in range(per_gpu // sub):
+            eng.run_host_segments(h_pages, SCALE, out, max_components=maxc, cc_majority=True)
+
+    host_step()
+    ms_host = _timed(env, host_step, steps)
+    hbm = peaks()[0]
+    px = Hs * Ws
+    # algorithmic bytes per page (SURVEY.md section 8d): cc_majority reads binary + class map, writes labels i32 + class map =
+    # 6.8 MB in an ideal single pass; segment extraction reads the class map once per class and writes the tables
+    cc_bytes, seg_bytes = 6.8e6, N_CLASSES * px + N_CLASSES * maxc * 20
+    cc_ms, seg_ms = st.get("cc_majority", 0.0), st.get("class_components", 0.0)
+    nb = sub                                                # the stage times are those of one sub-batch
+    return {
+        "config": f"BASELINE configs[3]: prepare_images + fcn_skip + cc_majority + per-class CC segment extraction (stats tables, "
+                  f"{maxc} rows per class) + colour masks; {per_gpu} A4 pages per GPU per step in sub-batches of {sub}",
+        "value": world * per_gpu / (ms / 1e3), "unit": "pages/s", "ms_per_step": ms, "steps": steps, "pages_per_gpu": per_gpu, "scaling": "weak",
+        "e2e": {"value": world * per_gpu / (ms_host / 1e3), "unit": "pages/s", "h2d_bytes_per_step": int(h_pages.nbytes) * (per_gpu // sub),
+                "d2h_bytes_per_step": int(sum(v.nbytes for v in out.values())) * (per_gpu // sub),
+                "call": "pcs_predict_pages_segments (host buffers, copies inside the timed region)"},
+        "roofline": {"bound": "hbm", "kernel": "cc_majority", "achieved": cc_bytes * nb / (cc_ms * 1e6) if cc_ms else None, "peak": hbm,
+                     "unit": "GB/s", "frac": cc_bytes * nb / (cc_ms * 1e6) / hbm if cc_ms else None, "traffic": None,
+                     "algorithmic_bytes_per_page": cc_bytes},
+        "segment_extraction": {"ms_per_launch": seg_ms, "algorithmic_bytes_per_page": seg_bytes,
+                               "achieved_gbs": seg_bytes * nb / (seg_ms * 1e6) if seg_ms else None},
+        "stage_ms_per_launch": {k: round(v, 4) for k, v in st.items()}, "pages_per_launch": sub,
+    }
+
+
+def bench_unet(env):
+    """BASELINE configs[2]: U-Net predict over 256 synthetic A4 pages, page-sharded across the ranks (strong scaling: each of
+    N ranks takes 256 / N pages, in sub-batches of 8 pages = 10 GB of activations)."""
+    torch, world, rank = env["torch"], env["world"], env["rank"]
+    from page_segmentation_b200.runtime import PageBatchEngine, shard_pages
+    total, sub, steps = 256, 8, 2
+    mine = len(shard_pages(total, rank, world))
+    eng = PageBatchEngine("unet", synth.make_weights("unet", N_CLASSES, seed=0), N_CLASSES, precision=env["precision"],
+                          device=env["local_rank"], lut=LUT)
+    d_pages, h_pages = env["d_pages"][:sub], env["h_pages_np"][:sub]
+    out = {k: v[:sub] for k, v in env["h_out_np"].items()}
+
+    def device_step():
+        for _ in range(mine // sub):
+            eng.run_device(d_pages, SCALE)
+
+    eng.run_device(d_pages, SCALE)
+    st = _stage_times(eng.ctx, lambda: eng.run_device(d_pages, SCALE))
+    ms = _timed(env, device_step, steps)
+    e2e_pages = min(mine, 32)
+
+    def host_step():
+        for _ in range(e2e_pages // sub):
+            eng.run_host(h_pages, SCALE, out)
+
+    host_step()
+    ms_host = _timed(env, host_step, steps)
+    Hs, Ws = synth.scaled_shape(synth.A4_H, synth.A4_W, SCALE)
+    hp, wp = Hs + (32 - Hs % 32) % 32, Ws + (32 - Ws % 32) % 32
+    g = unet_layer_gflop(hp, wp)
+    body = {k: v for k, v in st.items() if k in g}
+    dom = max(body, key=lambda k: body[k])
+    body_ms = sum(body.values())
+    res = {
+        "config": f"BASELINE configs[2]: unet predict, {total} synthetic A4 pages sharded page-wise over {world} GPU(s) "
+                  f"({mine} per GPU per step, sub-batches of {sub}), preprocess + network + argmax + colour masks, random-init weights",
+        "value": total / (ms / 1e3), "unit": "pages/s", "ms_per_step": ms, "steps": steps, "pages_total": total, "scaling": "strong",
+        "dtype": env["precision"],
+        "e2e": {"value": world * e2e_pages / (ms_host / 1e3), "unit": "pages/s", "pages_per_gpu": e2e_pages,
+                "h2d_bytes_per_step": int(h_pages.nbytes) * (e2e_pages // sub),
+                "d2h_bytes_per_step": int(sum(v.nbytes for v in out.values())) * (e2e_pages // sub),
+                "call": "pcs_predict_pages_host (host buffers, copies inside the timed region)"},
+        "roofline": tensor_roofline(dom, g[dom] * sub, body[dom], None, {
+            "whole_body_tflops": GFLOP_PER_PAGE["unet"] * sub / body_ms,
+            "whole_body_frac_burst": GFLOP_PER_PAGE["unet"] * sub / body_ms / peaks()[1],
+            "stage_ms_per_launch": {k: round(v, 4) for k, v in st.items()}, "pages_per_launch": sub}),
+    }
+    del eng
+    torch.cuda.empty_cache()
+    return res
+
+
+def bench_train_step(env):
+    """BASELINE configs[4]: one fcn_skip training step per page per rank (forward, sparse softmax cross entropy, backward,
+    gradient all-reduce over NCCL, Adam with per-variable clipnorm) -- lib/network.py:127-242."""
+    torch, world, rank = env["torch"], env["world"], env["rank"]
+    from page_segmentation_b200.lib.trainer import FcnTrainStep
+    from page_segmentation_b200.runtime import get_context
+    ctx = get_context(env["local_rank"])
+    Hs, Ws = synth.scaled_shape(synth.A4_H, synth.A4_W, SCALE)
+    d_img = torch.empty((1, Hs, Ws), dtype=torch.uint8, device=env["dev"])
+    d_bin = torch.empty((1, Hs, Ws), dtype=torch.uint8, device=env["dev"])
+    ctx.preprocess(env["d_pages"][:1], env["d_pages"][:1], 1, synth.A4_H, synth.A4_W, Hs, Ws, d_img, d_bin, None)
+    img, labels = d_img[0].cpu().numpy(), d_bin[0].cpu().numpy()      # ink / paper as a two-class target of three
+    step = FcnTrainStep("fcn_skip", synth.make_weights("fcn_skip", N_CLASSES, seed=0), N_CLASSES, l_rate=1e-4, device=env["local_rank"])
+    steps = 5
+    for _ in range(2):
+        step.step(img, labels)
+    losses = []
+    ms = _timed(env, lambda: losses.append(step.step(img, labels)), steps)
+    info = step.describe() if hasattr(step, "describe") else {}
+    return {"config": "BASELINE configs[4]: fcn_skip training step, one 1169x827 page per rank per step, data parallel with the NCCL "
+                      "gradient all-reduce (673 013 floats), Adam + per-variable clipnorm",
+            "value": world * 1e3 / ms, "unit": "pages/s (= steps/s x ranks)", "ms_per_step": ms, "steps": steps, "scaling": "weak",
+            "gflop_per_step": 3 * GFLOP_PER_PAGE["fcn_skip"], "tflops_per_gpu": 3 * GFLOP_PER_PAGE["fcn_skip"] / ms,
+            "loss_first_last": [losses[0], losses[-1]], **info}
+
+
+def bench_api(env):
+    """The reference-named per-page flow on host numpy pages, wall clock: DatasetLoader.load_data -> Predictor.predict with the
+    cc_majority post-processor -> output_data (three PNG files per page) -- lib/dataset.py:193-198, lib/predictor.py:27-42,
+    lib/output.py:20-41.  Every rank runs its own pages on its own GPU."""
+    import shutil
+    import tempfile
+    torch, world = env["torch"], env["world"]
+    from page_segmentation_b200.lib.colors import DEFAULT_COLOR_MAP
+    from page_segmentation_b200.lib.dataset import DatasetLoader, SingleData
+    from page_segmentation_b200.lib.network import Network
+    from page_segmentation_b200.lib.output import output_data
+    from page_segmentation_b200.lib.postprocess import find_postprocessor
+    from page_segmentation_b200.lib.predictor import Predictor
+    from page_segmentation_b200.lib.predictor_data import PredictSettings
+    n = 16
+    pages = [np.array(env["h_pages_np"][i % 8]) for i in range(n)]          # pageable numpy pages, as a caller holds them
+    root = tempfile.mkdtemp(prefix="pcseg_api_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        net = Network("Predict", n_classes=N_CLASSES, weights=synth.make_weights("fcn_skip", N_CLASSES, seed=0),
+                      precision=env["precision"], device=env["local_rank"])
+        settings = PredictSettings(n_classes=N_CLASSES, color_map=DEFAULT_COLOR_MAP, output=root,
+                                   post_process=[find_postprocessor("cc_majority")])
+        predictor = Predictor(settings, network=net)
+        loader = DatasetLoader(TARGET_LH, DEFAULT_COLOR_MAP, prediction=True)
+
+        def flow():
+            entries = [SingleData(image=p, line_height_px=LINE_HEIGHT, output_path=f"page{i:04d}.png") for i, p in enumerate(pages)]
+            dataset = loader.load_data(entries)
+            for pred in predictor.predict(dataset):
+                output_data(root, pred.labels, pred.data, DEFAULT_COLOR_MAP)
+
+        flow()
+        env["sync_all"]()
+        t0 = time.perf_counter()
+        flow()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device=env["dev"])
+        if world > 1:
+            env["dist"].all_reduce(t, op=env["dist"].ReduceOp.MAX)
+        return {"value": world * n / float(t.item()), "unit": "pages/s", "pages_per_gpu": n, "clock": "wall (perf_counter), max over ranks",
+                "flow": "DatasetLoader.load_data -> Predictor.predict(+cc_majority) -> output_data (3 PNG files per page, tmpfs), "
+                        "pageable numpy pages in, one pass after one warm-up pass"}
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -221,6 +459,9 @@ def main():
                          "rank with the NCCL gradient all-reduce (tools/bench_train.py)")
     ap.add_argument("--png-files", action="store_true",
                     help="adds e2e_png_files: the host-buffer call with the masks returned as PNG files (pcs_predict_pages_files)")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the sub-benchmarks of BASELINE configs[2] (unet), configs[3] (pipeline_cc), configs[4] (train) and the "
+                         "reference-named per-page API (e2e_api) that the default line carries as extra objects")
     ap.add_argument("--cc-majority", action="store_true",
                     help="also run the cc_majority post-processor (BASELINE configs[3] pipeline); not the default workload")
     args = ap.parse_args()
@@ -358,21 +599,27 @@ def main():
                      "d2h_bytes_per_step": int(f_out["labels"].nbytes + int(f_out["png_sizes"].sum()) + f_out["png_sizes"].nbytes),
                      "what": "pcs_predict_pages_files: class map + the three masks as PNG files (device encoder, level 1) per page"}
 
+    extras = {}
+    if not args.no_extras and arch == "fcn_skip" and not args.cc_majority:
+        env = dict(torch=torch, dist=dist, rank=rank, world=world, dev=dev, local_rank=local_rank, sync_all=sync_all,
+                   h_pages_np=h_pages_np, h_out_np=h_out_np, d_pages=d_pages, precision=args.precision)
+        extras["pipeline_cc"] = bench_pipeline_cc(eng, env)
+        extras["e2e_api"] = bench_api(env)
+        del eng
+        extras["unet"] = bench_unet(env)
+        extras["train"] = bench_train_step(env)
+
     if rank == 0:
-        hbm_peak, tf_peak, which = peaks()
         # dominant kernel = the slowest stage of the step
         per_step = {k: v / args.steps for k, v in stage_ms.items()}
         dom = max((k for k in per_step if k in LAYER_GFLOP), key=lambda k: per_step[k], default=None)
         roofline = None
         if dom is not None and arch == "fcn_skip":
-            tflops = LAYER_GFLOP[dom] * n / per_step[dom]          # GFLOP / ms == TFLOP/s
-            roofline = {"bound": "tensor", "kernel": dom, "achieved": tflops, "peak": tf_peak, "unit": "TFLOP/s",
-                        "frac": tflops / tf_peak, "traffic": measured_traffic(dom, n),
-                        "traffic_unit": "bytes per launch (ncu dram read + write)",
-                        "peak_source": f"{which} (sustained bf16: the kernel is timed inside a long step)",
-                        "whole_body_tflops": GFLOP_PER_PAGE[arch] * n / sum(
-                            v for k, v in per_step.items() if k not in ("preprocess",)),
-                        "stage_ms_per_step": {k: round(v, 4) for k, v in per_step.items()}}
+            body_ms = sum(v for k, v in per_step.items() if k in LAYER_GFLOP)
+            roofline = tensor_roofline(dom, LAYER_GFLOP[dom] * n, per_step[dom], measured_traffic(dom, n), {
+                "whole_body_tflops": GFLOP_PER_PAGE[arch] * n / body_ms,
+                "whole_body_frac_burst": GFLOP_PER_PAGE[arch] * n / body_ms / peaks()[1],
+                "stage_ms_per_step": {k: round(v, 4) for k, v in per_step.items()}})
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             v, cores = cpu_reference_pages_per_s(args.cpu_pages)
@@ -393,6 +640,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "pages/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "pcie_pinned_copy": pcie, "numa_binding": numa, **({"e2e_png_files": png_files} if png_files else {}),
+            **extras,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
