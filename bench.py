@@ -578,6 +578,41 @@ def main():
     h2d = int(h_pages_np.nbytes)
     d2h = int(sum(v.nbytes for v in h_out_np.values()))
 
+    # ---------------- the same call with compact transport formats (fewer PCIe bytes per page) ----------------
+    e2e_modes = {}
+    if not args.no_extras:
+        from page_segmentation_b200.runtime import pack_pages
+        bw = (Hs * Ws + 31) // 32
+        c_out = {"labels": h_out_np["labels"],
+                 "binary_bits": torch.empty((n, bw), dtype=torch.int32).pin_memory().numpy().view(np.uint32)}
+        pbits, l0, l1 = pack_pages(base)
+        h_bits = torch.empty((n, pbits.shape[1]), dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+        for i in range(n):
+            h_bits[i] = pbits[i % distinct]
+
+        def e2e_of(fn, h2d_bytes, d2h_bytes, what):
+            fn()
+            sync_all()
+            e0.record()
+            for _ in range(args.steps):
+                fn()
+            e1.record()
+            sync_all()
+            tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return {"value": world * n * args.steps / (float(tt.item()) / 1e3), "unit": "pages/s", "h2d_bytes_per_step": int(h2d_bytes),
+                    "d2h_bytes_per_step": int(d2h_bytes), "what": what}
+
+        cbytes = c_out["labels"].nbytes + c_out["binary_bits"].nbytes
+        e2e_modes["compact"] = e2e_of(lambda: eng.run_host_compact(h_pages_np, SCALE, c_out, cc_majority=args.cc_majority), h_pages_np.nbytes, cbytes,
+                                      "pcs_predict_pages_compact: uint8 pages in; class map + bit-packed binary out, colour masks "
+                                      "materialised on request on the device (pcs_unpack_bits + pcs_masks)")
+        e2e_modes["packed"] = e2e_of(lambda: eng.run_host_packed(h_bits, l0, l1, synth.A4_H, synth.A4_W, SCALE, c_out, cc_majority=args.cc_majority),
+                                     h_bits.nbytes, cbytes,
+                                     "pcs_predict_pages_packed: BIT-PACKED binarised pages in (1 bit per pixel, what a 1-bit scan file "
+                                     "decodes to); class map + bit-packed binary out")
+
     # ---------------- optional: the same call with the masks leaving the device as PNG files ----------------
     png_files = None
     if args.png_files:
@@ -640,7 +675,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "pages/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "pcie_pinned_copy": pcie, "numa_binding": numa, **({"e2e_png_files": png_files} if png_files else {}),
-            **extras,
+            **({"e2e_modes": e2e_modes} if e2e_modes else {}), **extras,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

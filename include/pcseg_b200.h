@@ -101,6 +101,18 @@ PCS_API int pcs_preprocess(pcs_ctx* ctx, const uint8_t* d_grey, const uint8_t* d
                    int n, int H, int W, int Hs, int Ws,
                    uint8_t* d_image, uint8_t* d_binary, uint8_t* d_orig_binary);
 
+/* ---- prepare_images for pages that arrive BIT-PACKED.  A binarised page is one bit per pixel by nature (the reference
+ * decodes it into a uint8 array, lib/dataset.py:169-172); a caller that holds it packed moves 1.1 MB per A4 page across
+ * PCIe instead of 8.7.  Layout: flat over the page, pixel i = bit (i & 31) of word (i >> 5) - numpy.packbits(page.ravel()
+ * != level0, bitorder='little') viewed as little-endian uint32 - words_per_page >= H * W / 32 + 1 (one readable pad
+ * word); a clear bit is a pixel of grey level `level0`, a set bit one of `level1`.  Results are exactly those of
+ * pcs_preprocess on the uint8 page `bit ? level1 : level0` used as grey and binary page (scale factors up to 4). */
+PCS_API int pcs_preprocess_bits(pcs_ctx* ctx, const uint32_t* d_bits, size_t words_per_page, int n, int H, int W,
+                        int level0, int level1, int Hs, int Ws, uint8_t* d_image, uint8_t* d_binary);
+/* uint8 planes <-> flat bit planes of the same layout: non-zero byte <-> set bit <-> byte 1; n planes of n_pixels */
+PCS_API int pcs_pack_bits(pcs_ctx* ctx, const uint8_t* d_src, int n, size_t n_pixels, uint32_t* d_bits, size_t words_per_page);
+PCS_API int pcs_unpack_bits(pcs_ctx* ctx, const uint32_t* d_bits, int n, size_t words_per_page, size_t n_pixels, uint8_t* d_dst);
+
 /* ---- prepare_images with max_width (lib/dataset.py:139-143): after the first
  * rescale to (H1, W1) = np.round(scale * (H, W)), `n_scale = max_width / W1 < 1`
  * triggers a second one to (H2, W2) = np.round(n_scale * (H1, W1)): order 0 for
@@ -205,6 +217,18 @@ PCS_API int pcs_predict_pages_host(pcs_ctx* ctx, const uint8_t* h_grey, const ui
 PCS_API int pcs_predict_pages_files(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h_bin,
                             int n, int H, int W, int Hs, int Ws, int cc_majority, const uint8_t* lut,
                             uint8_t* h_labels, uint8_t* h_png, size_t png_stride, uint64_t* h_png_sizes);
+
+/* The same pipeline with COMPACT results: what Predictor.predict yields per page (lib/predictor.py:27-42) is the class
+ * map; the colour masks are pure functions of (class map, binary page, LUT) and are produced on request (pcs_unpack_bits
+ * + pcs_masks) instead of crossing PCIe for every page: 1.1 MB per A4 page leave the device instead of 9.7.
+ *   h_labels      : [n][Hs][Ws] uint8
+ *   h_binary_bits : [n][ceil(Hs * Ws / 32)] uint32, `data.binary` bit-packed (layout of pcs_preprocess_bits), or NULL
+ * pcs_predict_pages_packed additionally takes the PAGES bit-packed ([n][ceil(H * W / 32)] words, levels as in
+ * pcs_preprocess_bits): 1.1 MB per page in, 1.1 MB out. */
+PCS_API int pcs_predict_pages_compact(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h_bin, int n, int H, int W,
+                              int Hs, int Ws, int cc_majority, uint8_t* h_labels, uint32_t* h_binary_bits);
+PCS_API int pcs_predict_pages_packed(pcs_ctx* ctx, const uint32_t* h_bits, int level0, int level1, int n, int H, int W,
+                             int Hs, int Ws, int cc_majority, uint8_t* h_labels, uint32_t* h_binary_bits);
 
 /* The same pipeline followed by segment extraction (pcs_class_components on the final class map): BASELINE configs[3],
  * "normalization rescale + FCN + connected-component segment extraction".  The masks are optional.

@@ -21,7 +21,7 @@ ENGINES = {"umma": 0, "direct": 1}
 EXPORTS = [
     "pcs_abi_version", "pcs_ctx_create", "pcs_ctx_destroy", "pcs_last_error", "pcs_set_stream",
     "pcs_synchronize", "pcs_launch_count", "pcs_model_load", "pcs_set_engine", "pcs_preprocess",
-    "pcs_preprocess_max_width",
+    "pcs_preprocess_max_width", "pcs_preprocess_bits", "pcs_pack_bits", "pcs_unpack_bits", "pcs_predict_pages_compact", "pcs_predict_pages_packed",
     "pcs_forward", "pcs_masks", "pcs_resize_nearest", "pcs_ccl", "pcs_cc_majority",
     "pcs_bounding_boxes", "pcs_class_components", "pcs_char_height", "pcs_png_bytes", "pcs_png_encode", "pcs_segment_masks", "pcs_dilate3x3", "pcs_integral_image", "pcs_text_regions", "pcs_predict_pages_host", "pcs_predict_pages_files", "pcs_predict_pages_segments", "pcs_eval_counts",
     "pcs_train_input", "pcs_train_corr2d", "pcs_train_wgrad", "pcs_train_bias_grad", "pcs_train_relu_bwd", "pcs_train_maxpool_fwd",
@@ -67,6 +67,11 @@ def load() -> C.CDLL:
     lib.pcs_set_engine.argtypes = [vp, i32]
     lib.pcs_preprocess.argtypes = [vp, u8p, u8p, i32, i32, i32, i32, i32, u8p, u8p, u8p]
     lib.pcs_preprocess_max_width.argtypes = [vp, u8p, u8p, i32, i32, i32, i32, i32, i32, i32, u8p, u8p, u8p]
+    lib.pcs_preprocess_bits.argtypes = [vp, vp, C.c_size_t, i32, i32, i32, i32, i32, i32, i32, u8p, u8p]
+    lib.pcs_pack_bits.argtypes = [vp, u8p, i32, C.c_size_t, vp, C.c_size_t]
+    lib.pcs_unpack_bits.argtypes = [vp, vp, i32, C.c_size_t, C.c_size_t, u8p]
+    lib.pcs_predict_pages_compact.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]
+    lib.pcs_predict_pages_packed.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]
     lib.pcs_forward.argtypes = [vp, u8p, u8p, i32, i32, i32, u8p, vp, vp, vp, u8p, u8p, u8p]
     lib.pcs_masks.argtypes = [vp, u8p, u8p, i32, i32, i32, vp, i32, u8p, u8p, u8p]
     lib.pcs_resize_nearest.argtypes = [vp, u8p, i32, i32, i32, u8p, i32, i32]
@@ -243,6 +248,16 @@ class Context:
                                                       _ptr(d_image), _ptr(d_binary), _ptr(d_orig_binary)),
                     "pcs_preprocess_max_width")
 
+    def preprocess_bits(self, d_bits, words_per_page, n, H, W, level0, level1, Hs, Ws, d_image, d_binary=None):
+        self._check(self.lib.pcs_preprocess_bits(self.h, _ptr(d_bits), words_per_page, n, H, W, int(level0), int(level1), Hs, Ws,
+                                                 _ptr(d_image), _ptr(d_binary)), "pcs_preprocess_bits")
+
+    def pack_bits(self, d_src, n, n_pixels, d_bits, words_per_page):
+        self._check(self.lib.pcs_pack_bits(self.h, _ptr(d_src), n, n_pixels, _ptr(d_bits), words_per_page), "pcs_pack_bits")
+
+    def unpack_bits(self, d_bits, n, words_per_page, n_pixels, d_dst):
+        self._check(self.lib.pcs_unpack_bits(self.h, _ptr(d_bits), n, words_per_page, n_pixels, _ptr(d_dst)), "pcs_unpack_bits")
+
     def forward(self, d_image, d_binary, n, Hs, Ws, d_labels, d_logits=None, d_prob=None, lut=None,
                 d_color=None, d_overlay=None, d_inverted=None):
         lut_arr = _lut256(lut, self.model[1] if self.model else None)
@@ -313,6 +328,15 @@ class Context:
             self.h, _ptr(h_grey), _ptr(h_bin), n, H, W, Hs, Ws, 1 if cc_majority else 0, _ptr(lut_arr),
             _ptr(h_image), _ptr(h_binary), _ptr(h_labels), _ptr(h_color), _ptr(h_overlay), _ptr(h_inverted)),
             "pcs_predict_pages_host")
+
+    def predict_pages_compact(self, h_grey, h_bin, n, H, W, Hs, Ws, cc_majority, h_labels, h_binary_bits=None):
+        self._check(self.lib.pcs_predict_pages_compact(self.h, _ptr(h_grey), _ptr(h_bin), n, H, W, Hs, Ws, 1 if cc_majority else 0,
+                                                       _ptr(h_labels), _ptr(h_binary_bits)), "pcs_predict_pages_compact")
+
+    def predict_pages_packed(self, h_bits, level0, level1, n, H, W, Hs, Ws, cc_majority, h_labels, h_binary_bits=None):
+        self._check(self.lib.pcs_predict_pages_packed(self.h, _ptr(h_bits), int(level0), int(level1), n, H, W, Hs, Ws,
+                                                      1 if cc_majority else 0, _ptr(h_labels), _ptr(h_binary_bits)),
+                    "pcs_predict_pages_packed")
 
     def predict_pages_files(self, h_grey, h_bin, n, H, W, Hs, Ws, cc_majority, lut, h_labels, h_png, png_stride, h_png_sizes):
         lut_arr = _lut256(lut, self.model[1] if self.model else None)

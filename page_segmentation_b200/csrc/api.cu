@@ -679,6 +679,27 @@ int pcs_preprocess(pcs_ctx* ctx, const uint8_t* d_grey, const uint8_t* d_bin, in
     return launch_preprocess(ctx, d_grey, d_bin, n, H, W, Hs, Ws, d_image, d_binary, d_orig_binary);
 }
 
+int pcs_preprocess_bits(pcs_ctx* ctx, const uint32_t* d_bits, size_t words_per_page, int n, int H, int W, int level0, int level1, int Hs, int Ws,
+                        uint8_t* d_image, uint8_t* d_binary) {
+    if (!ctx || !d_bits) return ctx ? set_err(ctx, PCS_ERR_ARG, "preprocess_bits: null input") : PCS_ERR_ARG;
+    PCS_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->timing_enabled) clear_stage_times(ctx);
+    StageScope ts(ctx, "preprocess");
+    return launch_preprocess_bits(ctx, d_bits, words_per_page, n, H, W, level0, level1, Hs, Ws, d_image, d_binary);
+}
+
+int pcs_pack_bits(pcs_ctx* ctx, const uint8_t* d_src, int n, size_t n_pixels, uint32_t* d_bits, size_t words_per_page) {
+    if (!ctx || !d_src || !d_bits) return ctx ? set_err(ctx, PCS_ERR_ARG, "pack_bits: null argument") : PCS_ERR_ARG;
+    PCS_CUDA(ctx, cudaSetDevice(ctx->device));
+    return launch_pack_bits(ctx, d_src, n, n_pixels, d_bits, words_per_page);
+}
+
+int pcs_unpack_bits(pcs_ctx* ctx, const uint32_t* d_bits, int n, size_t words_per_page, size_t n_pixels, uint8_t* d_dst) {
+    if (!ctx || !d_bits || !d_dst) return ctx ? set_err(ctx, PCS_ERR_ARG, "unpack_bits: null argument") : PCS_ERR_ARG;
+    PCS_CUDA(ctx, cudaSetDevice(ctx->device));
+    return launch_unpack_bits(ctx, d_bits, n, words_per_page, n_pixels, d_dst);
+}
+
 int pcs_preprocess_max_width(pcs_ctx* ctx, const uint8_t* d_grey, const uint8_t* d_bin, int n, int H, int W, int H1, int W1,
                              int H2, int W2, uint8_t* d_image, uint8_t* d_binary, uint8_t* d_orig_binary) {
     if (!ctx || !d_bin || !d_grey) return ctx ? set_err(ctx, PCS_ERR_ARG, "preprocess: null input") : PCS_ERR_ARG;
@@ -885,8 +906,10 @@ int pcs_png_encode(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, int 
 static int predict_pages_host_body(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h_bin, int n, int H, int W, int Hs, int Ws,
                                    int cc_majority, const uint8_t* lut, uint8_t* h_image, uint8_t* h_binary, uint8_t* h_labels,
                                    uint8_t* h_color, uint8_t* h_overlay, uint8_t* h_inverted, uint8_t* h_png, size_t png_stride,
-                                   uint64_t* h_png_sizes, int32_t* h_stats = nullptr, int max_components = 0, int32_t* h_ncomp = nullptr) {
-    if (!ctx || !h_grey || !h_bin) return ctx ? set_err(ctx, PCS_ERR_ARG, "predict_pages_host: null input") : PCS_ERR_ARG;
+                                   uint64_t* h_png_sizes, int32_t* h_stats = nullptr, int max_components = 0, int32_t* h_ncomp = nullptr,
+                                   const uint32_t* h_bits = nullptr, int level0 = 0, int level1 = 0, uint32_t* h_binary_bits = nullptr) {
+    // h_bits: the pages arrive bit-packed (pcs_preprocess_bits) instead of as uint8 pages; h_binary_bits: `data.binary` leaves bit-packed
+    if (!ctx || (!h_bits && (!h_grey || !h_bin))) return ctx ? set_err(ctx, PCS_ERR_ARG, "predict_pages_host: null input") : PCS_ERR_ARG;
     if (h_stats && (max_components <= 0 || !h_labels)) return set_err(ctx, PCS_ERR_ARG, "predict_pages_segments: max_components and the class map are required");
     if (!ctx->model_ready) return set_err(ctx, PCS_ERR_STATE, "pcs_predict_pages_host before pcs_model_load");
     if (n <= 0 || H <= 0 || W <= 0 || Hs <= 0 || Ws <= 0) return set_err(ctx, PCS_ERR_ARG, "predict_pages_host: bad shape");
@@ -948,11 +971,14 @@ static int predict_pages_host_body(pcs_ctx* ctx, const uint8_t* h_grey, const ui
     const size_t src1 = (size_t)H * W, dst1 = (size_t)Hs * Ws;
     const bool same = h_grey == h_bin;
     auto al = [](size_t b) { return (b + 255) / 256 * 256; };
-    const size_t in_bytes = al(src1 * chunk) * (same ? 1 : 2);
+    const size_t in_words = (src1 + 31) / 32, bm_words = (src1 / 32 + 1 + 3) / 4 * 4;       // packed page on the host / on the device (padded)
+    const size_t bb_words = (dst1 + 31) / 32;                                               // packed `binary` of one page
+    const size_t in_bytes = h_bits ? al(bm_words * 4 * chunk) : al(src1 * chunk) * (same ? 1 : 2);
     const size_t png_bytes = want_png ? 3 * (size_t)chunk * dpng_stride + al(3 * (size_t)chunk * 8) : 0;
     const size_t stats1 = h_stats ? (size_t)ctx->n_classes * max_components * 5 * sizeof(int32_t) : 0;      // per page
     const size_t seg_bytes = h_stats ? al(stats1 * chunk) + al((size_t)chunk * ctx->n_classes * sizeof(int32_t)) : 0;
-    const size_t out_bytes = al(dst1 * chunk) * 3 + al(dst1 * chunk * 3) * 3 + png_bytes + seg_bytes;
+    const size_t bb_bytes = h_binary_bits ? al(bb_words * 4 * chunk) : 0;
+    const size_t out_bytes = al(dst1 * chunk) * 3 + al(dst1 * chunk * 3) * 3 + png_bytes + seg_bytes + bb_bytes;
     const size_t need = (size_t)nbuf * (in_bytes + out_bytes) + 4096;
     if (want_png && !ctx->h_png_sizes) PCS_CUDA(ctx, cudaHostAlloc(&ctx->h_png_sizes, pcs_ctx::kHostBufs * 3 * 64 * sizeof(uint64_t), cudaHostAllocDefault));
     if (want_png && chunk > 64) return set_err(ctx, PCS_ERR_ARG, "predict_pages_files: chunks of more than 64 pages");
@@ -966,12 +992,12 @@ static int predict_pages_host_body(pcs_ctx* ctx, const uint8_t* h_grey, const ui
         }
         ctx->stage_bytes = need;
     }
-    struct Buf { uint8_t *grey, *bin, *image, *binary, *labels, *color, *overlay, *inverted, *png; uint64_t* png_sizes; int32_t *stats, *ncomp; } buf[pcs_ctx::kHostBufs];
+    struct Buf { uint8_t *grey, *bin, *image, *binary, *labels, *color, *overlay, *inverted, *png; uint64_t* png_sizes; int32_t *stats, *ncomp; uint32_t* bbits; } buf[pcs_ctx::kHostBufs];
     {
         uint8_t* p = reinterpret_cast<uint8_t*>(ctx->stage);
         for (int i = 0; i < nbuf; ++i) {
-            buf[i].grey = p; p += al(src1 * chunk);
-            buf[i].bin = same ? buf[i].grey : p; if (!same) p += al(src1 * chunk);
+            buf[i].grey = p; p += h_bits ? al(bm_words * 4 * chunk) : al(src1 * chunk);
+            buf[i].bin = (same || h_bits) ? buf[i].grey : p; if (!same && !h_bits) p += al(src1 * chunk);
             buf[i].image = p; p += al(dst1 * chunk);
             buf[i].binary = p; p += al(dst1 * chunk);
             buf[i].labels = p; p += al(dst1 * chunk);
@@ -980,6 +1006,7 @@ static int predict_pages_host_body(pcs_ctx* ctx, const uint8_t* h_grey, const ui
             buf[i].inverted = p; p += al(dst1 * chunk * 3);
             buf[i].png = p; buf[i].png_sizes = reinterpret_cast<uint64_t*>(p + 3 * (size_t)chunk * dpng_stride); p += png_bytes;
             buf[i].stats = reinterpret_cast<int32_t*>(p); buf[i].ncomp = reinterpret_cast<int32_t*>(p + al(stats1 * chunk)); p += seg_bytes;
+            buf[i].bbits = reinterpret_cast<uint32_t*>(p); p += bb_bytes;
         }
     }
     // PCSEG_TRACE_HOST: per-chunk device timeline (timing events on the three streams), printed at the end
@@ -994,8 +1021,14 @@ static int predict_pages_host_body(pcs_ctx* ctx, const uint8_t* h_grey, const ui
         const int b = c % nbuf, p0 = first[c], m = count[c];
         if (c >= nbuf) PCS_CUDA(ctx, cudaStreamWaitEvent(s_in, ctx->ev_comp[b], 0));   // input buffer consumed by chunk c-nbuf
         mark(s_in);
-        PCS_CUDA(ctx, cudaMemcpyAsync(buf[b].grey, h_grey + (size_t)p0 * src1, src1 * m, cudaMemcpyHostToDevice, s_in));
-        if (!same) PCS_CUDA(ctx, cudaMemcpyAsync(buf[b].bin, h_bin + (size_t)p0 * src1, src1 * m, cudaMemcpyHostToDevice, s_in));
+        if (h_bits) {       // packed rows of in_words words into the padded device pitch; the pad words read as zero
+            PCS_CUDA(ctx, cudaMemset2DAsync(buf[b].grey + in_words * 4, bm_words * 4, 0, (bm_words - in_words) * 4, m, s_in));
+            PCS_CUDA(ctx, cudaMemcpy2DAsync(buf[b].grey, bm_words * 4, h_bits + (size_t)p0 * in_words, in_words * 4, in_words * 4, m,
+                                            cudaMemcpyHostToDevice, s_in));
+        } else {
+            PCS_CUDA(ctx, cudaMemcpyAsync(buf[b].grey, h_grey + (size_t)p0 * src1, src1 * m, cudaMemcpyHostToDevice, s_in));
+            if (!same) PCS_CUDA(ctx, cudaMemcpyAsync(buf[b].bin, h_bin + (size_t)p0 * src1, src1 * m, cudaMemcpyHostToDevice, s_in));
+        }
         mark(s_in);
         PCS_CUDA(ctx, cudaEventRecord(ctx->ev_h2d[b], s_in));
         return PCS_OK;
@@ -1030,7 +1063,10 @@ static int predict_pages_host_body(pcs_ctx* ctx, const uint8_t* h_grey, const ui
         PCS_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_h2d[b], 0));
         if (c >= nbuf) PCS_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_d2h[b], 0));       // output buffer drained by chunk c-nbuf
         mark(st);
-        PCS_TRY(pcs_preprocess(ctx, buf[b].grey, buf[b].bin, m, H, W, Hs, Ws, buf[b].image, buf[b].binary, nullptr));
+        if (h_bits) PCS_TRY(pcs_preprocess_bits(ctx, reinterpret_cast<const uint32_t*>(buf[b].grey), bm_words, m, H, W, level0, level1, Hs, Ws,
+                                                buf[b].image, buf[b].binary));
+        else PCS_TRY(pcs_preprocess(ctx, buf[b].grey, buf[b].bin, m, H, W, Hs, Ws, buf[b].image, buf[b].binary, nullptr));
+        if (h_binary_bits) PCS_TRY(launch_pack_bits(ctx, buf[b].binary, m, dst1, buf[b].bbits, bb_words));
         if (cc_majority) {
             PCS_TRY(pcs_forward(ctx, buf[b].image, buf[b].binary, m, Hs, Ws, buf[b].labels, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
             PCS_TRY(pcs_cc_majority(ctx, buf[b].labels, buf[b].binary, m, Hs, Ws, ctx->n_classes));
@@ -1061,6 +1097,7 @@ static int predict_pages_host_body(pcs_ctx* ctx, const uint8_t* h_grey, const ui
         if (h_color) PCS_CUDA(ctx, cudaMemcpyAsync(h_color + o3, buf[b].color, dst1 * m * 3, cudaMemcpyDeviceToHost, s_out));
         if (h_overlay) PCS_CUDA(ctx, cudaMemcpyAsync(h_overlay + o3, buf[b].overlay, dst1 * m * 3, cudaMemcpyDeviceToHost, s_out));
         if (h_inverted) PCS_CUDA(ctx, cudaMemcpyAsync(h_inverted + o3, buf[b].inverted, dst1 * m * 3, cudaMemcpyDeviceToHost, s_out));
+        if (h_binary_bits) PCS_CUDA(ctx, cudaMemcpyAsync(h_binary_bits + (size_t)p0 * bb_words, buf[b].bbits, bb_words * 4 * m, cudaMemcpyDeviceToHost, s_out));
         if (h_stats) {
             PCS_CUDA(ctx, cudaMemcpyAsync(reinterpret_cast<char*>(h_stats) + (size_t)p0 * stats1, buf[b].stats, stats1 * m, cudaMemcpyDeviceToHost, s_out));
             if (h_ncomp) PCS_CUDA(ctx, cudaMemcpyAsync(h_ncomp + (size_t)p0 * ctx->n_classes, buf[b].ncomp, (size_t)m * ctx->n_classes * sizeof(int32_t),
@@ -1112,9 +1149,11 @@ static int predict_pages_host_body(pcs_ctx* ctx, const uint8_t* h_grey, const ui
 static int predict_pages_host_impl(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h_bin, int n, int H, int W, int Hs, int Ws,
                                    int cc_majority, const uint8_t* lut, uint8_t* h_image, uint8_t* h_binary, uint8_t* h_labels,
                                    uint8_t* h_color, uint8_t* h_overlay, uint8_t* h_inverted, uint8_t* h_png, size_t png_stride,
-                                   uint64_t* h_png_sizes, int32_t* h_stats = nullptr, int max_components = 0, int32_t* h_ncomp = nullptr) {
+                                   uint64_t* h_png_sizes, int32_t* h_stats = nullptr, int max_components = 0, int32_t* h_ncomp = nullptr,
+                                   const uint32_t* h_bits = nullptr, int level0 = 0, int level1 = 0, uint32_t* h_binary_bits = nullptr) {
     const int rc = predict_pages_host_body(ctx, h_grey, h_bin, n, H, W, Hs, Ws, cc_majority, lut, h_image, h_binary, h_labels, h_color,
-                                           h_overlay, h_inverted, h_png, png_stride, h_png_sizes, h_stats, max_components, h_ncomp);
+                                           h_overlay, h_inverted, h_png, png_stride, h_png_sizes, h_stats, max_components, h_ncomp,
+                                           h_bits, level0, level1, h_binary_bits);
     if (rc != PCS_OK && ctx) {
         for (cudaStream_t s : {ctx->copy_streams[0], ctx->copy_streams[1]})
             if (s) cudaStreamSynchronize(s);
@@ -1145,6 +1184,20 @@ int pcs_predict_pages_segments(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_
     if (ctx && (!h_stats || !h_labels)) return set_err(ctx, PCS_ERR_ARG, "predict_pages_segments: null output");
     return predict_pages_host_impl(ctx, h_grey, h_bin, n, H, W, Hs, Ws, cc_majority, lut, nullptr, nullptr, h_labels, h_color, h_overlay,
                                    h_inverted, nullptr, 0, nullptr, h_stats, max_components, h_ncomp);
+}
+
+int pcs_predict_pages_compact(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h_bin, int n, int H, int W, int Hs, int Ws, int cc_majority,
+                              uint8_t* h_labels, uint32_t* h_binary_bits) {
+    if (ctx && !h_labels) return set_err(ctx, PCS_ERR_ARG, "predict_pages_compact: null output");
+    return predict_pages_host_impl(ctx, h_grey, h_bin, n, H, W, Hs, Ws, cc_majority, nullptr, nullptr, nullptr, h_labels, nullptr, nullptr, nullptr,
+                                   nullptr, 0, nullptr, nullptr, 0, nullptr, nullptr, 0, 0, h_binary_bits);
+}
+
+int pcs_predict_pages_packed(pcs_ctx* ctx, const uint32_t* h_bits, int level0, int level1, int n, int H, int W, int Hs, int Ws, int cc_majority,
+                             uint8_t* h_labels, uint32_t* h_binary_bits) {
+    if (ctx && (!h_labels || !h_bits)) return set_err(ctx, PCS_ERR_ARG, "predict_pages_packed: null argument");
+    return predict_pages_host_impl(ctx, nullptr, nullptr, n, H, W, Hs, Ws, cc_majority, nullptr, nullptr, nullptr, h_labels, nullptr, nullptr, nullptr,
+                                   nullptr, 0, nullptr, nullptr, 0, nullptr, h_bits, level0, level1, h_binary_bits);
 }
 
 int pcs_debug_activation(pcs_ctx* ctx, const char* name, float* h_out, size_t capacity_floats, int32_t* shape4) {

@@ -179,6 +179,10 @@ int launch_preprocess(pcs_ctx* ctx, const uint8_t* d_grey, const uint8_t* d_bin,
                       int Hs, int Ws, uint8_t* d_image, uint8_t* d_binary, uint8_t* d_orig_binary);
 int launch_preprocess_max_width(pcs_ctx* ctx, const uint8_t* d_grey, const uint8_t* d_bin, int n, int H, int W, int H1, int W1,
                                 int H2, int W2, uint8_t* d_image, uint8_t* d_binary, uint8_t* d_orig_binary);
+int launch_preprocess_bits(pcs_ctx* ctx, const uint32_t* d_bitmap, size_t bitmap_words, int n, int H, int W, int level0, int level1,
+                           int Hs, int Ws, uint8_t* d_image, uint8_t* d_binary);
+int launch_pack_bits(pcs_ctx* ctx, const uint8_t* d_src, int n, size_t npix, uint32_t* d_dst, size_t words_per_page);
+int launch_unpack_bits(pcs_ctx* ctx, const uint32_t* d_src, int n, size_t words_per_page, size_t npix, uint8_t* d_dst);
 int launch_resize_nearest(pcs_ctx* ctx, const uint8_t* d_src, int n, int H, int W, uint8_t* d_dst,
                           int Ho, int Wo);
 

@@ -158,7 +158,8 @@ constexpr int RB_ROW_WORDS = 8;                  // staged words per source row:
 __global__ void __launch_bounds__(256)
 resample_bits_kernel(const uint8_t* __restrict__ grey, const uint8_t* __restrict__ bin, int bin_is_grey, int H, int W,
                      int Hs, int Ws, const uint32_t* __restrict__ level_bits, const uint32_t* __restrict__ bitmap,
-                     size_t bitmap_words, uint8_t* __restrict__ image_out, uint8_t* __restrict__ binary_out) {
+                     size_t bitmap_words, uint8_t* __restrict__ image_out, uint8_t* __restrict__ binary_out, int va_fixed /* >= 0: the level of a
+                     zero bit (packed input pages, no uint8 page to read it from) */) {
     __shared__ double s_lut[16][RB_T];            // [pattern][column]: a warp reads 32 consecutive doubles (no bank conflicts)
     __shared__ double s_cfrac[RB_T], s_rfrac[RB_TY];                  // fractional sampling offsets of columns / rows
     __shared__ uint32_t s_bm[RB_MAX_SPAN][RB_ROW_WORDS];
@@ -230,7 +231,7 @@ resample_bits_kernel(const uint8_t* __restrict__ grey, const uint8_t* __restrict
             l0 = lo;
         }
     }
-    const int va = (int)__ldg(grey + (size_t)page * H * W);
+    const int va = va_fixed >= 0 ? va_fixed : (int)__ldg(grey + (size_t)page * H * W);
     const int vb = va == l0 ? l1 : l0;
     const double vmin = (double)l0, vmax = (double)l1;
     if (image_out) {
@@ -570,7 +571,7 @@ static int preprocess_impl(pcs_ctx* ctx, const uint8_t* d_grey, const uint8_t* d
                 PCS_LAUNCH_CHECK(ctx, "scan_pack_kernel");
                 dim3 rgrid((Ws + RB_T - 1) / RB_T, (Hs + RB_TY - 1) / RB_TY, n);
                 resample_bits_kernel<<<rgrid, 256, 0, st>>>(d_grey, d_bin, d_bin == d_grey ? 1 : 0, H, W, Hs, Ws, d_bits, d_bitmap,
-                                                            bitmap_words, d_image, d_binary);
+                                                            bitmap_words, d_image, d_binary, -1);
                 PCS_LAUNCH_CHECK(ctx, "resample_bits_kernel");
             } else {
                 dim3 grid((unsigned)std::min<size_t>(296, (page_px / 16 + 255) / 256 + 1), n);
@@ -623,6 +624,82 @@ static int preprocess_impl(pcs_ctx* ctx, const uint8_t* d_grey, const uint8_t* d
                                                                                                           d_orig_binary);
         PCS_LAUNCH_CHECK(ctx, "orig_binary_kernel");
     }
+    return PCS_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Bit-packed pages.  A binarised page is one bit per pixel by nature; the two-level fast path above packs the uint8 page
+// into exactly that form before it resamples.  A caller that already holds the page packed (flat over the page, pixel i
+// = bit i & 31 of word i >> 5, i.e. numpy.packbits(..., bitorder='little') viewed as little-endian words; bit 0 = a
+// pixel of value level0, bit 1 = level1) skips the 8.7 MB page altogether.  Results are those of pcs_preprocess on the
+// uint8 page `bit ? level1 : level0` used as grey and binary page.
+// ---------------------------------------------------------------------------
+__global__ void set_levels_kernel(uint32_t* __restrict__ bits /*[n][8]*/, int n, int l0, int l1) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * 8) return;
+    const int w = i & 7;
+    bits[i] = ((l0 >> 5) == w ? 1u << (l0 & 31) : 0u) | ((l1 >> 5) == w ? 1u << (l1 & 31) : 0u);
+}
+
+int launch_preprocess_bits(pcs_ctx* ctx, const uint32_t* d_bitmap, size_t bitmap_words, int n, int H, int W, int level0, int level1,
+                           int Hs, int Ws, uint8_t* d_image, uint8_t* d_binary) {
+    if (n <= 0 || H <= 0 || W <= 0 || Hs <= 0 || Ws <= 0) return set_err(ctx, PCS_ERR_ARG, "preprocess_bits: bad shape");
+    if (level0 < 0 || level0 > 255 || level1 < 0 || level1 > 255 || level0 == level1)
+        return set_err(ctx, PCS_ERR_ARG, "preprocess_bits: the two grey levels must differ and lie in 0..255");
+    const size_t page_px = (size_t)H * W;
+    if (bitmap_words < page_px / 32 + 1) return set_err(ctx, PCS_ERR_ARG, "preprocess_bits: %zu words per page needed (incl. one pad word)", page_px / 32 + 1);
+    if ((double)H / Hs > 4.0 || (double)W / Ws > 4.0) return set_err(ctx, PCS_ERR_ARG, "preprocess_bits: scale factors above 4 are not supported");
+    if (!d_image) return set_err(ctx, PCS_ERR_ARG, "preprocess_bits: the image output is required");
+    PCS_TRY(scratch_reserve(ctx, (size_t)n * 8 * 4 + 256));
+    uint32_t* d_bits = reinterpret_cast<uint32_t*>(ctx->scratch);
+    set_levels_kernel<<<(n * 8 + 255) / 256, 256, 0, ctx->stream>>>(d_bits, n, level0, level1);
+    PCS_LAUNCH_CHECK(ctx, "set_levels_kernel");
+    dim3 rgrid((Ws + RB_T - 1) / RB_T, (Hs + RB_TY - 1) / RB_TY, n);
+    resample_bits_kernel<<<rgrid, 256, 0, ctx->stream>>>(nullptr, nullptr, 1, H, W, Hs, Ws, d_bits, d_bitmap, bitmap_words, d_image, d_binary,
+                                                         level0);
+    PCS_LAUNCH_CHECK(ctx, "resample_bits_kernel");
+    return PCS_OK;
+}
+
+// uint8 planes <-> flat bit planes (pixel i = bit i & 31 of word i >> 5; a non-zero byte is a set bit, a set bit is byte 1).
+// grid = (blocks, pages); words_per_page may exceed ceil(npix / 32) (padding is written as zero).
+__global__ void __launch_bounds__(256) pack_bits_kernel(const uint8_t* __restrict__ src, size_t npix, uint32_t* __restrict__ dst, size_t words_per_page) {
+    const uint8_t* p = src + (size_t)blockIdx.y * npix;
+    uint32_t* o = dst + (size_t)blockIdx.y * words_per_page;
+    const int lane = threadIdx.x & 31;
+    const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t w0 = warp0 * 32; w0 < words_per_page; w0 += nwarps * 32) {        // a warp packs 32 words = 1024 pixels per step
+        uint32_t mine = 0;
+#pragma unroll 4
+        for (int k = 0; k < 32; ++k) {
+            const size_t i = (w0 + k) * 32 + lane;
+            const uint32_t m = __ballot_sync(0xffffffffu, i < npix && p[i] != 0);
+            if (lane == k) mine = m;
+        }
+        if (w0 + lane < words_per_page) o[w0 + lane] = mine;
+    }
+}
+
+__global__ void __launch_bounds__(256) unpack_bits_kernel(const uint32_t* __restrict__ src, size_t words_per_page, size_t npix, uint8_t* __restrict__ dst) {
+    const uint32_t* p = src + (size_t)blockIdx.y * words_per_page;
+    uint8_t* o = dst + (size_t)blockIdx.y * npix;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x)
+        o[i] = (uint8_t)((__ldg(p + (i >> 5)) >> (i & 31)) & 1u);
+}
+
+int launch_pack_bits(pcs_ctx* ctx, const uint8_t* d_src, int n, size_t npix, uint32_t* d_dst, size_t words_per_page) {
+    if (n <= 0 || !npix || words_per_page < (npix + 31) / 32) return set_err(ctx, PCS_ERR_ARG, "pack_bits: bad shape");
+    const unsigned blocks = (unsigned)std::min<size_t>((size_t)ctx->sm_count * 4, (words_per_page + 255) / 256);
+    pack_bits_kernel<<<dim3(blocks, n), 256, 0, ctx->stream>>>(d_src, npix, d_dst, words_per_page);
+    PCS_LAUNCH_CHECK(ctx, "pack_bits_kernel");
+    return PCS_OK;
+}
+
+int launch_unpack_bits(pcs_ctx* ctx, const uint32_t* d_src, int n, size_t words_per_page, size_t npix, uint8_t* d_dst) {
+    if (n <= 0 || !npix || words_per_page < (npix + 31) / 32) return set_err(ctx, PCS_ERR_ARG, "unpack_bits: bad shape");
+    const unsigned blocks = (unsigned)std::min<size_t>((size_t)ctx->sm_count * 8, (npix + 255) / 256);
+    unpack_bits_kernel<<<dim3(blocks, n), 256, 0, ctx->stream>>>(d_src, words_per_page, npix, d_dst);
+    PCS_LAUNCH_CHECK(ctx, "unpack_bits_kernel");
     return PCS_OK;
 }
 

@@ -331,6 +331,45 @@ class PageBatchEngine:
                                         max_components, out.get("ncomp"), out.get("color"), out.get("overlay"), out.get("inverted"))
         return out
 
+    def run_host_compact(self, h_pages: np.ndarray, scale: float, out: dict, cc_majority: bool = False):
+        """pcs_predict_pages_compact: uint8 pages in; `out` holds 'labels' (n, Hs, Ws) uint8 and optionally 'binary_bits'
+        (n, ceil(Hs * Ws / 32)) uint32 -- `data.binary` bit-packed.  The colour masks are produced on request
+        (masks_from_compact) instead of crossing PCIe for every page."""
+        n, H, W = h_pages.shape
+        Hs, Ws = scaled_shape(H, W, scale)
+        self._ensure_model()
+        self.ctx.use_torch_stream()
+        self.ctx.predict_pages_compact(h_pages, h_pages, n, H, W, Hs, Ws, cc_majority, out["labels"], out.get("binary_bits"))
+        return out
+
+    def run_host_packed(self, h_bits: np.ndarray, level0: int, level1: int, H: int, W: int, scale: float, out: dict,
+                        cc_majority: bool = False):
+        """pcs_predict_pages_packed: BIT-PACKED pages in (pack_pages), compact results out (see run_host_compact)."""
+        n = h_bits.shape[0]
+        Hs, Ws = scaled_shape(H, W, scale)
+        if h_bits.dtype != np.uint32 or h_bits.shape[1] != (H * W + 31) // 32:
+            raise ValueError("h_bits must be (n, ceil(H * W / 32)) uint32 (pack_pages)")
+        self._ensure_model()
+        self.ctx.use_torch_stream()
+        self.ctx.predict_pages_packed(h_bits, level0, level1, n, H, W, Hs, Ws, cc_majority, out["labels"], out.get("binary_bits"))
+        return out
+
+    def masks_from_compact(self, labels: np.ndarray, binary_bits: np.ndarray) -> dict:
+        """The colour masks of compact results, materialised on request ON THE DEVICE (pcs_unpack_bits + pcs_masks =
+        generate_output_masks, output.py:44-60): {'color', 'overlay', 'inverted'} numpy (n, Hs, Ws, 3)."""
+        t = self.torch
+        dev = f"cuda:{self.ctx.device}"
+        n, Hs, Ws = labels.shape
+        self.ctx.use_torch_stream()
+        d_labels = t.from_numpy(np.ascontiguousarray(labels)).to(dev)
+        d_bits = t.from_numpy(np.ascontiguousarray(binary_bits).view(np.int32)).to(dev)
+        d_bin = t.empty((n, Hs, Ws), dtype=t.uint8, device=dev)
+        self.ctx.unpack_bits(d_bits, n, binary_bits.shape[1], Hs * Ws, d_bin)
+        outs = t.empty((3, n, Hs, Ws, 3), dtype=t.uint8, device=dev)
+        self.ctx.masks(d_labels, d_bin, n, Hs, Ws, self.lut, outs[0], outs[1], outs[2])
+        color, overlay, inverted = results_to_host(outs[0], outs[1], outs[2], site="masks")
+        return {"color": color, "overlay": overlay, "inverted": inverted}
+
     def run_host_files(self, h_pages: np.ndarray, scale: float, out: dict, cc_majority: bool = False):
         """Like run_host, but the three masks of every page come back as PNG files (pcs_predict_pages_files): `out` holds
         host arrays 'png' (n, 3, stride) uint8, 'png_sizes' (n, 3) uint64 and optionally 'labels' (ideally pinned).
@@ -342,6 +381,34 @@ class PageBatchEngine:
         self.ctx.predict_pages_files(h_pages, h_pages, n, H, W, Hs, Ws, cc_majority, self.lut, out.get("labels"), out["png"],
                                      out["png"].shape[2], out["png_sizes"])
         return out
+
+
+def pack_pages(pages: np.ndarray):
+    """Two-level uint8 pages (n, H, W) -> (bits (n, ceil(H * W / 32)) uint32, level0, level1): the layout
+    pcs_preprocess_bits / pcs_predict_pages_packed take (flat, pixel i = bit i & 31 of word i >> 5; clear bit = level0).
+    Host-side convenience for callers whose binarised pages are uint8 arrays; a loader that decodes 1-bit files
+    (PBM, TIFF G4, 1-bit PNG) produces this form directly."""
+    pages = np.ascontiguousarray(pages)
+    levels = np.unique(pages)
+    if pages.dtype != np.uint8 or pages.ndim != 3 or not 1 <= levels.size <= 2:
+        raise ValueError("pack_pages expects uint8 pages (n, H, W) with at most two grey levels")
+    level1 = int(levels[-1])
+    level0 = int(levels[0]) if levels.size == 2 else (0 if level1 else 255)
+    n = pages.shape[0]
+    flat = (pages.reshape(n, -1) == level1)
+    pad = (-flat.shape[1]) % 32
+    if pad:
+        flat = np.concatenate([flat, np.zeros((n, pad), dtype=bool)], axis=1)
+    bits = np.packbits(flat, axis=1, bitorder="little").view("<u4")
+    return np.ascontiguousarray(bits), level0, level1
+
+
+def unpack_bits_host(bits: np.ndarray, shape) -> np.ndarray:
+    """Inverse of the packed layout for one plane stack: (n, words) uint32 -> (n,) + shape uint8 {0,1} (host, tests)."""
+    n = bits.shape[0]
+    npix = int(np.prod(shape))
+    flat = np.unpackbits(np.ascontiguousarray(bits).view(np.uint8).reshape(n, -1), axis=1, bitorder="little")[:, :npix]
+    return flat.reshape((n,) + tuple(shape))
 
 
 def shard_pages(n_pages: int, rank: int, world: int) -> List[int]:

@@ -1,0 +1,106 @@
+"""Compact transport formats of the batch pipeline: bit-packed binarised pages in
+(pcs_preprocess_bits / pcs_predict_pages_packed), class map + bit-packed `data.binary` out (pcs_predict_pages_compact),
+colour masks materialised on request on the device.  Everything is held to the oracle's prepare_images
+(dataset.py:131-150), network (network.py:248-260) and generate_output_masks (output.py:44-60)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import network as onet
+from oracle import pipeline as opipe
+from page_segmentation_b200 import synth
+from page_segmentation_b200.runtime import pack_pages, unpack_bits_host
+
+pytestmark = pytest.mark.gpu
+LUT = {0: (255, 255, 255), 1: (255, 0, 0), 2: (0, 255, 0)}
+
+
+@pytest.mark.parametrize("npix", [1, 31, 32, 33, 1000, 966763, 1024 * 37])
+def test_pack_unpack_bits_roundtrip(ctx, npix):
+    rng = np.random.default_rng(npix)
+    n = 3
+    src = (rng.random((n, npix)) < 0.3).astype(np.uint8) * rng.integers(1, 255, size=(n, npix)).astype(np.uint8)
+    words = (npix + 31) // 32 + 2                                            # padded pitch: the padding must come back zero
+    d_src = torch.from_numpy(src).cuda()
+    d_bits = torch.full((n, words), -1, dtype=torch.int32, device="cuda")
+    ctx.pack_bits(d_src, n, npix, d_bits, words)
+    bits = d_bits.cpu().numpy().view(np.uint32)
+    exp = np.packbits(np.pad(src != 0, ((0, 0), (0, words * 32 - npix))), axis=1, bitorder="little").view("<u4")
+    np.testing.assert_array_equal(bits, exp)
+    d_back = torch.empty((n, npix), dtype=torch.uint8, device="cuda")
+    ctx.unpack_bits(d_bits, n, words, npix, d_back)
+    np.testing.assert_array_equal(d_back.cpu().numpy(), (src != 0).astype(np.uint8))
+
+
+@pytest.mark.parametrize("shape,lh,first_is_ink", [((3508, 2480), 18, False), ((700, 500), 18, False), ((333, 517), 11, True),
+                                                   ((1200, 900), 24, True), ((97, 131), 5, False)])
+def test_preprocess_from_packed_pages_is_bit_exact(ctx, shape, lh, first_is_ink):
+    """pcs_preprocess_bits == the oracle's prepare_images of the uint8 page; also for pages whose first pixel is ink (the
+    uint8 fast path keys its bit plane on page[0]; the packed entry point has fixed level semantics) and whose size is not
+    a multiple of 32 pixels."""
+    page = synth.make_page(3, shape[0], shape[1], lh)
+    if first_is_ink:
+        page = page.copy()
+        page[0, :7] = 0
+    bits, l0, l1 = pack_pages(page[None])
+    assert (l0, l1) == (0, 255)
+    H, W = shape
+    Hs, Ws = synth.scaled_shape(H, W, 6 / lh)
+    words = H * W // 32 + 1
+    padded = np.zeros((1, words), np.uint32)
+    padded[:, :bits.shape[1]] = bits
+    d_bits = torch.from_numpy(padded.view(np.int32)).cuda()
+    d_img = torch.empty((Hs, Ws), dtype=torch.uint8, device="cuda")
+    d_bin = torch.empty((Hs, Ws), dtype=torch.uint8, device="cuda")
+    ctx.preprocess_bits(d_bits, words, 1, H, W, l0, l1, Hs, Ws, d_img, d_bin)
+    eimg, eb = opipe.prepare_images(page, page, 6, lh)
+    np.testing.assert_array_equal(d_bin.cpu().numpy(), eb)
+    np.testing.assert_array_equal(d_img.cpu().numpy(), eimg)
+
+
+def test_pack_pages_layout():
+    page = np.full((2, 3, 40), 255, np.uint8)
+    page[0, 0, 1] = 0
+    page[1, 2, 39] = 0
+    bits, l0, l1 = pack_pages(page)
+    assert bits.shape == (2, 4) and bits.dtype == np.uint32 and (l0, l1) == (0, 255)
+    assert bits[0, 0] == 0xffffffff & ~2 and bits[1, 3] == 0x00ffffff & ~(1 << 23)
+    np.testing.assert_array_equal(unpack_bits_host(bits, (3, 40)), (page == 255).astype(np.uint8))
+
+
+@pytest.mark.parametrize("cc", [False, True])
+def test_compact_and_packed_calls_vs_oracle(ctx, cc, monkeypatch):
+    """uint8 pages in / packed pages in -> class map + packed binary out, over a chunked call: identical class maps from
+    both input forms, `binary` bits == the oracle's binary, class maps against the fp64 oracle (the vote against the
+    oracle's vote over the raw device map), and the masks materialised from the compact results == the oracle's."""
+    from page_segmentation_b200.runtime import PageBatchEngine
+    monkeypatch.setenv("PCSEG_HOST_CHUNK", "2")
+    n, H, W_ = 5, 393, 300                       # 117 900 pixels per page: not a multiple of 32
+    pages = np.stack([synth.make_page(40 + s, H, W_, 18) for s in range(n)])
+    weights = synth.make_weights("fcn_skip", 3, seed=9)
+    lut = np.array([LUT[i] for i in range(3)], dtype=np.uint8)
+    eng = PageBatchEngine("fcn_skip", weights, 3, precision="fp16", lut=lut)
+    Hs, Ws = synth.scaled_shape(H, W_, 6 / 18)
+    bw = (Hs * Ws + 31) // 32
+    a = {"labels": np.zeros((n, Hs, Ws), np.uint8), "binary_bits": np.zeros((n, bw), np.uint32)}
+    b = {"labels": np.zeros((n, Hs, Ws), np.uint8), "binary_bits": np.zeros((n, bw), np.uint32)}
+    eng.run_host_compact(pages, 6 / 18, a, cc_majority=cc)
+    bits, l0, l1 = pack_pages(pages)
+    eng.run_host_packed(bits, l0, l1, H, W_, 6 / 18, b, cc_majority=cc)
+    np.testing.assert_array_equal(a["labels"], b["labels"])
+    np.testing.assert_array_equal(a["binary_bits"], b["binary_bits"])
+    raw = {"labels": np.zeros((n, Hs, Ws), np.uint8)}
+    eng.run_host_compact(pages, 6 / 18, raw, cc_majority=False)
+    binary = unpack_bits_host(a["binary_bits"], (Hs, Ws))
+    masks = eng.masks_from_compact(a["labels"], a["binary_bits"])
+    for i in range(n):
+        eimg, eb = opipe.prepare_images(pages[i], pages[i], 6, 18)
+        np.testing.assert_array_equal(binary[i], eb)
+        l64 = onet.Forward("fcn_skip", weights, 3, dtype=torch.float64).logits(eimg)[0]
+        assert (raw["labels"][i] == l64.argmax(-1)).mean() >= 0.999
+        exp = opipe.vote_connected_component_class(raw["labels"][i].astype(np.int64), eb) if cc else raw["labels"][i]
+        np.testing.assert_array_equal(a["labels"][i], exp)
+        c, o, inv, _ = opipe.generate_output_masks(eb, a["labels"][i].astype(np.int64), LUT)
+        np.testing.assert_array_equal(masks["color"][i], c)
+        np.testing.assert_array_equal(masks["overlay"][i], o)
+        np.testing.assert_array_equal(masks["inverted"][i], inv)
