@@ -796,19 +796,31 @@ cstats_accum_kernel(const uint8_t* __restrict__ img, int H, int W, int cls, cons
             atomicAdd(&g[4], cnt);
         }
     }
-    if (!m) return;
+    // the runs of a warp's 32 segments are walked in lock step and runs that end in the same root are combined before
+    // the atomics (a page background or a picture block sends every run of a row to ONE record: without this its five
+    // words serialise 30 000 updates per page)
     const int base = y * W + x0;
     unsigned mm = m;
-    int s, len;
-    while (next_run(mm, s, len)) {
-        const int p = uf_find(parent + page_off, base + s);
-        int* a = acc + (page_off + p) * 5;
-        const int v0 = W - (x0 + s), v1 = H - y, v2 = x0 + s + len - 1, v3 = y;
-        if (v0 > __ldcg(a + 0)) atomicMax(&a[0], v0);
-        if (v1 > __ldcg(a + 1)) atomicMax(&a[1], v1);
-        if (v2 > __ldcg(a + 2)) atomicMax(&a[2], v2);
-        if (v3 > __ldcg(a + 3)) atomicMax(&a[3], v3);
-        atomicAdd(&a[4], len);
+    const unsigned lane = threadIdx.x & 31;
+    while (__any_sync(0xffffffffu, mm != 0u)) {
+        int s = 0, len = 0;
+        const bool has = next_run(mm, s, len);
+        const int p = has ? uf_find(parent + page_off, base + s) : -1 - (int)lane;       // idle lanes: unique keys
+        const unsigned peers = __match_any_sync(0xffffffffu, p);
+        int v0 = W - (x0 + s), v1 = H - y, v2 = x0 + s + len - 1, v3 = y, cnt = len;
+        if (peers & (peers - 1)) {                                                       // more than one lane on this root
+            v0 = __reduce_max_sync(peers, v0); v1 = __reduce_max_sync(peers, v1);
+            v2 = __reduce_max_sync(peers, v2); v3 = __reduce_max_sync(peers, v3);
+            cnt = __reduce_add_sync(peers, cnt);
+        }
+        if (has && lane == (unsigned)(__ffs(peers) - 1)) {
+            int* a = acc + (page_off + p) * 5;
+            if (v0 > __ldcg(a + 0)) atomicMax(&a[0], v0);
+            if (v1 > __ldcg(a + 1)) atomicMax(&a[1], v1);
+            if (v2 > __ldcg(a + 2)) atomicMax(&a[2], v2);
+            if (v3 > __ldcg(a + 3)) atomicMax(&a[3], v3);
+            atomicAdd(&a[4], cnt);
+        }
     }
 }
 

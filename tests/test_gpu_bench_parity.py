@@ -177,3 +177,36 @@ def test_two_owners_of_one_context_do_not_share_weights(ctx):
     assert np.abs(again - la).max() <= 1e-3
     d2 = eng.run_device(torch.from_numpy(page[None]).cuda(), 6 / 18, masks=False)      # and the engine reloads its own
     assert bool((d2["labels"] == d["labels"]).all())
+
+
+UNET_TOL = {"fp16": dict(f32_max=8e-3, agree=0.999), "bf16": dict(f32_max=6e-2, agree=0.998)}
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_unet_a4_vs_oracle(ctx, precision):
+    """U-Net (model.py:151-203) at the size BASELINE configs[2] names: two A4 pages in one pcs_forward, the first against
+    the fp32 / fp64 oracle.  Stated tolerances: logits max |d| <= 8e-3 (fp16 operands; 5.1e-3 measured) / 6e-2 (bf16 operands; 4.0e-2 measured) on logits
+    within +-3; class map >= 99.9 % of the fp64 oracle's with fp16 operands (99.978 % measured), >= 99.8 % with bf16 operands (99.878 % measured; He-normal weights give a median top-2
+    margin of 0.5), every disagreeing pixel a near-tie (fp64 margin <= 2 x the page's largest logit error)."""
+    from page_segmentation_b200.lib.architecture import Architecture
+    from page_segmentation_b200.lib.network import Network
+    imgs, _ = _a4_inputs()
+    imgs = imgs[:2]
+    n, h, w = imgs.shape
+    W = synth.make_weights("unet", 3, seed=0)
+    net = Network("Predict", n_classes=3, model_constructor=Architecture("unet"), weights=W, precision=precision)
+    c = net._context()
+    d_img = torch.from_numpy(imgs).cuda()
+    d_labels = torch.empty((n, h, w), dtype=torch.uint8, device="cuda")
+    d_logits = torch.empty((n, h, w, 3), dtype=torch.float32, device="cuda")
+    c.forward(d_img, None, n, h, w, d_labels, d_logits, None)
+    torch.cuda.synchronize()
+    l32, l64 = _oracle_logits("unet", W, imgs[0], ("a4", 0, 0))
+    logit, pred = d_logits[0].cpu().numpy(), d_labels[0].cpu().numpy()
+    print(f"unet {precision}: max |logit - fp32| = {np.abs(logit - l32).max():.3e}, agreement with fp64 = {(pred == l64.argmax(-1)).mean():.6f}")
+    _check_page(logit, pred, l32, l64, UNET_TOL[precision], f"unet {precision}")
+    assert bool((d_logits.argmax(-1).to(torch.uint8) == d_labels).all())
+    # the same page alone gives the same class map (batch independence at A4)
+    d_one = torch.empty((1, h, w), dtype=torch.uint8, device="cuda")
+    c.forward(d_img[1:2].contiguous(), None, 1, h, w, d_one)
+    assert bool((d_one[0] == d_labels[1]).all())
