@@ -227,8 +227,8 @@ static int run_conv1_u8(pcs_ctx* ctx, const char* lname, const uint8_t* d_image,
     Layer* L = find_layer(ctx, lname);
     if (!L) return set_err(ctx, PCS_ERR_STATE, "layer %s missing", lname);
     StageScope ts(ctx, lname);
-    if (ctx->engine == PCS_ENGINE_UMMA && L->d_wmma && L->k == 5 && L->cout == 20)
-        return launch_conv1_umma(ctx, d_image, n, hs, ws, out->h, out->w, L->d_wmma, L->h_b32.data(), out->p, out->cp);
+    if (ctx->engine == PCS_ENGINE_UMMA && L->d_wmma && conv1_umma_supported(L->k, L->cout))
+        return launch_conv1_umma(ctx, d_image, n, hs, ws, out->h, out->w, L->d_wmma, L->h_b32.data(), L->k, L->cout, out->p, out->cp);
     DirectConvArgs a;
     a.src[0].p = d_image; a.src[0].c = 1; a.src[0].cp = 1; a.nsrc = 1;
     a.src_u8 = 1; a.img_h = hs; a.img_w = ws;
@@ -557,11 +557,11 @@ int pcs_model_load(pcs_ctx* ctx, int arch, int n_classes, int precision, const p
         PCS_CUDA(ctx, cudaMemcpy(L.d_b32, L.h_b32.data(), L.h_b32.size() * 4, cudaMemcpyHostToDevice));
         ctx->layers.push_back(std::move(L));
     }
-    // first FCN layer (C_in = 1, 5x5, 20 outputs): tap-contraction operand image, weights split hi + lo
-    if (arch != PCS_ARCH_UNET) {
+    // first layer (C_in = 1; FCN 5x5 -> 20, U-Net 3x3 -> 64): tap-contraction operand image, weights split hi + lo
+    if (conv1_umma_supported(ctx->layers[0].k, ctx->layers[0].cout)) {
         Layer& L = ctx->layers[0];
         std::vector<uint16_t> img;
-        L.wmma_bytes = conv1_umma_weight_image(L.h_w32.data(), L.cout, precision, img);
+        L.wmma_bytes = conv1_umma_weight_image(L.h_w32.data(), L.k, L.cout, precision, img);
         PCS_CUDA(ctx, cudaMalloc(&L.d_wmma, L.wmma_bytes));
         PCS_CUDA(ctx, cudaMemcpy(L.d_wmma, img.data(), L.wmma_bytes, cudaMemcpyHostToDevice));
     }

@@ -351,8 +351,9 @@ size_t fold_weight_image(const float* w32 /*[25][cin_total][cout_total]*/, int c
 int launch_conv_fold(pcs_ctx* ctx, const FoldConvArgs& a);
 
 // conv1_umma.cu  (first FCN layer on the tensor cores)
-size_t conv1_umma_weight_image(const float* w32 /*[25][1][cout]*/, int cout, int precision, std::vector<uint16_t>& out);
+size_t conv1_umma_weight_image(const float* w32 /*[ksz*ksz][1][cout]*/, int ksz, int cout, int precision, std::vector<uint16_t>& out);
+bool conv1_umma_supported(int ksz, int cout);
 int launch_conv1_umma(pcs_ctx* ctx, const uint8_t* d_image, int n, int img_h, int img_w, int h, int w, const void* wimg,
-                      const float* h_bias, void* out, int out_cp);
+                      const float* h_bias, int ksz, int cout, void* out, int out_cp);
 
 }  // namespace pcs

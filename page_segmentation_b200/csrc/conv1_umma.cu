@@ -1,5 +1,7 @@
-// First layer of the FCN variants on the tensor cores:
-//   Conv2D(20, 5x5, 'same', relu) over the uint8 page  (model.py:50 / :211, x/255 of architecture.py:67-68).
+// First layer of the network on the tensor cores:
+//   FCN variants: Conv2D(20, 5x5, 'same', relu) over the uint8 page  (model.py:50 / :211, x/255 of architecture.py:67-68);
+//   U-Net:        Conv2D(64, 3x3, 'same', relu)                      (model.py:156, conv1a) -- same kernel, template
+//                 parameters <kernel size, padded C_out, rows per tile> = <5, 32, 8> / <3, 64, 4>.
 //
 // C_in = 1, so the contraction runs over the 25 taps.  The builder warps expand every input row rho
 // of the tile once into shared memory as   E_rho[x'] = (in[rho][x0-2+x' + 0..7])  -- one 16-byte unit
@@ -20,32 +22,38 @@ namespace pcs {
 namespace {
 using namespace ptx;
 
-constexpr int C1_R = 8;            // output rows per tile
-constexpr int C1_N = 32;           // padded C_out
-constexpr int C1_ROWS = C1_R + 5;  // expanded rows per stage (r + 2ks + 1 <= R - 1 + 5)
+// KSZ = kernel size (5 | 3), NP = padded C_out (32 | 64), R = output rows per tile (2 accumulator stages of R * NP TMEM columns)
+template <int KSZ, int NP, int R> struct C1Cfg {
+    static constexpr int KS = (KSZ + 1) / 2;                  // K = 16 steps: vertical tap pairs (2 ks, 2 ks + 1)
+    static constexpr int ROWS = R + 2 * KS - 1;               // expanded rows per stage (r + 2 ks + 1 <= R - 1 + 2 KS - 1)
+    static constexpr int STAGE_BYTES = ROWS * 128 * 16;
+    static constexpr int B_BYTES = 2 * KS * 2 * NP * 16;      // [hi|lo][ks][plane][n][8]
+    static constexpr int CVT_COPY = ROWS * 144 + 14;          // elements per converted copy: an odd number of words (943 for 13 rows, 511
+                                                              // for 7), so the windows of odd pixel slots (copy 1, word m+1) use other banks
+    static_assert(2 * R * NP <= 512, "two accumulator stages must fit TMEM");
+};
 constexpr int C1_SW = 124;         // valid output pixels per 128-pixel strip
 constexpr int C1_STAGES = 3;
 constexpr int C1_ROW_BYTES = 128 * 16;
-constexpr int C1_STAGE_BYTES = C1_ROWS * C1_ROW_BYTES;
-constexpr int C1_B_BYTES = 2 * 3 * 2 * C1_N * 16;      // [hi|lo][ks][plane][n][8]
 constexpr int C1_THREADS = 448;     // warp 0 weights, warp 1 MMA, warps 2-5 + 10-13 epilogue (2 per lane quarter), warps 6-9 builders
-constexpr int C1_RAW_W = 136;      // bytes per raw patch row: 128 pixel slots + 7 look-ahead (+1 pad)
 constexpr int C1_CVT_W = 144;      // operand elements per converted patch row (4-byte aligned rows)
-constexpr int C1_CVT_COPY = C1_ROWS * C1_CVT_W + 14;   // elements per converted copy: 943 words = 15 mod 32, so the windows of odd
-                                                       // pixel slots (copy 1, word m+1) use the 16 banks the even ones (word m) do not
+constexpr int C1_MAXN = 64;
 
 struct Conv1Params {
     const uint8_t* img; int img_h, img_w;   // real page
     int n, h, w;                            // padded grid
     const uint8_t* wimg;                    // C1_B_BYTES operand image
-    float bias[C1_N];                       // by value: read as constant-bank FFMA operands, no shared-memory traffic
+    float bias[C1_MAXN];                    // by value: read as constant-bank FFMA operands, no shared-memory traffic
     void* out; int out_cp;
     int strips, rowblocks, num_tiles;
     int dbg;                                // diagnosis only (PCSEG_C1_DEBUG): 1 = no output stores, 2 = hi MMAs only, 4 = no expansion
 };
 
-template <typename T>
+template <typename T, int KSZ, int NP, int C1_R>
 __global__ void __launch_bounds__(C1_THREADS, 1) conv1_umma_kernel(const Conv1Params p) {
+    using Cfg = C1Cfg<KSZ, NP, C1_R>;
+    constexpr int C1_N = NP, C1_ROWS = Cfg::ROWS, C1_STAGE_BYTES = Cfg::STAGE_BYTES, C1_B_BYTES = Cfg::B_BYTES, C1_CVT_COPY = Cfg::CVT_COPY;
+    constexpr int KS = Cfg::KS, PAD = KSZ / 2;
     constexpr uint32_t IDESC = (1u << 4) | ((std::is_same<T, __nv_bfloat16>::value ? 1u : 0u) << 7) |
                                ((std::is_same<T, __nv_bfloat16>::value ? 1u : 0u) << 10) |
                                ((uint32_t)(C1_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -106,9 +114,9 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv1_umma_kernel(const Conv1Pa
 #pragma unroll
                     for (int half = 0; half < ((p.dbg & 2) ? 1 : 2); ++half) {        // weights hi, then lo
 #pragma unroll
-                        for (int ks = 0; ks < 3; ++ks) {
+                        for (int ks = 0; ks < KS; ++ks) {
                             const uint32_t a_off = (uint32_t)((r + 2 * ks) * (C1_ROW_BYTES >> 4));
-                            const uint32_t b_off = (uint32_t)((half * 3 + ks) * (2 * C1_N));    // 16-byte units
+                            const uint32_t b_off = (uint32_t)((half * KS + ks) * (2 * C1_N));   // 16-byte units
                             tc_mma(d0 + (uint32_t)(r * C1_N), a_lo0 + a_off, hi, b_lo0 + b_off, hi, IDESC, (half | ks) ? 1u : 0u);
                         }
                     }
@@ -141,23 +149,22 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv1_umma_kernel(const Conv1Pa
             const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * C1_R * C1_N);
 #pragma unroll 1
             for (int r = rgroup; r < C1_R; r += 2) {
-                uint32_t v0[16], v1[16];
-                tmem_ld16(t_lane + (uint32_t)(r * C1_N), v0);
-                tmem_ld16(t_lane + (uint32_t)(r * C1_N + 16), v1);
-                tmem_ld_wait();
                 const int y = y0 + r;
-                if (xok && y < p.h && !(p.dbg & 1)) {
-                    float f[32];
+                const bool store = xok && y < p.h && !(p.dbg & 1);
+                uint32_t v[C1_N];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        f[i] = fmaxf(fmaf(__uint_as_float(v0[i]), inv255, p.bias[i]), 0.f);
-                        f[16 + i] = fmaxf(fmaf(__uint_as_float(v1[i]), inv255, p.bias[16 + i]), 0.f);
-                    }
+                for (int c16 = 0; c16 < C1_N / 16; ++c16)
+                    tmem_ld16(t_lane + (uint32_t)(r * C1_N + c16 * 16), *reinterpret_cast<uint32_t(*)[16]>(&v[c16 * 16]));
+                tmem_ld_wait();
+                if (!store) continue;
 #pragma unroll
-                    for (int g = 0; g < 4; ++g)
-                        if (g < nplanes) *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, p.h, p.w, g * 8, y, x)) =
-                            make_uint4(pack2<T>(f[g * 8 + 0], f[g * 8 + 1]), pack2<T>(f[g * 8 + 2], f[g * 8 + 3]),
-                                       pack2<T>(f[g * 8 + 4], f[g * 8 + 5]), pack2<T>(f[g * 8 + 6], f[g * 8 + 7]));
+                for (int g = 0; g < C1_N / 8; ++g) {
+                    if (g >= nplanes) break;
+                    float f[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) f[i] = fmaxf(fmaf(__uint_as_float(v[g * 8 + i]), inv255, p.bias[g * 8 + i]), 0.f);
+                    *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, p.h, p.w, g * 8, y, x)) =
+                        make_uint4(pack2<T>(f[0], f[1]), pack2<T>(f[2], f[3]), pack2<T>(f[4], f[5]), pack2<T>(f[6], f[7]));
                 }
             }
             tc_fence_before();
@@ -183,7 +190,7 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv1_umma_kernel(const Conv1Pa
             const int page = tile / tiles_per_page;
             const int rem = tile - page * tiles_per_page;
             const int rb = rem % p.rowblocks, strip = rem / p.rowblocks;
-            const int gxb = strip * C1_SW - 2, gy0 = rb * C1_R - 2;
+            const int gxb = strip * C1_SW - PAD, gy0 = rb * C1_R - PAD;
             const uint8_t* src = p.img + (size_t)page * p.img_h * p.img_w;
             const int gx = gxb + xq;
             const bool xin = gx >= 0 && gx < p.img_w;
@@ -240,9 +247,11 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv1_umma_kernel(const Conv1Pa
 
 }  // namespace
 
-// Operand image [hi|lo][ks 0..2][plane 0..1][n 0..31][e 0..7]: value W[dy = 2ks+plane][dx = e][n] for dy, e < 5.
-size_t conv1_umma_weight_image(const float* w32 /*[25][1][cout]*/, int cout, int precision, std::vector<uint16_t>& out) {
-    out.assign(C1_B_BYTES / 2, 0);
+// Operand image [hi|lo][ks][plane 0..1][n][e 0..7]: value W[dy = 2ks+plane][dx = e][n] for dy, e < ksz (ksz = 5: 3 K steps,
+// n < 32; ksz = 3: 2 K steps, n < 64).
+size_t conv1_umma_weight_image(const float* w32 /*[ksz*ksz][1][cout]*/, int ksz, int cout, int precision, std::vector<uint16_t>& out) {
+    const int KS = (ksz + 1) / 2, NP = ksz == 5 ? 32 : 64;
+    out.assign((size_t)2 * KS * 2 * NP * 8, 0);
     auto to16 = [&](float v) -> uint16_t {
         if (precision == PCS_PREC_BF16) { __nv_bfloat16 b = __float2bfloat16_rn(v); return *reinterpret_cast<uint16_t*>(&b); }
         __half h = __float2half_rn(v); return *reinterpret_cast<uint16_t*>(&h);
@@ -251,52 +260,57 @@ size_t conv1_umma_weight_image(const float* w32 /*[25][1][cout]*/, int cout, int
         if (precision == PCS_PREC_BF16) { uint32_t x = (uint32_t)u << 16; float f; memcpy(&f, &x, 4); return f; }
         __half_raw hr; hr.x = u; return __half2float(__half(hr));
     };
-    for (int ks = 0; ks < 3; ++ks)
+    for (int ks = 0; ks < KS; ++ks)
         for (int pl = 0; pl < 2; ++pl)
-            for (int n = 0; n < C1_N; ++n)
+            for (int n = 0; n < NP; ++n)
                 for (int e = 0; e < 8; ++e) {
                     const int dy = 2 * ks + pl;
-                    if (dy >= 5 || e >= 5 || n >= cout) continue;
-                    const float w = w32[(size_t)(dy * 5 + e) * cout + n];
+                    if (dy >= ksz || e >= ksz || n >= cout) continue;
+                    const float w = w32[(size_t)(dy * ksz + e) * cout + n];
                     const uint16_t hi = to16(w);
                     const uint16_t lo = to16(w - from16(hi));
-                    const size_t idx = (((size_t)ks * 2 + pl) * C1_N + n) * 8 + e;
+                    const size_t idx = (((size_t)ks * 2 + pl) * NP + n) * 8 + e;
                     out[idx] = hi;
-                    out[(size_t)3 * 2 * C1_N * 8 + idx] = lo;
+                    out[(size_t)KS * 2 * NP * 8 + idx] = lo;
                 }
     return out.size() * sizeof(uint16_t);
 }
 
+namespace {
+template <typename T, int KSZ, int NP, int R>
+int launch_conv1_t(pcs_ctx* ctx, Conv1Params& p) {
+    using Cfg = C1Cfg<KSZ, NP, R>;
+    p.strips = (p.w + C1_SW - 1) / C1_SW;
+    p.rowblocks = (p.h + R - 1) / R;
+    p.num_tiles = p.n * p.strips * p.rowblocks;
+    const size_t smem = std::max<size_t>(((Cfg::B_BYTES + 1023) / 1024) * 1024 + (size_t)C1_STAGES * Cfg::STAGE_BYTES + 1024, kSoloSmem);
+    const int grid = std::min(p.num_tiles, ctx->sm_count);
+    static bool set[64] = {};                // the attribute is per device (and per instantiation: this is a template)
+    if (ctx->device >= 64 || !set[ctx->device]) {
+        PCS_CUDA(ctx, cudaFuncSetAttribute(conv1_umma_kernel<T, KSZ, NP, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (ctx->device < 64) set[ctx->device] = true;
+    }
+    PCS_CUDA(ctx, launch_kernel_pdl(conv1_umma_kernel<T, KSZ, NP, R>, dim3(grid), dim3(C1_THREADS), smem, ctx->stream, ctx->pdl, p));
+    PCS_LAUNCH_CHECK(ctx, "conv1_umma_kernel");
+    return PCS_OK;
+}
+}  // namespace
+
+bool conv1_umma_supported(int ksz, int cout) { return (ksz == 5 && cout <= 32) || (ksz == 3 && cout <= 64); }
+
 int launch_conv1_umma(pcs_ctx* ctx, const uint8_t* d_image, int n, int img_h, int img_w, int h, int w, const void* wimg,
-                      const float* h_bias /*host, 20 values*/, void* out, int out_cp) {
-    if (out_cp != C1_N && out_cp != 24) return set_err(ctx, PCS_ERR_ARG, "conv1_umma: output stride must be 24 or %d channels", C1_N);
+                      const float* h_bias /*host, cout values*/, int ksz, int cout, void* out, int out_cp) {
+    if (!conv1_umma_supported(ksz, cout)) return set_err(ctx, PCS_ERR_ARG, "conv1_umma: no instantiation for a %dx%d kernel with %d outputs", ksz, ksz, cout);
+    if ((out_cp & 7) || out_cp < cout || out_cp > (ksz == 5 ? 32 : 64))
+        return set_err(ctx, PCS_ERR_ARG, "conv1_umma: output stride of %d channels", out_cp);
     Conv1Params p{};
     p.img = d_image; p.img_h = img_h; p.img_w = img_w; p.n = n; p.h = h; p.w = w;
     p.wimg = reinterpret_cast<const uint8_t*>(wimg); p.out = out; p.out_cp = out_cp;
-    for (int i = 0; i < C1_N; ++i) p.bias[i] = i < 20 ? h_bias[i] : 0.f;
-    p.strips = (w + C1_SW - 1) / C1_SW;
-    p.rowblocks = (h + C1_R - 1) / C1_R;
-    p.num_tiles = n * p.strips * p.rowblocks;
+    for (int i = 0; i < C1_MAXN; ++i) p.bias[i] = i < cout ? h_bias[i] : 0.f;
     { const char* e = getenv("PCSEG_C1_DEBUG"); p.dbg = e ? atoi(e) : 0; }
-    const size_t smem = std::max<size_t>(((C1_B_BYTES + 1023) / 1024) * 1024 + (size_t)C1_STAGES * C1_STAGE_BYTES + 1024, kSoloSmem);
-    const int grid = std::min(p.num_tiles, ctx->sm_count);
-    if (ctx->precision == PCS_PREC_BF16) {
-        static bool set[64] = {};                // the attribute is per device
-        if (ctx->device >= 64 || !set[ctx->device]) {
-            PCS_CUDA(ctx, cudaFuncSetAttribute(conv1_umma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            if (ctx->device < 64) set[ctx->device] = true;
-        }
-        PCS_CUDA(ctx, launch_kernel_pdl(conv1_umma_kernel<__nv_bfloat16>, dim3(grid), dim3(C1_THREADS), smem, ctx->stream, ctx->pdl, p));
-    } else {
-        static bool set[64] = {};
-        if (ctx->device >= 64 || !set[ctx->device]) {
-            PCS_CUDA(ctx, cudaFuncSetAttribute(conv1_umma_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            if (ctx->device < 64) set[ctx->device] = true;
-        }
-        PCS_CUDA(ctx, launch_kernel_pdl(conv1_umma_kernel<__half>, dim3(grid), dim3(C1_THREADS), smem, ctx->stream, ctx->pdl, p));
-    }
-    PCS_LAUNCH_CHECK(ctx, "conv1_umma_kernel");
-    return PCS_OK;
+    const bool bf = ctx->precision == PCS_PREC_BF16;
+    if (ksz == 5) return bf ? launch_conv1_t<__nv_bfloat16, 5, 32, 8>(ctx, p) : launch_conv1_t<__half, 5, 32, 8>(ctx, p);
+    return bf ? launch_conv1_t<__nv_bfloat16, 3, 64, 4>(ctx, p) : launch_conv1_t<__half, 3, 64, 4>(ctx, p);
 }
 
 }  // namespace pcs
