@@ -48,7 +48,8 @@ typedef enum {
     PCS_ERR_CUDA = -2,      /* CUDA runtime or driver error (see pcs_last_error) */
     PCS_ERR_STATE = -3,     /* call order: e.g. forward before model load */
     PCS_ERR_NOMEM = -4,     /* device allocation failed */
-    PCS_ERR_DEVICE = -5     /* not an sm_100 device */
+    PCS_ERR_DEVICE = -5,    /* not an sm_100 device */
+    PCS_ERR_IO = -6         /* a file of pcs_output_pages could not be written */
 } pcs_status;
 
 /* Architecture.value strings of lib/architecture.py:6-11 that are in scope. */
@@ -249,6 +250,18 @@ PCS_API int pcs_predict_pages_segments(pcs_ctx* ctx, const uint8_t* h_grey, cons
 PCS_API size_t pcs_png_bytes(int H, int W, int channels, int level);   /* exact (level 0) / upper bound (level 1); 0 = unsupported */
 PCS_API int pcs_png_encode(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, int channels, int level,
                    uint8_t* d_out, size_t stride, uint64_t* d_sizes);
+
+/* ---- output_data, lib/output.py:20-41, for n pages in one asynchronous call: generate_output_masks (pcs_masks) + the
+ * three PNG files of every page (pcs_png_encode, level 1; level 0 for scanlines beyond its limit).  d_labels /
+ * d_binary: [n][H][W] uint8 device pointers (class map, data.binary); lut: HOST [n_lut][3]; paths: HOST array of
+ * 3 n C strings, page-major (page p: paths[3 p] = color, [3 p + 1] = overlay, [3 p + 2] = inverted), copied by the call.
+ * The kernels run on the context's stream into buffers the library owns (the inputs may be released once work queued
+ * on the stream after this call has run); worker threads of the library fetch only the bytes of the files and write
+ * them.  1 <= n <= 64.  pcs_output_flush returns once every file handed over so far is on disk and reports the first
+ * write error (PCS_ERR_IO, also reported by the next pcs_output_pages); pcs_ctx_destroy flushes. */
+PCS_API int pcs_output_pages(pcs_ctx* ctx, const uint8_t* d_labels, const uint8_t* d_binary, int n, int H, int W,
+                             const uint8_t* lut, int n_lut, const char* const* paths);
+PCS_API int pcs_output_flush(pcs_ctx* ctx);
 
 /* ---- region extraction (downstream consumer of the `inverted` colour image):
  * the pixel work of lib/pc_segmentation.py and lib/xycut.py; the data-dependent

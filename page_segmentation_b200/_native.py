@@ -23,7 +23,7 @@ EXPORTS = [
     "pcs_synchronize", "pcs_launch_count", "pcs_model_load", "pcs_set_engine", "pcs_preprocess",
     "pcs_preprocess_max_width", "pcs_preprocess_bits", "pcs_pack_bits", "pcs_unpack_bits", "pcs_predict_pages_compact", "pcs_predict_pages_packed",
     "pcs_forward", "pcs_masks", "pcs_resize_nearest", "pcs_ccl", "pcs_cc_majority",
-    "pcs_bounding_boxes", "pcs_class_components", "pcs_char_height", "pcs_png_bytes", "pcs_png_encode", "pcs_segment_masks", "pcs_dilate3x3", "pcs_integral_image", "pcs_text_regions", "pcs_predict_pages_host", "pcs_predict_pages_files", "pcs_predict_pages_segments", "pcs_eval_counts",
+    "pcs_bounding_boxes", "pcs_class_components", "pcs_char_height", "pcs_png_bytes", "pcs_png_encode", "pcs_output_pages", "pcs_output_flush", "pcs_segment_masks", "pcs_dilate3x3", "pcs_integral_image", "pcs_text_regions", "pcs_predict_pages_host", "pcs_predict_pages_files", "pcs_predict_pages_segments", "pcs_eval_counts",
     "pcs_train_input", "pcs_train_corr2d", "pcs_train_wgrad", "pcs_train_bias_grad", "pcs_train_relu_bwd", "pcs_train_maxpool_fwd",
     "pcs_train_maxpool_bwd", "pcs_train_deconv2_fwd", "pcs_train_deconv2_bwd_data", "pcs_train_deconv2_wgrad", "pcs_train_softmax_ce",
     "pcs_train_adam", "pcs_debug_activation", "pcs_set_keep_activations", "pcs_set_timing", "pcs_set_pdl",
@@ -83,6 +83,8 @@ def load() -> C.CDLL:
     lib.pcs_png_bytes.argtypes = [i32, i32, i32, i32]
     lib.pcs_png_bytes.restype = C.c_size_t
     lib.pcs_png_encode.argtypes = [vp, u8p, i32, i32, i32, i32, i32, u8p, C.c_size_t, vp]
+    lib.pcs_output_pages.argtypes = [vp, u8p, u8p, i32, i32, i32, vp, i32, C.POINTER(C.c_char_p)]
+    lib.pcs_output_flush.argtypes = [vp]
     lib.pcs_segment_masks.argtypes = [vp, u8p, i32, i32, i32, i32, vp, i32, u8p]
     lib.pcs_dilate3x3.argtypes = [vp, u8p, i32, i32, i32, u8p]
     lib.pcs_integral_image.argtypes = [vp, u8p, i32, i32, i32, vp]
@@ -302,6 +304,19 @@ class Context:
     def png_encode(self, d_img, n, H, W, channels, d_out, stride, d_sizes=None, level=1):
         self._check(self.lib.pcs_png_encode(self.h, _ptr(d_img), n, H, W, channels, level, _ptr(d_out), stride, _ptr(d_sizes)),
                     "pcs_png_encode")
+
+    def output_pages(self, d_labels, d_binary, n, H, W, lut, paths):
+        """pcs_output_pages: masks + three PNG files per page, written by the library's worker threads; `paths` page-major
+        (color, overlay, inverted per page)."""
+        lut_arr = np.ascontiguousarray(lut, dtype=np.uint8).reshape(-1, 3)
+        if len(paths) != 3 * n:
+            raise PcsError(f"output_pages: {3 * n} paths expected, got {len(paths)}")
+        arr = (C.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
+        self._check(self.lib.pcs_output_pages(self.h, _ptr(d_labels), _ptr(d_binary), n, H, W, _ptr(lut_arr), lut_arr.shape[0], arr),
+                    "pcs_output_pages")
+
+    def output_flush(self):
+        self._check(self.lib.pcs_output_flush(self.h), "pcs_output_flush")
 
     # -- region extraction ---------------------------------------------------
     def segment_masks(self, d_rgb, H, W, Ho, Wo, colours, d_masks):

@@ -463,6 +463,7 @@ void pcs_ctx_destroy(pcs_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    output_writer_destroy(ctx);
     free_layers(ctx);
     clear_stage_times(ctx);
     if (ctx->arena) cudaFree(ctx->arena);
@@ -899,6 +900,22 @@ int pcs_png_encode(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, int 
     PCS_CUDA(ctx, cudaSetDevice(ctx->device));
     StageScope ts(ctx, "png_encode");
     return launch_png_encode(ctx, d_img, n, H, W, channels, level, d_out, stride, reinterpret_cast<unsigned long long*>(d_sizes));
+}
+
+int pcs_output_pages(pcs_ctx* ctx, const uint8_t* d_labels, const uint8_t* d_binary, int n, int H, int W, const uint8_t* lut, int n_lut,
+                     const char* const* paths) {
+    if (!ctx || !d_labels || !d_binary || !lut || !paths) return ctx ? set_err(ctx, PCS_ERR_ARG, "output_pages: null argument") : PCS_ERR_ARG;
+    if (n_lut < 0 || n_lut > 256) return set_err(ctx, PCS_ERR_ARG, "output_pages: LUT size %d", n_lut);
+    for (int i = 0; i < 3 * n; ++i)
+        if (!paths[i]) return set_err(ctx, PCS_ERR_ARG, "output_pages: null path");
+    PCS_CUDA(ctx, cudaSetDevice(ctx->device));
+    StageScope ts(ctx, "output_pages");
+    return output_pages(ctx, d_labels, d_binary, n, H, W, lut, n_lut, paths);
+}
+
+int pcs_output_flush(pcs_ctx* ctx) {
+    if (!ctx) return PCS_ERR_ARG;
+    return output_flush(ctx);
 }
 
 // h_png != nullptr: the three masks leave the device as PNG files (level 1) instead of raw arrays: file (page p, kind k)

@@ -114,6 +114,8 @@ struct pcs_ctx {
     cudaEvent_t ev_h2d[kHostBufs] = {}, ev_comp[kHostBufs] = {}, ev_d2h[kHostBufs] = {}, ev_sizes[kHostBufs] = {}, ev_fork = nullptr;
     uint64_t* h_png_sizes = nullptr;                       // pinned [kHostBufs][3][64]: file lengths of the chunk in flight (PNG mode)
 
+    void* writer = nullptr;                 // pcs::OutputWriter of pcs_output_pages (output.cu), created on first use
+
     std::string timings;
     std::vector<pcs::StageTime> stage_times;
     bool timing_enabled = false;
@@ -276,10 +278,21 @@ int launch_integral_image(pcs_ctx* ctx, const uint8_t* d_mask, int n, int H, int
 int launch_text_regions(pcs_ctx* ctx, const uint8_t* d_rgb, int H, int W, const uint8_t* colour, int k_close, int k_open,
                         int k_region, uint8_t* d_text_inv, uint8_t* d_region);
 
+// output.cu
+int output_pages(pcs_ctx* ctx, const uint8_t* d_labels, const uint8_t* d_binary, int n, int H, int W, const uint8_t* lut, int n_lut,
+                 const char* const* paths);
+int output_flush(pcs_ctx* ctx);
+void output_writer_destroy(pcs_ctx* ctx);
+
 // png.cu
 size_t png_file_bytes(int H, int W, int C, int level);
 int launch_png_encode(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, int C, int level, uint8_t* d_out, size_t stride,
                       unsigned long long* d_sizes);
+int png_index_depth(int ncolors);
+size_t png_indexed_file_bytes(int H, int W, int ncolors, int level);
+int launch_png_encode_indexed(pcs_ctx* ctx, const uint8_t* d_idx, int n, int H, int W, const uint8_t* h_palette, int ncolors, int level,
+                              uint8_t* d_out, size_t stride, unsigned long long* d_sizes);
+int launch_mask_indices(pcs_ctx* ctx, const uint8_t* d_labels, const uint8_t* d_binary, int n, int H, int W, int n_lut, uint8_t* d_out);
 
 // train.cu  (fp32 CUDA-core training primitives, planar [C][H][W])
 int train_corr2d(pcs_ctx* ctx, const float* x, const float* w, const float* b, float* y, int Ci, int Co, int H, int W, int k, int relu, int acc);

@@ -19,6 +19,7 @@
 // and any PNG reader decodes them to exactly the mask bytes (tests decode with OpenCV and zlib).
 #include "common.cuh"
 
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 
@@ -26,14 +27,17 @@ namespace pcs {
 namespace {
 
 constexpr uint32_t kCrcPoly = 0xedb88320u;
-constexpr size_t kHead = 8 + 25 + 8;            // signature, IHDR chunk, IDAT length + type
+constexpr size_t kHeadPlain = 8 + 25 + 8;       // signature, IHDR chunk, IDAT length + type
+constexpr size_t kMaxHead = 8 + 25 + (12 + 768) + 8;   // ... with a PLTE chunk of up to 256 colours in front of the IDAT
 
 struct PngPlan {
     int H, W, C;
     uint32_t line;                              // bytes per scanline incl. the filter byte
     uint32_t lines_per_block, nblocks;
     uint64_t zlib_bytes, file_bytes, stride;    // stride: bytes between the files of a batch
-    uint8_t head[kHead];                        // signature + IHDR + IDAT length/type, built on the host
+    uint32_t head_len;                          // bytes in front of the zlib stream (kHeadPlain, or more with a palette)
+    uint32_t filter_a;                          // level 1 costs every scanline with this filter (1 Sub, 0 None) and with Up
+    uint8_t head[kMaxHead];                     // signature + IHDR (+ PLTE) + IDAT length/type, built on the host
 };
 
 __host__ __device__ inline uint32_t crc_step(uint32_t c) {
@@ -70,6 +74,7 @@ __device__ uint32_t x8n_modp(uint64_t n, const uint32_t* x2n /*[32]: x^(2^k)*/) 
 // and stores it whole: the scanlines sit at arbitrary byte offsets, so byte stores would quarter the store throughput.
 // grid = (ceil(words / 256), n).  The word that straddles the Adler-32 is completed by png_adler_kernel afterwards.
 __global__ void __launch_bounds__(256) png_body_kernel(const uint8_t* __restrict__ img, uint8_t* __restrict__ out, const PngPlan pl) {
+    const uint32_t kHead = pl.head_len;
     const uint32_t limit = (uint32_t)(kHead + pl.zlib_bytes - 4);                       // first byte of the Adler-32
     const uint32_t o0 = (blockIdx.x * 256u + threadIdx.x) * 4u;
     if (o0 >= limit) return;
@@ -148,7 +153,7 @@ __global__ void __launch_bounds__(256) png_adler_kernel(const unsigned long long
         for (int k = 1; k < 8; ++k) { s1 += t1[k]; s2 += t2[k]; }
         const unsigned long long n = ((unsigned long long)pl.H * pl.line) % 65521ull;
         const uint32_t a = (uint32_t)((1 + s1) % 65521ull), b = (uint32_t)((n + s2) % 65521ull);
-        uint8_t* f = out + (uint64_t)page * pl.stride + kHead + (zbytes ? zbytes[page] : pl.zlib_bytes) - 4;
+        uint8_t* f = out + (uint64_t)page * pl.stride + pl.head_len + (zbytes ? zbytes[page] : pl.zlib_bytes) - 4;
         f[0] = (uint8_t)(b >> 8); f[1] = (uint8_t)b; f[2] = (uint8_t)(a >> 8); f[3] = (uint8_t)a;
     }
 }
@@ -174,7 +179,7 @@ __global__ void __launch_bounds__(kCrcThreads) png_crc_kernel(const uint8_t* __r
     const uint64_t tile_begin = (uint64_t)blockIdx.x * kCrcTile;
     if (tile_begin >= total) return;                                                     // level 1: the grid covers the worst case
     const int nbytes = (int)min((uint64_t)kCrcTile, total - tile_begin);
-    const uint8_t* src = out + (uint64_t)blockIdx.y * pl.stride + (kHead - 4) + tile_begin;
+    const uint8_t* src = out + (uint64_t)blockIdx.y * pl.stride + (pl.head_len - 4) + tile_begin;
     for (int i = tid; i < nbytes; i += kCrcThreads) tile[(i >> 8) * kCrcPitch + (i & 255)] = src[i];
     __syncthreads();
     if (tid < 7) lvl[tid] = x8n_modp((uint64_t)kCrcBytes << tid, x2n);
@@ -257,7 +262,8 @@ __device__ __forceinline__ uint32_t stage_row(const uint8_t* __restrict__ src, u
 
 // Filtered scanline and its run starts in shared memory; returns the number of runs (warp-uniform).  `raw` / `above`
 // are the staged rows (shared memory; `above` null on the first row).
-// fb[0] is the filter type: 1 (Sub) fb[i] = raw[i-1] - raw[i-1-C];  2 (Up) fb[i] = raw[i-1] - above[i-1]  (zeros above row 0).
+// fb[0] is the filter type: 0 (None) fb[i] = raw[i-1];  1 (Sub) fb[i] = raw[i-1] - raw[i-1-C];  2 (Up) fb[i] = raw[i-1] - above[i-1]
+// (zeros above row 0).
 // One pass: filter, Adler partial sums (ADLER: lane-local, of the FILTERED bytes incl. the filter byte) and run starts;
 // the previous byte comes from the neighbouring lane, not from shared memory.
 template <bool ADLER>
@@ -271,7 +277,7 @@ __device__ uint32_t rle_prepare(const uint8_t* raw, const uint8_t* above, uint32
         uint32_t v = ftype;
         if (i && i < line) {
             const uint32_t j = i - 1;
-            const uint32_t pred = ftype == 1u ? (j >= C ? (uint32_t)raw[j - C] : 0u) : (above ? (uint32_t)above[j] : 0u);
+            const uint32_t pred = ftype == 1u ? (j >= C ? (uint32_t)raw[j - C] : 0u) : (ftype == 2u && above ? (uint32_t)above[j] : 0u);
             v = ((uint32_t)raw[j] - pred) & 0xffu;
         }
         if (i < line) {
@@ -307,8 +313,9 @@ __global__ void __launch_bounds__(32) png_rle_count_kernel(const uint8_t* __rest
     const uint8_t* raw = sraw + stage_row(graw, npx, first, last, sraw);
     const uint8_t* above = row ? sabove + stage_row(graw - npx, npx, page == 0 && row == 1, false, sabove) : nullptr;
     unsigned long long best_a = 0, best_b = 0;
-    uint32_t best_t = 0xffffffffu, best_f = 1;
-    for (uint32_t ftype = 1; ftype <= 2; ++ftype) {
+    uint32_t best_t = 0xffffffffu, best_f = pl.filter_a;
+    for (uint32_t trial = 0; trial < 2; ++trial) {
+        const uint32_t ftype = trial ? 2u : pl.filter_a;
         unsigned long long a = 0, b = 0;
         const uint32_t R = rle_prepare<true>(raw, above, ftype, pl.line, (uint32_t)pl.C, fb, starts, a, b);
         uint32_t t = 0;
@@ -335,6 +342,7 @@ __global__ void __launch_bounds__(1024) png_rle_scan_kernel(const uint32_t* __re
                                                             unsigned long long* __restrict__ bitbase, unsigned long long* __restrict__ zbytes) {
     __shared__ unsigned long long s_warp[32], s_carry;
     const int page = blockIdx.x, tid = threadIdx.x;
+    const uint32_t kHead = pl.head_len;
     if (tid == 0) s_carry = (kHead + 2) * 8ull + 3ull;                                   // after BFINAL = 1, BTYPE = 01
     __syncthreads();
     for (int base = 0; base < pl.H; base += 1024) {
@@ -367,9 +375,13 @@ __global__ void __launch_bounds__(1024) png_rle_scan_kernel(const uint32_t* __re
         const unsigned long long zb = (end_bit + 7ull) / 8ull - kHead + 4ull;            // zlib header + deflate + Adler-32
         zbytes[page] = zb;
         uint8_t* f = out + (uint64_t)page * pl.stride;
-        for (int i = 0; i < (int)kHead; ++i) f[i] = pl.head[i];
-        f[33] = (uint8_t)(zb >> 24); f[34] = (uint8_t)(zb >> 16); f[35] = (uint8_t)(zb >> 8); f[36] = (uint8_t)zb;
+        f[kHead - 8] = (uint8_t)(zb >> 24); f[kHead - 7] = (uint8_t)(zb >> 16); f[kHead - 6] = (uint8_t)(zb >> 8); f[kHead - 5] = (uint8_t)zb;
         f[kHead] = 0x78; f[kHead + 1] = 0x01; f[kHead + 2] = 0x03;                       // BFINAL = 1, BTYPE = 01 (fixed Huffman)
+    }
+    {   // the fixed bytes in front (signature, IHDR, palette, "IDAT"); the IDAT length was written above
+        uint8_t* f = out + (uint64_t)page * pl.stride;
+        for (uint32_t i = tid; i < kHead; i += 1024)
+            if (i < kHead - 8 || i >= kHead - 4) f[i] = pl.head[i];
     }
 }
 
@@ -438,12 +450,12 @@ __global__ void png_finish_kernel(uint8_t* __restrict__ out, const PngPlan pl, c
     const int page = blockIdx.x * blockDim.x + threadIdx.x;
     if (page >= n) return;
     const uint64_t zb = zbytes ? zbytes[page] : pl.zlib_bytes;
-    uint8_t* f = out + (uint64_t)page * pl.stride + kHead + zb;
+    uint8_t* f = out + (uint64_t)page * pl.stride + pl.head_len + zb;
     const uint32_t c = crc[page];
     const uint8_t tail[16] = {(uint8_t)(c >> 24), (uint8_t)(c >> 16), (uint8_t)(c >> 8), (uint8_t)c,
                               0, 0, 0, 0, 'I', 'E', 'N', 'D', 0xae, 0x42, 0x60, 0x82};
     for (int i = 0; i < 16; ++i) f[i] = tail[i];
-    if (sizes) sizes[page] = kHead + zb + 16;
+    if (sizes) sizes[page] = pl.head_len + zb + 16;
 }
 
 uint32_t host_crc(const uint8_t* p, size_t n) {
@@ -453,49 +465,76 @@ uint32_t host_crc(const uint8_t* p, size_t n) {
 }
 void be32(uint8_t* p, uint32_t v) { p[0] = (uint8_t)(v >> 24); p[1] = (uint8_t)(v >> 16); p[2] = (uint8_t)(v >> 8); p[3] = (uint8_t)v; }
 
-bool make_plan(int H, int W, int C, PngPlan& pl) {
-    if (H <= 0 || W <= 0 || (C != 1 && C != 3 && C != 4)) return false;
-    const uint64_t line = 1 + (uint64_t)W * C;
+// depth == 0: 8-bit grey / RGB / RGBA with C channels.  depth in {1, 2, 4, 8}: colour type 3 (indexed), `palette` holds
+// ncolors RGB triples, the image is H rows of ceil(W * depth / 8) bytes (leftmost pixel in the high-order bits).
+bool make_plan(int H, int W, int C, PngPlan& pl, int depth = 0, const uint8_t* palette = nullptr, int ncolors = 0) {
+    if (H <= 0 || W <= 0) return false;
+    if (depth == 0 && C != 1 && C != 3 && C != 4) return false;
+    if (depth != 0 && (C != 1 || (depth != 1 && depth != 2 && depth != 4 && depth != 8) || ncolors < 1 || ncolors > (1 << depth) || !palette)) return false;
+    const uint64_t line = 1 + (depth ? ((uint64_t)W * depth + 7) / 8 : (uint64_t)W * C);
     if (line > 65535) return false;                                                      // one scanline must fit a stored block
     pl.H = H; pl.W = W; pl.C = C;
+    pl.filter_a = depth ? 0u : 1u;                                                       // packed indices: None, samples: Sub
     pl.line = (uint32_t)line;
     pl.lines_per_block = (uint32_t)(65535 / line);
     pl.nblocks = ((uint32_t)H + pl.lines_per_block - 1) / pl.lines_per_block;
     pl.zlib_bytes = 2 + (uint64_t)pl.nblocks * 5 + (uint64_t)H * line + 4;
     if (pl.zlib_bytes > 0x7fffffffull) return false;
-    pl.file_bytes = kHead + pl.zlib_bytes + 4 + 12;
+    pl.head_len = (uint32_t)(kHeadPlain + (depth ? 12 + 3 * (size_t)ncolors : 0));
+    pl.file_bytes = pl.head_len + pl.zlib_bytes + 4 + 12;
     static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
     uint8_t* h = pl.head;
     memcpy(h, sig, 8);
     be32(h + 8, 13); memcpy(h + 12, "IHDR", 4);
     be32(h + 16, (uint32_t)W); be32(h + 20, (uint32_t)H);
-    h[24] = 8; h[25] = (uint8_t)(C == 1 ? 0 : (C == 3 ? 2 : 6)); h[26] = 0; h[27] = 0; h[28] = 0;      // 8 bit, grey / RGB / RGBA
+    h[24] = (uint8_t)(depth ? depth : 8);
+    h[25] = (uint8_t)(depth ? 3 : (C == 1 ? 0 : (C == 3 ? 2 : 6))); h[26] = 0; h[27] = 0; h[28] = 0;   // indexed / grey / RGB / RGBA
     be32(h + 29, host_crc(h + 12, 17));
-    be32(h + 33, (uint32_t)pl.zlib_bytes); memcpy(h + 37, "IDAT", 4);
+    uint8_t* q = h + 33;
+    if (depth) {
+        be32(q, 3u * (uint32_t)ncolors); memcpy(q + 4, "PLTE", 4);
+        memcpy(q + 8, palette, 3 * (size_t)ncolors);
+        be32(q + 8 + 3 * ncolors, host_crc(q + 4, 4 + 3 * (size_t)ncolors));
+        q += 12 + 3 * ncolors;
+    }
+    be32(q, (uint32_t)pl.zlib_bytes); memcpy(q + 4, "IDAT", 4);
     return true;
 }
 
 }  // namespace
 
-size_t png_file_bytes(int H, int W, int C, int level) {
-    PngPlan pl{};
-    if (!make_plan(H, W, C, pl)) return 0;
+static size_t plan_file_bytes(const PngPlan& pl, int level) {
     if (level <= 0) return (size_t)pl.file_bytes;
     if (pl.line > kMaxRleLine) return 0;
     // worst case of level 1: every byte a 9-bit literal
-    const uint64_t zlib = 2 + (3 + 7 + 9 * (uint64_t)H * pl.line + 7) / 8 + 4;
-    return zlib > 0x7fffffffull ? 0 : (size_t)(kHead + zlib + 16);
+    const uint64_t zlib = 2 + (3 + 7 + 9 * (uint64_t)pl.H * pl.line + 7) / 8 + 4;
+    return zlib > 0x7fffffffull ? 0 : (size_t)(pl.head_len + zlib + 16);
 }
 
-int launch_png_encode(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, int C, int level, uint8_t* d_out, size_t stride,
-                      unsigned long long* d_sizes) {
+size_t png_file_bytes(int H, int W, int C, int level) {
     PngPlan pl{};
-    if (n <= 0 || !make_plan(H, W, C, pl)) return set_err(ctx, PCS_ERR_ARG, "png_encode: unsupported shape %d x %d x %d", H, W, C);
-    const size_t bound = png_file_bytes(H, W, C, level);
+    if (!make_plan(H, W, C, pl)) return 0;
+    return plan_file_bytes(pl, level);
+}
+
+int png_index_depth(int ncolors) { return ncolors <= 2 ? 1 : (ncolors <= 4 ? 2 : (ncolors <= 16 ? 4 : 8)); }
+
+size_t png_indexed_file_bytes(int H, int W, int ncolors, int level) {
+    PngPlan pl{};
+    uint8_t pal[768] = {};
+    if (ncolors < 1 || ncolors > 256 || !make_plan(H, W, 1, pl, png_index_depth(ncolors), pal, ncolors)) return 0;
+    return plan_file_bytes(pl, level);
+}
+
+static int encode_with_plan(pcs_ctx* ctx, PngPlan& pl, const uint8_t* d_img, int n, int level, uint8_t* d_out, size_t stride,
+                            unsigned long long* d_sizes) {
+    const int H = pl.H;
+    const size_t bound = plan_file_bytes(pl, level);
     if (!bound) return set_err(ctx, PCS_ERR_ARG, "png_encode: scanlines of %u bytes are too long for level %d", pl.line, level);
     if ((stride & 3) || (reinterpret_cast<uintptr_t>(d_out) & 3)) return set_err(ctx, PCS_ERR_ARG, "png_encode: output and stride must be 4-byte aligned");
     if (stride < ((bound + 3) & ~(size_t)3)) return set_err(ctx, PCS_ERR_ARG, "png_encode: %zu bytes per file needed, stride is %zu", bound, stride);
     if (H > 65535) return set_err(ctx, PCS_ERR_ARG, "png_encode: more than 65535 rows");
+    const size_t kHead = pl.head_len;
     pl.stride = stride;
     auto al = [](size_t b) { return (b + 255) / 256 * 256; };
     const size_t rows = (size_t)n * H;
@@ -546,6 +585,67 @@ int launch_png_encode(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, i
     PCS_LAUNCH_CHECK(ctx, "png_crc_kernel");
     png_finish_kernel<<<(n + 63) / 64, 64, 0, st>>>(d_out, pl, crc, n, zbytes, d_sizes);
     PCS_LAUNCH_CHECK(ctx, "png_finish_kernel");
+    return PCS_OK;
+}
+
+int launch_png_encode(pcs_ctx* ctx, const uint8_t* d_img, int n, int H, int W, int C, int level, uint8_t* d_out, size_t stride,
+                      unsigned long long* d_sizes) {
+    PngPlan pl{};
+    if (n <= 0 || !make_plan(H, W, C, pl)) return set_err(ctx, PCS_ERR_ARG, "png_encode: unsupported shape %d x %d x %d", H, W, C);
+    return encode_with_plan(ctx, pl, d_img, n, level, d_out, stride, d_sizes);
+}
+
+// Indexed-colour files (PNG colour type 3) of images whose pixels are palette indices packed `depth` bits each
+// (png_index_depth(ncolors); leftmost pixel in the high-order bits, rows of ceil(W * depth / 8) bytes).  What the colour
+// masks of a class map are: n_classes + 1 distinct colours, i.e. 2 bits per pixel for the default colour map instead of
+// 24 -- a twelfth of the bytes in every pass of the encoder, in the file, across PCIe and on disk; any PNG reader
+// expands the palette to the same RGB pixels.
+int launch_png_encode_indexed(pcs_ctx* ctx, const uint8_t* d_idx, int n, int H, int W, const uint8_t* h_palette, int ncolors, int level,
+                              uint8_t* d_out, size_t stride, unsigned long long* d_sizes) {
+    PngPlan pl{};
+    if (n <= 0 || ncolors < 1 || ncolors > 256 || !make_plan(H, W, 1, pl, png_index_depth(ncolors), h_palette, ncolors))
+        return set_err(ctx, PCS_ERR_ARG, "png_encode_indexed: unsupported shape %d x %d with %d colours", H, W, ncolors);
+    return encode_with_plan(ctx, pl, d_idx, n, level, d_out, stride, d_sizes);
+}
+
+// Palette indices of the three masks of generate_output_masks (lib/output.py:44-60) straight from the class map and
+// data.binary, packed for launch_png_encode_indexed: palette = the n_lut LUT colours + black at index n_lut;
+//   color    : label (labels outside the LUT -> black, like ColorMap.to_rgb_array)
+//   overlay  : black where (uint8)(1 - binary) == 0      inverted : black where binary == 0
+// out: [3][n][H][Wb] with Wb = ceil(W * depth / 8).  One thread per output byte of all three kinds.
+__global__ void __launch_bounds__(256) mask_index_kernel(const uint8_t* __restrict__ labels, const uint8_t* __restrict__ binary, int n, int H,
+                                                         int W, int n_lut, int depth, int Wb, uint8_t* __restrict__ out) {
+    const size_t total = (size_t)n * H * Wb, plane = total;
+    const int ppb = 8 / depth;
+    for (size_t t = (size_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (size_t)gridDim.x * 256) {
+        const size_t rowi = t / Wb;
+        const int xb = (int)(t - rowi * Wb);
+        const uint8_t* lrow = labels + rowi * W;
+        const uint8_t* brow = binary + rowi * W;
+        uint32_t c = 0, o = 0, v = 0;
+        for (int k = 0; k < ppb; ++k) {
+            const int x = xb * ppb + k;
+            uint32_t ic = 0, io = 0, iv = 0;
+            if (x < W) {
+                const uint32_t lab = __ldg(lrow + x), bin = __ldg(brow + x);
+                ic = lab < (uint32_t)n_lut ? lab : (uint32_t)n_lut;
+                io = ((uint8_t)(1u - bin) != 0) ? ic : (uint32_t)n_lut;
+                iv = bin != 0 ? ic : (uint32_t)n_lut;
+            }
+            const int sh = 8 - depth * (k + 1);
+            c |= ic << sh; o |= io << sh; v |= iv << sh;
+        }
+        out[t] = (uint8_t)c; out[plane + t] = (uint8_t)o; out[2 * plane + t] = (uint8_t)v;
+    }
+}
+
+int launch_mask_indices(pcs_ctx* ctx, const uint8_t* d_labels, const uint8_t* d_binary, int n, int H, int W, int n_lut, uint8_t* d_out) {
+    if (n <= 0 || H <= 0 || W <= 0 || n_lut < 0 || n_lut > 255) return set_err(ctx, PCS_ERR_ARG, "mask_indices: bad argument");
+    const int depth = png_index_depth(n_lut + 1), Wb = (W * depth + 7) / 8;
+    const size_t total = (size_t)n * H * Wb;
+    const unsigned blocks = (unsigned)std::min<size_t>((size_t)ctx->sm_count * 16, (total + 255) / 256);
+    mask_index_kernel<<<blocks, 256, 0, ctx->stream>>>(d_labels, d_binary, n, H, W, n_lut, depth, Wb, d_out);
+    PCS_LAUNCH_CHECK(ctx, "mask_index_kernel");
     return PCS_OK;
 }
 

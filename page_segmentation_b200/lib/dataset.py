@@ -14,6 +14,7 @@ import numpy as np
 import os
 
 from .colors import ColorMap
+from ..lazy import DeviceArray as _DeviceArray
 
 
 @dataclass
@@ -29,6 +30,16 @@ class SingleData:
     original_shape: Tuple[int, int] = None
     output_path: Optional[str] = None
     user_data: Any = None
+
+    def __getattribute__(self, name):
+        """Same fields as dataset.py:17-29.  The loader leaves `image` / `binary` / `orig_binary` on the device
+        (lazy.DeviceArray) for the predictor and the output stage; a caller reading the attribute gets a real numpy
+        array (one device-to-host copy at the first access), so code written against the reference - cv2 calls
+        included - sees what it expects.  The device stages read the fields through lazy.peek."""
+        v = object.__getattribute__(self, name)
+        if type(v) is _DeviceArray:
+            return v.to_host()
+        return v
 
 
 @dataclass
@@ -124,38 +135,74 @@ class DatasetLoader:
         self.color_map = color_map
         self.max_width = max_width
 
-    def load_images(self, dataset_file_entry: SingleData) -> SingleData:
-        """dataset.py:160-191, including its quirk that the binary page is
-        derived from `image` / `image_path` (attribute name 'image', :172)."""
-        def load_cached(data: SingleData, attr: str, loader: Callable[[str], np.ndarray]) -> np.ndarray:
-            file = getattr(data, attr)
-            if file is not None:
-                return file
-            return loader(getattr(data, attr + '_path'))
+    def _page_job(self, entry: SingleData):
+        """The page of one entry (dataset.py:160-172) as a staging job.  The reference derives the binary page from the
+        'image' attribute as well (:172): an in-memory `image` IS the binary page; a file is read once and thresholded,
+        and goes up as one plane when the scan is strictly two-level (imread_bin changes nothing then)."""
+        from ..pipeline import PageJob
+        if entry.image is not None:
+            img = np.asarray(entry.image)           # (an entry that was loaded before: its host copy)
+            grey, binary = (lambda a=img: a), None
+        else:
+            img = imread(entry.image_path, as_gray=True)
+            bin_ = np.where(img > 127, 255, 0).astype(np.uint8)             # imread_bin of the same file
+            grey = lambda a=img: a
+            binary = None if np.array_equal(bin_, img) else (lambda a=bin_: a)
+        if img.ndim != 2:
+            raise ValueError("prepare_images expects 2-D image and binary of equal shape")
+        if img.dtype != np.uint8:
+            raise NotImplementedError("the device preprocess takes uint8 grey pages (as imread(as_gray=True) of 8-bit scans yields)")
+        scale = self.target_line_height / entry.line_height_px
+        return PageJob(grey, binary, img.shape[0], img.shape[1], scale, self.max_width), img
 
-        img = load_cached(dataset_file_entry, 'image', lambda path: imread(path, as_gray=True))
-        original_shape = img.shape
-        bin = load_cached(dataset_file_entry, 'image', lambda path: imread_bin(path, True))
-        img, bin, orig_bin = prepare_images(img, bin, self.target_line_height, dataset_file_entry.line_height_px,
-                                            self.max_width, keep_orig_bin=True)
-        scaled_shape = img.shape
+    def _finish_entry(self, entry: SingleData, job, img: np.ndarray, device: int) -> SingleData:
+        from ..lazy import DeviceArray
+        from ..pipeline import staged_fields
+        image, binary = staged_fields(job, device)
+        bin_src = job.binary() if job.binary is not None else img
+
+        def orig_binary():
+            from ..runtime import prepare_images_tensors
+            return prepare_images_tensors(img, bin_src, self.target_line_height, entry.line_height_px, self.max_width,
+                                          keep_orig_bin=True, device=device)[2]
+
         if not self.prediction:
             from .util import preserving_resize
-            mask = load_cached(dataset_file_entry, 'mask', self.color_map.imread_labels)
-            mask = preserving_resize(mask, scaled_shape)
-            assert (mask.shape == img.shape)
-            dataset_file_entry.mask = mask.astype(np.uint8)
-        dataset_file_entry.binary = bin
-        dataset_file_entry.orig_binary = orig_bin
-        dataset_file_entry.image = img
-        dataset_file_entry.original_shape = original_shape
-        return dataset_file_entry
+            mask = entry.mask if entry.mask is not None else self.color_map.imread_labels(entry.mask_path)
+            mask = preserving_resize(mask, image.shape)
+            assert (mask.shape == image.shape)
+            entry.mask = mask.astype(np.uint8)
+        entry.binary = binary
+        entry.orig_binary = DeviceArray(img.shape, np.uint8, orig_binary, device, pinned=False)
+        entry.image = image
+        entry.original_shape = img.shape
+        return entry
+
+    def load_images(self, dataset_file_entry: SingleData) -> SingleData:
+        """dataset.py:160-191, including its quirk that the binary page is derived from `image` / `image_path`
+        (attribute name 'image', :172).  prepare_images runs on the device; `image`, `binary` and `orig_binary` come back
+        as DeviceArrays (lazy.py): ndarray stand-ins that stay on the GPU for the predictor and turn into host arrays
+        the first time the caller looks at their contents."""
+        from ..pipeline import stager
+        from ..runtime import default_device
+        device = default_device()
+        job, img = self._page_job(dataset_file_entry)
+        stager(device).submit([job])
+        return self._finish_entry(dataset_file_entry, job, img, device)
 
     def load_data(self, all_dataset_files) -> Dataset:
-        """dataset.py:193-198.  The reference fans pages out to a 12-process pool
-        because its rescale is CPU bound; here the rescale is a GPU kernel, so
-        pages are processed in order on the caller's device."""
-        out = [self.load_images(d) for d in all_dataset_files]
+        """dataset.py:193-198.  The reference fans pages out to a 12-process pool because decoding and rescaling are CPU
+        work; here files are decoded by a thread pool, pages are staged to the device in chunks by a background stager
+        (pipeline.PageStager: page-locked ring, one upload + one batched prepare_images per chunk) and this call returns
+        without waiting for them -- the Predictor picks every chunk up when it is ready."""
+        from ..pipeline import host_pool, stager
+        from ..runtime import default_device
+        device = default_device()
+        entries = list(all_dataset_files)
+        need_files = [e for e in entries if e.image is None]
+        prepared = list(host_pool().map(self._page_job, entries)) if need_files else [self._page_job(e) for e in entries]
+        stager(device).submit([job for job, _ in prepared])
+        out = [self._finish_entry(e, job, img, device) for e, (job, img) in zip(entries, prepared)]
         return Dataset(out, self.color_map)
 
     def load_data_from_json(self, files, type) -> Dataset:

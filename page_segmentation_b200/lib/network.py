@@ -108,18 +108,25 @@ class Network:
         """network.py:248-260 -> (logit f32 HWC, prob f32 HWC, pred int64 HW)."""
         return self._predict(data, want_logits=True)
 
+    def _device_image(self, data: SingleData, ctx):
+        from ..lazy import DeviceArray, device_tensor_of, peek
+        image = peek(data, "image")
+        if not isinstance(image, DeviceArray):
+            image = np.ascontiguousarray(image)
+        if image.dtype != np.uint8 or image.ndim != 2:
+            raise ValueError("data.image must be a 2-D uint8 array (DatasetLoader output)")
+        return device_tensor_of(image, ctx.device)
+
     def _predict(self, data: SingleData, want_logits: bool):
         """`want_logits=False` (Predictor: predictor.py:33 drops the logits at once) skips their 12 bytes per pixel of
         device-to-host traffic and returns None in their place."""
         import torch
         from ..runtime import results_to_host
         ctx = self._context()
-        image = np.ascontiguousarray(data.image)
-        if image.dtype != np.uint8 or image.ndim != 2:
-            raise ValueError("data.image must be a 2-D uint8 array (DatasetLoader output)")
-        h, w = image.shape
-        dev = f"cuda:{ctx.device}"
-        d_image = torch.from_numpy(image).to(dev)
+        ctx.use_torch_stream()
+        d_image = self._device_image(data, ctx)
+        h, w = d_image.shape
+        dev = d_image.device
         d_labels = torch.empty((h, w), dtype=torch.uint8, device=dev)
         d_logits = torch.empty((h, w, self.n_classes), dtype=torch.float32, device=dev) if want_logits else None
         d_prob = torch.empty((h, w, self.n_classes), dtype=torch.float32, device=dev)
@@ -127,6 +134,20 @@ class Network:
         # np.argmax yields int64; widened on the device, not by a host pass
         logit, prob, pred = results_to_host(d_logits, d_prob, d_labels.to(torch.int64))
         return logit, prob, pred
+
+    def _probabilities_device(self, data: SingleData):
+        """softmax(logits) of one page as an (H, W, n_classes) float32 device tensor: what a lazily evaluated
+        `Prediction.probabilities` runs when somebody reads it (the batched predict path does not keep 12 bytes per
+        pixel per page around for callers that never look)."""
+        import torch
+        ctx = self._context()
+        ctx.use_torch_stream()
+        d_image = self._device_image(data, ctx)
+        h, w = d_image.shape
+        d_labels = torch.empty((h, w), dtype=torch.uint8, device=d_image.device)
+        d_prob = torch.empty((h, w, self.n_classes), dtype=torch.float32, device=d_image.device)
+        ctx.forward(d_image, None, 1, h, w, d_labels, None, d_prob)
+        return d_prob
 
     def predict_labels_device(self, d_image, d_labels):
         """Device-resident variant: (n,H,W) uint8 CUDA tensors in/out."""

@@ -21,20 +21,36 @@ class Masks:
     fg_color_mask: Optional[np.ndarray] = None
 
 
-def _masks_on_device(data: SingleData, pred: np.ndarray, color_map: ColorMap):
+def _class_map_and_binary_on_device(data: SingleData, pred):
+    """(ctx, class map, data.binary) as contiguous (H, W) uint8 device tensors.  `pred` / `data.binary` that are still on
+    the device (lazy.DeviceArray, what Predictor.predict and DatasetLoader hand out) are used where they are."""
+    from ..lazy import DeviceArray, device_tensor_of, peek
+    from ..runtime import get_context
+    ctx = get_context()
+    h, w = pred.shape
+    from .postprocess import _pred_to_device
+    if isinstance(pred, DeviceArray) and pred.on_device:
+        d_pred = pred.device_tensor()
+    else:
+        d_pred, _ = _pred_to_device(np.asarray(pred), ctx.device)   # int64 from np.argmax: checked and narrowed on the device
+    binary = peek(data, "binary")
+    if not isinstance(binary, DeviceArray):
+        binary = np.asarray(binary)
+        if binary.dtype != np.uint8 and binary.dtype != np.bool_:
+            binary = (binary != 0)
+    d_bin = device_tensor_of(binary, ctx.device)
+    if tuple(d_bin.shape) != (h, w):
+        raise ValueError(f"data.binary {tuple(d_bin.shape)} and the class map {(h, w)} differ in shape")
+    return ctx, d_pred.contiguous(), d_bin.contiguous()
+
+
+def _masks_on_device(data: SingleData, pred, color_map: ColorMap):
     """The three masks as one (3, H, W, 3) uint8 device tensor: color, overlay, inverted."""
     import torch
-    from ..runtime import get_context, to_device_u8
-    ctx = get_context()
-    pred = np.asarray(pred)
-    h, w = pred.shape
-    lut = color_map.lut()
-    from .postprocess import _pred_to_device
-    binary = np.asarray(data.binary)
-    d_pred, _ = _pred_to_device(pred, ctx.device)        # int64 from Predictor.predict: checked and narrowed on the device
-    d_bin = to_device_u8(binary, ctx.device)
+    ctx, d_pred, d_bin = _class_map_and_binary_on_device(data, pred)
+    h, w = d_pred.shape
     outs = torch.empty((3, h, w, 3), dtype=torch.uint8, device=d_pred.device)
-    ctx.masks(d_pred, d_bin, 1, h, w, lut, outs[0], outs[1], outs[2])
+    ctx.masks(d_pred, d_bin, 1, h, w, color_map.lut(), outs[0], outs[1], outs[2])
     return ctx, outs
 
 
@@ -78,8 +94,10 @@ def generate_output_masks(data: SingleData, pred: np.ndarray, color_map: ColorMa
 
 
 def output_data(output_dir, pred, data: SingleData, color_map):
-    """output.py:20-41.  `.png` targets (the frontend's default) are encoded on the device (encode_png) and written
-    with one file write each; other extensions go through cv2.imwrite in place of skimage.io.imsave."""
+    """output.py:20-41.  `.png` targets (the frontend's default): ONE library call per page (pcs_output_pages) builds the
+    three masks and their PNG files on the device; the library's worker threads write them, so the call returns before
+    the files exist -- `flush_outputs()` waits for them (it also runs at interpreter exit; PCSEG_OUTPUT_ASYNC=0 makes
+    every call wait).  Other extensions go through cv2.imwrite in place of skimage.io.imsave."""
     if len(pred.shape) == 3:
         assert (pred.shape[0] == 1)
         pred = pred[0]
@@ -94,17 +112,27 @@ def output_data(output_dir, pred, data: SingleData, color_map):
     else:
         filename = os.path.basename(data.image_path)
     categories = ("color", "overlay", "inverted")
-    _, d_masks = _masks_on_device(data, pred, color_map)
     if filename.lower().endswith(".png"):
-        for category, blob in zip(categories, encode_png(d_masks)):
-            with open(os.path.join(output_dir, category, filename), "wb") as f:
-                f.write(blob)
+        from .. import pipeline
+        ctx, d_pred, d_bin = _class_map_and_binary_on_device(data, pred)
+        h, w = d_pred.shape
+        ctx.output_pages(d_pred, d_bin, 1, h, w, color_map.lut(), [os.path.join(output_dir, c, filename) for c in categories])
+        if not pipeline.OUTPUT_ASYNC:
+            ctx.output_flush()
         return
+    _, d_masks = _masks_on_device(data, pred, color_map)
     import cv2
     for category, img in zip(categories, d_masks.cpu().numpy()):
         path = os.path.join(output_dir, category, filename)
         if not cv2.imwrite(path, np.ascontiguousarray(img[..., ::-1])):
             raise IOError(f"could not write {path}")
+
+
+def flush_outputs():
+    """Waits until every PNG file handed to output_data is on disk (they are written by a background thread; also runs
+    at interpreter exit).  Not part of the reference API, whose output_data writes synchronously."""
+    from ..pipeline import flush_outputs as f
+    f()
 
 
 def scale_to_original_shape(data: SingleData, pred):

@@ -35,22 +35,38 @@ def _store(pred: np.ndarray, d_pred) -> np.ndarray:
     return pred
 
 
-def vote_connected_component_class(pred: np.ndarray, data: SingleData) -> np.ndarray:
-    """postprocess.py:9-26; like the reference, writes into `pred` and returns it."""
+def _binary_to_device(data: SingleData, device):
     import torch
-    from ..runtime import get_context
-    ctx = get_context()
-    h, w = pred.shape
-    d_pred, n_classes = _pred_to_device(pred, ctx.device)
+    from ..lazy import DeviceArray, device_tensor_of, peek
+    if isinstance(peek(data, "binary"), DeviceArray):
+        return device_tensor_of(peek(data, "binary"), device)
     binary = np.ascontiguousarray(data.binary)
     if binary.dtype == np.bool_:
         binary = binary.view(np.uint8)
-    if binary.dtype == np.uint8:
-        d_bin = torch.from_numpy(binary).to(d_pred.device)            # the kernels take non-zero as foreground
-    else:
-        d_bin = torch.from_numpy(np.ascontiguousarray(binary != 0).view(np.uint8)).to(d_pred.device)
+    if binary.dtype != np.uint8:
+        binary = np.ascontiguousarray(binary != 0).view(np.uint8)     # the kernels take non-zero as foreground
+    return torch.from_numpy(binary).to(device)
+
+
+def _lazy_pred(pred):
+    """(device tensor uint8, n_classes) of a class map that is still on the device, else None."""
+    from ..lazy import DeviceArray
+    if isinstance(pred, DeviceArray) and pred.on_device:
+        t = pred.device_tensor()
+        return t, (int(t.max()) + 1 if t.numel() else 1)
+    return None
+
+
+def vote_connected_component_class(pred: np.ndarray, data: SingleData) -> np.ndarray:
+    """postprocess.py:9-26; like the reference, writes into `pred` and returns it."""
+    from ..runtime import get_context
+    ctx = get_context()
+    h, w = pred.shape
+    lazy = _lazy_pred(pred)
+    d_pred, n_classes = lazy if lazy else _pred_to_device(np.asarray(pred), ctx.device)
+    d_bin = _binary_to_device(data, d_pred.device)
     ctx.cc_majority(d_pred, d_bin, 1, h, w, n_classes)
-    return _store(pred, d_pred)
+    return pred if lazy else _store(np.asarray(pred), d_pred)
 
 
 def add_bounding_boxes(pred: np.ndarray, data: SingleData) -> np.ndarray:
@@ -60,10 +76,14 @@ def add_bounding_boxes(pred: np.ndarray, data: SingleData) -> np.ndarray:
     from ..runtime import get_context
     ctx = get_context()
     h, w = pred.shape
-    d_pred, n_classes = _pred_to_device(pred, ctx.device)
+    lazy = _lazy_pred(pred)
+    d_pred, n_classes = lazy if lazy else _pred_to_device(np.asarray(pred), ctx.device)
     d_out = torch.empty((h, w), dtype=torch.uint8, device=d_pred.device)
     ctx.bounding_boxes(d_pred, 1, h, w, n_classes, d_out)
-    return _store(np.empty_like(pred), d_out)
+    if lazy:
+        from ..lazy import DeviceArray
+        return DeviceArray((h, w), pred.dtype, (lambda t=d_out: t), ctx.device)
+    return _store(np.empty_like(np.asarray(pred)), d_out)
 
 
 def class_components(pred: np.ndarray, n_classes: int = None, max_components: int = 65536):
@@ -75,7 +95,7 @@ def class_components(pred: np.ndarray, n_classes: int = None, max_components: in
     from ..runtime import get_context
     ctx = get_context()
     h, w = pred.shape
-    d_pred, seen = _pred_to_device(pred, ctx.device)
+    d_pred, seen = _lazy_pred(pred) or _pred_to_device(np.asarray(pred), ctx.device)
     n_classes = seen if n_classes is None else int(n_classes)
     d_stats = torch.empty((1, n_classes, max_components, 5), dtype=torch.int32, device=d_pred.device)
     d_ncomp = torch.empty((1, n_classes), dtype=torch.int32, device=d_pred.device)

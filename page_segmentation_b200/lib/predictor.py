@@ -26,9 +26,10 @@ class Predictor:
             os.makedirs(os.path.join(output_dir, "inverted"), exist_ok=True)
 
     def predict(self, dataset: Dataset) -> Generator[Prediction, None, None]:
-        for data in dataset.data:
-            prediction = self.predict_single(data)
-            yield prediction
+        """predictor.py:27-30.  Same generator contract; underneath, consecutive pages of one size run as one batch with
+        look-ahead and the results stay on the device until read (pipeline.predict_stream)."""
+        from ..pipeline import predict_stream
+        return predict_stream(self, dataset.data)
 
     def _post(self, data: SingleData, pred):
         if self.settings.high_res_output:
@@ -45,9 +46,13 @@ class Predictor:
         return fast(data, want_logits=False) if fast else self.network.predict_single_data(data)
 
     def predict_single(self, data: SingleData) -> Prediction:
-        logit, prob, pred = self._forward(data)
-        data, pred = self._post(data, pred)
-        return Prediction(pred, prob, data)
+        """predictor.py:32-42."""
+        if self.settings.high_res_output or not hasattr(self.network, "_context"):
+            logit, prob, pred = self._forward(data)
+            data, pred = self._post(data, pred)
+            return Prediction(pred, prob, data)
+        from ..pipeline import predict_stream
+        return next(iter(predict_stream(self, [data])))
 
     def predict_masks(self, data: SingleData) -> Masks:
         logit, prob, pred = self._forward(data)

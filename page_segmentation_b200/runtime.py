@@ -7,7 +7,6 @@ torch.distributed); all arithmetic is in libpcseg_b200.so.
 from __future__ import annotations
 
 import os
-import time
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -85,102 +84,29 @@ def to_host(t) -> np.ndarray:
     return results_to_host(t, site=None)[0]
 
 
-# Page-sized results (probabilities, class map, masks) of the per-page API.  A pageable copy of a page's 19 MB costs
-# ~9 ms (first-touch faults of a fresh block plus the driver's bounce buffers); page-locking a NEW block per result
-# costs more still.  torch's caching host allocator keeps freed page-locked blocks, so a caller that consumes a
-# Prediction and drops it (the reference's front ends: predict -> write masks -> next page) gets the same few blocks
-# back and the copy runs at PCIe speed (measured: 1 070 instead of 105 pages/s through Predictor.predict).  A caller
-# that keeps every result makes each allocation a cudaHostAlloc; that shows as a slow allocation, and after
-# `_PIN_MISSES` slow ones in a row the pageable copy is used for a while (doubling each time it happens again, back to
-# page-locked at the first fast allocation).  The arrays are ordinary numpy arrays the caller owns either way.
-_PIN_MISSES = 10
-_PIN_SLOW_S = 3e-4          # a cache hit takes ~10 us, a cudaHostAlloc of a page-sized block milliseconds
-_PIN_ENABLED = os.environ.get("PCSEG_PINNED_RESULTS", "1") != "0"
-_clock = time.perf_counter
+# Page-sized results (probabilities, class map, masks) of the per-page API land in blocks of an explicit, bounded pool of
+# page-locked memory (lazy.PinnedPool): a block comes back when the caller drops the array, so a caller that consumes a
+# Prediction and moves on (the reference's front ends: predict -> write masks -> next page) copies at PCIe speed; a
+# caller that keeps every result exhausts the pool's budget and gets ordinary pageable arrays, filled through one
+# page-locked bounce buffer.  Datasets are kept by design (DatasetLoader.load_data returns all pages), so their
+# host copies are pageable unless PCSEG_PINNED_LOAD=1.
 _PIN_LOAD = os.environ.get("PCSEG_PINNED_LOAD", "0") == "1"      # page-by-page loaders that drop each page may opt in
-_pin_sites: Dict[str, dict] = {}        # one state per call site: a dataset that is kept must not slow the predictions down
-
-
-def _pinned_empty(torch, shape, dtype, site):
-    if not _PIN_ENABLED or site is None:
-        return None
-    st = _pin_sites.setdefault(site, {"misses": 0, "skip": 0, "pause": 32})
-    if st["skip"] > 0:
-        st["skip"] -= 1
-        return None
-    t0 = _clock()
-    h = torch.empty(shape, dtype=dtype, pin_memory=True)
-    if _clock() - t0 > _PIN_SLOW_S:
-        st["misses"] += 1
-        if st["misses"] >= _PIN_MISSES:
-            st["pause"] = min(st["pause"] * 2, 8192)
-            st["skip"], st["misses"] = st["pause"], _PIN_MISSES // 2
-    else:
-        st["misses"], st["pause"] = 0, 32
-    return h
-
-
-_staging = {"buf": None, "lock": None}
-
-
-def _staging_buffer(torch, nbytes: int):
-    """One page-locked bounce buffer per process (grow-only) for results that end in fresh pageable arrays."""
-    buf = _staging["buf"]
-    if buf is None or buf.numel() < nbytes:
-        _staging["buf"] = buf = torch.empty((max(nbytes * 5 // 4, 32 << 20),), dtype=torch.uint8, pin_memory=True)
-    return buf
 
 
 def results_to_host(*tensors, site: Optional[str] = "predict"):
     """Device tensors (None allowed) -> fresh numpy arrays the caller owns, all copies issued before one
-    synchronisation.  Page-locked destination blocks where the policy above allows; otherwise the data crosses PCIe into
-    the process's page-locked bounce buffer at full speed and is copied into a fresh pageable array from there (the
-    driver's own pageable path manages ~2 GB/s into untouched memory)."""
-    import threading
-    torch = _torch()
-    if _staging["lock"] is None:
-        _staging["lock"] = threading.Lock()
-    outs, stream, bounce = [], None, []
-    for t in tensors:
-        if t is None:
-            outs.append(None)
-        elif t.numel() < (1 << 16):
-            outs.append(t.cpu().numpy())
-        else:
-            t = t.contiguous()
-            stream = torch.cuda.current_stream(t.device)
-            h = _pinned_empty(torch, t.shape, t.dtype, site)
-            if h is not None:
-                h.copy_(t, non_blocking=True)
-                outs.append(h.numpy())
-            else:
-                bounce.append((len(outs), t))
-                outs.append(None)
-    if not bounce:
-        if stream is not None:
-            stream.synchronize()
-        return outs
-    with _staging["lock"]:
-        sizes = [(t.numel() * t.element_size() + 255) // 256 * 256 for _, t in bounce]
-        buf = _staging_buffer(torch, sum(sizes))
-        views, off = [], 0
-        for (i, t), size in zip(bounce, sizes):
-            v = buf[off:off + t.numel() * t.element_size()].view(t.dtype).view(t.shape)
-            v.copy_(t, non_blocking=True)
-            views.append((i, v))
-            off += size
-        stream.synchronize()
-        for i, v in views:
-            outs[i] = np.array(v.numpy())                  # a copy in fresh memory: the bounce buffer is reused
-    return outs
+    synchronisation (lazy.tensors_to_host).  `site=None`: pageable destinations."""
+    _torch()
+    from .lazy import tensors_to_host
+    return tensors_to_host(tensors, pinned=site is not None)
 
 
 # ---------------------------------------------------------------------------
 # single-page helpers behind the reference-named functions
 # ---------------------------------------------------------------------------
-def prepare_images_device(image: np.ndarray, binary: np.ndarray, target_line_height: int, line_height_px: int,
-                          max_width: Optional[int] = None, keep_orig_bin: bool = False, device: Optional[int] = None):
-    """dataset.py:131-150 on the GPU; returns numpy uint8 arrays like the reference."""
+def prepare_images_tensors(image: np.ndarray, binary: np.ndarray, target_line_height: int, line_height_px: int,
+                           max_width: Optional[int] = None, keep_orig_bin: bool = False, device: Optional[int] = None):
+    """dataset.py:131-150 on the GPU -> (d_image, d_binary, d_orig_binary | None) uint8 device tensors."""
     torch = _torch()
     ctx = get_context(device)
     dev = ctx.device
@@ -203,12 +129,20 @@ def prepare_images_device(image: np.ndarray, binary: np.ndarray, target_line_hei
     d_image = torch.empty((Hs, Ws), dtype=torch.uint8, device=d_grey.device)
     d_binary = torch.empty((Hs, Ws), dtype=torch.uint8, device=d_grey.device)
     d_orig = torch.empty((H, W), dtype=torch.uint8, device=d_grey.device) if keep_orig_bin else None
-    if second:
-        ctx.preprocess_max_width(d_grey, d_bin, 1, H, W, H1, W1, Hs, Ws, d_image, d_binary, d_orig)
-    else:
-        ctx.preprocess(d_grey, d_bin, 1, H, W, Hs, Ws, d_image, d_binary, d_orig)
-    # datasets are kept (DatasetLoader.load_data returns all pages), and page-locking a fresh 8.7 MB block per page
-    # costs ~60 ms (measured: 38 instead of 170 pages/s), so these results are pageable unless the caller opts in
+    from .pipeline import _preprocess_lock
+    with _preprocess_lock:
+        if second:
+            ctx.preprocess_max_width(d_grey, d_bin, 1, H, W, H1, W1, Hs, Ws, d_image, d_binary, d_orig)
+        else:
+            ctx.preprocess(d_grey, d_bin, 1, H, W, Hs, Ws, d_image, d_binary, d_orig)
+    return d_image, d_binary, d_orig
+
+
+def prepare_images_device(image: np.ndarray, binary: np.ndarray, target_line_height: int, line_height_px: int,
+                          max_width: Optional[int] = None, keep_orig_bin: bool = False, device: Optional[int] = None):
+    """dataset.py:131-150 on the GPU; returns numpy uint8 arrays like the reference."""
+    d_image, d_binary, d_orig = prepare_images_tensors(image, binary, target_line_height, line_height_px, max_width,
+                                                       keep_orig_bin, device)
     img, bin_, orig = results_to_host(d_image, d_binary, d_orig, site="load" if _PIN_LOAD else None)
     if keep_orig_bin:
         return img, bin_, orig

@@ -65,11 +65,11 @@ def test_predictor_predict_and_masks_with_postprocessing(ctx):
 
 
 def test_results_are_owned_by_the_caller(ctx):
-    """Results travel through recycled page-locked blocks (runtime.results_to_host): an array a caller keeps must
-    never be rewritten by a later call, arrays that are dropped may be recycled, and the pageable path (forced, or
-    chosen after a run of slow allocations) gives the same values."""
+    """Host copies of results come from a bounded pool of page-locked blocks (lazy.PinnedPool): an array a caller keeps
+    must never be rewritten by a later call, blocks of dropped arrays go round, and the pageable path (pool exhausted
+    or disabled) gives the same values."""
     import gc
-    from page_segmentation_b200 import runtime
+    from page_segmentation_b200 import lazy
     from page_segmentation_b200.lib.network import Network
     from page_segmentation_b200.lib.predictor import Predictor
     from page_segmentation_b200.lib.predictor_data import PredictSettings
@@ -78,14 +78,18 @@ def test_results_are_owned_by_the_caller(ctx):
     pred = Predictor(PredictSettings(n_classes=3, color_map=DEFAULT_COLOR_MAP), network=net)
     datas = [_loaded(s, h=1350, w=990)[1] for s in (5, 6, 7)]        # large enough for the page-locked path
     kept = [pred.predict_single(d) for d in datas]
+    assert all(lazy.is_lazy(p.labels) and p.labels.dtype == np.int64 and p.probabilities.dtype == np.float32 for p in kept)
     snap = [(p.labels.copy(), p.probabilities.copy()) for p in kept]
+    assert not any(lazy.is_lazy(p.labels) for p in kept)
     assert len({p.labels.ctypes.data for p in kept}) == 3 and len({p.probabilities.ctypes.data for p in kept}) == 3
     for _ in range(3):                                         # dropped results: their blocks go round
         for d in datas:
             p = pred.predict_single(d)
+            q = np.asarray(p.labels), np.asarray(p.probabilities)
             m = pred.predict_masks(d)
-            del p, m
+            del p, q, m
         gc.collect()
+    assert lazy.pinned_pool().stats["hits"] > 0
     for p, (l, q), d in zip(kept, snap, datas):
         np.testing.assert_array_equal(p.labels, l)
         np.testing.assert_array_equal(p.probabilities, q)
@@ -93,14 +97,75 @@ def test_results_are_owned_by_the_caller(ctx):
         again = pred.predict_single(d)
         np.testing.assert_array_equal(again.labels, l)
         np.testing.assert_array_equal(again.probabilities, q)
-    saved = runtime._PIN_ENABLED
+        logit, prob, raw = net.predict_single_data(d)          # the eager reference-named call gives the same
+        np.testing.assert_array_equal(raw, l)
+        np.testing.assert_array_equal(prob, q)
+    saved = lazy._ENABLED
     try:
-        runtime._PIN_ENABLED = False                           # the pageable copy
+        lazy._ENABLED = False                                  # the pageable copy
         p = pred.predict_single(datas[0])
         np.testing.assert_array_equal(p.labels, snap[0][0])
         np.testing.assert_array_equal(p.probabilities, snap[0][1])
     finally:
-        runtime._PIN_ENABLED = saved
+        lazy._ENABLED = saved
+
+
+def test_lazy_flow_matches_page_by_page(ctx, tmp_path):
+    """load_data -> predict (+ cc_majority) -> output_data with everything staying on the device (pipeline.py) against the
+    same pages taken one at a time through host arrays and the oracle: pages of two sizes (chunks break at a size
+    change), more pages than one chunk, a foreign post-processor (runs on host arrays) after the registry's own."""
+    import cv2
+    from page_segmentation_b200 import lazy
+    from page_segmentation_b200.lib.dataset import Dataset, DatasetLoader, SingleData
+    from page_segmentation_b200.lib.network import Network
+    from page_segmentation_b200.lib.output import flush_outputs, output_data
+    from page_segmentation_b200.lib.postprocess import find_postprocessor
+    from page_segmentation_b200.lib.predictor import Predictor
+    from page_segmentation_b200.lib.predictor_data import PredictSettings
+    W = synth.make_weights("fcn_skip", 3, seed=4)
+    net = Network("Predict", n_classes=3, weights=W, precision="fp16")
+    shapes = [(420, 300)] * 11 + [(390, 330)] * 2 + [(420, 300)]
+    pages = [synth.make_page(40 + i, h, w, 18) for i, (h, w) in enumerate(shapes)]
+    entries = [SingleData(image=p, line_height_px=18, output_path=f"p{i:02d}.png") for i, p in enumerate(pages)]
+    loader = DatasetLoader(6, DEFAULT_COLOR_MAP, prediction=True)
+    ds = loader.load_data(entries)
+    assert isinstance(ds, Dataset) and len(ds) == len(pages)
+    assert all(lazy.is_lazy(lazy.peek(d, "image")) and lazy.is_lazy(lazy.peek(d, "binary")) and d.original_shape == s
+               for d, s in zip(ds.data, shapes))
+    seen = []
+
+    def foreign(pred, data):
+        assert isinstance(pred, np.ndarray) and pred.dtype == np.int64
+        seen.append(pred.shape)
+        return pred
+
+    out = str(tmp_path)
+    settings = PredictSettings(n_classes=3, color_map=DEFAULT_COLOR_MAP, output=out, post_process=[find_postprocessor("cc_majority")])
+    predictor = Predictor(settings, network=net)
+    preds = []
+    for p in predictor.predict(ds):
+        assert lazy.is_lazy(p.labels)
+        output_data(out, p.labels, p.data, DEFAULT_COLOR_MAP)
+        preds.append(p)
+    flush_outputs()
+    for i, (page, p) in enumerate(zip(pages, preds)):
+        eimg, ebin = opipe.prepare_images(page, page, 6, 18)
+        np.testing.assert_array_equal(p.data.image, eimg)
+        np.testing.assert_array_equal(p.data.binary, ebin)
+        _, _, raw = net.predict_single_data(SingleData(image=eimg))
+        exp = opipe.vote_connected_component_class(raw.copy(), ebin)
+        np.testing.assert_array_equal(p.labels, exp)
+        c, o, inv, _ = opipe.generate_output_masks(ebin, exp, LUT)
+        for cat, want in (("color", c), ("overlay", o), ("inverted", inv)):
+            got = cv2.imread(f"{out}/{cat}/p{i:02d}.png", cv2.IMREAD_COLOR)[..., ::-1]
+            np.testing.assert_array_equal(got, want)
+    settings2 = PredictSettings(n_classes=3, color_map=DEFAULT_COLOR_MAP, post_process=[find_postprocessor("cc_majority"), foreign])
+    ds2 = loader.load_data([SingleData(image=p, line_height_px=18) for p in pages[:3]])
+    for p, q in zip(Predictor(settings2, network=net).predict(ds2), preds):
+        assert isinstance(p.labels, np.ndarray)
+        np.testing.assert_array_equal(p.labels, q.labels)
+    assert len(seen) == 3
+    np.testing.assert_array_equal(ds2.data[0].orig_binary, (pages[0] == 0).astype(np.uint8))      # lazily, on request
 
 
 def test_high_res_output(ctx):
@@ -121,7 +186,7 @@ def test_high_res_output(ctx):
 
 
 def test_output_data_writes_three_images(ctx, tmp_path):
-    from page_segmentation_b200.lib.output import output_data
+    from page_segmentation_b200.lib.output import flush_outputs, output_data
     from page_segmentation_b200.lib.predictor import Predictor
     from page_segmentation_b200.lib.predictor_data import PredictSettings
     from page_segmentation_b200.lib.network import Network
@@ -134,6 +199,7 @@ def test_output_data_writes_three_images(ctx, tmp_path):
         assert os.path.isdir(os.path.join(out, sub))                     # predictor.py:21-25
     _, _, pred = net.predict_single_data(data)
     output_data(out, pred[None], data, DEFAULT_COLOR_MAP)                 # leading batch dim is squeezed (output.py:21-23)
+    flush_outputs()
     c, o, i, _ = opipe.generate_output_masks(data.binary, pred, LUT)
     for sub, exp in (("color", c), ("overlay", o), ("inverted", i)):
         img = cv2.imread(os.path.join(out, sub, "page_0001.png"), cv2.IMREAD_COLOR)[..., ::-1]

@@ -5,6 +5,8 @@ import struct
 import zlib
 
 import cv2
+import os
+
 import numpy as np
 import pytest
 
@@ -145,7 +147,7 @@ def test_output_data_writes_device_encoded_pngs(ctx, tmp_path):
     from oracle import pipeline as opipe
     from page_segmentation_b200.lib.colors import DEFAULT_COLOR_MAP
     from page_segmentation_b200.lib.dataset import SingleData
-    from page_segmentation_b200.lib.output import output_data
+    from page_segmentation_b200.lib.output import flush_outputs, output_data
     rng = np.random.default_rng(3)
     page = synth.make_page(2, 300, 240, 18)
     binary = (page == 0).astype(np.uint8)
@@ -154,10 +156,48 @@ def test_output_data_writes_device_encoded_pngs(ctx, tmp_path):
         (tmp_path / sub).mkdir()
     data = SingleData(binary=binary, image_path="/somewhere/page_0001.png")
     output_data(str(tmp_path), pred[None], data, DEFAULT_COLOR_MAP)
+    flush_outputs()                                                  # the library's worker threads write the files
     exp = opipe.generate_output_masks(binary, pred, {0: (255, 255, 255), 1: (255, 0, 0), 2: (0, 255, 0)})
     for sub, e in zip(("color", "overlay", "inverted"), exp[:3]):
         got = cv2.imread(str(tmp_path / sub / "page_0001.png"), cv2.IMREAD_COLOR)[..., ::-1]
         np.testing.assert_array_equal(got, e)
+
+
+def test_output_pages_batch_and_write_errors(ctx, tmp_path):
+    """pcs_output_pages for several pages in one call (paths page-major), more calls in flight than the library has
+    slots, and a path that cannot be written: the error surfaces at pcs_output_flush and the writer keeps working."""
+    import torch
+    from oracle import pipeline as opipe
+    from page_segmentation_b200._native import PcsError
+    rng = np.random.default_rng(5)
+    n, H, W = 5, 140, 200
+    lut = np.array([[255, 255, 255], [255, 0, 0], [0, 255, 0]], dtype=np.uint8)
+    kinds = ("color", "overlay", "inverted")
+    cases = []
+    for call in range(9):                                            # 9 calls > 6 slots
+        labels = rng.integers(0, 3, (n, H, W)).astype(np.uint8)
+        binary = (rng.random((n, H, W)) < 0.3).astype(np.uint8)
+        paths = [str(tmp_path / f"c{call}_p{p}_{k}.png") for p in range(n) for k in kinds]
+        ctx.output_pages(torch.from_numpy(labels).cuda(), torch.from_numpy(binary).cuda(), n, H, W, lut, paths)
+        cases.append((labels, binary, paths))
+    ctx.output_flush()
+    for labels, binary, paths in cases:
+        for p in range(n):
+            exp = opipe.generate_output_masks(binary[p], labels[p].astype(np.int64), {0: (255, 255, 255), 1: (255, 0, 0), 2: (0, 255, 0)})
+            for k in range(3):
+                got = cv2.imread(paths[3 * p + k], cv2.IMREAD_COLOR)[..., ::-1]
+                np.testing.assert_array_equal(got, exp[k])
+    labels, binary, _ = cases[0]
+    bad = [str(tmp_path / "no_such_dir" / f"x{k}.png") for k in range(3)]
+    ctx.output_pages(torch.from_numpy(labels[:1]).cuda(), torch.from_numpy(binary[:1]).cuda(), 1, H, W, lut, bad)
+    with pytest.raises(PcsError, match="cannot write"):
+        ctx.output_flush()
+    good = [str(tmp_path / f"again_{k}.png") for k in range(3)]
+    ctx.output_pages(torch.from_numpy(labels[:1]).cuda(), torch.from_numpy(binary[:1]).cuda(), 1, H, W, lut, good)
+    ctx.output_flush()
+    assert all(os.path.getsize(g) > 0 for g in good)
+    with pytest.raises(PcsError):
+        ctx.output_pages(torch.from_numpy(labels[:1]).cuda(), torch.from_numpy(binary[:1]).cuda(), 1, H, W, lut, good[:2])
 
 
 @pytest.mark.parametrize("cc", [False, True])

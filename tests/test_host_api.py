@@ -187,40 +187,66 @@ def test_synthetic_page_is_deterministic_and_binarised():
     assert len(np.unique(synth.make_grey_page(3, 200, 150))) > 2
 
 
-def test_page_locked_result_policy(monkeypatch):
-    """runtime._pinned_empty: fast allocations (blocks recycled by the caching host allocator) stay page-locked; a run of
-    slow ones (a caller that keeps every result: each block is a fresh cudaHostAlloc) switches to the pageable copy for a
-    doubling number of results and comes back at the first fast one; one state per call site."""
-    from page_segmentation_b200 import runtime
-    now = [0.0]
+def test_page_locked_pool_is_bounded_and_recycles():
+    """lazy.PinnedPool: blocks come back when the array handed out (and every view of it) has died; a caller that keeps
+    everything runs into the byte budget and is refused (-> pageable copy); no timing is involved."""
+    import gc
+    from page_segmentation_b200.lazy import PinnedPool
+    made = []
 
-    class FakeTorch:
-        slow = False
+    import torch
 
-        def empty(self, shape, dtype=None, pin_memory=False):
-            assert pin_memory
-            now[0] += runtime._PIN_SLOW_S * (4 if self.slow else 0.01)
-            return ("block", shape)
+    def block(n):                              # pageable here; the pool only needs `.numpy()` (base = the tensor)
+        made.append(n)
+        return torch.zeros(n, dtype=torch.uint8)
 
-    t = FakeTorch()
-    monkeypatch.setattr(runtime, "_clock", lambda: now[0])
-    monkeypatch.setattr(runtime, "_pin_sites", {})
-    monkeypatch.setattr(runtime, "_PIN_ENABLED", True)
-    assert runtime._pinned_empty(t, (4,), None, None) is None                     # site None: always pageable
-    for _ in range(3 * runtime._PIN_MISSES):
-        assert runtime._pinned_empty(t, (4,), None, "a") is not None              # streaming caller: hits
-    t.slow = True
-    got = [runtime._pinned_empty(t, (4,), None, "a") is not None for _ in range(runtime._PIN_MISSES + 64)]
-    assert all(got[:runtime._PIN_MISSES]) and not any(got[runtime._PIN_MISSES:])  # then 64 pageable results
-    t.slow = False
-    assert runtime._pinned_empty(t, (4,), None, "b") is not None                  # another site is unaffected
-    probes = [runtime._pinned_empty(t, (4,), None, "a") is not None for _ in range(4)]
-    assert all(probes) and runtime._pin_sites["a"]["misses"] == 0 and runtime._pin_sites["a"]["pause"] == 32
-    t.slow = True                                                                 # keep-all again: the pause doubles
-    n_pinned = sum(runtime._pinned_empty(t, (4,), None, "a") is not None for _ in range(400))
-    assert n_pinned <= runtime._PIN_MISSES + 3 * (runtime._PIN_MISSES - runtime._PIN_MISSES // 2)
-    monkeypatch.setattr(runtime, "_PIN_ENABLED", False)
-    assert runtime._pinned_empty(t, (4,), None, "b") is None
+    pool = PinnedPool(budget_bytes=4 << 20, allocator=block)
+    assert PinnedPool.size_class(1) == 1 << 16 and PinnedPool.size_class((1 << 20) + 1) == 2 << 20
+    a = pool.alloc(1 << 20)
+    view = a[:100].view(np.float32).reshape(5, 5)
+    del a
+    gc.collect()
+    assert pool.outstanding == 1 << 20 and not pool.free            # the view keeps the block out
+    del view
+    gc.collect()
+    assert pool.outstanding == 0 and len(pool.free[1 << 20]) == 1
+    b = pool.alloc(900_000)                                          # same size class: the block comes round
+    assert made == [1 << 20] and pool.stats["hits"] == 1
+    kept = [b] + [pool.alloc(1 << 20) for _ in range(3)]             # keep-all caller: the budget (4 MB) is reached
+    assert all(k is not None for k in kept) and pool.total == 4 << 20
+    assert pool.alloc(1 << 20) is None and pool.alloc(1) is None and pool.stats["refused"] == 2
+    del kept, b
+    gc.collect()
+    held = pool.alloc(1 << 20)
+    assert pool.outstanding == 1 << 20 and held is not None
+    pool.trim()
+    assert pool.total == 1 << 20                                      # only the block still handed out counts
+
+
+def test_device_array_is_an_ndarray_stand_in():
+    """lazy.DeviceArray: metadata without data access, one host copy at the first look, reported dtype wider than the
+    device dtype (class maps: uint8 on the device, int64 like np.argmax to the caller), numpy protocols."""
+    import torch
+    from page_segmentation_b200.lazy import DeviceArray, is_lazy
+    calls = []
+    t = torch.arange(12, dtype=torch.uint8).reshape(3, 4)
+
+    def source():
+        calls.append(1)
+        return t
+
+    a = DeviceArray((3, 4), np.int64, source, device=0)
+    assert a.shape == (3, 4) and a.dtype == np.int64 and a.ndim == 2 and a.size == 12 and len(a) == 3 and not calls
+    assert is_lazy(a) and "device" in repr(a)
+    assert a.device_tensor() is t and calls == [1] and is_lazy(a)
+    h = np.asarray(a)
+    assert h.dtype == np.int64 and h.tolist() == t.tolist() and not is_lazy(a) and calls == [1]
+    assert np.asarray(a) is h                                          # the host copy IS the array from now on
+    a[0, 0] = 7
+    assert h[0, 0] == 7 and int(a.max()) == 11 and a.astype(np.uint8).dtype == np.uint8
+    assert (a + 1)[0, 0] == 8 and (a == h).all() and np.array_equal(a, h) and np.stack([a, a]).shape == (2, 3, 4)
+    with pytest.raises(AttributeError):
+        a._missing
 
 
 def test_colour_lut_is_padded_and_checked_before_it_reaches_the_library():

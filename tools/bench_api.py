@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Throughput of the reference-named Python API on one GPU (what a caller of the drop-in sees):
-DatasetLoader.load_data -> Predictor.predict -> output_data on synthetic A4 pages.  Wall clock, host included."""
+DatasetLoader.load_data -> Predictor.predict -> output_data on synthetic A4 pages.  Wall clock, host included;
+every line ends with all device work finished and (where files are written) all files on disk."""
 import json
 import os
 import sys
@@ -19,13 +20,17 @@ def main():
     from page_segmentation_b200.lib.colors import DEFAULT_COLOR_MAP
     from page_segmentation_b200.lib.dataset import DatasetLoader, SingleData
     from page_segmentation_b200.lib.network import Network
-    from page_segmentation_b200.lib.output import output_data
+    from page_segmentation_b200.lib.output import flush_outputs, output_data
     from page_segmentation_b200.lib.postprocess import find_postprocessor
     from page_segmentation_b200.lib.predictor import Predictor
     from page_segmentation_b200.lib.predictor_data import PredictSettings
-    n = int(os.environ.get("PCSEG_API_PAGES", "32"))
-    pages = [synth.make_page(s) for s in range(8)]
-    entries = [SingleData(image=pages[i % 8], line_height_px=18, image_path=f"/in/page_{i:04d}.png") for i in range(n)]
+    n = int(os.environ.get("PCSEG_API_PAGES", "64"))
+    pages = [np.array(synth.make_page(s)) for s in range(8)]
+    pages = [pages[i % 8].copy() for i in range(n)]                         # n separate pageable arrays, as a caller holds them
+
+    def entries():
+        return [SingleData(image=pages[i], line_height_px=18, output_path=f"page_{i:04d}.png") for i in range(n)]
+
     loader = DatasetLoader(6, DEFAULT_COLOR_MAP, prediction=True)
     net = Network("Predict", n_classes=3, weights=synth.make_weights("fcn_skip", 3, seed=0))
 
@@ -36,46 +41,85 @@ def main():
         torch.cuda.synchronize()
         return out, time.perf_counter() - t
 
-    loader.load_data(entries[:2])                                           # warm-up
-    ds, t_load = clock(lambda: loader.load_data(entries))
+    def line(stage, t, **kw):
+        print(json.dumps({"stage": stage, "pages": n, "s": round(t, 4), "pages_per_s": round(n / t, 1), **kw}), flush=True)
+
+    def staged(ds):
+        # wait for the background stager: every page's image is on the device
+        from page_segmentation_b200.lazy import peek
+        for d in ds.data:
+            peek(d, "image").device_tensor()
+        return ds
+
+    staged(loader.load_data(entries()[:8]))                                 # warm-up
+    ds, t = clock(lambda: staged(loader.load_data(entries())))
+    line("DatasetLoader.load_data (in-memory pages) until every page is staged on the device", t)
+    ds, t = clock(lambda: (lambda d: [np.asarray(x.image) for x in d.data] and d)(loader.load_data(entries())))
+    line("DatasetLoader.load_data, every image read on the host afterwards", t)
     for label, post in (("predict", []), ("predict + cc_majority", [find_postprocessor("cc_majority")])):
         pred = Predictor(PredictSettings(n_classes=3, color_map=DEFAULT_COLOR_MAP, post_process=post), network=net)
-        list(pred.predict(type(ds)(ds.data[:2], ds.color_map)))
+        ds = staged(loader.load_data(entries()))
+        list(pred.predict(type(ds)(ds.data[:8], ds.color_map)))
+
+        def on_device():
+            for p in pred.predict(ds):
+                pass
+        on_device()
+        _, t = clock(on_device)
+        line(f"Predictor.{label}, results left on the device", t)
+
         def consume():
-            # what the reference's front ends do: use a Prediction, drop it, take the next one
+            # a front end that looks at every class map on the host, then drops the Prediction
             k = 0
             for p in pred.predict(ds):
                 k += int(p.labels[0, 0]) + 1
             return k
-        preds = None                                    # kept results of the previous round would hold page-locked blocks
         consume()
         _, t = clock(consume)
-        print(json.dumps({"stage": f"Predictor.{label}, each result consumed and dropped", "pages": n, "s": round(t, 4),
-                          "pages_per_s": round(n / t, 1)}), flush=True)
-        preds, t = clock(lambda: list(pred.predict(ds)))
-        print(json.dumps({"stage": f"Predictor.{label}, all results kept", "pages": n, "s": round(t, 4),
-                          "pages_per_s": round(n / t, 1)}), flush=True)
-    print(json.dumps({"stage": "DatasetLoader.load_data (in-memory pages)", "pages": n, "s": round(t_load, 4),
-                      "pages_per_s": round(n / t_load, 1)}), flush=True)
-    with tempfile.TemporaryDirectory() as out:
-        for sub in ("color", "overlay", "inverted"):
-            os.makedirs(os.path.join(out, sub))
+        line(f"Predictor.{label}, each class map read on the host and dropped", t)
+        _, t = clock(lambda: [np.asarray(p.labels) for p in pred.predict(ds)])
+        line(f"Predictor.{label}, all class maps read and kept", t)
+    with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as out:
+        pred = Predictor(PredictSettings(n_classes=3, color_map=DEFAULT_COLOR_MAP, output=out,
+                                         post_process=[find_postprocessor("cc_majority")]), network=net)
+        preds = list(pred.predict(ds))
+
+        def write_all():
+            for p in preds:
+                output_data(out, p.labels, p.data, DEFAULT_COLOR_MAP)
+            flush_outputs()
+        write_all()
+        from page_segmentation_b200.runtime import get_context
+        c = get_context()
+        c.set_timing(True)
         output_data(out, preds[0].labels, preds[0].data, DEFAULT_COLOR_MAP)
-        _, t = clock(lambda: [output_data(out, p.labels, p.data, DEFAULT_COLOR_MAP) for p in preds])
-        print(json.dumps({"stage": "output_data (three PNG files per page, device encoder)", "pages": n, "s": round(t, 4),
-                          "pages_per_s": round(n / t, 1)}), flush=True)
+        print(json.dumps({"output_pages_device_ms_per_page": dict(c.timings())}), flush=True)
+        c.set_timing(False)
+        _, t = clock(write_all)
+        size = sum(os.path.getsize(os.path.join(out, c, f)) for c in ("color", "overlay", "inverted") for f in os.listdir(os.path.join(out, c)))
+        line("output_data (three PNG files per page, device encoder) + flush_outputs", t, mb_per_page=round(size / n / 1e6, 2))
         del preds, ds
 
         def flow():
-            # one page at a time through the whole per-page API, nothing kept
-            for i in range(n):
-                e = SingleData(image=pages[i % 8], line_height_px=18, image_path=f"/in/page_{i:04d}.png")
+            ds = loader.load_data(entries())
+            for p in pred.predict(ds):
+                output_data(out, p.labels, p.data, DEFAULT_COLOR_MAP)
+            flush_outputs()
+        flow()
+        for _ in range(2):
+            _, t = clock(flow)
+            line("load_data -> predict (+ cc_majority) -> output_data -> flush_outputs (the drop-in flow)", t)
+
+        def page_by_page():
+            for e in entries():
                 p = pred.predict_single(loader.load_images(e))
                 output_data(out, p.labels, p.data, DEFAULT_COLOR_MAP)
-        flow()
-        _, t = clock(flow)
-        print(json.dumps({"stage": "load_images -> predict_single (+ cc_majority) -> output_data, page by page, nothing kept",
-                          "pages": n, "s": round(t, 4), "pages_per_s": round(n / t, 1)}), flush=True)
+            flush_outputs()
+        page_by_page()
+        _, t = clock(page_by_page)
+        line("load_images -> predict_single (+ cc_majority) -> output_data, page by page, + flush_outputs", t)
+    from page_segmentation_b200.lazy import pinned_pool
+    print(json.dumps({"pinned_pool": pinned_pool().stats}), flush=True)
 
 
 if __name__ == "__main__":
