@@ -24,8 +24,13 @@ never by literal layer name, because Keras layer names carry process-global
 counters (`conv2d_7`, ...).
 
 `write_keras_h5` authors files of the same old-style flavour (fixtures, export).
-PARITY UNPINNED: neither path could be cross-checked against h5py in this
-environment.
+Pins (tests/test_h5_pins.py): the reader is checked against a file written by the
+real HDF5 library (MATLAB's -v7.3 writer, shipped with scipy's test data) and
+against a Keras-layout file assembled byte by byte from the format specification
+by tests/golden/make_keras_h5_fixture.py (variable-length UTF-8 attributes,
+continuation blocks, multi-node groups, chunked / compact datasets).  h5py and
+Keras themselves are absent here, so a real `model.save()` file is still
+unseen; the writer is only pinned by this reader.
 """
 from __future__ import annotations
 
