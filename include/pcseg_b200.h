@@ -330,6 +330,27 @@ PCS_API int pcs_train_softmax_ce(pcs_ctx* ctx, const float* d_logits, const uint
 PCS_API int pcs_train_adam(pcs_ctx* ctx, float* d_params, const float* d_grads, float* d_m, float* d_v, const int64_t* d_offsets,
                    int n_vars, float lr_t, float beta1, float beta2, float eps, float clipnorm, float grad_scale);
 
+/* ---- training step on the tensor cores (csrc/train_tc.cu): the same step as the primitives above compose -- forward
+ * with kept activations, mean sparse cross entropy from logits (metrics.py:8-9), backward -- for ONE page of the
+ * fcn_skip / fcn graph (network.py:151-161 trains with batch 1), in mixed precision: bf16 activations and activation
+ * gradients, fp32 accumulation, fp32 master weights / gradients.  `offsets` (host, 27 entries) are the element offsets of
+ * kernel_0, bias_0, kernel_1, ... and the end in the flat parameter / gradient buffers, kernels in the layouts of the
+ * primitives above (w[C_out][C_in][k][k]; stride-1 transposed convolutions flipped; 2x2 stride-2 ones k2[tap][C_out][C_in]).
+ * pcs_train_tc_step fills d_grads (zeroed by phase 1) and *d_loss_sum (un-normalised: divide by h * w).  `phases`: bit 0 =
+ * forward + loss + backward of logits .. deconv1, bit 1 = backward of conv7 .. conv1 (two calls let the caller start the
+ * data-parallel all-reduce of the first half while the second runs); 3 = the whole step. */
+typedef struct pcs_train_tc pcs_train_tc;
+PCS_API int pcs_train_tc_create(pcs_ctx* ctx, int arch, int n_classes, int h, int w, const int64_t* offsets, int n_offsets,
+                                pcs_train_tc** out);
+PCS_API int pcs_train_tc_step(pcs_ctx* ctx, pcs_train_tc* step, int phases, const uint8_t* d_image, const uint8_t* d_labels,
+                              const float* d_params, float* d_grads, double* d_loss_sum);
+PCS_API int pcs_train_tc_destroy(pcs_ctx* ctx, pcs_train_tc* step);
+/* the weight-gradient kernel of that step on its own: d_dw[c_out][c_in][k][k] += sum over pixels of x[pixel + tap][c_in] *
+ * dy[pixel][c_out] ('same' zero border), k = 5 or 1, for bf16 tensors in the plane-major activation layout
+ * [planes][H][W][8 channels] (x_planes <= 16, k * max(32, c_out rounded up to 16) <= 512); fp32 accumulation. */
+PCS_API int pcs_train_tc_wgrad(pcs_ctx* ctx, const void* d_x, int x_planes, const void* d_dy, int dy_planes, int H, int W, int k,
+                               int c_in, int c_out, float* d_dw);
+
 /* ---- diagnostics ------------------------------------------------------ */
 /* copies one named internal activation of the last pcs_forward to a float32
  * NHWC host buffer (real channels only); returns the channel count or <0. */

@@ -26,7 +26,7 @@ EXPORTS = [
     "pcs_bounding_boxes", "pcs_class_components", "pcs_char_height", "pcs_png_bytes", "pcs_png_encode", "pcs_output_pages", "pcs_output_flush", "pcs_segment_masks", "pcs_dilate3x3", "pcs_integral_image", "pcs_text_regions", "pcs_predict_pages_host", "pcs_predict_pages_files", "pcs_predict_pages_segments", "pcs_eval_counts",
     "pcs_train_input", "pcs_train_corr2d", "pcs_train_wgrad", "pcs_train_bias_grad", "pcs_train_relu_bwd", "pcs_train_maxpool_fwd",
     "pcs_train_maxpool_bwd", "pcs_train_deconv2_fwd", "pcs_train_deconv2_bwd_data", "pcs_train_deconv2_wgrad", "pcs_train_softmax_ce",
-    "pcs_train_adam", "pcs_debug_activation", "pcs_set_keep_activations", "pcs_set_timing", "pcs_set_pdl",
+    "pcs_train_adam", "pcs_train_tc_create", "pcs_train_tc_step", "pcs_train_tc_destroy", "pcs_train_tc_wgrad", "pcs_debug_activation", "pcs_set_keep_activations", "pcs_set_timing", "pcs_set_pdl",
     "pcs_last_timings",
 ]
 
@@ -106,6 +106,10 @@ def load() -> C.CDLL:
     lib.pcs_train_deconv2_wgrad.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32]
     lib.pcs_train_softmax_ce.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]
     lib.pcs_train_adam.argtypes = [vp, vp, vp, vp, vp, vp, i32, f32, f32, f32, f32, f32, f32]
+    lib.pcs_train_tc_create.argtypes = [vp, i32, i32, i32, i32, vp, i32, C.POINTER(vp)]
+    lib.pcs_train_tc_step.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
+    lib.pcs_train_tc_destroy.argtypes = [vp, vp]
+    lib.pcs_train_tc_wgrad.argtypes = [vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.pcs_debug_activation.argtypes = [vp, C.c_char_p, vp, C.c_size_t, C.POINTER(C.c_int32)]
     lib.pcs_set_keep_activations.argtypes = [vp, i32]
     lib.pcs_set_timing.argtypes = [vp, i32]
@@ -376,6 +380,22 @@ class Context:
         fn = getattr(self.lib, "pcs_train_" + name)
         conv = [(_ptr(a) if (a is None or hasattr(a, "data_ptr") or isinstance(a, np.ndarray)) else a) for a in args]
         self._check(fn(self.h, *conv), "pcs_train_" + name)
+
+    # -- training step on the tensor cores (csrc/train_tc.cu) -----------------------
+    def train_tc_create(self, arch: str, n_classes: int, h: int, w: int, offsets) -> int:
+        offs = np.ascontiguousarray(offsets, dtype=np.int64)
+        handle = C.c_void_p()
+        self._check(self.lib.pcs_train_tc_create(self.h, ARCH_IDS[arch], int(n_classes), int(h), int(w), offs.ctypes.data, int(offs.size),
+                                                 C.byref(handle)), "pcs_train_tc_create")
+        return handle.value
+
+    def train_tc_step(self, handle: int, phases: int, d_image, d_labels, d_params, d_grads, d_loss):
+        self._check(self.lib.pcs_train_tc_step(self.h, handle, int(phases), _ptr(d_image), _ptr(d_labels), _ptr(d_params), _ptr(d_grads),
+                                               _ptr(d_loss)), "pcs_train_tc_step")
+
+    def train_tc_destroy(self, handle: int):
+        if handle and self.h:
+            self.lib.pcs_train_tc_destroy(self.h, handle)
 
     # -- diagnostics -----------------------------------------------------------
     def debug_activation(self, name: str) -> np.ndarray:

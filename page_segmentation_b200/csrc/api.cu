@@ -885,6 +885,29 @@ int pcs_train_adam(pcs_ctx* ctx, float* d_params, const float* d_grads, float* d
     return train_adam(ctx, d_params, d_grads, d_m, d_v, reinterpret_cast<const long long*>(d_offsets), n_vars, lr_t, beta1, beta2, eps, clipnorm, grad_scale);
 }
 
+int pcs_train_tc_create(pcs_ctx* ctx, int arch, int n_classes, int h, int w, const int64_t* offsets, int n_offsets, pcs_train_tc** out) {
+    PCS_TRAIN_ENTER(ctx, offsets && out, "train_tc_create");
+    TrainTc* t = nullptr;
+    PCS_TRY(train_tc_create(ctx, arch, n_classes, h, w, reinterpret_cast<const long long*>(offsets), n_offsets, &t));
+    *out = reinterpret_cast<pcs_train_tc*>(t);
+    return PCS_OK;
+}
+int pcs_train_tc_step(pcs_ctx* ctx, pcs_train_tc* step, int phases, const uint8_t* d_image, const uint8_t* d_labels, const float* d_params,
+                      float* d_grads, double* d_loss_sum) {
+    PCS_TRAIN_ENTER(ctx, step && d_params && d_grads && d_loss_sum && (phases & 3) && (!(phases & 1) || (d_image && d_labels)), "train_tc_step");
+    return train_tc_step(ctx, reinterpret_cast<TrainTc*>(step), phases, d_image, d_labels, d_params, d_grads, d_loss_sum);
+}
+int pcs_train_tc_wgrad(pcs_ctx* ctx, const void* d_x, int x_planes, const void* d_dy, int dy_planes, int H, int W, int k, int c_in, int c_out,
+                       float* d_dw) {
+    PCS_TRAIN_ENTER(ctx, d_x && d_dy && d_dw, "train_tc_wgrad");
+    return train_tc_wgrad(ctx, d_x, x_planes, d_dy, dy_planes, H, W, k, c_in, c_out, d_dw);
+}
+int pcs_train_tc_destroy(pcs_ctx* ctx, pcs_train_tc* step) {
+    if (!ctx) return PCS_ERR_ARG;
+    PCS_CUDA(ctx, cudaSetDevice(ctx->device));
+    return train_tc_destroy(ctx, reinterpret_cast<TrainTc*>(step));
+}
+
 int pcs_eval_counts(pcs_ctx* ctx, const uint8_t* d_pred, const uint8_t* d_mask, const uint8_t* d_bin, size_t n_pixels, int n_classes,
                     uint64_t* d_out) {
     if (!ctx || !d_pred || !d_mask || !d_bin || !d_out || !n_pixels) return ctx ? set_err(ctx, PCS_ERR_ARG, "eval_counts: null or empty argument") : PCS_ERR_ARG;

@@ -307,6 +307,14 @@ int train_input_plane(pcs_ctx* ctx, const uint8_t* img, int h, int w, float* out
 int train_adam(pcs_ctx* ctx, float* p, const float* g, float* m, float* v, const long long* d_offsets, int nvars, float lr_t, float b1,
                float b2, float eps, float clipnorm, float gscale);
 
+// train_tc.cu  (training step on the tensor cores)
+struct TrainTc;
+int train_tc_create(pcs_ctx* ctx, int arch, int n_classes, int h, int w, const long long* offsets, int n_offsets, TrainTc** out);
+int train_tc_step(pcs_ctx* ctx, TrainTc* t, int phases, const uint8_t* d_img, const uint8_t* d_labels, const float* d_params, float* d_grads,
+                  double* d_loss);
+int train_tc_destroy(pcs_ctx* ctx, TrainTc* t);
+int train_tc_wgrad(pcs_ctx* ctx, const void* d_x, int x_planes, const void* d_dy, int dy_planes, int H, int W, int k, int ci, int co, float* d_dw);
+
 // conv_umma.cu  (tcgen05 / TMEM / TMA implicit GEMM)
 struct UmmaHeadArgs {              // fused FCN head epilogue (conv_umma.cu mode 2)
     const void* plog = nullptr;         // device float4 [n][2h][2w]: conv2 share of the logits (fcn_skip) or null

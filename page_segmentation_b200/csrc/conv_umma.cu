@@ -540,6 +540,8 @@ int launch_npad(pcs_ctx* ctx, const UmmaConvArgs& a) {
         case 5080: return launch_t<T, 80, 5, EPI_STORE>(ctx, a);
         case 3064: return launch_t<T, 64, 3, EPI_STORE>(ctx, a);
         case 3128: return launch_t<T, 128, 3, EPI_STORE>(ctx, a);
+        case 1080: return launch_t<T, 80, 1, EPI_STORE>(ctx, a);         // input gradients of the stride-2 transposed convs (train_tc.cu)
+        case 1128: return launch_t<T, 128, 1, EPI_STORE>(ctx, a);
         case 101128: return launch_t<T, 128, 1, EPI_DECONV>(ctx, a);
         case 102128: return launch_t<T, 128, 2, EPI_DECONV>(ctx, a);      // UpSampling2D(2) + Conv2D(2x2) of the U-Net
         case 201032: return launch_t<T, 32, 1, EPI_HEAD>(ctx, a);
@@ -701,7 +703,8 @@ size_t umma_weight_image_head(const double* m /*[4][cin][4]*/, const int* src_c,
 int launch_conv_umma(pcs_ctx* ctx, const UmmaConvArgs& a) {
     if (a.mode >= EPI_HEAD && (!a.head || a.npad != 32 || a.head->n_classes > HEAD_NC))
         return set_err(ctx, PCS_ERR_ARG, "conv_umma: fused head needs the N=32 operand image and <= %d classes", HEAD_NC);
-    if (!umma_supported(a.k, a.npad)) return set_err(ctx, PCS_ERR_ARG, "conv_umma: unsupported k=%d N=%d", a.k, a.npad);
+    const bool plain_1x1 = a.mode == 0 && a.k == 1 && (a.npad == 80 || a.npad == 128);
+    if (!umma_supported(a.k, a.npad) && !plain_1x1) return set_err(ctx, PCS_ERR_ARG, "conv_umma: unsupported k=%d N=%d", a.k, a.npad);
     if (a.src[0].cp % 8 || (a.nsrc > 1 && a.src[1].cp % 8)) return set_err(ctx, PCS_ERR_ARG, "conv_umma: channel stride not a multiple of 8");
     if ((a.out && a.out_cp % 8) || (a.pool_out && a.pool_cp % 8)) return set_err(ctx, PCS_ERR_ARG, "conv_umma: output stride");
     if (ctx->precision == PCS_PREC_BF16) return launch_npad<__nv_bfloat16>(ctx, a);

@@ -4,9 +4,16 @@ one page per step (the reference's batch, network.py:151-161), mean sparse cross
 Adam with per-variable clipnorm (network.py:91-103), data-parallel gradient averaging over the ranks of
 torch.distributed.
 
-First version: fp32 on the CUDA cores (csrc/train.cu); `FcnTrainStep` walks the graph of lib/model.py:45-92 (fcn_skip)
-or :206-234 (fcn) over the pcs_train_* primitives.  Concatenations never copy: a skip tensor is allocated inside the
-buffer of the concatenation it feeds, and its gradient is the matching slice of that buffer's gradient.
+Two engines behind `FcnTrainStep` (same parameters, same flat fp32 gradient buffer, same Adam):
+  "tensor" (default)  csrc/train_tc.cu: mixed precision on the tensor cores -- bf16 activations and activation
+                      gradients, fp32 accumulation, fp32 master weights -- one library call per step
+                      (pcs_train_tc_step); with several ranks the gradient all-reduce of the decoder half starts while
+                      the encoder half is still in backward;
+  "fp32"              csrc/train.cu: fp32 on the CUDA cores; this module walks the graph of lib/model.py:45-92
+                      (fcn_skip) or :206-234 (fcn) over the pcs_train_* primitives.  The numerics reference of the
+                      tensor engine and the engine for more than four classes.
+Concatenations never copy: a skip tensor is allocated inside the buffer of the concatenation it feeds, and its gradient
+is the matching slice of that buffer's gradient.
 
 Out of scope (Keras training UX): callbacks, early stopping, LR plateau, TensorBoard, augmentation, the other
 optimizers and losses of lib/architecture.py:71-90 / lib/metrics.py.
@@ -96,11 +103,18 @@ class FcnTrainStep:
     flat fp32 buffer (variables in Keras order: kernel, bias per layer)."""
 
     def __init__(self, arch: str, weights: Sequence[Tuple[np.ndarray, np.ndarray]], n_classes: int, l_rate: float = 1e-3,
-                 clipnorm: Optional[float] = 1.0, device: Optional[int] = None):
+                 clipnorm: Optional[float] = 1.0, device: Optional[int] = None, engine: Optional[str] = None):
         from .. import runtime
         from ..synth import layer_table
         if arch not in ("fcn_skip", "fcn"):
             raise NotImplementedError("the device training step covers the fcn_skip and fcn graphs")
+        engine = engine or os.environ.get("PCSEG_TRAIN_ENGINE") or ("tensor" if n_classes <= 4 else "fp32")
+        if engine not in ("tensor", "fp32"):
+            raise ValueError(f"unknown training engine {engine!r} (tensor | fp32)")
+        if engine == "tensor" and n_classes > 4:
+            raise ValueError("the tensor-core training step covers up to 4 classes; use engine='fp32'")
+        self.engine = engine
+        self._tc, self._tc_shape = None, None
         self.torch = runtime._torch()
         self.ctx = runtime.get_context(device)
         self.arch, self.n_classes = arch, int(n_classes)
@@ -181,8 +195,44 @@ class FcnTrainStep:
         self._shape, self._padded = (h, w), (H, W)
 
     # -- one step ---------------------------------------------------------------
+    def __del__(self):
+        try:
+            if getattr(self, "_tc", None):
+                self.ctx.train_tc_destroy(self._tc)
+                self._tc = None
+        except Exception:
+            pass
+
+    def _upload_page(self, image_u8, labels_u8):
+        t, dev = self.torch, f"cuda:{self.ctx.device}"
+        image_u8, labels_u8 = np.asarray(image_u8), np.asarray(labels_u8)
+        if image_u8.ndim != 2 or labels_u8.shape != image_u8.shape:
+            raise ValueError(f"image {image_u8.shape} and labels {labels_u8.shape} must be equally sized 2-D arrays")
+        if labels_u8.size and int(labels_u8.max()) >= self.n_classes:
+            raise ValueError(f"label {int(labels_u8.max())} outside 0..{self.n_classes - 1}")
+        d_img = t.from_numpy(np.ascontiguousarray(image_u8, dtype=np.uint8)).to(dev)
+        d_lab = t.from_numpy(np.ascontiguousarray(labels_u8, dtype=np.uint8)).to(dev)
+        return d_img, d_lab
+
+    def _tc_enqueue(self, image_u8, labels_u8, phases: int = 3, page=None):
+        """pcs_train_tc_step for one page (uploaded here unless `page` = (d_img, d_lab) is given); no synchronisation."""
+        h, w = image_u8.shape
+        self.ctx.use_torch_stream()
+        if self._tc is None or self._tc_shape != (h, w):
+            if self._tc:
+                self.ctx.train_tc_destroy(self._tc)
+            self._tc = self.ctx.train_tc_create(self.arch, self.n_classes, h, w, self.offsets)
+            self._tc_shape = (h, w)
+        d_img, d_lab = page if page is not None else self._upload_page(image_u8, labels_u8)
+        self.ctx.train_tc_step(self._tc, phases, d_img, d_lab, self.params, self.grads, self.d_loss)
+        return d_img, d_lab
+
     def forward_backward(self, image_u8: np.ndarray, labels_u8: np.ndarray) -> float:
         """Fills self.grads with d loss / d parameters for one page and returns the loss."""
+        if self.engine == "tensor":
+            h, w = image_u8.shape
+            self._tc_enqueue(image_u8, labels_u8)
+            return float(self.d_loss.cpu()[0]) / (h * w)
         t, c = self.torch, self.ctx.train_call
         h, w = image_u8.shape
         self._alloc(h, w)
@@ -278,7 +328,32 @@ class FcnTrainStep:
         self.ctx.train_call("adam", self.params, self.grads, self.m, self.v, self.d_offsets, len(self.offsets) - 1,
                             float(lr_t), self.b1, self.b2, self.eps, self.clipnorm, float(grad_scale))
 
+    def describe(self) -> dict:
+        if self.engine == "tensor":
+            return {"engine": "tensor", "dtype": "bf16 activations / activation gradients, fp32 accumulation, fp32 master weights and Adam",
+                    "kernels": "conv_umma_kernel (forward, input gradients), wgrad_tc_kernel (tcgen05, MN-major operands)"}
+        return {"engine": "fp32", "dtype": "f32 (CUDA cores)"}
+
+    def _decoder_start(self) -> int:
+        """offset of the first variable the backward pass finishes in its first phase (deconv1 .. logits)"""
+        return self.offsets[self.slots["deconv1"][0]]
+
     def step(self, image_u8: np.ndarray, labels_u8: np.ndarray) -> float:
+        import torch.distributed as dist
+        world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        if self.engine == "tensor" and world > 1:
+            # data parallel: the decoder half of the gradients is all-reduced (NCCL, its own stream) while the encoder
+            # half is still being computed
+            h, w = image_u8.shape
+            cut = self._decoder_start()
+            page = self._tc_enqueue(image_u8, labels_u8, phases=1)
+            first = dist.all_reduce(self.grads[cut:], op=dist.ReduceOp.SUM, async_op=True)
+            self._tc_enqueue(image_u8, labels_u8, phases=2, page=page)
+            second = dist.all_reduce(self.grads[:cut], op=dist.ReduceOp.SUM, async_op=True)
+            first.wait()
+            second.wait()
+            self.apply_gradients(1.0 / world)
+            return float(self.d_loss.cpu()[0]) / (h * w)
         loss = self.forward_backward(image_u8, labels_u8)
         self.apply_gradients(self.allreduce_gradients())
         return loss

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--arch", default="fcn_skip")
+    ap.add_argument("--engine", default=None, help="tensor | fp32 (default: FcnTrainStep's)")
     ap.add_argument("--cpu-steps", type=int, default=1, help="steps of the torch-CPU oracle timed beside it (rank 0, single process)")
     args = ap.parse_args()
     import torch
@@ -36,7 +37,7 @@ def main():
     img, binary = opipe.prepare_images(page, page, 6, 18)                  # 1169 x 827, the scaled page the network sees
     labels = binary.astype(np.uint8)                                        # ink / paper as a two-class target of three
     W = synth.make_weights(args.arch, 3, seed=0)
-    eng = FcnTrainStep(args.arch, W, 3, l_rate=1e-4, device=local)
+    eng = FcnTrainStep(args.arch, W, 3, l_rate=1e-4, device=local, engine=args.engine)
     for _ in range(args.warmup):
         eng.step(img, labels)
     torch.cuda.synchronize()
@@ -62,7 +63,7 @@ def main():
             cpu = {"s_per_step": (time.perf_counter() - t0) / args.cpu_steps, "threads": torch.get_num_threads(),
                    "what": "torch-CPU autograd forward + backward of the same page (oracle), no optimizer"}
         print(json.dumps({"metric": "train_steps_per_sec", "value": world * 1e3 / ms, "unit": "pages/s (one page per rank per step)",
-                          "n_gpus": world, "ms_per_step": ms, "steps": args.steps, "dtype": "f32 (CUDA cores)", "arch": args.arch,
+                          "n_gpus": world, "ms_per_step": ms, "steps": args.steps, "dtype": eng.describe()["dtype"], "engine": eng.engine, "arch": args.arch,
                           "page": list(img.shape), "allreduce_floats": int(eng.params.numel()), "loss_first_last": [losses[0], losses[-1]],
                           "gflop_per_step": 3 * 112.0, "tflops": 3 * 112.0 / ms, "cpu_oracle": cpu}), flush=True)
     if world > 1:
