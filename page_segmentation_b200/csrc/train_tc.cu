@@ -718,9 +718,22 @@ int wgrad_launch_raw(pcs_ctx* ctx, const Ten& X, const Ten& dY, int kx, int npad
     }
     if (best_b < 1) return set_err(ctx, PCS_ERR_STATE, "train_tc: wgrad tile does not fit shared memory (P=%d N=%d)", p.P, p.npad);
     p.B = std::min(best_b, std::max(1, p.H)); p.nslots = best_s;
+    p.strips = (p.W + DT - 1) / DT;
+    {   // among the band heights that fit, the one that spreads strips x bands most evenly over the CTAs (ties: the taller band)
+        const int ctas = std::max(1, (ctx->sm_count + p.ntiles_m - 1) / p.ntiles_m);
+        double best_eff = -1.0;
+        int best = p.B;
+        for (int b = p.B; b >= std::max(1, p.B / 2); --b) {
+            const int items = p.strips * ((p.H + b - 1) / b);
+            const int grid = std::min(items, ctas);
+            const double rows_done = (double)((items + grid - 1) / grid) * b * grid;          // row-strips the slowest CTA pattern pays for
+            const double eff = (double)p.strips * p.H / rows_done;
+            if (eff > best_eff + 1e-9) { best_eff = eff; best = b; }
+        }
+        p.B = best;
+    }
     p.xr = p.B + nr_max - 1;
     p.x_alloc = ((uint32_t)p.xr * p.x_row_bytes + 1023) / 1024 * 1024;
-    p.strips = (p.W + DT - 1) / DT;
     p.bands = (p.H + p.B - 1) / p.B;
     p.dw = dw; p.m_off = m_off; p.n_off = n_off; p.s_tap = s_tap;
     { const char* e = getenv("PCSEG_WGRAD_SWAP"); p.swap_strides = e && e[0] == '1'; }

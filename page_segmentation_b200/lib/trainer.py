@@ -115,6 +115,7 @@ class FcnTrainStep:
             raise ValueError("the tensor-core training step covers up to 4 classes; use engine='fp32'")
         self.engine = engine
         self._tc, self._tc_shape = None, None
+        self._slots, self._copy_stream, self._turn, self._last_slot = None, None, 0, None
         self.torch = runtime._torch()
         self.ctx = runtime.get_context(device)
         self.arch, self.n_classes = arch, int(n_classes)
@@ -210,9 +211,34 @@ class FcnTrainStep:
             raise ValueError(f"image {image_u8.shape} and labels {labels_u8.shape} must be equally sized 2-D arrays")
         if labels_u8.size and int(labels_u8.max()) >= self.n_classes:
             raise ValueError(f"label {int(labels_u8.max())} outside 0..{self.n_classes - 1}")
-        d_img = t.from_numpy(np.ascontiguousarray(image_u8, dtype=np.uint8)).to(dev)
-        d_lab = t.from_numpy(np.ascontiguousarray(labels_u8, dtype=np.uint8)).to(dev)
-        return d_img, d_lab
+        if self.engine != "tensor":
+            return t.from_numpy(np.ascontiguousarray(image_u8, dtype=np.uint8)).to(dev), t.from_numpy(np.ascontiguousarray(labels_u8, dtype=np.uint8)).to(dev)
+        # Two page slots of page-locked host memory + device buffers, filled on a copy stream: a pageable copy on the compute
+        # stream would make the host wait for the previous step's kernels before it could enqueue this one (measured: 2.1 ms
+        # per step against 1.8 ms of kernels).  A slot is reused two steps later, after the step that read it.
+        n = image_u8.size
+        if self._slots is None or self._slots[0]["pin"].shape[1] < n:
+            self._copy_stream = t.cuda.Stream(self.ctx.device)
+            self._slots = [{"pin": t.empty((2, n), dtype=t.uint8, pin_memory=True), "dev": t.empty((2, n), dtype=t.uint8, device=dev),
+                            "copied": None, "consumed": None} for _ in range(2)]
+            self._turn = 0
+        slot = self._slots[self._turn % 2]
+        self._turn += 1
+        if slot["copied"] is not None:
+            slot["copied"].synchronize()                          # the page-locked block is free again
+        pin = slot["pin"].numpy()
+        np.copyto(pin[0, :n].reshape(image_u8.shape), image_u8, casting="unsafe")
+        np.copyto(pin[1, :n].reshape(image_u8.shape), labels_u8, casting="unsafe")
+        main = t.cuda.current_stream(self.ctx.device)
+        with t.cuda.stream(self._copy_stream):
+            if slot["consumed"] is not None:
+                self._copy_stream.wait_event(slot["consumed"])    # the step that read this slot's device buffers has run
+            slot["dev"][:, :n].copy_(slot["pin"][:, :n], non_blocking=True)
+            slot["copied"] = t.cuda.Event()
+            slot["copied"].record(self._copy_stream)
+        main.wait_event(slot["copied"])
+        self._last_slot = slot
+        return slot["dev"][0, :n].view(image_u8.shape), slot["dev"][1, :n].view(image_u8.shape)
 
     def _tc_enqueue(self, image_u8, labels_u8, phases: int = 3, page=None):
         """pcs_train_tc_step for one page (uploaded here unless `page` = (d_img, d_lab) is given); no synchronisation."""
@@ -225,6 +251,10 @@ class FcnTrainStep:
             self._tc_shape = (h, w)
         d_img, d_lab = page if page is not None else self._upload_page(image_u8, labels_u8)
         self.ctx.train_tc_step(self._tc, phases, d_img, d_lab, self.params, self.grads, self.d_loss)
+        if self._last_slot is not None and (phases & 1):
+            ev = self.torch.cuda.Event()
+            ev.record(self.torch.cuda.current_stream(self.ctx.device))
+            self._last_slot["consumed"] = ev
         return d_img, d_lab
 
     def forward_backward(self, image_u8: np.ndarray, labels_u8: np.ndarray) -> float:
@@ -338,7 +368,9 @@ class FcnTrainStep:
         """offset of the first variable the backward pass finishes in its first phase (deconv1 .. logits)"""
         return self.offsets[self.slots["deconv1"][0]]
 
-    def step(self, image_u8: np.ndarray, labels_u8: np.ndarray) -> float:
+    def step(self, image_u8: np.ndarray, labels_u8: np.ndarray, lazy_loss: bool = False):
+        """One optimisation step on one page; returns the loss as a float, or (tensor engine, lazy_loss=True) as a 0-d
+        device tensor that costs no synchronisation until somebody reads it."""
         import torch.distributed as dist
         world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
         if self.engine == "tensor" and world > 1:
@@ -353,7 +385,13 @@ class FcnTrainStep:
             first.wait()
             second.wait()
             self.apply_gradients(1.0 / world)
-            return float(self.d_loss.cpu()[0]) / (h * w)
+            loss = self.d_loss[0] / (h * w)
+            return loss if lazy_loss else float(loss.cpu())
+        if self.engine == "tensor" and lazy_loss:
+            h, w = image_u8.shape
+            self._tc_enqueue(image_u8, labels_u8)
+            self.apply_gradients(1.0)
+            return self.d_loss[0] / (h * w)
         loss = self.forward_backward(image_u8, labels_u8)
         self.apply_gradients(self.allreduce_gradients())
         return loss
@@ -389,7 +427,8 @@ class Trainer:
                 mask = np.asarray(d.mask, dtype=np.uint8).copy()
                 if s.foreground_masks:
                     mask[np.asarray(d.binary) != 1] = 0                          # network.py:148-149
-                self.losses.append(self.engine.step(np.asarray(d.image), mask))
+                self.losses.append(self.engine.step(np.asarray(d.image), mask, lazy_loss=True))
+            self.losses = [float(v) for v in self.losses]            # one synchronisation per epoch, not per page
         if s.output_dir:
             self.save(os.path.join(s.output_dir, s.model_name + s.model_suffix))
 

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--arch", default="fcn_skip")
+    ap.add_argument("--lazy-loss", action="store_true", help="do not read the loss back after every step (what Trainer.train does)")
     ap.add_argument("--engine", default=None, help="tensor | fp32 (default: FcnTrainStep's)")
     ap.add_argument("--cpu-steps", type=int, default=1, help="steps of the torch-CPU oracle timed beside it (rank 0, single process)")
     args = ap.parse_args()
@@ -45,9 +46,10 @@ def main():
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    losses = [eng.step(img, labels) for _ in range(args.steps)]
+    losses = [eng.step(img, labels, lazy_loss=args.lazy_loss) for _ in range(args.steps)]
     e1.record()
     torch.cuda.synchronize()
+    losses = [float(v) for v in losses]
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=f"cuda:{local}")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
