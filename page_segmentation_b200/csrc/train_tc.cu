@@ -339,12 +339,36 @@ struct WgradParams {
     int nslots;
     uint32_t x_row_bytes, x_alloc, dy_slot_bytes;
     int ntiles_m, d0[5], nr[5];
+    float* acc;                 // [ntiles_m][KX][npad][128] fp32 partial sums of all CTAs (zeroed by the caller), scattered into
+                                // the weight layout by tc_wgrad_scatter_kernel
+    int swap_strides;           // diagnosis: exchange LBO and SBO
+};
+
+// acc[tile][dx][n][m] -> dw[m_off[channel of row m] + n_off[n] + ((d0 + j) * kx + dx) * s_tap] += value
+struct ScatterDesc {
+    const float* acc;
     float* dw;
     const int* m_off;           // [P * 8]: X padded channel -> element offset of its weights or -1
     const int* n_off;           // [npad]
-    int s_tap;
-    int swap_strides;           // diagnosis: exchange LBO and SBO
+    int P, npad, kx, ntiles_m, d0[5], nr[5], s_tap;
+    unsigned total;
 };
+__global__ void __launch_bounds__(256) tc_wgrad_scatter_kernel(const ScatterDesc* __restrict__ descs) {
+    const ScatterDesc d = descs[blockIdx.y];
+    for (unsigned i = blockIdx.x * 256 + threadIdx.x; i < d.total; i += gridDim.x * 256) {
+        const int m = (int)(i & 127);
+        unsigned r = i >> 7;
+        const int n = (int)(r % d.npad); r /= d.npad;
+        const int dx = (int)(r % d.kx);
+        const int tile = (int)(r / d.kx);
+        const int g = m >> 3, j = g / d.P, pl = g - j * d.P;
+        if (j >= d.nr[tile]) continue;
+        const int moff = d.m_off[pl * 8 + (m & 7)], noff = d.n_off[n];
+        if (moff < 0 || noff < 0) continue;
+        const float v = d.acc[i];
+        if (v != 0.f) d.dw[moff + noff + ((d.d0[tile] + j) * d.kx + dx) * d.s_tap] += v;
+    }
+}
 
 template <int KX>
 __global__ void __launch_bounds__(kWgThreads, 1)
@@ -434,25 +458,26 @@ wgrad_tc_kernel(const WgradParams p, const __grid_constant__ CUtensorMap tmx, co
         if (leader) tc_commit(&s_done);
         __syncwarp();
     } else {
+        // one lane = one accumulator row; consecutive lanes add into consecutive floats of acc (a warp-wide reduction
+        // touches four 32-byte sectors; adding straight into the weight layout touched 32 and made this epilogue as long
+        // as the main loop of the low-resolution layers)
         const int quarter = warp & 3;
-        const int m = quarter * 32 + lane, g = m >> 3, e = m & 7;
-        const int j = g / p.P, pl = g - j * p.P;
-        const int moff = j < nr ? __ldg(p.m_off + pl * 8 + e) : -1;
+        const int m = quarter * 32 + lane;
+        const bool valid = ((m >> 3) / p.P) < nr;
         mbar_wait(&s_done, 0);
         tc_fence_after();
         const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        float* acc = p.acc + (size_t)blockIdx.y * KX * p.npad * 128 + m;
         for (int dx = 0; dx < KX; ++dx) {
-            const int tap_off = ((d0 + j) * KX + dx) * p.s_tap;
             for (int c16 = 0; c16 < p.npad / 16; ++c16) {
                 uint32_t v[16];
                 tmem_ld16(t_lane + (uint32_t)(dx * p.npad + c16 * 16), v);
                 tmem_ld_wait();
-                if (moff >= 0) {
+                if (valid) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const int noff = __ldg(p.n_off + c16 * 16 + i);
                         const float f = __uint_as_float(v[i]);
-                        if (noff >= 0 && f != 0.f) atomicAdd(p.dw + moff + noff + tap_off, f);
+                        if (f != 0.f) atomicAdd(acc + (size_t)(dx * p.npad + c16 * 16 + i) * 128, f);
                     }
                 }
             }
@@ -537,7 +562,20 @@ struct TcLayer {
     int co_t = 0;                // stride-2 layers: padded channels per tap of the forward GEMM
     const int* wg_m_off = nullptr; const int* wg_n_off = nullptr;
     int wg_npad = 0;
+    float* wg_acc = nullptr;     // partial-sum buffer of the weight-gradient kernel (inside TrainTc::d_wg_acc)
 };
+
+// groups of vertical taps of a weight-gradient launch: as many kernel rows as fit 16 eight-channel groups
+int wgrad_tiles(int P, int kx, int* d0, int* nr) {
+    const int per = kx == 1 ? 1 : std::min(5, 16 / P);
+    int n = 0;
+    for (int d = 0; d < kx; d += per) { d0[n] = d; nr[n] = std::min(per, kx - d); ++n; }
+    return n;
+}
+size_t wgrad_acc_floats(int P, int kx, int npad) {
+    int d0[5], nr[5];
+    return (size_t)wgrad_tiles(P, kx, d0, nr) * kx * npad * 128;
+}
 
 int npad_for(int cols) { return cols <= 32 ? 32 : cols <= 48 ? 48 : cols <= 64 ? 64 : cols <= 80 ? 80 : 64; }
 
@@ -551,6 +589,13 @@ struct TrainTc {
     WimgDesc* d_descs = nullptr;
     unsigned long long max_img_total = 0;
     float* d_zero_bias = nullptr;
+    float* d_wg_acc = nullptr;               // partial sums of all weight-gradient launches of a step
+    size_t wg_acc_floats = 0;
+    std::vector<ScatterDesc> h_scatter;      // decoder layers first (phase 1), then the encoder layers (phase 2)
+    int n_scatter_decoder = 0;
+    ScatterDesc* d_scatter = nullptr;
+    const float* scatter_grads = nullptr;    // gradient buffer the device scatter table was built for
+    unsigned max_scatter_total = 0;
     const int* d_logit_map = nullptr;
     float4* d_dl = nullptr;
     Ten x, conv1, d5cat, deconv5, conv2, pool2, d4cat, deconv4, conv3, conv4, pool4, d3cat, deconv3, conv5, d2cat, deconv2, conv6, pool6, conv7, deconv1;
@@ -691,21 +736,15 @@ int deconv_fwd_launch(pcs_ctx* ctx, const TcLayer& L, const Ten& src, const floa
     return launch_conv_umma(ctx, a);
 }
 
-int wgrad_launch_raw(pcs_ctx* ctx, const Ten& X, const Ten& dY, int kx, int npad, float* dw, const int* m_off, const int* n_off, int s_tap) {
+int wgrad_launch_raw(pcs_ctx* ctx, const Ten& X, const Ten& dY, int kx, int npad, float* acc) {
     const int DT = kx == 5 ? 112 : 128, XT = kx == 5 ? 120 : 128;
     WgradParams p{};
     p.H = dY.h; p.W = dY.w; p.P = X.planes(); p.npad = npad; p.nq = p.npad / 8; p.pad = (kx - 1) / 2;
     if (X.h != dY.h || X.w != dY.w) return set_err(ctx, PCS_ERR_STATE, "train_tc: wgrad operands differ in size");
     if (p.P < 1 || p.P > 16 || kx * p.npad > 512 || p.npad > 256 || (p.npad & 15)) return set_err(ctx, PCS_ERR_STATE, "train_tc: wgrad shape P=%d N=%d", p.P, p.npad);
-    // groups of vertical taps: as many kernel rows as fit 16 eight-channel groups
-    const int per = kx == 1 ? 1 : std::min(5, 16 / p.P);
-    p.ntiles_m = 0;
+    p.ntiles_m = wgrad_tiles(p.P, kx, p.d0, p.nr);
     int nr_max = 0;
-    for (int d = 0; d < kx; d += per) {
-        p.d0[p.ntiles_m] = d; p.nr[p.ntiles_m] = std::min(per, kx - d);
-        nr_max = std::max(nr_max, p.nr[p.ntiles_m]);
-        ++p.ntiles_m;
-    }
+    for (int i = 0; i < p.ntiles_m; ++i) nr_max = std::max(nr_max, p.nr[i]);
     p.x_row_bytes = (uint32_t)p.P * XT * 16;
     p.dy_slot_bytes = (uint32_t)p.nq * DT * 16;
     const uint32_t budget = 222 * 1024, slack = 16u * XT * 16;
@@ -735,7 +774,7 @@ int wgrad_launch_raw(pcs_ctx* ctx, const Ten& X, const Ten& dY, int kx, int npad
     p.xr = p.B + nr_max - 1;
     p.x_alloc = ((uint32_t)p.xr * p.x_row_bytes + 1023) / 1024 * 1024;
     p.bands = (p.H + p.B - 1) / p.B;
-    p.dw = dw; p.m_off = m_off; p.n_off = n_off; p.s_tap = s_tap;
+    p.acc = acc;
     { const char* e = getenv("PCSEG_WGRAD_SWAP"); p.swap_strides = e && e[0] == '1'; }
     CUtensorMap tmx, tmdy;
     PCS_TRY(make_row_map(ctx, &tmx, X, XT, p.P));
@@ -756,7 +795,23 @@ int wgrad_launch_raw(pcs_ctx* ctx, const Ten& X, const Ten& dY, int kx, int npad
 }
 
 int wgrad_launch(pcs_ctx* ctx, TrainTc* t, const TcLayer& L, const Ten& X, const Ten& dY) {
-    return wgrad_launch_raw(ctx, X, dY, L.def.kind == 2 ? 1 : 5, L.wg_npad, t->grads + L.w_off, L.wg_m_off, L.wg_n_off, L.def.kind == 2 ? 0 : 1);
+    (void)t;
+    return wgrad_launch_raw(ctx, X, dY, L.def.kind == 2 ? 1 : 5, L.wg_npad, L.wg_acc);
+}
+
+ScatterDesc scatter_desc(const float* acc, float* dw, const int* m_off, const int* n_off, int P, int npad, int kx, int s_tap) {
+    ScatterDesc d{};
+    d.acc = acc; d.dw = dw; d.m_off = m_off; d.n_off = n_off; d.P = P; d.npad = npad; d.kx = kx; d.s_tap = s_tap;
+    d.ntiles_m = wgrad_tiles(P, kx, d.d0, d.nr);
+    d.total = (unsigned)((size_t)d.ntiles_m * kx * npad * 128);
+    return d;
+}
+
+// launches tc_wgrad_scatter_kernel over descs[first, first + count) of the device table
+int scatter_launch(pcs_ctx* ctx, const ScatterDesc* d_descs, int first, int count, unsigned max_total) {
+    tc_wgrad_scatter_kernel<<<dim3(std::min<unsigned>((max_total + 255) / 256, 96), (unsigned)count), 256, 0, ctx->stream>>>(d_descs + first);
+    PCS_LAUNCH_CHECK(ctx, "tc_wgrad_scatter_kernel");
+    return PCS_OK;
 }
 
 int bias_grad_launch(pcs_ctx* ctx, TrainTc* t, const TcLayer& L, const Ten& g, int qp) {
@@ -792,15 +847,25 @@ int train_tc_wgrad(pcs_ctx* ctx, const void* d_x, int x_planes, const void* d_dy
     std::vector<int> mo(x_planes * 8, -1), no(npad, -1);
     for (int c = 0; c < ci; ++c) mo[c] = c * KK;
     for (int o = 0; o < co; ++o) no[o] = o * ci * KK;
-    PCS_TRY(scratch_reserve(ctx, (mo.size() + no.size()) * sizeof(int) + 256));
-    int* d_maps = reinterpret_cast<int*>(ctx->scratch);
+    const size_t acc_floats = wgrad_acc_floats(x_planes, k, npad);
+    const size_t maps_bytes = ((mo.size() + no.size()) * sizeof(int) + 255) / 256 * 256;
+    PCS_TRY(scratch_reserve(ctx, maps_bytes + 256 + acc_floats * sizeof(float)));
+    char* base = reinterpret_cast<char*>(ctx->scratch);
+    int* d_maps = reinterpret_cast<int*>(base);
+    ScatterDesc* d_desc = reinterpret_cast<ScatterDesc*>(base + maps_bytes);
+    float* d_acc = reinterpret_cast<float*>(base + maps_bytes + 256);
+    static_assert(sizeof(ScatterDesc) <= 256, "scatter descriptor slot");
+    const ScatterDesc desc = scatter_desc(d_acc, d_dw, d_maps, d_maps + mo.size(), x_planes, npad, k, 1);
     PCS_CUDA(ctx, cudaMemcpyAsync(d_maps, mo.data(), mo.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     PCS_CUDA(ctx, cudaMemcpyAsync(d_maps + mo.size(), no.data(), no.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    PCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));            // the maps are temporaries
+    PCS_CUDA(ctx, cudaMemcpyAsync(d_desc, &desc, sizeof(desc), cudaMemcpyHostToDevice, ctx->stream));
+    PCS_CUDA(ctx, cudaMemsetAsync(d_acc, 0, acc_floats * sizeof(float), ctx->stream));
+    PCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));            // the maps and the descriptor are temporaries
     Ten X, dY;
     X.p = reinterpret_cast<bf16*>(const_cast<void*>(d_x)); X.cp = x_planes * 8; X.h = H; X.w = W;
     dY.p = reinterpret_cast<bf16*>(const_cast<void*>(d_dy)); dY.cp = dy_planes * 8; dY.h = H; dY.w = W;
-    return wgrad_launch_raw(ctx, X, dY, k, npad, d_dw, d_maps, d_maps + mo.size(), 1);
+    PCS_TRY(wgrad_launch_raw(ctx, X, dY, k, npad, d_acc));
+    return scatter_launch(ctx, d_desc, 0, 1, desc.total);
 }
 
 int train_tc_destroy(pcs_ctx* ctx, TrainTc* t) {
@@ -871,6 +936,32 @@ int train_tc_create(pcs_ctx* ctx, int arch, int n_classes, int h, int w, const l
     }
     if (rc == PCS_OK) rc = tc_alloc(ctx, t, &p, t->h_descs.size() * sizeof(WimgDesc));
     t->d_descs = reinterpret_cast<WimgDesc*>(p);
+    if (rc == PCS_OK) {
+        // partial-sum buffers and the scatter table of the weight-gradient launches, in backward order
+        const int order[12] = {L_DECONV5, L_DECONV4, L_DECONV3, L_DECONV2, L_DECONV1, L_CONV7, L_CONV6, L_CONV5, L_CONV4, L_CONV3, L_CONV2, L_CONV1};
+        size_t total = 0;
+        for (int li : order) {
+            TcLayer& L = t->L[li];
+            total += wgrad_acc_floats(L.in_cp / 8, L.def.kind == 2 ? 1 : 5, L.wg_npad);
+        }
+        t->wg_acc_floats = total;
+        rc = tc_alloc(ctx, t, &p, total * sizeof(float));
+        t->d_wg_acc = reinterpret_cast<float*>(p);
+        size_t at = 0;
+        for (int k = 0; k < 12 && rc == PCS_OK; ++k) {
+            TcLayer& L = t->L[order[k]];
+            const int kx = L.def.kind == 2 ? 1 : 5;
+            L.wg_acc = t->d_wg_acc + at;
+            at += wgrad_acc_floats(L.in_cp / 8, kx, L.wg_npad);
+            // dw holds the OFFSET of the layer's kernel until the step rebases it on the gradient buffer
+            ScatterDesc d = scatter_desc(L.wg_acc, reinterpret_cast<float*>(L.w_off), L.wg_m_off, L.wg_n_off, L.in_cp / 8, L.wg_npad, kx, L.def.kind == 2 ? 0 : 1);
+            t->h_scatter.push_back(d);
+            t->max_scatter_total = std::max(t->max_scatter_total, d.total);
+            if (order[k] == L_DECONV1) t->n_scatter_decoder = k + 1;
+        }
+        if (rc == PCS_OK) rc = tc_alloc(ctx, t, &p, t->h_scatter.size() * sizeof(ScatterDesc));
+        t->d_scatter = reinterpret_cast<ScatterDesc*>(p);
+    }
     if (rc == PCS_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = set_err(ctx, PCS_ERR_CUDA, "train_tc: setup failed");
     if (rc != PCS_OK) { train_tc_destroy(ctx, t); return rc; }
     *out = t;
@@ -898,6 +989,14 @@ int train_tc_step(pcs_ctx* ctx, TrainTc* t, int phases, const uint8_t* d_img, co
         }
         tc_wimg_kernel<<<dim3((unsigned)std::min<unsigned long long>((t->max_img_total + 255) / 256, 64), (unsigned)t->h_descs.size()), 256, 0, ctx->stream>>>(t->d_descs);
         PCS_LAUNCH_CHECK(ctx, "tc_wimg_kernel");
+        if (t->scatter_grads != d_grads) {
+            std::vector<ScatterDesc> sd = t->h_scatter;
+            for (ScatterDesc& d : sd) d.dw = d_grads + reinterpret_cast<intptr_t>(d.dw);
+            PCS_CUDA(ctx, cudaMemcpyAsync(t->d_scatter, sd.data(), sd.size() * sizeof(ScatterDesc), cudaMemcpyHostToDevice, ctx->stream));
+            PCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));    // sd is a temporary
+            t->scatter_grads = d_grads;
+        }
+        PCS_CUDA(ctx, cudaMemsetAsync(t->d_wg_acc, 0, t->wg_acc_floats * sizeof(float), ctx->stream));
         size_t nparams = (size_t)L[L_LOGITS].b_off + t->ncls;
         PCS_CUDA(ctx, cudaMemsetAsync(d_grads, 0, nparams * sizeof(float), ctx->stream));
         PCS_CUDA(ctx, cudaMemsetAsync(d_loss, 0, sizeof(double), ctx->stream));
@@ -960,6 +1059,7 @@ int train_tc_step(pcs_ctx* ctx, TrainTc* t, int phases, const uint8_t* d_img, co
         PCS_TRY(wgrad_launch(ctx, t, L[L_DECONV1], t->conv7, t->g_deconv1));
         PCS_TRY(bias_grad_launch(ctx, t, L[L_DECONV1], t->g_deconv1, 10));
         PCS_TRY(conv_launch(ctx, L[L_DECONV1].dgrad, t->g_deconv1, zb, 80, 0, t->g_conv7, nullptr, 5));
+        PCS_TRY(scatter_launch(ctx, t->d_scatter, 0, t->n_scatter_decoder, t->max_scatter_total));
     }
     if (phases & 2) {
         const float* zb = t->d_zero_bias;
@@ -1000,6 +1100,8 @@ int train_tc_step(pcs_ctx* ctx, TrainTc* t, int phases, const uint8_t* d_img, co
         PCS_TRY(combine_launch(ctx, t->g_conv1, t->g_conv1, nullptr, &t->conv1, 0));
         PCS_TRY(wgrad_launch(ctx, t, L[L_CONV1], t->x, t->g_conv1));
         PCS_TRY(bias_grad_launch(ctx, t, L[L_CONV1], t->g_conv1, 3));
+        if (t->scatter_grads != d_grads) return set_err(ctx, PCS_ERR_STATE, "train_tc: phase 2 with a gradient buffer phase 1 has not seen");
+        PCS_TRY(scatter_launch(ctx, t->d_scatter, t->n_scatter_decoder, (int)t->h_scatter.size() - t->n_scatter_decoder, t->max_scatter_total));
     }
     return PCS_OK;
 }
