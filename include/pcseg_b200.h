@@ -352,6 +352,13 @@ PCS_API int pcs_train_tc_wgrad(pcs_ctx* ctx, const void* d_x, int x_planes, cons
                                int c_in, int c_out, float* d_dw);
 
 /* ---- diagnostics ------------------------------------------------------ */
+/* fp16 models (PCS_PREC_FP16, the default) store activations with a saturating conversion: a value beyond the fp16 range
+ * is stored as +-65504 instead of inf.  The stored activations of the FIRST forward after every pcs_model_load (mode 1,
+ * the default; 2 = of every forward, 0 = never) are scanned for such values; pcs_saturation_count returns how many were
+ * found since the model was loaded (synchronises the stream).  A non-zero count means the model needs PCS_PREC_BF16 for
+ * parity with the reference's fp32 arithmetic (keras models: network.py:75-84). */
+PCS_API int pcs_set_saturation_check(pcs_ctx* ctx, int mode);
+PCS_API int pcs_saturation_count(pcs_ctx* ctx, uint64_t* out);
 /* copies one named internal activation of the last pcs_forward to a float32
  * NHWC host buffer (real channels only); returns the channel count or <0. */
 PCS_API int pcs_debug_activation(pcs_ctx* ctx, const char* name, float* h_out, size_t capacity_floats,

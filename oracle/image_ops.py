@@ -1,3 +1,5 @@
+# Test infrastructure: restates functions of ocr4all_pixel_classifier (https://github.com/ocr-d-modul-2-segmentierung/page-segmentation,
+# (c) its authors, licensed Apache-2.0 OR GPL-3.0-or-later) on the CPU as the parity oracle; never imported by the product path.
 """CPU restatement of `compute_char_height` (test infrastructure, see oracle/__init__).
 
 Follows ocr4all_pixel_classifier/lib/image_ops.py:58-82 with cv2 (installed here, 4.13) as the live

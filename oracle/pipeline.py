@@ -1,3 +1,5 @@
+# Test infrastructure: restates functions of ocr4all_pixel_classifier (https://github.com/ocr-d-modul-2-segmentierung/page-segmentation,
+# (c) its authors, licensed Apache-2.0 OR GPL-3.0-or-later) on the CPU as the parity oracle; never imported by the product path.
 """CPU restatement of the page-level stages either side of the network
 (test infrastructure, see oracle/__init__).
 

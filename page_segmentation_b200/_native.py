@@ -26,7 +26,7 @@ EXPORTS = [
     "pcs_bounding_boxes", "pcs_class_components", "pcs_char_height", "pcs_png_bytes", "pcs_png_encode", "pcs_output_pages", "pcs_output_flush", "pcs_segment_masks", "pcs_dilate3x3", "pcs_integral_image", "pcs_text_regions", "pcs_predict_pages_host", "pcs_predict_pages_files", "pcs_predict_pages_segments", "pcs_eval_counts",
     "pcs_train_input", "pcs_train_corr2d", "pcs_train_wgrad", "pcs_train_bias_grad", "pcs_train_relu_bwd", "pcs_train_maxpool_fwd",
     "pcs_train_maxpool_bwd", "pcs_train_deconv2_fwd", "pcs_train_deconv2_bwd_data", "pcs_train_deconv2_wgrad", "pcs_train_softmax_ce",
-    "pcs_train_adam", "pcs_train_tc_create", "pcs_train_tc_step", "pcs_train_tc_destroy", "pcs_train_tc_wgrad", "pcs_debug_activation", "pcs_set_keep_activations", "pcs_set_timing", "pcs_set_pdl",
+    "pcs_train_adam", "pcs_train_tc_create", "pcs_train_tc_step", "pcs_train_tc_destroy", "pcs_train_tc_wgrad", "pcs_set_saturation_check", "pcs_saturation_count", "pcs_debug_activation", "pcs_set_keep_activations", "pcs_set_timing", "pcs_set_pdl",
     "pcs_last_timings",
 ]
 
@@ -109,6 +109,8 @@ def load() -> C.CDLL:
     lib.pcs_train_tc_create.argtypes = [vp, i32, i32, i32, i32, vp, i32, C.POINTER(vp)]
     lib.pcs_train_tc_step.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
     lib.pcs_train_tc_destroy.argtypes = [vp, vp]
+    lib.pcs_set_saturation_check.argtypes = [vp, i32]
+    lib.pcs_saturation_count.argtypes = [vp, vp]
     lib.pcs_train_tc_wgrad.argtypes = [vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.pcs_debug_activation.argtypes = [vp, C.c_char_p, vp, C.c_size_t, C.POINTER(C.c_int32)]
     lib.pcs_set_keep_activations.argtypes = [vp, i32]
@@ -242,6 +244,7 @@ class Context:
         self._check(self.lib.pcs_model_load(self.h, ARCH_IDS[arch], int(n_classes), PRECISIONS[precision],
                                             arr, len(weights)), "pcs_model_load")
         self.model = (arch, int(n_classes), precision)
+        self._sat_unchecked = precision == "fp16"
         self.loaded_key = key
 
     # -- stages (device pointers) ----------------------------------------------
@@ -270,6 +273,7 @@ class Context:
         self._check(self.lib.pcs_forward(self.h, _ptr(d_image), _ptr(d_binary), n, Hs, Ws, _ptr(d_labels),
                                          _ptr(d_logits), _ptr(d_prob), _ptr(lut_arr), _ptr(d_color),
                                          _ptr(d_overlay), _ptr(d_inverted)), "pcs_forward")
+        self._after_forward()
 
     def masks(self, d_labels, d_binary, n, H, W, lut, d_color, d_overlay, d_inverted):
         lut_arr = np.ascontiguousarray(lut, dtype=np.uint8)
@@ -347,21 +351,25 @@ class Context:
             self.h, _ptr(h_grey), _ptr(h_bin), n, H, W, Hs, Ws, 1 if cc_majority else 0, _ptr(lut_arr),
             _ptr(h_image), _ptr(h_binary), _ptr(h_labels), _ptr(h_color), _ptr(h_overlay), _ptr(h_inverted)),
             "pcs_predict_pages_host")
+        self._after_forward()
 
     def predict_pages_compact(self, h_grey, h_bin, n, H, W, Hs, Ws, cc_majority, h_labels, h_binary_bits=None):
         self._check(self.lib.pcs_predict_pages_compact(self.h, _ptr(h_grey), _ptr(h_bin), n, H, W, Hs, Ws, 1 if cc_majority else 0,
                                                        _ptr(h_labels), _ptr(h_binary_bits)), "pcs_predict_pages_compact")
+        self._after_forward()
 
     def predict_pages_packed(self, h_bits, level0, level1, n, H, W, Hs, Ws, cc_majority, h_labels, h_binary_bits=None):
         self._check(self.lib.pcs_predict_pages_packed(self.h, _ptr(h_bits), int(level0), int(level1), n, H, W, Hs, Ws,
                                                       1 if cc_majority else 0, _ptr(h_labels), _ptr(h_binary_bits)),
                     "pcs_predict_pages_packed")
+        self._after_forward()
 
     def predict_pages_files(self, h_grey, h_bin, n, H, W, Hs, Ws, cc_majority, lut, h_labels, h_png, png_stride, h_png_sizes):
         lut_arr = _lut256(lut, self.model[1] if self.model else None)
         self._check(self.lib.pcs_predict_pages_files(
             self.h, _ptr(h_grey), _ptr(h_bin), n, H, W, Hs, Ws, 1 if cc_majority else 0, _ptr(lut_arr),
             _ptr(h_labels), _ptr(h_png), png_stride, _ptr(h_png_sizes)), "pcs_predict_pages_files")
+        self._after_forward()
 
     def predict_pages_segments(self, h_grey, h_bin, n, H, W, Hs, Ws, cc_majority, lut, h_labels, h_stats, max_components,
                                h_ncomp=None, h_color=None, h_overlay=None, h_inverted=None):
@@ -370,6 +378,7 @@ class Context:
             self.h, _ptr(h_grey), _ptr(h_bin), n, H, W, Hs, Ws, 1 if cc_majority else 0, _ptr(lut_arr), _ptr(h_labels),
             _ptr(h_color), _ptr(h_overlay), _ptr(h_inverted), _ptr(h_stats), int(max_components), _ptr(h_ncomp)),
             "pcs_predict_pages_segments")
+        self._after_forward()
 
     def eval_counts(self, d_pred, d_mask, d_bin, n_pixels, n_classes, d_out):
         self._check(self.lib.pcs_eval_counts(self.h, _ptr(d_pred), _ptr(d_mask), _ptr(d_bin), n_pixels, n_classes, _ptr(d_out)), "pcs_eval_counts")
@@ -398,6 +407,26 @@ class Context:
             self.lib.pcs_train_tc_destroy(self.h, handle)
 
     # -- diagnostics -----------------------------------------------------------
+    def _after_forward(self):
+        """First forward after a model load: the library has scanned the stored fp16 activations for saturated values."""
+        if getattr(self, "_sat_unchecked", False):
+            self._sat_unchecked = False
+            n = self.saturation_count()
+            if n:
+                import warnings
+                warnings.warn(f"{n} fp16 activation values of this model saturated at +-65504 on the first page(s); its class maps "
+                              "may differ from the reference's fp32 arithmetic.  Use precision='bf16' (Network(precision=...), "
+                              "PCSEG_PRECISION=bf16).", RuntimeWarning, stacklevel=3)
+
+    def set_saturation_check(self, mode: int):
+        self._check(self.lib.pcs_set_saturation_check(self.h, int(mode)), "pcs_set_saturation_check")
+
+    def saturation_count(self) -> int:
+        """fp16 activation stores that hit the +-65504 bound since the model was loaded (pcseg_b200.h)"""
+        out = C.c_uint64(0)
+        self._check(self.lib.pcs_saturation_count(self.h, C.byref(out)), "pcs_saturation_count")
+        return int(out.value)
+
     def debug_activation(self, name: str) -> np.ndarray:
         shape = (C.c_int32 * 4)()
         c = self.lib.pcs_debug_activation(self.h, name.encode(), None, 0, shape)

@@ -469,6 +469,7 @@ void pcs_ctx_destroy(pcs_ctx* ctx) {
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->scratch2) cudaFree(ctx->scratch2);
+    if (ctx->d_sat_count) cudaFree(ctx->d_sat_count);
     if (ctx->stage) cudaFree(ctx->stage);
     if (ctx->h_png_sizes) cudaFreeHost(ctx->h_png_sizes);
     for (int i = 0; i < 2; ++i)
@@ -514,6 +515,8 @@ int pcs_model_load(pcs_ctx* ctx, int arch, int n_classes, int precision, const p
     free_layers(ctx);
     ctx->arch = arch; ctx->n_classes = n_classes; ctx->precision = precision;
     { static int64_t next_stamp = 0; ctx->model_stamp = ++next_stamp; }
+    ctx->sat_pending = true;
+    if (ctx->d_sat_count) PCS_CUDA(ctx, cudaMemsetAsync(ctx->d_sat_count, 0, sizeof(unsigned long long), ctx->stream));
     for (int li = 0; li < nt; ++li) {
         const LayerSpec& s = table[li];
         const pcs_layer_weights& w = layers[li];
@@ -732,8 +735,39 @@ int pcs_forward(pcs_ctx* ctx, const uint8_t* d_image, const uint8_t* d_binary, i
         PCS_CUDA(ctx, cudaMemcpyAsync(d_lut, lut, (size_t)ctx->n_classes * 3, cudaMemcpyHostToDevice, ctx->stream));
         io.d_lut = d_lut;
     }
-    if (ctx->arch == PCS_ARCH_UNET) return forward_unet(ctx, d_image, n, Hs, Ws, io);
-    return forward_fcn(ctx, ctx->arch == PCS_ARCH_FCN_SKIP, d_image, n, Hs, Ws, io);
+    if (ctx->arch == PCS_ARCH_UNET) PCS_TRY(forward_unet(ctx, d_image, n, Hs, Ws, io));
+    else PCS_TRY(forward_fcn(ctx, ctx->arch == PCS_ARCH_FCN_SKIP, d_image, n, Hs, Ws, io));
+    if (ctx->precision == PCS_PREC_FP16 && (ctx->sat_mode == 2 || (ctx->sat_mode == 1 && ctx->sat_pending))) {
+        // every activation this forward stored (the arena is one contiguous range, untouched parts are whatever an
+        // earlier forward stored): saturated fp16 stores show up as +-65504
+        if (!ctx->d_sat_count) {
+            PCS_CUDA(ctx, cudaMalloc(&ctx->d_sat_count, sizeof(unsigned long long)));
+            PCS_CUDA(ctx, cudaMemsetAsync(ctx->d_sat_count, 0, sizeof(unsigned long long), ctx->stream));
+        }
+        for (const auto& kv : ctx->acts)
+            PCS_TRY(launch_saturation_scan(ctx, kv.second.p, kv.second.bytes() / 2, ctx->d_sat_count));
+        ctx->sat_pending = false;
+    }
+    return PCS_OK;
+}
+
+int pcs_set_saturation_check(pcs_ctx* ctx, int mode) {
+    if (!ctx) return PCS_ERR_ARG;
+    if (mode < 0 || mode > 2) return set_err(ctx, PCS_ERR_ARG, "saturation check mode %d (0 never, 1 first forward after a model load, 2 every forward)", mode);
+    ctx->sat_mode = mode;
+    return PCS_OK;
+}
+
+int pcs_saturation_count(pcs_ctx* ctx, uint64_t* out) {
+    if (!ctx || !out) return ctx ? set_err(ctx, PCS_ERR_ARG, "saturation_count: null argument") : PCS_ERR_ARG;
+    *out = 0;
+    if (!ctx->d_sat_count) return PCS_OK;
+    PCS_CUDA(ctx, cudaSetDevice(ctx->device));
+    unsigned long long v = 0;
+    PCS_CUDA(ctx, cudaMemcpyAsync(&v, ctx->d_sat_count, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
+    PCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = v;
+    return PCS_OK;
 }
 
 int pcs_masks(pcs_ctx* ctx, const uint8_t* d_labels, const uint8_t* d_binary, int n, int H, int W, const uint8_t* lut,

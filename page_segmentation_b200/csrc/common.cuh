@@ -122,6 +122,12 @@ struct pcs_ctx {
     bool pdl = false;                       // launch the tensor-core kernels with programmatic dependent launch (PCSEG_PDL=1 / pcs_set_pdl);
                                             // measured neutral on B200 (interleaved A/B), so off by default
     bool keep_acts = false;                 // diagnostics: also store activations the fused kernels normally skip
+
+    // fp16 stores saturate at +-65504 (umma_ptx.cuh pack2<__half>): the stored activations of a forward are scanned for
+    // saturated values -- mode 1 (default): on the first forward after every model load, 2: on every forward, 0: never
+    int sat_mode = 1;
+    bool sat_pending = false;               // a model has been loaded and not yet checked
+    unsigned long long* d_sat_count = nullptr;   // saturated stored values found since the model was loaded
 };
 
 namespace pcs {
@@ -256,6 +262,7 @@ int launch_head(pcs_ctx* ctx, const HeadArgs& a);
 int launch_masks(pcs_ctx* ctx, const uint8_t* d_labels, const uint8_t* d_binary, int n, int H, int W,
                  const uint8_t* d_lut, int n_lut, uint8_t* d_color, uint8_t* d_overlay, uint8_t* d_inverted);
 
+int launch_saturation_scan(pcs_ctx* ctx, const void* d_act, size_t n_halves, unsigned long long* d_count);
 int launch_eval_counts(pcs_ctx* ctx, const uint8_t* d_pred, const uint8_t* d_mask, const uint8_t* d_bin, size_t n, int n_classes,
                        unsigned long long* d_out);
 

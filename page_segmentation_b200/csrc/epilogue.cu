@@ -283,6 +283,29 @@ eval_counts_kernel(const uint8_t* __restrict__ pred, const uint8_t* __restrict__
         if (s_cnt[i]) atomicAdd(&out[i], (unsigned long long)s_cnt[i]);
 }
 
+// counts the fp16 values of an activation tensor that sit at the saturation bound +-65504 (0x7BFF): pack2<__half> stores
+// anything beyond the fp16 range there (umma_ptx.cuh), and an exact 65504 in a healthy network is as good as impossible
+__global__ void __launch_bounds__(256) saturation_scan_kernel(const uint4* __restrict__ a, size_t units, unsigned long long* __restrict__ count) {
+    unsigned local = 0;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < units; i += (size_t)gridDim.x * 256) {
+        const uint4 v = __ldg(a + i);
+        const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) local += __popc(__vcmpeq2(w[k] & 0x7fff7fffu, 0x7bff7bffu)) >> 4;
+    }
+    for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, (unsigned long long)local);
+}
+
+int launch_saturation_scan(pcs_ctx* ctx, const void* d_act, size_t n_halves, unsigned long long* d_count) {
+    const size_t units = n_halves / 8;
+    if (!units) return PCS_OK;
+    const unsigned blocks = (unsigned)std::min<size_t>((units + 255) / 256, 148 * 16);
+    saturation_scan_kernel<<<blocks, 256, 0, ctx->stream>>>(reinterpret_cast<const uint4*>(d_act), units, d_count);
+    PCS_LAUNCH_CHECK(ctx, "saturation_scan_kernel");
+    return PCS_OK;
+}
+
 int launch_eval_counts(pcs_ctx* ctx, const uint8_t* d_pred, const uint8_t* d_mask, const uint8_t* d_bin, size_t n, int n_classes,
                        unsigned long long* d_out) {
     if (n_classes < 1 || n_classes > 62) return set_err(ctx, PCS_ERR_ARG, "eval_counts: 1..62 classes");

@@ -1,3 +1,7 @@
+# API mirror: the class / field / function names and argument lists in this file follow ocr4all_pixel_classifier
+# (https://github.com/ocr-d-modul-2-segmentierung/page-segmentation, (c) its authors, licensed Apache-2.0 OR
+# GPL-3.0-or-later) so that it drops in for the reference; the arithmetic underneath is this repository's own
+# (pcs_* calls into libpcseg_b200.so).
 """Mirror of ocr4all_pixel_classifier/lib/dataset.py for the prediction path:
 SingleData (:17-29), Dataset (:32-41), prepare_images (:131-150) and
 DatasetLoader (:153-208) and the directory listing `list_dataset` (:44-111) that

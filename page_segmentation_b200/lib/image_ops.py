@@ -1,3 +1,7 @@
+# API mirror: the class / field / function names and argument lists in this file follow ocr4all_pixel_classifier
+# (https://github.com/ocr-d-modul-2-segmentierung/page-segmentation, (c) its authors, licensed Apache-2.0 OR
+# GPL-3.0-or-later) so that it drops in for the reference; the arithmetic underneath is this repository's own
+# (pcs_* calls into libpcseg_b200.so).
 """Mirror of ocr4all_pixel_classifier/lib/image_ops.py on the B200 path: `compute_char_height` (:58-82, the producer of
 the `line_height_px` normalisation input; pcs_char_height) and the evaluation metrics `fgpa` (:8-19) and
 `fgoverlap_per_class` (:22-55) as one masked counting pass (pcs_eval_counts)."""

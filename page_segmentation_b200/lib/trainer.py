@@ -1,3 +1,7 @@
+# API mirror: the class / field / function names and argument lists in this file follow ocr4all_pixel_classifier
+# (https://github.com/ocr-d-modul-2-segmentierung/page-segmentation, (c) its authors, licensed Apache-2.0 OR
+# GPL-3.0-or-later) so that it drops in for the reference; the arithmetic underneath is this repository's own
+# (pcs_* calls into libpcseg_b200.so).
 """Training step of the FCN graphs on the device: mirror of ocr4all_pixel_classifier/lib/trainer.py (`TrainSettings`
 :59-106, `Trainer` :109-159) over `Network.train_dataset` (lib/network.py:167-242) for what BASELINE configs[4] names:
 one page per step (the reference's batch, network.py:151-161), mean sparse cross entropy from logits (metrics.py:8-9),

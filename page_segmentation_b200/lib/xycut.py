@@ -1,3 +1,7 @@
+# API mirror: the class / field / function names and argument lists in this file follow ocr4all_pixel_classifier
+# (https://github.com/ocr-d-modul-2-segmentierung/page-segmentation, (c) its authors, licensed Apache-2.0 OR
+# GPL-3.0-or-later) so that it drops in for the reference; the arithmetic underneath is this repository's own
+# (pcs_* calls into libpcseg_b200.so).
 """Mirror of ocr4all_pixel_classifier/lib/xycut.py: region types (:14-67) and the recursive XY-cut
 (`do_xy_cut` :95-109, `recursive_cut` :127-161, `_get_gaps` :112-117, `_get_segments` :164-173).
 

@@ -120,3 +120,42 @@ def test_c_abi_reports_errors_instead_of_crashing(ctx):
     # the Python layer turns the status into an exception with the library's message
     with pytest.raises(_native.PcsError):
         ctx.ccl(torch.zeros((4, 4), dtype=torch.uint8, device="cuda"), 1, 0, 4, torch.zeros((4, 4), dtype=torch.int32, device="cuda"), None, 0, None)
+
+
+def test_fp16_saturation_is_counted_and_reported(ctx):
+    """fp16 stores saturate at +-65504 (umma_ptx.cuh); the first forward after a model load scans the stored activations
+    and the host side warns and points at bf16.  A sane model counts zero, and bf16 (no saturation bound in reach) is
+    never scanned."""
+    import warnings
+    from page_segmentation_b200.lib.dataset import SingleData
+    from page_segmentation_b200.lib.network import Network
+    page = synth.make_page(4, 96, 128, 6)
+    data = SingleData(image=255 - page, binary=(page == 0).astype(np.uint8))
+    W = synth.make_weights("fcn_skip", 3, seed=2)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")                                   # a sane model must not warn
+        Network("Predict", n_classes=3, weights=W, precision="fp16").predict_single_data(data)
+    assert ctx.saturation_count() == 0
+    hot = [(k.copy(), b.copy()) for k, b in W]
+    hot[2] = (hot[2][0] * 3e5, hot[2][1])                                # conv3: activations far beyond 65504
+    with pytest.warns(RuntimeWarning, match="saturated"):
+        Network("Predict", n_classes=3, weights=hot, precision="fp16").predict_single_data(data)
+    assert ctx.saturation_count() > 0
+    n_first = ctx.saturation_count()
+    net = Network("Predict", n_classes=3, weights=hot, precision="fp16")
+    with pytest.warns(RuntimeWarning):
+        net.predict_single_data(data)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")                                   # reported once per model load, scanned once
+        net.predict_single_data(data)
+    assert ctx.saturation_count() == n_first
+    ctx.set_saturation_check(2)
+    try:
+        net.predict_single_data(data)
+        assert ctx.saturation_count() == 2 * n_first                      # mode 2: every forward
+    finally:
+        ctx.set_saturation_check(1)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        Network("Predict", n_classes=3, weights=hot, precision="bf16").predict_single_data(data)
+    assert ctx.saturation_count() == 0
