@@ -477,6 +477,9 @@ void pcs_ctx_destroy(pcs_ctx* ctx) {
     for (int i = 0; i < pcs_ctx::kHostBufs; ++i)
         if (ctx->ev_h2d[i]) { cudaEventDestroy(ctx->ev_h2d[i]); cudaEventDestroy(ctx->ev_comp[i]); cudaEventDestroy(ctx->ev_d2h[i]); cudaEventDestroy(ctx->ev_sizes[i]); }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+    if (ctx->ev_aux_fork) cudaEventDestroy(ctx->ev_aux_fork);
+    if (ctx->ev_aux_join) cudaEventDestroy(ctx->ev_aux_join);
     delete ctx;
 }
 

@@ -112,6 +112,8 @@ struct pcs_ctx {
     cudaStream_t copy_streams[2] = {nullptr, nullptr};     // H2D / D2H streams of the host pipeline
     static constexpr int kHostBufs = 4;                    // staging buffers the host pipeline may rotate over
     cudaEvent_t ev_h2d[kHostBufs] = {}, ev_comp[kHostBufs] = {}, ev_d2h[kHostBufs] = {}, ev_sizes[kHostBufs] = {}, ev_fork = nullptr;
+    cudaStream_t aux_stream = nullptr;                     // side stream of the preprocess: the (normally empty) general-path launches
+    cudaEvent_t ev_aux_fork = nullptr, ev_aux_join = nullptr;  // run beside the two-level resampler instead of after it
     uint64_t* h_png_sizes = nullptr;                       // pinned [kHostBufs][3][64]: file lengths of the chunk in flight (PNG mode)
 
     void* writer = nullptr;                 // pcs::OutputWriter of pcs_output_pages (output.cu), created on first use

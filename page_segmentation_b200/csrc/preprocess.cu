@@ -14,7 +14,9 @@ namespace pcs {
 // per-page grey-level presence bitmap (256 bits) -> min, max, #levels
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) level_bits_kernel(const uint8_t* __restrict__ src, size_t page_bytes,
-                                                         uint32_t* __restrict__ bits /*[n][8]*/) {
+                                                         uint32_t* __restrict__ bits /*[n][8]*/,
+                                                         const int4* __restrict__ page_lv /* or null: pages with .z set are skipped */) {
+    if (page_lv && page_lv[blockIdx.y].z) return;
     __shared__ uint32_t s_bits[8];
     if (threadIdx.x < 8) s_bits[threadIdx.x] = 0;
     __syncthreads();
@@ -82,216 +84,369 @@ __device__ __forceinline__ int level_count(const uint32_t* bits) {
 
 // ---------------------------------------------------------------------------
 // Fast path for pages with at most two grey levels (binarised scans: the case dataset.py:169-172 makes
-// the normal one).  One streaming pass over the page produces the level bitmap AND a 1-bit-per-pixel
-// plane  bit(i) = (page[i] != page[0]);  the resampler then never touches the 8.7 MB page again: a
-// source value is  bit ? other level : page[0].
+// the normal one).  One streaming pass over the page produces a 1-bit-per-pixel plane
+// bit(i) = (page[i] != page[0])  and three sums per page that decide exactly whether the page has at most
+// two levels; the resampler then never touches the 8.7 MB page again: a source value is
+// bit ? other level : page[0].
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t ne_bits4(uint32_t w, uint32_t ref4) {
-    const uint32_t x = w ^ ref4;
-    const uint32_t t = (x | ((x | 0x80808080u) - 0x01010101u)) & 0x80808080u;      // high bit set iff byte != 0
-    return (((t >> 7) * 0x01020408u) >> 24) & 0xfu;                                 // byte k -> bit k
-}
-__device__ __forceinline__ uint32_t ne_bits16(const uint4 v, uint32_t ref4) {
-    return ne_bits4(v.x, ref4) | (ne_bits4(v.y, ref4) << 4) | (ne_bits4(v.z, ref4) << 8) | (ne_bits4(v.w, ref4) << 12);
+// High bit of every byte of x that is not zero.
+__device__ __forceinline__ uint32_t nz_flags(uint32_t x) { return (x | ((x | 0x80808080u) - 0x01010101u)) & 0x80808080u; }
+
+// The 16 bytes of v compared with the bytes of ref4: bit i (of 16) = byte i differs.  Flags of two words are
+// interleaved at a spacing of four bits and gathered by ONE multiplication (32 partial products, no two on the
+// same bit, so no carries): the eight result bits arrive in the top byte of the product.
+__device__ __forceinline__ uint32_t ne_bits16(const uint4 v, uint32_t ref4, uint32_t& s1, uint32_t& s2) {
+    const uint32_t x0 = v.x ^ ref4, x1 = v.y ^ ref4, x2 = v.z ^ ref4, x3 = v.w ^ ref4;
+    s1 = __dp4a(x0, 0x01010101u, s1); s2 = __dp4a(x0, x0, s2);
+    s1 = __dp4a(x1, 0x01010101u, s1); s2 = __dp4a(x1, x1, s2);
+    s1 = __dp4a(x2, 0x01010101u, s1); s2 = __dp4a(x2, x2, s2);
+    s1 = __dp4a(x3, 0x01010101u, s1); s2 = __dp4a(x3, x3, s2);
+    const uint32_t p01 = ((nz_flags(x0) >> 4) | nz_flags(x1)) * 0x00204081u;       // top byte: bytes of x0, then of x1
+    const uint32_t p23 = ((nz_flags(x2) >> 4) | nz_flags(x3)) * 0x00204081u;
+    return __byte_perm(p01, p23, 0x4473) & 0xffffu;                                // byte 0 = p01 >> 24, byte 1 = p23 >> 24
 }
 
-// grid = (blocks, pages); every thread turns 32 page bytes into one bitmap word.  Requires 16-byte aligned
-// pages whose size is a multiple of 32 bytes (checked by the host; other shapes take the general kernels).
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+// Per-page sums over x = byte ^ page[0]: [0] = number of non-zero x, [1] = sum of x, [2] = sum of x^2.  The non-zero x
+// are all equal (the page has at most two levels) iff  [0] * [2] == [1]^2  (Cauchy-Schwarz, exact in integers).
+constexpr int kScanUnroll = 2;
+
+// grid = (blocks, pages); a warp turns 2 KB of page into 64 bitmap words per step: lane l loads the 16-byte groups
+// l, 32 + l, 64 + l, 96 + l (fully coalesced), neighbouring lanes exchange half words so that every lane holds whole
+// 32-pixel words.  Requires 16-byte aligned pages whose size is a multiple of 32 bytes (checked by the host; other
+// shapes take the general kernels).
 __global__ void __launch_bounds__(256) scan_pack_kernel(const uint8_t* __restrict__ src, size_t page_bytes,
-                                                        uint32_t* __restrict__ bits /*[n][8]*/,
+                                                        unsigned long long* __restrict__ stats /*[n][gridDim.x][3]*/,
                                                         uint32_t* __restrict__ bitmap, size_t bitmap_words /*per page, padded*/) {
-    __shared__ uint32_t s_bits[8];
-    if (threadIdx.x < 8) s_bits[threadIdx.x] = 0;
-    __syncthreads();
     const int page = blockIdx.y;
     const uint8_t* p = src + (size_t)page * page_bytes;
     const uint4* pv = reinterpret_cast<const uint4*>(p);
     uint32_t* bm = bitmap + (size_t)page * bitmap_words;
     const uint32_t ref4 = (uint32_t)__ldg(p) * 0x01010101u;
-    const size_t nwords = page_bytes / 32;
-    auto mark = [&](uint32_t val) {
-        if (!((s_bits[val >> 5] >> (val & 31)) & 1u)) atomicOr(&s_bits[val >> 5], 1u << (val & 31));
-    };
-    // high bit of every byte of w that is NOT zero
-    auto nz = [](uint32_t w) -> uint32_t { return (w | ((w | 0x80808080u) - 0x01010101u)) & 0x80808080u; };
-    // per-thread cache of the second value: words made of {page[0], oth} bytes only need no set update
-    uint32_t oth4 = ref4;
-    bool have_oth = false;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (size_t)gridDim.x * blockDim.x) {
-        const uint4 a = __ldg(pv + 2 * i), b = __ldg(pv + 2 * i + 1);
-        const uint32_t words[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        uint32_t out = 0;
+    const size_t nvec = page_bytes / 16;                  // even
+    const int lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    uint32_t cnt = 0, s1 = 0, s2 = 0;
+    constexpr int U = 2 * kScanUnroll;                    // 16-byte groups per lane and step
+    for (size_t base = warp * (32 * U); base < nvec; base += nwarps * (32 * U)) {
+        uint4 v[U];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const uint32_t wv = words[k];
-            const uint32_t dif = nz(wv ^ ref4);                         // bytes that differ from page[0]
-            out |= ((((dif >> 7) * 0x01020408u) >> 24) & 0xfu) << (4 * k);
-            if (dif & nz(wv ^ oth4)) {                                  // some byte is neither page[0] nor oth
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint32_t v = (wv >> (8 * q)) & 0xff;
-                    if (v != (ref4 & 0xff)) { mark(v); if (!have_oth) { oth4 = v * 0x01010101u; have_oth = true; } }
-                }
-            }
+        for (int u = 0; u < U; ++u) {
+            const size_t i = base + 32 * u + lane;
+            v[u] = i < nvec ? ldg_stream(pv + i) : make_uint4(ref4, ref4, ref4, ref4);
         }
-        bm[i] = out;
+#pragma unroll
+        for (int u = 0; u < U; u += 2) {
+            const uint32_t h0 = ne_bits16(v[u], ref4, s1, s2), h1 = ne_bits16(v[u + 1], ref4, s1, s2);
+            // even lane 2j: word j of the first 32 groups = h0(2j) | h0(2j+1) << 16; odd lane 2j+1: word j of the next 32 groups
+            const uint32_t got = __shfl_xor_sync(0xffffffffu, (lane & 1) ? h0 : h1, 1);
+            const uint32_t word = (lane & 1) ? (got | (h1 << 16)) : (h0 | (got << 16));
+            cnt += __popc(h0) + __popc(h1);
+            const size_t wi = (base + 32 * u) / 2 + (lane >> 1) + ((lane & 1) ? 16 : 0);
+            if (wi < nvec / 2) bm[wi] = word;
+        }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) { mark(ref4 & 0xff); bm[nwords] = 0; }       // pad word read by the funnel shift
+    if (blockIdx.x == 0 && threadIdx.x == 0) bm[nvec / 2] = 0;       // pad word read by the funnel shift
+    // one partial result per block (plain stores: thousands of atomics on one sector per page serialise in L2)
+    __shared__ unsigned long long s_part[8][3];
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    s1 = __reduce_add_sync(0xffffffffu, s1);
+    unsigned long long q = s2;                           // s2 <= 65025 * 16 * U per lane and step: 64 bits across the warp
+    for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    if (lane == 0) { s_part[threadIdx.x >> 5][0] = cnt; s_part[threadIdx.x >> 5][1] = s1; s_part[threadIdx.x >> 5][2] = q; }
     __syncthreads();
-    if (threadIdx.x < 8 && s_bits[threadIdx.x]) atomicOr(&bits[page * 8 + threadIdx.x], s_bits[threadIdx.x]);
+    if (threadIdx.x < 3) {
+        unsigned long long t = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += s_part[w][threadIdx.x];
+        stats[((size_t)page * gridDim.x + blockIdx.x) * 3 + threadIdx.x] = t;
+    }
 }
 
-constexpr int RB_T = 32, RB_TY = 128;            // output tile of the fast resampler: 32 x 128 (256 threads, 16 rows each): the
-                                                 // per-block setup (coordinates, 16-pattern table) is a quarter of the work at 64 rows
-constexpr int RB_RW = RB_TY / 32;                // warps that set up the rows
-constexpr int RB_MAX_SPAN = 4 * RB_TY + 8;       // staged source rows for scale factors up to 4
-constexpr int RB_ROW_WORDS = 8;                  // staged words per source row: (4*32 + 8 + 31 + 31) / 32
+// A warp per page, a block (16 warps) per group of pages: the verdict of the sums.  lv[page] = {level of a zero bit
+// (= page[0]), level of a set bit, 1 iff at most two levels, -}.  Pages with at most two levels get their level bitmap
+// here; the others are scanned by level_bits_kernel (gated on lv).  Also the per-group flag "some page of the group
+// has more than two levels".
+__global__ void __launch_bounds__(512)
+levels_from_stats_kernel(const uint8_t* __restrict__ src, size_t page_bytes, const unsigned long long* __restrict__ stats, int parts,
+                         int n, int group /* <= 16 */, uint32_t* __restrict__ bits /*[n][8], zeroed*/, int4* __restrict__ lv,
+                         int* __restrict__ gflags) {
+    __shared__ int s_many[16];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, pg = blockIdx.x * group + w;
+    if (w < 16) s_many[w] = 0;
+    __syncthreads();
+    if (w < group && pg < n) {
+        unsigned long long c = 0, s1 = 0, s2 = 0;
+        for (int i = lane; i < parts; i += 32) {
+            const unsigned long long* p = stats + ((size_t)pg * parts + i) * 3;
+            c += p[0]; s1 += p[1]; s2 += p[2];
+        }
+        for (int o = 16; o; o >>= 1) {
+            c += __shfl_xor_sync(0xffffffffu, c, o);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        if (lane == 0) {
+            const int a = src[(size_t)pg * page_bytes];
+            // c * s2 and s1 * s1 as 128-bit products
+            const bool two = c == 0 || (c * s2 == s1 * s1 && __umul64hi(c, s2) == __umul64hi(s1, s1));
+            const int b = (two && c) ? a ^ (int)(s1 / c) : a;
+            lv[pg] = make_int4(a, b, two ? 1 : 0, 0);
+            if (two) {
+                atomicOr(&bits[pg * 8 + (a >> 5)], 1u << (a & 31));
+                atomicOr(&bits[pg * 8 + (b >> 5)], 1u << (b & 31));
+            } else {
+                s_many[w] = 1;
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int f = 0;
+        for (int k = 0; k < 16; ++k) f |= s_many[k];
+        gflags[blockIdx.x] = f;
+    }
+}
 
-// grid = (ceil(Ws/32), ceil(Hs/64), pages).  Pages with more than two grey levels return at once (the
-// general kernel below handles them).  Bit-identical to the general kernel:
-//   * the horizontal cubic of a two-level row has only 16 possible operand patterns per output column;
-//     they are evaluated once per block with the same fp64 operation order (cubic_rn) and looked up;
-//   * a pixel whose 4x4 neighbourhood is all one level v gets cubic(v,v,v,v) = v exactly (every
-//     intermediate of cubic_rn is an exact small integer or zero), so warps over blank paper or solid ink
-//     store the precomputed constant and skip the fp64 arithmetic;
+__global__ void set_levels_kernel(int4* __restrict__ lv, int n, int l0, int l1) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) lv[i] = make_int4(l0, l1, 1, 0);
+}
+
+// v / 255 correctly rounded without the division sequence: q0 = RN(v * RN(1/255)), exact residual r = v - 255 q0 by one
+// FMA, q = RN(q0 + r * RN(1/255)) (Markstein; checked against `/` on 2e9 doubles of [0, 255], incl. subnormals).
+__device__ __forceinline__ double div255_rn(double v) {
+    const double c = 1.0 / 255.0;
+    const double q0 = __dmul_rn(v, c);
+    return __fma_rn(__fma_rn(-255.0, q0, v), c, q0);
+}
+// clip=True, then img = 1.0 - v/255 ; (img*255).astype(uint8)
+__device__ __forceinline__ uint8_t finish_image(double v, double vmin, double vmax) {
+    v = fmin(fmax(v, vmin), vmax);
+    return (uint8_t)(int)__dmul_rn(__dsub_rn(1.0, div255_rn(v)), 255.0);
+}
+
+constexpr int R2_TW = 128, R2_TH = 32;                     // output tile: 32 quads of columns x 32 rows
+constexpr int R2_MAXF = 4;                                 // largest scale factor (source pixels per output pixel)
+constexpr int R2_ROWS = R2_MAXF * (R2_TH - 1) + 6;         // staged source rows: first tap of the first row .. last tap of the last
+constexpr int R2_WORDS = (R2_MAXF * (R2_TW - 1) + 5 + 31) / 32 + 2;      // staged words per source row (+1 for the funnel shift)
+
+// grid = (ceil(Ws/128), ceil(tiles_y / tiles_per_block), pages).  Bit-identical to the general kernel:
+//   * the horizontal cubic of a two-level row has only 16 possible operand patterns per output column; they are
+//     evaluated once per block with the same fp64 operation order (cubic_rn) and looked up;
+//   * a pixel whose 4x4 neighbourhood is all one level v gets cubic(v,v,v,v) = v exactly (every intermediate of
+//     cubic_rn is an exact small integer or zero);
 //   * the vertical cubic, clip and the (1 - v/255) * 255 truncation are otherwise unchanged.
+// Source bit rows are staged in LOGICAL coordinates (reflection applied while staging), so that the taps of a pixel are
+// four consecutive bits of four consecutive staged rows.  A thread owns a quad of four adjacent output columns: one
+// funnel shift per tap row gives the bits of all four neighbourhoods, and a quad whose window is all paper or all ink
+// (three of four) is finished with integer work only.  The other quads go to a list in shared memory and are
+// evaluated afterwards, one pixel per thread, with every lane busy (phase B).
 __global__ void __launch_bounds__(256)
-resample_bits_kernel(const uint8_t* __restrict__ grey, const uint8_t* __restrict__ bin, int bin_is_grey, int H, int W,
-                     int Hs, int Ws, const uint32_t* __restrict__ level_bits, const uint32_t* __restrict__ bitmap,
-                     size_t bitmap_words, uint8_t* __restrict__ image_out, uint8_t* __restrict__ binary_out, int va_fixed /* >= 0: the level of a
-                     zero bit (packed input pages, no uint8 page to read it from) */) {
-    __shared__ double s_lut[16][RB_T];            // [pattern][column]: a warp reads 32 consecutive doubles (no bank conflicts)
-    __shared__ double s_cfrac[RB_T], s_rfrac[RB_TY];                  // fractional sampling offsets of columns / rows
-    __shared__ uint32_t s_bm[RB_MAX_SPAN][RB_ROW_WORDS];
-    __shared__ __align__(16) int s_ctap[RB_T][4], s_rtap[RB_TY][4];   // the four (reflected) source columns / rows
-    __shared__ int s_cnn[RB_T], s_rnn[RB_TY], s_off[RB_MAX_SPAN], s_rng[2 + 2 * RB_RW];
-    // bit address (within the flat staged bitmap) of column 0 of the four tap rows / the nearest row of every output
-    // row: the per-pixel work is then one add, one shift and a funnel shift per tap row
-    __shared__ __align__(16) int s_tapbit[RB_TY][4];
-    __shared__ int s_nnbit[RB_TY];
+resample_bits_kernel(const uint8_t* __restrict__ bin, int bin_is_grey, int H, int W, int Hs, int Ws, double f_r, double t_r,
+                     double f_c, double t_c, const int4* __restrict__ page_lv, const uint32_t* __restrict__ bitmap,
+                     size_t bitmap_words, uint8_t* __restrict__ image_out, uint8_t* __restrict__ binary_out, int tiles_per_block) {
+    __shared__ double s_lut[16][R2_TW];                   // [pattern][column]
+    __shared__ double s_cfrac[R2_TW], s_rfrac[R2_TH];
+    __shared__ uint32_t s_bm[R2_ROWS * R2_WORDS];
+    __shared__ uint32_t s_list[(R2_TW / 4) * R2_TH * 3];
+    __shared__ int s_c0[R2_TW], s_cnn[R2_TW], s_r0[R2_TH], s_rnn[R2_TH];      // floor / round of the sampling position (logical)
+    __shared__ int s_count;
     const int page = blockIdx.z;
-    const uint32_t* bits = level_bits + (size_t)page * 8;
-    if (level_count(bits) > 2) return;
+    const int4 lv = page_lv[page];
+    if (!lv.z) return;                                     // more than two levels: the general kernels do this page
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
-    if (wrp < 1 + RB_RW) {                        // warp 0: the 32 columns, warps 1..: the rows of the tile
-        const int n_in = wrp == 0 ? W : H, n_out = wrp == 0 ? Ws : Hs;
-        const int o = min(wrp == 0 ? blockIdx.x * RB_T + lane : blockIdx.y * RB_TY + (wrp - 1) * 32 + lane, n_out - 1);   // replicate past the edge
-        const double f = __ddiv_rn((double)n_in, (double)n_out);
-        const double pc = __dadd_rn(__dmul_rn(f, (double)o), __dsub_rn(__dmul_rn(0.5, f), 0.5));
-        const int nn = reflect_coord((long long)round(pc), n_in);        // order 0: C round(), then reflect
+    const int X0 = blockIdx.x * R2_TW;
+    const int va = lv.x, vb = lv.y;
+    const double vmin = (double)min(va, vb), vmax = (double)max(va, vb);
+    if (tid < R2_TW) {
+        const int o = min(X0 + tid, Ws - 1);               // replicate past the edge
+        const double pc = __dadd_rn(__dmul_rn(f_c, (double)o), t_c);
         const double pf = floor(pc);
-        const int ti = wrp == 0 ? lane : (wrp - 1) * 32 + lane;
-        (wrp == 0 ? s_cfrac : s_rfrac)[ti] = __dsub_rn(pc, pf);
-        (wrp == 0 ? s_cnn : s_rnn)[ti] = nn;
-        int lo = nn, hi = nn;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int c = reflect_coord((long long)pf - 1 + k, n_in);
-            (wrp == 0 ? s_ctap : s_rtap)[ti][k] = c;
-            lo = min(lo, c); hi = max(hi, c);
-        }
-        lo = __reduce_min_sync(0xffffffffu, lo);
-        hi = __reduce_max_sync(0xffffffffu, hi);
-        if (lane == 0) { s_rng[2 * wrp] = lo; s_rng[2 * wrp + 1] = hi; }
+        s_c0[tid] = (int)pf;
+        s_cnn[tid] = (int)round(pc);                       // order 0: C round()
+        s_cfrac[tid] = __dsub_rn(pc, pf);
     }
     __syncthreads();
-    const int cmin = s_rng[0], cmax = s_rng[1];
-    int rmin = s_rng[2], rmax = s_rng[3];
-#pragma unroll
-    for (int k = 1; k < RB_RW; ++k) { rmin = min(rmin, s_rng[2 + 2 * k]); rmax = max(rmax, s_rng[3 + 2 * k]); }
-    const int nrows = rmax - rmin + 1;
-    if (nrows > RB_MAX_SPAN || cmax - cmin + 1 + 62 > RB_ROW_WORDS * 32) { __trap(); }      // host guarantees scale <= 4
-    const uint32_t* bm = bitmap + (size_t)page * bitmap_words;
-    const size_t last_word = (size_t)H * W / 32;
-    for (int i = tid; i < nrows * RB_ROW_WORDS; i += 256) {
-        const int r = i / RB_ROW_WORDS, wq = i - r * RB_ROW_WORDS;
-        const size_t b0 = (size_t)(rmin + r) * W + cmin;
-        const size_t w0 = (b0 >> 5) + wq;
-        s_bm[r][wq] = w0 <= last_word ? __ldg(bm + w0) : 0u;
-        if (wq == 0) s_off[r] = (int)(b0 & 31) - cmin;        // bit (r, c) sits at bit s_off[r] + c of the staged row
-    }
-    __syncthreads();
-    if (tid < RB_TY) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int rl = s_rtap[tid][k] - rmin;
-            s_tapbit[tid][k] = rl * (RB_ROW_WORDS * 32) + s_off[rl];
-        }
-        const int rl = s_rnn[tid] - rmin;
-        s_nnbit[tid] = rl * (RB_ROW_WORDS * 32) + s_off[rl];
-    }
-    // the two levels: a = page[0] (bit 0), b = the other one (bit 1)
-    int l0 = -1, l1 = -1;
-#pragma unroll
-    for (int wv = 7; wv >= 0; --wv) {
-        const uint32_t m = bits[wv];
-        if (m) {
-            const int hi = wv * 32 + 31 - __clz(m), lo = wv * 32 + __ffs(m) - 1;
-            if (l1 < 0) l1 = hi;
-            l0 = lo;
-        }
-    }
-    const int va = va_fixed >= 0 ? va_fixed : (int)__ldg(grey + (size_t)page * H * W);
-    const int vb = va == l0 ? l1 : l0;
-    const double vmin = (double)l0, vmax = (double)l1;
-    if (image_out) {
+    {
         const double fa = (double)va, fb = (double)vb;
-        for (int i = tid; i < RB_T * 16; i += 256) {
-            const int c = i & 31, pat = i >> 5;
+        for (int i = tid; i < R2_TW * 16; i += 256) {
+            const int c = i & (R2_TW - 1), pat = i / R2_TW;
             s_lut[pat][c] = cubic_rn(s_cfrac[c], (pat & 1) ? fb : fa, (pat & 2) ? fb : fa, (pat & 4) ? fb : fa, (pat & 8) ? fb : fa);
         }
     }
-    __syncthreads();
-    const int x = blockIdx.x * RB_T + lane;
-    const uint32_t* bmflat = &s_bm[0][0];
-    auto bit_at = [&](int rowbit, int c) -> uint32_t {          // rowbit: flat bit address of column 0 of a staged row
-        const int b = rowbit + c;
-        return (bmflat[b >> 5] >> (b & 31)) & 1u;
-    };
-    auto finish = [&](double v) -> uint8_t {          // clip=True, then img = 1.0 - v/255 ; (img*255).astype(uint8)
-        v = fmin(fmax(v, vmin), vmax);
-        return (uint8_t)(int)__dmul_rn(__dsub_rn(1.0, __ddiv_rn(v, 255.0)), 255.0);
-    };
-    const uint8_t out_a = finish((double)va), out_b = finish((double)vb);
-    const int c0 = s_ctap[lane][0], c1 = s_ctap[lane][1], c2 = s_ctap[lane][2], c3 = s_ctap[lane][3];
-    const bool consec = c1 == c0 + 1 && c2 == c0 + 2 && c3 == c0 + 3;
-    const int nnc = s_cnn[lane];
-    const bool xok = x < Ws;
-    const uint8_t bin_a = va == 0 ? 1 : 0, bin_b = vb == 0 ? 1 : 0;   // bin = (1.0 - NN(binary/255 or binary)).astype(uint8)
-    const int y_first = blockIdx.y * RB_TY + wrp;
-    size_t dst = (size_t)page * Hs * Ws + (size_t)y_first * Ws + x;
-    const size_t dst_step = (size_t)8 * Ws;
-#pragma unroll 1
-    for (int ty = wrp; ty < RB_TY && blockIdx.y * RB_TY + ty < Hs; ty += 8, dst += dst_step) {     // warp-uniform bounds
-        if (binary_out && xok) {
-            uint8_t v;
-            if (bin_is_grey) v = bit_at(s_nnbit[ty], nnc) ? bin_b : bin_a;
-            else v = bin[(size_t)page * H * W + (size_t)s_rnn[ty] * W + nnc] == 0 ? 1 : 0;
-            binary_out[dst] = v;
-        }
-        if (image_out) {
-            const int4 rr = *reinterpret_cast<const int4*>(s_tapbit[ty]);
-            const int rb[4] = {rr.x, rr.y, rr.z, rr.w};
-            uint32_t pat[4];
+    // the quad of this thread: bit offset of its window in a staged row, offsets of the four neighbourhoods inside the
+    // window, positions of the four nearest-neighbour columns inside the window
+    const int cl = s_c0[0] - 1;                            // logical source column of staged bit 0
+    const int ch = s_c0[R2_TW - 1] + 2;                    // last logical source column needed
+    const int q = s_c0[4 * lane] - 1 - cl;
+    const int qw = q >> 5, qs = q & 31;
+    int off[4], nnb[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (consec) {
-                    const int b = rb[k] + c0;
-                    pat[k] = __funnelshift_r(bmflat[b >> 5], bmflat[(b >> 5) + 1], b & 31) & 15u;
-                } else {
-                    pat[k] = bit_at(rb[k], c0) | (bit_at(rb[k], c1) << 1) | (bit_at(rb[k], c2) << 2) | (bit_at(rb[k], c3) << 3);
+    for (int j = 0; j < 4; ++j) {
+        off[j] = s_c0[4 * lane + j] - s_c0[4 * lane];
+        nnb[j] = s_cnn[4 * lane + j] - (s_c0[4 * lane] - 1);
+    }
+    const uint32_t span = (2u << (off[3] + 3)) - 1u;       // window bits 0 .. off[3] + 3
+    uint32_t out_a4 = finish_image((double)va, vmin, vmax) * 0x01010101u, out_b4 = finish_image((double)vb, vmin, vmax) * 0x01010101u;
+    asm volatile("" : "+r"(out_a4), "+r"(out_b4));         // keep the two bytes in registers (not re-derived from doubles per row)
+    const uint32_t bin_a = va == 0 ? 1u : 0u, bin_b = vb == 0 ? 1u : 0u;      // bin = (1.0 - NN(binary/255 or binary)).astype(uint8)
+    const int x0 = X0 + 4 * lane;
+    const int nvalid = min(4, max(0, Ws - x0));            // columns of the quad that exist
+    const uint32_t* bm = bitmap + (size_t)page * bitmap_words;
+    uint8_t* img_page = image_out + (size_t)page * Hs * Ws;
+    uint8_t* bin_page = binary_out ? binary_out + (size_t)page * Hs * Ws : nullptr;
+    const int nwq = min(R2_WORDS, (ch - cl + 1 + 31) / 32 + 1);
+    if (ch - cl + 1 + 32 > R2_WORDS * 32) __trap();        // host guarantees scale factors <= 4
+    auto store4 = [&](uint8_t* p, uint32_t v4) {
+        if (nvalid == 4) {
+            p[0] = (uint8_t)v4; p[1] = (uint8_t)(v4 >> 8); p[2] = (uint8_t)(v4 >> 16); p[3] = (uint8_t)(v4 >> 24);
+        } else {
+            for (int j = 0; j < nvalid; ++j) p[j] = (uint8_t)(v4 >> (8 * j));
+        }
+    };
+
+    const int tiles_y = (Hs + R2_TH - 1) / R2_TH;
+    for (int t = 0; t < tiles_per_block; ++t) {
+        const int tile_y = blockIdx.y * tiles_per_block + t;
+        if (tile_y >= tiles_y) break;
+        const int Y0 = tile_y * R2_TH;
+        __syncthreads();                                   // phase B of the previous tile is done with the tables
+        if (tid < R2_TH) {
+            const int o = min(Y0 + tid, Hs - 1);
+            const double pr = __dadd_rn(__dmul_rn(f_r, (double)o), t_r);
+            const double pf = floor(pr);
+            s_r0[tid] = (int)pf;
+            s_rnn[tid] = (int)round(pr);
+            s_rfrac[tid] = __dsub_rn(pr, pf);
+        }
+        if (tid == 0) s_count = 0;
+        __syncthreads();
+        const int rl = s_r0[0] - 1;                        // logical source row of staged row 0
+        const int nrows = s_r0[R2_TH - 1] + 2 - rl + 1;
+        if (nrows > R2_ROWS) __trap();
+        // staging: 16 threads per source row (one word each; a second round for the widest rows), 16 rows per step.  The
+        // columns of a word that lie on the page come from one funnel shift (clamped at the page borders)
+        for (int r = tid >> 4; r < nrows; r += 16) {
+            int prow = rl + r;
+            if ((unsigned)prow >= (unsigned)H) prow = reflect_coord((long long)prow, H);
+            const size_t rowbit = (size_t)prow * W;
+            for (int wq = tid & 15; wq < nwq; wq += 16) {
+                const int lc = cl + 32 * wq;               // logical column of bit 0 of this word
+                const int lo = max(lc, 0), hi = min(lc + 31, W - 1);
+                uint32_t word = 0;
+                if (lo <= hi) {
+                    const size_t b0 = rowbit + lo;
+                    const uint32_t raw = __funnelshift_r(__ldg(bm + (b0 >> 5)), __ldg(bm + (b0 >> 5) + 1), (uint32_t)(b0 & 31));
+                    word = (raw & (0xffffffffu >> (31 - (hi - lo)))) << (lo - lc);
+                }
+                s_bm[r * R2_WORDS + wq] = word;
+            }
+        }
+        if (cl < 0 || ch > W - 1) {                        // block-uniform: tiles at the left / right page border
+            // the (at most two on either side) needed columns beyond the border are reflected one by one, a row per thread
+            __syncthreads();
+            for (int r = tid; r < nrows; r += 256) {
+                int prow = rl + r;
+                if ((unsigned)prow >= (unsigned)H) prow = reflect_coord((long long)prow, H);
+                const size_t rowbit = (size_t)prow * W;
+                for (int c = cl; c < 0; ++c) {
+                    const size_t b = rowbit + reflect_coord((long long)c, W);
+                    s_bm[r * R2_WORDS + ((c - cl) >> 5)] |= ((__ldg(bm + (b >> 5)) >> (b & 31)) & 1u) << ((c - cl) & 31);
+                }
+                for (int c = max(W, cl); c <= ch; ++c) {
+                    const size_t b = rowbit + reflect_coord((long long)c, W);
+                    s_bm[r * R2_WORDS + ((c - cl) >> 5)] |= ((__ldg(bm + (b >> 5)) >> (b & 31)) & 1u) << ((c - cl) & 31);
                 }
             }
-            const bool all_a = (pat[0] | pat[1] | pat[2] | pat[3]) == 0u;
-            const bool all_b = (pat[0] & pat[1] & pat[2] & pat[3]) == 15u;
-            uint8_t o = all_a ? out_a : out_b;
-            if (!__all_sync(0xffffffffu, all_a || all_b)) {
-                const double v = cubic_rn(s_rfrac[ty], s_lut[pat[0]][lane], s_lut[pat[1]][lane], s_lut[pat[2]][lane], s_lut[pat[3]][lane]);
-                o = finish(v);
+        }
+        __syncthreads();
+        // ---- phase A: a quad per thread, a row per warp ----
+#pragma unroll 1
+        for (int ty = wrp; ty < R2_TH; ty += 8) {
+            const int y = Y0 + ty;
+            if (y >= Hs) break;                            // warp-uniform
+            const int r0 = s_r0[ty];
+            const uint32_t* rowp = s_bm + (r0 - 1 - rl) * R2_WORDS + qw;
+            uint32_t w[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) w[k] = __funnelshift_r(rowp[k * R2_WORDS], rowp[k * R2_WORDS + 1], qs);
+            const uint32_t any = (w[0] | w[1] | w[2] | w[3]) & span, all = w[0] & w[1] & w[2] & w[3] & span;
+            const bool pending = any != 0u && all != span;
+            const int rowoff = y * Ws + x0;
+            const unsigned pm = __ballot_sync(0xffffffffu, pending);
+            uint32_t bin4 = (any ? bin_b : bin_a) * 0x01010101u;
+            if (pm) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_count, __popc(pm));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (pending) {
+                    const int e = 3 * (base + __popc(pm & ((1u << lane) - 1u)));
+                    s_list[e] = __byte_perm(w[0], w[1], 0x5410);
+                    s_list[e + 1] = __byte_perm(w[2], w[3], 0x5410);
+                    s_list[e + 2] = (uint32_t)(ty << 5 | lane);
+                    const uint32_t wn = (s_rnn[ty] != r0) ? w[2] : w[1];        // the nearest row is tap row 1 or 2
+                    const uint32_t m = ((wn >> nnb[0]) & 1u) | (((wn >> nnb[1]) & 1u) << 8) | (((wn >> nnb[2]) & 1u) << 16) |
+                                       (((wn >> nnb[3]) & 1u) << 24);
+                    bin4 = (bin_a * 0x01010101u) ^ (m * (bin_a ^ bin_b));
+                }
             }
-            if (xok) image_out[dst] = o;
+            if (!pending) store4(img_page + rowoff, any ? out_b4 : out_a4);
+            if (bin_page) {
+                if (!bin_is_grey) {                        // a binary page of its own: sampled from the uint8 page
+                    const int prow = reflect_coord((long long)s_rnn[ty], H);
+                    bin4 = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int pcol = reflect_coord((long long)s_cnn[min(4 * lane + j, R2_TW - 1)], W);
+                        bin4 |= (bin[(size_t)page * H * W + (size_t)prow * W + pcol] == 0 ? 1u : 0u) << (8 * j);
+                    }
+                }
+                store4(bin_page + rowoff, bin4);
+            }
+        }
+        __syncthreads();
+        // ---- phase B: the pixels of the listed quads, one per thread ----
+        const int npx = 4 * s_count;
+        for (int i = tid; i < npx; i += 256) {
+            const uint32_t* ent = s_list + 3 * (i >> 2);
+            const uint32_t meta = ent[2];
+            const int tx = 4 * (int)(meta & 31u) + (i & 3), ty = (int)(meta >> 5);
+            if (X0 + tx >= Ws) continue;
+            const int o = s_c0[tx] - s_c0[tx & ~3];
+            const uint32_t w01 = ent[0] >> o, w23 = ent[1] >> o;         // tap rows 0, 2 at bit 0, rows 1, 3 at bit 16
+            const char* lut = reinterpret_cast<const char*>(&s_lut[0][tx]);
+            constexpr uint32_t kPat = 15u * R2_TW * 8;                   // pattern index scaled to the byte stride of s_lut
+            const double f0 = *reinterpret_cast<const double*>(lut + ((w01 * (R2_TW * 8)) & kPat));
+            const double f1 = *reinterpret_cast<const double*>(lut + ((w01 >> 16) * (R2_TW * 8) & kPat));
+            const double f2 = *reinterpret_cast<const double*>(lut + ((w23 * (R2_TW * 8)) & kPat));
+            const double f3 = *reinterpret_cast<const double*>(lut + ((w23 >> 16) * (R2_TW * 8) & kPat));
+            img_page[(Y0 + ty) * Ws + X0 + tx] = finish_image(cubic_rn(s_rfrac[ty], f0, f1, f2, f3), vmin, vmax);
         }
     }
+}
+
+static int g_r2_tiles_per_block = 4;
+static int launch_resample_bits(pcs_ctx* ctx, const uint8_t* d_bin, int bin_is_grey, int n, int H, int W, int Hs, int Ws, const int4* d_lv,
+                                const uint32_t* d_bitmap, size_t bitmap_words, uint8_t* d_image, uint8_t* d_binary) {
+    if ((size_t)Hs * Ws >= (size_t)1 << 31) return set_err(ctx, PCS_ERR_ARG, "preprocess: scaled pages of 2^31 pixels and more are not supported");
+    // sampling positions  p = f * o + (0.5 f - 0.5), every operation rounded to nearest (host doubles = the device's)
+    const double f_r = (double)H / (double)Hs, f_c = (double)W / (double)Ws;
+    const volatile double h_r = 0.5 * f_r, h_c = 0.5 * f_c;
+    const double t_r = h_r - 0.5, t_c = h_c - 0.5;
+    static const int tpb_env = [] { const char* e = getenv("PCSEG_RESAMPLE_TILES"); return e ? atoi(e) : 0; }();
+    const int tpb = tpb_env > 0 ? tpb_env : g_r2_tiles_per_block;
+    const int tiles_y = (Hs + R2_TH - 1) / R2_TH;
+    dim3 grid((Ws + R2_TW - 1) / R2_TW, (tiles_y + tpb - 1) / tpb, n);
+    resample_bits_kernel<<<grid, 256, 0, ctx->stream>>>(d_bin, bin_is_grey, H, W, Hs, Ws, f_r, t_r, f_c, t_c, d_lv, d_bitmap, bitmap_words,
+                                                        d_image, d_binary, tpb);
+    PCS_LAUNCH_CHECK(ctx, "resample_bits_kernel");
+    return PCS_OK;
 }
 
 // General resampler: one thread per output pixel, persistent grid over 32x8 tiles of the pages of a group.
@@ -535,6 +690,7 @@ static int preprocess_impl(pcs_ctx* ctx, const uint8_t* d_grey, const uint8_t* d
     if (d_image_f64 && (d_image || n > kAaGroup)) return set_err(ctx, PCS_ERR_ARG, "preprocess: fp64 image output is per group");
     const bool want_image = d_image || d_image_f64;
     cudaStream_t st = ctx->stream;
+    bool forked = false;
     const size_t page_px = (size_t)H * W;
     dim3 block(32, 8);
     if (want_image || d_binary) {
@@ -549,37 +705,56 @@ static int preprocess_impl(pcs_ctx* ctx, const uint8_t* d_grey, const uint8_t* d
             return set_err(ctx, PCS_ERR_ARG, "preprocess: anti-aliasing radius %d/%d exceeds %d", r0, r1, kMaxGaussRadius);
         const int group = std::min(n, kAaGroup);
         // two-level fast path: 16-byte aligned pages of a multiple of 32 bytes, scale factors up to 4
-        const bool fast = d_image && (reinterpret_cast<uintptr_t>(d_grey) & 15) == 0 && page_px % 32 == 0 && fr <= 4.0 && fc <= 4.0;
+        const bool fast = d_image && (reinterpret_cast<uintptr_t>(d_grey) & 15) == 0 && page_px % 32 == 0 && fr <= 4.0 && fc <= 4.0 &&
+                          (size_t)Hs * Ws < (size_t)1 << 31;
         const size_t bitmap_words = fast ? (page_px / 32 + 1 + 3) / 4 * 4 : 0;
         const int ngroups = (n + group - 1) / group;
-        const size_t head = (((size_t)n * 8 * 4 + (size_t)ngroups * 4 + 255) / 256) * 256;     // level bitmaps, then group flags
+        // level bitmaps, group flags, then (fast path) the sums of scan_pack_kernel and its verdict per page
+        const size_t head_bits = (((size_t)n * 8 * 4 + (size_t)ngroups * 4 + 255) / 256) * 256;
+        const unsigned scan_blocks = fast ? (unsigned)std::min<size_t>((size_t)ctx->sm_count * 4, (page_px / (1024 * kScanUnroll) + 7) / 8 + 1) : 0;
+        const size_t head = head_bits + (((size_t)n * (16 + (size_t)scan_blocks * 3 * 8) + 255) / 256) * 256;
         const size_t mm_bytes = (((size_t)group * 16 + 255) / 256) * 256;
         const size_t bm_bytes = (((size_t)n * bitmap_words * 4 + 255) / 256) * 256;
         const size_t plane_bytes = may_aa ? (size_t)group * page_px * sizeof(double) : 0;
         PCS_TRY(scratch_reserve(ctx, head + mm_bytes + bm_bytes + 2 * plane_bytes + 256));
         uint32_t* d_bits = reinterpret_cast<uint32_t*>(ctx->scratch);
         int* d_gflags = reinterpret_cast<int*>(d_bits + (size_t)n * 8);
+        int4* d_lv = reinterpret_cast<int4*>(reinterpret_cast<char*>(ctx->scratch) + head_bits);
+        unsigned long long* d_stats = reinterpret_cast<unsigned long long*>(d_lv + n);
         unsigned long long* d_mm = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(ctx->scratch) + head);
         uint32_t* d_bitmap = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ctx->scratch) + head + mm_bytes);
         double* t0 = reinterpret_cast<double*>(reinterpret_cast<char*>(ctx->scratch) + head + mm_bytes + bm_bytes);
         double* t1 = t0 + (size_t)group * page_px;
         if (want_image) {
-            PCS_CUDA(ctx, cudaMemsetAsync(d_bits, 0, (size_t)n * 8 * sizeof(uint32_t), st));
+            PCS_CUDA(ctx, cudaMemsetAsync(d_bits, 0, head_bits, st));
             if (fast) {
-                dim3 grid((unsigned)std::min<size_t>((size_t)ctx->sm_count * 4, (page_px / 32 + 255) / 256), n);
-                scan_pack_kernel<<<grid, 256, 0, st>>>(d_grey, page_px, d_bits, d_bitmap, bitmap_words);
+                scan_pack_kernel<<<dim3(scan_blocks, n), 256, 0, st>>>(d_grey, page_px, d_stats, d_bitmap, bitmap_words);
                 PCS_LAUNCH_CHECK(ctx, "scan_pack_kernel");
-                dim3 rgrid((Ws + RB_T - 1) / RB_T, (Hs + RB_TY - 1) / RB_TY, n);
-                resample_bits_kernel<<<rgrid, 256, 0, st>>>(d_grey, d_bin, d_bin == d_grey ? 1 : 0, H, W, Hs, Ws, d_bits, d_bitmap,
-                                                            bitmap_words, d_image, d_binary, -1);
-                PCS_LAUNCH_CHECK(ctx, "resample_bits_kernel");
+                levels_from_stats_kernel<<<ngroups, 512, 0, st>>>(d_grey, page_px, d_stats, (int)scan_blocks, n, group, d_bits, d_lv, d_gflags);
+                PCS_LAUNCH_CHECK(ctx, "levels_from_stats_kernel");
+                // From here the two-level resampler runs on the main stream and everything for pages with more than two levels
+                // (normally a row of launches that leave at once, ~3 us each) beside it on the side stream.  The two write
+                // different pages.
+                if (!ctx->aux_stream) {
+                    PCS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+                    PCS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_aux_fork, cudaEventDisableTiming));
+                    PCS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_aux_join, cudaEventDisableTiming));
+                }
+                PCS_CUDA(ctx, cudaEventRecord(ctx->ev_aux_fork, st));
+                PCS_TRY(launch_resample_bits(ctx, d_bin, d_bin == d_grey ? 1 : 0, n, H, W, Hs, Ws, d_lv, d_bitmap, bitmap_words, d_image, d_binary));
+                st = ctx->aux_stream;
+                forked = true;
+                PCS_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_aux_fork, 0));
+                // the level sets of the pages that have more than two levels (every block of the others leaves at once)
+                level_bits_kernel<<<dim3(74, n), 256, 0, st>>>(d_grey, page_px, d_bits, d_lv);
+                PCS_LAUNCH_CHECK(ctx, "level_bits_kernel");
             } else {
                 dim3 grid((unsigned)std::min<size_t>(296, (page_px / 16 + 255) / 256 + 1), n);
-                level_bits_kernel<<<grid, 256, 0, st>>>(d_grey, page_px, d_bits);
+                level_bits_kernel<<<grid, 256, 0, st>>>(d_grey, page_px, d_bits, nullptr);
                 PCS_LAUNCH_CHECK(ctx, "level_bits_kernel");
+                group_flags_kernel<<<(ngroups + 63) / 64, 64, 0, st>>>(d_bits, n, group, d_gflags);
+                PCS_LAUNCH_CHECK(ctx, "group_flags_kernel");
             }
-            group_flags_kernel<<<(ngroups + 63) / 64, 64, 0, st>>>(d_bits, n, group, d_gflags);
-            PCS_LAUNCH_CHECK(ctx, "group_flags_kernel");
             if (may_aa) {
                 // pageable host -> constant: staged synchronously, ordered on the stream
                 if (r0 >= 0) PCS_CUDA(ctx, cudaMemcpyToSymbolAsync(c_gauss_w, w0.data(), w0.size() * 8, 0, cudaMemcpyHostToDevice, st));
@@ -617,6 +792,11 @@ static int preprocess_impl(pcs_ctx* ctx, const uint8_t* d_grey, const uint8_t* d
                                                      want_image ? d_gflags + p0 / group : nullptr, m, d_image_f64);
             PCS_LAUNCH_CHECK(ctx, "resample_kernel");
         }
+        if (forked) {
+            PCS_CUDA(ctx, cudaEventRecord(ctx->ev_aux_join, st));
+            st = ctx->stream;
+            PCS_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_aux_join, 0));
+        }
     }
     if (d_orig_binary) {
         const size_t nbytes = (size_t)n * page_px;
@@ -634,13 +814,6 @@ static int preprocess_impl(pcs_ctx* ctx, const uint8_t* d_grey, const uint8_t* d
 // pixel of value level0, bit 1 = level1) skips the 8.7 MB page altogether.  Results are those of pcs_preprocess on the
 // uint8 page `bit ? level1 : level0` used as grey and binary page.
 // ---------------------------------------------------------------------------
-__global__ void set_levels_kernel(uint32_t* __restrict__ bits /*[n][8]*/, int n, int l0, int l1) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n * 8) return;
-    const int w = i & 7;
-    bits[i] = ((l0 >> 5) == w ? 1u << (l0 & 31) : 0u) | ((l1 >> 5) == w ? 1u << (l1 & 31) : 0u);
-}
-
 int launch_preprocess_bits(pcs_ctx* ctx, const uint32_t* d_bitmap, size_t bitmap_words, int n, int H, int W, int level0, int level1,
                            int Hs, int Ws, uint8_t* d_image, uint8_t* d_binary) {
     if (n <= 0 || H <= 0 || W <= 0 || Hs <= 0 || Ws <= 0) return set_err(ctx, PCS_ERR_ARG, "preprocess_bits: bad shape");
@@ -650,15 +823,11 @@ int launch_preprocess_bits(pcs_ctx* ctx, const uint32_t* d_bitmap, size_t bitmap
     if (bitmap_words < page_px / 32 + 1) return set_err(ctx, PCS_ERR_ARG, "preprocess_bits: %zu words per page needed (incl. one pad word)", page_px / 32 + 1);
     if ((double)H / Hs > 4.0 || (double)W / Ws > 4.0) return set_err(ctx, PCS_ERR_ARG, "preprocess_bits: scale factors above 4 are not supported");
     if (!d_image) return set_err(ctx, PCS_ERR_ARG, "preprocess_bits: the image output is required");
-    PCS_TRY(scratch_reserve(ctx, (size_t)n * 8 * 4 + 256));
-    uint32_t* d_bits = reinterpret_cast<uint32_t*>(ctx->scratch);
-    set_levels_kernel<<<(n * 8 + 255) / 256, 256, 0, ctx->stream>>>(d_bits, n, level0, level1);
+    PCS_TRY(scratch_reserve(ctx, (size_t)n * 16 + 256));
+    int4* d_lv = reinterpret_cast<int4*>(ctx->scratch);
+    set_levels_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_lv, n, level0, level1);
     PCS_LAUNCH_CHECK(ctx, "set_levels_kernel");
-    dim3 rgrid((Ws + RB_T - 1) / RB_T, (Hs + RB_TY - 1) / RB_TY, n);
-    resample_bits_kernel<<<rgrid, 256, 0, ctx->stream>>>(nullptr, nullptr, 1, H, W, Hs, Ws, d_bits, d_bitmap, bitmap_words, d_image, d_binary,
-                                                         level0);
-    PCS_LAUNCH_CHECK(ctx, "resample_bits_kernel");
-    return PCS_OK;
+    return launch_resample_bits(ctx, nullptr, 1, n, H, W, Hs, Ws, d_lv, d_bitmap, bitmap_words, d_image, d_binary);
 }
 
 // uint8 planes <-> flat bit planes (pixel i = bit i & 31 of word i >> 5; a non-zero byte is a set bit, a set bit is byte 1).
