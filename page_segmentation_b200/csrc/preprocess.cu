@@ -335,13 +335,13 @@ resample_bits_kernel(const uint8_t* __restrict__ bin, int bin_is_grey, int H, in
         for (int r = tid >> 4; r < nrows; r += 16) {
             int prow = rl + r;
             if ((unsigned)prow >= (unsigned)H) prow = reflect_coord((long long)prow, H);
-            const size_t rowbit = (size_t)prow * W;
+            const uint32_t rowbit = (uint32_t)prow * (uint32_t)W;          // pages have fewer than 2^32 pixels (host check)
             for (int wq = tid & 15; wq < nwq; wq += 16) {
                 const int lc = cl + 32 * wq;               // logical column of bit 0 of this word
                 const int lo = max(lc, 0), hi = min(lc + 31, W - 1);
                 uint32_t word = 0;
                 if (lo <= hi) {
-                    const size_t b0 = rowbit + lo;
+                    const uint32_t b0 = rowbit + lo;
                     const uint32_t raw = __funnelshift_r(__ldg(bm + (b0 >> 5)), __ldg(bm + (b0 >> 5) + 1), (uint32_t)(b0 & 31));
                     word = (raw & (0xffffffffu >> (31 - (hi - lo)))) << (lo - lc);
                 }
@@ -367,7 +367,7 @@ resample_bits_kernel(const uint8_t* __restrict__ bin, int bin_is_grey, int H, in
         }
         __syncthreads();
         // ---- phase A: a quad per thread, a row per warp ----
-#pragma unroll 1
+#pragma unroll
         for (int ty = wrp; ty < R2_TH; ty += 8) {
             const int y = Y0 + ty;
             if (y >= Hs) break;                            // warp-uniform
@@ -434,7 +434,8 @@ resample_bits_kernel(const uint8_t* __restrict__ bin, int bin_is_grey, int H, in
 static int g_r2_tiles_per_block = 4;
 static int launch_resample_bits(pcs_ctx* ctx, const uint8_t* d_bin, int bin_is_grey, int n, int H, int W, int Hs, int Ws, const int4* d_lv,
                                 const uint32_t* d_bitmap, size_t bitmap_words, uint8_t* d_image, uint8_t* d_binary) {
-    if ((size_t)Hs * Ws >= (size_t)1 << 31) return set_err(ctx, PCS_ERR_ARG, "preprocess: scaled pages of 2^31 pixels and more are not supported");
+    if ((size_t)Hs * Ws >= (size_t)1 << 31 || (size_t)H * W >= (size_t)1 << 32)
+        return set_err(ctx, PCS_ERR_ARG, "preprocess: pages of 2^32 pixels (2^31 after scaling) and more are not supported");
     // sampling positions  p = f * o + (0.5 f - 0.5), every operation rounded to nearest (host doubles = the device's)
     const double f_r = (double)H / (double)Hs, f_c = (double)W / (double)Ws;
     const volatile double h_r = 0.5 * f_r, h_c = 0.5 * f_c;
@@ -706,7 +707,7 @@ static int preprocess_impl(pcs_ctx* ctx, const uint8_t* d_grey, const uint8_t* d
         const int group = std::min(n, kAaGroup);
         // two-level fast path: 16-byte aligned pages of a multiple of 32 bytes, scale factors up to 4
         const bool fast = d_image && (reinterpret_cast<uintptr_t>(d_grey) & 15) == 0 && page_px % 32 == 0 && fr <= 4.0 && fc <= 4.0 &&
-                          (size_t)Hs * Ws < (size_t)1 << 31;
+                          (size_t)Hs * Ws < (size_t)1 << 31 && page_px < (size_t)1 << 32;
         const size_t bitmap_words = fast ? (page_px / 32 + 1 + 3) / 4 * 4 : 0;
         const int ngroups = (n + group - 1) / group;
         // level bitmaps, group flags, then (fast path) the sums of scan_pack_kernel and its verdict per page
