@@ -607,15 +607,20 @@ int pcs_model_load(pcs_ctx* ctx, int arch, int n_classes, int precision, const p
                 L.fold.push_back(part);
                 return PCS_OK;
             };
-            if (L.k == 5 && nsrc == 1 && fold_supported(5, L.npad, pad8(L.cin) / 8)) {
-                PCS_TRY(add_part(0, 0, L.cin, 0, L.cout, L.npad, 0));
+            // C_out of an odd number of planes (40): the folded kernel takes it unpadded
+            static const bool fold40 = !(getenv("PCSEG_FOLD40") && !strcmp(getenv("PCSEG_FOLD40"), "0"));
+            const int fnp1 = (fold40 && pad8(L.cout) % 16 == 8 && fold_supported(5, pad8(L.cout), pad8(L.cin) / 8)) ? pad8(L.cout) : L.npad;
+            const int fnp2 = (fold40 && pad8(L.cout) % 16 == 8 && nsrc == 2 && fold_supported(5, pad8(L.cout), pad8(src_c[0]) / 8) &&
+                              fold_supported(5, pad8(L.cout), pad8(src_c[1]) / 8)) ? pad8(L.cout) : L.npad;
+            if (L.k == 5 && nsrc == 1 && fold_supported(5, fnp1, pad8(L.cin) / 8)) {
+                PCS_TRY(add_part(0, 0, L.cin, 0, L.cout, fnp1, 0));
             } else if (L.k == 5 && nsrc == 1 && L.cout > 32 && L.cout <= 64 && fold_supported(5, 32, pad8(L.cin) / 8)) {
                 PCS_TRY(add_part(0, 0, L.cin, 0, 32, 32, 0));
                 PCS_TRY(add_part(0, 0, L.cin, 32, L.cout - 32, 32, 0));
-            } else if (L.k == 5 && nsrc == 2 && fold_supported(5, L.npad, pad8(src_c[0]) / 8) &&
-                       fold_supported(5, L.npad, pad8(src_c[1]) / 8)) {
-                PCS_TRY(add_part(0, 0, src_c[0], 0, L.cout, L.npad, 1));
-                PCS_TRY(add_part(1, src_c[0], src_c[1], 0, L.cout, L.npad, 2));
+            } else if (L.k == 5 && nsrc == 2 && fold_supported(5, fnp2, pad8(src_c[0]) / 8) &&
+                       fold_supported(5, fnp2, pad8(src_c[1]) / 8)) {
+                PCS_TRY(add_part(0, 0, src_c[0], 0, L.cout, fnp2, 1));
+                PCS_TRY(add_part(1, src_c[0], src_c[1], 0, L.cout, fnp2, 2));
             }
         } else if (L.kind == K_DECONV_S2 && L.name == "deconv5") {
             // fused head: deconv5 composed with the logits layer on the host (conv_umma.cu EPI_HEAD)
@@ -1030,10 +1035,23 @@ static int predict_pages_host_body(pcs_ctx* ctx, const uint8_t* h_grey, const ui
     tail = std::max(1, std::min(tail, chunk));
     nbuf = std::max(2, std::min(nbuf, (int)pcs_ctx::kHostBufs));
     std::vector<int> first, count;             // first page and page count of every chunk
+    std::vector<int> fixed;                    // PCSEG_HOST_CHUNKS=a,b,c,...: an explicit schedule (the last size repeats)
+    if (const char* e = getenv("PCSEG_HOST_CHUNKS")) {
+        for (const char* q = e; *q;) {
+            char* end = nullptr;
+            const long v = strtol(q, &end, 10);
+            if (end == q) break;
+            if (v > 0) fixed.push_back((int)std::min<long>(v, n));
+            q = *end ? end + 1 : end;
+        }
+        for (int v : fixed) chunk = std::max(chunk, v);
+    }
     {
         int p = 0;
         auto push = [&](int m) { first.push_back(p); count.push_back(m); p += m; };
-        if (n <= chunk) push(n);
+        if (!fixed.empty()) {
+            for (size_t i = 0; p < n; ++i) push(std::min(fixed[std::min(i, fixed.size() - 1)], n - p));
+        } else if (n <= chunk) push(n);
         else {
             push(head);
             // grow geometrically to the steady size, keep `tail` pages (and a shrinking ramp) for the end

@@ -41,7 +41,28 @@ __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
         ::"r"(taddr), "r"(z) : "memory");
 }
+__device__ __forceinline__ void tmem_st8_zero(uint32_t taddr) {
+    const uint32_t z = 0u;
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(z) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// NPAD columns of one accumulator slot: whole 16-column pieces, then one of 8 (NPAD is a multiple of 8)
+template <int NPAD> __device__ __forceinline__ void tmem_ld_slot(uint32_t taddr, uint32_t (&v)[NPAD]) {
+#pragma unroll
+    for (int c = 0; c + 16 <= NPAD; c += 16) tmem_ld16(taddr + (uint32_t)c, *reinterpret_cast<uint32_t(*)[16]>(&v[c]));
+    if constexpr (NPAD % 16 == 8) tmem_ld8(taddr + (uint32_t)(NPAD - 8), *reinterpret_cast<uint32_t(*)[8]>(&v[NPAD - 8]));
+}
+template <int NPAD> __device__ __forceinline__ void tmem_zero_slot(uint32_t taddr) {
+#pragma unroll
+    for (int c = 0; c + 16 <= NPAD; c += 16) tmem_st16_zero(taddr + (uint32_t)c);
+    if constexpr (NPAD % 16 == 8) tmem_st8_zero(taddr + (uint32_t)(NPAD - 8));
+}
+constexpr int fold_up16(int v) { return (v + 15) / 16 * 16; }
 
 // threads = warp 0 producer, warp 1 MMA issuer, then EG epilogue groups of 4 warps (4 TMEM lane quarters)
 constexpr int F_RING_MAX = 20;              // input-row ring entries (one row is consumed per step)
@@ -90,14 +111,22 @@ template <int NPL> struct FoldK {
 template <typename T, int NPAD, int NPL, int RING, int SLOTS, int EG>
 __global__ void __launch_bounds__(64 + EG * 128, 1)
 conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
-    constexpr int NF = 5 * NPAD;                                     // folded N
+    // Folded N.  NPAD need not be a multiple of 16 (C_out = 40: five whole planes): the five slots of a window are then
+    // 5 * NPAD = 200 accumulator columns and every MMA rounds ITS part of the window up to a legal N.  The extra columns
+    // of a part that ends inside the ring belong to the slot after the window and take zero weight rows (the weight
+    // image is padded to NF rows): D += 0 there, which is why the issuer also waits for THAT slot to be drained and
+    // re-zeroed (a read-modify-write of the tensor pipe racing with the epilogue's zeroing store would undo it).  The
+    // extra columns of a part that ends at the ring's end fall behind the ring (columns SLOTS * NPAD ...: unused).
+    constexpr int NF = fold_up16(5 * NPAD);
+    constexpr bool SPILL = (NPAD % 16) != 0;
     constexpr uint32_t ROW_BYTES = NPL * 2048;                       // one ring entry: all planes of one input row
     constexpr uint32_t WDX_BYTES = 2 * NF * 16;                      // weights of one K step
     constexpr int NMMA = FoldK<NPL>::NMMA;
     constexpr uint32_t IDESC0 = (1u << 4) | ((std::is_same<T, __nv_bfloat16>::value ? 1u : 0u) << 7) |
                                 ((std::is_same<T, __nv_bfloat16>::value ? 1u : 0u) << 10) | ((uint32_t)(128 >> 4) << 24);
     static_assert(NF <= 256 && NF % 16 == 0, "folded N must be a legal UMMA N");
-    static_assert(SLOTS * NPAD <= 512 && SLOTS <= F_SLOTS_MAX && SLOTS >= 8, "accumulator ring must fit TMEM");
+    static_assert(SLOTS * NPAD + (SPILL ? 16 : 0) <= 512 && SLOTS <= F_SLOTS_MAX && SLOTS >= 8, "accumulator ring must fit TMEM");
+    static_assert(NPAD % 8 == 0, "whole planes");
     constexpr int PERIOD = RING / fold_gcd(RING, SLOTS) * SLOTS;     // least common multiple
     static_assert(PERIOD % RING == 0 && PERIOD % SLOTS == 0 && PERIOD <= 20 && RING <= F_RING_MAX,
                   "the issue loop is unrolled over one common period of the input ring and the accumulator ring");
@@ -186,6 +215,7 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
                     // the newest output slot of the window must have been drained and re-zeroed by the epilogue:
                     // tempty phase 0 = initial zeroing, phase n = drain of use n-1: use n waits for phase n
                     mbar_wait(&s_tempty[(u + 4) % SLOTS], ((kk + u + 4) / SLOTS) & 1u);
+                    if constexpr (SPILL) mbar_wait(&s_tempty[(u + 5) % SLOTS], ((kk + u + 5) / SLOTS) & 1u);
                     tc_fence_after();
                     // opaque copies: keeps the descriptor arithmetic (base + immediate) next to its MMA instead of
                     // having every one of the RING x NCH x 5 sums hoisted out of the loop into spilled registers
@@ -194,8 +224,8 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
                                  : "=r"(a_step), "=r"(b_step), "=r"(d_step) : "r"(a_lo0), "r"(b_lo0), "r"(tmem_base));
                     const int s0 = u % SLOTS;
                     const int n1 = (SLOTS - s0) < 5 ? (SLOTS - s0) : 5;           // blocks before the ring wraps
-                    const uint32_t idesc1 = IDESC0 | ((uint32_t)((n1 * NPAD) >> 3) << 17);
-                    const uint32_t idesc2 = IDESC0 | ((uint32_t)(((5 - n1) * NPAD) >> 3) << 17);
+                    const uint32_t idesc1 = IDESC0 | ((uint32_t)(fold_up16(n1 * NPAD) >> 3) << 17);
+                    const uint32_t idesc2 = IDESC0 | ((uint32_t)(fold_up16((5 - n1) * NPAD) >> 3) << 17);
 #pragma unroll
                     for (int q = 0; q < NMMA; ++q) {
                         // K step q: plane pair (q / 5) at tap q % 5, or the odd last plane at taps {0, 2, 3} (+1)
@@ -224,8 +254,8 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
         T* pool = reinterpret_cast<T*>(p.pool);
         // group 0 zeroes the whole accumulator ring once
         if (group == 0) {
-            for (int s = 0; s < SLOTS; ++s)
-                for (int c = 0; c < NPAD; c += 16) tmem_st16_zero(t_lane + (uint32_t)(s * NPAD + c));
+            for (int s = 0; s < SLOTS; ++s) tmem_zero_slot<NPAD>(t_lane + (uint32_t)(s * NPAD));
+            if constexpr (SPILL) tmem_st16_zero(t_lane + (uint32_t)(SLOTS * NPAD));       // defined values behind the ring
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
@@ -253,11 +283,9 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
                     tc_fence_after();
                     const uint32_t tacc = t_lane + slot * NPAD;
                     uint32_t v[NPAD];
-#pragma unroll
-                    for (int c = 0; c < NPAD; c += 16) tmem_ld16(tacc + (uint32_t)c, *reinterpret_cast<uint32_t(*)[16]>(&v[c]));
+                    tmem_ld_slot<NPAD>(tacc, v);
                     tmem_ld_wait();
-#pragma unroll
-                    for (int c = 0; c < NPAD; c += 16) tmem_st16_zero(tacc + (uint32_t)c);
+                    tmem_zero_slot<NPAD>(tacc);
                     tmem_st_wait();
                     tc_fence_before();
                     __syncwarp();
@@ -303,37 +331,32 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
                         }
                     }
 #pragma unroll
-                    for (int hb = 0; hb < NPAD / 16; ++hb) {
-                        uint32_t pk[8];
+                    for (int pl = 0; pl < NPAD / 8; ++pl) {                 // one 8-channel plane = one 16-byte unit per pixel
+                        uint32_t pk[4];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            float a = __uint_as_float(v[hb * 16 + 2 * i]) + p.bias[hb * 16 + 2 * i];
-                            float b = __uint_as_float(v[hb * 16 + 2 * i + 1]) + p.bias[hb * 16 + 2 * i + 1];
+                        for (int i = 0; i < 4; ++i) {
+                            float a = __uint_as_float(v[pl * 8 + 2 * i]) + p.bias[pl * 8 + 2 * i];
+                            float b = __uint_as_float(v[pl * 8 + 2 * i + 1]) + p.bias[pl * 8 + 2 * i + 1];
                             if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
                             pk[i] = pack2<T>(a, b);
                         }
-                        const int oc = p.out_c0 + hb * 16;            // first of the 16 output channels of this block
-                        if (out && xok && y < p.h && oc < p.out_cp) {
+                        const int oc = p.out_c0 + pl * 8;             // first of the 8 output channels of this plane
+                        if (out && xok && y < p.h && oc < p.out_cp)
                             *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, p.h, p.w, oc, y, x)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                            if (oc + 8 < p.out_cp)
-                                *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, p.h, p.w, oc + 8, y, x)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-                        }
                         if (pool) {
                             if (st == 0) {
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) kept[hb * 8 + i] = pk[i];
+                                for (int i = 0; i < 4; ++i) kept[pl * 4 + i] = pk[i];
                             } else {
-                                uint32_t pm[8];
+                                uint32_t pm[4];
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    const uint32_t m = max2<T>(pk[i], kept[hb * 8 + i]);
+                                for (int i = 0; i < 4; ++i) {
+                                    const uint32_t m = max2<T>(pk[i], kept[pl * 4 + i]);
                                     pm[i] = max2<T>(m, __shfl_xor_sync(0xffffffffu, m, 1));
                                 }
                                 if (!(lane & 1) && xok && y < p.h && oc < p.pool_cp) {
                                     const int ph = p.h >> 1, pw = p.w >> 1;
                                     *reinterpret_cast<uint4*>(pool + act_idx(page, p.pool_cp, ph, pw, oc, y >> 1, x >> 1)) = make_uint4(pm[0], pm[1], pm[2], pm[3]);
-                                    if (oc + 8 < p.pool_cp)
-                                        *reinterpret_cast<uint4*>(pool + act_idx(page, p.pool_cp, ph, pw, oc + 8, y >> 1, x >> 1)) = make_uint4(pm[4], pm[5], pm[6], pm[7]);
                                 }
                             }
                         }
@@ -369,7 +392,7 @@ EncodeTiledFn fold_get_encode() {
 
 template <typename T, int NPAD, int NPL, int RING, int SLOTS, int EG>
 int launch_fold_t(pcs_ctx* ctx, const FoldConvArgs& a) {
-    constexpr int NF = 5 * NPAD;
+    constexpr int NF = fold_up16(5 * NPAD);
     FoldParams p{};
     p.n = a.n; p.h = a.h; p.w = a.w;
     p.wimg = reinterpret_cast<const uint8_t*>(a.wimg); p.cout = a.cout; p.relu = a.relu;
@@ -436,6 +459,10 @@ int launch_fold_dispatch(pcs_ctx* ctx, const FoldConvArgs& a) {
         case 325: return launch_fold_t<T, 32, 5, 8, 16, 4>(ctx, a);      // conv5: 40(40) -> 60 as 32 + 28 output channels
         case 328: return launch_fold_t<T, 32, 8, 4, 16, 4>(ctx, a);       // conv6: 60(64) -> 60 as 32 + 28 output channels
         case 488: return launch_fold_t<T, 48, 8, 4, 8, 3>(ctx, a);       // deconv3: 60(64) [+ 60(64)] -> 40(48), one launch per source
+        // C_out = 40 as five whole planes (N' = 208 instead of 240: 13 % fewer tensor cycles), twelve slots of 40 columns
+        case 404: return launch_fold_t<T, 40, 4, 12, 12, 3>(ctx, a);     // conv3: 30(32) -> 40
+        case 405: return launch_fold_t<T, 40, 5, 6, 12, 3>(ctx, a);      // conv4: 40 -> 40
+        case 408: return launch_fold_t<T, 40, 8, 4, 12, 3>(ctx, a);      // deconv3: 60(64) [+ 60(64)] -> 40, one launch per source
         default: return set_err(ctx, PCS_ERR_ARG, "conv_fold: no instantiation for N=%d planes=%d", a.npad, a.nplanes);
     }
 }
@@ -446,15 +473,15 @@ int launch_fold_dispatch(pcs_ctx* ctx, const FoldConvArgs& a) {
 bool fold_supported(int k, int npad, int nplanes) {
     if (k != 5) return false;
     const int key = npad * 10 + nplanes;
-    return key == 323 || key == 484 || key == 485 || key == 325 || key == 328 || key == 488;
+    return key == 323 || key == 484 || key == 485 || key == 325 || key == 328 || key == 488 || key == 404 || key == 405 || key == 408;
 }
 
-// Resident operand image [K step][K half][row = (4-dy)*NPAD + o][8] (K steps as in FoldK) for the input channels
+// Resident operand image [K step][K half][row = (4-dy)*NPAD + o][8] (rows padded with zeros to a multiple of 16; K steps as in FoldK) for the input channels
 // [ci0, ci0 + cin) and the output channels [o0, o0 + ncols) of a layer with weights w32[25][cin_total][cout_total]:
 // the N blocks run from the oldest output row of the window (dy = 4) to the newest (dy = 0).
 size_t fold_weight_image(const float* w32, int cin_total, int cout_total, int ci0, int cin, int o0, int ncols, int npad,
                          int precision, std::vector<uint16_t>& out) {
-    const int npl = pad8(cin) / 8, pairs = npl / 2, odd = npl & 1, nmma = pairs * 5 + odd * 3, nf = 5 * npad;
+    const int npl = pad8(cin) / 8, pairs = npl / 2, odd = npl & 1, nmma = pairs * 5 + odd * 3, nf = (5 * npad + 15) / 16 * 16;
     out.assign((size_t)nmma * 2 * nf * 8, 0);
     auto conv = [&](float v) -> uint16_t {
         if (precision == PCS_PREC_BF16) { __nv_bfloat16 b = __float2bfloat16_rn(v); return *reinterpret_cast<uint16_t*>(&b); }

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--trace", action="store_true")
     ap.add_argument("--precision", default="bf16")
+    ap.add_argument("--mode", default="raw", choices=["raw", "compact", "packed"], help="raw masks out / class map + bit-packed binary out")
     ap.add_argument("--scheds", default="8,8,8,2;2,8,2,2;2,8,2,3;2,8,2,4;2,16,2,3;4,16,4,3;1,8,1,3;2,12,2,3;2,10,2,4;2,16,2,4")
     args = ap.parse_args()
     import torch
@@ -38,6 +39,17 @@ def main():
     h_out = {k: torch.empty((n, Hs, Ws) + ((3,) if k != "labels" else ()), dtype=torch.uint8).pin_memory().numpy()
              for k in ("labels", "color", "overlay", "inverted")}
     hp = h_pages.numpy()
+    if args.mode != "raw":
+        h_out = {"labels": h_out["labels"],
+                 "binary_bits": torch.empty((n, (Hs * Ws + 31) // 32), dtype=torch.int32).pin_memory().numpy().view(np.uint32)}
+    run_host = (lambda: eng.run_host(hp, 1 / 3, h_out)) if args.mode == "raw" else (lambda: eng.run_host_compact(hp, 1 / 3, h_out))
+    if args.mode == "packed":
+        from page_segmentation_b200.runtime import pack_pages
+        pbits, l0, l1 = pack_pages(base)
+        h_bits = torch.empty((n, pbits.shape[1]), dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+        for i in range(n):
+            h_bits[i] = pbits[i % 8]
+        run_host = lambda: eng.run_host_packed(h_bits, l0, l1, synth.A4_H, synth.A4_W, 1 / 3, h_out)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     # device-resident time per batch size
@@ -58,14 +70,15 @@ def main():
 
     ref = None
     for sched in args.scheds.split(";"):
-        os.environ["PCSEG_HOST_SCHED"] = sched
+        os.environ.pop("PCSEG_HOST_CHUNKS", None)
+        os.environ["PCSEG_HOST_CHUNKS" if sched.startswith("L") else "PCSEG_HOST_SCHED"] = sched.lstrip("L")
         os.environ.pop("PCSEG_TRACE_HOST", None)
         for _ in range(2):
-            eng.run_host(hp, 1 / 3, h_out)
+            run_host()
         torch.cuda.synchronize()
         e0.record()
         for _ in range(args.steps):
-            eng.run_host(hp, 1 / 3, h_out)
+            run_host()
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.steps
@@ -79,7 +92,7 @@ def main():
             os.environ["PCSEG_TRACE_HOST"] = "1"
             sys.stderr.write(f"--- trace sched {sched}\n")
             sys.stderr.flush()
-            eng.run_host(hp, 1 / 3, h_out)
+            run_host()
             os.environ.pop("PCSEG_TRACE_HOST", None)
 
 
