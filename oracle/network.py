@@ -17,7 +17,9 @@ TF semantics restated:
 
 `bf16=True` gives the numerics twin of the device path: weights of every layer
 but conv1 and logits are rounded to bf16, every stored activation is rounded to
-bf16, accumulation stays fp32 (see DESIGN.md "precision").  `fused_head=True`
+bf16, accumulation stays fp32 (see DESIGN.md "precision").  `conv1_rounded=True`
+rounds the weights of the first layer as well: the tensor engine with fp16 operands
+uses them as ONE operand (conv1_umma.cu; with bf16 operands they are split hi + lo).  `fused_head=True`
 additionally mirrors the tensor-engine head: deconv5 keeps its fp32 weights (it is
 composed with the logits layer on the host and split into two bf16 operand halves)
 and the conv2 skip enters the logits unrounded (taken from conv2's fp32 accumulators).
@@ -67,7 +69,7 @@ class Forward:
     """Runs one of the three reference graphs on a single page."""
 
     def __init__(self, arch: str, weights: Sequence[Tuple[np.ndarray, np.ndarray]], n_classes: int,
-                 dtype=torch.float32, bf16: bool = False, fused_head: bool = False):
+                 dtype=torch.float32, bf16: bool = False, fused_head: bool = False, conv1_rounded: bool = False):
         from page_segmentation_b200.synth import layer_table
         self.arch = arch
         self.table = layer_table(arch, n_classes)
@@ -79,7 +81,8 @@ class Forward:
         for (name, kind, k, ci, co, act), (w, b) in zip(self.table, weights):
             wt = torch.from_numpy(np.ascontiguousarray(w)).to(dtype)
             bt = torch.from_numpy(np.ascontiguousarray(b)).to(dtype)
-            if bf16 and name not in ("conv1", "conv1a", "logits") and not (self.fused_head and name == "deconv5"):
+            if bf16 and name not in ("logits",) + (() if conv1_rounded else ("conv1", "conv1a")) and \
+                    not (self.fused_head and name == "deconv5"):
                 wt = _bf16(wt)
             self.params[name] = (wt, bt, (kind, k, ci, co, act))
 

@@ -9,8 +9,8 @@
 // layout.  Output row r then needs K = (dy, dx-slot): its A operand for the K=16 step ks is the pair of
 // expanded rows (r+2ks, r+2ks+1) -- the same smem rows serve five different output rows -- and the B
 // operand holds W[dy][dx] in slot dx < 5 and zeros elsewhere.  Pixels 0..255 are exact in bf16/fp16; the
-// fp32 weights are split into hi + lo operand halves (two MMAs, ~16 mantissa bits) and 1/255 is applied
-// to the fp32 accumulator, so the result matches the fp32 CUDA-core kernel to fp32 rounding.
+// fp32 weights are split into hi + lo operand halves (two MMAs, ~16 mantissa bits; bf16 operands) or used as one fp16
+// operand (11 bits, like the weights of every other layer) and 1/255 is applied to the fp32 accumulator.
 //
 // Warp roles (320 threads): warp 0 loads the weight image; warp 1 = MMA issuer + TMEM owner;
 // warps 2-5 and 10-13 = epilogue (bias, ReLU, pack, plane-major stores; two warps per TMEM lane quarter
@@ -46,6 +46,8 @@ struct Conv1Params {
     float bias[C1_MAXN];                    // by value: read as constant-bank FFMA operands, no shared-memory traffic
     void* out; int out_cp;
     int strips, rowblocks, num_tiles;
+    int halves;                             // operand halves of the weights: 2 = hi + lo (bf16 operands: ~16 mantissa bits), 1 = hi only
+                                            // (fp16 operands: 11 bits, what every other layer's weights have)
     int dbg;                                // diagnosis only (PCSEG_C1_DEBUG): 1 = no output stores, 2 = hi MMAs only, 4 = no expansion
 };
 
@@ -112,7 +114,7 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv1_umma_kernel(const Conv1Pa
 #pragma unroll
                 for (int r = 0; r < C1_R; ++r) {
 #pragma unroll
-                    for (int half = 0; half < ((p.dbg & 2) ? 1 : 2); ++half) {        // weights hi, then lo
+                    for (int half = 0; half < ((p.dbg & 2) ? 1 : p.halves); ++half) {        // weights hi, then lo
 #pragma unroll
                         for (int ks = 0; ks < KS; ++ks) {
                             const uint32_t a_off = (uint32_t)((r + 2 * ks) * (C1_ROW_BYTES >> 4));
@@ -309,6 +311,12 @@ int launch_conv1_umma(pcs_ctx* ctx, const uint8_t* d_image, int n, int img_h, in
     for (int i = 0; i < C1_MAXN; ++i) p.bias[i] = i < cout ? h_bias[i] : 0.f;
     { const char* e = getenv("PCSEG_C1_DEBUG"); p.dbg = e ? atoi(e) : 0; }
     const bool bf = ctx->precision == PCS_PREC_BF16;
+    // fp16 operands carry 11 mantissa bits: the weights of this layer are used like those of every other layer (one operand).
+    // With bf16 operands (8 bits) the hi + lo split keeps the first layer, whose inputs are exact, out of the error budget.
+    // PCSEG_C1_SPLIT=1 / 0 forces either (measured on A4 pages, fp16: class-map agreement with the fp64 oracle 99.982 % with
+    // the split, 99.980 % without; conv1 1.02 -> 0.79 ms per 64 pages).
+    static const int split_env = [] { const char* e = getenv("PCSEG_C1_SPLIT"); return e ? atoi(e) : -1; }();
+    p.halves = split_env >= 0 ? (split_env ? 2 : 1) : (bf ? 2 : 1);
     if (ksz == 5) return bf ? launch_conv1_t<__nv_bfloat16, 5, 32, 8>(ctx, p) : launch_conv1_t<__half, 5, 32, 8>(ctx, p);
     return bf ? launch_conv1_t<__nv_bfloat16, 3, 64, 4>(ctx, p) : launch_conv1_t<__half, 3, 64, 4>(ctx, p);
 }

@@ -18,7 +18,7 @@ def _twin_fp16(arch, W, n_classes, img):
     saved = onet._bf16
     onet._bf16 = lambda t: t.to(torch.float16).to(t.dtype)
     try:
-        return onet.Forward(arch, W, n_classes, bf16=True, fused_head=True).logits(img)[0]
+        return onet.Forward(arch, W, n_classes, bf16=True, fused_head=True, conv1_rounded=True).logits(img)[0]
     finally:
         onet._bf16 = saved
 

@@ -62,7 +62,7 @@ def test_fcn_logits_and_argmax(ctx, arch, hw, precision, engine):
     if precision == "fp16":
         onet._bf16, saved = (lambda t: t.to(torch.float16).to(t.dtype)), onet._bf16
         try:
-            twin = onet.Forward(arch, W, 3, bf16=True, fused_head=fused)
+            twin = onet.Forward(arch, W, 3, bf16=True, fused_head=fused, conv1_rounded=fused)   # fp16 tensor engine: one operand
             lt, _ = twin.logits(img)
         finally:
             onet._bf16 = saved
@@ -133,7 +133,7 @@ def test_unet_small(ctx, engine, hw):
     _, (logit, prob, pred) = _device_predict("unet", W, 3, img, "fp16", engine)
     onet._bf16, saved = (lambda t: t.to(torch.float16).to(t.dtype)), onet._bf16
     try:
-        lt, _ = onet.Forward("unet", W, 3, bf16=True).logits(img)
+        lt, _ = onet.Forward("unet", W, 3, bf16=True, conv1_rounded=engine == "umma").logits(img)
     finally:
         onet._bf16 = saved
     scale = np.abs(lt).max()
