@@ -428,17 +428,21 @@ def bench_api(env):
             flush_outputs()                                                   # every file is on disk when the clock stops
 
         flow()
-        env["sync_all"]()
-        t0 = time.perf_counter()
-        flow()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        t = torch.tensor([dt], dtype=torch.float64, device=env["dev"])
-        if world > 1:
-            env["dist"].all_reduce(t, op=env["dist"].ReduceOp.MAX)
-        return {"value": world * n / float(t.item()), "unit": "pages/s", "pages_per_gpu": n, "clock": "wall (perf_counter), max over ranks",
+        passes = []
+        for _ in range(3):                                                    # one 64-page pass is ~30 ms of wall clock: report the median of three
+            env["sync_all"]()
+            t0 = time.perf_counter()
+            flow()
+            torch.cuda.synchronize()
+            t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=env["dev"])
+            if world > 1:
+                env["dist"].all_reduce(t, op=env["dist"].ReduceOp.MAX)
+            passes.append(float(t.item()))
+        med = sorted(passes)[1]
+        return {"value": world * n / med, "unit": "pages/s", "pages_per_gpu": n, "clock": "wall (perf_counter), max over ranks",
+                "passes_pages_per_s": [round(world * n / p, 1) for p in passes],
                 "flow": "DatasetLoader.load_data -> Predictor.predict(+cc_majority) -> output_data (3 PNG files per page, tmpfs) -> "
-                        "flush_outputs; pageable numpy pages in, all files on disk at the end; one pass after one warm-up pass"}
+                        "flush_outputs; pageable numpy pages in, all files on disk at the end; median of three passes after one warm-up pass"}
     finally:
         shutil.rmtree(root, ignore_errors=True)
 
