@@ -236,3 +236,51 @@ def test_scratch_growth_between_two_max_width_calls():
         np.testing.assert_array_equal(first[1], second[1])
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("case", ["one_stray_pixel_last", "one_stray_pixel_first_row", "sum_neutral_pair", "levels_around_mean",
+                                  "one_level", "one_pixel_differs"])
+def test_two_level_verdict_is_exact(ctx, case):
+    """The fast path decides "at most two grey levels" from three sums per page (scan_pack_kernel: count, sum and sum of
+    squares of byte ^ page[0]).  Pages built to fool anything weaker than the exact test -- a single pixel of a third
+    level, third levels that leave the sum unchanged -- must take the anti-aliased general path like the oracle
+    (`len(np.unique(image)) > 2`, dataset.py:127); pages with one or two levels must stay bit-exact."""
+    H, W, lh = 480, 352, 18
+    page = synth.make_page(21, H, W, lh)                     # levels {0, 255}, page[0, 0] == 255
+    exact = True
+    if case == "one_stray_pixel_last":
+        page[-1, -1] = 254
+        exact = False
+    elif case == "one_stray_pixel_first_row":
+        page[0, 5] = 1
+        exact = False
+    elif case == "sum_neutral_pair":                         # two ink pixels 0 -> 1 and 0 -> 255 ^ ... keep the count, move the sums
+        ys, xs = np.nonzero(page == 0)
+        page[ys[0], xs[0]] = 1
+        page[ys[1], xs[1]] = 2
+        exact = False
+    elif case == "levels_around_mean":                       # x = byte ^ 255 in {127, 128, 129} in equal numbers: mean 128
+        page[:] = 255
+        page[10:40, 10:40] = 255 ^ 128
+        page[10:20, 10:40] = 255 ^ 127
+        page[30:40, 10:40] = 255 ^ 129
+        exact = False
+    elif case == "one_level":
+        page[:] = 77
+    elif case == "one_pixel_differs":
+        page[:] = 255
+        page[H // 2, W // 2] = 0
+    img, b, ob = _run(page, page, 6, lh)
+    eimg, eb, eob = opipe.prepare_images(page, page, 6, lh, keep_orig_bin=True)
+    np.testing.assert_array_equal(b, eb)
+    np.testing.assert_array_equal(ob, eob)
+    if exact:
+        np.testing.assert_array_equal(img, eimg)
+    else:
+        assert len(np.unique(page)) > 2
+        diff = np.abs(img.astype(int) - eimg.astype(int))
+        assert diff.max() <= 1 and (diff > 0).mean() <= 1e-4
+        # and the anti-aliased result differs from what the two-level kernel would have produced
+        two = np.where(page == page[0, 0], page[0, 0], page[page != page[0, 0]][0]).astype(np.uint8)
+        timg = opipe.prepare_images(two, two, 6, lh)[0]
+        assert (timg != eimg).any()
