@@ -32,7 +32,7 @@ SCALE = TARGET_LH / LINE_HEIGHT
 LUT = np.array([[255, 255, 255], [255, 0, 0], [0, 255, 0]], dtype=np.uint8)
 GFLOP_PER_PAGE = {"fcn_skip": 111.999, "fcn": 101.97, "unet": 1639.684}
 # algorithmic GFLOP of the single layers at the 1184x832 grid (2 * GMAC of appendix E)
-LAYER_GFLOP = {"conv1": 0.985, "conv2": 29.553, "conv3": 14.776, "conv4": 19.702, "conv5": 7.388, "conv6": 11.082,
+LAYER_GFLOP = {"conv1": 0.985, "conv2": 29.553, "conv1+conv2": 0.985 + 29.553, "conv3": 14.776, "conv4": 19.702, "conv5": 7.388, "conv6": 11.082,
                "conv7": 3.694, "deconv1": 4.925, "deconv2": 0.591, "deconv3": 14.776, "deconv4": 1.478, "head": 3.048}
 
 

@@ -104,6 +104,7 @@ static void free_layers(pcs_ctx* ctx) {
         if (l.d_b32) cudaFree(l.d_b32);
         if (l.d_wmma) cudaFree(l.d_wmma);
         for (auto& f : l.fold) if (f.d_w) cudaFree(f.d_w);
+        if (l.d_w12) cudaFree(l.d_w12);
         if (l.d_head_lw) cudaFree(l.d_head_lw);
         if (l.d_head_lb) cudaFree(l.d_head_lb);
     }
@@ -269,8 +270,6 @@ struct HeadIO {
 static int forward_fcn(pcs_ctx* ctx, bool skip, const uint8_t* d_image, int n, int hs, int ws, const HeadIO& io) {
     const int hp = hs + (32 - hs % 32) % 32, wp = ws + (32 - ws % 32) % 32;    // model.py:10-26
     Act conv1, conv2, pool2, conv3, pool4, conv5, conv6, pool6, conv7, d1, d2, d3, d4;
-    PCS_TRY(new_act(ctx, "conv1", n, hp, wp, 20, &conv1));
-    PCS_TRY(run_conv1_u8(ctx, "conv1", d_image, n, hs, ws, &conv1));
     // fused head (<= 4 classes, tensor engine): conv2 hands its share of the logits to the head as fp32
     // partial sums and its full-resolution tensor is not stored at all
     Layer* L2 = find_layer(ctx, "conv2");
@@ -286,7 +285,26 @@ static int forward_fcn(pcs_ctx* ctx, bool skip, const uint8_t* d_image, int n, i
     const bool store_conv2 = (skip && !fused_head) || ctx->keep_acts;
     if (store_conv2) PCS_TRY(new_act(ctx, "conv2", n, hp, wp, 30, &conv2));
     PCS_TRY(new_act(ctx, "pool2", n, hp / 2, wp / 2, 30, &pool2));
-    PCS_TRY(run_conv(ctx, "conv2", &conv1, nullptr, store_conv2 ? &conv2 : nullptr, &pool2, false, plog, plog ? LL->d_head_lw : nullptr));
+    // conv1 never leaves the SM when the fused kernel applies (tensor engine, folded conv2, activations not kept for inspection)
+    // Opt-in (PCSEG_FUSE12=1): measured on B200 the fused kernel takes as long as conv1 + conv2 apart (2.8 ms per 64 A4 pages) --
+    // the pair is bound by the issue slots of its epilogues, not by the 94 MB per page of HBM traffic the fusion removes
+    // (DESIGN.md section 3.2a).
+    static const bool no_fuse12 = !(getenv("PCSEG_FUSE12") && !strcmp(getenv("PCSEG_FUSE12"), "1"));
+    Layer* L1 = find_layer(ctx, "conv1");
+    if (ctx->engine == PCS_ENGINE_UMMA && !no_fuse12 && !ctx->keep_acts && conv2_folds && L1 && L1->d_w12 && L2->d_w12 && (hp % 4) == 0) {
+        StageScope ts(ctx, "conv1+conv2");
+        Conv12Args f;
+        f.d_image = d_image; f.n = n; f.img_h = hs; f.img_w = ws; f.h = hp; f.w = wp;
+        f.w1img = L1->d_w12; f.w2img = L2->d_w12; f.h_bias1 = L1->h_b32.data(); f.h_bias2 = L2->h_b32.data(); f.cout2 = L2->cout;
+        f.out = store_conv2 ? conv2.p : nullptr; f.out_cp = store_conv2 ? conv2.cp : 0;
+        f.pool_out = pool2.p; f.pool_cp = pool2.cp;
+        f.plog = plog; f.skip_lw = plog ? LL->d_head_lw : nullptr;
+        PCS_TRY(launch_conv12_fused(ctx, f));
+    } else {
+        PCS_TRY(new_act(ctx, "conv1", n, hp, wp, 20, &conv1));
+        PCS_TRY(run_conv1_u8(ctx, "conv1", d_image, n, hs, ws, &conv1));
+        PCS_TRY(run_conv(ctx, "conv2", &conv1, nullptr, store_conv2 ? &conv2 : nullptr, &pool2, false, plog, plog ? LL->d_head_lw : nullptr));
+    }
     PCS_TRY(new_act(ctx, "conv3", n, hp / 2, wp / 2, 40, &conv3));
     PCS_TRY(run_conv(ctx, "conv3", &pool2, nullptr, &conv3, nullptr));
     PCS_TRY(new_act(ctx, "pool4", n, hp / 4, wp / 4, 40, &pool4));
@@ -571,6 +589,19 @@ int pcs_model_load(pcs_ctx* ctx, int arch, int n_classes, int precision, const p
         L.wmma_bytes = conv1_umma_weight_image(L.h_w32.data(), L.k, L.cout, precision, img);
         PCS_CUDA(ctx, cudaMalloc(&L.d_wmma, L.wmma_bytes));
         PCS_CUDA(ctx, cudaMemcpy(L.d_wmma, img.data(), L.wmma_bytes, cudaMemcpyHostToDevice));
+    }
+    // conv1 + conv2 of the FCN variants as one kernel (conv12_fused.cu)
+    if (ctx->layers.size() > 1 && ctx->layers[0].name == "conv1" && ctx->layers[1].name == "conv2" && ctx->layers[1].kind == K_CONV &&
+        !ctx->layers[1].relu &&
+        conv12_fused_supported(ctx->layers[0].k, ctx->layers[0].cout, ctx->layers[1].k, ctx->layers[1].cin, ctx->layers[1].cout)) {
+        Layer &L1 = ctx->layers[0], &L2 = ctx->layers[1];
+        std::vector<uint16_t> img;
+        size_t nb = conv12_weight_image1(L1.h_w32.data(), precision, img);
+        PCS_CUDA(ctx, cudaMalloc(&L1.d_w12, nb));
+        PCS_CUDA(ctx, cudaMemcpy(L1.d_w12, img.data(), nb, cudaMemcpyHostToDevice));
+        nb = conv12_weight_image2(L2.h_w32.data(), L2.cout, precision, img);
+        PCS_CUDA(ctx, cudaMalloc(&L2.d_w12, nb));
+        PCS_CUDA(ctx, cudaMemcpy(L2.d_w12, img.data(), nb, cudaMemcpyHostToDevice));
     }
     // tensor-core operand images: stride-1 convolutions with C_in > 1 and the 2x2 stride-2
     // transposed convolutions that are not fused into the head

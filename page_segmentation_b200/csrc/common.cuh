@@ -71,6 +71,7 @@ struct Layer {
         int psum = 0;             // 0 complete, 1 writes partial sums, 2 adds them
     };
     std::vector<FoldPart> fold;
+    void* d_w12 = nullptr;        // conv1 / conv2 of the FCN variants: operand image of the fused kernel (conv12_fused.cu)
     std::vector<float> h_w32_raw; // deconv5, U-Net up*: weights before rounding (composed / summed on the host, rounded once)
     float* d_head_lw = nullptr;   // logits layer: [32][4] rows of the conv2 skip channels, zero padded (fcn_skip)
     float* d_head_lb = nullptr;   // logits layer: [4] bias with the deconv5 / conv2 biases folded in
@@ -379,6 +380,25 @@ bool fold_supported(int k, int npad, int nplanes);
 size_t fold_weight_image(const float* w32 /*[25][cin_total][cout_total]*/, int cin_total, int cout_total, int ci0, int cin,
                          int o0, int ncols, int npad, int precision, std::vector<uint16_t>& out);
 int launch_conv_fold(pcs_ctx* ctx, const FoldConvArgs& a);
+
+// conv12_fused.cu  (conv1 + conv2 + MaxPool of the FCN variants in one marching kernel; conv1 never leaves the SM)
+struct Conv12Args {
+    const uint8_t* d_image = nullptr;
+    int n = 0, img_h = 0, img_w = 0, h = 0, w = 0;
+    const void* w1img = nullptr;       // conv12_weight_image1
+    const void* w2img = nullptr;       // conv12_weight_image2
+    const float* h_bias1 = nullptr;    // HOST pointers: the biases travel in the kernel parameter block
+    const float* h_bias2 = nullptr;
+    int cout2 = 0;
+    void* out = nullptr; int out_cp = 0;             // full-resolution conv2 (optional)
+    void* pool_out = nullptr; int pool_cp = 0;
+    void* plog = nullptr;              // optional float4 [n][h][w]: conv2's share of the logits (fcn_skip)
+    const float* skip_lw = nullptr;    // device [32][4]
+};
+bool conv12_fused_supported(int k1, int cout1, int k2, int cin2, int cout2);
+size_t conv12_weight_image1(const float* w32 /*[25][1][20]*/, int precision, std::vector<uint16_t>& out);
+size_t conv12_weight_image2(const float* w32 /*[25][20][cout]*/, int cout, int precision, std::vector<uint16_t>& out);
+int launch_conv12_fused(pcs_ctx* ctx, const Conv12Args& a);
 
 // conv1_umma.cu  (first FCN layer on the tensor cores)
 size_t conv1_umma_weight_image(const float* w32 /*[ksz*ksz][1][cout]*/, int ksz, int cout, int precision, std::vector<uint16_t>& out);
