@@ -338,12 +338,17 @@ resample_bits_kernel(const uint8_t* __restrict__ bin, int bin_is_grey, int H, in
             const uint32_t rowbit = (uint32_t)prow * (uint32_t)W;          // pages have fewer than 2^32 pixels (host check)
             for (int wq = tid & 15; wq < nwq; wq += 16) {
                 const int lc = cl + 32 * wq;               // logical column of bit 0 of this word
-                const int lo = max(lc, 0), hi = min(lc + 31, W - 1);
                 uint32_t word = 0;
-                if (lo <= hi) {
-                    const uint32_t b0 = rowbit + lo;
-                    const uint32_t raw = __funnelshift_r(__ldg(bm + (b0 >> 5)), __ldg(bm + (b0 >> 5) + 1), (uint32_t)(b0 & 31));
-                    word = (raw & (0xffffffffu >> (31 - (hi - lo)))) << (lo - lc);
+                if (lc >= 0 && lc + 31 < W) {              // a word inside the page (all of them except in border tiles)
+                    const uint32_t b0 = rowbit + (uint32_t)lc;
+                    word = __funnelshift_r(__ldg(bm + (b0 >> 5)), __ldg(bm + (b0 >> 5) + 1), b0 & 31u);
+                } else {
+                    const int lo = max(lc, 0), hi = min(lc + 31, W - 1);
+                    if (lo <= hi) {
+                        const uint32_t b0 = rowbit + lo;
+                        const uint32_t raw = __funnelshift_r(__ldg(bm + (b0 >> 5)), __ldg(bm + (b0 >> 5) + 1), (uint32_t)(b0 & 31));
+                        word = (raw & (0xffffffffu >> (31 - (hi - lo)))) << (lo - lc);
+                    }
                 }
                 s_bm[r * R2_WORDS + wq] = word;
             }
