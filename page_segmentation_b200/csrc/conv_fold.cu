@@ -73,7 +73,7 @@ constexpr int F_SW = 124;                   // valid output pixels per strip
 // in conv2, so its share  P[y,x,k] = sum_o conv2[y,x,o] * lw[20+o][k]  is taken here from the fp32
 // accumulators (before the bf16 rounding) and the full-resolution conv2 tensor is never written.
 constexpr int F_LOGC = 32, F_NC = 4;
-__constant__ float c_skip_lw[F_LOGC * F_NC];
+__constant__ float4 c_skip_lw[F_LOGC];       // [channel] -> the logits weights of (up to) four classes: ONE 128-bit constant load per channel
 int64_t g_skip_owner[64] = {0};
 
 struct FoldParams {
@@ -313,51 +313,63 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
                             v[4 * c4 + 3] = __float_as_uint(__uint_as_float(v[4 * c4 + 3]) + q.w);
                         }
                     }
+                    const bool rowok = xok && y < p.h;
                     if constexpr (NPAD == F_LOGC) {
                         if (p.plog) {
                             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                             for (int o = 0; o < NPAD; ++o) {
                                 const float a = __uint_as_float(v[o]);
-                                acc.x = fmaf(a, c_skip_lw[o * F_NC + 0], acc.x);
-                                acc.y = fmaf(a, c_skip_lw[o * F_NC + 1], acc.y);
-                                acc.z = fmaf(a, c_skip_lw[o * F_NC + 2], acc.z);
+                                const float4 lw = c_skip_lw[o];
+                                acc.x = fmaf(a, lw.x, acc.x);
+                                acc.y = fmaf(a, lw.y, acc.y);
+                                acc.z = fmaf(a, lw.z, acc.z);
                             }
                             if (p.plog_nc > 3) {
 #pragma unroll
-                                for (int o = 0; o < NPAD; ++o) acc.w = fmaf(__uint_as_float(v[o]), c_skip_lw[o * F_NC + 3], acc.w);
+                                for (int o = 0; o < NPAD; ++o) acc.w = fmaf(__uint_as_float(v[o]), c_skip_lw[o].w, acc.w);
                             }
-                            if (xok && y < p.h) p.plog[((size_t)page * p.h + y) * p.w + x] = acc;
+                            if (rowok) p.plog[((size_t)page * p.h + y) * p.w + x] = acc;
                         }
                     }
+                    // bias, activation, pack: one 8-channel plane = one 16-byte unit per pixel.  The activation switch is uniform:
+                    // hoisted out of the element loop (a select per element was 6 % of conv2's instructions)
+                    uint32_t pk[NPAD / 2];
+                    if (p.relu) {
 #pragma unroll
-                    for (int pl = 0; pl < NPAD / 8; ++pl) {                 // one 8-channel plane = one 16-byte unit per pixel
-                        uint32_t pk[4];
+                        for (int i = 0; i < NPAD / 2; ++i)
+                            pk[i] = pack2<T>(fmaxf(__uint_as_float(v[2 * i]) + p.bias[2 * i], 0.f), fmaxf(__uint_as_float(v[2 * i + 1]) + p.bias[2 * i + 1], 0.f));
+                    } else {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            float a = __uint_as_float(v[pl * 8 + 2 * i]) + p.bias[pl * 8 + 2 * i];
-                            float b = __uint_as_float(v[pl * 8 + 2 * i + 1]) + p.bias[pl * 8 + 2 * i + 1];
-                            if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-                            pk[i] = pack2<T>(a, b);
-                        }
-                        const int oc = p.out_c0 + pl * 8;             // first of the 8 output channels of this plane
-                        if (out && xok && y < p.h && oc < p.out_cp)
-                            *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, p.h, p.w, oc, y, x)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                        if (pool) {
-                            if (st == 0) {
+                        for (int i = 0; i < NPAD / 2; ++i)
+                            pk[i] = pack2<T>(__uint_as_float(v[2 * i]) + p.bias[2 * i], __uint_as_float(v[2 * i + 1]) + p.bias[2 * i + 1]);
+                    }
+                    if (out && rowok) {
+                        T* o0 = out + act_idx(page, p.out_cp, p.h, p.w, p.out_c0, y, x);
+                        const size_t plane = (size_t)p.h * p.w * 8;
 #pragma unroll
-                                for (int i = 0; i < 4; ++i) kept[pl * 4 + i] = pk[i];
-                            } else {
-                                uint32_t pm[4];
+                        for (int pl = 0; pl < NPAD / 8; ++pl)
+                            if (p.out_c0 + pl * 8 < p.out_cp)
+                                *reinterpret_cast<uint4*>(o0 + pl * plane) = make_uint4(pk[4 * pl], pk[4 * pl + 1], pk[4 * pl + 2], pk[4 * pl + 3]);
+                    }
+                    if (pool) {
+                        if (st == 0) {
 #pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    const uint32_t m = max2<T>(pk[i], kept[pl * 4 + i]);
-                                    pm[i] = max2<T>(m, __shfl_xor_sync(0xffffffffu, m, 1));
-                                }
-                                if (!(lane & 1) && xok && y < p.h && oc < p.pool_cp) {
-                                    const int ph = p.h >> 1, pw = p.w >> 1;
-                                    *reinterpret_cast<uint4*>(pool + act_idx(page, p.pool_cp, ph, pw, oc, y >> 1, x >> 1)) = make_uint4(pm[0], pm[1], pm[2], pm[3]);
-                                }
+                            for (int i = 0; i < NPAD / 2; ++i) kept[i] = pk[i];
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < NPAD / 2; ++i) {
+                                const uint32_t m = max2<T>(pk[i], kept[i]);
+                                pk[i] = max2<T>(m, __shfl_xor_sync(0xffffffffu, m, 1));
+                            }
+                            if (!(lane & 1) && rowok) {
+                                const int ph = p.h >> 1, pw = p.w >> 1;
+                                T* q0 = pool + act_idx(page, p.pool_cp, ph, pw, p.out_c0, y >> 1, x >> 1);
+                                const size_t plane = (size_t)ph * pw * 8;
+#pragma unroll
+                                for (int pl = 0; pl < NPAD / 8; ++pl)
+                                    if (p.out_c0 + pl * 8 < p.pool_cp)
+                                        *reinterpret_cast<uint4*>(q0 + pl * plane) = make_uint4(pk[4 * pl], pk[4 * pl + 1], pk[4 * pl + 2], pk[4 * pl + 3]);
                             }
                         }
                     }
