@@ -71,6 +71,9 @@ def main():
     ref = None
     for sched in args.scheds.split(";"):
         os.environ.pop("PCSEG_HOST_CHUNKS", None)
+        if sched.startswith("L") and ":" in sched:          # "La,b,c:nbuf"
+            sched, nb = sched.split(":")
+            os.environ["PCSEG_HOST_SCHED"] = f"8,32,8,{nb}"
         os.environ["PCSEG_HOST_CHUNKS" if sched.startswith("L") else "PCSEG_HOST_SCHED"] = sched.lstrip("L")
         os.environ.pop("PCSEG_TRACE_HOST", None)
         for _ in range(2):
