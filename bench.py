@@ -420,16 +420,24 @@ def bench_api(env):
         predictor = Predictor(settings, network=net)
         loader = DatasetLoader(TARGET_LH, DEFAULT_COLOR_MAP, prediction=True)
 
+        dbg = os.environ.get("PCSEG_API_DEBUG") is not None
+
         def flow():
+            ta = time.perf_counter()
             entries = [SingleData(image=p, line_height_px=LINE_HEIGHT, output_path=f"page{i:04d}.png") for i, p in enumerate(pages)]
             dataset = loader.load_data(entries)
+            tb = time.perf_counter()
             for pred in predictor.predict(dataset):
                 output_data(root, pred.labels, pred.data, DEFAULT_COLOR_MAP)
+            tc = time.perf_counter()
             flush_outputs()                                                   # every file is on disk when the clock stops
+            if dbg:
+                sys.stderr.write(f"[e2e_api] load_data {1e3 * (tb - ta):.1f} ms, predict + output_data {1e3 * (tc - tb):.1f} ms, flush "
+                                 f"{1e3 * (time.perf_counter() - tc):.1f} ms, cuda {torch.cuda.memory_allocated() >> 20} MB\n")
 
         flow()
         passes = []
-        for _ in range(3):                                                    # one 64-page pass is ~30 ms of wall clock: report the median of three
+        for _ in range(6 if dbg else 3):                                      # one 64-page pass is ~30 ms of wall clock: report the median of three
             env["sync_all"]()
             t0 = time.perf_counter()
             flow()

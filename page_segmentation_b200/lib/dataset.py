@@ -165,10 +165,13 @@ class DatasetLoader:
         image, binary = staged_fields(job, device)
         bin_src = job.binary() if job.binary is not None else img
 
+        # (the closure must not hold `entry`: entry -> DeviceArray -> closure -> entry would keep the page's device tensors
+        # alive until a pass of the cyclic collector -- 118 MB per 64 pages piling up between collections)
+        tlh, lh, mw = self.target_line_height, entry.line_height_px, self.max_width
+
         def orig_binary():
             from ..runtime import prepare_images_tensors
-            return prepare_images_tensors(img, bin_src, self.target_line_height, entry.line_height_px, self.max_width,
-                                          keep_orig_bin=True, device=device)[2]
+            return prepare_images_tensors(img, bin_src, tlh, lh, mw, keep_orig_bin=True, device=device)[2]
 
         if not self.prediction:
             from .util import preserving_resize
