@@ -645,6 +645,11 @@ int pcs_model_load(pcs_ctx* ctx, int arch, int n_classes, int precision, const p
                               fold_supported(5, pad8(L.cout), pad8(src_c[1]) / 8)) ? pad8(L.cout) : L.npad;
             if (L.k == 5 && nsrc == 1 && fold_supported(5, fnp1, pad8(L.cin) / 8)) {
                 PCS_TRY(add_part(0, 0, L.cin, 0, L.cout, fnp1, 0));
+            } else if (fold40 && L.k == 5 && nsrc == 1 && L.cout == 80 && fold_supported(5, 40, pad8(L.cin) / 8)) {
+                // conv7 (60 -> 80): two launches of 40 output channels each on the 40-column kernel (N' = 208) instead of the
+                // plain kernel, whose N = 80 leaves room for one accumulator stage only (tensor pipe 56 %)
+                PCS_TRY(add_part(0, 0, L.cin, 0, 40, 40, 0));
+                PCS_TRY(add_part(0, 0, L.cin, 40, 40, 40, 0));
             } else if (L.k == 5 && nsrc == 1 && L.cout > 32 && L.cout <= 64 && fold_supported(5, 32, pad8(L.cin) / 8)) {
                 PCS_TRY(add_part(0, 0, L.cin, 0, 32, 32, 0));
                 PCS_TRY(add_part(0, 0, L.cin, 32, L.cout - 32, 32, 0));
