@@ -239,6 +239,27 @@ conv_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm0, co
             const bool xok = m < p.sw && x < p.w;
             const int y0 = rb * R;
             const int cbase = nt * NPAD;
+            // fused head: conv2's share of the logits of the 2x2 output block of input row yy is requested one row of this
+            // warp AHEAD of its use -- the first one here, before the waits (the first use of a freshly requested value was
+            // 37 % of this kernel's stall samples)
+            const HeadEpi& hd = p.head;
+            const int oh = 2 * p.h, ow = 2 * p.w;
+            auto request = [&](int yy, float4 (&q)[2][2]) {
+#pragma unroll
+                for (int i2 = 0; i2 < 2; ++i2) {
+                    const int oy = 2 * yy + i2;
+                    if (MODE >= EPI_HEAD && hd.plog && xok && yy < p.h && oy < hd.hs) {
+                        // the two pixels of an output row: 32 contiguous bytes per thread, 1 KB per warp
+                        const float4* src = hd.plog + ((size_t)page * oh + oy) * ow + 2 * x;
+                        q[i2][0] = __ldg(src);
+                        q[i2][1] = __ldg(src + 1);
+                    } else {
+                        q[i2][0] = q[i2][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+            };
+            float4 nx[2][2];
+            if constexpr (MODE >= EPI_HEAD) request(y0 + group, nx);
             // per-column bias of this N tile (named barrier 1 over the epilogue warps)
             asm volatile("bar.sync 1, %0;" ::"r"(epi_threads) : "memory");
             for (int i = threadIdx.x - 64; i < NPAD; i += epi_threads) {
@@ -255,8 +276,6 @@ conv_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm0, co
 
             if constexpr (MODE >= EPI_HEAD) {
                 // one thread = one input pixel of deconv5 = a 2x2 block of output pixels x 4 classes
-                const HeadEpi& hd = p.head;
-                const int oh = 2 * p.h, ow = 2 * p.w;
 #pragma unroll 1
                 for (int r = group; r < R; r += ngroups) {
                     const int y = y0 + r;
@@ -266,17 +285,8 @@ conv_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm0, co
                     const bool rok = xok && y < p.h;
                     float4 pl[2][2];
 #pragma unroll
-                    for (int i2 = 0; i2 < 2; ++i2) {
-                        const int oy = 2 * y + i2;
-                        if (hd.plog && rok && oy < hd.hs) {
-                            // the two pixels of an output row: 32 contiguous bytes per thread, 1 KB per warp
-                            const float4* src = hd.plog + ((size_t)page * oh + oy) * ow + 2 * x;
-                            pl[i2][0] = __ldg(src);
-                            pl[i2][1] = __ldg(src + 1);
-                        } else {
-                            pl[i2][0] = pl[i2][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        }
-                    }
+                    for (int i2 = 0; i2 < 2; ++i2) { pl[i2][0] = nx[i2][0]; pl[i2][1] = nx[i2][1]; }
+                    if (r + ngroups < R) request(y + ngroups, nx);
                     tmem_ld_wait();
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {                      // tap = 2*i2 + j -> output pixel (2y+i2, 2x+j)
