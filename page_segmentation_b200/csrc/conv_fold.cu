@@ -279,6 +279,16 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
                     const uint32_t slot = gg % SLOTS;
                     const int y = ys + o2 + st - 4;                   // < ys: virtual row
                     const bool real = o2 >= 4;
+                    // K split, last part: what the first part left is requested BEFORE the wait for this row's accumulator
+                    // (the epilogue of a tensor-bound layer spends most of its time in that wait)
+                    float4 ps[NPAD / 4];
+                    if (p.psum_in && real) {
+                        const bool ok = xok && y < p.h;
+#pragma unroll
+                        for (int c4 = 0; c4 < NPAD / 4; ++c4)
+                            ps[c4] = ok ? __ldg(p.psum_in + (((size_t)page * (NPAD / 4) + c4) * p.h + y) * p.w + x)
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
                     mbar_wait(&s_tfull[slot], (gg / SLOTS) & 1u);
                     tc_fence_after();
                     const uint32_t tacc = t_lane + slot * NPAD;
@@ -302,15 +312,12 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
                         continue;
                     }
                     if (p.psum_in) {                                    // K split, last part: add what the first part left
-                        const bool ok = xok && y < p.h;
 #pragma unroll
                         for (int c4 = 0; c4 < NPAD / 4; ++c4) {
-                            const float4 q = ok ? __ldg(p.psum_in + (((size_t)page * (NPAD / 4) + c4) * p.h + y) * p.w + x)
-                                                : make_float4(0.f, 0.f, 0.f, 0.f);
-                            v[4 * c4] = __float_as_uint(__uint_as_float(v[4 * c4]) + q.x);
-                            v[4 * c4 + 1] = __float_as_uint(__uint_as_float(v[4 * c4 + 1]) + q.y);
-                            v[4 * c4 + 2] = __float_as_uint(__uint_as_float(v[4 * c4 + 2]) + q.z);
-                            v[4 * c4 + 3] = __float_as_uint(__uint_as_float(v[4 * c4 + 3]) + q.w);
+                            v[4 * c4] = __float_as_uint(__uint_as_float(v[4 * c4]) + ps[c4].x);
+                            v[4 * c4 + 1] = __float_as_uint(__uint_as_float(v[4 * c4 + 1]) + ps[c4].y);
+                            v[4 * c4 + 2] = __float_as_uint(__uint_as_float(v[4 * c4 + 2]) + ps[c4].z);
+                            v[4 * c4 + 3] = __float_as_uint(__uint_as_float(v[4 * c4 + 3]) + ps[c4].w);
                         }
                     }
                     const bool rowok = xok && y < p.h;
