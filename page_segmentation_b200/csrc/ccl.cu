@@ -851,10 +851,397 @@ __global__ void cstats_ncomp_kernel(const int* __restrict__ ncomp_tmp, int n, in
     if (i < n) d_ncomp[(size_t)i * n_classes + cls] = ncomp_tmp[i];
 }
 
+// ---------------------------------------------------------------------------
+// Segment extraction, every class in ONE labelling (n_classes <= kMcMaxClasses).  The per-class path above labels
+// (pred == c) once per class: three tile / border / accumulate / rank rounds per page, each reading the whole class
+// map, and one set of five global atomics per run.  Every pixel belongs to exactly one of those labellings, so the
+// class map is labelled once with "same byte" as the neighbour relation:
+//   mc_tile   : 256 x 32 tiles in shared memory as in ccl_tile_kernel, the run structure taken from byte compares
+//               (run start = differs from the left pixel, vertical union = equals the upper pixel where either row
+//               starts a run); the statistics of every tile-local component (area, x extent, row mask) are gathered
+//               with shared-memory atomics in a table indexed by the rank of the root among the tile's root
+//               candidates (run starts without an equal upper pixel; candidates beyond the table go to global
+//               atomics), and written once per tile-local root together with a bit mask of those roots;
+//   mc_border : unions across tile borders on the global parents;
+//   mc_fold   : tile-local roots that lost their root status add their record to the component's root (one set of
+//               atomics per tile and component, not per run); roots counted per class and warp (= 1024 pixels in
+//               raster order), box and pixel count of every class for row 0 of the tables;
+//   scan, mc_write : label = rank of the root among the roots of ITS class (cv2's numbering of that class's
+//               labelling), stats row written from the root's record.
+// ---------------------------------------------------------------------------
+constexpr int kMcMaxClasses = 8;
+constexpr int kMcCap = 1024;                        // tile-local root candidates with shared-memory accumulators
+
+__device__ __forceinline__ unsigned eq_bits32(const unsigned (&a)[8], const unsigned (&b)[8]) {
+    unsigned m = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        unsigned c = __vcmpeq4(a[k], b[k]) & 0x08040201u;
+        c |= c >> 8;
+        c |= c >> 16;
+        m |= (c & 0xfu) << (4 * k);
+    }
+    return m;
+}
+
+// bit k = pixel k equals its left neighbour; the neighbour of pixel 0 is the low byte of `prev`
+__device__ __forceinline__ unsigned eq_left_bits32(const unsigned (&w)[8], unsigned prev) {
+    unsigned s[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[k] = (w[k] << 8) | (k ? w[k - 1] >> 24 : (prev & 0xffu));
+    return eq_bits32(w, s);
+}
+
+struct McTileSmem {
+    int lpar[kTileRows * kTileSegs * 32];
+    union {
+        uint4 bytes[256][2];                        // the tile's class bytes (phase 1 only)
+        int tab[4][kMcCap];                         // area, 255 - min x, max x, row mask of the tile-local components
+    } u;
+    unsigned hs[256];                               // run starts (tile sense) of every segment
+    unsigned cand[256];                             // root candidates of every segment
+    int off[256];                                   // exclusive scan of the candidate counts
+    int wsum[8];
+};
+
+__global__ void __launch_bounds__(256)
+mc_tile_kernel(const uint8_t* __restrict__ img, int H, int W, int* __restrict__ parent, unsigned* __restrict__ rootmask,
+               int* __restrict__ acc /*[px][5]: W - min x, H - min y, max x, max y, area*/) {
+    extern __shared__ __align__(16) unsigned char mc_smem_raw[];
+    McTileSmem& sm = *reinterpret_cast<McTileSmem*>(mc_smem_raw);
+    int* lpar = sm.lpar;
+    const int tid = threadIdx.x, lane = tid & 31, sx = tid & (kTileSegs - 1), ry = tid / kTileSegs;
+    const int ty0 = blockIdx.y * kTileRows, tx0 = blockIdx.x * kTileSegs * 32;
+    const int y = ty0 + ry, x0 = tx0 + sx * 32;
+    const size_t page_off = (size_t)blockIdx.z * H * W;
+    const bool valid = y < H && x0 < W;
+    const bool last_row = y == H - 1 && blockIdx.z == gridDim.z - 1;
+    const int nx = valid ? min(32, W - x0) : 0;
+    const unsigned m = nx >= 32 ? 0xffffffffu : ((1u << nx) - 1u);     // pixels of the segment inside the page
+    unsigned w[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    if (valid) load_seg32(img + page_off + (size_t)y * W, x0, W, last_row, 0u, w);
+    sm.u.bytes[tid][0] = make_uint4(w[0], w[1], w[2], w[3]);
+    sm.u.bytes[tid][1] = make_uint4(w[4], w[5], w[6], w[7]);
+    __syncthreads();
+    const int l0 = tid * 32;
+    unsigned eql = eq_left_bits32(w, sx > 0 ? sm.u.bytes[tid - 1][1].w >> 24 : 0u);
+    if (sx == 0) eql &= ~1u;                                            // the tile's first column starts a run
+    const unsigned hs_true = ~eql & m;                                  // run starts, tile sense
+    const unsigned hs_seg = (hs_true | 1u) & m;                         // run starts, segment sense
+    const bool cont0 = (eql & m & 1u) != 0u;                            // the first run continues the left segment's last
+    unsigned vsame = 0u;
+    if (ry > 0 && valid) {
+        const uint4 u0 = sm.u.bytes[tid - kTileSegs][0], u1 = sm.u.bytes[tid - kTileSegs][1];
+        const unsigned wu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+        vsame = eq_bits32(w, wu) & m;
+    }
+    const unsigned cand = hs_true & ~vsame;
+    sm.hs[tid] = hs_true;
+    sm.cand[tid] = cand;
+    const unsigned nzv = __ballot_sync(0xffffffffu, m != 0u);
+    for (unsigned todo = nzv; todo; todo &= todo - 1) {                 // warp-uniform loop
+        const int j = __ffs(todo) - 1;
+        const unsigned hj = __shfl_sync(0xffffffffu, hs_seg, j), mj = __shfl_sync(0xffffffffu, m, j);
+        if ((mj >> lane) & 1u) {
+            const int lb = (tid - lane + j) * 32;
+            lpar[lb + lane] = lb + 31 - __clz(hj & (0xffffffffu >> (31 - lane)));
+        }
+    }
+    int cnt = __popc(cand), incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) sm.wsum[tid >> 5] = incl;
+    __syncthreads();
+    if (cont0) suf_union(lpar, l0, l0 - 1);
+    if (vsame) {
+        unsigned v = vsame & (hs_true | sm.hs[tid - kTileSegs]);
+        while (v) {
+            const int k = __ffs(v) - 1;
+            v &= v - 1;
+            suf_union(lpar, l0 + k, l0 + k - 256);
+        }
+    }
+    int coff = incl - cnt;
+    for (int k = 0; k < (tid >> 5); ++k) coff += sm.wsum[k];
+    sm.off[tid] = coff;
+    for (int k = tid; k < 4 * kMcCap; k += 256) (&sm.u.tab[0][0])[k] = 0;   // the byte copy was last read before the barrier
+    auto gidx = [&](int r) { return (ty0 + (r >> 8)) * W + tx0 + (r & 255); };
+    if (coff + cnt > kMcCap) {                                          // candidates without a table slot: records in global memory
+        unsigned c2 = cand;
+        for (int i = coff; c2; ++i, c2 &= c2 - 1) {
+            if (i < kMcCap) continue;
+            int* z = acc + (page_off + gidx(l0 + __ffs(c2) - 1)) * 5;
+            z[0] = 0; z[1] = 0; z[2] = 0; z[3] = 0; z[4] = 0;
+        }
+    }
+    __syncthreads();
+    {   // one find per run, kept at the run's first pixel (a concurrent walker reads the old or the new ancestor)
+        unsigned mm = hs_seg;
+        while (mm) {
+            const int s = __ffs(mm) - 1;
+            mm &= mm - 1;
+            lpar[l0 + s] = suf_find(lpar, l0 + s);
+        }
+    }
+    __syncthreads();
+    {   // statistics: runs that end in the same root are combined across the warp before the atomics
+        unsigned mm = hs_seg;
+        while (__any_sync(0xffffffffu, mm != 0u)) {
+            const bool has = mm != 0u;
+            const int s = has ? __ffs(mm) - 1 : 0;
+            mm &= mm - 1;
+            const int e = mm ? __ffs(mm) - 1 : nx;
+            const int r = has ? lpar[l0 + s] : -1 - lane;               // idle lanes: unique keys
+            const unsigned peers = __match_any_sync(0xffffffffu, r);
+            int a = e - s, v0 = 255 - (sx * 32 + s), v2 = sx * 32 + e - 1;
+            unsigned rows = 1u << ry;
+            if (peers & (peers - 1)) {
+                a = __reduce_add_sync(peers, a);
+                v0 = __reduce_max_sync(peers, v0);
+                v2 = __reduce_max_sync(peers, v2);
+                rows = __reduce_or_sync(peers, rows);
+            }
+            if (has && lane == __ffs(peers) - 1) {
+                const int rt = r >> 5;
+                const int ci = sm.off[rt] + __popc(sm.cand[rt] & ((1u << (r & 31)) - 1u));
+                if (ci < kMcCap) {
+                    atomicAdd(&sm.u.tab[0][ci], a);
+                    atomicMax(&sm.u.tab[1][ci], v0);
+                    atomicMax(&sm.u.tab[2][ci], v2);
+                    atomicOr(reinterpret_cast<unsigned*>(&sm.u.tab[3][ci]), rows);
+                } else {
+                    int* g = acc + (page_off + gidx(r)) * 5;
+                    atomicMax(&g[0], W - (tx0 + 255 - v0));
+                    atomicMax(&g[1], H - (ty0 + __ffs(rows) - 1));
+                    atomicMax(&g[2], tx0 + v2);
+                    atomicMax(&g[3], ty0 + 31 - __clz(rows));
+                    atomicAdd(&g[4], a);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    int* par = parent + page_off;
+    for (unsigned todo = nzv; todo; todo &= todo - 1) {                 // every store writes 32 consecutive parents
+        const int j = __ffs(todo) - 1;
+        const unsigned hj = __shfl_sync(0xffffffffu, hs_seg, j), mj = __shfl_sync(0xffffffffu, m, j);
+        const int tj = tid - lane + j;
+        const int bj = (ty0 + tj / kTileSegs) * W + tx0 + (tj & (kTileSegs - 1)) * 32;
+        if ((mj >> lane) & 1u) par[bj + lane] = gidx(lpar[tj * 32 + 31 - __clz(hj & (0xffffffffu >> (31 - lane)))]);
+    }
+    if (valid) {
+        unsigned roots = 0u, c2 = cand;
+        for (int i = coff; c2; ++i, c2 &= c2 - 1) {
+            const int k = __ffs(c2) - 1;
+            if (lpar[l0 + k] != l0 + k) continue;
+            roots |= 1u << k;
+            if (i < kMcCap) {
+                const unsigned rows = (unsigned)sm.u.tab[3][i];
+                int* g = acc + (page_off + gidx(l0 + k)) * 5;
+                g[0] = W - (tx0 + 255 - sm.u.tab[1][i]);
+                g[1] = H - (ty0 + __ffs(rows) - 1);
+                g[2] = tx0 + sm.u.tab[2][i];
+                g[3] = ty0 + 31 - __clz(rows);
+                g[4] = sm.u.tab[0][i];
+            }
+        }
+        rootmask[((size_t)blockIdx.z * H + y) * ((W + 31) >> 5) + (x0 >> 5)] = roots;
+    }
+}
+
+template <bool COMPRESS>
+__global__ void __launch_bounds__(256)
+mc_border_kernel(const uint8_t* __restrict__ img, int H, int W, int* __restrict__ parent) {
+    PCS_SEG_THREAD();
+    if (!valid) return;
+    const int sx = (x0 >> 5) & (kTileSegs - 1);
+    const bool hrow = (y & (kTileRows - 1)) == 0 && y > 0;
+    const bool hcol = sx == 0 && x0 > 0;
+    if (!hrow && !hcol) return;
+    const uint8_t* row = img + page_off + (size_t)y * W;
+    const int nx = min(32, W - x0);
+    const unsigned m = nx >= 32 ? 0xffffffffu : ((1u << nx) - 1u);
+    unsigned w[8];
+    load_seg32(row, x0, W, last_row, 0u, w);
+    unsigned eql = eq_left_bits32(w, x0 > 0 ? __ldg(row + x0 - 1) : 0u);
+    if (x0 == 0) eql &= ~1u;
+    int* par = parent + page_off;
+    const int idx0 = y * W + x0;
+    if (hcol && (eql & 1u)) uf_union<COMPRESS>(par, idx0, idx0 - 1);    // run crosses a tile border
+    if (!hrow) return;
+    const uint8_t* rup = row - W;
+    unsigned wu[8];
+    load_seg32(rup, x0, W, false, 0u, wu);
+    unsigned equ = eq_left_bits32(wu, x0 > 0 ? __ldg(rup + x0 - 1) : 0u);
+    if (x0 == 0) equ &= ~1u;
+    unsigned v = eq_bits32(w, wu) & m & ~(eql & equ);                   // equal to the upper pixel where either row starts a run
+    while (v) {
+        const int k = __ffs(v) - 1;
+        v &= v - 1;
+        uf_union<COMPRESS>(par, idx0 + k, idx0 + k - W);
+    }
+}
+
+// clsbox: [page][n_classes + 1][5] = W - min x, H - min y, max x, max y, pixel count of every class (last: other bytes)
+__global__ void __launch_bounds__(256)
+mc_fold_kernel(const uint8_t* __restrict__ img, int H, int W, int n_classes, int* __restrict__ parent, unsigned* __restrict__ rootmask,
+               int* __restrict__ acc, int* __restrict__ warpcnt /*[page][class][warp]*/, int* __restrict__ clsbox) {
+    PCS_SEG_THREAD();
+    __shared__ int sbox[(kMcMaxClasses + 1) * 5];
+    if (threadIdx.x < (kMcMaxClasses + 1) * 5) sbox[threadIdx.x] = 0;
+    __syncthreads();
+    const size_t mask_off = (size_t)blockIdx.y * H * segs + t;
+    unsigned rm = valid ? rootmask[mask_off] : 0u, gm = 0u;
+    int* par = parent + page_off;
+    const int base = y * W + x0;
+    while (rm) {
+        const int k = __ffs(rm) - 1;
+        rm &= rm - 1;
+        const int r = uf_find(par, base + k);
+        if (r == base + k) { gm |= 1u << k; continue; }
+        const int* a = acc + (page_off + base + k) * 5;
+        int* g = acc + (page_off + r) * 5;
+        const int v0 = a[0], v1 = a[1], v2 = a[2], v3 = a[3];
+        if (v0 > __ldcg(g + 0)) atomicMax(&g[0], v0);
+        if (v1 > __ldcg(g + 1)) atomicMax(&g[1], v1);
+        if (v2 > __ldcg(g + 2)) atomicMax(&g[2], v2);
+        if (v3 > __ldcg(g + 3)) atomicMax(&g[3], v3);
+        atomicAdd(&g[4], a[4]);
+    }
+    if (valid) rootmask[mask_off] = gm;                                 // from here on: the roots of whole components
+    const int nx = valid ? min(32, W - x0) : 0;
+    const unsigned m = nx >= 32 ? 0xffffffffu : ((1u << nx) - 1u);
+    unsigned w[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    if (valid) load_seg32(img + page_off + (size_t)y * W, x0, W, last_row, 0u, w);
+    const int nw = gridDim.x * 8, wid = t >> 5;
+    unsigned seen = 0u;
+    for (int c = 0; c <= n_classes; ++c) {
+        const unsigned b = c < n_classes ? seg_bits<1>(w, c) & m : m & ~seen;
+        seen |= b;
+        if (c < n_classes) {
+            const int wc = __reduce_add_sync(0xffffffffu, __popc(gm & b));
+            if ((threadIdx.x & 31) == 0) warpcnt[((size_t)blockIdx.y * n_classes + c) * nw + wid] = wc;
+        }
+        if (!__any_sync(0xffffffffu, b != 0u)) continue;
+        const int v0 = b ? W - (x0 + __ffs(b) - 1) : 0, v1 = b ? H - y : 0, v2 = b ? x0 + 31 - __clz(b) : -1, v3 = b ? y : -1;
+        const int r0 = __reduce_max_sync(0xffffffffu, v0), r1 = __reduce_max_sync(0xffffffffu, v1);
+        const int r2 = __reduce_max_sync(0xffffffffu, v2), r3 = __reduce_max_sync(0xffffffffu, v3);
+        const int pc = __reduce_add_sync(0xffffffffu, __popc(b));
+        if ((threadIdx.x & 31) == 0) {
+            int* s = sbox + c * 5;
+            if (r0 > s[0]) atomicMax(&s[0], r0);
+            if (r1 > s[1]) atomicMax(&s[1], r1);
+            if (r2 > s[2]) atomicMax(&s[2], r2);
+            if (r3 > s[3]) atomicMax(&s[3], r3);
+            atomicAdd(&s[4], pc);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < (n_classes + 1) * 5) {
+        const int c = threadIdx.x / 5, f = threadIdx.x - c * 5;
+        if (sbox[c * 5 + 4] > 0) {
+            int* g = clsbox + ((size_t)blockIdx.y * (n_classes + 1) + c) * 5 + f;
+            if (f == 4) atomicAdd(g, sbox[threadIdx.x]);
+            else if (sbox[threadIdx.x] > __ldcg(g)) atomicMax(g, sbox[threadIdx.x]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+mc_write_kernel(const uint8_t* __restrict__ img, int H, int W, int n_classes, const unsigned* __restrict__ rootmask, const int* __restrict__ acc,
+                const int* __restrict__ warpoff, const int* __restrict__ clsbox, int32_t* __restrict__ stats, int max_components) {
+    PCS_SEG_THREAD();
+    int32_t* st = stats + (size_t)blockIdx.y * n_classes * max_components * 5;
+    if (blockIdx.x == 0 && (int)threadIdx.x < n_classes) {
+        // row 0 of class c's table: box and count of every pixel that is NOT c (cv2's label 0 of that labelling)
+        int g0 = 0, g1 = 0, g2 = -1, g3 = -1, cnt = 0;
+        for (int o = 0; o <= n_classes; ++o) {
+            if (o == (int)threadIdx.x) continue;
+            const int* b = clsbox + ((size_t)blockIdx.y * (n_classes + 1) + o) * 5;
+            if (b[4] <= 0) continue;
+            g0 = max(g0, b[0]); g1 = max(g1, b[1]); g2 = max(g2, b[2]); g3 = max(g3, b[3]); cnt += b[4];
+        }
+        int32_t* o = st + (size_t)threadIdx.x * max_components * 5;
+        if (cnt > 0) { o[0] = W - g0; o[1] = H - g1; o[2] = g2 - (W - g0) + 1; o[3] = g3 - (H - g1) + 1; o[4] = cnt; }
+        else { o[0] = 0; o[1] = 0; o[2] = 0; o[3] = 0; o[4] = 0; }      // cv2 leaves an empty label's box at zero extent
+    }
+    const unsigned gm = valid ? rootmask[(size_t)blockIdx.y * H * segs + t] : 0u;
+    if (!__any_sync(0xffffffffu, gm != 0u)) return;
+    unsigned w[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    if (gm) load_seg32(img + page_off + (size_t)y * W, x0, W, last_row, 0u, w);
+    const int nw = gridDim.x * 8, wid = t >> 5, lane = threadIdx.x & 31;
+    const int base = y * W + x0;
+    for (int c = 0; c < n_classes; ++c) {
+        unsigned b = gm ? gm & seg_bits<1>(w, c) : 0u;
+        if (!__any_sync(0xffffffffu, b != 0u)) continue;
+        const int cnt = __popc(b);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        int l = __ldg(warpoff + ((size_t)blockIdx.y * n_classes + c) * nw + wid) + incl - cnt;
+        int32_t* sc = st + (size_t)c * max_components * 5;
+        while (b) {
+            const int k = __ffs(b) - 1;
+            b &= b - 1;
+            if (++l >= max_components) break;
+            const int* a = acc + (page_off + base + k) * 5;
+            int32_t* o = sc + (size_t)l * 5;
+            const int left = W - a[0], top = H - a[1];
+            o[0] = left; o[1] = top; o[2] = a[2] - left + 1; o[3] = a[3] - top + 1; o[4] = a[4];
+        }
+    }
+}
+
+static int launch_class_components_mc(pcs_ctx* ctx, const uint8_t* d_pred, int n, int H, int W, int n_classes, int32_t* d_stats,
+                                      int max_components, int32_t* d_ncomp) {
+    const size_t page_px = (size_t)H * W, total = page_px * n;
+    const int segs = (W + 31) >> 5;
+    const dim3 g = seg_grid(H, W, n);
+    const int nw = (int)g.x * 8;
+    const size_t mask_words = (size_t)n * H * segs, cnt_words = (size_t)n * n_classes * nw, box_words = (size_t)n * (n_classes + 1) * 5;
+    PCS_TRY(scratch_reserve(ctx, (total * 6 + mask_words + cnt_words + box_words + (size_t)n * n_classes) * 4 + 512));
+    int* parent = reinterpret_cast<int*>(ctx->scratch);
+    int* acc = parent + total;
+    unsigned* rootmask = reinterpret_cast<unsigned*>(acc + total * 5);
+    int* warpcnt = reinterpret_cast<int*>(rootmask + mask_words);
+    int* clsbox = warpcnt + cnt_words;
+    int* ncomp_tmp = clsbox + box_words;
+    cudaStream_t st = ctx->stream;
+    static bool attr_set = false;
+    if (!attr_set) {
+        PCS_CUDA(ctx, cudaFuncSetAttribute(mc_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(McTileSmem)));
+        attr_set = true;
+    }
+    PCS_CUDA(ctx, cudaMemsetAsync(d_stats, 0, (size_t)n * n_classes * max_components * 5 * sizeof(int32_t), st));
+    PCS_CUDA(ctx, cudaMemsetAsync(clsbox, 0, box_words * sizeof(int), st));
+    const dim3 gt((W + kTileSegs * 32 - 1) / (kTileSegs * 32), (H + kTileRows - 1) / kTileRows, n);
+    mc_tile_kernel<<<gt, 256, sizeof(McTileSmem), st>>>(d_pred, H, W, parent, rootmask, acc);
+    PCS_LAUNCH_CHECK(ctx, "mc_tile_kernel");
+    if (ccl_compress(true)) mc_border_kernel<true><<<g, 256, 0, st>>>(d_pred, H, W, parent);
+    else mc_border_kernel<false><<<g, 256, 0, st>>>(d_pred, H, W, parent);
+    PCS_LAUNCH_CHECK(ctx, "mc_border_kernel");
+    mc_fold_kernel<<<g, 256, 0, st>>>(d_pred, H, W, n_classes, parent, rootmask, acc, warpcnt, clsbox);
+    PCS_LAUNCH_CHECK(ctx, "mc_fold_kernel");
+    ccl_scan_blocks_kernel<<<n * n_classes, 1024, 0, st>>>(warpcnt, nw, d_ncomp ? d_ncomp : ncomp_tmp);
+    PCS_LAUNCH_CHECK(ctx, "ccl_scan_blocks_kernel");
+    mc_write_kernel<<<g, 256, 0, st>>>(d_pred, H, W, n_classes, rootmask, acc, warpcnt, clsbox, d_stats, max_components);
+    PCS_LAUNCH_CHECK(ctx, "mc_write_kernel");
+    return PCS_OK;
+}
+
 int launch_class_components(pcs_ctx* ctx, const uint8_t* d_pred, int n, int H, int W, int n_classes, int32_t* d_stats, int max_components,
                             int32_t* d_ncomp) {
     if (n <= 0 || H <= 0 || W <= 0 || n_classes <= 0 || n_classes > 255 || (size_t)H * W >= (size_t)INT_MAX || max_components <= 0)
         return set_err(ctx, PCS_ERR_ARG, "class_components: bad argument");
+    static const char* per_class = getenv("PCSEG_SEGMENTS_PER_CLASS");   // A/B switch: one labelling per class
+    if (n_classes <= kMcMaxClasses && !(per_class && atoi(per_class) != 0))
+        return launch_class_components_mc(ctx, d_pred, n, H, W, n_classes, d_stats, max_components, d_ncomp);
     const size_t page_px = (size_t)H * W, total = page_px * n;
     const int nblocks = (int)((page_px + kScanBlock - 1) / kScanBlock);
     PCS_TRY(scratch_reserve(ctx, total * 4 * 7 + ((size_t)n * nblocks + n + (size_t)n * 5) * 4 + 512));

@@ -158,3 +158,83 @@ def test_class_components_batched_and_truncated(ctx):
             np.testing.assert_array_equal(stats[p, c, :k], exp[:k])
             assert not stats[p, c, k:].any()
     assert ncomp[1, 2] == 1 and stats[1, 2, 0].tolist() == [0, 0, 203, 150, 150 * 203]
+
+
+def _cv2_class_tables(pred, n_classes):
+    return [cv2.connectedComponentsWithStats((pred == c).astype(np.uint8), connectivity=4)[::2] for c in range(n_classes)]
+
+
+def _device_class_tables(ctx, preds, n_classes, maxc):
+    import torch
+    d = torch.from_numpy(np.stack(preds).astype(np.uint8)).cuda()
+    n, h, w = d.shape
+    d_stats = torch.full((n, n_classes, maxc, 5), -7, dtype=torch.int32, device="cuda")
+    d_ncomp = torch.zeros((n, n_classes), dtype=torch.int32, device="cuda")
+    ctx.class_components(d, n, h, w, n_classes, d_stats, maxc, d_ncomp)
+    return d_stats.cpu().numpy(), d_ncomp.cpu().numpy()
+
+
+def _check_class_tables(ctx, preds, n_classes, maxc=1 << 17):
+    stats, ncomp = _device_class_tables(ctx, preds, n_classes, maxc)
+    for p, pred in enumerate(preds):
+        for c, (n, exp) in enumerate(_cv2_class_tables(pred, n_classes)):
+            assert ncomp[p, c] == n, (p, c, ncomp[p, c], n)
+            k = min(n, maxc)
+            np.testing.assert_array_equal(stats[p, c, :k], exp[:k], err_msg=f"page {p} class {c}")
+            assert not stats[p, c, k:].any()
+
+
+@pytest.mark.parametrize("hw", [(33, 257), (64, 512), (97, 530), (300, 700)])
+def test_class_components_pure_noise(ctx, hw):
+    """Uniform three-class noise: ~3 600 root candidates per 256 x 32 labelling tile, far beyond the 1 024 records a
+    tile accumulates in shared memory, so most components take the global-atomics path of the one-pass labelling."""
+    rng = np.random.default_rng(5)
+    preds = [rng.integers(0, 3, size=hw).astype(np.uint8) for _ in range(2)]
+    _check_class_tables(ctx, preds, 3)
+
+
+def test_class_components_shapes_across_tiles(ctx):
+    """Components that leave a labelling tile and come back (a spiral, a comb, nested frames): tile-local roots that
+    merge through neighbouring tiles, whose records have to be folded into one."""
+    h, w = 200, 700
+    spiral = np.zeros((h, w), np.uint8)
+    y0, y1, x0, x1 = 2, h - 3, 2, w - 3
+    while y1 - y0 > 8 and x1 - x0 > 8:
+        spiral[y0, x0:x1 + 1] = 1
+        spiral[y0:y1 + 1, x1] = 1
+        spiral[y1, x0 + 4:x1 + 1] = 1
+        spiral[y0 + 4:y1 + 1, x0 + 4] = 1
+        spiral[y0 + 4, x0 + 4:x1 - 3] = 1
+        y0 += 4; y1 -= 4; x0 += 4; x1 -= 4                                   # noqa: E702
+    comb = np.zeros((h, w), np.uint8)
+    comb[h - 2, :] = 2
+    comb[3:h - 2, ::3] = 2
+    comb[5:h - 40:2, 1::3] = 1
+    frames = np.zeros((h, w), np.uint8)
+    for k in range(0, 90, 2):
+        frames[k:h - k, k:w - k] = (k // 2) % 3
+    _check_class_tables(ctx, [spiral, comb, frames, np.full((h, w), 2, np.uint8)], 3)
+
+
+def test_class_components_other_bytes_and_class_counts(ctx, monkeypatch):
+    """Bytes outside 0 .. n_classes-1 belong to no class but count as 'not c' in every row 0; nine classes take the
+    per-class path (the one-pass labelling handles up to eight); PCSEG_SEGMENTS_PER_CLASS is read once per process,
+    so the A/B switch itself is exercised by tools/probe_segments.py."""
+    rng = np.random.default_rng(11)
+    coarse = rng.integers(0, 6, size=(40, 60))
+    pred = np.kron(coarse, np.ones((5, 9), np.uint8))[:170, :530].astype(np.uint8)
+    pred[rng.random(pred.shape) < 0.1] = 250
+    _check_class_tables(ctx, [pred], 3)                                      # classes 3, 4, 5 and 250 are 'other'
+    _check_class_tables(ctx, [pred], 6)
+    _check_class_tables(ctx, [pred % 9, (pred + 3) % 9], 9)
+    _check_class_tables(ctx, [pred % 8], 8)
+    _check_class_tables(ctx, [np.where(pred == 250, 1, 0).astype(np.uint8)], 1)
+
+
+def test_class_components_a4_noise_like_truncated(ctx):
+    """Full scaled page, class map with letter-sized and page-sized components, table shorter than the label count."""
+    preds = []
+    for s in range(2):
+        pred, b = _pred_and_binary(40 + s, 1169, 827)
+        preds.append(np.where(b > 0, pred, 0).astype(np.uint8))
+    _check_class_tables(ctx, preds, 3, maxc=4096)
