@@ -180,6 +180,12 @@ def _check_class_tables(ctx, preds, n_classes, maxc=1 << 17):
         for c, (n, exp) in enumerate(_cv2_class_tables(pred, n_classes)):
             assert ncomp[p, c] == n, (p, c, ncomp[p, c], n)
             k = min(n, maxc)
+            if exp[0, 4] == 0:
+                # class c covers the page: cv2 4.13 reports [-1, INT_MAX, 0, 0, 0] for the empty label 0 (its untouched
+                # min / max initialisers); the reference never reads row 0 (postprocess.py:35), the device writes zeros
+                assert not stats[p, c, 0].any()
+                exp = exp.copy()
+                exp[0] = 0
             np.testing.assert_array_equal(stats[p, c, :k], exp[:k], err_msg=f"page {p} class {c}")
             assert not stats[p, c, k:].any()
 
