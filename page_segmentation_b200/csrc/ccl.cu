@@ -161,6 +161,32 @@ __device__ __forceinline__ void suf_union(int* lp, int a, int b) {
     }
 }
 
+// path halving: every node on the walk is re-linked to its grandparent (plain stores of an ANCESTOR into a node that
+// is not a root: roots change through atomicMin only, and a node that stopped being a root never becomes one again)
+__device__ __forceinline__ int suf_find_h(volatile int* lp, int x) {
+    int p = lp[x];
+    while (p != x) {
+        const int g = lp[p];
+        if (g == p) return p;
+        lp[x] = g;
+        x = g;
+        p = lp[x];
+    }
+    return x;
+}
+
+__device__ __forceinline__ void suf_union_h(int* lp, int a, int b) {
+    while (true) {
+        a = suf_find_h(lp, a);
+        b = suf_find_h(lp, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }
+        const int old = atomicMin(&lp[a], b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
 constexpr int kTileSegs = 8, kTileRows = 32;        // a block labels a tile of 256 x 32 pixels
 
 // A  tile: every 256 x 32 tile is labelled on its own in shared memory (pixels outside the tile count as
@@ -955,13 +981,13 @@ mc_tile_kernel(const uint8_t* __restrict__ img, int H, int W, int* __restrict__ 
     }
     if (lane == 31) sm.wsum[tid >> 5] = incl;
     __syncthreads();
-    if (cont0) suf_union(lpar, l0, l0 - 1);
+    if (cont0) suf_union_h(lpar, l0, l0 - 1);
     if (vsame) {
         unsigned v = vsame & (hs_true | sm.hs[tid - kTileSegs]);
         while (v) {
             const int k = __ffs(v) - 1;
             v &= v - 1;
-            suf_union(lpar, l0 + k, l0 + k - 256);
+            suf_union_h(lpar, l0 + k, l0 + k - 256);
         }
     }
     int coff = incl - cnt;
@@ -983,54 +1009,72 @@ mc_tile_kernel(const uint8_t* __restrict__ img, int H, int W, int* __restrict__ 
         while (mm) {
             const int s = __ffs(mm) - 1;
             mm &= mm - 1;
-            lpar[l0 + s] = suf_find(lpar, l0 + s);
+            lpar[l0 + s] = suf_find(lpar, l0 + s);                     // read-only walk: a halving store could land after another thread's final one
         }
     }
     __syncthreads();
-    {   // statistics: runs that end in the same root are combined across the warp before the atomics
-        unsigned mm = hs_seg;
-        while (__any_sync(0xffffffffu, mm != 0u)) {
-            const bool has = mm != 0u;
-            const int s = has ? __ffs(mm) - 1 : 0;
+    {   // statistics.  A thread adds up the runs that share the root of its longest run in registers (the page
+        // background or a picture block owns most segments of a tile: its record would serialise thousands of
+        // atomics), those sums are combined across the warp; the other runs (letters, specks) update their record.
+        auto update = [&](int r, int a, int v0, int v2, unsigned rows) {
+            const int rt = r >> 5;
+            const int ci = sm.off[rt] + __popc(sm.cand[rt] & ((1u << (r & 31)) - 1u));
+            if (ci < kMcCap) {
+                atomicAdd(&sm.u.tab[0][ci], a);
+                atomicMax(&sm.u.tab[1][ci], v0);
+                atomicMax(&sm.u.tab[2][ci], v2);
+                atomicOr(reinterpret_cast<unsigned*>(&sm.u.tab[3][ci]), rows);
+            } else {
+                int* g = acc + (page_off + gidx(r)) * 5;
+                atomicMax(&g[0], W - (tx0 + 255 - v0));
+                atomicMax(&g[1], H - (ty0 + __ffs(rows) - 1));
+                atomicMax(&g[2], tx0 + v2);
+                atomicMax(&g[3], ty0 + 31 - __clz(rows));
+                atomicAdd(&g[4], a);
+            }
+        };
+        int best_s = 0, best_len = 0;
+        for (unsigned mm = hs_seg; mm;) {
+            const int s = __ffs(mm) - 1;
+            mm &= mm - 1;
+            const int len = (mm ? __ffs(mm) - 1 : nx) - s;
+            if (len > best_len) { best_len = len; best_s = s; }
+        }
+        const int rkey = valid ? lpar[l0 + best_s] : -1 - lane;         // idle lanes: unique keys
+        int a = 0, v0 = 0, v2 = -1;
+        for (unsigned mm = hs_seg; mm;) {
+            const int s = __ffs(mm) - 1;
             mm &= mm - 1;
             const int e = mm ? __ffs(mm) - 1 : nx;
-            const int r = has ? lpar[l0 + s] : -1 - lane;               // idle lanes: unique keys
-            const unsigned peers = __match_any_sync(0xffffffffu, r);
-            int a = e - s, v0 = 255 - (sx * 32 + s), v2 = sx * 32 + e - 1;
-            unsigned rows = 1u << ry;
-            if (peers & (peers - 1)) {
-                a = __reduce_add_sync(peers, a);
-                v0 = __reduce_max_sync(peers, v0);
-                v2 = __reduce_max_sync(peers, v2);
-                rows = __reduce_or_sync(peers, rows);
-            }
-            if (has && lane == __ffs(peers) - 1) {
-                const int rt = r >> 5;
-                const int ci = sm.off[rt] + __popc(sm.cand[rt] & ((1u << (r & 31)) - 1u));
-                if (ci < kMcCap) {
-                    atomicAdd(&sm.u.tab[0][ci], a);
-                    atomicMax(&sm.u.tab[1][ci], v0);
-                    atomicMax(&sm.u.tab[2][ci], v2);
-                    atomicOr(reinterpret_cast<unsigned*>(&sm.u.tab[3][ci]), rows);
-                } else {
-                    int* g = acc + (page_off + gidx(r)) * 5;
-                    atomicMax(&g[0], W - (tx0 + 255 - v0));
-                    atomicMax(&g[1], H - (ty0 + __ffs(rows) - 1));
-                    atomicMax(&g[2], tx0 + v2);
-                    atomicMax(&g[3], ty0 + 31 - __clz(rows));
-                    atomicAdd(&g[4], a);
-                }
-            }
+            const int r = s == best_s ? rkey : lpar[l0 + s];
+            if (r == rkey) { a += e - s; v0 = max(v0, 255 - (sx * 32 + s)); v2 = max(v2, sx * 32 + e - 1); }
+            else update(r, e - s, 255 - (sx * 32 + s), sx * 32 + e - 1, 1u << ry);
         }
+        const unsigned peers = __match_any_sync(0xffffffffu, rkey);
+        unsigned rows = 1u << ry;
+        if (peers & (peers - 1)) {
+            a = __reduce_add_sync(peers, a);
+            v0 = __reduce_max_sync(peers, v0);
+            v2 = __reduce_max_sync(peers, v2);
+            rows = __reduce_or_sync(peers, rows);
+        }
+        if (valid && lane == __ffs(peers) - 1) update(rkey, a, v0, v2, rows);
     }
     __syncthreads();
     int* par = parent + page_off;
-    for (unsigned todo = nzv; todo; todo &= todo - 1) {                 // every store writes 32 consecutive parents
+    // Parents are written where later passes read them: the tile's first and last row and its first and last column
+    // (operands of the border unions) and the tile-local roots (the ends of those walks, the pixels mc_fold visits).
+    const unsigned edge_rows = __ballot_sync(0xffffffffu, m != 0u && (ry == 0 || ry == kTileRows - 1));
+    for (unsigned todo = edge_rows; todo; todo &= todo - 1) {           // every store writes 32 consecutive parents
         const int j = __ffs(todo) - 1;
         const unsigned hj = __shfl_sync(0xffffffffu, hs_seg, j), mj = __shfl_sync(0xffffffffu, m, j);
         const int tj = tid - lane + j;
         const int bj = (ty0 + tj / kTileSegs) * W + tx0 + (tj & (kTileSegs - 1)) * 32;
         if ((mj >> lane) & 1u) par[bj + lane] = gidx(lpar[tj * 32 + 31 - __clz(hj & (0xffffffffu >> (31 - lane)))]);
+    }
+    if (valid && ry != 0 && ry != kTileRows - 1) {
+        if (sx == 0) par[y * W + x0] = gidx(lpar[l0]);
+        if (sx == kTileSegs - 1 && nx == 32) par[y * W + x0 + 31] = gidx(lpar[l0 + 31 - __clz(hs_seg)]);
     }
     if (valid) {
         unsigned roots = 0u, c2 = cand;
@@ -1038,6 +1082,7 @@ mc_tile_kernel(const uint8_t* __restrict__ img, int H, int W, int* __restrict__ 
             const int k = __ffs(c2) - 1;
             if (lpar[l0 + k] != l0 + k) continue;
             roots |= 1u << k;
+            par[y * W + x0 + k] = y * W + x0 + k;
             if (i < kMcCap) {
                 const unsigned rows = (unsigned)sm.u.tab[3][i];
                 int* g = acc + (page_off + gidx(l0 + k)) * 5;
