@@ -59,6 +59,32 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
     }
 }
 
+// the same walk with path halving (see suf_find_h below: every store puts an ANCESTOR into a node that is not a root)
+__device__ __forceinline__ int uf_find_h(int* parent, int x) {
+    int p = __ldcg(parent + x);
+    while (p != x) {
+        const int g = __ldcg(parent + p);
+        if (g == p) return p;
+        __stcg(parent + x, g);
+        x = g;
+        p = __ldcg(parent + x);
+    }
+    return x;
+}
+
+// union with halving walks; the starting nodes end up one or two links from their roots, so no separate re-linking
+__device__ __forceinline__ void uf_union_h(int* parent, int a, int b) {
+    while (true) {
+        a = uf_find_h(parent, a);
+        b = uf_find_h(parent, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }
+        const int old = atomicMin(&parent[a], b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Segment-wise passes.  A page is nine tenths background, so the passes over the image do not spend a thread per
 // pixel: a thread owns one 32-pixel segment of a row, reads it with two 128-bit loads (32-bit words and a funnel
@@ -1097,7 +1123,7 @@ mc_tile_kernel(const uint8_t* __restrict__ img, int H, int W, int* __restrict__ 
     }
 }
 
-template <bool COMPRESS>
+template <bool HALVE>
 __global__ void __launch_bounds__(256)
 mc_border_kernel(const uint8_t* __restrict__ img, int H, int W, int* __restrict__ parent) {
     PCS_SEG_THREAD();
@@ -1115,7 +1141,7 @@ mc_border_kernel(const uint8_t* __restrict__ img, int H, int W, int* __restrict_
     if (x0 == 0) eql &= ~1u;
     int* par = parent + page_off;
     const int idx0 = y * W + x0;
-    if (hcol && (eql & 1u)) uf_union<COMPRESS>(par, idx0, idx0 - 1);    // run crosses a tile border
+    if (hcol && (eql & 1u)) { if (HALVE) uf_union_h(par, idx0, idx0 - 1); else uf_union<false>(par, idx0, idx0 - 1); }    // run crosses a tile border
     if (!hrow) return;
     const uint8_t* rup = row - W;
     unsigned wu[8];
@@ -1126,7 +1152,8 @@ mc_border_kernel(const uint8_t* __restrict__ img, int H, int W, int* __restrict_
     while (v) {
         const int k = __ffs(v) - 1;
         v &= v - 1;
-        uf_union<COMPRESS>(par, idx0 + k, idx0 + k - W);
+        if (HALVE) uf_union_h(par, idx0 + k, idx0 + k - W);
+        else uf_union<false>(par, idx0 + k, idx0 + k - W);
     }
 }
 
@@ -1145,7 +1172,7 @@ mc_fold_kernel(const uint8_t* __restrict__ img, int H, int W, int n_classes, int
     while (rm) {
         const int k = __ffs(rm) - 1;
         rm &= rm - 1;
-        const int r = uf_find(par, base + k);
+        const int r = uf_find_h(par, base + k);                         // no unions any more: only ancestors are stored
         if (r == base + k) { gm |= 1u << k; continue; }
         const int* a = acc + (page_off + base + k) * 5;
         int* g = acc + (page_off + r) * 5;
