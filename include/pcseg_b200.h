@@ -239,6 +239,14 @@ PCS_API int pcs_predict_pages_segments(pcs_ctx* ctx, const uint8_t* h_grey, cons
                                uint8_t* h_labels, uint8_t* h_color, uint8_t* h_overlay, uint8_t* h_inverted,
                                int32_t* h_stats, int max_components, int32_t* h_ncomp);
 
+/* The segment call with the compact transport of pcs_predict_pages_compact: uint8 pages in; class map, bit-packed
+ * `binary` (or NULL), stats tables and label counts out -- 1.3 MB per page instead of 9.9 MB with the three masks,
+ * which are a function of the class map, the binary and the colour table (pcs_unpack_bits + pcs_masks). */
+PCS_API int pcs_predict_pages_segments_compact(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h_bin,
+                               int n, int H, int W, int Hs, int Ws, int cc_majority,
+                               uint8_t* h_labels, uint32_t* h_binary_bits,
+                               int32_t* h_stats, int max_components, int32_t* h_ncomp);
+
 /* ---- image files: the encoder of output_data, lib/output.py:38-41 (skimage.io.imsave of the three masks).
  * Builds n complete PNG files on the device from [n][H][W][channels] uint8 images (channels 1 = grey, 3 = RGB,
  * 4 = RGBA): signature, IHDR, one IDAT, Adler-32, CRC-32, IEND.  level 0: stored deflate blocks, the file is the

@@ -1325,6 +1325,14 @@ int pcs_predict_pages_segments(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_
                                    h_inverted, nullptr, 0, nullptr, h_stats, max_components, h_ncomp);
 }
 
+int pcs_predict_pages_segments_compact(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h_bin, int n, int H, int W, int Hs, int Ws,
+                                       int cc_majority, uint8_t* h_labels, uint32_t* h_binary_bits, int32_t* h_stats, int max_components,
+                                       int32_t* h_ncomp) {
+    if (ctx && (!h_stats || !h_labels)) return set_err(ctx, PCS_ERR_ARG, "predict_pages_segments_compact: null output");
+    return predict_pages_host_impl(ctx, h_grey, h_bin, n, H, W, Hs, Ws, cc_majority, nullptr, nullptr, nullptr, h_labels, nullptr, nullptr,
+                                   nullptr, nullptr, 0, nullptr, h_stats, max_components, h_ncomp, nullptr, 0, 0, h_binary_bits);
+}
+
 int pcs_predict_pages_compact(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h_bin, int n, int H, int W, int Hs, int Ws, int cc_majority,
                               uint8_t* h_labels, uint32_t* h_binary_bits) {
     if (ctx && !h_labels) return set_err(ctx, PCS_ERR_ARG, "predict_pages_compact: null output");

@@ -265,6 +265,17 @@ class PageBatchEngine:
                                         max_components, out.get("ncomp"), out.get("color"), out.get("overlay"), out.get("inverted"))
         return out
 
+    def run_host_segments_compact(self, h_pages: np.ndarray, scale: float, out: dict, max_components: int, cc_majority: bool = True):
+        """pcs_predict_pages_segments_compact: the segment call with compact results -- `out` holds 'labels', 'stats',
+        optionally 'ncomp' and 'binary_bits' (see run_host_compact); no mask crosses PCIe."""
+        n, H, W = h_pages.shape
+        Hs, Ws = scaled_shape(H, W, scale)
+        self._ensure_model()
+        self.ctx.use_torch_stream()
+        self.ctx.predict_pages_segments_compact(h_pages, h_pages, n, H, W, Hs, Ws, cc_majority, out["labels"], out.get("binary_bits"),
+                                                out["stats"], max_components, out.get("ncomp"))
+        return out
+
     def run_host_compact(self, h_pages: np.ndarray, scale: float, out: dict, cc_majority: bool = False):
         """pcs_predict_pages_compact: uint8 pages in; `out` holds 'labels' (n, Hs, Ws) uint8 and optionally 'binary_bits'
         (n, ceil(Hs * Ws / 32)) uint32 -- `data.binary` bit-packed.  The colour masks are produced on request

@@ -306,6 +306,18 @@ def test_host_batch_pipeline_with_segment_extraction(ctx, cc, monkeypatch):
             kk = min(m, maxc)
             np.testing.assert_array_equal(out["stats"][i, k, :kk], stats[:kk])
             assert not out["stats"][i, k, kk:].any()
+    # the same call with compact results (pcs_predict_pages_segments_compact): class map, bit-packed binary, tables
+    from page_segmentation_b200.runtime import unpack_bits_host
+    comp = {"labels": np.zeros((n, Hs, Ws), np.uint8), "binary_bits": np.zeros((n, (Hs * Ws + 31) // 32), np.uint32),
+            "stats": np.full((n, 3, maxc, 5), -1, np.int32), "ncomp": np.zeros((n, 3), np.int32)}
+    eng.run_host_segments_compact(pages, 6 / 18, comp, max_components=maxc, cc_majority=cc)
+    np.testing.assert_array_equal(comp["labels"], out["labels"])
+    np.testing.assert_array_equal(comp["stats"], out["stats"])
+    np.testing.assert_array_equal(comp["ncomp"], out["ncomp"])
+    binary = unpack_bits_host(comp["binary_bits"], (Hs, Ws))
+    for i in range(n):
+        _, eb = opipe.prepare_images(pages[i], pages[i], 6, 18)
+        np.testing.assert_array_equal(binary[i], eb)
 
 
 def test_loaded_pages_are_freed_without_the_cyclic_collector(ctx):
