@@ -249,7 +249,7 @@ ccl_tile_kernel(const uint8_t* __restrict__ img, int H, int W, int cls, int* __r
     __syncthreads();
     if (m) {
         const unsigned lb = sx > 0 ? smask[ry][sx - 1] >> 31 : 0u;
-        if ((m & 1u) && lb) suf_union(lpar, l0, l0 - 1);                // run crosses a segment border
+        if ((m & 1u) && lb) suf_union_h(lpar, l0, l0 - 1);                // run crosses a segment border
         if (ry > 0) {
             const unsigned up = smask[ry - 1][sx];
             const unsigned ulb = sx > 0 ? smask[ry - 1][sx - 1] >> 31 : 0u;
@@ -258,7 +258,7 @@ ccl_tile_kernel(const uint8_t* __restrict__ img, int H, int W, int cls, int* __r
             while (v) {
                 const int k = __ffs(v) - 1;
                 v &= v - 1;
-                suf_union(lpar, l0 + k, l0 + k - 256);
+                suf_union_h(lpar, l0 + k, l0 + k - 256);
             }
             if (CONN8) {
                 // 8-connectivity: the diagonal neighbours matter only when the pixel above is background (otherwise
@@ -267,7 +267,7 @@ ccl_tile_kernel(const uint8_t* __restrict__ img, int H, int W, int cls, int* __r
                 while (d1) {
                     const int k = __ffs(d1) - 1;
                     d1 &= d1 - 1;
-                    suf_union(lpar, l0 + k, l0 + k - 256 - 1);
+                    suf_union_h(lpar, l0 + k, l0 + k - 256 - 1);
                 }
                 const unsigned rb = sx + 1 < kTileSegs ? smask[ry][sx + 1] & 1u : 0u;
                 const unsigned urb = sx + 1 < kTileSegs ? smask[ry - 1][sx + 1] & 1u : 0u;
@@ -275,7 +275,7 @@ ccl_tile_kernel(const uint8_t* __restrict__ img, int H, int W, int cls, int* __r
                 while (d2) {
                     const int k = __ffs(d2) - 1;
                     d2 &= d2 - 1;
-                    suf_union(lpar, l0 + k, l0 + k - 256 + 1);
+                    suf_union_h(lpar, l0 + k, l0 + k - 256 + 1);
                 }
             }
         }
