@@ -754,6 +754,12 @@ __global__ void __launch_bounds__(256) diff_rowscan_kernel(int* __restrict__ dif
 // column scan in kColBands row bands (a thread walking all H rows of its column leaves the device idle):
 // per-band column sums first, then every band scans its rows from the sum of the bands above it.
 constexpr int kColBands = 16;
+constexpr int kMcMaxClasses = 8;                    // classes the one-pass labelling (mc_*, below) handles
+static int launch_bounding_boxes_mc(pcs_ctx* ctx, const uint8_t* d_pred, int n, int H, int W, int n_classes, uint8_t* d_out);
+static bool mc_per_class() {                        // A/B switch: one labelling per class instead of one for all
+    static const char* e = getenv("PCSEG_SEGMENTS_PER_CLASS");
+    return e && atoi(e) != 0;
+}
 
 __global__ void __launch_bounds__(256)
 diff_colband_sum_kernel(const int* __restrict__ diff, int H, int W, int* __restrict__ bandsum) {
@@ -787,6 +793,7 @@ diff_colscan_paint_kernel(const int* __restrict__ diff, int H, int W, int cls, c
 int launch_bounding_boxes(pcs_ctx* ctx, const uint8_t* d_pred, int n, int H, int W, int n_classes, uint8_t* d_out) {
     if (n <= 0 || H <= 0 || W <= 0 || n_classes <= 0 || n_classes > 255 || (size_t)H * W >= (size_t)INT_MAX)
         return set_err(ctx, PCS_ERR_ARG, "bounding_boxes: bad argument");
+    if (n_classes <= kMcMaxClasses && !mc_per_class()) return launch_bounding_boxes_mc(ctx, d_pred, n, H, W, n_classes, d_out);
     const size_t page_px = (size_t)H * W, total = page_px * n;
     const size_t diff_elems = (size_t)n * (H + 1) * (W + 1);
     const size_t total4 = (total + 3) / 4 * 4;                           // keeps the int4 box records 16-byte aligned
@@ -921,7 +928,6 @@ __global__ void cstats_ncomp_kernel(const int* __restrict__ ncomp_tmp, int n, in
 //   scan, mc_write : label = rank of the root among the roots of ITS class (cv2's numbering of that class's
 //               labelling), stats row written from the root's record.
 // ---------------------------------------------------------------------------
-constexpr int kMcMaxClasses = 8;
 constexpr int kMcCap = 1024;                        // tile-local root candidates with shared-memory accumulators
 
 __device__ __forceinline__ unsigned eq_bits32(const unsigned (&a)[8], const unsigned (&b)[8]) {
@@ -1270,39 +1276,124 @@ mc_write_kernel(const uint8_t* __restrict__ img, int H, int W, int n_classes, co
     }
 }
 
-static int launch_class_components_mc(pcs_ctx* ctx, const uint8_t* d_pred, int n, int H, int W, int n_classes, int32_t* d_stats,
-                                      int max_components, int32_t* d_ncomp) {
-    const size_t page_px = (size_t)H * W, total = page_px * n;
+// the labelling shared by segment extraction and add_bounding_boxes: parents, root records, root masks, per-class counts
+struct McBuffers { int* parent; int* acc; unsigned* rootmask; int* warpcnt; int* clsbox; int* extra; int nw; };
+
+static int mc_label(pcs_ctx* ctx, const uint8_t* d_pred, int n, int H, int W, int n_classes, size_t extra_words, McBuffers& b) {
+    const size_t total = (size_t)H * W * n;
     const int segs = (W + 31) >> 5;
     const dim3 g = seg_grid(H, W, n);
-    const int nw = (int)g.x * 8;
-    const size_t mask_words = (size_t)n * H * segs, cnt_words = (size_t)n * n_classes * nw, box_words = (size_t)n * (n_classes + 1) * 5;
-    PCS_TRY(scratch_reserve(ctx, (total * 6 + mask_words + cnt_words + box_words + (size_t)n * n_classes) * 4 + 512));
-    int* parent = reinterpret_cast<int*>(ctx->scratch);
-    int* acc = parent + total;
-    unsigned* rootmask = reinterpret_cast<unsigned*>(acc + total * 5);
-    int* warpcnt = reinterpret_cast<int*>(rootmask + mask_words);
-    int* clsbox = warpcnt + cnt_words;
-    int* ncomp_tmp = clsbox + box_words;
+    b.nw = (int)g.x * 8;
+    const size_t mask_words = (size_t)n * H * segs, cnt_words = (size_t)n * n_classes * b.nw, box_words = (size_t)n * (n_classes + 1) * 5;
+    PCS_TRY(scratch_reserve(ctx, (total * 6 + mask_words + cnt_words + box_words + extra_words) * 4 + 512));
+    b.parent = reinterpret_cast<int*>(ctx->scratch);
+    b.acc = b.parent + total;
+    b.rootmask = reinterpret_cast<unsigned*>(b.acc + total * 5);
+    b.warpcnt = reinterpret_cast<int*>(b.rootmask + mask_words);
+    b.clsbox = b.warpcnt + cnt_words;
+    b.extra = b.clsbox + box_words;
     cudaStream_t st = ctx->stream;
     static bool attr_set = false;
     if (!attr_set) {
         PCS_CUDA(ctx, cudaFuncSetAttribute(mc_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(McTileSmem)));
         attr_set = true;
     }
-    PCS_CUDA(ctx, cudaMemsetAsync(d_stats, 0, (size_t)n * n_classes * max_components * 5 * sizeof(int32_t), st));
-    PCS_CUDA(ctx, cudaMemsetAsync(clsbox, 0, box_words * sizeof(int), st));
+    PCS_CUDA(ctx, cudaMemsetAsync(b.clsbox, 0, box_words * sizeof(int), st));
     const dim3 gt((W + kTileSegs * 32 - 1) / (kTileSegs * 32), (H + kTileRows - 1) / kTileRows, n);
-    mc_tile_kernel<<<gt, 256, sizeof(McTileSmem), st>>>(d_pred, H, W, parent, rootmask, acc);
+    mc_tile_kernel<<<gt, 256, sizeof(McTileSmem), st>>>(d_pred, H, W, b.parent, b.rootmask, b.acc);
     PCS_LAUNCH_CHECK(ctx, "mc_tile_kernel");
-    if (ccl_compress(true)) mc_border_kernel<true><<<g, 256, 0, st>>>(d_pred, H, W, parent);
-    else mc_border_kernel<false><<<g, 256, 0, st>>>(d_pred, H, W, parent);
+    if (ccl_compress(true)) mc_border_kernel<true><<<g, 256, 0, st>>>(d_pred, H, W, b.parent);
+    else mc_border_kernel<false><<<g, 256, 0, st>>>(d_pred, H, W, b.parent);
     PCS_LAUNCH_CHECK(ctx, "mc_border_kernel");
-    mc_fold_kernel<<<g, 256, 0, st>>>(d_pred, H, W, n_classes, parent, rootmask, acc, warpcnt, clsbox);
+    mc_fold_kernel<<<g, 256, 0, st>>>(d_pred, H, W, n_classes, b.parent, b.rootmask, b.acc, b.warpcnt, b.clsbox);
     PCS_LAUNCH_CHECK(ctx, "mc_fold_kernel");
-    ccl_scan_blocks_kernel<<<n * n_classes, 1024, 0, st>>>(warpcnt, nw, d_ncomp ? d_ncomp : ncomp_tmp);
+    return PCS_OK;
+}
+
+// add_bounding_boxes on the one-pass labelling: the box of every component goes into the difference array of ITS class
+// (four corner updates per component), the arrays of all classes are scanned together and a pixel takes the highest
+// class whose boxes cover it (the reference paints the classes in ascending order over zeros, postprocess.py:29-42)
+__global__ void __launch_bounds__(256)
+mc_bbox_diff_kernel(const uint8_t* __restrict__ img, int H, int W, int n_classes, const unsigned* __restrict__ rootmask, const int* __restrict__ acc,
+                    int* __restrict__ diff /*[page][class][(H + 1) * (W + 1)]*/) {
+    PCS_SEG_THREAD();
+    if (!valid) return;
+    unsigned gm = rootmask[(size_t)blockIdx.y * H * segs + t];
+    if (!gm) return;
+    const uint8_t* row = img + page_off + (size_t)y * W;
+    const int base = y * W + x0;
+    const size_t plane = (size_t)(H + 1) * (W + 1);
+    while (gm) {
+        const int k = __ffs(gm) - 1;
+        gm &= gm - 1;
+        const int cls = __ldg(row + x0 + k);
+        if (cls >= n_classes) continue;
+        const int* a = acc + (page_off + base + k) * 5;
+        const int bx0 = W - a[0], by0 = H - a[1], bx1 = a[2], by1 = a[3];
+        int* d = diff + ((size_t)blockIdx.y * n_classes + cls) * plane;
+        atomicAdd(&d[(size_t)by0 * (W + 1) + bx0], 1);
+        atomicAdd(&d[(size_t)by0 * (W + 1) + bx1 + 1], -1);
+        atomicAdd(&d[(size_t)(by1 + 1) * (W + 1) + bx0], -1);
+        atomicAdd(&d[(size_t)(by1 + 1) * (W + 1) + bx1 + 1], 1);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+mc_colscan_paint_kernel(const int* __restrict__ diff, int H, int W, int n_classes, const int* __restrict__ bandsum, uint8_t* __restrict__ out) {
+    const int x = blockIdx.x * 256 + threadIdx.x;
+    if (x >= W) return;
+    const int rows = (H + kColBands - 1) / kColBands;
+    const int y0 = blockIdx.y * rows, y1 = min(H, y0 + rows);
+    const size_t plane = (size_t)(H + 1) * (W + 1);
+    const int* d = diff + (size_t)blockIdx.z * n_classes * plane;
+    uint8_t* o = out + (size_t)blockIdx.z * H * W;
+    int cov[kMcMaxClasses];
+#pragma unroll
+    for (int c = 0; c < kMcMaxClasses; ++c) {
+        cov[c] = 0;
+        if (c < n_classes)
+            for (int b = 0; b < (int)blockIdx.y; ++b) cov[c] += bandsum[(((size_t)blockIdx.z * n_classes + c) * kColBands + b) * W + x];
+    }
+    for (int y = y0; y < y1; ++y) {
+        int best = 0;
+#pragma unroll
+        for (int c = 0; c < kMcMaxClasses; ++c)
+            if (c < n_classes) {
+                cov[c] += d[(size_t)c * plane + (size_t)y * (W + 1) + x];
+                if (cov[c] > 0) best = c;
+            }
+        o[(size_t)y * W + x] = (uint8_t)best;
+    }
+}
+
+static int launch_bounding_boxes_mc(pcs_ctx* ctx, const uint8_t* d_pred, int n, int H, int W, int n_classes, uint8_t* d_out) {
+    const size_t diff_elems = (size_t)n * n_classes * (H + 1) * (W + 1), band_elems = (size_t)n * n_classes * kColBands * W;
+    McBuffers b;
+    PCS_TRY(mc_label(ctx, d_pred, n, H, W, n_classes, diff_elems + band_elems, b));
+    int* diff = b.extra;
+    int* bandsum = diff + diff_elems;
+    cudaStream_t st = ctx->stream;
+    PCS_CUDA(ctx, cudaMemsetAsync(diff, 0, diff_elems * 4, st));
+    mc_bbox_diff_kernel<<<seg_grid(H, W, n), 256, 0, st>>>(d_pred, H, W, n_classes, b.rootmask, b.acc, diff);
+    PCS_LAUNCH_CHECK(ctx, "mc_bbox_diff_kernel");
+    diff_rowscan_kernel<<<dim3((H + 1 + 7) / 8, n * n_classes), 256, 0, st>>>(diff, H + 1, W + 1);
+    PCS_LAUNCH_CHECK(ctx, "diff_rowscan_kernel");
+    diff_colband_sum_kernel<<<dim3((W + 255) / 256, kColBands, n * n_classes), 256, 0, st>>>(diff, H, W, bandsum);
+    PCS_LAUNCH_CHECK(ctx, "diff_colband_sum_kernel");
+    mc_colscan_paint_kernel<<<dim3((W + 255) / 256, kColBands, n), 256, 0, st>>>(diff, H, W, n_classes, bandsum, d_out);
+    PCS_LAUNCH_CHECK(ctx, "mc_colscan_paint_kernel");
+    return PCS_OK;
+}
+
+static int launch_class_components_mc(pcs_ctx* ctx, const uint8_t* d_pred, int n, int H, int W, int n_classes, int32_t* d_stats,
+                                      int max_components, int32_t* d_ncomp) {
+    McBuffers b;
+    cudaStream_t st = ctx->stream;
+    PCS_CUDA(ctx, cudaMemsetAsync(d_stats, 0, (size_t)n * n_classes * max_components * 5 * sizeof(int32_t), st));
+    PCS_TRY(mc_label(ctx, d_pred, n, H, W, n_classes, (size_t)n * n_classes, b));
+    ccl_scan_blocks_kernel<<<n * n_classes, 1024, 0, st>>>(b.warpcnt, b.nw, d_ncomp ? d_ncomp : b.extra);
     PCS_LAUNCH_CHECK(ctx, "ccl_scan_blocks_kernel");
-    mc_write_kernel<<<g, 256, 0, st>>>(d_pred, H, W, n_classes, rootmask, acc, warpcnt, clsbox, d_stats, max_components);
+    mc_write_kernel<<<seg_grid(H, W, n), 256, 0, st>>>(d_pred, H, W, n_classes, b.rootmask, b.acc, b.warpcnt, b.clsbox, d_stats, max_components);
     PCS_LAUNCH_CHECK(ctx, "mc_write_kernel");
     return PCS_OK;
 }
@@ -1311,8 +1402,7 @@ int launch_class_components(pcs_ctx* ctx, const uint8_t* d_pred, int n, int H, i
                             int32_t* d_ncomp) {
     if (n <= 0 || H <= 0 || W <= 0 || n_classes <= 0 || n_classes > 255 || (size_t)H * W >= (size_t)INT_MAX || max_components <= 0)
         return set_err(ctx, PCS_ERR_ARG, "class_components: bad argument");
-    static const char* per_class = getenv("PCSEG_SEGMENTS_PER_CLASS");   // A/B switch: one labelling per class
-    if (n_classes <= kMcMaxClasses && !(per_class && atoi(per_class) != 0))
+    if (n_classes <= kMcMaxClasses && !mc_per_class())
         return launch_class_components_mc(ctx, d_pred, n, H, W, n_classes, d_stats, max_components, d_ncomp);
     const size_t page_px = (size_t)H * W, total = page_px * n;
     const int nblocks = (int)((page_px + kScanBlock - 1) / kScanBlock);

@@ -244,3 +244,25 @@ def test_class_components_a4_noise_like_truncated(ctx):
         pred, b = _pred_and_binary(40 + s, 1169, 827)
         preds.append(np.where(b > 0, pred, 0).astype(np.uint8))
     _check_class_tables(ctx, preds, 3, maxc=4096)
+
+
+def test_bounding_boxes_batched_a4_and_many_classes(ctx):
+    """pcs_bounding_boxes on a batch of scaled A4 class maps (one labelling for all classes, one scan of the per-class
+    difference arrays) and with nine classes (one labelling per class)."""
+    import torch
+    preds = []
+    for s in range(3):
+        pred, b = _pred_and_binary(50 + s, 1169, 827, n_classes=4)
+        preds.append(np.where(b > 0, pred, 0).astype(np.uint8))
+    preds[2][:] = 3                                                          # one component covering the page
+    d = torch.from_numpy(np.stack(preds)).cuda()
+    out = torch.full_like(d, 77)
+    ctx.bounding_boxes(d, 3, 1169, 827, 4, out)
+    for i in range(3):
+        np.testing.assert_array_equal(out[i].cpu().numpy(), opipe.add_bounding_boxes(preds[i].astype(np.int64)))
+    rng = np.random.default_rng(3)
+    p9 = np.kron(rng.integers(0, 9, size=(30, 40)), np.ones((6, 8), np.int64))[:170, :300].astype(np.uint8)
+    d9 = torch.from_numpy(p9[None]).cuda()
+    out9 = torch.full_like(d9, 77)
+    ctx.bounding_boxes(d9, 1, 170, 300, 9, out9)
+    np.testing.assert_array_equal(out9[0].cpu().numpy(), opipe.add_bounding_boxes(p9.astype(np.int64)))
