@@ -105,6 +105,8 @@ static void free_layers(pcs_ctx* ctx) {
         if (l.d_wmma) cudaFree(l.d_wmma);
         for (auto& f : l.fold) if (f.d_w) cudaFree(f.d_w);
         if (l.d_w12) cudaFree(l.d_w12);
+        if (l.d_wmma_px) cudaFree(l.d_wmma_px);
+        for (auto& part : l.fold) if (part.d_w_px) cudaFree(part.d_w_px);
         if (l.d_head_lw) cudaFree(l.d_head_lw);
         if (l.d_head_lb) cudaFree(l.d_head_lb);
     }
@@ -162,7 +164,7 @@ static bool fold_disabled() {
 }
 
 static int run_conv(pcs_ctx* ctx, const char* lname, const Act* s0, const Act* s1, Act* out, Act* pool_out,
-                    bool upsample = false, void* plog = nullptr, const float* skip_lw = nullptr) {
+                    bool upsample = false, void* plog = nullptr, const float* skip_lw = nullptr, const void* pair_src = nullptr) {
     Layer* L = find_layer(ctx, lname);
     if (!L) return set_err(ctx, PCS_ERR_STATE, "layer %s missing", lname);
     StageScope ts(ctx, lname);
@@ -183,6 +185,10 @@ static int run_conv(pcs_ctx* ctx, const char* lname, const Act* s0, const Act* s
             f.n = n; f.h = h; f.w = w; f.k = L->k;
             f.wimg = part.d_w; f.h_bias = L->h_b32.data() + part.o0; f.cout = part.ncols; f.npad = part.npad;
             f.nplanes = src->cp / 8; f.relu = L->relu; f.o0 = part.o0;
+            if (pair_src) {
+                if (!part.d_w_px) return set_err(ctx, PCS_ERR_STATE, "layer %s: no weight image for a pixel-pair source", lname);
+                f.pair_src = pair_src; f.wimg = part.d_w_px; f.nplanes += 1;
+            }
             f.out = out ? out->p : nullptr; f.out_cp = out ? out->cp : 0;
             f.pool_out = pool_out ? pool_out->p : nullptr; f.pool_cp = pool_out ? pool_out->cp : 0;
             f.psum_out = part.psum == 1 ? psum : nullptr;
@@ -193,6 +199,7 @@ static int run_conv(pcs_ctx* ctx, const char* lname, const Act* s0, const Act* s
         return PCS_OK;
     }
     if (plog) return set_err(ctx, PCS_ERR_STATE, "layer %s: partial logits requested off the folded kernel", lname);
+    if (pair_src) return set_err(ctx, PCS_ERR_STATE, "layer %s: pixel-pair source off the folded kernel", lname);
     if (ctx->engine == PCS_ENGINE_UMMA && upsample && L->d_wmma && L->k == 2 && !s1 && out) {
         // UpSampling2D(2) + Conv2D(2x2) as a 2x2 convolution on the low-resolution grid, N = (parity, C_out)
         UmmaConvArgs a;
@@ -224,10 +231,12 @@ static int run_conv(pcs_ctx* ctx, const char* lname, const Act* s0, const Act* s
     return launch_conv_direct(ctx, a);
 }
 
-static int run_conv1_u8(pcs_ctx* ctx, const char* lname, const uint8_t* d_image, int n, int hs, int ws, Act* out) {
+static int run_conv1_u8(pcs_ctx* ctx, const char* lname, const uint8_t* d_image, int n, int hs, int ws, Act* out, void* pair_out = nullptr) {
     Layer* L = find_layer(ctx, lname);
     if (!L) return set_err(ctx, PCS_ERR_STATE, "layer %s missing", lname);
     StageScope ts(ctx, lname);
+    if (pair_out)
+        return launch_conv1_umma(ctx, d_image, n, hs, ws, out->h, out->w, L->d_wmma_px, L->h_b32.data(), L->k, L->cout, out->p, out->cp, pair_out);
     if (ctx->engine == PCS_ENGINE_UMMA && L->d_wmma && conv1_umma_supported(L->k, L->cout))
         return launch_conv1_umma(ctx, d_image, n, hs, ws, out->h, out->w, L->d_wmma, L->h_b32.data(), L->k, L->cout, out->p, out->cp);
     DirectConvArgs a;
@@ -290,6 +299,7 @@ static int forward_fcn(pcs_ctx* ctx, bool skip, const uint8_t* d_image, int n, i
     // the pair is bound by the issue slots of its epilogues, not by the 94 MB per page of HBM traffic the fusion removes
     // (DESIGN.md section 3.2a).
     static const bool no_fuse12 = !(getenv("PCSEG_FUSE12") && !strcmp(getenv("PCSEG_FUSE12"), "1"));
+    static const bool pairplane = !(getenv("PCSEG_PAIRPLANE") && !strcmp(getenv("PCSEG_PAIRPLANE"), "0"));
     Layer* L1 = find_layer(ctx, "conv1");
     if (ctx->engine == PCS_ENGINE_UMMA && !no_fuse12 && !ctx->keep_acts && conv2_folds && L1 && L1->d_w12 && L2->d_w12 && (hp % 4) == 0) {
         StageScope ts(ctx, "conv1+conv2");
@@ -300,6 +310,16 @@ static int forward_fcn(pcs_ctx* ctx, bool skip, const uint8_t* d_image, int n, i
         f.pool_out = pool2.p; f.pool_cp = pool2.cp;
         f.plog = plog; f.skip_lw = plog ? LL->d_head_lw : nullptr;
         PCS_TRY(launch_conv12_fused(ctx, f));
+    } else if (pairplane && ctx->engine == PCS_ENGINE_UMMA && !ctx->keep_acts && conv2_folds && L1 && L1->d_wmma_px && L2->fold[0].d_w_px &&
+               (hp % 4) == 0) {
+        // conv1 hands channels 0..15 over as two whole planes and channels 16..19 as pixel-pair units (w + 1 per row): conv2
+        // spends 7 instead of 8 MMAs per input row; the inspection path (keep_acts) keeps three planes
+        Act c1; c1.n = n; c1.h = hp; c1.w = wp; c1.c = 16; c1.cp = 16;
+        c1.p = arena_alloc(ctx, c1.bytes());
+        void* pairs = arena_alloc(ctx, (size_t)n * hp * (wp + 1) * 16);
+        if (!c1.p || !pairs) return set_err(ctx, PCS_ERR_NOMEM, "activation arena exhausted at conv1");
+        PCS_TRY(run_conv1_u8(ctx, "conv1", d_image, n, hs, ws, &c1, pairs));
+        PCS_TRY(run_conv(ctx, "conv2", &c1, nullptr, store_conv2 ? &conv2 : nullptr, &pool2, false, plog, plog ? LL->d_head_lw : nullptr, pairs));
     } else {
         PCS_TRY(new_act(ctx, "conv1", n, hp, wp, 20, &conv1));
         PCS_TRY(run_conv1_u8(ctx, "conv1", d_image, n, hs, ws, &conv1));
@@ -589,6 +609,11 @@ int pcs_model_load(pcs_ctx* ctx, int arch, int n_classes, int precision, const p
         L.wmma_bytes = conv1_umma_weight_image(L.h_w32.data(), L.k, L.cout, precision, img);
         PCS_CUDA(ctx, cudaMalloc(&L.d_wmma, L.wmma_bytes));
         PCS_CUDA(ctx, cudaMemcpy(L.d_wmma, img.data(), L.wmma_bytes, cudaMemcpyHostToDevice));
+        if (L.k == 5 && L.cout == 20) {         // FCN conv1: the image with channels 16..19 of the right neighbour in columns 20..23
+            const size_t nb = conv1_umma_weight_image(L.h_w32.data(), L.k, L.cout, precision, img, true);
+            PCS_CUDA(ctx, cudaMalloc(&L.d_wmma_px, nb));
+            PCS_CUDA(ctx, cudaMemcpy(L.d_wmma_px, img.data(), nb, cudaMemcpyHostToDevice));
+        }
     }
     // conv1 + conv2 of the FCN variants as one kernel (conv12_fused.cu)
     if (ctx->layers.size() > 1 && ctx->layers[0].name == "conv1" && ctx->layers[1].name == "conv2" && ctx->layers[1].kind == K_CONV &&
@@ -635,6 +660,14 @@ int pcs_model_load(pcs_ctx* ctx, int arch, int n_classes, int precision, const p
                 part.src = src; part.o0 = o0; part.ncols = ncols; part.npad = npad; part.nplanes = pad8(cin) / 8; part.psum = psum;
                 PCS_CUDA(ctx, cudaMalloc(&part.d_w, fb));
                 PCS_CUDA(ctx, cudaMemcpy(part.d_w, fimg.data(), fb, cudaMemcpyHostToDevice));
+                if (L.name == "conv2" && cin == 20 && npad == 32 && ci0 == 0 && o0 == 0) {
+                    // the same weights for a source whose channels 16..19 arrive as pixel-pair units (7 K steps per row instead of 8)
+                    const size_t pb = fold_weight_image(L.h_w32.data(), L.cin, L.cout, ci0, cin, o0, ncols, npad, precision, fimg, true);
+                    if (pb) {
+                        PCS_CUDA(ctx, cudaMalloc(&part.d_w_px, pb));
+                        PCS_CUDA(ctx, cudaMemcpy(part.d_w_px, fimg.data(), pb, cudaMemcpyHostToDevice));
+                    }
+                }
                 L.fold.push_back(part);
                 return PCS_OK;
             };

@@ -65,12 +65,14 @@ struct Layer {
     // concatenated source, fp32 partial sums handed from the first part to the last)
     struct FoldPart {
         void* d_w = nullptr;      // resident operand image
+        void* d_w_px = nullptr;   // ... for a source whose odd last plane arrives as pixel-pair units (conv2 <- conv1)
         int src = 0;              // concatenated source read by this part
         int o0 = 0, ncols = 0;    // output channels [o0, o0 + ncols)
         int npad = 0, nplanes = 0;
         int psum = 0;             // 0 complete, 1 writes partial sums, 2 adds them
     };
     std::vector<FoldPart> fold;
+    void* d_wmma_px = nullptr;    // conv1 (5x5, 20 channels): operand image with the pixel-pair columns 20..23
     void* d_w12 = nullptr;        // conv1 / conv2 of the FCN variants: operand image of the fused kernel (conv12_fused.cu)
     std::vector<float> h_w32_raw; // deconv5, U-Net up*: weights before rounding (composed / summed on the host, rounded once)
     float* d_head_lw = nullptr;   // logits layer: [32][4] rows of the conv2 skip channels, zero padded (fcn_skip)
@@ -375,10 +377,12 @@ struct FoldConvArgs {
     const void* psum_in = nullptr;     // ... and added by the last part before bias / activation
     void* plog = nullptr;              // optional float4 [n][h][w]: this layer's share of the logits (fcn_skip conv2)
     const float* skip_lw = nullptr;    // device [32][4]: logits rows of this layer's channels, zero padded
+    const void* pair_src = nullptr;    // the source's last (odd) plane as pixel-pair units [n][h][w + 1][8] (conv1_umma.cu): src holds the
+                                       // whole planes before it, nplanes counts it, wimg is the image built with pairx
 };
 bool fold_supported(int k, int npad, int nplanes);
 size_t fold_weight_image(const float* w32 /*[25][cin_total][cout_total]*/, int cin_total, int cout_total, int ci0, int cin,
-                         int o0, int ncols, int npad, int precision, std::vector<uint16_t>& out);
+                         int o0, int ncols, int npad, int precision, std::vector<uint16_t>& out, bool pairx = false);
 int launch_conv_fold(pcs_ctx* ctx, const FoldConvArgs& a);
 
 // conv12_fused.cu  (conv1 + conv2 + MaxPool of the FCN variants in one marching kernel; conv1 never leaves the SM)
@@ -401,9 +405,10 @@ size_t conv12_weight_image2(const float* w32 /*[25][20][cout]*/, int cout, int p
 int launch_conv12_fused(pcs_ctx* ctx, const Conv12Args& a);
 
 // conv1_umma.cu  (first FCN layer on the tensor cores)
-size_t conv1_umma_weight_image(const float* w32 /*[ksz*ksz][1][cout]*/, int ksz, int cout, int precision, std::vector<uint16_t>& out);
+size_t conv1_umma_weight_image(const float* w32 /*[ksz*ksz][1][cout]*/, int ksz, int cout, int precision, std::vector<uint16_t>& out,
+                               bool pairx = false);
 bool conv1_umma_supported(int ksz, int cout);
 int launch_conv1_umma(pcs_ctx* ctx, const uint8_t* d_image, int n, int img_h, int img_w, int h, int w, const void* wimg,
-                      const float* h_bias, int ksz, int cout, void* out, int out_cp);
+                      const float* h_bias, int ksz, int cout, void* out, int out_cp, void* pair_out = nullptr);
 
 }  // namespace pcs

@@ -45,6 +45,7 @@ struct Conv1Params {
     const uint8_t* wimg;                    // C1_B_BYTES operand image
     float bias[C1_MAXN];                    // by value: read as constant-bank FFMA operands, no shared-memory traffic
     void* out; int out_cp;
+    void* pair_out;                         // 5x5 / 20 channels only: [n][h][w + 1][8] pixel-pair units of channels 16..19 (see the epilogue), or null
     int strips, rowblocks, num_tiles;
     int halves;                             // operand halves of the weights: 2 = hi + lo (bf16 operands: ~16 mantissa bits), 1 = hi only
                                             // (fp16 operands: 11 bits, what every other layer's weights have)
@@ -168,6 +169,23 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv1_umma_kernel(const Conv1Pa
                     *reinterpret_cast<uint4*>(out + act_idx(page, p.out_cp, p.h, p.w, g * 8, y, x)) =
                         make_uint4(pack2<T>(f[0], f[1]), pack2<T>(f[2], f[3]), pack2<T>(f[4], f[5]), pack2<T>(f[6], f[7]));
                 }
+                if constexpr (KSZ == 5) {
+                    if (p.pair_out) {
+                        // Channels 16..19 travel as pixel-pair units: unit i of a row holds [ch 16..19 of pixel i - 1 | of pixel i],
+                        // i = 0 .. w (w + 1 units: the first and the last are half padding), so that one 16-byte K half of conv2's
+                        // MMA covers TWO horizontal taps of these four channels (conv_fold.cu, PX).  Columns 20..23 of this layer's
+                        // GEMM are channels 16..19 of the pixel to the RIGHT (weights shifted by one tap), so a lane builds the unit
+                        // x + 1 from its own accumulators; lane x = 0 also writes unit 0.
+                        float f[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) f[i] = fmaxf(fmaf(__uint_as_float(v[16 + i]), inv255, p.bias[16 + i]), 0.f);
+                        if (x + 1 >= p.w) { f[4] = 0.f; f[5] = 0.f; f[6] = 0.f; f[7] = 0.f; }      // 'same' padding of conv2's input
+                        T* unit = reinterpret_cast<T*>(p.pair_out) + (((size_t)page * p.h + y) * (p.w + 1) + x + 1) * 8;
+                        *reinterpret_cast<uint4*>(unit) =
+                            make_uint4(pack2<T>(f[0], f[1]), pack2<T>(f[2], f[3]), pack2<T>(f[4], f[5]), pack2<T>(f[6], f[7]));
+                        if (x == 0) *reinterpret_cast<uint4*>(unit - 8) = make_uint4(0u, 0u, pack2<T>(f[0], f[1]), pack2<T>(f[2], f[3]));
+                    }
+                }
             }
             tc_fence_before();
             __syncwarp();
@@ -251,7 +269,8 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv1_umma_kernel(const Conv1Pa
 
 // Operand image [hi|lo][ks][plane 0..1][n][e 0..7]: value W[dy = 2ks+plane][dx = e][n] for dy, e < ksz (ksz = 5: 3 K steps,
 // n < 32; ksz = 3: 2 K steps, n < 64).
-size_t conv1_umma_weight_image(const float* w32 /*[ksz*ksz][1][cout]*/, int ksz, int cout, int precision, std::vector<uint16_t>& out) {
+// pairx (5x5, 20 channels): columns 20..23 = channels 16..19 of the pixel one to the right, W[dy][dx = e - 1][16 + n - 20].
+size_t conv1_umma_weight_image(const float* w32 /*[ksz*ksz][1][cout]*/, int ksz, int cout, int precision, std::vector<uint16_t>& out, bool pairx) {
     const int KS = (ksz + 1) / 2, NP = ksz == 5 ? 32 : 64;
     out.assign((size_t)2 * KS * 2 * NP * 8, 0);
     auto to16 = [&](float v) -> uint16_t {
@@ -267,8 +286,14 @@ size_t conv1_umma_weight_image(const float* w32 /*[ksz*ksz][1][cout]*/, int ksz,
             for (int n = 0; n < NP; ++n)
                 for (int e = 0; e < 8; ++e) {
                     const int dy = 2 * ks + pl;
-                    if (dy >= ksz || e >= ksz || n >= cout) continue;
-                    const float w = w32[(size_t)(dy * ksz + e) * cout + n];
+                    if (dy >= ksz) continue;
+                    float w;
+                    if (n < cout) {
+                        if (e >= ksz) continue;
+                        w = w32[(size_t)(dy * ksz + e) * cout + n];
+                    } else if (pairx && n < cout + 4 && e >= 1 && e <= ksz) {
+                        w = w32[(size_t)(dy * ksz + e - 1) * cout + (n - 4)];
+                    } else continue;
                     const uint16_t hi = to16(w);
                     const uint16_t lo = to16(w - from16(hi));
                     const size_t idx = (((size_t)ks * 2 + pl) * NP + n) * 8 + e;
@@ -301,14 +326,18 @@ int launch_conv1_t(pcs_ctx* ctx, Conv1Params& p) {
 bool conv1_umma_supported(int ksz, int cout) { return (ksz == 5 && cout <= 32) || (ksz == 3 && cout <= 64); }
 
 int launch_conv1_umma(pcs_ctx* ctx, const uint8_t* d_image, int n, int img_h, int img_w, int h, int w, const void* wimg,
-                      const float* h_bias /*host, cout values*/, int ksz, int cout, void* out, int out_cp) {
+                      const float* h_bias /*host, cout values*/, int ksz, int cout, void* out, int out_cp, void* pair_out) {
     if (!conv1_umma_supported(ksz, cout)) return set_err(ctx, PCS_ERR_ARG, "conv1_umma: no instantiation for a %dx%d kernel with %d outputs", ksz, ksz, cout);
-    if ((out_cp & 7) || out_cp < cout || out_cp > (ksz == 5 ? 32 : 64))
+    if (pair_out && (ksz != 5 || cout != 20 || out_cp != 16))
+        return set_err(ctx, PCS_ERR_ARG, "conv1_umma: the pixel-pair hand-off is for 5x5 / 20 channels with two whole planes");
+    if ((out_cp & 7) || (!pair_out && out_cp < cout) || out_cp > (ksz == 5 ? 32 : 64))
         return set_err(ctx, PCS_ERR_ARG, "conv1_umma: output stride of %d channels", out_cp);
     Conv1Params p{};
     p.img = d_image; p.img_h = img_h; p.img_w = img_w; p.n = n; p.h = h; p.w = w;
     p.wimg = reinterpret_cast<const uint8_t*>(wimg); p.out = out; p.out_cp = out_cp;
     for (int i = 0; i < C1_MAXN; ++i) p.bias[i] = i < cout ? h_bias[i] : 0.f;
+    p.pair_out = pair_out;
+    if (pair_out) for (int i = 0; i < 4; ++i) p.bias[20 + i] = h_bias[16 + i];
     { const char* e = getenv("PCSEG_C1_DEBUG"); p.dbg = e ? atoi(e) : 0; }
     const bool bf = ctx->precision == PCS_PREC_BF16;
     // fp16 operands carry 11 mantissa bits: the weights of this layer are used like those of every other layer (one operand).

@@ -103,14 +103,20 @@ struct FoldParams {
 // repeated tap 3 -- instead of the 5 that padding the plane count to even would cost.
 constexpr int fold_gcd(int a, int b) { return b == 0 ? a : fold_gcd(b, a % b); }
 
-template <int NPL> struct FoldK {
+//
+// PX: the odd last plane holds at most FOUR channels and arrives as pixel-pair units (unit i = [channels of pixel i - 1 |
+// of pixel i], w + 1 units per row, conv1_umma.cu): one 16-byte K half then covers two taps, and the five taps cost TWO
+// MMAs -- K halves (0,1) | (2,3) two units apart, then (3,4) | (4,5) with zero weights for everything but tap 4 (every
+// unit read lies inside the row's box, so the zero weights meet finite values) -- instead of three.
+template <int NPL, bool PX = false> struct FoldK {
     static constexpr int PAIRS = NPL / 2, ODD = NPL & 1;
-    static constexpr int NMMA = PAIRS * 5 + ODD * 3;
+    static constexpr int NMMA = PAIRS * 5 + ODD * (PX ? 2 : 3);
 };
 
-template <typename T, int NPAD, int NPL, int RING, int SLOTS, int EG>
+template <typename T, int NPAD, int NPL, int RING, int SLOTS, int EG, bool PX>
 __global__ void __launch_bounds__(64 + EG * 128, 1)
-conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
+conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm2) {
+    static_assert(!PX || (NPL & 1), "the pixel-pair plane is the odd last plane");
     // Folded N.  NPAD need not be a multiple of 16 (C_out = 40: five whole planes): the five slots of a window are then
     // 5 * NPAD = 200 accumulator columns and every MMA rounds ITS part of the window up to a legal N.  The extra columns
     // of a part that ends inside the ring belong to the slot after the window and take zero weight rows (the weight
@@ -121,7 +127,7 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
     constexpr bool SPILL = (NPAD % 16) != 0;
     constexpr uint32_t ROW_BYTES = NPL * 2048;                       // one ring entry: all planes of one input row
     constexpr uint32_t WDX_BYTES = 2 * NF * 16;                      // weights of one K step
-    constexpr int NMMA = FoldK<NPL>::NMMA;
+    constexpr int NMMA = FoldK<NPL, PX>::NMMA;
     constexpr uint32_t IDESC0 = (1u << 4) | ((std::is_same<T, __nv_bfloat16>::value ? 1u : 0u) << 7) |
                                 ((std::is_same<T, __nv_bfloat16>::value ? 1u : 0u) << 10) | ((uint32_t)(128 >> 4) << 24);
     static_assert(NF <= 256 && NF % 16 == 0, "folded N must be a legal UMMA N");
@@ -178,8 +184,11 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
                     const uint32_t slot = k % (uint32_t)RING, pass = k / (uint32_t)RING;
                     mbar_wait(&s_empty[slot], (pass & 1u) ^ 1u);
                     mbar_expect_tx(&s_full[slot], ROW_BYTES);
-                    // box = 256 u64 (128 px x 16 B) x 1 row x NPL planes
+                    // box = 256 u64 (128 px x 16 B) x 1 row x NPL planes (PX: the whole planes, then the pair units from one
+                    // unit further: unit j + dx of the box = pixels (x - 2 + dx, x - 1 + dx) of output pixel x = strip start + j)
                     tma_load_4d(ring + (size_t)slot * ROW_BYTES, &tm, &s_full[slot], x0 * 2, ys - 2 + i, 0, page);
+                    if constexpr (PX)
+                        tma_load_4d(ring + (size_t)slot * ROW_BYTES + (NPL - 1) * 2048, &tm2, &s_full[slot], (x0 + 1) * 2, ys - 2 + i, 0, page);
                 }
             }
         }
@@ -201,6 +210,7 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
             const uint32_t hi = (uint32_t)(make_desc(0, 0, 128) >> 32);
             constexpr uint32_t a_lbo_pair = ((2048u >> 4) & 0x3fffu) << 16;               // K halves = two planes
             constexpr uint32_t a_lbo_self = ((16u >> 4) & 0x3fffu) << 16;                 // K halves = two taps of one plane
+            constexpr uint32_t a_lbo_two = ((32u >> 4) & 0x3fffu) << 16;                  // K halves = pair units two pixels apart
             constexpr uint32_t b_lbo = (((uint32_t)NF * 16u >> 4) & 0x3fffu) << 16;
             mbar_wait(&s_wfull, 0);
             const uint32_t a_lo0 = (smem_u32(ring) >> 4) & 0x3fffu;
@@ -232,9 +242,9 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm) {
                         const bool pair = q < FoldK<NPL>::PAIRS * 5;
                         const int t = q - FoldK<NPL>::PAIRS * 5;
                         const int plane = pair ? 2 * (q / 5) : NPL - 1;
-                        const int dx = pair ? q % 5 : (t == 0 ? 0 : t + 1);
+                        const int dx = pair ? q % 5 : PX ? (t == 0 ? 0 : 3) : (t == 0 ? 0 : t + 1);
                         const uint32_t a_lo = (a_step + (uint32_t)((u % RING) * (ROW_BYTES >> 4) + plane * (2048 >> 4) + dx)) |
-                                              (pair ? a_lbo_pair : a_lbo_self);
+                                              (pair ? a_lbo_pair : (PX && t == 0) ? a_lbo_two : a_lbo_self);
                         const uint32_t b_lo = b_step + (uint32_t)(q * (WDX_BYTES >> 4));
                         tc_mma(d_step + (uint32_t)(s0 * NPAD), a_lo, hi, b_lo, hi, idesc1, 1u);   // slots are pre-zeroed
                         if (n1 < 5) tc_mma(d_step, a_lo, hi, b_lo + (uint32_t)(n1 * NPAD), hi, idesc2, 1u);
@@ -409,7 +419,7 @@ EncodeTiledFn fold_get_encode() {
     return fn;
 }
 
-template <typename T, int NPAD, int NPL, int RING, int SLOTS, int EG>
+template <typename T, int NPAD, int NPL, int RING, int SLOTS, int EG, bool PX = false>
 int launch_fold_t(pcs_ctx* ctx, const FoldConvArgs& a) {
     constexpr int NF = fold_up16(5 * NPAD);
     FoldParams p{};
@@ -432,7 +442,7 @@ int launch_fold_t(pcs_ctx* ctx, const FoldConvArgs& a) {
             if (ctx->device < 64) g_skip_owner[ctx->device] = ctx->model_stamp;
         }
     }
-    p.w_bytes = (uint32_t)FoldK<NPL>::NMMA * 2 * NF * 16;  // [K step][K half][N' rows][16 B]
+    p.w_bytes = (uint32_t)FoldK<NPL, PX>::NMMA * 2 * NF * 16;  // [K step][K half][N' rows][16 B]
     p.strips = (a.w + F_SW - 1) / F_SW;
     // equal ranges of whole row quads (row pairs for the pooling, pair rotation over the epilogue groups)
     p.total_rows = (long long)a.n * p.strips * a.h;
@@ -442,28 +452,39 @@ int launch_fold_t(pcs_ctx* ctx, const FoldConvArgs& a) {
     EncodeTiledFn enc = fold_get_encode();
     if (!enc) return set_err(ctx, PCS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     const cuuint64_t planes = (cuuint64_t)a.src.cp / 8;
-    if ((int)planes != NPL) return set_err(ctx, PCS_ERR_ARG, "conv_fold: source has %d planes, kernel expects %d", (int)planes, NPL);
+    if ((int)planes != NPL - (PX ? 1 : 0) || PX != (a.pair_src != nullptr))
+        return set_err(ctx, PCS_ERR_ARG, "conv_fold: source has %d planes%s, kernel expects %d", (int)planes, a.pair_src ? " + pair units" : "", NPL);
     const cuuint64_t dims[4] = {(cuuint64_t)a.w * 2, (cuuint64_t)a.h, planes, (cuuint64_t)a.n};
     const cuuint64_t strides[3] = {(cuuint64_t)a.w * 16, (cuuint64_t)a.h * a.w * 16, planes * a.h * a.w * 16};
-    const cuuint32_t box[4] = {256, 1, (cuuint32_t)NPL, 1};
+    const cuuint32_t box[4] = {256, 1, (cuuint32_t)planes, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     CUtensorMap tm;
     CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(a.src.p), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_err(ctx, PCS_ERR_CUDA, "conv_fold: cuTensorMapEncodeTiled failed with %d", (int)r);
+    CUtensorMap tm2 = tm;
+    if (PX) {       // the pair units: w + 1 per row, one "plane"
+        const cuuint64_t pdims[4] = {(cuuint64_t)(a.w + 1) * 2, (cuuint64_t)a.h, 1, (cuuint64_t)a.n};
+        const cuuint64_t pstrides[3] = {(cuuint64_t)(a.w + 1) * 16, (cuuint64_t)a.h * (a.w + 1) * 16, (cuuint64_t)a.h * (a.w + 1) * 16};
+        const cuuint32_t pbox[4] = {256, 1, 1, 1};
+        r = enc(&tm2, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(a.pair_src), pdims, pstrides, pbox, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return set_err(ctx, PCS_ERR_CUDA, "conv_fold: cuTensorMapEncodeTiled (pair units) failed with %d", (int)r);
+    }
     const size_t w_al = ((p.w_bytes + 1023) / 1024) * 1024;
     p.ring = RING;
     const size_t smem = std::max<size_t>(w_al + (size_t)RING * NPL * 2048 + 1024, kSoloSmem);
     if (smem + 2 * 1024 > 227 * 1024) return set_err(ctx, PCS_ERR_ARG, "conv_fold: %zu bytes of shared memory needed", smem);
     static size_t attr_set[64] = {};             // the attribute is per device
     if (ctx->device >= 64 || attr_set[ctx->device] < smem) {
-        PCS_CUDA(ctx, cudaFuncSetAttribute(conv_fold_kernel<T, NPAD, NPL, RING, SLOTS, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PCS_CUDA(ctx, cudaFuncSetAttribute(conv_fold_kernel<T, NPAD, NPL, RING, SLOTS, EG, PX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (ctx->device < 64) attr_set[ctx->device] = smem;
     }
     const int grid = (int)((p.total_rows + p.rows_per_cta - 1) / p.rows_per_cta);
-    PCS_CUDA(ctx, launch_kernel_pdl(conv_fold_kernel<T, NPAD, NPL, RING, SLOTS, EG>, dim3(grid), dim3(64 + EG * 128), smem, ctx->stream,
-                                    ctx->pdl, p, tm));
+    PCS_CUDA(ctx, launch_kernel_pdl(conv_fold_kernel<T, NPAD, NPL, RING, SLOTS, EG, PX>, dim3(grid), dim3(64 + EG * 128), smem, ctx->stream,
+                                    ctx->pdl, p, tm, tm2));
     PCS_LAUNCH_CHECK(ctx, "conv_fold_kernel");
     return PCS_OK;
 }
@@ -471,6 +492,10 @@ int launch_fold_t(pcs_ctx* ctx, const FoldConvArgs& a) {
 template <typename T>
 int launch_fold_dispatch(pcs_ctx* ctx, const FoldConvArgs& a) {
     const int key = a.npad * 10 + a.nplanes;
+    if (a.pair_src) {
+        if (key == 323) return launch_fold_t<T, 32, 3, 16, 16, 4, true>(ctx, a);    // conv2 <- conv1 with channels 16..19 as pixel-pair units
+        return set_err(ctx, PCS_ERR_ARG, "conv_fold: no pixel-pair instantiation for N=%d planes=%d", a.npad, a.nplanes);
+    }
     switch (key) {          //               NPAD planes RING SLOTS epilogue groups
         case 323: return launch_fold_t<T, 32, 3, 16, 16, 4>(ctx, a);     // conv2: 20(24) -> 30(32)
         case 484: return launch_fold_t<T, 48, 4, 10, 10, 3>(ctx, a);     // conv3: 30(32) -> 40(48)
@@ -499,8 +524,9 @@ bool fold_supported(int k, int npad, int nplanes) {
 // [ci0, ci0 + cin) and the output channels [o0, o0 + ncols) of a layer with weights w32[25][cin_total][cout_total]:
 // the N blocks run from the oldest output row of the window (dy = 4) to the newest (dy = 0).
 size_t fold_weight_image(const float* w32, int cin_total, int cout_total, int ci0, int cin, int o0, int ncols, int npad,
-                         int precision, std::vector<uint16_t>& out) {
-    const int npl = pad8(cin) / 8, pairs = npl / 2, odd = npl & 1, nmma = pairs * 5 + odd * 3, nf = (5 * npad + 15) / 16 * 16;
+                         int precision, std::vector<uint16_t>& out, bool pairx) {
+    const int npl = pad8(cin) / 8, pairs = npl / 2, odd = npl & 1, nmma = pairs * 5 + odd * (pairx ? 2 : 3), nf = (5 * npad + 15) / 16 * 16;
+    if (pairx && (!odd || cin - (npl - 1) * 8 > 4)) { out.clear(); return 0; }      // pair units carry four channels
     out.assign((size_t)nmma * 2 * nf * 8, 0);
     auto conv = [&](float v) -> uint16_t {
         if (precision == PCS_PREC_BF16) { __nv_bfloat16 b = __float2bfloat16_rn(v); return *reinterpret_cast<uint16_t*>(&b); }
@@ -510,7 +536,20 @@ size_t fold_weight_image(const float* w32, int cin_total, int cout_total, int ci
         for (int half = 0; half < 2; ++half) {
             int plane, dx;
             if (q < pairs * 5) { plane = 2 * (q / 5) + half; dx = q % 5; }
-            else {
+            else if (pairx) {
+                // K half = one pair unit = [4 channels at tap d | the same channels at tap d + 1]: step 0 holds the taps
+                // (0,1) | (2,3), step 1 the taps (3,4) | (4,5) of which only tap 4 of the first half carries weights
+                const int t = q - pairs * 5;
+                for (int dy = 0; dy < 5; ++dy)
+                    for (int o = 0; o < ncols; ++o)
+                        for (int e = 0; e < 8; ++e) {
+                            const int ci = (npl - 1) * 8 + (e & 3), tap = (t == 0 ? 2 * half : 3 + half) + (e >> 2);
+                            if (ci >= cin || tap > 4 || (t == 1 && (half == 1 || tap != 4))) continue;
+                            const float v = w32[((size_t)(dy * 5 + tap) * cin_total + ci0 + ci) * cout_total + o0 + o];
+                            out[(((size_t)q * 2 + half) * nf + (4 - dy) * npad + o) * 8 + e] = conv(v);
+                        }
+                continue;
+            } else {
                 const int t = q - pairs * 5;                  // taps (0,1), (2,3), (3,4); the repeated tap 3 gets zeros
                 plane = npl - 1;
                 dx = (t == 0 ? 0 : t + 1) + half;

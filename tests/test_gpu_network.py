@@ -194,3 +194,29 @@ def test_umma_one_hot_tap_is_a_shifted_copy(ctx, tap, precision):
         print("mismatch tile map:\n" + "\n".join(lines))
     np.testing.assert_array_equal(conv2, exp)
     np.testing.assert_array_equal(pool2, exp.reshape(H // 2, 2, Wd // 2, 2, 30).max(axis=(1, 3)))
+
+
+@pytest.mark.parametrize("tap", [(2, 0), (2, 1), (2, 2), (2, 3), (2, 4), (0, 4), (4, 0), (1, 3)])
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+def test_pixel_pair_handoff_one_hot_tap(ctx, tap, precision):
+    """The default tensor path hands conv1's channels 16..19 to conv2 as pixel-pair units (w + 1 units per row, two taps per
+    K half, 7 MMAs per input row): with one-hot conv2 weights pool2 must be the bit-exact 2x2 maximum of a shifted copy of
+    conv1 (closed form), for every horizontal tap, across strip borders and at both page edges."""
+    ty, tx = tap
+    img, _ = _small_input(4, 70, 300)
+    W = [(np.zeros_like(k), np.zeros_like(b)) for k, b in synth.make_weights("fcn_skip", 3, seed=0)]
+    for c in range(20):
+        W[0][0][2, 2, 0, c] = (c + 1) / 32.0
+        W[1][0][ty, tx, c, c] = 1.0
+    net, _ = _device_predict("fcn_skip", W, 3, img, precision, "umma", keep=False)
+    pool2 = net._context().debug_activation("pool2")[0]
+    H, Wd = pool2.shape[0] * 2, pool2.shape[1] * 2
+    x32 = (np.pad(img, ((0, H - img.shape[0]), (0, Wd - img.shape[1]))).astype(np.float64) / 255.0).astype(np.float32)
+    c1 = torch.from_numpy(x32[..., None] * (np.arange(1, 21, dtype=np.float32) / np.float32(32.0)))
+    c1 = c1.to(torch.bfloat16 if precision == "bf16" else torch.float16).to(torch.float32).numpy()
+    assert c1.max() > 0
+    exp = np.zeros((H, Wd, 30), np.float32)
+    ys, xs = np.arange(H)[:, None] + ty - 2, np.arange(Wd)[None, :] + tx - 2
+    ok = (ys >= 0) & (ys < H) & (xs >= 0) & (xs < Wd)
+    exp[..., :20] = np.where(ok[..., None], c1[np.clip(ys, 0, H - 1), np.clip(xs, 0, Wd - 1), :], 0.0)
+    np.testing.assert_array_equal(pool2, exp.reshape(H // 2, 2, Wd // 2, 2, 30).max(axis=(1, 3)))
