@@ -447,7 +447,7 @@ int launch_fold_t(pcs_ctx* ctx, const FoldConvArgs& a) {
     // equal ranges of whole row quads (row pairs for the pooling, pair rotation over the epilogue groups)
     p.total_rows = (long long)a.n * p.strips * a.h;
     p.rows_per_cta = ((p.total_rows + ctx->sm_count - 1) / ctx->sm_count + 3) / 4 * 4;
-    if (p.rows_per_cta < 16) p.rows_per_cta = 16;
+    if (p.rows_per_cta < 8) p.rows_per_cta = 8;           // 8 + 4 virtual rows per CTA at least: an 8-page launch of the 1/8-resolution layers still fills the SMs
     if ((a.h & 3) || (a.w & 1)) return set_err(ctx, PCS_ERR_ARG, "conv_fold: grid %dx%d must be a multiple of 4 x 2", a.h, a.w);
     EncodeTiledFn enc = fold_get_encode();
     if (!enc) return set_err(ctx, PCS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
