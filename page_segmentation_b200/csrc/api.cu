@@ -1099,7 +1099,9 @@ static int predict_pages_host_body(pcs_ctx* ctx, const uint8_t* h_grey, const ui
     int head = light ? 8 : 2, chunk = light ? 32 : 8, tail = light ? 8 : 2, nbuf = 3;
     // uint8 pages in, compact results out: the 8.7 MB per page going up are the longest stage (0.158 ms per page against 0.145 of
     // kernels), so the upload stream must never wait: short fill, chunks of 8 (4 940 -> 5 100 pages/s on one B200)
-    if (light && !h_bits && !h_stats) { head = 4; chunk = 8; tail = 8; }
+    // -- and at 10 pages per launch the kernels keep up with it: 4, 10, 10 ... (5 100 -> 5 240; tools/sweep_chunks.py)
+    const bool upload_bound = light && !h_bits && !h_stats;
+    if (upload_bound) { head = 4; chunk = 10; tail = 10; }
     if (const char* e = getenv("PCSEG_HOST_SCHED")) sscanf(e, "%d,%d,%d,%d", &head, &chunk, &tail, &nbuf);
     if (const char* e = getenv("PCSEG_HOST_CHUNK")) head = chunk = tail = std::max(1, atoi(e));
     chunk = std::max(1, std::min(chunk, n));
@@ -1117,6 +1119,8 @@ static int predict_pages_host_body(pcs_ctx* ctx, const uint8_t* h_grey, const ui
             q = *end ? end + 1 : end;
         }
         for (int v : fixed) chunk = std::max(chunk, v);
+    } else if (upload_bound && !getenv("PCSEG_HOST_SCHED") && !getenv("PCSEG_HOST_CHUNK")) {
+        fixed = {std::min(4, n), std::min(10, n)};
     }
     {
         int p = 0;
