@@ -1129,38 +1129,39 @@ mc_tile_kernel(const uint8_t* __restrict__ img, int H, int W, int* __restrict__ 
     }
 }
 
+// Unions across tile borders.  The walks to the roots are chains of dependent L2 round trips, so the work is spread as
+// thinly as possible: one LANE per pixel of a row that starts a tile (a thread per 32-pixel segment spent up to 32
+// unions one after the other: 210 us per launch on noise-like maps whatever the number of pages), one thread per row
+// and vertical tile border.
 template <bool HALVE>
 __global__ void __launch_bounds__(256)
-mc_border_kernel(const uint8_t* __restrict__ img, int H, int W, int* __restrict__ parent) {
-    PCS_SEG_THREAD();
-    if (!valid) return;
-    const int sx = (x0 >> 5) & (kTileSegs - 1);
-    const bool hrow = (y & (kTileRows - 1)) == 0 && y > 0;
-    const bool hcol = sx == 0 && x0 > 0;
-    if (!hrow && !hcol) return;
+mc_border_rows_kernel(const uint8_t* __restrict__ img, int H, int W, int* __restrict__ parent) {
+    const int segs = (W + 31) >> 5;
+    const int wid = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;     // warp -> (tile row, segment)
+    const int tr = wid / segs + 1, x = (wid - (tr - 1) * segs) * 32 + lane, y = tr * kTileRows;
+    if (y >= H || x >= W) return;
+    const size_t page_off = (size_t)blockIdx.y * H * W;
     const uint8_t* row = img + page_off + (size_t)y * W;
-    const int nx = min(32, W - x0);
-    const unsigned m = nx >= 32 ? 0xffffffffu : ((1u << nx) - 1u);
-    unsigned w[8];
-    load_seg32(row, x0, W, last_row, 0u, w);
-    unsigned eql = eq_left_bits32(w, x0 > 0 ? __ldg(row + x0 - 1) : 0u);
-    if (x0 == 0) eql &= ~1u;
+    const uint8_t me = __ldg(row + x), up = __ldg(row - W + x);
+    if (me != up) return;
+    if (x > 0 && __ldg(row + x - 1) == me && __ldg(row - W + x - 1) == up) return;  // the pixel to the left unites the same two runs
     int* par = parent + page_off;
-    const int idx0 = y * W + x0;
-    if (hcol && (eql & 1u)) { if (HALVE) uf_union_h(par, idx0, idx0 - 1); else uf_union<false>(par, idx0, idx0 - 1); }    // run crosses a tile border
-    if (!hrow) return;
-    const uint8_t* rup = row - W;
-    unsigned wu[8];
-    load_seg32(rup, x0, W, false, 0u, wu);
-    unsigned equ = eq_left_bits32(wu, x0 > 0 ? __ldg(rup + x0 - 1) : 0u);
-    if (x0 == 0) equ &= ~1u;
-    unsigned v = eq_bits32(w, wu) & m & ~(eql & equ);                   // equal to the upper pixel where either row starts a run
-    while (v) {
-        const int k = __ffs(v) - 1;
-        v &= v - 1;
-        if (HALVE) uf_union_h(par, idx0 + k, idx0 + k - W);
-        else uf_union<false>(par, idx0 + k, idx0 + k - W);
-    }
+    if (HALVE) uf_union_h(par, y * W + x, (y - 1) * W + x);
+    else uf_union<false>(par, y * W + x, (y - 1) * W + x);
+}
+
+template <bool HALVE>
+__global__ void __launch_bounds__(256)
+mc_border_cols_kernel(const uint8_t* __restrict__ img, int H, int W, int* __restrict__ parent) {
+    const int ncols = (W - 1) / (kTileSegs * 32);                        // vertical tile borders inside the page
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= ncols * H) return;
+    const int y = t / ncols, x = (t - y * ncols + 1) * kTileSegs * 32;
+    const size_t page_off = (size_t)blockIdx.y * H * W;
+    const uint8_t* row = img + page_off + (size_t)y * W;
+    if (__ldg(row + x) != __ldg(row + x - 1)) return;
+    if (HALVE) uf_union_h(parent + page_off, y * W + x, y * W + x - 1);
+    else uf_union<false>(parent + page_off, y * W + x, y * W + x - 1);
 }
 
 // clsbox: [page][n_classes + 1][5] = W - min x, H - min y, max x, max y, pixel count of every class (last: other bytes)
@@ -1302,9 +1303,20 @@ static int mc_label(pcs_ctx* ctx, const uint8_t* d_pred, int n, int H, int W, in
     const dim3 gt((W + kTileSegs * 32 - 1) / (kTileSegs * 32), (H + kTileRows - 1) / kTileRows, n);
     mc_tile_kernel<<<gt, 256, sizeof(McTileSmem), st>>>(d_pred, H, W, b.parent, b.rootmask, b.acc);
     PCS_LAUNCH_CHECK(ctx, "mc_tile_kernel");
-    if (ccl_compress(true)) mc_border_kernel<true><<<g, 256, 0, st>>>(d_pred, H, W, b.parent);
-    else mc_border_kernel<false><<<g, 256, 0, st>>>(d_pred, H, W, b.parent);
-    PCS_LAUNCH_CHECK(ctx, "mc_border_kernel");
+    const int ncols = (W - 1) / (kTileSegs * 32), trows = (H - 1) / kTileRows;     // tile borders inside the page
+    const bool halve = ccl_compress(true);
+    if (ncols > 0) {
+        const dim3 gc((unsigned)(((size_t)ncols * H + 255) / 256), n);
+        if (halve) mc_border_cols_kernel<true><<<gc, 256, 0, st>>>(d_pred, H, W, b.parent);
+        else mc_border_cols_kernel<false><<<gc, 256, 0, st>>>(d_pred, H, W, b.parent);
+        PCS_LAUNCH_CHECK(ctx, "mc_border_cols_kernel");
+    }
+    if (trows > 0) {
+        const dim3 gr((unsigned)(((size_t)trows * segs + 7) / 8), n);
+        if (halve) mc_border_rows_kernel<true><<<gr, 256, 0, st>>>(d_pred, H, W, b.parent);
+        else mc_border_rows_kernel<false><<<gr, 256, 0, st>>>(d_pred, H, W, b.parent);
+        PCS_LAUNCH_CHECK(ctx, "mc_border_rows_kernel");
+    }
     mc_fold_kernel<<<g, 256, 0, st>>>(d_pred, H, W, n_classes, b.parent, b.rootmask, b.acc, b.warpcnt, b.clsbox);
     PCS_LAUNCH_CHECK(ctx, "mc_fold_kernel");
     return PCS_OK;
