@@ -1173,15 +1173,37 @@ mc_fold_kernel(const uint8_t* __restrict__ img, int H, int W, int n_classes, int
     if (threadIdx.x < (kMcMaxClasses + 1) * 5) sbox[threadIdx.x] = 0;
     __syncthreads();
     const size_t mask_off = (size_t)blockIdx.y * H * segs + t;
-    unsigned rm = valid ? rootmask[mask_off] : 0u, gm = 0u;
+    const unsigned rm = valid ? rootmask[mask_off] : 0u;
     int* par = parent + page_off;
     const int base = y * W + x0;
-    while (rm) {
-        const int k = __ffs(rm) - 1;
-        rm &= rm - 1;
-        const int r = uf_find_h(par, base + k);                         // no unions any more: only ancestors are stored
-        if (r == base + k) { gm |= 1u << k; continue; }
-        const int* a = acc + (page_off + base + k) * 5;
+    // The tile roots of a warp's 32 segments are dealt out evenly over its lanes: a segment on a tile border of a noisy map
+    // holds a dozen roots that lost their status, each a walk plus a record merge (dependent L2 round trips), its
+    // neighbours none -- one thread doing them in turn set the duration of the whole launch.
+    __shared__ unsigned short s_list[8][1024];
+    __shared__ unsigned s_gm[8][32];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    s_gm[wib][lane] = 0u;
+    const int cnt = __popc(rm);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    {
+        unsigned r2 = rm;
+        for (int i = incl - cnt; r2; ++i, r2 &= r2 - 1) s_list[wib][i] = (unsigned short)((lane << 5) | (__ffs(r2) - 1));
+    }
+    __syncwarp();
+    for (int i0 = 0; i0 < total; i0 += 32) {
+        const bool has = i0 + lane < total;
+        const int e = has ? s_list[wib][i0 + lane] : 0;
+        const int k = e & 31, p = __shfl_sync(0xffffffffu, base, e >> 5) + k;
+        if (!has) continue;
+        const int r = uf_find_h(par, p);                                // no unions any more: only ancestors are stored
+        if (r == p) { atomicOr(&s_gm[wib][e >> 5], 1u << k); continue; }
+        const int* a = acc + (page_off + p) * 5;
         int* g = acc + (page_off + r) * 5;
         const int v0 = a[0], v1 = a[1], v2 = a[2], v3 = a[3];
         if (v0 > __ldcg(g + 0)) atomicMax(&g[0], v0);
@@ -1190,6 +1212,8 @@ mc_fold_kernel(const uint8_t* __restrict__ img, int H, int W, int n_classes, int
         if (v3 > __ldcg(g + 3)) atomicMax(&g[3], v3);
         atomicAdd(&g[4], a[4]);
     }
+    __syncwarp();
+    const unsigned gm = s_gm[wib][lane];
     if (valid) rootmask[mask_off] = gm;                                 // from here on: the roots of whole components
     const int nx = valid ? min(32, W - x0) : 0;
     const unsigned m = nx >= 32 ? 0xffffffffu : ((1u << nx) - 1u);
