@@ -655,7 +655,7 @@ cc_apply_kernel(uint8_t* __restrict__ pred, const uint8_t* __restrict__ fg, int 
     const int base = y * W + x0;
     int s, len;
     while (next_run(mm, s, len)) {
-        const int* h = hist + (page_off + parent[page_off + base + s]) * n_classes;
+        const int* h = hist + (page_off + uf_find(parent + page_off, base + s)) * n_classes;   // run start -> (tile root ->) root
         int best = 0, bv = h[0];
         for (int c = 1; c < n_classes; ++c)
             if (h[c] > bv) { bv = h[c]; best = c; }          // ties -> lowest class (np.argmax)
@@ -664,15 +664,193 @@ cc_apply_kernel(uint8_t* __restrict__ pred, const uint8_t* __restrict__ fg, int 
     }
 }
 
+// ---------------------------------------------------------------------------
+// The vote with tile-local histograms (n_classes <= kVoteClasses).  cc_vote_kernel above walks from every run to its root
+// through L2 and adds to the root's histogram with global atomics.  Letters rarely leave a 256 x 32 tile, so the tile
+// kernel counts the classes of every tile-local component in shared memory (a table indexed by the rank of the root among
+// the tile's root candidates = run starts without foreground above; candidates beyond the table take global atomics),
+// writes one histogram per tile-local root and a bit mask of those roots; after the border unions the roots that lost
+// their status add their histogram to the component's root (ccv_fold_kernel) -- one update per tile and component.
+// ---------------------------------------------------------------------------
+constexpr int kVoteCap = 1024, kVoteClasses = 4;
+
+struct VoteTileSmem {
+    int lpar[kTileRows * kTileSegs * 32];
+    int tab[kVoteClasses][kVoteCap];
+    unsigned smask[kTileRows][kTileSegs];
+    unsigned cand[256];
+    int off[256];
+    int wsum[8];
+};
+
+__global__ void __launch_bounds__(256)
+ccv_tile_kernel(const uint8_t* __restrict__ fg, const uint8_t* __restrict__ pred, int H, int W, int n_classes, int* __restrict__ parent,
+                unsigned* __restrict__ rootmask, int* __restrict__ hist /*[px][n_classes]*/) {
+    extern __shared__ __align__(16) unsigned char ccv_smem_raw[];
+    VoteTileSmem& sm = *reinterpret_cast<VoteTileSmem*>(ccv_smem_raw);
+    int* lpar = sm.lpar;
+    const int tid = threadIdx.x, lane = tid & 31, sx = tid & (kTileSegs - 1), ry = tid / kTileSegs;
+    const int ty0 = blockIdx.y * kTileRows, tx0 = blockIdx.x * kTileSegs * 32;
+    const int y = ty0 + ry, x0 = tx0 + sx * 32;
+    const size_t page_off = (size_t)blockIdx.z * H * W;
+    const bool valid = y < H && x0 < W;
+    const bool last_row = y == H - 1 && blockIdx.z == gridDim.z - 1;
+    const unsigned m = valid ? fg_bits<0>(fg + page_off + (size_t)y * W, x0, W, 0, last_row) : 0u;
+    sm.smask[ry][sx] = m;
+    for (int k = tid; k < kVoteClasses * kVoteCap; k += 256) (&sm.tab[0][0])[k] = 0;
+    const int l0 = tid * 32;
+    const unsigned nz = __ballot_sync(0xffffffffu, m != 0);
+    for (unsigned todo = nz; todo; todo &= todo - 1) {                  // warp-uniform loop
+        const int j = __ffs(todo) - 1;
+        const unsigned mj = __shfl_sync(0xffffffffu, m, j);
+        if ((mj >> lane) & 1u) {
+            const unsigned below = ~mj & ((1u << lane) - 1u);
+            const int lb = (tid - lane + j) * 32;
+            lpar[lb + lane] = lb + (below ? 32 - __clz(below) : 0);
+        }
+    }
+    __syncthreads();
+    const unsigned lb = sx > 0 ? sm.smask[ry][sx - 1] >> 31 : 0u;
+    const unsigned up = ry > 0 ? sm.smask[ry - 1][sx] : 0u;
+    const unsigned ulb = (ry > 0 && sx > 0) ? sm.smask[ry - 1][sx - 1] >> 31 : 0u;
+    const unsigned leftm = (m << 1) | lb, upleftm = (up << 1) | ulb;
+    const unsigned cand = m & ~leftm & ~up;                             // run starts (tile sense) without foreground above
+    sm.cand[tid] = cand;
+    const int cnt = __popc(cand);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) sm.wsum[tid >> 5] = incl;
+    if (m) {
+        if ((m & 1u) && lb) suf_union_h(lpar, l0, l0 - 1);              // run crosses a segment border
+        unsigned v = m & up & ~(leftm & upleftm);
+        while (v) {
+            const int k = __ffs(v) - 1;
+            v &= v - 1;
+            suf_union_h(lpar, l0 + k, l0 + k - 256);
+        }
+    }
+    __syncthreads();
+    int coff = incl - cnt;
+    for (int k = 0; k < (tid >> 5); ++k) coff += sm.wsum[k];
+    sm.off[tid] = coff;
+    auto gidx = [&](int r) { return (ty0 + (r >> 8)) * W + tx0 + (r & 255); };
+    if (coff + cnt > kVoteCap) {                                        // candidates without a table slot: histograms in global memory
+        unsigned c2 = cand;
+        for (int i = coff; c2; ++i, c2 &= c2 - 1) {
+            if (i < kVoteCap) continue;
+            int* z = hist + (page_off + gidx(l0 + __ffs(c2) - 1)) * n_classes;
+            for (int c = 0; c < n_classes; ++c) z[c] = 0;
+        }
+    }
+    {   // one find per run, kept at the run's first pixel (read-only walks)
+        unsigned mm = m;
+        int s, len;
+        while (next_run(mm, s, len)) lpar[l0 + s] = suf_find(lpar, l0 + s);
+    }
+    __syncthreads();
+    if (m) {
+        unsigned w[8];
+        load_seg32(pred + page_off + (size_t)y * W, x0, W, last_row, 0xffu, w);
+        unsigned cb[kVoteClasses];
+#pragma unroll
+        for (int c = 0; c < kVoteClasses; ++c) cb[c] = c < n_classes ? seg_bits<1>(w, c) & m : 0u;
+        unsigned mm = m;
+        int s, len;
+        while (next_run(mm, s, len)) {
+            const unsigned run = (len >= 32 ? 0xffffffffu : ((1u << len) - 1u)) << s;
+            const int r = lpar[l0 + s], rt = r >> 5;
+            const int ci = sm.off[rt] + __popc(sm.cand[rt] & ((1u << (r & 31)) - 1u));
+#pragma unroll
+            for (int c = 0; c < kVoteClasses; ++c) {
+                const int v = __popc(cb[c] & run);
+                if (!v) continue;
+                if (ci < kVoteCap) atomicAdd(&sm.tab[c][ci], v);
+                else atomicAdd(&hist[(page_off + gidx(r)) * n_classes + c], v);
+            }
+        }
+    }
+    __syncthreads();
+    int* par = parent + page_off;
+    for (unsigned todo = nz; todo; todo &= todo - 1) {                  // every store writes up to 32 consecutive parents
+        const int j = __ffs(todo) - 1;
+        const unsigned mj = __shfl_sync(0xffffffffu, m, j);
+        const int tj = tid - lane + j;
+        const int bj = (ty0 + tj / kTileSegs) * W + tx0 + (tj & (kTileSegs - 1)) * 32;
+        if ((mj >> lane) & 1u) {
+            const unsigned below = ~mj & ((1u << lane) - 1u);
+            par[bj + lane] = gidx(lpar[tj * 32 + (below ? 32 - __clz(below) : 0)]);
+        }
+    }
+    if (valid) {
+        unsigned roots = 0u, c2 = cand;
+        for (int i = coff; c2; ++i, c2 &= c2 - 1) {
+            const int k = __ffs(c2) - 1;
+            if (lpar[l0 + k] != l0 + k) continue;
+            roots |= 1u << k;
+            if (i < kVoteCap) {
+                int* g = hist + (page_off + gidx(l0 + k)) * n_classes;
+                for (int c = 0; c < n_classes; ++c) g[c] = sm.tab[c][i];
+            }
+        }
+        rootmask[((size_t)blockIdx.z * H + y) * ((W + 31) >> 5) + (x0 >> 5)] = roots;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+ccv_fold_kernel(int H, int W, int n_classes, int* __restrict__ parent, const unsigned* __restrict__ rootmask, int* __restrict__ hist) {
+    PCS_SEG_THREAD();
+    (void)last_row;
+    if (!valid) return;
+    unsigned rm = rootmask[(size_t)blockIdx.y * H * segs + t];
+    int* par = parent + page_off;
+    const int base = y * W + x0;
+    while (rm) {
+        const int k = __ffs(rm) - 1;
+        rm &= rm - 1;
+        const int r = uf_find_h(par, base + k);                         // no unions any more: only ancestors are stored
+        if (r == base + k) continue;
+        const int* a = hist + (page_off + base + k) * n_classes;
+        int* g = hist + (page_off + r) * n_classes;
+        for (int c = 0; c < n_classes; ++c)
+            if (a[c]) atomicAdd(&g[c], a[c]);
+    }
+}
+
 int launch_cc_majority(pcs_ctx* ctx, uint8_t* d_pred, const uint8_t* d_binary, int n, int H, int W, int n_classes) {
     if (n <= 0 || H <= 0 || W <= 0 || n_classes <= 0 || n_classes > 255 || (size_t)H * W >= (size_t)INT_MAX)
         return set_err(ctx, PCS_ERR_ARG, "cc_majority: bad argument");
     const size_t page_px = (size_t)H * W, total = page_px * n;
-    PCS_TRY(scratch_reserve(ctx, total * 4 * (1 + (size_t)n_classes) + 256));
+    const size_t mask_words = (size_t)n * H * ((W + 31) >> 5);
+    PCS_TRY(scratch_reserve(ctx, total * 4 * (1 + (size_t)n_classes) + mask_words * 4 + 256));
     int* parent = reinterpret_cast<int*>(ctx->scratch);
     int* hist = parent + total;
-    PCS_TRY(ccl_roots(ctx, d_binary, n, H, W, 0, false, parent, hist, n_classes, false, /*fg_only=*/true, /*flatten=*/false));
     const dim3 grid = seg_grid(H, W, n);
+    static const bool vote_global = [] { const char* e = getenv("PCSEG_VOTE_GLOBAL"); return e && atoi(e) != 0; }();   // A/B switch
+    if (n_classes <= kVoteClasses && !vote_global) {
+        unsigned* rootmask = reinterpret_cast<unsigned*>(hist + total * n_classes);
+        cudaStream_t st = ctx->stream;
+        static bool attr_set = false;
+        if (!attr_set) {
+            PCS_CUDA(ctx, cudaFuncSetAttribute(ccv_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VoteTileSmem)));
+            attr_set = true;
+        }
+        const dim3 gt((W + kTileSegs * 32 - 1) / (kTileSegs * 32), (H + kTileRows - 1) / kTileRows, n);
+        ccv_tile_kernel<<<gt, 256, sizeof(VoteTileSmem), st>>>(d_binary, d_pred, H, W, n_classes, parent, rootmask, hist);
+        PCS_LAUNCH_CHECK(ctx, "ccv_tile_kernel");
+        if (ccl_compress(false)) ccl_border_kernel<0, false, true><<<grid, 256, 0, st>>>(d_binary, H, W, 0, parent);
+        else ccl_border_kernel<0, false, false><<<grid, 256, 0, st>>>(d_binary, H, W, 0, parent);
+        PCS_LAUNCH_CHECK(ctx, "ccl_border_kernel");
+        ccv_fold_kernel<<<grid, 256, 0, st>>>(H, W, n_classes, parent, rootmask, hist);
+        PCS_LAUNCH_CHECK(ctx, "ccv_fold_kernel");
+        cc_apply_kernel<<<grid, 256, 0, st>>>(d_pred, d_binary, H, W, parent, n_classes, hist);
+        PCS_LAUNCH_CHECK(ctx, "cc_apply_kernel");
+        return PCS_OK;
+    }
+    PCS_TRY(ccl_roots(ctx, d_binary, n, H, W, 0, false, parent, hist, n_classes, false, /*fg_only=*/true, /*flatten=*/false));
     cc_vote_kernel<<<grid, 256, 0, ctx->stream>>>(d_pred, d_binary, H, W, parent, n_classes, hist);
     PCS_LAUNCH_CHECK(ctx, "cc_vote_kernel");
     cc_apply_kernel<<<grid, 256, 0, ctx->stream>>>(d_pred, d_binary, H, W, parent, n_classes, hist);

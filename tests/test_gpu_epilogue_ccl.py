@@ -266,3 +266,38 @@ def test_bounding_boxes_batched_a4_and_many_classes(ctx):
     out9 = torch.full_like(d9, 77)
     ctx.bounding_boxes(d9, 1, 170, 300, 9, out9)
     np.testing.assert_array_equal(out9[0].cpu().numpy(), opipe.add_bounding_boxes(p9.astype(np.int64)))
+
+
+def test_vote_noise_binary_and_shapes_across_tiles(ctx):
+    """vote_connected_component_class with tile-local histograms: salt-and-pepper foreground (more root candidates per
+    labelling tile than the shared-memory table holds), a spiral and a comb that leave tiles and come back, a page of
+    foreground only; batched, against the restated reference."""
+    import torch
+    rng = np.random.default_rng(21)
+    h, w = 200, 700
+    noise = (rng.random((h, w)) < 0.4).astype(np.uint8)
+    spiral = np.zeros((h, w), np.uint8)
+    y0, y1, x0, x1 = 2, h - 3, 2, w - 3
+    while y1 - y0 > 8 and x1 - x0 > 8:
+        spiral[y0, x0:x1 + 1] = 1
+        spiral[y0:y1 + 1, x1] = 1
+        spiral[y1, x0 + 4:x1 + 1] = 1
+        spiral[y0 + 4:y1 + 1, x0 + 4] = 1
+        spiral[y0 + 4, x0 + 4:x1 - 3] = 1
+        y0 += 4; y1 -= 4; x0 += 4; x1 -= 4                                   # noqa: E702
+    comb = np.zeros((h, w), np.uint8)
+    comb[h - 2, :] = 1
+    comb[3:h - 2, ::3] = 1
+    binaries = [noise, spiral, comb, np.ones((h, w), np.uint8)]
+    preds = [rng.integers(0, 3, size=(h, w)).astype(np.uint8) for _ in binaries]
+    d_pred = torch.from_numpy(np.stack(preds)).cuda()
+    d_bin = torch.from_numpy(np.stack(binaries)).cuda()
+    ctx.cc_majority(d_pred, d_bin, len(binaries), h, w, 3)
+    got = d_pred.cpu().numpy()
+    for i, (p, b) in enumerate(zip(preds, binaries)):
+        np.testing.assert_array_equal(got[i], opipe.vote_connected_component_class(p.astype(np.int64), b), err_msg=f"page {i}")
+    # five classes: the per-run global path
+    p5 = rng.integers(0, 5, size=(h, w)).astype(np.uint8)
+    d5 = torch.from_numpy(p5[None]).cuda()
+    ctx.cc_majority(d5, torch.from_numpy(spiral[None]).cuda(), 1, h, w, 5)
+    np.testing.assert_array_equal(d5[0].cpu().numpy(), opipe.vote_connected_component_class(p5.astype(np.int64), spiral))
