@@ -301,3 +301,23 @@ def test_vote_noise_binary_and_shapes_across_tiles(ctx):
     d5 = torch.from_numpy(p5[None]).cuda()
     ctx.cc_majority(d5, torch.from_numpy(spiral[None]).cuda(), 1, h, w, 5)
     np.testing.assert_array_equal(d5[0].cpu().numpy(), opipe.vote_connected_component_class(p5.astype(np.int64), spiral))
+
+
+@pytest.mark.parametrize("hw", [(1, 1), (1, 40), (40, 1), (2, 33), (32, 256), (31, 255), (64, 257)])
+def test_class_components_and_boxes_degenerate_shapes(ctx, hw):
+    """One-pixel pages, single rows / columns, pages that are exactly one labelling tile or one pixel more."""
+    import torch
+    rng = np.random.default_rng(hw[0] * 1000 + hw[1])
+    preds = [rng.integers(0, 3, size=hw).astype(np.uint8), np.zeros(hw, np.uint8),
+             (np.add.outer(np.arange(hw[0]), np.arange(hw[1])) % 3).astype(np.uint8)]
+    _check_class_tables(ctx, preds, 3)
+    d = torch.from_numpy(np.stack(preds)).cuda()
+    out = torch.full_like(d, 9)
+    ctx.bounding_boxes(d, len(preds), hw[0], hw[1], 3, out)
+    binaries = [(p > 0).astype(np.uint8) for p in preds]
+    d_bin = torch.from_numpy(np.stack(binaries)).cuda()
+    d_vote = d.clone()
+    ctx.cc_majority(d_vote, d_bin, len(preds), hw[0], hw[1], 3)
+    for i, p in enumerate(preds):
+        np.testing.assert_array_equal(out[i].cpu().numpy(), opipe.add_bounding_boxes(p.astype(np.int64)))
+        np.testing.assert_array_equal(d_vote[i].cpu().numpy(), opipe.vote_connected_component_class(p.astype(np.int64), binaries[i]))
