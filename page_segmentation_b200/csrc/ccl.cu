@@ -838,6 +838,8 @@ int launch_cc_majority(pcs_ctx* ctx, uint8_t* d_pred, const uint8_t* d_binary, i
             PCS_CUDA(ctx, cudaFuncSetAttribute(ccv_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VoteTileSmem)));
             attr_set = true;
         }
+        static const bool poison = [] { const char* e = getenv("PCSEG_CCL_POISON"); return e && e[0] == '1'; }();
+        if (poison) PCS_CUDA(ctx, cudaMemsetAsync(parent, 0x7f, (total * (1 + (size_t)n_classes) + mask_words) * 4, st));
         const dim3 gt((W + kTileSegs * 32 - 1) / (kTileSegs * 32), (H + kTileRows - 1) / kTileRows, n);
         ccv_tile_kernel<<<gt, 256, sizeof(VoteTileSmem), st>>>(d_binary, d_pred, H, W, n_classes, parent, rootmask, hist);
         PCS_LAUNCH_CHECK(ctx, "ccv_tile_kernel");
@@ -1501,6 +1503,11 @@ static int mc_label(pcs_ctx* ctx, const uint8_t* d_pred, int n, int H, int W, in
         PCS_CUDA(ctx, cudaFuncSetAttribute(mc_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(McTileSmem)));
         attr_set = true;
     }
+    // diagnosis (PCSEG_CCL_POISON=1): parents / records / root masks start as 0x7f7f7f7f, so a pass that reads one the
+    // labelling did not write (parents exist only on tile edges and at roots) walks out of the page instead of finding a
+    // plausible stale value from an earlier call
+    static const bool poison = [] { const char* e = getenv("PCSEG_CCL_POISON"); return e && e[0] == '1'; }();
+    if (poison) PCS_CUDA(ctx, cudaMemsetAsync(b.parent, 0x7f, (total * 6 + mask_words + cnt_words) * 4, st));
     PCS_CUDA(ctx, cudaMemsetAsync(b.clsbox, 0, box_words * sizeof(int), st));
     const dim3 gt((W + kTileSegs * 32 - 1) / (kTileSegs * 32), (H + kTileRows - 1) / kTileRows, n);
     mc_tile_kernel<<<gt, 256, sizeof(McTileSmem), st>>>(d_pred, H, W, b.parent, b.rootmask, b.acc);
