@@ -1,3 +1,5 @@
+"""U-Net device time against the number of pages per launch (8 / 16 / 32): no gain beyond 8 (557 / 566 / 547 pages/s on one
+B200), which is why bench.py runs the 256 pages of BASELINE configs[2] in sub-batches of 8.  Development tool."""
 import os, sys, json
 import numpy as np
 sys.path.insert(0, os.getcwd())
