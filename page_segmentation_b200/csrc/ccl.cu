@@ -1108,7 +1108,7 @@ __global__ void cstats_ncomp_kernel(const int* __restrict__ ncomp_tmp, int n, in
 //   scan, mc_write : label = rank of the root among the roots of ITS class (cv2's numbering of that class's
 //               labelling), stats row written from the root's record.
 // ---------------------------------------------------------------------------
-constexpr int kMcCap = 1024;                        // tile-local root candidates with shared-memory accumulators
+// tile-local root candidates with shared-memory accumulators: 512 records leave room for five tiles per SM (1 024: four)
 
 __device__ __forceinline__ unsigned eq_bits32(const unsigned (&a)[8], const unsigned (&b)[8]) {
     unsigned m = 0;
@@ -1130,7 +1130,7 @@ __device__ __forceinline__ unsigned eq_left_bits32(const unsigned (&w)[8], unsig
     return eq_bits32(w, s);
 }
 
-struct McTileSmem {
+template <int kMcCap> struct McTileSmem {
     int lpar[kTileRows * kTileSegs * 32];
     union {
         uint4 bytes[256][2];                        // the tile's class bytes (phase 1 only)
@@ -1142,11 +1142,12 @@ struct McTileSmem {
     int wsum[8];
 };
 
+template <int kMcCap>
 __global__ void __launch_bounds__(256)
 mc_tile_kernel(const uint8_t* __restrict__ img, int H, int W, int* __restrict__ parent, unsigned* __restrict__ rootmask,
                int* __restrict__ acc /*[px][5]: W - min x, H - min y, max x, max y, area*/) {
     extern __shared__ __align__(16) unsigned char mc_smem_raw[];
-    McTileSmem& sm = *reinterpret_cast<McTileSmem*>(mc_smem_raw);
+    McTileSmem<kMcCap>& sm = *reinterpret_cast<McTileSmem<kMcCap>*>(mc_smem_raw);
     int* lpar = sm.lpar;
     const int tid = threadIdx.x, lane = tid & 31, sx = tid & (kTileSegs - 1), ry = tid / kTileSegs;
     const int ty0 = blockIdx.y * kTileRows, tx0 = blockIdx.x * kTileSegs * 32;
@@ -1498,9 +1499,11 @@ static int mc_label(pcs_ctx* ctx, const uint8_t* d_pred, int n, int H, int W, in
     b.clsbox = b.warpcnt + cnt_words;
     b.extra = b.clsbox + box_words;
     cudaStream_t st = ctx->stream;
+    static const bool big_table = [] { const char* e = getenv("PCSEG_MC_CAP"); return e && atoi(e) >= 1024; }();   // A/B switch
     static bool attr_set = false;
     if (!attr_set) {
-        PCS_CUDA(ctx, cudaFuncSetAttribute(mc_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(McTileSmem)));
+        PCS_CUDA(ctx, cudaFuncSetAttribute(mc_tile_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(McTileSmem<512>)));
+        PCS_CUDA(ctx, cudaFuncSetAttribute(mc_tile_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(McTileSmem<1024>)));
         attr_set = true;
     }
     // diagnosis (PCSEG_CCL_POISON=1): parents / records / root masks start as 0x7f7f7f7f, so a pass that reads one the
@@ -1510,7 +1513,8 @@ static int mc_label(pcs_ctx* ctx, const uint8_t* d_pred, int n, int H, int W, in
     if (poison) PCS_CUDA(ctx, cudaMemsetAsync(b.parent, 0x7f, (total * 6 + mask_words + cnt_words) * 4, st));
     PCS_CUDA(ctx, cudaMemsetAsync(b.clsbox, 0, box_words * sizeof(int), st));
     const dim3 gt((W + kTileSegs * 32 - 1) / (kTileSegs * 32), (H + kTileRows - 1) / kTileRows, n);
-    mc_tile_kernel<<<gt, 256, sizeof(McTileSmem), st>>>(d_pred, H, W, b.parent, b.rootmask, b.acc);
+    if (big_table) mc_tile_kernel<1024><<<gt, 256, sizeof(McTileSmem<1024>), st>>>(d_pred, H, W, b.parent, b.rootmask, b.acc);
+    else mc_tile_kernel<512><<<gt, 256, sizeof(McTileSmem<512>), st>>>(d_pred, H, W, b.parent, b.rootmask, b.acc);
     PCS_LAUNCH_CHECK(ctx, "mc_tile_kernel");
     const int ncols = (W - 1) / (kTileSegs * 32), trows = (H - 1) / kTileRows;     // tile borders inside the page
     const bool halve = ccl_compress(true);
