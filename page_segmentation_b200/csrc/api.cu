@@ -185,6 +185,10 @@ static int run_conv(pcs_ctx* ctx, const char* lname, const Act* s0, const Act* s
             f.n = n; f.h = h; f.w = w; f.k = L->k;
             f.wimg = part.d_w; f.h_bias = L->h_b32.data() + part.o0; f.cout = part.ncols; f.npad = part.npad;
             f.nplanes = src->cp / 8; f.relu = L->relu; f.o0 = part.o0;
+            if (part.both) {
+                if (!s1) return set_err(ctx, PCS_ERR_STATE, "layer %s: folded part reads a missing second source", lname);
+                f.src2 = src_of(*s1); f.nplanes += s1->cp / 8;
+            }
             if (pair_src) {
                 if (!part.d_w_px) return set_err(ctx, PCS_ERR_STATE, "layer %s: no weight image for a pixel-pair source", lname);
                 f.pair_src = pair_src; f.wimg = part.d_w_px; f.nplanes += 1;
@@ -655,7 +659,7 @@ int pcs_model_load(pcs_ctx* ctx, int arch, int n_classes, int precision, const p
             // channels, two launches) or along K (one launch per concatenated source)
             auto add_part = [&](int src, int ci0, int cin, int o0, int ncols, int npad, int psum) -> int {
                 std::vector<uint16_t> fimg;
-                const size_t fb = fold_weight_image(L.h_w32.data(), L.cin, L.cout, ci0, cin, o0, ncols, npad, precision, fimg);
+                const size_t fb = fold_weight_image(L.h_w32.data(), L.cin, L.cout, ci0, cin, o0, ncols, npad, precision, fimg, false, L.k);
                 Layer::FoldPart part;
                 part.src = src; part.o0 = o0; part.ncols = ncols; part.npad = npad; part.nplanes = pad8(cin) / 8; part.psum = psum;
                 PCS_CUDA(ctx, cudaMalloc(&part.d_w, fb));
@@ -676,7 +680,13 @@ int pcs_model_load(pcs_ctx* ctx, int arch, int n_classes, int precision, const p
             const int fnp1 = (fold40 && pad8(L.cout) % 16 == 8 && fold_supported(5, pad8(L.cout), pad8(L.cin) / 8)) ? pad8(L.cout) : L.npad;
             const int fnp2 = (fold40 && pad8(L.cout) % 16 == 8 && nsrc == 2 && fold_supported(5, pad8(L.cout), pad8(src_c[0]) / 8) &&
                               fold_supported(5, pad8(L.cout), pad8(src_c[1]) / 8)) ? pad8(L.cout) : L.npad;
-            if (L.k == 5 && nsrc == 1 && fold_supported(5, fnp1, pad8(L.cin) / 8)) {
+            static const bool fold3 = !(getenv("PCSEG_FOLD3") && !strcmp(getenv("PCSEG_FOLD3"), "0"));
+            if (fold3 && L.k == 3 && L.kind == K_CONV && L.cout == 64 && ((nsrc == 1 && L.cin == 64) || (nsrc == 2 && src_c[0] == 64 && src_c[1] == 64))) {
+                // U-Net conv1b / conv9b / conv9a: 64 output channels at full resolution, dy-folded (N' = 192); the two sources of
+                // conv9a's concatenation are read by one launch through two tensor maps
+                PCS_TRY(add_part(0, 0, L.cin, 0, 64, 64, 0));
+                L.fold.back().both = nsrc == 2;
+            } else if (L.k == 5 && nsrc == 1 && fold_supported(5, fnp1, pad8(L.cin) / 8)) {
                 PCS_TRY(add_part(0, 0, L.cin, 0, L.cout, fnp1, 0));
             } else if (fold40 && L.k == 5 && nsrc == 1 && L.cout == 80 && fold_supported(5, 40, pad8(L.cin) / 8)) {
                 // conv7 (60 -> 80): two launches of 40 output channels each on the 40-column kernel (N' = 208) instead of the

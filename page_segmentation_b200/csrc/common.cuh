@@ -70,6 +70,7 @@ struct Layer {
         int o0 = 0, ncols = 0;    // output channels [o0, o0 + ncols)
         int npad = 0, nplanes = 0;
         int psum = 0;             // 0 complete, 1 writes partial sums, 2 adds them
+        bool both = false;        // reads BOTH concatenated sources in one launch (3x3, U-Net conv9a)
     };
     std::vector<FoldPart> fold;
     void* d_wmma_px = nullptr;    // conv1 (5x5, 20 channels): operand image with the pixel-pair columns 20..23
@@ -377,12 +378,13 @@ struct FoldConvArgs {
     const void* psum_in = nullptr;     // ... and added by the last part before bias / activation
     void* plog = nullptr;              // optional float4 [n][h][w]: this layer's share of the logits (fcn_skip conv2)
     const float* skip_lw = nullptr;    // device [32][4]: logits rows of this layer's channels, zero padded
+    ConvSrc src2;                      // 3x3 layers on a concatenation: the second tensor (same geometry and plane count as src)
     const void* pair_src = nullptr;    // the source's last (odd) plane as pixel-pair units [n][h][w + 1][8] (conv1_umma.cu): src holds the
                                        // whole planes before it, nplanes counts it, wimg is the image built with pairx
 };
 bool fold_supported(int k, int npad, int nplanes);
 size_t fold_weight_image(const float* w32 /*[25][cin_total][cout_total]*/, int cin_total, int cout_total, int ci0, int cin,
-                         int o0, int ncols, int npad, int precision, std::vector<uint16_t>& out, bool pairx = false);
+                         int o0, int ncols, int npad, int precision, std::vector<uint16_t>& out, bool pairx = false, int ks = 5);
 int launch_conv_fold(pcs_ctx* ctx, const FoldConvArgs& a);
 
 // conv12_fused.cu  (conv1 + conv2 + MaxPool of the FCN variants in one marching kernel; conv1 never leaves the SM)

@@ -83,7 +83,7 @@ struct FoldParams {
                                             // perfect balance, and a strip restart (4 virtual rows) only where a range or a
                                             // strip begins
     const uint8_t* wimg;                    // [chunk][dx][plane][row = (4-dy)*NPAD + o][8]: resident operand image
-    float bias[48];                         // by value (zero padded): constant-bank operands of the epilogue's adds
+    float bias[64];                         // by value (zero padded): constant-bank operands of the epilogue's adds
     int cout, relu;
     void* out; int out_cp;
     void* pool; int pool_cp;
@@ -108,26 +108,33 @@ constexpr int fold_gcd(int a, int b) { return b == 0 ? a : fold_gcd(b, a % b); }
 // of pixel i], w + 1 units per row, conv1_umma.cu): one 16-byte K half then covers two taps, and the five taps cost TWO
 // MMAs -- K halves (0,1) | (2,3) two units apart, then (3,4) | (4,5) with zero weights for everything but tap 4 (every
 // unit read lies inside the row's box, so the zero weights meet finite values) -- instead of three.
-template <int NPL, bool PX = false> struct FoldK {
+//
+// KS: kernel size, 5 (the FCN layers) or 3 (the U-Net's 64-channel full-resolution layers: N' = 3 * 64 = 192 instead of one
+// N = 64 MMA per tap, whose fixed cost caps the plain kernel at 56 % tensor activity); the window of a row is KS slots, a
+// strip starts with KS - 1 virtual rows, the halo is KS / 2.  SRC2: the planes are the concatenation of two tensors
+// (conv9a: [conv1b, up9]), each loaded with its own tensor map into the same ring entry.
+template <int NPL, bool PX = false, int KS = 5> struct FoldK {
     static constexpr int PAIRS = NPL / 2, ODD = NPL & 1;
-    static constexpr int NMMA = PAIRS * 5 + ODD * (PX ? 2 : 3);
+    static constexpr int NMMA = PAIRS * KS + ODD * (PX ? 2 : 3);
+    static_assert(KS == 5 || ODD == 0, "the self-paired odd plane is laid out for five taps");
 };
 
-template <typename T, int NPAD, int NPL, int RING, int SLOTS, int EG, bool PX>
+template <typename T, int NPAD, int NPL, int RING, int SLOTS, int EG, bool PX, int KS, bool SRC2>
 __global__ void __launch_bounds__(64 + EG * 128, 1)
 conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm2) {
     static_assert(!PX || (NPL & 1), "the pixel-pair plane is the odd last plane");
+    static_assert((KS == 5 || KS == 3) && !(PX && SRC2) && (!SRC2 || (NPL & 1) == 0), "kernel size / source layout");
     // Folded N.  NPAD need not be a multiple of 16 (C_out = 40: five whole planes): the five slots of a window are then
     // 5 * NPAD = 200 accumulator columns and every MMA rounds ITS part of the window up to a legal N.  The extra columns
     // of a part that ends inside the ring belong to the slot after the window and take zero weight rows (the weight
     // image is padded to NF rows): D += 0 there, which is why the issuer also waits for THAT slot to be drained and
     // re-zeroed (a read-modify-write of the tensor pipe racing with the epilogue's zeroing store would undo it).  The
     // extra columns of a part that ends at the ring's end fall behind the ring (columns SLOTS * NPAD ...: unused).
-    constexpr int NF = fold_up16(5 * NPAD);
+    constexpr int NF = fold_up16(KS * NPAD);
     constexpr bool SPILL = (NPAD % 16) != 0;
     constexpr uint32_t ROW_BYTES = NPL * 2048;                       // one ring entry: all planes of one input row
     constexpr uint32_t WDX_BYTES = 2 * NF * 16;                      // weights of one K step
-    constexpr int NMMA = FoldK<NPL, PX>::NMMA;
+    constexpr int NMMA = FoldK<NPL, PX, KS>::NMMA;
     constexpr uint32_t IDESC0 = (1u << 4) | ((std::is_same<T, __nv_bfloat16>::value ? 1u : 0u) << 7) |
                                 ((std::is_same<T, __nv_bfloat16>::value ? 1u : 0u) << 10) | ((uint32_t)(128 >> 4) << 24);
     static_assert(NF <= 256 && NF % 16 == 0, "folded N must be a legal UMMA N");
@@ -179,16 +186,18 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm, con
                 const int rows = (int)((long long)(p.h - ys) < pos1 - pos ? (long long)(p.h - ys) : pos1 - pos);
                 const int page = sg / p.strips, strip = sg - page * p.strips;
                 pos += rows;
-                const int x0 = strip * F_SW - 2;
-                for (int i = 0; i < rows + 4; ++i, ++k) {
+                const int x0 = strip * F_SW - KS / 2;
+                for (int i = 0; i < rows + KS - 1; ++i, ++k) {
                     const uint32_t slot = k % (uint32_t)RING, pass = k / (uint32_t)RING;
                     mbar_wait(&s_empty[slot], (pass & 1u) ^ 1u);
                     mbar_expect_tx(&s_full[slot], ROW_BYTES);
                     // box = 256 u64 (128 px x 16 B) x 1 row x NPL planes (PX: the whole planes, then the pair units from one
                     // unit further: unit j + dx of the box = pixels (x - 2 + dx, x - 1 + dx) of output pixel x = strip start + j)
-                    tma_load_4d(ring + (size_t)slot * ROW_BYTES, &tm, &s_full[slot], x0 * 2, ys - 2 + i, 0, page);
+                    tma_load_4d(ring + (size_t)slot * ROW_BYTES, &tm, &s_full[slot], x0 * 2, ys - KS / 2 + i, 0, page);
                     if constexpr (PX)
-                        tma_load_4d(ring + (size_t)slot * ROW_BYTES + (NPL - 1) * 2048, &tm2, &s_full[slot], (x0 + 1) * 2, ys - 2 + i, 0, page);
+                        tma_load_4d(ring + (size_t)slot * ROW_BYTES + (NPL - 1) * 2048, &tm2, &s_full[slot], (x0 + 1) * 2, ys - KS / 2 + i, 0, page);
+                    if constexpr (SRC2)
+                        tma_load_4d(ring + (size_t)slot * ROW_BYTES + (NPL / 2) * 2048, &tm2, &s_full[slot], x0 * 2, ys - KS / 2 + i, 0, page);
                 }
             }
         }
@@ -205,7 +214,7 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm, con
                 const int ys = (int)(pos % p.h);
                 const int rows = (int)((long long)(p.h - ys) < pos1 - pos ? (long long)(p.h - ys) : pos1 - pos);
                 pos += rows;
-                total += (uint32_t)(rows + 4);
+                total += (uint32_t)(rows + KS - 1);
             }
             const uint32_t hi = (uint32_t)(make_desc(0, 0, 128) >> 32);
             constexpr uint32_t a_lbo_pair = ((2048u >> 4) & 0x3fffu) << 16;               // K halves = two planes
@@ -224,8 +233,8 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm, con
                     mbar_wait(&s_full[u % RING], ((kk + u) / RING) & 1u);
                     // the newest output slot of the window must have been drained and re-zeroed by the epilogue:
                     // tempty phase 0 = initial zeroing, phase n = drain of use n-1: use n waits for phase n
-                    mbar_wait(&s_tempty[(u + 4) % SLOTS], ((kk + u + 4) / SLOTS) & 1u);
-                    if constexpr (SPILL) mbar_wait(&s_tempty[(u + 5) % SLOTS], ((kk + u + 5) / SLOTS) & 1u);
+                    mbar_wait(&s_tempty[(u + KS - 1) % SLOTS], ((kk + u + KS - 1) / SLOTS) & 1u);
+                    if constexpr (SPILL) mbar_wait(&s_tempty[(u + KS) % SLOTS], ((kk + u + KS) / SLOTS) & 1u);
                     tc_fence_after();
                     // opaque copies: keeps the descriptor arithmetic (base + immediate) next to its MMA instead of
                     // having every one of the RING x NCH x 5 sums hoisted out of the loop into spilled registers
@@ -233,21 +242,21 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm, con
                     asm volatile("mov.u32 %0, %3;\n\tmov.u32 %1, %4;\n\tmov.u32 %2, %5;"
                                  : "=r"(a_step), "=r"(b_step), "=r"(d_step) : "r"(a_lo0), "r"(b_lo0), "r"(tmem_base));
                     const int s0 = u % SLOTS;
-                    const int n1 = (SLOTS - s0) < 5 ? (SLOTS - s0) : 5;           // blocks before the ring wraps
+                    const int n1 = (SLOTS - s0) < KS ? (SLOTS - s0) : KS;         // blocks before the ring wraps
                     const uint32_t idesc1 = IDESC0 | ((uint32_t)(fold_up16(n1 * NPAD) >> 3) << 17);
-                    const uint32_t idesc2 = IDESC0 | ((uint32_t)(fold_up16((5 - n1) * NPAD) >> 3) << 17);
+                    const uint32_t idesc2 = IDESC0 | ((uint32_t)(fold_up16((KS - n1) * NPAD) >> 3) << 17);
 #pragma unroll
                     for (int q = 0; q < NMMA; ++q) {
                         // K step q: plane pair (q / 5) at tap q % 5, or the odd last plane at taps {0, 2, 3} (+1)
-                        const bool pair = q < FoldK<NPL>::PAIRS * 5;
-                        const int t = q - FoldK<NPL>::PAIRS * 5;
-                        const int plane = pair ? 2 * (q / 5) : NPL - 1;
-                        const int dx = pair ? q % 5 : PX ? (t == 0 ? 0 : 3) : (t == 0 ? 0 : t + 1);
+                        const bool pair = q < FoldK<NPL>::PAIRS * KS;
+                        const int t = q - FoldK<NPL>::PAIRS * KS;
+                        const int plane = pair ? 2 * (q / KS) : NPL - 1;
+                        const int dx = pair ? q % KS : PX ? (t == 0 ? 0 : 3) : (t == 0 ? 0 : t + 1);
                         const uint32_t a_lo = (a_step + (uint32_t)((u % RING) * (ROW_BYTES >> 4) + plane * (2048 >> 4) + dx)) |
                                               (pair ? a_lbo_pair : (PX && t == 0) ? a_lbo_two : a_lbo_self);
                         const uint32_t b_lo = b_step + (uint32_t)(q * (WDX_BYTES >> 4));
                         tc_mma(d_step + (uint32_t)(s0 * NPAD), a_lo, hi, b_lo, hi, idesc1, 1u);   // slots are pre-zeroed
-                        if (n1 < 5) tc_mma(d_step, a_lo, hi, b_lo + (uint32_t)(n1 * NPAD), hi, idesc2, 1u);
+                        if (n1 < KS) tc_mma(d_step, a_lo, hi, b_lo + (uint32_t)(n1 * NPAD), hi, idesc2, 1u);
                     }
                     tc_commit(&s_empty[u % RING]);                                        // input row consumed
                     tc_commit(&s_tfull[s0]);                                              // output slot k is complete
@@ -281,18 +290,18 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm, con
             const int x = strip * F_SW + j;
             const bool xok = j < F_SW && x < p.w;
             // row pairs (o = o2 - 4 + st) go round-robin over the epilogue groups, across work items
-            for (int o2 = 2 * (int)((EG + group - (g >> 1) % EG) % EG); o2 < rows + 4; o2 += 2 * EG) {
+            for (int o2 = 2 * (int)((EG + group - (g >> 1) % EG) % EG); o2 < rows + KS - 1; o2 += 2 * EG) {
                 uint32_t kept[NPAD / 2];
 #pragma unroll
                 for (int st = 0; st < 2; ++st) {
                     const uint32_t gg = g + (uint32_t)(o2 + st);
                     const uint32_t slot = gg % SLOTS;
-                    const int y = ys + o2 + st - 4;                   // < ys: virtual row
-                    const bool real = o2 >= 4;
+                    const int y = ys + o2 + st - (KS - 1);            // < ys: virtual row
+                    const bool real = o2 >= KS - 1;
                     // K split, last part: what the first part left is requested BEFORE the wait for this row's accumulator
                     // (the epilogue of a tensor-bound layer spends most of its time in that wait)
-                    float4 ps[NPAD / 4];
-                    if (p.psum_in && real) {
+                    float4 ps[KS == 5 ? NPAD / 4 : 1];
+                    if constexpr (KS == 5) if (p.psum_in && real) {
                         const bool ok = xok && y < p.h;
 #pragma unroll
                         for (int c4 = 0; c4 < NPAD / 4; ++c4)
@@ -311,7 +320,7 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm, con
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&s_tempty[slot]);      // slot free for the window of input row gg+4
                     if (!real) continue;
-                    if (p.psum_out) {                                   // K split, first part: raw fp32 sums, nothing else
+                    if constexpr (KS == 5) if (p.psum_out) {                // K split, first part: raw fp32 sums, nothing else
                         if (xok && y < p.h) {
 #pragma unroll
                             for (int c4 = 0; c4 < NPAD / 4; ++c4)
@@ -321,7 +330,7 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm, con
                         }
                         continue;
                     }
-                    if (p.psum_in) {                                    // K split, last part: add what the first part left
+                    if constexpr (KS == 5) if (p.psum_in) {                 // K split, last part: add what the first part left
 #pragma unroll
                         for (int c4 = 0; c4 < NPAD / 4; ++c4) {
                             v[4 * c4] = __float_as_uint(__uint_as_float(v[4 * c4]) + ps[c4].x);
@@ -392,7 +401,7 @@ conv_fold_kernel(const FoldParams p, const __grid_constant__ CUtensorMap tm, con
                     }
                 }
             }
-            g += (uint32_t)(rows + 4);
+            g += (uint32_t)(rows + KS - 1);
         }
     }
 
@@ -419,14 +428,15 @@ EncodeTiledFn fold_get_encode() {
     return fn;
 }
 
-template <typename T, int NPAD, int NPL, int RING, int SLOTS, int EG, bool PX = false>
+template <typename T, int NPAD, int NPL, int RING, int SLOTS, int EG, bool PX = false, int KS = 5, bool SRC2 = false>
 int launch_fold_t(pcs_ctx* ctx, const FoldConvArgs& a) {
-    constexpr int NF = fold_up16(5 * NPAD);
+    constexpr int NF = fold_up16(KS * NPAD);
     FoldParams p{};
     p.n = a.n; p.h = a.h; p.w = a.w;
     p.wimg = reinterpret_cast<const uint8_t*>(a.wimg); p.cout = a.cout; p.relu = a.relu;
-    static_assert(NPAD <= 48, "bias travels in the parameter block");
-    for (int i = 0; i < 48; ++i) p.bias[i] = i < a.cout ? a.h_bias[i] : 0.f;
+    static_assert(NPAD <= 64, "bias travels in the parameter block");
+    for (int i = 0; i < 64; ++i) p.bias[i] = i < a.cout ? a.h_bias[i] : 0.f;
+    if (KS != 5 && (a.psum_in || a.psum_out || a.plog)) return set_err(ctx, PCS_ERR_ARG, "conv_fold: partial sums / logits share are for the 5x5 kernels");
     p.out = a.out; p.out_cp = a.out_cp; p.pool = a.pool_out; p.pool_cp = a.pool_cp;
     p.out_c0 = a.o0;
     p.psum_out = reinterpret_cast<float4*>(a.psum_out);
@@ -442,7 +452,7 @@ int launch_fold_t(pcs_ctx* ctx, const FoldConvArgs& a) {
             if (ctx->device < 64) g_skip_owner[ctx->device] = ctx->model_stamp;
         }
     }
-    p.w_bytes = (uint32_t)FoldK<NPL, PX>::NMMA * 2 * NF * 16;  // [K step][K half][N' rows][16 B]
+    p.w_bytes = (uint32_t)FoldK<NPL, PX, KS>::NMMA * 2 * NF * 16;  // [K step][K half][N' rows][16 B]
     p.strips = (a.w + F_SW - 1) / F_SW;
     // equal ranges of whole row quads (row pairs for the pooling, pair rotation over the epilogue groups)
     p.total_rows = (long long)a.n * p.strips * a.h;
@@ -452,7 +462,9 @@ int launch_fold_t(pcs_ctx* ctx, const FoldConvArgs& a) {
     EncodeTiledFn enc = fold_get_encode();
     if (!enc) return set_err(ctx, PCS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     const cuuint64_t planes = (cuuint64_t)a.src.cp / 8;
-    if ((int)planes != NPL - (PX ? 1 : 0) || PX != (a.pair_src != nullptr))
+    if (SRC2 != (a.src2.p != nullptr) || (SRC2 && (a.src2.cp != a.src.cp || (int)planes * 2 != NPL)))
+        return set_err(ctx, PCS_ERR_ARG, "conv_fold: two sources of %d planes each expected", NPL / 2);
+    if ((!SRC2 && (int)planes != NPL - (PX ? 1 : 0)) || PX != (a.pair_src != nullptr))
         return set_err(ctx, PCS_ERR_ARG, "conv_fold: source has %d planes%s, kernel expects %d", (int)planes, a.pair_src ? " + pair units" : "", NPL);
     const cuuint64_t dims[4] = {(cuuint64_t)a.w * 2, (cuuint64_t)a.h, planes, (cuuint64_t)a.n};
     const cuuint64_t strides[3] = {(cuuint64_t)a.w * 16, (cuuint64_t)a.h * a.w * 16, planes * a.h * a.w * 16};
@@ -464,6 +476,12 @@ int launch_fold_t(pcs_ctx* ctx, const FoldConvArgs& a) {
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_err(ctx, PCS_ERR_CUDA, "conv_fold: cuTensorMapEncodeTiled failed with %d", (int)r);
     CUtensorMap tm2 = tm;
+    if (SRC2) {     // the second tensor of the concatenation: same geometry
+        r = enc(&tm2, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(a.src2.p), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return set_err(ctx, PCS_ERR_CUDA, "conv_fold: cuTensorMapEncodeTiled (second source) failed with %d", (int)r);
+    }
     if (PX) {       // the pair units: w + 1 per row, one "plane"
         const cuuint64_t pdims[4] = {(cuuint64_t)(a.w + 1) * 2, (cuuint64_t)a.h, 1, (cuuint64_t)a.n};
         const cuuint64_t pstrides[3] = {(cuuint64_t)(a.w + 1) * 16, (cuuint64_t)a.h * (a.w + 1) * 16, (cuuint64_t)a.h * (a.w + 1) * 16};
@@ -479,11 +497,11 @@ int launch_fold_t(pcs_ctx* ctx, const FoldConvArgs& a) {
     if (smem + 2 * 1024 > 227 * 1024) return set_err(ctx, PCS_ERR_ARG, "conv_fold: %zu bytes of shared memory needed", smem);
     static size_t attr_set[64] = {};             // the attribute is per device
     if (ctx->device >= 64 || attr_set[ctx->device] < smem) {
-        PCS_CUDA(ctx, cudaFuncSetAttribute(conv_fold_kernel<T, NPAD, NPL, RING, SLOTS, EG, PX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PCS_CUDA(ctx, cudaFuncSetAttribute(conv_fold_kernel<T, NPAD, NPL, RING, SLOTS, EG, PX, KS, SRC2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (ctx->device < 64) attr_set[ctx->device] = smem;
     }
     const int grid = (int)((p.total_rows + p.rows_per_cta - 1) / p.rows_per_cta);
-    PCS_CUDA(ctx, launch_kernel_pdl(conv_fold_kernel<T, NPAD, NPL, RING, SLOTS, EG, PX>, dim3(grid), dim3(64 + EG * 128), smem, ctx->stream,
+    PCS_CUDA(ctx, launch_kernel_pdl(conv_fold_kernel<T, NPAD, NPL, RING, SLOTS, EG, PX, KS, SRC2>, dim3(grid), dim3(64 + EG * 128), smem, ctx->stream,
                                     ctx->pdl, p, tm, tm2));
     PCS_LAUNCH_CHECK(ctx, "conv_fold_kernel");
     return PCS_OK;
@@ -492,6 +510,11 @@ int launch_fold_t(pcs_ctx* ctx, const FoldConvArgs& a) {
 template <typename T>
 int launch_fold_dispatch(pcs_ctx* ctx, const FoldConvArgs& a) {
     const int key = a.npad * 10 + a.nplanes;
+    if (a.k == 3) {         // U-Net, 64 output channels at full resolution: N' = 192, eight slots of 64 columns, two epilogue groups
+        if (a.npad == 64 && a.nplanes == 8 && !a.src2.p) return launch_fold_t<T, 64, 8, 4, 8, 2, false, 3, false>(ctx, a);
+        if (a.npad == 64 && a.nplanes == 16 && a.src2.p) return launch_fold_t<T, 64, 16, 2, 8, 2, false, 3, true>(ctx, a);
+        return set_err(ctx, PCS_ERR_ARG, "conv_fold: no 3x3 instantiation for N=%d planes=%d", a.npad, a.nplanes);
+    }
     if (a.pair_src) {
         if (key == 323) return launch_fold_t<T, 32, 3, 16, 16, 4, true>(ctx, a);    // conv2 <- conv1 with channels 16..19 as pixel-pair units
         return set_err(ctx, PCS_ERR_ARG, "conv_fold: no pixel-pair instantiation for N=%d planes=%d", a.npad, a.nplanes);
@@ -515,6 +538,7 @@ int launch_fold_dispatch(pcs_ctx* ctx, const FoldConvArgs& a) {
 
 // (N tile, source planes) pairs with an instantiation; the resident weights + input ring must fit shared memory
 bool fold_supported(int k, int npad, int nplanes) {
+    if (k == 3) return npad == 64 && (nplanes == 8 || nplanes == 16);       // 16 planes = two concatenated sources of 8
     if (k != 5) return false;
     const int key = npad * 10 + nplanes;
     return key == 323 || key == 484 || key == 485 || key == 325 || key == 328 || key == 488 || key == 404 || key == 405 || key == 408;
@@ -524,8 +548,9 @@ bool fold_supported(int k, int npad, int nplanes) {
 // [ci0, ci0 + cin) and the output channels [o0, o0 + ncols) of a layer with weights w32[25][cin_total][cout_total]:
 // the N blocks run from the oldest output row of the window (dy = 4) to the newest (dy = 0).
 size_t fold_weight_image(const float* w32, int cin_total, int cout_total, int ci0, int cin, int o0, int ncols, int npad,
-                         int precision, std::vector<uint16_t>& out, bool pairx) {
-    const int npl = pad8(cin) / 8, pairs = npl / 2, odd = npl & 1, nmma = pairs * 5 + odd * (pairx ? 2 : 3), nf = (5 * npad + 15) / 16 * 16;
+                         int precision, std::vector<uint16_t>& out, bool pairx, int ks) {
+    const int npl = pad8(cin) / 8, pairs = npl / 2, odd = npl & 1, nmma = pairs * ks + odd * (pairx ? 2 : 3), nf = (ks * npad + 15) / 16 * 16;
+    if (ks != 5 && (odd || pairx)) { out.clear(); return 0; }
     if (pairx && (!odd || cin - (npl - 1) * 8 > 4)) { out.clear(); return 0; }      // pair units carry four channels
     out.assign((size_t)nmma * 2 * nf * 8, 0);
     auto conv = [&](float v) -> uint16_t {
@@ -535,7 +560,7 @@ size_t fold_weight_image(const float* w32, int cin_total, int cout_total, int ci
     for (int q = 0; q < nmma; ++q)
         for (int half = 0; half < 2; ++half) {
             int plane, dx;
-            if (q < pairs * 5) { plane = 2 * (q / 5) + half; dx = q % 5; }
+            if (q < pairs * ks) { plane = 2 * (q / ks) + half; dx = q % ks; }
             else if (pairx) {
                 // K half = one pair unit = [4 channels at tap d | the same channels at tap d + 1]: step 0 holds the taps
                 // (0,1) | (2,3), step 1 the taps (3,4) | (4,5) of which only tap 4 of the first half carries weights
@@ -555,13 +580,13 @@ size_t fold_weight_image(const float* w32, int cin_total, int cout_total, int ci
                 dx = (t == 0 ? 0 : t + 1) + half;
                 if (t == 2 && half == 0) continue;
             }
-            for (int dy = 0; dy < 5; ++dy)
+            for (int dy = 0; dy < ks; ++dy)
                 for (int o = 0; o < ncols; ++o)
                     for (int e = 0; e < 8; ++e) {
                         const int ci = plane * 8 + e;
                         if (ci >= cin) continue;
-                        const float v = w32[((size_t)(dy * 5 + dx) * cin_total + ci0 + ci) * cout_total + o0 + o];
-                        out[(((size_t)q * 2 + half) * nf + (4 - dy) * npad + o) * 8 + e] = conv(v);
+                        const float v = w32[((size_t)(dy * ks + dx) * cin_total + ci0 + ci) * cout_total + o0 + o];
+                        out[(((size_t)q * 2 + half) * nf + (ks - 1 - dy) * npad + o) * 8 + e] = conv(v);
                     }
         }
     return out.size() * sizeof(uint16_t);
