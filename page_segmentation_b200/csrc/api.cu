@@ -686,6 +686,10 @@ int pcs_model_load(pcs_ctx* ctx, int arch, int n_classes, int precision, const p
                 // conv9a's concatenation are read by one launch through two tensor maps
                 PCS_TRY(add_part(0, 0, L.cin, 0, 64, 64, 0));
                 L.fold.back().both = nsrc == 2;
+            } else if (fold3 && L.k == 3 && L.kind == K_CONV && L.cout == 128 && nsrc == 1 && (L.cin == 64 || L.cin == 128)) {
+                // conv2a / conv2b / conv8b (half resolution, 128 output channels): two launches of 64 output channels each
+                PCS_TRY(add_part(0, 0, L.cin, 0, 64, 64, 0));
+                PCS_TRY(add_part(0, 0, L.cin, 64, 64, 64, 0));
             } else if (L.k == 5 && nsrc == 1 && fold_supported(5, fnp1, pad8(L.cin) / 8)) {
                 PCS_TRY(add_part(0, 0, L.cin, 0, L.cout, fnp1, 0));
             } else if (fold40 && L.k == 5 && nsrc == 1 && L.cout == 80 && fold_supported(5, 40, pad8(L.cin) / 8)) {

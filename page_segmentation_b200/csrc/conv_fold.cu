@@ -513,6 +513,7 @@ int launch_fold_dispatch(pcs_ctx* ctx, const FoldConvArgs& a) {
     if (a.k == 3) {         // U-Net, 64 output channels at full resolution: N' = 192, eight slots of 64 columns, two epilogue groups
         if (a.npad == 64 && a.nplanes == 8 && !a.src2.p) return launch_fold_t<T, 64, 8, 4, 8, 2, false, 3, false>(ctx, a);
         if (a.npad == 64 && a.nplanes == 16 && a.src2.p) return launch_fold_t<T, 64, 16, 2, 8, 2, false, 3, true>(ctx, a);
+        if (a.npad == 64 && a.nplanes == 16) return launch_fold_t<T, 64, 16, 2, 8, 2, false, 3, false>(ctx, a);
         return set_err(ctx, PCS_ERR_ARG, "conv_fold: no 3x3 instantiation for N=%d planes=%d", a.npad, a.nplanes);
     }
     if (a.pair_src) {

@@ -7,11 +7,12 @@ from page_segmentation_b200 import synth
 import torch
 from page_segmentation_b200.runtime import PageBatchEngine
 lut = np.array([[255, 255, 255], [255, 0, 0], [0, 255, 0]], np.uint8)
-eng = PageBatchEngine("fcn_skip", synth.make_weights("fcn_skip", 3, seed=0), 3, lut=lut)
+ARCH = "unet" if "unet" in sys.argv[1:] else "fcn_skip"
+eng = PageBatchEngine(ARCH, synth.make_weights(ARCH, 3, seed=0), 3, lut=lut)
 base = np.stack([synth.make_page(s) for s in range(8)])
 Hs, Ws = synth.scaled_shape(synth.A4_H, synth.A4_W, 1 / 3)
-CC = len(sys.argv) > 1 and sys.argv[1] == "cc"          # with cc_majority + segment extraction (BASELINE configs[3])
-for n in (4, 8, 16, 32, 64):
+CC = "cc" in sys.argv[1:]          # with cc_majority + segment extraction (BASELINE configs[3])
+for n in ((8,) if ARCH == "unet" else (4, 8, 16, 32, 64)):
     d = torch.from_numpy(np.concatenate([base] * max(1, n // 8))[:n]).cuda()
     d_stats = torch.empty((n, 3, 4096, 5), dtype=torch.int32, device="cuda")
     d_ncomp = torch.empty((n, 3), dtype=torch.int32, device="cuda")
