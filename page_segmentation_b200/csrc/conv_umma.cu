@@ -186,6 +186,16 @@ conv_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm0, co
         constexpr uint32_t b_lo_c = (((uint32_t)NPAD * 16u >> 4) & 0x3fffu) << 16;   // LBO field of B
         constexpr uint32_t B_TAP16 = 2u * NPAD;                                      // 16-byte units per tap
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            // UpSampling2D + 2x2 convolution on the low-resolution grid (KS = 2, N column = parity * co_t + o): parity (i, j)
+            // of the output pixel only sees the low-resolution taps dy <= i, dx <= j -- 9 of the 16 (parity, tap) blocks
+            // of the operand image are non-zero -- so the taps beyond the largest i / j of this N tile's parities are skipped
+            int tap_dy = KS - 1, tap_dx = KS - 1;
+            if (MODE == EPI_DECONV && KS == 2) {
+                const int nt = (tile % tiles_per_page) % p.ntiles_n;
+                const int par_lo = (nt * NPAD) / p.co_t, par_hi = min(3, (nt * NPAD + NPAD - 1) / p.co_t);
+                tap_dy = par_hi >> 1;
+                tap_dx = par_lo != par_hi ? 1 : (par_lo & 1);
+            }
             mbar_wait(&s_tempty[acc], acc_phase ^ 1u);
             tc_fence_after();
             for (int kc = 0; kc < p.nchunks; ++kc) {
@@ -203,7 +213,7 @@ conv_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm0, co
                         for (int dy = 0; dy < KS; ++dy) {
 #pragma unroll
                             for (int dx = 0; dx < KS; ++dx) {
-                                constexpr int dummy = 0; (void)dummy;
+                                if (dy > tap_dy || dx > tap_dx) continue;
                                 const uint32_t a_off = (uint32_t)((r + dy) * TILE_M + dx);      // 16-byte units
                                 const uint32_t b_off = (uint32_t)(dy * KS + dx) * B_TAP16;
                                 tc_mma(d0 + (uint32_t)(r * NPAD), a_lo0 + a_off, a_hi, b_lo0 + b_off, b_hi, IDESC,
