@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpcseg_b200.so")
 OBJ_DIR = os.path.join(HERE, "build")
-SOURCES = ["api.cu", "preprocess.cu", "conv_direct.cu", "conv_umma.cu", "conv1_umma.cu", "conv_fold.cu", "conv12_fused.cu", "epilogue.cu", "ccl.cu", "regions.cu", "png.cu", "output.cu", "train.cu", "train_tc.cu"]
+SOURCES = ["api.cu", "preprocess.cu", "conv_direct.cu", "conv_umma.cu", "conv1_umma.cu", "conv_fold.cu", "conv12_fused.cu", "epilogue.cu", "ccl.cu", "ccl_onepass.cu", "regions.cu", "png.cu", "output.cu", "train.cu", "train_tc.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
