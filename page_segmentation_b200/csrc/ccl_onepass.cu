@@ -5,7 +5,7 @@
 namespace pcs {
 
 // ---------------------------------------------------------------------------
-// Segment extraction, every class in ONE labelling (n_classes <= kMcMaxClasses).  The per-class path above labels
+// Segment extraction, every class in ONE labelling (n_classes <= kMcMaxClasses).  The per-class path (ccl.cu) labels
 // (pred == c) once per class: three tile / border / accumulate / rank rounds per page, each reading the whole class
 // map, and one set of five global atomics per run.  Every pixel belongs to exactly one of those labellings, so the
 // class map is labelled once with "same byte" as the neighbour relation:
@@ -15,14 +15,16 @@ namespace pcs {
 //               with shared-memory atomics in a table indexed by the rank of the root among the tile's root
 //               candidates (run starts without an equal upper pixel; candidates beyond the table go to global
 //               atomics), and written once per tile-local root together with a bit mask of those roots;
-//   mc_border : unions across tile borders on the global parents;
+//   mc_border : unions across tile borders on the global parents, one lane per pixel of a tile's first row and one
+//               thread per row and vertical tile border;
 //   mc_fold   : tile-local roots that lost their root status add their record to the component's root (one set of
 //               atomics per tile and component, not per run); roots counted per class and warp (= 1024 pixels in
 //               raster order), box and pixel count of every class for row 0 of the tables;
 //   scan, mc_write : label = rank of the root among the roots of ITS class (cv2's numbering of that class's
 //               labelling), stats row written from the root's record.
+// The table of tile-local root candidates holds 512 records: room for five tiles per SM (1 024 records: four tiles, 5-8 %
+// slower; PCSEG_MC_CAP=1024).
 // ---------------------------------------------------------------------------
-// tile-local root candidates with shared-memory accumulators: 512 records leave room for five tiles per SM (1 024: four)
 
 __device__ __forceinline__ unsigned eq_bits32(const unsigned (&a)[8], const unsigned (&b)[8]) {
     unsigned m = 0;
