@@ -636,10 +636,10 @@ int launch_cc_majority(pcs_ctx* ctx, uint8_t* d_pred, const uint8_t* d_binary, i
     if (n_classes <= kVoteClasses && !vote_global) {
         unsigned* rootmask = reinterpret_cast<unsigned*>(hist + total * n_classes);
         cudaStream_t st = ctx->stream;
-        static bool attr_set = false;
-        if (!attr_set) {
+        static bool attr_set[64] = {};          // the attribute is per device
+        if (ctx->device >= 64 || !attr_set[ctx->device]) {
             PCS_CUDA(ctx, cudaFuncSetAttribute(ccv_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VoteTileSmem)));
-            attr_set = true;
+            if (ctx->device < 64) attr_set[ctx->device] = true;
         }
         static const bool poison = [] { const char* e = getenv("PCSEG_CCL_POISON"); return e && e[0] == '1'; }();
         if (poison) PCS_CUDA(ctx, cudaMemsetAsync(parent, 0x7f, (total * (1 + (size_t)n_classes) + mask_words) * 4, st));

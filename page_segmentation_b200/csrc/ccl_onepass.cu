@@ -416,11 +416,11 @@ static int mc_label(pcs_ctx* ctx, const uint8_t* d_pred, int n, int H, int W, in
     b.extra = b.clsbox + box_words;
     cudaStream_t st = ctx->stream;
     static const bool big_table = [] { const char* e = getenv("PCSEG_MC_CAP"); return e && atoi(e) >= 1024; }();   // A/B switch
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};          // the attribute is per device
+    if (ctx->device >= 64 || !attr_set[ctx->device]) {
         PCS_CUDA(ctx, cudaFuncSetAttribute(mc_tile_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(McTileSmem<512>)));
         PCS_CUDA(ctx, cudaFuncSetAttribute(mc_tile_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(McTileSmem<1024>)));
-        attr_set = true;
+        if (ctx->device < 64) attr_set[ctx->device] = true;
     }
     // diagnosis (PCSEG_CCL_POISON=1): parents / records / root masks start as 0x7f7f7f7f, so a pass that reads one the
     // labelling did not write (parents exist only on tile edges and at roots) walks out of the page instead of finding a
