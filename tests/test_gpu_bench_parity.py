@@ -210,3 +210,48 @@ def test_unet_a4_vs_oracle(ctx, precision):
     d_one = torch.empty((1, h, w), dtype=torch.uint8, device="cuda")
     c.forward(d_img[1:2].contiguous(), None, 1, h, w, d_one)
     assert bool((d_one[0] == d_labels[1]).all())
+
+
+def test_stress_variant_full_resolution_page(ctx):
+    """SURVEY section 8(d)'s stress variant: `line_height_px = 6`, i.e. scale 1 -- the network runs on the 3508x2480 page
+    itself (padded grid 3520x2496: 21 strips, 8.9x the pixels of a normalised page, planes of > 2^27 elements).  The largest
+    single-page size the path is specified for: device preprocess bit-exact against the oracle (prepare_images,
+    dataset.py:131-150, at scale 1), device logits within the fp16-operand tolerance of the fp32 oracle
+    (network.py:248-260), class map = first-max argmax of the device logits, and every pixel whose class differs from the
+    fp32 oracle's a near-tie (fp32 top-2 margin <= 2 x the page's largest logit error).  (No fp64 run at this size: it costs
+    a minute of CPU; the fp64 near-tie analysis is done at A4 above.)"""
+    from page_segmentation_b200.lib.network import Network
+    page = synth.make_page(7)
+    H, W_ = page.shape
+    img, binary = opipe.prepare_images(page, page, 6, 6)
+    assert img.shape == (H, W_)
+    W = synth.make_weights("fcn_skip", 3, seed=0)
+    net = Network("Predict", n_classes=3, weights=W, precision="fp16")
+    c = net._context()
+    d_page = torch.from_numpy(page[None]).cuda()
+    d_img = torch.empty((1, H, W_), dtype=torch.uint8, device="cuda")
+    d_bin = torch.empty((1, H, W_), dtype=torch.uint8, device="cuda")
+    c.preprocess(d_page, d_page, 1, H, W_, H, W_, d_img, d_bin)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(d_img[0].cpu().numpy(), img)
+    np.testing.assert_array_equal(d_bin[0].cpu().numpy(), binary)
+    d_labels = torch.empty((1, H, W_), dtype=torch.uint8, device="cuda")
+    d_logits = torch.empty((1, H, W_, 3), dtype=torch.float32, device="cuda")
+    c.forward(d_img, None, 1, H, W_, d_labels, d_logits, None)
+    torch.cuda.synchronize()
+    logit, pred = d_logits[0].cpu().numpy(), d_labels[0].cpu().numpy()
+    l32 = onet.Forward("fcn_skip", W, 3).logits(img)[0]
+    err = np.abs(logit - l32).max()
+    print(f"stress variant: max |logit - fp32| = {err:.3e}, agreement with the fp32 oracle = {(pred == l32.argmax(-1)).mean():.6f}")
+    assert err <= TOL["fp16"]["f32_max"], err
+    np.testing.assert_array_equal(pred, logit.argmax(-1))
+    ref = l32.argmax(-1)
+    assert (pred == ref).mean() >= TOL["fp16"]["agree"]
+    bad = pred != ref
+    if bad.any():
+        s = np.sort(l32, -1)
+        assert (s[..., -1] - s[..., -2])[bad].max() <= 2 * err
+    # labels-only schedule (the bench's) on the same page
+    d_labels2 = torch.empty_like(d_labels)
+    c.forward(d_img, None, 1, H, W_, d_labels2)
+    assert bool((d_labels2 == d_labels).all())
