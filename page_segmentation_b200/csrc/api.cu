@@ -505,6 +505,8 @@ void pcs_ctx_destroy(pcs_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    for (cudaStream_t cs : ctx->copy_streams)
+        if (cs) cudaStreamSynchronize(cs);                 // submitted host calls may still be downloading
     output_writer_destroy(ctx);
     free_layers(ctx);
     clear_stage_times(ctx);
@@ -519,6 +521,8 @@ void pcs_ctx_destroy(pcs_ctx* ctx) {
     for (int i = 0; i < pcs_ctx::kHostBufs; ++i)
         if (ctx->ev_h2d[i]) { cudaEventDestroy(ctx->ev_h2d[i]); cudaEventDestroy(ctx->ev_comp[i]); cudaEventDestroy(ctx->ev_d2h[i]); cudaEventDestroy(ctx->ev_sizes[i]); }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    for (cudaEvent_t e : ctx->ev_call)
+        if (e) cudaEventDestroy(e);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->ev_aux_fork) cudaEventDestroy(ctx->ev_aux_fork);
     if (ctx->ev_aux_join) cudaEventDestroy(ctx->ev_aux_join);
@@ -536,6 +540,8 @@ int pcs_set_stream(pcs_ctx* ctx, void* cuda_stream) {
 int pcs_synchronize(pcs_ctx* ctx) {
     if (!ctx) return PCS_ERR_ARG;
     PCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // submitted host calls (pcs_predict_pages_*_submit) do not join the compute stream to their downloads
+    if (ctx->call_seq) PCS_CUDA(ctx, cudaEventSynchronize(ctx->ev_call[(ctx->call_seq - 1) % pcs_ctx::kCallRing]));
     return PCS_OK;
 }
 
@@ -1072,13 +1078,19 @@ static int predict_pages_host_body(pcs_ctx* ctx, const uint8_t* h_grey, const ui
                                    int cc_majority, const uint8_t* lut, uint8_t* h_image, uint8_t* h_binary, uint8_t* h_labels,
                                    uint8_t* h_color, uint8_t* h_overlay, uint8_t* h_inverted, uint8_t* h_png, size_t png_stride,
                                    uint64_t* h_png_sizes, int32_t* h_stats = nullptr, int max_components = 0, int32_t* h_ncomp = nullptr,
-                                   const uint32_t* h_bits = nullptr, int level0 = 0, int level1 = 0, uint32_t* h_binary_bits = nullptr) {
+                                   const uint32_t* h_bits = nullptr, int level0 = 0, int level1 = 0, uint32_t* h_binary_bits = nullptr,
+                                   uint64_t* ticket = nullptr) {
+    // ticket: the streaming form (pcs_predict_pages_*_submit): return once the work is queued, *ticket names the call for pcs_wait_pages
     // h_bits: the pages arrive bit-packed (pcs_preprocess_bits) instead of as uint8 pages; h_binary_bits: `data.binary` leaves bit-packed
     if (!ctx || (!h_bits && (!h_grey || !h_bin))) return ctx ? set_err(ctx, PCS_ERR_ARG, "predict_pages_host: null input") : PCS_ERR_ARG;
     if (h_stats && (max_components <= 0 || !h_labels)) return set_err(ctx, PCS_ERR_ARG, "predict_pages_segments: max_components and the class map are required");
     if (!ctx->model_ready) return set_err(ctx, PCS_ERR_STATE, "pcs_predict_pages_host before pcs_model_load");
     if (n <= 0 || H <= 0 || W <= 0 || Hs <= 0 || Ws <= 0) return set_err(ctx, PCS_ERR_ARG, "predict_pages_host: bad shape");
     const bool want_png = h_png != nullptr;
+    const bool submit = ticket != nullptr;
+    if (submit && want_png) return set_err(ctx, PCS_ERR_ARG, "predict_pages: the file call has no streaming form (the host places the files)");
+    const bool was_chain = ctx->host_chain_ok;
+    ctx->host_chain_ok = false;                 // set again when this call has queued completely
     const bool want_masks = h_color || h_overlay || h_inverted || want_png;
     if (want_masks && !lut) return set_err(ctx, PCS_ERR_ARG, "predict_pages_host: colour outputs need a LUT");
     const size_t png_bound = want_png ? png_file_bytes(Hs, Ws, 3, 1) : 0;
@@ -1102,6 +1114,7 @@ static int predict_pages_host_body(pcs_ctx* ctx, const uint8_t* h_grey, const ui
             PCS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_sizes[i], cudaEventDisableTiming));
         }
         PCS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        for (int i = 0; i < pcs_ctx::kCallRing; ++i) PCS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_call[i], cudaEventDisableTiming));
     }
     cudaStream_t s_in = ctx->copy_streams[0], s_out = ctx->copy_streams[1], st = ctx->stream;
     // schedule "head,chunk,tail[,nbuf]": pages of the first chunk, of the steady chunks, of the last chunk
@@ -1135,6 +1148,7 @@ static int predict_pages_host_body(pcs_ctx* ctx, const uint8_t* h_grey, const ui
         for (int v : fixed) chunk = std::max(chunk, v);
     } else if (upload_bound && !getenv("PCSEG_HOST_SCHED") && !getenv("PCSEG_HOST_CHUNK")) {
         fixed = {std::min(4, n), std::min(10, n)};
+        if (submit && was_chain) fixed = {std::min(10, n)};       // a chained call has no fill to keep short
     } else if (h_stats && !h_bits && !want_masks && !getenv("PCSEG_HOST_SCHED") && !getenv("PCSEG_HOST_CHUNK")) {
         // segment call with compact results: kernel-bound (190 us per page against 158 us of upload), so a short fill and then
         // launches large enough for the labelling kernels: 6, 12, 16, 16 ... (4 180 -> 4 310 pages/s; tools/sweep_chunks.py segments)
@@ -1187,6 +1201,14 @@ static int predict_pages_host_body(pcs_ctx* ctx, const uint8_t* h_grey, const ui
         }
         ctx->stage_bytes = need;
     }
+    // A submit chains onto the submit before it when both carve the staging memory the same way: the buffers then keep
+    // rotating across the call boundary (buffer = running chunk number % nbuf) and only the per-buffer events order the
+    // three streams, so this call's upload runs under the kernels of the call before.  Any other call starts behind
+    // everything queued so far (the fork below).
+    const std::vector<size_t> layout = {(size_t)reinterpret_cast<uintptr_t>(ctx->stage), (size_t)reinterpret_cast<uintptr_t>(ctx->stream), (size_t)nbuf, (size_t)chunk, src1, dst1, (size_t)same,
+                                        (size_t)(h_bits != nullptr), in_bytes, out_bytes, png_bytes, seg_bytes, bb_bytes};
+    const bool chained = submit && was_chain && layout == ctx->host_layout;
+    const uint64_t seq0 = chained ? ctx->host_seq : 0;
     struct Buf { uint8_t *grey, *bin, *image, *binary, *labels, *color, *overlay, *inverted, *png; uint64_t* png_sizes; int32_t *stats, *ncomp; uint32_t* bbits; } buf[pcs_ctx::kHostBufs];
     {
         uint8_t* p = reinterpret_cast<uint8_t*>(ctx->stage);
@@ -1205,7 +1227,7 @@ static int predict_pages_host_body(pcs_ctx* ctx, const uint8_t* h_grey, const ui
         }
     }
     // PCSEG_TRACE_HOST: per-chunk device timeline (timing events on the three streams), printed at the end
-    const bool trace = getenv("PCSEG_TRACE_HOST") != nullptr;
+    const bool trace = getenv("PCSEG_TRACE_HOST") != nullptr && !submit;
     std::vector<cudaEvent_t> tev;
     cudaEvent_t t0 = nullptr;
     auto mark = [&](cudaStream_t s) {
@@ -1213,8 +1235,8 @@ static int predict_pages_host_body(pcs_ctx* ctx, const uint8_t* h_grey, const ui
         cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); tev.push_back(e);
     };
     auto enqueue_h2d = [&](int c) -> int {
-        const int b = c % nbuf, p0 = first[c], m = count[c];
-        if (c >= nbuf) PCS_CUDA(ctx, cudaStreamWaitEvent(s_in, ctx->ev_comp[b], 0));   // input buffer consumed by chunk c-nbuf
+        const int b = (int)((seq0 + c) % nbuf), p0 = first[c], m = count[c];
+        if (c >= nbuf || chained) PCS_CUDA(ctx, cudaStreamWaitEvent(s_in, ctx->ev_comp[b], 0));   // input buffer consumed by the chunk nbuf before
         mark(s_in);
         if (h_bits) {       // packed rows of in_words words into the padded device pitch; the pad words read as zero
             PCS_CUDA(ctx, cudaMemset2DAsync(buf[b].grey + in_words * 4, bm_words * 4, 0, (bm_words - in_words) * 4, m, s_in));
@@ -1230,14 +1252,18 @@ static int predict_pages_host_body(pcs_ctx* ctx, const uint8_t* h_grey, const ui
     };
     // order the pipeline after whatever the caller already queued on the compute stream
     if (trace) { cudaEventCreate(&t0); cudaEventRecord(t0, st); }
-    PCS_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
-    PCS_CUDA(ctx, cudaStreamWaitEvent(s_in, ctx->ev_fork, 0));
-    PCS_CUDA(ctx, cudaStreamWaitEvent(s_out, ctx->ev_fork, 0));
+    if (!chained) {
+        // (a submit does not join the compute stream to its downloads: wait for the last one here)
+        if (ctx->call_seq) PCS_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_call[(ctx->call_seq - 1) % pcs_ctx::kCallRing], 0));
+        PCS_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+        PCS_CUDA(ctx, cudaStreamWaitEvent(s_in, ctx->ev_fork, 0));
+        PCS_CUDA(ctx, cudaStreamWaitEvent(s_out, ctx->ev_fork, 0));
+    }
     const int ahead = nbuf - 1;                                                        // copies in flight ahead of the compute
     // PNG mode: the file lengths of a chunk reach the host first; once they are there the files themselves are copied
     // (only their bytes, not the worst-case buffers).  The host waits for chunk c-1 after it has queued chunk c.
     auto finish_files = [&](int c) -> int {
-        const int b = c % nbuf, p0 = first[c], m = count[c];
+        const int b = c % nbuf, p0 = first[c], m = count[c];             // (PNG mode never chains: seq0 = 0)
         PCS_CUDA(ctx, cudaEventSynchronize(ctx->ev_sizes[b]));
         const uint64_t* sz = ctx->h_png_sizes + (size_t)b * 3 * 64;
         for (int k = 0; k < 3; ++k)
@@ -1253,10 +1279,10 @@ static int predict_pages_host_body(pcs_ctx* ctx, const uint8_t* h_grey, const ui
     };
     for (int c = 0; c < std::min(ahead, nchunks); ++c) PCS_TRY(enqueue_h2d(c));
     for (int c = 0; c < nchunks; ++c) {
-        const int b = c % nbuf, p0 = first[c], m = count[c];
+        const int b = (int)((seq0 + c) % nbuf), p0 = first[c], m = count[c];
         if (c + ahead < nchunks) PCS_TRY(enqueue_h2d(c + ahead));
         PCS_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_h2d[b], 0));
-        if (c >= nbuf) PCS_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_d2h[b], 0));       // output buffer drained by chunk c-nbuf
+        if (c >= nbuf || chained) PCS_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_d2h[b], 0));       // output buffer drained by the chunk nbuf before
         mark(st);
         if (h_bits) PCS_TRY(pcs_preprocess_bits(ctx, reinterpret_cast<const uint32_t*>(buf[b].grey), bm_words, m, H, W, level0, level1, Hs, Ws,
                                                 buf[b].image, buf[b].binary));
@@ -1310,6 +1336,16 @@ static int predict_pages_host_body(pcs_ctx* ctx, const uint8_t* h_grey, const ui
         }
     }
     if (want_png) PCS_TRY(finish_files(nchunks - 1));
+    if (submit) {
+        // streaming form: nothing waits here.  The call's ticket is an event behind its last download; the compute stream is
+        // NOT joined to the downloads (the next chained call's kernels need not wait for them), pcs_wait_pages is the join
+        PCS_CUDA(ctx, cudaEventRecord(ctx->ev_call[ctx->call_seq % pcs_ctx::kCallRing], s_out));
+        *ticket = ctx->call_seq++;
+        ctx->host_seq = seq0 + (uint64_t)nchunks;
+        ctx->host_layout = layout;
+        ctx->host_chain_ok = true;
+        return PCS_OK;
+    }
     // the compute stream joins the output stream, so the caller's stream order covers the whole call
     PCS_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_d2h[(nchunks - 1) % nbuf], 0));
     PCS_CUDA(ctx, cudaStreamSynchronize(s_out));
@@ -1345,10 +1381,11 @@ static int predict_pages_host_impl(pcs_ctx* ctx, const uint8_t* h_grey, const ui
                                    int cc_majority, const uint8_t* lut, uint8_t* h_image, uint8_t* h_binary, uint8_t* h_labels,
                                    uint8_t* h_color, uint8_t* h_overlay, uint8_t* h_inverted, uint8_t* h_png, size_t png_stride,
                                    uint64_t* h_png_sizes, int32_t* h_stats = nullptr, int max_components = 0, int32_t* h_ncomp = nullptr,
-                                   const uint32_t* h_bits = nullptr, int level0 = 0, int level1 = 0, uint32_t* h_binary_bits = nullptr) {
+                                   const uint32_t* h_bits = nullptr, int level0 = 0, int level1 = 0, uint32_t* h_binary_bits = nullptr,
+                                   uint64_t* ticket = nullptr) {
     const int rc = predict_pages_host_body(ctx, h_grey, h_bin, n, H, W, Hs, Ws, cc_majority, lut, h_image, h_binary, h_labels, h_color,
                                            h_overlay, h_inverted, h_png, png_stride, h_png_sizes, h_stats, max_components, h_ncomp,
-                                           h_bits, level0, level1, h_binary_bits);
+                                           h_bits, level0, level1, h_binary_bits, ticket);
     if (rc != PCS_OK && ctx) {
         for (cudaStream_t s : {ctx->copy_streams[0], ctx->copy_streams[1]})
             if (s) cudaStreamSynchronize(s);
@@ -1394,6 +1431,29 @@ int pcs_predict_pages_compact(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t
     if (ctx && !h_labels) return set_err(ctx, PCS_ERR_ARG, "predict_pages_compact: null output");
     return predict_pages_host_impl(ctx, h_grey, h_bin, n, H, W, Hs, Ws, cc_majority, nullptr, nullptr, nullptr, h_labels, nullptr, nullptr, nullptr,
                                    nullptr, 0, nullptr, nullptr, 0, nullptr, nullptr, 0, 0, h_binary_bits);
+}
+
+int pcs_predict_pages_compact_submit(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h_bin, int n, int H, int W, int Hs, int Ws,
+                                     int cc_majority, uint8_t* h_labels, uint32_t* h_binary_bits, uint64_t* ticket) {
+    if (ctx && (!h_labels || !ticket)) return set_err(ctx, PCS_ERR_ARG, "predict_pages_compact_submit: null output");
+    return predict_pages_host_impl(ctx, h_grey, h_bin, n, H, W, Hs, Ws, cc_majority, nullptr, nullptr, nullptr, h_labels, nullptr, nullptr, nullptr,
+                                   nullptr, 0, nullptr, nullptr, 0, nullptr, nullptr, 0, 0, h_binary_bits, ticket);
+}
+
+int pcs_predict_pages_segments_compact_submit(pcs_ctx* ctx, const uint8_t* h_grey, const uint8_t* h_bin, int n, int H, int W, int Hs, int Ws,
+                                              int cc_majority, uint8_t* h_labels, uint32_t* h_binary_bits, int32_t* h_stats,
+                                              int max_components, int32_t* h_ncomp, uint64_t* ticket) {
+    if (ctx && (!h_stats || !h_labels || !ticket)) return set_err(ctx, PCS_ERR_ARG, "predict_pages_segments_compact_submit: null output");
+    return predict_pages_host_impl(ctx, h_grey, h_bin, n, H, W, Hs, Ws, cc_majority, nullptr, nullptr, nullptr, h_labels, nullptr, nullptr,
+                                   nullptr, nullptr, 0, nullptr, h_stats, max_components, h_ncomp, nullptr, 0, 0, h_binary_bits, ticket);
+}
+
+int pcs_wait_pages(pcs_ctx* ctx, uint64_t ticket) {
+    if (!ctx) return PCS_ERR_ARG;
+    if (ticket >= ctx->call_seq) return set_err(ctx, PCS_ERR_ARG, "wait_pages: ticket %llu was never issued", (unsigned long long)ticket);
+    // a slot re-recorded by a later submit lies behind this one on the (in-order) download stream: waiting on it is enough
+    PCS_CUDA(ctx, cudaEventSynchronize(ctx->ev_call[ticket % pcs_ctx::kCallRing]));
+    return PCS_OK;
 }
 
 int pcs_predict_pages_packed(pcs_ctx* ctx, const uint32_t* h_bits, int level0, int level1, int n, int H, int W, int Hs, int Ws, int cc_majority,

@@ -119,6 +119,15 @@ struct pcs_ctx {
     cudaStream_t aux_stream = nullptr;                     // side stream of the preprocess: the (normally empty) general-path launches
     cudaEvent_t ev_aux_fork = nullptr, ev_aux_join = nullptr;  // run beside the two-level resampler instead of after it
     uint64_t* h_png_sizes = nullptr;                       // pinned [kHostBufs][3][64]: file lengths of the chunk in flight (PNG mode)
+    // streaming form of the host-buffer calls (pcs_predict_pages_*_submit / pcs_wait_pages): a submitted call returns once
+    // its work is queued; the next submit with the same staging layout CHAINS onto it (the staging buffers keep rotating,
+    // ordered by the per-buffer events only), so its upload runs under the kernels of the call before
+    static constexpr int kCallRing = 8;
+    cudaEvent_t ev_call[kCallRing] = {};                   // "results of submit t are in the caller's buffers" (slot t % kCallRing)
+    uint64_t call_seq = 0;                                 // submits so far = the next ticket
+    uint64_t host_seq = 0;                                 // chunks queued by the chain so far (staging buffer = seq % nbuf)
+    bool host_chain_ok = false;                            // the last host call was a submit that queued completely
+    std::vector<size_t> host_layout;                       // staging layout of that call
 
     void* writer = nullptr;                 // pcs::OutputWriter of pcs_output_pages (output.cu), created on first use
 

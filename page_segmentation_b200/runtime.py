@@ -287,6 +287,25 @@ class PageBatchEngine:
         self.ctx.predict_pages_compact(h_pages, h_pages, n, H, W, Hs, Ws, cc_majority, out["labels"], out.get("binary_bits"))
         return out
 
+    def submit_host_compact(self, h_pages: np.ndarray, scale: float, out: dict, cc_majority: bool = False, max_components: int = 0) -> int:
+        """Streaming form of run_host_compact (and, with `max_components` and out['stats'], of run_host_segments_compact):
+        queues the call and returns its ticket; `wait(ticket)` returns when `out` holds the results.  A submit that follows
+        a submit of the same shapes is chained onto it -- its upload runs under the kernels of the call before -- so a
+        caller that feeds batch after batch (Predictor.predict is a generator, predictor.py:27-30) pays the fill and the
+        drain of the pipeline once, not once per batch.  Keep `h_pages` and `out` untouched until the wait; rotate over
+        two or more sets of buffers to keep a batch in flight while the one before is consumed."""
+        n, H, W = h_pages.shape
+        Hs, Ws = scaled_shape(H, W, scale)
+        self._ensure_model()
+        self.ctx.use_torch_stream()
+        if max_components:
+            return self.ctx.predict_pages_segments_compact_submit(h_pages, h_pages, n, H, W, Hs, Ws, cc_majority, out["labels"],
+                                                                  out.get("binary_bits"), out["stats"], max_components, out.get("ncomp"))
+        return self.ctx.predict_pages_compact_submit(h_pages, h_pages, n, H, W, Hs, Ws, cc_majority, out["labels"], out.get("binary_bits"))
+
+    def wait(self, ticket: int):
+        self.ctx.wait_pages(ticket)
+
     def run_host_packed(self, h_bits: np.ndarray, level0: int, level1: int, H: int, W: int, scale: float, out: dict,
                         cc_majority: bool = False):
         """pcs_predict_pages_packed: BIT-PACKED pages in (pack_pages), compact results out (see run_host_compact)."""
