@@ -1148,11 +1148,18 @@ static int predict_pages_host_body(pcs_ctx* ctx, const uint8_t* h_grey, const ui
         for (int v : fixed) chunk = std::max(chunk, v);
     } else if (upload_bound && !getenv("PCSEG_HOST_SCHED") && !getenv("PCSEG_HOST_CHUNK")) {
         fixed = {std::min(4, n), std::min(10, n)};
-        if (submit && was_chain) fixed = {std::min(10, n)};       // a chained call has no fill to keep short
+        if (submit) {
+            // streaming form: a chained call has no fill to keep short and its kernels hide under the upload at 16 pages per
+            // launch (10: 5 690, 12: 5 870, 16: 6 020, 20: 5 980, 32: 5 950 pages/s, tools/sweep_stream.sh); the first call of a
+            // chain ramps up to that size.  Staging is sized for 16 either way, so that the two layouts agree
+            fixed = was_chain ? std::vector<int>{std::min(16, n)} : std::vector<int>{std::min(4, n), std::min(12, n), std::min(16, n)};
+            chunk = std::max(chunk, std::min(16, n));
+        }
     } else if (h_stats && !h_bits && !want_masks && !getenv("PCSEG_HOST_SCHED") && !getenv("PCSEG_HOST_CHUNK")) {
         // segment call with compact results: kernel-bound (190 us per page against 158 us of upload), so a short fill and then
         // launches large enough for the labelling kernels: 6, 12, 16, 16 ... (4 180 -> 4 310 pages/s; tools/sweep_chunks.py segments)
         fixed = {std::min(6, n), std::min(12, n), std::min(16, n)};
+        if (submit && was_chain) fixed = {std::min(16, n)};
         chunk = std::max(chunk, std::min(16, n));
     }
     {

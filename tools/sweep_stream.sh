@@ -1,0 +1,5 @@
+for cfg in "10,3" "12,3" "16,3" "16,4" "20,4" "8,4" "32,3"; do
+  c=${cfg%,*}; nb=${cfg#*,}
+  echo "chunks=$c nbuf=$nb"
+  PCSEG_HOST_SCHED=4,$c,$c,$nb PCSEG_HOST_CHUNKS=$c timeout 100 python tools/stream_bench.py 10 2>/dev/null | grep streaming
+done
