@@ -260,7 +260,7 @@ def _pinned_like(torch, d):
     return out
 
 
-def _timed_stream(env, eng, h_pages, outs, ncalls, **kw):
+def _timed_stream(env, eng, h_pages, outs, ncalls, submit=None, **kw):
     """ms per call of `ncalls` STREAMED host-buffer calls (PageBatchEngine.submit_host_compact / wait): the results of call
     k - 2 are waited for (they are in host memory then) before call k is submitted into the same host buffers; all calls are
     waited for before the closing event, so every call's upload, kernels and download lie inside the timed region."""
@@ -271,7 +271,8 @@ def _timed_stream(env, eng, h_pages, outs, ncalls, **kw):
         for i in range(k):
             if i >= len(outs):
                 eng.wait(t[i - len(outs)])
-            t.append(eng.submit_host_compact(h_pages, SCALE, outs[i % len(outs)], **kw))
+            o = outs[i % len(outs)]
+            t.append(submit(o) if submit else eng.submit_host_compact(h_pages, SCALE, o, **kw))
         for x in t[-len(outs):]:
             eng.wait(x)
 
@@ -692,6 +693,10 @@ def main():
                                      h_bits.nbytes, cbytes,
                                      "pcs_predict_pages_packed: BIT-PACKED binarised pages in (1 bit per pixel, what a 1-bit scan file "
                                      "decodes to); class map + bit-packed binary out")
+        ms_p = _timed_stream(env0, eng, None, [c_out, _pinned_like(torch, c_out)], args.steps,
+                             submit=lambda o: eng.submit_host_packed(h_bits, l0, l1, synth.A4_H, synth.A4_W, SCALE, o, cc_majority=args.cc_majority))
+        e2e_modes["packed_streaming"] = {"value": world * n / (ms_p / 1e3), "unit": "pages/s", "h2d_bytes_per_step": int(h_bits.nbytes),
+                                         "d2h_bytes_per_step": int(cbytes), "what": "pcs_predict_pages_packed_submit + pcs_wait_pages: the packed call streamed two deep"}
 
     # ---------------- optional: the same call with the masks leaving the device as PNG files ----------------
     png_files = None

@@ -231,7 +231,7 @@ PCS_API int pcs_predict_pages_compact(pcs_ctx* ctx, const uint8_t* h_grey, const
 PCS_API int pcs_predict_pages_packed(pcs_ctx* ctx, const uint32_t* h_bits, int level0, int level1, int n, int H, int W,
                              int Hs, int Ws, int cc_majority, uint8_t* h_labels, uint32_t* h_binary_bits);
 
-/* STREAMING form of the two compact calls: Predictor.predict is a generator (lib/predictor.py:27-30), a caller with a
+/* STREAMING form of the compact calls: Predictor.predict is a generator (lib/predictor.py:27-30), a caller with a
  * long page list feeds it batch after batch.  `_submit` queues the whole call and returns; *ticket names it.  A submit
  * that follows a submit of the same shapes is chained onto it: its upload runs under the kernels of the call before, so
  * the fill and the drain of the three-stage pipeline are paid once per run of submits instead of once per call.
@@ -244,6 +244,8 @@ PCS_API int pcs_predict_pages_segments_compact_submit(pcs_ctx* ctx, const uint8_
                                int n, int H, int W, int Hs, int Ws, int cc_majority,
                                uint8_t* h_labels, uint32_t* h_binary_bits,
                                int32_t* h_stats, int max_components, int32_t* h_ncomp, uint64_t* ticket);
+PCS_API int pcs_predict_pages_packed_submit(pcs_ctx* ctx, const uint32_t* h_bits, int level0, int level1, int n, int H, int W,
+                             int Hs, int Ws, int cc_majority, uint8_t* h_labels, uint32_t* h_binary_bits, uint64_t* ticket);
 PCS_API int pcs_wait_pages(pcs_ctx* ctx, uint64_t ticket);
 
 /* The same pipeline followed by segment extraction (pcs_class_components on the final class map): BASELINE configs[3],

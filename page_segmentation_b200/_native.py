@@ -23,7 +23,7 @@ EXPORTS = [
     "pcs_synchronize", "pcs_launch_count", "pcs_model_load", "pcs_set_engine", "pcs_preprocess",
     "pcs_preprocess_max_width", "pcs_preprocess_bits", "pcs_pack_bits", "pcs_unpack_bits", "pcs_predict_pages_compact", "pcs_predict_pages_packed",
     "pcs_forward", "pcs_masks", "pcs_resize_nearest", "pcs_ccl", "pcs_cc_majority",
-    "pcs_bounding_boxes", "pcs_class_components", "pcs_char_height", "pcs_png_bytes", "pcs_png_encode", "pcs_output_pages", "pcs_output_flush", "pcs_segment_masks", "pcs_dilate3x3", "pcs_integral_image", "pcs_text_regions", "pcs_predict_pages_host", "pcs_predict_pages_files", "pcs_predict_pages_segments", "pcs_predict_pages_segments_compact", "pcs_predict_pages_compact_submit", "pcs_predict_pages_segments_compact_submit", "pcs_wait_pages", "pcs_eval_counts",
+    "pcs_bounding_boxes", "pcs_class_components", "pcs_char_height", "pcs_png_bytes", "pcs_png_encode", "pcs_output_pages", "pcs_output_flush", "pcs_segment_masks", "pcs_dilate3x3", "pcs_integral_image", "pcs_text_regions", "pcs_predict_pages_host", "pcs_predict_pages_files", "pcs_predict_pages_segments", "pcs_predict_pages_segments_compact", "pcs_predict_pages_compact_submit", "pcs_predict_pages_segments_compact_submit", "pcs_predict_pages_packed_submit", "pcs_wait_pages", "pcs_eval_counts",
     "pcs_train_input", "pcs_train_corr2d", "pcs_train_wgrad", "pcs_train_bias_grad", "pcs_train_relu_bwd", "pcs_train_maxpool_fwd",
     "pcs_train_maxpool_bwd", "pcs_train_deconv2_fwd", "pcs_train_deconv2_bwd_data", "pcs_train_deconv2_wgrad", "pcs_train_softmax_ce",
     "pcs_train_adam", "pcs_train_tc_create", "pcs_train_tc_step", "pcs_train_tc_destroy", "pcs_train_tc_wgrad", "pcs_set_saturation_check", "pcs_saturation_count", "pcs_debug_activation", "pcs_set_keep_activations", "pcs_set_timing", "pcs_set_pdl",
@@ -95,6 +95,7 @@ def load() -> C.CDLL:
     lib.pcs_predict_pages_segments_compact.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp]
     lib.pcs_predict_pages_compact_submit.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp]
     lib.pcs_predict_pages_segments_compact_submit.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp]
+    lib.pcs_predict_pages_packed_submit.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp]
     lib.pcs_wait_pages.argtypes = [vp, C.c_uint64]
     lib.pcs_eval_counts.argtypes = [vp, vp, vp, vp, C.c_size_t, i32, vp]
     f32 = C.c_float
@@ -406,6 +407,14 @@ class Context:
         self._check(self.lib.pcs_predict_pages_segments_compact_submit(
             self.h, _ptr(h_grey), _ptr(h_bin), n, H, W, Hs, Ws, 1 if cc_majority else 0, _ptr(h_labels), _ptr(h_binary_bits),
             _ptr(h_stats), int(max_components), _ptr(h_ncomp), C.byref(ticket)), "pcs_predict_pages_segments_compact_submit")
+        self._after_forward()
+        return int(ticket.value)
+
+    def predict_pages_packed_submit(self, h_bits, level0, level1, n, H, W, Hs, Ws, cc_majority, h_labels, h_binary_bits=None) -> int:
+        ticket = C.c_uint64(0)
+        self._check(self.lib.pcs_predict_pages_packed_submit(self.h, _ptr(h_bits), int(level0), int(level1), n, H, W, Hs, Ws,
+                                                             1 if cc_majority else 0, _ptr(h_labels), _ptr(h_binary_bits), C.byref(ticket)),
+                    "pcs_predict_pages_packed_submit")
         self._after_forward()
         return int(ticket.value)
 

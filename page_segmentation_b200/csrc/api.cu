@@ -1135,6 +1135,7 @@ static int predict_pages_host_body(pcs_ctx* ctx, const uint8_t* h_grey, const ui
     head = std::max(1, std::min(head, chunk));
     tail = std::max(1, std::min(tail, chunk));
     nbuf = std::max(2, std::min(nbuf, (int)pcs_ctx::kHostBufs));
+    const bool steady_only = submit && was_chain && !getenv("PCSEG_HOST_SCHED") && !getenv("PCSEG_HOST_CHUNK");   // a chained call: no fill, no drain
     std::vector<int> first, count;             // first page and page count of every chunk
     std::vector<int> fixed;                    // PCSEG_HOST_CHUNKS=a,b,c,...: an explicit schedule (the last size repeats)
     if (const char* e = getenv("PCSEG_HOST_CHUNKS")) {
@@ -1168,7 +1169,9 @@ static int predict_pages_host_body(pcs_ctx* ctx, const uint8_t* h_grey, const ui
         if (!fixed.empty()) {
             for (size_t i = 0; p < n; ++i) push(std::min(fixed[std::min(i, fixed.size() - 1)], n - p));
         } else if (n <= chunk) push(n);
-        else {
+        else if (steady_only) {
+            while (p < n) push(std::min(chunk, n - p));
+        } else {
             push(head);
             // grow geometrically to the steady size, keep `tail` pages (and a shrinking ramp) for the end
             int m = head;
@@ -1453,6 +1456,13 @@ int pcs_predict_pages_segments_compact_submit(pcs_ctx* ctx, const uint8_t* h_gre
     if (ctx && (!h_stats || !h_labels || !ticket)) return set_err(ctx, PCS_ERR_ARG, "predict_pages_segments_compact_submit: null output");
     return predict_pages_host_impl(ctx, h_grey, h_bin, n, H, W, Hs, Ws, cc_majority, nullptr, nullptr, nullptr, h_labels, nullptr, nullptr,
                                    nullptr, nullptr, 0, nullptr, h_stats, max_components, h_ncomp, nullptr, 0, 0, h_binary_bits, ticket);
+}
+
+int pcs_predict_pages_packed_submit(pcs_ctx* ctx, const uint32_t* h_bits, int level0, int level1, int n, int H, int W, int Hs, int Ws,
+                                    int cc_majority, uint8_t* h_labels, uint32_t* h_binary_bits, uint64_t* ticket) {
+    if (ctx && (!h_labels || !h_bits || !ticket)) return set_err(ctx, PCS_ERR_ARG, "predict_pages_packed_submit: null argument");
+    return predict_pages_host_impl(ctx, nullptr, nullptr, n, H, W, Hs, Ws, cc_majority, nullptr, nullptr, nullptr, h_labels, nullptr, nullptr, nullptr,
+                                   nullptr, 0, nullptr, nullptr, 0, nullptr, h_bits, level0, level1, h_binary_bits, ticket);
 }
 
 int pcs_wait_pages(pcs_ctx* ctx, uint64_t ticket) {

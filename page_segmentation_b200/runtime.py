@@ -303,6 +303,17 @@ class PageBatchEngine:
                                                                   out.get("binary_bits"), out["stats"], max_components, out.get("ncomp"))
         return self.ctx.predict_pages_compact_submit(h_pages, h_pages, n, H, W, Hs, Ws, cc_majority, out["labels"], out.get("binary_bits"))
 
+    def submit_host_packed(self, h_bits: np.ndarray, level0: int, level1: int, H: int, W: int, scale: float, out: dict,
+                           cc_majority: bool = False) -> int:
+        """Streaming form of run_host_packed (see submit_host_compact)."""
+        n = h_bits.shape[0]
+        Hs, Ws = scaled_shape(H, W, scale)
+        if h_bits.dtype != np.uint32 or h_bits.shape[1] != (H * W + 31) // 32:
+            raise ValueError("h_bits must be (n, ceil(H * W / 32)) uint32 (pack_pages)")
+        self._ensure_model()
+        self.ctx.use_torch_stream()
+        return self.ctx.predict_pages_packed_submit(h_bits, level0, level1, n, H, W, Hs, Ws, cc_majority, out["labels"], out.get("binary_bits"))
+
     def wait(self, ticket: int):
         self.ctx.wait_pages(ticket)
 

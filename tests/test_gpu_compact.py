@@ -185,8 +185,16 @@ def test_streaming_submits_match_blocking_calls_and_oracle(ctx, cc, monkeypatch)
     sb = {"labels": np.zeros((3, hs2, ws2), np.uint8)}
     eng.run_host_compact(small, 6 / 18, sb, cc_majority=cc)
     np.testing.assert_array_equal(so["labels"], sb["labels"])
+    # the packed form, two chained submits
+    pb = [pack_pages(batches[k]) for k in (0, 1)]
+    po = [{"labels": _pinned((n, Hs, Ws), np.uint8), "binary_bits": _pinned((n, bw), np.uint32)} for _ in range(2)]
+    tp = [eng.submit_host_packed(pb[k][0], pb[k][1], pb[k][2], H, W_, 6 / 18, po[k], cc_majority=cc) for k in (0, 1)]
+    for k in (1, 0):
+        eng.wait(tp[k])
+        np.testing.assert_array_equal(po[k]["labels"], blocking[k]["labels"])
+        np.testing.assert_array_equal(po[k]["binary_bits"], blocking[k]["binary_bits"])
     with pytest.raises(PcsError):
-        eng.wait(t2 + 1)                                # never issued
+        eng.wait(tp[1] + 1)                             # never issued
     eng.ctx.synchronize()
 
 
