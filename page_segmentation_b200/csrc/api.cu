@@ -1160,8 +1160,13 @@ static int predict_pages_host_body(pcs_ctx* ctx, const uint8_t* h_grey, const ui
         // segment call with compact results: kernel-bound (190 us per page against 158 us of upload), so a short fill and then
         // launches large enough for the labelling kernels: 6, 12, 16, 16 ... (4 180 -> 4 310 pages/s; tools/sweep_chunks.py segments)
         fixed = {std::min(6, n), std::min(12, n), std::min(16, n)};
-        if (submit && was_chain) fixed = {std::min(16, n)};
         chunk = std::max(chunk, std::min(16, n));
+        if (submit) {
+            // streaming form: chained calls are kernel-bound with nothing to fill or drain, so the largest launches win
+            // (16: 5 030, 24: 5 120, 32: 5 260, 64 with two buffers: 5 040 pages/s; tools/sweep_stream.sh segments)
+            fixed = was_chain ? std::vector<int>{std::min(32, n)} : std::vector<int>{std::min(6, n), std::min(12, n), std::min(16, n), std::min(32, n)};
+            chunk = std::max(chunk, std::min(32, n));
+        }
     }
     {
         int p = 0;
